@@ -1,0 +1,312 @@
+/*
+ * riichienv_b200.h — C ABI of the B200-native batched Riichi mahjong simulator.
+ *
+ * This is the drop-in boundary for the reference's hot path (SURVEY.md §8 b).
+ * The reference (smly/RiichiEnv) has no C ABI of its own: its boundary is the
+ * PyO3 class `riichienv._riichienv.RiichiEnv` over `GameStateVariant`
+ * (riichienv-python/src/env.rs:74-118).  Every entry point below names the
+ * reference interface it replaces (file:line relative to /root/reference).
+ * INTEGRATION.md shows the Rust `extern "C"` block + PyO3 shim a maintainer
+ * would add on the reference side.
+ *
+ * Conventions: plain pointers and sizes, no torch / CUDA types.  Pointers named
+ * `d_*` are DEVICE pointers (caller-allocated, e.g. torch tensors' data_ptr);
+ * everything else is host memory.  All functions return 0 on success or a
+ * negative RV_ERR_* code; rv_last_error() gives a message.  A handle is bound
+ * to one CUDA device and one stream and is not thread-safe (one host thread +
+ * one stream per GPU, as in the north star).
+ */
+#ifndef RIICHIENV_B200_H
+#define RIICHIENV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------- */
+#define RV_OK 0
+#define RV_ERR_INVALID -1   /* bad argument (maps to PyValueError, env.rs:815-823) */
+#define RV_ERR_CUDA -2      /* CUDA runtime failure / no device: the product has NO CPU fallback */
+#define RV_ERR_UNSUPPORTED -3
+
+/* ---- enums (values identical to the reference) ------------------------- */
+/* action.rs:55-68 */
+enum rv_action_type {
+  RV_DISCARD = 0, RV_CHI = 1, RV_PON = 2, RV_DAIMINKAN = 3, RV_RON = 4, RV_RIICHI = 5,
+  RV_TSUMO = 6, RV_PASS = 7, RV_ANKAN = 8, RV_KAKAN = 9, RV_KYUSHU_KYUHAI = 10, RV_KITA = 11,
+  RV_NO_ACTION = 255 /* seat supplies no action this step (missing dict key in env.step) */
+};
+/* types.rs:57-63 */
+enum rv_meld_type { RV_MELD_CHI = 0, RV_MELD_PON = 1, RV_MELD_DAIMINKAN = 2, RV_MELD_ANKAN = 3, RV_MELD_KAKAN = 4 };
+/* action.rs:30-33 */
+enum rv_phase { RV_WAIT_ACT = 0, RV_WAIT_RESPONSE = 1 };
+/* env.rs:93-101 */
+enum rv_game_mode {
+  RV_4P_RED_SINGLE = 0, RV_4P_RED_EAST = 1, RV_4P_RED_HALF = 2,
+  RV_3P_RED_SINGLE = 3, RV_3P_RED_EAST = 4, RV_3P_RED_HALF = 5
+};
+/* rule.rs:10-20 — one bit per GameRule field, in declaration order */
+#define RV_RULE_RON_ON_ANKAN_KOKUSHI 0x01u
+#define RV_RULE_KOKUSHI13_DOUBLE 0x02u
+#define RV_RULE_SUUANKOU_TANKI_DOUBLE 0x04u
+#define RV_RULE_JUNSEI_CHUUREN_DOUBLE 0x08u
+#define RV_RULE_DAISUUSHII_DOUBLE 0x10u
+#define RV_RULE_PAO_LIABILITY_ONLY 0x20u
+#define RV_RULE_SANCHAHO_IS_DRAW 0x40u
+#define RV_RULE_KUIKAE_FORBIDDEN 0x80u
+#define RV_RULE_DEFAULT_TENHOU (RV_RULE_SANCHAHO_IS_DRAW | RV_RULE_KUIKAE_FORBIDDEN)           /* rule.rs:29-42 */
+#define RV_RULE_DEFAULT_MJSOUL (0x3Fu | RV_RULE_KUIKAE_FORBIDDEN)                               /* rule.rs:44-57 */
+
+#define RV_NONE 0xFFu /* Option::None for u8 fields */
+#define RV_NP 4
+#define RV_HAND_CAP 14
+#define RV_RIVER_CAP 32
+#define RV_MAX_CLAIMS 48
+#define RV_MAX_LEGAL 64
+
+/* per-seat flag bits (state/player.rs:14-34) */
+#define RV_F_RIICHI_DECLARED 0x01u
+#define RV_F_RIICHI_STAGE 0x02u
+#define RV_F_DOUBLE_RIICHI 0x04u
+#define RV_F_MISSED_AGARI_RIICHI 0x08u
+#define RV_F_MISSED_AGARI_DOUJUN 0x10u
+#define RV_F_NAGASHI_ELIGIBLE 0x20u
+#define RV_F_IPPATSU_CYCLE 0x40u
+
+/* ---- Action (action.rs:82-105) ------------------------------------------ */
+typedef struct rv_action {
+  uint8_t type;       /* rv_action_type */
+  uint8_t tile;       /* tid 0..135 or RV_NONE */
+  uint8_t n_consume;  /* 0..4 */
+  uint8_t consume[4]; /* sorted ascending (Action::new sorts, action.rs:97-98) */
+  uint8_t actor;      /* seat or RV_NONE */
+} rv_action;
+
+/* ---- per-game state: the HBM record AND the snapshot format --------------
+ * Replaces GameState / PlayerState / WallState (state/mod.rs:31-91,
+ * state/player.rs:6-39, state/wall.rs:9-19).  One record per game, array of
+ * records in HBM.  `wall` holds the reference's `wall.tiles` Vec as a fixed
+ * array: the Vec's front (rinshan side) is wall[rinshan_draw_count], its back
+ * (live-draw side) is wall[wall_top-1].                                      */
+typedef struct rv_game_state {
+  uint8_t wall[136];
+  uint8_t wall_len;               /* 136 (4P) or 108 (3P) */
+  uint8_t wall_top;               /* tiles not yet popped from the back (absolute index + 1) */
+  uint8_t rinshan_draw_count;     /* wall.rs:12 */
+  uint8_t pending_kan_dora_count; /* wall.rs:13 */
+  uint8_t drawable_count;         /* wall.rs:14 */
+  uint8_t n_dora;
+  uint8_t dora_ind[5];            /* wall.dora_indicators (tids) */
+  uint8_t phase;                  /* rv_phase */
+
+  uint8_t hand[RV_NP][RV_HAND_CAP]; /* ordered as the reference's Vec (legal_actions.rs:102-110 lists discards in this order) */
+  uint8_t hand_len[RV_NP];
+  uint8_t meld_tiles[RV_NP][4][4];  /* tids, order as stored by the reference (sorted); RV_NONE pad */
+  uint8_t meld_type[RV_NP][4];      /* rv_meld_type */
+  uint8_t meld_from[RV_NP][4];      /* from_who, RV_NONE == -1 */
+  uint8_t meld_called[RV_NP][4];    /* called_tile or RV_NONE */
+  uint8_t n_melds[RV_NP];
+  uint8_t river[RV_NP][RV_RIVER_CAP]; /* discards */
+  uint8_t n_river[RV_NP];
+  uint32_t river_tedashi[RV_NP];    /* bit i = discard_from_hand[i] */
+  uint32_t river_riichi[RV_NP];     /* bit i = discard_is_riichi[i] */
+  uint8_t riichi_decl_idx[RV_NP];   /* riichi_declaration_index or RV_NONE */
+  uint8_t flags[RV_NP];             /* RV_F_* */
+  uint8_t pao[RV_NP][2];            /* [seat][0]: liable seat for yaku 37, [1]: for yaku 50; RV_NONE */
+  uint8_t forbidden[RV_NP][2];      /* forbidden_discards (tids), RV_NONE pad */
+  uint8_t riichi_sutehai[RV_NP];    /* state/mod.rs:89 */
+  uint8_t last_tedashi[RV_NP];      /* state/mod.rs:90 */
+  int32_t score[RV_NP];
+  int32_t score_delta[RV_NP];
+
+  uint8_t current_player, oya, honba, kyoku_idx;
+  uint8_t round_wind, is_done, needs_tsumo, is_first_turn;
+  uint8_t is_rinshan_flag, riichi_pending_acceptance, drawn_tile, last_discard_pid;
+  uint8_t last_discard_tile, pending_kan_pid, pending_kan_type, pending_kan_tile;
+  uint8_t active_mask;            /* active_players as a seat bitmask (always ascending seat order in the reference) */
+  uint8_t last_error;             /* RV_NONE or offending seat (state/mod.rs:395-399) */
+  uint8_t game_mode, rule_bits;
+  uint8_t overflow;               /* set if a fixed capacity (river/claims/log) was exceeded */
+  uint8_t n_kita[RV_NP];          /* 3P: kita count per seat */
+  uint8_t _pad0[3];
+  uint32_t riichi_sticks;
+  uint32_t turn_count;
+
+  uint64_t seed;                  /* wall.seed */
+  uint64_t hand_index;            /* wall.hand_index */
+
+  /* current_claims (state/mod.rs:47): packed type | tile<<8 | c0<<16 | c1<<24 */
+  uint8_t n_claims[RV_NP];
+  uint32_t claims[RV_NP][RV_MAX_CLAIMS];
+
+  /* counters (not in the reference): */
+  uint32_t step_count;            /* env steps taken (RiichiEnv.step calls that were not no-ops on a done game) */
+  uint32_t kyoku_count;           /* rounds dealt since reset */
+  uint32_t ev_count;              /* events pushed since reset */
+  uint32_t _pad1;
+  uint64_t ev_hash;               /* FNV-1a-64 over the 32-bit words of the binary event stream */
+} rv_game_state;
+
+/* ---- binary event stream (replaces _push_mjai_event, state/mod.rs:2094-2148)
+ * A sequence of 32-bit words.  word0 = type | nwords<<8 | a<<16 | b<<24.
+ * Host code (rv_event_to_json) renders MJAI JSON with alphabetical keys.     */
+enum rv_event_type {
+  RV_EV_START_GAME = 1,   /* 1 word */
+  RV_EV_START_KYOKU = 2,  /* a=bakaze(round_wind%4) b=oya; w1=honba|dora_marker<<8|kyotaku<<16; w2..5=scores; w6..18=tehais 4x13 bytes */
+  RV_EV_TSUMO = 3,        /* a=actor b=tile */
+  RV_EV_DAHAI = 4,        /* a=actor b=tile; tsumogiri=false */
+  RV_EV_DAHAI_TSUMOGIRI = 5,
+  RV_EV_REACH = 6,        /* a=actor */
+  RV_EV_REACH_ACCEPTED = 7,
+  RV_EV_PON = 8,          /* a=actor b=tile; w1=target|c0<<8|c1<<16|0xFF<<24 */
+  RV_EV_CHI = 9,
+  RV_EV_DAIMINKAN = 10,   /* w1=target|c0<<8|c1<<16|c2<<24 */
+  RV_EV_ANKAN = 11,       /* a=actor b=pai; w1=c0..c3 */
+  RV_EV_KAKAN = 12,       /* a=actor b=pai; w1=c0|c1<<8|c2<<16|0xFF<<24 */
+  RV_EV_DORA = 13,        /* b=dora_marker */
+  RV_EV_HORA = 14,        /* a=actor b=target; w1=tsumo|n_ura<<8|han<<16|fu<<24; w2=ura0..3; w3=ura4|yakuman<<8; w4..7=deltas; w8,w9=yaku bitmask lo,hi */
+  RV_EV_RYUKYOKU = 15,    /* a=reason code; w1..4=deltas */
+  RV_EV_END_KYOKU = 16,
+  RV_EV_END_GAME = 17,
+  RV_EV_KITA = 18         /* a=actor b=tile */
+};
+enum rv_ryukyoku_reason {
+  RV_RK_EXHAUSTIVE = 0, RV_RK_NAGASHI = 1, RV_RK_KYUSHU = 2, RV_RK_SUFUURENTA = 3,
+  RV_RK_SUUKANSANSEN = 4, RV_RK_SUUCHA_RIICHI = 5, RV_RK_SANCHAHO = 6,
+  RV_RK_ILLEGAL_BASE = 8 /* + offending seat: "Error: Illegal Action by Player N" */
+};
+
+/* ---- hand evaluation (config 2) ------------------------------------------
+ * Replaces HandEvaluator::{new,calc,get_waits_u8,is_tenpai}
+ * (hand_evaluator.rs:24-213), agari::is_agari (agari.rs:63),
+ * yaku::calculate_yaku (yaku.rs:232), score::calculate_score (score.rs:13),
+ * shanten::calculate_shanten (shanten.rs:250).                              */
+#define RV_C_TSUMO 0x001u
+#define RV_C_RIICHI 0x002u
+#define RV_C_DOUBLE_RIICHI 0x004u
+#define RV_C_IPPATSU 0x008u
+#define RV_C_HAITEI 0x010u
+#define RV_C_HOUTEI 0x020u
+#define RV_C_RINSHAN 0x040u
+#define RV_C_CHANKAN 0x080u
+#define RV_C_TSUMO_FIRST_TURN 0x100u
+
+typedef struct rv_hand_query {  /* 56 bytes */
+  uint8_t tiles[14];       /* concealed tids, RV_NONE pad */
+  uint8_t n_tiles;
+  uint8_t n_melds;
+  uint8_t meld_type[4];    /* rv_meld_type */
+  uint8_t meld_tiles[4][4];/* tids (RV_NONE pad for 3-tile melds) */
+  uint8_t win_tile;        /* tid */
+  uint8_t n_dora, n_ura;
+  uint8_t dora_ind[5];     /* tids */
+  uint8_t ura_ind[5];
+  uint8_t player_wind, round_wind; /* 0..3 */
+  uint8_t honba;
+  uint16_t cond;           /* RV_C_* */
+  uint8_t _pad[2];
+} rv_hand_query;
+
+typedef struct rv_hand_result { /* 40 bytes */
+  uint64_t yaku_mask;      /* bit id set for every yaku id in WinResult.yaku */
+  uint64_t wait_mask;      /* get_waits_u8 of the 3n+1 hand (tiles without win tile when 3n+2), bit t34 */
+  uint32_t ron_agari, tsumo_agari_oya, tsumo_agari_ko;
+  uint8_t is_win, yakuman, has_win_shape, han;
+  uint8_t fu;
+  int8_t shanten;          /* calculate_shanten(tiles [+ win tile when 3n+1]) */
+  int8_t shanten13;        /* calculate_shanten of the 3n+1 hand */
+  uint8_t n_yaku;
+  uint8_t _pad[4];
+} rv_hand_result;
+
+typedef struct rv_ctx rv_ctx; /* opaque: device tables + stream */
+
+const char* rv_last_error(void);
+int rv_version(void);
+
+/* Create / destroy a context on CUDA device `device` (uploads lookup tables). */
+int rv_ctx_create(int device, rv_ctx** out);
+int rv_ctx_destroy(rv_ctx* ctx);
+int rv_ctx_sync(rv_ctx* ctx);
+
+/* Batched hand evaluation with HOST buffers (copies inside the call). */
+int rv_hand_eval_batch(rv_ctx* ctx, const rv_hand_query* q, rv_hand_result* out, int64_t n);
+/* Same with DEVICE buffers; asynchronous on the context's stream. */
+int rv_hand_eval_batch_device(rv_ctx* ctx, const rv_hand_query* d_q, rv_hand_result* d_out, int64_t n);
+/* score.rs:13-52 on host (no device work): out[0]=pay_ron out[1]=pay_tsumo_oya out[2]=pay_tsumo_ko out[3]=total */
+int rv_calculate_score(int han, int fu, int is_oya, int is_tsumo, uint32_t honba, int num_players, uint32_t out[4]);
+
+/* ---- the vectorised environment -------------------------------------------
+ * N independent games, SoA-of-records in HBM.  Replaces a Python list of
+ * RiichiEnv objects (riichienv-ml/.../_ppo_worker.py:39).                    */
+typedef struct rv_vec rv_vec; /* opaque */
+
+/* RiichiEnv::new (env.rs:82-118) for n games: game g gets seed seeds[g]
+ * (seeds==NULL -> seed_base+g).  The constructor's shuffle #0 is consumed as
+ * in the reference (state/mod.rs:165).  log_cap_words: per-game capacity of
+ * the binary event log in 32-bit words, 0 == skip_mjai_logging=True (only the
+ * rolling hash is kept).                                                     */
+int rv_vec_create(rv_ctx* ctx, int64_t n, int game_mode, uint32_t rule_bits, const uint64_t* seeds,
+                  uint64_t seed_base, uint32_t log_cap_words, rv_vec** out);
+int rv_vec_destroy(rv_vec* v);
+int64_t rv_vec_size(const rv_vec* v);
+
+/* RiichiEnv::reset (env.rs:799-851) for every game.  Optional per-game arrays
+ * (NULL = default): oya[n], round_wind[n], honba[n], kyotaku[n], scores[n*NP],
+ * walls[n*wall_len] (reset(wall=) -> load_wall, wall.rs:69-80).              */
+int rv_vec_reset(rv_vec* v, const uint8_t* oya, const uint8_t* round_wind, const uint8_t* honba,
+                 const uint32_t* kyotaku, const int32_t* scores, const uint8_t* walls);
+
+/* Legal actions of every seat that owes an action (Observation.legal_actions,
+ * observation/mod.rs:113-115; order of state/legal_actions.rs:11-508).
+ * out_actions: [n][NP][RV_MAX_LEGAL], out_counts: [n][NP] (0 for idle seats). */
+int rv_vec_legal_actions(rv_vec* v, rv_action* out_actions, uint8_t* out_counts);
+
+/* RiichiEnv::step (env.rs:857-872 -> state/mod.rs:330-1315).  actions:
+ * [n][NP]; type RV_NO_ACTION == key absent.  Illegal actions trigger the
+ * reference's penalty ryukyoku and set last_error.                           */
+int rv_vec_step(rv_vec* v, const rv_action* actions);
+
+/* Persistent on-device rollout with the keyed random agent (SURVEY.md §8 d):
+ * every game takes up to max_steps env steps (stopping at done):
+ *   idx = mix64(agent_seed ^ game_id*0x9E3779B97F4A7C15 ^ (step_count<<8) ^ seat) % n_legal.
+ * Returns the number of env steps executed by all games in *steps_done.      */
+int rv_vec_step_random(rv_vec* v, uint64_t agent_seed, uint32_t max_steps, uint64_t* steps_done);
+/* Asynchronous variant on the context stream: accumulates into a device counter; read with rv_vec_steps_total. */
+int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps);
+int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done);
+
+/* RiichiEnv::{done,scores,ranks} (env.rs:353,401,673-689).  Host outputs:
+ * done[n], scores[n*NP], ranks[n*NP] (1-based), any may be NULL.            */
+int rv_vec_results(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks);
+/* per-game counters: step_count[n], kyoku_count[n], ev_count[n], ev_hash[n] (any may be NULL) */
+int rv_vec_counters(rv_vec* v, uint32_t* step_count, uint32_t* kyoku_count, uint32_t* ev_count, uint64_t* ev_hash);
+
+/* Snapshot get/set (RiichiEnv getters/setters, env.rs:134-635; clone() 358-372). */
+int rv_vec_get_state(rv_vec* v, int64_t game, rv_game_state* out);
+int rv_vec_set_state(rv_vec* v, int64_t game, const rv_game_state* in);
+/* Device pointer to the state records (for zero-copy consumers). */
+int rv_vec_state_device_ptr(rv_vec* v, void** d_states);
+
+/* Binary event log of one game (mjai_log, env.rs:729-739).  Copies up to cap
+ * words; *n_words receives the full length.                                 */
+int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, uint32_t* n_words);
+/* Render one binary event as MJAI JSON (alphabetical keys, as serde_json
+ * without preserve_order).  viewer = seat for the per-player masked log
+ * (state/mod.rs:2109-2143) or -1 for the global log.  Returns words consumed. */
+int rv_event_to_json(const uint32_t* words, uint32_t n_words, int viewer, char* out, uint32_t out_cap);
+
+/* Seeded wall (state/wall.rs:36-67): host implementation for tests / tools. */
+int rv_wall_from_seed(uint64_t seed, uint64_t hand_index, int n_tiles /*136|108*/, uint8_t* out_tiles_reversed);
+
+/* Observation tensors (Observation::encode observation/python.rs:457-806,
+ * mask 98-111).  d_obs: [n][NP][74][34] f32, d_mask: [n][NP][82] u8 device
+ * buffers; rows of seats that owe no action are zero.                        */
+int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1557 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see hand.hpp header).
+//
+// CPU restatement of the reference's 4-player game state machine, following
+// (paths relative to /root/reference/riichienv-core/src):
+//   state/mod.rs:98-187     GameState::new / reset
+//   state/mod.rs:330-1315   step (validation, WaitAct, WaitResponse)
+//   state/mod.rs:1317-1413  _resolve_discard
+//   state/mod.rs:1415-1547  _resolve_kan
+//   state/mod.rs:1549-1593  _accept_riichi / _deal_next
+//   state/mod.rs:1595-1844  _initialize_next_round / _initialize_round
+//   state/mod.rs:1846-2081  _trigger_ryukyoku / check_abortive_draw / kan dora / ura / end game
+//   state/legal_actions.rs:11-508
+//   state/player.rs, state/wall.rs
+// Data structures deliberately mirror the reference (Vec per player, claim map) so
+// that quirks (hand order, stale current_claims, score_delta semantics) carry over.
+// Events are emitted in the binary format of include/riichienv_b200.h.
+#pragma once
+#include <cstring>
+#include <optional>
+
+#include "../include/riichienv_b200.h"
+#include "hand.hpp"
+#include "wall.hpp"
+
+namespace orc {
+
+constexpr int NP = 4;
+
+struct Action {
+  uint8_t type = RV_PASS;
+  int tile = -1;  // -1 == None
+  std::vector<uint8_t> consume;
+  int actor = -1;
+  Action() {}
+  // action.rs:91-105 (sorts consume_tiles)
+  Action(uint8_t ty, int t, std::vector<uint8_t> c, int a) : type(ty), tile(t), consume(std::move(c)), actor(a) {
+    std::sort(consume.begin(), consume.end());
+  }
+};
+
+// state/player.rs:6-39
+struct PlayerState {
+  std::vector<uint8_t> hand;
+  std::vector<Meld> melds;
+  std::vector<uint8_t> discards;
+  std::vector<bool> discard_from_hand, discard_is_riichi;
+  int riichi_declaration_index = -1;
+  int32_t score = 25000, score_delta = 0;
+  bool riichi_declared = false, riichi_stage = false, double_riichi_declared = false;
+  bool missed_agari_riichi = false, missed_agari_doujun = false, nagashi_eligible = true, ippatsu_cycle = false;
+  int pao37 = -1, pao50 = -1;  // pao: HashMap<u8,u8> only ever holds keys 37 and 50
+  std::vector<uint8_t> forbidden_discards;
+  // state/player.rs:66-86
+  void reset_round() {
+    hand.clear(); melds.clear(); discards.clear(); discard_from_hand.clear(); discard_is_riichi.clear();
+    riichi_declaration_index = -1;
+    riichi_declared = riichi_stage = double_riichi_declared = false;
+    missed_agari_riichi = missed_agari_doujun = false;
+    nagashi_eligible = true;
+    ippatsu_cycle = false;
+    forbidden_discards.clear();
+    score_delta = 0;
+    pao37 = pao50 = -1;
+  }
+};
+
+inline bool is_terminal_tile(uint8_t t) {  // types.rs:364-369
+  int tt = t / 4;
+  return tt / 9 == 3 || tt % 9 == 0 || tt % 9 == 8;
+}
+
+struct GameState {
+  // wall (state/wall.rs:9-19)
+  std::vector<uint8_t> wall_tiles;
+  std::vector<uint8_t> dora_indicators;
+  uint8_t rinshan_draw_count = 0, pending_kan_dora_count = 0, drawable_count = 0;
+  uint64_t wall_seed = 0, hand_index = 0;
+  std::vector<uint8_t> wall_abs;  // absolute (never shrinking) copy for snapshots
+
+  PlayerState players[NP];
+  uint8_t current_player = 0;
+  uint32_t turn_count = 0;
+  bool is_done = false, needs_tsumo = false;
+  uint32_t riichi_sticks = 0;
+  uint8_t phase = RV_WAIT_ACT;
+  std::vector<uint8_t> active_players;
+  int last_discard_pid = -1, last_discard_tile = -1;
+  std::vector<Action> current_claims[NP];
+  bool has_claims_entry[NP] = {false, false, false, false};
+  bool pending_kan = false;
+  uint8_t pending_kan_pid = 0;
+  Action pending_kan_act;
+  uint8_t oya = 0, honba = 0, kyoku_idx = 0, round_wind = 0;
+  bool is_rinshan_flag = false, is_first_turn = true;
+  int riichi_pending_acceptance = -1;
+  int drawn_tile = -1;
+  uint8_t game_mode = 0;
+  uint32_t rule = RV_RULE_DEFAULT_TENHOU;
+  int last_error = -1;
+  int riichi_sutehais[NP] = {-1, -1, -1, -1}, last_tedashis[NP] = {-1, -1, -1, -1};
+
+  // event stream
+  bool keep_log = true;
+  std::vector<uint32_t> log;
+  uint64_t ev_hash = 0xcbf29ce484222325ull;
+  uint32_t ev_count = 0, step_count = 0, kyoku_count = 0;
+  // per-winner results of the last settlement (win_results, state/mod.rs:60)
+  std::vector<std::pair<int, WinResult>> win_results;
+
+  bool rb(uint32_t bit) const { return (rule & bit) != 0; }
+
+  // ------------------------------------------------------------ events
+  void push_words(const uint32_t* w, int n) {
+    for (int i = 0; i < n; i++) {
+      ev_hash = (ev_hash ^ w[i]) * 0x100000001b3ull;
+      if (keep_log) log.push_back(w[i]);
+    }
+    ev_count++;
+  }
+  static uint32_t w0(int type, int n, int a, int b) {
+    return (uint32_t)type | ((uint32_t)n << 8) | ((uint32_t)(a & 0xFF) << 16) | ((uint32_t)(b & 0xFF) << 24);
+  }
+  void ev_simple(int type, int a = 0, int b = 0) {
+    uint32_t w = w0(type, 1, a, b);
+    push_words(&w, 1);
+  }
+  void ev_deltas(int type, int a, const int32_t* d) {
+    uint32_t w[5] = {w0(type, 5, a, 0), (uint32_t)d[0], (uint32_t)d[1], (uint32_t)d[2], (uint32_t)d[3]};
+    push_words(w, 5);
+  }
+
+  // ------------------------------------------------------------ ctor / reset
+  // state/mod.rs:98-167
+  GameState(uint8_t mode, uint64_t seed, uint8_t rw, uint32_t rule_bits, bool log_events = true)
+      : wall_seed(seed), round_wind(rw), game_mode(mode), rule(rule_bits), keep_log(log_events) {
+    for (auto& p : players) p.score = 25000;
+    ev_simple(RV_EV_START_GAME);
+    _initialize_round(0, rw, 0, 0, nullptr, nullptr);
+  }
+  // state/mod.rs:171-187 + env.rs:799-851
+  void reset(uint8_t oya_ = 0, uint8_t rw = 0, uint8_t honba_ = 0, uint32_t kyotaku = 0,
+             const std::vector<uint8_t>* wall = nullptr, const int32_t* scores = nullptr) {
+    log.clear();
+    ev_hash = 0xcbf29ce484222325ull;
+    ev_count = 0;
+    step_count = 0;
+    kyoku_count = 0;
+    ev_simple(RV_EV_START_GAME);
+    int32_t def[NP] = {25000, 25000, 25000, 25000};
+    _initialize_round(oya_, rw, honba_, kyotaku, wall, scores ? scores : def);
+  }
+
+  // state/wall.rs:36-67 / 69-80
+  void wall_shuffle() {
+    wall_tiles = wall_from_seed(wall_seed, hand_index, 136);
+    hand_index++;
+    wall_loaded();
+  }
+  void load_wall(const std::vector<uint8_t>& t) {
+    wall_tiles.assign(t.rbegin(), t.rend());
+    wall_loaded();
+  }
+  void wall_loaded() {
+    wall_abs = wall_tiles;
+    dora_indicators.clear();
+    if (wall_tiles.size() > 5) dora_indicators.push_back(wall_tiles[4]);
+    rinshan_draw_count = 0;
+    pending_kan_dora_count = 0;
+    drawable_count = 0;
+  }
+
+  // state/mod.rs:1695-1844
+  void _initialize_round(uint8_t oya_, uint8_t rw, uint8_t honba_, uint32_t kyotaku,
+                         const std::vector<uint8_t>* wall, const int32_t* scores) {
+    oya = oya_;
+    kyoku_idx = oya_;
+    current_player = oya_;
+    honba = honba_;
+    riichi_sticks = kyotaku;
+    round_wind = rw;
+    for (auto& p : players) p.reset_round();
+    is_done = false;
+    for (int i = 0; i < NP; i++) {
+      current_claims[i].clear();
+      has_claims_entry[i] = false;
+    }
+    pending_kan = false;
+    is_rinshan_flag = false;
+    rinshan_draw_count = 0;
+    pending_kan_dora_count = 0;
+    is_first_turn = true;
+    riichi_pending_acceptance = -1;
+    turn_count = 0;
+    needs_tsumo = true;
+    last_discard_pid = last_discard_tile = -1;
+    win_results.clear();
+    for (int i = 0; i < NP; i++) riichi_sutehais[i] = last_tedashis[i] = -1;
+    if (scores)
+      for (int i = 0; i < NP; i++) players[i].score = scores[i];
+    if (wall)
+      load_wall(*wall);
+    else
+      wall_shuffle();
+    kyoku_count++;
+    for (int r = 0; r < 3; r++)
+      for (int idx = 0; idx < NP; idx++) {
+        int p = (idx + oya) % NP;
+        for (int k = 0; k < 4; k++)
+          if (!wall_tiles.empty()) {
+            players[p].hand.push_back(wall_tiles.back());
+            wall_tiles.pop_back();
+          }
+      }
+    for (int idx = 0; idx < NP; idx++) {
+      int p = (idx + oya) % NP;
+      if (!wall_tiles.empty()) {
+        players[p].hand.push_back(wall_tiles.back());
+        wall_tiles.pop_back();
+      }
+    }
+    for (auto& p : players) std::sort(p.hand.begin(), p.hand.end());
+    drawable_count = (uint8_t)(wall_tiles.size() - 14);
+
+    {  // start_kyoku (state/mod.rs:1785-1820)
+      uint32_t w[19];
+      w[0] = w0(RV_EV_START_KYOKU, 19, round_wind % 4, oya);
+      w[1] = (uint32_t)honba | ((uint32_t)dora_indicators[0] << 8) | ((kyotaku & 0xFFFF) << 16);
+      for (int i = 0; i < NP; i++) w[2 + i] = (uint32_t)players[i].score;
+      uint8_t th[52];
+      memset(th, 0xFF, sizeof th);
+      for (int i = 0; i < NP; i++)
+        for (size_t k = 0; k < players[i].hand.size() && k < 13; k++) th[i * 13 + k] = players[i].hand[k];
+      memcpy(&w[6], th, 52);
+      push_words(w, 19);
+    }
+    current_player = oya;
+    phase = RV_WAIT_ACT;
+    active_players = {oya};
+    if (!wall_tiles.empty()) {
+      uint8_t t = wall_tiles.back();
+      wall_tiles.pop_back();
+      drawable_count -= 1;
+      players[oya].hand.push_back(t);
+      drawn_tile = t;
+      needs_tsumo = false;
+      ev_simple(RV_EV_TSUMO, oya, t);
+    } else {
+      needs_tsumo = true;
+      drawn_tile = -1;
+    }
+  }
+
+  // ------------------------------------------------------------ helpers
+  Conditions base_cond(int pid) const {
+    Conditions c;
+    c.riichi = players[pid].riichi_declared;
+    c.double_riichi = players[pid].double_riichi_declared;
+    c.ippatsu = players[pid].ippatsu_cycle;
+    c.player_wind = (uint8_t)((pid + NP - oya) % NP);
+    c.round_wind = (uint8_t)(round_wind % 4);
+    c.riichi_sticks = riichi_sticks;
+    c.honba = honba;
+    return c;
+  }
+  // state/mod.rs:2048-2069
+  std::vector<uint8_t> _get_ura_indicators() const {
+    std::vector<uint8_t> out;
+    for (size_t i = 0; i < dora_indicators.size(); i++) {
+      size_t raw = 5 + 2 * i;
+      size_t idx = raw >= rinshan_draw_count ? raw - rinshan_draw_count : 0;
+      if (idx < wall_tiles.size()) out.push_back(wall_tiles[idx]);
+    }
+    return out;
+  }
+  // state/mod.rs:2021-2046
+  void _reveal_kan_dora() {
+    size_t count = dora_indicators.size();
+    if (count < 5) {
+      size_t raw = 4 + 2 * count;
+      size_t base = raw >= rinshan_draw_count ? raw - rinshan_draw_count : 0;
+      if (base < wall_tiles.size()) {
+        dora_indicators.push_back(wall_tiles[base]);
+        ev_simple(RV_EV_DORA, 0, dora_indicators.back());
+      }
+    }
+  }
+  static bool vec_remove_first(std::vector<uint8_t>& v, uint8_t t) {
+    for (size_t i = 0; i < v.size(); i++)
+      if (v[i] == t) {
+        v.erase(v.begin() + i);
+        return true;
+      }
+    return false;
+  }
+
+  // ------------------------------------------------------------ legal actions
+  // state/legal_actions.rs:11-252
+  std::vector<Action> _get_legal_actions_internal(int pid) const {
+    std::vector<Action> legals;
+    const PlayerState& P = players[pid];
+    if (is_done) return legals;
+    if (phase == RV_WAIT_ACT) {
+      if (pid != current_player) return legals;
+      // 1. Tsumo
+      if (drawn_tile >= 0 && !P.riichi_stage) {
+        Conditions cond = base_cond(pid);
+        cond.tsumo = true;
+        cond.haitei = drawable_count == 0 && !is_rinshan_flag;
+        cond.rinshan = is_rinshan_flag;
+        cond.tsumo_first_turn = is_first_turn && P.discards.empty();
+        std::vector<uint8_t> hand = P.hand;
+        for (int i = (int)hand.size() - 1; i >= 0; i--)
+          if (hand[i] == drawn_tile) {
+            hand.erase(hand.begin() + i);
+            break;
+          }
+        HandEvaluator calc(hand, P.melds);
+        WinResult res = calc.calc((uint8_t)drawn_tile, dora_indicators, {}, cond);
+        if (res.is_win && (res.yakuman || res.han >= 1)) legals.emplace_back(RV_TSUMO, drawn_tile, std::vector<uint8_t>{}, pid);
+      }
+      // 2. Discard / Riichi
+      auto forbidden = [&](uint8_t t) {
+        for (uint8_t f : P.forbidden_discards)
+          if (f / 4 == t / 4) return true;
+        return false;
+      };
+      if (P.riichi_declared) {
+        if (drawn_tile >= 0) legals.emplace_back(RV_DISCARD, drawn_tile, std::vector<uint8_t>{}, pid);
+      } else if (P.riichi_stage) {
+        for (uint8_t t : P.hand) {
+          if (forbidden(t)) continue;
+          std::vector<uint8_t> tmp = P.hand;
+          vec_remove_first(tmp, t);
+          HandEvaluator calc(tmp, P.melds);
+          if (calc.is_tenpai()) legals.emplace_back(RV_DISCARD, t, std::vector<uint8_t>{}, pid);
+        }
+      } else {
+        for (uint8_t t : P.hand)
+          if (!forbidden(t)) legals.emplace_back(RV_DISCARD, t, std::vector<uint8_t>{}, pid);
+        bool all_closed = true;
+        for (auto& m : P.melds)
+          if (m.opened) all_closed = false;
+        if (P.score >= 1000 && drawable_count >= 4 && all_closed) {
+          bool can = false;
+          for (size_t skip = 0; skip < P.hand.size(); skip++) {
+            std::vector<uint8_t> tmp = P.hand;
+            tmp.erase(tmp.begin() + skip);
+            HandEvaluator calc(tmp, P.melds);
+            if (calc.is_tenpai()) {
+              can = true;
+              break;
+            }
+          }
+          if (can) legals.emplace_back(RV_RIICHI, -1, std::vector<uint8_t>{}, pid);
+        }
+      }
+      // 3. Kan
+      if (drawable_count > 0 && drawn_tile >= 0) {
+        int counts[34] = {0};
+        for (uint8_t t : P.hand) counts[t / 4]++;
+        if (!P.riichi_declared && !P.riichi_stage) {
+          for (int tv = 0; tv < 34; tv++)
+            if (counts[tv] == 4) {
+              uint8_t lo = (uint8_t)(tv * 4);
+              legals.emplace_back(RV_ANKAN, lo, std::vector<uint8_t>{lo, (uint8_t)(lo + 1), (uint8_t)(lo + 2), (uint8_t)(lo + 3)}, pid);
+            }
+          for (auto& m : P.melds)
+            if (m.meld_type == Pon) {
+              uint8_t target = m.tiles[0] / 4;
+              for (uint8_t t : P.hand)
+                if (t / 4 == target) legals.emplace_back(RV_KAKAN, t, m.tiles, pid);
+            }
+        } else if (P.riichi_declared) {
+          uint8_t t = (uint8_t)drawn_tile, t34 = t / 4;
+          if (counts[t34] == 4) {
+            std::vector<uint8_t> pre = P.hand;
+            vec_remove_first(pre, t);
+            HandEvaluator cpre(pre, P.melds);
+            auto wpre = cpre.get_waits_u8();
+            std::vector<uint8_t> post;
+            for (uint8_t x : P.hand)
+              if (x / 4 != t34) post.push_back(x);
+            std::vector<Meld> mpost = P.melds;
+            uint8_t lo = t34 * 4;
+            Meld am;
+            am.meld_type = Ankan;
+            am.tiles = {lo, (uint8_t)(lo + 1), (uint8_t)(lo + 2), (uint8_t)(lo + 3)};
+            am.opened = false;
+            mpost.push_back(am);
+            HandEvaluator cpost(post, mpost);
+            auto wpost = cpost.get_waits_u8();
+            if (wpre == wpost && !wpre.empty())
+              legals.emplace_back(RV_ANKAN, lo, am.tiles, pid);
+          }
+        }
+      }
+      // 4. Kyushu kyuhai
+      bool no_calls = true;
+      for (auto& p : players)
+        if (!p.melds.empty()) no_calls = false;
+      if (is_first_turn && no_calls && !P.riichi_stage) {
+        bool seen[34] = {false};
+        int distinct = 0;
+        for (uint8_t t : P.hand)
+          if (is_terminal_tile(t) && !seen[t / 4]) {
+            seen[t / 4] = true;
+            distinct++;
+          }
+        if (distinct >= 9) legals.emplace_back(RV_KYUSHU_KYUHAI, -1, std::vector<uint8_t>{}, pid);
+      }
+    } else {
+      if (has_claims_entry[pid])
+        for (auto& a : current_claims[pid]) legals.push_back(a);
+      legals.emplace_back(RV_PASS, -1, std::vector<uint8_t>{}, pid);
+    }
+    return legals;
+  }
+
+  // state/legal_actions.rs:254-508
+  std::pair<std::vector<Action>, bool> _get_claim_actions_for_player(int i, int pid, uint8_t tile) const {
+    std::vector<Action> legals;
+    bool missed_agari = false;
+    const PlayerState& P = players[i];
+    const auto& hand = P.hand;
+    uint8_t tile_class = tile / 4;
+    bool in_discards = false;
+    for (uint8_t d : P.discards)
+      if (d / 4 == tile_class) in_discards = true;
+    bool in_missed = P.missed_agari_doujun || (P.riichi_declared && P.missed_agari_riichi);
+    if (!in_discards && !in_missed) {
+      HandEvaluator calc(hand, P.melds);
+      Conditions cond = base_cond(i);
+      cond.houtei = drawable_count == 0 && !is_rinshan_flag;
+      bool furiten = false;
+      for (uint8_t w : calc.get_waits_u8()) {
+        for (uint8_t d : P.discards)
+          if (d / 4 == w) furiten = true;
+        if (furiten) break;
+      }
+      if (P.missed_agari_riichi || P.missed_agari_doujun) furiten = true;
+      if (!furiten) {
+        WinResult res = calc.calc(tile, dora_indicators, {}, cond);
+        if (res.is_win)
+          legals.emplace_back(RV_RON, tile, std::vector<uint8_t>{}, i);
+        else if (res.has_win_shape)
+          missed_agari = true;
+      }
+    }
+    // 2. Pon / Kan
+    if (!P.riichi_declared && drawable_count > 0) {
+      std::vector<uint8_t> matching;
+      for (uint8_t t : hand)
+        if (t / 4 == tile / 4) matching.push_back(t);
+      size_t count = matching.size();
+      if (count >= 2 && hand.size() >= 3) {
+        auto check_pon_kuikae = [&](const std::vector<uint8_t>& consumes) {
+          std::vector<bool> used(consumes.size(), false);
+          for (uint8_t t : hand) {
+            bool consumed_this = false;
+            for (size_t k = 0; k < consumes.size(); k++)
+              if (!used[k] && consumes[k] == t) {
+                used[k] = true;
+                consumed_this = true;
+                break;
+              }
+            if (consumed_this) continue;
+            bool forb = rb(RV_RULE_KUIKAE_FORBIDDEN) && (t / 4 == tile / 4);
+            if (!forb) return true;
+          }
+          return false;
+        };
+        for (size_t a = 0; a < matching.size(); a++)
+          for (size_t b = a + 1; b < matching.size(); b++) {
+            std::vector<uint8_t> consumes = {matching[a], matching[b]};
+            if (check_pon_kuikae(consumes)) legals.emplace_back(RV_PON, tile, consumes, i);
+          }
+      }
+      if (count >= 3) {
+        std::vector<uint8_t> consumes(matching.begin(), matching.begin() + 3);
+        legals.emplace_back(RV_DAIMINKAN, tile, consumes, i);
+      }
+    }
+    // 3. Chi
+    bool is_shimocha = i == (pid + 1) % 4;
+    if (!P.riichi_declared && drawable_count > 0 && is_shimocha && hand.size() >= 3) {
+      int t_val = tile / 4;
+      if (t_val < 27) {
+        auto check_chi_kuikae = [&](uint8_t c1, uint8_t c2) {
+          int forb[2] = {-1, -1};
+          if (rb(RV_RULE_KUIKAE_FORBIDDEN)) {
+            forb[0] = t_val;
+            int a = c1 / 4, b = c2 / 4;
+            if (a > b) std::swap(a, b);
+            if (a == t_val + 1 && b == t_val + 2) {
+              if (t_val % 9 <= 5) forb[1] = t_val + 3;
+            } else if (t_val >= 2 && b == t_val - 1 && a == t_val - 2 && t_val % 9 >= 3) {
+              forb[1] = t_val - 3;
+            }
+          }
+          bool used1 = false, used2 = false;
+          for (uint8_t t : hand) {
+            if (!used1 && t == c1) {
+              used1 = true;
+              continue;
+            }
+            if (!used2 && t == c2) {
+              used2 = true;
+              continue;
+            }
+            int tt = t / 4;
+            if (tt != forb[0] && tt != forb[1]) return true;
+          }
+          return false;
+        };
+        auto pattern = [&](int ta, int tb) {
+          std::vector<uint8_t> o1, o2;
+          for (uint8_t t : hand) {
+            if (t / 4 == ta) o1.push_back(t);
+          }
+          for (uint8_t t : hand) {
+            if (t / 4 == tb) o2.push_back(t);
+          }
+          for (uint8_t c1 : o1)
+            for (uint8_t c2 : o2)
+              if (check_chi_kuikae(c1, c2)) legals.emplace_back(RV_CHI, tile, std::vector<uint8_t>{c1, c2}, i);
+        };
+        if (t_val % 9 >= 2) pattern(t_val - 2, t_val - 1);
+        if (t_val % 9 >= 1 && t_val % 9 <= 7) pattern(t_val - 1, t_val + 1);
+        if (t_val % 9 <= 6) pattern(t_val + 1, t_val + 2);
+      }
+    }
+    return {legals, missed_agari};
+  }
+
+  // ------------------------------------------------------------ step
+  // state/mod.rs:344-392: fuzzy legality match
+  static bool action_matches(const Action& l, const Action& act) {
+    if (l.type != act.type) return false;
+    bool tiles_match = l.tile == act.tile;
+    bool consumes_match = l.consume == act.consume;
+    if (tiles_match) {
+      if (consumes_match) return true;
+      if (act.consume.empty() && l.type == RV_KAKAN) return true;
+      if (act.consume.empty() &&
+          (l.type == RV_DISCARD || l.type == RV_RIICHI || l.type == RV_TSUMO || l.type == RV_RON || l.type == RV_PASS))
+        return true;
+    }
+    if (consumes_match && (l.type == RV_ANKAN || l.type == RV_KAKAN)) return true;
+    if (act.tile < 0)
+      return l.type == RV_TSUMO || l.type == RV_RON || l.type == RV_RIICHI || l.type == RV_KYUSHU_KYUHAI || l.type == RV_KITA;
+    return false;
+  }
+
+  void cap_double_yakuman(WinResult& res, bool is_oya, bool tsumo, uint32_t hb) const {
+    // state/mod.rs:720-745 / 1009-1034
+    if (res.yakuman && res.han > 13) {
+      uint32_t cap = 0;
+      for (uint32_t y : res.yaku) {
+        if (y == 47 && !rb(RV_RULE_JUNSEI_CHUUREN_DOUBLE)) cap += 13;
+        if (y == 48 && !rb(RV_RULE_SUUANKOU_TANKI_DOUBLE)) cap += 13;
+        if (y == 49 && !rb(RV_RULE_KOKUSHI13_DOUBLE)) cap += 13;
+        if (y == 50 && !rb(RV_RULE_DAISUUSHII_DOUBLE)) cap += 13;
+      }
+      if (cap > 0) {
+        uint32_t h = res.han > cap ? res.han - cap : 0;
+        res.han = std::max<uint32_t>(h, 13);
+        Score c = calculate_score((uint8_t)res.han, 0, is_oya, tsumo, hb, NP);
+        res.ron_agari = c.pay_ron;
+        res.tsumo_agari_oya = c.pay_tsumo_oya;
+        res.tsumo_agari_ko = c.pay_tsumo_ko;
+      }
+    }
+  }
+  int yakuman_val(uint32_t yid) const {
+    if (yid == 47 && rb(RV_RULE_JUNSEI_CHUUREN_DOUBLE)) return 2;
+    if (yid == 48 && rb(RV_RULE_SUUANKOU_TANKI_DOUBLE)) return 2;
+    if (yid == 49 && rb(RV_RULE_KOKUSHI13_DOUBLE)) return 2;
+    if (yid == 50 && rb(RV_RULE_DAISUUSHII_DOUBLE)) return 2;
+    return 1;
+  }
+  int pao_for(int pid, uint32_t yid) const {
+    if (yid == 37) return players[pid].pao37;
+    if (yid == 50) return players[pid].pao50;
+    return -1;
+  }
+  void ev_hora(int actor, int target, bool tsumo, const WinResult& res, const int32_t* deltas, bool with_ura) {
+    std::vector<uint8_t> ura;
+    if (with_ura) ura = _get_ura_indicators();
+    uint32_t w[10];
+    w[0] = w0(RV_EV_HORA, 10, actor, target);
+    w[1] = (tsumo ? 1u : 0u) | ((uint32_t)ura.size() << 8) | ((res.han & 0xFF) << 16) | ((res.fu & 0xFF) << 24);
+    uint8_t ub[8];
+    memset(ub, 0xFF, 8);
+    for (size_t i = 0; i < ura.size() && i < 5; i++) ub[i] = ura[i];
+    ub[5] = res.yakuman ? 1 : 0;
+    ub[6] = ub[7] = 0;
+    memcpy(&w[2], ub, 8);
+    for (int i = 0; i < 4; i++) w[4 + i] = (uint32_t)deltas[i];
+    uint64_t mask = 0;
+    for (uint32_t y : res.yaku) mask |= 1ull << y;
+    w[8] = (uint32_t)mask;
+    w[9] = (uint32_t)(mask >> 32);
+    push_words(w, 10);
+  }
+
+  // acts[pid].has_value() <=> key present in the reference's HashMap
+  void step(const std::optional<Action> acts[NP]) {
+    if (is_done) return;
+    step_count++;
+    // validation (state/mod.rs:340-402)
+    for (int pid = 0; pid < NP; pid++) {
+      if (!acts[pid]) continue;
+      auto legals = _get_legal_actions_internal(pid);
+      bool ok = false;
+      for (auto& l : legals)
+        if (action_matches(l, *acts[pid])) {
+          ok = true;
+          break;
+        }
+      if (!ok) {
+        last_error = pid;
+        _trigger_ryukyoku(RV_RK_ILLEGAL_BASE + pid);
+        return;
+      }
+    }
+    if (phase == RV_WAIT_ACT) {
+      int pid = current_player;
+      if (!acts[pid]) return;
+      const Action& act = *acts[pid];
+      PlayerState& P = players[pid];
+      switch (act.type) {
+        case RV_DISCARD: {
+          if (act.tile < 0) break;
+          uint8_t tile = (uint8_t)act.tile;
+          bool tsumogiri = false, valid = false;
+          if (drawn_tile >= 0 && drawn_tile == tile) {
+            tsumogiri = true;
+            valid = true;
+          }
+          if (vec_remove_first(P.hand, tile)) {
+            std::sort(P.hand.begin(), P.hand.end());
+            valid = true;
+            if (drawn_tile >= 0 && drawn_tile == tile) tsumogiri = true;
+          }
+          if (valid) _resolve_discard(pid, tile, tsumogiri);
+          break;
+        }
+        case RV_KYUSHU_KYUHAI:
+          _trigger_ryukyoku(RV_RK_KYUSHU);
+          break;
+        case RV_RIICHI: {
+          if (P.score >= 1000 && drawable_count >= 4 && !P.riichi_declared && !P.riichi_stage) {
+            P.riichi_stage = true;
+            ev_simple(RV_EV_REACH, pid);
+            if (act.tile >= 0) {
+              uint8_t t = (uint8_t)act.tile;
+              bool tsumogiri = drawn_tile >= 0 && drawn_tile == t;
+              riichi_sutehais[pid] = t;
+              if (!tsumogiri) last_tedashis[pid] = t;
+              if (vec_remove_first(P.hand, t)) std::sort(P.hand.begin(), P.hand.end());
+              _resolve_discard(pid, t, tsumogiri);
+            }
+          }
+          break;
+        }
+        case RV_ANKAN: {
+          uint8_t tile = act.tile >= 0 ? (uint8_t)act.tile : (act.consume.empty() ? 0 : act.consume[0]);
+          std::vector<uint8_t> ronners;
+          if (rb(RV_RULE_RON_ON_ANKAN_KOKUSHI)) {
+            for (int i = 0; i < NP; i++) {
+              if (i == pid) continue;
+              bool in_disc = false;
+              for (uint8_t d : players[i].discards)
+                if (d / 4 == tile / 4) in_disc = true;
+              if (in_disc) continue;
+              Conditions cond;
+              cond.riichi = players[i].riichi_declared;
+              cond.chankan = true;
+              cond.player_wind = (uint8_t)((i + NP - oya) % NP);
+              cond.round_wind = (uint8_t)(round_wind % 4);
+              HandEvaluator calc(players[i].hand, players[i].melds);
+              WinResult res = calc.calc(tile, dora_indicators, {}, cond);
+              bool kok = false;
+              for (uint32_t y : res.yaku)
+                if (y == 42 || y == 49) kok = true;
+              if (res.is_win && kok) {
+                ronners.push_back((uint8_t)i);
+                has_claims_entry[i] = true;
+                current_claims[i].emplace_back(RV_RON, tile, std::vector<uint8_t>{}, i);
+              }
+            }
+          }
+          if (!ronners.empty()) {
+            pending_kan = true;
+            pending_kan_pid = (uint8_t)pid;
+            pending_kan_act = act;
+            phase = RV_WAIT_RESPONSE;
+            active_players = ronners;
+            last_discard_pid = pid;
+            last_discard_tile = tile;
+          } else {
+            _resolve_kan(pid, act);
+          }
+          break;
+        }
+        case RV_KAKAN: {
+          uint8_t tile = act.tile >= 0 ? (uint8_t)act.tile : (act.consume.empty() ? 0 : act.consume[0]);
+          vec_remove_first(P.hand, tile);
+          for (auto& m : P.melds)
+            if (m.meld_type == Pon && m.tiles[0] / 4 == tile / 4) {
+              m.meld_type = Kakan;
+              m.tiles.push_back(tile);
+              std::sort(m.tiles.begin(), m.tiles.end());
+              break;
+            }
+          {
+            uint8_t c[4] = {0xFF, 0xFF, 0xFF, 0xFF};
+            for (size_t k = 0; k < act.consume.size() && k < 4; k++) c[k] = act.consume[k];
+            uint32_t w[2] = {w0(RV_EV_KAKAN, 2, pid, tile), 0};
+            memcpy(&w[1], c, 4);
+            push_words(w, 2);
+          }
+          while (pending_kan_dora_count > 0) {
+            pending_kan_dora_count--;
+            _reveal_kan_dora();
+          }
+          std::vector<uint8_t> ronners;
+          for (int i = 0; i < NP; i++) {
+            if (i == pid) continue;
+            Conditions cond = base_cond(i);
+            cond.chankan = true;
+            HandEvaluator calc(players[i].hand, players[i].melds);
+            bool furiten = false;
+            for (uint8_t w : calc.get_waits_u8()) {
+              for (uint8_t d : players[i].discards)
+                if (d / 4 == w) furiten = true;
+              if (furiten) break;
+            }
+            if (players[i].missed_agari_riichi || players[i].missed_agari_doujun) furiten = true;
+            WinResult res;
+            if (!furiten) res = calc.calc(tile, dora_indicators, {}, cond);
+            if (res.is_win && (res.yakuman || res.han >= 1)) {
+              ronners.push_back((uint8_t)i);
+              has_claims_entry[i] = true;
+              current_claims[i].emplace_back(RV_RON, tile, std::vector<uint8_t>{}, i);
+            }
+          }
+          if (!ronners.empty()) {
+            pending_kan = true;
+            pending_kan_pid = (uint8_t)pid;
+            pending_kan_act = act;
+            phase = RV_WAIT_RESPONSE;
+            active_players = ronners;
+            last_discard_pid = pid;
+            last_discard_tile = tile;
+          } else {
+            _resolve_kan(pid, act);
+          }
+          break;
+        }
+        case RV_TSUMO: {
+          Conditions cond = base_cond(pid);
+          cond.tsumo = true;
+          cond.haitei = drawable_count == 0 && !is_rinshan_flag;
+          cond.rinshan = is_rinshan_flag;
+          bool all_meldless = true;
+          for (auto& p : players)
+            if (!p.melds.empty()) all_meldless = false;
+          cond.tsumo_first_turn = is_first_turn && all_meldless;
+          HandEvaluator calc(P.hand, P.melds);
+          uint8_t win_tile = drawn_tile >= 0 ? (uint8_t)drawn_tile : 0;
+          std::vector<uint8_t> ura;
+          if (P.riichi_declared) ura = _get_ura_indicators();
+          WinResult res = calc.calc(win_tile, dora_indicators, ura, cond);
+          cap_double_yakuman(res, pid == oya, true, cond.honba);
+          if (res.is_win) {
+            int32_t deltas[NP] = {0, 0, 0, 0};
+            int32_t total_win = 0;
+            int pao_payer = -1;
+            int pao_val = 0, total_val = 0;
+            if (res.yakuman)
+              for (uint32_t y : res.yaku) {
+                int v = yakuman_val(y);
+                total_val += v;
+                int liable = pao_for(pid, y);
+                if (liable >= 0) {
+                  pao_val += v;
+                  pao_payer = liable;
+                }
+              }
+            if (pao_val > 0) {
+              int32_t unit = pid == oya ? 48000 : 32000;
+              int32_t honba_total = (int32_t)honba * (NP - 1) * 100;
+              if (pao_payer >= 0) {
+                if (rb(RV_RULE_PAO_LIABILITY_ONLY)) {
+                  int32_t pao_amt = pao_val * unit + honba_total;
+                  int non_pao = total_val - pao_val;
+                  deltas[pao_payer] -= pao_amt;
+                  total_win += pao_amt;
+                  if (non_pao > 0) {
+                    if (pid == oya) {
+                      int32_t share = non_pao * 16000;
+                      for (int i = 0; i < NP; i++)
+                        if (i != pid) {
+                          deltas[i] -= share;
+                          total_win += share;
+                        }
+                    } else {
+                      for (int i = 0; i < NP; i++)
+                        if (i != pid) {
+                          int32_t pay = (i == oya) ? non_pao * 16000 : non_pao * 8000;
+                          deltas[i] -= pay;
+                          total_win += pay;
+                        }
+                    }
+                  }
+                } else {
+                  int32_t full = total_val * unit + honba_total;
+                  deltas[pao_payer] -= full;
+                  total_win += full;
+                }
+              }
+            } else {
+              for (int i = 0; i < NP; i++)
+                if (i != pid) {
+                  int32_t pay = (pid == oya || i != oya) ? (int32_t)res.tsumo_agari_ko : (int32_t)res.tsumo_agari_oya;
+                  deltas[i] = -pay;
+                  total_win += pay;
+                }
+            }
+            total_win += (int32_t)(riichi_sticks * 1000);
+            riichi_sticks = 0;
+            deltas[pid] += total_win;
+            for (int i = 0; i < NP; i++) {
+              players[i].score += deltas[i];
+              players[i].score_delta = deltas[i];
+            }
+            for (uint32_t y : res.yaku)
+              if (pao_for(pid, y) >= 0) {
+                res.pao_payer = pao_for(pid, y);
+                break;
+              }
+            win_results.push_back({pid, res});
+            ev_hora(pid, pid, true, res, deltas, P.riichi_declared);
+            _initialize_next_round(pid == oya, false);
+          } else {
+            current_player = (current_player + 1) % NP;
+            _deal_next();
+          }
+          break;
+        }
+        default:
+          break;
+      }
+    } else {  // WaitResponse (state/mod.rs:900-1314)
+      for (int pid = 0; pid < NP; pid++) {
+        if (!has_claims_entry[pid]) continue;
+        bool has_ron = false;
+        for (auto& a : current_claims[pid])
+          if (a.type == RV_RON) has_ron = true;
+        if (has_ron) {
+          bool roned = acts[pid] && acts[pid]->type == RV_RON;
+          if (!roned) {
+            players[pid].missed_agari_doujun = true;
+            if (players[pid].riichi_declared) players[pid].missed_agari_riichi = true;
+          }
+        }
+      }
+      std::vector<uint8_t> ron_claims;
+      int call_pid = -1;
+      Action call_act;
+      for (uint8_t pid : active_players) {
+        if (!acts[pid]) continue;
+        const Action& act = *acts[pid];
+        if (act.type == RV_RON) {
+          ron_claims.push_back(pid);
+        } else if (act.type == RV_PON || act.type == RV_DAIMINKAN || act.type == RV_CHI) {
+          if (call_pid >= 0) {
+            bool old_is_pon = call_act.type == RV_PON || call_act.type == RV_DAIMINKAN;
+            bool new_is_pon = act.type == RV_PON || act.type == RV_DAIMINKAN;
+            if (!old_is_pon && new_is_pon) {
+              call_pid = pid;
+              call_act = act;
+            }
+          } else {
+            call_pid = pid;
+            call_act = act;
+          }
+        }
+      }
+      if (!ron_claims.empty()) {
+        if ((int)ron_claims.size() >= NP - 1 && rb(RV_RULE_SANCHAHO_IS_DRAW)) {
+          _trigger_ryukyoku(RV_RK_SANCHAHO);
+          return;
+        }
+        int target_pid = last_discard_pid >= 0 ? last_discard_pid : current_player;
+        uint8_t win_tile = last_discard_pid >= 0 ? (uint8_t)last_discard_tile : 0;
+        std::stable_sort(ron_claims.begin(), ron_claims.end(), [&](uint8_t a, uint8_t b) {
+          return (a + NP - target_pid) % NP < (b + NP - target_pid) % NP;
+        });
+        int32_t total_deltas[NP] = {0, 0, 0, 0};
+        bool oya_won = false, deposit_taken = false, honba_taken = false;
+        for (uint8_t w_pid : ron_claims) {
+          PlayerState& W = players[w_pid];
+          bool is_chankan = pending_kan;
+          uint32_t ron_honba = 0;
+          if (!honba_taken) {
+            honba_taken = true;
+            ron_honba = honba;
+          }
+          Conditions cond = base_cond(w_pid);
+          cond.houtei = drawable_count == 0 && !is_rinshan_flag;
+          cond.chankan = is_chankan;
+          cond.honba = ron_honba;
+          HandEvaluator calc(W.hand, W.melds);
+          std::vector<uint8_t> ura;
+          if (W.riichi_declared) ura = _get_ura_indicators();
+          WinResult res = calc.calc(win_tile, dora_indicators, ura, cond);
+          cap_double_yakuman(res, w_pid == oya, false, ron_honba);
+          if (res.is_win) {
+            int32_t score = (int32_t)res.ron_agari;
+            int pao_payer = target_pid;
+            int32_t pao_amt = 0;
+            if (res.yakuman) {
+              bool has_pao = false;
+              int total_val = 0, pao_val = 0;
+              for (uint32_t y : res.yaku) {
+                int v = yakuman_val(y);
+                total_val += v;
+                int liable = pao_for(w_pid, y);
+                if (liable >= 0) {
+                  has_pao = true;
+                  pao_payer = liable;
+                  pao_val += v;
+                }
+              }
+              if (has_pao) {
+                int32_t unit = (w_pid == oya) ? 48000 : 32000;
+                int32_t honba_ron = (int32_t)ron_honba * (NP - 1) * 100;
+                int32_t split_base = rb(RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
+                pao_amt = split_base / 2 + honba_ron;
+              }
+            }
+            int32_t this_d[NP] = {0, 0, 0, 0};
+            this_d[w_pid] += score;
+            this_d[pao_payer] -= pao_amt;
+            this_d[target_pid] -= score - pao_amt;
+            total_deltas[w_pid] += score;
+            total_deltas[pao_payer] -= pao_amt;
+            total_deltas[target_pid] -= score - pao_amt;
+            if (!deposit_taken) {
+              int32_t stick = (int32_t)(riichi_sticks * 1000);
+              total_deltas[w_pid] += stick;
+              this_d[w_pid] += stick;
+              riichi_sticks = 0;
+              deposit_taken = true;
+            }
+            for (uint32_t y : res.yaku)
+              if (pao_for(w_pid, y) >= 0) {
+                res.pao_payer = pao_for(w_pid, y);
+                break;
+              }
+            win_results.push_back({w_pid, res});
+            if (w_pid == oya) oya_won = true;
+            ev_hora(w_pid, target_pid, false, res, this_d, W.riichi_declared);
+          }
+        }
+        for (int i = 0; i < NP; i++) {
+          players[i].score += total_deltas[i];
+          players[i].score_delta = total_deltas[i];
+        }
+        _initialize_next_round(oya_won, false);
+      } else if (call_pid >= 0) {
+        int claimer = call_pid;
+        const Action& action = call_act;
+        PlayerState& C = players[claimer];
+        _accept_riichi();
+        is_rinshan_flag = false;
+        is_first_turn = false;
+        C.missed_agari_doujun = false;
+        if (last_discard_pid >= 0) players[last_discard_pid].nagashi_eligible = false;
+        for (auto& p : players) p.ippatsu_cycle = false;
+        if (action.type == RV_DAIMINKAN) {
+          current_player = (uint8_t)claimer;
+          active_players = {(uint8_t)claimer};
+          C.forbidden_discards.clear();
+          _resolve_kan(claimer, action);
+          return;
+        }
+        for (uint8_t t : action.consume) vec_remove_first(C.hand, t);
+        int discarder = last_discard_pid;
+        uint8_t tile = (uint8_t)last_discard_tile;
+        std::vector<uint8_t> tiles = action.consume;
+        tiles.push_back(tile);
+        std::sort(tiles.begin(), tiles.end());
+        Meld m;
+        m.meld_type = action.type == RV_PON ? Pon : Chi;
+        m.tiles = tiles;
+        m.opened = true;
+        m.from_who = (int8_t)discarder;
+        m.called_tile = tile;
+        C.melds.push_back(m);
+        {
+          uint8_t c[4] = {(uint8_t)discarder, 0xFF, 0xFF, 0xFF};
+          for (size_t k = 0; k < action.consume.size() && k < 3; k++) c[1 + k] = action.consume[k];
+          uint32_t w[2] = {w0(action.type == RV_PON ? RV_EV_PON : RV_EV_CHI, 2, claimer, tile), 0};
+          memcpy(&w[1], c, 4);
+          push_words(w, 2);
+        }
+        if (m.meld_type == Pon) register_pao(claimer, tile, discarder);
+        current_player = (uint8_t)claimer;
+        phase = RV_WAIT_ACT;
+        active_players = {(uint8_t)claimer};
+        C.forbidden_discards.clear();
+        if (action.type == RV_PON) {
+          C.forbidden_discards.push_back(tile);
+        } else {
+          C.forbidden_discards.push_back(tile);
+          int t34 = tile / 4;
+          std::vector<int> c34;
+          for (uint8_t x : action.consume) c34.push_back(x / 4);
+          std::sort(c34.begin(), c34.end());
+          if (c34[0] == t34 + 1 && c34[1] == t34 + 2) {
+            if (t34 % 9 <= 5) C.forbidden_discards.push_back((uint8_t)((t34 + 3) * 4));
+          } else if (t34 >= 2 && c34[1] == t34 - 1 && c34[0] == t34 - 2 && t34 % 9 >= 3) {
+            C.forbidden_discards.push_back((uint8_t)((t34 - 3) * 4));
+          }
+        }
+        needs_tsumo = false;
+        drawn_tile = -1;
+      } else {
+        for (int i = 0; i < NP; i++) {
+          current_claims[i].clear();
+          has_claims_entry[i] = false;
+        }
+        active_players.clear();
+        if (pending_kan) {
+          pending_kan = false;
+          Action a = pending_kan_act;
+          _resolve_kan(pending_kan_pid, a);
+        } else {
+          _accept_riichi();
+          turn_count += 1;
+          current_player = (current_player + 1) % NP;
+          _deal_next();
+          if (turn_count >= (uint32_t)NP) is_first_turn = false;
+        }
+      }
+    }
+  }
+
+  // state/mod.rs:1229-1259 / 1444-1472
+  void register_pao(int claimer, uint8_t tile, int discarder) {
+    int tv = tile / 4;
+    auto& ms = players[claimer].melds;
+    if (tv >= 31 && tv <= 33) {
+      int n = 0;
+      for (auto& m : ms) {
+        int t = m.tiles[0] / 4;
+        if (t >= 31 && t <= 33 && m.meld_type != Chi) n++;
+      }
+      if (n == 3) players[claimer].pao37 = discarder;
+    } else if (tv >= 27 && tv <= 30) {
+      int n = 0;
+      for (auto& m : ms) {
+        int t = m.tiles[0] / 4;
+        if (t >= 27 && t <= 30 && m.meld_type != Chi) n++;
+      }
+      if (n == 4) players[claimer].pao50 = discarder;
+    }
+  }
+
+  // state/mod.rs:1317-1413
+  void _resolve_discard(int pid, uint8_t tile, bool tsumogiri) {
+    PlayerState& P = players[pid];
+    is_rinshan_flag = false;
+    P.ippatsu_cycle = false;
+    P.discards.push_back(tile);
+    last_discard_pid = pid;
+    last_discard_tile = tile;
+    drawn_tile = -1;
+    P.discard_from_hand.push_back(!tsumogiri);
+    P.discard_is_riichi.push_back(P.riichi_stage);
+    if (!tsumogiri) last_tedashis[pid] = tile;
+    needs_tsumo = true;
+    if (P.riichi_stage) {
+      P.riichi_declared = true;
+      if (is_first_turn) P.double_riichi_declared = true;
+      P.riichi_declaration_index = (int)P.discards.size() - 1;
+      P.riichi_stage = false;
+      riichi_pending_acceptance = pid;
+    }
+    while (pending_kan_dora_count > 0) {
+      pending_kan_dora_count--;
+      _reveal_kan_dora();
+    }
+    ev_simple(tsumogiri ? RV_EV_DAHAI_TSUMOGIRI : RV_EV_DAHAI, pid, tile);
+    P.missed_agari_doujun = false;
+    P.nagashi_eligible = P.nagashi_eligible && is_terminal_tile(tile);
+    for (int i = 0; i < NP; i++) {
+      current_claims[i].clear();
+      has_claims_entry[i] = false;
+    }
+    active_players.clear();
+    bool has_claims = false;
+    std::vector<uint8_t> claim_active;
+    for (int i = 0; i < NP; i++) {
+      if (i == pid) continue;
+      auto [legals, missed] = _get_claim_actions_for_player(i, pid, tile);
+      if (missed) players[i].missed_agari_doujun = true;
+      if (!legals.empty()) {
+        has_claims = true;
+        claim_active.push_back((uint8_t)i);
+        current_claims[i] = legals;
+        has_claims_entry[i] = true;
+      }
+    }
+    if (has_claims) {
+      phase = RV_WAIT_RESPONSE;
+      active_players = claim_active;
+    } else {
+      if (riichi_pending_acceptance >= 0) _accept_riichi();
+      if (!check_abortive_draw()) {
+        turn_count += 1;
+        current_player = (uint8_t)((pid + 1) % NP);
+        _deal_next();
+        if (turn_count >= (uint32_t)NP) is_first_turn = false;
+      }
+    }
+  }
+
+  // state/mod.rs:1415-1547
+  void _resolve_kan(int pid, const Action& action) {
+    PlayerState& P = players[pid];
+    if (action.type != RV_KAKAN) {
+      for (uint8_t t : action.consume) vec_remove_first(P.hand, t);
+      Meld m;
+      if (action.type == RV_ANKAN) {
+        m.meld_type = Ankan;
+        m.tiles = action.consume;
+        m.from_who = -1;
+        m.called_tile = -1;
+        m.opened = false;
+      } else {
+        m.meld_type = Daiminkan;
+        m.tiles = action.consume;
+        m.tiles.push_back((uint8_t)last_discard_tile);
+        std::sort(m.tiles.begin(), m.tiles.end());
+        m.from_who = (int8_t)last_discard_pid;
+        m.called_tile = last_discard_tile;
+        m.opened = true;
+      }
+      P.melds.push_back(m);
+      if (action.type == RV_DAIMINKAN) register_pao(pid, (uint8_t)last_discard_tile, last_discard_pid);
+    }
+    is_first_turn = false;
+    for (auto& p : players) p.ippatsu_cycle = false;
+    if (drawable_count > 0) {
+      uint8_t t = wall_tiles.front();
+      wall_tiles.erase(wall_tiles.begin());
+      drawable_count -= 1;
+      P.hand.push_back(t);
+      drawn_tile = t;
+      rinshan_draw_count += 1;
+      is_rinshan_flag = true;
+      if (action.type == RV_ANKAN) {
+        uint8_t tile = action.tile >= 0 ? (uint8_t)action.tile : action.consume[0];
+        uint8_t c[4] = {0xFF, 0xFF, 0xFF, 0xFF};
+        for (size_t k = 0; k < action.consume.size() && k < 4; k++) c[k] = action.consume[k];
+        uint32_t w[2] = {w0(RV_EV_ANKAN, 2, pid, tile), 0};
+        memcpy(&w[1], c, 4);
+        push_words(w, 2);
+      } else if (action.type == RV_DAIMINKAN) {
+        uint8_t c[4] = {(uint8_t)last_discard_pid, 0xFF, 0xFF, 0xFF};
+        for (size_t k = 0; k < action.consume.size() && k < 3; k++) c[1 + k] = action.consume[k];
+        uint32_t w[2] = {w0(RV_EV_DAIMINKAN, 2, pid, last_discard_tile), 0};
+        memcpy(&w[1], c, 4);
+        push_words(w, 2);
+      }
+      while (pending_kan_dora_count > 0) {
+        pending_kan_dora_count--;
+        _reveal_kan_dora();
+      }
+      if (action.type == RV_ANKAN)
+        _reveal_kan_dora();
+      else
+        pending_kan_dora_count += 1;
+      ev_simple(RV_EV_TSUMO, pid, t);
+      phase = RV_WAIT_ACT;
+      active_players = {(uint8_t)pid};
+    }
+  }
+
+  // state/mod.rs:1549-1567
+  void _accept_riichi() {
+    if (riichi_pending_acceptance >= 0) {
+      int p = riichi_pending_acceptance;
+      players[p].score -= 1000;
+      players[p].score_delta -= 1000;
+      riichi_sticks += 1;
+      players[p].riichi_declared = true;
+      players[p].ippatsu_cycle = true;
+      ev_simple(RV_EV_REACH_ACCEPTED, p);
+      riichi_pending_acceptance = -1;
+    }
+  }
+
+  // state/mod.rs:1569-1593
+  void _deal_next() {
+    is_rinshan_flag = false;
+    if (drawable_count == 0) {
+      _trigger_ryukyoku(RV_RK_EXHAUSTIVE);
+      return;
+    }
+    if (!wall_tiles.empty()) {
+      uint8_t t = wall_tiles.back();
+      wall_tiles.pop_back();
+      drawable_count -= 1;
+      int pid = current_player;
+      players[pid].hand.push_back(t);
+      drawn_tile = t;
+      needs_tsumo = false;
+      phase = RV_WAIT_ACT;
+      active_players = {(uint8_t)pid};
+      ev_simple(RV_EV_TSUMO, pid, t);
+      players[pid].forbidden_discards.clear();
+    }
+  }
+
+  // state/mod.rs:2071-2081
+  void _process_end_game() {
+    is_done = true;
+    ev_simple(RV_EV_END_KYOKU);
+    ev_simple(RV_EV_END_GAME);
+  }
+
+  // state/mod.rs:1595-1688
+  void _initialize_next_round(bool oya_won, bool is_draw) {
+    if (is_done) return;
+    for (auto& p : players)
+      if (p.score < 0) {
+        _process_end_game();
+        return;
+      }
+    int32_t dealer_score = players[oya].score;
+    bool dealer_is_top = true;
+    for (int seat = 0; seat < NP; seat++) {
+      bool ok = seat == oya || dealer_score > players[seat].score || (dealer_score == players[seat].score && oya <= seat);
+      if (!ok) dealer_is_top = false;
+    }
+    bool is_last_regular = false;
+    if (game_mode == 1 || game_mode == 4) is_last_regular = round_wind == 0 && oya == NP - 1;
+    if (game_mode == 2 || game_mode == 5) is_last_regular = round_wind == 1 && oya == NP - 1;
+    if (oya_won && is_last_regular && dealer_is_top && dealer_score >= 30000) {
+      _process_end_game();
+      return;
+    }
+    uint8_t next_honba = honba, next_oya = oya, next_rw = round_wind;
+    if (oya_won) {
+      next_honba = next_honba == 255 ? 255 : next_honba + 1;
+    } else if (is_draw) {
+      next_honba = next_honba == 255 ? 255 : next_honba + 1;
+      next_oya = (next_oya + 1) % NP;
+      if (next_oya == 0) next_rw += 1;
+    } else {
+      next_honba = 0;
+      next_oya = (next_oya + 1) % NP;
+      if (next_oya == 0) next_rw += 1;
+    }
+    int32_t max_score = players[0].score;
+    for (auto& p : players) max_score = std::max(max_score, p.score);
+    switch (game_mode) {
+      case 1:
+      case 4:
+        if (next_rw >= 1 && (max_score >= 30000 || next_rw > 1)) {
+          _process_end_game();
+          return;
+        }
+        break;
+      case 2:
+      case 5:
+        if (next_rw >= 2 && (max_score >= 30000 || next_rw > 2)) {
+          _process_end_game();
+          return;
+        }
+        break;
+      case 0:
+      case 3:
+        _process_end_game();
+        return;
+      default:
+        if (next_rw >= 1) {
+          _process_end_game();
+          return;
+        }
+    }
+    ev_simple(RV_EV_END_KYOKU);
+    int32_t sc[NP];
+    for (int i = 0; i < NP; i++) sc[i] = players[i].score;
+    _initialize_round(next_oya, next_rw, next_honba, riichi_sticks, nullptr, sc);
+  }
+
+  // state/mod.rs:1846-1968   (reason: rv_ryukyoku_reason code)
+  void _trigger_ryukyoku(int reason) {
+    _accept_riichi();
+    bool tenpai[NP] = {false, false, false, false};
+    int final_reason = reason;
+    std::vector<uint8_t> nagashi;
+    if (reason == RV_RK_EXHAUSTIVE) {
+      for (int i = 0; i < NP; i++) {
+        HandEvaluator calc(players[i].hand, players[i].melds);
+        if (calc.is_tenpai()) tenpai[i] = true;
+      }
+      for (int i = 0; i < NP; i++)
+        if (players[i].nagashi_eligible) nagashi.push_back((uint8_t)i);
+      if (!nagashi.empty()) {
+        final_reason = RV_RK_NAGASHI;
+        for (uint8_t w : nagashi) {
+          bool is_oya = w == oya;
+          Score sr = calculate_score(5, 30, is_oya, true, 0, NP);
+          for (int i = 0; i < NP; i++) {
+            if (i == w) continue;
+            int32_t pay = (is_oya || i != oya) ? (int32_t)sr.pay_tsumo_ko : (int32_t)sr.pay_tsumo_oya;
+            players[i].score -= pay;
+            players[i].score_delta -= pay;
+            players[w].score += pay;
+            players[w].score_delta += pay;
+          }
+        }
+      } else {
+        int num_tp = 0;
+        for (bool t : tenpai) num_tp += t;
+        if (num_tp > 0 && num_tp < NP) {
+          int32_t pk = 3000 / num_tp, pn = 3000 / (NP - num_tp);
+          for (int i = 0; i < NP; i++) {
+            int32_t d = tenpai[i] ? pk : -pn;
+            players[i].score += d;
+            players[i].score_delta = d;
+          }
+        }
+      }
+    } else if (reason >= RV_RK_ILLEGAL_BASE && reason - RV_RK_ILLEGAL_BASE < NP) {
+      int pid = reason - RV_RK_ILLEGAL_BASE;
+      if (pid == oya) {
+        int32_t penalty = 4000 * (NP - 1), each = penalty / (NP - 1);
+        for (int i = 0; i < NP; i++) {
+          if (i == pid) {
+            players[i].score -= penalty;
+            players[i].score_delta = -penalty;
+          } else {
+            players[i].score += each;
+            players[i].score_delta = each;
+          }
+        }
+      } else {
+        int32_t total = 4000 + 2000 * (NP - 2);
+        for (int i = 0; i < NP; i++) {
+          if (i == pid) {
+            players[i].score -= total;
+            players[i].score_delta = -total;
+          } else if (i == oya) {
+            players[i].score += 4000;
+            players[i].score_delta = 4000;
+          } else {
+            players[i].score += 2000;
+            players[i].score_delta = 2000;
+          }
+        }
+      }
+    }
+    bool is_renchan;
+    if (final_reason == RV_RK_EXHAUSTIVE)
+      is_renchan = tenpai[oya];
+    else if (final_reason == RV_RK_NAGASHI)
+      is_renchan = std::find(nagashi.begin(), nagashi.end(), oya) != nagashi.end();
+    else
+      is_renchan = true;
+    int32_t d[NP];
+    for (int i = 0; i < NP; i++) d[i] = players[i].score_delta;
+    ev_deltas(RV_EV_RYUKYOKU, final_reason, d);
+    _initialize_next_round(is_renchan, true);
+  }
+
+  // state/mod.rs:1970-2019
+  bool check_abortive_draw() {
+    bool turns_ok = true, melds_empty = true;
+    for (auto& p : players) {
+      if (p.discards.size() != 1) turns_ok = false;
+      if (!p.melds.empty()) melds_empty = false;
+    }
+    if (turns_ok && melds_empty && !players[0].discards.empty()) {
+      int first = players[0].discards[0] / 4;
+      if (first >= 27 && first <= 30) {
+        bool all = true;
+        for (auto& p : players)
+          if (p.discards.empty() || p.discards[0] / 4 != first) all = false;
+        if (all) {
+          _trigger_ryukyoku(RV_RK_SUFUURENTA);
+          return true;
+        }
+      }
+    }
+    std::vector<int> owners;
+    for (int pid = 0; pid < NP; pid++)
+      for (auto& m : players[pid].melds)
+        if (m.meld_type == Daiminkan || m.meld_type == Ankan || m.meld_type == Kakan) owners.push_back(pid);
+    if (owners.size() == 4) {
+      bool same = true;
+      for (int o : owners)
+        if (o != owners[0]) same = false;
+      if (!same) {
+        _trigger_ryukyoku(RV_RK_SUUKANSANSEN);
+        return true;
+      }
+    }
+    bool all_riichi = true;
+    for (auto& p : players)
+      if (!p.riichi_declared) all_riichi = false;
+    if (all_riichi) {
+      _trigger_ryukyoku(RV_RK_SUUCHA_RIICHI);
+      return true;
+    }
+    return false;
+  }
+
+  // env.rs:673-689
+  void ranks(uint8_t out[NP]) const {
+    int idx[NP] = {0, 1, 2, 3};
+    std::stable_sort(idx, idx + NP, [&](int a, int b) { return players[a].score > players[b].score; });
+    for (int r = 0; r < NP; r++) out[idx[r]] = (uint8_t)(r + 1);
+  }
+
+  // ------------------------------------------------------------ snapshot
+  static uint32_t pack_claim(const Action& a) {
+    uint32_t c0 = a.consume.size() > 0 ? a.consume[0] : 0xFF, c1 = a.consume.size() > 1 ? a.consume[1] : 0xFF;
+    return (uint32_t)a.type | ((uint32_t)(a.tile & 0xFF) << 8) | (c0 << 16) | (c1 << 24);
+  }
+  void to_snapshot(rv_game_state& s) const {
+    memset(&s, 0, sizeof s);
+    memset(s.wall, 0xFF, sizeof s.wall);
+    for (size_t i = 0; i < wall_abs.size() && i < 136; i++) s.wall[i] = wall_abs[i];
+    s.wall_len = (uint8_t)wall_abs.size();
+    s.wall_top = (uint8_t)(wall_tiles.size() + rinshan_draw_count);
+    s.rinshan_draw_count = rinshan_draw_count;
+    s.pending_kan_dora_count = pending_kan_dora_count;
+    s.drawable_count = drawable_count;
+    s.n_dora = (uint8_t)dora_indicators.size();
+    memset(s.dora_ind, 0xFF, 5);
+    for (size_t i = 0; i < dora_indicators.size() && i < 5; i++) s.dora_ind[i] = dora_indicators[i];
+    s.phase = phase;
+    memset(s.hand, 0xFF, sizeof s.hand);
+    memset(s.meld_tiles, 0xFF, sizeof s.meld_tiles);
+    memset(s.meld_type, 0xFF, sizeof s.meld_type);
+    memset(s.meld_from, 0xFF, sizeof s.meld_from);
+    memset(s.meld_called, 0xFF, sizeof s.meld_called);
+    memset(s.river, 0xFF, sizeof s.river);
+    memset(s.forbidden, 0xFF, sizeof s.forbidden);
+    memset(s.claims, 0, sizeof s.claims);
+    for (int p = 0; p < NP; p++) {
+      const PlayerState& P = players[p];
+      s.hand_len[p] = (uint8_t)P.hand.size();
+      for (size_t k = 0; k < P.hand.size() && k < RV_HAND_CAP; k++) s.hand[p][k] = P.hand[k];
+      s.n_melds[p] = (uint8_t)P.melds.size();
+      for (size_t m = 0; m < P.melds.size() && m < 4; m++) {
+        for (size_t k = 0; k < P.melds[m].tiles.size() && k < 4; k++) s.meld_tiles[p][m][k] = P.melds[m].tiles[k];
+        s.meld_type[p][m] = P.melds[m].meld_type;
+        s.meld_from[p][m] = (uint8_t)P.melds[m].from_who;
+        s.meld_called[p][m] = (uint8_t)(P.melds[m].called_tile < 0 ? 0xFF : P.melds[m].called_tile);
+      }
+      s.n_river[p] = (uint8_t)P.discards.size();
+      for (size_t k = 0; k < P.discards.size(); k++) {
+        if (k < RV_RIVER_CAP) {
+          s.river[p][k] = P.discards[k];
+          if (P.discard_from_hand[k]) s.river_tedashi[p] |= 1u << k;
+          if (P.discard_is_riichi[k]) s.river_riichi[p] |= 1u << k;
+        } else {
+          s.overflow = 1;
+        }
+      }
+      s.riichi_decl_idx[p] = (uint8_t)(P.riichi_declaration_index < 0 ? 0xFF : P.riichi_declaration_index);
+      s.flags[p] = (P.riichi_declared ? RV_F_RIICHI_DECLARED : 0) | (P.riichi_stage ? RV_F_RIICHI_STAGE : 0) |
+                   (P.double_riichi_declared ? RV_F_DOUBLE_RIICHI : 0) | (P.missed_agari_riichi ? RV_F_MISSED_AGARI_RIICHI : 0) |
+                   (P.missed_agari_doujun ? RV_F_MISSED_AGARI_DOUJUN : 0) | (P.nagashi_eligible ? RV_F_NAGASHI_ELIGIBLE : 0) |
+                   (P.ippatsu_cycle ? RV_F_IPPATSU_CYCLE : 0);
+      s.pao[p][0] = (uint8_t)(P.pao37 < 0 ? 0xFF : P.pao37);
+      s.pao[p][1] = (uint8_t)(P.pao50 < 0 ? 0xFF : P.pao50);
+      for (size_t k = 0; k < P.forbidden_discards.size() && k < 2; k++) s.forbidden[p][k] = P.forbidden_discards[k];
+      s.riichi_sutehai[p] = (uint8_t)(riichi_sutehais[p] < 0 ? 0xFF : riichi_sutehais[p]);
+      s.last_tedashi[p] = (uint8_t)(last_tedashis[p] < 0 ? 0xFF : last_tedashis[p]);
+      s.score[p] = P.score;
+      s.score_delta[p] = P.score_delta;
+      s.n_claims[p] = has_claims_entry[p] ? (uint8_t)current_claims[p].size() : 0;
+      for (size_t k = 0; k < current_claims[p].size() && k < RV_MAX_CLAIMS; k++) s.claims[p][k] = pack_claim(current_claims[p][k]);
+    }
+    s.current_player = current_player;
+    s.oya = oya;
+    s.honba = honba;
+    s.kyoku_idx = kyoku_idx;
+    s.round_wind = round_wind;
+    s.is_done = is_done;
+    s.needs_tsumo = needs_tsumo;
+    s.is_first_turn = is_first_turn;
+    s.is_rinshan_flag = is_rinshan_flag;
+    s.riichi_pending_acceptance = (uint8_t)(riichi_pending_acceptance < 0 ? 0xFF : riichi_pending_acceptance);
+    s.drawn_tile = (uint8_t)(drawn_tile < 0 ? 0xFF : drawn_tile);
+    s.last_discard_pid = (uint8_t)(last_discard_pid < 0 ? 0xFF : last_discard_pid);
+    s.last_discard_tile = (uint8_t)(last_discard_tile < 0 ? 0xFF : last_discard_tile);
+    s.pending_kan_pid = pending_kan ? pending_kan_pid : 0xFF;
+    s.pending_kan_type = pending_kan ? pending_kan_act.type : 0xFF;
+    s.pending_kan_tile = pending_kan ? (uint8_t)(pending_kan_act.tile >= 0 ? pending_kan_act.tile : pending_kan_act.consume[0]) : 0xFF;
+    s.active_mask = 0;
+    for (uint8_t a : active_players) s.active_mask |= (uint8_t)(1u << a);
+    s.last_error = (uint8_t)(last_error < 0 ? 0xFF : last_error);
+    s.game_mode = game_mode;
+    s.rule_bits = (uint8_t)rule;
+    s.riichi_sticks = riichi_sticks;
+    s.turn_count = turn_count;
+    s.seed = wall_seed;
+    s.hand_index = hand_index;
+    s.step_count = step_count;
+    s.kyoku_count = kyoku_count;
+    s.ev_count = ev_count;
+    s.ev_hash = ev_hash;
+  }
+};
+
+// keyed random agent shared with the CUDA path (SURVEY.md §8 d)
+inline uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+inline uint32_t agent_pick(uint64_t agent_seed, uint64_t game_id, uint32_t step_count, int seat, uint32_t n_legal) {
+  uint64_t k = agent_seed ^ (game_id * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)step_count << 8) ^ (uint64_t)seat;
+  return (uint32_t)(mix64(k) % n_legal);
+}
+
+// One env step with the keyed agent. Returns false if the game is done.
+inline bool random_step(GameState& g, uint64_t agent_seed, uint64_t game_id) {
+  if (g.is_done) return false;
+  std::optional<Action> acts[NP];
+  uint32_t sc = g.step_count;
+  if (g.phase == RV_WAIT_ACT) {
+    int pid = g.current_player;
+    auto legals = g._get_legal_actions_internal(pid);
+    if (!legals.empty()) acts[pid] = legals[agent_pick(agent_seed, game_id, sc, pid, (uint32_t)legals.size())];
+  } else {
+    for (uint8_t pid : g.active_players) {
+      auto legals = g._get_legal_actions_internal(pid);
+      if (!legals.empty()) acts[pid] = legals[agent_pick(agent_seed, game_id, sc, pid, (uint32_t)legals.size())];
+    }
+  }
+  g.step(acts);
+  return true;
+}
+
+}  // namespace orc

@@ -1,0 +1,101 @@
+"""ctypes mirror of include/riichienv_b200.h (structs + constants).
+
+Host-side plumbing only: the layouts must match the C header byte for byte
+(tests/test_abi.py checks sizeof() against the library).
+"""
+import ctypes as C
+
+NP = 4
+HAND_CAP = 14
+RIVER_CAP = 32
+MAX_CLAIMS = 48
+MAX_LEGAL = 64
+NONE = 0xFF
+
+# action.rs:55-68
+DISCARD, CHI, PON, DAIMINKAN, RON, RIICHI, TSUMO, PASS, ANKAN, KAKAN, KYUSHU_KYUHAI, KITA = range(12)
+NO_ACTION = 255
+# rule.rs:10-20
+RULE_RON_ON_ANKAN_KOKUSHI = 0x01
+RULE_KOKUSHI13_DOUBLE = 0x02
+RULE_SUUANKOU_TANKI_DOUBLE = 0x04
+RULE_JUNSEI_CHUUREN_DOUBLE = 0x08
+RULE_DAISUUSHII_DOUBLE = 0x10
+RULE_PAO_LIABILITY_ONLY = 0x20
+RULE_SANCHAHO_IS_DRAW = 0x40
+RULE_KUIKAE_FORBIDDEN = 0x80
+RULE_DEFAULT_TENHOU = RULE_SANCHAHO_IS_DRAW | RULE_KUIKAE_FORBIDDEN
+RULE_DEFAULT_MJSOUL = 0x3F | RULE_KUIKAE_FORBIDDEN
+
+F_RIICHI_DECLARED = 0x01
+F_RIICHI_STAGE = 0x02
+F_DOUBLE_RIICHI = 0x04
+F_MISSED_AGARI_RIICHI = 0x08
+F_MISSED_AGARI_DOUJUN = 0x10
+F_NAGASHI_ELIGIBLE = 0x20
+F_IPPATSU_CYCLE = 0x40
+
+C_TSUMO, C_RIICHI, C_DOUBLE_RIICHI, C_IPPATSU, C_HAITEI, C_HOUTEI, C_RINSHAN, C_CHANKAN, C_TSUMO_FIRST_TURN = (
+    0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040, 0x080, 0x100)
+
+(EV_START_GAME, EV_START_KYOKU, EV_TSUMO, EV_DAHAI, EV_DAHAI_TSUMOGIRI, EV_REACH, EV_REACH_ACCEPTED, EV_PON, EV_CHI,
+ EV_DAIMINKAN, EV_ANKAN, EV_KAKAN, EV_DORA, EV_HORA, EV_RYUKYOKU, EV_END_KYOKU, EV_END_GAME, EV_KITA) = range(1, 19)
+
+u8, u32, i32, u64, u16, i8 = C.c_uint8, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint16, C.c_int8
+
+
+class Action(C.Structure):
+    _fields_ = [("type", u8), ("tile", u8), ("n_consume", u8), ("consume", u8 * 4), ("actor", u8)]
+
+
+class GameState(C.Structure):
+    _fields_ = [
+        ("wall", u8 * 136), ("wall_len", u8), ("wall_top", u8), ("rinshan_draw_count", u8),
+        ("pending_kan_dora_count", u8), ("drawable_count", u8), ("n_dora", u8), ("dora_ind", u8 * 5), ("phase", u8),
+        ("hand", (u8 * HAND_CAP) * NP), ("hand_len", u8 * NP), ("meld_tiles", ((u8 * 4) * 4) * NP),
+        ("meld_type", (u8 * 4) * NP), ("meld_from", (u8 * 4) * NP), ("meld_called", (u8 * 4) * NP),
+        ("n_melds", u8 * NP), ("river", (u8 * RIVER_CAP) * NP), ("n_river", u8 * NP),
+        ("river_tedashi", u32 * NP), ("river_riichi", u32 * NP), ("riichi_decl_idx", u8 * NP), ("flags", u8 * NP),
+        ("pao", (u8 * 2) * NP), ("forbidden", (u8 * 2) * NP), ("riichi_sutehai", u8 * NP), ("last_tedashi", u8 * NP),
+        ("score", i32 * NP), ("score_delta", i32 * NP),
+        ("current_player", u8), ("oya", u8), ("honba", u8), ("kyoku_idx", u8),
+        ("round_wind", u8), ("is_done", u8), ("needs_tsumo", u8), ("is_first_turn", u8),
+        ("is_rinshan_flag", u8), ("riichi_pending_acceptance", u8), ("drawn_tile", u8), ("last_discard_pid", u8),
+        ("last_discard_tile", u8), ("pending_kan_pid", u8), ("pending_kan_type", u8), ("pending_kan_tile", u8),
+        ("active_mask", u8), ("last_error", u8), ("game_mode", u8), ("rule_bits", u8),
+        ("overflow", u8), ("n_kita", u8 * NP), ("_pad0", u8 * 3),
+        ("riichi_sticks", u32), ("turn_count", u32), ("seed", u64), ("hand_index", u64),
+        ("n_claims", u8 * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
+        ("step_count", u32), ("kyoku_count", u32), ("ev_count", u32), ("_pad1", u32), ("ev_hash", u64),
+    ]
+
+
+class HandQuery(C.Structure):
+    _fields_ = [
+        ("tiles", u8 * 14), ("n_tiles", u8), ("n_melds", u8), ("meld_type", u8 * 4), ("meld_tiles", (u8 * 4) * 4),
+        ("win_tile", u8), ("n_dora", u8), ("n_ura", u8), ("dora_ind", u8 * 5), ("ura_ind", u8 * 5),
+        ("player_wind", u8), ("round_wind", u8), ("honba", u8), ("cond", u16), ("_pad", u8 * 2),
+    ]
+
+
+class HandResult(C.Structure):
+    _fields_ = [
+        ("yaku_mask", u64), ("wait_mask", u64), ("ron_agari", u32), ("tsumo_agari_oya", u32), ("tsumo_agari_ko", u32),
+        ("is_win", u8), ("yakuman", u8), ("has_win_shape", u8), ("han", u8), ("fu", u8), ("shanten", i8),
+        ("shanten13", i8), ("n_yaku", u8), ("_pad", u8 * 4),
+    ]
+
+
+def state_fields_equal(a: "GameState", b: "GameState", skip=("_pad0", "_pad1")):
+    """Field-by-field comparison; returns list of differing field names."""
+    diff = []
+    for name, _ in GameState._fields_:
+        if name in skip:
+            continue
+        va, vb = getattr(a, name), getattr(b, name)
+        if isinstance(va, C.Array):
+            if bytes(va) != bytes(vb):
+                diff.append(name)
+        elif va != vb:
+            diff.append(name)
+    return diff
