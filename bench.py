@@ -1,0 +1,293 @@
+#!/usr/bin/env python3
+"""Headline benchmark: env steps/sec of seeded random-agent 4p hanchan (BASELINE.json).
+
+One bench "step" = one pass of the hot path over one batch: G games per GPU are re-seeded,
+reset (wall shuffle + deal) and played to `done` by the on-device keyed random agent.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference arm: the CPU oracle
+        (restatement of riichienv-core — the reference itself is Rust and cannot be built in
+         this image) on all host cores, bounded sample per step
+
+For N > 1 the driver launches this file under torchrun (one rank per GPU, NCCL).  Games are
+independent: rank r owns a disjoint range of global game ids ("scaling": "weak"); the only
+collective is the end-of-run reduction of timing / episode statistics.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_STEP = 1024  # algorithmic bytes per env step without observations (SURVEY.md §8 d)
+METRIC = "env_steps_per_sec"
+UNIT = "env steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=65536, help="games per GPU per bench step")
+    ap.add_argument("--mode", type=int, default=2, help="2 = 4p-red-half")
+    ap.add_argument("--cpu-sample-games", type=int, default=0, help="games in the cpu_baseline sample (0 = sized by time)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.2 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_oracle_sample(mode, n_games, seed_base, agent_seed, threads):
+    import numpy as np
+
+    import oracle
+    from riichienv_b200 import _abi as A
+
+    lib = oracle.load()
+    t0 = time.perf_counter()
+    steps = lib.orc_run_random(mode, A.RULE_DEFAULT_TENHOU, seed_base, n_games, agent_seed, 1 << 30, threads, None, None, None, None,
+                               None, None, None, None)
+    return int(steps), time.perf_counter() - t0
+
+
+def cpu_baseline(mode, sample_games):
+    threads = os.cpu_count() or 1
+    if sample_games <= 0:
+        # probe, then size the sample for ~12 s of CPU work
+        s, dt = run_oracle_sample(mode, 4 * threads, 10_000_000, 1, threads)
+        rate = s / max(dt, 1e-6)
+        sample_games = max(4 * threads, int(12.0 * rate / 1060))
+    steps, dt = run_oracle_sample(mode, sample_games, 20_000_000, 1, threads)
+    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample_games} seeded 4p-red-half hanchan ({steps} env steps, {dt:.1f} s) through the C++ oracle "
+                      f"(restatement of riichienv-core; the Rust reference cannot be built here), {threads} threads"}
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = args.cpu_sample_games or max(2 * threads, 256)
+    for w in range(args.warmup):
+        run_oracle_sample(args.mode, max(threads, per_step // 8), 30_000_000 + w * per_step, 1, threads)
+    tot_steps, tot_t = 0, 0.0
+    for k in range(args.steps):
+        s, dt = run_oracle_sample(args.mode, per_step, 40_000_000 + k * per_step, 1, threads)
+        tot_steps += s
+        tot_t += dt
+    val = tot_steps / tot_t
+    sample = (f"{per_step} seeded hanchan per step x {args.steps} steps ({tot_steps} env steps) through the C++ oracle "
+              f"(CPU restatement of riichienv-core; Rust toolchain absent so oracle/_ref cannot exist), {threads} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
+        "config": {"workload": "4p-red-half hanchan, default Tenhou rules, seeded keyed random agents (bounded CPU sample)",
+                   "games_per_step": per_step, "game_mode": args.mode},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+
+    from riichienv_b200._lib import Context
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    torch.cuda.set_device(local_rank)
+    ctx = Context.get(local_rank)
+    ext_stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    G = args.games
+    v = VecRiichiEnv(G, args.mode, device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    agent_seed = 0x5EED
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def one_step(k, timed):
+        """returns (step_ms, kernel_ms, env_steps)"""
+        base = (k * world + rank) * G          # disjoint global game ids per (bench step, rank)
+        with torch.cuda.stream(ext_stream):
+            flush.fill_(k & 0xFF)              # L2 flush between iterations (outside the timed events)
+        s_before, _ = v.steps_total()
+        ctx.timer_mark(0)
+        v.reseed(None, base)
+        v.reset()                              # synchronises the stream internally
+        ctx.timer_mark(1)
+        v.step_random_async(agent_seed, 1 << 30)
+        ctx.timer_mark(2)
+        kernel_ms = ctx.timer_elapsed(1, 2)
+        step_ms = ctx.timer_elapsed(0, 2)
+        s_after, _ = v.steps_total()
+        # reset zeroes the device counter, so s_after is this step's count
+        return step_ms, kernel_ms, s_after
+
+    for w in range(args.warmup):
+        one_step(1000 + w, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    t0 = time.time()
+    tot_ms = tot_kernel_ms = 0.0
+    tot_steps = 0
+    launches = 0
+    for k in range(args.steps):
+        ms, kms, st = one_step(k, True)
+        tot_ms += ms
+        tot_kernel_ms += kms
+        tot_steps += st
+        launches += 3                         # reseed_kernel + reset_kernel + step_random_kernel
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    done, scores, ranks = v.results()
+    assert done.all(), "a game did not finish inside the timed region"
+
+    # ---- e2e: the public host-buffer API, H2D seeds in and D2H results out every step ----------
+    pinned = torch.empty(G, dtype=torch.int64).pin_memory()
+    e2e_t = 0.0
+    e2e_steps = 0
+    for k in range(args.steps):
+        base = ((5000 + k) * world + rank) * G
+        pinned.copy_(torch.arange(base, base + G, dtype=torch.int64))
+        seeds = pinned.numpy().view(np.uint64)
+        ctx.sync()
+        a = time.perf_counter()
+        v.reseed(seeds, 0)                     # H2D: 8 B / game
+        v.reset()
+        n = v.step_random(agent_seed, 1 << 30)
+        d_, s_, r_ = v.results()               # D2H: done + scores + ranks
+        c_ = v.counters()                      # D2H: step / kyoku / event counters + event hash
+        e2e_t += time.perf_counter() - a
+        e2e_steps += n
+    h2d = G * 8
+    d2h = G * (1 + 16 + 4 + 4 + 4 + 4 + 8)
+
+    # ---- reduce over ranks: max time, sum of steps (the only collective) -----------------------
+    stats = torch.tensor([tot_ms, tot_kernel_ms, e2e_t, float(tot_steps), float(e2e_steps)], dtype=torch.float64,
+                         device=f"cuda:{local_rank}")
+    if dist is not None:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        tot_ms, tot_kernel_ms_max, e2e_t = mx[0].item(), mx[1].item(), mx[2].item()
+        all_steps, all_e2e_steps = sm[3].item(), sm[4].item()
+    else:
+        tot_kernel_ms_max = tot_kernel_ms
+        all_steps, all_e2e_steps = float(tot_steps), float(e2e_steps)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = all_steps / (tot_ms / 1000.0)
+        achieved = (tot_steps * B_STEP) / (tot_kernel_ms / 1000.0) / 1e9  # this rank's dominant kernel
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tot_ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/i32", "data": "synthetic",
+            "config": {"workload": "4p-red-half hanchan, default Tenhou rules, 65,536 parallel seeded random-agent games per GPU "
+                                   "(BASELINE.json configs[2]), reset -> done",
+                       "games_per_gpu": G, "game_mode": args.mode, "l2": "256 MiB flush write between timed iterations",
+                       "games_per_sec": (G * args.steps * world) / (tot_ms / 1000.0),
+                       "env_steps_per_game": all_steps / (G * args.steps * world)},
+            "e2e": {"value": all_e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "step_random_kernel", "peak_source": peak_src,
+                         "bytes_per_env_step": B_STEP, "kernel_share_of_step": tot_kernel_ms / tot_ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.mode, args.cpu_sample_games)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -145,7 +145,7 @@ typedef struct rv_game_state {
   uint32_t step_count;            /* env steps taken (RiichiEnv.step calls that were not no-ops on a done game) */
   uint32_t kyoku_count;           /* rounds dealt since reset */
   uint32_t ev_count;              /* events pushed since reset */
-  uint32_t _pad1;
+  uint32_t ev_words;             /* 32-bit words pushed since reset (log length, even when the log is capped/off) */
   uint64_t ev_hash;               /* FNV-1a-64 over the 32-bit words of the binary event stream */
 } rv_game_state;
 
@@ -230,6 +230,13 @@ int rv_version(void);
 int rv_ctx_create(int device, rv_ctx** out);
 int rv_ctx_destroy(rv_ctx* ctx);
 int rv_ctx_sync(rv_ctx* ctx);
+/* The context's cudaStream_t (as void*), so callers can order their own work (e.g. torch.cuda.ExternalStream). */
+void* rv_ctx_stream(rv_ctx* ctx);
+/* CUDA-event timers on the context stream: mark records event idx; elapsed synchronises on idx_b and returns ms. */
+int rv_timer_mark(rv_ctx* ctx, int idx /*0..7*/);
+int rv_timer_elapsed(rv_ctx* ctx, int idx_a, int idx_b, float* ms);
+/* sizeof() of the public structs as compiled: 0 rv_game_state, 1 rv_hand_query, 2 rv_hand_result, 3 rv_action */
+int rv_sizeof(int which);
 
 /* Batched hand evaluation with HOST buffers (copies inside the call). */
 int rv_hand_eval_batch(rv_ctx* ctx, const rv_hand_query* q, rv_hand_result* out, int64_t n);
@@ -251,6 +258,9 @@ typedef struct rv_vec rv_vec; /* opaque */
 int rv_vec_create(rv_ctx* ctx, int64_t n, int game_mode, uint32_t rule_bits, const uint64_t* seeds,
                   uint64_t seed_base, uint32_t log_cap_words, rv_vec** out);
 int rv_vec_destroy(rv_vec* v);
+/* Re-seed every game as if freshly constructed with RiichiEnv(seed=...) (hand_index back to 1); asynchronous.
+ * seeds: HOST array of n u64 (copied H2D) or NULL -> seed_base + g.  Follow with rv_vec_reset.            */
+int rv_vec_reseed(rv_vec* v, const uint64_t* seeds, uint64_t seed_base);
 int64_t rv_vec_size(const rv_vec* v);
 
 /* RiichiEnv::reset (env.rs:799-851) for every game.  Optional per-game arrays

@@ -127,6 +127,7 @@ static void load_snapshot(GameState& g, const rv_game_state& s) {
   g.step_count = s.step_count;
   g.kyoku_count = s.kyoku_count;
   g.ev_count = s.ev_count;
+  g.ev_words = s.ev_words;
   g.ev_hash = s.ev_hash;
 }
 

@@ -103,7 +103,7 @@ struct GameState {
   bool keep_log = true;
   std::vector<uint32_t> log;
   uint64_t ev_hash = 0xcbf29ce484222325ull;
-  uint32_t ev_count = 0, step_count = 0, kyoku_count = 0;
+  uint32_t ev_count = 0, step_count = 0, kyoku_count = 0, ev_words = 0;
   // per-winner results of the last settlement (win_results, state/mod.rs:60)
   std::vector<std::pair<int, WinResult>> win_results;
 
@@ -116,6 +116,7 @@ struct GameState {
       if (keep_log) log.push_back(w[i]);
     }
     ev_count++;
+    ev_words += (uint32_t)n;
   }
   static uint32_t w0(int type, int n, int a, int b) {
     return (uint32_t)type | ((uint32_t)n << 8) | ((uint32_t)(a & 0xFF) << 16) | ((uint32_t)(b & 0xFF) << 24);
@@ -143,6 +144,7 @@ struct GameState {
     log.clear();
     ev_hash = 0xcbf29ce484222325ull;
     ev_count = 0;
+    ev_words = 0;
     step_count = 0;
     kyoku_count = 0;
     ev_simple(RV_EV_START_GAME);
@@ -1520,6 +1522,7 @@ struct GameState {
     s.step_count = step_count;
     s.kyoku_count = kyoku_count;
     s.ev_count = ev_count;
+    s.ev_words = ev_words;
     s.ev_hash = ev_hash;
   }
 };

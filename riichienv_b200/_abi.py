@@ -66,7 +66,7 @@ class GameState(C.Structure):
         ("overflow", u8), ("n_kita", u8 * NP), ("_pad0", u8 * 3),
         ("riichi_sticks", u32), ("turn_count", u32), ("seed", u64), ("hand_index", u64),
         ("n_claims", u8 * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
-        ("step_count", u32), ("kyoku_count", u32), ("ev_count", u32), ("_pad1", u32), ("ev_hash", u64),
+        ("step_count", u32), ("kyoku_count", u32), ("ev_count", u32), ("ev_words", u32), ("ev_hash", u64),
     ]
 
 
@@ -86,13 +86,20 @@ class HandResult(C.Structure):
     ]
 
 
-def state_fields_equal(a: "GameState", b: "GameState", skip=("_pad0", "_pad1")):
+def state_fields_equal(a: "GameState", b: "GameState", skip=("_pad0",)):
     """Field-by-field comparison; returns list of differing field names."""
     diff = []
     for name, _ in GameState._fields_:
         if name in skip:
             continue
         va, vb = getattr(a, name), getattr(b, name)
+        if name == "claims":  # entries past n_claims are dead storage
+            for p in range(NP):
+                n = min(a.n_claims[p], MAX_CLAIMS)
+                if list(va[p][:n]) != list(vb[p][:n]):
+                    diff.append(name)
+                    break
+            continue
         if isinstance(va, C.Array):
             if bytes(va) != bytes(vb):
                 diff.append(name)

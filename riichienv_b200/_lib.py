@@ -1,0 +1,127 @@
+"""ctypes binding of libriichienv_b200.so (the C ABI in include/riichienv_b200.h).
+
+The product has no CPU fallback: if the CUDA library is missing this module raises
+ImportError loudly, and every compute call fails with RuntimeError when no GPU is
+visible (RV_ERR_CUDA).
+"""
+import ctypes as C
+import os
+
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libriichienv_b200.so")
+_LIB = None
+
+
+class RvError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). riichienv_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp = C.c_void_p
+    L.rv_last_error.restype = C.c_char_p
+    L.rv_ctx_create.argtypes = [C.c_int, P(vp)]
+    L.rv_ctx_destroy.argtypes = [vp]
+    L.rv_ctx_sync.argtypes = [vp]
+    L.rv_ctx_stream.restype = vp
+    L.rv_ctx_stream.argtypes = [vp]
+    L.rv_timer_mark.argtypes = [vp, C.c_int]
+    L.rv_timer_elapsed.argtypes = [vp, C.c_int, C.c_int, P(C.c_float)]
+    L.rv_vec_reseed.argtypes = [vp, P(C.c_uint64), C.c_uint64]
+    L.rv_hand_eval_batch.argtypes = [vp, P(A.HandQuery), P(A.HandResult), C.c_int64]
+    L.rv_hand_eval_batch_device.argtypes = [vp, vp, vp, C.c_int64]
+    L.rv_calculate_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, P(C.c_uint32)]
+    L.rv_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]
+    L.rv_vec_create.argtypes = [vp, C.c_int64, C.c_int, C.c_uint32, P(C.c_uint64), C.c_uint64, C.c_uint32, P(vp)]
+    L.rv_vec_destroy.argtypes = [vp]
+    L.rv_vec_size.restype = C.c_int64
+    L.rv_vec_size.argtypes = [vp]
+    L.rv_vec_reset.argtypes = [vp, P(C.c_uint8), P(C.c_uint8), P(C.c_uint8), P(C.c_uint32), P(C.c_int32), P(C.c_uint8)]
+    L.rv_vec_legal_actions.argtypes = [vp, P(A.Action), P(C.c_uint8)]
+    L.rv_vec_step.argtypes = [vp, P(A.Action)]
+    L.rv_vec_step_random.argtypes = [vp, C.c_uint64, C.c_uint32, P(C.c_uint64)]
+    L.rv_vec_step_random_async.argtypes = [vp, C.c_uint64, C.c_uint32]
+    L.rv_vec_steps_total.argtypes = [vp, P(C.c_uint64), P(C.c_int64)]
+    L.rv_vec_results.argtypes = [vp, P(C.c_uint8), P(C.c_int32), P(C.c_uint8)]
+    L.rv_vec_counters.argtypes = [vp, P(C.c_uint32), P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]
+    L.rv_vec_get_state.argtypes = [vp, C.c_int64, P(A.GameState)]
+    L.rv_vec_set_state.argtypes = [vp, C.c_int64, P(A.GameState)]
+    L.rv_vec_state_device_ptr.argtypes = [vp, P(vp)]
+    L.rv_vec_events.argtypes = [vp, C.c_int64, P(C.c_uint32), C.c_uint32, P(C.c_uint32)]
+    L.rv_event_to_json.argtypes = [P(C.c_uint32), C.c_uint32, C.c_int, C.c_char_p, C.c_uint32]
+    L.rv_vec_encode.argtypes = [vp, vp, vp]
+    L.rv_sizeof.argtypes = [C.c_int]
+    for i, T in enumerate((A.GameState, A.HandQuery, A.HandResult, A.Action)):
+        if L.rv_sizeof(i) != C.sizeof(T):
+            raise ImportError(f"ABI mismatch for {T.__name__}: C {L.rv_sizeof(i)} != ctypes {C.sizeof(T)}")
+    _LIB = L
+    return L
+
+
+def check(rc: int):
+    if rc == 0:
+        return
+    msg = lib().rv_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(msg)
+    raise RvError(f"riichienv_b200 error {rc}: {msg}")
+
+
+class Context:
+    """One CUDA device + stream + lookup tables (rv_ctx)."""
+
+    _cache = {}
+
+    def __init__(self, device: int = 0):
+        self.handle = C.c_void_p()
+        check(lib().rv_ctx_create(int(device), C.byref(self.handle)))
+        self.device = int(device)
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Context":
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+    def sync(self):
+        check(lib().rv_ctx_sync(self.handle))
+
+    def timer_mark(self, idx: int):
+        check(lib().rv_timer_mark(self.handle, idx))
+
+    def timer_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        check(lib().rv_timer_elapsed(self.handle, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def stream(self) -> int:
+        return int(lib().rv_ctx_stream(self.handle) or 0)
+
+
+def events_to_json(words, viewer: int = -1):
+    """Render a binary event stream (sequence of u32) as a list of MJAI JSON strings."""
+    L = lib()
+    n = len(words)
+    arr = (C.c_uint32 * n)(*words) if not isinstance(words, C.Array) else words
+    buf = C.create_string_buffer(2048)
+    out = []
+    i = 0
+    while i < n:
+        sub = C.cast(C.byref(arr, 4 * i), C.POINTER(C.c_uint32))
+        used = L.rv_event_to_json(sub, n - i, viewer, buf, 2048)
+        if used <= 0:
+            raise ValueError(f"malformed event stream at word {i}")
+        out.append(buf.value.decode())
+        i += used
+    return out

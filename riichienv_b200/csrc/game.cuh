@@ -1,0 +1,1448 @@
+// Device-side game state machine for 4-player Riichi (one rv_game_state record per game).
+//
+// Replaces (reference paths relative to riichienv-core/src):
+//   state/mod.rs:330-1315  GameState::step            -> step_apply()
+//   state/mod.rs:1317-1413 _resolve_discard           -> resolve_discard()
+//   state/mod.rs:1415-1547 _resolve_kan               -> resolve_kan()
+//   state/mod.rs:1549-1593 _accept_riichi/_deal_next  -> accept_riichi()/deal_next()
+//   state/mod.rs:1595-1844 round / game flow          -> next_round()/init_round()
+//   state/mod.rs:1846-2081 ryukyoku, abortive draws, kan dora, ura, end game
+//   state/legal_actions.rs:11-252  turn actions       -> TurnInfo + enum_turn_actions()
+//   state/legal_actions.rs:254-508 claim actions      -> gen_claims()
+//   state/wall.rs:36-88    seeded wall                -> wall_shuffle()
+// The reference walks Vec/HashMap structures and re-runs a backtracking agari test
+// up to 14x34 times per turn; here hands are fixed byte arrays in the HBM record and
+// every agari / tenpai / wait question is answered from the suit tables (hand.cuh).
+#pragma once
+#include "hand.cuh"
+
+namespace rv {
+
+typedef rv_game_state G;
+constexpr int NP = 4;
+
+struct Ctx {
+  Tables T;
+  uint32_t* log;      // this game's event log region or nullptr
+  uint32_t log_cap;   // words
+};
+
+__device__ __forceinline__ bool rule(const G& g, uint32_t bit) { return (g.rule_bits & bit) != 0; }
+
+// ------------------------------------------------------------------ events
+__device__ inline void ev_push(const Ctx& cx, G& g, const uint32_t* w, int n) {
+  uint64_t h = g.ev_hash;
+  uint32_t base = g.ev_words;
+  for (int i = 0; i < n; i++) {
+    h = (h ^ w[i]) * 0x100000001b3ull;
+    if (cx.log && base + i < cx.log_cap) cx.log[base + i] = w[i];
+  }
+  g.ev_hash = h;
+  g.ev_words = base + n;
+  g.ev_count++;
+}
+__device__ __forceinline__ uint32_t ev_w0(int type, int n, int a, int b) {
+  return (uint32_t)type | ((uint32_t)n << 8) | ((uint32_t)(a & 0xFF) << 16) | ((uint32_t)(b & 0xFF) << 24);
+}
+__device__ __forceinline__ void ev_simple(const Ctx& cx, G& g, int type, int a = 0, int b = 0) {
+  uint32_t w = ev_w0(type, 1, a, b);
+  ev_push(cx, g, &w, 1);
+}
+__device__ __forceinline__ void ev_meld(const Ctx& cx, G& g, int type, int actor, int tile, int b0, int b1, int b2, int b3) {
+  uint32_t w[2] = {ev_w0(type, 2, actor, tile),
+                   (uint32_t)(b0 & 0xFF) | ((uint32_t)(b1 & 0xFF) << 8) | ((uint32_t)(b2 & 0xFF) << 16) | ((uint32_t)(b3 & 0xFF) << 24)};
+  ev_push(cx, g, w, 2);
+}
+
+// ------------------------------------------------------------------ hand helpers
+__device__ inline bool hand_remove_first(G& g, int p, int tile) {
+  int n = g.hand_len[p];
+  for (int i = 0; i < n; i++)
+    if (g.hand[p][i] == tile) {
+      for (int j = i; j + 1 < n; j++) g.hand[p][j] = g.hand[p][j + 1];
+      g.hand[p][n - 1] = RV_NONE;
+      g.hand_len[p] = (uint8_t)(n - 1);
+      return true;
+    }
+  return false;
+}
+__device__ inline void hand_push(G& g, int p, int tile) {
+  int n = g.hand_len[p];
+  if (n < RV_HAND_CAP) {
+    g.hand[p][n] = (uint8_t)tile;
+    g.hand_len[p] = (uint8_t)(n + 1);
+  } else {
+    g.overflow = 1;
+  }
+}
+__device__ inline void hand_sort(G& g, int p) {
+  int n = g.hand_len[p];
+  for (int i = 1; i < n; i++) {
+    uint8_t v = g.hand[p][i];
+    int j = i - 1;
+    while (j >= 0 && g.hand[p][j] > v) {
+      g.hand[p][j + 1] = g.hand[p][j];
+      j--;
+    }
+    g.hand[p][j + 1] = v;
+  }
+}
+__device__ inline Cnt hand_cnt(const G& g, int p) {
+  Cnt c;
+  cnt_zero(c);
+  int n = g.hand_len[p];
+  for (int i = 0; i < n; i++) cnt_add(c, g.hand[p][i] >> 2);
+  return c;
+}
+__device__ inline uint64_t river_kinds(const G& g, int p) {
+  uint64_t m = 0;
+  int n = min((int)g.n_river[p], RV_RIVER_CAP);
+  for (int i = 0; i < n; i++) m |= 1ull << (g.river[p][i] >> 2);
+  return m;
+}
+__device__ __forceinline__ bool tid_terminal(int t) {  // types.rs:364-369
+  int k = t >> 2;
+  return k >= 27 || k % 9 == 0 || k % 9 == 8;
+}
+__device__ __forceinline__ bool any_open_meld(const G& g, int p) {
+  for (int m = 0; m < g.n_melds[p]; m++)
+    if (g.meld_type[p][m] != RV_MELD_ANKAN) return true;
+  return false;
+}
+__device__ __forceinline__ bool all_meldless(const G& g) {
+  return (g.n_melds[0] | g.n_melds[1] | g.n_melds[2] | g.n_melds[3]) == 0;
+}
+
+// Conditions common to every calc call site (riichi flags, winds, honba)
+__device__ __forceinline__ uint32_t base_cond(const G& g, int p) {
+  uint32_t f = g.flags[p], c = 0;
+  if (f & RV_F_RIICHI_DECLARED) c |= RV_C_RIICHI;
+  if (f & RV_F_DOUBLE_RIICHI) c |= RV_C_DOUBLE_RIICHI;
+  if (f & RV_F_IPPATSU_CYCLE) c |= RV_C_IPPATSU;
+  return c;
+}
+// HandEvaluator::new(hand, melds).calc(win_tile, dora, ura, cond) for a seat
+__device__ inline WinRes seat_calc(const Ctx& cx, const G& g, int p, int win_tile, uint32_t cond, bool with_ura, uint32_t honba) {
+  uint8_t ura[5];
+  int n_ura = 0;
+  if (with_ura)
+    for (int i = 0; i < g.n_dora; i++) {
+      int idx = 5 + 2 * i;                       // state/mod.rs:2048-2058 (absolute index: the Vec lost
+      if (idx < g.wall_top) ura[n_ura++] = g.wall[idx];  //  rinshan_draw_count front tiles)
+    }
+  return hand_calc(cx.T, g.hand[p], g.hand_len[p], g.n_melds[p], g.meld_type[p], g.meld_tiles[p], win_tile, g.dora_ind,
+                   g.n_dora, ura, n_ura, cond, (p + NP - g.oya) % NP, g.round_wind % 4, honba);
+}
+
+// ------------------------------------------------------------------ wall (state/wall.rs:36-88)
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  uint64_t z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct ChaCha12 {
+  uint32_t key[8];
+  uint32_t buf[16];
+  uint64_t counter;
+  int idx;
+  __host__ __device__ static inline uint32_t rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+  __host__ __device__ inline void init(uint64_t state) {
+    // rand_core SeedableRng::seed_from_u64: PCG32 (XSH-RR) expansion
+    for (int i = 0; i < 8; i++) {
+      state = state * 6364136223846793005ull + 11634580027462260723ull;
+      uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
+      uint32_t rot = (uint32_t)(state >> 59);
+      key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+    counter = 0;
+    idx = 16;
+  }
+  __host__ __device__ inline void refill() {
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                       key[4], key[5], key[6], key[7], (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+    uint32_t s[16];
+    for (int i = 0; i < 16; i++) s[i] = in[i];
+#define RV_QR(a, b, c, d)                                                  \
+  s[a] += s[b]; s[d] ^= s[a]; s[d] = rotl(s[d], 16); s[c] += s[d]; s[b] ^= s[c]; s[b] = rotl(s[b], 12); \
+  s[a] += s[b]; s[d] ^= s[a]; s[d] = rotl(s[d], 8);  s[c] += s[d]; s[b] ^= s[c]; s[b] = rotl(s[b], 7);
+    for (int r = 0; r < 6; r++) {
+      RV_QR(0, 4, 8, 12) RV_QR(1, 5, 9, 13) RV_QR(2, 6, 10, 14) RV_QR(3, 7, 11, 15)
+      RV_QR(0, 5, 10, 15) RV_QR(1, 6, 11, 12) RV_QR(2, 7, 8, 13) RV_QR(3, 4, 9, 14)
+    }
+#undef RV_QR
+    for (int i = 0; i < 16; i++) buf[i] = s[i] + in[i];
+    counter++;
+    idx = 0;
+  }
+  __host__ __device__ inline uint32_t next_u32() {
+    if (idx >= 16) refill();
+    return buf[idx++];
+  }
+};
+// rand UniformInt<u32>::sample_single_inclusive(0, range-1): widening multiply + one bias-correction draw
+__host__ __device__ inline uint32_t random_below(ChaCha12& rng, uint32_t range) {
+  uint64_t m = (uint64_t)rng.next_u32() * range;
+  uint32_t hi = (uint32_t)(m >> 32), lo = (uint32_t)m;
+  if (lo > (uint32_t)(0u - range)) {
+    uint64_t m2 = (uint64_t)rng.next_u32() * range;
+    if ((uint64_t)lo + (uint32_t)(m2 >> 32) > 0xFFFFFFFFull) hi += 1;
+  }
+  return hi;
+}
+// SliceRandom::shuffle via IncreasingUniform (one u32 draw feeds several indices), then reverse.
+// `out` receives the reference's `wall.tiles` order.  n = 136 (4P) or 108 (3P tile set).
+__host__ __device__ __noinline__ void wall_from_seed(uint64_t seed, uint64_t hand_index, int n, uint8_t* out) {
+  uint8_t w[136];
+  if (n == 136) {
+    for (int i = 0; i < 136; i++) w[i] = (uint8_t)i;
+  } else {
+    int k = 0;
+    for (int i = 0; i < 136; i++) {
+      int t = i >> 2;
+      if (t >= 1 && t <= 7) continue;
+      w[k++] = (uint8_t)i;
+    }
+  }
+  ChaCha12 rng;
+  rng.init(splitmix64(seed + hand_index));
+  uint32_t cur_n = 0, chunk = 0, remaining = 1;
+  for (int i = 0; i < n; i++) {
+    uint32_t next_n = cur_n + 1, rem;
+    if (remaining == 0) {
+      uint32_t product = next_n, current = next_n + 1;
+      while (true) {
+        uint64_t p = (uint64_t)product * current;
+        if (p > 0xFFFFFFFFull) break;
+        product = (uint32_t)p;
+        current++;
+      }
+      chunk = random_below(rng, product);
+      rem = (current - next_n) - 1;
+    } else {
+      rem = remaining - 1;
+    }
+    uint32_t j;
+    if (rem == 0) {
+      j = chunk;
+    } else {
+      j = chunk % next_n;
+      chunk /= next_n;
+    }
+    remaining = rem;
+    cur_n = next_n;
+    uint8_t t = w[i];
+    w[i] = w[j];
+    w[j] = t;
+  }
+  for (int i = 0; i < n; i++) out[i] = w[n - 1 - i];
+}
+
+// ------------------------------------------------------------------ forward decls
+__device__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason);
+__device__ void next_round(const Ctx& cx, G& g, bool oya_won, bool is_draw);
+
+// state/mod.rs:2021-2046
+__device__ inline void reveal_kan_dora(const Ctx& cx, G& g) {
+  int count = g.n_dora;
+  if (count < 5) {
+    int idx = 4 + 2 * count;
+    if (idx < g.wall_top) {
+      g.dora_ind[count] = g.wall[idx];
+      g.n_dora = (uint8_t)(count + 1);
+      ev_simple(cx, g, RV_EV_DORA, 0, g.wall[idx]);
+    }
+  }
+}
+__device__ inline void flush_pending_kan_dora(const Ctx& cx, G& g) {
+  while (g.pending_kan_dora_count > 0) {
+    g.pending_kan_dora_count--;
+    reveal_kan_dora(cx, g);
+  }
+}
+// state/mod.rs:1549-1567
+__device__ inline void accept_riichi(const Ctx& cx, G& g) {
+  int p = g.riichi_pending_acceptance;
+  if (p != RV_NONE) {
+    g.score[p] -= 1000;
+    g.score_delta[p] -= 1000;
+    g.riichi_sticks += 1;
+    g.flags[p] |= RV_F_RIICHI_DECLARED | RV_F_IPPATSU_CYCLE;
+    ev_simple(cx, g, RV_EV_REACH_ACCEPTED, p);
+    g.riichi_pending_acceptance = RV_NONE;
+  }
+}
+// state/mod.rs:1569-1593
+__device__ inline void deal_next(const Ctx& cx, G& g) {
+  g.is_rinshan_flag = 0;
+  if (g.drawable_count == 0) {
+    trigger_ryukyoku(cx, g, RV_RK_EXHAUSTIVE);
+    return;
+  }
+  if (g.wall_top > g.rinshan_draw_count) {
+    int t = g.wall[g.wall_top - 1];
+    g.wall_top--;
+    g.drawable_count--;
+    int pid = g.current_player;
+    hand_push(g, pid, t);
+    g.drawn_tile = (uint8_t)t;
+    g.needs_tsumo = 0;
+    g.phase = RV_WAIT_ACT;
+    g.active_mask = (uint8_t)(1u << pid);
+    ev_simple(cx, g, RV_EV_TSUMO, pid, t);
+    g.forbidden[pid][0] = g.forbidden[pid][1] = RV_NONE;
+  }
+}
+
+// ------------------------------------------------------------------ round setup (state/mod.rs:1695-1844)
+// `custom_wall`: nullptr -> seeded shuffle; else 136 tids in the order passed to reset(wall=) (load_wall reverses).
+__device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_wind, int honba, uint32_t kyotaku,
+                                  const uint8_t* custom_wall, const int32_t* scores) {
+  g.oya = g.kyoku_idx = g.current_player = (uint8_t)oya;
+  g.honba = (uint8_t)honba;
+  g.riichi_sticks = kyotaku;
+  g.round_wind = (uint8_t)round_wind;
+  for (int p = 0; p < NP; p++) {  // PlayerState::reset_round (state/player.rs:66-86)
+    for (int i = 0; i < RV_HAND_CAP; i++) g.hand[p][i] = RV_NONE;
+    g.hand_len[p] = 0;
+    for (int m = 0; m < 4; m++) {
+      for (int k = 0; k < 4; k++) g.meld_tiles[p][m][k] = RV_NONE;
+      g.meld_type[p][m] = g.meld_from[p][m] = g.meld_called[p][m] = RV_NONE;
+    }
+    g.n_melds[p] = 0;
+    for (int i = 0; i < RV_RIVER_CAP; i++) g.river[p][i] = RV_NONE;
+    g.n_river[p] = 0;
+    g.river_tedashi[p] = g.river_riichi[p] = 0;
+    g.riichi_decl_idx[p] = RV_NONE;
+    g.flags[p] = RV_F_NAGASHI_ELIGIBLE;
+    g.pao[p][0] = g.pao[p][1] = RV_NONE;
+    g.forbidden[p][0] = g.forbidden[p][1] = RV_NONE;
+    g.score_delta[p] = 0;
+    g.n_claims[p] = 0;
+    g.riichi_sutehai[p] = g.last_tedashi[p] = RV_NONE;
+    g.n_kita[p] = 0;
+    if (scores) g.score[p] = scores[p];
+  }
+  g.is_done = 0;
+  g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
+  g.is_rinshan_flag = 0;
+  g.rinshan_draw_count = 0;
+  g.pending_kan_dora_count = 0;
+  g.is_first_turn = 1;
+  g.riichi_pending_acceptance = RV_NONE;
+  g.turn_count = 0;
+  g.needs_tsumo = 1;
+  g.last_discard_pid = g.last_discard_tile = RV_NONE;
+  if (custom_wall) {
+    for (int i = 0; i < 136; i++) g.wall[i] = custom_wall[135 - i];  // wall.rs:69-72
+  } else {
+    uint8_t w[136];
+    wall_from_seed(g.seed, g.hand_index, 136, w);
+    g.hand_index++;
+    for (int i = 0; i < 136; i++) g.wall[i] = w[i];
+  }
+  g.wall_len = 136;
+  g.wall_top = 136;
+  g.n_dora = 1;
+  g.dora_ind[0] = g.wall[4];
+  for (int i = 1; i < 5; i++) g.dora_ind[i] = RV_NONE;
+  g.kyoku_count++;
+  // deal: 3 x (4 tiles per seat from oya), then 1 each; tiles pop from the back
+  for (int r = 0; r < 3; r++)
+    for (int idx = 0; idx < NP; idx++) {
+      int p = (idx + oya) % NP;
+      for (int k = 0; k < 4; k++) hand_push(g, p, g.wall[--g.wall_top]);
+    }
+  for (int idx = 0; idx < NP; idx++) {
+    int p = (idx + oya) % NP;
+    hand_push(g, p, g.wall[--g.wall_top]);
+  }
+  for (int p = 0; p < NP; p++) hand_sort(g, p);
+  g.drawable_count = (uint8_t)(g.wall_top - 14);
+  {
+    uint32_t w[19];
+    w[0] = ev_w0(RV_EV_START_KYOKU, 19, round_wind % 4, oya);
+    w[1] = (uint32_t)honba | ((uint32_t)g.dora_ind[0] << 8) | ((kyotaku & 0xFFFF) << 16);
+    for (int i = 0; i < NP; i++) w[2 + i] = (uint32_t)g.score[i];
+    for (int k = 0; k < 13; k++) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; b++) {
+        int flat = k * 4 + b, p = flat / 13, i = flat % 13;
+        v |= (uint32_t)g.hand[p][i] << (8 * b);
+      }
+      w[6 + k] = v;
+    }
+    ev_push(cx, g, w, 19);
+  }
+  g.phase = RV_WAIT_ACT;
+  g.active_mask = (uint8_t)(1u << oya);
+  {
+    int t = g.wall[--g.wall_top];
+    g.drawable_count--;
+    hand_push(g, oya, t);
+    g.drawn_tile = (uint8_t)t;
+    g.needs_tsumo = 0;
+    ev_simple(cx, g, RV_EV_TSUMO, oya, t);
+  }
+}
+
+// RiichiEnv::new + reset (env.rs:82-118, 799-851): fresh game, logs cleared
+__device__ inline void game_reset(const Ctx& cx, G& g, int oya, int round_wind, int honba, uint32_t kyotaku,
+                                  const uint8_t* custom_wall, const int32_t* scores) {
+  g.ev_hash = 0xcbf29ce484222325ull;
+  g.ev_count = g.ev_words = g.step_count = g.kyoku_count = 0;
+  g.last_error = RV_NONE;   // NOTE: the reference never clears last_error on reset (state/mod.rs:171-187); a fresh
+                            // VecEnv has none, and rv_vec_reset is documented to clear it.
+  g.overflow = 0;
+  ev_simple(cx, g, RV_EV_START_GAME);
+  int32_t def[NP] = {25000, 25000, 25000, 25000};
+  init_round(cx, g, oya, round_wind, honba, kyotaku, custom_wall, scores ? scores : def);
+}
+
+// state/mod.rs:2071-2081
+__device__ inline void end_game(const Ctx& cx, G& g) {
+  g.is_done = 1;
+  ev_simple(cx, g, RV_EV_END_KYOKU);
+  ev_simple(cx, g, RV_EV_END_GAME);
+}
+
+// state/mod.rs:1595-1688
+__device__ __noinline__ void next_round(const Ctx& cx, G& g, bool oya_won, bool is_draw) {
+  if (g.is_done) return;
+  int32_t mx = g.score[0];
+  bool tobi = false;
+  for (int p = 0; p < NP; p++) {
+    if (g.score[p] < 0) tobi = true;
+    mx = max(mx, g.score[p]);
+  }
+  if (tobi) {
+    end_game(cx, g);
+    return;
+  }
+  int oya = g.oya;
+  int32_t ds = g.score[oya];
+  bool top = true;
+  for (int s = 0; s < NP; s++)
+    if (!(s == oya || ds > g.score[s] || (ds == g.score[s] && oya <= s))) top = false;
+  int gm = g.game_mode;
+  bool last = false;
+  if (gm == 1 || gm == 4) last = g.round_wind == 0 && oya == NP - 1;
+  if (gm == 2 || gm == 5) last = g.round_wind == 1 && oya == NP - 1;
+  if (oya_won && last && top && ds >= 30000) {
+    end_game(cx, g);
+    return;
+  }
+  int nh = g.honba, no = oya, nw = g.round_wind;
+  if (oya_won) {
+    nh = nh == 255 ? 255 : nh + 1;
+  } else {
+    nh = is_draw ? (nh == 255 ? 255 : nh + 1) : 0;
+    no = (no + 1) % NP;
+    if (no == 0) nw += 1;
+  }
+  bool fin;
+  if (gm == 1 || gm == 4) fin = nw >= 1 && (mx >= 30000 || nw > 1);
+  else if (gm == 2 || gm == 5) fin = nw >= 2 && (mx >= 30000 || nw > 2);
+  else if (gm == 0 || gm == 3) fin = true;
+  else fin = nw >= 1;
+  if (fin) {
+    end_game(cx, g);
+    return;
+  }
+  ev_simple(cx, g, RV_EV_END_KYOKU);
+  init_round(cx, g, no, nw, nh, g.riichi_sticks, nullptr, nullptr);
+}
+
+// is_tenpai of a seat's 13-tile-equivalent hand (hand_evaluator.rs:178-194)
+__device__ inline bool seat_tenpai(const Ctx& cx, const G& g, int p) {
+  if (g.hand_len[p] + 3 * g.n_melds[p] != 13) return false;
+  Cnt c = hand_cnt(g, p);
+  return waits13(cx.T, c) != 0;
+}
+
+// state/mod.rs:1846-1968
+__device__ __noinline__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason) {
+  accept_riichi(cx, g);
+  bool tenpai[NP] = {false, false, false, false};
+  int final_reason = reason;
+  int nagashi_mask = 0;
+  int oya = g.oya;
+  if (reason == RV_RK_EXHAUSTIVE) {
+    for (int p = 0; p < NP; p++) {
+      tenpai[p] = seat_tenpai(cx, g, p);
+      if (g.flags[p] & RV_F_NAGASHI_ELIGIBLE) nagashi_mask |= 1 << p;
+    }
+    if (nagashi_mask) {
+      final_reason = RV_RK_NAGASHI;
+      for (int w = 0; w < NP; w++) {
+        if (!(nagashi_mask & (1 << w))) continue;
+        bool is_oya = w == oya;   // mangan tsumo: calculate_score(5,30,is_oya,true,0,4) -> oya 4000 / ko 2000
+        for (int i = 0; i < NP; i++) {
+          if (i == w) continue;
+          int32_t pay = is_oya ? 4000 : (i == oya ? 4000 : 2000);
+          g.score[i] -= pay;
+          g.score_delta[i] -= pay;
+          g.score[w] += pay;
+          g.score_delta[w] += pay;
+        }
+      }
+    } else {
+      int ntp = tenpai[0] + tenpai[1] + tenpai[2] + tenpai[3];
+      if (ntp > 0 && ntp < NP) {
+        int32_t pk = 3000 / ntp, pn = 3000 / (NP - ntp);
+        for (int i = 0; i < NP; i++) {
+          int32_t d = tenpai[i] ? pk : -pn;
+          g.score[i] += d;
+          g.score_delta[i] = d;
+        }
+      }
+    }
+  } else if (reason >= RV_RK_ILLEGAL_BASE && reason - RV_RK_ILLEGAL_BASE < NP) {
+    int pid = reason - RV_RK_ILLEGAL_BASE;
+    for (int i = 0; i < NP; i++) {
+      int32_t d;
+      if (pid == oya) d = (i == pid) ? -12000 : 4000;
+      else d = (i == pid) ? -8000 : (i == oya ? 4000 : 2000);
+      g.score[i] += d;
+      g.score_delta[i] = d;
+    }
+  }
+  bool renchan = final_reason == RV_RK_EXHAUSTIVE ? tenpai[oya]
+               : final_reason == RV_RK_NAGASHI ? ((nagashi_mask >> oya) & 1) != 0 : true;
+  uint32_t w[5] = {ev_w0(RV_EV_RYUKYOKU, 5, final_reason, 0), (uint32_t)g.score_delta[0], (uint32_t)g.score_delta[1],
+                   (uint32_t)g.score_delta[2], (uint32_t)g.score_delta[3]};
+  ev_push(cx, g, w, 5);
+  next_round(cx, g, renchan, true);
+}
+
+// state/mod.rs:1970-2019
+__device__ __noinline__ bool check_abortive_draw(const Ctx& cx, G& g) {
+  bool turns_ok = true;
+  for (int p = 0; p < NP; p++)
+    if (g.n_river[p] != 1) turns_ok = false;
+  if (turns_ok && all_meldless(g)) {
+    int first = g.river[0][0] >> 2;
+    if (first >= 27 && first <= 30 && (g.river[1][0] >> 2) == first && (g.river[2][0] >> 2) == first &&
+        (g.river[3][0] >> 2) == first) {
+      trigger_ryukyoku(cx, g, RV_RK_SUFUURENTA);
+      return true;
+    }
+  }
+  int kans = 0, first_owner = -1;
+  bool same = true;
+  for (int p = 0; p < NP; p++)
+    for (int m = 0; m < g.n_melds[p]; m++)
+      if (g.meld_type[p][m] >= RV_MELD_DAIMINKAN) {
+        kans++;
+        if (first_owner < 0) first_owner = p;
+        else if (p != first_owner) same = false;
+      }
+  if (kans == 4 && !same) {
+    trigger_ryukyoku(cx, g, RV_RK_SUUKANSANSEN);
+    return true;
+  }
+  if ((g.flags[0] & g.flags[1] & g.flags[2] & g.flags[3]) & RV_F_RIICHI_DECLARED) {
+    trigger_ryukyoku(cx, g, RV_RK_SUUCHA_RIICHI);
+    return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------ claims (state/legal_actions.rs:254-508)
+__device__ __forceinline__ uint32_t pack_act(int type, int tile, int c0, int c1) {
+  return (uint32_t)type | ((uint32_t)(tile & 0xFF) << 8) | ((uint32_t)(c0 & 0xFF) << 16) | ((uint32_t)(c1 & 0xFF) << 24);
+}
+__device__ inline void claim_push(G& g, int i, uint32_t a) {
+  int n = g.n_claims[i];
+  if (n < RV_MAX_CLAIMS) {
+    g.claims[i][n] = a;
+    g.n_claims[i] = (uint8_t)(n + 1);
+  } else {
+    g.overflow = 1;
+  }
+}
+// Fills g.claims[i]; returns the reference's `missed_agari` flag.
+__device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int tile) {
+  bool missed = false;
+  g.n_claims[i] = 0;
+  int kind = tile >> 2;
+  int hl = g.hand_len[i];
+  uint32_t f = g.flags[i];
+  bool riichi = f & RV_F_RIICHI_DECLARED;
+  // 1. Ron
+  uint64_t rk = river_kinds(g, i);
+  bool in_discards = (rk >> kind) & 1;
+  bool in_missed = (f & RV_F_MISSED_AGARI_DOUJUN) || (riichi && (f & RV_F_MISSED_AGARI_RIICHI));
+  if (!in_discards && !in_missed && hl + 3 * g.n_melds[i] == 13) {
+    Cnt c = hand_cnt(g, i);
+    SuitInfo si;
+    load_info(cx.T, c, si);
+    uint64_t waits = waits13(c, si);
+    if ((waits >> kind) & 1) {   // hand + tile has a winning shape (calc would pass is_agari)
+      bool furiten = (waits & rk) != 0 || (f & (RV_F_MISSED_AGARI_RIICHI | RV_F_MISSED_AGARI_DOUJUN));
+      if (!furiten) {
+        uint32_t cond = base_cond(g, i);
+        if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
+        WinRes r = seat_calc(cx, g, i, tile, cond, false, g.honba);
+        if (r.is_win) claim_push(g, i, pack_act(RV_RON, tile, RV_NONE, RV_NONE));
+        else if (r.has_shape) missed = true;
+      }
+    }
+  }
+  // 2. Pon / Daiminkan
+  if (!riichi && g.drawable_count > 0) {
+    uint8_t match[4];
+    int cnt = 0;
+    bool other_kind = false;
+    for (int k = 0; k < hl; k++) {
+      int t = g.hand[i][k];
+      if ((t >> 2) == kind) { if (cnt < 4) match[cnt++] = (uint8_t)t; }
+      else other_kind = true;
+    }
+    if (cnt >= 2 && hl >= 3) {
+      // kuikae: some tile other than the consumed pair must be discardable
+      bool ok = rule(g, RV_RULE_KUIKAE_FORBIDDEN) ? other_kind : true;
+      if (ok)
+        for (int a = 0; a < cnt; a++)
+          for (int b = a + 1; b < cnt; b++) claim_push(g, i, pack_act(RV_PON, tile, match[a], match[b]));
+    }
+    if (cnt >= 3) claim_push(g, i, pack_act(RV_DAIMINKAN, tile, match[0], match[1]));
+  }
+  // 3. Chi
+  if (!riichi && g.drawable_count > 0 && i == (pid + 1) % NP && hl >= 3 && kind < 27) {
+    int r9 = kind % 9;
+    bool kuikae = rule(g, RV_RULE_KUIKAE_FORBIDDEN);
+    for (int pat = 0; pat < 3; pat++) {
+      int ka, kb, forb2 = -1;
+      if (pat == 0) { if (r9 < 2) continue; ka = kind - 2; kb = kind - 1; if (r9 >= 3) forb2 = kind - 3; }
+      else if (pat == 1) { if (r9 < 1 || r9 > 7) continue; ka = kind - 1; kb = kind + 1; }
+      else { if (r9 > 6) continue; ka = kind + 1; kb = kind + 2; if (r9 <= 5) forb2 = kind + 3; }
+      // leftover tiles (hand minus c1,c2) need one tile that is neither `kind` nor forb2
+      int free_tiles = 0;
+      for (int k = 0; k < hl; k++) {
+        int tk = g.hand[i][k] >> 2;
+        if (!kuikae || (tk != kind && tk != forb2)) free_tiles++;
+      }
+      if (free_tiles - 2 <= 0) continue;
+      for (int a = 0; a < hl; a++) {
+        int c1 = g.hand[i][a];
+        if ((c1 >> 2) != ka) continue;
+        for (int b = 0; b < hl; b++) {
+          int c2 = g.hand[i][b];
+          if ((c2 >> 2) != kb) continue;
+          claim_push(g, i, pack_act(RV_CHI, tile, c1, c2));
+        }
+      }
+    }
+  }
+  return missed;
+}
+
+// Expand a packed claim / turn action into the public rv_action (consume lists as the reference builds them)
+__device__ inline rv_action expand_act(const G& g, int seat, uint32_t a) {
+  rv_action r;
+  r.type = (uint8_t)(a & 0xFF);
+  r.tile = (uint8_t)((a >> 8) & 0xFF);
+  r.actor = (uint8_t)seat;
+  r.n_consume = 0;
+  for (int k = 0; k < 4; k++) r.consume[k] = RV_NONE;
+  int c0 = (a >> 16) & 0xFF, c1 = (a >> 24) & 0xFF;
+  switch (r.type) {
+    case RV_PON:
+    case RV_CHI:
+      r.consume[0] = (uint8_t)min(c0, c1);
+      r.consume[1] = (uint8_t)max(c0, c1);
+      r.n_consume = 2;
+      break;
+    case RV_DAIMINKAN: {  // first three matching tiles in hand order, sorted
+      int n = 0, kind = r.tile >> 2;
+      for (int k = 0; k < g.hand_len[seat] && n < 3; k++)
+        if ((g.hand[seat][k] >> 2) == kind) r.consume[n++] = g.hand[seat][k];
+      r.n_consume = (uint8_t)n;
+      for (int x = 1; x < n; x++)
+        for (int y = x; y > 0 && r.consume[y - 1] > r.consume[y]; y--) {
+          uint8_t t = r.consume[y]; r.consume[y] = r.consume[y - 1]; r.consume[y - 1] = t;
+        }
+      break;
+    }
+    case RV_ANKAN: {
+      int lo = (r.tile >> 2) << 2;
+      for (int k = 0; k < 4; k++) r.consume[k] = (uint8_t)(lo + k);
+      r.n_consume = 4;
+      break;
+    }
+    case RV_KAKAN: {  // consume = the pon's tiles (legal_actions.rs:158-172)
+      int kind = r.tile >> 2;
+      for (int m = 0; m < g.n_melds[seat]; m++)
+        if (g.meld_type[seat][m] == RV_MELD_PON && (g.meld_tiles[seat][m][0] >> 2) == kind) {
+          for (int k = 0; k < 3; k++) r.consume[k] = g.meld_tiles[seat][m][k];
+          r.n_consume = 3;
+          break;
+        }
+      break;
+    }
+    default:
+      break;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------ turn actions (state/legal_actions.rs:11-252)
+struct TurnInfo {
+  bool can_tsumo, can_riichi, riichi_ankan, kyushu;
+  uint16_t tenpai_keep;   // bit k: hand minus hand[k] is tenpai (valid when riichi_stage or can_riichi was evaluated)
+  uint64_t quads;         // kinds with four tiles in hand
+};
+
+// bit k set iff removing hand[k] leaves a tenpai hand
+__device__ __noinline__ uint16_t tenpai_discard_mask(const Ctx& cx, const G& g, int p, bool stop_at_first) {
+  int hl = g.hand_len[p];
+  if (hl - 1 + 3 * g.n_melds[p] != 13) return 0;
+  Cnt c = hand_cnt(g, p);
+  SuitInfo si;
+  load_info(cx.T, c, si);
+  uint16_t mask = 0;
+  uint64_t done = 0, good = 0;
+  for (int k = 0; k < hl; k++) {
+    int kind = g.hand[p][k] >> 2;
+    if (!((done >> kind) & 1)) {
+      done |= 1ull << kind;
+      Cnt c2 = c;
+      cnt_sub(c2, kind);
+      SuitInfo s2 = si;
+      int su = kind / 9;
+      uint32_t e = load_info_suit(cx.T, cnt_suit(c2, su), su);
+      s2.e[0] = su == 0 ? e : si.e[0];
+      s2.e[1] = su == 1 ? e : si.e[1];
+      s2.e[2] = su == 2 ? e : si.e[2];
+      s2.e[3] = su == 3 ? e : si.e[3];
+      if (waits13(c2, s2) != 0) good |= 1ull << kind;
+    }
+    if ((good >> kind) & 1) {
+      mask |= (uint16_t)(1u << k);
+      if (stop_at_first) return mask;
+    }
+  }
+  return mask;
+}
+
+__device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnInfo& ti) {
+  ti.can_tsumo = ti.can_riichi = ti.riichi_ankan = ti.kyushu = false;
+  ti.tenpai_keep = 0;
+  ti.quads = 0;
+  uint32_t f = g.flags[pid];
+  bool riichi = f & RV_F_RIICHI_DECLARED, stage = f & RV_F_RIICHI_STAGE;
+  int drawn = g.drawn_tile;
+  int hl = g.hand_len[pid];
+  if (drawn != RV_NONE && !stage) {
+    Cnt c = hand_cnt(g, pid);
+    if (hl + 3 * g.n_melds[pid] == 14 && agari14(cx.T, c)) {
+      uint32_t cond = base_cond(g, pid) | RV_C_TSUMO;
+      if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HAITEI;
+      if (g.is_rinshan_flag) cond |= RV_C_RINSHAN;
+      if (g.is_first_turn && g.n_river[pid] == 0) cond |= RV_C_TSUMO_FIRST_TURN;
+      WinRes r = seat_calc(cx, g, pid, drawn, cond, false, g.honba);
+      ti.can_tsumo = r.is_win && (r.yakuman || r.han >= 1);
+    }
+  }
+  if (stage) {
+    ti.tenpai_keep = tenpai_discard_mask(cx, g, pid, false);
+  } else if (!riichi) {
+    if (g.score[pid] >= 1000 && g.drawable_count >= 4 && !any_open_meld(g, pid))
+      ti.can_riichi = tenpai_discard_mask(cx, g, pid, true) != 0;
+  }
+  if (g.drawable_count > 0 && drawn != RV_NONE) {
+    Cnt c = hand_cnt(g, pid);
+    if (!riichi && !stage) {
+      #pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint64_t x = c.s[k] & 0x4444444444444444ull;   // nibble == 4
+        for (int i = 0; i < 9; i++)
+          if ((x >> (4 * i + 2)) & 1) ti.quads |= 1ull << (9 * k + i);
+      }
+    } else if (riichi) {
+      int kind = drawn >> 2;
+      if (cnt_get(c, kind) == 4 && hl + 3 * g.n_melds[pid] == 14) {
+        Cnt pre = c;
+        cnt_sub(pre, kind);
+        uint64_t wpre = waits13(cx.T, pre);
+        Cnt post = c;
+        cnt_sub(post, kind, 4);
+        uint64_t wpost = waits13(cx.T, post);
+        ti.riichi_ankan = wpre == wpost && wpre != 0;
+      }
+    }
+  }
+  if (g.is_first_turn && all_meldless(g) && !stage) {
+    uint64_t pres = 0;
+    for (int k = 0; k < hl; k++) pres |= 1ull << (g.hand[pid][k] >> 2);
+    ti.kyushu = __popcll(pres & MASK_TERMINAL_HONOR) >= 9;
+  }
+}
+
+__device__ __forceinline__ bool discard_forbidden(const G& g, int p, int tile) {
+  int k = tile >> 2;
+  return (g.forbidden[p][0] != RV_NONE && (g.forbidden[p][0] >> 2) == k) ||
+         (g.forbidden[p][1] != RV_NONE && (g.forbidden[p][1] >> 2) == k);
+}
+
+// Calls f(packed_action) for every legal turn action in the reference's order; returns the count.
+template <class F>
+__device__ inline int enum_turn_actions(const G& g, int pid, const TurnInfo& ti, F&& f) {
+  int n = 0;
+  uint32_t fl = g.flags[pid];
+  bool riichi = fl & RV_F_RIICHI_DECLARED, stage = fl & RV_F_RIICHI_STAGE;
+  int drawn = g.drawn_tile, hl = g.hand_len[pid];
+  if (ti.can_tsumo) { f(pack_act(RV_TSUMO, drawn, RV_NONE, RV_NONE)); n++; }
+  if (riichi) {
+    if (drawn != RV_NONE) { f(pack_act(RV_DISCARD, drawn, RV_NONE, RV_NONE)); n++; }
+  } else if (stage) {
+    for (int k = 0; k < hl; k++) {
+      int t = g.hand[pid][k];
+      if (discard_forbidden(g, pid, t)) continue;
+      if ((ti.tenpai_keep >> k) & 1) { f(pack_act(RV_DISCARD, t, RV_NONE, RV_NONE)); n++; }
+    }
+  } else {
+    for (int k = 0; k < hl; k++) {
+      int t = g.hand[pid][k];
+      if (!discard_forbidden(g, pid, t)) { f(pack_act(RV_DISCARD, t, RV_NONE, RV_NONE)); n++; }
+    }
+    if (ti.can_riichi) { f(pack_act(RV_RIICHI, RV_NONE, RV_NONE, RV_NONE)); n++; }
+  }
+  if (g.drawable_count > 0 && drawn != RV_NONE) {
+    if (!riichi && !stage) {
+      uint64_t q = ti.quads;
+      while (q) {
+        int kind = __ffsll((long long)q) - 1;
+        q &= q - 1;
+        f(pack_act(RV_ANKAN, kind * 4, RV_NONE, RV_NONE));
+        n++;
+      }
+      for (int m = 0; m < g.n_melds[pid]; m++)
+        if (g.meld_type[pid][m] == RV_MELD_PON) {
+          int target = g.meld_tiles[pid][m][0] >> 2;
+          for (int k = 0; k < hl; k++)
+            if ((g.hand[pid][k] >> 2) == target) { f(pack_act(RV_KAKAN, g.hand[pid][k], RV_NONE, RV_NONE)); n++; }
+        }
+    } else if (riichi && ti.riichi_ankan) {
+      f(pack_act(RV_ANKAN, (drawn >> 2) * 4, RV_NONE, RV_NONE));
+      n++;
+    }
+  }
+  if (ti.kyushu) { f(pack_act(RV_KYUSHU_KYUHAI, RV_NONE, RV_NONE, RV_NONE)); n++; }
+  return n;
+}
+
+// Legal actions of `pid` as the reference's _get_legal_actions_internal would list them (packed).
+// Returns count; out may be nullptr (count only).  `pick` >= 0: stores only that index into *picked.
+__device__ inline int legal_actions(const Ctx& cx, const G& g, int pid, uint32_t* out, int pick, uint32_t* picked) {
+  if (g.is_done) return 0;
+  if (g.phase == RV_WAIT_ACT) {
+    if (pid != g.current_player) return 0;
+    TurnInfo ti;
+    turn_info(cx, g, pid, ti);
+    int idx = 0;
+    return enum_turn_actions(g, pid, ti, [&](uint32_t a) {
+      if (out && idx < RV_MAX_LEGAL) out[idx] = a;
+      if (idx == pick && picked) *picked = a;
+      idx++;
+    });
+  }
+  int n = g.n_claims[pid];
+  for (int k = 0; k < n; k++) {
+    if (out) out[k] = g.claims[pid][k];
+    if (k == pick && picked) *picked = g.claims[pid][k];
+  }
+  uint32_t pass = pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
+  if (out && n < RV_MAX_LEGAL) out[n] = pass;
+  if (n == pick && picked) *picked = pass;
+  return n + 1;
+}
+
+// ------------------------------------------------------------------ settlement helpers
+__device__ inline void register_pao(G& g, int claimer, int tile, int discarder) {  // state/mod.rs:1229-1259
+  int tv = tile >> 2;
+  int dragons = 0, winds = 0;
+  for (int m = 0; m < g.n_melds[claimer]; m++) {
+    if (g.meld_type[claimer][m] == RV_MELD_CHI) continue;
+    int t = g.meld_tiles[claimer][m][0] >> 2;
+    if (t >= 31 && t <= 33) dragons++;
+    if (t >= 27 && t <= 30) winds++;
+  }
+  if (tv >= 31 && tv <= 33) {
+    if (dragons == 3) g.pao[claimer][0] = (uint8_t)discarder;
+  } else if (tv >= 27 && tv <= 30) {
+    if (winds == 4) g.pao[claimer][1] = (uint8_t)discarder;
+  }
+}
+__device__ __forceinline__ int yakuman_val(const G& g, int yid) {
+  if (yid == 47 && rule(g, RV_RULE_JUNSEI_CHUUREN_DOUBLE)) return 2;
+  if (yid == 48 && rule(g, RV_RULE_SUUANKOU_TANKI_DOUBLE)) return 2;
+  if (yid == 49 && rule(g, RV_RULE_KOKUSHI13_DOUBLE)) return 2;
+  if (yid == 50 && rule(g, RV_RULE_DAISUUSHII_DOUBLE)) return 2;
+  return 1;
+}
+// state/mod.rs:720-745 / 1009-1034
+__device__ inline void cap_double_yakuman(const G& g, WinRes& r, bool is_oya, bool tsumo, uint32_t honba) {
+  if (r.yakuman && r.han > 13) {
+    int cap = 0;
+    if (((r.yaku_mask >> 47) & 1) && !rule(g, RV_RULE_JUNSEI_CHUUREN_DOUBLE)) cap += 13;
+    if (((r.yaku_mask >> 48) & 1) && !rule(g, RV_RULE_SUUANKOU_TANKI_DOUBLE)) cap += 13;
+    if (((r.yaku_mask >> 49) & 1) && !rule(g, RV_RULE_KOKUSHI13_DOUBLE)) cap += 13;
+    if (((r.yaku_mask >> 50) & 1) && !rule(g, RV_RULE_DAISUUSHII_DOUBLE)) cap += 13;
+    if (cap > 0) {
+      r.han = max(r.han - cap, 13);
+      ScoreRes s = calc_score(r.han, 0, is_oya, tsumo, honba, NP);
+      r.ron = s.pay_ron;
+      r.oya = s.pay_oya;
+      r.ko = s.pay_ko;
+    }
+  }
+}
+__device__ inline void ev_hora(const Ctx& cx, G& g, int actor, int target, bool tsumo, const WinRes& r, const int32_t* d,
+                               bool with_ura) {
+  uint8_t ub[8] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE, RV_NONE, 0, 0, 0};
+  int n_ura = 0;
+  if (with_ura)
+    for (int i = 0; i < g.n_dora; i++) {
+      int idx = 5 + 2 * i;
+      if (idx < g.wall_top) ub[n_ura++] = g.wall[idx];
+    }
+  ub[5] = r.yakuman ? 1 : 0;
+  uint32_t w[10];
+  w[0] = ev_w0(RV_EV_HORA, 10, actor, target);
+  w[1] = (tsumo ? 1u : 0u) | ((uint32_t)n_ura << 8) | ((uint32_t)(r.han & 0xFF) << 16) | ((uint32_t)(r.fu & 0xFF) << 24);
+  w[2] = ub[0] | (ub[1] << 8) | (ub[2] << 16) | ((uint32_t)ub[3] << 24);
+  w[3] = ub[4] | (ub[5] << 8);
+  for (int i = 0; i < 4; i++) w[4 + i] = (uint32_t)d[i];
+  w[8] = (uint32_t)r.yaku_mask;
+  w[9] = (uint32_t)(r.yaku_mask >> 32);
+  ev_push(cx, g, w, 10);
+}
+
+// ------------------------------------------------------------------ kan (state/mod.rs:1415-1547)
+__device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_action& act) {
+  int c_ev[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
+  for (int k = 0; k < act.n_consume && k < 4; k++) c_ev[k] = act.consume[k];
+  if (act.type != RV_KAKAN) {
+    for (int k = 0; k < act.n_consume && k < 4; k++) hand_remove_first(g, pid, act.consume[k]);
+    int m = g.n_melds[pid];
+    if (m < 4) {
+      uint8_t tl[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
+      int n = 0;
+      for (int k = 0; k < act.n_consume && k < 4; k++) tl[n++] = act.consume[k];
+      if (act.type == RV_ANKAN) {
+        g.meld_type[pid][m] = RV_MELD_ANKAN;
+        g.meld_from[pid][m] = RV_NONE;
+        g.meld_called[pid][m] = RV_NONE;
+      } else {
+        if (n < 4) tl[n++] = g.last_discard_tile;
+        for (int x = 1; x < n; x++)
+          for (int y = x; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
+        g.meld_type[pid][m] = RV_MELD_DAIMINKAN;
+        g.meld_from[pid][m] = g.last_discard_pid;
+        g.meld_called[pid][m] = g.last_discard_tile;
+      }
+      for (int k = 0; k < 4; k++) g.meld_tiles[pid][m][k] = tl[k];
+      g.n_melds[pid] = (uint8_t)(m + 1);
+    } else {
+      g.overflow = 1;
+    }
+    if (act.type == RV_DAIMINKAN) register_pao(g, pid, g.last_discard_tile, g.last_discard_pid);
+  }
+  g.is_first_turn = 0;
+  for (int p = 0; p < NP; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
+  if (g.drawable_count > 0) {
+    int t = g.wall[g.rinshan_draw_count];   // Vec::remove(0)
+    g.drawable_count--;
+    hand_push(g, pid, t);
+    g.drawn_tile = (uint8_t)t;
+    g.rinshan_draw_count++;
+    g.is_rinshan_flag = 1;
+    if (act.type == RV_ANKAN) {
+      int tile = act.tile != RV_NONE ? act.tile : act.consume[0];
+      ev_meld(cx, g, RV_EV_ANKAN, pid, tile, c_ev[0], c_ev[1], c_ev[2], c_ev[3]);
+    } else if (act.type == RV_DAIMINKAN) {
+      ev_meld(cx, g, RV_EV_DAIMINKAN, pid, g.last_discard_tile, g.last_discard_pid, c_ev[0], c_ev[1], c_ev[2]);
+    }
+    flush_pending_kan_dora(cx, g);
+    if (act.type == RV_ANKAN) reveal_kan_dora(cx, g);
+    else g.pending_kan_dora_count++;
+    ev_simple(cx, g, RV_EV_TSUMO, pid, t);
+    g.phase = RV_WAIT_ACT;
+    g.active_mask = (uint8_t)(1u << pid);
+  }
+}
+
+// ------------------------------------------------------------------ discard (state/mod.rs:1317-1413)
+__device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int tile, bool tsumogiri) {
+  g.is_rinshan_flag = 0;
+  g.flags[pid] &= ~RV_F_IPPATSU_CYCLE;
+  int nr = g.n_river[pid];
+  bool stage = g.flags[pid] & RV_F_RIICHI_STAGE;
+  if (nr < RV_RIVER_CAP) {
+    g.river[pid][nr] = (uint8_t)tile;
+    if (!tsumogiri) g.river_tedashi[pid] |= 1u << nr;
+    if (stage) g.river_riichi[pid] |= 1u << nr;
+  } else {
+    g.overflow = 1;
+  }
+  g.n_river[pid] = (uint8_t)(nr + 1);
+  g.last_discard_pid = (uint8_t)pid;
+  g.last_discard_tile = (uint8_t)tile;
+  g.drawn_tile = RV_NONE;
+  if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)tile;
+  g.needs_tsumo = 1;
+  if (stage) {
+    g.flags[pid] |= RV_F_RIICHI_DECLARED;
+    if (g.is_first_turn) g.flags[pid] |= RV_F_DOUBLE_RIICHI;
+    g.riichi_decl_idx[pid] = (uint8_t)nr;
+    g.flags[pid] &= ~RV_F_RIICHI_STAGE;
+    g.riichi_pending_acceptance = (uint8_t)pid;
+  }
+  flush_pending_kan_dora(cx, g);
+  ev_simple(cx, g, tsumogiri ? RV_EV_DAHAI_TSUMOGIRI : RV_EV_DAHAI, pid, tile);
+  g.flags[pid] &= ~RV_F_MISSED_AGARI_DOUJUN;
+  if (!tid_terminal(tile)) g.flags[pid] &= ~RV_F_NAGASHI_ELIGIBLE;
+  for (int i = 0; i < NP; i++) g.n_claims[i] = 0;
+  g.active_mask = 0;
+  int claim_mask = 0;
+  for (int i = 0; i < NP; i++) {
+    if (i == pid) continue;
+    bool missed = gen_claims(cx, g, i, pid, tile);
+    if (missed) g.flags[i] |= RV_F_MISSED_AGARI_DOUJUN;
+    if (g.n_claims[i] > 0) claim_mask |= 1 << i;
+  }
+  if (claim_mask) {
+    g.phase = RV_WAIT_RESPONSE;
+    g.active_mask = (uint8_t)claim_mask;
+  } else {
+    accept_riichi(cx, g);
+    if (!check_abortive_draw(cx, g)) {
+      g.turn_count++;
+      g.current_player = (uint8_t)((pid + 1) % NP);
+      deal_next(cx, g);
+      if (g.turn_count >= (uint32_t)NP) g.is_first_turn = 0;
+    }
+  }
+}
+
+// chankan candidates after a kakan (state/mod.rs:588-684) / kokushi-on-ankan (485-547)
+__device__ __noinline__ int chankan_ronners(const Ctx& cx, G& g, int pid, int tile, bool ankan_kokushi_only) {
+  int mask = 0;
+  int kind = tile >> 2;
+  for (int i = 0; i < NP; i++) {
+    if (i == pid) continue;
+    if (g.hand_len[i] + 3 * g.n_melds[i] != 13) continue;
+    uint64_t rk = river_kinds(g, i);
+    uint32_t f = g.flags[i];
+    Cnt c = hand_cnt(g, i);
+    uint64_t waits = waits13(cx.T, c);
+    if (!((waits >> kind) & 1)) continue;
+    WinRes r;
+    if (ankan_kokushi_only) {
+      if ((rk >> kind) & 1) continue;
+      uint32_t cond = RV_C_CHANKAN | ((f & RV_F_RIICHI_DECLARED) ? RV_C_RIICHI : 0);
+      r = hand_calc(cx.T, g.hand[i], g.hand_len[i], g.n_melds[i], g.meld_type[i], g.meld_tiles[i], tile, g.dora_ind,
+                    g.n_dora, nullptr, 0, cond, (i + NP - g.oya) % NP, g.round_wind % 4, 0);
+      if (!(r.is_win && ((r.yaku_mask >> 42) & 1 || (r.yaku_mask >> 49) & 1))) continue;
+    } else {
+      bool furiten = (waits & rk) != 0 || (f & (RV_F_MISSED_AGARI_RIICHI | RV_F_MISSED_AGARI_DOUJUN));
+      if (furiten) continue;
+      r = seat_calc(cx, g, i, tile, base_cond(g, i) | RV_C_CHANKAN, false, g.honba);
+      if (!(r.is_win && (r.yakuman || r.han >= 1))) continue;
+    }
+    mask |= 1 << i;
+    claim_push(g, i, pack_act(RV_RON, tile, RV_NONE, RV_NONE));   // appended to (possibly stale) current_claims
+  }
+  return mask;
+}
+
+// ------------------------------------------------------------------ step (state/mod.rs:330-1315)
+// acts[p].type == RV_NO_ACTION  <=>  key p absent from the reference's HashMap.  No validation here.
+__device__ __noinline__ void step_apply(const Ctx& cx, G& g, const rv_action* acts) {
+  if (g.phase == RV_WAIT_ACT) {
+    int pid = g.current_player;
+    const rv_action& act = acts[pid];
+    switch (act.type) {
+      case RV_DISCARD: {
+        if (act.tile == RV_NONE) break;
+        int tile = act.tile;
+        bool tsumogiri = false, valid = false;
+        if (g.drawn_tile != RV_NONE && g.drawn_tile == tile) { tsumogiri = true; valid = true; }
+        if (hand_remove_first(g, pid, tile)) {
+          hand_sort(g, pid);
+          valid = true;
+        }
+        if (valid) resolve_discard(cx, g, pid, tile, tsumogiri);
+        break;
+      }
+      case RV_KYUSHU_KYUHAI:
+        trigger_ryukyoku(cx, g, RV_RK_KYUSHU);
+        break;
+      case RV_RIICHI: {
+        uint32_t f = g.flags[pid];
+        if (g.score[pid] >= 1000 && g.drawable_count >= 4 && !(f & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE))) {
+          g.flags[pid] |= RV_F_RIICHI_STAGE;
+          ev_simple(cx, g, RV_EV_REACH, pid);
+          if (act.tile != RV_NONE) {
+            int t = act.tile;
+            bool tsumogiri = g.drawn_tile != RV_NONE && g.drawn_tile == t;
+            g.riichi_sutehai[pid] = (uint8_t)t;
+            if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)t;
+            if (hand_remove_first(g, pid, t)) hand_sort(g, pid);
+            resolve_discard(cx, g, pid, t, tsumogiri);
+          }
+        }
+        break;
+      }
+      case RV_ANKAN: {
+        int tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
+        int ron_mask = 0;
+        if (rule(g, RV_RULE_RON_ON_ANKAN_KOKUSHI)) ron_mask = chankan_ronners(cx, g, pid, tile, true);
+        if (ron_mask) {
+          g.pending_kan_pid = (uint8_t)pid;
+          g.pending_kan_type = RV_ANKAN;
+          g.pending_kan_tile = (uint8_t)tile;
+          g.phase = RV_WAIT_RESPONSE;
+          g.active_mask = (uint8_t)ron_mask;
+          g.last_discard_pid = (uint8_t)pid;
+          g.last_discard_tile = (uint8_t)tile;
+        } else {
+          resolve_kan(cx, g, pid, act);
+        }
+        break;
+      }
+      case RV_KAKAN: {
+        int tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
+        hand_remove_first(g, pid, tile);
+        for (int m = 0; m < g.n_melds[pid]; m++)
+          if (g.meld_type[pid][m] == RV_MELD_PON && (g.meld_tiles[pid][m][0] >> 2) == (tile >> 2)) {
+            g.meld_type[pid][m] = RV_MELD_KAKAN;
+            uint8_t* tl = g.meld_tiles[pid][m];
+            tl[3] = (uint8_t)tile;
+            for (int y = 3; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
+            break;
+          }
+        {
+          int c[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
+          for (int k = 0; k < act.n_consume && k < 4; k++) c[k] = act.consume[k];
+          ev_meld(cx, g, RV_EV_KAKAN, pid, tile, c[0], c[1], c[2], c[3]);
+        }
+        flush_pending_kan_dora(cx, g);
+        int ron_mask = chankan_ronners(cx, g, pid, tile, false);
+        if (ron_mask) {
+          g.pending_kan_pid = (uint8_t)pid;
+          g.pending_kan_type = RV_KAKAN;
+          g.pending_kan_tile = (uint8_t)tile;
+          g.phase = RV_WAIT_RESPONSE;
+          g.active_mask = (uint8_t)ron_mask;
+          g.last_discard_pid = (uint8_t)pid;
+          g.last_discard_tile = (uint8_t)tile;
+        } else {
+          resolve_kan(cx, g, pid, act);
+        }
+        break;
+      }
+      case RV_TSUMO: {
+        uint32_t cond = base_cond(g, pid) | RV_C_TSUMO;
+        if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HAITEI;
+        if (g.is_rinshan_flag) cond |= RV_C_RINSHAN;
+        if (g.is_first_turn && all_meldless(g)) cond |= RV_C_TSUMO_FIRST_TURN;
+        bool riichi = g.flags[pid] & RV_F_RIICHI_DECLARED;
+        int win_tile = g.drawn_tile != RV_NONE ? g.drawn_tile : 0;
+        WinRes r = seat_calc(cx, g, pid, win_tile, cond, riichi, g.honba);
+        int oya = g.oya;
+        cap_double_yakuman(g, r, pid == oya, true, g.honba);
+        if (r.is_win) {
+          int32_t d[NP] = {0, 0, 0, 0};
+          int32_t total_win = 0;
+          int pao_payer = -1, pao_val = 0, total_val = 0;
+          if (r.yakuman) {
+            uint64_t m = r.yaku_mask;
+            while (m) {
+              int y = __ffsll((long long)m) - 1;
+              m &= m - 1;
+              int v = yakuman_val(g, y);
+              total_val += v;
+              int liable = y == 37 ? g.pao[pid][0] : y == 50 ? g.pao[pid][1] : RV_NONE;
+              if (liable != RV_NONE) { pao_val += v; pao_payer = liable; }
+            }
+          }
+          if (pao_val > 0) {
+            int32_t unit = pid == oya ? 48000 : 32000;
+            int32_t honba_total = (int32_t)g.honba * (NP - 1) * 100;
+            if (rule(g, RV_RULE_PAO_LIABILITY_ONLY)) {
+              int32_t pao_amt = pao_val * unit + honba_total;
+              int non_pao = total_val - pao_val;
+              d[pao_payer] -= pao_amt;
+              total_win += pao_amt;
+              if (non_pao > 0)
+                for (int i = 0; i < NP; i++)
+                  if (i != pid) {
+                    int32_t pay = (pid == oya || i == oya) ? non_pao * 16000 : non_pao * 8000;
+                    d[i] -= pay;
+                    total_win += pay;
+                  }
+            } else {
+              int32_t full = total_val * unit + honba_total;
+              d[pao_payer] -= full;
+              total_win += full;
+            }
+          } else {
+            for (int i = 0; i < NP; i++)
+              if (i != pid) {
+                int32_t pay = (pid == oya || i != oya) ? (int32_t)r.ko : (int32_t)r.oya;
+                d[i] = -pay;
+                total_win += pay;
+              }
+          }
+          total_win += (int32_t)(g.riichi_sticks * 1000);
+          g.riichi_sticks = 0;
+          d[pid] += total_win;
+          for (int i = 0; i < NP; i++) {
+            g.score[i] += d[i];
+            g.score_delta[i] = d[i];
+          }
+          ev_hora(cx, g, pid, pid, true, r, d, riichi);
+          next_round(cx, g, pid == oya, false);
+        } else {
+          g.current_player = (uint8_t)((g.current_player + 1) % NP);
+          deal_next(cx, g);
+        }
+        break;
+      }
+      default:
+        break;
+    }
+  } else {
+    // missed agari (state/mod.rs:902-917): every seat holding a Ron claim (stale ones included) that did not ron
+    for (int p = 0; p < NP; p++) {
+      bool has_ron = false;
+      for (int k = 0; k < g.n_claims[p]; k++)
+        if ((g.claims[p][k] & 0xFF) == RV_RON) has_ron = true;
+      if (has_ron && acts[p].type != RV_RON) {
+        g.flags[p] |= RV_F_MISSED_AGARI_DOUJUN;
+        if (g.flags[p] & RV_F_RIICHI_DECLARED) g.flags[p] |= RV_F_MISSED_AGARI_RIICHI;
+      }
+    }
+    int ron_mask = 0, call_pid = -1;
+    for (int p = 0; p < NP; p++) {
+      if (!((g.active_mask >> p) & 1)) continue;
+      int ty = acts[p].type;
+      if (ty == RV_RON) ron_mask |= 1 << p;
+      else if (ty == RV_PON || ty == RV_DAIMINKAN || ty == RV_CHI) {
+        if (call_pid >= 0) {
+          int oty = acts[call_pid].type;
+          bool old_pon = oty == RV_PON || oty == RV_DAIMINKAN, new_pon = ty == RV_PON || ty == RV_DAIMINKAN;
+          if (!old_pon && new_pon) call_pid = p;
+        } else {
+          call_pid = p;
+        }
+      }
+    }
+    if (ron_mask) {
+      if (__popc(ron_mask) >= NP - 1 && rule(g, RV_RULE_SANCHAHO_IS_DRAW)) {
+        trigger_ryukyoku(cx, g, RV_RK_SANCHAHO);
+        return;
+      }
+      int target = g.last_discard_pid != RV_NONE ? g.last_discard_pid : g.current_player;
+      int win_tile = g.last_discard_pid != RV_NONE ? g.last_discard_tile : 0;
+      int32_t total[NP] = {0, 0, 0, 0};
+      bool oya_won = false, deposit_taken = false, honba_taken = false;
+      bool is_chankan = g.pending_kan_pid != RV_NONE;
+      int oya = g.oya;
+      for (int dist = 1; dist < NP; dist++) {   // winners sorted by distance from the discarder
+        int w = (target + dist) % NP;
+        if (!((ron_mask >> w) & 1)) continue;
+        uint32_t ron_honba = 0;
+        if (!honba_taken) { honba_taken = true; ron_honba = g.honba; }
+        uint32_t cond = base_cond(g, w);
+        if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
+        if (is_chankan) cond |= RV_C_CHANKAN;
+        bool riichi = g.flags[w] & RV_F_RIICHI_DECLARED;
+        WinRes r = seat_calc(cx, g, w, win_tile, cond, riichi, ron_honba);
+        cap_double_yakuman(g, r, w == oya, false, ron_honba);
+        if (r.is_win) {
+          int32_t score = (int32_t)r.ron;
+          int pao_payer = target;
+          int32_t pao_amt = 0;
+          if (r.yakuman) {
+            bool has_pao = false;
+            int total_val = 0, pao_val = 0;
+            uint64_t m = r.yaku_mask;
+            while (m) {
+              int y = __ffsll((long long)m) - 1;
+              m &= m - 1;
+              int v = yakuman_val(g, y);
+              total_val += v;
+              int liable = y == 37 ? g.pao[w][0] : y == 50 ? g.pao[w][1] : RV_NONE;
+              if (liable != RV_NONE) { has_pao = true; pao_payer = liable; pao_val += v; }
+            }
+            if (has_pao) {
+              int32_t unit = w == oya ? 48000 : 32000;
+              int32_t honba_ron = (int32_t)ron_honba * (NP - 1) * 100;
+              int32_t split = rule(g, RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
+              pao_amt = split / 2 + honba_ron;
+            }
+          }
+          int32_t td[NP] = {0, 0, 0, 0};
+          td[w] += score;
+          td[pao_payer] -= pao_amt;
+          td[target] -= score - pao_amt;
+          if (!deposit_taken) {
+            td[w] += (int32_t)(g.riichi_sticks * 1000);
+            g.riichi_sticks = 0;
+            deposit_taken = true;
+          }
+          for (int i = 0; i < NP; i++) total[i] += td[i];
+          if (w == oya) oya_won = true;
+          ev_hora(cx, g, w, target, false, r, td, riichi);
+        }
+      }
+      for (int i = 0; i < NP; i++) {
+        g.score[i] += total[i];
+        g.score_delta[i] = total[i];
+      }
+      next_round(cx, g, oya_won, false);
+    } else if (call_pid >= 0) {
+      int claimer = call_pid;
+      const rv_action& act = acts[claimer];
+      accept_riichi(cx, g);
+      g.is_rinshan_flag = 0;
+      g.is_first_turn = 0;
+      g.flags[claimer] &= ~RV_F_MISSED_AGARI_DOUJUN;
+      if (g.last_discard_pid != RV_NONE) g.flags[g.last_discard_pid] &= ~RV_F_NAGASHI_ELIGIBLE;
+      for (int p = 0; p < NP; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
+      if (act.type == RV_DAIMINKAN) {
+        g.current_player = (uint8_t)claimer;
+        g.active_mask = (uint8_t)(1u << claimer);
+        g.forbidden[claimer][0] = g.forbidden[claimer][1] = RV_NONE;
+        resolve_kan(cx, g, claimer, act);
+        return;
+      }
+      for (int k = 0; k < act.n_consume && k < 4; k++) hand_remove_first(g, claimer, act.consume[k]);
+      int discarder = g.last_discard_pid, tile = g.last_discard_tile;
+      int m = g.n_melds[claimer];
+      if (m < 4) {
+        uint8_t tl[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
+        int n = 0;
+        for (int k = 0; k < act.n_consume && k < 3; k++) tl[n++] = act.consume[k];
+        tl[n++] = (uint8_t)tile;
+        for (int x = 1; x < n; x++)
+          for (int y = x; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
+        for (int k = 0; k < 4; k++) g.meld_tiles[claimer][m][k] = tl[k];
+        g.meld_type[claimer][m] = act.type == RV_PON ? RV_MELD_PON : RV_MELD_CHI;
+        g.meld_from[claimer][m] = (uint8_t)discarder;
+        g.meld_called[claimer][m] = (uint8_t)tile;
+        g.n_melds[claimer] = (uint8_t)(m + 1);
+      } else {
+        g.overflow = 1;
+      }
+      {
+        int c0 = act.n_consume > 0 ? act.consume[0] : RV_NONE, c1 = act.n_consume > 1 ? act.consume[1] : RV_NONE,
+            c2 = act.n_consume > 2 ? act.consume[2] : RV_NONE;
+        ev_meld(cx, g, act.type == RV_PON ? RV_EV_PON : RV_EV_CHI, claimer, tile, discarder, c0, c1, c2);
+      }
+      if (act.type == RV_PON) register_pao(g, claimer, tile, discarder);
+      g.current_player = (uint8_t)claimer;
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << claimer);
+      g.forbidden[claimer][0] = (uint8_t)tile;
+      g.forbidden[claimer][1] = RV_NONE;
+      if (act.type == RV_CHI && act.n_consume >= 2) {
+        int t34 = tile >> 2;
+        int a = act.consume[0] >> 2, b = act.consume[1] >> 2;
+        if (a > b) { int t = a; a = b; b = t; }
+        if (a == t34 + 1 && b == t34 + 2) {
+          if (t34 % 9 <= 5) g.forbidden[claimer][1] = (uint8_t)((t34 + 3) * 4);
+        } else if (t34 >= 2 && b == t34 - 1 && a == t34 - 2 && t34 % 9 >= 3) {
+          g.forbidden[claimer][1] = (uint8_t)((t34 - 3) * 4);
+        }
+      }
+      g.needs_tsumo = 0;
+      g.drawn_tile = RV_NONE;
+    } else {
+      for (int i = 0; i < NP; i++) g.n_claims[i] = 0;
+      g.active_mask = 0;
+      if (g.pending_kan_pid != RV_NONE) {
+        int pk = g.pending_kan_pid;
+        rv_action a = expand_act(g, pk, pack_act(g.pending_kan_type, g.pending_kan_tile, RV_NONE, RV_NONE));
+        g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
+        resolve_kan(cx, g, pk, a);
+      } else {
+        accept_riichi(cx, g);
+        g.turn_count++;
+        g.current_player = (uint8_t)((g.current_player + 1) % NP);
+        deal_next(cx, g);
+        if (g.turn_count >= (uint32_t)NP) g.is_first_turn = 0;
+      }
+    }
+  }
+}
+
+// state/mod.rs:344-392
+__device__ inline bool action_matches(const rv_action& l, const rv_action& a) {
+  if (l.type != a.type) return false;
+  bool tiles_match = l.tile == a.tile;
+  bool cons_match = l.n_consume == a.n_consume;
+  if (cons_match)
+    for (int k = 0; k < l.n_consume && k < 4; k++)
+      if (l.consume[k] != a.consume[k]) cons_match = false;
+  if (tiles_match) {
+    if (cons_match) return true;
+    if (a.n_consume == 0 && l.type == RV_KAKAN) return true;
+    if (a.n_consume == 0 && (l.type == RV_DISCARD || l.type == RV_RIICHI || l.type == RV_TSUMO || l.type == RV_RON || l.type == RV_PASS))
+      return true;
+  }
+  if (cons_match && (l.type == RV_ANKAN || l.type == RV_KAKAN)) return true;
+  if (a.tile == RV_NONE)
+    return l.type == RV_TSUMO || l.type == RV_RON || l.type == RV_RIICHI || l.type == RV_KYUSHU_KYUHAI || l.type == RV_KITA;
+  return false;
+}
+
+// keyed random agent shared with the oracle (SURVEY.md §8 d)
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uint64_t game_id, uint32_t step, int seat, uint32_t n) {
+  uint64_t k = agent_seed ^ (game_id * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)step << 8) ^ (uint64_t)seat;
+  return (uint32_t)(mix64(k) % n);
+}
+
+// One env step with the on-device random agent.
+__device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+  rv_action acts[NP];
+  for (int p = 0; p < NP; p++) acts[p].type = RV_NO_ACTION;
+  uint32_t sc = g.step_count;
+  if (g.phase == RV_WAIT_ACT) {
+    int pid = g.current_player;
+    TurnInfo ti;
+    turn_info(cx, g, pid, ti);
+    int n = enum_turn_actions(g, pid, ti, [](uint32_t) {});
+    if (n > 0) {
+      int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
+      uint32_t chosen = 0;
+      int idx = 0;
+      enum_turn_actions(g, pid, ti, [&](uint32_t a) {
+        if (idx == pick) chosen = a;
+        idx++;
+      });
+      acts[pid] = expand_act(g, pid, chosen);
+    }
+  } else {
+    for (int p = 0; p < NP; p++) {
+      if (!((g.active_mask >> p) & 1)) continue;
+      int n = g.n_claims[p] + 1;
+      int pick = (int)agent_pick(agent_seed, game_id, sc, p, (uint32_t)n);
+      uint32_t chosen = pick < g.n_claims[p] ? g.claims[p][pick] : pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
+      acts[p] = expand_act(g, p, chosen);
+    }
+  }
+  g.step_count = sc + 1;
+  step_apply(cx, g, acts);
+}
+
+}  // namespace rv

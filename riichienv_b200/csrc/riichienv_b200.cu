@@ -1,0 +1,598 @@
+// Kernels + extern "C" entry points of libriichienv_b200.so (see include/riichienv_b200.h).
+// There is NO CPU fallback in this file: every compute entry point launches CUDA kernels
+// and returns RV_ERR_CUDA if the device is unavailable.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "game.cuh"
+
+using namespace rv;
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(RV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+struct rv_ctx {
+  int device;
+  cudaStream_t stream;
+  cudaEvent_t ev[8];
+  uint32_t *suit_info, *honor_info;
+  uint64_t *suit_cost, *honor_cost;
+  Tables T;
+  int sm_count;
+};
+
+struct rv_vec {
+  rv_ctx* ctx;
+  int64_t n;
+  int game_mode;
+  uint32_t rule_bits;
+  G* d_states;
+  uint32_t* d_log;  // n * log_cap words or nullptr
+  uint32_t log_cap;
+  uint64_t* d_seeds;            // scratch for rv_vec_reseed
+  unsigned long long* d_steps;  // [0] = env steps executed, [1] = games finished (by step kernels)
+};
+
+// ------------------------------------------------------------------ kernels
+__global__ void hand_eval_kernel(Tables T, const rv_hand_query* __restrict__ q, rv_hand_result* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rv_hand_query h = q[i];
+  WinRes r = hand_calc(T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
+                       h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba);
+  rv_hand_result o;
+  memset(&o, 0, sizeof o);
+  o.is_win = r.is_win;
+  o.yakuman = r.yakuman;
+  o.has_win_shape = r.has_shape;
+  o.han = (uint8_t)r.han;
+  o.fu = (uint8_t)r.fu;
+  o.ron_agari = r.ron;
+  o.tsumo_agari_oya = r.oya;
+  o.tsumo_agari_ko = r.ko;
+  o.yaku_mask = r.yaku_mask;
+  o.n_yaku = (uint8_t)__popcll(r.yaku_mask);
+  // concealed histogram (kan melds whose tiles are also listed count 3, as HandEvaluator::new)
+  Cnt c;
+  cnt_zero(c);
+  for (int k = 0; k < h.n_tiles; k++) cnt_add(c, h.tiles[k] >> 2);
+  Cnt raw = c;
+  for (int m = 0; m < h.n_melds; m++)
+    if (h.meld_type[m] >= RV_MELD_DAIMINKAN) {
+      int kind = h.meld_tiles[m][0] >> 2;
+      if (cnt_get(c, kind) == 4) cnt_sub(c, kind, 1);
+    }
+  int total = cnt_total(c) + 3 * h.n_melds;
+  int win34 = h.win_tile >> 2;
+  Cnt c13 = c, r13 = raw;
+  bool ok13 = total == 13;
+  if (total == 14 && cnt_get(c, win34) > 0) {
+    cnt_sub(c13, win34);
+    cnt_sub(r13, win34);
+    ok13 = true;
+  }
+  o.wait_mask = ok13 ? waits13(T, c13) : 0;
+  Cnt r14 = raw;
+  int n14 = h.n_tiles;
+  if (total == 13) {
+    cnt_add(r14, win34);
+    n14++;
+  }
+  o.shanten = (int8_t)shanten_counts(T, r14, n14 / 3);
+  o.shanten13 = ok13 ? (int8_t)shanten_counts(T, r13, cnt_total(r13) / 3) : (int8_t)127;
+  out[i] = o;
+}
+
+__device__ __forceinline__ Ctx make_ctx(const Tables& T, uint32_t* log, uint32_t cap, int64_t i) {
+  Ctx cx;
+  cx.T = T;
+  cx.log = log ? log + (size_t)i * cap : nullptr;
+  cx.log_cap = cap;
+  return cx;
+}
+
+__global__ void create_kernel(G* states, int64_t n, int game_mode, uint32_t rule_bits, const uint64_t* seeds, uint64_t seed_base) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G& g = states[i];
+  uint8_t* p = (uint8_t*)&g;
+  for (size_t k = 0; k < sizeof(G); k++) p[k] = 0;
+  g.game_mode = (uint8_t)game_mode;
+  g.rule_bits = (uint8_t)rule_bits;
+  g.seed = seeds ? seeds[i] : seed_base + (uint64_t)i;
+  g.hand_index = 1;   // GameState::new consumed shuffle #0 (state/mod.rs:165)
+  g.last_error = RV_NONE;
+  g.is_done = 1;      // until reset
+  for (int s = 0; s < NP; s++) g.score[s] = 25000;
+}
+
+__global__ void reseed_kernel(G* states, int64_t n, const uint64_t* seeds, uint64_t seed_base) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  states[i].seed = seeds ? seeds[i] : seed_base + (uint64_t)i;
+  states[i].hand_index = 1;   // as a freshly constructed RiichiEnv(seed=...) (state/mod.rs:165)
+}
+
+__global__ void reset_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, const uint8_t* oya, const uint8_t* rw,
+                             const uint8_t* honba, const uint32_t* kyotaku, const int32_t* scores, const uint8_t* walls) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ctx cx = make_ctx(T, log, cap, i);
+  game_reset(cx, states[i], oya ? oya[i] : 0, rw ? rw[i] : 0, honba ? honba[i] : 0, kyotaku ? kyotaku[i] : 0,
+             walls ? walls + (size_t)i * 136 : nullptr, scores ? scores + (size_t)i * NP : nullptr);
+}
+
+// Persistent rollout: each thread owns one game and advances it up to max_steps env steps.
+__global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
+                                                          uint64_t agent_seed, uint32_t max_steps, unsigned long long* counters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long my_steps = 0, my_done = 0;
+  if (i < n) {
+    Ctx cx = make_ctx(T, log, cap, i);
+    G& g = states[i];
+    uint64_t gid = g.seed;
+    for (uint32_t s = 0; s < max_steps && !g.is_done; s++) {
+      random_step(cx, g, agent_seed, gid);
+      my_steps++;
+    }
+    if (g.is_done && my_steps > 0) my_done = 1;
+  }
+  // block reduction -> one atomic per block
+  __shared__ unsigned long long sh[2];
+  if (threadIdx.x == 0) sh[0] = sh[1] = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) {
+    my_steps += __shfl_down_sync(0xFFFFFFFFu, my_steps, o);
+    my_done += __shfl_down_sync(0xFFFFFFFFu, my_done, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sh[0], my_steps);
+    atomicAdd(&sh[1], my_done);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&counters[0], sh[0]);
+    atomicAdd(&counters[1], sh[1]);
+  }
+}
+
+__global__ void legal_kernel(Tables T, const G* states, int64_t n, rv_action* out, uint8_t* counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const G& g = states[i];
+  Ctx cx = make_ctx(T, nullptr, 0, i);
+  for (int p = 0; p < NP; p++) {
+    bool owes = !g.is_done && ((g.phase == RV_WAIT_ACT && g.current_player == p) ||
+                               (g.phase == RV_WAIT_RESPONSE && ((g.active_mask >> p) & 1)));
+    int cnt = 0;
+    if (owes) {
+      uint32_t packed[RV_MAX_LEGAL];
+      cnt = legal_actions(cx, g, p, packed, -1, nullptr);
+      if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+      for (int k = 0; k < cnt; k++) out[((size_t)i * NP + p) * RV_MAX_LEGAL + k] = expand_act(g, p, packed[k]);
+    }
+    counts[(size_t)i * NP + p] = (uint8_t)cnt;
+  }
+}
+
+__global__ void step_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, const rv_action* actions,
+                            unsigned long long* counters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G& g = states[i];
+  if (g.is_done) return;
+  Ctx cx = make_ctx(T, log, cap, i);
+  rv_action acts[NP];
+  for (int p = 0; p < NP; p++) {
+    acts[p] = actions[(size_t)i * NP + p];
+    if (acts[p].type != RV_NO_ACTION) {   // Action::new sorts consume_tiles (action.rs:97-98)
+      int nc = acts[p].n_consume > 4 ? 4 : acts[p].n_consume;
+      for (int x = 1; x < nc; x++)
+        for (int y = x; y > 0 && acts[p].consume[y - 1] > acts[p].consume[y]; y--) {
+          uint8_t t = acts[p].consume[y]; acts[p].consume[y] = acts[p].consume[y - 1]; acts[p].consume[y - 1] = t;
+        }
+    }
+  }
+  g.step_count++;
+  atomicAdd(&counters[0], 1ull);
+  for (int p = 0; p < NP; p++) {
+    if (acts[p].type == RV_NO_ACTION) continue;
+    uint32_t packed[RV_MAX_LEGAL];
+    int cnt = legal_actions(cx, g, p, packed, -1, nullptr);
+    if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+    bool ok = false;
+    for (int k = 0; k < cnt && !ok; k++) ok = action_matches(expand_act(g, p, packed[k]), acts[p]);
+    if (!ok) {
+      g.last_error = (uint8_t)p;
+      trigger_ryukyoku(cx, g, RV_RK_ILLEGAL_BASE + p);
+      if (g.is_done) atomicAdd(&counters[1], 1ull);
+      return;
+    }
+  }
+  step_apply(cx, g, acts);
+  if (g.is_done) atomicAdd(&counters[1], 1ull);
+}
+
+__global__ void results_kernel(const G* states, int64_t n, uint8_t* done, int32_t* scores, uint8_t* ranks, uint32_t* step_count,
+                               uint32_t* kyoku_count, uint32_t* ev_count, uint64_t* ev_hash) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const G& g = states[i];
+  if (done) done[i] = g.is_done;
+  if (scores)
+    for (int p = 0; p < NP; p++) scores[i * NP + p] = g.score[p];
+  if (ranks)   // env.rs:673-689: score desc, seat asc
+    for (int p = 0; p < NP; p++) {
+      int r = 1;
+      for (int q = 0; q < NP; q++)
+        if (g.score[q] > g.score[p] || (g.score[q] == g.score[p] && q < p)) r++;
+      ranks[i * NP + p] = (uint8_t)r;
+    }
+  if (step_count) step_count[i] = g.step_count;
+  if (kyoku_count) kyoku_count[i] = g.kyoku_count;
+  if (ev_count) ev_count[i] = g.ev_count;
+  if (ev_hash) ev_hash[i] = g.ev_hash;
+}
+
+// ------------------------------------------------------------------ host API
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+template <class T>
+static int upload(rv_ctx* c, const T* h, size_t count, T** d) {
+  *d = nullptr;
+  if (!h) return RV_OK;
+  CK(cudaMalloc(d, sizeof(T) * count));
+  CK(cudaMemcpyAsync(*d, h, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
+  return RV_OK;
+}
+
+extern "C" {
+
+const char* rv_last_error(void) { return g_err.c_str(); }
+int rv_version(void) { return 1; }
+
+int rv_ctx_create(int device, rv_ctx** out) {
+  if (!out) return fail(RV_ERR_INVALID, "out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(RV_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(RV_ERR_INVALID, "bad device index");
+  CK(cudaSetDevice(device));
+  rv_ctx* c = new rv_ctx();
+  c->device = device;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->ev[i]));
+  CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CK(cudaMalloc(&c->suit_info, sizeof(uint32_t) * SUIT_KEYS));
+  CK(cudaMalloc(&c->honor_info, sizeof(uint32_t) * HONOR_KEYS));
+  CK(cudaMalloc(&c->suit_cost, sizeof(uint64_t) * SUIT_KEYS));
+  CK(cudaMalloc(&c->honor_cost, sizeof(uint64_t) * HONOR_KEYS));
+  gen_cost_kernel<9, true><<<grid_for(SUIT_KEYS, 128), 128, 0, c->stream>>>(c->suit_cost, c->suit_info, SUIT_KEYS);
+  gen_cost_kernel<7, false><<<grid_for(HONOR_KEYS, 128), 128, 0, c->stream>>>(c->honor_cost, c->honor_info, HONOR_KEYS);
+  gen_wait_kernel<9><<<grid_for(SUIT_KEYS, 128), 128, 0, c->stream>>>(c->suit_info, SUIT_KEYS);
+  gen_wait_kernel<7><<<grid_for(HONOR_KEYS, 128), 128, 0, c->stream>>>(c->honor_info, HONOR_KEYS);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  c->T.suit_info = c->suit_info;
+  c->T.honor_info = c->honor_info;
+  c->T.suit_cost = c->suit_cost;
+  c->T.honor_cost = c->honor_cost;
+  *out = c;
+  return RV_OK;
+}
+int rv_ctx_destroy(rv_ctx* c) {
+  if (!c) return RV_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->suit_info);
+  cudaFree(c->honor_info);
+  cudaFree(c->suit_cost);
+  cudaFree(c->honor_cost);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return RV_OK;
+}
+int rv_ctx_sync(rv_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
+void* rv_ctx_stream(rv_ctx* c) { return (void*)c->stream; }
+int rv_timer_mark(rv_ctx* c, int idx) {
+  if (idx < 0 || idx >= 8) return fail(RV_ERR_INVALID, "timer index must be 0..7");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev[idx], c->stream));
+  return RV_OK;
+}
+int rv_timer_elapsed(rv_ctx* c, int a, int b, float* ms) {
+  if (a < 0 || a >= 8 || b < 0 || b >= 8) return fail(RV_ERR_INVALID, "timer index must be 0..7");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->ev[b]));
+  CK(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
+  return RV_OK;
+}
+
+int rv_hand_eval_batch_device(rv_ctx* c, const rv_hand_query* d_q, rv_hand_result* d_out, int64_t n) {
+  if (n <= 0) return RV_OK;
+  CK(cudaSetDevice(c->device));
+  hand_eval_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, d_q, d_out, n);
+  CK(cudaGetLastError());
+  return RV_OK;
+}
+int rv_hand_eval_batch(rv_ctx* c, const rv_hand_query* q, rv_hand_result* out, int64_t n) {
+  if (n <= 0) return RV_OK;
+  CK(cudaSetDevice(c->device));
+  rv_hand_query* dq;
+  rv_hand_result* dr;
+  CK(cudaMalloc(&dq, sizeof(rv_hand_query) * n));
+  CK(cudaMalloc(&dr, sizeof(rv_hand_result) * n));
+  CK(cudaMemcpyAsync(dq, q, sizeof(rv_hand_query) * n, cudaMemcpyHostToDevice, c->stream));
+  int rc = rv_hand_eval_batch_device(c, dq, dr, n);
+  if (rc == RV_OK) {
+    CK(cudaMemcpyAsync(out, dr, sizeof(rv_hand_result) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(dq);
+  cudaFree(dr);
+  return rc;
+}
+int rv_calculate_score(int han, int fu, int is_oya, int is_tsumo, uint32_t honba, int num_players, uint32_t out[4]) {
+  uint32_t total = 0;
+  ScoreRes s = calc_score(han & 0xFF, fu & 0xFF, is_oya != 0, is_tsumo != 0, honba, (uint32_t)num_players, &total);
+  out[0] = s.pay_ron;
+  out[1] = is_tsumo ? s.pay_oya : 0;
+  out[2] = is_tsumo ? s.pay_ko : 0;
+  out[3] = total;
+  return RV_OK;
+}
+int rv_wall_from_seed(uint64_t seed, uint64_t hand_index, int n_tiles, uint8_t* out) {
+  if (n_tiles != 136 && n_tiles != 108) return fail(RV_ERR_INVALID, "n_tiles must be 136 or 108");
+  wall_from_seed(seed, hand_index, n_tiles, out);
+  return RV_OK;
+}
+
+int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const uint64_t* seeds, uint64_t seed_base,
+                  uint32_t log_cap_words, rv_vec** out) {
+  if (!c || !out || n <= 0) return fail(RV_ERR_INVALID, "bad arguments");
+  if (game_mode < 0 || game_mode > 5) return fail(RV_ERR_INVALID, "game_mode must be 0..5");
+  if (game_mode >= 3) return fail(RV_ERR_UNSUPPORTED, "3-player (sanma) modes are not implemented yet");
+  CK(cudaSetDevice(c->device));
+  rv_vec* v = new rv_vec();
+  v->ctx = c;
+  v->n = n;
+  v->game_mode = game_mode;
+  v->rule_bits = rule_bits;
+  v->log_cap = log_cap_words;
+  v->d_log = nullptr;
+  v->d_seeds = nullptr;
+  CK(cudaMalloc(&v->d_states, sizeof(G) * n));
+  if (log_cap_words) CK(cudaMalloc(&v->d_log, sizeof(uint32_t) * (size_t)n * log_cap_words));
+  CK(cudaMalloc(&v->d_steps, sizeof(unsigned long long) * 2));
+  CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 2, c->stream));
+  uint64_t* d_seeds = nullptr;
+  if (seeds) {
+    CK(cudaMalloc(&d_seeds, sizeof(uint64_t) * n));
+    CK(cudaMemcpyAsync(d_seeds, seeds, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
+  }
+  create_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, game_mode, rule_bits, d_seeds, seed_base);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  if (d_seeds) cudaFree(d_seeds);
+  *out = v;
+  return RV_OK;
+}
+int rv_vec_reseed(rv_vec* v, const uint64_t* seeds, uint64_t seed_base) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  if (seeds) {
+    if (!v->d_seeds) CK(cudaMalloc(&v->d_seeds, sizeof(uint64_t) * v->n));
+    CK(cudaMemcpyAsync(v->d_seeds, seeds, sizeof(uint64_t) * v->n, cudaMemcpyHostToDevice, c->stream));
+  }
+  reseed_kernel<<<grid_for(v->n, 256), 256, 0, c->stream>>>(v->d_states, v->n, seeds ? v->d_seeds : nullptr, seed_base);
+  CK(cudaGetLastError());
+  return RV_OK;
+}
+int rv_vec_destroy(rv_vec* v) {
+  if (!v) return RV_OK;
+  cudaSetDevice(v->ctx->device);
+  cudaFree(v->d_states);
+  if (v->d_log) cudaFree(v->d_log);
+  if (v->d_seeds) cudaFree(v->d_seeds);
+  cudaFree(v->d_steps);
+  delete v;
+  return RV_OK;
+}
+int64_t rv_vec_size(const rv_vec* v) { return v ? v->n : 0; }
+
+int rv_vec_reset(rv_vec* v, const uint8_t* oya, const uint8_t* round_wind, const uint8_t* honba, const uint32_t* kyotaku,
+                 const int32_t* scores, const uint8_t* walls) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  uint8_t *d_oya, *d_rw, *d_honba, *d_walls;
+  uint32_t* d_ky;
+  int32_t* d_sc;
+  int rc;
+  if ((rc = upload(c, oya, v->n, &d_oya))) return rc;
+  if ((rc = upload(c, round_wind, v->n, &d_rw))) return rc;
+  if ((rc = upload(c, honba, v->n, &d_honba))) return rc;
+  if ((rc = upload(c, kyotaku, v->n, &d_ky))) return rc;
+  if ((rc = upload(c, scores, v->n * NP, &d_sc))) return rc;
+  if ((rc = upload(c, walls, v->n * 136, &d_walls))) return rc;
+  CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 2, c->stream));
+  reset_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_oya, d_rw, d_honba,
+                                                           d_ky, d_sc, d_walls);
+  CK(cudaGetLastError());
+  bool any = oya || round_wind || honba || kyotaku || scores || walls;
+  if (any) CK(cudaStreamSynchronize(c->stream));   // staging buffers are freed below; default reset stays asynchronous
+  cudaFree(d_oya);
+  cudaFree(d_rw);
+  cudaFree(d_honba);
+  cudaFree(d_ky);
+  cudaFree(d_sc);
+  cudaFree(d_walls);
+  return RV_OK;
+}
+
+int rv_vec_legal_actions(rv_vec* v, rv_action* out_actions, uint8_t* out_counts) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  rv_action* d_a;
+  uint8_t* d_c;
+  size_t na = (size_t)v->n * NP * RV_MAX_LEGAL;
+  CK(cudaMalloc(&d_a, sizeof(rv_action) * na));
+  CK(cudaMalloc(&d_c, (size_t)v->n * NP));
+  legal_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, d_a, d_c);
+  CK(cudaGetLastError());
+  if (out_actions) CK(cudaMemcpyAsync(out_actions, d_a, sizeof(rv_action) * na, cudaMemcpyDeviceToHost, c->stream));
+  if (out_counts) CK(cudaMemcpyAsync(out_counts, d_c, (size_t)v->n * NP, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_a);
+  cudaFree(d_c);
+  return RV_OK;
+}
+
+int rv_vec_step(rv_vec* v, const rv_action* actions) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  rv_action* d_a;
+  CK(cudaMalloc(&d_a, sizeof(rv_action) * v->n * NP));
+  CK(cudaMemcpyAsync(d_a, actions, sizeof(rv_action) * v->n * NP, cudaMemcpyHostToDevice, c->stream));
+  step_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_a, v->d_steps);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_a);
+  return RV_OK;
+}
+
+int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  step_random_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, agent_seed,
+                                                                 max_steps, v->d_steps);
+  CK(cudaGetLastError());
+  return RV_OK;
+}
+int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  unsigned long long h[2];
+  CK(cudaMemcpyAsync(h, v->d_steps, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (steps_total) *steps_total = h[0];
+  if (games_done) *games_done = (int64_t)h[1];
+  return RV_OK;
+}
+int rv_vec_step_random(rv_vec* v, uint64_t agent_seed, uint32_t max_steps, uint64_t* steps_done) {
+  uint64_t before = 0, after = 0;
+  int rc = rv_vec_steps_total(v, &before, nullptr);
+  if (rc) return rc;
+  if ((rc = rv_vec_step_random_async(v, agent_seed, max_steps))) return rc;
+  if ((rc = rv_vec_steps_total(v, &after, nullptr))) return rc;
+  if (steps_done) *steps_done = after - before;
+  return RV_OK;
+}
+
+static int gather(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks, uint32_t* sc, uint32_t* kc, uint32_t* ec, uint64_t* eh) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  int64_t n = v->n;
+  uint8_t *d_done = nullptr, *d_ranks = nullptr;
+  int32_t* d_scores = nullptr;
+  uint32_t *d_sc = nullptr, *d_kc = nullptr, *d_ec = nullptr;
+  uint64_t* d_eh = nullptr;
+  if (done) CK(cudaMalloc(&d_done, n));
+  if (scores) CK(cudaMalloc(&d_scores, sizeof(int32_t) * n * NP));
+  if (ranks) CK(cudaMalloc(&d_ranks, n * NP));
+  if (sc) CK(cudaMalloc(&d_sc, sizeof(uint32_t) * n));
+  if (kc) CK(cudaMalloc(&d_kc, sizeof(uint32_t) * n));
+  if (ec) CK(cudaMalloc(&d_ec, sizeof(uint32_t) * n));
+  if (eh) CK(cudaMalloc(&d_eh, sizeof(uint64_t) * n));
+  results_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, d_done, d_scores, d_ranks, d_sc, d_kc, d_ec, d_eh);
+  CK(cudaGetLastError());
+  if (done) CK(cudaMemcpyAsync(done, d_done, n, cudaMemcpyDeviceToHost, c->stream));
+  if (scores) CK(cudaMemcpyAsync(scores, d_scores, sizeof(int32_t) * n * NP, cudaMemcpyDeviceToHost, c->stream));
+  if (ranks) CK(cudaMemcpyAsync(ranks, d_ranks, n * NP, cudaMemcpyDeviceToHost, c->stream));
+  if (sc) CK(cudaMemcpyAsync(sc, d_sc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (kc) CK(cudaMemcpyAsync(kc, d_kc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (ec) CK(cudaMemcpyAsync(ec, d_ec, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (eh) CK(cudaMemcpyAsync(eh, d_eh, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_done);
+  cudaFree(d_scores);
+  cudaFree(d_ranks);
+  cudaFree(d_sc);
+  cudaFree(d_kc);
+  cudaFree(d_ec);
+  cudaFree(d_eh);
+  return RV_OK;
+}
+int rv_vec_results(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks) {
+  return gather(v, done, scores, ranks, nullptr, nullptr, nullptr, nullptr);
+}
+int rv_vec_counters(rv_vec* v, uint32_t* step_count, uint32_t* kyoku_count, uint32_t* ev_count, uint64_t* ev_hash) {
+  return gather(v, nullptr, nullptr, nullptr, step_count, kyoku_count, ev_count, ev_hash);
+}
+
+int rv_vec_get_state(rv_vec* v, int64_t game, rv_game_state* out) {
+  if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(out, v->d_states + game, sizeof(G), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
+int rv_vec_set_state(rv_vec* v, int64_t game, const rv_game_state* in) {
+  if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(v->d_states + game, in, sizeof(G), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
+int rv_vec_state_device_ptr(rv_vec* v, void** d_states) {
+  *d_states = v->d_states;
+  return RV_OK;
+}
+int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, uint32_t* n_words) {
+  if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  G g;
+  CK(cudaMemcpyAsync(&g, v->d_states + game, sizeof(G), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (n_words) *n_words = g.ev_words;
+  if (!v->d_log) return fail(RV_ERR_INVALID, "event logging is off for this VecEnv (log_cap_words == 0)");
+  uint32_t have = g.ev_words < v->log_cap ? g.ev_words : v->log_cap;
+  uint32_t ncopy = have < cap ? have : cap;
+  if (out_words && ncopy) {
+    CK(cudaMemcpyAsync(out_words, v->d_log + (size_t)game * v->log_cap, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return RV_OK;
+}
+int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask) {
+  (void)v; (void)d_obs; (void)d_mask;
+  return fail(RV_ERR_UNSUPPORTED, "observation encoding is not implemented yet");
+}
+int rv_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(rv_game_state);
+    case 1: return (int)sizeof(rv_hand_query);
+    case 2: return (int)sizeof(rv_hand_result);
+    case 3: return (int)sizeof(rv_action);
+  }
+  return -1;
+}
+}  // extern "C"

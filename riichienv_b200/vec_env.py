@@ -1,0 +1,124 @@
+"""VecRiichiEnv — N independent Riichi games resident in HBM, advanced by CUDA kernels.
+
+Host-side mirror of a *list* of the reference's `RiichiEnv` objects
+(riichienv-ml/src/riichienv_ml/.../_ppo_worker.py:39) behind one handle.  All compute
+happens in libriichienv_b200.so; this file only marshals numpy buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from ._lib import Context, check, events_to_json, lib
+
+GAME_MODES = {"4p-red-single": 0, "4p-red-east": 1, "4p-red-half": 2, "3p-red-single": 3, "3p-red-east": 4, "3p-red-half": 5}
+
+
+def _ptr(a, ty):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ty))
+
+
+class VecRiichiEnv:
+    def __init__(self, n, game_mode="4p-red-half", rule_bits=A.RULE_DEFAULT_TENHOU, seeds=None, seed_base=0,
+                 log_cap_words=0, device=0):
+        if isinstance(game_mode, str):
+            game_mode = GAME_MODES.get(game_mode, 0)  # unknown string -> mode 0 (env.rs:100)
+        self.ctx = Context.get(device)
+        self.n = int(n)
+        self.game_mode = int(game_mode)
+        self.handle = C.c_void_p()
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        check(lib().rv_vec_create(self.ctx.handle, self.n, self.game_mode, int(rule_bits), _ptr(s, C.c_uint64),
+                                  int(seed_base), int(log_cap_words), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            lib().rv_vec_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # RiichiEnv.reset (env.rs:799-851) for all games
+    def reset(self, oya=None, round_wind=None, honba=None, kyotaku=None, scores=None, walls=None):
+        def arr(x, dt, shape):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dt), shape))
+            return a
+        n = self.n
+        if scores is not None and np.asarray(scores).shape[-1] != A.NP:
+            raise ValueError(f"scores length {np.asarray(scores).shape[-1]} does not match number of players {A.NP}")
+        a_oya, a_rw, a_hb = arr(oya, np.uint8, (n,)), arr(round_wind, np.uint8, (n,)), arr(honba, np.uint8, (n,))
+        a_ky, a_sc, a_w = arr(kyotaku, np.uint32, (n,)), arr(scores, np.int32, (n, A.NP)), arr(walls, np.uint8, (n, 136))
+        check(lib().rv_vec_reset(self.handle, _ptr(a_oya, C.c_uint8), _ptr(a_rw, C.c_uint8), _ptr(a_hb, C.c_uint8),
+                                 _ptr(a_ky, C.c_uint32), _ptr(a_sc, C.c_int32), _ptr(a_w, C.c_uint8)))
+
+    def reseed(self, seeds=None, seed_base=0):
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        check(lib().rv_vec_reseed(self.handle, _ptr(s, C.c_uint64), int(seed_base)))
+
+    def step_random(self, agent_seed, max_steps=1):
+        done = C.c_uint64(0)
+        check(lib().rv_vec_step_random(self.handle, int(agent_seed), int(max_steps), C.byref(done)))
+        return int(done.value)
+
+    def step_random_async(self, agent_seed, max_steps):
+        check(lib().rv_vec_step_random_async(self.handle, int(agent_seed), int(max_steps)))
+
+    def steps_total(self):
+        s, g = C.c_uint64(0), C.c_int64(0)
+        check(lib().rv_vec_steps_total(self.handle, C.byref(s), C.byref(g)))
+        return int(s.value), int(g.value)
+
+    def step(self, actions):
+        """actions: ctypes array (A.Action * (n*NP)) or numpy structured bytes of the same layout."""
+        check(lib().rv_vec_step(self.handle, C.cast(actions, C.POINTER(A.Action))))
+
+    def legal_actions(self):
+        acts = (A.Action * (self.n * A.NP * A.MAX_LEGAL))()
+        counts = np.zeros((self.n, A.NP), np.uint8)
+        check(lib().rv_vec_legal_actions(self.handle, acts, _ptr(counts, C.c_uint8)))
+        return acts, counts
+
+    def results(self):
+        done = np.zeros(self.n, np.uint8)
+        scores = np.zeros((self.n, A.NP), np.int32)
+        ranks = np.zeros((self.n, A.NP), np.uint8)
+        check(lib().rv_vec_results(self.handle, _ptr(done, C.c_uint8), _ptr(scores, C.c_int32), _ptr(ranks, C.c_uint8)))
+        return done, scores, ranks
+
+    def counters(self):
+        sc = np.zeros(self.n, np.uint32)
+        kc = np.zeros(self.n, np.uint32)
+        ec = np.zeros(self.n, np.uint32)
+        eh = np.zeros(self.n, np.uint64)
+        check(lib().rv_vec_counters(self.handle, _ptr(sc, C.c_uint32), _ptr(kc, C.c_uint32), _ptr(ec, C.c_uint32),
+                                    _ptr(eh, C.c_uint64)))
+        return sc, kc, ec, eh
+
+    def get_state(self, game=0):
+        s = A.GameState()
+        check(lib().rv_vec_get_state(self.handle, int(game), C.byref(s)))
+        return s
+
+    def set_state(self, game, state):
+        check(lib().rv_vec_set_state(self.handle, int(game), C.byref(state)))
+
+    def state_device_ptr(self):
+        p = C.c_void_p()
+        check(lib().rv_vec_state_device_ptr(self.handle, C.byref(p)))
+        return int(p.value)
+
+    def events(self, game=0):
+        n = C.c_uint32(0)
+        check(lib().rv_vec_events(self.handle, int(game), None, 0, C.byref(n)))
+        buf = (C.c_uint32 * max(1, n.value))()
+        check(lib().rv_vec_events(self.handle, int(game), buf, n.value, C.byref(n)))
+        return list(buf[: n.value])
+
+    def mjai_log(self, game=0, viewer=-1):
+        return events_to_json(self.events(game), viewer)

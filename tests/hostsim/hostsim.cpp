@@ -1,0 +1,268 @@
+// TEST INFRASTRUCTURE ONLY (see cuda_shim.h).  Host compile of the device sources with a
+// C surface parallel to oracle/capi.cpp, so tests can diff kernel logic vs oracle on CPU.
+#include "cuda_shim.h"
+
+#include <atomic>
+#include <cstdio>
+#include <thread>
+#include <vector>
+
+#include "../../riichienv_b200/csrc/game.cuh"
+
+using namespace rv;
+
+static std::vector<uint32_t> g_suit_info, g_honor_info;
+static std::vector<uint64_t> g_suit_cost, g_honor_cost;
+static Tables g_T;
+static bool g_ready = false;
+
+template <int N, bool SEQ>
+static void gen(std::vector<uint64_t>& cost, std::vector<uint32_t>& info, int n_keys, int threads) {
+  cost.assign(n_keys, 0xFFFFFFFFFFull);
+  info.assign(n_keys, 0);
+  std::atomic<int> next{0};
+  auto work = [&] {
+    while (true) {
+      int b = next.fetch_add(1024);
+      if (b >= n_keys) break;
+      for (int key = b; key < std::min(n_keys, b + 1024); key++) {
+        uint8_t c[9];
+        int k = key, sum = 0;
+        for (int i = 0; i < N; i++) {
+          c[i] = k % 5;
+          k /= 5;
+          sum += c[i];
+        }
+        if (sum > 14) continue;
+        uint8_t best[5][2];
+        suit_cost_dp<N, SEQ>(c, best);
+        uint64_t packed = 0;
+        for (int m = 0; m < 5; m++) {
+          uint64_t a = best[m][0] > 15 ? 15 : best[m][0], b2 = best[m][1] > 15 ? 15 : best[m][1];
+          packed |= a << (8 * m);
+          packed |= b2 << (8 * m + 4);
+        }
+        cost[key] = packed;
+        uint32_t e = 0;
+        if (sum % 3 == 0 && best[sum / 3][0] == 0) e |= 1u;
+        if (sum % 3 == 2 && best[sum / 3][1] == 0) e |= 2u;
+        info[key] = e;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) th.emplace_back(work);
+  for (auto& t : th) t.join();
+  std::vector<uint32_t> base = info;
+  for (int key = 0; key < n_keys; key++) {
+    uint8_t c[9];
+    int k = key, sum = 0;
+    for (int i = 0; i < N; i++) {
+      c[i] = k % 5;
+      k /= 5;
+      sum += c[i];
+    }
+    if (sum > 13) continue;
+    uint32_t e = base[key] & 3u;
+    for (int i = 0; i < N; i++) {
+      if (c[i] >= 4) continue;
+      uint32_t o = base[key + pow5(i)] & 3u;
+      if (o & 1u) e |= 1u << (2 + i);
+      if (o & 2u) e |= 1u << (11 + i);
+    }
+    info[key] = e;
+  }
+}
+
+extern "C" {
+int hs_init(const char* cache_path, int threads) {
+  if (g_ready) return 0;
+  bool loaded = false;
+  if (cache_path) {
+    FILE* f = fopen(cache_path, "rb");
+    if (f) {
+      g_suit_info.resize(SUIT_KEYS);
+      g_honor_info.resize(HONOR_KEYS);
+      g_suit_cost.resize(SUIT_KEYS);
+      g_honor_cost.resize(HONOR_KEYS);
+      size_t ok = fread(g_suit_info.data(), 4, SUIT_KEYS, f) + fread(g_honor_info.data(), 4, HONOR_KEYS, f) +
+                  fread(g_suit_cost.data(), 8, SUIT_KEYS, f) + fread(g_honor_cost.data(), 8, HONOR_KEYS, f);
+      fclose(f);
+      loaded = ok == (size_t)2 * SUIT_KEYS + 2 * HONOR_KEYS;
+    }
+  }
+  if (!loaded) {
+    gen<9, true>(g_suit_cost, g_suit_info, SUIT_KEYS, threads);
+    gen<7, false>(g_honor_cost, g_honor_info, HONOR_KEYS, threads);
+    if (cache_path) {
+      FILE* f = fopen(cache_path, "wb");
+      if (f) {
+        fwrite(g_suit_info.data(), 4, SUIT_KEYS, f);
+        fwrite(g_honor_info.data(), 4, HONOR_KEYS, f);
+        fwrite(g_suit_cost.data(), 8, SUIT_KEYS, f);
+        fwrite(g_honor_cost.data(), 8, HONOR_KEYS, f);
+        fclose(f);
+      }
+    }
+  }
+  g_T.suit_info = g_suit_info.data();
+  g_T.honor_info = g_honor_info.data();
+  g_T.suit_cost = g_suit_cost.data();
+  g_T.honor_cost = g_honor_cost.data();
+  g_ready = true;
+  return 0;
+}
+
+int hs_hand_eval(const rv_hand_query* q, rv_hand_result* out, int64_t n) {
+  for (int64_t i = 0; i < n; i++) {
+    rv_hand_query h = q[i];
+    WinRes r = hand_calc(g_T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
+                         h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba);
+    rv_hand_result o;
+    memset(&o, 0, sizeof o);
+    o.is_win = r.is_win;
+    o.yakuman = r.yakuman;
+    o.has_win_shape = r.has_shape;
+    o.han = (uint8_t)r.han;
+    o.fu = (uint8_t)r.fu;
+    o.ron_agari = r.ron;
+    o.tsumo_agari_oya = r.oya;
+    o.tsumo_agari_ko = r.ko;
+    o.yaku_mask = r.yaku_mask;
+    o.n_yaku = (uint8_t)__popcll(r.yaku_mask);
+    Cnt c;
+    cnt_zero(c);
+    for (int k = 0; k < h.n_tiles; k++) cnt_add(c, h.tiles[k] >> 2);
+    Cnt raw = c;
+    for (int m = 0; m < h.n_melds; m++)
+      if (h.meld_type[m] >= RV_MELD_DAIMINKAN) {
+        int kind = h.meld_tiles[m][0] >> 2;
+        if (cnt_get(c, kind) == 4) cnt_sub(c, kind, 1);
+      }
+    int total = cnt_total(c) + 3 * h.n_melds;
+    int win34 = h.win_tile >> 2;
+    Cnt c13 = c, r13 = raw;
+    bool ok13 = total == 13;
+    if (total == 14 && cnt_get(c, win34) > 0) {
+      cnt_sub(c13, win34);
+      cnt_sub(r13, win34);
+      ok13 = true;
+    }
+    o.wait_mask = ok13 ? waits13(g_T, c13) : 0;
+    Cnt r14 = raw;
+    int n14 = h.n_tiles;
+    if (total == 13) {
+      cnt_add(r14, win34);
+      n14++;
+    }
+    o.shanten = (int8_t)shanten_counts(g_T, r14, n14 / 3);
+    o.shanten13 = ok13 ? (int8_t)shanten_counts(g_T, r13, cnt_total(r13) / 3) : (int8_t)127;
+    out[i] = o;
+  }
+  return 0;
+}
+int hs_shanten_counts(const uint8_t* cnt34, int len_div3) {
+  Cnt c;
+  cnt_zero(c);
+  for (int i = 0; i < 34; i++) cnt_add(c, i, cnt34[i]);
+  return shanten_counts(g_T, c, len_div3);
+}
+int hs_is_agari(const uint8_t* cnt34) {
+  Cnt c;
+  cnt_zero(c);
+  for (int i = 0; i < 34; i++) cnt_add(c, i, cnt34[i]);
+  return agari14(g_T, c) ? 1 : 0;
+}
+uint64_t hs_waits(const uint8_t* cnt34) {
+  Cnt c;
+  cnt_zero(c);
+  for (int i = 0; i < 34; i++) cnt_add(c, i, cnt34[i]);
+  return waits13(g_T, c);
+}
+
+// one game
+struct HS { G g; std::vector<uint32_t> log; };
+void* hs_game_new(int mode, uint64_t seed, uint32_t rule, uint32_t log_cap) {
+  HS* h = new HS();
+  memset(&h->g, 0, sizeof(G));
+  h->g.game_mode = (uint8_t)mode;
+  h->g.rule_bits = (uint8_t)rule;
+  h->g.seed = seed;
+  h->g.hand_index = 1;
+  h->g.last_error = RV_NONE;
+  h->g.is_done = 1;
+  for (int s = 0; s < NP; s++) h->g.score[s] = 25000;
+  h->log.assign(log_cap, 0);
+  return h;
+}
+static Ctx hs_ctx(HS* h) {
+  Ctx cx;
+  cx.T = g_T;
+  cx.log = h->log.empty() ? nullptr : h->log.data();
+  cx.log_cap = (uint32_t)h->log.size();
+  return cx;
+}
+void hs_game_free(void* p) { delete (HS*)p; }
+void hs_game_reset(void* p, int oya, int rw, int honba, uint32_t kyotaku, const uint8_t* wall, const int32_t* scores) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  game_reset(cx, h->g, oya, rw, honba, kyotaku, wall, scores);
+}
+int hs_game_legal(void* p, int pid, rv_action* out) {
+  HS* h = (HS*)p;
+  G& g = h->g;
+  Ctx cx = hs_ctx(h);
+  bool owes = !g.is_done && ((g.phase == RV_WAIT_ACT && g.current_player == pid) ||
+                             (g.phase == RV_WAIT_RESPONSE && ((g.active_mask >> pid) & 1)));
+  if (!owes) return 0;
+  uint32_t packed[RV_MAX_LEGAL];
+  int n = legal_actions(cx, g, pid, packed, -1, nullptr);
+  if (n > RV_MAX_LEGAL) n = RV_MAX_LEGAL;
+  for (int k = 0; k < n; k++) out[k] = expand_act(g, pid, packed[k]);
+  return n;
+}
+void hs_game_step(void* p, const rv_action* in) {
+  HS* h = (HS*)p;
+  G& g = h->g;
+  if (g.is_done) return;
+  Ctx cx = hs_ctx(h);
+  rv_action acts[NP];
+  for (int s = 0; s < NP; s++) {
+    acts[s] = in[s];
+    int nc = acts[s].n_consume > 4 ? 4 : acts[s].n_consume;
+    if (acts[s].type != RV_NO_ACTION) std::sort(acts[s].consume, acts[s].consume + nc);
+  }
+  g.step_count++;
+  for (int s = 0; s < NP; s++) {
+    if (acts[s].type == RV_NO_ACTION) continue;
+    uint32_t packed[RV_MAX_LEGAL];
+    int cnt = legal_actions(cx, g, s, packed, -1, nullptr);
+    if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+    bool ok = false;
+    for (int k = 0; k < cnt && !ok; k++) ok = action_matches(expand_act(g, s, packed[k]), acts[s]);
+    if (!ok) {
+      g.last_error = (uint8_t)s;
+      trigger_ryukyoku(cx, g, RV_RK_ILLEGAL_BASE + s);
+      return;
+    }
+  }
+  step_apply(cx, g, acts);
+}
+void hs_game_random_step(void* p, uint64_t agent_seed, uint64_t game_id) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  if (!h->g.is_done) random_step(cx, h->g, agent_seed, game_id);
+}
+void hs_game_snapshot(void* p, rv_game_state* out) { *out = ((HS*)p)->g; }
+void hs_game_load_snapshot(void* p, const rv_game_state* in) { ((HS*)p)->g = *in; }
+uint32_t hs_game_events(void* p, uint32_t* out, uint32_t cap) {
+  HS* h = (HS*)p;
+  uint32_t n = std::min<uint32_t>(h->g.ev_words, (uint32_t)h->log.size());
+  if (out) memcpy(out, h->log.data(), 4 * std::min(n, cap));
+  return h->g.ev_words;
+}
+int hs_wall_from_seed(uint64_t seed, uint64_t hand_index, int n, uint8_t* out) {
+  wall_from_seed(seed, hand_index, n, out);
+  return n;
+}
+}

@@ -1,0 +1,189 @@
+"""Parity tests proper: the CUDA library, called through its C ABI, against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from riichienv_b200 import _abi as A
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return oracle.load()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from riichienv_b200._lib import Context
+
+    return Context.get(0)
+
+
+def gpu_eval(ctx, arr, n):
+    from riichienv_b200._lib import check, lib
+
+    out = (A.HandResult * n)()
+    check(lib().rv_hand_eval_batch(ctx.handle, arr, out, n))
+    return out
+
+
+def test_hand_eval_golden(ctx, orc):
+    cases = H.load_agari_cases()
+    arr = H.query_array([c[0] for c in cases])
+    out = gpu_eval(ctx, arr, len(cases))
+    ref = (A.HandResult * len(cases))()
+    orc.orc_hand_eval(arr, ref, len(cases))
+    for i, (_, exp, yaku) in enumerate(cases):
+        assert (out[i].is_win, out[i].han, out[i].fu) == exp, f"case {i}"
+        assert H.yaku_ids(out[i].yaku_mask) == yaku, f"case {i}"
+        assert bytes(out[i]) == bytes(ref[i]), f"case {i}"
+
+
+def test_hand_eval_random_vs_oracle(ctx, orc):
+    n = 200_000
+    qs = H.random_hand_queries(n, seed=11)
+    arr = H.query_array(qs)
+    out = gpu_eval(ctx, arr, n)
+    ref = (A.HandResult * n)()
+    orc.orc_hand_eval_mt(arr, ref, n, 16)
+    a = np.frombuffer(out, dtype=np.uint8).reshape(n, C.sizeof(A.HandResult))
+    b = np.frombuffer(ref, dtype=np.uint8).reshape(n, C.sizeof(A.HandResult))
+    bad = np.nonzero((a != b).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} hands differ, first {bad[:5]}"
+    assert int(a[:, 28].sum()) > 10_000  # is_win column: positive stratum exercised
+
+
+def test_shanten_golden_via_hand_eval(ctx):
+    cases = H.load_counts_file("shanten_golden.txt")
+    qs = []
+    keep = []
+    for cnt, sh in cases:
+        tiles = [t * 4 + k for t in range(34) for k in range(cnt[t])]
+        if len(tiles) % 3 != 2 or len(tiles) > 14:
+            continue
+        qs.append(H.make_query(tiles, [], tiles[-1], [], [], 0, 0, 0, 0))
+        keep.append(sh)
+    out = gpu_eval(ctx, H.query_array(qs), len(qs))
+    assert len(qs) > 1500
+    for i, sh in enumerate(keep):
+        assert out[i].shanten == sh, f"hand {i}"
+
+
+def run_both(orc, n, mode, rule, seed_base, agent_seed, max_steps=100000):
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    v = VecRiichiEnv(n, mode, rule, seed_base=seed_base)
+    v.reset()
+    total = v.step_random(agent_seed, max_steps)
+    done, scores, ranks = v.results()
+    sc, kc, ec, eh = v.counters()
+    v.close()
+    o_scores = np.zeros((n, 4), np.int32)
+    o_ranks = np.zeros((n, 4), np.uint8)
+    o_done = np.zeros(n, np.uint8)
+    o_steps = np.zeros(n, np.uint32)
+    o_ky = np.zeros(n, np.uint32)
+    o_ec = np.zeros(n, np.uint32)
+    o_h = np.zeros(n, np.uint64)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    o_total = orc.orc_run_random(mode, rule, seed_base, n, agent_seed, max_steps, 32, p(o_scores, C.c_int32), p(o_ranks, C.c_uint8),
+                                 p(o_done, C.c_uint8), p(o_steps, C.c_uint32), p(o_ky, C.c_uint32), p(o_ec, C.c_uint32),
+                                 p(o_h, C.c_uint64), None)
+    return (total, done, scores, ranks, sc, kc, ec, eh), (o_total, o_done, o_scores, o_ranks, o_steps, o_ky, o_ec, o_h)
+
+
+@pytest.mark.parametrize("mode,rule,n", [(2, A.RULE_DEFAULT_TENHOU, 4096), (2, A.RULE_DEFAULT_MJSOUL, 1024),
+                                          (1, A.RULE_DEFAULT_TENHOU, 1024), (0, A.RULE_DEFAULT_TENHOU, 4096)])
+def test_random_games_vs_oracle(orc, mode, rule, n):
+    g, o = run_both(orc, n, mode, rule, seed_base=1000 * mode, agent_seed=0xABCDEF)
+    assert g[0] == o[0], "total env steps"
+    names = ["done", "scores", "ranks", "step_count", "kyoku_count", "ev_count", "ev_hash"]
+    for name, a, b in zip(names, g[1:], o[1:]):
+        assert np.array_equal(a, b), f"{name} differs in {int((a != b).sum())} entries"
+    assert g[1].all()
+
+
+def test_partial_rollout_and_resume(orc):
+    """max_steps < game length: state must carry over between launches exactly."""
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n = 512
+    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=77)
+    v.reset()
+    total = 0
+    for _ in range(40):
+        total += v.step_random(5, 100)
+    done, scores, ranks = v.results()
+    sc, kc, ec, eh = v.counters()
+    o_scores = np.zeros((n, 4), np.int32)
+    o_h = np.zeros(n, np.uint64)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    o_total = orc.orc_run_random(2, A.RULE_DEFAULT_TENHOU, 77, n, 5, 4000, 32, p(o_scores, C.c_int32), None, None, None, None, None,
+                                 p(o_h, C.c_uint64), None)
+    assert total == o_total and np.array_equal(scores, o_scores) and np.array_equal(eh, o_h)
+
+
+def test_lockstep_snapshots_legal_and_events(orc):
+    """Per-step: full state record, legal-action lists; at the end: event log words and MJAI JSON."""
+    from tests.backends import GpuBackend, OracleBackend
+
+    for seed in (3, 4):
+        g, o = GpuBackend(2, seed), OracleBackend(2, seed)
+        g.reset()
+        o.reset()
+        steps = 0
+        while True:
+            sg, so = g.get_state(), o.get_state()
+            d = A.state_fields_equal(so, sg)
+            assert not d, f"seed {seed} step {steps}: {d}"
+            if so.is_done:
+                break
+            if steps % 7 == 0:
+                for p in range(4):
+                    assert g.legal_tuples(p) == o.legal_tuples(p)
+            g.random_step(99, seed)
+            o.random_step(99, seed)
+            steps += 1
+        assert g.events() == o.events()
+        assert g.events_json() == o.events_json()
+
+
+def test_external_actions_step(orc):
+    """rv_vec_step with host-chosen actions (legal list -> keyed pick on the host) matches the on-device agent."""
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n = 64
+    a = VecRiichiEnv(n, 0, A.RULE_DEFAULT_TENHOU, seed_base=500)
+    b = VecRiichiEnv(n, 0, A.RULE_DEFAULT_TENHOU, seed_base=500)
+    a.reset()
+    b.reset()
+    mix = lambda z: ((((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9 % 2**64) ^ ((((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) % 2**64) >> 27)) * 0x94D049BB133111EB) % 2**64
+    def mix64(z):
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) % 2**64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) % 2**64
+        return z ^ (z >> 31)
+    for it in range(400):
+        done, _, _ = a.results()
+        if done.all():
+            break
+        acts, counts = a.legal_actions()
+        sc, _, _, _ = a.counters()
+        chosen = (A.Action * (n * 4))()
+        for g in range(n):
+            for p in range(4):
+                k = int(counts[g, p])
+                if k == 0:
+                    chosen[g * 4 + p].type = A.NO_ACTION
+                    continue
+                key = (0x1234 ^ (((500 + g) * 0x9E3779B97F4A7C15) % 2**64) ^ (int(sc[g]) << 8) ^ p) % 2**64
+                chosen[g * 4 + p] = acts[(g * 4 + p) * A.MAX_LEGAL + mix64(key) % k]
+        a.step(chosen)
+        b.step_random(0x1234, 1)
+    ra, rb = a.results(), b.results()
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a.counters()[3], b.counters()[3])

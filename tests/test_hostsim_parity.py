@@ -1,0 +1,97 @@
+"""Kernel-source-vs-oracle parity on CPU (no GPU needed): the CUDA device code of
+riichienv_b200/csrc is compiled for the host by tests/hostsim and diffed against the oracle.
+The same comparisons run against the real GPU library in tests/test_gpu_parity.py."""
+import ctypes as C
+
+import pytest
+
+import oracle
+from riichienv_b200 import _abi as A
+from tests import helpers as H
+from tests import hostsim
+from tests.backends import HostsimBackend, OracleBackend
+
+
+@pytest.fixture(scope="module")
+def libs():
+    return oracle.load(), hostsim.load()
+
+
+def test_hand_eval_golden(libs):
+    orc, hs = libs
+    for i, (q, exp, yaku) in enumerate(H.load_agari_cases()):
+        r, ro = A.HandResult(), A.HandResult()
+        hs.hs_hand_eval(C.byref(q), C.byref(r), 1)
+        orc.orc_hand_eval(C.byref(q), C.byref(ro), 1)
+        assert (r.is_win, r.han, r.fu) == exp and H.yaku_ids(r.yaku_mask) == yaku, f"case {i}"
+        assert bytes(r) == bytes(ro), f"case {i}"
+
+
+def test_hand_eval_random(libs):
+    orc, hs = libs
+    qs = H.random_hand_queries(20000, seed=7)
+    arr = H.query_array(qs)
+    a = (A.HandResult * len(qs))()
+    b = (A.HandResult * len(qs))()
+    hs.hs_hand_eval(arr, a, len(qs))
+    orc.orc_hand_eval_mt(arr, b, len(qs), 8)
+    wins = 0
+    for i in range(len(qs)):
+        assert bytes(a[i]) == bytes(b[i]), f"hand {i}"
+        wins += a[i].is_win
+    assert wins > 1000  # the positive stratum is exercised
+
+
+def test_shanten_and_waits_golden(libs):
+    _, hs = libs
+    for cnt, sh in H.load_counts_file("shanten_golden.txt"):
+        assert hs.hs_shanten_counts((C.c_uint8 * 34)(*cnt), sum(cnt) // 3) == sh
+    for cnt, tenpai in H.load_counts_file("hands_negative.txt"):
+        arr = (C.c_uint8 * 34)(*cnt)
+        if sum(cnt) == 14:
+            assert hs.hs_is_agari(arr) == 0
+        else:
+            assert (hs.hs_waits(arr) != 0) == bool(tenpai)
+
+
+def test_wall_matches_oracle(libs):
+    orc, hs = libs
+    for seed in (0, 1, 2, 42, 123, 2 ** 32, 2 ** 63 + 1):
+        for hi in (0, 1, 5):
+            for n in (136, 108):
+                a = (C.c_uint8 * 136)()
+                b = (C.c_uint8 * 136)()
+                orc.orc_wall_from_seed(seed, hi, n, a)
+                hs.hs_wall_from_seed(seed, hi, n, b)
+                assert bytes(a)[:n] == bytes(b)[:n]
+                assert len(set(bytes(a)[:n])) == n
+
+
+def lockstep(seed, mode, rule, agent_seed, check_legal=True):
+    o, h = OracleBackend(mode, seed, rule), HostsimBackend(mode, seed, rule)
+    o.reset()
+    h.reset()
+    steps = 0
+    while True:
+        so, sh = o.get_state(), h.get_state()
+        d = A.state_fields_equal(so, sh)
+        assert not d, f"seed {seed} step {steps}: state differs in {d}"
+        if so.is_done:
+            break
+        if check_legal:
+            for p in range(4):
+                assert o.legal_tuples(p) == h.legal_tuples(p), f"seed {seed} step {steps} seat {p}"
+        o.random_step(agent_seed, seed)
+        h.random_step(agent_seed, seed)
+        steps += 1
+    assert o.events() == h.events()
+    return steps
+
+
+@pytest.mark.parametrize("mode,rule,n", [(2, A.RULE_DEFAULT_TENHOU, 24), (2, A.RULE_DEFAULT_MJSOUL, 12),
+                                          (1, A.RULE_DEFAULT_TENHOU, 8), (0, A.RULE_DEFAULT_TENHOU, 16)])
+def test_random_games_lockstep(mode, rule, n):
+    total = 0
+    for seed in range(100 * mode, 100 * mode + n):
+        total += lockstep(seed, mode, rule, agent_seed=0xC0FFEE + mode)
+    assert total > 50 * n

@@ -1,0 +1,128 @@
+"""Pins the ORACLE (CPU restatement) on the reference's own golden vectors / known answers.
+
+Sources: riichienv-core/benches/data/*.json (via tests/golden/*.txt),
+riichienv-core/tests/agari_correctness.rs:286-348 (score table),
+tests/test_agari_calculator.py:41-97, README.md:221-223, tests/test_shanten.py.
+"""
+import ctypes as C
+
+import pytest
+
+import oracle
+from riichienv_b200 import _abi as A
+from tests import helpers as H
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return oracle.load()
+
+
+def test_agari_4p_golden(orc):
+    cases = H.load_agari_cases()
+    assert len(cases) == 816
+    for i, (q, exp, yaku) in enumerate(cases):
+        r = A.HandResult()
+        orc.orc_hand_eval(C.byref(q), C.byref(r), 1)
+        assert (r.is_win, r.han, r.fu) == exp, f"case {i}"
+        assert H.yaku_ids(r.yaku_mask) == yaku, f"case {i}"
+        assert r.has_win_shape == 1
+
+
+def test_negative_hands(orc):
+    cases = H.load_counts_file("hands_negative.txt")
+    assert len(cases) == 200
+    for cnt, tenpai in cases:
+        arr = (C.c_uint8 * 34)(*cnt)
+        assert orc.orc_is_agari(arr) == 0
+        if sum(cnt) == 13:
+            assert orc.orc_is_tenpai_counts(arr) == tenpai
+
+
+def test_shanten_golden(orc):
+    cases = H.load_counts_file("shanten_golden.txt")
+    assert len(cases) == 6000
+    for cnt, sh in cases:
+        assert orc.orc_shanten_counts((C.c_uint8 * 34)(*cnt), sum(cnt) // 3) == sh
+
+
+SHANTEN_KNOWN = [  # tests/test_shanten.py
+    ("1111m111122233z", 1), ("111m111z222z333z44z", -1), ("123456789p11222z", -1), ("111m123456789s11z", -1),
+    ("19m19p19s1234567z", 0), ("111m999m123p789s1z", 0), ("1199m1199p1199s1z", 0), ("11m99m123p456s111z", 0),
+    ("111m999m123p13s7z", 1), ("11119999m22345s", 1), ("1111m9m1234567z", 3), ("111m999m111p11z", -1),
+    ("111m123456789p1z", 0), ("999m111222333z1p", 0), ("11m99m11p99p11s99s1z", 0), ("111999m111999p1z", 0),
+    ("19m147p258s12345z", 5),
+]
+
+
+@pytest.mark.parametrize("hand,expected", SHANTEN_KNOWN)
+def test_shanten_known_answers(orc, hand, expected):
+    cnt = [0] * 34
+    for t in H.parse_hand(hand):
+        cnt[t // 4] += 1
+    assert orc.orc_shanten_counts((C.c_uint8 * 34)(*cnt), sum(cnt) // 3) == expected
+
+
+SCORE_TABLE = [  # tests/agari_correctness.rs:290-331
+    (1, 30, 0, 0, 0, 4, 1000, 0, 0), (1, 30, 0, 1, 0, 4, 0, 500, 300), (3, 30, 1, 0, 0, 4, 5800, 0, 0),
+    (5, 0, 0, 0, 0, 4, 8000, 0, 0), (5, 0, 1, 1, 0, 4, 0, 0, 4000), (5, 0, 0, 1, 0, 4, 0, 4000, 2000),
+    (6, 0, 0, 0, 0, 4, 12000, 0, 0), (8, 0, 0, 0, 0, 4, 16000, 0, 0), (11, 0, 0, 0, 0, 4, 24000, 0, 0),
+    (13, 0, 0, 0, 0, 4, 32000, 0, 0), (13, 0, 1, 0, 0, 4, 48000, 0, 0), (13, 0, 0, 1, 0, 4, 0, 16000, 8000),
+    (13, 0, 1, 1, 0, 4, 0, 0, 16000), (26, 0, 0, 0, 0, 4, 64000, 0, 0), (26, 0, 1, 0, 0, 4, 96000, 0, 0),
+    (26, 0, 0, 1, 0, 4, 0, 32000, 16000), (26, 0, 1, 1, 0, 4, 0, 0, 32000), (26, 0, 0, 0, 2, 4, 64600, 0, 0),
+    (26, 0, 1, 1, 2, 4, 0, 200, 32200), (39, 0, 0, 0, 0, 4, 96000, 0, 0), (39, 0, 1, 1, 0, 4, 0, 0, 48000),
+    (52, 0, 0, 0, 0, 4, 128000, 0, 0), (65, 0, 0, 0, 0, 4, 160000, 0, 0), (13, 0, 0, 0, 0, 3, 32000, 0, 0),
+    (13, 0, 0, 1, 0, 3, 0, 16000, 8000), (26, 0, 0, 0, 0, 3, 64000, 0, 0), (26, 0, 1, 1, 0, 3, 0, 0, 32000),
+]
+
+
+@pytest.mark.parametrize("case", SCORE_TABLE)
+def test_score_table(orc, case):
+    han, fu, oya, tsumo, honba, np_, ron, p_oya, p_ko = case
+    out = (C.c_uint32 * 4)()
+    orc.orc_calculate_score(han, fu, oya, tsumo, honba, np_, out)
+    assert (out[0], out[1], out[2]) == (ron, p_oya, p_ko)
+
+
+def _calc(orc, hand, win, cond=0, pw=0, rw=0, melds=(), dora=()):
+    q = H.make_query(H.parse_hand(hand), list(melds), win, list(dora), [], cond, pw, rw, 0)
+    r = A.HandResult()
+    orc.orc_hand_eval(C.byref(q), C.byref(r), 1)
+    return r
+
+
+def test_readme_example(orc):
+    # README.md:221-223: 111m33p12s111666z + 3s ron -> 12000 for dealer?  yaku [8, 11, 10, 22], 5 han 60 fu
+    # (hatsu triplet 666z is kind 32 -> id 8; 111z is East: round + seat wind)
+    tiles = H.parse_hand("111m33p12s111666z")
+    q = H.make_query(tiles, [], 18 * 4 + 2 * 4, [], [], 0, 0, 0, 0)  # 3s
+    r = A.HandResult()
+    orc.orc_hand_eval(C.byref(q), C.byref(r), 1)
+    assert r.is_win and r.han == 5 and r.fu == 60
+    assert H.yaku_ids(r.yaku_mask) == [8, 10, 11, 22]
+    assert r.ron_agari == 12000
+
+
+def test_agari_calculator_known(orc):
+    # tests/test_agari_calculator.py:41-97: 123m456p789s111z + 2z pair wait, winds vary the yakuhai count
+    tiles = H.parse_hand("123m456p789s111z2z")
+    win = 28 * 4 + 1
+    # seat East, round East: double-wind triplet -> 2 han
+    q = H.make_query(tiles, [], win, [], [], 0, 0, 0, 0)
+    r = A.HandResult()
+    orc.orc_hand_eval(C.byref(q), C.byref(r), 1)
+    assert r.is_win and r.han == 2 and r.fu == 40
+    # seat South, round South: 111z is no yakuhai -> no yaku on ron
+    q = H.make_query(tiles, [], win, [], [], 0, 1, 1, 0)
+    orc.orc_hand_eval(C.byref(q), C.byref(r), 1)
+    assert r.has_win_shape and not r.is_win
+
+
+def test_kokushi_and_chiitoi(orc):
+    r = _calc(orc, "19m19p19s1234567z", 0 * 4 + 1)  # 13-sided
+    assert r.is_win and r.yakuman and r.han == 26 and H.yaku_ids(r.yaku_mask) == [49]
+    r = _calc(orc, "1122m3344p5566s7z", 33 * 4 + 1)
+    assert r.is_win and r.fu == 25 and 25 in H.yaku_ids(r.yaku_mask)
+    # ryanpeikou shape is never scored as chiitoitsu (yaku.rs:236-296)
+    r = _calc(orc, "112233m445566p7s", 24 * 4 + 1, cond=A.C_RIICHI)
+    assert r.is_win and 28 in H.yaku_ids(r.yaku_mask) and 25 not in H.yaku_ids(r.yaku_mask)

@@ -1,0 +1,244 @@
+"""Rule scenarios re-expressed from the reference's own pytest suite (state injection through
+snapshot get/set instead of PyO3 setters).  Each scenario runs on the oracle and on the kernel
+source compiled for the host; the same scenarios run on the GPU through the C ABI under -m gpu.
+
+Sources (relative to /root/reference/tests): env/rule_validation/test_claim_priority.py,
+env/test_illegal_actions.py, test_midway_draw.py, env/test_kan_dora_timing_events.py,
+env/actions/test_kyushu_kyuhai.py, env/rule_validation/test_kuikae.py, env/test_riichienv.py.
+"""
+import json
+
+import pytest
+
+from riichienv_b200 import _abi as A
+from tests.backends import BACKENDS, act, setup_env
+
+CPU_BACKENDS = ["oracle", "hostsim"]
+ALL = [pytest.param(b) for b in CPU_BACKENDS] + [pytest.param("gpu", marks=pytest.mark.gpu)]
+
+
+def ev(env):
+    return [json.loads(s) for s in env.events_json()]
+
+
+def active(s):
+    return [p for p in range(4) if (s.active_mask >> p) & 1]
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_initialization(backend):  # env/test_riichienv.py:9-64
+    env = BACKENDS[backend](0, 42)
+    env.reset()
+    s = env.get_state()
+    assert s.wall_top - s.rinshan_draw_count == 83
+    assert [s.hand_len[p] for p in range(4)] == [14, 13, 13, 13]
+    assert s.current_player == 0 and s.turn_count == 0 and not s.is_done and not s.needs_tsumo
+    assert s.drawable_count == 69
+    assert active(s) == [0]
+    assert len(env.legal_tuples(0)) == 14 and env.legal_tuples(1) == []
+    e = ev(env)
+    assert [x["type"] for x in e] == ["start_game", "start_kyoku", "tsumo"]
+    masked = [json.loads(x) for x in env.events_json(viewer=1)]
+    assert masked[1]["tehais"][0][0] == "?" and masked[1]["tehais"][1][0] != "?" and masked[2]["pai"] == "?"
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_basic_step(backend):  # env/test_riichienv.py:66-126
+    env = BACKENDS[backend](0, 42)
+    env.reset()
+    s = env.get_state()
+    tile = s.hand[0][s.hand_len[0] - 1]
+    env.step({0: act(A.DISCARD, tile)})
+    while env.get_state().phase == 1:
+        env.step({p: act(A.PASS) for p in active(env.get_state())})
+    s = env.get_state()
+    assert s.phase == 0 and s.current_player == 1 and s.hand_len[1] == 14 and s.drawn_tile != 255
+    assert [x["type"] for x in ev(env)][:5] == ["start_game", "start_kyoku", "tsumo", "dahai", "tsumo"]
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_pon_priority_over_chi(backend):  # env/rule_validation/test_claim_priority.py:11-54
+    env = setup_env(BACKENDS[backend], seed=1,
+                    hands=[[57] + [2] * 12, [62, 65] + [0] * 11, [56, 58] + [1] * 11,
+                           [12, 16, 19, 21, 48, 59, 64, 77, 81, 89, 104, 130, 133]],
+                    current_player=0, active_players=[0], drawn_tile=100)
+    env.step({0: act(A.DISCARD, 57)})
+    s = env.get_state()
+    assert s.phase == 1 and active(s) == [1, 2]
+    env.step({1: act(A.CHI, 57, [62, 65]), 2: act(A.PON, 57, [56, 58])})
+    s = env.get_state()
+    assert s.phase == 0 and active(s) == [2]
+    assert ev(env)[-1]["type"] == "pon"
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_illegal_discard_penalty(backend):  # env/test_illegal_actions.py:5-60
+    env = BACKENDS[backend](1, 42)
+    env.reset()
+    s = env.get_state()
+    hand = [s.hand[0][k] for k in range(s.hand_len[0])]
+    bad = 0
+    while bad in hand:
+        bad += 1
+    env.step({0: act(A.DISCARD, bad)})
+    s = env.get_state()
+    assert s.last_error == 0 and not s.is_done
+    e = ev(env)
+    ry = [x for x in e if x["type"] == "ryukyoku"][-1]
+    assert "Error: Illegal Action" in ry["reason"] and ry["deltas"] == [-12000, 4000, 4000, 4000]
+    assert [s.score[p] for p in range(4)] == [13000, 29000, 29000, 29000]
+    assert s.oya == 0 and s.honba == 1 and s.kyoku_idx == 0 and s.hand_len[0] == 14
+    assert any(x["type"] == "end_kyoku" for x in e)
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_illegal_out_of_turn(backend):  # env/test_illegal_actions.py:62-100 (ko offender: -8000 / oya +4000 / ko +2000)
+    env = BACKENDS[backend](1, 42)
+    env.reset()
+    s = env.get_state()
+    env.step({0: act(A.DISCARD, s.hand[0][13]), 1: act(A.DISCARD, 0)})
+    s = env.get_state()
+    assert s.last_error == 1
+    assert [s.score[p] for p in range(4)] == [29000, 17000, 27000, 27000]
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_sufuurenta(backend):  # test_midway_draw.py:7-31
+    tiles = [108, 109, 110, 111]
+    scattered = [0, 4, 8, 36, 40, 44, 72, 76, 80, 112, 116, 120, 124]
+    env = setup_env(BACKENDS[backend], hands=[scattered[:] for _ in range(4)], wall=list(range(136)))
+    for i in range(4):
+        s = env.get_state()
+        p = s.current_player
+        hand = sorted([s.hand[p][k] for k in range(s.hand_len[p])])
+        hand[0] = tiles[i]
+        for k in range(s.hand_len[p]):
+            s.hand[p][k] = hand[k]
+        s.drawn_tile = tiles[i]
+        env.set_state(s)
+        env.step({p: act(A.DISCARD, tiles[i])})
+        if i < 3:
+            assert not env.get_state().is_done
+    assert env.get_state().is_done
+    assert any(x.get("reason") == "sufuurenta" for x in ev(env))
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_suukansansen(backend):  # test_midway_draw.py:33-56
+    scattered = [0, 4, 8, 36, 40, 44, 72, 76, 80, 112, 116, 120, 124]
+    ank = lambda lo: (3, [lo, lo + 1, lo + 2, lo + 3], -1, None)
+    env = setup_env(BACKENDS[backend], hands=[scattered[:] for _ in range(4)],
+                    melds=[[ank(0), ank(4)], [ank(8), ank(12)], [], []], current_player=1, drawn_tile=108,
+                    wall=list(range(136)))
+    env.step({1: act(A.DISCARD, 108)})
+    assert env.get_state().is_done
+    assert any(x.get("reason") == "suukansansen" for x in ev(env))
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_kyushu_kyuhai(backend):  # env/actions/test_kyushu_kyuhai.py
+    hand = [0, 32, 36, 68, 72, 104, 108, 112, 116, 4, 8, 12, 40]  # 9 distinct terminal/honor kinds
+    env = setup_env(BACKENDS[backend], hands=[hand, None, None, None], current_player=0, drawn_tile=44)
+    legal = env.legal_tuples(0)
+    assert (A.KYUSHU_KYUHAI, None, ()) in legal
+    env.step({0: act(A.KYUSHU_KYUHAI)})
+    e = ev(env)
+    assert any(x.get("reason") == "kyushu_kyuhai" for x in e)
+    assert env.get_state().is_done  # single-kyoku mode
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_kuikae_forbidden_after_chi(backend):  # env/rule_validation/test_kuikae.py
+    # P1 holds 2m3m (+ 1m,4m); P0 discards 4m -> chi 2m3m+4m forbids discarding 4m and 1m (suji kuikae)
+    p1 = [0 * 4, 1 * 4, 2 * 4, 3 * 4 + 1, 40, 44, 72, 76, 80, 112, 116, 120, 124]
+    p0 = [3 * 4, 41, 45, 73, 77, 81, 113, 117, 121, 125, 100, 101, 102]
+    env = setup_env(BACKENDS[backend], hands=[p0, p1, None, None], current_player=0, drawn_tile=133)
+    env.step({0: act(A.DISCARD, 12)})
+    s = env.get_state()
+    assert s.phase == 1 and 1 in active(s)
+    chis = [a for a in env.legal_tuples(1) if a[0] == A.CHI]
+    assert (A.CHI, 12, (4, 8)) in chis
+    acts = {p: act(A.PASS) for p in active(s)}
+    acts[1] = act(A.CHI, 12, [4, 8])
+    env.step(acts)
+    s = env.get_state()
+    assert s.phase == 0 and s.current_player == 1
+    discards = [a[1] for a in env.legal_tuples(1) if a[0] == A.DISCARD]
+    assert 13 not in discards and 0 not in discards  # 4m (other copy) and 1m are forbidden
+    assert 40 in discards
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_kan_dora_timing(backend):  # env/test_kan_dora_timing_events.py
+    # ankan: dora event BEFORE the rinshan tsumo
+    h0 = [0, 1, 2, 36, 40, 44, 72, 76, 80, 112, 116, 120, 124]
+    env = setup_env(BACKENDS[backend], hands=[h0, None, None, None], current_player=0, drawn_tile=3, wall=list(range(136)))
+    assert (A.ANKAN, 0, (0, 1, 2, 3)) in env.legal_tuples(0)
+    env.step({0: act(A.ANKAN, 0, [0, 1, 2, 3])})
+    types = [x["type"] for x in ev(env)]
+    assert types[-3:] == ["ankan", "dora", "tsumo"]
+    s = env.get_state()
+    assert s.n_dora == 2 and s.rinshan_draw_count == 1 and s.is_rinshan_flag == 1
+    # kakan: tsumo first, dora revealed right before the next dahai
+    pon = (1, [4, 5, 6], 1, 4)
+    h0 = [7, 36, 40, 44, 72, 76, 80, 112, 116, 120]
+    env = setup_env(BACKENDS[backend], hands=[h0, None, None, None], melds=[[pon], [], [], []], current_player=0,
+                    drawn_tile=124, wall=list(range(136)))
+    kakans = [a for a in env.legal_tuples(0) if a[0] == A.KAKAN]
+    assert kakans == [(A.KAKAN, 7, (4, 5, 6))]
+    env.step({0: act(A.KAKAN, 7, [4, 5, 6])})
+    s = env.get_state()
+    if s.phase == 1:  # somebody may chankan: everyone passes
+        env.step({p: act(A.PASS) for p in active(s)})
+    types = [x["type"] for x in ev(env)]
+    assert types[-2:] == ["kakan", "tsumo"]
+    s = env.get_state()
+    assert s.pending_kan_dora_count == 1 and s.n_dora == 1
+    env.step({0: act(A.DISCARD, s.drawn_tile)})
+    types = [x["type"] for x in ev(env)]
+    i = max(k for k, t in enumerate(types) if t == "dahai")
+    assert types[i - 1] == "dora"
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_ron_and_scores(backend):  # tests/test_env_scoring.py style: P1 rons P0's discard
+    # P1: 123m 456m 789m 11p + 23p waiting 1p/4p ; menzen pinfu-ish + ittsu
+    p1 = [0, 4, 8, 12, 17, 20, 24, 28, 32, 36, 37, 40, 44]
+    p0 = [48, 72, 76, 80, 84, 88, 112, 116, 120, 124, 128, 132, 100]
+    env = setup_env(BACKENDS[backend], hands=[p0, p1, None, None], current_player=0, drawn_tile=52, game_mode=1)
+    env.step({0: act(A.DISCARD, 48)})  # 4p
+    s = env.get_state()
+    assert s.phase == 1 and 1 in active(s)
+    assert (A.RON, 48, ()) in env.legal_tuples(1)
+    env.step({p: (act(A.RON, 48) if p == 1 else act(A.PASS)) for p in active(s)})
+    e = ev(env)
+    hora = [x for x in e if x["type"] == "hora"][-1]
+    assert hora["actor"] == 1 and hora["target"] == 0 and sum(hora["deltas"]) == 0 and hora["deltas"][1] > 0
+    s = env.get_state()
+    assert s.score[0] + s.score[1] == 50000 and s.oya == 1 and s.honba == 0
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_tsumo_and_riichi_flow(backend):  # env/rule_validation/test_riichi_sequence.py style
+    # P0 tenpai after discarding 9s: 123m 456m 789m 11p 23p + junk 9s; riichi -> discard -> accepted
+    p0 = [0, 4, 8, 12, 17, 20, 24, 28, 32, 36, 37, 40, 44]
+    env = setup_env(BACKENDS[backend], hands=[p0, None, None, None], current_player=0, drawn_tile=104, wall=list(range(136)))
+    legal = env.legal_tuples(0)
+    assert (A.RIICHI, None, ()) in legal
+    env.step({0: act(A.RIICHI)})
+    s = env.get_state()
+    assert s.flags[0] & A.F_RIICHI_STAGE
+    legal = env.legal_tuples(0)
+    # tenpai-keeping discards only: 9s (wait 1p/4p) or a 1p (tanki on 9s)
+    assert [a for a in legal if a[0] == A.DISCARD] == [(A.DISCARD, 36, ()), (A.DISCARD, 37, ()), (A.DISCARD, 104, ())]
+    assert A.RIICHI not in [a[0] for a in legal] and A.TSUMO not in [a[0] for a in legal]
+    env.step({0: act(A.DISCARD, 104)})
+    s = env.get_state()
+    while s.phase == 1:
+        env.step({p: act(A.PASS) for p in active(s)})
+        s = env.get_state()
+    types = [x["type"] for x in ev(env)]
+    assert "reach" in types and "reach_accepted" in types
+    assert types.index("reach") < types.index("reach_accepted")
+    assert s.score[0] == 24000 and s.riichi_sticks == 1 and (s.flags[0] & A.F_RIICHI_DECLARED)
+    assert s.flags[0] & A.F_DOUBLE_RIICHI  # declared on the first turn
