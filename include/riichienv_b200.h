@@ -147,6 +147,13 @@ typedef struct rv_game_state {
   uint32_t ev_count;              /* events pushed since reset */
   uint32_t ev_words;             /* 32-bit words pushed since reset (log length, even when the log is capped/off) */
   uint64_t ev_hash;               /* FNV-1a-64 over the 32-bit words of the binary event stream */
+
+  /* derived caches, kept consistent by every mutation (the oracle recomputes them from scratch in its
+   * snapshot, so state-parity tests also check the incremental maintenance):                          */
+  uint64_t c_cnt[RV_NP][4];       /* concealed-hand histogram, 4-bit count per tile kind; [seat][m,p,s,z] */
+  uint64_t c_river_kinds[RV_NP];  /* bit k: some own discard has kind k (furiten test)                     */
+  uint64_t c_waits[RV_NP];        /* get_waits_u8 of the seat's hand when it is 13-tile-equivalent, else 0 */
+  uint32_t c_key[RV_NP][4];       /* base-5 suit keys of c_cnt (table indices)                             */
 } rv_game_state;
 
 /* ---- binary event stream (replaces _push_mjai_event, state/mod.rs:2094-2148)

@@ -1523,6 +1523,19 @@ struct GameState {
     s.kyoku_count = kyoku_count;
     s.ev_count = ev_count;
     s.ev_words = ev_words;
+    // derived caches recomputed from scratch (the CUDA path maintains them incrementally)
+    for (int p = 0; p < NP; p++) {
+      const PlayerState& P = players[p];
+      static const uint32_t P5[9] = {1, 5, 25, 125, 625, 3125, 15625, 78125, 390625};
+      for (uint8_t t : P.hand) {
+        int kind = t / 4, su = kind / 9, pos = kind % 9;
+        s.c_cnt[p][su] += 1ull << (4 * pos);
+        s.c_key[p][su] += P5[pos];
+      }
+      for (uint8_t d : P.discards) s.c_river_kinds[p] |= 1ull << (d / 4);
+      HandEvaluator he(P.hand, P.melds);
+      for (uint8_t w : he.get_waits_u8()) s.c_waits[p] |= 1ull << w;
+    }
     s.ev_hash = ev_hash;
   }
 };

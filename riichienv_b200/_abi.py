@@ -67,6 +67,7 @@ class GameState(C.Structure):
         ("riichi_sticks", u32), ("turn_count", u32), ("seed", u64), ("hand_index", u64),
         ("n_claims", u8 * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
         ("step_count", u32), ("kyoku_count", u32), ("ev_count", u32), ("ev_words", u32), ("ev_hash", u64),
+        ("c_cnt", (u64 * 4) * NP), ("c_river_kinds", u64 * NP), ("c_waits", u64 * NP), ("c_key", (u32 * 4) * NP),
     ]
 
 

@@ -55,6 +55,16 @@ __device__ __forceinline__ void ev_meld(const Ctx& cx, G& g, int type, int actor
 }
 
 // ------------------------------------------------------------------ hand helpers
+__device__ __forceinline__ void cache_add(G& g, int p, int kind) {
+  int su = kind / 9, pos = kind - 9 * su;
+  g.c_cnt[p][su] += 1ull << (4 * pos);
+  g.c_key[p][su] += (uint32_t)pow5(pos);
+}
+__device__ __forceinline__ void cache_sub(G& g, int p, int kind) {
+  int su = kind / 9, pos = kind - 9 * su;
+  g.c_cnt[p][su] -= 1ull << (4 * pos);
+  g.c_key[p][su] -= (uint32_t)pow5(pos);
+}
 __device__ inline bool hand_remove_first(G& g, int p, int tile) {
   int n = g.hand_len[p];
   for (int i = 0; i < n; i++)
@@ -62,6 +72,7 @@ __device__ inline bool hand_remove_first(G& g, int p, int tile) {
       for (int j = i; j + 1 < n; j++) g.hand[p][j] = g.hand[p][j + 1];
       g.hand[p][n - 1] = RV_NONE;
       g.hand_len[p] = (uint8_t)(n - 1);
+      cache_sub(g, p, tile >> 2);
       return true;
     }
   return false;
@@ -71,6 +82,7 @@ __device__ inline void hand_push(G& g, int p, int tile) {
   if (n < RV_HAND_CAP) {
     g.hand[p][n] = (uint8_t)tile;
     g.hand_len[p] = (uint8_t)(n + 1);
+    cache_add(g, p, tile >> 2);
   } else {
     g.overflow = 1;
   }
@@ -87,18 +99,46 @@ __device__ inline void hand_sort(G& g, int p) {
     g.hand[p][j + 1] = v;
   }
 }
-__device__ inline Cnt hand_cnt(const G& g, int p) {
+__device__ __forceinline__ Cnt hand_cnt(const G& g, int p) {
   Cnt c;
-  cnt_zero(c);
-  int n = g.hand_len[p];
-  for (int i = 0; i < n; i++) cnt_add(c, g.hand[p][i] >> 2);
+  c.s[0] = g.c_cnt[p][0];
+  c.s[1] = g.c_cnt[p][1];
+  c.s[2] = g.c_cnt[p][2];
+  c.s[3] = g.c_cnt[p][3];
   return c;
 }
-__device__ inline uint64_t river_kinds(const G& g, int p) {
-  uint64_t m = 0;
-  int n = min((int)g.n_river[p], RV_RIVER_CAP);
-  for (int i = 0; i < n; i++) m |= 1ull << (g.river[p][i] >> 2);
-  return m;
+__device__ __forceinline__ void hand_info(const Tables& T, const G& g, int p, SuitInfo& si) {
+  si.e[0] = __ldg(&T.suit_info[g.c_key[p][0]]);
+  si.e[1] = __ldg(&T.suit_info[g.c_key[p][1]]);
+  si.e[2] = __ldg(&T.suit_info[g.c_key[p][2]]);
+  si.e[3] = __ldg(&T.honor_info[g.c_key[p][3]]);
+}
+__device__ __forceinline__ uint64_t river_kinds(const G& g, int p) { return g.c_river_kinds[p]; }
+// c_waits[p] = get_waits_u8 when the hand is 13-tile-equivalent, else 0 (hand_evaluator.rs:196-201)
+__device__ inline void waits_update(const Tables& T, G& g, int p) {
+  uint64_t w = 0;
+  if (g.hand_len[p] + 3 * g.n_melds[p] == 13) {
+    SuitInfo si;
+    hand_info(T, g, p, si);
+    w = waits13(hand_cnt(g, p), si);
+  }
+  g.c_waits[p] = w;
+}
+// Rebuild every derived cache from the canonical fields (after rv_vec_set_state)
+__device__ inline void refresh_caches(const Tables& T, G& g) {
+  for (int p = 0; p < 4; p++) {
+    for (int k = 0; k < 4; k++) g.c_cnt[p][k] = 0, g.c_key[p][k] = 0;
+    for (int i = 0; i < g.hand_len[p]; i++) {
+      int kind = g.hand[p][i] >> 2, su = kind / 9, pos = kind - 9 * su;
+      g.c_cnt[p][su] += 1ull << (4 * pos);
+      g.c_key[p][su] += (uint32_t)pow5(pos);
+    }
+    uint64_t m = 0;
+    int n = min((int)g.n_river[p], RV_RIVER_CAP);
+    for (int i = 0; i < n; i++) m |= 1ull << (g.river[p][i] >> 2);
+    g.c_river_kinds[p] = m;
+    waits_update(T, g, p);
+  }
 }
 __device__ __forceinline__ bool tid_terminal(int t) {  // types.rs:364-369
   int k = t >> 2;
@@ -285,6 +325,7 @@ __device__ inline void deal_next(const Ctx& cx, G& g) {
     g.drawable_count--;
     int pid = g.current_player;
     hand_push(g, pid, t);
+    g.c_waits[pid] = 0;   // 14-tile-equivalent now
     g.drawn_tile = (uint8_t)t;
     g.needs_tsumo = 0;
     g.phase = RV_WAIT_ACT;
@@ -321,6 +362,9 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
     g.n_claims[p] = 0;
     g.riichi_sutehai[p] = g.last_tedashi[p] = RV_NONE;
     g.n_kita[p] = 0;
+    for (int k = 0; k < 4; k++) g.c_cnt[p][k] = 0, g.c_key[p][k] = 0;
+    g.c_river_kinds[p] = 0;
+    g.c_waits[p] = 0;
     if (scores) g.score[p] = scores[p];
   }
   g.is_done = 0;
@@ -357,7 +401,10 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
     int p = (idx + oya) % NP;
     hand_push(g, p, g.wall[--g.wall_top]);
   }
-  for (int p = 0; p < NP; p++) hand_sort(g, p);
+  for (int p = 0; p < NP; p++) {
+    hand_sort(g, p);
+    if (p != oya) waits_update(cx.T, g, p);   // the dealer draws a 14th tile right below
+  }
   g.drawable_count = (uint8_t)(g.wall_top - 14);
   {
     uint32_t w[19];
@@ -454,11 +501,7 @@ __device__ __noinline__ void next_round(const Ctx& cx, G& g, bool oya_won, bool 
 }
 
 // is_tenpai of a seat's 13-tile-equivalent hand (hand_evaluator.rs:178-194)
-__device__ inline bool seat_tenpai(const Ctx& cx, const G& g, int p) {
-  if (g.hand_len[p] + 3 * g.n_melds[p] != 13) return false;
-  Cnt c = hand_cnt(g, p);
-  return waits13(cx.T, c) != 0;
-}
+__device__ __forceinline__ bool seat_tenpai(const Ctx& cx, const G& g, int p) { return g.c_waits[p] != 0; }
 
 // state/mod.rs:1846-1968
 __device__ __noinline__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason) {
@@ -562,6 +605,8 @@ __device__ inline void claim_push(G& g, int i, uint32_t a) {
   }
 }
 // Fills g.claims[i]; returns the reference's `missed_agari` flag.
+// Fast path: the cached wait mask / histogram answer "nothing to claim" with a few bit tests;
+// the hand is only scanned for tile ids when a pon / chi pattern actually exists.
 __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int tile) {
   bool missed = false;
   g.n_claims[i] = 0;
@@ -570,15 +615,12 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
   uint32_t f = g.flags[i];
   bool riichi = f & RV_F_RIICHI_DECLARED;
   // 1. Ron
-  uint64_t rk = river_kinds(g, i);
-  bool in_discards = (rk >> kind) & 1;
-  bool in_missed = (f & RV_F_MISSED_AGARI_DOUJUN) || (riichi && (f & RV_F_MISSED_AGARI_RIICHI));
-  if (!in_discards && !in_missed && hl + 3 * g.n_melds[i] == 13) {
-    Cnt c = hand_cnt(g, i);
-    SuitInfo si;
-    load_info(cx.T, c, si);
-    uint64_t waits = waits13(c, si);
-    if ((waits >> kind) & 1) {   // hand + tile has a winning shape (calc would pass is_agari)
+  uint64_t rk = g.c_river_kinds[i];
+  uint64_t waits = g.c_waits[i];
+  if ((waits >> kind) & 1) {   // hand + tile has a winning shape (calc would pass is_agari)
+    bool in_discards = (rk >> kind) & 1;
+    bool in_missed = (f & RV_F_MISSED_AGARI_DOUJUN) || (riichi && (f & RV_F_MISSED_AGARI_RIICHI));
+    if (!in_discards && !in_missed) {
       bool furiten = (waits & rk) != 0 || (f & (RV_F_MISSED_AGARI_RIICHI | RV_F_MISSED_AGARI_DOUJUN));
       if (!furiten) {
         uint32_t cond = base_cond(g, i);
@@ -589,48 +631,48 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
       }
     }
   }
+  if (riichi || g.drawable_count == 0 || hl < 3) return missed;
+  int su = kind / 9, r9 = kind - 9 * su;
+  uint64_t sc = g.c_cnt[i][su];
+  int n_same = (int)((sc >> (4 * r9)) & 15);
+  bool kuikae = rule(g, RV_RULE_KUIKAE_FORBIDDEN);
   // 2. Pon / Daiminkan
-  if (!riichi && g.drawable_count > 0) {
+  if (n_same >= 2) {
     uint8_t match[4];
     int cnt = 0;
-    bool other_kind = false;
     for (int k = 0; k < hl; k++) {
       int t = g.hand[i][k];
-      if ((t >> 2) == kind) { if (cnt < 4) match[cnt++] = (uint8_t)t; }
-      else other_kind = true;
+      if ((t >> 2) == kind && cnt < 4) match[cnt++] = (uint8_t)t;
     }
-    if (cnt >= 2 && hl >= 3) {
-      // kuikae: some tile other than the consumed pair must be discardable
-      bool ok = rule(g, RV_RULE_KUIKAE_FORBIDDEN) ? other_kind : true;
-      if (ok)
-        for (int a = 0; a < cnt; a++)
-          for (int b = a + 1; b < cnt; b++) claim_push(g, i, pack_act(RV_PON, tile, match[a], match[b]));
-    }
+    // kuikae: some tile other than the consumed pair must be discardable (legal_actions.rs:316-338)
+    bool ok = kuikae ? (hl - cnt) > 0 : true;
+    if (ok)
+      for (int a = 0; a < cnt; a++)
+        for (int b = a + 1; b < cnt; b++) claim_push(g, i, pack_act(RV_PON, tile, match[a], match[b]));
     if (cnt >= 3) claim_push(g, i, pack_act(RV_DAIMINKAN, tile, match[0], match[1]));
   }
-  // 3. Chi
-  if (!riichi && g.drawable_count > 0 && i == (pid + 1) % NP && hl >= 3 && kind < 27) {
-    int r9 = kind % 9;
-    bool kuikae = rule(g, RV_RULE_KUIKAE_FORBIDDEN);
-    for (int pat = 0; pat < 3; pat++) {
-      int ka, kb, forb2 = -1;
-      if (pat == 0) { if (r9 < 2) continue; ka = kind - 2; kb = kind - 1; if (r9 >= 3) forb2 = kind - 3; }
-      else if (pat == 1) { if (r9 < 1 || r9 > 7) continue; ka = kind - 1; kb = kind + 1; }
-      else { if (r9 > 6) continue; ka = kind + 1; kb = kind + 2; if (r9 <= 5) forb2 = kind + 3; }
-      // leftover tiles (hand minus c1,c2) need one tile that is neither `kind` nor forb2
-      int free_tiles = 0;
-      for (int k = 0; k < hl; k++) {
-        int tk = g.hand[i][k] >> 2;
-        if (!kuikae || (tk != kind && tk != forb2)) free_tiles++;
-      }
-      if (free_tiles - 2 <= 0) continue;
-      for (int a = 0; a < hl; a++) {
-        int c1 = g.hand[i][a];
-        if ((c1 >> 2) != ka) continue;
-        for (int b = 0; b < hl; b++) {
-          int c2 = g.hand[i][b];
-          if ((c2 >> 2) != kb) continue;
-          claim_push(g, i, pack_act(RV_CHI, tile, c1, c2));
+  // 3. Chi (shimocha only, number suits)
+  if (i == (pid + 1) % NP && su < 3) {
+    auto at = [&](int r) -> int { return (r < 0 || r > 8) ? 0 : (int)((sc >> (4 * r)) & 15); };
+    int m2 = at(r9 - 2), m1 = at(r9 - 1), p1 = at(r9 + 1), p2 = at(r9 + 2);
+    if ((m2 && m1) || (m1 && p1) || (p1 && p2)) {
+      for (int pat = 0; pat < 3; pat++) {
+        int ka, kb, forb2 = -1;
+        if (pat == 0) { if (!(m2 && m1)) continue; ka = kind - 2; kb = kind - 1; if (r9 >= 3) forb2 = kind - 3; }
+        else if (pat == 1) { if (!(m1 && p1)) continue; ka = kind - 1; kb = kind + 1; }
+        else { if (!(p1 && p2)) continue; ka = kind + 1; kb = kind + 2; if (r9 <= 5) forb2 = kind + 3; }
+        // leftover tiles (hand minus c1,c2) need one tile that is neither `kind` nor forb2 (legal_actions.rs:394-431)
+        int free_tiles = hl;
+        if (kuikae) free_tiles -= n_same + (forb2 >= 0 ? at(forb2 - 9 * su) : 0);
+        if (free_tiles - 2 <= 0) continue;
+        for (int a = 0; a < hl; a++) {
+          int c1 = g.hand[i][a];
+          if ((c1 >> 2) != ka) continue;
+          for (int b = 0; b < hl; b++) {
+            int c2 = g.hand[i][b];
+            if ((c2 >> 2) != kb) continue;
+            claim_push(g, i, pack_act(RV_CHI, tile, c1, c2));
+          }
         }
       }
     }
@@ -694,13 +736,13 @@ struct TurnInfo {
   uint64_t quads;         // kinds with four tiles in hand
 };
 
-// bit k set iff removing hand[k] leaves a tenpai hand
+// bit k set iff removing hand[k] leaves a tenpai hand (exact per-tile answer; used in riichi_stage)
 __device__ __noinline__ uint16_t tenpai_discard_mask(const Ctx& cx, const G& g, int p, bool stop_at_first) {
   int hl = g.hand_len[p];
   if (hl - 1 + 3 * g.n_melds[p] != 13) return 0;
   Cnt c = hand_cnt(g, p);
   SuitInfo si;
-  load_info(cx.T, c, si);
+  hand_info(cx.T, g, p, si);
   uint16_t mask = 0;
   uint64_t done = 0, good = 0;
   for (int k = 0; k < hl; k++) {
@@ -711,7 +753,8 @@ __device__ __noinline__ uint16_t tenpai_discard_mask(const Ctx& cx, const G& g, 
       cnt_sub(c2, kind);
       SuitInfo s2 = si;
       int su = kind / 9;
-      uint32_t e = load_info_suit(cx.T, cnt_suit(c2, su), su);
+      uint32_t key = g.c_key[p][su] - (uint32_t)pow5(kind - 9 * su);
+      uint32_t e = su == 3 ? __ldg(&cx.T.honor_info[key]) : __ldg(&cx.T.suit_info[key]);
       s2.e[0] = su == 0 ? e : si.e[0];
       s2.e[1] = su == 1 ? e : si.e[1];
       s2.e[2] = su == 2 ? e : si.e[2];
@@ -726,6 +769,82 @@ __device__ __noinline__ uint16_t tenpai_discard_mask(const Ctx& cx, const G& g, 
   return mask;
 }
 
+// "Does some discard leave the hand tenpai?" (legal_actions.rs:112-132) from the four suit entries of the
+// 14-tile-equivalent hand: the D-bits say whether a tile can leave a suit so that it becomes M / P / waitM / waitP.
+__device__ __forceinline__ bool any_tenpai_discard(const Cnt& c, const SuitInfo& si, int hl, int n_melds) {
+  if (hl + 3 * n_melds != 14) return false;
+  uint32_t M = 0, P = 0, WM = 0, WP = 0, DM = 0, DP = 0, DWM = 0, DWP = 0;
+  #pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint32_t e = si.e[k];
+    M |= (e & 1u) << k;
+    P |= ((e >> 1) & 1u) << k;
+    WM |= (((e >> 2) & 0x1FFu) != 0 ? 1u : 0u) << k;
+    WP |= (((e >> 11) & 0x1FFu) != 0 ? 1u : 0u) << k;
+    DM |= ((e >> 20) & 1u) << k;
+    DP |= ((e >> 21) & 1u) << k;
+    DWM |= ((e >> 22) & 1u) << k;
+    DWP |= ((e >> 23) & 1u) << k;
+  }
+  bool ok = false;
+  #pragma unroll
+  for (int s = 0; s < 4; s++) {
+    uint32_t others = 0xFu & ~(1u << s);
+    uint32_t mo = M & others, po = P & others;
+    int nM = __popc(mo), nP = __popc(po);
+    // the discard suit also holds the wait
+    if (((DWP >> s) & 1) && nM == 3) ok = true;
+    if (((DWM >> s) & 1) && nP == 1 && nM == 2) ok = true;
+    // the discard suit ends complete (M or P); another suit u holds the wait
+    #pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (u == s) continue;
+      uint32_t rest = others & ~(1u << u);
+      int rM = __popc(M & rest), rP = __popc(P & rest);
+      if ((DM >> s) & 1) {
+        if (((WP >> u) & 1) && rM == 2) ok = true;
+        if (((WM >> u) & 1) && rM == 1 && rP == 1) ok = true;
+      }
+      if ((DP >> s) & 1) {
+        if (((WM >> u) & 1) && rM == 2) ok = true;
+      }
+    }
+  }
+  if (ok || n_melds != 0) return ok;
+  // chiitoitsu: 7 pairs | 6 pairs + 2 singles | 5 pairs + triplet + single (all kinds distinct)
+  {
+    int n1 = 0, n2 = 0, n3 = 0;
+    uint64_t bad = 0;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint64_t x = c.s[k];
+      uint64_t b0 = x & 0x1111111111111111ull, b1 = (x >> 1) & 0x1111111111111111ull;
+      bad |= x & 0xCCCCCCCCCCCCCCCCull;
+      n3 += __popcll(b0 & b1);
+      n1 += __popcll(b0 & ~b1);
+      n2 += __popcll(b1 & ~b0);
+    }
+    if (bad == 0 && ((n2 == 7 && n1 == 0 && n3 == 0) || (n2 == 6 && n1 == 2 && n3 == 0) || (n2 == 5 && n3 == 1 && n1 == 1)))
+      return true;
+  }
+  // kokushi: at least 13 terminal/honor tiles covering at least 12 kinds
+  {
+    const uint64_t TM = 0xF0000000Full;
+    uint64_t xs[4] = {c.s[0] & TM, c.s[1] & TM, c.s[2] & TM, c.s[3] & 0xFFFFFFFull};
+    int tiles = 0, kinds = 0;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint64_t x = xs[k];
+      uint64_t nz = (x | (x >> 1) | (x >> 2)) & 0x1111111111111111ull;
+      kinds += __popcll(nz);
+      uint64_t y = (x & 0x0F0F0F0F0F0F0F0Full) + ((x >> 4) & 0x0F0F0F0F0F0F0F0Full);
+      tiles += (int)((y * 0x0101010101010101ull) >> 56);
+    }
+    if (tiles >= 13 && kinds >= 12) return true;
+  }
+  return false;
+}
+
 __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnInfo& ti) {
   ti.can_tsumo = ti.can_riichi = ti.riichi_ankan = ti.kyushu = false;
   ti.tenpai_keep = 0;
@@ -733,10 +852,12 @@ __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnI
   uint32_t f = g.flags[pid];
   bool riichi = f & RV_F_RIICHI_DECLARED, stage = f & RV_F_RIICHI_STAGE;
   int drawn = g.drawn_tile;
-  int hl = g.hand_len[pid];
+  int hl = g.hand_len[pid], nm = g.n_melds[pid];
+  Cnt c = hand_cnt(g, pid);
+  SuitInfo si;
+  hand_info(cx.T, g, pid, si);
   if (drawn != RV_NONE && !stage) {
-    Cnt c = hand_cnt(g, pid);
-    if (hl + 3 * g.n_melds[pid] == 14 && agari14(cx.T, c)) {
+    if (hl + 3 * nm == 14 && (standard_agari(si) || chiitoi14(c) || kokushi14(c))) {
       uint32_t cond = base_cond(g, pid) | RV_C_TSUMO;
       if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HAITEI;
       if (g.is_rinshan_flag) cond |= RV_C_RINSHAN;
@@ -749,20 +870,22 @@ __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnI
     ti.tenpai_keep = tenpai_discard_mask(cx, g, pid, false);
   } else if (!riichi) {
     if (g.score[pid] >= 1000 && g.drawable_count >= 4 && !any_open_meld(g, pid))
-      ti.can_riichi = tenpai_discard_mask(cx, g, pid, true) != 0;
+      ti.can_riichi = any_tenpai_discard(c, si, hl, nm);
   }
   if (g.drawable_count > 0 && drawn != RV_NONE) {
-    Cnt c = hand_cnt(g, pid);
     if (!riichi && !stage) {
       #pragma unroll
       for (int k = 0; k < 4; k++) {
-        uint64_t x = c.s[k] & 0x4444444444444444ull;   // nibble == 4
-        for (int i = 0; i < 9; i++)
-          if ((x >> (4 * i + 2)) & 1) ti.quads |= 1ull << (9 * k + i);
+        uint64_t x = (c.s[k] >> 2) & 0x1111111111111111ull;   // nibble == 4
+        while (x) {
+          int b = __ffsll((long long)x) - 1;
+          x &= x - 1;
+          ti.quads |= 1ull << (9 * k + (b >> 2));
+        }
       }
     } else if (riichi) {
       int kind = drawn >> 2;
-      if (cnt_get(c, kind) == 4 && hl + 3 * g.n_melds[pid] == 14) {
+      if (cnt_get(c, kind) == 4 && hl + 3 * nm == 14) {
         Cnt pre = c;
         cnt_sub(pre, kind);
         uint64_t wpre = waits13(cx.T, pre);
@@ -773,11 +896,8 @@ __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnI
       }
     }
   }
-  if (g.is_first_turn && all_meldless(g) && !stage) {
-    uint64_t pres = 0;
-    for (int k = 0; k < hl; k++) pres |= 1ull << (g.hand[pid][k] >> 2);
-    ti.kyushu = __popcll(pres & MASK_TERMINAL_HONOR) >= 9;
-  }
+  if (g.is_first_turn && all_meldless(g) && !stage)
+    ti.kyushu = __popcll(cnt_present(c) & MASK_TERMINAL_HONOR) >= 9;
 }
 
 __device__ __forceinline__ bool discard_forbidden(const G& g, int p, int tile) {
@@ -972,6 +1092,7 @@ __device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_
     g.phase = RV_WAIT_ACT;
     g.active_mask = (uint8_t)(1u << pid);
   }
+  waits_update(cx.T, g, pid);
 }
 
 // ------------------------------------------------------------------ discard (state/mod.rs:1317-1413)
@@ -988,6 +1109,8 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
     g.overflow = 1;
   }
   g.n_river[pid] = (uint8_t)(nr + 1);
+  g.c_river_kinds[pid] |= 1ull << (tile >> 2);
+  waits_update(cx.T, g, pid);   // the discarder is back to 13 tiles
   g.last_discard_pid = (uint8_t)pid;
   g.last_discard_tile = (uint8_t)tile;
   g.drawn_tile = RV_NONE;
@@ -1033,12 +1156,10 @@ __device__ __noinline__ int chankan_ronners(const Ctx& cx, G& g, int pid, int ti
   int kind = tile >> 2;
   for (int i = 0; i < NP; i++) {
     if (i == pid) continue;
-    if (g.hand_len[i] + 3 * g.n_melds[i] != 13) continue;
-    uint64_t rk = river_kinds(g, i);
-    uint32_t f = g.flags[i];
-    Cnt c = hand_cnt(g, i);
-    uint64_t waits = waits13(cx.T, c);
+    uint64_t waits = g.c_waits[i];
     if (!((waits >> kind) & 1)) continue;
+    uint64_t rk = g.c_river_kinds[i];
+    uint32_t f = g.flags[i];
     WinRes r;
     if (ankan_kokushi_only) {
       if ((rk >> kind) & 1) continue;
@@ -1130,6 +1251,7 @@ __device__ __noinline__ void step_apply(const Ctx& cx, G& g, const rv_action* ac
           ev_meld(cx, g, RV_EV_KAKAN, pid, tile, c[0], c[1], c[2], c[3]);
         }
         flush_pending_kan_dora(cx, g);
+        waits_update(cx.T, g, pid);
         int ron_mask = chankan_ronners(cx, g, pid, tile, false);
         if (ron_mask) {
           g.pending_kan_pid = (uint8_t)pid;
@@ -1362,6 +1484,7 @@ __device__ __noinline__ void step_apply(const Ctx& cx, G& g, const rv_action* ac
       }
       g.needs_tsumo = 0;
       g.drawn_tile = RV_NONE;
+      g.c_waits[claimer] = 0;
     } else {
       for (int i = 0; i < NP; i++) g.n_claims[i] = 0;
       g.active_mask = 0;

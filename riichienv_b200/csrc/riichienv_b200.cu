@@ -118,6 +118,8 @@ __global__ void create_kernel(G* states, int64_t n, int game_mode, uint32_t rule
   for (int s = 0; s < NP; s++) g.score[s] = 25000;
 }
 
+__global__ void refresh_kernel(Tables T, G* state) { refresh_caches(T, *state); }
+
 __global__ void reseed_kernel(G* states, int64_t n, const uint64_t* seeds, uint64_t seed_base) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -284,6 +286,8 @@ int rv_ctx_create(int device, rv_ctx** out) {
   gen_cost_kernel<7, false><<<grid_for(HONOR_KEYS, 128), 128, 0, c->stream>>>(c->honor_cost, c->honor_info, HONOR_KEYS);
   gen_wait_kernel<9><<<grid_for(SUIT_KEYS, 128), 128, 0, c->stream>>>(c->suit_info, SUIT_KEYS);
   gen_wait_kernel<7><<<grid_for(HONOR_KEYS, 128), 128, 0, c->stream>>>(c->honor_info, HONOR_KEYS);
+  gen_discard_kernel<9><<<grid_for(SUIT_KEYS, 128), 128, 0, c->stream>>>(c->suit_info, SUIT_KEYS);
+  gen_discard_kernel<7><<<grid_for(HONOR_KEYS, 128), 128, 0, c->stream>>>(c->honor_info, HONOR_KEYS);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->T.suit_info = c->suit_info;
@@ -558,6 +562,8 @@ int rv_vec_set_state(rv_vec* v, int64_t game, const rv_game_state* in) {
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   CK(cudaMemcpyAsync(v->d_states + game, in, sizeof(G), cudaMemcpyHostToDevice, c->stream));
+  refresh_kernel<<<1, 1, 0, c->stream>>>(c->T, v->d_states + game);   // derived caches follow the canonical fields
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   return RV_OK;
 }

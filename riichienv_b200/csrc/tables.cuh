@@ -11,6 +11,9 @@
 //                     bit1  P : the suit splits into mentsu + exactly one pair
 //                     bits 2..10   waitM[i] : count[i] < 4 and (suit + tile i) is M
 //                     bits 11..19  waitP[i] : count[i] < 4 and (suit + tile i) is P
+//                     bits 20..23  DM, DP, DWM, DWP : some tile i of the suit can be removed so that
+//                                  (suit - tile i) is M / is P / has a non-empty waitM / waitP
+//                                  (answers "does any discard leave the hand tenpai" in 4 loads)
 //   cost[key]  (u64)  ten nibbles: min #tiles missing to hold k mentsu (k=0..4),
 //                     without (nibble 2k) / with (nibble 2k+1) a pair, when no tile
 //                     may be used more than four times — the quantity nyanten encodes.
@@ -36,8 +39,23 @@ struct Tables {
 };
 
 __host__ __device__ inline int pow5(int i) {
-  const int p[10] = {1, 5, 25, 125, 625, 3125, 15625, 78125, 390625, 1953125};
-  return p[i];
+  // computed, not tabulated: keeps the value in registers (no local/constant array indexing)
+  int v = 1;
+  if (i & 1) v *= 5;
+  if (i & 2) v *= 25;
+  if (i & 4) v *= 625;
+  if (i & 8) v *= 390625;
+  return v;
+}
+
+// D-bits contributed by the entry `o` of (suit - one tile)
+__host__ __device__ inline uint32_t discard_bits(uint32_t o) {
+  uint32_t e = 0;
+  if (o & 1u) e |= 1u << 20;
+  if (o & 2u) e |= 1u << 21;
+  if ((o >> 2) & 0x1FFu) e |= 1u << 22;
+  if ((o >> 11) & 0x1FFu) e |= 1u << 23;
+  return e;
 }
 
 // DP over tile positions.  State: (s1 = sequences started at i-1, s2 = sequences
@@ -138,6 +156,27 @@ __global__ void gen_wait_kernel(uint32_t* info, int n_keys) {
     uint32_t o = info[key + pow5(i)] & 3u;   // written by gen_cost_kernel (previous launch)
     if (o & 1u) e |= 1u << (2 + i);
     if (o & 2u) e |= 1u << (11 + i);
+  }
+  info[key] = e;
+}
+
+template <int N>
+__global__ void gen_discard_kernel(uint32_t* info, int n_keys) {
+  int key = blockIdx.x * blockDim.x + threadIdx.x;
+  if (key >= n_keys) return;
+  int k = key, sum = 0;
+  uint8_t c[9];
+  for (int i = 0; i < N; i++) {
+    c[i] = (uint8_t)(k % 5);
+    k /= 5;
+    sum += c[i];
+  }
+  if (sum > 14 || sum == 0) return;
+  uint32_t e = info[key] & 0xFFFFFu;
+  for (int i = 0; i < N; i++) {
+    if (c[i] == 0) continue;
+    uint32_t o = info[key - pow5(i)];   // bits 0..19 were final after gen_wait_kernel (previous launch)
+    e |= discard_bits(o);
   }
   info[key] = e;
 }

@@ -72,6 +72,21 @@ static void gen(std::vector<uint64_t>& cost, std::vector<uint32_t>& info, int n_
     }
     info[key] = e;
   }
+  std::vector<uint32_t> base2 = info;
+  for (int key = 0; key < n_keys; key++) {
+    uint8_t c[9];
+    int k = key, sum = 0;
+    for (int i = 0; i < N; i++) {
+      c[i] = k % 5;
+      k /= 5;
+      sum += c[i];
+    }
+    if (sum > 14 || sum == 0) continue;
+    uint32_t e = base2[key];
+    for (int i = 0; i < N; i++)
+      if (c[i] > 0) e |= discard_bits(base2[key - pow5(i)]);
+    info[key] = e;
+  }
 }
 
 extern "C" {
@@ -254,7 +269,10 @@ void hs_game_random_step(void* p, uint64_t agent_seed, uint64_t game_id) {
   if (!h->g.is_done) random_step(cx, h->g, agent_seed, game_id);
 }
 void hs_game_snapshot(void* p, rv_game_state* out) { *out = ((HS*)p)->g; }
-void hs_game_load_snapshot(void* p, const rv_game_state* in) { ((HS*)p)->g = *in; }
+void hs_game_load_snapshot(void* p, const rv_game_state* in) {
+  ((HS*)p)->g = *in;
+  refresh_caches(g_T, ((HS*)p)->g);
+}
 uint32_t hs_game_events(void* p, uint32_t* out, uint32_t cap) {
   HS* h = (HS*)p;
   uint32_t n = std::min<uint32_t>(h->g.ev_words, (uint32_t)h->log.size());
