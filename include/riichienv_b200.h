@@ -130,7 +130,8 @@ typedef struct rv_game_state {
   uint8_t game_mode, rule_bits;
   uint8_t overflow;               /* set if a fixed capacity (river/claims/log) was exceeded */
   uint8_t n_kita[RV_NP];          /* 3P: kita count per seat */
-  uint8_t _pad0[3];
+  uint8_t pending_init[3];        /* {oya, round_wind, honba} of a round whose deal is deferred inside a rollout kernel;
+                                     pending_init[0]==RV_NONE outside kernels (always, as seen through this API)      */
   uint32_t riichi_sticks;
   uint32_t turn_count;
 

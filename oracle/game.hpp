@@ -1513,6 +1513,7 @@ struct GameState {
     s.active_mask = 0;
     for (uint8_t a : active_players) s.active_mask |= (uint8_t)(1u << a);
     s.last_error = (uint8_t)(last_error < 0 ? 0xFF : last_error);
+    s.pending_init[0] = s.pending_init[1] = s.pending_init[2] = 0xFF;
     s.game_mode = game_mode;
     s.rule_bits = (uint8_t)rule;
     s.riichi_sticks = riichi_sticks;

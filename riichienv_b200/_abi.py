@@ -63,7 +63,7 @@ class GameState(C.Structure):
         ("is_rinshan_flag", u8), ("riichi_pending_acceptance", u8), ("drawn_tile", u8), ("last_discard_pid", u8),
         ("last_discard_tile", u8), ("pending_kan_pid", u8), ("pending_kan_type", u8), ("pending_kan_tile", u8),
         ("active_mask", u8), ("last_error", u8), ("game_mode", u8), ("rule_bits", u8),
-        ("overflow", u8), ("n_kita", u8 * NP), ("_pad0", u8 * 3),
+        ("overflow", u8), ("n_kita", u8 * NP), ("pending_init", u8 * 3),
         ("riichi_sticks", u32), ("turn_count", u32), ("seed", u64), ("hand_index", u64),
         ("n_claims", u8 * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
         ("step_count", u32), ("kyoku_count", u32), ("ev_count", u32), ("ev_words", u32), ("ev_hash", u64),
@@ -87,7 +87,7 @@ class HandResult(C.Structure):
     ]
 
 
-def state_fields_equal(a: "GameState", b: "GameState", skip=("_pad0",)):
+def state_fields_equal(a: "GameState", b: "GameState", skip=()):
     """Field-by-field comparison; returns list of differing field names."""
     diff = []
     for name, _ in GameState._fields_:

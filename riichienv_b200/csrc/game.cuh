@@ -25,6 +25,7 @@ struct Ctx {
   Tables T;
   uint32_t* log;      // this game's event log region or nullptr
   uint32_t log_cap;   // words
+  bool defer_init;    // rollout kernels: next_round() parks the deal in g.pending_init so warps can batch it
 };
 
 __device__ __forceinline__ bool rule(const G& g, uint32_t bit) { return (g.rule_bits & bit) != 0; }
@@ -339,6 +340,7 @@ __device__ inline void deal_next(const Ctx& cx, G& g) {
 // `custom_wall`: nullptr -> seeded shuffle; else 136 tids in the order passed to reset(wall=) (load_wall reverses).
 __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_wind, int honba, uint32_t kyotaku,
                                   const uint8_t* custom_wall, const int32_t* scores) {
+  RV_STAT(2);
   g.oya = g.kyoku_idx = g.current_player = (uint8_t)oya;
   g.honba = (uint8_t)honba;
   g.riichi_sticks = kyotaku;
@@ -377,6 +379,7 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   g.turn_count = 0;
   g.needs_tsumo = 1;
   g.last_discard_pid = g.last_discard_tile = RV_NONE;
+  g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
   if (custom_wall) {
     for (int i = 0; i < 136; i++) g.wall[i] = custom_wall[135 - i];  // wall.rs:69-72
   } else {
@@ -497,6 +500,16 @@ __device__ __noinline__ void next_round(const Ctx& cx, G& g, bool oya_won, bool 
     return;
   }
   ev_simple(cx, g, RV_EV_END_KYOKU);
+  if (cx.defer_init) {   // the (expensive, rare) shuffle + deal is batched across the warp by the rollout kernel
+    g.pending_init[0] = (uint8_t)no;
+    g.pending_init[1] = (uint8_t)nw;
+    g.pending_init[2] = (uint8_t)nh;
+    return;
+  }
+  init_round(cx, g, no, nw, nh, g.riichi_sticks, nullptr, nullptr);
+}
+__device__ inline void run_pending_init(const Ctx& cx, G& g) {
+  int no = g.pending_init[0], nw = g.pending_init[1], nh = g.pending_init[2];
   init_round(cx, g, no, nw, nh, g.riichi_sticks, nullptr, nullptr);
 }
 
@@ -632,12 +645,14 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
     }
   }
   if (riichi || g.drawable_count == 0 || hl < 3) return missed;
+  RV_STAT(6);
   int su = kind / 9, r9 = kind - 9 * su;
   uint64_t sc = g.c_cnt[i][su];
   int n_same = (int)((sc >> (4 * r9)) & 15);
   bool kuikae = rule(g, RV_RULE_KUIKAE_FORBIDDEN);
   // 2. Pon / Daiminkan
   if (n_same >= 2) {
+    RV_STAT(7);
     uint8_t match[4];
     int cnt = 0;
     for (int k = 0; k < hl; k++) {
@@ -656,6 +671,7 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
     auto at = [&](int r) -> int { return (r < 0 || r > 8) ? 0 : (int)((sc >> (4 * r)) & 15); };
     int m2 = at(r9 - 2), m1 = at(r9 - 1), p1 = at(r9 + 1), p2 = at(r9 + 2);
     if ((m2 && m1) || (m1 && p1) || (p1 && p2)) {
+      RV_STAT(8);
       for (int pat = 0; pat < 3; pat++) {
         int ka, kb, forb2 = -1;
         if (pat == 0) { if (!(m2 && m1)) continue; ka = kind - 2; kb = kind - 1; if (r9 >= 3) forb2 = kind - 3; }
@@ -738,6 +754,7 @@ struct TurnInfo {
 
 // bit k set iff removing hand[k] leaves a tenpai hand (exact per-tile answer; used in riichi_stage)
 __device__ __noinline__ uint16_t tenpai_discard_mask(const Ctx& cx, const G& g, int p, bool stop_at_first) {
+  RV_STAT(5);
   int hl = g.hand_len[p];
   if (hl - 1 + 3 * g.n_melds[p] != 13) return 0;
   Cnt c = hand_cnt(g, p);
@@ -1540,7 +1557,9 @@ __device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uin
   rv_action acts[NP];
   for (int p = 0; p < NP; p++) acts[p].type = RV_NO_ACTION;
   uint32_t sc = g.step_count;
+  RV_STAT(3);
   if (g.phase == RV_WAIT_ACT) {
+    RV_STAT(4);
     int pid = g.current_player;
     TurnInfo ti;
     turn_info(cx, g, pid, ti);

@@ -14,6 +14,13 @@
 #include "../../include/riichienv_b200.h"
 #include "tables.cuh"
 
+#ifdef RV_HOSTSIM_STATS
+extern unsigned long long g_rv_stats[16];
+#define RV_STAT(i) (g_rv_stats[i]++)
+#else
+#define RV_STAT(i)
+#endif
+
 namespace rv {
 
 // ------------------------------------------------------------------ counts
@@ -713,6 +720,7 @@ __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, 
                                    const uint8_t* ura, int n_ura, uint32_t cond, int player_wind, int round_wind,
                                    uint32_t honba) {
   WinRes out{false, false, false, 0, 0, 0, 0, 0, 0};
+  RV_STAT(0);
   Cnt hand, full;
   cnt_zero(hand);
   int aka = 0;
@@ -757,6 +765,7 @@ __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, 
   bool std_shape = standard_agari(si);
   if (!std_shape && !chiitoi14(hand) && !kokushi14(hand)) return out;
   out.has_shape = true;
+  RV_STAT(1);
   WinCtx x;
   x.tsumo = cond & RV_C_TSUMO;
   x.riichi = cond & RV_C_RIICHI;

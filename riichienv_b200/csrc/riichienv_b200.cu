@@ -100,6 +100,7 @@ __device__ __forceinline__ Ctx make_ctx(const Tables& T, uint32_t* log, uint32_t
   cx.T = T;
   cx.log = log ? log + (size_t)i * cap : nullptr;
   cx.log_cap = cap;
+  cx.defer_init = false;
   return cx;
 }
 
@@ -114,6 +115,7 @@ __global__ void create_kernel(G* states, int64_t n, int game_mode, uint32_t rule
   g.seed = seeds ? seeds[i] : seed_base + (uint64_t)i;
   g.hand_index = 1;   // GameState::new consumed shuffle #0 (state/mod.rs:165)
   g.last_error = RV_NONE;
+  g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
   g.is_done = 1;      // until reset
   for (int s = 0; s < NP; s++) g.score[s] = 25000;
 }
@@ -137,20 +139,40 @@ __global__ void reset_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint
 }
 
 // Persistent rollout: each thread owns one game and advances it up to max_steps env steps.
+// Divergence control: the one rare, expensive transition — shuffling and dealing the next round
+// (~1 in 88 steps per game, ~10k instructions) — is not run inline.  A game whose round ended parks
+// (g.pending_init) and the warp deals parked games together once INIT_BATCH lanes are waiting, or when
+// no lane can make progress otherwise, so the deal runs convergent on many lanes instead of on one.
+#ifndef RV_INIT_BATCH
+#define RV_INIT_BATCH 8
+#endif
 __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
                                                           uint64_t agent_seed, uint32_t max_steps, unsigned long long* counters) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long my_steps = 0, my_done = 0;
-  if (i < n) {
-    Ctx cx = make_ctx(T, log, cap, i);
-    G& g = states[i];
-    uint64_t gid = g.seed;
-    for (uint32_t s = 0; s < max_steps && !g.is_done; s++) {
+  bool alive = i < n;
+  G& g = states[alive ? i : 0];
+  Ctx cx = make_ctx(T, log, cap, alive ? i : 0);
+  cx.defer_init = true;
+  uint64_t gid = alive ? g.seed : 0;
+  uint32_t taken = 0;
+  while (true) {
+    bool parked = alive && g.pending_init[0] != RV_NONE;
+    bool can = alive && !parked && !g.is_done && taken < max_steps;
+    if (can) {
       random_step(cx, g, agent_seed, gid);
+      taken++;
       my_steps++;
+      parked = g.pending_init[0] != RV_NONE;
+      can = !parked && !g.is_done && taken < max_steps;
     }
-    if (g.is_done && my_steps > 0) my_done = 1;
+    unsigned pm = __ballot_sync(0xFFFFFFFFu, parked), wm = __ballot_sync(0xFFFFFFFFu, can);
+    if (pm == 0 && wm == 0) break;
+    if (__popc(pm) >= RV_INIT_BATCH || wm == 0) {
+      if (parked) run_pending_init(cx, g);
+    }
   }
+  if (alive && g.is_done && my_steps > 0) my_done = 1;
   // block reduction -> one atomic per block
   __shared__ unsigned long long sh[2];
   if (threadIdx.x == 0) sh[0] = sh[1] = 0;

@@ -205,6 +205,7 @@ void* hs_game_new(int mode, uint64_t seed, uint32_t rule, uint32_t log_cap) {
   h->g.seed = seed;
   h->g.hand_index = 1;
   h->g.last_error = RV_NONE;
+  h->g.pending_init[0] = h->g.pending_init[1] = h->g.pending_init[2] = RV_NONE;
   h->g.is_done = 1;
   for (int s = 0; s < NP; s++) h->g.score[s] = 25000;
   h->log.assign(log_cap, 0);
@@ -215,6 +216,7 @@ static Ctx hs_ctx(HS* h) {
   cx.T = g_T;
   cx.log = h->log.empty() ? nullptr : h->log.data();
   cx.log_cap = (uint32_t)h->log.size();
+  cx.defer_init = false;
   return cx;
 }
 void hs_game_free(void* p) { delete (HS*)p; }
@@ -267,6 +269,17 @@ void hs_game_random_step(void* p, uint64_t agent_seed, uint64_t game_id) {
   HS* h = (HS*)p;
   Ctx cx = hs_ctx(h);
   if (!h->g.is_done) random_step(cx, h->g, agent_seed, game_id);
+}
+void hs_game_random_step_deferred(void* p, uint64_t agent_seed, uint64_t game_id, int flush) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  cx.defer_init = true;
+  if (h->g.pending_init[0] != RV_NONE) {
+    if (flush) run_pending_init(cx, h->g);
+    return;
+  }
+  if (!h->g.is_done) random_step(cx, h->g, agent_seed, game_id);
+  if (flush && h->g.pending_init[0] != RV_NONE) run_pending_init(cx, h->g);
 }
 void hs_game_snapshot(void* p, rv_game_state* out) { *out = ((HS*)p)->g; }
 void hs_game_load_snapshot(void* p, const rv_game_state* in) {
