@@ -681,15 +681,16 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
         int free_tiles = hl;
         if (kuikae) free_tiles -= n_same + (forb2 >= 0 ? at(forb2 - 9 * su) : 0);
         if (free_tiles - 2 <= 0) continue;
-        for (int a = 0; a < hl; a++) {
-          int c1 = g.hand[i][a];
-          if ((c1 >> 2) != ka) continue;
-          for (int b = 0; b < hl; b++) {
-            int c2 = g.hand[i][b];
-            if ((c2 >> 2) != kb) continue;
-            claim_push(g, i, pack_act(RV_CHI, tile, c1, c2));
-          }
+        // one pass over the hand collects the candidate tile ids (hand order), then the cross product
+        uint8_t ta[4], tb[4];
+        int na = 0, nb = 0;
+        for (int k = 0; k < hl; k++) {
+          int t = g.hand[i][k], tk = t >> 2;
+          if (tk == ka && na < 4) ta[na++] = (uint8_t)t;
+          if (tk == kb && nb < 4) tb[nb++] = (uint8_t)t;
         }
+        for (int a = 0; a < na; a++)
+          for (int b = 0; b < nb; b++) claim_push(g, i, pack_act(RV_CHI, tile, ta[a], tb[b]));
       }
     }
   }
@@ -750,6 +751,7 @@ struct TurnInfo {
   bool can_tsumo, can_riichi, riichi_ankan, kyushu;
   uint16_t tenpai_keep;   // bit k: hand minus hand[k] is tenpai (valid when riichi_stage or can_riichi was evaluated)
   uint64_t quads;         // kinds with four tiles in hand
+  uint64_t present;       // kinds present in hand
 };
 
 // bit k set iff removing hand[k] leaves a tenpai hand (exact per-tile answer; used in riichi_stage)
@@ -866,6 +868,7 @@ __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnI
   ti.can_tsumo = ti.can_riichi = ti.riichi_ankan = ti.kyushu = false;
   ti.tenpai_keep = 0;
   ti.quads = 0;
+  ti.present = 0;
   uint32_t f = g.flags[pid];
   bool riichi = f & RV_F_RIICHI_DECLARED, stage = f & RV_F_RIICHI_STAGE;
   int drawn = g.drawn_tile;
@@ -913,8 +916,9 @@ __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnI
       }
     }
   }
+  ti.present = cnt_present(c);
   if (g.is_first_turn && all_meldless(g) && !stage)
-    ti.kyushu = __popcll(cnt_present(c) & MASK_TERMINAL_HONOR) >= 9;
+    ti.kyushu = __popcll(ti.present & MASK_TERMINAL_HONOR) >= 9;
 }
 
 __device__ __forceinline__ bool discard_forbidden(const G& g, int p, int tile) {
@@ -958,6 +962,7 @@ __device__ inline int enum_turn_actions(const G& g, int pid, const TurnInfo& ti,
       for (int m = 0; m < g.n_melds[pid]; m++)
         if (g.meld_type[pid][m] == RV_MELD_PON) {
           int target = g.meld_tiles[pid][m][0] >> 2;
+          if (!((ti.present >> target) & 1)) continue;   // no 4th tile in hand: skip the scan
           for (int k = 0; k < hl; k++)
             if ((g.hand[pid][k] >> 2) == target) { f(pack_act(RV_KAKAN, g.hand[pid][k], RV_NONE, RV_NONE)); n++; }
         }
@@ -1563,16 +1568,48 @@ __device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uin
     int pid = g.current_player;
     TurnInfo ti;
     turn_info(cx, g, pid, ti);
-    int n = enum_turn_actions(g, pid, ti, [](uint32_t) {});
-    if (n > 0) {
+    uint32_t fl = g.flags[pid];
+    bool plain = !(fl & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) && g.forbidden[pid][0] == RV_NONE &&
+                 g.forbidden[pid][1] == RV_NONE;
+    bool has_pon = false;
+    for (int m = 0; m < g.n_melds[pid]; m++) has_pon |= g.meld_type[pid][m] == RV_MELD_PON;
+    if (plain && !has_pon) {
+      // common case, closed form: [Tsumo] + every hand tile + [Riichi] + ankans + [Kyushu]
+      int hl = g.hand_len[pid];
+      int nq = (g.drawable_count > 0 && g.drawn_tile != RV_NONE) ? __popcll(ti.quads) : 0;
+      int n = (ti.can_tsumo ? 1 : 0) + hl + (ti.can_riichi ? 1 : 0) + nq + (ti.kyushu ? 1 : 0);
       int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
-      uint32_t chosen = 0;
-      int idx = 0;
-      enum_turn_actions(g, pid, ti, [&](uint32_t a) {
-        if (idx == pick) chosen = a;
-        idx++;
-      });
+      uint32_t chosen;
+      int k = pick - (ti.can_tsumo ? 1 : 0);
+      if (k < 0) chosen = pack_act(RV_TSUMO, g.drawn_tile, RV_NONE, RV_NONE);
+      else if (k < hl) chosen = pack_act(RV_DISCARD, g.hand[pid][k], RV_NONE, RV_NONE);
+      else {
+        k -= hl;
+        if (ti.can_riichi && k == 0) chosen = pack_act(RV_RIICHI, RV_NONE, RV_NONE, RV_NONE);
+        else {
+          k -= ti.can_riichi ? 1 : 0;
+          if (k < nq) {
+            uint64_t q = ti.quads;
+            for (int z = 0; z < k; z++) q &= q - 1;
+            chosen = pack_act(RV_ANKAN, (__ffsll((long long)q) - 1) * 4, RV_NONE, RV_NONE);
+          } else {
+            chosen = pack_act(RV_KYUSHU_KYUHAI, RV_NONE, RV_NONE, RV_NONE);
+          }
+        }
+      }
       acts[pid] = expand_act(g, pid, chosen);
+    } else {
+      int n = enum_turn_actions(g, pid, ti, [](uint32_t) {});
+      if (n > 0) {
+        int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
+        uint32_t chosen = 0;
+        int idx = 0;
+        enum_turn_actions(g, pid, ti, [&](uint32_t a) {
+          if (idx == pick) chosen = a;
+          idx++;
+        });
+        acts[pid] = expand_act(g, pid, chosen);
+      }
     }
   } else {
     for (int p = 0; p < NP; p++) {
