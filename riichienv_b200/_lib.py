@@ -10,7 +10,7 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libriichienv_b200.so")
+LIB_PATH = os.environ.get("RV_LIB_PATH") or os.path.join(_HERE, "libriichienv_b200.so")  # override: A/B builds
 _LIB = None
 
 

@@ -31,7 +31,7 @@ struct Ctx {
 __device__ __forceinline__ bool rule(const G& g, uint32_t bit) { return (g.rule_bits & bit) != 0; }
 
 // ------------------------------------------------------------------ events
-__device__ inline void ev_push(const Ctx& cx, G& g, const uint32_t* w, int n) {
+__device__ __noinline__ void ev_push(const Ctx& cx, G& g, const uint32_t* w, int n) {
   uint64_t h = g.ev_hash;
   uint32_t base = g.ev_words;
   for (int i = 0; i < n; i++) {
@@ -45,11 +45,11 @@ __device__ inline void ev_push(const Ctx& cx, G& g, const uint32_t* w, int n) {
 __device__ __forceinline__ uint32_t ev_w0(int type, int n, int a, int b) {
   return (uint32_t)type | ((uint32_t)n << 8) | ((uint32_t)(a & 0xFF) << 16) | ((uint32_t)(b & 0xFF) << 24);
 }
-__device__ __forceinline__ void ev_simple(const Ctx& cx, G& g, int type, int a = 0, int b = 0) {
+__device__ __noinline__ void ev_simple(const Ctx& cx, G& g, int type, int a = 0, int b = 0) {
   uint32_t w = ev_w0(type, 1, a, b);
   ev_push(cx, g, &w, 1);
 }
-__device__ __forceinline__ void ev_meld(const Ctx& cx, G& g, int type, int actor, int tile, int b0, int b1, int b2, int b3) {
+__device__ __noinline__ void ev_meld(const Ctx& cx, G& g, int type, int actor, int tile, int b0, int b1, int b2, int b3) {
   uint32_t w[2] = {ev_w0(type, 2, actor, tile),
                    (uint32_t)(b0 & 0xFF) | ((uint32_t)(b1 & 0xFF) << 8) | ((uint32_t)(b2 & 0xFF) << 16) | ((uint32_t)(b3 & 0xFF) << 24)};
   ev_push(cx, g, w, 2);
@@ -66,7 +66,7 @@ __device__ __forceinline__ void cache_sub(G& g, int p, int kind) {
   g.c_cnt[p][su] -= 1ull << (4 * pos);
   g.c_key[p][su] -= (uint32_t)pow5(pos);
 }
-__device__ inline bool hand_remove_first(G& g, int p, int tile) {
+__device__ __noinline__ bool hand_remove_first(G& g, int p, int tile) {
   int n = g.hand_len[p];
   for (int i = 0; i < n; i++)
     if (g.hand[p][i] == tile) {
@@ -78,7 +78,7 @@ __device__ inline bool hand_remove_first(G& g, int p, int tile) {
     }
   return false;
 }
-__device__ inline void hand_push(G& g, int p, int tile) {
+__device__ __noinline__ void hand_push(G& g, int p, int tile) {
   int n = g.hand_len[p];
   if (n < RV_HAND_CAP) {
     g.hand[p][n] = (uint8_t)tile;
@@ -88,7 +88,7 @@ __device__ inline void hand_push(G& g, int p, int tile) {
     g.overflow = 1;
   }
 }
-__device__ inline void hand_sort(G& g, int p) {
+__device__ __noinline__ void hand_sort(G& g, int p) {
   int n = g.hand_len[p];
   for (int i = 1; i < n; i++) {
     uint8_t v = g.hand[p][i];
@@ -116,7 +116,7 @@ __device__ __forceinline__ void hand_info(const Tables& T, const G& g, int p, Su
 }
 __device__ __forceinline__ uint64_t river_kinds(const G& g, int p) { return g.c_river_kinds[p]; }
 // c_waits[p] = get_waits_u8 when the hand is 13-tile-equivalent, else 0 (hand_evaluator.rs:196-201)
-__device__ inline void waits_update(const Tables& T, G& g, int p) {
+__device__ __noinline__ void waits_update(const Tables& T, G& g, int p) {
   uint64_t w = 0;
   if (g.hand_len[p] + 3 * g.n_melds[p] == 13) {
     SuitInfo si;
@@ -126,7 +126,7 @@ __device__ inline void waits_update(const Tables& T, G& g, int p) {
   g.c_waits[p] = w;
 }
 // Rebuild every derived cache from the canonical fields (after rv_vec_set_state)
-__device__ inline void refresh_caches(const Tables& T, G& g) {
+__device__ __noinline__ void refresh_caches(const Tables& T, G& g) {
   for (int p = 0; p < 4; p++) {
     for (int k = 0; k < 4; k++) g.c_cnt[p][k] = 0, g.c_key[p][k] = 0;
     for (int i = 0; i < g.hand_len[p]; i++) {
@@ -284,7 +284,7 @@ __device__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason);
 __device__ void next_round(const Ctx& cx, G& g, bool oya_won, bool is_draw);
 
 // state/mod.rs:2021-2046
-__device__ inline void reveal_kan_dora(const Ctx& cx, G& g) {
+__device__ __noinline__ void reveal_kan_dora(const Ctx& cx, G& g) {
   int count = g.n_dora;
   if (count < 5) {
     int idx = 4 + 2 * count;
@@ -302,7 +302,7 @@ __device__ inline void flush_pending_kan_dora(const Ctx& cx, G& g) {
   }
 }
 // state/mod.rs:1549-1567
-__device__ inline void accept_riichi(const Ctx& cx, G& g) {
+__device__ __noinline__ void accept_riichi(const Ctx& cx, G& g) {
   int p = g.riichi_pending_acceptance;
   if (p != RV_NONE) {
     g.score[p] -= 1000;
@@ -314,7 +314,7 @@ __device__ inline void accept_riichi(const Ctx& cx, G& g) {
   }
 }
 // state/mod.rs:1569-1593
-__device__ inline void deal_next(const Ctx& cx, G& g) {
+__device__ __noinline__ void deal_next(const Ctx& cx, G& g) {
   g.is_rinshan_flag = 0;
   if (g.drawable_count == 0) {
     trigger_ryukyoku(cx, g, RV_RK_EXHAUSTIVE);
@@ -437,7 +437,7 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
 }
 
 // RiichiEnv::new + reset (env.rs:82-118, 799-851): fresh game, logs cleared
-__device__ inline void game_reset(const Ctx& cx, G& g, int oya, int round_wind, int honba, uint32_t kyotaku,
+__device__ __noinline__ void game_reset(const Ctx& cx, G& g, int oya, int round_wind, int honba, uint32_t kyotaku,
                                   const uint8_t* custom_wall, const int32_t* scores) {
   g.ev_hash = 0xcbf29ce484222325ull;
   g.ev_count = g.ev_words = g.step_count = g.kyoku_count = 0;
@@ -450,7 +450,7 @@ __device__ inline void game_reset(const Ctx& cx, G& g, int oya, int round_wind, 
 }
 
 // state/mod.rs:2071-2081
-__device__ inline void end_game(const Ctx& cx, G& g) {
+__device__ __noinline__ void end_game(const Ctx& cx, G& g) {
   g.is_done = 1;
   ev_simple(cx, g, RV_EV_END_KYOKU);
   ev_simple(cx, g, RV_EV_END_GAME);
@@ -508,7 +508,7 @@ __device__ __noinline__ void next_round(const Ctx& cx, G& g, bool oya_won, bool 
   }
   init_round(cx, g, no, nw, nh, g.riichi_sticks, nullptr, nullptr);
 }
-__device__ inline void run_pending_init(const Ctx& cx, G& g) {
+__device__ __noinline__ void run_pending_init(const Ctx& cx, G& g) {
   int no = g.pending_init[0], nw = g.pending_init[1], nh = g.pending_init[2];
   init_round(cx, g, no, nw, nh, g.riichi_sticks, nullptr, nullptr);
 }
@@ -698,7 +698,7 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
 }
 
 // Expand a packed claim / turn action into the public rv_action (consume lists as the reference builds them)
-__device__ inline rv_action expand_act(const G& g, int seat, uint32_t a) {
+__device__ __noinline__ rv_action expand_act(const G& g, int seat, uint32_t a) {
   rv_action r;
   r.type = (uint8_t)(a & 0xFF);
   r.tile = (uint8_t)((a >> 8) & 0xFF);
@@ -790,7 +790,7 @@ __device__ __noinline__ uint16_t tenpai_discard_mask(const Ctx& cx, const G& g, 
 
 // "Does some discard leave the hand tenpai?" (legal_actions.rs:112-132) from the four suit entries of the
 // 14-tile-equivalent hand: the D-bits say whether a tile can leave a suit so that it becomes M / P / waitM / waitP.
-__device__ __forceinline__ bool any_tenpai_discard(const Cnt& c, const SuitInfo& si, int hl, int n_melds) {
+__device__ __noinline__ bool any_tenpai_discard(const Cnt& c, const SuitInfo& si, int hl, int n_melds) {
   if (hl + 3 * n_melds != 14) return false;
   uint32_t M = 0, P = 0, WM = 0, WP = 0, DM = 0, DP = 0, DWM = 0, DWP = 0;
   #pragma unroll
@@ -977,7 +977,7 @@ __device__ inline int enum_turn_actions(const G& g, int pid, const TurnInfo& ti,
 
 // Legal actions of `pid` as the reference's _get_legal_actions_internal would list them (packed).
 // Returns count; out may be nullptr (count only).  `pick` >= 0: stores only that index into *picked.
-__device__ inline int legal_actions(const Ctx& cx, const G& g, int pid, uint32_t* out, int pick, uint32_t* picked) {
+__device__ __noinline__ int legal_actions(const Ctx& cx, const G& g, int pid, uint32_t* out, int pick, uint32_t* picked) {
   if (g.is_done) return 0;
   if (g.phase == RV_WAIT_ACT) {
     if (pid != g.current_player) return 0;
@@ -1002,7 +1002,7 @@ __device__ inline int legal_actions(const Ctx& cx, const G& g, int pid, uint32_t
 }
 
 // ------------------------------------------------------------------ settlement helpers
-__device__ inline void register_pao(G& g, int claimer, int tile, int discarder) {  // state/mod.rs:1229-1259
+__device__ __noinline__ void register_pao(G& g, int claimer, int tile, int discarder) {  // state/mod.rs:1229-1259
   int tv = tile >> 2;
   int dragons = 0, winds = 0;
   for (int m = 0; m < g.n_melds[claimer]; m++) {
@@ -1025,7 +1025,7 @@ __device__ __forceinline__ int yakuman_val(const G& g, int yid) {
   return 1;
 }
 // state/mod.rs:720-745 / 1009-1034
-__device__ inline void cap_double_yakuman(const G& g, WinRes& r, bool is_oya, bool tsumo, uint32_t honba) {
+__device__ __noinline__ void cap_double_yakuman(const G& g, WinRes& r, bool is_oya, bool tsumo, uint32_t honba) {
   if (r.yakuman && r.han > 13) {
     int cap = 0;
     if (((r.yaku_mask >> 47) & 1) && !rule(g, RV_RULE_JUNSEI_CHUUREN_DOUBLE)) cap += 13;
@@ -1041,7 +1041,7 @@ __device__ inline void cap_double_yakuman(const G& g, WinRes& r, bool is_oya, bo
     }
   }
 }
-__device__ inline void ev_hora(const Ctx& cx, G& g, int actor, int target, bool tsumo, const WinRes& r, const int32_t* d,
+__device__ __noinline__ void ev_hora(const Ctx& cx, G& g, int actor, int target, bool tsumo, const WinRes& r, const int32_t* d,
                                bool with_ura) {
   uint8_t ub[8] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE, RV_NONE, 0, 0, 0};
   int n_ura = 0;
@@ -1558,7 +1558,7 @@ __host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uin
 }
 
 // One env step with the on-device random agent.
-__device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+__device__ __noinline__ void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   rv_action acts[NP];
   for (int p = 0; p < NP; p++) acts[p].type = RV_NO_ACTION;
   uint32_t sc = g.step_count;
