@@ -1,0 +1,26 @@
+"""riichienv_b200 — B200-native batched Riichi mahjong simulator (hot path of smly/RiichiEnv).
+
+Python is a thin shim: every game-logic call goes to libriichienv_b200.so (CUDA, sm_100a) through the
+C ABI in include/riichienv_b200.h.  Importing this package does not need a GPU; computing does.
+"""
+from . import _abi  # noqa: F401
+
+__all__ = ["RiichiEnv", "VecRiichiEnv", "Observation", "Action", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
+           "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "tid_to_mjai"]
+
+
+def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
+    if name in ("RiichiEnv", "Observation", "Action", "ActionType", "Phase", "Meld", "MeldType", "GameRule", "GameType", "Wind",
+                "tid_to_mjai"):
+        from . import env
+
+        return getattr(env, name)
+    if name == "VecRiichiEnv":
+        from .vec_env import VecRiichiEnv
+
+        return VecRiichiEnv
+    if name in ("HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "WinResult"):
+        from . import hand
+
+        return getattr(hand, name)
+    raise AttributeError(name)

@@ -1,0 +1,626 @@
+"""Drop-in mirror of the reference's Python surface for the hot path, over the CUDA library.
+
+Same names, argument meaning and error behaviour as `riichienv._riichienv` (PyO3):
+  RiichiEnv        riichienv-python/src/env.rs:74-118, 353-401, 673-872
+  Observation      riichienv-core/src/observation/mod.rs:24-160, observation/mjai_select.rs:87-193
+  Action/ActionType/Phase   riichienv-core/src/action.rs:30-227, src/riichienv/action.py:6-17
+  Meld/MeldType    riichienv-core/src/types.rs:57-108
+  GameRule         riichienv-core/src/rule.rs:10-112
+A single env is a VecRiichiEnv of size 1; all game logic runs in libriichienv_b200.so (no CPU fallback).
+"""
+import ctypes as C
+import enum
+import json
+
+from . import _abi as A
+from ._lib import events_to_json
+from .vec_env import GAME_MODES, VecRiichiEnv
+
+
+class ActionType(enum.IntEnum):  # action.rs:55-68
+    DISCARD = 0
+    CHI = 1
+    PON = 2
+    DAIMINKAN = 3
+    RON = 4
+    RIICHI = 5
+    TSUMO = 6
+    PASS = 7
+    ANKAN = 8
+    KAKAN = 9
+    KYUSHU_KYUHAI = 10
+    KITA = 11
+
+
+# PascalCase aliases (src/riichienv/action.py:6-17)
+for _n, _alias in [("DISCARD", "Discard"), ("CHI", "Chi"), ("PON", "Pon"), ("DAIMINKAN", "Daiminkan"), ("RON", "Ron"),
+                   ("RIICHI", "Riichi"), ("TSUMO", "Tsumo"), ("PASS", "Pass"), ("ANKAN", "Ankan"), ("KAKAN", "Kakan"),
+                   ("KYUSHU_KYUHAI", "KyushuKyuhai"), ("KITA", "Kita")]:
+    setattr(ActionType, _alias, ActionType[_n])
+
+
+class Phase(enum.IntEnum):  # action.rs:30-33
+    WaitAct = 0
+    WaitResponse = 1
+
+
+class MeldType(enum.IntEnum):  # types.rs:57-63
+    Chi = 0
+    Pon = 1
+    Daiminkan = 2
+    Ankan = 3
+    Kakan = 4
+
+
+class Wind(enum.IntEnum):
+    East = 0
+    South = 1
+    West = 2
+    North = 3
+
+
+class GameType(enum.IntEnum):  # src/riichienv/game_mode.py:4-10
+    YON_IKKYOKU = 0
+    YON_TONPUSEN = 1
+    YON_HANCHAN = 2
+    SAN_IKKYOKU = 3
+    SAN_TONPUSEN = 4
+    SAN_HANCHAN = 5
+
+
+def tid_to_mjai(tid: int) -> str:  # parser.rs:301-334
+    if tid == 16:
+        return "5mr"
+    if tid == 52:
+        return "5pr"
+    if tid == 88:
+        return "5sr"
+    if tid < 108:
+        return f"{(tid % 36) // 4 + 1}{'mps'[tid // 36]}"
+    return "ESWNPFC"[(tid - 108) // 4]
+
+
+class Action:
+    """action.rs:82-105 — consume_tiles are stored sorted."""
+
+    __slots__ = ("action_type", "tile", "consume_tiles", "actor")
+
+    def __init__(self, type=ActionType.PASS, tile=None, consume_tiles=(), actor=None):
+        self.action_type = ActionType(int(type))
+        self.tile = None if tile is None else int(tile)
+        self.consume_tiles = sorted(int(t) for t in consume_tiles)
+        self.actor = None if actor is None else int(actor)
+
+    def __eq__(self, o):
+        return (isinstance(o, Action) and self.action_type == o.action_type and self.tile == o.tile
+                and self.consume_tiles == o.consume_tiles and self.actor == o.actor)
+
+    def __repr__(self):
+        return (f"Action(action_type={self.action_type.name}, tile={self.tile}, consume_tiles={self.consume_tiles}, "
+                f"actor={self.actor})")
+
+    def to_dict(self):
+        return {"type": int(self.action_type), "tile": self.tile, "consume_tiles": list(self.consume_tiles), "actor": self.actor}
+
+    def to_mjai(self) -> str:  # action.rs:107-150 (serde_json: keys alphabetical)
+        t = {ActionType.DISCARD: "dahai", ActionType.CHI: "chi", ActionType.PON: "pon", ActionType.DAIMINKAN: "daiminkan",
+             ActionType.ANKAN: "ankan", ActionType.KAKAN: "kakan", ActionType.RIICHI: "reach", ActionType.TSUMO: "hora",
+             ActionType.RON: "hora", ActionType.KYUSHU_KYUHAI: "ryukyoku", ActionType.KITA: "kita",
+             ActionType.PASS: "none"}[self.action_type]
+        d = {"type": t}
+        if self.actor is not None:
+            d["actor"] = self.actor
+        if self.tile is not None and self.action_type not in (ActionType.TSUMO, ActionType.RON, ActionType.RIICHI):
+            d["pai"] = tid_to_mjai(self.tile)
+        if self.consume_tiles:
+            d["consumed"] = [tid_to_mjai(t) for t in self.consume_tiles]
+        return json.dumps(d, sort_keys=True, separators=(",", ":"))
+
+    def encode(self) -> int:  # action.rs:158-227 (82-id space)
+        at = self.action_type
+        if at == ActionType.DISCARD:
+            if self.tile is None:
+                raise ValueError("Discard action requires a tile")
+            return self.tile // 4
+        if at == ActionType.RIICHI:
+            return 37
+        if at == ActionType.CHI:
+            if self.tile is None:
+                raise ValueError("Chi action requires a target tile")
+            kinds = sorted(set([t // 4 for t in self.consume_tiles] + [self.tile // 4]))
+            if len(kinds) != 3:
+                raise ValueError(f"Invalid Chi tiles: target={self.tile}, consumed={self.consume_tiles}")
+            return 38 + kinds.index(self.tile // 4)
+        if at == ActionType.PON:
+            return 41
+        if at == ActionType.DAIMINKAN:
+            if self.tile is None:
+                raise ValueError("Daiminkan action requires a tile")
+            return 42 + self.tile // 4
+        if at in (ActionType.ANKAN, ActionType.KAKAN):
+            if not self.consume_tiles:
+                raise ValueError("Ankan/Kakan action requires consumed tiles")
+            return 42 + self.consume_tiles[0] // 4
+        if at in (ActionType.RON, ActionType.TSUMO):
+            return 79
+        if at == ActionType.KYUSHU_KYUHAI:
+            return 80
+        if at == ActionType.PASS:
+            return 81
+        raise ValueError("Kita action is not valid in 4-player mode")
+
+    # -- ABI marshalling
+    def _to_abi(self) -> A.Action:
+        a = A.Action()
+        a.type = int(self.action_type)
+        a.tile = 255 if self.tile is None else self.tile
+        a.n_consume = min(4, len(self.consume_tiles))
+        for k in range(4):
+            a.consume[k] = self.consume_tiles[k] if k < a.n_consume else 255
+        a.actor = 255 if self.actor is None else self.actor
+        return a
+
+    @staticmethod
+    def _from_abi(a: A.Action) -> "Action":
+        return Action(a.type, None if a.tile == 255 else a.tile, [a.consume[k] for k in range(a.n_consume)],
+                      None if a.actor == 255 else a.actor)
+
+
+class Meld:  # types.rs:98-190
+    __slots__ = ("meld_type", "tiles", "opened", "from_who", "called_tile")
+
+    def __init__(self, meld_type, tiles, opened, from_who=-1, called_tile=None):
+        self.meld_type = MeldType(int(meld_type))
+        self.tiles = [int(t) for t in tiles]
+        self.opened = bool(opened)
+        self.from_who = int(from_who)
+        self.called_tile = called_tile
+
+    def __repr__(self):
+        return f"Meld({self.meld_type.name}, {self.tiles}, opened={self.opened}, from_who={self.from_who})"
+
+    def __eq__(self, o):
+        return isinstance(o, Meld) and (self.meld_type, self.tiles, self.opened, self.from_who) == (
+            o.meld_type, o.tiles, o.opened, o.from_who)
+
+
+class GameRule:  # rule.rs:10-112
+    _FIELDS = ["allows_ron_on_ankan_for_kokushi_musou", "is_kokushi_musou_13machi_double", "is_suuankou_tanki_double",
+               "is_junsei_chuurenpoutou_double", "is_daisuushii_double", "yakuman_pao_is_liability_only", "sanchaho_is_draw",
+               "kuikae_forbidden"]
+
+    def __init__(self, allows_ron_on_ankan_for_kokushi_musou=False, is_kokushi_musou_13machi_double=False,
+                 is_suuankou_tanki_double=False, is_junsei_chuurenpoutou_double=False, is_daisuushii_double=False,
+                 yakuman_pao_is_liability_only=False, sanchaho_is_draw=False, kuikae_forbidden=True):
+        loc = locals()
+        for f in self._FIELDS:
+            setattr(self, f, bool(loc[f]))
+
+    @staticmethod
+    def default_tenhou():
+        return GameRule(sanchaho_is_draw=True, kuikae_forbidden=True)
+
+    @staticmethod
+    def default_mjsoul():
+        return GameRule(True, True, True, True, True, True, False, True)
+
+    def bits(self) -> int:
+        return sum((1 << i) for i, f in enumerate(self._FIELDS) if getattr(self, f))
+
+    def __eq__(self, o):
+        return isinstance(o, GameRule) and self.bits() == o.bits()
+
+    def __repr__(self):
+        return "GameRule(" + ", ".join(f"{f}={str(getattr(self, f)).lower()}" for f in self._FIELDS) + ")"
+
+
+def _melds_of(s: A.GameState, p: int):
+    out = []
+    for m in range(s.n_melds[p]):
+        tiles = [t for t in s.meld_tiles[p][m] if t != 255]
+        ty = s.meld_type[p][m]
+        fw = s.meld_from[p][m]
+        ct = s.meld_called[p][m]
+        out.append(Meld(ty, tiles, ty != MeldType.Ankan, -1 if fw == 255 else fw, None if ct == 255 else ct))
+    return out
+
+
+class Observation:
+    """observation/mod.rs:24-160 — a by-value snapshot for one seat."""
+
+    def __init__(self, env: "RiichiEnv", s: A.GameState, pid: int, legal, new_events):
+        self.player_id = pid
+        self.hands = [[s.hand[p][k] for k in range(s.hand_len[p])] if p == pid else [] for p in range(4)]
+        self.melds = [_melds_of(s, p) for p in range(4)]
+        self.discards = [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(4)]
+        self.dora_indicators = [s.dora_ind[k] for k in range(s.n_dora)]
+        self.scores = [s.score[p] for p in range(4)]
+        self.riichi_declared = [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(4)]
+        self._legal_actions = legal
+        self._new_events = new_events
+        self._env = env
+        self.honba = s.honba
+        self.riichi_sticks = s.riichi_sticks
+        self.round_wind = s.round_wind
+        self.oya = s.oya
+        self.kyoku_index = s.kyoku_idx
+        self.waits = [k for k in range(34) if (s.c_waits[pid] >> k) & 1]
+        self.is_tenpai = bool(self.waits)
+        self.tsumogiri_flags = [[], [], [], []]  # always empty in the live env (observation/mod.rs:105)
+        self.riichi_sutehais = [None if s.riichi_sutehai[p] == 255 else s.riichi_sutehai[p] for p in range(4)]
+        self.last_tedashis = [None if s.last_tedashi[p] == 255 else s.last_tedashi[p] for p in range(4)]
+        # state/mod.rs:252 destructures (pid, tile) as (tile, _pid): the field carries the DISCARDER'S SEAT
+        self.last_discard = None if s.last_discard_pid == 255 else s.last_discard_pid
+        self.drawn_tile = None if s.drawn_tile == 255 else s.drawn_tile
+
+    @property
+    def hand(self):
+        return list(self.hands[self.player_id])
+
+    @property
+    def events(self):
+        """Full per-player masked log up to this observation (parsed dicts)."""
+        return [json.loads(x) for x in self._env._masked_log(self.player_id)]
+
+    def legal_actions(self):
+        return list(self._legal_actions)
+
+    def new_events(self):
+        return list(self._new_events)
+
+    def mask(self):  # observation/python.rs:98-111
+        m = bytearray(82)
+        for a in self._legal_actions:
+            try:
+                m[a.encode()] = 1
+            except ValueError:
+                pass
+        return bytes(m)
+
+    def find_action(self, action_id: int):  # observation/mod.rs:117-129
+        for a in self._legal_actions:
+            try:
+                if a.encode() == action_id:
+                    return a
+            except ValueError:
+                pass
+        return None
+
+    def select_action_from_mjai(self, mjai):  # observation/mjai_select.rs:19-193
+        if isinstance(mjai, str):
+            try:
+                v = json.loads(mjai)
+            except ValueError:
+                return None
+            tile_str = v.get("pai") or ""
+        elif isinstance(mjai, dict):
+            v = mjai
+            tile_str = v.get("pai") or v.get("tile") or ""
+        else:
+            return None
+        atype = v.get("type", "")
+        tsumogiri = v.get("tsumogiri") if isinstance(v.get("tsumogiri"), bool) else None
+        consumed = v.get("consumed") if isinstance(v.get("consumed"), list) else None
+        la = self._legal_actions
+        if atype == "hora":
+            return next((a for a in la if a.action_type in (ActionType.TSUMO, ActionType.RON)), None)
+        if atype == "none":
+            return next((a for a in la if a.action_type == ActionType.PASS), None)
+        tt = {"dahai": ActionType.DISCARD, "chi": ActionType.CHI, "pon": ActionType.PON, "kakan": ActionType.KAKAN,
+              "daiminkan": ActionType.DAIMINKAN, "ankan": ActionType.ANKAN, "reach": ActionType.RIICHI,
+              "ryukyoku": ActionType.KYUSHU_KYUHAI}.get(atype)
+        if tt is None:
+            return None
+        if tt == ActionType.DISCARD:
+            cands = [a for a in la if a.action_type == ActionType.DISCARD and
+                     (not tile_str or (a.tile is not None and tid_to_mjai(a.tile) == tile_str))]
+            if not cands:
+                return None
+            if tsumogiri is not None and self.drawn_tile is not None:
+                for a in cands:
+                    if (a.tile == self.drawn_tile) == tsumogiri:
+                        return a
+            return cands[0]
+        for a in la:
+            if a.action_type != tt:
+                continue
+            if consumed is not None:
+                if sorted(tid_to_mjai(t) for t in a.consume_tiles) != sorted(consumed):
+                    continue
+                if tile_str and tt in (ActionType.CHI, ActionType.PON, ActionType.DAIMINKAN, ActionType.KAKAN):
+                    if a.tile is None or tid_to_mjai(a.tile) != tile_str:
+                        continue
+                return a
+            if tile_str:
+                if a.tile is not None and tid_to_mjai(a.tile) == tile_str:
+                    return a
+                continue
+            return a
+        return None
+
+    def to_dict(self):
+        return {"player_id": self.player_id, "hands": self.hands, "discards": self.discards,
+                "dora_indicators": self.dora_indicators, "scores": self.scores, "riichi_declared": self.riichi_declared,
+                "legal_actions": [a.to_dict() for a in self._legal_actions], "events": self.new_events(), "honba": self.honba,
+                "riichi_sticks": self.riichi_sticks, "round_wind": self.round_wind, "oya": self.oya}
+
+    def encode(self):
+        """(74, 34) float32 FEATURE_ENCODING tensor bytes (observation/python.rs:457-806), computed on the GPU."""
+        return self._env._encode(self.player_id)
+
+
+class RiichiEnv:
+    """env.rs:74-118 / 799-872 over a VecRiichiEnv of one game."""
+
+    def __init__(self, game_mode=None, skip_mjai_logging=False, seed=None, round_wind=None, rule=None, device=0):
+        if game_mode is None:
+            gm = 0
+        elif isinstance(game_mode, str):
+            gm = GAME_MODES.get(game_mode, 0)  # unknown string silently -> 0 (env.rs:100)
+        else:
+            gm = int(game_mode)
+        self.game_mode = gm
+        self.skip_mjai_logging = bool(skip_mjai_logging)
+        self.rule = rule or GameRule.default_tenhou()
+        if seed is None:
+            import os
+
+            seed = int.from_bytes(os.urandom(8), "little")
+        self.seed = int(seed)
+        self._round_wind0 = 0 if round_wind is None else int(round_wind)
+        self._v = VecRiichiEnv(1, gm, self.rule.bits(), seeds=[self.seed], log_cap_words=0 if skip_mjai_logging else 1 << 16,
+                               device=device)
+        self._event_counts = [0, 0, 0, 0]
+        # GameState::new deals a first round immediately (state/mod.rs:165); mirror it so getters work before reset().
+        # That constructor deal uses shuffle #0; the library's create already accounts for it (hand_index = 1), so we
+        # temporarily rewind to reproduce the same wall, as a freshly constructed reference env would show.
+        s = self._v.get_state(0)
+        s.hand_index = 0
+        self._v.set_state(0, s)
+        self._v.reset(round_wind=self._round_wind0)
+
+    # ---- core API -------------------------------------------------------------------------------
+    def reset(self, oya=None, wall=None, round_wind=None, scores=None, honba=None, kyotaku=None, seed=None):
+        if scores is not None and len(scores) != 4:
+            raise ValueError(f"scores length {len(scores)} does not match number of players 4")
+        # reset(seed=) sets GameState.seed which nothing reads (env.rs:835-837): the wall is NOT reseeded.
+        self._event_counts = [0, 0, 0, 0]
+        self._v.reset(oya=0 if oya is None else oya, round_wind=0 if round_wind is None else round_wind,
+                      honba=0 if honba is None else honba, kyotaku=0 if kyotaku is None else kyotaku,
+                      scores=None if scores is None else [list(scores)], walls=None if wall is None else [list(wall)])
+        return self._observations(self.active_players)
+
+    def step(self, actions):
+        arr = (A.Action * 4)()
+        for p in range(4):
+            a = actions.get(p) if actions else None
+            if a is None:
+                arr[p].type = A.NO_ACTION
+            else:
+                arr[p] = a._to_abi()
+        self._v.step(arr)
+        s = self._state()
+        if s.last_error != 255:
+            return {}
+        return self._observations(self._active(s), s)
+
+    def done(self):
+        return bool(self._state().is_done)
+
+    def scores(self):
+        s = self._state()
+        return [s.score[p] for p in range(4)]
+
+    def ranks(self):  # env.rs:673-689
+        sc = self.scores()
+        order = sorted(range(4), key=lambda p: (-sc[p], p))
+        out = [0] * 4
+        for r, p in enumerate(order):
+            out[p] = r + 1
+        return out
+
+    def points(self, rule_name: str):  # env.rs:691-727
+        presets = {"basic": (1.0, 25000.0, [50.0, 10.0, -10.0, -50.0]),
+                   "ouza-tyoujyo": (0.0, 25000.0, [100.0, 40.0, -40.0, -100.0]),
+                   "ouza-normal": (0.0, 25000.0, [50.0, 20.0, -20.0, -50.0])}
+        if rule_name not in presets:
+            raise ValueError(f"Unknown preset rule: {rule_name}")
+        w, base, uma = presets[rule_name]
+        sc, rk = self.scores(), self.ranks()
+        return [(sc[i] - base) / 1000.0 * w + uma[rk[i] - 1] for i in range(4)]
+
+    def get_observation(self, player_id: int):
+        return self._observations([player_id])[player_id]
+
+    def get_observations(self, players=None):
+        return self._observations(list(range(4)) if players is None else list(players))
+
+    def _get_legal_actions(self, pid: int):
+        acts, counts = self._v.legal_actions()
+        return [Action._from_abi(acts[pid * A.MAX_LEGAL + k]) for k in range(int(counts[0, pid]))]
+
+    # ---- logs -----------------------------------------------------------------------------------
+    @property
+    def mjai_log(self):
+        if self.skip_mjai_logging:
+            return []
+        return [json.loads(x) for x in self._v.mjai_log(0)]
+
+    def _masked_log(self, pid):
+        if self.skip_mjai_logging:
+            return []
+        return events_to_json(self._v.events(0), pid)
+
+    # ---- internals ------------------------------------------------------------------------------
+    def _state(self) -> A.GameState:
+        return self._v.get_state(0)
+
+    @staticmethod
+    def _active(s):
+        return [p for p in range(4) if (s.active_mask >> p) & 1]
+
+    def _observations(self, players, s=None):
+        s = s or self._state()
+        acts, counts = self._v.legal_actions()
+        out = {}
+        logs = {}
+        for p in players:
+            legal = [Action._from_abi(acts[p * A.MAX_LEGAL + k]) for k in range(int(counts[0, p]))]
+            full = logs.setdefault(p, self._masked_log(p))
+            new = full[self._event_counts[p]:]
+            self._event_counts[p] = len(full)  # state/mod.rs:211-218: the delta advances on every observation
+            out[p] = Observation(self, s, p, legal, new)
+        return out
+
+    def _encode(self, pid):
+        raise NotImplementedError("Observation.encode(): FEATURE_ENCODING kernel is not built yet in this round")
+
+    # ---- getters / setters used by callers and by the reference's tests (env.rs:134-635) --------------
+    kyoku_idx = property(lambda self: self._state().kyoku_idx)
+    round_wind = property(lambda self: self._state().round_wind)
+    oya = property(lambda self: self._state().oya)
+    honba = property(lambda self: self._state().honba)
+    riichi_sticks = property(lambda self: self._state().riichi_sticks)
+    turn_count = property(lambda self: self._state().turn_count)
+    is_done = property(lambda self: bool(self._state().is_done))
+    num_players = property(lambda self: 4)
+    action_space_size = property(lambda self: 82)
+    last_error = property(lambda self: None if self._state().last_error == 255 else
+                          f"Error: Illegal Action by Player {self._state().last_error}")
+    dora_indicators = property(lambda self: [self._state().dora_ind[k] for k in range(self._state().n_dora)])
+
+    def _mutate(self, fn):
+        s = self._state()
+        fn(s)
+        self._v.set_state(0, s)
+
+    @property
+    def phase(self):
+        return Phase(self._state().phase)
+
+    @phase.setter
+    def phase(self, v):
+        self._mutate(lambda s: setattr(s, "phase", int(v)))
+
+    @property
+    def current_player(self):
+        return self._state().current_player
+
+    @current_player.setter
+    def current_player(self, v):
+        self._mutate(lambda s: setattr(s, "current_player", int(v)))
+
+    @property
+    def active_players(self):
+        return self._active(self._state())
+
+    @active_players.setter
+    def active_players(self, v):
+        self._mutate(lambda s: setattr(s, "active_mask", sum(1 << int(p) for p in v)))
+
+    @property
+    def needs_tsumo(self):
+        return bool(self._state().needs_tsumo)
+
+    @needs_tsumo.setter
+    def needs_tsumo(self, v):
+        self._mutate(lambda s: setattr(s, "needs_tsumo", int(bool(v))))
+
+    @property
+    def drawn_tile(self):
+        t = self._state().drawn_tile
+        return None if t == 255 else t
+
+    @drawn_tile.setter
+    def drawn_tile(self, v):
+        self._mutate(lambda s: setattr(s, "drawn_tile", 255 if v is None else int(v)))
+
+    @property
+    def hands(self):
+        s = self._state()
+        return [[s.hand[p][k] for k in range(s.hand_len[p])] for p in range(4)]
+
+    @hands.setter
+    def hands(self, v):
+        def f(s):
+            for p in range(4):
+                tiles = list(v[p])[: A.HAND_CAP]
+                for k in range(A.HAND_CAP):
+                    s.hand[p][k] = tiles[k] if k < len(tiles) else 255
+                s.hand_len[p] = len(tiles)
+        self._mutate(f)
+
+    @property
+    def melds(self):
+        s = self._state()
+        return [_melds_of(s, p) for p in range(4)]
+
+    @melds.setter
+    def melds(self, v):
+        def f(s):
+            for p in range(4):
+                ms = list(v[p])[:4]
+                s.n_melds[p] = len(ms)
+                for m in range(4):
+                    for k in range(4):
+                        s.meld_tiles[p][m][k] = 255
+                    s.meld_type[p][m] = s.meld_from[p][m] = s.meld_called[p][m] = 255
+                for m, md in enumerate(ms):
+                    for k, t in enumerate(md.tiles[:4]):
+                        s.meld_tiles[p][m][k] = t
+                    s.meld_type[p][m] = int(md.meld_type)
+                    s.meld_from[p][m] = 255 if md.from_who < 0 else md.from_who
+                    s.meld_called[p][m] = 255 if md.called_tile is None else md.called_tile
+        self._mutate(f)
+
+    @property
+    def discards(self):
+        s = self._state()
+        return [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(4)]
+
+    @discards.setter
+    def discards(self, v):
+        def f(s):
+            for p in range(4):
+                d = list(v[p])[: A.RIVER_CAP]
+                s.n_river[p] = len(d)
+                s.river_tedashi[p] = (1 << len(d)) - 1
+                for k in range(A.RIVER_CAP):
+                    s.river[p][k] = d[k] if k < len(d) else 255
+        self._mutate(f)
+
+    @property
+    def riichi_declared(self):
+        s = self._state()
+        return [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(4)]
+
+    @riichi_declared.setter
+    def riichi_declared(self, v):
+        def f(s):
+            for p in range(4):
+                s.flags[p] = (s.flags[p] | A.F_RIICHI_DECLARED) if v[p] else (s.flags[p] & ~A.F_RIICHI_DECLARED)
+        self._mutate(f)
+
+    @property
+    def wall(self):
+        """The reference's `wall.tiles` Vec: front = rinshan side, back = next live draw."""
+        s = self._state()
+        return [s.wall[i] for i in range(s.rinshan_draw_count, s.wall_top)]
+
+    def set_scores(self, pts):
+        self._mutate(lambda s: [s.score.__setitem__(p, int(pts[p])) for p in range(4)])
+
+    def set_state(self, oya=None, round_wind=None, honba=None, kyotaku=None, scores=None):  # env.rs:636-671
+        def f(s):
+            if oya is not None:
+                s.oya = s.kyoku_idx = int(oya)
+            if round_wind is not None:
+                s.round_wind = int(round_wind)
+            if honba is not None:
+                s.honba = int(honba)
+            if kyotaku is not None:
+                s.riichi_sticks = int(kyotaku)
+            if scores is not None and len(scores) == 4:
+                for p in range(4):
+                    s.score[p] = int(scores[p])
+        self._mutate(f)
