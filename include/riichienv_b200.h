@@ -319,10 +319,14 @@ int rv_event_to_json(const uint32_t* words, uint32_t n_words, int viewer, char* 
 /* Seeded wall (state/wall.rs:36-67): host implementation for tests / tools. */
 int rv_wall_from_seed(uint64_t seed, uint64_t hand_index, int n_tiles /*136|108*/, uint8_t* out_tiles_reversed);
 
-/* Observation tensors (Observation::encode observation/python.rs:457-806,
- * mask 98-111).  d_obs: [n][NP][74][34] f32, d_mask: [n][NP][82] u8 device
- * buffers; rows of seats that owe no action are zero.                        */
-int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask);
+/* Observation tensors for every seat that owes an action (what RiichiEnv.step returns observations for):
+ * Observation::encode (observation/python.rs:457-806) and Observation::mask (98-111).  Rows are written
+ * compactly in ascending (game, seat) order:
+ *   d_obs   [max_obs][74][34] f32   (device, 16-byte aligned)      — may be NULL
+ *   d_mask  [max_obs][82] u8        (device)                       — may be NULL
+ *   d_index [max_obs] i32           (device) game*4 + seat per row — may be NULL
+ * *n_obs (host, may be NULL -> fully asynchronous) receives the number of rows; rows beyond max_obs are dropped. */
+int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
 
 #ifdef __cplusplus
 }

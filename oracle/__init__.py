@@ -15,7 +15,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "game.hpp", "hand.hpp", "wall.hpp", "shanten.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "game.hpp", "hand.hpp", "wall.hpp", "shanten.hpp", "obs.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "riichienv_b200.h"))
     stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
     if force or stale:
@@ -49,6 +49,7 @@ def load():
     lib.orc_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.orc_game_events.restype = C.c_uint32
     lib.orc_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
+    lib.orc_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]
     lib.orc_run_random.restype = C.c_int64
     lib.orc_run_random.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_int,
                                    P(C.c_int32), P(C.c_uint8), P(C.c_uint8), P(C.c_uint32), P(C.c_uint32),

@@ -6,6 +6,7 @@
 #include <thread>
 
 #include "game.hpp"
+#include "obs.hpp"
 #include "shanten.hpp"
 
 using namespace orc;
@@ -342,6 +343,11 @@ int64_t orc_run_random(int mode, uint32_t rule, uint64_t seed_base, int64_t n, u
   }
   return total.load();
 }
+}
+extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {
+  GameState* g = (GameState*)h;
+  if (obs) encode_obs(*g, pid, obs);
+  if (mask) encode_mask(*g, pid, mask);
 }
 extern "C" int orc_sizeof(int which) {
   switch (which) {

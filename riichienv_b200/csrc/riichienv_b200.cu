@@ -6,7 +6,9 @@
 #include <string>
 #include <vector>
 
-#include "game.cuh"
+#include <cub/device/device_scan.cuh>
+
+#include "obs.cuh"
 
 using namespace rv;
 
@@ -42,6 +44,9 @@ struct rv_vec {
   uint32_t* d_log;  // n * log_cap words or nullptr
   uint32_t log_cap;
   uint64_t* d_seeds;            // scratch for rv_vec_reseed
+  int32_t *d_obs_counts, *d_obs_offsets;   // encode: active seats per game and their exclusive scan (n + 1)
+  void* d_scan_tmp;
+  size_t scan_tmp_bytes;
   unsigned long long* d_steps;  // [0] = env steps executed, [1] = games finished (by step kernels)
 };
 
@@ -249,6 +254,77 @@ __global__ void step_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint3
   if (g.is_done) atomicAdd(&counters[1], 1ull);
 }
 
+// ---- observation encoding ------------------------------------------------------------------
+__global__ void obs_count_kernel(const G* states, int64_t n, int32_t* counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int c = 0;
+  if (i < n && !states[i].is_done) c = __popc(states[i].active_mask & 0xF);
+  counts[i] = c;   // counts[n] = 0 so that offsets[n] is the total
+}
+
+// One warp per game; for each seat that owes an action the warp (1) describes the 74 channels
+// (lane L takes channels L, L+32, L+64), (2) streams the 2,516 floats out with 16-byte stores.
+__global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* states, int64_t n, const int32_t* offsets,
+                                                         float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
+  __shared__ uint64_t s_mask[4][OBS_CH];
+  __shared__ float s_val[4][OBS_CH];
+  __shared__ uint8_t s_kind[4][OBS_CH];
+  __shared__ uint8_t s_seen[4][36];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t gi = (int64_t)blockIdx.x * 4 + w;
+  if (gi >= n) return;
+  const G& g = states[gi];
+  if (g.is_done) return;
+  int row = offsets[gi];
+  for (int pid = 0; pid < NP; pid++) {
+    if (!((g.active_mask >> pid) & 1)) continue;
+    if (row >= max_obs) break;
+    if (obs) {
+      for (int ch = lane; ch < OBS_CH; ch += 32) {
+        int kind;
+        uint64_t m;
+        float v;
+        obs_channel(g, pid, ch, kind, m, v);
+        s_kind[w][ch] = (uint8_t)kind;
+        s_mask[w][ch] = m;
+        s_val[w][ch] = v;
+      }
+      for (int k = lane; k < OBS_W; k += 32) s_seen[w][k] = (uint8_t)obs_seen(g, pid, k);
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(obs + (size_t)row * (OBS_CH * OBS_W));
+      for (int j = lane; j < OBS_CH * OBS_W / 4; j += 32) {
+        float o[4];
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int e = 4 * j + q, ch = e / OBS_W, col = e - ch * OBS_W;
+          o[q] = obs_value(s_kind[w][ch], s_mask[w][ch], s_val[w][ch], s_seen[w][col], col);
+        }
+        __stcs(&dst[j], make_float4(o[0], o[1], o[2], o[3]));   // streaming store: write-once data
+      }
+      __syncwarp();
+    }
+    if (mask) {
+      uint8_t* mrow = mask + (size_t)row * 82;
+      for (int k = lane; k < 82; k += 32) mrow[k] = 0;
+      __syncwarp();
+      if (lane == 0) {
+        Ctx cx = make_ctx(T, nullptr, 0, gi);
+        uint32_t packed[RV_MAX_LEGAL];
+        int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
+        if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+        for (int k = 0; k < cnt; k++) {
+          int id = action_id(expand_act(g, pid, packed[k]));
+          if (id >= 0 && id < 82) mrow[id] = 1;
+        }
+      }
+      __syncwarp();
+    }
+    if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
+    row++;
+  }
+}
+
 __global__ void results_kernel(const G* states, int64_t n, uint8_t* done, int32_t* scores, uint8_t* ranks, uint32_t* step_count,
                                uint32_t* kyoku_count, uint32_t* ev_count, uint64_t* ev_hash) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,6 +479,9 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->log_cap = log_cap_words;
   v->d_log = nullptr;
   v->d_seeds = nullptr;
+  v->d_obs_counts = v->d_obs_offsets = nullptr;
+  v->d_scan_tmp = nullptr;
+  v->scan_tmp_bytes = 0;
   CK(cudaMalloc(&v->d_states, sizeof(G) * n));
   if (log_cap_words) CK(cudaMalloc(&v->d_log, sizeof(uint32_t) * (size_t)n * log_cap_words));
   CK(cudaMalloc(&v->d_steps, sizeof(unsigned long long) * 2));
@@ -436,6 +515,9 @@ int rv_vec_destroy(rv_vec* v) {
   cudaFree(v->d_states);
   if (v->d_log) cudaFree(v->d_log);
   if (v->d_seeds) cudaFree(v->d_seeds);
+  if (v->d_obs_counts) cudaFree(v->d_obs_counts);
+  if (v->d_obs_offsets) cudaFree(v->d_obs_offsets);
+  if (v->d_scan_tmp) cudaFree(v->d_scan_tmp);
   cudaFree(v->d_steps);
   delete v;
   return RV_OK;
@@ -610,9 +692,28 @@ int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, ui
   }
   return RV_OK;
 }
-int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask) {
-  (void)v; (void)d_obs; (void)d_mask;
-  return fail(RV_ERR_UNSUPPORTED, "observation encoding is not implemented yet");
+int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  int64_t n = v->n;
+  if (!v->d_obs_counts) {
+    CK(cudaMalloc(&v->d_obs_counts, sizeof(int32_t) * (n + 1)));
+    CK(cudaMalloc(&v->d_obs_offsets, sizeof(int32_t) * (n + 1)));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, v->scan_tmp_bytes, v->d_obs_counts, v->d_obs_offsets, (int)(n + 1), c->stream));
+    CK(cudaMalloc(&v->d_scan_tmp, v->scan_tmp_bytes));
+  }
+  obs_count_kernel<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(v->d_states, n, v->d_obs_counts);
+  CK(cub::DeviceScan::ExclusiveSum(v->d_scan_tmp, v->scan_tmp_bytes, v->d_obs_counts, v->d_obs_offsets, (int)(n + 1), c->stream));
+  if (d_obs || d_mask || d_index)
+    obs_encode_kernel<<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_obs_offsets, d_obs, d_mask, d_index, max_obs);
+  CK(cudaGetLastError());
+  if (n_obs) {
+    int32_t total = 0;
+    CK(cudaMemcpyAsync(&total, v->d_obs_offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *n_obs = total;
+  }
+  return RV_OK;
 }
 int rv_sizeof(int which) {
   switch (which) {

@@ -473,7 +473,17 @@ class RiichiEnv:
         return out
 
     def _encode(self, pid):
-        raise NotImplementedError("Observation.encode(): FEATURE_ENCODING kernel is not built yet in this round")
+        """bytes of the (74, 34) float32 tensor for seat `pid` (must owe an action), computed by obs_encode_kernel."""
+        import torch
+
+        dev = f"cuda:{self._v.ctx.device}"
+        obs = torch.zeros((4, 74, 34), dtype=torch.float32, device=dev)
+        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
+        n = self._v.encode(obs=obs, index=idx, max_obs=4)
+        rows = idx[:n].tolist()
+        if pid not in rows:
+            raise ValueError(f"seat {pid} owes no action; encode() is defined for the observations step()/reset() return")
+        return obs[rows.index(pid)].cpu().numpy().tobytes()
 
     # ---- getters / setters used by callers and by the reference's tests (env.rs:134-635) --------------
     kyoku_idx = property(lambda self: self._state().kyoku_idx)

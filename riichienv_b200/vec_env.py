@@ -84,6 +84,17 @@ class VecRiichiEnv:
         check(lib().rv_vec_legal_actions(self.handle, acts, _ptr(counts, C.c_uint8)))
         return acts, counts
 
+    def encode(self, obs=None, mask=None, index=None, max_obs=None, sync=True):
+        """Write FEATURE_ENCODING tensors / 82-id masks of every seat that owes an action into DEVICE buffers
+        (torch tensors): obs [max_obs,74,34] f32, mask [max_obs,82] u8, index [max_obs] i32.  Returns the row count."""
+        def ptr(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        if max_obs is None:
+            max_obs = min(t.shape[0] for t in (obs, mask, index) if t is not None)
+        n = C.c_int64(0)
+        check(lib().rv_vec_encode(self.handle, ptr(obs), ptr(mask), ptr(index), int(max_obs), C.byref(n) if sync else None))
+        return int(n.value) if sync else None
+
     def results(self):
         done = np.zeros(self.n, np.uint8)
         scores = np.zeros((self.n, A.NP), np.int32)

@@ -7,7 +7,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../riichienv_b200/csrc/game.cuh"
+#include "../../riichienv_b200/csrc/obs.cuh"
 
 using namespace rv;
 
@@ -291,6 +291,32 @@ uint32_t hs_game_events(void* p, uint32_t* out, uint32_t cap) {
   uint32_t n = std::min<uint32_t>(h->g.ev_words, (uint32_t)h->log.size());
   if (out) memcpy(out, h->log.data(), 4 * std::min(n, cap));
   return h->g.ev_words;
+}
+void hs_game_encode(void* p, int pid, float* obs, uint8_t* mask) {
+  HS* h = (HS*)p;
+  const G& g = h->g;
+  if (obs) {
+    int seen[34];
+    for (int k = 0; k < 34; k++) seen[k] = obs_seen(g, pid, k);
+    for (int ch = 0; ch < OBS_CH; ch++) {
+      int kind;
+      uint64_t m;
+      float v;
+      obs_channel(g, pid, ch, kind, m, v);
+      for (int col = 0; col < OBS_W; col++) obs[ch * OBS_W + col] = obs_value(kind, m, v, seen[col], col);
+    }
+  }
+  if (mask) {
+    memset(mask, 0, 82);
+    Ctx cx = hs_ctx(h);
+    uint32_t packed[RV_MAX_LEGAL];
+    int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
+    if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+    for (int k = 0; k < cnt; k++) {
+      int id = action_id(expand_act(g, pid, packed[k]));
+      if (id >= 0 && id < 82) mask[id] = 1;
+    }
+  }
 }
 int hs_wall_from_seed(uint64_t seed, uint64_t hand_index, int n, uint8_t* out) {
   wall_from_seed(seed, hand_index, n, out);

@@ -187,3 +187,64 @@ def test_external_actions_step(orc):
     for x, y in zip(ra, rb):
         assert np.array_equal(x, y)
     assert np.array_equal(a.counters()[3], b.counters()[3])
+
+
+def test_observation_encode_vs_oracle(orc):
+    """rv_vec_encode: every acting seat of 256 games at several points of the rollout, bytes equal to the oracle's
+    Observation::encode / mask restatement; row order ascending (game, seat)."""
+    import torch
+
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n = 256
+    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=9000)
+    v.reset()
+    games = [orc.orc_game_new(2, 9000 + g, 0, A.RULE_DEFAULT_TENHOU, 0) for g in range(n)]
+    for h in games:
+        orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    obs = torch.empty((n * 3, 74, 34), dtype=torch.float32, device="cuda")
+    mask = torch.empty((n * 3, 82), dtype=torch.uint8, device="cuda")
+    idx = torch.empty((n * 3,), dtype=torch.int32, device="cuda")
+    a = np.zeros(74 * 34, np.float32)
+    m = np.zeros(82, np.uint8)
+    checked = 0
+    for it in range(60):
+        rows = v.encode(obs=obs, mask=mask, index=idx)
+        h_obs, h_mask, h_idx = obs[:rows].cpu().numpy(), mask[:rows].cpu().numpy(), idx[:rows].cpu().numpy()
+        assert (np.diff(h_idx) > 0).all()
+        st = A.GameState()
+        expect_rows = 0
+        for g in range(n):
+            orc.orc_game_snapshot(games[g], C.byref(st))
+            if st.is_done:
+                continue
+            for p in range(4):
+                if (st.active_mask >> p) & 1:
+                    assert h_idx[expect_rows] == g * 4 + p
+                    orc.orc_game_encode(games[g], p, a.ctypes.data_as(C.POINTER(C.c_float)), m.ctypes.data_as(C.POINTER(C.c_uint8)))
+                    assert h_obs[expect_rows].tobytes() == a.tobytes(), f"iter {it} game {g} seat {p}"
+                    assert h_mask[expect_rows].tobytes() == m.tobytes(), f"iter {it} game {g} seat {p} mask"
+                    expect_rows += 1
+                    checked += 1
+        assert expect_rows == rows
+        stride = 1 if it < 30 else 37
+        v.step_random(21, stride)
+        for g in range(n):
+            for _ in range(stride):
+                orc.orc_game_random_step(games[g], 21, 9000 + g)
+    for h in games:
+        orc.orc_game_free(h)
+    assert checked > 15000
+
+
+def test_shim_observation_encode(orc):
+    from riichienv_b200 import RiichiEnv
+
+    env = RiichiEnv(game_mode=0, seed=5)
+    obs = env.reset()
+    b = obs[0].encode()
+    assert len(b) == 74 * 34 * 4
+    arr = np.frombuffer(b, dtype=np.float32).reshape(74, 34)
+    assert arr[0].sum() == len({t // 4 for t in obs[0].hand})
+    assert arr[30, 0] == np.float32(136 - 14 - 1) / np.float32(70.0)
+    assert bytes(obs[0].mask()) == bytes(bytearray(1 if i in {a.encode() for a in obs[0].legal_actions()} else 0 for i in range(82)))

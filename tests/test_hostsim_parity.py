@@ -95,3 +95,37 @@ def test_random_games_lockstep(mode, rule, n):
     for seed in range(100 * mode, 100 * mode + n):
         total += lockstep(seed, mode, rule, agent_seed=0xC0FFEE + mode)
     assert total > 50 * n
+
+
+def test_observation_encode_lockstep(libs):
+    """encode() (74x34 f32) and mask() (82) of every acting seat, at every step of seeded games: bit-equal."""
+    import numpy as np
+
+    orc, hs = libs
+    n_obs = 0
+    for seed in (11, 12, 13):
+        o, h = OracleBackend(2, seed), HostsimBackend(2, seed)
+        o.reset()
+        h.reset()
+        a = np.zeros(74 * 34, np.float32)
+        b = np.zeros(74 * 34, np.float32)
+        ma = np.zeros(82, np.uint8)
+        mb = np.zeros(82, np.uint8)
+        fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        up = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint8))
+        step = 0
+        while True:
+            s = o.get_state()
+            if s.is_done:
+                break
+            for p in range(4):
+                if (s.active_mask >> p) & 1:
+                    orc.orc_game_encode(o.h, p, fp(a), up(ma))
+                    hs.hs_game_encode(h.h, p, fp(b), up(mb))
+                    assert a.tobytes() == b.tobytes(), f"seed {seed} step {step} seat {p}: channels {sorted(set(np.nonzero(a != b)[0] // 34))}"
+                    assert ma.tobytes() == mb.tobytes(), f"seed {seed} step {step} seat {p}: mask"
+                    n_obs += 1
+            o.random_step(5, seed)
+            h.random_step(5, seed)
+            step += 1
+    assert n_obs > 3000
