@@ -164,6 +164,7 @@ def main():
     import torch
 
     from riichienv_b200._lib import Context
+    from riichienv_b200.multi_gpu import RunStats, reduce_stats, shard_range
     from riichienv_b200.vec_env import VecRiichiEnv
 
     dist = None
@@ -190,7 +191,7 @@ def main():
 
     def one_step(k, timed):
         """returns (step_ms, kernel_ms, env_steps)"""
-        base = (k * world + rank) * G          # disjoint global game ids per (bench step, rank)
+        base, _ = shard_range(k, world, rank, G)  # disjoint global game ids per (bench step, rank)
         with torch.cuda.stream(ext_stream):
             flush.fill_(k & 0xFF)              # L2 flush between iterations (outside the timed events)
         s_before, _ = v.steps_total()
@@ -233,7 +234,7 @@ def main():
     e2e_t = 0.0
     e2e_steps = 0
     for k in range(args.steps):
-        base = ((5000 + k) * world + rank) * G
+        base, _ = shard_range(5000 + k, world, rank, G)
         pinned.copy_(torch.arange(base, base + G, dtype=torch.int64))
         seeds = pinned.numpy().view(np.uint64)
         ctx.sync()
@@ -249,18 +250,11 @@ def main():
     d2h = G * (1 + 16 + 4 + 4 + 4 + 4 + 8)
 
     # ---- reduce over ranks: max time, sum of steps (the only collective) -----------------------
-    stats = torch.tensor([tot_ms, tot_kernel_ms, e2e_t, float(tot_steps), float(e2e_steps)], dtype=torch.float64,
-                         device=f"cuda:{local_rank}")
-    if dist is not None:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        tot_ms, tot_kernel_ms_max, e2e_t = mx[0].item(), mx[1].item(), mx[2].item()
-        all_steps, all_e2e_steps = sm[3].item(), sm[4].item()
-    else:
-        tot_kernel_ms_max = tot_kernel_ms
-        all_steps, all_e2e_steps = float(tot_steps), float(e2e_steps)
+    mine = RunStats(elapsed_ms=tot_ms, kernel_ms=tot_kernel_ms, e2e_s=e2e_t, env_steps=float(tot_steps),
+                    e2e_steps=float(e2e_steps), games=float(G * args.steps), score_sum=float(scores.sum()))
+    red = reduce_stats(mine, dist, torch, f"cuda:{local_rank}")
+    tot_ms, e2e_t = red.elapsed_ms, red.e2e_s
+    all_steps, all_e2e_steps = red.env_steps, red.e2e_steps
 
     if rank == 0:
         peak, peak_src = measured_peaks()
