@@ -1203,327 +1203,332 @@ __device__ __noinline__ int chankan_ronners(const Ctx& cx, G& g, int pid, int ti
 
 // ------------------------------------------------------------------ step (state/mod.rs:330-1315)
 // acts[p].type == RV_NO_ACTION  <=>  key p absent from the reference's HashMap.  No validation here.
-__device__ __noinline__ void step_apply(const Ctx& cx, G& g, const rv_action* acts) {
-  if (g.phase == RV_WAIT_ACT) {
-    int pid = g.current_player;
-    const rv_action& act = acts[pid];
-    switch (act.type) {
-      case RV_DISCARD: {
-        if (act.tile == RV_NONE) break;
-        int tile = act.tile;
-        bool tsumogiri = false, valid = false;
-        if (g.drawn_tile != RV_NONE && g.drawn_tile == tile) { tsumogiri = true; valid = true; }
-        if (hand_remove_first(g, pid, tile)) {
-          hand_sort(g, pid);
-          valid = true;
-        }
-        if (valid) resolve_discard(cx, g, pid, tile, tsumogiri);
-        break;
+__device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action* acts) {
+  int pid = g.current_player;
+  const rv_action& act = acts[pid];
+  switch (act.type) {
+    case RV_DISCARD: {
+      if (act.tile == RV_NONE) break;
+      int tile = act.tile;
+      bool tsumogiri = false, valid = false;
+      if (g.drawn_tile != RV_NONE && g.drawn_tile == tile) { tsumogiri = true; valid = true; }
+      if (hand_remove_first(g, pid, tile)) {
+        hand_sort(g, pid);
+        valid = true;
       }
-      case RV_KYUSHU_KYUHAI:
-        trigger_ryukyoku(cx, g, RV_RK_KYUSHU);
-        break;
-      case RV_RIICHI: {
-        uint32_t f = g.flags[pid];
-        if (g.score[pid] >= 1000 && g.drawable_count >= 4 && !(f & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE))) {
-          g.flags[pid] |= RV_F_RIICHI_STAGE;
-          ev_simple(cx, g, RV_EV_REACH, pid);
-          if (act.tile != RV_NONE) {
-            int t = act.tile;
-            bool tsumogiri = g.drawn_tile != RV_NONE && g.drawn_tile == t;
-            g.riichi_sutehai[pid] = (uint8_t)t;
-            if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)t;
-            if (hand_remove_first(g, pid, t)) hand_sort(g, pid);
-            resolve_discard(cx, g, pid, t, tsumogiri);
-          }
-        }
-        break;
-      }
-      case RV_ANKAN: {
-        int tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
-        int ron_mask = 0;
-        if (rule(g, RV_RULE_RON_ON_ANKAN_KOKUSHI)) ron_mask = chankan_ronners(cx, g, pid, tile, true);
-        if (ron_mask) {
-          g.pending_kan_pid = (uint8_t)pid;
-          g.pending_kan_type = RV_ANKAN;
-          g.pending_kan_tile = (uint8_t)tile;
-          g.phase = RV_WAIT_RESPONSE;
-          g.active_mask = (uint8_t)ron_mask;
-          g.last_discard_pid = (uint8_t)pid;
-          g.last_discard_tile = (uint8_t)tile;
-        } else {
-          resolve_kan(cx, g, pid, act);
-        }
-        break;
-      }
-      case RV_KAKAN: {
-        int tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
-        hand_remove_first(g, pid, tile);
-        for (int m = 0; m < g.n_melds[pid]; m++)
-          if (g.meld_type[pid][m] == RV_MELD_PON && (g.meld_tiles[pid][m][0] >> 2) == (tile >> 2)) {
-            g.meld_type[pid][m] = RV_MELD_KAKAN;
-            uint8_t* tl = g.meld_tiles[pid][m];
-            tl[3] = (uint8_t)tile;
-            for (int y = 3; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
-            break;
-          }
-        {
-          int c[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
-          for (int k = 0; k < act.n_consume && k < 4; k++) c[k] = act.consume[k];
-          ev_meld(cx, g, RV_EV_KAKAN, pid, tile, c[0], c[1], c[2], c[3]);
-        }
-        flush_pending_kan_dora(cx, g);
-        waits_update(cx.T, g, pid);
-        int ron_mask = chankan_ronners(cx, g, pid, tile, false);
-        if (ron_mask) {
-          g.pending_kan_pid = (uint8_t)pid;
-          g.pending_kan_type = RV_KAKAN;
-          g.pending_kan_tile = (uint8_t)tile;
-          g.phase = RV_WAIT_RESPONSE;
-          g.active_mask = (uint8_t)ron_mask;
-          g.last_discard_pid = (uint8_t)pid;
-          g.last_discard_tile = (uint8_t)tile;
-        } else {
-          resolve_kan(cx, g, pid, act);
-        }
-        break;
-      }
-      case RV_TSUMO: {
-        uint32_t cond = base_cond(g, pid) | RV_C_TSUMO;
-        if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HAITEI;
-        if (g.is_rinshan_flag) cond |= RV_C_RINSHAN;
-        if (g.is_first_turn && all_meldless(g)) cond |= RV_C_TSUMO_FIRST_TURN;
-        bool riichi = g.flags[pid] & RV_F_RIICHI_DECLARED;
-        int win_tile = g.drawn_tile != RV_NONE ? g.drawn_tile : 0;
-        WinRes r = seat_calc(cx, g, pid, win_tile, cond, riichi, g.honba);
-        int oya = g.oya;
-        cap_double_yakuman(g, r, pid == oya, true, g.honba);
-        if (r.is_win) {
-          int32_t d[NP] = {0, 0, 0, 0};
-          int32_t total_win = 0;
-          int pao_payer = -1, pao_val = 0, total_val = 0;
-          if (r.yakuman) {
-            uint64_t m = r.yaku_mask;
-            while (m) {
-              int y = __ffsll((long long)m) - 1;
-              m &= m - 1;
-              int v = yakuman_val(g, y);
-              total_val += v;
-              int liable = y == 37 ? g.pao[pid][0] : y == 50 ? g.pao[pid][1] : RV_NONE;
-              if (liable != RV_NONE) { pao_val += v; pao_payer = liable; }
-            }
-          }
-          if (pao_val > 0) {
-            int32_t unit = pid == oya ? 48000 : 32000;
-            int32_t honba_total = (int32_t)g.honba * (NP - 1) * 100;
-            if (rule(g, RV_RULE_PAO_LIABILITY_ONLY)) {
-              int32_t pao_amt = pao_val * unit + honba_total;
-              int non_pao = total_val - pao_val;
-              d[pao_payer] -= pao_amt;
-              total_win += pao_amt;
-              if (non_pao > 0)
-                for (int i = 0; i < NP; i++)
-                  if (i != pid) {
-                    int32_t pay = (pid == oya || i == oya) ? non_pao * 16000 : non_pao * 8000;
-                    d[i] -= pay;
-                    total_win += pay;
-                  }
-            } else {
-              int32_t full = total_val * unit + honba_total;
-              d[pao_payer] -= full;
-              total_win += full;
-            }
-          } else {
-            for (int i = 0; i < NP; i++)
-              if (i != pid) {
-                int32_t pay = (pid == oya || i != oya) ? (int32_t)r.ko : (int32_t)r.oya;
-                d[i] = -pay;
-                total_win += pay;
-              }
-          }
-          total_win += (int32_t)(g.riichi_sticks * 1000);
-          g.riichi_sticks = 0;
-          d[pid] += total_win;
-          for (int i = 0; i < NP; i++) {
-            g.score[i] += d[i];
-            g.score_delta[i] = d[i];
-          }
-          ev_hora(cx, g, pid, pid, true, r, d, riichi);
-          next_round(cx, g, pid == oya, false);
-        } else {
-          g.current_player = (uint8_t)((g.current_player + 1) % NP);
-          deal_next(cx, g);
-        }
-        break;
-      }
-      default:
-        break;
+      if (valid) resolve_discard(cx, g, pid, tile, tsumogiri);
+      break;
     }
-  } else {
-    // missed agari (state/mod.rs:902-917): every seat holding a Ron claim (stale ones included) that did not ron
-    for (int p = 0; p < NP; p++) {
-      bool has_ron = false;
-      for (int k = 0; k < g.n_claims[p]; k++)
-        if ((g.claims[p][k] & 0xFF) == RV_RON) has_ron = true;
-      if (has_ron && acts[p].type != RV_RON) {
-        g.flags[p] |= RV_F_MISSED_AGARI_DOUJUN;
-        if (g.flags[p] & RV_F_RIICHI_DECLARED) g.flags[p] |= RV_F_MISSED_AGARI_RIICHI;
-      }
-    }
-    int ron_mask = 0, call_pid = -1;
-    for (int p = 0; p < NP; p++) {
-      if (!((g.active_mask >> p) & 1)) continue;
-      int ty = acts[p].type;
-      if (ty == RV_RON) ron_mask |= 1 << p;
-      else if (ty == RV_PON || ty == RV_DAIMINKAN || ty == RV_CHI) {
-        if (call_pid >= 0) {
-          int oty = acts[call_pid].type;
-          bool old_pon = oty == RV_PON || oty == RV_DAIMINKAN, new_pon = ty == RV_PON || ty == RV_DAIMINKAN;
-          if (!old_pon && new_pon) call_pid = p;
-        } else {
-          call_pid = p;
+    case RV_KYUSHU_KYUHAI:
+      trigger_ryukyoku(cx, g, RV_RK_KYUSHU);
+      break;
+    case RV_RIICHI: {
+      uint32_t f = g.flags[pid];
+      if (g.score[pid] >= 1000 && g.drawable_count >= 4 && !(f & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE))) {
+        g.flags[pid] |= RV_F_RIICHI_STAGE;
+        ev_simple(cx, g, RV_EV_REACH, pid);
+        if (act.tile != RV_NONE) {
+          int t = act.tile;
+          bool tsumogiri = g.drawn_tile != RV_NONE && g.drawn_tile == t;
+          g.riichi_sutehai[pid] = (uint8_t)t;
+          if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)t;
+          if (hand_remove_first(g, pid, t)) hand_sort(g, pid);
+          resolve_discard(cx, g, pid, t, tsumogiri);
         }
       }
+      break;
     }
-    if (ron_mask) {
-      if (__popc(ron_mask) >= NP - 1 && rule(g, RV_RULE_SANCHAHO_IS_DRAW)) {
-        trigger_ryukyoku(cx, g, RV_RK_SANCHAHO);
-        return;
-      }
-      int target = g.last_discard_pid != RV_NONE ? g.last_discard_pid : g.current_player;
-      int win_tile = g.last_discard_pid != RV_NONE ? g.last_discard_tile : 0;
-      int32_t total[NP] = {0, 0, 0, 0};
-      bool oya_won = false, deposit_taken = false, honba_taken = false;
-      bool is_chankan = g.pending_kan_pid != RV_NONE;
-      int oya = g.oya;
-      for (int dist = 1; dist < NP; dist++) {   // winners sorted by distance from the discarder
-        int w = (target + dist) % NP;
-        if (!((ron_mask >> w) & 1)) continue;
-        uint32_t ron_honba = 0;
-        if (!honba_taken) { honba_taken = true; ron_honba = g.honba; }
-        uint32_t cond = base_cond(g, w);
-        if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
-        if (is_chankan) cond |= RV_C_CHANKAN;
-        bool riichi = g.flags[w] & RV_F_RIICHI_DECLARED;
-        WinRes r = seat_calc(cx, g, w, win_tile, cond, riichi, ron_honba);
-        cap_double_yakuman(g, r, w == oya, false, ron_honba);
-        if (r.is_win) {
-          int32_t score = (int32_t)r.ron;
-          int pao_payer = target;
-          int32_t pao_amt = 0;
-          if (r.yakuman) {
-            bool has_pao = false;
-            int total_val = 0, pao_val = 0;
-            uint64_t m = r.yaku_mask;
-            while (m) {
-              int y = __ffsll((long long)m) - 1;
-              m &= m - 1;
-              int v = yakuman_val(g, y);
-              total_val += v;
-              int liable = y == 37 ? g.pao[w][0] : y == 50 ? g.pao[w][1] : RV_NONE;
-              if (liable != RV_NONE) { has_pao = true; pao_payer = liable; pao_val += v; }
-            }
-            if (has_pao) {
-              int32_t unit = w == oya ? 48000 : 32000;
-              int32_t honba_ron = (int32_t)ron_honba * (NP - 1) * 100;
-              int32_t split = rule(g, RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
-              pao_amt = split / 2 + honba_ron;
-            }
-          }
-          int32_t td[NP] = {0, 0, 0, 0};
-          td[w] += score;
-          td[pao_payer] -= pao_amt;
-          td[target] -= score - pao_amt;
-          if (!deposit_taken) {
-            td[w] += (int32_t)(g.riichi_sticks * 1000);
-            g.riichi_sticks = 0;
-            deposit_taken = true;
-          }
-          for (int i = 0; i < NP; i++) total[i] += td[i];
-          if (w == oya) oya_won = true;
-          ev_hora(cx, g, w, target, false, r, td, riichi);
-        }
-      }
-      for (int i = 0; i < NP; i++) {
-        g.score[i] += total[i];
-        g.score_delta[i] = total[i];
-      }
-      next_round(cx, g, oya_won, false);
-    } else if (call_pid >= 0) {
-      int claimer = call_pid;
-      const rv_action& act = acts[claimer];
-      accept_riichi(cx, g);
-      g.is_rinshan_flag = 0;
-      g.is_first_turn = 0;
-      g.flags[claimer] &= ~RV_F_MISSED_AGARI_DOUJUN;
-      if (g.last_discard_pid != RV_NONE) g.flags[g.last_discard_pid] &= ~RV_F_NAGASHI_ELIGIBLE;
-      for (int p = 0; p < NP; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
-      if (act.type == RV_DAIMINKAN) {
-        g.current_player = (uint8_t)claimer;
-        g.active_mask = (uint8_t)(1u << claimer);
-        g.forbidden[claimer][0] = g.forbidden[claimer][1] = RV_NONE;
-        resolve_kan(cx, g, claimer, act);
-        return;
-      }
-      for (int k = 0; k < act.n_consume && k < 4; k++) hand_remove_first(g, claimer, act.consume[k]);
-      int discarder = g.last_discard_pid, tile = g.last_discard_tile;
-      int m = g.n_melds[claimer];
-      if (m < 4) {
-        uint8_t tl[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
-        int n = 0;
-        for (int k = 0; k < act.n_consume && k < 3; k++) tl[n++] = act.consume[k];
-        tl[n++] = (uint8_t)tile;
-        for (int x = 1; x < n; x++)
-          for (int y = x; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
-        for (int k = 0; k < 4; k++) g.meld_tiles[claimer][m][k] = tl[k];
-        g.meld_type[claimer][m] = act.type == RV_PON ? RV_MELD_PON : RV_MELD_CHI;
-        g.meld_from[claimer][m] = (uint8_t)discarder;
-        g.meld_called[claimer][m] = (uint8_t)tile;
-        g.n_melds[claimer] = (uint8_t)(m + 1);
+    case RV_ANKAN: {
+      int tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
+      int ron_mask = 0;
+      if (rule(g, RV_RULE_RON_ON_ANKAN_KOKUSHI)) ron_mask = chankan_ronners(cx, g, pid, tile, true);
+      if (ron_mask) {
+        g.pending_kan_pid = (uint8_t)pid;
+        g.pending_kan_type = RV_ANKAN;
+        g.pending_kan_tile = (uint8_t)tile;
+        g.phase = RV_WAIT_RESPONSE;
+        g.active_mask = (uint8_t)ron_mask;
+        g.last_discard_pid = (uint8_t)pid;
+        g.last_discard_tile = (uint8_t)tile;
       } else {
-        g.overflow = 1;
+        resolve_kan(cx, g, pid, act);
       }
+      break;
+    }
+    case RV_KAKAN: {
+      int tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
+      hand_remove_first(g, pid, tile);
+      for (int m = 0; m < g.n_melds[pid]; m++)
+        if (g.meld_type[pid][m] == RV_MELD_PON && (g.meld_tiles[pid][m][0] >> 2) == (tile >> 2)) {
+          g.meld_type[pid][m] = RV_MELD_KAKAN;
+          uint8_t* tl = g.meld_tiles[pid][m];
+          tl[3] = (uint8_t)tile;
+          for (int y = 3; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
+          break;
+        }
       {
-        int c0 = act.n_consume > 0 ? act.consume[0] : RV_NONE, c1 = act.n_consume > 1 ? act.consume[1] : RV_NONE,
-            c2 = act.n_consume > 2 ? act.consume[2] : RV_NONE;
-        ev_meld(cx, g, act.type == RV_PON ? RV_EV_PON : RV_EV_CHI, claimer, tile, discarder, c0, c1, c2);
+        int c[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
+        for (int k = 0; k < act.n_consume && k < 4; k++) c[k] = act.consume[k];
+        ev_meld(cx, g, RV_EV_KAKAN, pid, tile, c[0], c[1], c[2], c[3]);
       }
-      if (act.type == RV_PON) register_pao(g, claimer, tile, discarder);
-      g.current_player = (uint8_t)claimer;
-      g.phase = RV_WAIT_ACT;
-      g.active_mask = (uint8_t)(1u << claimer);
-      g.forbidden[claimer][0] = (uint8_t)tile;
-      g.forbidden[claimer][1] = RV_NONE;
-      if (act.type == RV_CHI && act.n_consume >= 2) {
-        int t34 = tile >> 2;
-        int a = act.consume[0] >> 2, b = act.consume[1] >> 2;
-        if (a > b) { int t = a; a = b; b = t; }
-        if (a == t34 + 1 && b == t34 + 2) {
-          if (t34 % 9 <= 5) g.forbidden[claimer][1] = (uint8_t)((t34 + 3) * 4);
-        } else if (t34 >= 2 && b == t34 - 1 && a == t34 - 2 && t34 % 9 >= 3) {
-          g.forbidden[claimer][1] = (uint8_t)((t34 - 3) * 4);
-        }
-      }
-      g.needs_tsumo = 0;
-      g.drawn_tile = RV_NONE;
-      g.c_waits[claimer] = 0;
-    } else {
-      for (int i = 0; i < NP; i++) g.n_claims[i] = 0;
-      g.active_mask = 0;
-      if (g.pending_kan_pid != RV_NONE) {
-        int pk = g.pending_kan_pid;
-        rv_action a = expand_act(g, pk, pack_act(g.pending_kan_type, g.pending_kan_tile, RV_NONE, RV_NONE));
-        g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
-        resolve_kan(cx, g, pk, a);
+      flush_pending_kan_dora(cx, g);
+      waits_update(cx.T, g, pid);
+      int ron_mask = chankan_ronners(cx, g, pid, tile, false);
+      if (ron_mask) {
+        g.pending_kan_pid = (uint8_t)pid;
+        g.pending_kan_type = RV_KAKAN;
+        g.pending_kan_tile = (uint8_t)tile;
+        g.phase = RV_WAIT_RESPONSE;
+        g.active_mask = (uint8_t)ron_mask;
+        g.last_discard_pid = (uint8_t)pid;
+        g.last_discard_tile = (uint8_t)tile;
       } else {
-        accept_riichi(cx, g);
-        g.turn_count++;
+        resolve_kan(cx, g, pid, act);
+      }
+      break;
+    }
+    case RV_TSUMO: {
+      uint32_t cond = base_cond(g, pid) | RV_C_TSUMO;
+      if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HAITEI;
+      if (g.is_rinshan_flag) cond |= RV_C_RINSHAN;
+      if (g.is_first_turn && all_meldless(g)) cond |= RV_C_TSUMO_FIRST_TURN;
+      bool riichi = g.flags[pid] & RV_F_RIICHI_DECLARED;
+      int win_tile = g.drawn_tile != RV_NONE ? g.drawn_tile : 0;
+      WinRes r = seat_calc(cx, g, pid, win_tile, cond, riichi, g.honba);
+      int oya = g.oya;
+      cap_double_yakuman(g, r, pid == oya, true, g.honba);
+      if (r.is_win) {
+        int32_t d[NP] = {0, 0, 0, 0};
+        int32_t total_win = 0;
+        int pao_payer = -1, pao_val = 0, total_val = 0;
+        if (r.yakuman) {
+          uint64_t m = r.yaku_mask;
+          while (m) {
+            int y = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            int v = yakuman_val(g, y);
+            total_val += v;
+            int liable = y == 37 ? g.pao[pid][0] : y == 50 ? g.pao[pid][1] : RV_NONE;
+            if (liable != RV_NONE) { pao_val += v; pao_payer = liable; }
+          }
+        }
+        if (pao_val > 0) {
+          int32_t unit = pid == oya ? 48000 : 32000;
+          int32_t honba_total = (int32_t)g.honba * (NP - 1) * 100;
+          if (rule(g, RV_RULE_PAO_LIABILITY_ONLY)) {
+            int32_t pao_amt = pao_val * unit + honba_total;
+            int non_pao = total_val - pao_val;
+            d[pao_payer] -= pao_amt;
+            total_win += pao_amt;
+            if (non_pao > 0)
+              for (int i = 0; i < NP; i++)
+                if (i != pid) {
+                  int32_t pay = (pid == oya || i == oya) ? non_pao * 16000 : non_pao * 8000;
+                  d[i] -= pay;
+                  total_win += pay;
+                }
+          } else {
+            int32_t full = total_val * unit + honba_total;
+            d[pao_payer] -= full;
+            total_win += full;
+          }
+        } else {
+          for (int i = 0; i < NP; i++)
+            if (i != pid) {
+              int32_t pay = (pid == oya || i != oya) ? (int32_t)r.ko : (int32_t)r.oya;
+              d[i] = -pay;
+              total_win += pay;
+            }
+        }
+        total_win += (int32_t)(g.riichi_sticks * 1000);
+        g.riichi_sticks = 0;
+        d[pid] += total_win;
+        for (int i = 0; i < NP; i++) {
+          g.score[i] += d[i];
+          g.score_delta[i] = d[i];
+        }
+        ev_hora(cx, g, pid, pid, true, r, d, riichi);
+        next_round(cx, g, pid == oya, false);
+      } else {
         g.current_player = (uint8_t)((g.current_player + 1) % NP);
         deal_next(cx, g);
-        if (g.turn_count >= (uint32_t)NP) g.is_first_turn = 0;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+__device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_action* acts) {
+  // missed agari (state/mod.rs:902-917): every seat holding a Ron claim (stale ones included) that did not ron
+  for (int p = 0; p < NP; p++) {
+    bool has_ron = false;
+    for (int k = 0; k < g.n_claims[p]; k++)
+      if ((g.claims[p][k] & 0xFF) == RV_RON) has_ron = true;
+    if (has_ron && acts[p].type != RV_RON) {
+      g.flags[p] |= RV_F_MISSED_AGARI_DOUJUN;
+      if (g.flags[p] & RV_F_RIICHI_DECLARED) g.flags[p] |= RV_F_MISSED_AGARI_RIICHI;
+    }
+  }
+  int ron_mask = 0, call_pid = -1;
+  for (int p = 0; p < NP; p++) {
+    if (!((g.active_mask >> p) & 1)) continue;
+    int ty = acts[p].type;
+    if (ty == RV_RON) ron_mask |= 1 << p;
+    else if (ty == RV_PON || ty == RV_DAIMINKAN || ty == RV_CHI) {
+      if (call_pid >= 0) {
+        int oty = acts[call_pid].type;
+        bool old_pon = oty == RV_PON || oty == RV_DAIMINKAN, new_pon = ty == RV_PON || ty == RV_DAIMINKAN;
+        if (!old_pon && new_pon) call_pid = p;
+      } else {
+        call_pid = p;
       }
     }
   }
+  if (ron_mask) {
+    if (__popc(ron_mask) >= NP - 1 && rule(g, RV_RULE_SANCHAHO_IS_DRAW)) {
+      trigger_ryukyoku(cx, g, RV_RK_SANCHAHO);
+      return;
+    }
+    int target = g.last_discard_pid != RV_NONE ? g.last_discard_pid : g.current_player;
+    int win_tile = g.last_discard_pid != RV_NONE ? g.last_discard_tile : 0;
+    int32_t total[NP] = {0, 0, 0, 0};
+    bool oya_won = false, deposit_taken = false, honba_taken = false;
+    bool is_chankan = g.pending_kan_pid != RV_NONE;
+    int oya = g.oya;
+    for (int dist = 1; dist < NP; dist++) {   // winners sorted by distance from the discarder
+      int w = (target + dist) % NP;
+      if (!((ron_mask >> w) & 1)) continue;
+      uint32_t ron_honba = 0;
+      if (!honba_taken) { honba_taken = true; ron_honba = g.honba; }
+      uint32_t cond = base_cond(g, w);
+      if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
+      if (is_chankan) cond |= RV_C_CHANKAN;
+      bool riichi = g.flags[w] & RV_F_RIICHI_DECLARED;
+      WinRes r = seat_calc(cx, g, w, win_tile, cond, riichi, ron_honba);
+      cap_double_yakuman(g, r, w == oya, false, ron_honba);
+      if (r.is_win) {
+        int32_t score = (int32_t)r.ron;
+        int pao_payer = target;
+        int32_t pao_amt = 0;
+        if (r.yakuman) {
+          bool has_pao = false;
+          int total_val = 0, pao_val = 0;
+          uint64_t m = r.yaku_mask;
+          while (m) {
+            int y = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            int v = yakuman_val(g, y);
+            total_val += v;
+            int liable = y == 37 ? g.pao[w][0] : y == 50 ? g.pao[w][1] : RV_NONE;
+            if (liable != RV_NONE) { has_pao = true; pao_payer = liable; pao_val += v; }
+          }
+          if (has_pao) {
+            int32_t unit = w == oya ? 48000 : 32000;
+            int32_t honba_ron = (int32_t)ron_honba * (NP - 1) * 100;
+            int32_t split = rule(g, RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
+            pao_amt = split / 2 + honba_ron;
+          }
+        }
+        int32_t td[NP] = {0, 0, 0, 0};
+        td[w] += score;
+        td[pao_payer] -= pao_amt;
+        td[target] -= score - pao_amt;
+        if (!deposit_taken) {
+          td[w] += (int32_t)(g.riichi_sticks * 1000);
+          g.riichi_sticks = 0;
+          deposit_taken = true;
+        }
+        for (int i = 0; i < NP; i++) total[i] += td[i];
+        if (w == oya) oya_won = true;
+        ev_hora(cx, g, w, target, false, r, td, riichi);
+      }
+    }
+    for (int i = 0; i < NP; i++) {
+      g.score[i] += total[i];
+      g.score_delta[i] = total[i];
+    }
+    next_round(cx, g, oya_won, false);
+  } else if (call_pid >= 0) {
+    int claimer = call_pid;
+    const rv_action& act = acts[claimer];
+    accept_riichi(cx, g);
+    g.is_rinshan_flag = 0;
+    g.is_first_turn = 0;
+    g.flags[claimer] &= ~RV_F_MISSED_AGARI_DOUJUN;
+    if (g.last_discard_pid != RV_NONE) g.flags[g.last_discard_pid] &= ~RV_F_NAGASHI_ELIGIBLE;
+    for (int p = 0; p < NP; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
+    if (act.type == RV_DAIMINKAN) {
+      g.current_player = (uint8_t)claimer;
+      g.active_mask = (uint8_t)(1u << claimer);
+      g.forbidden[claimer][0] = g.forbidden[claimer][1] = RV_NONE;
+      resolve_kan(cx, g, claimer, act);
+      return;
+    }
+    for (int k = 0; k < act.n_consume && k < 4; k++) hand_remove_first(g, claimer, act.consume[k]);
+    int discarder = g.last_discard_pid, tile = g.last_discard_tile;
+    int m = g.n_melds[claimer];
+    if (m < 4) {
+      uint8_t tl[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
+      int n = 0;
+      for (int k = 0; k < act.n_consume && k < 3; k++) tl[n++] = act.consume[k];
+      tl[n++] = (uint8_t)tile;
+      for (int x = 1; x < n; x++)
+        for (int y = x; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
+      for (int k = 0; k < 4; k++) g.meld_tiles[claimer][m][k] = tl[k];
+      g.meld_type[claimer][m] = act.type == RV_PON ? RV_MELD_PON : RV_MELD_CHI;
+      g.meld_from[claimer][m] = (uint8_t)discarder;
+      g.meld_called[claimer][m] = (uint8_t)tile;
+      g.n_melds[claimer] = (uint8_t)(m + 1);
+    } else {
+      g.overflow = 1;
+    }
+    {
+      int c0 = act.n_consume > 0 ? act.consume[0] : RV_NONE, c1 = act.n_consume > 1 ? act.consume[1] : RV_NONE,
+          c2 = act.n_consume > 2 ? act.consume[2] : RV_NONE;
+      ev_meld(cx, g, act.type == RV_PON ? RV_EV_PON : RV_EV_CHI, claimer, tile, discarder, c0, c1, c2);
+    }
+    if (act.type == RV_PON) register_pao(g, claimer, tile, discarder);
+    g.current_player = (uint8_t)claimer;
+    g.phase = RV_WAIT_ACT;
+    g.active_mask = (uint8_t)(1u << claimer);
+    g.forbidden[claimer][0] = (uint8_t)tile;
+    g.forbidden[claimer][1] = RV_NONE;
+    if (act.type == RV_CHI && act.n_consume >= 2) {
+      int t34 = tile >> 2;
+      int a = act.consume[0] >> 2, b = act.consume[1] >> 2;
+      if (a > b) { int t = a; a = b; b = t; }
+      if (a == t34 + 1 && b == t34 + 2) {
+        if (t34 % 9 <= 5) g.forbidden[claimer][1] = (uint8_t)((t34 + 3) * 4);
+      } else if (t34 >= 2 && b == t34 - 1 && a == t34 - 2 && t34 % 9 >= 3) {
+        g.forbidden[claimer][1] = (uint8_t)((t34 - 3) * 4);
+      }
+    }
+    g.needs_tsumo = 0;
+    g.drawn_tile = RV_NONE;
+    g.c_waits[claimer] = 0;
+  } else {
+    for (int i = 0; i < NP; i++) g.n_claims[i] = 0;
+    g.active_mask = 0;
+    if (g.pending_kan_pid != RV_NONE) {
+      int pk = g.pending_kan_pid;
+      rv_action a = expand_act(g, pk, pack_act(g.pending_kan_type, g.pending_kan_tile, RV_NONE, RV_NONE));
+      g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
+      resolve_kan(cx, g, pk, a);
+    } else {
+      accept_riichi(cx, g);
+      g.turn_count++;
+      g.current_player = (uint8_t)((g.current_player + 1) % NP);
+      deal_next(cx, g);
+      if (g.turn_count >= (uint32_t)NP) g.is_first_turn = 0;
+    }
+  }
+}
+
+__device__ inline void step_apply(const Ctx& cx, G& g, const rv_action* acts) {
+  if (g.phase == RV_WAIT_ACT) step_apply_act(cx, g, acts);
+  else step_apply_resp(cx, g, acts);
 }
 
 // state/mod.rs:344-392
@@ -1557,71 +1562,81 @@ __host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uin
   return (uint32_t)(mix64(k) % n);
 }
 
-// One env step with the on-device random agent.
-__device__ __noinline__ void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+// One env step with the on-device random agent, split by phase so that phase-sorted kernels only carry
+// the code of their own phase.
+__device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   rv_action acts[NP];
   for (int p = 0; p < NP; p++) acts[p].type = RV_NO_ACTION;
   uint32_t sc = g.step_count;
   RV_STAT(3);
-  if (g.phase == RV_WAIT_ACT) {
-    RV_STAT(4);
-    int pid = g.current_player;
-    TurnInfo ti;
-    turn_info(cx, g, pid, ti);
-    uint32_t fl = g.flags[pid];
-    bool plain = !(fl & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) && g.forbidden[pid][0] == RV_NONE &&
-                 g.forbidden[pid][1] == RV_NONE;
-    bool has_pon = false;
-    for (int m = 0; m < g.n_melds[pid]; m++) has_pon |= g.meld_type[pid][m] == RV_MELD_PON;
-    if (plain && !has_pon) {
-      // common case, closed form: [Tsumo] + every hand tile + [Riichi] + ankans + [Kyushu]
-      int hl = g.hand_len[pid];
-      int nq = (g.drawable_count > 0 && g.drawn_tile != RV_NONE) ? __popcll(ti.quads) : 0;
-      int n = (ti.can_tsumo ? 1 : 0) + hl + (ti.can_riichi ? 1 : 0) + nq + (ti.kyushu ? 1 : 0);
-      int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
-      uint32_t chosen;
-      int k = pick - (ti.can_tsumo ? 1 : 0);
-      if (k < 0) chosen = pack_act(RV_TSUMO, g.drawn_tile, RV_NONE, RV_NONE);
-      else if (k < hl) chosen = pack_act(RV_DISCARD, g.hand[pid][k], RV_NONE, RV_NONE);
+  RV_STAT(4);
+  int pid = g.current_player;
+  TurnInfo ti;
+  turn_info(cx, g, pid, ti);
+  uint32_t fl = g.flags[pid];
+  bool plain = !(fl & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) && g.forbidden[pid][0] == RV_NONE &&
+               g.forbidden[pid][1] == RV_NONE;
+  bool has_pon = false;
+  for (int m = 0; m < g.n_melds[pid]; m++) has_pon |= g.meld_type[pid][m] == RV_MELD_PON;
+  if (plain && !has_pon) {
+    // common case, closed form: [Tsumo] + every hand tile + [Riichi] + ankans + [Kyushu]
+    int hl = g.hand_len[pid];
+    int nq = (g.drawable_count > 0 && g.drawn_tile != RV_NONE) ? __popcll(ti.quads) : 0;
+    int n = (ti.can_tsumo ? 1 : 0) + hl + (ti.can_riichi ? 1 : 0) + nq + (ti.kyushu ? 1 : 0);
+    int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
+    uint32_t chosen;
+    int k = pick - (ti.can_tsumo ? 1 : 0);
+    if (k < 0) chosen = pack_act(RV_TSUMO, g.drawn_tile, RV_NONE, RV_NONE);
+    else if (k < hl) chosen = pack_act(RV_DISCARD, g.hand[pid][k], RV_NONE, RV_NONE);
+    else {
+      k -= hl;
+      if (ti.can_riichi && k == 0) chosen = pack_act(RV_RIICHI, RV_NONE, RV_NONE, RV_NONE);
       else {
-        k -= hl;
-        if (ti.can_riichi && k == 0) chosen = pack_act(RV_RIICHI, RV_NONE, RV_NONE, RV_NONE);
-        else {
-          k -= ti.can_riichi ? 1 : 0;
-          if (k < nq) {
-            uint64_t q = ti.quads;
-            for (int z = 0; z < k; z++) q &= q - 1;
-            chosen = pack_act(RV_ANKAN, (__ffsll((long long)q) - 1) * 4, RV_NONE, RV_NONE);
-          } else {
-            chosen = pack_act(RV_KYUSHU_KYUHAI, RV_NONE, RV_NONE, RV_NONE);
-          }
+        k -= ti.can_riichi ? 1 : 0;
+        if (k < nq) {
+          uint64_t q = ti.quads;
+          for (int z = 0; z < k; z++) q &= q - 1;
+          chosen = pack_act(RV_ANKAN, (__ffsll((long long)q) - 1) * 4, RV_NONE, RV_NONE);
+        } else {
+          chosen = pack_act(RV_KYUSHU_KYUHAI, RV_NONE, RV_NONE, RV_NONE);
         }
       }
-      acts[pid] = expand_act(g, pid, chosen);
-    } else {
-      int n = enum_turn_actions(g, pid, ti, [](uint32_t) {});
-      if (n > 0) {
-        int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
-        uint32_t chosen = 0;
-        int idx = 0;
-        enum_turn_actions(g, pid, ti, [&](uint32_t a) {
-          if (idx == pick) chosen = a;
-          idx++;
-        });
-        acts[pid] = expand_act(g, pid, chosen);
-      }
     }
+    acts[pid] = expand_act(g, pid, chosen);
   } else {
-    for (int p = 0; p < NP; p++) {
-      if (!((g.active_mask >> p) & 1)) continue;
-      int n = g.n_claims[p] + 1;
-      int pick = (int)agent_pick(agent_seed, game_id, sc, p, (uint32_t)n);
-      uint32_t chosen = pick < g.n_claims[p] ? g.claims[p][pick] : pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
-      acts[p] = expand_act(g, p, chosen);
+    int n = enum_turn_actions(g, pid, ti, [](uint32_t) {});
+    if (n > 0) {
+      int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
+      uint32_t chosen = 0;
+      int idx = 0;
+      enum_turn_actions(g, pid, ti, [&](uint32_t a) {
+        if (idx == pick) chosen = a;
+        idx++;
+      });
+      acts[pid] = expand_act(g, pid, chosen);
     }
   }
   g.step_count = sc + 1;
-  step_apply(cx, g, acts);
+  step_apply_act(cx, g, acts);
+}
+__device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+  rv_action acts[NP];
+  for (int p = 0; p < NP; p++) acts[p].type = RV_NO_ACTION;
+  uint32_t sc = g.step_count;
+  RV_STAT(3);
+  for (int p = 0; p < NP; p++) {
+    if (!((g.active_mask >> p) & 1)) continue;
+    int n = g.n_claims[p] + 1;
+    int pick = (int)agent_pick(agent_seed, game_id, sc, p, (uint32_t)n);
+    uint32_t chosen = pick < g.n_claims[p] ? g.claims[p][pick] : pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
+    acts[p] = expand_act(g, p, chosen);
+  }
+  g.step_count = sc + 1;
+  step_apply_resp(cx, g, acts);
+}
+__device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+  if (g.phase == RV_WAIT_ACT) random_step_act(cx, g, agent_seed, game_id);
+  else random_step_resp(cx, g, agent_seed, game_id);
 }
 
 }  // namespace rv

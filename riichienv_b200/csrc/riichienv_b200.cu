@@ -2,6 +2,7 @@
 // There is NO CPU fallback in this file: every compute entry point launches CUDA kernels
 // and returns RV_ERR_CUDA if the device is unavailable.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +30,8 @@ struct rv_ctx {
   int device;
   cudaStream_t stream;
   cudaEvent_t ev[8];
+  cudaStream_t aux[2];          // phase pipeline: RESPOND and DEAL kernels run beside ACT
+  cudaEvent_t fork_ev, join_ev[2];
   uint32_t *suit_info, *honor_info;
   uint64_t *suit_cost, *honor_cost;
   Tables T;
@@ -47,6 +50,11 @@ struct rv_vec {
   int32_t *d_obs_counts, *d_obs_offsets;   // encode: active seats per game and their exclusive scan (n + 1)
   void* d_scan_tmp;
   size_t scan_tmp_bytes;
+  // phase pipeline (rv_vec_step_random): per-phase game lists, double buffered, and per-game step budgets
+  int32_t* d_lists;             // [2 buffers][3 phases][n]
+  uint32_t* d_list_counts;      // [2][4]
+  uint32_t* d_budget;           // [n]
+  uint32_t* h_counts;           // pinned [4]
   unsigned long long* d_steps;  // [0] = env steps executed, [1] = games finished (by step kernels)
 };
 
@@ -194,6 +202,86 @@ __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, i
   if (threadIdx.x == 0) {
     atomicAdd(&counters[0], sh[0]);
     atomicAdd(&counters[1], sh[1]);
+  }
+}
+
+// ---- phase-sorted rollout -------------------------------------------------------------------
+// Games are compacted by phase into index lists (warp ballot + prefix, one atomic per warp and phase),
+// and each phase runs as its own kernel over its list, so a warp holds 32 games that all execute the
+// same transition and a kernel only carries the code of its phase:
+//   PH_ACT   the seat to move picks and applies a turn action (discard / riichi / kan / tsumo ...)
+//   PH_RESP  the claim window: every active seat answers (pass / chi / pon / kan / ron)
+//   PH_DEAL  shuffle + deal of the next round for games parked by next_round()
+// After stepping its game a thread files it into the NEXT iteration's list (double buffering), so an
+// iteration is {memset counts; ACT | RESP | DEAL concurrently on three streams}.
+enum { PH_ACT = 0, PH_RESP = 1, PH_DEAL = 2, PH_NONE = 3 };
+
+__device__ __forceinline__ int classify(const G& g, uint32_t budget) {
+  if (g.pending_init[0] != RV_NONE) return PH_DEAL;      // must be flushed even when the budget is spent
+  if (g.is_done || budget == 0) return PH_NONE;
+  return g.phase == RV_WAIT_ACT ? PH_ACT : PH_RESP;
+}
+// every lane of the warp must call this (cls = PH_NONE for lanes without a game)
+__device__ __forceinline__ void file_game(int cls, int32_t gi, int32_t* lists, uint32_t* counts, int64_t n) {
+  int lane = threadIdx.x & 31;
+  #pragma unroll
+  for (int c = 0; c < 3; c++) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+    if (m == 0) continue;
+    int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&counts[c], (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (cls == c) lists[(size_t)c * n + base + __popc(m & ((1u << lane) - 1))] = gi;
+  }
+}
+__global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, int32_t* lists,
+                                  uint32_t* counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int cls = PH_NONE;
+  if (i < n) {
+    budget[i] = max_steps;
+    cls = classify(states[i], max_steps);
+  }
+  file_game(cls, (int32_t)i, lists, counts, n);
+}
+template <int PH>
+__global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
+                                                    uint32_t* budget, const int32_t* cur_lists, const uint32_t* cur_counts,
+                                                    int32_t* next_lists, uint32_t* next_counts, unsigned long long* counters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t count = cur_counts[PH];
+  if ((int64_t)blockIdx.x * blockDim.x >= count) return;     // whole block idle (block-uniform)
+  int cls = PH_NONE;
+  int32_t gi = -1;
+  unsigned long long stepped = 0, finished = 0;
+  if (i < count) {
+    gi = cur_lists[(size_t)PH * n + i];
+    G& g = states[gi];
+    Ctx cx = make_ctx(T, log, cap, gi);
+    cx.defer_init = true;
+    uint32_t b = budget[gi];
+    if (PH == PH_DEAL) {
+      run_pending_init(cx, g);
+    } else {
+      if (PH == PH_ACT) random_step_act(cx, g, agent_seed, g.seed);
+      else random_step_resp(cx, g, agent_seed, g.seed);
+      budget[gi] = --b;
+      stepped = 1;
+      finished = g.is_done ? 1 : 0;
+    }
+    cls = classify(g, b);
+  }
+  file_game(cls, gi, next_lists, next_counts, n);
+  if (PH != PH_DEAL) {
+    for (int o = 16; o > 0; o >>= 1) {
+      stepped += __shfl_down_sync(0xFFFFFFFFu, stepped, o);
+      finished += __shfl_down_sync(0xFFFFFFFFu, finished, o);
+    }
+    if ((threadIdx.x & 31) == 0 && stepped) {
+      atomicAdd(&counters[0], stepped);
+      if (finished) atomicAdd(&counters[1], finished);
+    }
   }
 }
 
@@ -375,6 +463,11 @@ int rv_ctx_create(int device, rv_ctx** out) {
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
   CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   CK(cudaMalloc(&c->suit_info, sizeof(uint32_t) * SUIT_KEYS));
   CK(cudaMalloc(&c->honor_info, sizeof(uint32_t) * HONOR_KEYS));
@@ -482,6 +575,10 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_obs_counts = v->d_obs_offsets = nullptr;
   v->d_scan_tmp = nullptr;
   v->scan_tmp_bytes = 0;
+  v->d_lists = nullptr;
+  v->d_list_counts = nullptr;
+  v->d_budget = nullptr;
+  v->h_counts = nullptr;
   CK(cudaMalloc(&v->d_states, sizeof(G) * n));
   if (log_cap_words) CK(cudaMalloc(&v->d_log, sizeof(uint32_t) * (size_t)n * log_cap_words));
   CK(cudaMalloc(&v->d_steps, sizeof(unsigned long long) * 2));
@@ -518,6 +615,10 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_obs_counts) cudaFree(v->d_obs_counts);
   if (v->d_obs_offsets) cudaFree(v->d_obs_offsets);
   if (v->d_scan_tmp) cudaFree(v->d_scan_tmp);
+  if (v->d_lists) cudaFree(v->d_lists);
+  if (v->d_list_counts) cudaFree(v->d_list_counts);
+  if (v->d_budget) cudaFree(v->d_budget);
+  if (v->h_counts) cudaFreeHost(v->h_counts);
   cudaFree(v->d_steps);
   delete v;
   return RV_OK;
@@ -584,13 +685,73 @@ int rv_vec_step(rv_vec* v, const rv_action* actions) {
   return RV_OK;
 }
 
-int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
+static int rollout_mono(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
-  CK(cudaSetDevice(c->device));
   step_random_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, agent_seed,
                                                                  max_steps, v->d_steps);
   CK(cudaGetLastError());
   return RV_OK;
+}
+// Phase-sorted pipeline; returns after every game has used its budget (or finished) and no deal is pending.
+static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
+  rv_ctx* c = v->ctx;
+  int64_t n = v->n;
+  if (!v->d_lists) {
+    CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * 3 * n));
+    CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 8));
+    CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
+    CK(cudaMallocHost(&v->h_counts, sizeof(uint32_t) * 4));
+  }
+  auto lists = [&](int b) { return v->d_lists + (size_t)b * 3 * n; };
+  auto counts = [&](int b) { return v->d_list_counts + b * 4; };
+  CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 8, c->stream));
+  sched_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, lists(0), counts(0));
+  int grid = grid_for(n, 128);
+  int cur = 0;
+  uint64_t done_iters = 0;
+  // the host cannot see the list sizes without a sync, so it runs iterations in chunks and polls in between
+  while (true) {
+    uint64_t chunk = max_steps - done_iters > 64 ? 64 : (max_steps > done_iters ? max_steps - done_iters : 2);
+    if (chunk == 0) chunk = 2;
+    for (uint64_t it = 0; it < chunk; it++) {
+      int nxt = cur ^ 1;
+      CK(cudaMemsetAsync(counts(nxt), 0, sizeof(uint32_t) * 4, c->stream));
+      CK(cudaEventRecord(c->fork_ev, c->stream));
+      CK(cudaStreamWaitEvent(c->aux[0], c->fork_ev, 0));
+      CK(cudaStreamWaitEvent(c->aux[1], c->fork_ev, 0));
+      phase_kernel<PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                        lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
+      phase_kernel<PH_RESP><<<grid, 128, 0, c->aux[0]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                         lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
+      phase_kernel<PH_DEAL><<<grid, 128, 0, c->aux[1]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                         lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
+      CK(cudaEventRecord(c->join_ev[0], c->aux[0]));
+      CK(cudaEventRecord(c->join_ev[1], c->aux[1]));
+      CK(cudaStreamWaitEvent(c->stream, c->join_ev[0], 0));
+      CK(cudaStreamWaitEvent(c->stream, c->join_ev[1], 0));
+      cur = nxt;
+    }
+    done_iters += chunk;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(v->h_counts, counts(cur), sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (v->h_counts[0] == 0 && v->h_counts[1] == 0 && v->h_counts[2] == 0) break;
+  }
+  return RV_OK;
+}
+static bool use_phased() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("RV_ROLLOUT");
+    mode = (e && strcmp(e, "mono") == 0) ? 0 : 1;
+  }
+  return mode == 1;
+}
+int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  if (max_steps == 0) return RV_OK;
+  return use_phased() ? rollout_phased(v, agent_seed, max_steps) : rollout_mono(v, agent_seed, max_steps);
 }
 int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done) {
   rv_ctx* c = v->ctx;
