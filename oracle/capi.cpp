@@ -157,7 +157,11 @@ static void eval_one(const rv_hand_query& q, rv_hand_result& r) {
   c.player_wind = q.player_wind;
   c.round_wind = q.round_wind;
   c.honba = q.honba;
-  HandEvaluator he(tiles, melds);
+  bool sanma = q._pad[0] & 1;            // rv_hand_query._pad[0]: bit0 = sanma, _pad[1] = kita_count
+  c.kita_count = q._pad[1];
+  c.is_sanma = sanma;
+  c.num_players = sanma ? 3 : 4;
+  HandEvaluator he(tiles, melds, sanma);
   std::vector<uint8_t> dora(q.dora_ind, q.dora_ind + q.n_dora), ura(q.ura_ind, q.ura_ind + q.n_ura);
   WinResult w = he.calc(q.win_tile, dora, ura, c);
   r.is_win = w.is_win;
@@ -183,7 +187,7 @@ static void eval_one(const rv_hand_query& q, rv_hand_result& r) {
       }
   }
   if (ok13) {
-    HandEvaluator h13(t13, melds);
+    HandEvaluator h13(t13, melds, sanma);
     for (uint8_t x : h13.get_waits_u8()) r.wait_mask |= 1ull << x;
   }
   // shanten (shanten.rs:250-261) over the concealed tiles (+ win tile when 3n+1)

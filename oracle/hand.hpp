@@ -278,6 +278,7 @@ struct YakuContext {
   bool is_haitei = false, is_houtei = false, is_rinshan = false, is_chankan = false;
   bool is_tsumo_first_turn = false, is_daburu_reach = false;
   uint8_t dora_count = 0, aka_dora = 0, ura_dora_count = 0;
+  uint8_t nukidora_count = 0;  // yaku_3p.rs:30 (3P only)
   uint8_t round_wind = 27, seat_wind = 27;
 };
 
@@ -621,6 +622,10 @@ inline void apply_static_yaku(YakuResult& res, const YakuContext& ctx) {
     res.han += ctx.ura_dora_count;
     res.yaku_ids.push_back(33);
   }
+  if (ctx.nukidora_count > 0) {  // yaku_3p.rs:706-709
+    res.han += ctx.nukidora_count;
+    res.yaku_ids.push_back(34);
+  }
 }
 
 inline bool body_has_koutsu(const Division& div, uint8_t t) {
@@ -934,13 +939,23 @@ inline uint8_t get_next_tile(uint8_t t) {
   return t + 1;
 }
 
+// hand_evaluator_3p.rs:300-311
+inline uint8_t get_next_tile_sanma(uint8_t t) {
+  if (t == 0) return 8;
+  if (t == 8) return 0;
+  if (t >= 1 && t <= 7) return t;
+  return get_next_tile(t);
+}
+
+// HandEvaluator (4P) and HandEvaluator3P (hand_evaluator_3p.rs) differ only in `calc`; `sanma` selects.
 struct HandEvaluator {
+  bool sanma = false;
   Hand hand, full_hand;
   std::vector<Meld> melds;  // tiles in 34-space
   uint8_t aka_dora_count = 0;
 
   // hand_evaluator.rs:24-75
-  HandEvaluator(const std::vector<uint8_t>& tiles_136, const std::vector<Meld>& in_melds) {
+  HandEvaluator(const std::vector<uint8_t>& tiles_136, const std::vector<Meld>& in_melds, bool sanma_ = false) : sanma(sanma_) {
     for (uint8_t t : tiles_136) {
       if (is_aka(t)) aka_dora_count++;
       full_hand.add(t / 4);
@@ -983,8 +998,16 @@ struct HandEvaluator {
     WinResult out;
     if (!is_agari(hand_14)) return out;
     uint8_t dora = 0, ura = 0;
-    for (uint8_t ind : dora_ind) dora += full_14.counts[get_next_tile(ind / 4)];
-    for (uint8_t ind : ura_ind) ura += full_14.counts[get_next_tile(ind / 4)];
+    for (uint8_t ind : dora_ind) {
+      uint8_t nt = sanma ? get_next_tile_sanma(ind / 4) : get_next_tile(ind / 4);
+      dora += full_14.counts[nt];
+      if (sanma && nt == 30) dora += cond.kita_count;  // hand_evaluator_3p.rs:108-115
+    }
+    for (uint8_t ind : ura_ind) {
+      uint8_t nt = sanma ? get_next_tile_sanma(ind / 4) : get_next_tile(ind / 4);
+      ura += full_14.counts[nt];
+      if (sanma && nt == 30) ura += cond.kita_count;
+    }
     uint8_t aka = aka_dora_count;
     if (total == 13 && is_aka(win_tile_136)) aka++;
     YakuContext ctx;
@@ -1000,6 +1023,7 @@ struct HandEvaluator {
     ctx.dora_count = dora;
     ctx.aka_dora = aka;
     ctx.ura_dora_count = ura;
+    ctx.nukidora_count = sanma ? cond.kita_count : 0;
     ctx.round_wind = 27 + cond.round_wind;
     ctx.seat_wind = 27 + cond.player_wind;
     ctx.is_menzen = true;
@@ -1008,10 +1032,10 @@ struct HandEvaluator {
     YakuResult yr = calculate_yaku(hand_14, melds, ctx, win34);
     bool is_oya = cond.player_wind == 0;
     uint8_t scoring_han = (yr.yakuman_count == 0 && yr.han >= 13) ? 13 : yr.han;
-    Score sc = calculate_score(scoring_han, yr.fu, is_oya, cond.tsumo, cond.honba, 4);
+    Score sc = calculate_score(scoring_han, yr.fu, is_oya, cond.tsumo, cond.honba, sanma ? 3 : 4);
     bool has_yaku = false;
     for (uint32_t id : yr.yaku_ids)
-      if (id != 31 && id != 32 && id != 33) has_yaku = true;
+      if (id != 31 && id != 32 && id != 33 && !(sanma && id == 34)) has_yaku = true;
     out.is_win = (has_yaku || yr.yakuman_count > 0) && yr.han >= 1;
     out.yakuman = yr.yakuman_count > 0;
     out.ron_agari = sc.pay_ron;

@@ -1562,6 +1562,153 @@ __host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uin
   return (uint32_t)(mix64(k) % n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path of the ACT phase.  The rollout is bound by instruction fetch (the generic step is ~90 KB
+// of hot SASS), so the overwhelmingly common transition — "a concealed-or-open hand draws, discards a
+// random tile, nobody can claim it, the next seat draws" — is restated here as one compact routine that
+// stays resident in the SM instruction cache.  It either performs the WHOLE env step exactly as
+// random_step_act would, or returns false BEFORE touching the state so the game is handed to the
+// generic kernel.  Everything it does not recognise (agari shape, riichi/kan/kyushu options, kuikae,
+// first turn, claims, exhausted wall, kan doras) is a demotion, not an approximation.
+__device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+  RV_STAT(10);
+  const int pid = g.current_player;
+  const int drawn = g.drawn_tile;
+  const int hl = g.hand_len[pid], nm = g.n_melds[pid];
+  if (drawn == RV_NONE || g.is_first_turn || g.is_rinshan_flag || g.drawable_count == 0) return false;
+  if (g.n_dora != 1 || g.pending_kan_dora_count != 0) return false;          // some kan happened: generic path
+  if (g.flags[pid] & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) return false;
+  if ((g.forbidden[pid][0] & g.forbidden[pid][1]) != RV_NONE) return false;
+  if (hl + 3 * nm != 14) return false;
+  const uint64_t c0 = g.c_cnt[pid][0], c1 = g.c_cnt[pid][1], c2 = g.c_cnt[pid][2], c3 = g.c_cnt[pid][3];
+  if ((c0 | c1 | c2 | c3) & 0x4444444444444444ull) return false;             // four of a kind: ankan is legal
+  const uint32_t e0 = __ldg(&cx.T.suit_info[g.c_key[pid][0]]), e1 = __ldg(&cx.T.suit_info[g.c_key[pid][1]]),
+                 e2 = __ldg(&cx.T.suit_info[g.c_key[pid][2]]), e3 = __ldg(&cx.T.honor_info[g.c_key[pid][3]]);
+  // suits that are complete (M or P).  agari needs 4 of them, "some discard leaves tenpai" needs >= 2
+  const int complete = ((e0 | (e0 >> 1)) & 1) + ((e1 | (e1 >> 1)) & 1) + ((e2 | (e2 >> 1)) & 1) + ((e3 | (e3 >> 1)) & 1);
+  bool open_meld = false;
+  #pragma unroll 1
+  for (int m = 0; m < nm; m++) {
+    int ty = g.meld_type[pid][m];
+    if (ty != RV_MELD_ANKAN) open_meld = true;
+    if (ty == RV_MELD_PON) {                                                  // kakan possible?
+      int k = g.meld_tiles[pid][m][0] >> 2, su = k / 9;
+      uint64_t x = su == 0 ? c0 : su == 1 ? c1 : su == 2 ? c2 : c3;
+      if ((x >> (4 * (k - 9 * su))) & 15) return false;
+    }
+  }
+  if (nm == 0) {
+    // chiitoitsu / kokushi shapes (agari now, or tenpai after a discard) need >= 5 pairs / >= 12 terminal kinds
+    const uint64_t L = 0x1111111111111111ull;
+    int pairs = __popcll(((c0 >> 1) | (c0 >> 2)) & L) + __popcll(((c1 >> 1) | (c1 >> 2)) & L) +
+                __popcll(((c2 >> 1) | (c2 >> 2)) & L) + __popcll(((c3 >> 1) | (c3 >> 2)) & L);
+    if (pairs >= 5) return false;
+    const uint64_t TM = 0xF0000000Full;
+    uint64_t t0 = c0 & TM, t1 = c1 & TM, t2 = c2 & TM;
+    int tk = __popcll((t0 | (t0 >> 1) | (t0 >> 2)) & L) + __popcll((t1 | (t1 >> 1) | (t1 >> 2)) & L) +
+             __popcll((t2 | (t2 >> 1) | (t2 >> 2)) & L) + __popcll((c3 | (c3 >> 1) | (c3 >> 2)) & L & 0xFFFFFFFull);
+    if (tk >= 12) return false;
+  }
+  if (complete == 4) return false;                                            // standard agari shape: tsumo evaluation
+  if (complete >= 2 && !open_meld && g.score[pid] >= 1000 && g.drawable_count >= 4) return false;   // riichi may be legal
+  // ---- the action: every hand tile is a legal discard, nothing else is legal
+  const uint32_t sc = g.step_count;
+  const int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)hl);
+  const int tile = g.hand[pid][pick];
+  const int kind = tile >> 2, ksu = kind / 9, kr = kind - 9 * ksu;
+  // ---- would anybody be offered a claim?  (legal_actions.rs:254-508, decided from the caches)
+  #pragma unroll 1
+  for (int d = 1; d < NP; d++) {
+    int i = (pid + d) & 3;
+    if ((g.c_waits[i] >> kind) & 1) return false;                             // ron shape
+    if (g.flags[i] & RV_F_RIICHI_DECLARED) continue;
+    if (g.hand_len[i] < 3) continue;
+    uint64_t x = g.c_cnt[i][ksu];
+    if (((x >> (4 * kr)) & 15) >= 2) return false;                            // pon / daiminkan
+    if (d == 1 && ksu < 3) {                                                  // chi (shimocha)
+      uint64_t y = x << 8;                                                    // nibble kr+2 of y == nibble kr of x
+      int m2 = (y >> (4 * kr)) & 15, m1 = (y >> (4 * kr + 4)) & 15, p1 = (y >> (4 * kr + 12)) & 15, p2 = (y >> (4 * kr + 16)) & 15;
+      if (kr >= 8) p1 = 0;
+      if (kr >= 7) p2 = 0;
+      if ((m2 && m1) || (m1 && p1) || (p1 && p2)) return false;
+    }
+  }
+  // ================= commit: nothing below can fail =================
+  RV_STAT(9);
+  g.step_count = sc + 1;
+  const bool tsumogiri = tile == drawn;
+  // hand: remove `pick`, then place the drawn tile (stored last) into the sorted 13
+  if (!tsumogiri) {
+    uint8_t* h = g.hand[pid];
+    int pos = 0;
+    #pragma unroll 1
+    for (int j = 0; j < hl - 1; j++) pos += (j != pick && h[j] < drawn) ? 1 : 0;
+    // shift: out[j] for j < hl-1 built from in[] skipping `pick`, inserting drawn at pos
+    uint8_t out[RV_HAND_CAP];
+    int src = 0;
+    #pragma unroll 1
+    for (int j = 0; j < hl - 1; j++) {
+      if (j == pos) out[j] = (uint8_t)drawn;
+      else {
+        if (src == pick) src++;
+        out[j] = h[src++];
+      }
+    }
+    #pragma unroll 1
+    for (int j = 0; j < hl - 1; j++) h[j] = out[j];
+    h[hl - 1] = RV_NONE;
+  } else {
+    g.hand[pid][hl - 1] = RV_NONE;
+  }
+  g.hand_len[pid] = (uint8_t)(hl - 1);
+  cache_sub(g, pid, kind);
+  // _resolve_discard (state/mod.rs:1317-1413), no-claims branch
+  g.flags[pid] &= ~(RV_F_IPPATSU_CYCLE | RV_F_MISSED_AGARI_DOUJUN);
+  if (!tid_terminal(tile)) g.flags[pid] &= ~RV_F_NAGASHI_ELIGIBLE;
+  const int nr = g.n_river[pid];
+  if (nr < RV_RIVER_CAP) {
+    g.river[pid][nr] = (uint8_t)tile;
+    if (!tsumogiri) g.river_tedashi[pid] |= 1u << nr;
+  } else {
+    g.overflow = 1;
+  }
+  g.n_river[pid] = (uint8_t)(nr + 1);
+  g.c_river_kinds[pid] |= 1ull << kind;
+  waits_update(cx.T, g, pid);
+  g.last_discard_pid = (uint8_t)pid;
+  g.last_discard_tile = (uint8_t)tile;
+  if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)tile;
+  g.n_claims[0] = g.n_claims[1] = g.n_claims[2] = g.n_claims[3] = 0;
+  // the next seat draws (_deal_next, state/mod.rs:1569-1593)
+  g.turn_count++;
+  const int nxt = (pid + 1) & 3;
+  g.current_player = (uint8_t)nxt;
+  const int t2 = g.wall[g.wall_top - 1];
+  g.wall_top--;
+  g.drawable_count--;
+  hand_push(g, nxt, t2);
+  g.c_waits[nxt] = 0;
+  g.drawn_tile = (uint8_t)t2;
+  g.needs_tsumo = 0;
+  g.phase = RV_WAIT_ACT;
+  g.active_mask = (uint8_t)(1u << nxt);
+  g.forbidden[nxt][0] = g.forbidden[nxt][1] = RV_NONE;
+  // events: dahai, tsumo
+  uint32_t w[2] = {ev_w0(tsumogiri ? RV_EV_DAHAI_TSUMOGIRI : RV_EV_DAHAI, 1, pid, tile), ev_w0(RV_EV_TSUMO, 1, nxt, t2)};
+  uint64_t hsh = g.ev_hash;
+  uint32_t base = g.ev_words;
+  hsh = (hsh ^ w[0]) * 0x100000001b3ull;
+  hsh = (hsh ^ w[1]) * 0x100000001b3ull;
+  if (cx.log) {
+    if (base < cx.log_cap) cx.log[base] = w[0];
+    if (base + 1 < cx.log_cap) cx.log[base + 1] = w[1];
+  }
+  g.ev_hash = hsh;
+  g.ev_words = base + 2;
+  g.ev_count += 2;
+  return true;
+}
+
 // One env step with the on-device random agent, split by phase so that phase-sorted kernels only carry
 // the code of their own phase.
 __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
@@ -1635,7 +1782,9 @@ __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agen
   step_apply_resp(cx, g, acts);
 }
 __device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
-  if (g.phase == RV_WAIT_ACT) random_step_act(cx, g, agent_seed, game_id);
+  if (g.phase == RV_WAIT_ACT) {
+    if (!act_fast(cx, g, agent_seed, game_id)) random_step_act(cx, g, agent_seed, game_id);
+  }
   else random_step_resp(cx, g, agent_seed, game_id);
 }
 

@@ -30,8 +30,8 @@ struct rv_ctx {
   int device;
   cudaStream_t stream;
   cudaEvent_t ev[8];
-  cudaStream_t aux[2];          // phase pipeline: RESPOND and DEAL kernels run beside ACT
-  cudaEvent_t fork_ev, join_ev[2];
+  cudaStream_t aux[3];          // phase pipeline: RESPOND, DEAL and SLOW kernels run beside ACT
+  cudaEvent_t fork_ev, join_ev[3];
   uint32_t *suit_info, *honor_info;
   uint64_t *suit_cost, *honor_cost;
   Tables T;
@@ -212,9 +212,12 @@ __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, i
 //   PH_ACT   the seat to move picks and applies a turn action (discard / riichi / kan / tsumo ...)
 //   PH_RESP  the claim window: every active seat answers (pass / chi / pon / kan / ron)
 //   PH_DEAL  shuffle + deal of the next round for games parked by next_round()
+//   PH_SLOW  ACT games the fast path declined (see act_fast): the generic, large-footprint turn code.
+// The ACT kernel only carries act_fast (a few KB of SASS, instruction-cache resident); a game it cannot
+// handle is re-filed under PH_SLOW and takes its step one iteration later.
 // After stepping its game a thread files it into the NEXT iteration's list (double buffering), so an
 // iteration is {memset counts; ACT | RESP | DEAL concurrently on three streams}.
-enum { PH_ACT = 0, PH_RESP = 1, PH_DEAL = 2, PH_NONE = 3 };
+enum { PH_ACT = 0, PH_RESP = 1, PH_DEAL = 2, PH_SLOW = 3, PH_NONE = 4, N_LISTS = 4 };
 
 __device__ __forceinline__ int classify(const G& g, uint32_t budget) {
   if (g.pending_init[0] != RV_NONE) return PH_DEAL;      // must be flushed even when the budget is spent
@@ -225,7 +228,7 @@ __device__ __forceinline__ int classify(const G& g, uint32_t budget) {
 __device__ __forceinline__ void file_game(int cls, int32_t gi, int32_t* lists, uint32_t* counts, int64_t n) {
   int lane = threadIdx.x & 31;
   #pragma unroll
-  for (int c = 0; c < 3; c++) {
+  for (int c = 0; c < N_LISTS; c++) {
     unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
     if (m == 0) continue;
     int leader = __ffs(m) - 1;
@@ -261,19 +264,27 @@ __global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t
     Ctx cx = make_ctx(T, log, cap, gi);
     cx.defer_init = true;
     uint32_t b = budget[gi];
+    bool did_step = false;
     if (PH == PH_DEAL) {
       run_pending_init(cx, g);
+    } else if (PH == PH_ACT) {
+      did_step = act_fast(cx, g, agent_seed, g.seed);
+    } else if (PH == PH_SLOW) {
+      random_step_act(cx, g, agent_seed, g.seed);
+      did_step = true;
     } else {
-      if (PH == PH_ACT) random_step_act(cx, g, agent_seed, g.seed);
-      else random_step_resp(cx, g, agent_seed, g.seed);
+      random_step_resp(cx, g, agent_seed, g.seed);
+      did_step = true;
+    }
+    if (did_step) {
       budget[gi] = --b;
       stepped = 1;
       finished = g.is_done ? 1 : 0;
     }
-    cls = classify(g, b);
+    cls = (PH == PH_ACT && !did_step) ? PH_SLOW : classify(g, b);
   }
   file_game(cls, gi, next_lists, next_counts, n);
-  if (PH != PH_DEAL) {
+  if (PH != PH_DEAL) {   // (uniform per kernel)
     for (int o = 16; o > 0; o >>= 1) {
       stepped += __shfl_down_sync(0xFFFFFFFFu, stepped, o);
       finished += __shfl_down_sync(0xFFFFFFFFu, finished, o);
@@ -463,7 +474,7 @@ int rv_ctx_create(int device, rv_ctx** out) {
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->ev[i]));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
   }
@@ -697,14 +708,14 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
   int64_t n = v->n;
   if (!v->d_lists) {
-    CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * 3 * n));
-    CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 8));
+    CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * N_LISTS * n));
+    CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 16));
     CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
     CK(cudaMallocHost(&v->h_counts, sizeof(uint32_t) * 4));
   }
-  auto lists = [&](int b) { return v->d_lists + (size_t)b * 3 * n; };
-  auto counts = [&](int b) { return v->d_list_counts + b * 4; };
-  CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 8, c->stream));
+  auto lists = [&](int b) { return v->d_lists + (size_t)b * N_LISTS * n; };
+  auto counts = [&](int b) { return v->d_list_counts + b * 8; };
+  CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 16, c->stream));
   sched_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, lists(0), counts(0));
   int grid = grid_for(n, 128);
   int cur = 0;
@@ -715,27 +726,28 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
     if (chunk == 0) chunk = 2;
     for (uint64_t it = 0; it < chunk; it++) {
       int nxt = cur ^ 1;
-      CK(cudaMemsetAsync(counts(nxt), 0, sizeof(uint32_t) * 4, c->stream));
+      CK(cudaMemsetAsync(counts(nxt), 0, sizeof(uint32_t) * 8, c->stream));
       CK(cudaEventRecord(c->fork_ev, c->stream));
-      CK(cudaStreamWaitEvent(c->aux[0], c->fork_ev, 0));
-      CK(cudaStreamWaitEvent(c->aux[1], c->fork_ev, 0));
+      for (int a = 0; a < 3; a++) CK(cudaStreamWaitEvent(c->aux[a], c->fork_ev, 0));
       phase_kernel<PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
                                                         lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
       phase_kernel<PH_RESP><<<grid, 128, 0, c->aux[0]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
                                                          lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
       phase_kernel<PH_DEAL><<<grid, 128, 0, c->aux[1]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
                                                          lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
-      CK(cudaEventRecord(c->join_ev[0], c->aux[0]));
-      CK(cudaEventRecord(c->join_ev[1], c->aux[1]));
-      CK(cudaStreamWaitEvent(c->stream, c->join_ev[0], 0));
-      CK(cudaStreamWaitEvent(c->stream, c->join_ev[1], 0));
+      phase_kernel<PH_SLOW><<<grid, 128, 0, c->aux[2]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                         lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
+      for (int a = 0; a < 3; a++) {
+        CK(cudaEventRecord(c->join_ev[a], c->aux[a]));
+        CK(cudaStreamWaitEvent(c->stream, c->join_ev[a], 0));
+      }
       cur = nxt;
     }
     done_iters += chunk;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(v->h_counts, counts(cur), sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (v->h_counts[0] == 0 && v->h_counts[1] == 0 && v->h_counts[2] == 0) break;
+    if (v->h_counts[0] == 0 && v->h_counts[1] == 0 && v->h_counts[2] == 0 && v->h_counts[3] == 0) break;
   }
   return RV_OK;
 }
