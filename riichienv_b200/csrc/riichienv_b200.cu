@@ -224,8 +224,17 @@ __device__ __forceinline__ int classify(const G& g, uint32_t budget) {
   if (g.is_done || budget == 0) return PH_NONE;
   return g.phase == RV_WAIT_ACT ? PH_ACT : PH_RESP;
 }
-// every lane of the warp must call this (cls = PH_NONE for lanes without a game)
-__device__ __forceinline__ void file_game(int cls, int32_t gi, int32_t* lists, uint32_t* counts, int64_t n) {
+// every lane of the warp must call this (cls = PH_NONE for lanes without a game).
+// ACT games go to the per-iteration ACT list; RESP / DEAL / SLOW games go to the accumulating slow lists,
+// which are only drained every few iterations (their kernels carry the large generic code and would
+// otherwise put ~100 us of instruction-fetch latency on the critical path of every iteration).
+struct Lists {
+  int32_t* act;        // [n]
+  uint32_t* act_count; // [1]
+  int32_t* slow;       // [3][n]  (RESP, DEAL, SLOW) -> index cls - 1
+  uint32_t* slow_count;// [3]
+};
+__device__ __forceinline__ void file_game(int cls, int32_t gi, const Lists& L, int64_t n) {
   int lane = threadIdx.x & 31;
   #pragma unroll
   for (int c = 0; c < N_LISTS; c++) {
@@ -233,33 +242,36 @@ __device__ __forceinline__ void file_game(int cls, int32_t gi, int32_t* lists, u
     if (m == 0) continue;
     int leader = __ffs(m) - 1;
     uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&counts[c], (uint32_t)__popc(m));
+    uint32_t* cnt = c == PH_ACT ? L.act_count : &L.slow_count[c - 1];
+    if (lane == leader) base = atomicAdd(cnt, (uint32_t)__popc(m));
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (cls == c) lists[(size_t)c * n + base + __popc(m & ((1u << lane) - 1))] = gi;
+    if (cls == c) {
+      int32_t* dst = c == PH_ACT ? L.act : L.slow + (size_t)(c - 1) * n;
+      dst[base + __popc(m & ((1u << lane) - 1))] = gi;
+    }
   }
 }
-__global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, int32_t* lists,
-                                  uint32_t* counts) {
+__global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, Lists out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cls = PH_NONE;
   if (i < n) {
     budget[i] = max_steps;
     cls = classify(states[i], max_steps);
   }
-  file_game(cls, (int32_t)i, lists, counts, n);
+  file_game(cls, (int32_t)i, out, n);
 }
 template <int PH>
 __global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
-                                                    uint32_t* budget, const int32_t* cur_lists, const uint32_t* cur_counts,
-                                                    int32_t* next_lists, uint32_t* next_counts, unsigned long long* counters) {
+                                                    uint32_t* budget, const int32_t* in_list, const uint32_t* in_count, Lists out,
+                                                    unsigned long long* counters) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t count = cur_counts[PH];
+  uint32_t count = *in_count;
   if ((int64_t)blockIdx.x * blockDim.x >= count) return;     // whole block idle (block-uniform)
   int cls = PH_NONE;
   int32_t gi = -1;
   unsigned long long stepped = 0, finished = 0;
   if (i < count) {
-    gi = cur_lists[(size_t)PH * n + i];
+    gi = in_list[i];
     G& g = states[gi];
     Ctx cx = make_ctx(T, log, cap, gi);
     cx.defer_init = true;
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t
     }
     cls = (PH == PH_ACT && !did_step) ? PH_SLOW : classify(g, b);
   }
-  file_game(cls, gi, next_lists, next_counts, n);
+  file_game(cls, gi, out, n);
   if (PH != PH_DEAL) {   // (uniform per kernel)
     for (int o = 16; o > 0; o >>= 1) {
       stepped += __shfl_down_sync(0xFFFFFFFFu, stepped, o);
@@ -707,47 +719,72 @@ static int rollout_mono(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
 static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
   int64_t n = v->n;
-  if (!v->d_lists) {
-    CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * N_LISTS * n));
-    CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 16));
-    CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
-    CK(cudaMallocHost(&v->h_counts, sizeof(uint32_t) * 4));
+  static int slow_every = -1;
+  if (slow_every < 0) {
+    const char* e = getenv("RV_SLOW_EVERY");
+    slow_every = e ? atoi(e) : 4;
+    if (slow_every < 1) slow_every = 1;
   }
-  auto lists = [&](int b) { return v->d_lists + (size_t)b * N_LISTS * n; };
-  auto counts = [&](int b) { return v->d_list_counts + b * 8; };
+  if (!v->d_lists) {
+    CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * (2 + 2 * 3) * n));      // act[2][n] + slow[2][3][n]
+    CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 16));            // act_count[2] @0,1 ; slow_count[2][3] @4..6, 8..10
+    CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
+    CK(cudaMallocHost(&v->h_counts, sizeof(uint32_t) * 16));
+  }
+  auto act_list = [&](int b) { return v->d_lists + (size_t)b * n; };
+  auto act_count = [&](int b) { return v->d_list_counts + b; };
+  auto slow_list = [&](int b, int ph) { return v->d_lists + (size_t)(2 + b * 3 + (ph - 1)) * n; };
+  auto slow_count = [&](int b) { return v->d_list_counts + 4 + b * 4; };
+  auto mk = [&](int ab, int sb) {
+    Lists L;
+    L.act = act_list(ab);
+    L.act_count = act_count(ab);
+    L.slow = slow_list(sb, 1);
+    L.slow_count = slow_count(sb);
+    return L;
+  };
   CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 16, c->stream));
-  sched_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, lists(0), counts(0));
   int grid = grid_for(n, 128);
-  int cur = 0;
-  uint64_t done_iters = 0;
-  // the host cannot see the list sizes without a sync, so it runs iterations in chunks and polls in between
+  int cur = 0, sw = 0;   // cur: ACT list being read; sw: slow lists being WRITTEN (accumulated)
+  sched_init_kernel<<<grid, 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, mk(cur, sw));
+  uint64_t it_total = 0;
   while (true) {
-    uint64_t chunk = max_steps - done_iters > 64 ? 64 : (max_steps > done_iters ? max_steps - done_iters : 2);
-    if (chunk == 0) chunk = 2;
-    for (uint64_t it = 0; it < chunk; it++) {
+    for (int it = 0; it < 64; it++, it_total++) {
       int nxt = cur ^ 1;
-      CK(cudaMemsetAsync(counts(nxt), 0, sizeof(uint32_t) * 8, c->stream));
-      CK(cudaEventRecord(c->fork_ev, c->stream));
-      for (int a = 0; a < 3; a++) CK(cudaStreamWaitEvent(c->aux[a], c->fork_ev, 0));
+      bool slow_iter = (it_total % slow_every) == (uint64_t)(slow_every - 1);
+      CK(cudaMemsetAsync(act_count(nxt), 0, sizeof(uint32_t), c->stream));
+      int sr = sw;                       // slow lists to drain this iteration (if slow_iter)
+      if (slow_iter) {
+        sw ^= 1;                         // producers now write the other set (emptied when it was last drained)
+        CK(cudaMemsetAsync(slow_count(sw), 0, sizeof(uint32_t) * 3, c->stream));
+      }
+      Lists out = mk(nxt, sw);
+      if (slow_iter) {
+        CK(cudaEventRecord(c->fork_ev, c->stream));
+        for (int a = 0; a < 3; a++) CK(cudaStreamWaitEvent(c->aux[a], c->fork_ev, 0));
+      }
       phase_kernel<PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                        lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
-      phase_kernel<PH_RESP><<<grid, 128, 0, c->aux[0]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                         lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
-      phase_kernel<PH_DEAL><<<grid, 128, 0, c->aux[1]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                         lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
-      phase_kernel<PH_SLOW><<<grid, 128, 0, c->aux[2]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                         lists(cur), counts(cur), lists(nxt), counts(nxt), v->d_steps);
-      for (int a = 0; a < 3; a++) {
-        CK(cudaEventRecord(c->join_ev[a], c->aux[a]));
-        CK(cudaStreamWaitEvent(c->stream, c->join_ev[a], 0));
+                                                        act_list(cur), act_count(cur), out, v->d_steps);
+      if (slow_iter) {
+        phase_kernel<PH_RESP><<<grid, 128, 0, c->aux[0]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                           slow_list(sr, PH_RESP), slow_count(sr) + (PH_RESP - 1), out, v->d_steps);
+        phase_kernel<PH_DEAL><<<grid, 128, 0, c->aux[1]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                           slow_list(sr, PH_DEAL), slow_count(sr) + (PH_DEAL - 1), out, v->d_steps);
+        phase_kernel<PH_SLOW><<<grid, 128, 0, c->aux[2]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                           slow_list(sr, PH_SLOW), slow_count(sr) + (PH_SLOW - 1), out, v->d_steps);
+        for (int a = 0; a < 3; a++) {
+          CK(cudaEventRecord(c->join_ev[a], c->aux[a]));
+          CK(cudaStreamWaitEvent(c->stream, c->join_ev[a], 0));
+        }
       }
       cur = nxt;
     }
-    done_iters += chunk;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(v->h_counts, counts(cur), sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(v->h_counts, v->d_list_counts, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (v->h_counts[0] == 0 && v->h_counts[1] == 0 && v->h_counts[2] == 0 && v->h_counts[3] == 0) break;
+    uint32_t* hc = v->h_counts;
+    // pending work: the ACT list just produced and the slow set being accumulated (the other slow set was drained)
+    if (hc[cur] == 0 && hc[4 + sw * 4] == 0 && hc[4 + sw * 4 + 1] == 0 && hc[4 + sw * 4 + 2] == 0) break;
   }
   return RV_OK;
 }
