@@ -229,10 +229,8 @@ __device__ __forceinline__ int classify(const G& g, uint32_t budget) {
 // which are only drained every few iterations (their kernels carry the large generic code and would
 // otherwise put ~100 us of instruction-fetch latency on the critical path of every iteration).
 struct Lists {
-  int32_t* act;        // [n]
-  uint32_t* act_count; // [1]
-  int32_t* slow;       // [3][n]  (RESP, DEAL, SLOW) -> index cls - 1
-  uint32_t* slow_count;// [3]
+  int32_t* dst[N_LISTS];     // where games of each class are appended
+  uint32_t* cnt[N_LISTS];
 };
 __device__ __forceinline__ void file_game(int cls, int32_t gi, const Lists& L, int64_t n) {
   int lane = threadIdx.x & 31;
@@ -242,13 +240,9 @@ __device__ __forceinline__ void file_game(int cls, int32_t gi, const Lists& L, i
     if (m == 0) continue;
     int leader = __ffs(m) - 1;
     uint32_t base = 0;
-    uint32_t* cnt = c == PH_ACT ? L.act_count : &L.slow_count[c - 1];
-    if (lane == leader) base = atomicAdd(cnt, (uint32_t)__popc(m));
+    if (lane == leader) base = atomicAdd(L.cnt[c], (uint32_t)__popc(m));
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (cls == c) {
-      int32_t* dst = c == PH_ACT ? L.act : L.slow + (size_t)(c - 1) * n;
-      dst[base + __popc(m & ((1u << lane) - 1))] = gi;
-    }
+    if (cls == c) L.dst[c][base + __popc(m & ((1u << lane) - 1))] = gi;
   }
 }
 __global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, Lists out) {
@@ -716,75 +710,83 @@ static int rollout_mono(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   return RV_OK;
 }
 // Phase-sorted pipeline; returns after every game has used its budget (or finished) and no deal is pending.
+// Every class has a double-buffered list.  The ACT list is swapped every iteration; RESP/SLOW lists are
+// drained every `slow_every` iterations and the DEAL list every `deal_every` (their kernels are long
+// single-warp latencies — a deal is ~270 us — that must not sit on the critical path of every iteration).
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  int v = e ? atoi(e) : dflt;
+  return v < 1 ? 1 : v;
+}
 static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
   int64_t n = v->n;
-  static int slow_every = -1;
-  if (slow_every < 0) {
-    const char* e = getenv("RV_SLOW_EVERY");
-    slow_every = e ? atoi(e) : 4;
-    if (slow_every < 1) slow_every = 1;
-  }
+  static int slow_every = env_int("RV_SLOW_EVERY", 4), deal_every = env_int("RV_DEAL_EVERY", 16);
   if (!v->d_lists) {
-    CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * (2 + 2 * 3) * n));      // act[2][n] + slow[2][3][n]
-    CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 16));            // act_count[2] @0,1 ; slow_count[2][3] @4..6, 8..10
+    CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * N_LISTS * n));      // [class][buffer][n]
+    CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 16));            // [class][buffer]
     CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
     CK(cudaMallocHost(&v->h_counts, sizeof(uint32_t) * 16));
   }
-  auto act_list = [&](int b) { return v->d_lists + (size_t)b * n; };
-  auto act_count = [&](int b) { return v->d_list_counts + b; };
-  auto slow_list = [&](int b, int ph) { return v->d_lists + (size_t)(2 + b * 3 + (ph - 1)) * n; };
-  auto slow_count = [&](int b) { return v->d_list_counts + 4 + b * 4; };
-  auto mk = [&](int ab, int sb) {
+  auto list = [&](int ph, int b) { return v->d_lists + (size_t)(ph * 2 + b) * n; };
+  auto count = [&](int ph, int b) { return v->d_list_counts + ph * 2 + b; };
+  int wr[N_LISTS] = {0, 0, 0, 0};     // buffer currently being WRITTEN for each class
+  auto mk = [&]() {
     Lists L;
-    L.act = act_list(ab);
-    L.act_count = act_count(ab);
-    L.slow = slow_list(sb, 1);
-    L.slow_count = slow_count(sb);
+    for (int ph = 0; ph < N_LISTS; ph++) {
+      L.dst[ph] = list(ph, wr[ph]);
+      L.cnt[ph] = count(ph, wr[ph]);
+    }
     return L;
   };
   CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 16, c->stream));
   int grid = grid_for(n, 128);
-  int cur = 0, sw = 0;   // cur: ACT list being read; sw: slow lists being WRITTEN (accumulated)
-  sched_init_kernel<<<grid, 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, mk(cur, sw));
+  sched_init_kernel<<<grid, 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, mk());
   uint64_t it_total = 0;
   while (true) {
     for (int it = 0; it < 64; it++, it_total++) {
-      int nxt = cur ^ 1;
-      bool slow_iter = (it_total % slow_every) == (uint64_t)(slow_every - 1);
-      CK(cudaMemsetAsync(act_count(nxt), 0, sizeof(uint32_t), c->stream));
-      int sr = sw;                       // slow lists to drain this iteration (if slow_iter)
-      if (slow_iter) {
-        sw ^= 1;                         // producers now write the other set (emptied when it was last drained)
-        CK(cudaMemsetAsync(slow_count(sw), 0, sizeof(uint32_t) * 3, c->stream));
+      // which classes are drained this iteration
+      bool drain[N_LISTS];
+      drain[PH_ACT] = true;
+      drain[PH_RESP] = drain[PH_SLOW] = (it_total % slow_every) == (uint64_t)(slow_every - 1);
+      drain[PH_DEAL] = (it_total % deal_every) == (uint64_t)(deal_every - 1);
+      int rd[N_LISTS];
+      for (int ph = 0; ph < N_LISTS; ph++) {
+        rd[ph] = wr[ph];
+        if (drain[ph]) {
+          wr[ph] ^= 1;             // producers switch to the other buffer (drained earlier), cleared now
+          CK(cudaMemsetAsync(count(ph, wr[ph]), 0, sizeof(uint32_t), c->stream));
+        }
       }
-      Lists out = mk(nxt, sw);
-      if (slow_iter) {
+      Lists out = mk();
+      bool any_aux = drain[PH_RESP] || drain[PH_DEAL] || drain[PH_SLOW];
+      if (any_aux) {
         CK(cudaEventRecord(c->fork_ev, c->stream));
         for (int a = 0; a < 3; a++) CK(cudaStreamWaitEvent(c->aux[a], c->fork_ev, 0));
       }
       phase_kernel<PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                        act_list(cur), act_count(cur), out, v->d_steps);
-      if (slow_iter) {
+                                                        list(PH_ACT, rd[PH_ACT]), count(PH_ACT, rd[PH_ACT]), out, v->d_steps);
+      if (drain[PH_RESP])
         phase_kernel<PH_RESP><<<grid, 128, 0, c->aux[0]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                           slow_list(sr, PH_RESP), slow_count(sr) + (PH_RESP - 1), out, v->d_steps);
+                                                           list(PH_RESP, rd[PH_RESP]), count(PH_RESP, rd[PH_RESP]), out, v->d_steps);
+      if (drain[PH_DEAL])
         phase_kernel<PH_DEAL><<<grid, 128, 0, c->aux[1]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                           slow_list(sr, PH_DEAL), slow_count(sr) + (PH_DEAL - 1), out, v->d_steps);
+                                                           list(PH_DEAL, rd[PH_DEAL]), count(PH_DEAL, rd[PH_DEAL]), out, v->d_steps);
+      if (drain[PH_SLOW])
         phase_kernel<PH_SLOW><<<grid, 128, 0, c->aux[2]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                           slow_list(sr, PH_SLOW), slow_count(sr) + (PH_SLOW - 1), out, v->d_steps);
+                                                           list(PH_SLOW, rd[PH_SLOW]), count(PH_SLOW, rd[PH_SLOW]), out, v->d_steps);
+      if (any_aux)
         for (int a = 0; a < 3; a++) {
           CK(cudaEventRecord(c->join_ev[a], c->aux[a]));
           CK(cudaStreamWaitEvent(c->stream, c->join_ev[a], 0));
         }
-      }
-      cur = nxt;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(v->h_counts, v->d_list_counts, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    uint32_t* hc = v->h_counts;
-    // pending work: the ACT list just produced and the slow set being accumulated (the other slow set was drained)
-    if (hc[cur] == 0 && hc[4 + sw * 4] == 0 && hc[4 + sw * 4 + 1] == 0 && hc[4 + sw * 4 + 2] == 0) break;
+    bool pending = false;
+    for (int ph = 0; ph < N_LISTS; ph++) pending |= v->h_counts[ph * 2 + wr[ph]] != 0;
+    if (!pending) break;
   }
   return RV_OK;
 }
