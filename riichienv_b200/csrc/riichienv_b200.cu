@@ -213,11 +213,14 @@ __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, i
 //   PH_RESP  the claim window: every active seat answers (pass / chi / pon / kan / ron)
 //   PH_DEAL  shuffle + deal of the next round for games parked by next_round()
 //   PH_SLOW  ACT games the fast path declined (see act_fast): the generic, large-footprint turn code.
+//   PH_REACT / PH_REACT_D  games that return to the ACT phase out of a RESP/SLOW kernel / a DEAL kernel.
+// The big-code kernels (RESP, SLOW, DEAL) run ASYNCHRONOUSLY on side streams, overlapping the following fast
+// iterations; they are only joined right before the lists they append to are swapped.
 // The ACT kernel only carries act_fast (a few KB of SASS, instruction-cache resident); a game it cannot
 // handle is re-filed under PH_SLOW and takes its step one iteration later.
 // After stepping its game a thread files it into the NEXT iteration's list (double buffering), so an
 // iteration is {memset counts; ACT | RESP | DEAL concurrently on three streams}.
-enum { PH_ACT = 0, PH_RESP = 1, PH_DEAL = 2, PH_SLOW = 3, PH_NONE = 4, N_LISTS = 4 };
+enum { PH_ACT = 0, PH_RESP = 1, PH_DEAL = 2, PH_SLOW = 3, PH_REACT = 4, PH_REACT_D = 5, N_LISTS = 6, PH_NONE = 7 };
 
 __device__ __forceinline__ int classify(const G& g, uint32_t budget) {
   if (g.pending_init[0] != RV_NONE) return PH_DEAL;      // must be flushed even when the budget is spent
@@ -254,7 +257,7 @@ __global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, 
   }
   file_game(cls, (int32_t)i, out, n);
 }
-template <int PH>
+template <int PH, int OUT_ACT>
 __global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
                                                     uint32_t* budget, const int32_t* in_list, const uint32_t* in_count, Lists out,
                                                     unsigned long long* counters) {
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t
       finished = g.is_done ? 1 : 0;
     }
     cls = (PH == PH_ACT && !did_step) ? PH_SLOW : classify(g, b);
+    if (cls == PH_ACT && OUT_ACT != PH_ACT) cls = OUT_ACT;   // async kernels return ACT games through their own list
   }
   file_game(cls, gi, out, n);
   if (PH != PH_DEAL) {   // (uniform per kernel)
@@ -721,7 +725,8 @@ static int env_int(const char* name, int dflt) {
 static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
   int64_t n = v->n;
-  static int slow_every = env_int("RV_SLOW_EVERY", 4), deal_every = env_int("RV_DEAL_EVERY", 16);
+  static int slow_every = env_int("RV_SLOW_EVERY", 4), deal_mult = env_int("RV_DEAL_MULT", 8);
+  const int deal_every = slow_every * deal_mult;   // deal drains coincide with slow drains
   if (!v->d_lists) {
     CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * N_LISTS * n));      // [class][buffer][n]
     CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 16));            // [class][buffer]
@@ -730,7 +735,7 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   }
   auto list = [&](int ph, int b) { return v->d_lists + (size_t)(ph * 2 + b) * n; };
   auto count = [&](int ph, int b) { return v->d_list_counts + ph * 2 + b; };
-  int wr[N_LISTS] = {0, 0, 0, 0};     // buffer currently being WRITTEN for each class
+  int wr[N_LISTS] = {0, 0, 0, 0, 0, 0};     // buffer currently being WRITTEN for each class
   auto mk = [&]() {
     Lists L;
     for (int ph = 0; ph < N_LISTS; ph++) {
@@ -739,55 +744,83 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
     }
     return L;
   };
+  bool inflight[3] = {false, false, false};   // aux[0]=RESP, aux[1]=DEAL, aux[2]=SLOW
+  auto join = [&](int a) -> int {
+    if (inflight[a]) {
+      CK(cudaStreamWaitEvent(c->stream, c->join_ev[a], 0));
+      inflight[a] = false;
+    }
+    return RV_OK;
+  };
+  auto swap_class = [&](int ph) -> int {
+    wr[ph] ^= 1;             // producers switch to the other buffer (drained earlier), cleared now
+    CK(cudaMemsetAsync(count(ph, wr[ph]), 0, sizeof(uint32_t), c->stream));
+    return RV_OK;
+  };
+#define LAUNCH(PH, OUT, STREAM, RD)                                                                                   \
+  phase_kernel<PH, OUT><<<grid, 128, 0, STREAM>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, \
+                                                  list(PH, RD), count(PH, RD), out, v->d_steps)
   CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 16, c->stream));
   int grid = grid_for(n, 128);
   sched_init_kernel<<<grid, 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, mk());
   uint64_t it_total = 0;
+  int rc;
   while (true) {
     for (int it = 0; it < 64; it++, it_total++) {
-      // which classes are drained this iteration
-      bool drain[N_LISTS];
-      drain[PH_ACT] = true;
-      drain[PH_RESP] = drain[PH_SLOW] = (it_total % slow_every) == (uint64_t)(slow_every - 1);
-      drain[PH_DEAL] = (it_total % deal_every) == (uint64_t)(deal_every - 1);
-      int rd[N_LISTS];
-      for (int ph = 0; ph < N_LISTS; ph++) {
-        rd[ph] = wr[ph];
-        if (drain[ph]) {
-          wr[ph] ^= 1;             // producers switch to the other buffer (drained earlier), cleared now
-          CK(cudaMemsetAsync(count(ph, wr[ph]), 0, sizeof(uint32_t), c->stream));
-        }
+      bool slow_drain = (it_total % slow_every) == (uint64_t)(slow_every - 1);
+      bool deal_drain = (it_total % deal_every) == (uint64_t)(deal_every - 1);
+      int rd_act = wr[PH_ACT];
+      if ((rc = swap_class(PH_ACT))) return rc;
+      int rd_resp = 0, rd_slow = 0, rd_react = 0, rd_deal = 0, rd_react_d = 0;
+      if (slow_drain) {
+        // the RESP / SLOW kernels of the previous period append to RESP, DEAL, REACT: finish them before swapping
+        if ((rc = join(0)) || (rc = join(2))) return rc;
+        rd_resp = wr[PH_RESP];
+        rd_slow = wr[PH_SLOW];
+        rd_react = wr[PH_REACT];
+        if ((rc = swap_class(PH_RESP)) || (rc = swap_class(PH_SLOW)) || (rc = swap_class(PH_REACT))) return rc;
+      }
+      if (deal_drain) {
+        if ((rc = join(1))) return rc;        // previous deal kernel appends to REACT_D and reads the other DEAL buffer
+        rd_deal = wr[PH_DEAL];
+        rd_react_d = wr[PH_REACT_D];
+        if ((rc = swap_class(PH_DEAL)) || (rc = swap_class(PH_REACT_D))) return rc;
       }
       Lists out = mk();
-      bool any_aux = drain[PH_RESP] || drain[PH_DEAL] || drain[PH_SLOW];
-      if (any_aux) {
-        CK(cudaEventRecord(c->fork_ev, c->stream));
-        for (int a = 0; a < 3; a++) CK(cudaStreamWaitEvent(c->aux[a], c->fork_ev, 0));
+      if (slow_drain || deal_drain) CK(cudaEventRecord(c->fork_ev, c->stream));
+      LAUNCH(PH_ACT, PH_ACT, c->stream, rd_act);
+      if (slow_drain) {
+        // games returning from the previous period's RESP/SLOW kernels re-enter through the fast kernel
+        phase_kernel<PH_ACT, PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                                   list(PH_REACT, rd_react), count(PH_REACT, rd_react), out, v->d_steps);
+        CK(cudaStreamWaitEvent(c->aux[0], c->fork_ev, 0));
+        CK(cudaStreamWaitEvent(c->aux[2], c->fork_ev, 0));
+        LAUNCH(PH_RESP, PH_REACT, c->aux[0], rd_resp);
+        LAUNCH(PH_SLOW, PH_REACT, c->aux[2], rd_slow);
+        CK(cudaEventRecord(c->join_ev[0], c->aux[0]));
+        CK(cudaEventRecord(c->join_ev[2], c->aux[2]));
+        inflight[0] = inflight[2] = true;
       }
-      phase_kernel<PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                        list(PH_ACT, rd[PH_ACT]), count(PH_ACT, rd[PH_ACT]), out, v->d_steps);
-      if (drain[PH_RESP])
-        phase_kernel<PH_RESP><<<grid, 128, 0, c->aux[0]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                           list(PH_RESP, rd[PH_RESP]), count(PH_RESP, rd[PH_RESP]), out, v->d_steps);
-      if (drain[PH_DEAL])
-        phase_kernel<PH_DEAL><<<grid, 128, 0, c->aux[1]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                           list(PH_DEAL, rd[PH_DEAL]), count(PH_DEAL, rd[PH_DEAL]), out, v->d_steps);
-      if (drain[PH_SLOW])
-        phase_kernel<PH_SLOW><<<grid, 128, 0, c->aux[2]>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                           list(PH_SLOW, rd[PH_SLOW]), count(PH_SLOW, rd[PH_SLOW]), out, v->d_steps);
-      if (any_aux)
-        for (int a = 0; a < 3; a++) {
-          CK(cudaEventRecord(c->join_ev[a], c->aux[a]));
-          CK(cudaStreamWaitEvent(c->stream, c->join_ev[a], 0));
-        }
+      if (deal_drain) {
+        phase_kernel<PH_ACT, PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                                   list(PH_REACT_D, rd_react_d), count(PH_REACT_D, rd_react_d), out,
+                                                                   v->d_steps);
+        CK(cudaStreamWaitEvent(c->aux[1], c->fork_ev, 0));
+        LAUNCH(PH_DEAL, PH_REACT_D, c->aux[1], rd_deal);
+        CK(cudaEventRecord(c->join_ev[1], c->aux[1]));
+        inflight[1] = true;
+      }
     }
     CK(cudaGetLastError());
+    for (int a = 0; a < 3; a++)
+      if ((rc = join(a))) return rc;
     CK(cudaMemcpyAsync(v->h_counts, v->d_list_counts, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     bool pending = false;
     for (int ph = 0; ph < N_LISTS; ph++) pending |= v->h_counts[ph * 2 + wr[ph]] != 0;
     if (!pending) break;
   }
+#undef LAUNCH
   return RV_OK;
 }
 static bool use_phased() {
