@@ -214,7 +214,8 @@ typedef struct rv_hand_query {  /* 56 bytes */
   uint8_t player_wind, round_wind; /* 0..3 */
   uint8_t honba;
   uint16_t cond;           /* RV_C_* */
-  uint8_t _pad[2];
+  uint8_t sanma;           /* 1: HandEvaluator3P semantics (hand_evaluator_3p.rs: 1m<->9m dora wrap, nukidora, 3-player score) */
+  uint8_t kita_count;      /* Conditions.kita_count (3P) */
 } rv_hand_query;
 
 typedef struct rv_hand_result { /* 40 bytes */

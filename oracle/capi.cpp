@@ -25,6 +25,16 @@ static Action from_rv_action(const rv_action& a) {
 }
 
 static void load_snapshot(GameState& g, const rv_game_state& s) {
+  g.game_mode = s.game_mode;
+  g.sanma = s.game_mode >= 3;
+  g.np = g.sanma ? 3 : 4;
+  const int NP = g.np;
+  if (g.sanma && s.wall_len == 108)
+    for (int i = 0; i < 5; i++) {
+      g.dora_tiles3[i] = s.wall[8 + 2 * i];
+      g.ura_tiles3[i] = s.wall[9 + 2 * i];
+    }
+  for (int p = 0; p < 4; p++) g.n_kita[p] = s.n_kita[p];
   g.wall_abs.assign(s.wall, s.wall + s.wall_len);
   g.wall_tiles.assign(s.wall + s.rinshan_draw_count, s.wall + s.wall_top);
   g.rinshan_draw_count = s.rinshan_draw_count;
@@ -119,6 +129,7 @@ static void load_snapshot(GameState& g, const rv_game_state& s) {
   for (int p = 0; p < NP; p++)
     if (s.active_mask & (1u << p)) g.active_players.push_back((uint8_t)p);
   g.last_error = s.last_error == 0xFF ? -1 : s.last_error;
+  g.stalled = (s.overflow & 2) != 0;
   g.game_mode = s.game_mode;
   g.rule = s.rule_bits;
   g.riichi_sticks = s.riichi_sticks;
@@ -157,8 +168,8 @@ static void eval_one(const rv_hand_query& q, rv_hand_result& r) {
   c.player_wind = q.player_wind;
   c.round_wind = q.round_wind;
   c.honba = q.honba;
-  bool sanma = q._pad[0] & 1;            // rv_hand_query._pad[0]: bit0 = sanma, _pad[1] = kita_count
-  c.kita_count = q._pad[1];
+  bool sanma = q.sanma & 1;
+  c.kita_count = q.kita_count;
   c.is_sanma = sanma;
   c.num_players = sanma ? 3 : 4;
   HandEvaluator he(tiles, melds, sanma);
@@ -274,7 +285,7 @@ void orc_game_free(void* h) { delete (GameState*)h; }
 void orc_game_reset(void* h, int oya, int rw, int honba, uint32_t kyotaku, const uint8_t* wall, const int32_t* scores) {
   GameState* g = (GameState*)h;
   std::vector<uint8_t> w;
-  if (wall) w.assign(wall, wall + 136);
+  if (wall) w.assign(wall, wall + (g->sanma ? 108 : 136));
   g->reset((uint8_t)oya, (uint8_t)rw, (uint8_t)honba, kyotaku, wall ? &w : nullptr, scores);
 }
 int orc_game_legal(void* h, int pid, rv_action* out) {
@@ -290,8 +301,8 @@ int orc_game_legal(void* h, int pid, rv_action* out) {
 }
 void orc_game_step(void* h, const rv_action* acts) {
   GameState* g = (GameState*)h;
-  std::optional<Action> a[NP];
-  for (int p = 0; p < NP; p++)
+  std::optional<Action> a[MAXP];
+  for (int p = 0; p < g->np; p++)
     if (acts[p].type != RV_NO_ACTION) a[p] = from_rv_action(acts[p]);
   g->step(a);
 }
@@ -328,8 +339,8 @@ int64_t orc_run_random(int mode, uint32_t rule, uint64_t seed_base, int64_t n, u
       }
       total += gs.step_count;
       if (scores)
-        for (int i = 0; i < NP; i++) scores[g * NP + i] = gs.players[i].score;
-      if (ranks) gs.ranks(ranks + g * NP);
+        for (int i = 0; i < gs.np; i++) scores[g * MAXP + i] = gs.players[i].score;
+      if (ranks) gs.ranks(ranks + g * MAXP);
       if (done) done[g] = gs.is_done;
       if (steps) steps[g] = gs.step_count;
       if (kyoku) kyoku[g] = gs.kyoku_count;

@@ -24,7 +24,7 @@
 
 namespace orc {
 
-constexpr int NP = 4;
+constexpr int MAXP = 4;  // array capacity; the number of seats is GameState::np (4, or 3 for sanma)
 
 struct Action {
   uint8_t type = RV_PASS;
@@ -77,16 +77,17 @@ struct GameState {
   uint64_t wall_seed = 0, hand_index = 0;
   std::vector<uint8_t> wall_abs;  // absolute (never shrinking) copy for snapshots
 
-  PlayerState players[NP];
+  PlayerState players[MAXP];
   uint8_t current_player = 0;
   uint32_t turn_count = 0;
   bool is_done = false, needs_tsumo = false;
+  bool stalled = false;   // rollout only: the seat to move had no legal action (see random_step)
   uint32_t riichi_sticks = 0;
   uint8_t phase = RV_WAIT_ACT;
   std::vector<uint8_t> active_players;
   int last_discard_pid = -1, last_discard_tile = -1;
-  std::vector<Action> current_claims[NP];
-  bool has_claims_entry[NP] = {false, false, false, false};
+  std::vector<Action> current_claims[MAXP];
+  bool has_claims_entry[MAXP] = {false, false, false, false};
   bool pending_kan = false;
   uint8_t pending_kan_pid = 0;
   Action pending_kan_act;
@@ -95,9 +96,13 @@ struct GameState {
   int riichi_pending_acceptance = -1;
   int drawn_tile = -1;
   uint8_t game_mode = 0;
+  int np = 4;          // state_3p/mod.rs:25 (3) vs state/mod.rs:27 (4)
+  bool sanma = false;
+  uint8_t dora_tiles3[5] = {0, 0, 0, 0, 0}, ura_tiles3[5] = {0, 0, 0, 0, 0};   // state_3p/wall.rs:46-49
+  uint8_t n_kita[MAXP] = {0, 0, 0, 0};   // kita_tiles.len() (state_3p/player.rs:38)
   uint32_t rule = RV_RULE_DEFAULT_TENHOU;
   int last_error = -1;
-  int riichi_sutehais[NP] = {-1, -1, -1, -1}, last_tedashis[NP] = {-1, -1, -1, -1};
+  int riichi_sutehais[MAXP] = {-1, -1, -1, -1}, last_tedashis[MAXP] = {-1, -1, -1, -1};
 
   // event stream
   bool keep_log = true;
@@ -108,6 +113,8 @@ struct GameState {
   std::vector<std::pair<int, WinResult>> win_results;
 
   bool rb(uint32_t bit) const { return (rule & bit) != 0; }
+  int32_t starting_score() const { return sanma ? 35000 : 25000; }   // state_3p/game_mode.rs:31-33
+  int32_t target_score() const { return sanma ? 40000 : 30000; }     // state_3p/mod.rs:1524,1553,1561
 
   // ------------------------------------------------------------ events
   void push_words(const uint32_t* w, int n) {
@@ -125,16 +132,18 @@ struct GameState {
     uint32_t w = w0(type, 1, a, b);
     push_words(&w, 1);
   }
-  void ev_deltas(int type, int a, const int32_t* d) {
-    uint32_t w[5] = {w0(type, 5, a, 0), (uint32_t)d[0], (uint32_t)d[1], (uint32_t)d[2], (uint32_t)d[3]};
-    push_words(w, 5);
+  void ev_deltas(int type, int a, const int32_t* d) {   // 1 + np words
+    uint32_t w[5] = {w0(type, 1 + np, a, 0), (uint32_t)d[0], (uint32_t)d[1], (uint32_t)d[2], (uint32_t)d[3]};
+    push_words(w, 1 + np);
   }
 
   // ------------------------------------------------------------ ctor / reset
   // state/mod.rs:98-167
   GameState(uint8_t mode, uint64_t seed, uint8_t rw, uint32_t rule_bits, bool log_events = true)
       : wall_seed(seed), round_wind(rw), game_mode(mode), rule(rule_bits), keep_log(log_events) {
-    for (auto& p : players) p.score = 25000;
+    sanma = mode >= 3;    // game_variant.rs:12-36
+    np = sanma ? 3 : 4;
+    for (auto& p : players) p.score = starting_score();
     ev_simple(RV_EV_START_GAME);
     _initialize_round(0, rw, 0, 0, nullptr, nullptr);
   }
@@ -142,19 +151,20 @@ struct GameState {
   void reset(uint8_t oya_ = 0, uint8_t rw = 0, uint8_t honba_ = 0, uint32_t kyotaku = 0,
              const std::vector<uint8_t>* wall = nullptr, const int32_t* scores = nullptr) {
     log.clear();
+    stalled = false;
     ev_hash = 0xcbf29ce484222325ull;
     ev_count = 0;
     ev_words = 0;
     step_count = 0;
     kyoku_count = 0;
     ev_simple(RV_EV_START_GAME);
-    int32_t def[NP] = {25000, 25000, 25000, 25000};
+    int32_t def[MAXP] = {starting_score(), starting_score(), starting_score(), starting_score()};
     _initialize_round(oya_, rw, honba_, kyotaku, wall, scores ? scores : def);
   }
 
   // state/wall.rs:36-67 / 69-80
   void wall_shuffle() {
-    wall_tiles = wall_from_seed(wall_seed, hand_index, 136);
+    wall_tiles = wall_from_seed(wall_seed, hand_index, sanma ? 108 : 136);
     hand_index++;
     wall_loaded();
   }
@@ -165,7 +175,17 @@ struct GameState {
   void wall_loaded() {
     wall_abs = wall_tiles;
     dora_indicators.clear();
-    if (wall_tiles.size() > 5) dora_indicators.push_back(wall_tiles[4]);
+    if (sanma) {
+      // state_3p/wall.rs:104-112 (shuffle) and 141-146 (load_wall: t[99],t[97].. == reversed index 8+2i)
+      if (wall_tiles.size() == 108)
+        for (int i = 0; i < 5; i++) {
+          dora_tiles3[i] = wall_tiles[8 + 2 * i];
+          ura_tiles3[i] = wall_tiles[9 + 2 * i];
+        }
+      dora_indicators.push_back(dora_tiles3[0]);
+    } else if (wall_tiles.size() > 5) {
+      dora_indicators.push_back(wall_tiles[4]);
+    }
     rinshan_draw_count = 0;
     pending_kan_dora_count = 0;
     drawable_count = 0;
@@ -181,8 +201,9 @@ struct GameState {
     riichi_sticks = kyotaku;
     round_wind = rw;
     for (auto& p : players) p.reset_round();
+    for (int i = 0; i < MAXP; i++) n_kita[i] = 0;
     is_done = false;
-    for (int i = 0; i < NP; i++) {
+    for (int i = 0; i < np; i++) {
       current_claims[i].clear();
       has_claims_entry[i] = false;
     }
@@ -196,25 +217,25 @@ struct GameState {
     needs_tsumo = true;
     last_discard_pid = last_discard_tile = -1;
     win_results.clear();
-    for (int i = 0; i < NP; i++) riichi_sutehais[i] = last_tedashis[i] = -1;
+    for (int i = 0; i < np; i++) riichi_sutehais[i] = last_tedashis[i] = -1;
     if (scores)
-      for (int i = 0; i < NP; i++) players[i].score = scores[i];
+      for (int i = 0; i < np; i++) players[i].score = scores[i];
     if (wall)
       load_wall(*wall);
     else
       wall_shuffle();
     kyoku_count++;
     for (int r = 0; r < 3; r++)
-      for (int idx = 0; idx < NP; idx++) {
-        int p = (idx + oya) % NP;
+      for (int idx = 0; idx < np; idx++) {
+        int p = (idx + oya) % np;
         for (int k = 0; k < 4; k++)
           if (!wall_tiles.empty()) {
             players[p].hand.push_back(wall_tiles.back());
             wall_tiles.pop_back();
           }
       }
-    for (int idx = 0; idx < NP; idx++) {
-      int p = (idx + oya) % NP;
+    for (int idx = 0; idx < np; idx++) {
+      int p = (idx + oya) % np;
       if (!wall_tiles.empty()) {
         players[p].hand.push_back(wall_tiles.back());
         wall_tiles.pop_back();
@@ -223,17 +244,18 @@ struct GameState {
     for (auto& p : players) std::sort(p.hand.begin(), p.hand.end());
     drawable_count = (uint8_t)(wall_tiles.size() - 14);
 
-    {  // start_kyoku (state/mod.rs:1785-1820)
+    {  // start_kyoku (state/mod.rs:1785-1820); 4P: 19 words, 3P: 15 words (3 scores, 39 tehai bytes)
       uint32_t w[19];
-      w[0] = w0(RV_EV_START_KYOKU, 19, round_wind % 4, oya);
+      int nb = 13 * np, nwords = 2 + np + (nb + 3) / 4;
+      w[0] = w0(RV_EV_START_KYOKU, nwords, round_wind % 4, oya);
       w[1] = (uint32_t)honba | ((uint32_t)dora_indicators[0] << 8) | ((kyotaku & 0xFFFF) << 16);
-      for (int i = 0; i < NP; i++) w[2 + i] = (uint32_t)players[i].score;
+      for (int i = 0; i < np; i++) w[2 + i] = (uint32_t)players[i].score;
       uint8_t th[52];
       memset(th, 0xFF, sizeof th);
-      for (int i = 0; i < NP; i++)
+      for (int i = 0; i < np; i++)
         for (size_t k = 0; k < players[i].hand.size() && k < 13; k++) th[i * 13 + k] = players[i].hand[k];
-      memcpy(&w[6], th, 52);
-      push_words(w, 19);
+      memcpy(&w[2 + np], th, (size_t)((nb + 3) / 4) * 4);
+      push_words(w, nwords);
     }
     current_player = oya;
     phase = RV_WAIT_ACT;
@@ -258,15 +280,21 @@ struct GameState {
     c.riichi = players[pid].riichi_declared;
     c.double_riichi = players[pid].double_riichi_declared;
     c.ippatsu = players[pid].ippatsu_cycle;
-    c.player_wind = (uint8_t)((pid + NP - oya) % NP);
+    c.player_wind = (uint8_t)((pid + np - oya) % np);
     c.round_wind = (uint8_t)(round_wind % 4);
     c.riichi_sticks = riichi_sticks;
     c.honba = honba;
+    c.is_sanma = sanma;
+    c.num_players = (uint8_t)np;
     return c;
   }
   // state/mod.rs:2048-2069
   std::vector<uint8_t> _get_ura_indicators() const {
     std::vector<uint8_t> out;
+    if (sanma) {  // state_3p/mod.rs:1925-1931
+      for (size_t i = 0; i < dora_indicators.size() && i < 5; i++) out.push_back(ura_tiles3[i]);
+      return out;
+    }
     for (size_t i = 0; i < dora_indicators.size(); i++) {
       size_t raw = 5 + 2 * i;
       size_t idx = raw >= rinshan_draw_count ? raw - rinshan_draw_count : 0;
@@ -274,10 +302,15 @@ struct GameState {
     }
     return out;
   }
-  // state/mod.rs:2021-2046
+  // state/mod.rs:2021-2046 ; 3P: state_3p/mod.rs:1893-1915
   void _reveal_kan_dora() {
     size_t count = dora_indicators.size();
     if (count < 5) {
+      if (sanma) {
+        dora_indicators.push_back(dora_tiles3[count]);
+        ev_simple(RV_EV_DORA, 0, dora_indicators.back());
+        return;
+      }
       size_t raw = 4 + 2 * count;
       size_t base = raw >= rinshan_draw_count ? raw - rinshan_draw_count : 0;
       if (base < wall_tiles.size()) {
@@ -316,7 +349,7 @@ struct GameState {
             hand.erase(hand.begin() + i);
             break;
           }
-        HandEvaluator calc(hand, P.melds);
+        HandEvaluator calc(hand, P.melds, sanma);
         WinResult res = calc.calc((uint8_t)drawn_tile, dora_indicators, {}, cond);
         if (res.is_win && (res.yakuman || res.han >= 1)) legals.emplace_back(RV_TSUMO, drawn_tile, std::vector<uint8_t>{}, pid);
       }
@@ -333,7 +366,7 @@ struct GameState {
           if (forbidden(t)) continue;
           std::vector<uint8_t> tmp = P.hand;
           vec_remove_first(tmp, t);
-          HandEvaluator calc(tmp, P.melds);
+          HandEvaluator calc(tmp, P.melds, sanma);
           if (calc.is_tenpai()) legals.emplace_back(RV_DISCARD, t, std::vector<uint8_t>{}, pid);
         }
       } else {
@@ -342,12 +375,12 @@ struct GameState {
         bool all_closed = true;
         for (auto& m : P.melds)
           if (m.opened) all_closed = false;
-        if (P.score >= 1000 && drawable_count >= 4 && all_closed) {
+        if (P.score >= 1000 && (sanma ? drawable_count > 0 : drawable_count >= 4) && all_closed) {   // state_3p/legal_actions.rs:116
           bool can = false;
           for (size_t skip = 0; skip < P.hand.size(); skip++) {
             std::vector<uint8_t> tmp = P.hand;
             tmp.erase(tmp.begin() + skip);
-            HandEvaluator calc(tmp, P.melds);
+            HandEvaluator calc(tmp, P.melds, sanma);
             if (calc.is_tenpai()) {
               can = true;
               break;
@@ -377,7 +410,7 @@ struct GameState {
           if (counts[t34] == 4) {
             std::vector<uint8_t> pre = P.hand;
             vec_remove_first(pre, t);
-            HandEvaluator cpre(pre, P.melds);
+            HandEvaluator cpre(pre, P.melds, sanma);
             auto wpre = cpre.get_waits_u8();
             std::vector<uint8_t> post;
             for (uint8_t x : P.hand)
@@ -389,7 +422,7 @@ struct GameState {
             am.tiles = {lo, (uint8_t)(lo + 1), (uint8_t)(lo + 2), (uint8_t)(lo + 3)};
             am.opened = false;
             mpost.push_back(am);
-            HandEvaluator cpost(post, mpost);
+            HandEvaluator cpost(post, mpost, sanma);
             auto wpost = cpost.get_waits_u8();
             if (wpre == wpost && !wpre.empty())
               legals.emplace_back(RV_ANKAN, lo, am.tiles, pid);
@@ -410,6 +443,10 @@ struct GameState {
           }
         if (distinct >= 9) legals.emplace_back(RV_KYUSHU_KYUHAI, -1, std::vector<uint8_t>{}, pid);
       }
+      // 5. Kita (state_3p/legal_actions.rs:240-243, sanma.rs:146-169)
+      if (sanma && drawn_tile >= 0 && drawable_count > 0)
+        for (uint8_t t : P.hand)
+          if (t / 4 == 30) legals.emplace_back(RV_KITA, t, std::vector<uint8_t>{}, pid);
     } else {
       if (has_claims_entry[pid])
         for (auto& a : current_claims[pid]) legals.push_back(a);
@@ -430,7 +467,7 @@ struct GameState {
       if (d / 4 == tile_class) in_discards = true;
     bool in_missed = P.missed_agari_doujun || (P.riichi_declared && P.missed_agari_riichi);
     if (!in_discards && !in_missed) {
-      HandEvaluator calc(hand, P.melds);
+      HandEvaluator calc(hand, P.melds, sanma);
       Conditions cond = base_cond(i);
       cond.houtei = drawable_count == 0 && !is_rinshan_flag;
       bool furiten = false;
@@ -483,7 +520,7 @@ struct GameState {
       }
     }
     // 3. Chi
-    bool is_shimocha = i == (pid + 1) % 4;
+    bool is_shimocha = !sanma && i == (pid + 1) % 4;   // no chi in 3P (state_3p/legal_actions.rs:386)
     if (!P.riichi_declared && drawable_count > 0 && is_shimocha && hand.size() >= 3) {
       int t_val = tile / 4;
       if (t_val < 27) {
@@ -566,7 +603,7 @@ struct GameState {
       if (cap > 0) {
         uint32_t h = res.han > cap ? res.han - cap : 0;
         res.han = std::max<uint32_t>(h, 13);
-        Score c = calculate_score((uint8_t)res.han, 0, is_oya, tsumo, hb, NP);
+        Score c = calculate_score((uint8_t)res.han, 0, is_oya, tsumo, hb, np);
         res.ron_agari = c.pay_ron;
         res.tsumo_agari_oya = c.pay_tsumo_oya;
         res.tsumo_agari_ko = c.pay_tsumo_ko;
@@ -589,7 +626,8 @@ struct GameState {
     std::vector<uint8_t> ura;
     if (with_ura) ura = _get_ura_indicators();
     uint32_t w[10];
-    w[0] = w0(RV_EV_HORA, 10, actor, target);
+    int nw = 6 + np;   // 4P: 10 words, 3P: 9 words (np deltas)
+    w[0] = w0(RV_EV_HORA, nw, actor, target);
     w[1] = (tsumo ? 1u : 0u) | ((uint32_t)ura.size() << 8) | ((res.han & 0xFF) << 16) | ((res.fu & 0xFF) << 24);
     uint8_t ub[8];
     memset(ub, 0xFF, 8);
@@ -597,20 +635,20 @@ struct GameState {
     ub[5] = res.yakuman ? 1 : 0;
     ub[6] = ub[7] = 0;
     memcpy(&w[2], ub, 8);
-    for (int i = 0; i < 4; i++) w[4 + i] = (uint32_t)deltas[i];
+    for (int i = 0; i < np; i++) w[4 + i] = (uint32_t)deltas[i];
     uint64_t mask = 0;
     for (uint32_t y : res.yaku) mask |= 1ull << y;
-    w[8] = (uint32_t)mask;
-    w[9] = (uint32_t)(mask >> 32);
-    push_words(w, 10);
+    w[4 + np] = (uint32_t)mask;
+    w[5 + np] = (uint32_t)(mask >> 32);
+    push_words(w, nw);
   }
 
   // acts[pid].has_value() <=> key present in the reference's HashMap
-  void step(const std::optional<Action> acts[NP]) {
+  void step(const std::optional<Action> acts[MAXP]) {
     if (is_done) return;
     step_count++;
     // validation (state/mod.rs:340-402)
-    for (int pid = 0; pid < NP; pid++) {
+    for (int pid = 0; pid < np; pid++) {
       if (!acts[pid]) continue;
       auto legals = _get_legal_actions_internal(pid);
       bool ok = false;
@@ -651,7 +689,7 @@ struct GameState {
           _trigger_ryukyoku(RV_RK_KYUSHU);
           break;
         case RV_RIICHI: {
-          if (P.score >= 1000 && drawable_count >= 4 && !P.riichi_declared && !P.riichi_stage) {
+          if (P.score >= 1000 && (sanma ? drawable_count > 0 : drawable_count >= 4) && !P.riichi_declared && !P.riichi_stage) {
             P.riichi_stage = true;
             ev_simple(RV_EV_REACH, pid);
             if (act.tile >= 0) {
@@ -669,7 +707,7 @@ struct GameState {
           uint8_t tile = act.tile >= 0 ? (uint8_t)act.tile : (act.consume.empty() ? 0 : act.consume[0]);
           std::vector<uint8_t> ronners;
           if (rb(RV_RULE_RON_ON_ANKAN_KOKUSHI)) {
-            for (int i = 0; i < NP; i++) {
+            for (int i = 0; i < np; i++) {
               if (i == pid) continue;
               bool in_disc = false;
               for (uint8_t d : players[i].discards)
@@ -678,9 +716,11 @@ struct GameState {
               Conditions cond;
               cond.riichi = players[i].riichi_declared;
               cond.chankan = true;
-              cond.player_wind = (uint8_t)((i + NP - oya) % NP);
+              cond.player_wind = (uint8_t)((i + np - oya) % np);
               cond.round_wind = (uint8_t)(round_wind % 4);
-              HandEvaluator calc(players[i].hand, players[i].melds);
+              cond.is_sanma = sanma;
+              cond.num_players = (uint8_t)np;
+              HandEvaluator calc(players[i].hand, players[i].melds, sanma);
               WinResult res = calc.calc(tile, dora_indicators, {}, cond);
               bool kok = false;
               for (uint32_t y : res.yaku)
@@ -727,11 +767,11 @@ struct GameState {
             _reveal_kan_dora();
           }
           std::vector<uint8_t> ronners;
-          for (int i = 0; i < NP; i++) {
+          for (int i = 0; i < np; i++) {
             if (i == pid) continue;
             Conditions cond = base_cond(i);
             cond.chankan = true;
-            HandEvaluator calc(players[i].hand, players[i].melds);
+            HandEvaluator calc(players[i].hand, players[i].melds, sanma);
             bool furiten = false;
             for (uint8_t w : calc.get_waits_u8()) {
               for (uint8_t d : players[i].discards)
@@ -769,14 +809,15 @@ struct GameState {
           for (auto& p : players)
             if (!p.melds.empty()) all_meldless = false;
           cond.tsumo_first_turn = is_first_turn && all_meldless;
-          HandEvaluator calc(P.hand, P.melds);
+          cond.kita_count = n_kita[pid];   // state_3p/mod.rs:635
+          HandEvaluator calc(P.hand, P.melds, sanma);
           uint8_t win_tile = drawn_tile >= 0 ? (uint8_t)drawn_tile : 0;
           std::vector<uint8_t> ura;
           if (P.riichi_declared) ura = _get_ura_indicators();
           WinResult res = calc.calc(win_tile, dora_indicators, ura, cond);
           cap_double_yakuman(res, pid == oya, true, cond.honba);
           if (res.is_win) {
-            int32_t deltas[NP] = {0, 0, 0, 0};
+            int32_t deltas[MAXP] = {0, 0, 0, 0};
             int32_t total_win = 0;
             int pao_payer = -1;
             int pao_val = 0, total_val = 0;
@@ -791,8 +832,9 @@ struct GameState {
                 }
               }
             if (pao_val > 0) {
-              int32_t unit = pid == oya ? 48000 : 32000;
-              int32_t honba_total = (int32_t)honba * (NP - 1) * 100;
+              // state_3p/mod.rs:713-721: per-yakuman tsumo total depends on the player count
+              int32_t unit = pid == oya ? (np - 1) * 16000 : 16000 + (np - 2) * 8000;
+              int32_t honba_total = (int32_t)honba * (np - 1) * 100;
               if (pao_payer >= 0) {
                 if (rb(RV_RULE_PAO_LIABILITY_ONLY)) {
                   int32_t pao_amt = pao_val * unit + honba_total;
@@ -802,13 +844,13 @@ struct GameState {
                   if (non_pao > 0) {
                     if (pid == oya) {
                       int32_t share = non_pao * 16000;
-                      for (int i = 0; i < NP; i++)
+                      for (int i = 0; i < np; i++)
                         if (i != pid) {
                           deltas[i] -= share;
                           total_win += share;
                         }
                     } else {
-                      for (int i = 0; i < NP; i++)
+                      for (int i = 0; i < np; i++)
                         if (i != pid) {
                           int32_t pay = (i == oya) ? non_pao * 16000 : non_pao * 8000;
                           deltas[i] -= pay;
@@ -823,7 +865,7 @@ struct GameState {
                 }
               }
             } else {
-              for (int i = 0; i < NP; i++)
+              for (int i = 0; i < np; i++)
                 if (i != pid) {
                   int32_t pay = (pid == oya || i != oya) ? (int32_t)res.tsumo_agari_ko : (int32_t)res.tsumo_agari_oya;
                   deltas[i] = -pay;
@@ -833,7 +875,7 @@ struct GameState {
             total_win += (int32_t)(riichi_sticks * 1000);
             riichi_sticks = 0;
             deltas[pid] += total_win;
-            for (int i = 0; i < NP; i++) {
+            for (int i = 0; i < np; i++) {
               players[i].score += deltas[i];
               players[i].score_delta = deltas[i];
             }
@@ -846,16 +888,19 @@ struct GameState {
             ev_hora(pid, pid, true, res, deltas, P.riichi_declared);
             _initialize_next_round(pid == oya, false);
           } else {
-            current_player = (current_player + 1) % NP;
+            current_player = (current_player + 1) % np;
             _deal_next();
           }
           break;
         }
+        case RV_KITA:
+          if (sanma) handle_kita(pid, act);
+          break;
         default:
           break;
       }
     } else {  // WaitResponse (state/mod.rs:900-1314)
-      for (int pid = 0; pid < NP; pid++) {
+      for (int pid = 0; pid < np; pid++) {
         if (!has_claims_entry[pid]) continue;
         bool has_ron = false;
         for (auto& a : current_claims[pid])
@@ -891,20 +936,20 @@ struct GameState {
         }
       }
       if (!ron_claims.empty()) {
-        if ((int)ron_claims.size() >= NP - 1 && rb(RV_RULE_SANCHAHO_IS_DRAW)) {
+        if (!sanma && (int)ron_claims.size() >= np - 1 && rb(RV_RULE_SANCHAHO_IS_DRAW)) {   // 3P has no sanchaho branch
           _trigger_ryukyoku(RV_RK_SANCHAHO);
           return;
         }
         int target_pid = last_discard_pid >= 0 ? last_discard_pid : current_player;
         uint8_t win_tile = last_discard_pid >= 0 ? (uint8_t)last_discard_tile : 0;
         std::stable_sort(ron_claims.begin(), ron_claims.end(), [&](uint8_t a, uint8_t b) {
-          return (a + NP - target_pid) % NP < (b + NP - target_pid) % NP;
+          return (a + np - target_pid) % np < (b + np - target_pid) % np;
         });
-        int32_t total_deltas[NP] = {0, 0, 0, 0};
+        int32_t total_deltas[MAXP] = {0, 0, 0, 0};
         bool oya_won = false, deposit_taken = false, honba_taken = false;
         for (uint8_t w_pid : ron_claims) {
           PlayerState& W = players[w_pid];
-          bool is_chankan = pending_kan;
+          bool is_chankan = pending_kan && pending_kan_act.type != RV_KITA;   // state_3p/mod.rs:896-902
           uint32_t ron_honba = 0;
           if (!honba_taken) {
             honba_taken = true;
@@ -914,7 +959,8 @@ struct GameState {
           cond.houtei = drawable_count == 0 && !is_rinshan_flag;
           cond.chankan = is_chankan;
           cond.honba = ron_honba;
-          HandEvaluator calc(W.hand, W.melds);
+          cond.kita_count = n_kita[w_pid];   // state_3p/mod.rs:926
+          HandEvaluator calc(W.hand, W.melds, sanma);
           std::vector<uint8_t> ura;
           if (W.riichi_declared) ura = _get_ura_indicators();
           WinResult res = calc.calc(win_tile, dora_indicators, ura, cond);
@@ -938,12 +984,12 @@ struct GameState {
               }
               if (has_pao) {
                 int32_t unit = (w_pid == oya) ? 48000 : 32000;
-                int32_t honba_ron = (int32_t)ron_honba * (NP - 1) * 100;
+                int32_t honba_ron = (int32_t)ron_honba * (np - 1) * 100;
                 int32_t split_base = rb(RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
                 pao_amt = split_base / 2 + honba_ron;
               }
             }
-            int32_t this_d[NP] = {0, 0, 0, 0};
+            int32_t this_d[MAXP] = {0, 0, 0, 0};
             this_d[w_pid] += score;
             this_d[pao_payer] -= pao_amt;
             this_d[target_pid] -= score - pao_amt;
@@ -967,7 +1013,7 @@ struct GameState {
             ev_hora(w_pid, target_pid, false, res, this_d, W.riichi_declared);
           }
         }
-        for (int i = 0; i < NP; i++) {
+        for (int i = 0; i < np; i++) {
           players[i].score += total_deltas[i];
           players[i].score_delta = total_deltas[i];
         }
@@ -1031,7 +1077,7 @@ struct GameState {
         needs_tsumo = false;
         drawn_tile = -1;
       } else {
-        for (int i = 0; i < NP; i++) {
+        for (int i = 0; i < np; i++) {
           current_claims[i].clear();
           has_claims_entry[i] = false;
         }
@@ -1039,13 +1085,18 @@ struct GameState {
         if (pending_kan) {
           pending_kan = false;
           Action a = pending_kan_act;
-          _resolve_kan(pending_kan_pid, a);
+          if (a.type == RV_KITA) {   // state_3p/mod.rs:1201-1207
+            for (auto& p : players) p.ippatsu_cycle = false;
+            resolve_kita_rinshan(pending_kan_pid);
+          } else {
+            _resolve_kan(pending_kan_pid, a);
+          }
         } else {
           _accept_riichi();
           turn_count += 1;
-          current_player = (current_player + 1) % NP;
+          current_player = (current_player + 1) % np;
           _deal_next();
-          if (turn_count >= (uint32_t)NP) is_first_turn = false;
+          if (turn_count >= (uint32_t)np) is_first_turn = false;
         }
       }
     }
@@ -1075,6 +1126,7 @@ struct GameState {
   // state/mod.rs:1317-1413
   void _resolve_discard(int pid, uint8_t tile, bool tsumogiri) {
     PlayerState& P = players[pid];
+    if (sanma) pending_kan = false;   // state_3p/mod.rs:1224-1227
     is_rinshan_flag = false;
     P.ippatsu_cycle = false;
     P.discards.push_back(tile);
@@ -1099,14 +1151,14 @@ struct GameState {
     ev_simple(tsumogiri ? RV_EV_DAHAI_TSUMOGIRI : RV_EV_DAHAI, pid, tile);
     P.missed_agari_doujun = false;
     P.nagashi_eligible = P.nagashi_eligible && is_terminal_tile(tile);
-    for (int i = 0; i < NP; i++) {
+    for (int i = 0; i < np; i++) {
       current_claims[i].clear();
       has_claims_entry[i] = false;
     }
     active_players.clear();
     bool has_claims = false;
     std::vector<uint8_t> claim_active;
-    for (int i = 0; i < NP; i++) {
+    for (int i = 0; i < np; i++) {
       if (i == pid) continue;
       auto [legals, missed] = _get_claim_actions_for_player(i, pid, tile);
       if (missed) players[i].missed_agari_doujun = true;
@@ -1124,9 +1176,9 @@ struct GameState {
       if (riichi_pending_acceptance >= 0) _accept_riichi();
       if (!check_abortive_draw()) {
         turn_count += 1;
-        current_player = (uint8_t)((pid + 1) % NP);
+        current_player = (uint8_t)((pid + 1) % np);
         _deal_next();
-        if (turn_count >= (uint32_t)NP) is_first_turn = false;
+        if (turn_count >= (uint32_t)np) is_first_turn = false;
       }
     }
   }
@@ -1193,6 +1245,83 @@ struct GameState {
     }
   }
 
+  // state_3p/sanma.rs:9-144
+  void handle_kita(int pid, const Action& act) {
+    PlayerState& P = players[pid];
+    int tile = -1;
+    if (act.tile >= 0 && act.tile / 4 == 30) {
+      tile = act.tile;
+    } else {
+      for (uint8_t t : P.hand)
+        if (t / 4 == 30) {
+          tile = t;
+          break;
+        }
+      if (tile < 0) tile = act.tile >= 0 ? act.tile : (act.consume.empty() ? 0 : act.consume[0]);
+    }
+    vec_remove_first(P.hand, (uint8_t)tile);
+    n_kita[pid]++;
+    is_first_turn = false;
+    ev_simple(RV_EV_KITA, pid, tile);
+    while (pending_kan_dora_count > 0) {
+      pending_kan_dora_count--;
+      _reveal_kan_dora();
+    }
+    std::vector<uint8_t> ronners;
+    for (int i = 0; i < np; i++) {
+      if (i == pid) continue;
+      HandEvaluator calc(players[i].hand, players[i].melds, sanma);
+      bool furiten = false;
+      for (uint8_t w : calc.get_waits_u8()) {
+        for (uint8_t d : players[i].discards)
+          if (d / 4 == w) furiten = true;
+        if (furiten) break;
+      }
+      if (players[i].missed_agari_riichi || players[i].missed_agari_doujun) furiten = true;
+      if (furiten) continue;
+      Conditions cond = base_cond(i);   // chankan stays false: kita does not award chankan
+      cond.kita_count = n_kita[i];
+      WinResult res = calc.calc((uint8_t)tile, dora_indicators, {}, cond);
+      if (res.is_win && (res.yakuman || res.han >= 1)) {
+        ronners.push_back((uint8_t)i);
+        has_claims_entry[i] = true;
+        current_claims[i].emplace_back(RV_RON, tile, std::vector<uint8_t>{}, i);
+      }
+    }
+    if (!ronners.empty()) {
+      phase = RV_WAIT_RESPONSE;
+      active_players = ronners;
+      last_discard_pid = pid;
+      last_discard_tile = tile;
+      pending_kan = true;
+      pending_kan_pid = (uint8_t)pid;
+      pending_kan_act = Action(RV_KITA, tile, {}, pid);
+    } else {
+      for (auto& p : players) p.ippatsu_cycle = false;
+      resolve_kita_rinshan(pid);
+    }
+  }
+  // state_3p/sanma.rs:171-204
+  void resolve_kita_rinshan(int pid) {
+    if (drawable_count > 0) {
+      while (pending_kan_dora_count > 0) {
+        pending_kan_dora_count--;
+        _reveal_kan_dora();
+      }
+      if (wall_tiles.empty()) return;
+      uint8_t t = wall_tiles.front();
+      wall_tiles.erase(wall_tiles.begin());
+      drawable_count = drawable_count > 0 ? drawable_count - 1 : 0;
+      players[pid].hand.push_back(t);
+      drawn_tile = t;
+      rinshan_draw_count += 1;
+      is_rinshan_flag = true;
+      ev_simple(RV_EV_TSUMO, pid, t);
+      phase = RV_WAIT_ACT;
+      active_players = {(uint8_t)pid};
+    }
+  }
+
   // state/mod.rs:1549-1567
   void _accept_riichi() {
     if (riichi_pending_acceptance >= 0) {
@@ -1239,21 +1368,21 @@ struct GameState {
   // state/mod.rs:1595-1688
   void _initialize_next_round(bool oya_won, bool is_draw) {
     if (is_done) return;
-    for (auto& p : players)
-      if (p.score < 0) {
+    for (int i = 0; i < np; i++)
+      if (players[i].score < 0) {
         _process_end_game();
         return;
       }
     int32_t dealer_score = players[oya].score;
     bool dealer_is_top = true;
-    for (int seat = 0; seat < NP; seat++) {
+    for (int seat = 0; seat < np; seat++) {
       bool ok = seat == oya || dealer_score > players[seat].score || (dealer_score == players[seat].score && oya <= seat);
       if (!ok) dealer_is_top = false;
     }
     bool is_last_regular = false;
-    if (game_mode == 1 || game_mode == 4) is_last_regular = round_wind == 0 && oya == NP - 1;
-    if (game_mode == 2 || game_mode == 5) is_last_regular = round_wind == 1 && oya == NP - 1;
-    if (oya_won && is_last_regular && dealer_is_top && dealer_score >= 30000) {
+    if (game_mode == 1 || game_mode == 4) is_last_regular = round_wind == 0 && oya == np - 1;
+    if (game_mode == 2 || game_mode == 5) is_last_regular = round_wind == 1 && oya == np - 1;
+    if (oya_won && is_last_regular && dealer_is_top && dealer_score >= target_score()) {
       _process_end_game();
       return;
     }
@@ -1262,26 +1391,26 @@ struct GameState {
       next_honba = next_honba == 255 ? 255 : next_honba + 1;
     } else if (is_draw) {
       next_honba = next_honba == 255 ? 255 : next_honba + 1;
-      next_oya = (next_oya + 1) % NP;
+      next_oya = (next_oya + 1) % np;
       if (next_oya == 0) next_rw += 1;
     } else {
       next_honba = 0;
-      next_oya = (next_oya + 1) % NP;
+      next_oya = (next_oya + 1) % np;
       if (next_oya == 0) next_rw += 1;
     }
     int32_t max_score = players[0].score;
-    for (auto& p : players) max_score = std::max(max_score, p.score);
+    for (int i = 0; i < np; i++) max_score = std::max(max_score, players[i].score);
     switch (game_mode) {
       case 1:
       case 4:
-        if (next_rw >= 1 && (max_score >= 30000 || next_rw > 1)) {
+        if (next_rw >= 1 && (max_score >= target_score() || next_rw > 1)) {
           _process_end_game();
           return;
         }
         break;
       case 2:
       case 5:
-        if (next_rw >= 2 && (max_score >= 30000 || next_rw > 2)) {
+        if (next_rw >= 2 && (max_score >= target_score() || next_rw > 2)) {
           _process_end_game();
           return;
         }
@@ -1297,30 +1426,30 @@ struct GameState {
         }
     }
     ev_simple(RV_EV_END_KYOKU);
-    int32_t sc[NP];
-    for (int i = 0; i < NP; i++) sc[i] = players[i].score;
+    int32_t sc[MAXP];
+    for (int i = 0; i < np; i++) sc[i] = players[i].score;
     _initialize_round(next_oya, next_rw, next_honba, riichi_sticks, nullptr, sc);
   }
 
   // state/mod.rs:1846-1968   (reason: rv_ryukyoku_reason code)
   void _trigger_ryukyoku(int reason) {
     _accept_riichi();
-    bool tenpai[NP] = {false, false, false, false};
+    bool tenpai[MAXP] = {false, false, false, false};
     int final_reason = reason;
     std::vector<uint8_t> nagashi;
     if (reason == RV_RK_EXHAUSTIVE) {
-      for (int i = 0; i < NP; i++) {
-        HandEvaluator calc(players[i].hand, players[i].melds);
+      for (int i = 0; i < np; i++) {
+        HandEvaluator calc(players[i].hand, players[i].melds, sanma);
         if (calc.is_tenpai()) tenpai[i] = true;
       }
-      for (int i = 0; i < NP; i++)
+      for (int i = 0; i < np; i++)
         if (players[i].nagashi_eligible) nagashi.push_back((uint8_t)i);
       if (!nagashi.empty()) {
         final_reason = RV_RK_NAGASHI;
         for (uint8_t w : nagashi) {
           bool is_oya = w == oya;
-          Score sr = calculate_score(5, 30, is_oya, true, 0, NP);
-          for (int i = 0; i < NP; i++) {
+          Score sr = calculate_score(5, 30, is_oya, true, 0, np);
+          for (int i = 0; i < np; i++) {
             if (i == w) continue;
             int32_t pay = (is_oya || i != oya) ? (int32_t)sr.pay_tsumo_ko : (int32_t)sr.pay_tsumo_oya;
             players[i].score -= pay;
@@ -1332,20 +1461,21 @@ struct GameState {
       } else {
         int num_tp = 0;
         for (bool t : tenpai) num_tp += t;
-        if (num_tp > 0 && num_tp < NP) {
-          int32_t pk = 3000 / num_tp, pn = 3000 / (NP - num_tp);
-          for (int i = 0; i < NP; i++) {
+        if (num_tp > 0 && num_tp < np) {
+          int32_t pool = sanma ? 2000 : 3000;   // state_3p/game_mode.rs:39-41
+          int32_t pk = pool / num_tp, pn = pool / (np - num_tp);
+          for (int i = 0; i < np; i++) {
             int32_t d = tenpai[i] ? pk : -pn;
             players[i].score += d;
             players[i].score_delta = d;
           }
         }
       }
-    } else if (reason >= RV_RK_ILLEGAL_BASE && reason - RV_RK_ILLEGAL_BASE < NP) {
+    } else if (reason >= RV_RK_ILLEGAL_BASE && reason - RV_RK_ILLEGAL_BASE < np) {
       int pid = reason - RV_RK_ILLEGAL_BASE;
       if (pid == oya) {
-        int32_t penalty = 4000 * (NP - 1), each = penalty / (NP - 1);
-        for (int i = 0; i < NP; i++) {
+        int32_t penalty = 4000 * (np - 1), each = penalty / (np - 1);
+        for (int i = 0; i < np; i++) {
           if (i == pid) {
             players[i].score -= penalty;
             players[i].score_delta = -penalty;
@@ -1355,8 +1485,8 @@ struct GameState {
           }
         }
       } else {
-        int32_t total = 4000 + 2000 * (NP - 2);
-        for (int i = 0; i < NP; i++) {
+        int32_t total = 4000 + 2000 * (np - 2);
+        for (int i = 0; i < np; i++) {
           if (i == pid) {
             players[i].score -= total;
             players[i].score_delta = -total;
@@ -1377,15 +1507,15 @@ struct GameState {
       is_renchan = std::find(nagashi.begin(), nagashi.end(), oya) != nagashi.end();
     else
       is_renchan = true;
-    int32_t d[NP];
-    for (int i = 0; i < NP; i++) d[i] = players[i].score_delta;
+    int32_t d[MAXP];
+    for (int i = 0; i < np; i++) d[i] = players[i].score_delta;
     ev_deltas(RV_EV_RYUKYOKU, final_reason, d);
     _initialize_next_round(is_renchan, true);
   }
 
   // state/mod.rs:1970-2019
   bool check_abortive_draw() {
-    bool turns_ok = true, melds_empty = true;
+    bool turns_ok = !sanma, melds_empty = true;   // sufuurenta is disabled in 3P (state_3p/mod.rs:1860-1863)
     for (auto& p : players) {
       if (p.discards.size() != 1) turns_ok = false;
       if (!p.melds.empty()) melds_empty = false;
@@ -1403,7 +1533,7 @@ struct GameState {
       }
     }
     std::vector<int> owners;
-    for (int pid = 0; pid < NP; pid++)
+    for (int pid = 0; pid < np; pid++)
       for (auto& m : players[pid].melds)
         if (m.meld_type == Daiminkan || m.meld_type == Ankan || m.meld_type == Kakan) owners.push_back(pid);
     if (owners.size() == 4) {
@@ -1415,9 +1545,9 @@ struct GameState {
         return true;
       }
     }
-    bool all_riichi = true;
-    for (auto& p : players)
-      if (!p.riichi_declared) all_riichi = false;
+    bool all_riichi = !sanma;   // suucha riichi is disabled in 3P (state_3p/mod.rs:1886-1888)
+    for (int i = 0; i < np; i++)
+      if (!players[i].riichi_declared) all_riichi = false;
     if (all_riichi) {
       _trigger_ryukyoku(RV_RK_SUUCHA_RIICHI);
       return true;
@@ -1426,10 +1556,10 @@ struct GameState {
   }
 
   // env.rs:673-689
-  void ranks(uint8_t out[NP]) const {
-    int idx[NP] = {0, 1, 2, 3};
-    std::stable_sort(idx, idx + NP, [&](int a, int b) { return players[a].score > players[b].score; });
-    for (int r = 0; r < NP; r++) out[idx[r]] = (uint8_t)(r + 1);
+  void ranks(uint8_t out[MAXP]) const {
+    int idx[MAXP] = {0, 1, 2, 3};
+    std::stable_sort(idx, idx + np, [&](int a, int b) { return players[a].score > players[b].score; });
+    for (int r = 0; r < np; r++) out[idx[r]] = (uint8_t)(r + 1);
   }
 
   // ------------------------------------------------------------ snapshot
@@ -1457,8 +1587,12 @@ struct GameState {
     memset(s.meld_called, 0xFF, sizeof s.meld_called);
     memset(s.river, 0xFF, sizeof s.river);
     memset(s.forbidden, 0xFF, sizeof s.forbidden);
+    memset(s.riichi_decl_idx, 0xFF, sizeof s.riichi_decl_idx);   // unused 3P seat slot reads as None everywhere
+    memset(s.pao, 0xFF, sizeof s.pao);
+    memset(s.riichi_sutehai, 0xFF, sizeof s.riichi_sutehai);
+    memset(s.last_tedashi, 0xFF, sizeof s.last_tedashi);
     memset(s.claims, 0, sizeof s.claims);
-    for (int p = 0; p < NP; p++) {
+    for (int p = 0; p < np; p++) {
       const PlayerState& P = players[p];
       s.hand_len[p] = (uint8_t)P.hand.size();
       for (size_t k = 0; k < P.hand.size() && k < RV_HAND_CAP; k++) s.hand[p][k] = P.hand[k];
@@ -1510,11 +1644,13 @@ struct GameState {
     s.pending_kan_pid = pending_kan ? pending_kan_pid : 0xFF;
     s.pending_kan_type = pending_kan ? pending_kan_act.type : 0xFF;
     s.pending_kan_tile = pending_kan ? (uint8_t)(pending_kan_act.tile >= 0 ? pending_kan_act.tile : pending_kan_act.consume[0]) : 0xFF;
+    for (int p = 0; p < np; p++) s.n_kita[p] = n_kita[p];
     s.active_mask = 0;
     for (uint8_t a : active_players) s.active_mask |= (uint8_t)(1u << a);
     s.last_error = (uint8_t)(last_error < 0 ? 0xFF : last_error);
     s.pending_init[0] = s.pending_init[1] = s.pending_init[2] = 0xFF;
     s.game_mode = game_mode;
+    s.overflow = stalled ? 2 : s.overflow;
     s.rule_bits = (uint8_t)rule;
     s.riichi_sticks = riichi_sticks;
     s.turn_count = turn_count;
@@ -1525,7 +1661,7 @@ struct GameState {
     s.ev_count = ev_count;
     s.ev_words = ev_words;
     // derived caches recomputed from scratch (the CUDA path maintains them incrementally)
-    for (int p = 0; p < NP; p++) {
+    for (int p = 0; p < np; p++) {
       const PlayerState& P = players[p];
       static const uint32_t P5[9] = {1, 5, 25, 125, 625, 3125, 15625, 78125, 390625};
       for (uint8_t t : P.hand) {
@@ -1534,7 +1670,7 @@ struct GameState {
         s.c_key[p][su] += P5[pos];
       }
       for (uint8_t d : P.discards) s.c_river_kinds[p] |= 1ull << (d / 4);
-      HandEvaluator he(P.hand, P.melds);
+      HandEvaluator he(P.hand, P.melds, sanma);
       for (uint8_t w : he.get_waits_u8()) s.c_waits[p] |= 1ull << w;
     }
     s.ev_hash = ev_hash;
@@ -1555,12 +1691,20 @@ inline uint32_t agent_pick(uint64_t agent_seed, uint64_t game_id, uint32_t step_
 // One env step with the keyed agent. Returns false if the game is done.
 inline bool random_step(GameState& g, uint64_t agent_seed, uint64_t game_id) {
   if (g.is_done) return false;
-  std::optional<Action> acts[NP];
+  std::optional<Action> acts[MAXP];
   uint32_t sc = g.step_count;
   if (g.phase == RV_WAIT_ACT) {
     int pid = g.current_player;
     auto legals = g._get_legal_actions_internal(pid);
-    if (!legals.empty()) acts[pid] = legals[agent_pick(agent_seed, game_id, sc, pid, (uint32_t)legals.size())];
+    if (legals.empty()) {
+      // Dead end of the reference (3P: riichi declared, then kita + rinshan draws leave no tenpai-keeping discard;
+      // `random.choice([])` raises in RandomAgent).  The rollout retires the game: done + stalled flag.
+      g.step_count++;
+      g.is_done = true;
+      g.stalled = true;
+      return true;
+    }
+    acts[pid] = legals[agent_pick(agent_seed, game_id, sc, pid, (uint32_t)legals.size())];
   } else {
     for (uint8_t pid : g.active_players) {
       auto legals = g._get_legal_actions_internal(pid);

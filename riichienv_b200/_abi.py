@@ -75,7 +75,7 @@ class HandQuery(C.Structure):
     _fields_ = [
         ("tiles", u8 * 14), ("n_tiles", u8), ("n_melds", u8), ("meld_type", u8 * 4), ("meld_tiles", (u8 * 4) * 4),
         ("win_tile", u8), ("n_dora", u8), ("n_ura", u8), ("dora_ind", u8 * 5), ("ura_ind", u8 * 5),
-        ("player_wind", u8), ("round_wind", u8), ("honba", u8), ("cond", u16), ("_pad", u8 * 2),
+        ("player_wind", u8), ("round_wind", u8), ("honba", u8), ("cond", u16), ("sanma", u8), ("kita_count", u8),
     ]
 
 

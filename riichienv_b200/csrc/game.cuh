@@ -19,7 +19,9 @@
 namespace rv {
 
 typedef rv_game_state G;
-constexpr int NP = 4;
+constexpr int MAXP = 4;   // seat capacity of the record; the seat count is num_players(g): 4, or 3 for sanma
+__device__ __forceinline__ bool is_sanma(const rv_game_state& g) { return g.game_mode >= 3; }   // game_variant.rs:12-36
+__device__ __forceinline__ int num_players(const rv_game_state& g) { return g.game_mode >= 3 ? 3 : 4; }
 
 struct Ctx {
   Tables T;
@@ -163,16 +165,25 @@ __device__ __forceinline__ uint32_t base_cond(const G& g, int p) {
   return c;
 }
 // HandEvaluator::new(hand, melds).calc(win_tile, dora, ura, cond) for a seat
-__device__ inline WinRes seat_calc(const Ctx& cx, const G& g, int p, int win_tile, uint32_t cond, bool with_ura, uint32_t honba) {
+// ura indicators of the revealed doras.  4P: wall[5+2i] while still in the Vec (state/mod.rs:2048-2058; absolute index:
+// the Vec lost rinshan_draw_count front tiles).  3P: pre-extracted tiles[9+2i] (state_3p/wall.rs:104-112).
+__device__ __forceinline__ int ura_indicators(const G& g, uint8_t* ura) {
+  int n = 0;
+  bool sanma = is_sanma(g);
+  for (int i = 0; i < g.n_dora; i++) {
+    int idx = (sanma ? 9 : 5) + 2 * i;
+    if (sanma || idx < g.wall_top) ura[n++] = g.wall[idx];
+  }
+  return n;
+}
+__device__ inline WinRes seat_calc(const Ctx& cx, const G& g, int p, int win_tile, uint32_t cond, bool with_ura, uint32_t honba,
+                                   bool with_kita = false) {
+  const int np = num_players(g);
   uint8_t ura[5];
-  int n_ura = 0;
-  if (with_ura)
-    for (int i = 0; i < g.n_dora; i++) {
-      int idx = 5 + 2 * i;                       // state/mod.rs:2048-2058 (absolute index: the Vec lost
-      if (idx < g.wall_top) ura[n_ura++] = g.wall[idx];  //  rinshan_draw_count front tiles)
-    }
+  int n_ura = with_ura ? ura_indicators(g, ura) : 0;
   return hand_calc(cx.T, g.hand[p], g.hand_len[p], g.n_melds[p], g.meld_type[p], g.meld_tiles[p], win_tile, g.dora_ind,
-                   g.n_dora, ura, n_ura, cond, (p + NP - g.oya) % NP, g.round_wind % 4, honba);
+                   g.n_dora, ura, n_ura, cond, (p + np - g.oya) % np, g.round_wind % 4, honba, is_sanma(g),
+                   with_kita ? g.n_kita[p] : 0);
 }
 
 // ------------------------------------------------------------------ wall (state/wall.rs:36-88)
@@ -287,8 +298,9 @@ __device__ void next_round(const Ctx& cx, G& g, bool oya_won, bool is_draw);
 __device__ __noinline__ void reveal_kan_dora(const Ctx& cx, G& g) {
   int count = g.n_dora;
   if (count < 5) {
-    int idx = 4 + 2 * count;
-    if (idx < g.wall_top) {
+    bool sanma = is_sanma(g);
+    int idx = (sanma ? 8 : 4) + 2 * count;   // 3P: pre-extracted dora_indicator_tiles (state_3p/mod.rs:1893-1915)
+    if (sanma || idx < g.wall_top) {
       g.dora_ind[count] = g.wall[idx];
       g.n_dora = (uint8_t)(count + 1);
       ev_simple(cx, g, RV_EV_DORA, 0, g.wall[idx]);
@@ -340,12 +352,13 @@ __device__ __noinline__ void deal_next(const Ctx& cx, G& g) {
 // `custom_wall`: nullptr -> seeded shuffle; else 136 tids in the order passed to reset(wall=) (load_wall reverses).
 __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_wind, int honba, uint32_t kyotaku,
                                   const uint8_t* custom_wall, const int32_t* scores) {
+  const int np = num_players(g);
   RV_STAT(2);
   g.oya = g.kyoku_idx = g.current_player = (uint8_t)oya;
   g.honba = (uint8_t)honba;
   g.riichi_sticks = kyotaku;
   g.round_wind = (uint8_t)round_wind;
-  for (int p = 0; p < NP; p++) {  // PlayerState::reset_round (state/player.rs:66-86)
+  for (int p = 0; p < MAXP; p++) {  // PlayerState::reset_round (state/player.rs:66-86); the unused 3P slot is reset too
     for (int i = 0; i < RV_HAND_CAP; i++) g.hand[p][i] = RV_NONE;
     g.hand_len[p] = 0;
     for (int m = 0; m < 4; m++) {
@@ -367,7 +380,11 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
     for (int k = 0; k < 4; k++) g.c_cnt[p][k] = 0, g.c_key[p][k] = 0;
     g.c_river_kinds[p] = 0;
     g.c_waits[p] = 0;
-    if (scores) g.score[p] = scores[p];
+    if (scores && p < np) g.score[p] = scores[p];
+  }
+  if (np == 3) {   // the record has four seat slots; the unused one stays inert
+    g.flags[3] = 0;
+    g.score[3] = 0;
   }
   g.is_done = 0;
   g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
@@ -380,49 +397,53 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   g.needs_tsumo = 1;
   g.last_discard_pid = g.last_discard_tile = RV_NONE;
   g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
+  const int wl = np == 3 ? 108 : 136;
   if (custom_wall) {
-    for (int i = 0; i < 136; i++) g.wall[i] = custom_wall[135 - i];  // wall.rs:69-72
+    for (int i = 0; i < wl; i++) g.wall[i] = custom_wall[wl - 1 - i];  // wall.rs:69-72 / state_3p/wall.rs:148-149
   } else {
     uint8_t w[136];
-    wall_from_seed(g.seed, g.hand_index, 136, w);
+    wall_from_seed(g.seed, g.hand_index, wl, w);
     g.hand_index++;
-    for (int i = 0; i < 136; i++) g.wall[i] = w[i];
+    for (int i = 0; i < wl; i++) g.wall[i] = w[i];
   }
-  g.wall_len = 136;
-  g.wall_top = 136;
+  for (int i = wl; i < 136; i++) g.wall[i] = RV_NONE;
+  g.wall_len = (uint8_t)wl;
+  g.wall_top = (uint8_t)wl;
   g.n_dora = 1;
-  g.dora_ind[0] = g.wall[4];
+  g.dora_ind[0] = g.wall[np == 3 ? 8 : 4];   // state_3p/wall.rs:104-112
   for (int i = 1; i < 5; i++) g.dora_ind[i] = RV_NONE;
   g.kyoku_count++;
   // deal: 3 x (4 tiles per seat from oya), then 1 each; tiles pop from the back
   for (int r = 0; r < 3; r++)
-    for (int idx = 0; idx < NP; idx++) {
-      int p = (idx + oya) % NP;
+    for (int idx = 0; idx < np; idx++) {
+      int p = (idx + oya) % np;
       for (int k = 0; k < 4; k++) hand_push(g, p, g.wall[--g.wall_top]);
     }
-  for (int idx = 0; idx < NP; idx++) {
-    int p = (idx + oya) % NP;
+  for (int idx = 0; idx < np; idx++) {
+    int p = (idx + oya) % np;
     hand_push(g, p, g.wall[--g.wall_top]);
   }
-  for (int p = 0; p < NP; p++) {
+  for (int p = 0; p < np; p++) {
     hand_sort(g, p);
     if (p != oya) waits_update(cx.T, g, p);   // the dealer draws a 14th tile right below
   }
   g.drawable_count = (uint8_t)(g.wall_top - 14);
-  {
+  {  // start_kyoku: 4P 19 words, 3P 15 words (np scores, 13*np tehai bytes)
     uint32_t w[19];
-    w[0] = ev_w0(RV_EV_START_KYOKU, 19, round_wind % 4, oya);
+    const int nb = 13 * np, ntw = (nb + 3) / 4, nwords = 2 + np + ntw;
+    w[0] = ev_w0(RV_EV_START_KYOKU, nwords, round_wind % 4, oya);
     w[1] = (uint32_t)honba | ((uint32_t)g.dora_ind[0] << 8) | ((kyotaku & 0xFFFF) << 16);
-    for (int i = 0; i < NP; i++) w[2 + i] = (uint32_t)g.score[i];
-    for (int k = 0; k < 13; k++) {
+    for (int i = 0; i < np; i++) w[2 + i] = (uint32_t)g.score[i];
+    for (int k = 0; k < ntw; k++) {
       uint32_t v = 0;
       for (int b = 0; b < 4; b++) {
-        int flat = k * 4 + b, p = flat / 13, i = flat % 13;
-        v |= (uint32_t)g.hand[p][i] << (8 * b);
+        int flat = k * 4 + b;
+        int t = flat < nb ? g.hand[flat / 13][flat % 13] : RV_NONE;
+        v |= (uint32_t)t << (8 * b);
       }
-      w[6 + k] = v;
+      w[2 + np + k] = v;
     }
-    ev_push(cx, g, w, 19);
+    ev_push(cx, g, w, nwords);
   }
   g.phase = RV_WAIT_ACT;
   g.active_mask = (uint8_t)(1u << oya);
@@ -439,13 +460,15 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
 // RiichiEnv::new + reset (env.rs:82-118, 799-851): fresh game, logs cleared
 __device__ __noinline__ void game_reset(const Ctx& cx, G& g, int oya, int round_wind, int honba, uint32_t kyotaku,
                                   const uint8_t* custom_wall, const int32_t* scores) {
+  const int np = num_players(g);
   g.ev_hash = 0xcbf29ce484222325ull;
   g.ev_count = g.ev_words = g.step_count = g.kyoku_count = 0;
   g.last_error = RV_NONE;   // NOTE: the reference never clears last_error on reset (state/mod.rs:171-187); a fresh
                             // VecEnv has none, and rv_vec_reset is documented to clear it.
   g.overflow = 0;
   ev_simple(cx, g, RV_EV_START_GAME);
-  int32_t def[NP] = {25000, 25000, 25000, 25000};
+  const int32_t st = np == 3 ? 35000 : 25000;   // state_3p/game_mode.rs:31-33
+  int32_t def[MAXP] = {st, st, st, st};
   init_round(cx, g, oya, round_wind, honba, kyotaku, custom_wall, scores ? scores : def);
 }
 
@@ -458,10 +481,11 @@ __device__ __noinline__ void end_game(const Ctx& cx, G& g) {
 
 // state/mod.rs:1595-1688
 __device__ __noinline__ void next_round(const Ctx& cx, G& g, bool oya_won, bool is_draw) {
+  const int np = num_players(g);
   if (g.is_done) return;
   int32_t mx = g.score[0];
   bool tobi = false;
-  for (int p = 0; p < NP; p++) {
+  for (int p = 0; p < np; p++) {
     if (g.score[p] < 0) tobi = true;
     mx = max(mx, g.score[p]);
   }
@@ -472,13 +496,14 @@ __device__ __noinline__ void next_round(const Ctx& cx, G& g, bool oya_won, bool 
   int oya = g.oya;
   int32_t ds = g.score[oya];
   bool top = true;
-  for (int s = 0; s < NP; s++)
+  for (int s = 0; s < np; s++)
     if (!(s == oya || ds > g.score[s] || (ds == g.score[s] && oya <= s))) top = false;
   int gm = g.game_mode;
   bool last = false;
-  if (gm == 1 || gm == 4) last = g.round_wind == 0 && oya == NP - 1;
-  if (gm == 2 || gm == 5) last = g.round_wind == 1 && oya == NP - 1;
-  if (oya_won && last && top && ds >= 30000) {
+  if (gm == 1 || gm == 4) last = g.round_wind == 0 && oya == np - 1;
+  if (gm == 2 || gm == 5) last = g.round_wind == 1 && oya == np - 1;
+  const int32_t target = np == 3 ? 40000 : 30000;   // state_3p/mod.rs:1524,1553,1561
+  if (oya_won && last && top && ds >= target) {
     end_game(cx, g);
     return;
   }
@@ -487,12 +512,12 @@ __device__ __noinline__ void next_round(const Ctx& cx, G& g, bool oya_won, bool 
     nh = nh == 255 ? 255 : nh + 1;
   } else {
     nh = is_draw ? (nh == 255 ? 255 : nh + 1) : 0;
-    no = (no + 1) % NP;
+    no = (no + 1) % np;
     if (no == 0) nw += 1;
   }
   bool fin;
-  if (gm == 1 || gm == 4) fin = nw >= 1 && (mx >= 30000 || nw > 1);
-  else if (gm == 2 || gm == 5) fin = nw >= 2 && (mx >= 30000 || nw > 2);
+  if (gm == 1 || gm == 4) fin = nw >= 1 && (mx >= target || nw > 1);
+  else if (gm == 2 || gm == 5) fin = nw >= 2 && (mx >= target || nw > 2);
   else if (gm == 0 || gm == 3) fin = true;
   else fin = nw >= 1;
   if (fin) {
@@ -518,22 +543,23 @@ __device__ __forceinline__ bool seat_tenpai(const Ctx& cx, const G& g, int p) { 
 
 // state/mod.rs:1846-1968
 __device__ __noinline__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason) {
+  const int np = num_players(g);
   accept_riichi(cx, g);
-  bool tenpai[NP] = {false, false, false, false};
+  bool tenpai[MAXP] = {false, false, false, false};
   int final_reason = reason;
   int nagashi_mask = 0;
   int oya = g.oya;
   if (reason == RV_RK_EXHAUSTIVE) {
-    for (int p = 0; p < NP; p++) {
+    for (int p = 0; p < np; p++) {
       tenpai[p] = seat_tenpai(cx, g, p);
       if (g.flags[p] & RV_F_NAGASHI_ELIGIBLE) nagashi_mask |= 1 << p;
     }
     if (nagashi_mask) {
       final_reason = RV_RK_NAGASHI;
-      for (int w = 0; w < NP; w++) {
+      for (int w = 0; w < np; w++) {
         if (!(nagashi_mask & (1 << w))) continue;
         bool is_oya = w == oya;   // mangan tsumo: calculate_score(5,30,is_oya,true,0,4) -> oya 4000 / ko 2000
-        for (int i = 0; i < NP; i++) {
+        for (int i = 0; i < np; i++) {
           if (i == w) continue;
           int32_t pay = is_oya ? 4000 : (i == oya ? 4000 : 2000);
           g.score[i] -= pay;
@@ -543,38 +569,41 @@ __device__ __noinline__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason) {
         }
       }
     } else {
-      int ntp = tenpai[0] + tenpai[1] + tenpai[2] + tenpai[3];
-      if (ntp > 0 && ntp < NP) {
-        int32_t pk = 3000 / ntp, pn = 3000 / (NP - ntp);
-        for (int i = 0; i < NP; i++) {
+      int ntp = 0;
+      for (int i = 0; i < np; i++) ntp += tenpai[i];
+      if (ntp > 0 && ntp < np) {
+        const int32_t pool = np == 3 ? 2000 : 3000;   // state_3p/game_mode.rs:39-41
+        int32_t pk = pool / ntp, pn = pool / (np - ntp);
+        for (int i = 0; i < np; i++) {
           int32_t d = tenpai[i] ? pk : -pn;
           g.score[i] += d;
           g.score_delta[i] = d;
         }
       }
     }
-  } else if (reason >= RV_RK_ILLEGAL_BASE && reason - RV_RK_ILLEGAL_BASE < NP) {
+  } else if (reason >= RV_RK_ILLEGAL_BASE && reason - RV_RK_ILLEGAL_BASE < np) {
     int pid = reason - RV_RK_ILLEGAL_BASE;
-    for (int i = 0; i < NP; i++) {
+    for (int i = 0; i < np; i++) {
       int32_t d;
-      if (pid == oya) d = (i == pid) ? -12000 : 4000;
-      else d = (i == pid) ? -8000 : (i == oya ? 4000 : 2000);
+      if (pid == oya) d = (i == pid) ? -4000 * (np - 1) : 4000;
+      else d = (i == pid) ? -(4000 + 2000 * (np - 2)) : (i == oya ? 4000 : 2000);
       g.score[i] += d;
       g.score_delta[i] = d;
     }
   }
   bool renchan = final_reason == RV_RK_EXHAUSTIVE ? tenpai[oya]
                : final_reason == RV_RK_NAGASHI ? ((nagashi_mask >> oya) & 1) != 0 : true;
-  uint32_t w[5] = {ev_w0(RV_EV_RYUKYOKU, 5, final_reason, 0), (uint32_t)g.score_delta[0], (uint32_t)g.score_delta[1],
+  uint32_t w[5] = {ev_w0(RV_EV_RYUKYOKU, 1 + np, final_reason, 0), (uint32_t)g.score_delta[0], (uint32_t)g.score_delta[1],
                    (uint32_t)g.score_delta[2], (uint32_t)g.score_delta[3]};
-  ev_push(cx, g, w, 5);
+  ev_push(cx, g, w, 1 + np);
   next_round(cx, g, renchan, true);
 }
 
 // state/mod.rs:1970-2019
 __device__ __noinline__ bool check_abortive_draw(const Ctx& cx, G& g) {
-  bool turns_ok = true;
-  for (int p = 0; p < NP; p++)
+  const int np = num_players(g);
+  bool turns_ok = np == 4;   // sufuurenta and suucha riichi do not exist in 3P (state_3p/mod.rs:1860-1888)
+  for (int p = 0; p < np; p++)
     if (g.n_river[p] != 1) turns_ok = false;
   if (turns_ok && all_meldless(g)) {
     int first = g.river[0][0] >> 2;
@@ -586,7 +615,7 @@ __device__ __noinline__ bool check_abortive_draw(const Ctx& cx, G& g) {
   }
   int kans = 0, first_owner = -1;
   bool same = true;
-  for (int p = 0; p < NP; p++)
+  for (int p = 0; p < np; p++)
     for (int m = 0; m < g.n_melds[p]; m++)
       if (g.meld_type[p][m] >= RV_MELD_DAIMINKAN) {
         kans++;
@@ -597,7 +626,7 @@ __device__ __noinline__ bool check_abortive_draw(const Ctx& cx, G& g) {
     trigger_ryukyoku(cx, g, RV_RK_SUUKANSANSEN);
     return true;
   }
-  if ((g.flags[0] & g.flags[1] & g.flags[2] & g.flags[3]) & RV_F_RIICHI_DECLARED) {
+  if (np == 4 && ((g.flags[0] & g.flags[1] & g.flags[2] & g.flags[3]) & RV_F_RIICHI_DECLARED)) {
     trigger_ryukyoku(cx, g, RV_RK_SUUCHA_RIICHI);
     return true;
   }
@@ -621,6 +650,7 @@ __device__ inline void claim_push(G& g, int i, uint32_t a) {
 // Fast path: the cached wait mask / histogram answer "nothing to claim" with a few bit tests;
 // the hand is only scanned for tile ids when a pon / chi pattern actually exists.
 __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int tile) {
+  const int np = num_players(g);
   bool missed = false;
   g.n_claims[i] = 0;
   int kind = tile >> 2;
@@ -667,7 +697,7 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
     if (cnt >= 3) claim_push(g, i, pack_act(RV_DAIMINKAN, tile, match[0], match[1]));
   }
   // 3. Chi (shimocha only, number suits)
-  if (i == (pid + 1) % NP && su < 3) {
+  if (np == 4 && i == (pid + 1) % np && su < 3) {   // no chi in 3P (state_3p/legal_actions.rs:386)
     auto at = [&](int r) -> int { return (r < 0 || r > 8) ? 0 : (int)((sc >> (4 * r)) & 15); };
     int m2 = at(r9 - 2), m1 = at(r9 - 1), p1 = at(r9 + 1), p2 = at(r9 + 2);
     if ((m2 && m1) || (m1 && p1) || (p1 && p2)) {
@@ -889,7 +919,8 @@ __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnI
   if (stage) {
     ti.tenpai_keep = tenpai_discard_mask(cx, g, pid, false);
   } else if (!riichi) {
-    if (g.score[pid] >= 1000 && g.drawable_count >= 4 && !any_open_meld(g, pid))
+    // 3P needs only one drawable tile (state_3p/legal_actions.rs:116)
+    if (g.score[pid] >= 1000 && (is_sanma(g) ? g.drawable_count > 0 : g.drawable_count >= 4) && !any_open_meld(g, pid))
       ti.can_riichi = any_tenpai_discard(c, si, hl, nm);
   }
   if (g.drawable_count > 0 && drawn != RV_NONE) {
@@ -972,6 +1003,10 @@ __device__ inline int enum_turn_actions(const G& g, int pid, const TurnInfo& ti,
     }
   }
   if (ti.kyushu) { f(pack_act(RV_KYUSHU_KYUHAI, RV_NONE, RV_NONE, RV_NONE)); n++; }
+  // Kita: one action per North tile in hand (state_3p/sanma.rs:146-169)
+  if (is_sanma(g) && drawn != RV_NONE && g.drawable_count > 0)
+    for (int k = 0; k < hl; k++)
+      if ((g.hand[pid][k] >> 2) == 30) { f(pack_act(RV_KITA, g.hand[pid][k], RV_NONE, RV_NONE)); n++; }
   return n;
 }
 
@@ -1026,6 +1061,7 @@ __device__ __forceinline__ int yakuman_val(const G& g, int yid) {
 }
 // state/mod.rs:720-745 / 1009-1034
 __device__ __noinline__ void cap_double_yakuman(const G& g, WinRes& r, bool is_oya, bool tsumo, uint32_t honba) {
+  const int np = num_players(g);
   if (r.yakuman && r.han > 13) {
     int cap = 0;
     if (((r.yaku_mask >> 47) & 1) && !rule(g, RV_RULE_JUNSEI_CHUUREN_DOUBLE)) cap += 13;
@@ -1034,7 +1070,7 @@ __device__ __noinline__ void cap_double_yakuman(const G& g, WinRes& r, bool is_o
     if (((r.yaku_mask >> 50) & 1) && !rule(g, RV_RULE_DAISUUSHII_DOUBLE)) cap += 13;
     if (cap > 0) {
       r.han = max(r.han - cap, 13);
-      ScoreRes s = calc_score(r.han, 0, is_oya, tsumo, honba, NP);
+      ScoreRes s = calc_score(r.han, 0, is_oya, tsumo, honba, np);
       r.ron = s.pay_ron;
       r.oya = s.pay_oya;
       r.ko = s.pay_ko;
@@ -1043,27 +1079,26 @@ __device__ __noinline__ void cap_double_yakuman(const G& g, WinRes& r, bool is_o
 }
 __device__ __noinline__ void ev_hora(const Ctx& cx, G& g, int actor, int target, bool tsumo, const WinRes& r, const int32_t* d,
                                bool with_ura) {
+  const int np = num_players(g);
   uint8_t ub[8] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE, RV_NONE, 0, 0, 0};
-  int n_ura = 0;
-  if (with_ura)
-    for (int i = 0; i < g.n_dora; i++) {
-      int idx = 5 + 2 * i;
-      if (idx < g.wall_top) ub[n_ura++] = g.wall[idx];
-    }
+  int n_ura = with_ura ? ura_indicators(g, ub) : 0;
+  for (int i = n_ura; i < 5; i++) ub[i] = RV_NONE;
   ub[5] = r.yakuman ? 1 : 0;
   uint32_t w[10];
-  w[0] = ev_w0(RV_EV_HORA, 10, actor, target);
+  const int nw = 6 + np;   // 4P: 10 words, 3P: 9 words
+  w[0] = ev_w0(RV_EV_HORA, nw, actor, target);
   w[1] = (tsumo ? 1u : 0u) | ((uint32_t)n_ura << 8) | ((uint32_t)(r.han & 0xFF) << 16) | ((uint32_t)(r.fu & 0xFF) << 24);
   w[2] = ub[0] | (ub[1] << 8) | (ub[2] << 16) | ((uint32_t)ub[3] << 24);
   w[3] = ub[4] | (ub[5] << 8);
-  for (int i = 0; i < 4; i++) w[4 + i] = (uint32_t)d[i];
-  w[8] = (uint32_t)r.yaku_mask;
-  w[9] = (uint32_t)(r.yaku_mask >> 32);
-  ev_push(cx, g, w, 10);
+  for (int i = 0; i < np; i++) w[4 + i] = (uint32_t)d[i];
+  w[4 + np] = (uint32_t)r.yaku_mask;
+  w[5 + np] = (uint32_t)(r.yaku_mask >> 32);
+  ev_push(cx, g, w, nw);
 }
 
 // ------------------------------------------------------------------ kan (state/mod.rs:1415-1547)
 __device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_action& act) {
+  const int np = num_players(g);
   int c_ev[4] = {RV_NONE, RV_NONE, RV_NONE, RV_NONE};
   for (int k = 0; k < act.n_consume && k < 4; k++) c_ev[k] = act.consume[k];
   if (act.type != RV_KAKAN) {
@@ -1093,7 +1128,7 @@ __device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_
     if (act.type == RV_DAIMINKAN) register_pao(g, pid, g.last_discard_tile, g.last_discard_pid);
   }
   g.is_first_turn = 0;
-  for (int p = 0; p < NP; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
+  for (int p = 0; p < np; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
   if (g.drawable_count > 0) {
     int t = g.wall[g.rinshan_draw_count];   // Vec::remove(0)
     g.drawable_count--;
@@ -1119,6 +1154,8 @@ __device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_
 
 // ------------------------------------------------------------------ discard (state/mod.rs:1317-1413)
 __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int tile, bool tsumogiri) {
+  const int np = num_players(g);
+  if (np == 3) g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;   // state_3p/mod.rs:1224-1227
   g.is_rinshan_flag = 0;
   g.flags[pid] &= ~RV_F_IPPATSU_CYCLE;
   int nr = g.n_river[pid];
@@ -1149,10 +1186,10 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
   ev_simple(cx, g, tsumogiri ? RV_EV_DAHAI_TSUMOGIRI : RV_EV_DAHAI, pid, tile);
   g.flags[pid] &= ~RV_F_MISSED_AGARI_DOUJUN;
   if (!tid_terminal(tile)) g.flags[pid] &= ~RV_F_NAGASHI_ELIGIBLE;
-  for (int i = 0; i < NP; i++) g.n_claims[i] = 0;
+  for (int i = 0; i < np; i++) g.n_claims[i] = 0;
   g.active_mask = 0;
   int claim_mask = 0;
-  for (int i = 0; i < NP; i++) {
+  for (int i = 0; i < np; i++) {
     if (i == pid) continue;
     bool missed = gen_claims(cx, g, i, pid, tile);
     if (missed) g.flags[i] |= RV_F_MISSED_AGARI_DOUJUN;
@@ -1165,34 +1202,36 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
     accept_riichi(cx, g);
     if (!check_abortive_draw(cx, g)) {
       g.turn_count++;
-      g.current_player = (uint8_t)((pid + 1) % NP);
+      g.current_player = (uint8_t)((pid + 1) % np);
       deal_next(cx, g);
-      if (g.turn_count >= (uint32_t)NP) g.is_first_turn = 0;
+      if (g.turn_count >= (uint32_t)np) g.is_first_turn = 0;
     }
   }
 }
 
 // chankan candidates after a kakan (state/mod.rs:588-684) / kokushi-on-ankan (485-547)
-__device__ __noinline__ int chankan_ronners(const Ctx& cx, G& g, int pid, int tile, bool ankan_kokushi_only) {
+// mode 0: kakan (chankan yaku), 1: kokushi-only ron on ankan, 2: ron on a kita tile (no chankan yaku, sanma.rs:66-126)
+__device__ __noinline__ int chankan_ronners(const Ctx& cx, G& g, int pid, int tile, int mode) {
+  const int np = num_players(g);
   int mask = 0;
   int kind = tile >> 2;
-  for (int i = 0; i < NP; i++) {
+  for (int i = 0; i < np; i++) {
     if (i == pid) continue;
     uint64_t waits = g.c_waits[i];
     if (!((waits >> kind) & 1)) continue;
     uint64_t rk = g.c_river_kinds[i];
     uint32_t f = g.flags[i];
     WinRes r;
-    if (ankan_kokushi_only) {
+    if (mode == 1) {
       if ((rk >> kind) & 1) continue;
       uint32_t cond = RV_C_CHANKAN | ((f & RV_F_RIICHI_DECLARED) ? RV_C_RIICHI : 0);
       r = hand_calc(cx.T, g.hand[i], g.hand_len[i], g.n_melds[i], g.meld_type[i], g.meld_tiles[i], tile, g.dora_ind,
-                    g.n_dora, nullptr, 0, cond, (i + NP - g.oya) % NP, g.round_wind % 4, 0);
+                    g.n_dora, nullptr, 0, cond, (i + np - g.oya) % np, g.round_wind % 4, 0, is_sanma(g), 0);
       if (!(r.is_win && ((r.yaku_mask >> 42) & 1 || (r.yaku_mask >> 49) & 1))) continue;
     } else {
       bool furiten = (waits & rk) != 0 || (f & (RV_F_MISSED_AGARI_RIICHI | RV_F_MISSED_AGARI_DOUJUN));
       if (furiten) continue;
-      r = seat_calc(cx, g, i, tile, base_cond(g, i) | RV_C_CHANKAN, false, g.honba);
+      r = seat_calc(cx, g, i, tile, base_cond(g, i) | (mode == 0 ? RV_C_CHANKAN : 0), false, g.honba, mode == 2);
       if (!(r.is_win && (r.yakuman || r.han >= 1))) continue;
     }
     mask |= 1 << i;
@@ -1203,7 +1242,57 @@ __device__ __noinline__ int chankan_ronners(const Ctx& cx, G& g, int pid, int ti
 
 // ------------------------------------------------------------------ step (state/mod.rs:330-1315)
 // acts[p].type == RV_NO_ACTION  <=>  key p absent from the reference's HashMap.  No validation here.
+// state_3p/sanma.rs:171-204 — rinshan draw after a kita; no new dora
+__device__ __noinline__ void resolve_kita_rinshan(const Ctx& cx, G& g, int pid) {
+  if (g.drawable_count > 0) {
+    flush_pending_kan_dora(cx, g);
+    if (g.wall_top <= g.rinshan_draw_count) return;
+    int t = g.wall[g.rinshan_draw_count];
+    g.drawable_count--;
+    hand_push(g, pid, t);
+    g.drawn_tile = (uint8_t)t;
+    g.rinshan_draw_count++;
+    g.is_rinshan_flag = 1;
+    ev_simple(cx, g, RV_EV_TSUMO, pid, t);
+    g.phase = RV_WAIT_ACT;
+    g.active_mask = (uint8_t)(1u << pid);
+  }
+  waits_update(cx.T, g, pid);
+}
+// state_3p/sanma.rs:9-144
+__device__ __noinline__ void handle_kita(const Ctx& cx, G& g, int pid, const rv_action& act) {
+  const int np = num_players(g);
+  int tile = -1;
+  if (act.tile != RV_NONE && (act.tile >> 2) == 30) {
+    tile = act.tile;
+  } else {
+    for (int k = 0; k < g.hand_len[pid] && tile < 0; k++)
+      if ((g.hand[pid][k] >> 2) == 30) tile = g.hand[pid][k];
+    if (tile < 0) tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
+  }
+  hand_remove_first(g, pid, tile);
+  g.n_kita[pid]++;
+  g.is_first_turn = 0;
+  ev_simple(cx, g, RV_EV_KITA, pid, tile);
+  flush_pending_kan_dora(cx, g);
+  waits_update(cx.T, g, pid);
+  int ron_mask = chankan_ronners(cx, g, pid, tile, 2);
+  if (ron_mask) {
+    g.phase = RV_WAIT_RESPONSE;
+    g.active_mask = (uint8_t)ron_mask;
+    g.last_discard_pid = (uint8_t)pid;
+    g.last_discard_tile = (uint8_t)tile;
+    g.pending_kan_pid = (uint8_t)pid;
+    g.pending_kan_type = RV_KITA;
+    g.pending_kan_tile = (uint8_t)tile;
+  } else {
+    for (int p = 0; p < np; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
+    resolve_kita_rinshan(cx, g, pid);
+  }
+}
+
 __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action* acts) {
+  const int np = num_players(g);
   int pid = g.current_player;
   const rv_action& act = acts[pid];
   switch (act.type) {
@@ -1224,7 +1313,8 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
       break;
     case RV_RIICHI: {
       uint32_t f = g.flags[pid];
-      if (g.score[pid] >= 1000 && g.drawable_count >= 4 && !(f & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE))) {
+      if (g.score[pid] >= 1000 && (np == 3 ? g.drawable_count > 0 : g.drawable_count >= 4) &&
+          !(f & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE))) {
         g.flags[pid] |= RV_F_RIICHI_STAGE;
         ev_simple(cx, g, RV_EV_REACH, pid);
         if (act.tile != RV_NONE) {
@@ -1241,7 +1331,7 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
     case RV_ANKAN: {
       int tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
       int ron_mask = 0;
-      if (rule(g, RV_RULE_RON_ON_ANKAN_KOKUSHI)) ron_mask = chankan_ronners(cx, g, pid, tile, true);
+      if (rule(g, RV_RULE_RON_ON_ANKAN_KOKUSHI)) ron_mask = chankan_ronners(cx, g, pid, tile, 1);
       if (ron_mask) {
         g.pending_kan_pid = (uint8_t)pid;
         g.pending_kan_type = RV_ANKAN;
@@ -1273,7 +1363,7 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
       }
       flush_pending_kan_dora(cx, g);
       waits_update(cx.T, g, pid);
-      int ron_mask = chankan_ronners(cx, g, pid, tile, false);
+      int ron_mask = chankan_ronners(cx, g, pid, tile, 0);
       if (ron_mask) {
         g.pending_kan_pid = (uint8_t)pid;
         g.pending_kan_type = RV_KAKAN;
@@ -1287,6 +1377,9 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
       }
       break;
     }
+    case RV_KITA:
+      if (np == 3) handle_kita(cx, g, pid, act);
+      break;
     case RV_TSUMO: {
       uint32_t cond = base_cond(g, pid) | RV_C_TSUMO;
       if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HAITEI;
@@ -1294,11 +1387,11 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
       if (g.is_first_turn && all_meldless(g)) cond |= RV_C_TSUMO_FIRST_TURN;
       bool riichi = g.flags[pid] & RV_F_RIICHI_DECLARED;
       int win_tile = g.drawn_tile != RV_NONE ? g.drawn_tile : 0;
-      WinRes r = seat_calc(cx, g, pid, win_tile, cond, riichi, g.honba);
+      WinRes r = seat_calc(cx, g, pid, win_tile, cond, riichi, g.honba, true);   // kita_count: state_3p/mod.rs:635
       int oya = g.oya;
       cap_double_yakuman(g, r, pid == oya, true, g.honba);
       if (r.is_win) {
-        int32_t d[NP] = {0, 0, 0, 0};
+        int32_t d[MAXP] = {0, 0, 0, 0};
         int32_t total_win = 0;
         int pao_payer = -1, pao_val = 0, total_val = 0;
         if (r.yakuman) {
@@ -1313,15 +1406,15 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
           }
         }
         if (pao_val > 0) {
-          int32_t unit = pid == oya ? 48000 : 32000;
-          int32_t honba_total = (int32_t)g.honba * (NP - 1) * 100;
+          int32_t unit = pid == oya ? (np - 1) * 16000 : 16000 + (np - 2) * 8000;   // state_3p/mod.rs:713-721
+          int32_t honba_total = (int32_t)g.honba * (np - 1) * 100;
           if (rule(g, RV_RULE_PAO_LIABILITY_ONLY)) {
             int32_t pao_amt = pao_val * unit + honba_total;
             int non_pao = total_val - pao_val;
             d[pao_payer] -= pao_amt;
             total_win += pao_amt;
             if (non_pao > 0)
-              for (int i = 0; i < NP; i++)
+              for (int i = 0; i < np; i++)
                 if (i != pid) {
                   int32_t pay = (pid == oya || i == oya) ? non_pao * 16000 : non_pao * 8000;
                   d[i] -= pay;
@@ -1333,7 +1426,7 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
             total_win += full;
           }
         } else {
-          for (int i = 0; i < NP; i++)
+          for (int i = 0; i < np; i++)
             if (i != pid) {
               int32_t pay = (pid == oya || i != oya) ? (int32_t)r.ko : (int32_t)r.oya;
               d[i] = -pay;
@@ -1343,14 +1436,14 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
         total_win += (int32_t)(g.riichi_sticks * 1000);
         g.riichi_sticks = 0;
         d[pid] += total_win;
-        for (int i = 0; i < NP; i++) {
+        for (int i = 0; i < np; i++) {
           g.score[i] += d[i];
           g.score_delta[i] = d[i];
         }
         ev_hora(cx, g, pid, pid, true, r, d, riichi);
         next_round(cx, g, pid == oya, false);
       } else {
-        g.current_player = (uint8_t)((g.current_player + 1) % NP);
+        g.current_player = (uint8_t)((g.current_player + 1) % np);
         deal_next(cx, g);
       }
       break;
@@ -1361,8 +1454,9 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
 }
 
 __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_action* acts) {
+  const int np = num_players(g);
   // missed agari (state/mod.rs:902-917): every seat holding a Ron claim (stale ones included) that did not ron
-  for (int p = 0; p < NP; p++) {
+  for (int p = 0; p < np; p++) {
     bool has_ron = false;
     for (int k = 0; k < g.n_claims[p]; k++)
       if ((g.claims[p][k] & 0xFF) == RV_RON) has_ron = true;
@@ -1372,7 +1466,7 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
     }
   }
   int ron_mask = 0, call_pid = -1;
-  for (int p = 0; p < NP; p++) {
+  for (int p = 0; p < np; p++) {
     if (!((g.active_mask >> p) & 1)) continue;
     int ty = acts[p].type;
     if (ty == RV_RON) ron_mask |= 1 << p;
@@ -1387,18 +1481,18 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
     }
   }
   if (ron_mask) {
-    if (__popc(ron_mask) >= NP - 1 && rule(g, RV_RULE_SANCHAHO_IS_DRAW)) {
+    if (np == 4 && __popc(ron_mask) >= np - 1 && rule(g, RV_RULE_SANCHAHO_IS_DRAW)) {   // no sanchaho branch in 3P
       trigger_ryukyoku(cx, g, RV_RK_SANCHAHO);
       return;
     }
     int target = g.last_discard_pid != RV_NONE ? g.last_discard_pid : g.current_player;
     int win_tile = g.last_discard_pid != RV_NONE ? g.last_discard_tile : 0;
-    int32_t total[NP] = {0, 0, 0, 0};
+    int32_t total[MAXP] = {0, 0, 0, 0};
     bool oya_won = false, deposit_taken = false, honba_taken = false;
-    bool is_chankan = g.pending_kan_pid != RV_NONE;
+    bool is_chankan = g.pending_kan_pid != RV_NONE && g.pending_kan_type != RV_KITA;   // state_3p/mod.rs:896-902
     int oya = g.oya;
-    for (int dist = 1; dist < NP; dist++) {   // winners sorted by distance from the discarder
-      int w = (target + dist) % NP;
+    for (int dist = 1; dist < np; dist++) {   // winners sorted by distance from the discarder
+      int w = (target + dist) % np;
       if (!((ron_mask >> w) & 1)) continue;
       uint32_t ron_honba = 0;
       if (!honba_taken) { honba_taken = true; ron_honba = g.honba; }
@@ -1406,7 +1500,7 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
       if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
       if (is_chankan) cond |= RV_C_CHANKAN;
       bool riichi = g.flags[w] & RV_F_RIICHI_DECLARED;
-      WinRes r = seat_calc(cx, g, w, win_tile, cond, riichi, ron_honba);
+      WinRes r = seat_calc(cx, g, w, win_tile, cond, riichi, ron_honba, true);   // kita_count: state_3p/mod.rs:926
       cap_double_yakuman(g, r, w == oya, false, ron_honba);
       if (r.is_win) {
         int32_t score = (int32_t)r.ron;
@@ -1426,12 +1520,12 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
           }
           if (has_pao) {
             int32_t unit = w == oya ? 48000 : 32000;
-            int32_t honba_ron = (int32_t)ron_honba * (NP - 1) * 100;
+            int32_t honba_ron = (int32_t)ron_honba * (np - 1) * 100;
             int32_t split = rule(g, RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
             pao_amt = split / 2 + honba_ron;
           }
         }
-        int32_t td[NP] = {0, 0, 0, 0};
+        int32_t td[MAXP] = {0, 0, 0, 0};
         td[w] += score;
         td[pao_payer] -= pao_amt;
         td[target] -= score - pao_amt;
@@ -1440,12 +1534,12 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
           g.riichi_sticks = 0;
           deposit_taken = true;
         }
-        for (int i = 0; i < NP; i++) total[i] += td[i];
+        for (int i = 0; i < np; i++) total[i] += td[i];
         if (w == oya) oya_won = true;
         ev_hora(cx, g, w, target, false, r, td, riichi);
       }
     }
-    for (int i = 0; i < NP; i++) {
+    for (int i = 0; i < np; i++) {
       g.score[i] += total[i];
       g.score_delta[i] = total[i];
     }
@@ -1458,7 +1552,7 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
     g.is_first_turn = 0;
     g.flags[claimer] &= ~RV_F_MISSED_AGARI_DOUJUN;
     if (g.last_discard_pid != RV_NONE) g.flags[g.last_discard_pid] &= ~RV_F_NAGASHI_ELIGIBLE;
-    for (int p = 0; p < NP; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
+    for (int p = 0; p < np; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
     if (act.type == RV_DAIMINKAN) {
       g.current_player = (uint8_t)claimer;
       g.active_mask = (uint8_t)(1u << claimer);
@@ -1509,19 +1603,24 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
     g.drawn_tile = RV_NONE;
     g.c_waits[claimer] = 0;
   } else {
-    for (int i = 0; i < NP; i++) g.n_claims[i] = 0;
+    for (int i = 0; i < np; i++) g.n_claims[i] = 0;
     g.active_mask = 0;
     if (g.pending_kan_pid != RV_NONE) {
-      int pk = g.pending_kan_pid;
-      rv_action a = expand_act(g, pk, pack_act(g.pending_kan_type, g.pending_kan_tile, RV_NONE, RV_NONE));
+      int pk = g.pending_kan_pid, pty = g.pending_kan_type;
+      rv_action a = expand_act(g, pk, pack_act(pty, g.pending_kan_tile, RV_NONE, RV_NONE));
       g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
-      resolve_kan(cx, g, pk, a);
+      if (pty == RV_KITA) {   // state_3p/mod.rs:1201-1207
+        for (int p = 0; p < np; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
+        resolve_kita_rinshan(cx, g, pk);
+      } else {
+        resolve_kan(cx, g, pk, a);
+      }
     } else {
       accept_riichi(cx, g);
       g.turn_count++;
-      g.current_player = (uint8_t)((g.current_player + 1) % NP);
+      g.current_player = (uint8_t)((g.current_player + 1) % np);
       deal_next(cx, g);
-      if (g.turn_count >= (uint32_t)NP) g.is_first_turn = 0;
+      if (g.turn_count >= (uint32_t)np) g.is_first_turn = 0;
     }
   }
 }
@@ -1571,10 +1670,12 @@ __host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uin
 // generic kernel.  Everything it does not recognise (agari shape, riichi/kan/kyushu options, kuikae,
 // first turn, claims, exhausted wall, kan doras) is a demotion, not an approximation.
 __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+  const int np = num_players(g);
   RV_STAT(10);
   const int pid = g.current_player;
   const int drawn = g.drawn_tile;
   const int hl = g.hand_len[pid], nm = g.n_melds[pid];
+  if (np != 4) return false;   // sanma takes the generic path (kita, seat arithmetic mod 3)
   if (drawn == RV_NONE || g.is_first_turn || g.is_rinshan_flag || g.drawable_count == 0) return false;
   if (g.n_dora != 1 || g.pending_kan_dora_count != 0) return false;          // some kan happened: generic path
   if (g.flags[pid] & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) return false;
@@ -1618,7 +1719,7 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
   const int kind = tile >> 2, ksu = kind / 9, kr = kind - 9 * ksu;
   // ---- would anybody be offered a claim?  (legal_actions.rs:254-508, decided from the caches)
   #pragma unroll 1
-  for (int d = 1; d < NP; d++) {
+  for (int d = 1; d < np; d++) {
     int i = (pid + d) & 3;
     if ((g.c_waits[i] >> kind) & 1) return false;                             // ron shape
     if (g.flags[i] & RV_F_RIICHI_DECLARED) continue;
@@ -1712,8 +1813,9 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
 // One env step with the on-device random agent, split by phase so that phase-sorted kernels only carry
 // the code of their own phase.
 __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
-  rv_action acts[NP];
-  for (int p = 0; p < NP; p++) acts[p].type = RV_NO_ACTION;
+  const int np = num_players(g);
+  rv_action acts[MAXP];
+  for (int p = 0; p < np; p++) acts[p].type = RV_NO_ACTION;
   uint32_t sc = g.step_count;
   RV_STAT(3);
   RV_STAT(4);
@@ -1722,7 +1824,7 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
   turn_info(cx, g, pid, ti);
   uint32_t fl = g.flags[pid];
   bool plain = !(fl & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) && g.forbidden[pid][0] == RV_NONE &&
-               g.forbidden[pid][1] == RV_NONE;
+               g.forbidden[pid][1] == RV_NONE && !(is_sanma(g) && ((ti.present >> 30) & 1));
   bool has_pon = false;
   for (int m = 0; m < g.n_melds[pid]; m++) has_pon |= g.meld_type[pid][m] == RV_MELD_PON;
   if (plain && !has_pon) {
@@ -1752,6 +1854,14 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
     acts[pid] = expand_act(g, pid, chosen);
   } else {
     int n = enum_turn_actions(g, pid, ti, [](uint32_t) {});
+    if (n == 0) {
+      // Dead end of the reference (3P: riichi declared, then kita + rinshan draws leave no tenpai-keeping discard;
+      // RandomAgent's random.choice([]) raises).  The rollout retires the game: done + stalled flag (overflow bit 1).
+      g.step_count = sc + 1;
+      g.is_done = 1;
+      g.overflow |= 2;
+      return;
+    }
     if (n > 0) {
       int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n);
       uint32_t chosen = 0;
@@ -1767,11 +1877,12 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
   step_apply_act(cx, g, acts);
 }
 __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
-  rv_action acts[NP];
-  for (int p = 0; p < NP; p++) acts[p].type = RV_NO_ACTION;
+  const int np = num_players(g);
+  rv_action acts[MAXP];
+  for (int p = 0; p < np; p++) acts[p].type = RV_NO_ACTION;
   uint32_t sc = g.step_count;
   RV_STAT(3);
-  for (int p = 0; p < NP; p++) {
+  for (int p = 0; p < np; p++) {
     if (!((g.active_mask >> p) & 1)) continue;
     int n = g.n_claims[p] + 1;
     int pick = (int)agent_pick(agent_seed, game_id, sc, p, (uint32_t)n);

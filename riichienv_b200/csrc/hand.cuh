@@ -310,7 +310,7 @@ struct MeldView {           // melds in 34-space, as HandEvaluator::new normalis
 };
 struct WinCtx {
   bool tsumo, riichi, double_riichi, ippatsu, haitei, houtei, rinshan, chankan, first_turn, menzen;
-  uint8_t dora, aka, ura;
+  uint8_t dora, aka, ura, nuki;   // nuki: nukidora (kita) count, 3P only (yaku_3p.rs:706-709)
   uint8_t round_wind, seat_wind;  // 27..30
 };
 struct YakuRes {
@@ -339,6 +339,7 @@ __device__ __forceinline__ void static_yaku(YakuRes& r, const WinCtx& x) {  // y
   if (x.dora > 0) { r.han += x.dora; r.mask |= 1ull << 31; }
   if (x.aka > 0) { r.han += x.aka; r.mask |= 1ull << 32; }
   if (x.ura > 0) { r.han += x.ura; r.mask |= 1ull << 33; }
+  if (x.nuki > 0) { r.han += x.nuki; r.mask |= 1ull << 34; }
 }
 
 struct Division {
@@ -709,6 +710,12 @@ __device__ __forceinline__ int next_dora_tile(int t) {  // hand_evaluator.rs:286
   if (t < 31) return t == 30 ? 27 : t + 1;
   return t == 33 ? 31 : t + 1;
 }
+__device__ __forceinline__ int next_dora_tile_sanma(int t) {  // hand_evaluator_3p.rs:300-311
+  if (t == 0) return 8;
+  if (t == 8) return 0;
+  if (t >= 1 && t <= 7) return t;
+  return next_dora_tile(t);
+}
 __device__ __forceinline__ bool tid_is_aka(int tid) { return tid == 16 || tid == 52 || tid == 88; }
 
 // HandEvaluator::new + calc (hand_evaluator.rs:24-176).
@@ -718,7 +725,7 @@ __device__ __forceinline__ bool tid_is_aka(int tid) { return tid == 16 || tid ==
 __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, int n, int n_melds, const uint8_t* meld_type,
                                    const uint8_t (*meld_tiles)[4], int win_tid, const uint8_t* dora, int n_dora,
                                    const uint8_t* ura, int n_ura, uint32_t cond, int player_wind, int round_wind,
-                                   uint32_t honba) {
+                                   uint32_t honba, bool sanma = false, int kita_count = 0) {
   WinRes out{false, false, false, 0, 0, 0, 0, 0, 0};
   RV_STAT(0);
   Cnt hand, full;
@@ -778,19 +785,26 @@ __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, 
   x.first_turn = cond & RV_C_TSUMO_FIRST_TURN;
   x.menzen = menzen;
   int dc = 0, uc = 0;
-  for (int i = 0; i < n_dora; i++) dc += cnt_get(full, next_dora_tile(dora[i] >> 2));
-  for (int i = 0; i < n_ura; i++) uc += cnt_get(full, next_dora_tile(ura[i] >> 2));
+  for (int i = 0; i < n_dora; i++) {
+    int nt = sanma ? next_dora_tile_sanma(dora[i] >> 2) : next_dora_tile(dora[i] >> 2);
+    dc += cnt_get(full, nt) + ((sanma && nt == 30) ? kita_count : 0);   // hand_evaluator_3p.rs:108-115
+  }
+  for (int i = 0; i < n_ura; i++) {
+    int nt = sanma ? next_dora_tile_sanma(ura[i] >> 2) : next_dora_tile(ura[i] >> 2);
+    uc += cnt_get(full, nt) + ((sanma && nt == 30) ? kita_count : 0);
+  }
   x.dora = (uint8_t)dc;
   x.ura = (uint8_t)uc;
   x.aka = (uint8_t)aka;
+  x.nuki = (uint8_t)(sanma ? kita_count : 0);
   x.round_wind = (uint8_t)(27 + round_wind);
   x.seat_wind = (uint8_t)(27 + player_wind);
   uint64_t all = cnt_present(hand) | meld_present;
   YakuRes y = calculate_yaku(T, hand, all, mv, x, win34, std_shape);
   bool is_oya = player_wind == 0;
   int scoring_han = (y.yakuman == 0 && y.han >= 13) ? 13 : y.han;
-  ScoreRes sc = calc_score(scoring_han & 0xFF, y.fu, is_oya, x.tsumo, honba, 4);
-  bool has_yaku = (y.mask & ~((1ull << 31) | (1ull << 32) | (1ull << 33))) != 0;
+  ScoreRes sc = calc_score(scoring_han & 0xFF, y.fu, is_oya, x.tsumo, honba, sanma ? 3 : 4);
+  bool has_yaku = (y.mask & ~((1ull << 31) | (1ull << 32) | (1ull << 33) | (sanma ? (1ull << 34) : 0ull))) != 0;
   out.is_win = (has_yaku || y.yakuman > 0) && y.han >= 1;
   out.yakuman = y.yakuman > 0;
   out.han = y.han;

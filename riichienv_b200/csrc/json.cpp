@@ -65,10 +65,12 @@ extern "C" int rv_event_to_json(const uint32_t* w, uint32_t n_words, int viewer,
     case RV_EV_START_KYOKU: {
       static const char* winds[4] = {"E", "S", "W", "N"};
       int honba = w[1] & 0xFF, dora = (w[1] >> 8) & 0xFF, kyotaku = (w[1] >> 16) & 0xFFFF;
-      int32_t sc[4] = {(int32_t)w[2], (int32_t)w[3], (int32_t)w[4], (int32_t)w[5]};
-      const uint8_t* th = (const uint8_t*)&w[6];
+      int np = nw == 19 ? 4 : 3;   // 4P: 19 words, 3P: 15 words
+      int32_t sc[4] = {0, 0, 0, 0};
+      for (int p = 0; p < np; p++) sc[p] = (int32_t)w[2 + p];
+      const uint8_t* th = (const uint8_t*)&w[2 + np];
       std::string tehais = "[";
-      for (int p = 0; p < 4; p++) {
+      for (int p = 0; p < np; p++) {
         tehais += p ? ",[" : "[";
         bool first = true;
         for (int k = 0; k < 13; k++) {
@@ -82,7 +84,7 @@ extern "C" int rv_event_to_json(const uint32_t* w, uint32_t n_words, int viewer,
       tehais += "]";
       s = "{\"bakaze\":" + q(winds[a & 3]) + ",\"dora_marker\":" + q(tid_to_mjai(dora)) + ",\"honba\":" + std::to_string(honba) +
           ",\"kyoku\":" + std::to_string(b + 1) + ",\"kyotaku\":" + std::to_string(kyotaku) + ",\"oya\":" + std::to_string(b) +
-          ",\"scores\":" + ilist(sc, 4) + ",\"tehais\":" + tehais + ",\"type\":\"start_kyoku\"}";
+          ",\"scores\":" + ilist(sc, np) + ",\"tehais\":" + tehais + ",\"type\":\"start_kyoku\"}";
       break;
     }
     case RV_EV_TSUMO:
@@ -114,17 +116,21 @@ extern "C" int rv_event_to_json(const uint32_t* w, uint32_t n_words, int viewer,
       bool tsumo = w[1] & 1;
       int n_ura = (w[1] >> 8) & 0xFF;
       const uint8_t* ub = (const uint8_t*)&w[2];
-      int32_t d[4] = {(int32_t)w[4], (int32_t)w[5], (int32_t)w[6], (int32_t)w[7]};
+      int np = nw - 6;   // 4P: 10 words, 3P: 9 words
+      int32_t d[4] = {0, 0, 0, 0};
+      for (int p = 0; p < np && p < 4; p++) d[p] = (int32_t)w[4 + p];
       std::string ura = "[";
       for (int k = 0; k < n_ura && k < 5; k++) ura += (k ? "," : "") + q(tid_to_mjai(ub[k]));
       ura += "]";
-      s = "{\"actor\":" + std::to_string(a) + ",\"deltas\":" + ilist(d, 4) + ",\"target\":" + std::to_string(b) +
+      s = "{\"actor\":" + std::to_string(a) + ",\"deltas\":" + ilist(d, np) + ",\"target\":" + std::to_string(b) +
           (tsumo ? ",\"tsumo\":true" : "") + ",\"type\":\"hora\",\"ura_markers\":" + ura + "}";
       break;
     }
     case RV_EV_RYUKYOKU: {
-      int32_t d[4] = {(int32_t)w[1], (int32_t)w[2], (int32_t)w[3], (int32_t)w[4]};
-      s = "{\"deltas\":" + ilist(d, 4) + ",\"reason\":" + q(reason_str(a, tmp)) + ",\"type\":\"ryukyoku\"}";
+      int np = nw - 1;
+      int32_t d[4] = {0, 0, 0, 0};
+      for (int p = 0; p < np && p < 4; p++) d[p] = (int32_t)w[1 + p];
+      s = "{\"deltas\":" + ilist(d, np) + ",\"reason\":" + q(reason_str(a, tmp)) + ",\"type\":\"ryukyoku\"}";
       break;
     }
     default:

@@ -64,7 +64,7 @@ __global__ void hand_eval_kernel(Tables T, const rv_hand_query* __restrict__ q, 
   if (i >= n) return;
   rv_hand_query h = q[i];
   WinRes r = hand_calc(T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
-                       h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba);
+                       h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count);
   rv_hand_result o;
   memset(&o, 0, sizeof o);
   o.is_win = r.is_win;
@@ -130,7 +130,7 @@ __global__ void create_kernel(G* states, int64_t n, int game_mode, uint32_t rule
   g.last_error = RV_NONE;
   g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
   g.is_done = 1;      // until reset
-  for (int s = 0; s < NP; s++) g.score[s] = 25000;
+  for (int s = 0; s < MAXP; s++) g.score[s] = game_mode >= 3 ? (s < 3 ? 35000 : 0) : 25000;   // state_3p/game_mode.rs:31-33
 }
 
 __global__ void refresh_kernel(Tables T, G* state) { refresh_caches(T, *state); }
@@ -148,7 +148,7 @@ __global__ void reset_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint
   if (i >= n) return;
   Ctx cx = make_ctx(T, log, cap, i);
   game_reset(cx, states[i], oya ? oya[i] : 0, rw ? rw[i] : 0, honba ? honba[i] : 0, kyotaku ? kyotaku[i] : 0,
-             walls ? walls + (size_t)i * 136 : nullptr, scores ? scores + (size_t)i * NP : nullptr);
+             walls ? walls + (size_t)i * (states[i].game_mode >= 3 ? 108 : 136) : nullptr, scores ? scores + (size_t)i * MAXP : nullptr);
 }
 
 // Persistent rollout: each thread owns one game and advances it up to max_steps env steps.
@@ -311,7 +311,7 @@ __global__ void legal_kernel(Tables T, const G* states, int64_t n, rv_action* ou
   if (i >= n) return;
   const G& g = states[i];
   Ctx cx = make_ctx(T, nullptr, 0, i);
-  for (int p = 0; p < NP; p++) {
+  for (int p = 0; p < MAXP; p++) {
     bool owes = !g.is_done && ((g.phase == RV_WAIT_ACT && g.current_player == p) ||
                                (g.phase == RV_WAIT_RESPONSE && ((g.active_mask >> p) & 1)));
     int cnt = 0;
@@ -319,9 +319,9 @@ __global__ void legal_kernel(Tables T, const G* states, int64_t n, rv_action* ou
       uint32_t packed[RV_MAX_LEGAL];
       cnt = legal_actions(cx, g, p, packed, -1, nullptr);
       if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
-      for (int k = 0; k < cnt; k++) out[((size_t)i * NP + p) * RV_MAX_LEGAL + k] = expand_act(g, p, packed[k]);
+      for (int k = 0; k < cnt; k++) out[((size_t)i * MAXP + p) * RV_MAX_LEGAL + k] = expand_act(g, p, packed[k]);
     }
-    counts[(size_t)i * NP + p] = (uint8_t)cnt;
+    counts[(size_t)i * MAXP + p] = (uint8_t)cnt;
   }
 }
 
@@ -332,9 +332,9 @@ __global__ void step_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint3
   G& g = states[i];
   if (g.is_done) return;
   Ctx cx = make_ctx(T, log, cap, i);
-  rv_action acts[NP];
-  for (int p = 0; p < NP; p++) {
-    acts[p] = actions[(size_t)i * NP + p];
+  rv_action acts[MAXP];
+  for (int p = 0; p < MAXP; p++) {
+    acts[p] = actions[(size_t)i * MAXP + p];
     if (acts[p].type != RV_NO_ACTION) {   // Action::new sorts consume_tiles (action.rs:97-98)
       int nc = acts[p].n_consume > 4 ? 4 : acts[p].n_consume;
       for (int x = 1; x < nc; x++)
@@ -345,7 +345,7 @@ __global__ void step_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint3
   }
   g.step_count++;
   atomicAdd(&counters[0], 1ull);
-  for (int p = 0; p < NP; p++) {
+  for (int p = 0; p < MAXP; p++) {
     if (acts[p].type == RV_NO_ACTION) continue;
     uint32_t packed[RV_MAX_LEGAL];
     int cnt = legal_actions(cx, g, p, packed, -1, nullptr);
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* stat
   const G& g = states[gi];
   if (g.is_done) return;
   int row = offsets[gi];
-  for (int pid = 0; pid < NP; pid++) {
+  for (int pid = 0; pid < MAXP; pid++) {
     if (!((g.active_mask >> pid) & 1)) continue;
     if (row >= max_obs) break;
     if (obs) {
@@ -441,13 +441,13 @@ __global__ void results_kernel(const G* states, int64_t n, uint8_t* done, int32_
   const G& g = states[i];
   if (done) done[i] = g.is_done;
   if (scores)
-    for (int p = 0; p < NP; p++) scores[i * NP + p] = g.score[p];
+    for (int p = 0; p < MAXP; p++) scores[i * MAXP + p] = g.score[p];
   if (ranks)   // env.rs:673-689: score desc, seat asc
-    for (int p = 0; p < NP; p++) {
-      int r = 1;
-      for (int q = 0; q < NP; q++)
+    for (int p = 0; p < MAXP; p++) {
+      int r = 1, np = num_players(g);
+      for (int q = 0; q < np; q++)
         if (g.score[q] > g.score[p] || (g.score[q] == g.score[p] && q < p)) r++;
-      ranks[i * NP + p] = (uint8_t)r;
+      ranks[i * MAXP + p] = (uint8_t)(p < np ? r : 0);
     }
   if (step_count) step_count[i] = g.step_count;
   if (kyoku_count) kyoku_count[i] = g.kyoku_count;
@@ -583,7 +583,6 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
                   uint32_t log_cap_words, rv_vec** out) {
   if (!c || !out || n <= 0) return fail(RV_ERR_INVALID, "bad arguments");
   if (game_mode < 0 || game_mode > 5) return fail(RV_ERR_INVALID, "game_mode must be 0..5");
-  if (game_mode >= 3) return fail(RV_ERR_UNSUPPORTED, "3-player (sanma) modes are not implemented yet");
   CK(cudaSetDevice(c->device));
   rv_vec* v = new rv_vec();
   v->ctx = c;
@@ -658,8 +657,8 @@ int rv_vec_reset(rv_vec* v, const uint8_t* oya, const uint8_t* round_wind, const
   if ((rc = upload(c, round_wind, v->n, &d_rw))) return rc;
   if ((rc = upload(c, honba, v->n, &d_honba))) return rc;
   if ((rc = upload(c, kyotaku, v->n, &d_ky))) return rc;
-  if ((rc = upload(c, scores, v->n * NP, &d_sc))) return rc;
-  if ((rc = upload(c, walls, v->n * 136, &d_walls))) return rc;
+  if ((rc = upload(c, scores, v->n * MAXP, &d_sc))) return rc;
+  if ((rc = upload(c, walls, v->n * (v->game_mode >= 3 ? 108 : 136), &d_walls))) return rc;
   CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 2, c->stream));
   reset_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_oya, d_rw, d_honba,
                                                            d_ky, d_sc, d_walls);
@@ -680,13 +679,13 @@ int rv_vec_legal_actions(rv_vec* v, rv_action* out_actions, uint8_t* out_counts)
   CK(cudaSetDevice(c->device));
   rv_action* d_a;
   uint8_t* d_c;
-  size_t na = (size_t)v->n * NP * RV_MAX_LEGAL;
+  size_t na = (size_t)v->n * MAXP * RV_MAX_LEGAL;
   CK(cudaMalloc(&d_a, sizeof(rv_action) * na));
-  CK(cudaMalloc(&d_c, (size_t)v->n * NP));
+  CK(cudaMalloc(&d_c, (size_t)v->n * MAXP));
   legal_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, d_a, d_c);
   CK(cudaGetLastError());
   if (out_actions) CK(cudaMemcpyAsync(out_actions, d_a, sizeof(rv_action) * na, cudaMemcpyDeviceToHost, c->stream));
-  if (out_counts) CK(cudaMemcpyAsync(out_counts, d_c, (size_t)v->n * NP, cudaMemcpyDeviceToHost, c->stream));
+  if (out_counts) CK(cudaMemcpyAsync(out_counts, d_c, (size_t)v->n * MAXP, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   cudaFree(d_a);
   cudaFree(d_c);
@@ -697,8 +696,8 @@ int rv_vec_step(rv_vec* v, const rv_action* actions) {
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   rv_action* d_a;
-  CK(cudaMalloc(&d_a, sizeof(rv_action) * v->n * NP));
-  CK(cudaMemcpyAsync(d_a, actions, sizeof(rv_action) * v->n * NP, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMalloc(&d_a, sizeof(rv_action) * v->n * MAXP));
+  CK(cudaMemcpyAsync(d_a, actions, sizeof(rv_action) * v->n * MAXP, cudaMemcpyHostToDevice, c->stream));
   step_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_a, v->d_steps);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
@@ -725,7 +724,7 @@ static int env_int(const char* name, int dflt) {
 static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
   int64_t n = v->n;
-  static int slow_every = env_int("RV_SLOW_EVERY", 4), deal_mult = env_int("RV_DEAL_MULT", 8);
+  static int slow_every = env_int("RV_SLOW_EVERY", 3), deal_mult = env_int("RV_DEAL_MULT", 8);
   const int deal_every = slow_every * deal_mult;   // deal drains coincide with slow drains
   if (!v->d_lists) {
     CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * N_LISTS * n));      // [class][buffer][n]
@@ -866,8 +865,8 @@ static int gather(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks, uin
   uint32_t *d_sc = nullptr, *d_kc = nullptr, *d_ec = nullptr;
   uint64_t* d_eh = nullptr;
   if (done) CK(cudaMalloc(&d_done, n));
-  if (scores) CK(cudaMalloc(&d_scores, sizeof(int32_t) * n * NP));
-  if (ranks) CK(cudaMalloc(&d_ranks, n * NP));
+  if (scores) CK(cudaMalloc(&d_scores, sizeof(int32_t) * n * MAXP));
+  if (ranks) CK(cudaMalloc(&d_ranks, n * MAXP));
   if (sc) CK(cudaMalloc(&d_sc, sizeof(uint32_t) * n));
   if (kc) CK(cudaMalloc(&d_kc, sizeof(uint32_t) * n));
   if (ec) CK(cudaMalloc(&d_ec, sizeof(uint32_t) * n));
@@ -875,8 +874,8 @@ static int gather(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks, uin
   results_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, d_done, d_scores, d_ranks, d_sc, d_kc, d_ec, d_eh);
   CK(cudaGetLastError());
   if (done) CK(cudaMemcpyAsync(done, d_done, n, cudaMemcpyDeviceToHost, c->stream));
-  if (scores) CK(cudaMemcpyAsync(scores, d_scores, sizeof(int32_t) * n * NP, cudaMemcpyDeviceToHost, c->stream));
-  if (ranks) CK(cudaMemcpyAsync(ranks, d_ranks, n * NP, cudaMemcpyDeviceToHost, c->stream));
+  if (scores) CK(cudaMemcpyAsync(scores, d_scores, sizeof(int32_t) * n * MAXP, cudaMemcpyDeviceToHost, c->stream));
+  if (ranks) CK(cudaMemcpyAsync(ranks, d_ranks, n * MAXP, cudaMemcpyDeviceToHost, c->stream));
   if (sc) CK(cudaMemcpyAsync(sc, d_sc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
   if (kc) CK(cudaMemcpyAsync(kc, d_kc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
   if (ec) CK(cudaMemcpyAsync(ec, d_ec, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -938,6 +937,8 @@ int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, ui
   return RV_OK;
 }
 int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
+  if (v->game_mode >= 3)
+    return fail(RV_ERR_UNSUPPORTED, "3P observation tensors (observation_3p, 27 compact columns) are not built yet");
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   int64_t n = v->n;

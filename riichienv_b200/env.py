@@ -230,12 +230,13 @@ class Observation:
 
     def __init__(self, env: "RiichiEnv", s: A.GameState, pid: int, legal, new_events):
         self.player_id = pid
-        self.hands = [[s.hand[p][k] for k in range(s.hand_len[p])] if p == pid else [] for p in range(4)]
-        self.melds = [_melds_of(s, p) for p in range(4)]
-        self.discards = [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(4)]
+        n = env._np
+        self.hands = [[s.hand[p][k] for k in range(s.hand_len[p])] if p == pid else [] for p in range(n)]
+        self.melds = [_melds_of(s, p) for p in range(n)]
+        self.discards = [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(n)]
         self.dora_indicators = [s.dora_ind[k] for k in range(s.n_dora)]
-        self.scores = [s.score[p] for p in range(4)]
-        self.riichi_declared = [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(4)]
+        self.scores = [s.score[p] for p in range(n)]
+        self.riichi_declared = [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(n)]
         self._legal_actions = legal
         self._new_events = new_events
         self._env = env
@@ -247,8 +248,8 @@ class Observation:
         self.waits = [k for k in range(34) if (s.c_waits[pid] >> k) & 1]
         self.is_tenpai = bool(self.waits)
         self.tsumogiri_flags = [[], [], [], []]  # always empty in the live env (observation/mod.rs:105)
-        self.riichi_sutehais = [None if s.riichi_sutehai[p] == 255 else s.riichi_sutehai[p] for p in range(4)]
-        self.last_tedashis = [None if s.last_tedashi[p] == 255 else s.last_tedashi[p] for p in range(4)]
+        self.riichi_sutehais = [None if s.riichi_sutehai[p] == 255 else s.riichi_sutehai[p] for p in range(n)]
+        self.last_tedashis = [None if s.last_tedashi[p] == 255 else s.last_tedashi[p] for p in range(n)]
         # state/mod.rs:252 destructures (pid, tile) as (tile, _pid): the field carries the DISCARDER'S SEAT
         self.last_discard = None if s.last_discard_pid == 255 else s.last_discard_pid
         self.drawn_tile = None if s.drawn_tile == 255 else s.drawn_tile
@@ -360,6 +361,7 @@ class RiichiEnv:
         else:
             gm = int(game_mode)
         self.game_mode = gm
+        self._np = 3 if gm >= 3 else 4
         self.skip_mjai_logging = bool(skip_mjai_logging)
         self.rule = rule or GameRule.default_tenhou()
         if seed is None:
@@ -381,8 +383,8 @@ class RiichiEnv:
 
     # ---- core API -------------------------------------------------------------------------------
     def reset(self, oya=None, wall=None, round_wind=None, scores=None, honba=None, kyotaku=None, seed=None):
-        if scores is not None and len(scores) != 4:
-            raise ValueError(f"scores length {len(scores)} does not match number of players 4")
+        if scores is not None and len(scores) != self._np:
+            raise ValueError(f"scores length {len(scores)} does not match number of players {self._np}")
         # reset(seed=) sets GameState.seed which nothing reads (env.rs:835-837): the wall is NOT reseeded.
         self._event_counts = [0, 0, 0, 0]
         self._v.reset(oya=0 if oya is None else oya, round_wind=0 if round_wind is None else round_wind,
@@ -393,6 +395,8 @@ class RiichiEnv:
     def step(self, actions):
         arr = (A.Action * 4)()
         for p in range(4):
+            arr[p].type = A.NO_ACTION
+        for p in range(self._np):
             a = actions.get(p) if actions else None
             if a is None:
                 arr[p].type = A.NO_ACTION
@@ -409,31 +413,34 @@ class RiichiEnv:
 
     def scores(self):
         s = self._state()
-        return [s.score[p] for p in range(4)]
+        return [s.score[p] for p in range(self._np)]
 
     def ranks(self):  # env.rs:673-689
         sc = self.scores()
-        order = sorted(range(4), key=lambda p: (-sc[p], p))
-        out = [0] * 4
+        order = sorted(range(self._np), key=lambda p: (-sc[p], p))
+        out = [0] * self._np
         for r, p in enumerate(order):
             out[p] = r + 1
         return out
 
     def points(self, rule_name: str):  # env.rs:691-727
-        presets = {"basic": (1.0, 25000.0, [50.0, 10.0, -10.0, -50.0]),
-                   "ouza-tyoujyo": (0.0, 25000.0, [100.0, 40.0, -40.0, -100.0]),
-                   "ouza-normal": (0.0, 25000.0, [50.0, 20.0, -20.0, -50.0])}
+        if self._np == 3:
+            presets = {"basic": (1.0, 35000.0, [40.0, 0.0, -40.0])}
+        else:
+            presets = {"basic": (1.0, 25000.0, [50.0, 10.0, -10.0, -50.0]),
+                       "ouza-tyoujyo": (0.0, 25000.0, [100.0, 40.0, -40.0, -100.0]),
+                       "ouza-normal": (0.0, 25000.0, [50.0, 20.0, -20.0, -50.0])}
         if rule_name not in presets:
-            raise ValueError(f"Unknown preset rule: {rule_name}")
+            raise ValueError(f"Unknown preset rule{' for 3P' if self._np == 3 else ''}: {rule_name}")
         w, base, uma = presets[rule_name]
         sc, rk = self.scores(), self.ranks()
-        return [(sc[i] - base) / 1000.0 * w + uma[rk[i] - 1] for i in range(4)]
+        return [(sc[i] - base) / 1000.0 * w + uma[rk[i] - 1] for i in range(self._np)]
 
     def get_observation(self, player_id: int):
         return self._observations([player_id])[player_id]
 
     def get_observations(self, players=None):
-        return self._observations(list(range(4)) if players is None else list(players))
+        return self._observations(list(range(self._np)) if players is None else list(players))
 
     def _get_legal_actions(self, pid: int):
         acts, counts = self._v.legal_actions()
@@ -493,8 +500,8 @@ class RiichiEnv:
     riichi_sticks = property(lambda self: self._state().riichi_sticks)
     turn_count = property(lambda self: self._state().turn_count)
     is_done = property(lambda self: bool(self._state().is_done))
-    num_players = property(lambda self: 4)
-    action_space_size = property(lambda self: 82)
+    num_players = property(lambda self: self._np)
+    action_space_size = property(lambda self: 60 if self._np == 3 else 82)
     last_error = property(lambda self: None if self._state().last_error == 255 else
                           f"Error: Illegal Action by Player {self._state().last_error}")
     dora_indicators = property(lambda self: [self._state().dora_ind[k] for k in range(self._state().n_dora)])
@@ -548,12 +555,12 @@ class RiichiEnv:
     @property
     def hands(self):
         s = self._state()
-        return [[s.hand[p][k] for k in range(s.hand_len[p])] for p in range(4)]
+        return [[s.hand[p][k] for k in range(s.hand_len[p])] for p in range(self._np)]
 
     @hands.setter
     def hands(self, v):
         def f(s):
-            for p in range(4):
+            for p in range(self._np):
                 tiles = list(v[p])[: A.HAND_CAP]
                 for k in range(A.HAND_CAP):
                     s.hand[p][k] = tiles[k] if k < len(tiles) else 255
@@ -563,16 +570,16 @@ class RiichiEnv:
     @property
     def melds(self):
         s = self._state()
-        return [_melds_of(s, p) for p in range(4)]
+        return [_melds_of(s, p) for p in range(self._np)]
 
     @melds.setter
     def melds(self, v):
         def f(s):
-            for p in range(4):
+            for p in range(self._np):
                 ms = list(v[p])[:4]
                 s.n_melds[p] = len(ms)
-                for m in range(4):
-                    for k in range(4):
+                for m in range(self._np):
+                    for k in range(self._np):
                         s.meld_tiles[p][m][k] = 255
                     s.meld_type[p][m] = s.meld_from[p][m] = s.meld_called[p][m] = 255
                 for m, md in enumerate(ms):
@@ -586,12 +593,12 @@ class RiichiEnv:
     @property
     def discards(self):
         s = self._state()
-        return [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(4)]
+        return [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(self._np)]
 
     @discards.setter
     def discards(self, v):
         def f(s):
-            for p in range(4):
+            for p in range(self._np):
                 d = list(v[p])[: A.RIVER_CAP]
                 s.n_river[p] = len(d)
                 s.river_tedashi[p] = (1 << len(d)) - 1
@@ -602,12 +609,12 @@ class RiichiEnv:
     @property
     def riichi_declared(self):
         s = self._state()
-        return [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(4)]
+        return [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(self._np)]
 
     @riichi_declared.setter
     def riichi_declared(self, v):
         def f(s):
-            for p in range(4):
+            for p in range(self._np):
                 s.flags[p] = (s.flags[p] | A.F_RIICHI_DECLARED) if v[p] else (s.flags[p] & ~A.F_RIICHI_DECLARED)
         self._mutate(f)
 
@@ -618,7 +625,7 @@ class RiichiEnv:
         return [s.wall[i] for i in range(s.rinshan_draw_count, s.wall_top)]
 
     def set_scores(self, pts):
-        self._mutate(lambda s: [s.score.__setitem__(p, int(pts[p])) for p in range(4)])
+        self._mutate(lambda s: [s.score.__setitem__(p, int(pts[p])) for p in range(self._np)])
 
     def set_state(self, oya=None, round_wind=None, honba=None, kyotaku=None, scores=None):  # env.rs:636-671
         def f(s):
@@ -630,7 +637,7 @@ class RiichiEnv:
                 s.honba = int(honba)
             if kyotaku is not None:
                 s.riichi_sticks = int(kyotaku)
-            if scores is not None and len(scores) == 4:
-                for p in range(4):
+            if scores is not None and len(scores) == self._np:
+                for p in range(self._np):
                     s.score[p] = int(scores[p])
         self._mutate(f)

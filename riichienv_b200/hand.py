@@ -69,6 +69,7 @@ def make_query(tiles_136, melds, win_tile, dora, ura, cond: Conditions) -> A.Han
         q.ura_ind[i] = t
     q.cond = cond.bits()
     q.player_wind, q.round_wind, q.honba = int(cond.player_wind), int(cond.round_wind), int(cond.honba)
+    q.sanma, q.kita_count = int(bool(cond.is_sanma)), int(cond.kita_count)
     return q
 
 

@@ -50,10 +50,17 @@ class VecRiichiEnv:
             a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dt), shape))
             return a
         n = self.n
-        if scores is not None and np.asarray(scores).shape[-1] != A.NP:
-            raise ValueError(f"scores length {np.asarray(scores).shape[-1]} does not match number of players {A.NP}")
+        nplayers = 3 if self.game_mode >= 3 else 4
+        wall_len = 108 if self.game_mode >= 3 else 136
+        if scores is not None:
+            sc = np.asarray(scores, dtype=np.int32)
+            if sc.shape[-1] != nplayers:
+                raise ValueError(f"scores length {sc.shape[-1]} does not match number of players {nplayers}")
+            sc = np.broadcast_to(sc, (n, nplayers))
+            scores = np.zeros((n, A.NP), np.int32)   # the C ABI strides scores by 4 seats
+            scores[:, :nplayers] = sc
         a_oya, a_rw, a_hb = arr(oya, np.uint8, (n,)), arr(round_wind, np.uint8, (n,)), arr(honba, np.uint8, (n,))
-        a_ky, a_sc, a_w = arr(kyotaku, np.uint32, (n,)), arr(scores, np.int32, (n, A.NP)), arr(walls, np.uint8, (n, 136))
+        a_ky, a_sc, a_w = arr(kyotaku, np.uint32, (n,)), arr(scores, np.int32, (n, A.NP)), arr(walls, np.uint8, (n, wall_len))
         check(lib().rv_vec_reset(self.handle, _ptr(a_oya, C.c_uint8), _ptr(a_rw, C.c_uint8), _ptr(a_hb, C.c_uint8),
                                  _ptr(a_ky, C.c_uint32), _ptr(a_sc, C.c_int32), _ptr(a_w, C.c_uint8)))
 

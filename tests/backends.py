@@ -53,8 +53,8 @@ class OracleBackend(Backend):
         self.h = self.lib.orc_game_new(mode, seed, 0, rule, 1)
 
     def reset(self, wall=None, oya=0, scores=None, honba=0, kyotaku=0, round_wind=0):
-        w = (C.c_uint8 * 136)(*wall) if wall is not None else None
-        s = (C.c_int32 * 4)(*scores) if scores is not None else None
+        w = (C.c_uint8 * len(wall))(*wall) if wall is not None else None
+        s = (C.c_int32 * 4)(*(list(scores) + [0] * (4 - len(scores)))) if scores is not None else None
         self.lib.orc_game_reset(self.h, oya, round_wind, honba, kyotaku, w, s)
 
     def get_state(self):
@@ -93,8 +93,8 @@ class HostsimBackend(Backend):
         self.h = self.lib.hs_game_new(mode, seed, rule, 1 << 16)
 
     def reset(self, wall=None, oya=0, scores=None, honba=0, kyotaku=0, round_wind=0):
-        w = (C.c_uint8 * 136)(*wall) if wall is not None else None
-        s = (C.c_int32 * 4)(*scores) if scores is not None else None
+        w = (C.c_uint8 * len(wall))(*wall) if wall is not None else None
+        s = (C.c_int32 * 4)(*(list(scores) + [0] * (4 - len(scores)))) if scores is not None else None
         self.lib.hs_game_reset(self.h, oya, round_wind, honba, kyotaku, w, s)
 
     def get_state(self):
@@ -166,6 +166,7 @@ def setup_env(backend_cls, seed=42, game_mode=0, hands=None, melds=None, active_
     env = backend_cls(game_mode, seed, rule)
     env.reset(wall=wall, oya=oya or 0)
     s = env.get_state()
+    nseats = 3 if game_mode >= 3 else 4
 
     def set_hand(p, tiles):
         tiles = sorted(tiles)
@@ -174,11 +175,11 @@ def setup_env(backend_cls, seed=42, game_mode=0, hands=None, melds=None, active_
         s.hand_len[p] = len(tiles)
 
     if hands is not None:
-        for p in range(4):
+        for p in range(nseats):
             if hands[p] is not None:
                 set_hand(p, hands[p])
     if melds is not None:
-        for p in range(4):
+        for p in range(nseats):
             if melds[p]:
                 s.n_melds[p] = len(melds[p])
                 for m, (ty, tiles, from_who, called) in enumerate(melds[p]):
@@ -201,19 +202,19 @@ def setup_env(backend_cls, seed=42, game_mode=0, hands=None, melds=None, active_
         cur = [s.hand[current_player][k] for k in range(s.hand_len[current_player])]
         set_hand(current_player, cur + [drawn_tile])
     if discards is not None:
-        for p in range(4):
+        for p in range(nseats):
             s.n_river[p] = len(discards[p])
             s.river_tedashi[p] = (1 << len(discards[p])) - 1
             for k, t in enumerate(discards[p]):
                 s.river[p][k] = t
     if riichi_declared is not None:
-        for p in range(4):
+        for p in range(nseats):
             if riichi_declared[p]:
                 s.flags[p] |= A.F_RIICHI_DECLARED
             else:
                 s.flags[p] &= ~A.F_RIICHI_DECLARED
     if points is not None:
-        for p in range(4):
+        for p in range(nseats):
             s.score[p] = points[p]
     if oya is not None:
         s.oya = oya

@@ -132,7 +132,7 @@ int hs_hand_eval(const rv_hand_query* q, rv_hand_result* out, int64_t n) {
   for (int64_t i = 0; i < n; i++) {
     rv_hand_query h = q[i];
     WinRes r = hand_calc(g_T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
-                         h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba);
+                         h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count);
     rv_hand_result o;
     memset(&o, 0, sizeof o);
     o.is_win = r.is_win;
@@ -207,7 +207,7 @@ void* hs_game_new(int mode, uint64_t seed, uint32_t rule, uint32_t log_cap) {
   h->g.last_error = RV_NONE;
   h->g.pending_init[0] = h->g.pending_init[1] = h->g.pending_init[2] = RV_NONE;
   h->g.is_done = 1;
-  for (int s = 0; s < NP; s++) h->g.score[s] = 25000;
+  for (int s = 0; s < MAXP; s++) h->g.score[s] = mode >= 3 ? (s < 3 ? 35000 : 0) : 25000;
   h->log.assign(log_cap, 0);
   return h;
 }
@@ -243,14 +243,14 @@ void hs_game_step(void* p, const rv_action* in) {
   G& g = h->g;
   if (g.is_done) return;
   Ctx cx = hs_ctx(h);
-  rv_action acts[NP];
-  for (int s = 0; s < NP; s++) {
+  rv_action acts[MAXP];
+  for (int s = 0; s < MAXP; s++) {
     acts[s] = in[s];
     int nc = acts[s].n_consume > 4 ? 4 : acts[s].n_consume;
     if (acts[s].type != RV_NO_ACTION) std::sort(acts[s].consume, acts[s].consume + nc);
   }
   g.step_count++;
-  for (int s = 0; s < NP; s++) {
+  for (int s = 0; s < MAXP; s++) {
     if (acts[s].type == RV_NO_ACTION) continue;
     uint32_t packed[RV_MAX_LEGAL];
     int cnt = legal_actions(cx, g, s, packed, -1, nullptr);

@@ -43,6 +43,22 @@ def test_hand_eval_golden(ctx, orc):
         assert bytes(out[i]) == bytes(ref[i]), f"case {i}"
 
 
+def test_hand_eval_golden_3p(ctx, orc):
+    import os
+
+    cases = H.load_agari_cases("agari_3p.txt")
+    lines = [l for l in open(os.path.join(H.GOLDEN, "agari_3p.txt")) if not l.startswith("#")]
+    for (q, _, _), line in zip(cases, lines):
+        q.sanma, q.kita_count = 1, [int(x) for x in line.split("|")[5].split()][4]
+    arr = H.query_array([c[0] for c in cases])
+    out = gpu_eval(ctx, arr, len(cases))
+    ref = (A.HandResult * len(cases))()
+    orc.orc_hand_eval(arr, ref, len(cases))
+    for i, (_, exp, yaku) in enumerate(cases):
+        assert (out[i].is_win, out[i].han, out[i].fu) == exp and H.yaku_ids(out[i].yaku_mask) == yaku, f"case {i}"
+        assert bytes(out[i]) == bytes(ref[i]), f"case {i}"
+
+
 def test_hand_eval_random_vs_oracle(ctx, orc):
     n = 200_000
     qs = H.random_hand_queries(n, seed=11)
@@ -97,14 +113,16 @@ def run_both(orc, n, mode, rule, seed_base, agent_seed, max_steps=100000):
 
 
 @pytest.mark.parametrize("mode,rule,n", [(2, A.RULE_DEFAULT_TENHOU, 4096), (2, A.RULE_DEFAULT_MJSOUL, 1024),
-                                          (1, A.RULE_DEFAULT_TENHOU, 1024), (0, A.RULE_DEFAULT_TENHOU, 4096)])
+                                          (1, A.RULE_DEFAULT_TENHOU, 1024), (0, A.RULE_DEFAULT_TENHOU, 4096),
+                                          (5, A.RULE_DEFAULT_TENHOU, 4096), (5, A.RULE_DEFAULT_MJSOUL, 1024),
+                                          (4, A.RULE_DEFAULT_TENHOU, 1024), (3, A.RULE_DEFAULT_TENHOU, 4096)])
 def test_random_games_vs_oracle(orc, mode, rule, n):
     g, o = run_both(orc, n, mode, rule, seed_base=1000 * mode, agent_seed=0xABCDEF)
     assert g[0] == o[0], "total env steps"
     names = ["done", "scores", "ranks", "step_count", "kyoku_count", "ev_count", "ev_hash"]
     for name, a, b in zip(names, g[1:], o[1:]):
         assert np.array_equal(a, b), f"{name} differs in {int((a != b).sum())} entries"
-    assert g[1].all()
+    assert g[1].all()   # incl. the rare stalled 3P games, which the rollout retires (overflow bit 1)
 
 
 def test_partial_rollout_and_resume(orc):
@@ -131,8 +149,8 @@ def test_lockstep_snapshots_legal_and_events(orc):
     """Per-step: full state record, legal-action lists; at the end: event log words and MJAI JSON."""
     from tests.backends import GpuBackend, OracleBackend
 
-    for seed in (3, 4):
-        g, o = GpuBackend(2, seed), OracleBackend(2, seed)
+    for mode, seed in ((2, 3), (2, 4), (5, 6), (3, 7)):
+        g, o = GpuBackend(mode, seed), OracleBackend(mode, seed)
         g.reset()
         o.reset()
         steps = 0

@@ -113,3 +113,24 @@ def test_hand_front_end():  # tests/test_agari_calculator.py, tests/test_shanten
     assert calculate_shanten(parse_hand("1111m111122233z")) == 1
     assert HandEvaluator(parse_hand("123m456p789s1122z")).get_waits() == [27, 28]
     assert calculate_score(3, 30, True, False).pay_ron == 5800
+
+
+def test_sanma_shim():  # tests/env/test_sanma.py:50-118, 390-401, 480-500
+    from riichienv_b200 import Action, ActionType, GameType, Phase, RiichiEnv
+    from riichienv_b200.agents import RandomAgent
+
+    env = RiichiEnv(game_mode=GameType.SAN_HANCHAN, seed=42)
+    obs = env.reset()
+    assert env.num_players == 3 and env.scores() == [35000, 35000, 35000]
+    assert [len(h) for h in env.hands] == [14, 13, 13] and len(env.wall) == 68
+    assert env.points("basic") == [40.0, 0.0, -40.0] and set(env.ranks()) == {1, 2, 3}
+    agent = RandomAgent(seed=1)
+    steps = 0
+    while not env.done() and steps < 3000:
+        for o in obs.values():
+            assert all(a.action_type != ActionType.CHI for a in o.legal_actions())
+        obs = env.step({pid: agent.act(o) for pid, o in obs.items()})
+        steps += 1
+    assert env.done()
+    assert sum(env.scores()) + 1000 * env.riichi_sticks == 105000
+    assert all(len(e["deltas"]) == 3 for e in env.mjai_log if e["type"] in ("hora", "ryukyoku"))

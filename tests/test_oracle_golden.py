@@ -29,6 +29,21 @@ def test_agari_4p_golden(orc):
         assert r.has_win_shape == 1
 
 
+def test_agari_3p_golden(orc):
+    """402 sanma cases (benches/data/agari_3p.json; tests/agari_correctness.rs:201-262) through HandEvaluator3P semantics."""
+    import os
+
+    cases = H.load_agari_cases("agari_3p.txt")
+    lines = [l for l in open(os.path.join(H.GOLDEN, "agari_3p.txt")) if not l.startswith("#")]
+    assert len(cases) == 402
+    for i, ((q, exp, yaku), line) in enumerate(zip(cases, lines)):
+        c = [int(x) for x in line.split("|")[5].split()]
+        q.sanma, q.kita_count = 1, c[4]
+        r = A.HandResult()
+        orc.orc_hand_eval(C.byref(q), C.byref(r), 1)
+        assert (r.is_win, r.han, r.fu) == exp and H.yaku_ids(r.yaku_mask) == yaku, f"case {i}"
+
+
 def test_negative_hands(orc):
     cases = H.load_counts_file("hands_negative.txt")
     assert len(cases) == 200

@@ -242,3 +242,109 @@ def test_tsumo_and_riichi_flow(backend):  # env/rule_validation/test_riichi_sequ
     assert types.index("reach") < types.index("reach_accepted")
     assert s.score[0] == 24000 and s.riichi_sticks == 1 and (s.flags[0] & A.F_RIICHI_DECLARED)
     assert s.flags[0] & A.F_DOUBLE_RIICHI  # declared on the first turn
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 3-player (sanma) scenarios — re-expressed from tests/env/test_sanma.py
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_sanma_initialization(backend):  # test_sanma.py:50-118
+    for mode in (3, 4, 5):
+        env = BACKENDS[backend](mode, 42)
+        env.reset()
+        s = env.get_state()
+        assert [s.hand_len[p] for p in range(4)] == [14, 13, 13, 0]
+        assert [s.score[p] for p in range(3)] == [35000, 35000, 35000]
+        assert s.wall_top - s.rinshan_draw_count == 68 and s.wall_len == 108 and s.drawable_count == 54
+        tiles = [s.hand[p][k] for p in range(3) for k in range(s.hand_len[p])] + [s.wall[i] for i in range(s.wall_top)]
+        assert all(not (1 <= t // 4 <= 7) for t in tiles) and len(set(tiles)) == 108   # no 2m-8m
+        e = ev(env)
+        assert [x["type"] for x in e] == ["start_game", "start_kyoku", "tsumo"]
+        assert len(e[1]["tehais"]) == 3 and len(e[1]["scores"]) == 3
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_sanma_rotation_and_no_chi(backend):  # test_sanma.py:120-175
+    env = BACKENDS[backend](5, 42)
+    env.reset()
+    for expected in (0, 1, 2, 0):
+        s = env.get_state()
+        assert s.current_player == expected
+        assert all(a[0] != A.CHI for a in env.legal_tuples(expected))
+        env.step({expected: act(A.DISCARD, s.hand[expected][s.hand_len[expected] - 1])})
+        while env.get_state().phase == 1:
+            st = env.get_state()
+            for p in active(st):
+                assert all(a[0] != A.CHI for a in env.legal_tuples(p))
+            env.step({p: act(A.PASS) for p in active(st)})
+    # shimocha holding 2p3p cannot chi a 1p
+    h0 = [36, 40, 44, 48, 52, 56, 60, 64, 68, 72, 76, 80, 84]
+    h1 = [37, 41, 45, 49, 53, 57, 61, 65, 69, 73, 77, 81, 85]
+    env = setup_env(BACKENDS[backend], game_mode=5, hands=[h0, h1, None], current_player=0, drawn_tile=88)
+    env.step({0: act(A.DISCARD, 36)})
+    st = env.get_state()
+    for p in active(st) if st.phase == 1 else []:
+        assert all(a[0] != A.CHI for a in env.legal_tuples(p))
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_sanma_pon_claim(backend):  # test_sanma.py:177-205
+    h0 = [36, 40, 44, 48, 52, 56, 60, 64, 68, 72, 76, 80, 84]
+    h1 = [37, 38, 49, 53, 57, 61, 65, 69, 73, 77, 81, 85, 89]
+    env = setup_env(BACKENDS[backend], game_mode=5, hands=[h0, h1, None], current_player=0, drawn_tile=88)
+    env.step({0: act(A.DISCARD, 36)})
+    s = env.get_state()
+    assert s.phase == 1 and 1 in active(s)
+    pons = [a for a in env.legal_tuples(1) if a[0] == A.PON]
+    assert pons == [(A.PON, 36, (37, 38))]
+    acts = {p: act(A.PASS) for p in active(s)}
+    acts[1] = act(A.PON, 36, [37, 38])
+    env.step(acts)
+    s = env.get_state()
+    assert s.current_player == 1 and s.phase == 0 and s.n_melds[1] == 1
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_sanma_tsumo_and_ron_deltas(backend):  # test_sanma.py:403-466
+    hand = [36, 37, 38, 40, 41, 42, 44, 45, 46, 32, 33, 34, 0]
+    env = setup_env(BACKENDS[backend], game_mode=5, hands=[hand, None, None], current_player=0, drawn_tile=1,
+                    discards=[[100], [], []])
+    s = env.get_state()
+    s.is_first_turn = 0
+    env.set_state(s)
+    assert (A.TSUMO, 1, ()) in env.legal_tuples(0)
+    env.step({0: act(A.TSUMO)})
+    hora = [x for x in ev(env) if x["type"] == "hora"][-1]
+    d = hora["deltas"]
+    assert hora["tsumo"] is True and len(d) == 3 and d[0] > 0 and d[1] < 0 and d[2] < 0 and sum(d) == 0
+    # ron
+    p0 = [1, 48, 52, 56, 60, 64, 68, 72, 76, 80, 84, 88, 92]
+    env = setup_env(BACKENDS[backend], game_mode=5, hands=[p0, hand, None], current_player=0, drawn_tile=96)
+    env.step({0: act(A.DISCARD, 1)})
+    s = env.get_state()
+    assert s.phase == 1 and 1 in active(s)
+    assert [a for a in env.legal_tuples(1) if a[0] == A.RON] == [(A.RON, 1, ())]
+    env.step({p: (act(A.RON, 1) if p == 1 else act(A.PASS)) for p in active(s)})
+    d = [x for x in ev(env) if x["type"] == "hora"][-1]["deltas"]
+    assert len(d) == 3 and d[1] > 0 and d[0] < 0 and d[2] == 0 and sum(d) == 0
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_sanma_kita(backend):  # state_3p/sanma.rs:9-204, tests/env/test_sanma.py (kita flow)
+    hand = [36, 40, 44, 48, 52, 56, 60, 64, 68, 72, 76, 80, 120]   # holds N (120)
+    env = setup_env(BACKENDS[backend], game_mode=5, hands=[hand, None, None], current_player=0, drawn_tile=121)
+    legal = env.legal_tuples(0)
+    kitas = [a for a in legal if a[0] == A.KITA]
+    assert kitas == [(A.KITA, 120, ()), (A.KITA, 121, ())] and legal[-1][0] == A.KITA
+    before = env.get_state()
+    env.step({0: act(A.KITA, 120)})
+    s = env.get_state()
+    if s.phase == 1:   # somebody may ron the kita tile: everyone passes
+        env.step({p: act(A.PASS) for p in active(s)})
+        s = env.get_state()
+    assert s.n_kita[0] == 1 and s.hand_len[0] == 14 and s.rinshan_draw_count == 1 and s.is_rinshan_flag == 1
+    assert s.drawable_count == before.drawable_count - 1 and s.n_dora == 1      # no new dora for kita
+    types = [x["type"] for x in ev(env)]
+    assert types[-2:] == ["kita", "tsumo"]
+    assert s.is_first_turn == 0
