@@ -26,6 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_STEP = 1024  # algorithmic bytes per env step without observations (SURVEY.md §8 d)
+# dram__bytes_read.sum + dram__bytes_write.sum of one 65,536-game rollout from the ncu --set full capture
+# (profiles/r01_final_*); None until measured for the current kernels
+TRAFFIC_BYTES_PER_LAUNCH = None
+MODE_NAMES = {0: "4p-red-single kyoku", 1: "4p-red-east", 2: "4p-red-half hanchan", 3: "3p-red-single kyoku", 4: "3p-red-east",
+              5: "3p-red-half hanchan (sanma)"}
 METRIC = "env_steps_per_sec"
 UNIT = "env steps/s"
 
@@ -40,6 +45,9 @@ def parse_args():
     ap.add_argument("--mode", type=int, default=2, help="2 = 4p-red-half")
     ap.add_argument("--cpu-sample-games", type=int, default=0, help="games in the cpu_baseline sample (0 = sized by time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "rollout_obs", "hands"],
+                    help="rollout: BASELINE configs[2]/[3] (headline); rollout_obs: configs[4] (encode()+mask() every step); "
+                         "hands: configs[1] (batched shanten + agari/yaku/fu/score)")
     return ap.parse_args()
 
 
@@ -167,6 +175,11 @@ def main():
     from riichienv_b200.multi_gpu import RunStats, reduce_stats, shard_range
     from riichienv_b200.vec_env import VecRiichiEnv
 
+    if args.workload != "rollout":
+        import bench_extra
+
+        return bench_extra.run(args, rank, world, local_rank)
+
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -264,8 +277,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot_ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/i32", "data": "synthetic",
-            "config": {"workload": "4p-red-half hanchan, default Tenhou rules, 65,536 parallel seeded random-agent games per GPU "
-                                   "(BASELINE.json configs[2]), reset -> done",
+            "config": {"workload": (f"{MODE_NAMES[args.mode]}, default Tenhou rules, {G:,} parallel seeded random-agent games per GPU "
+                                    f"(BASELINE.json configs[{3 if args.mode >= 3 else 2}]), reset -> done"),
                        "games_per_gpu": G, "game_mode": args.mode, "l2": "256 MiB flush write between timed iterations",
                        "games_per_sec": (G * args.steps * world) / (tot_ms / 1000.0),
                        "env_steps_per_game": all_steps / (G * args.steps * world)},
@@ -273,7 +286,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "step_random_kernel", "peak_source": peak_src,
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "kernel": "phase_kernel<ACT|RESP|DEAL|SLOW> pipeline (rollout region)", "peak_source": peak_src,
                          "bytes_per_env_step": B_STEP, "kernel_share_of_step": tot_kernel_ms / tot_ms},
         }
         if world == 1 and not args.no_cpu_baseline:

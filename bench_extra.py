@@ -1,0 +1,135 @@
+"""Secondary benchmark workloads (same JSON contract as bench.py; not the headline):
+
+  --workload rollout_obs   BASELINE.json configs[4]: 4p-red-half rollout with FEATURE_ENCODING tensors
+                           (74x34 f32) + 82-id masks written for every acting seat at every env step
+  --workload hands         BASELINE.json configs[1]: batched shanten + agari/yaku/fu/score over seeded hands
+"""
+import ctypes as C
+import json
+import os
+import time
+
+B_OBS = 74 * 34 * 4 + 82   # algorithmic bytes per observation written (SURVEY.md §8 d)
+B_HAND = 56 + 40           # rv_hand_query in + rv_hand_result out
+
+
+def _peak():
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def run(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    from riichienv_b200 import _abi as A
+    from riichienv_b200._lib import Context, check, lib
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    assert world == 1, "secondary workloads are single-GPU"
+    torch.cuda.set_device(local_rank)
+    ctx = Context.get(local_rank)
+    peak, peak_src = _peak()
+    if args.workload == "hands":
+        import sys
+
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+        from tests import helpers as H
+
+        n = 10_000_000
+        base = H.random_hand_queries(100_000, seed=0xA6A21)     # seeded stratum, tiled to 10^7 hands on the device
+        arr = np.frombuffer(H.query_array(base), dtype=np.uint8).reshape(len(base), C.sizeof(A.HandQuery))
+        d_q = torch.from_numpy(np.ascontiguousarray(arr)).cuda().repeat(n // len(base), 1).contiguous()
+        d_r = torch.empty((n, C.sizeof(A.HandResult)), dtype=torch.uint8, device="cuda")
+        ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+        def go():
+            check(lib().rv_hand_eval_batch_device(ctx.handle, C.c_void_p(d_q.data_ptr()), C.c_void_p(d_r.data_ptr()), n))
+
+        for _ in range(args.warmup):
+            go()
+        ctx.sync()
+        ctx.timer_mark(0)
+        for _ in range(args.steps):
+            go()
+        ctx.timer_mark(1)
+        ms = ctx.timer_elapsed(0, 1)
+        # e2e: host buffers through rv_hand_eval_batch (H2D + kernel + D2H inside the call)
+        hq = (A.HandQuery * len(base)).from_buffer_copy(arr.tobytes())
+        ho = (A.HandResult * len(base))()
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            check(lib().rv_hand_eval_batch(ctx.handle, hq, ho, len(base)))
+        e2e = reps * len(base) / (time.perf_counter() - t0)
+        val = n * args.steps / (ms / 1000)
+        ach = val * B_HAND / 1e9
+        print(json.dumps({
+            "metric": "hands_per_sec", "value": val, "unit": "hands/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32",
+            "data": "synthetic",
+            "config": {"workload": "10^7 seeded 14-tile hands: shanten(14), shanten(13), waits, agari, yaku/han/fu/score "
+                                   "(BASELINE.json configs[1]); 50% uniform random, 50% near-complete stratum", "hands": n,
+                       "l2": "inputs+outputs 960 MB per step > 126 MB L2"},
+            "e2e": {"value": e2e, "unit": "hands/s", "h2d_bytes_per_step": len(base) * 56, "d2h_bytes_per_step": len(base) * 40},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": "hand_eval_kernel", "peak_source": peak_src, "bytes_per_hand": B_HAND},
+        }))
+        return
+    # ---- rollout with observations every step
+    G = args.games
+    v = VecRiichiEnv(G, args.mode, device=local_rank)
+    max_obs = G * 2
+    obs = torch.empty((max_obs, 74, 34), dtype=torch.float32, device="cuda")
+    mask = torch.empty((max_obs, 82), dtype=torch.uint8, device="cuda")
+    idx = torch.empty((max_obs,), dtype=torch.int32, device="cuda")
+
+    def one(k):
+        v.reseed(None, k * G)
+        v.reset()
+        n_obs = 0
+        it = 0
+        while True:
+            sync = (it % 64) == 63
+            r = v.encode(obs=obs, mask=mask, index=idx, max_obs=max_obs, sync=sync)
+            if sync:
+                n_obs += r * 64          # sampled row count (rows/iteration is nearly constant)
+                if r == 0:
+                    break
+            v.step_random_async(0x5EED, 1)
+            it += 1
+        return it, n_obs
+
+    for w in range(max(1, args.warmup // 3)):
+        one(1000 + w)
+    ctx.sync()
+    tot_ms, tot_steps, tot_obs, iters = 0.0, 0, 0, 0
+    for k in range(args.steps):
+        ctx.sync()
+        ctx.timer_mark(0)
+        it, n_obs = one(k)
+        ctx.timer_mark(1)
+        tot_ms += ctx.timer_elapsed(0, 1)
+        s, _ = v.steps_total()
+        tot_steps += s
+        tot_obs += n_obs
+        iters += it
+    val = tot_steps / (tot_ms / 1000)
+    ach = (tot_steps * 1024 + tot_obs * B_OBS) / (tot_ms / 1000) / 1e9
+    print(json.dumps({
+        "metric": "env_steps_per_sec", "value": val, "unit": "env steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 + f32 obs",
+        "data": "synthetic",
+        "config": {"workload": f"4p-red-half hanchan, {G:,} games, encode() (74x34 f32) + mask() for every acting seat at every "
+                               "env step (BASELINE.json configs[4] on one GPU)", "games_per_gpu": G,
+                   "observations_per_env_step": tot_obs / max(1, tot_steps), "l2": "observation buffer 1.3 GB per iteration > L2"},
+        "e2e": {"value": val, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (iters // 64)},
+        "gpu_launches": iters * 4,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "obs_encode_kernel + step_random_kernel", "peak_source": peak_src,
+                     "bytes_per_observation": B_OBS},
+    }))

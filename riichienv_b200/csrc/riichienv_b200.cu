@@ -834,7 +834,9 @@ int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps)
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   if (max_steps == 0) return RV_OK;
-  return use_phased() ? rollout_phased(v, agent_seed, max_steps) : rollout_mono(v, agent_seed, max_steps);
+  // short calls (lock-step drivers, per-step observation loops) use the single persistent kernel: the phase pipeline
+  // needs a few dozen iterations to drain its deferred lists and only pays off for long rollouts
+  return (use_phased() && max_steps >= 32) ? rollout_phased(v, agent_seed, max_steps) : rollout_mono(v, agent_seed, max_steps);
 }
 int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done) {
   rv_ctx* c = v->ctx;
