@@ -54,7 +54,10 @@ struct rv_vec {
   int32_t* d_lists;             // [2 buffers][3 phases][n]
   uint32_t* d_list_counts;      // [2][4]
   uint32_t* d_budget;           // [n]
-  uint32_t* h_counts;           // pinned [4]
+  uint32_t* h_counts;           // pinned [16]
+  cudaGraphExec_t graph_exec;   // one period of the phase pipeline, captured once per agent seed
+  uint64_t graph_seed;
+  int graph_period;
   unsigned long long* d_steps;  // [0] = env steps executed, [1] = games finished (by step kernels)
 };
 
@@ -599,6 +602,9 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_list_counts = nullptr;
   v->d_budget = nullptr;
   v->h_counts = nullptr;
+  v->graph_exec = nullptr;
+  v->graph_seed = 0;
+  v->graph_period = 0;
   CK(cudaMalloc(&v->d_states, sizeof(G) * n));
   if (log_cap_words) CK(cudaMalloc(&v->d_log, sizeof(uint32_t) * (size_t)n * log_cap_words));
   CK(cudaMalloc(&v->d_steps, sizeof(unsigned long long) * 2));
@@ -639,6 +645,7 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_list_counts) cudaFree(v->d_list_counts);
   if (v->d_budget) cudaFree(v->d_budget);
   if (v->h_counts) cudaFreeHost(v->h_counts);
+  if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
   cudaFree(v->d_steps);
   delete v;
   return RV_OK;
@@ -759,20 +766,21 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
 #define LAUNCH(PH, OUT, STREAM, RD)                                                                                   \
   phase_kernel<PH, OUT><<<grid, 128, 0, STREAM>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, \
                                                   list(PH, RD), count(PH, RD), out, v->d_steps)
-  CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 16, c->stream));
   int grid = grid_for(n, 128);
-  sched_init_kernel<<<grid, 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, mk());
-  uint64_t it_total = 0;
   int rc;
-  while (true) {
-    for (int it = 0; it < 64; it++, it_total++) {
-      bool slow_drain = (it_total % slow_every) == (uint64_t)(slow_every - 1);
-      bool deal_drain = (it_total % deal_every) == (uint64_t)(deal_every - 1);
+  // One period of the pipeline = lcm of the buffer-flip periods (ACT 2, RESP/SLOW/REACT 2*slow_every, DEAL 2*deal_every):
+  // after it every write-buffer index is back where it started, so the whole period is captured once into a CUDA graph
+  // (the rollout needs ~3,000 iterations x ~8 stream operations; issuing them one by one makes the HOST the bottleneck).
+  const int period = 2 * deal_every;
+  auto issue_period = [&]() -> int {
+    for (int it = 0; it < period; it++) {
+      bool slow_drain = (it % slow_every) == slow_every - 1;
+      bool deal_drain = (it % deal_every) == deal_every - 1;
       int rd_act = wr[PH_ACT];
       if ((rc = swap_class(PH_ACT))) return rc;
       int rd_resp = 0, rd_slow = 0, rd_react = 0, rd_deal = 0, rd_react_d = 0;
       if (slow_drain) {
-        // the RESP / SLOW kernels of the previous period append to RESP, DEAL, REACT: finish them before swapping
+        // the RESP / SLOW kernels of the previous drain append to RESP, DEAL, REACT: finish them before swapping
         if ((rc = join(0)) || (rc = join(2))) return rc;
         rd_resp = wr[PH_RESP];
         rd_slow = wr[PH_SLOW];
@@ -789,7 +797,7 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
       if (slow_drain || deal_drain) CK(cudaEventRecord(c->fork_ev, c->stream));
       LAUNCH(PH_ACT, PH_ACT, c->stream, rd_act);
       if (slow_drain) {
-        // games returning from the previous period's RESP/SLOW kernels re-enter through the fast kernel
+        // games returning from the previous drain's RESP/SLOW kernels re-enter through the fast kernel
         phase_kernel<PH_ACT, PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
                                                                    list(PH_REACT, rd_react), count(PH_REACT, rd_react), out, v->d_steps);
         CK(cudaStreamWaitEvent(c->aux[0], c->fork_ev, 0));
@@ -810,9 +818,39 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
         inflight[1] = true;
       }
     }
-    CK(cudaGetLastError());
     for (int a = 0; a < 3; a++)
-      if ((rc = join(a))) return rc;
+      if ((rc = join(a))) return rc;          // the period is self-contained: side streams rejoin the main stream
+    return RV_OK;
+  };
+  static int use_graph = getenv("RV_GRAPH") ? atoi(getenv("RV_GRAPH")) : 1;
+  if (use_graph == 1 && (!v->graph_exec || v->graph_seed != agent_seed || v->graph_period != period)) {
+    if (v->graph_exec) {
+      cudaGraphExecDestroy(v->graph_exec);
+      v->graph_exec = nullptr;
+    }
+    cudaGraph_t graph;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    rc = issue_period();
+    cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(RV_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    CK(cudaGraphInstantiate(&v->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    v->graph_seed = agent_seed;
+    v->graph_period = period;
+    for (int ph = 0; ph < N_LISTS; ph++) wr[ph] = 0;   // capture leaves every class back at buffer 0 (period property)
+  }
+  CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 16, c->stream));
+  sched_init_kernel<<<grid, 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, mk());
+  uint64_t it_total = 0;
+  while (true) {
+    if (use_graph == 1) {
+      CK(cudaGraphLaunch(v->graph_exec, c->stream));
+    } else if ((rc = issue_period())) {
+      return rc;
+    }
+    it_total += period;
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(v->h_counts, v->d_list_counts, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     bool pending = false;
@@ -820,6 +858,7 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
     if (!pending) break;
   }
 #undef LAUNCH
+  if (getenv("RV_DEBUG")) fprintf(stderr, "[rollout_phased] iterations=%llu slow_every=%d deal_every=%d\n", (unsigned long long)it_total, slow_every, deal_every);
   return RV_OK;
 }
 static bool use_phased() {
