@@ -91,7 +91,44 @@ typedef struct rv_action {
  * array: the Vec's front (rinshan side) is wall[rinshan_draw_count], its back
  * (live-draw side) is wall[wall_top-1].                                      */
 typedef struct rv_game_state {
-  uint8_t wall[136];
+  /* ---- hot part: the first RV_HOT_BYTES bytes.  The rollout kernels stage exactly this prefix in shared
+   * memory (one bulk copy per game in, one out) and reach the cold arrays below through the HBM record. ---- */
+  /* derived caches, kept consistent by every mutation (the oracle recomputes them from scratch in its
+   * snapshot, so state-parity tests also check the incremental maintenance):                          */
+  uint64_t c_cnt[RV_NP][4];       /* concealed-hand histogram, 4-bit count per tile kind; [seat][m,p,s,z] */
+  uint64_t c_river_kinds[RV_NP];  /* bit k: some own discard has kind k (furiten test)                     */
+  uint64_t c_waits[RV_NP];        /* get_waits_u8 of the seat's hand when it is 13-tile-equivalent, else 0 */
+  uint64_t seed;                  /* wall.seed */
+  uint64_t hand_index;            /* wall.hand_index */
+  uint64_t ev_hash;               /* FNV-1a-64 over the 32-bit words of the binary event stream */
+  uint32_t c_key[RV_NP][4];       /* base-5 suit keys of c_cnt (table indices)                             */
+  uint32_t river_tedashi[RV_NP];  /* bit i = discard_from_hand[i] */
+  uint32_t river_riichi[RV_NP];   /* bit i = discard_is_riichi[i] */
+  int32_t score[RV_NP];
+  int32_t score_delta[RV_NP];
+  uint32_t riichi_sticks;
+  uint32_t turn_count;
+  /* counters (not in the reference): */
+  uint32_t step_count;            /* env steps taken (RiichiEnv.step calls that were not no-ops on a done game) */
+  uint32_t kyoku_count;           /* rounds dealt since reset */
+  uint32_t ev_count;              /* events pushed since reset */
+  uint32_t ev_words;              /* 32-bit words pushed since reset (log length, even when the log is capped/off) */
+
+  uint8_t hand[RV_NP][RV_HAND_CAP]; /* ordered as the reference's Vec (legal_actions.rs:102-110 lists discards in this order) */
+  uint8_t hand_len[RV_NP];
+  uint8_t meld_tiles[RV_NP][4][4];  /* tids, order as stored by the reference (sorted); RV_NONE pad */
+  uint8_t meld_type[RV_NP][4];      /* rv_meld_type */
+  uint8_t meld_from[RV_NP][4];      /* from_who, RV_NONE == -1 */
+  uint8_t meld_called[RV_NP][4];    /* called_tile or RV_NONE */
+  uint8_t n_melds[RV_NP];
+  uint8_t n_river[RV_NP];
+  uint8_t riichi_decl_idx[RV_NP];   /* riichi_declaration_index or RV_NONE */
+  uint8_t flags[RV_NP];             /* RV_F_* */
+  uint8_t pao[RV_NP][2];            /* [seat][0]: liable seat for yaku 37, [1]: for yaku 50; RV_NONE */
+  uint8_t forbidden[RV_NP][2];      /* forbidden_discards (tids), RV_NONE pad */
+  uint8_t riichi_sutehai[RV_NP];    /* state/mod.rs:89 */
+  uint8_t last_tedashi[RV_NP];      /* state/mod.rs:90 */
+
   uint8_t wall_len;               /* 136 (4P) or 108 (3P) */
   uint8_t wall_top;               /* tiles not yet popped from the back (absolute index + 1) */
   uint8_t rinshan_draw_count;     /* wall.rs:12 */
@@ -101,26 +138,6 @@ typedef struct rv_game_state {
   uint8_t dora_ind[5];            /* wall.dora_indicators (tids) */
   uint8_t phase;                  /* rv_phase */
 
-  uint8_t hand[RV_NP][RV_HAND_CAP]; /* ordered as the reference's Vec (legal_actions.rs:102-110 lists discards in this order) */
-  uint8_t hand_len[RV_NP];
-  uint8_t meld_tiles[RV_NP][4][4];  /* tids, order as stored by the reference (sorted); RV_NONE pad */
-  uint8_t meld_type[RV_NP][4];      /* rv_meld_type */
-  uint8_t meld_from[RV_NP][4];      /* from_who, RV_NONE == -1 */
-  uint8_t meld_called[RV_NP][4];    /* called_tile or RV_NONE */
-  uint8_t n_melds[RV_NP];
-  uint8_t river[RV_NP][RV_RIVER_CAP]; /* discards */
-  uint8_t n_river[RV_NP];
-  uint32_t river_tedashi[RV_NP];    /* bit i = discard_from_hand[i] */
-  uint32_t river_riichi[RV_NP];     /* bit i = discard_is_riichi[i] */
-  uint8_t riichi_decl_idx[RV_NP];   /* riichi_declaration_index or RV_NONE */
-  uint8_t flags[RV_NP];             /* RV_F_* */
-  uint8_t pao[RV_NP][2];            /* [seat][0]: liable seat for yaku 37, [1]: for yaku 50; RV_NONE */
-  uint8_t forbidden[RV_NP][2];      /* forbidden_discards (tids), RV_NONE pad */
-  uint8_t riichi_sutehai[RV_NP];    /* state/mod.rs:89 */
-  uint8_t last_tedashi[RV_NP];      /* state/mod.rs:90 */
-  int32_t score[RV_NP];
-  int32_t score_delta[RV_NP];
-
   uint8_t current_player, oya, honba, kyoku_idx;
   uint8_t round_wind, is_done, needs_tsumo, is_first_turn;
   uint8_t is_rinshan_flag, riichi_pending_acceptance, drawn_tile, last_discard_pid;
@@ -128,34 +145,23 @@ typedef struct rv_game_state {
   uint8_t active_mask;            /* active_players as a seat bitmask (always ascending seat order in the reference) */
   uint8_t last_error;             /* RV_NONE or offending seat (state/mod.rs:395-399) */
   uint8_t game_mode, rule_bits;
-  uint8_t overflow;               /* set if a fixed capacity (river/claims/log) was exceeded */
+  uint8_t overflow;               /* bit0: a fixed capacity (river/claims/log) was exceeded; bit1: game retired on a dead end */
   uint8_t n_kita[RV_NP];          /* 3P: kita count per seat */
   uint8_t pending_init[3];        /* {oya, round_wind, honba} of a round whose deal is deferred inside a rollout kernel;
                                      pending_init[0]==RV_NONE outside kernels (always, as seen through this API)      */
-  uint32_t riichi_sticks;
-  uint32_t turn_count;
+  uint8_t n_claims[RV_NP];        /* lengths of claims[] below */
+  uint8_t pending_tail[2];        /* {tile, tsumogiri} of a discard whose follow-up (_resolve_discard) is deferred inside a rollout
+                                     kernel; pending_tail[0]==RV_NONE outside kernels (always, as seen through this API) */
+  uint8_t hot_reserved[14];
 
-  uint64_t seed;                  /* wall.seed */
-  uint64_t hand_index;            /* wall.hand_index */
-
+  /* ---- cold part (offset RV_HOT_BYTES): large arrays touched a byte or a few words at a time ---- */
+  uint8_t wall[136];
+  uint8_t river[RV_NP][RV_RIVER_CAP]; /* discards */
   /* current_claims (state/mod.rs:47): packed type | tile<<8 | c0<<16 | c1<<24 */
-  uint8_t n_claims[RV_NP];
   uint32_t claims[RV_NP][RV_MAX_CLAIMS];
-
-  /* counters (not in the reference): */
-  uint32_t step_count;            /* env steps taken (RiichiEnv.step calls that were not no-ops on a done game) */
-  uint32_t kyoku_count;           /* rounds dealt since reset */
-  uint32_t ev_count;              /* events pushed since reset */
-  uint32_t ev_words;             /* 32-bit words pushed since reset (log length, even when the log is capped/off) */
-  uint64_t ev_hash;               /* FNV-1a-64 over the 32-bit words of the binary event stream */
-
-  /* derived caches, kept consistent by every mutation (the oracle recomputes them from scratch in its
-   * snapshot, so state-parity tests also check the incremental maintenance):                          */
-  uint64_t c_cnt[RV_NP][4];       /* concealed-hand histogram, 4-bit count per tile kind; [seat][m,p,s,z] */
-  uint64_t c_river_kinds[RV_NP];  /* bit k: some own discard has kind k (furiten test)                     */
-  uint64_t c_waits[RV_NP];        /* get_waits_u8 of the seat's hand when it is 13-tile-equivalent, else 0 */
-  uint32_t c_key[RV_NP][4];       /* base-5 suit keys of c_cnt (table indices)                             */
+  uint8_t reserved[8];            /* keeps sizeof a multiple of 16 (bulk-copy granularity) */
 } rv_game_state;
+#define RV_HOT_BYTES 640          /* == offsetof(rv_game_state, wall); a multiple of 16 */
 
 /* ---- binary event stream (replaces _push_mjai_event, state/mod.rs:2094-2148)
  * A sequence of 32-bit words.  word0 = type | nwords<<8 | a<<16 | b<<24.

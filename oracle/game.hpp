@@ -1649,6 +1649,8 @@ struct GameState {
     for (uint8_t a : active_players) s.active_mask |= (uint8_t)(1u << a);
     s.last_error = (uint8_t)(last_error < 0 ? 0xFF : last_error);
     s.pending_init[0] = s.pending_init[1] = s.pending_init[2] = 0xFF;
+    s.pending_tail[0] = 0xFF;
+    s.pending_tail[1] = 0;
     s.game_mode = game_mode;
     s.overflow = stalled ? 2 : s.overflow;
     s.rule_bits = (uint8_t)rule;

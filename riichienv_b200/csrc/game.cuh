@@ -28,7 +28,22 @@ struct Ctx {
   uint32_t* log;      // this game's event log region or nullptr
   uint32_t log_cap;   // words
   bool defer_init;    // rollout kernels: next_round() parks the deal in g.pending_init so warps can batch it
+  bool defer_tail;    // rollout kernels: act_fast() parks the follow-up of a discard it cannot finish inline in g.pending_tail
 };
+
+// The rollout kernels run on a shared-memory copy of the record's hot prefix (RV_HOT_BYTES); the word after that prefix
+// holds the address of the HBM record, where the cold arrays (wall, river, claims) stay.  Everywhere else &g IS the record.
+#ifndef RV_COLD_HOOK
+__device__ __forceinline__ G& cold(G& g) {
+#ifdef __CUDA_ARCH__
+  if (__isShared(&g)) return **reinterpret_cast<G**>(reinterpret_cast<char*>(&g) + RV_HOT_BYTES);
+#endif
+  return g;
+}
+#else
+__device__ __forceinline__ G& cold(G& g) { return RV_COLD_HOOK(g); }
+#endif
+__device__ __forceinline__ const G& cold(const G& g) { return cold(const_cast<G&>(g)); }
 
 __device__ __forceinline__ bool rule(const G& g, uint32_t bit) { return (g.rule_bits & bit) != 0; }
 
@@ -138,7 +153,7 @@ __device__ __noinline__ void refresh_caches(const Tables& T, G& g) {
     }
     uint64_t m = 0;
     int n = min((int)g.n_river[p], RV_RIVER_CAP);
-    for (int i = 0; i < n; i++) m |= 1ull << (g.river[p][i] >> 2);
+    for (int i = 0; i < n; i++) m |= 1ull << (cold(g).river[p][i] >> 2);
     g.c_river_kinds[p] = m;
     waits_update(T, g, p);
   }
@@ -172,7 +187,7 @@ __device__ __forceinline__ int ura_indicators(const G& g, uint8_t* ura) {
   bool sanma = is_sanma(g);
   for (int i = 0; i < g.n_dora; i++) {
     int idx = (sanma ? 9 : 5) + 2 * i;
-    if (sanma || idx < g.wall_top) ura[n++] = g.wall[idx];
+    if (sanma || idx < g.wall_top) ura[n++] = cold(g).wall[idx];
   }
   return n;
 }
@@ -301,9 +316,9 @@ __device__ __noinline__ void reveal_kan_dora(const Ctx& cx, G& g) {
     bool sanma = is_sanma(g);
     int idx = (sanma ? 8 : 4) + 2 * count;   // 3P: pre-extracted dora_indicator_tiles (state_3p/mod.rs:1893-1915)
     if (sanma || idx < g.wall_top) {
-      g.dora_ind[count] = g.wall[idx];
+      g.dora_ind[count] = cold(g).wall[idx];
       g.n_dora = (uint8_t)(count + 1);
-      ev_simple(cx, g, RV_EV_DORA, 0, g.wall[idx]);
+      ev_simple(cx, g, RV_EV_DORA, 0, cold(g).wall[idx]);
     }
   }
 }
@@ -333,7 +348,7 @@ __device__ __noinline__ void deal_next(const Ctx& cx, G& g) {
     return;
   }
   if (g.wall_top > g.rinshan_draw_count) {
-    int t = g.wall[g.wall_top - 1];
+    int t = cold(g).wall[g.wall_top - 1];
     g.wall_top--;
     g.drawable_count--;
     int pid = g.current_player;
@@ -366,7 +381,7 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
       g.meld_type[p][m] = g.meld_from[p][m] = g.meld_called[p][m] = RV_NONE;
     }
     g.n_melds[p] = 0;
-    for (int i = 0; i < RV_RIVER_CAP; i++) g.river[p][i] = RV_NONE;
+    for (int i = 0; i < RV_RIVER_CAP; i++) cold(g).river[p][i] = RV_NONE;
     g.n_river[p] = 0;
     g.river_tedashi[p] = g.river_riichi[p] = 0;
     g.riichi_decl_idx[p] = RV_NONE;
@@ -397,31 +412,33 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   g.needs_tsumo = 1;
   g.last_discard_pid = g.last_discard_tile = RV_NONE;
   g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
+  g.pending_tail[0] = RV_NONE;
+  g.pending_tail[1] = 0;
   const int wl = np == 3 ? 108 : 136;
   if (custom_wall) {
-    for (int i = 0; i < wl; i++) g.wall[i] = custom_wall[wl - 1 - i];  // wall.rs:69-72 / state_3p/wall.rs:148-149
+    for (int i = 0; i < wl; i++) cold(g).wall[i] = custom_wall[wl - 1 - i];  // wall.rs:69-72 / state_3p/wall.rs:148-149
   } else {
     uint8_t w[136];
     wall_from_seed(g.seed, g.hand_index, wl, w);
     g.hand_index++;
-    for (int i = 0; i < wl; i++) g.wall[i] = w[i];
+    for (int i = 0; i < wl; i++) cold(g).wall[i] = w[i];
   }
-  for (int i = wl; i < 136; i++) g.wall[i] = RV_NONE;
+  for (int i = wl; i < 136; i++) cold(g).wall[i] = RV_NONE;
   g.wall_len = (uint8_t)wl;
   g.wall_top = (uint8_t)wl;
   g.n_dora = 1;
-  g.dora_ind[0] = g.wall[np == 3 ? 8 : 4];   // state_3p/wall.rs:104-112
+  g.dora_ind[0] = cold(g).wall[np == 3 ? 8 : 4];   // state_3p/wall.rs:104-112
   for (int i = 1; i < 5; i++) g.dora_ind[i] = RV_NONE;
   g.kyoku_count++;
   // deal: 3 x (4 tiles per seat from oya), then 1 each; tiles pop from the back
   for (int r = 0; r < 3; r++)
     for (int idx = 0; idx < np; idx++) {
       int p = (idx + oya) % np;
-      for (int k = 0; k < 4; k++) hand_push(g, p, g.wall[--g.wall_top]);
+      for (int k = 0; k < 4; k++) hand_push(g, p, cold(g).wall[--g.wall_top]);
     }
   for (int idx = 0; idx < np; idx++) {
     int p = (idx + oya) % np;
-    hand_push(g, p, g.wall[--g.wall_top]);
+    hand_push(g, p, cold(g).wall[--g.wall_top]);
   }
   for (int p = 0; p < np; p++) {
     hand_sort(g, p);
@@ -448,7 +465,7 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   g.phase = RV_WAIT_ACT;
   g.active_mask = (uint8_t)(1u << oya);
   {
-    int t = g.wall[--g.wall_top];
+    int t = cold(g).wall[--g.wall_top];
     g.drawable_count--;
     hand_push(g, oya, t);
     g.drawn_tile = (uint8_t)t;
@@ -606,9 +623,9 @@ __device__ __noinline__ bool check_abortive_draw(const Ctx& cx, G& g) {
   for (int p = 0; p < np; p++)
     if (g.n_river[p] != 1) turns_ok = false;
   if (turns_ok && all_meldless(g)) {
-    int first = g.river[0][0] >> 2;
-    if (first >= 27 && first <= 30 && (g.river[1][0] >> 2) == first && (g.river[2][0] >> 2) == first &&
-        (g.river[3][0] >> 2) == first) {
+    int first = cold(g).river[0][0] >> 2;
+    if (first >= 27 && first <= 30 && (cold(g).river[1][0] >> 2) == first && (cold(g).river[2][0] >> 2) == first &&
+        (cold(g).river[3][0] >> 2) == first) {
       trigger_ryukyoku(cx, g, RV_RK_SUFUURENTA);
       return true;
     }
@@ -640,13 +657,13 @@ __device__ __forceinline__ uint32_t pack_act(int type, int tile, int c0, int c1)
 __device__ inline void claim_push(G& g, int i, uint32_t a) {
   int n = g.n_claims[i];
   if (n < RV_MAX_CLAIMS) {
-    g.claims[i][n] = a;
+    cold(g).claims[i][n] = a;
     g.n_claims[i] = (uint8_t)(n + 1);
   } else {
     g.overflow = 1;
   }
 }
-// Fills g.claims[i]; returns the reference's `missed_agari` flag.
+// Fills cold(g).claims[i]; returns the reference's `missed_agari` flag.
 // Fast path: the cached wait mask / histogram answer "nothing to claim" with a few bit tests;
 // the hand is only scanned for tile ids when a pon / chi pattern actually exists.
 __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int tile) {
@@ -1027,8 +1044,8 @@ __device__ __noinline__ int legal_actions(const Ctx& cx, const G& g, int pid, ui
   }
   int n = g.n_claims[pid];
   for (int k = 0; k < n; k++) {
-    if (out) out[k] = g.claims[pid][k];
-    if (k == pick && picked) *picked = g.claims[pid][k];
+    if (out) out[k] = cold(g).claims[pid][k];
+    if (k == pick && picked) *picked = cold(g).claims[pid][k];
   }
   uint32_t pass = pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
   if (out && n < RV_MAX_LEGAL) out[n] = pass;
@@ -1130,7 +1147,7 @@ __device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_
   g.is_first_turn = 0;
   for (int p = 0; p < np; p++) g.flags[p] &= ~RV_F_IPPATSU_CYCLE;
   if (g.drawable_count > 0) {
-    int t = g.wall[g.rinshan_draw_count];   // Vec::remove(0)
+    int t = cold(g).wall[g.rinshan_draw_count];   // Vec::remove(0)
     g.drawable_count--;
     hand_push(g, pid, t);
     g.drawn_tile = (uint8_t)t;
@@ -1161,7 +1178,7 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
   int nr = g.n_river[pid];
   bool stage = g.flags[pid] & RV_F_RIICHI_STAGE;
   if (nr < RV_RIVER_CAP) {
-    g.river[pid][nr] = (uint8_t)tile;
+    cold(g).river[pid][nr] = (uint8_t)tile;
     if (!tsumogiri) g.river_tedashi[pid] |= 1u << nr;
     if (stage) g.river_riichi[pid] |= 1u << nr;
   } else {
@@ -1247,7 +1264,7 @@ __device__ __noinline__ void resolve_kita_rinshan(const Ctx& cx, G& g, int pid) 
   if (g.drawable_count > 0) {
     flush_pending_kan_dora(cx, g);
     if (g.wall_top <= g.rinshan_draw_count) return;
-    int t = g.wall[g.rinshan_draw_count];
+    int t = cold(g).wall[g.rinshan_draw_count];
     g.drawable_count--;
     hand_push(g, pid, t);
     g.drawn_tile = (uint8_t)t;
@@ -1459,7 +1476,7 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
   for (int p = 0; p < np; p++) {
     bool has_ron = false;
     for (int k = 0; k < g.n_claims[p]; k++)
-      if ((g.claims[p][k] & 0xFF) == RV_RON) has_ron = true;
+      if ((cold(g).claims[p][k] & 0xFF) == RV_RON) has_ron = true;
     if (has_ron && acts[p].type != RV_RON) {
       g.flags[p] |= RV_F_MISSED_AGARI_DOUJUN;
       if (g.flags[p] & RV_F_RIICHI_DECLARED) g.flags[p] |= RV_F_MISSED_AGARI_RIICHI;
@@ -1650,6 +1667,11 @@ __device__ inline bool action_matches(const rv_action& l, const rv_action& a) {
   return false;
 }
 
+#ifdef RV_HOSTSIM_STATS
+#define RV_DECLINE(i) (RV_STAT(i), false)
+#else
+#define RV_DECLINE(i) false
+#endif
 // keyed random agent shared with the oracle (SURVEY.md §8 d)
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -1662,31 +1684,93 @@ __host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fast path of the ACT phase.  The rollout is bound by instruction fetch (the generic step is ~90 KB
-// of hot SASS), so the overwhelmingly common transition — "a concealed-or-open hand draws, discards a
-// random tile, nobody can claim it, the next seat draws" — is restated here as one compact routine that
-// stays resident in the SM instruction cache.  It either performs the WHOLE env step exactly as
-// random_step_act would, or returns false BEFORE touching the state so the game is handed to the
-// generic kernel.  Everything it does not recognise (agari shape, riichi/kan/kyushu options, kuikae,
-// first turn, claims, exhausted wall, kan doras) is a demotion, not an approximation.
+// Fast path of the ACT phase.  The generic turn code (legal-action enumeration, action expansion, the
+// apply switch) is ~90 KB of hot SASS and a long chain of dependent loads; the overwhelmingly common
+// turn — "the only legal actions are discards" — is restated here as one compact routine.  It either
+// performs the WHOLE env step exactly as random_step_act would, or returns false BEFORE touching the
+// state so the game is handed to the generic kernel (agari shape, riichi / kan / kyushu options, a
+// declared riichi, sanma).  The discard itself is committed here; what FOLLOWS the discard is
+//   * inline, when it is the plain case (nobody can claim, ordinary draw, no kan dora business), or
+//   * the generic resolve_discard() (claims, first turn, after a call or a kan, last tile) — the very
+//     function the generic path runs, entered with the same state.
+// A hand row (14 tile ids, RV_NONE padded) held in two registers: bytes 0..7 in lo, 8..13 in hi (hi's top 16 bits stay 0xFFFF).
+struct Row14 {
+  uint64_t lo, hi;
+};
+__device__ __forceinline__ Row14 row_load(const uint8_t* h) {       // hand rows are 2-byte aligned (offset 368 + 14 p)
+  const uint16_t* q = reinterpret_cast<const uint16_t*>(h);
+  Row14 r;
+  r.lo = (uint64_t)q[0] | ((uint64_t)q[1] << 16) | ((uint64_t)q[2] << 32) | ((uint64_t)q[3] << 48);
+  r.hi = (uint64_t)q[4] | ((uint64_t)q[5] << 16) | ((uint64_t)q[6] << 32) | 0xFFFF000000000000ull;
+  return r;
+}
+__device__ __forceinline__ void row_store(uint8_t* h, const Row14& r) {
+  uint16_t* q = reinterpret_cast<uint16_t*>(h);
+  q[0] = (uint16_t)r.lo, q[1] = (uint16_t)(r.lo >> 16), q[2] = (uint16_t)(r.lo >> 32), q[3] = (uint16_t)(r.lo >> 48);
+  q[4] = (uint16_t)r.hi, q[5] = (uint16_t)(r.hi >> 16), q[6] = (uint16_t)(r.hi >> 32);
+}
+__device__ __forceinline__ int row_get(const Row14& r, int j) {
+  return (int)(((j < 8 ? r.lo : r.hi) >> (8 * (j & 7))) & 0xFF);
+}
+__device__ __forceinline__ void row_pad(Row14& r, int j) {            // entry j := RV_NONE
+  const uint64_t m = 0xFFull << (8 * (j & 7));
+  if (j < 8) r.lo |= m;
+  else r.hi |= m;
+}
+__device__ __forceinline__ void row_drop(Row14& r, int k) {           // remove entry k, shift the rest down, pad with RV_NONE
+  const uint64_t below = (1ull << (8 * (k & 7))) - 1;
+  if (k < 8) {
+    r.lo = (r.lo & below) | ((r.lo >> 8) & ~below);
+    r.lo = (r.lo & 0x00FFFFFFFFFFFFFFull) | (r.hi << 56);
+    r.hi = (r.hi >> 8) | 0xFF00000000000000ull;
+  } else {
+    r.hi = (r.hi & below) | ((r.hi >> 8) & ~below) | 0xFF00000000000000ull;
+  }
+}
+__device__ __forceinline__ void row_insert(Row14& r, int pos, int v) {   // entries pos.. move up by one (row holds <= 13 entries)
+  const uint64_t below = (1ull << (8 * (pos & 7))) - 1, val = (uint64_t)(uint32_t)v << (8 * (pos & 7));
+  if (pos < 8) {
+    const uint64_t carry = r.lo >> 56;
+    r.lo = (r.lo & below) | val | ((r.lo & ~below) << 8);
+    r.hi = (r.hi << 8) | carry;
+  } else {
+    r.hi = (r.hi & below) | val | ((r.hi & ~below) << 8);
+  }
+}
+// What follows a committed discard that is not the plain case: the generic _resolve_discard — run here, or parked for
+// the TAIL class of the rollout scheduler (so the fast kernel does not carry the claim / abortive-draw / round-end code).
+__device__ __forceinline__ bool act_fast_tail(const Ctx& cx, G& g, int pid, int tile, bool tsumogiri) {
+  RV_STAT(11);
+  if (cx.defer_tail) {
+    g.pending_tail[0] = (uint8_t)tile;
+    g.pending_tail[1] = tsumogiri ? 1 : 0;
+  } else {
+    resolve_discard(cx, g, pid, tile, tsumogiri);
+  }
+  return true;
+}
+__device__ __noinline__ void run_pending_tail(const Ctx& cx, G& g) {
+  const int tile = g.pending_tail[0];
+  const bool tsumogiri = g.pending_tail[1] != 0;
+  g.pending_tail[0] = RV_NONE;
+  g.pending_tail[1] = 0;
+  resolve_discard(cx, g, g.current_player, tile, tsumogiri);
+}
 __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   const int np = num_players(g);
   RV_STAT(10);
   const int pid = g.current_player;
   const int drawn = g.drawn_tile;
   const int hl = g.hand_len[pid], nm = g.n_melds[pid];
-  if (np != 4) return false;   // sanma takes the generic path (kita, seat arithmetic mod 3)
-  if (drawn == RV_NONE || g.is_first_turn || g.is_rinshan_flag || g.drawable_count == 0) return false;
-  if (g.n_dora != 1 || g.pending_kan_dora_count != 0) return false;          // some kan happened: generic path
-  if (g.flags[pid] & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) return false;
-  if ((g.forbidden[pid][0] & g.forbidden[pid][1]) != RV_NONE) return false;
-  if (hl + 3 * nm != 14) return false;
+  if (np != 4) return RV_DECLINE(16);   // sanma takes the generic path (kita, seat arithmetic mod 3)
+  if (g.flags[pid] & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) return RV_DECLINE(19);
+  if (hl + 3 * nm != 14) return RV_DECLINE(21);
   const uint64_t c0 = g.c_cnt[pid][0], c1 = g.c_cnt[pid][1], c2 = g.c_cnt[pid][2], c3 = g.c_cnt[pid][3];
-  if ((c0 | c1 | c2 | c3) & 0x4444444444444444ull) return false;             // four of a kind: ankan is legal
-  const uint32_t e0 = __ldg(&cx.T.suit_info[g.c_key[pid][0]]), e1 = __ldg(&cx.T.suit_info[g.c_key[pid][1]]),
-                 e2 = __ldg(&cx.T.suit_info[g.c_key[pid][2]]), e3 = __ldg(&cx.T.honor_info[g.c_key[pid][3]]);
+  if ((c0 | c1 | c2 | c3) & 0x4444444444444444ull) return RV_DECLINE(22);             // four of a kind: ankan may be legal
+  uint32_t e[4] = {__ldg(&cx.T.suit_info[g.c_key[pid][0]]), __ldg(&cx.T.suit_info[g.c_key[pid][1]]),
+                   __ldg(&cx.T.suit_info[g.c_key[pid][2]]), __ldg(&cx.T.honor_info[g.c_key[pid][3]])};
   // suits that are complete (M or P).  agari needs 4 of them, "some discard leaves tenpai" needs >= 2
-  const int complete = ((e0 | (e0 >> 1)) & 1) + ((e1 | (e1 >> 1)) & 1) + ((e2 | (e2 >> 1)) & 1) + ((e3 | (e3 >> 1)) & 1);
+  const int complete = ((e[0] | (e[0] >> 1)) & 1) + ((e[1] | (e[1] >> 1)) & 1) + ((e[2] | (e[2] >> 1)) & 1) + ((e[3] | (e[3] >> 1)) & 1);
   bool open_meld = false;
   #pragma unroll 1
   for (int m = 0; m < nm; m++) {
@@ -1695,87 +1779,131 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
     if (ty == RV_MELD_PON) {                                                  // kakan possible?
       int k = g.meld_tiles[pid][m][0] >> 2, su = k / 9;
       uint64_t x = su == 0 ? c0 : su == 1 ? c1 : su == 2 ? c2 : c3;
-      if ((x >> (4 * (k - 9 * su))) & 15) return false;
+      if ((x >> (4 * (k - 9 * su))) & 15) return RV_DECLINE(23);
     }
   }
+  const bool first = g.is_first_turn;
   if (nm == 0) {
-    // chiitoitsu / kokushi shapes (agari now, or tenpai after a discard) need >= 5 pairs / >= 12 terminal kinds
+    // chiitoitsu / kokushi shapes (agari now, or tenpai after a discard) need >= 5 pairs / >= 12 terminal kinds;
+    // kyushu kyuhai (first turn) needs >= 9 terminal kinds
     const uint64_t L = 0x1111111111111111ull;
     int pairs = __popcll(((c0 >> 1) | (c0 >> 2)) & L) + __popcll(((c1 >> 1) | (c1 >> 2)) & L) +
                 __popcll(((c2 >> 1) | (c2 >> 2)) & L) + __popcll(((c3 >> 1) | (c3 >> 2)) & L);
-    if (pairs >= 5) return false;
+    if (pairs >= 5) return RV_DECLINE(24);
     const uint64_t TM = 0xF0000000Full;
     uint64_t t0 = c0 & TM, t1 = c1 & TM, t2 = c2 & TM;
     int tk = __popcll((t0 | (t0 >> 1) | (t0 >> 2)) & L) + __popcll((t1 | (t1 >> 1) | (t1 >> 2)) & L) +
              __popcll((t2 | (t2 >> 1) | (t2 >> 2)) & L) + __popcll((c3 | (c3 >> 1) | (c3 >> 2)) & L & 0xFFFFFFFull);
-    if (tk >= 12) return false;
+    if (tk >= (first ? 9 : 12)) return RV_DECLINE(25);
   }
-  if (complete == 4) return false;                                            // standard agari shape: tsumo evaluation
-  if (complete >= 2 && !open_meld && g.score[pid] >= 1000 && g.drawable_count >= 4) return false;   // riichi may be legal
-  // ---- the action: every hand tile is a legal discard, nothing else is legal
+  if (complete == 4) return RV_DECLINE(26);                                            // standard agari shape: tsumo evaluation
+  if (complete >= 2 && !open_meld && g.score[pid] >= 1000 && g.drawable_count >= 4) return RV_DECLINE(27);   // riichi may be legal
+  // ---- the action: every hand tile that kuikae does not forbid is a legal discard, nothing else is legal
+  uint8_t* const hrow = g.hand[pid];
+  Row14 hx = row_load(hrow);
   const uint32_t sc = g.step_count;
-  const int pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)hl);
-  const int tile = g.hand[pid][pick];
+  int pick;
+  const int f0 = g.forbidden[pid][0], f1 = g.forbidden[pid][1];
+  if ((f0 & f1) == RV_NONE) {
+    pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)hl);
+  } else {
+    const int k0 = f0 == RV_NONE ? 99 : f0 >> 2, k1 = f1 == RV_NONE ? 99 : f1 >> 2;
+    uint32_t ok = 0;
+    #pragma unroll
+    for (int j = 0; j < RV_HAND_CAP; j++) {
+      int k = row_get(hx, j) >> 2;
+      if (j < hl && k != k0 && k != k1) ok |= 1u << j;
+    }
+    const int n_ok = __popc(ok);
+    if (n_ok == 0) return RV_DECLINE(20);
+    int r = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n_ok);
+    for (; r > 0; r--) ok &= ok - 1;              // r-th set bit
+    pick = __ffs(ok) - 1;
+  }
+  const int tile = row_get(hx, pick);
   const int kind = tile >> 2, ksu = kind / 9, kr = kind - 9 * ksu;
   // ---- would anybody be offered a claim?  (legal_actions.rs:254-508, decided from the caches)
+  bool claims = false;
   #pragma unroll 1
   for (int d = 1; d < np; d++) {
     int i = (pid + d) & 3;
-    if ((g.c_waits[i] >> kind) & 1) return false;                             // ron shape
+    if ((g.c_waits[i] >> kind) & 1) claims = true;                            // ron shape
     if (g.flags[i] & RV_F_RIICHI_DECLARED) continue;
     if (g.hand_len[i] < 3) continue;
     uint64_t x = g.c_cnt[i][ksu];
-    if (((x >> (4 * kr)) & 15) >= 2) return false;                            // pon / daiminkan
+    if (((x >> (4 * kr)) & 15) >= 2) claims = true;                           // pon / daiminkan
     if (d == 1 && ksu < 3) {                                                  // chi (shimocha)
       uint64_t y = x << 8;                                                    // nibble kr+2 of y == nibble kr of x
       int m2 = (y >> (4 * kr)) & 15, m1 = (y >> (4 * kr + 4)) & 15, p1 = (y >> (4 * kr + 12)) & 15, p2 = (y >> (4 * kr + 16)) & 15;
       if (kr >= 8) p1 = 0;
       if (kr >= 7) p2 = 0;
-      if ((m2 && m1) || (m1 && p1) || (p1 && p2)) return false;
+      if ((m2 && m1) || (m1 && p1) || (p1 && p2)) claims = true;
     }
   }
   // ================= commit: nothing below can fail =================
   RV_STAT(9);
   g.step_count = sc + 1;
-  const bool tsumogiri = tile == drawn;
-  // hand: remove `pick`, then place the drawn tile (stored last) into the sorted 13
-  if (!tsumogiri) {
-    uint8_t* h = g.hand[pid];
-    int pos = 0;
-    #pragma unroll 1
-    for (int j = 0; j < hl - 1; j++) pos += (j != pick && h[j] < drawn) ? 1 : 0;
-    // shift: out[j] for j < hl-1 built from in[] skipping `pick`, inserting drawn at pos
-    uint8_t out[RV_HAND_CAP];
-    int src = 0;
-    #pragma unroll 1
-    for (int j = 0; j < hl - 1; j++) {
-      if (j == pos) out[j] = (uint8_t)drawn;
-      else {
-        if (src == pick) src++;
-        out[j] = h[src++];
-      }
-    }
-    #pragma unroll 1
-    for (int j = 0; j < hl - 1; j++) h[j] = out[j];
-    h[hl - 1] = RV_NONE;
-  } else {
-    g.hand[pid][hl - 1] = RV_NONE;
+  const bool tsumogiri = drawn != RV_NONE && tile == drawn;
+  // hand: the drawn tile (if any) sits last, the rest is sorted.  Remove the pick, re-insert the drawn tile in order.
+  if (g.is_rinshan_flag) {
+    // after a kan the tile drawn before it may still sit unsorted in the row: generic remove + full sort
+    hand_remove_first(g, pid, tile);
+    hand_sort(g, pid);
+    return act_fast_tail(cx, g, pid, tile, tsumogiri);
   }
+  if (tsumogiri) {
+    row_pad(hx, hl - 1);
+  } else if (drawn == RV_NONE) {
+    row_drop(hx, pick);
+  } else {
+    row_pad(hx, hl - 1);                           // lift the drawn tile out ...
+    row_drop(hx, pick);                            // ... drop the pick (pick < hl - 1 here) ...
+    int pos = 0;                                   // ... and count the tiles below the drawn one (pads are 0xFF)
+    #pragma unroll
+    for (int j = 0; j < RV_HAND_CAP - 2; j++) pos += row_get(hx, j) < drawn ? 1 : 0;
+    row_insert(hx, pos, drawn);
+  }
+  row_store(hrow, hx);
   g.hand_len[pid] = (uint8_t)(hl - 1);
   cache_sub(g, pid, kind);
+#ifdef RV_DEBUG_CHECK
+  {
+    uint64_t cc[4] = {0, 0, 0, 0};
+    for (int j = 0; j < hl - 1; j++) {
+      int k = hrow[j] >> 2, su = k / 9;
+      cc[su] += 1ull << (4 * (k - 9 * su));
+    }
+    if (cc[0] != g.c_cnt[pid][0] || cc[1] != g.c_cnt[pid][1] || cc[2] != g.c_cnt[pid][2] || cc[3] != g.c_cnt[pid][3])
+      printf("act_fast mismatch: pid %d hl %d nm %d drawn %d pick %d tile %d tsumogiri %d f0 %d f1 %d | row %d %d %d %d %d %d %d %d %d %d %d %d %d %d | cnt %llx %llx %llx %llx vs %llx %llx %llx %llx\n",
+             pid, hl, nm, drawn, pick, tile, (int)tsumogiri, f0, f1, hrow[0], hrow[1], hrow[2], hrow[3], hrow[4], hrow[5], hrow[6], hrow[7],
+             hrow[8], hrow[9], hrow[10], hrow[11], hrow[12], hrow[13], cc[0], cc[1], cc[2], cc[3], g.c_cnt[pid][0], g.c_cnt[pid][1],
+             g.c_cnt[pid][2], g.c_cnt[pid][3]);
+  }
+#endif
+  if (claims || drawn == RV_NONE || first || g.drawable_count == 0 || g.n_dora != 1 ||
+      g.pending_kan_dora_count != 0) {
+    return act_fast_tail(cx, g, pid, tile, tsumogiri);
+  }
   // _resolve_discard (state/mod.rs:1317-1413), no-claims branch
   g.flags[pid] &= ~(RV_F_IPPATSU_CYCLE | RV_F_MISSED_AGARI_DOUJUN);
   if (!tid_terminal(tile)) g.flags[pid] &= ~RV_F_NAGASHI_ELIGIBLE;
   const int nr = g.n_river[pid];
   if (nr < RV_RIVER_CAP) {
-    g.river[pid][nr] = (uint8_t)tile;
+    cold(g).river[pid][nr] = (uint8_t)tile;
     if (!tsumogiri) g.river_tedashi[pid] |= 1u << nr;
   } else {
     g.overflow = 1;
   }
   g.n_river[pid] = (uint8_t)(nr + 1);
   g.c_river_kinds[pid] |= 1ull << kind;
-  waits_update(cx.T, g, pid);
+  {
+    // waits of the 13-tile hand: only the discarded tile's suit entry changed
+    const uint32_t key = g.c_key[pid][ksu];
+    e[ksu] = ksu == 3 ? __ldg(&cx.T.honor_info[key]) : __ldg(&cx.T.suit_info[key]);
+    SuitInfo si;
+    si.e[0] = e[0], si.e[1] = e[1], si.e[2] = e[2], si.e[3] = e[3];
+    g.c_waits[pid] = waits13(hand_cnt(g, pid), si);
+  }
   g.last_discard_pid = (uint8_t)pid;
   g.last_discard_tile = (uint8_t)tile;
   if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)tile;
@@ -1784,10 +1912,15 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
   g.turn_count++;
   const int nxt = (pid + 1) & 3;
   g.current_player = (uint8_t)nxt;
-  const int t2 = g.wall[g.wall_top - 1];
+  const int t2 = cold(g).wall[g.wall_top - 1];
   g.wall_top--;
   g.drawable_count--;
-  hand_push(g, nxt, t2);
+  {
+    const int n2 = g.hand_len[nxt];
+    g.hand[nxt][n2] = (uint8_t)t2;
+    g.hand_len[nxt] = (uint8_t)(n2 + 1);
+    cache_add(g, nxt, t2 >> 2);
+  }
   g.c_waits[nxt] = 0;
   g.drawn_tile = (uint8_t)t2;
   g.needs_tsumo = 0;
@@ -1886,7 +2019,7 @@ __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agen
     if (!((g.active_mask >> p) & 1)) continue;
     int n = g.n_claims[p] + 1;
     int pick = (int)agent_pick(agent_seed, game_id, sc, p, (uint32_t)n);
-    uint32_t chosen = pick < g.n_claims[p] ? g.claims[p][pick] : pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
+    uint32_t chosen = pick < g.n_claims[p] ? cold(g).claims[p][pick] : pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
     acts[p] = expand_act(g, p, chosen);
   }
   g.step_count = sc + 1;

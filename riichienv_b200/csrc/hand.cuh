@@ -15,7 +15,7 @@
 #include "tables.cuh"
 
 #ifdef RV_HOSTSIM_STATS
-extern unsigned long long g_rv_stats[16];
+extern unsigned long long g_rv_stats[48];
 #define RV_STAT(i) (g_rv_stats[i]++)
 #else
 #define RV_STAT(i)

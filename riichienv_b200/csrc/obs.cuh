@@ -22,7 +22,7 @@ __device__ __forceinline__ uint64_t river_tail_mask(const G& g, int p, int from_
   // kind of the (from_last)-th most recent discard, as a one-hot mask (0 if absent)
   int n = min((int)g.n_river[p], RV_RIVER_CAP);
   int i = n - 1 - from_last;
-  return i >= 0 ? 1ull << (g.river[p][i] >> 2) : 0;
+  return i >= 0 ? 1ull << (cold(g).river[p][i] >> 2) : 0;
 }
 __device__ __forceinline__ int obs_next_kind(int k) {  // observation/helpers.rs:25-50
   if (k < 27) return (k % 9 == 8) ? k - 8 : k + 1;
@@ -41,7 +41,7 @@ __device__ inline int obs_dora_count(const G& g, int pid, int q) {
       }
     int n = min((int)g.n_river[q], RV_RIVER_CAP);
     for (int i = 0; i < n; i++)
-      if ((g.river[q][i] >> 2) == dk) cnt++;
+      if ((cold(g).river[q][i] >> 2) == dk) cnt++;
     if (q == pid) cnt += (int)((g.c_cnt[pid][dk / 9] >> (4 * (dk % 9))) & 15);
   }
   return cnt & 0xFF;
@@ -144,7 +144,7 @@ __device__ inline int obs_seen(const G& g, int pid, int kind) {
       }
     int n = min((int)g.n_river[p], RV_RIVER_CAP);
     for (int i = 0; i < n; i++)
-      if ((g.river[p][i] >> 2) == kind) c++;
+      if ((cold(g).river[p][i] >> 2) == kind) c++;
   }
   for (int d = 0; d < g.n_dora; d++)
     if ((g.dora_ind[d] >> 2) == kind) c++;

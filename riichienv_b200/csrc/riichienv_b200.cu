@@ -55,6 +55,10 @@ struct rv_vec {
   uint32_t* d_list_counts;      // [2][4]
   uint32_t* d_budget;           // [n]
   uint32_t* h_counts;           // pinned [16]
+  // persistent scheduler (rollout_persistent): ring queue per class + live-game counter
+  int32_t* d_q_slots;           // [4][q_cap]
+  uint32_t* d_q_ctl;            // head[4], tail[4] (one 128-byte line each), live, error
+  uint32_t q_cap;
   cudaGraphExec_t graph_exec;   // one period of the phase pipeline, captured once per agent seed
   uint64_t graph_seed;
   int graph_period;
@@ -117,6 +121,7 @@ __device__ __forceinline__ Ctx make_ctx(const Tables& T, uint32_t* log, uint32_t
   cx.log = log ? log + (size_t)i * cap : nullptr;
   cx.log_cap = cap;
   cx.defer_init = false;
+  cx.defer_tail = false;
   return cx;
 }
 
@@ -132,6 +137,7 @@ __global__ void create_kernel(G* states, int64_t n, int game_mode, uint32_t rule
   g.hand_index = 1;   // GameState::new consumed shuffle #0 (state/mod.rs:165)
   g.last_error = RV_NONE;
   g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
+  g.pending_tail[0] = RV_NONE;
   g.is_done = 1;      // until reset
   for (int s = 0; s < MAXP; s++) g.score[s] = game_mode >= 3 ? (s < 3 ? 35000 : 0) : 25000;   // state_3p/game_mode.rs:31-33
 }
@@ -224,8 +230,11 @@ __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, i
 // After stepping its game a thread files it into the NEXT iteration's list (double buffering), so an
 // iteration is {memset counts; ACT | RESP | DEAL concurrently on three streams}.
 enum { PH_ACT = 0, PH_RESP = 1, PH_DEAL = 2, PH_SLOW = 3, PH_REACT = 4, PH_REACT_D = 5, N_LISTS = 6, PH_NONE = 7 };
+// persistent scheduler only: a committed discard whose follow-up is parked (g.pending_tail).  Queue index 4 there.
+enum { PH_TAIL = 4, N_QUEUES = 5 };
 
 __device__ __forceinline__ int classify(const G& g, uint32_t budget) {
+  if (g.pending_tail[0] != RV_NONE) return PH_TAIL;      // (persistent scheduler only; flushed even when the budget is spent)
   if (g.pending_init[0] != RV_NONE) return PH_DEAL;      // must be flushed even when the budget is spent
   if (g.is_done || budget == 0) return PH_NONE;
   return g.phase == RV_WAIT_ACT ? PH_ACT : PH_RESP;
@@ -260,41 +269,97 @@ __global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, 
   }
   file_game(cls, (int32_t)i, out, n);
 }
+// ---- shared-memory staging of the hot prefix (per-lane bulk copies, TMA engine) ----
+// A lane's game record is 13 cache lines of HBM and a step touches most of the hot ones through dependent, uncoalesced
+// loads (every warp-level load waits for its slowest lane: ncu showed ~20 warps stalled on long_scoreboard per issue).
+// So each lane pulls its record's hot prefix (RV_HOT_BYTES = 624 B) into shared memory with ONE cp.async.bulk, all 32
+// copies of the warp in flight together, runs the step(s) there, and writes the prefix back with one bulk store.
+// The cold arrays (wall, river, claims) stay in HBM; game code reaches them through cold(g) (game.cuh).
+constexpr int PHB = 32;                              // threads (= games) per block: one warp, own barrier, own exit
+constexpr int STG_STRIDE = RV_HOT_BYTES + 32;        // 656 B = 164 words (== 4 mod 32: same-field accesses are 4-way conflicts)
+static_assert(offsetof(G, wall) == RV_HOT_BYTES && RV_HOT_BYTES % 16 == 0 && sizeof(G) % 16 == 0, "hot prefix layout");
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_in(unsigned char* slot, const G* src, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(slot)),
+               "l"(src), "r"((uint32_t)RV_HOT_BYTES), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void stage_out(G* dst, const unsigned char* slot) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's generic-proxy writes -> visible to the copy engine
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(slot)),
+               "r"((uint32_t)RV_HOT_BYTES)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 template <int PH, int OUT_ACT>
-__global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
+__global__ void __launch_bounds__(PHB) phase_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
                                                     uint32_t* budget, const int32_t* in_list, const uint32_t* in_count, Lists out,
-                                                    unsigned long long* counters) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                    unsigned long long* counters, int reps) {
+  __shared__ __align__(128) unsigned char stage[PHB * STG_STRIDE];
+  __shared__ __align__(8) uint64_t mbar;
+  const int lane = threadIdx.x;
+  int64_t i = (int64_t)blockIdx.x * PHB + lane;
   uint32_t count = *in_count;
-  if ((int64_t)blockIdx.x * blockDim.x >= count) return;     // whole block idle (block-uniform)
+  if ((int64_t)blockIdx.x * PHB >= count) return;     // whole block idle (block-uniform)
+  const bool have = i < count;
   int cls = PH_NONE;
-  int32_t gi = -1;
+  int32_t gi = have ? in_list[i] : -1;
+  unsigned char* slot = stage + lane * STG_STRIDE;
+  const uint32_t bar = smem_u32(&mbar);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t live = min((uint32_t)PHB, count - (uint32_t)blockIdx.x * PHB);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(live * (uint32_t)RV_HOT_BYTES) : "memory");
+  }
+  __syncwarp();
+  if (have) {
+    stage_in(slot, &states[gi], bar);
+    *reinterpret_cast<G**>(slot + RV_HOT_BYTES) = &states[gi];    // cold(g) finds the HBM record here
+  }
+  {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok)
+                   : "r"(bar), "r"(0)
+                   : "memory");
+  }
   unsigned long long stepped = 0, finished = 0;
-  if (i < count) {
-    gi = in_list[i];
-    G& g = states[gi];
+  if (have) {
+    G& g = *reinterpret_cast<G*>(slot);
     Ctx cx = make_ctx(T, log, cap, gi);
     cx.defer_init = true;
     uint32_t b = budget[gi];
-    bool did_step = false;
+    const uint32_t b0 = b;
     if (PH == PH_DEAL) {
       run_pending_init(cx, g);
+      cls = classify(g, b);
     } else if (PH == PH_ACT) {
-      did_step = act_fast(cx, g, agent_seed, g.seed);
-    } else if (PH == PH_SLOW) {
-      random_step_act(cx, g, agent_seed, g.seed);
-      did_step = true;
+      // up to `reps` consecutive fast steps while the game stays in the ACT class (most discards draw no claim)
+      for (int r = 0; r < reps; r++) {
+        if (!act_fast(cx, g, agent_seed, g.seed)) {
+          cls = PH_SLOW;
+          break;
+        }
+        b--;
+        cls = classify(g, b);
+        if (cls != PH_ACT) break;
+      }
     } else {
-      random_step_resp(cx, g, agent_seed, g.seed);
-      did_step = true;
+      if (PH == PH_SLOW) random_step_act(cx, g, agent_seed, g.seed);
+      else random_step_resp(cx, g, agent_seed, g.seed);
+      b--;
+      cls = classify(g, b);
     }
-    if (did_step) {
-      budget[gi] = --b;
-      stepped = 1;
+    if (b != b0) {
+      budget[gi] = b;
+      stepped = b0 - b;
       finished = g.is_done ? 1 : 0;
     }
-    cls = (PH == PH_ACT && !did_step) ? PH_SLOW : classify(g, b);
     if (cls == PH_ACT && OUT_ACT != PH_ACT) cls = OUT_ACT;   // async kernels return ACT games through their own list
+    stage_out(&states[gi], slot);
   }
   file_game(cls, gi, out, n);
   if (PH != PH_DEAL) {   // (uniform per kernel)
@@ -302,10 +367,267 @@ __global__ void __launch_bounds__(128) phase_kernel(Tables T, G* states, int64_t
       stepped += __shfl_down_sync(0xFFFFFFFFu, stepped, o);
       finished += __shfl_down_sync(0xFFFFFFFFu, finished, o);
     }
-    if ((threadIdx.x & 31) == 0 && stepped) {
+    if (lane == 0 && stepped) {
       atomicAdd(&counters[0], stepped);
       if (finished) atomicAdd(&counters[1], finished);
     }
+  }
+}
+
+
+// ---- persistent rollout: device-side class queues, no grid-wide barrier ------------------------------------------
+// The list pipeline above advances every game of a class in one kernel and waits for the slowest warp before the next
+// iteration starts (ncu: the SMs hold a resident warp for ~40 % of a kernel's duration).  Here a fixed crew of warps
+// stays resident for the whole rollout; each warp repeatedly claims up to 32 games of ONE class from that class's ring
+// queue, stages them, steps them, stores them and pushes each into the queue of its next class.  Nothing waits for
+// anything but work.  Per-SM class preference (from %smid) keeps one class's code hot in an SM's instruction cache;
+// a warp whose class has no full batch takes another class's, and only then a partial batch.
+//   push:  state stores -> __threadfence() -> ticket = atomicAdd(tail) -> slot[ticket] = game
+//   pop :  CAS on head (lane 0) -> lanes spin on their slots -> fence.acq_rel.gpu (invalidates L1: cold arrays and the
+//          budget are read with plain loads) -> bulk copy in
+enum { Q_HEAD = 0, Q_TAIL = 256, Q_LIVE = 512, Q_ERR = 513, Q_SMCLASS = 544, Q_CTL_WORDS = 544 + 256 };   // word offsets into d_q_ctl; heads/tails on own 128 B lines
+struct Queues {
+  int32_t* slots;      // [N_QUEUES][cap], -1 = empty
+  uint32_t* ctl;
+  uint32_t mask;       // cap - 1
+};
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+// Slot states: -1 empty, -2 abandoned by its consumer, >= 0 a game.  Ticket k of the producers and ticket k of the
+// consumers meet in slot k & mask.  Consumers take tickets with a plain fetch-add (no CAS loop: with ~1,500 warps on
+// one head word a CAS retries ~40 times per success); a consumer whose ticket is not served within a few polls marks the
+// slot abandoned and moves on, and the producer that later draws that ticket clears the mark and draws another ticket.
+// every lane calls; cls in {PH_ACT, PH_RESP, PH_DEAL, PH_SLOW, PH_TAIL} or PH_NONE
+__device__ __forceinline__ void q_push(const Queues& q, int cls, int32_t gi) {
+  const int lane = threadIdx.x & 31;
+  #pragma unroll
+  for (int c = 0; c < N_QUEUES; c++) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+    if (m == 0) continue;
+    int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&q.ctl[Q_TAIL + 32 * c], (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (cls == c) {
+      uint32_t t = base + __popc(m & ((1u << lane) - 1));
+      while (true) {
+        int32_t* sl = q.slots + (size_t)c * (q.mask + 1) + (t & q.mask);
+        int32_t old = atomicCAS(sl, -1, gi);
+        if (old == -1) break;
+        if (old == -2) {                                   // the consumer of this ticket gave up: clear, draw a new ticket
+          *reinterpret_cast<volatile int32_t*>(sl) = -1;
+          t = atomicAdd(&q.ctl[Q_TAIL + 32 * c], 1u);
+        }
+        // old >= 0: previous lap not consumed yet (cap >= 2n: practically never) -> retry the same slot
+      }
+    }
+  }
+}
+__global__ void q_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, Queues q) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int cls = PH_NONE;
+  if (i < n) {
+    budget[i] = max_steps;
+    cls = classify(states[i], max_steps);
+  }
+  if (i < 256) {
+    // initial class of every SM; shares follow the measured per-class warp time
+    const int r = (int)i & 15;
+    q.ctl[Q_SMCLASS + i] = r < 7 ? PH_ACT : r < 10 ? PH_TAIL : r < 13 ? PH_RESP : r < 15 ? PH_SLOW : PH_DEAL;
+  }
+  unsigned m = __ballot_sync(0xFFFFFFFFu, cls != PH_NONE);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&q.ctl[Q_LIVE], (uint32_t)__popc(m));
+  q_push(q, cls, (int32_t)i);
+}
+// lane 0 only: take up to PHB consumer tickets of class c if the queue looks non-empty; returns the count and the first ticket
+__device__ __forceinline__ int q_claim(const Queues& q, int c, uint32_t& h, unsigned long long* dbg = nullptr) {
+  uint32_t hh = ld_volatile_u32(&q.ctl[Q_HEAD + 32 * c]), tt = ld_volatile_u32(&q.ctl[Q_TAIL + 32 * c]);
+  int avail = (int)(tt - hh);
+  if (avail <= 0) {
+    if (dbg) dbg[1]++;
+    return 0;
+  }
+  int want = avail < PHB ? avail : PHB;
+  h = atomicAdd(&q.ctl[Q_HEAD + 32 * c], (uint32_t)want);
+  return want;
+}
+__global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
+                                                                 uint64_t agent_seed, uint32_t* budget, Queues q,
+                                                                 unsigned long long* counters, int reps) {
+  __shared__ __align__(128) unsigned char stage[PHB * STG_STRIDE];
+  __shared__ __align__(8) uint64_t mbar;
+  const int lane = threadIdx.x;
+  unsigned char* slot = stage + lane * STG_STRIDE;
+  const uint32_t bar = smem_u32(&mbar);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  // All warps of an SM work on the SAME class (its code stays in the SM's instruction cache: the per-class hot code is
+  // tens of KB, the L1.5 I-cache 32 KB).  The class is a per-SM word in global memory; a warp that finds its SM's class
+  // empty twice in a row moves the whole SM to the class with the longest queue.
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  uint32_t* const my_class = &q.ctl[Q_SMCLASS + (smid & 255)];
+  unsigned long long stepped_total = 0, finished_total = 0;
+  uint32_t idle = 0;
+#ifdef RV_QPROF
+  // per-warp cycle accounting: [0] idle polls, [1] claim+slots+fence, [2] stage in, [3..7] compute per class, [8] stage out+fence,
+  // [9] push; [10..14] batches per class, [15..19] games per class
+  unsigned long long prof[20] = {0};
+  unsigned long long dbg[4] = {0, 0, 0, 0};   // CAS retries, empty looks, claims given up, SM class switches
+#define QDBG dbg
+  long long t0 = clock64();
+#define QP(i) { long long t1 = clock64(); prof[i] += (unsigned long long)(t1 - t0); t0 = t1; }
+#else
+#define QP(i)
+#define QDBG nullptr
+#endif
+  while (true) {
+    int cls = PH_NONE, take = 0;
+    uint32_t h = 0;
+    if (lane == 0) {
+      cls = (int)ld_volatile_u32(my_class);
+      take = q_claim(q, cls, h, QDBG);
+      if (take == 0 && idle >= 3) {
+        // move the SM: longest queue wins
+        int best = -1, best_len = 0;
+        for (int c = 0; c < N_QUEUES; c++) {
+          int len = (int)(ld_volatile_u32(&q.ctl[Q_TAIL + 32 * c]) - ld_volatile_u32(&q.ctl[Q_HEAD + 32 * c]));
+          if (len > best_len) best_len = len, best = c;
+        }
+        if (best >= 0) {
+          *reinterpret_cast<volatile uint32_t*>(my_class) = (uint32_t)best;
+          cls = best;
+          take = q_claim(q, cls, h, QDBG);
+          idle = 0;
+#ifdef RV_QPROF
+          dbg[3]++;
+#endif
+        }
+      }
+    }
+    take = __shfl_sync(0xFFFFFFFFu, take, 0);
+    if (take == 0) {
+      uint32_t live = 0, err = 0;
+      if (lane == 0) {
+        live = ld_volatile_u32(&q.ctl[Q_LIVE]);
+        err = ld_volatile_u32(&q.ctl[Q_ERR]);
+        if (live != 0 && err == 0 && ++idle > (1u << 22)) {     // watchdog: seconds without work while games are live
+          atomicExch(&q.ctl[Q_ERR], 1u);
+          err = 1;
+        }
+      }
+      live = __shfl_sync(0xFFFFFFFFu, live, 0);
+      err = __shfl_sync(0xFFFFFFFFu, err, 0);
+      if (live == 0 || err != 0) break;
+      __nanosleep(300);
+      QP(0);
+      continue;
+    }
+    idle = 0;
+    cls = __shfl_sync(0xFFFFFFFFu, cls, 0);
+    h = __shfl_sync(0xFFFFFFFFu, h, 0);
+    int32_t gi = -1;
+    if (lane < take) {
+      int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + ((h + (uint32_t)lane) & q.mask);
+      for (int poll = 0; poll < 6 && gi < 0; poll++) gi = *reinterpret_cast<volatile int32_t*>(sl);
+      if (gi < 0) {
+        gi = atomicCAS(sl, -1, -2);          // racing consumers over-claimed, or the producer is slow: abandon the ticket
+#ifdef RV_QPROF
+        if (gi < 0) dbg[2]++;
+#endif
+      }
+      if (gi >= 0) *reinterpret_cast<volatile int32_t*>(sl) = -1;
+    }
+    const bool have = gi >= 0;
+    const unsigned have_mask = __ballot_sync(0xFFFFFFFFu, have);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    QP(1);
+    if (have_mask == 0) continue;
+    take = __popc(have_mask);
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)take * (uint32_t)RV_HOT_BYTES) : "memory");
+    __syncwarp();
+    if (have) {
+      stage_in(slot, &states[gi], bar);
+      *reinterpret_cast<G**>(slot + RV_HOT_BYTES) = &states[gi];
+    }
+    {
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+      parity ^= 1;
+    }
+    QP(2);
+    int next = PH_NONE;
+    if (have) {
+      G& g = *reinterpret_cast<G*>(slot);
+      Ctx cx = make_ctx(T, log, cap, gi);
+      cx.defer_init = true;
+      cx.defer_tail = true;
+      uint32_t b = budget[gi];
+      const uint32_t b0 = b;
+      if (cls == PH_ACT) {
+        for (int r = 0; r < reps; r++) {
+          if (!act_fast(cx, g, agent_seed, g.seed)) {
+            next = PH_SLOW;
+            break;
+          }
+          b--;
+          next = classify(g, b);
+          if (next != PH_ACT) break;
+        }
+      } else {
+        if (cls == PH_TAIL) run_pending_tail(cx, g);
+        else if (cls == PH_DEAL) run_pending_init(cx, g);
+        else if (cls == PH_SLOW) random_step_act(cx, g, agent_seed, g.seed), b--;
+        else random_step_resp(cx, g, agent_seed, g.seed), b--;
+        next = classify(g, b);
+      }
+      if (b != b0) {
+        budget[gi] = b;
+        stepped_total += b0 - b;
+        finished_total += g.is_done ? 1 : 0;
+      }
+    }
+#ifdef RV_QPROF
+    __syncwarp();
+    QP(3 + cls);
+    prof[10 + cls]++;
+    prof[15 + cls] += take;
+#endif
+    if (have) {
+      stage_out(&states[gi], slot);
+      __threadfence();
+    }
+    __syncwarp();
+    QP(8);
+    {
+      unsigned retired = __ballot_sync(0xFFFFFFFFu, have && next == PH_NONE);
+      q_push(q, next, gi);
+      if (lane == 0 && retired) atomicSub(&q.ctl[Q_LIVE], (uint32_t)__popc(retired));
+    }
+    QP(9);
+  }
+#ifdef RV_QPROF
+  if (lane == 0)
+  {
+    for (int i = 0; i < 20; i++) atomicAdd(&counters[8 + i], prof[i]);
+    for (int i = 0; i < 4; i++) atomicAdd(&counters[28 + i], dbg[i]);
+  }
+#endif
+  for (int o = 16; o > 0; o >>= 1) {
+    stepped_total += __shfl_down_sync(0xFFFFFFFFu, stepped_total, o);
+    finished_total += __shfl_down_sync(0xFFFFFFFFu, finished_total, o);
+  }
+  if (lane == 0 && stepped_total) {
+    atomicAdd(&counters[0], stepped_total);
+    if (finished_total) atomicAdd(&counters[1], finished_total);
   }
 }
 
@@ -603,12 +925,15 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_budget = nullptr;
   v->h_counts = nullptr;
   v->graph_exec = nullptr;
+  v->d_q_slots = nullptr;
+  v->d_q_ctl = nullptr;
+  v->q_cap = 0;
   v->graph_seed = 0;
   v->graph_period = 0;
   CK(cudaMalloc(&v->d_states, sizeof(G) * n));
   if (log_cap_words) CK(cudaMalloc(&v->d_log, sizeof(uint32_t) * (size_t)n * log_cap_words));
-  CK(cudaMalloc(&v->d_steps, sizeof(unsigned long long) * 2));
-  CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 2, c->stream));
+  CK(cudaMalloc(&v->d_steps, sizeof(unsigned long long) * 32));
+  CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 32, c->stream));
   uint64_t* d_seeds = nullptr;
   if (seeds) {
     CK(cudaMalloc(&d_seeds, sizeof(uint64_t) * n));
@@ -646,6 +971,8 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_budget) cudaFree(v->d_budget);
   if (v->h_counts) cudaFreeHost(v->h_counts);
   if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
+  if (v->d_q_slots) cudaFree(v->d_q_slots);
+  if (v->d_q_ctl) cudaFree(v->d_q_ctl);
   cudaFree(v->d_steps);
   delete v;
   return RV_OK;
@@ -666,7 +993,7 @@ int rv_vec_reset(rv_vec* v, const uint8_t* oya, const uint8_t* round_wind, const
   if ((rc = upload(c, kyotaku, v->n, &d_ky))) return rc;
   if ((rc = upload(c, scores, v->n * MAXP, &d_sc))) return rc;
   if ((rc = upload(c, walls, v->n * (v->game_mode >= 3 ? 108 : 136), &d_walls))) return rc;
-  CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 2, c->stream));
+  CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 32, c->stream));
   reset_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_oya, d_rw, d_honba,
                                                            d_ky, d_sc, d_walls);
   CK(cudaGetLastError());
@@ -731,12 +1058,12 @@ static int env_int(const char* name, int dflt) {
 static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
   int64_t n = v->n;
-  static int slow_every = env_int("RV_SLOW_EVERY", 3), deal_mult = env_int("RV_DEAL_MULT", 8);
+  static int slow_every = env_int("RV_SLOW_EVERY", 1), deal_mult = env_int("RV_DEAL_MULT", 8);
   const int deal_every = slow_every * deal_mult;   // deal drains coincide with slow drains
   if (!v->d_lists) {
     CK(cudaMalloc(&v->d_lists, sizeof(int32_t) * 2 * N_LISTS * n));      // [class][buffer][n]
     CK(cudaMalloc(&v->d_list_counts, sizeof(uint32_t) * 16));            // [class][buffer]
-    CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
+    if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
     CK(cudaMallocHost(&v->h_counts, sizeof(uint32_t) * 16));
   }
   auto list = [&](int ph, int b) { return v->d_lists + (size_t)(ph * 2 + b) * n; };
@@ -764,9 +1091,11 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
     return RV_OK;
   };
 #define LAUNCH(PH, OUT, STREAM, RD)                                                                                   \
-  phase_kernel<PH, OUT><<<grid, 128, 0, STREAM>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, \
-                                                  list(PH, RD), count(PH, RD), out, v->d_steps)
+  phase_kernel<PH, OUT><<<pgrid, PHB, 0, STREAM>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, \
+                                                  list(PH, RD), count(PH, RD), out, v->d_steps, act_reps)
   int grid = grid_for(n, 128);
+  const int pgrid = grid_for(n, PHB);
+  static int act_reps = env_int("RV_ACT_REPS", 4);
   int rc;
   // One period of the pipeline = lcm of the buffer-flip periods (ACT 2, RESP/SLOW/REACT 2*slow_every, DEAL 2*deal_every):
   // after it every write-buffer index is back where it started, so the whole period is captured once into a CUDA graph
@@ -798,8 +1127,8 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
       LAUNCH(PH_ACT, PH_ACT, c->stream, rd_act);
       if (slow_drain) {
         // games returning from the previous drain's RESP/SLOW kernels re-enter through the fast kernel
-        phase_kernel<PH_ACT, PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
-                                                                   list(PH_REACT, rd_react), count(PH_REACT, rd_react), out, v->d_steps);
+        phase_kernel<PH_ACT, PH_ACT><<<pgrid, PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+                                                                   list(PH_REACT, rd_react), count(PH_REACT, rd_react), out, v->d_steps, act_reps);
         CK(cudaStreamWaitEvent(c->aux[0], c->fork_ev, 0));
         CK(cudaStreamWaitEvent(c->aux[2], c->fork_ev, 0));
         LAUNCH(PH_RESP, PH_REACT, c->aux[0], rd_resp);
@@ -809,9 +1138,9 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
         inflight[0] = inflight[2] = true;
       }
       if (deal_drain) {
-        phase_kernel<PH_ACT, PH_ACT><<<grid, 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
+        phase_kernel<PH_ACT, PH_ACT><<<pgrid, PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget,
                                                                    list(PH_REACT_D, rd_react_d), count(PH_REACT_D, rd_react_d), out,
-                                                                   v->d_steps);
+                                                                   v->d_steps, act_reps);
         CK(cudaStreamWaitEvent(c->aux[1], c->fork_ev, 0));
         LAUNCH(PH_DEAL, PH_REACT_D, c->aux[1], rd_deal);
         CK(cudaEventRecord(c->join_ev[1], c->aux[1]));
@@ -823,7 +1152,7 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
     return RV_OK;
   };
   static int use_graph = getenv("RV_GRAPH") ? atoi(getenv("RV_GRAPH")) : 1;
-  if (use_graph == 1 && (!v->graph_exec || v->graph_seed != agent_seed || v->graph_period != period)) {
+  if (use_graph == 1 && (!v->graph_exec || v->graph_seed != agent_seed || v->graph_period != period * 64 + act_reps)) {
     if (v->graph_exec) {
       cudaGraphExecDestroy(v->graph_exec);
       v->graph_exec = nullptr;
@@ -837,7 +1166,7 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
     CK(cudaGraphInstantiate(&v->graph_exec, graph, 0));
     cudaGraphDestroy(graph);
     v->graph_seed = agent_seed;
-    v->graph_period = period;
+    v->graph_period = period * 64 + act_reps;
     for (int ph = 0; ph < N_LISTS; ph++) wr[ph] = 0;   // capture leaves every class back at buffer 0 (period property)
   }
   CK(cudaMemsetAsync(v->d_list_counts, 0, sizeof(uint32_t) * 16, c->stream));
@@ -861,13 +1190,37 @@ static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   if (getenv("RV_DEBUG")) fprintf(stderr, "[rollout_phased] iterations=%llu slow_every=%d deal_every=%d\n", (unsigned long long)it_total, slow_every, deal_every);
   return RV_OK;
 }
-static bool use_phased() {
+
+// Persistent scheduler: one launch for the whole rollout (see rollout_persistent_kernel).
+static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
+  rv_ctx* c = v->ctx;
+  int64_t n = v->n;
+  if (!v->d_q_slots) {
+    uint32_t capq = 64;
+    while ((int64_t)capq < 2 * n) capq <<= 1;
+    v->q_cap = capq;
+    CK(cudaMalloc(&v->d_q_slots, sizeof(int32_t) * N_QUEUES * (size_t)capq));
+    CK(cudaMalloc(&v->d_q_ctl, sizeof(uint32_t) * Q_CTL_WORDS));
+    if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
+  }
+  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 6);
+  Queues q{v->d_q_slots, v->d_q_ctl, v->q_cap - 1};
+  CK(cudaMemsetAsync(v->d_q_ctl, 0, sizeof(uint32_t) * Q_CTL_WORDS, c->stream));
+  CK(cudaMemsetAsync(v->d_q_slots, 0xFF, sizeof(int32_t) * N_QUEUES * (size_t)v->q_cap, c->stream));   // every slot empty (abandoned marks of the last call included)
+  q_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, q);
+  int64_t crew = (int64_t)c->sm_count * warps_per_sm, need = (n + PHB - 1) / PHB;
+  rollout_persistent_kernel<<<(int)(crew < need ? crew : need), PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed,
+                                                                                    v->d_budget, q, v->d_steps, act_reps);
+  CK(cudaGetLastError());
+  return RV_OK;
+}
+static int rollout_mode() {   // RV_ROLLOUT = mono | phased | persistent (default)
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("RV_ROLLOUT");
-    mode = (e && strcmp(e, "mono") == 0) ? 0 : 1;
+    mode = (e && strcmp(e, "mono") == 0) ? 0 : (e && strcmp(e, "phased") == 0) ? 1 : 2;
   }
-  return mode == 1;
+  return mode;
 }
 int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
@@ -875,14 +1228,34 @@ int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps)
   if (max_steps == 0) return RV_OK;
   // short calls (lock-step drivers, per-step observation loops) use the single persistent kernel: the phase pipeline
   // needs a few dozen iterations to drain its deferred lists and only pays off for long rollouts
-  return (use_phased() && max_steps >= 32) ? rollout_phased(v, agent_seed, max_steps) : rollout_mono(v, agent_seed, max_steps);
+  const int mode = rollout_mode();
+  if (mode == 0 || max_steps < 32) return rollout_mono(v, agent_seed, max_steps);
+  return mode == 1 ? rollout_phased(v, agent_seed, max_steps) : rollout_persistent(v, agent_seed, max_steps);
 }
 int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done) {
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   unsigned long long h[2];
+  uint32_t sched_err = 0;
   CK(cudaMemcpyAsync(h, v->d_steps, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  if (v->d_q_ctl) CK(cudaMemcpyAsync(&sched_err, v->d_q_ctl + Q_ERR, sizeof sched_err, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (sched_err) return fail(RV_ERR_CUDA, "rollout scheduler watchdog: live games but no queued work");
+#ifdef RV_QPROF
+  {
+    unsigned long long p[32];
+    CK(cudaMemcpy(p, v->d_steps, sizeof p, cudaMemcpyDeviceToHost));
+    const char* nm[10] = {"idle", "claim", "stage_in", "ACT", "RESP", "DEAL", "SLOW", "TAIL", "stage_out", "push"};
+    unsigned long long tot = 0;
+    for (int i = 0; i < 10; i++) tot += p[8 + i];
+    if (tot) fprintf(stderr, "[qprof] steps=%llu total warp-cycles=%llu\n", h[0], tot);
+    for (int i = 0; i < 10 && tot; i++) fprintf(stderr, "[qprof] %-9s %6.2f%%\n", nm[i], 100.0 * p[8 + i] / (tot ? tot : 1));
+    if (tot) fprintf(stderr, "[qprof] (unused)=%llu empty_looks=%llu tickets_abandoned=%llu sm_switches=%llu\n", p[28], p[29], p[30], p[31]);
+    for (int c2 = 0; c2 < 5 && tot; c2++)
+      fprintf(stderr, "[qprof] class %s: batches=%llu games=%llu (%.1f/batch) cycles/batch=%.0f\n", nm[3 + c2], p[18 + c2], p[23 + c2],
+              p[18 + c2] ? (double)p[23 + c2] / p[18 + c2] : 0.0, p[18 + c2] ? (double)p[11 + c2] / p[18 + c2] : 0.0);
+  }
+#endif
   if (steps_total) *steps_total = h[0];
   if (games_done) *games_done = (int64_t)h[1];
   return RV_OK;

@@ -111,6 +111,10 @@ class HostsimBackend(Backend):
     def random_step(self, agent_seed, game_id):
         self.lib.hs_game_random_step(self.h, agent_seed, game_id)
 
+    def visit_deferred(self, agent_seed, game_id):
+        """One scheduler visit of the rollout kernels (parked discard tails / deals run on their own visit)."""
+        return self.lib.hs_game_random_step_deferred(self.h, agent_seed, game_id)
+
     def legal(self, pid):
         out = (A.Action * A.MAX_LEGAL)()
         n = self.lib.hs_game_legal(self.h, pid, out)

@@ -39,7 +39,8 @@ def load():
     lib.hs_game_legal.argtypes = [C.c_void_p, C.c_int, P(A.Action)]
     lib.hs_game_step.argtypes = [C.c_void_p, P(A.Action)]
     lib.hs_game_random_step.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
-    lib.hs_game_random_step_deferred.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
+    lib.hs_game_random_step_deferred.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.hs_game_random_step_deferred.restype = C.c_int
     lib.hs_game_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.hs_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.hs_game_events.restype = C.c_uint32

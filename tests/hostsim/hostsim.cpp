@@ -1,6 +1,13 @@
 // TEST INFRASTRUCTURE ONLY (see cuda_shim.h).  Host compile of the device sources with a
 // C surface parallel to oracle/capi.cpp, so tests can diff kernel logic vs oracle on CPU.
 #include "cuda_shim.h"
+#include "../../include/riichienv_b200.h"
+// Emulation of the rollout kernels' shared-memory staging: the random-step entry points run the game code on a
+// copy of the record's hot prefix followed by poison, with cold(g) redirected to the real record — a device-code
+// access to a cold array that forgets cold(g) reads poison (parity with the oracle breaks) or trips the poison check.
+static thread_local rv_game_state* hs_staged = nullptr;
+static thread_local rv_game_state* hs_home = nullptr;
+#define RV_COLD_HOOK(g) (&(g) == hs_staged ? *hs_home : (g))
 
 #include <atomic>
 #include <cstdio>
@@ -206,6 +213,7 @@ void* hs_game_new(int mode, uint64_t seed, uint32_t rule, uint32_t log_cap) {
   h->g.hand_index = 1;
   h->g.last_error = RV_NONE;
   h->g.pending_init[0] = h->g.pending_init[1] = h->g.pending_init[2] = RV_NONE;
+  h->g.pending_tail[0] = RV_NONE;
   h->g.is_done = 1;
   for (int s = 0; s < MAXP; s++) h->g.score[s] = mode >= 3 ? (s < 3 ? 35000 : 0) : 25000;
   h->log.assign(log_cap, 0);
@@ -217,6 +225,7 @@ static Ctx hs_ctx(HS* h) {
   cx.log = h->log.empty() ? nullptr : h->log.data();
   cx.log_cap = (uint32_t)h->log.size();
   cx.defer_init = false;
+  cx.defer_tail = false;
   return cx;
 }
 void hs_game_free(void* p) { delete (HS*)p; }
@@ -265,21 +274,53 @@ void hs_game_step(void* p, const rv_action* in) {
   }
   step_apply(cx, g, acts);
 }
+struct Staged {
+  alignas(16) unsigned char buf[sizeof(G) + 64];
+  G* home;
+  explicit Staged(G& real) : home(&real) {
+    memset(buf, 0xAB, sizeof buf);
+    memcpy(buf, &real, RV_HOT_BYTES);
+    hs_staged = reinterpret_cast<G*>(buf);
+    hs_home = home;
+  }
+  G& g() { return *reinterpret_cast<G*>(buf); }
+  ~Staged() {
+    for (size_t k = RV_HOT_BYTES; k < sizeof buf; k++)
+      if (buf[k] != 0xAB) {
+        fprintf(stderr, "hostsim: device code wrote a cold field through the staged copy (offset %zu)\n", k);
+        abort();
+      }
+    memcpy(home, buf, RV_HOT_BYTES);
+    hs_staged = hs_home = nullptr;
+  }
+};
 void hs_game_random_step(void* p, uint64_t agent_seed, uint64_t game_id) {
   HS* h = (HS*)p;
   Ctx cx = hs_ctx(h);
-  if (!h->g.is_done) random_step(cx, h->g, agent_seed, game_id);
+  if (h->g.is_done) return;
+  Staged st(h->g);
+  random_step(cx, st.g(), agent_seed, game_id);
 }
-void hs_game_random_step_deferred(void* p, uint64_t agent_seed, uint64_t game_id, int flush) {
+// One scheduler visit as the rollout kernels make it: a parked discard tail or a parked deal is run on its own visit,
+// otherwise the game takes one random step with both deferrals armed.  Returns 1 if an env step was taken.
+int hs_game_random_step_deferred(void* p, uint64_t agent_seed, uint64_t game_id) {
   HS* h = (HS*)p;
   Ctx cx = hs_ctx(h);
   cx.defer_init = true;
-  if (h->g.pending_init[0] != RV_NONE) {
-    if (flush) run_pending_init(cx, h->g);
-    return;
+  cx.defer_tail = true;
+  Staged st(h->g);
+  G& g = st.g();
+  if (g.pending_tail[0] != RV_NONE) {
+    run_pending_tail(cx, g);
+    return 0;
   }
-  if (!h->g.is_done) random_step(cx, h->g, agent_seed, game_id);
-  if (flush && h->g.pending_init[0] != RV_NONE) run_pending_init(cx, h->g);
+  if (g.pending_init[0] != RV_NONE) {
+    run_pending_init(cx, g);
+    return 0;
+  }
+  if (g.is_done) return 0;
+  random_step(cx, g, agent_seed, game_id);
+  return 1;
 }
 void hs_game_snapshot(void* p, rv_game_state* out) { *out = ((HS*)p)->g; }
 void hs_game_load_snapshot(void* p, const rv_game_state* in) {
