@@ -1880,7 +1880,9 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
              g.c_cnt[pid][2], g.c_cnt[pid][3]);
   }
 #endif
-  if (claims || drawn == RV_NONE || first || g.drawable_count == 0 || g.n_dora != 1 ||
+  // (first turn: only a wind discard can complete a sufuurenta; 4-kan / 4-riichi draws need a kan or a riichi discard)
+  // four kans (every kan draws a rinshan tile in 4P) can end the round at this discard; a pending kan dora is flipped by it
+  if (claims || (first && kind >= 27 && kind <= 30) || g.drawable_count == 0 || g.n_dora >= 5 || g.rinshan_draw_count >= 4 ||
       g.pending_kan_dora_count != 0) {
     return act_fast_tail(cx, g, pid, tile, tsumogiri);
   }
@@ -1910,6 +1912,7 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
   g.n_claims[0] = g.n_claims[1] = g.n_claims[2] = g.n_claims[3] = 0;
   // the next seat draws (_deal_next, state/mod.rs:1569-1593)
   g.turn_count++;
+  if (first && g.turn_count >= 4) g.is_first_turn = 0;
   const int nxt = (pid + 1) & 3;
   g.current_player = (uint8_t)nxt;
   const int t2 = cold(g).wall[g.wall_top - 1];

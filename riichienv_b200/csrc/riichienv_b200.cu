@@ -583,8 +583,14 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
           if (next != PH_ACT) break;
         }
       } else {
-        if (cls == PH_TAIL) run_pending_tail(cx, g);
-        else if (cls == PH_DEAL) run_pending_init(cx, g);
+        if (cls == PH_TAIL) {
+          // the parked follow-up of a discard; when it opens a claim window the answers are taken in the same visit
+          run_pending_tail(cx, g);
+          if (b > 0 && !g.is_done && g.pending_init[0] == RV_NONE && g.phase == RV_WAIT_RESPONSE) {
+            random_step_resp(cx, g, agent_seed, g.seed);
+            b--;
+          }
+        } else if (cls == PH_DEAL) run_pending_init(cx, g);
         else if (cls == PH_SLOW) random_step_act(cx, g, agent_seed, g.seed), b--;
         else random_step_resp(cx, g, agent_seed, g.seed), b--;
         next = classify(g, b);
@@ -1203,7 +1209,7 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
     CK(cudaMalloc(&v->d_q_ctl, sizeof(uint32_t) * Q_CTL_WORDS));
     if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
   }
-  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 6);
+  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 10);
   Queues q{v->d_q_slots, v->d_q_ctl, v->q_cap - 1};
   CK(cudaMemsetAsync(v->d_q_ctl, 0, sizeof(uint32_t) * Q_CTL_WORDS, c->stream));
   CK(cudaMemsetAsync(v->d_q_slots, 0xFF, sizeof(int32_t) * N_QUEUES * (size_t)v->q_cap, c->stream));   // every slot empty (abandoned marks of the last call included)
