@@ -335,6 +335,24 @@ int rv_wall_from_seed(uint64_t seed, uint64_t hand_index, int n_tiles /*136|108*
  * *n_obs (host, may be NULL -> fully asynchronous) receives the number of rows; rows beyond max_obs are dropped. */
 int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
 
+/* Sequence features (observation/sequence_features.rs:331-835; docs/SEQUENCE_FEATURE_ENCODING.md) for every seat that
+ * owes an action, rows in the same (game, seat) order as rv_vec_encode.  4P only (as in the reference); the vector
+ * must have been created with an event log (log_cap_words > 0).
+ *   d_sparse  [max_obs][25] u16     encode_seq_sparse(game_style), padded with 441            — may be NULL
+ *   d_numeric [max_obs][12] f32     encode_seq_numeric                                       — may be NULL
+ *   d_prog    [max_obs][max_prog][5] u16  encode_seq_progression, padded with (4,276,2,2,4)   — may be NULL
+ *   d_cand    [max_obs][64][4] u16  encode_seq_candidates, padded with (279,2,2,3)            — may be NULL
+ *   d_lens    [max_obs][3] u16      lengths the reference would return: sparse, progression (<= 512), candidates
+ *   d_index   [max_obs] i32         game*4 + seat                                             — may be NULL
+ * The features are functions of the seat's EVENT DELTA: the events pushed since that seat's previous observation
+ * (state/mod.rs:211-218; the live env never enables the progression cache, state/mod.rs:146).
+ *   start_words == NULL: the library keeps one cursor per (game, seat) — zeroed by rv_vec_reset, advanced to the end
+ *                        of the log by every rv_vec_encode_seq call for the seats it observed;
+ *   start_words != NULL: host array [n][4] of word offsets into each game's event log; internal cursors untouched. */
+int rv_vec_encode_seq(rv_vec* v, int game_style, const uint32_t* start_words, uint16_t* d_sparse, float* d_numeric,
+                      uint16_t* d_prog, int max_prog, uint16_t* d_cand, uint16_t* d_lens, int32_t* d_index, int64_t max_obs,
+                      int64_t* n_obs);
+
 #ifdef __cplusplus
 }
 #endif

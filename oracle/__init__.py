@@ -50,6 +50,12 @@ def load():
     lib.orc_game_events.restype = C.c_uint32
     lib.orc_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.orc_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]
+    lib.orc_game_encode_seq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(C.c_uint16), P(C.c_float),
+                                        P(C.c_uint16), C.c_int, P(C.c_uint16), P(C.c_uint16)]
+    for name in ("orc_seq_encode_chi", "orc_seq_encode_pon"):
+        getattr(lib, name).argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.orc_seq_kan37.argtypes = [C.c_int]
+    lib.orc_seq_relative_from.argtypes = [C.c_int, C.c_int]
     lib.orc_run_random.restype = C.c_int64
     lib.orc_run_random.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_int,
                                    P(C.c_int32), P(C.c_uint8), P(C.c_uint8), P(C.c_uint32), P(C.c_uint32),

@@ -7,6 +7,7 @@
 
 #include "game.hpp"
 #include "obs.hpp"
+#include "seq.hpp"
 #include "shanten.hpp"
 
 using namespace orc;
@@ -364,6 +365,26 @@ extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {
   if (obs) encode_obs(*g, pid, obs);
   if (mask) encode_mask(*g, pid, mask);
 }
+// sequence features of seat pid over the event delta [w0, w1) (words); fixed-size outputs padded like the device path
+extern "C" void orc_game_encode_seq(void* h, int pid, uint32_t w0, uint32_t w1, int game_style, uint16_t* sparse, float* numeric,
+                                    uint16_t* prog, int max_prog, uint16_t* cand, uint16_t* lens) {
+  GameState* g = (GameState*)h;
+  SeqFeatures f = encode_seq(*g, pid, w0, w1, game_style);
+  for (int k = 0; k < 25; k++) sparse[k] = k < (int)f.sparse.size() ? f.sparse[k] : 441;
+  for (int k = 0; k < 12; k++) numeric[k] = f.numeric[k];
+  static const uint16_t PP[5] = {4, 276, 2, 2, 4}, CP[4] = {279, 2, 2, 3};
+  for (int k = 0; k < max_prog; k++)
+    for (int j = 0; j < 5; j++) prog[5 * k + j] = k < (int)f.prog.size() ? f.prog[k][j] : PP[j];
+  for (int k = 0; k < 64; k++)
+    for (int j = 0; j < 4; j++) cand[4 * k + j] = k < (int)f.cand.size() ? f.cand[k][j] : CP[j];
+  lens[0] = (uint16_t)f.sparse.size();
+  lens[1] = (uint16_t)f.prog.size();
+  lens[2] = (uint16_t)f.cand.size();
+}
+extern "C" int orc_seq_encode_chi(int c0, int c1, int called) { return seq_encode_chi({(uint8_t)c0, (uint8_t)c1}, called); }
+extern "C" int orc_seq_encode_pon(int c0, int c1, int called) { return seq_encode_pon({(uint8_t)c0, (uint8_t)c1}, called); }
+extern "C" int orc_seq_kan37(int tid) { return seq_tile_id_to_kan37(tid); }
+extern "C" int orc_seq_relative_from(int actor, int target) { return seq_relative_from(actor, target); }
 extern "C" int orc_sizeof(int which) {
   switch (which) {
     case 0: return (int)sizeof(rv_game_state);

@@ -1767,10 +1767,10 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
   if (hl + 3 * nm != 14) return RV_DECLINE(21);
   const uint64_t c0 = g.c_cnt[pid][0], c1 = g.c_cnt[pid][1], c2 = g.c_cnt[pid][2], c3 = g.c_cnt[pid][3];
   if ((c0 | c1 | c2 | c3) & 0x4444444444444444ull) return RV_DECLINE(22);             // four of a kind: ankan may be legal
-  uint32_t e[4] = {__ldg(&cx.T.suit_info[g.c_key[pid][0]]), __ldg(&cx.T.suit_info[g.c_key[pid][1]]),
-                   __ldg(&cx.T.suit_info[g.c_key[pid][2]]), __ldg(&cx.T.honor_info[g.c_key[pid][3]])};
+  const uint32_t e0 = __ldg(&cx.T.suit_info[g.c_key[pid][0]]), e1 = __ldg(&cx.T.suit_info[g.c_key[pid][1]]),
+                 e2 = __ldg(&cx.T.suit_info[g.c_key[pid][2]]), e3 = __ldg(&cx.T.honor_info[g.c_key[pid][3]]);
   // suits that are complete (M or P).  agari needs 4 of them, "some discard leaves tenpai" needs >= 2
-  const int complete = ((e[0] | (e[0] >> 1)) & 1) + ((e[1] | (e[1] >> 1)) & 1) + ((e[2] | (e[2] >> 1)) & 1) + ((e[3] | (e[3] >> 1)) & 1);
+  const int complete = ((e0 | (e0 >> 1)) & 1) + ((e1 | (e1 >> 1)) & 1) + ((e2 | (e2 >> 1)) & 1) + ((e3 | (e3 >> 1)) & 1);
   bool open_meld = false;
   #pragma unroll 1
   for (int m = 0; m < nm; m++) {
@@ -1901,10 +1901,13 @@ __device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, 
   {
     // waits of the 13-tile hand: only the discarded tile's suit entry changed
     const uint32_t key = g.c_key[pid][ksu];
-    e[ksu] = ksu == 3 ? __ldg(&cx.T.honor_info[key]) : __ldg(&cx.T.suit_info[key]);
+    const uint32_t en = ksu == 3 ? __ldg(&cx.T.honor_info[key]) : __ldg(&cx.T.suit_info[key]);
     SuitInfo si;
-    si.e[0] = e[0], si.e[1] = e[1], si.e[2] = e[2], si.e[3] = e[3];
-    g.c_waits[pid] = waits13(hand_cnt(g, pid), si);
+    si.e[0] = ksu == 0 ? en : e0, si.e[1] = ksu == 1 ? en : e1, si.e[2] = ksu == 2 ? en : e2, si.e[3] = ksu == 3 ? en : e3;
+    Cnt cn;
+    cn.s[0] = c0, cn.s[1] = c1, cn.s[2] = c2, cn.s[3] = c3;
+    cnt_sub(cn, kind);
+    g.c_waits[pid] = waits13_inl(cn, si);
   }
   g.last_discard_pid = (uint8_t)pid;
   g.last_discard_tile = (uint8_t)tile;

@@ -153,7 +153,7 @@ __device__ __forceinline__ bool agari14(const Tables& T, const Cnt& c) {
 
 // get_waits_u8 (hand_evaluator.rs:196-213) of a 3n+1 concealed hand: 34-bit mask.
 // `si` holds the suit entries of `c`.
-__device__ __noinline__ uint64_t waits13(const Cnt& c, const SuitInfo& si) {
+__device__ __forceinline__ uint64_t waits13_inl(const Cnt& c, const SuitInfo& si) {
   int nM = (si.e[0] & 1) + (si.e[1] & 1) + (si.e[2] & 1) + (si.e[3] & 1);
   int nP = ((si.e[0] >> 1) & 1) + ((si.e[1] >> 1) & 1) + ((si.e[2] >> 1) & 1) + ((si.e[3] >> 1) & 1);
   uint64_t w = 0;
@@ -207,6 +207,7 @@ __device__ __noinline__ uint64_t waits13(const Cnt& c, const SuitInfo& si) {
   }
   return w;
 }
+__device__ __noinline__ uint64_t waits13(const Cnt& c, const SuitInfo& si) { return waits13_inl(c, si); }
 __device__ __forceinline__ uint64_t waits13(const Tables& T, const Cnt& c) {
   SuitInfo si;
   load_info(T, c, si);

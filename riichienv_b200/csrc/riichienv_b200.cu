@@ -10,6 +10,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "obs.cuh"
+#include "seq.cuh"
 
 using namespace rv;
 
@@ -49,6 +50,8 @@ struct rv_vec {
   uint64_t* d_seeds;            // scratch for rv_vec_reseed
   int32_t *d_obs_counts, *d_obs_offsets;   // encode: active seats per game and their exclusive scan (n + 1)
   void* d_scan_tmp;
+  uint32_t* d_seq_cursor;       // [n][4] event-log word offset of each seat's previous observation (rv_vec_encode_seq)
+  uint32_t* d_seq_start;        // [n][4] scratch for caller-supplied cursors
   size_t scan_tmp_bytes;
   // phase pipeline (rv_vec_step_random): per-phase game lists, double buffered, and per-game step budgets
   int32_t* d_lists;             // [2 buffers][3 phases][n]
@@ -765,6 +768,39 @@ __global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* stat
   }
 }
 
+
+// ---- sequence features: one thread per game, one row per seat that owes an action ----------------------------------
+__global__ void seq_encode_kernel(Tables T, const G* states, int64_t n, const uint32_t* log, uint32_t cap, const int32_t* offsets,
+                                  const uint32_t* start, uint32_t* cursor, int game_style, uint16_t* sparse, float* numeric,
+                                  uint16_t* prog, int max_prog, uint16_t* cand, uint16_t* lens, int32_t* index, int64_t max_obs) {
+  int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n) return;
+  const G& g = states[gi];
+  if (g.is_done) return;
+  Ctx cx = make_ctx(T, nullptr, 0, gi);
+  const uint32_t* glog = log + (size_t)gi * cap;
+  const uint32_t end = g.ev_words < cap ? g.ev_words : cap;
+  int64_t row = offsets[gi];
+  for (int pid = 0; pid < MAXP; pid++) {
+    if (!((g.active_mask >> pid) & 1)) continue;
+    if (row < max_obs) {
+      uint32_t w0 = start ? start[gi * 4 + pid] : cursor[gi * 4 + pid];
+      if (w0 > end) w0 = end;
+      SeqOut o;
+      o.sparse = sparse ? sparse + row * SEQ_MAX_SPARSE : nullptr;
+      o.numeric = numeric ? numeric + row * SEQ_NUMERIC : nullptr;
+      o.prog = prog ? prog + row * (int64_t)max_prog * 5 : nullptr;
+      o.cand = cand ? cand + row * SEQ_MAX_CAND * 4 : nullptr;
+      o.lens = lens ? lens + row * 3 : nullptr;
+      o.max_prog = max_prog;
+      seq_encode(cx, g, pid, glog, w0, end, game_style, o);
+      if (index) index[row] = (int32_t)(gi * 4 + pid);
+    }
+    if (!start) cursor[gi * 4 + pid] = end;      // the delta advances on every observation (state/mod.rs:218)
+    row++;
+  }
+}
+
 __global__ void results_kernel(const G* states, int64_t n, uint8_t* done, int32_t* scores, uint8_t* ranks, uint32_t* step_count,
                                uint32_t* kyoku_count, uint32_t* ev_count, uint64_t* ev_hash) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -931,6 +967,8 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_budget = nullptr;
   v->h_counts = nullptr;
   v->graph_exec = nullptr;
+  v->d_seq_cursor = nullptr;
+  v->d_seq_start = nullptr;
   v->d_q_slots = nullptr;
   v->d_q_ctl = nullptr;
   v->q_cap = 0;
@@ -977,6 +1015,8 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_budget) cudaFree(v->d_budget);
   if (v->h_counts) cudaFreeHost(v->h_counts);
   if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
+  if (v->d_seq_cursor) cudaFree(v->d_seq_cursor);
+  if (v->d_seq_start) cudaFree(v->d_seq_start);
   if (v->d_q_slots) cudaFree(v->d_q_slots);
   if (v->d_q_ctl) cudaFree(v->d_q_ctl);
   cudaFree(v->d_steps);
@@ -999,6 +1039,7 @@ int rv_vec_reset(rv_vec* v, const uint8_t* oya, const uint8_t* round_wind, const
   if ((rc = upload(c, kyotaku, v->n, &d_ky))) return rc;
   if ((rc = upload(c, scores, v->n * MAXP, &d_sc))) return rc;
   if ((rc = upload(c, walls, v->n * (v->game_mode >= 3 ? 108 : 136), &d_walls))) return rc;
+  if (v->d_seq_cursor) CK(cudaMemsetAsync(v->d_seq_cursor, 0, sizeof(uint32_t) * 4 * v->n, c->stream));   // player_event_counts = [0; NP]
   CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 32, c->stream));
   reset_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_oya, d_rw, d_honba,
                                                            d_ky, d_sc, d_walls);
@@ -1378,6 +1419,44 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
     CK(cudaMemcpyAsync(&total, v->d_obs_offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     *n_obs = total;
+  }
+  return RV_OK;
+}
+int rv_vec_encode_seq(rv_vec* v, int game_style, const uint32_t* start_words, uint16_t* d_sparse, float* d_numeric, uint16_t* d_prog,
+                      int max_prog, uint16_t* d_cand, uint16_t* d_lens, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
+  if (v->game_mode >= 3) return fail(RV_ERR_UNSUPPORTED, "sequence features are 4P only (observation/sequence_features.rs:811)");
+  if (!v->d_log || v->log_cap == 0) return fail(RV_ERR_INVALID, "sequence features read the event log: create the vector with log_cap_words > 0");
+  if (max_prog < 0 || (d_prog && max_prog == 0)) return fail(RV_ERR_INVALID, "max_prog must be positive");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  int64_t n = v->n;
+  if (!v->d_obs_counts) {
+    CK(cudaMalloc(&v->d_obs_counts, sizeof(int32_t) * (n + 1)));
+    CK(cudaMalloc(&v->d_obs_offsets, sizeof(int32_t) * (n + 1)));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, v->scan_tmp_bytes, v->d_obs_counts, v->d_obs_offsets, (int)(n + 1), c->stream));
+    CK(cudaMalloc(&v->d_scan_tmp, v->scan_tmp_bytes));
+  }
+  if (!v->d_seq_cursor) {
+    CK(cudaMalloc(&v->d_seq_cursor, sizeof(uint32_t) * 4 * n));
+    CK(cudaMemsetAsync(v->d_seq_cursor, 0, sizeof(uint32_t) * 4 * n, c->stream));
+  }
+  const uint32_t* d_start = nullptr;
+  if (start_words) {
+    if (!v->d_seq_start) CK(cudaMalloc(&v->d_seq_start, sizeof(uint32_t) * 4 * n));
+    CK(cudaMemcpyAsync(v->d_seq_start, start_words, sizeof(uint32_t) * 4 * n, cudaMemcpyHostToDevice, c->stream));
+    d_start = v->d_seq_start;
+  }
+  obs_count_kernel<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(v->d_states, n, v->d_obs_counts);
+  CK(cub::DeviceScan::ExclusiveSum(v->d_scan_tmp, v->scan_tmp_bytes, v->d_obs_counts, v->d_obs_offsets, (int)(n + 1), c->stream));
+  seq_encode_kernel<<<grid_for(n, 64), 64, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, v->d_obs_offsets, d_start,
+                                                          v->d_seq_cursor, game_style, d_sparse, d_numeric, d_prog, max_prog, d_cand,
+                                                          d_lens, d_index, max_obs);
+  CK(cudaGetLastError());
+  if (n_obs || start_words) {      // (the caller's start_words must stay valid until the copy has run)
+    int32_t total = 0;
+    CK(cudaMemcpyAsync(&total, v->d_obs_offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_obs) *n_obs = total;
   }
   return RV_OK;
 }

@@ -102,6 +102,27 @@ class VecRiichiEnv:
         check(lib().rv_vec_encode(self.handle, ptr(obs), ptr(mask), ptr(index), int(max_obs), C.byref(n) if sync else None))
         return int(n.value) if sync else None
 
+    def encode_seq(self, sparse=None, numeric=None, prog=None, cand=None, lens=None, index=None, game_style=1, max_obs=None,
+                   start_words=None, sync=True):
+        """Sequence features (Observation.encode_seq_sparse/numeric/progression/candidates) of every seat that owes an
+        action, into DEVICE buffers (torch tensors): sparse [max_obs,25] u16 (pad 441), numeric [max_obs,12] f32,
+        prog [max_obs,max_prog,5] u16 (pad 4,276,2,2,4), cand [max_obs,64,4] u16 (pad 279,2,2,3), lens [max_obs,3] u16,
+        index [max_obs] i32.  The features cover each seat's event delta since its previous observation: by default the
+        library's per-seat cursors are used and advanced; `start_words` (numpy u32 [n,4]) overrides them."""
+        def ptr(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        if max_obs is None:
+            max_obs = min(t.shape[0] for t in (sparse, numeric, prog, cand, lens, index) if t is not None)
+        max_prog = int(prog.shape[1]) if prog is not None else 0
+        sw = None
+        if start_words is not None:
+            start_words = np.ascontiguousarray(start_words, np.uint32).reshape(self.n, A.NP)
+            sw = _ptr(start_words, C.c_uint32)
+        n = C.c_int64(0)
+        check(lib().rv_vec_encode_seq(self.handle, int(game_style), sw, ptr(sparse), ptr(numeric), ptr(prog), max_prog, ptr(cand),
+                                      ptr(lens), ptr(index), int(max_obs), C.byref(n) if (sync or sw is not None) else None))
+        return int(n.value) if (sync or sw is not None) else None
+
     def results(self):
         done = np.zeros(self.n, np.uint8)
         scores = np.zeros((self.n, A.NP), np.int32)

@@ -46,6 +46,8 @@ def load():
     lib.hs_game_events.restype = C.c_uint32
     lib.hs_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.hs_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]
+    lib.hs_game_encode_seq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(C.c_uint16), P(C.c_float),
+                                       P(C.c_uint16), C.c_int, P(C.c_uint16), P(C.c_uint16)]
     lib.hs_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]
     cache = os.environ.get("RV_HOSTSIM_CACHE", "/tmp/rv_hostsim_tables.bin")
     lib.hs_init(cache.encode(), os.cpu_count() or 1)

@@ -15,6 +15,7 @@ static thread_local rv_game_state* hs_home = nullptr;
 #include <vector>
 
 #include "../../riichienv_b200/csrc/obs.cuh"
+#include "../../riichienv_b200/csrc/seq.cuh"
 
 using namespace rv;
 
@@ -358,6 +359,13 @@ void hs_game_encode(void* p, int pid, float* obs, uint8_t* mask) {
       if (id >= 0 && id < 82) mask[id] = 1;
     }
   }
+}
+void hs_game_encode_seq(void* p, int pid, uint32_t w0, uint32_t w1, int game_style, uint16_t* sparse, float* numeric, uint16_t* prog,
+                        int max_prog, uint16_t* cand, uint16_t* lens) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  SeqOut o{sparse, numeric, prog, cand, lens, max_prog};
+  seq_encode(cx, h->g, pid, h->log.data(), w0, w1, game_style, o);
 }
 int hs_wall_from_seed(uint64_t seed, uint64_t hand_index, int n, uint8_t* out) {
   wall_from_seed(seed, hand_index, n, out);

@@ -125,6 +125,17 @@ def test_random_games_vs_oracle(orc, mode, rule, n):
     assert g[1].all()   # incl. the rare stalled 3P games, which the rollout retires (overflow bit 1)
 
 
+def test_parity_gate_100k_games(orc):
+    """The parity gate that accompanies the headline number (SURVEY.md section 8 d): >= 10^5 hanchan, final done / scores /
+    ranks / step count / round count / event count / 64-bit event-stream hash equal between the CUDA rollout and the oracle."""
+    n = 102400
+    g, o = run_both(orc, n, 2, A.RULE_DEFAULT_TENHOU, seed_base=5_000_000, agent_seed=0x5EED)
+    assert g[0] == o[0], "total env steps"
+    for name, a, b in zip(["done", "scores", "ranks", "step_count", "kyoku_count", "ev_count", "ev_hash"], g[1:], o[1:]):
+        assert np.array_equal(a, b), f"{name} differs in {int((a != b).sum())} entries"
+    assert g[1].all() and g[0] > 1000 * n
+
+
 def test_partial_rollout_and_resume(orc):
     """max_steps < game length: state must carry over between launches exactly."""
     from riichienv_b200.vec_env import VecRiichiEnv
@@ -253,6 +264,66 @@ def test_observation_encode_vs_oracle(orc):
     for h in games:
         orc.orc_game_free(h)
     assert checked > 10000
+
+
+def test_sequence_features_vs_oracle(orc):
+    """rv_vec_encode_seq: sparse / numeric / progression / candidates of every acting seat of 128 games, observed after
+    single steps and after multi-step strides (so the per-seat event deltas span several steps), bytes equal to the
+    oracle; once more with caller-supplied cursors."""
+    import torch
+
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n, MP = 128, 96
+    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=7700, log_cap_words=8192)
+    v.reset()
+    games = [orc.orc_game_new(2, 7700 + g, 0, A.RULE_DEFAULT_TENHOU, 1) for g in range(n)]
+    for h in games:
+        orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    dev = dict(device="cuda")
+    sparse = torch.empty((n * 3, 25), dtype=torch.uint16, **dev)
+    numeric = torch.empty((n * 3, 12), dtype=torch.float32, **dev)
+    prog = torch.empty((n * 3, MP, 5), dtype=torch.uint16, **dev)
+    cand = torch.empty((n * 3, 64, 4), dtype=torch.uint16, **dev)
+    lens = torch.empty((n * 3, 3), dtype=torch.uint16, **dev)
+    idx = torch.empty((n * 3,), dtype=torch.int32, **dev)
+    o_sp, o_nu, o_pr, o_ca, o_le = (np.zeros(25, np.uint16), np.zeros(12, np.float32), np.zeros(MP * 5, np.uint16),
+                                    np.zeros(64 * 4, np.uint16), np.zeros(3, np.uint16))
+    u16 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint16))
+    cursor = np.zeros((n, 4), np.uint32)
+    checked = long_delta = 0
+    st = A.GameState()
+    for it in range(70):
+        explicit = it % 7 == 6          # this round passes the cursors explicitly and must not advance the internal ones
+        rows = v.encode_seq(sparse=sparse, numeric=numeric, prog=prog, cand=cand, lens=lens, index=idx, game_style=1,
+                            start_words=cursor.copy() if explicit else None)
+        h = [t[:rows].cpu().numpy() for t in (sparse, numeric, prog, cand, lens, idx)]
+        row = 0
+        for g in range(n):
+            orc.orc_game_snapshot(games[g], C.byref(st))
+            if st.is_done:
+                continue
+            for p in range(4):
+                if (st.active_mask >> p) & 1:
+                    assert h[5][row] == g * 4 + p
+                    orc.orc_game_encode_seq(games[g], p, int(cursor[g, p]), st.ev_words, 1, u16(o_sp), o_nu.ctypes.data_as(C.POINTER(C.c_float)),
+                                            u16(o_pr), MP, u16(o_ca), u16(o_le))
+                    for k, ref in enumerate((o_sp, o_nu, o_pr, o_ca, o_le)):
+                        assert h[k][row].tobytes() == ref.tobytes(), f"iter {it} game {g} seat {p} output {k}"
+                    long_delta += int(o_le[1] > 8)
+                    if not explicit:
+                        cursor[g, p] = st.ev_words
+                    row += 1
+                    checked += 1
+        assert row == rows
+        stride = 1 if it < 35 else 11
+        v.step_random(33, stride)
+        for g in range(n):
+            for _ in range(stride):
+                orc.orc_game_random_step(games[g], 33, 7700 + g)
+    for hnd in games:
+        orc.orc_game_free(hnd)
+    assert checked > 6000 and long_delta > 500
 
 
 def test_shim_observation_encode(orc):

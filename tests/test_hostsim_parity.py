@@ -175,3 +175,42 @@ def test_observation_encode_lockstep(libs):
             h.random_step(5, seed)
             step += 1
     assert n_obs > 3000
+
+
+def test_sequence_features_lockstep(libs):
+    """encode_seq_{sparse,numeric,progression,candidates} of every acting seat at every step, over the seat's event delta
+    since its previous observation (state/mod.rs:211-218): kernel source vs oracle, byte-equal."""
+    import numpy as np
+
+    orc, hs = libs
+    u16 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint16))
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    n_obs = n_prog = n_calls = 0
+    for seed in (21, 22, 23, 24):
+        o, h = OracleBackend(2, seed), HostsimBackend(2, seed)
+        o.reset()
+        h.reset()
+        cursor = [0, 0, 0, 0]
+        outs = []
+        for _ in range(2):
+            outs.append((np.zeros(25, np.uint16), np.zeros(12, np.float32), np.zeros(512 * 5, np.uint16), np.zeros(64 * 4, np.uint16),
+                         np.zeros(3, np.uint16)))
+        while True:
+            s = o.get_state()
+            if s.is_done:
+                break
+            end = s.ev_words
+            for p in range(4):
+                if (s.active_mask >> p) & 1:
+                    for lib_, fn, hnd, out in ((orc, "orc_game_encode_seq", o.h, outs[0]), (hs, "hs_game_encode_seq", h.h, outs[1])):
+                        getattr(lib_, fn)(hnd, p, cursor[p], end, 1, u16(out[0]), fp(out[1]), u16(out[2]), 512, u16(out[3]), u16(out[4]))
+                    for k, name in enumerate(("sparse", "numeric", "progression", "candidates", "lens")):
+                        assert outs[0][k].tobytes() == outs[1][k].tobytes(), f"seed {seed} seat {p} step {s.step_count}: {name}"
+                    cursor[p] = end          # the delta advances on every observation
+                    n_obs += 1
+                    n_prog += int(outs[0][4][1])
+                    n_calls += int((outs[0][2].reshape(512, 5)[: outs[0][4][1], 1] >= 38).sum())
+                    assert 5 <= outs[0][4][0] <= 25 and outs[0][4][2] >= 1
+            o.random_step(9, seed)
+            h.random_step(9, seed)
+    assert n_obs > 4000 and n_prog > 10000 and n_calls > 100

@@ -141,3 +141,36 @@ def test_kokushi_and_chiitoi(orc):
     # ryanpeikou shape is never scored as chiitoitsu (yaku.rs:236-296)
     r = _calc(orc, "112233m445566p7s", 24 * 4 + 1, cond=A.C_RIICHI)
     assert r.is_win and 28 in H.yaku_ids(r.yaku_mask) and 25 not in H.yaku_ids(r.yaku_mask)
+
+
+def test_sequence_feature_known_answers():
+    """Known answers of the reference's own unit tests (observation/sequence_features.rs:845-930)."""
+    o = oracle.load()
+    # test_tile_id_to_kan37
+    for tid, k in ((16, 0), (52, 10), (88, 20), (0, 1), (3, 1), (17, 5), (32, 9), (36, 11), (72, 21), (108, 30), (132, 36)):
+        assert o.orc_seq_kan37(tid) == k
+    # test_relative_from
+    for (a, t), r in (((0, 3), 2), ((0, 1), 0), ((0, 2), 1), ((2, 3), 0)):
+        assert o.orc_seq_relative_from(a, t) == r
+    # test_encode_chi_basic
+    assert o.orc_seq_encode_chi(4, 8, 0) == 0
+    assert o.orc_seq_encode_chi(0, 8, 4) == 1
+    # test_encode_pon_honor / test_encode_pon_five_red
+    assert o.orc_seq_encode_pon(109, 110, 108) == 33
+    assert o.orc_seq_encode_pon(16, 17, 18) == 5
+    assert o.orc_seq_encode_pon(17, 18, 16) == 6
+    # bounds (test_progression_type_bounds / test_candidate_type_bounds): chi 0..89, pon 0..39 over every legal call
+    chis, pons = set(), set()
+    for suit in range(3):
+        for start in range(7):
+            kinds = [suit * 9 + start + d for d in range(3)]
+            for call in range(3):
+                for copies in ((0, 0, 0), (1, 1, 1)):
+                    t = [4 * k + c for k, c in zip(kinds, copies)]
+                    rest = [x for i, x in enumerate(t) if i != call]
+                    chis.add(o.orc_seq_encode_chi(rest[0], rest[1], t[call]))
+    for kind in range(34):
+        for c in ((0, 1, 2), (1, 2, 0), (1, 2, 3)):
+            pons.add(o.orc_seq_encode_pon(4 * kind + c[0], 4 * kind + c[1], 4 * kind + c[2]))
+    assert min(chis) == 0 and max(chis) == 89 and len(chis) == 90
+    assert min(pons) == 0 and max(pons) == 39 and len(pons) == 40
