@@ -26,9 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_STEP = 1024  # algorithmic bytes per env step without observations (SURVEY.md §8 d)
-# dram__bytes_read.sum + dram__bytes_write.sum of one 65,536-game rollout from the ncu --set full capture
-# (profiles/r01_final_*); None until measured for the current kernels
-TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_persistent_kernel launch (65,536 hanchan, 69.3 M env steps)
+# from the ncu --set full capture profiles/r01_persist_raw.csv: 1.97 GB read + 9.57 GB written
+TRAFFIC_BYTES_PER_LAUNCH = 11.54e9
 MODE_NAMES = {0: "4p-red-single kyoku", 1: "4p-red-east", 2: "4p-red-half hanchan", 3: "3p-red-single kyoku", 4: "3p-red-east",
               5: "3p-red-half hanchan (sanma)"}
 METRIC = "env_steps_per_sec"
@@ -235,7 +235,7 @@ def main():
         tot_ms += ms
         tot_kernel_ms += kms
         tot_steps += st
-        launches += 3                         # reseed_kernel + reset_kernel + step_random_kernel
+        launches += 4                         # reseed_kernel + reset_kernel + q_init_kernel + rollout_persistent_kernel
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
@@ -286,7 +286,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "kernel": "phase_kernel<ACT|RESP|DEAL|SLOW> pipeline (rollout region)", "peak_source": peak_src,
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "kernel": "rollout_persistent_kernel (one launch per rollout)", "peak_source": peak_src,
                          "bytes_per_env_step": B_STEP, "kernel_share_of_step": tot_kernel_ms / tot_ms},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -1756,7 +1756,7 @@ __device__ __noinline__ void run_pending_tail(const Ctx& cx, G& g) {
   g.pending_tail[1] = 0;
   resolve_discard(cx, g, g.current_player, tile, tsumogiri);
 }
-__device__ __noinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
+__device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   const int np = num_players(g);
   RV_STAT(10);
   const int pid = g.current_player;

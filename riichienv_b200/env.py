@@ -228,7 +228,7 @@ def _melds_of(s: A.GameState, p: int):
 class Observation:
     """observation/mod.rs:24-160 — a by-value snapshot for one seat."""
 
-    def __init__(self, env: "RiichiEnv", s: A.GameState, pid: int, legal, new_events):
+    def __init__(self, env: "RiichiEnv", s: A.GameState, pid: int, legal, new_events, seq_start_word=0):
         self.player_id = pid
         n = env._np
         self.hands = [[s.hand[p][k] for k in range(s.hand_len[p])] if p == pid else [] for p in range(n)]
@@ -240,6 +240,9 @@ class Observation:
         self._legal_actions = legal
         self._new_events = new_events
         self._env = env
+        self._seq_start_word = seq_start_word
+        self._token = env._token
+        self._seq = None
         self.honba = s.honba
         self.riichi_sticks = s.riichi_sticks
         self.round_wind = s.round_wind
@@ -349,6 +352,32 @@ class Observation:
         """(74, 34) float32 FEATURE_ENCODING tensor bytes (observation/python.rs:457-806), computed on the GPU."""
         return self._env._encode(self.player_id)
 
+    # ---- sequence features (observation/python.rs:1297-1364): raw bytes, as the reference returns them ----
+    def _seq_features(self):
+        if self._seq is None:
+            if self._token != self._env._token:
+                raise RuntimeError("sequence features are computed on the device from the live game: call them on the "
+                                   "observations of the latest reset()/step()")
+            self._seq = self._env._encode_seq(self.player_id, self._seq_start_word)
+        return self._seq
+
+    def encode_seq_sparse(self, game_style=1):
+        sp, _, _, _, lens = self._seq_features()
+        sp = sp.copy()
+        sp[0] = min(int(game_style), 1)
+        return sp[: lens[0]].tobytes()
+
+    def encode_seq_numeric(self):
+        return self._seq_features()[1].tobytes()
+
+    def encode_seq_progression(self):
+        _, _, pr, _, lens = self._seq_features()
+        return pr[: lens[1]].tobytes()
+
+    def encode_seq_candidates(self):
+        _, _, _, ca, lens = self._seq_features()
+        return ca[: lens[2]].tobytes()
+
 
 class RiichiEnv:
     """env.rs:74-118 / 799-872 over a VecRiichiEnv of one game."""
@@ -373,6 +402,7 @@ class RiichiEnv:
         self._v = VecRiichiEnv(1, gm, self.rule.bits(), seeds=[self.seed], log_cap_words=0 if skip_mjai_logging else 1 << 16,
                                device=device)
         self._event_counts = [0, 0, 0, 0]
+        self._token = getattr(self, "_token", 0) + 1
         # GameState::new deals a first round immediately (state/mod.rs:165); mirror it so getters work before reset().
         # That constructor deal uses shuffle #0; the library's create already accounts for it (hand_index = 1), so we
         # temporarily rewind to reproduce the same wall, as a freshly constructed reference env would show.
@@ -387,12 +417,14 @@ class RiichiEnv:
             raise ValueError(f"scores length {len(scores)} does not match number of players {self._np}")
         # reset(seed=) sets GameState.seed which nothing reads (env.rs:835-837): the wall is NOT reseeded.
         self._event_counts = [0, 0, 0, 0]
+        self._token = getattr(self, "_token", 0) + 1
         self._v.reset(oya=0 if oya is None else oya, round_wind=0 if round_wind is None else round_wind,
                       honba=0 if honba is None else honba, kyotaku=0 if kyotaku is None else kyotaku,
                       scores=None if scores is None else [list(scores)], walls=None if wall is None else [list(wall)])
         return self._observations(self.active_players)
 
     def step(self, actions):
+        self._token += 1
         arr = (A.Action * 4)()
         for p in range(4):
             arr[p].type = A.NO_ACTION
@@ -475,9 +507,43 @@ class RiichiEnv:
             legal = [Action._from_abi(acts[p * A.MAX_LEGAL + k]) for k in range(int(counts[0, p]))]
             full = logs.setdefault(p, self._masked_log(p))
             new = full[self._event_counts[p]:]
+            start_word = self._event_word_offset(self._event_counts[p])
             self._event_counts[p] = len(full)  # state/mod.rs:211-218: the delta advances on every observation
-            out[p] = Observation(self, s, p, legal, new)
+            out[p] = Observation(self, s, p, legal, new, start_word)
         return out
+
+    def _event_word_offset(self, k):
+        """word offset of the k-th event of this game's binary log (every seat's masked log has the same event count)"""
+        if self.skip_mjai_logging or k == 0:
+            return 0
+        words = self._v.events(0)
+        i = 0
+        for _ in range(k):
+            i += max(1, (int(words[i]) >> 8) & 0xFF)
+        return i
+
+    def _encode_seq(self, pid, start_word):
+        import numpy as np
+        import torch
+
+        if self.skip_mjai_logging:
+            raise ValueError("sequence features need the MJAI log (skip_mjai_logging=False)")
+        dev = f"cuda:{self._v.ctx.device}"
+        sp = torch.zeros((4, 25), dtype=torch.uint16, device=dev)
+        nu = torch.zeros((4, 12), dtype=torch.float32, device=dev)
+        pr = torch.zeros((4, 512, 5), dtype=torch.uint16, device=dev)
+        ca = torch.zeros((4, 64, 4), dtype=torch.uint16, device=dev)
+        le = torch.zeros((4, 3), dtype=torch.uint16, device=dev)
+        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
+        start = np.zeros((1, 4), np.uint32)
+        start[0, pid] = start_word
+        n = self._v.encode_seq(sparse=sp, numeric=nu, prog=pr, cand=ca, lens=le, index=idx, game_style=1, max_obs=4, start_words=start)
+        rows = idx[:n].tolist()
+        if pid not in rows:
+            raise ValueError(f"seat {pid} owes no action")
+        r = rows.index(pid)
+        lens = le[r].cpu().numpy()
+        return sp[r].cpu().numpy(), nu[r].cpu().numpy(), pr[r].cpu().numpy(), ca[r].cpu().numpy(), lens
 
     def _encode(self, pid):
         """bytes of the (74, 34) float32 tensor for seat `pid` (must owe an action), computed by obs_encode_kernel."""

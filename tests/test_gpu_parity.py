@@ -326,6 +326,46 @@ def test_sequence_features_vs_oracle(orc):
     assert checked > 6000 and long_delta > 500
 
 
+def test_shim_sequence_features(orc):
+    """Observation.encode_seq_* of the single-env shim (the reference's method names and byte formats) against the oracle,
+    driving a whole game through RiichiEnv.step with the first legal action."""
+    from riichienv_b200 import RiichiEnv
+
+    env = RiichiEnv(game_mode="4p-red-half", seed=31)
+    h = orc.orc_game_new(2, 31, 0, A.RULE_DEFAULT_TENHOU, 1)
+    orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    obs = env.reset()
+    cursor = [0, 0, 0, 0]
+    o_sp, o_nu, o_pr, o_ca, o_le = (np.zeros(25, np.uint16), np.zeros(12, np.float32), np.zeros(512 * 5, np.uint16),
+                                    np.zeros(64 * 4, np.uint16), np.zeros(3, np.uint16))
+    u16 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint16))
+    st = A.GameState()
+    checked = 0
+    for _ in range(120):
+        if env.done():
+            break
+        orc.orc_game_snapshot(h, C.byref(st))
+        acts = (A.Action * 4)()
+        for p in range(4):
+            acts[p].type = A.NO_ACTION
+        for p, ob in obs.items():
+            orc.orc_game_encode_seq(h, p, cursor[p], st.ev_words, 0, u16(o_sp), o_nu.ctypes.data_as(C.POINTER(C.c_float)), u16(o_pr), 512,
+                                    u16(o_ca), u16(o_le))
+            cursor[p] = st.ev_words
+            assert ob.encode_seq_sparse(0) == o_sp[: o_le[0]].tobytes()
+            assert ob.encode_seq_numeric() == o_nu.tobytes()
+            assert ob.encode_seq_progression() == o_pr[: 5 * o_le[1]].tobytes()
+            assert ob.encode_seq_candidates() == o_ca[: 4 * o_le[2]].tobytes()
+            checked += 1
+        chosen = {p: ob.legal_actions()[-1] for p, ob in obs.items()}
+        for p, a in chosen.items():
+            acts[p] = a._to_abi()
+        orc.orc_game_step(h, acts)
+        obs = env.step(chosen)
+    orc.orc_game_free(h)
+    assert checked > 100
+
+
 def test_shim_observation_encode(orc):
     from riichienv_b200 import RiichiEnv
 
