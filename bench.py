@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 
 B_STEP = 1024  # algorithmic bytes per env step without observations (SURVEY.md §8 d)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_persistent_kernel launch (65,536 hanchan, 69.3 M env steps)
-# from the ncu --set full capture profiles/r01_persist_raw.csv: 1.97 GB read + 9.57 GB written
-TRAFFIC_BYTES_PER_LAUNCH = 11.54e9
+# from the ncu --set full capture profiles/r01_persist_full_raw.csv: 1.49 GB read + 6.36 GB written
+TRAFFIC_BYTES_PER_LAUNCH = 7.85e9
 MODE_NAMES = {0: "4p-red-single kyoku", 1: "4p-red-east", 2: "4p-red-half hanchan", 3: "3p-red-single kyoku", 4: "3p-red-east",
               5: "3p-red-half hanchan (sanma)"}
 METRIC = "env_steps_per_sec"
@@ -254,10 +254,15 @@ def main():
         a = time.perf_counter()
         v.reseed(seeds, 0)                     # H2D: 8 B / game
         v.reset()
+        t_r = time.perf_counter()
         n = v.step_random(agent_seed, 1 << 30)
+        t_s = time.perf_counter()
         d_, s_, r_ = v.results()               # D2H: done + scores + ranks
         c_ = v.counters()                      # D2H: step / kyoku / event counters + event hash
         e2e_t += time.perf_counter() - a
+        if os.environ.get("RV_DEBUG"):
+            print(f"[e2e] reseed+reset {1e3 * (t_r - a):.1f} ms, rollout {1e3 * (t_s - t_r):.1f} ms, results+counters "
+                  f"{1e3 * (time.perf_counter() - t_s):.1f} ms", file=sys.stderr)
         e2e_steps += n
     h2d = G * 8
     d2h = G * (1 + 16 + 4 + 4 + 4 + 4 + 8)

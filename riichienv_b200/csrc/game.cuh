@@ -1170,7 +1170,9 @@ __device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_
 }
 
 // ------------------------------------------------------------------ discard (state/mod.rs:1317-1413)
-__device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int tile, bool tsumogiri) {
+// `claim_seats`: seats that may have something to claim or a ron shape to miss (act_fast knows from the caches); the
+// others are skipped — gen_claims would leave them with an empty list and missed = false.
+__device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int tile, bool tsumogiri, uint32_t claim_seats = 0xF) {
   const int np = num_players(g);
   if (np == 3) g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;   // state_3p/mod.rs:1224-1227
   g.is_rinshan_flag = 0;
@@ -1207,7 +1209,7 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
   g.active_mask = 0;
   int claim_mask = 0;
   for (int i = 0; i < np; i++) {
-    if (i == pid) continue;
+    if (i == pid || !((claim_seats >> i) & 1)) continue;
     bool missed = gen_claims(cx, g, i, pid, tile);
     if (missed) g.flags[i] |= RV_F_MISSED_AGARI_DOUJUN;
     if (g.n_claims[i] > 0) claim_mask |= 1 << i;
@@ -1739,22 +1741,23 @@ __device__ __forceinline__ void row_insert(Row14& r, int pos, int v) {   // entr
 }
 // What follows a committed discard that is not the plain case: the generic _resolve_discard — run here, or parked for
 // the TAIL class of the rollout scheduler (so the fast kernel does not carry the claim / abortive-draw / round-end code).
-__device__ __forceinline__ bool act_fast_tail(const Ctx& cx, G& g, int pid, int tile, bool tsumogiri) {
+__device__ __forceinline__ bool act_fast_tail(const Ctx& cx, G& g, int pid, int tile, bool tsumogiri, uint32_t claim_seats) {
   RV_STAT(11);
   if (cx.defer_tail) {
     g.pending_tail[0] = (uint8_t)tile;
-    g.pending_tail[1] = tsumogiri ? 1 : 0;
+    g.pending_tail[1] = (uint8_t)((tsumogiri ? 1 : 0) | (claim_seats << 1));
   } else {
-    resolve_discard(cx, g, pid, tile, tsumogiri);
+    resolve_discard(cx, g, pid, tile, tsumogiri, claim_seats);
   }
   return true;
 }
 __device__ __noinline__ void run_pending_tail(const Ctx& cx, G& g) {
   const int tile = g.pending_tail[0];
-  const bool tsumogiri = g.pending_tail[1] != 0;
+  const bool tsumogiri = (g.pending_tail[1] & 1) != 0;
+  const uint32_t claim_seats = g.pending_tail[1] >> 1;
   g.pending_tail[0] = RV_NONE;
   g.pending_tail[1] = 0;
-  resolve_discard(cx, g, g.current_player, tile, tsumogiri);
+  resolve_discard(cx, g, g.current_player, tile, tsumogiri, claim_seats);
 }
 __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   const int np = num_players(g);
@@ -1823,23 +1826,24 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   const int tile = row_get(hx, pick);
   const int kind = tile >> 2, ksu = kind / 9, kr = kind - 9 * ksu;
   // ---- would anybody be offered a claim?  (legal_actions.rs:254-508, decided from the caches)
-  bool claims = false;
+  uint32_t claim_seats = 0;                                                   // seats gen_claims has to look at
   #pragma unroll 1
   for (int d = 1; d < np; d++) {
     int i = (pid + d) & 3;
-    if ((g.c_waits[i] >> kind) & 1) claims = true;                            // ron shape
+    if ((g.c_waits[i] >> kind) & 1) claim_seats |= 1u << i;                   // ron shape
     if (g.flags[i] & RV_F_RIICHI_DECLARED) continue;
     if (g.hand_len[i] < 3) continue;
     uint64_t x = g.c_cnt[i][ksu];
-    if (((x >> (4 * kr)) & 15) >= 2) claims = true;                           // pon / daiminkan
+    if (((x >> (4 * kr)) & 15) >= 2) claim_seats |= 1u << i;                  // pon / daiminkan
     if (d == 1 && ksu < 3) {                                                  // chi (shimocha)
       uint64_t y = x << 8;                                                    // nibble kr+2 of y == nibble kr of x
       int m2 = (y >> (4 * kr)) & 15, m1 = (y >> (4 * kr + 4)) & 15, p1 = (y >> (4 * kr + 12)) & 15, p2 = (y >> (4 * kr + 16)) & 15;
       if (kr >= 8) p1 = 0;
       if (kr >= 7) p2 = 0;
-      if ((m2 && m1) || (m1 && p1) || (p1 && p2)) claims = true;
+      if ((m2 && m1) || (m1 && p1) || (p1 && p2)) claim_seats |= 1u << i;
     }
   }
+  const bool claims = claim_seats != 0;
   // ================= commit: nothing below can fail =================
   RV_STAT(9);
   g.step_count = sc + 1;
@@ -1849,7 +1853,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     // after a kan the tile drawn before it may still sit unsorted in the row: generic remove + full sort
     hand_remove_first(g, pid, tile);
     hand_sort(g, pid);
-    return act_fast_tail(cx, g, pid, tile, tsumogiri);
+    return act_fast_tail(cx, g, pid, tile, tsumogiri, claim_seats);
   }
   if (tsumogiri) {
     row_pad(hx, hl - 1);
@@ -1884,7 +1888,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   // four kans (every kan draws a rinshan tile in 4P) can end the round at this discard; a pending kan dora is flipped by it
   if (claims || (first && kind >= 27 && kind <= 30) || g.drawable_count == 0 || g.n_dora >= 5 || g.rinshan_draw_count >= 4 ||
       g.pending_kan_dora_count != 0) {
-    return act_fast_tail(cx, g, pid, tile, tsumogiri);
+    return act_fast_tail(cx, g, pid, tile, tsumogiri, claim_seats);
   }
   // _resolve_discard (state/mod.rs:1317-1413), no-claims branch
   g.flags[pid] &= ~(RV_F_IPPATSU_CYCLE | RV_F_MISSED_AGARI_DOUJUN);

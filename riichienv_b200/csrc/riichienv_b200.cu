@@ -50,6 +50,7 @@ struct rv_vec {
   uint64_t* d_seeds;            // scratch for rv_vec_reseed
   int32_t *d_obs_counts, *d_obs_offsets;   // encode: active seats per game and their exclusive scan (n + 1)
   void* d_scan_tmp;
+  unsigned char *d_gather, *h_gather;   // results/counters staging (device, pinned host)
   uint32_t* d_seq_cursor;       // [n][4] event-log word offset of each seat's previous observation (rv_vec_encode_seq)
   uint32_t* d_seq_start;        // [n][4] scratch for caller-supplied cursors
   size_t scan_tmp_bytes;
@@ -968,6 +969,8 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->h_counts = nullptr;
   v->graph_exec = nullptr;
   v->d_seq_cursor = nullptr;
+  v->d_gather = nullptr;
+  v->h_gather = nullptr;
   v->d_seq_start = nullptr;
   v->d_q_slots = nullptr;
   v->d_q_ctl = nullptr;
@@ -1016,6 +1019,8 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->h_counts) cudaFreeHost(v->h_counts);
   if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
   if (v->d_seq_cursor) cudaFree(v->d_seq_cursor);
+  if (v->d_gather) cudaFree(v->d_gather);
+  if (v->h_gather) cudaFreeHost(v->h_gather);
   if (v->d_seq_start) cudaFree(v->d_seq_start);
   if (v->d_q_slots) cudaFree(v->d_q_slots);
   if (v->d_q_ctl) cudaFree(v->d_q_ctl);
@@ -1317,38 +1322,37 @@ int rv_vec_step_random(rv_vec* v, uint64_t agent_seed, uint32_t max_steps, uint6
   return RV_OK;
 }
 
+// Results leave through a device gather buffer and a PINNED host staging buffer owned by the vector (allocated once):
+// one kernel, one D2H copy, then plain memcpy into the caller's arrays (which may be pageable, freshly allocated numpy).
 static int gather(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks, uint32_t* sc, uint32_t* kc, uint32_t* ec, uint64_t* eh) {
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
-  int64_t n = v->n;
-  uint8_t *d_done = nullptr, *d_ranks = nullptr;
-  int32_t* d_scores = nullptr;
-  uint32_t *d_sc = nullptr, *d_kc = nullptr, *d_ec = nullptr;
-  uint64_t* d_eh = nullptr;
-  if (done) CK(cudaMalloc(&d_done, n));
-  if (scores) CK(cudaMalloc(&d_scores, sizeof(int32_t) * n * MAXP));
-  if (ranks) CK(cudaMalloc(&d_ranks, n * MAXP));
-  if (sc) CK(cudaMalloc(&d_sc, sizeof(uint32_t) * n));
-  if (kc) CK(cudaMalloc(&d_kc, sizeof(uint32_t) * n));
-  if (ec) CK(cudaMalloc(&d_ec, sizeof(uint32_t) * n));
-  if (eh) CK(cudaMalloc(&d_eh, sizeof(uint64_t) * n));
-  results_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, d_done, d_scores, d_ranks, d_sc, d_kc, d_ec, d_eh);
+  const size_t n = (size_t)v->n;
+  // layout (8-byte aligned sections): eh u64[n] | scores i32[4n] | sc, kc, ec u32[n] each | ranks u8[4n] | done u8[n]
+  const size_t o_eh = 0, o_scores = o_eh + 8 * n, o_sc = o_scores + 16 * n, o_kc = o_sc + 4 * n, o_ec = o_kc + 4 * n,
+               o_ranks = o_ec + 4 * n, o_done = o_ranks + 4 * n, total = o_done + n;
+  if (!v->d_gather) {
+    CK(cudaMalloc(&v->d_gather, total));
+    CK(cudaMallocHost(&v->h_gather, total));
+  }
+  unsigned char *d = v->d_gather, *h = v->h_gather;
+  const bool res = done || scores || ranks, cnt = sc || kc || ec || eh;
+  results_kernel<<<grid_for((int64_t)n, 128), 128, 0, c->stream>>>(
+      v->d_states, (int64_t)n, res ? d + o_done : nullptr, res ? (int32_t*)(d + o_scores) : nullptr, res ? d + o_ranks : nullptr,
+      cnt ? (uint32_t*)(d + o_sc) : nullptr, cnt ? (uint32_t*)(d + o_kc) : nullptr, cnt ? (uint32_t*)(d + o_ec) : nullptr,
+      cnt ? (uint64_t*)(d + o_eh) : nullptr);
   CK(cudaGetLastError());
-  if (done) CK(cudaMemcpyAsync(done, d_done, n, cudaMemcpyDeviceToHost, c->stream));
-  if (scores) CK(cudaMemcpyAsync(scores, d_scores, sizeof(int32_t) * n * MAXP, cudaMemcpyDeviceToHost, c->stream));
-  if (ranks) CK(cudaMemcpyAsync(ranks, d_ranks, n * MAXP, cudaMemcpyDeviceToHost, c->stream));
-  if (sc) CK(cudaMemcpyAsync(sc, d_sc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
-  if (kc) CK(cudaMemcpyAsync(kc, d_kc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
-  if (ec) CK(cudaMemcpyAsync(ec, d_ec, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
-  if (eh) CK(cudaMemcpyAsync(eh, d_eh, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  // one contiguous copy covering what was asked for
+  const size_t from = cnt ? o_eh : o_scores, to = res ? total : o_ranks;
+  CK(cudaMemcpyAsync(h + from, d + from, to - from, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_done);
-  cudaFree(d_scores);
-  cudaFree(d_ranks);
-  cudaFree(d_sc);
-  cudaFree(d_kc);
-  cudaFree(d_ec);
-  cudaFree(d_eh);
+  if (done) memcpy(done, h + o_done, n);
+  if (scores) memcpy(scores, h + o_scores, 16 * n);
+  if (ranks) memcpy(ranks, h + o_ranks, 4 * n);
+  if (sc) memcpy(sc, h + o_sc, 4 * n);
+  if (kc) memcpy(kc, h + o_kc, 4 * n);
+  if (ec) memcpy(ec, h + o_ec, 4 * n);
+  if (eh) memcpy(eh, h + o_eh, 8 * n);
   return RV_OK;
 }
 int rv_vec_results(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks) {
