@@ -85,8 +85,10 @@ __device__ __forceinline__ void cache_sub(G& g, int p, int kind) {
 }
 __device__ __noinline__ bool hand_remove_first(G& g, int p, int tile) {
   int n = g.hand_len[p];
+  #pragma unroll 1
   for (int i = 0; i < n; i++)
     if (g.hand[p][i] == tile) {
+      #pragma unroll 1
       for (int j = i; j + 1 < n; j++) g.hand[p][j] = g.hand[p][j + 1];
       g.hand[p][n - 1] = RV_NONE;
       g.hand_len[p] = (uint8_t)(n - 1);
@@ -654,7 +656,7 @@ __device__ __noinline__ bool check_abortive_draw(const Ctx& cx, G& g) {
 __device__ __forceinline__ uint32_t pack_act(int type, int tile, int c0, int c1) {
   return (uint32_t)type | ((uint32_t)(tile & 0xFF) << 8) | ((uint32_t)(c0 & 0xFF) << 16) | ((uint32_t)(c1 & 0xFF) << 24);
 }
-__device__ inline void claim_push(G& g, int i, uint32_t a) {
+__device__ __noinline__ void claim_push(G& g, int i, uint32_t a) {
   int n = g.n_claims[i];
   if (n < RV_MAX_CLAIMS) {
     cold(g).claims[i][n] = a;
@@ -662,6 +664,26 @@ __device__ inline void claim_push(G& g, int i, uint32_t a) {
   } else {
     g.overflow = 1;
   }
+}
+// Ron part of gen_claims (legal_actions.rs:262-300): furiten tests, then the yaku evaluation.  Returns `missed_agari`.
+__device__ __noinline__ bool claim_ron(const Ctx& cx, G& g, int i, int tile) {
+  const int kind = tile >> 2;
+  const uint32_t f = g.flags[i];
+  const bool riichi = f & RV_F_RIICHI_DECLARED;
+  const uint64_t rk = g.c_river_kinds[i], waits = g.c_waits[i];
+  bool in_discards = (rk >> kind) & 1;
+  bool in_missed = (f & RV_F_MISSED_AGARI_DOUJUN) || (riichi && (f & RV_F_MISSED_AGARI_RIICHI));
+  if (in_discards || in_missed) return false;
+  bool furiten = (waits & rk) != 0 || (f & (RV_F_MISSED_AGARI_RIICHI | RV_F_MISSED_AGARI_DOUJUN));
+  if (furiten) return false;
+  uint32_t cond = base_cond(g, i);
+  if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
+  WinRes r = seat_calc(cx, g, i, tile, cond, false, g.honba);
+  if (r.is_win) {
+    claim_push(g, i, pack_act(RV_RON, tile, RV_NONE, RV_NONE));
+    return false;
+  }
+  return r.has_shape;
 }
 // Fills cold(g).claims[i]; returns the reference's `missed_agari` flag.
 // Fast path: the cached wait mask / histogram answer "nothing to claim" with a few bit tests;
@@ -675,22 +697,8 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
   uint32_t f = g.flags[i];
   bool riichi = f & RV_F_RIICHI_DECLARED;
   // 1. Ron
-  uint64_t rk = g.c_river_kinds[i];
   uint64_t waits = g.c_waits[i];
-  if ((waits >> kind) & 1) {   // hand + tile has a winning shape (calc would pass is_agari)
-    bool in_discards = (rk >> kind) & 1;
-    bool in_missed = (f & RV_F_MISSED_AGARI_DOUJUN) || (riichi && (f & RV_F_MISSED_AGARI_RIICHI));
-    if (!in_discards && !in_missed) {
-      bool furiten = (waits & rk) != 0 || (f & (RV_F_MISSED_AGARI_RIICHI | RV_F_MISSED_AGARI_DOUJUN));
-      if (!furiten) {
-        uint32_t cond = base_cond(g, i);
-        if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
-        WinRes r = seat_calc(cx, g, i, tile, cond, false, g.honba);
-        if (r.is_win) claim_push(g, i, pack_act(RV_RON, tile, RV_NONE, RV_NONE));
-        else if (r.has_shape) missed = true;
-      }
-    }
-  }
+  if ((waits >> kind) & 1) missed = claim_ron(cx, g, i, tile);   // hand + tile has a winning shape (rare: kept out of line)
   if (riichi || g.drawable_count == 0 || hl < 3) return missed;
   RV_STAT(6);
   int su = kind / 9, r9 = kind - 9 * su;
@@ -702,6 +710,7 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
     RV_STAT(7);
     uint8_t match[4];
     int cnt = 0;
+    #pragma unroll 1
     for (int k = 0; k < hl; k++) {
       int t = g.hand[i][k];
       if ((t >> 2) == kind && cnt < 4) match[cnt++] = (uint8_t)t;
@@ -709,7 +718,9 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
     // kuikae: some tile other than the consumed pair must be discardable (legal_actions.rs:316-338)
     bool ok = kuikae ? (hl - cnt) > 0 : true;
     if (ok)
+      #pragma unroll 1
       for (int a = 0; a < cnt; a++)
+        #pragma unroll 1
         for (int b = a + 1; b < cnt; b++) claim_push(g, i, pack_act(RV_PON, tile, match[a], match[b]));
     if (cnt >= 3) claim_push(g, i, pack_act(RV_DAIMINKAN, tile, match[0], match[1]));
   }
@@ -719,6 +730,7 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
     int m2 = at(r9 - 2), m1 = at(r9 - 1), p1 = at(r9 + 1), p2 = at(r9 + 2);
     if ((m2 && m1) || (m1 && p1) || (p1 && p2)) {
       RV_STAT(8);
+      #pragma unroll 1
       for (int pat = 0; pat < 3; pat++) {
         int ka, kb, forb2 = -1;
         if (pat == 0) { if (!(m2 && m1)) continue; ka = kind - 2; kb = kind - 1; if (r9 >= 3) forb2 = kind - 3; }
@@ -731,12 +743,15 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
         // one pass over the hand collects the candidate tile ids (hand order), then the cross product
         uint8_t ta[4], tb[4];
         int na = 0, nb = 0;
+        #pragma unroll 1
         for (int k = 0; k < hl; k++) {
           int t = g.hand[i][k], tk = t >> 2;
           if (tk == ka && na < 4) ta[na++] = (uint8_t)t;
           if (tk == kb && nb < 4) tb[nb++] = (uint8_t)t;
         }
+        #pragma unroll 1
         for (int a = 0; a < na; a++)
+          #pragma unroll 1
           for (int b = 0; b < nb; b++) claim_push(g, i, pack_act(RV_CHI, tile, ta[a], tb[b]));
       }
     }
@@ -1472,6 +1487,73 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
   }
 }
 
+// Ron settlement of a claim window (state/mod.rs:945-1142): kept out of line, a claim window rarely ends in a win.
+__device__ __noinline__ void resp_ron(const Ctx& cx, G& g, int ron_mask) {
+  const int np = num_players(g);
+  if (np == 4 && __popc(ron_mask) >= np - 1 && rule(g, RV_RULE_SANCHAHO_IS_DRAW)) {   // no sanchaho branch in 3P
+    trigger_ryukyoku(cx, g, RV_RK_SANCHAHO);
+    return;
+  }
+  int target = g.last_discard_pid != RV_NONE ? g.last_discard_pid : g.current_player;
+  int win_tile = g.last_discard_pid != RV_NONE ? g.last_discard_tile : 0;
+  int32_t total[MAXP] = {0, 0, 0, 0};
+  bool oya_won = false, deposit_taken = false, honba_taken = false;
+  bool is_chankan = g.pending_kan_pid != RV_NONE && g.pending_kan_type != RV_KITA;   // state_3p/mod.rs:896-902
+  int oya = g.oya;
+  for (int dist = 1; dist < np; dist++) {   // winners sorted by distance from the discarder
+    int w = (target + dist) % np;
+    if (!((ron_mask >> w) & 1)) continue;
+    uint32_t ron_honba = 0;
+    if (!honba_taken) { honba_taken = true; ron_honba = g.honba; }
+    uint32_t cond = base_cond(g, w);
+    if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
+    if (is_chankan) cond |= RV_C_CHANKAN;
+    bool riichi = g.flags[w] & RV_F_RIICHI_DECLARED;
+    WinRes r = seat_calc(cx, g, w, win_tile, cond, riichi, ron_honba, true);   // kita_count: state_3p/mod.rs:926
+    cap_double_yakuman(g, r, w == oya, false, ron_honba);
+    if (r.is_win) {
+      int32_t score = (int32_t)r.ron;
+      int pao_payer = target;
+      int32_t pao_amt = 0;
+      if (r.yakuman) {
+        bool has_pao = false;
+        int total_val = 0, pao_val = 0;
+        uint64_t m = r.yaku_mask;
+        while (m) {
+          int y = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          int v = yakuman_val(g, y);
+          total_val += v;
+          int liable = y == 37 ? g.pao[w][0] : y == 50 ? g.pao[w][1] : RV_NONE;
+          if (liable != RV_NONE) { has_pao = true; pao_payer = liable; pao_val += v; }
+        }
+        if (has_pao) {
+          int32_t unit = w == oya ? 48000 : 32000;
+          int32_t honba_ron = (int32_t)ron_honba * (np - 1) * 100;
+          int32_t split = rule(g, RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
+          pao_amt = split / 2 + honba_ron;
+        }
+      }
+      int32_t td[MAXP] = {0, 0, 0, 0};
+      td[w] += score;
+      td[pao_payer] -= pao_amt;
+      td[target] -= score - pao_amt;
+      if (!deposit_taken) {
+        td[w] += (int32_t)(g.riichi_sticks * 1000);
+        g.riichi_sticks = 0;
+        deposit_taken = true;
+      }
+      for (int i = 0; i < np; i++) total[i] += td[i];
+      if (w == oya) oya_won = true;
+      ev_hora(cx, g, w, target, false, r, td, riichi);
+    }
+  }
+  for (int i = 0; i < np; i++) {
+    g.score[i] += total[i];
+    g.score_delta[i] = total[i];
+  }
+  next_round(cx, g, oya_won, false);
+}
 __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_action* acts) {
   const int np = num_players(g);
   // missed agari (state/mod.rs:902-917): every seat holding a Ron claim (stale ones included) that did not ron
@@ -1500,69 +1582,7 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
     }
   }
   if (ron_mask) {
-    if (np == 4 && __popc(ron_mask) >= np - 1 && rule(g, RV_RULE_SANCHAHO_IS_DRAW)) {   // no sanchaho branch in 3P
-      trigger_ryukyoku(cx, g, RV_RK_SANCHAHO);
-      return;
-    }
-    int target = g.last_discard_pid != RV_NONE ? g.last_discard_pid : g.current_player;
-    int win_tile = g.last_discard_pid != RV_NONE ? g.last_discard_tile : 0;
-    int32_t total[MAXP] = {0, 0, 0, 0};
-    bool oya_won = false, deposit_taken = false, honba_taken = false;
-    bool is_chankan = g.pending_kan_pid != RV_NONE && g.pending_kan_type != RV_KITA;   // state_3p/mod.rs:896-902
-    int oya = g.oya;
-    for (int dist = 1; dist < np; dist++) {   // winners sorted by distance from the discarder
-      int w = (target + dist) % np;
-      if (!((ron_mask >> w) & 1)) continue;
-      uint32_t ron_honba = 0;
-      if (!honba_taken) { honba_taken = true; ron_honba = g.honba; }
-      uint32_t cond = base_cond(g, w);
-      if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HOUTEI;
-      if (is_chankan) cond |= RV_C_CHANKAN;
-      bool riichi = g.flags[w] & RV_F_RIICHI_DECLARED;
-      WinRes r = seat_calc(cx, g, w, win_tile, cond, riichi, ron_honba, true);   // kita_count: state_3p/mod.rs:926
-      cap_double_yakuman(g, r, w == oya, false, ron_honba);
-      if (r.is_win) {
-        int32_t score = (int32_t)r.ron;
-        int pao_payer = target;
-        int32_t pao_amt = 0;
-        if (r.yakuman) {
-          bool has_pao = false;
-          int total_val = 0, pao_val = 0;
-          uint64_t m = r.yaku_mask;
-          while (m) {
-            int y = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            int v = yakuman_val(g, y);
-            total_val += v;
-            int liable = y == 37 ? g.pao[w][0] : y == 50 ? g.pao[w][1] : RV_NONE;
-            if (liable != RV_NONE) { has_pao = true; pao_payer = liable; pao_val += v; }
-          }
-          if (has_pao) {
-            int32_t unit = w == oya ? 48000 : 32000;
-            int32_t honba_ron = (int32_t)ron_honba * (np - 1) * 100;
-            int32_t split = rule(g, RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
-            pao_amt = split / 2 + honba_ron;
-          }
-        }
-        int32_t td[MAXP] = {0, 0, 0, 0};
-        td[w] += score;
-        td[pao_payer] -= pao_amt;
-        td[target] -= score - pao_amt;
-        if (!deposit_taken) {
-          td[w] += (int32_t)(g.riichi_sticks * 1000);
-          g.riichi_sticks = 0;
-          deposit_taken = true;
-        }
-        for (int i = 0; i < np; i++) total[i] += td[i];
-        if (w == oya) oya_won = true;
-        ev_hora(cx, g, w, target, false, r, td, riichi);
-      }
-    }
-    for (int i = 0; i < np; i++) {
-      g.score[i] += total[i];
-      g.score_delta[i] = total[i];
-    }
-    next_round(cx, g, oya_won, false);
+    resp_ron(cx, g, ron_mask);
   } else if (call_pid >= 0) {
     int claimer = call_pid;
     const rv_action& act = acts[claimer];
@@ -1908,10 +1928,9 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     const uint32_t en = ksu == 3 ? __ldg(&cx.T.honor_info[key]) : __ldg(&cx.T.suit_info[key]);
     SuitInfo si;
     si.e[0] = ksu == 0 ? en : e0, si.e[1] = ksu == 1 ? en : e1, si.e[2] = ksu == 2 ? en : e2, si.e[3] = ksu == 3 ? en : e3;
-    Cnt cn;
-    cn.s[0] = c0, cn.s[1] = c1, cn.s[2] = c2, cn.s[3] = c3;
-    cnt_sub(cn, kind);
-    g.c_waits[pid] = waits13_inl(cn, si);
+    // standard-form waits only: a seven-pairs or kokushi wait after this discard needs >= 6 pairs / >= 12 terminal kinds in
+    // the 14 tiles, and those hands were declined above
+    g.c_waits[pid] = waits13_std(si);
   }
   g.last_discard_pid = (uint8_t)pid;
   g.last_discard_tile = (uint8_t)tile;

@@ -153,6 +153,20 @@ __device__ __forceinline__ bool agari14(const Tables& T, const Cnt& c) {
 
 // get_waits_u8 (hand_evaluator.rs:196-213) of a 3n+1 concealed hand: 34-bit mask.
 // `si` holds the suit entries of `c`.
+// the standard-form part of waits13 (4 mentsu + pair), from the four suit entries alone
+__device__ __forceinline__ uint64_t waits13_std(const SuitInfo& si) {
+  int nM = (si.e[0] & 1) + (si.e[1] & 1) + (si.e[2] & 1) + (si.e[3] & 1);
+  int nP = ((si.e[0] >> 1) & 1) + ((si.e[1] >> 1) & 1) + ((si.e[2] >> 1) & 1) + ((si.e[3] >> 1) & 1);
+  uint64_t w = 0;
+  #pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int m = si.e[k] & 1, p = (si.e[k] >> 1) & 1;
+    uint64_t wm = (si.e[k] >> 2) & 0x1FF, wp = (si.e[k] >> 11) & 0x1FF;
+    if (nM - m == 3 && nP - p == 0) w |= wp << (9 * k);   // others all M: this suit supplies the pair
+    if (nM - m == 2 && nP - p == 1) w |= wm << (9 * k);   // one other suit holds the pair
+  }
+  return w;
+}
 __device__ __forceinline__ uint64_t waits13_inl(const Cnt& c, const SuitInfo& si) {
   int nM = (si.e[0] & 1) + (si.e[1] & 1) + (si.e[2] & 1) + (si.e[3] & 1);
   int nP = ((si.e[0] >> 1) & 1) + ((si.e[1] >> 1) & 1) + ((si.e[2] >> 1) & 1) + ((si.e[3] >> 1) & 1);
