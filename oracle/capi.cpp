@@ -362,7 +362,7 @@ int64_t orc_run_random(int mode, uint32_t rule, uint64_t seed_base, int64_t n, u
 }
 extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {
   GameState* g = (GameState*)h;
-  if (obs) encode_obs(*g, pid, obs);
+  if (obs) g->np == 3 ? encode_obs_3p(*g, pid, obs) : encode_obs(*g, pid, obs);   // 74x34 (4P) / 74x27 (3P) floats
   if (mask) encode_mask(*g, pid, mask);
 }
 // sequence features of seat pid over the event delta [w0, w1) (words); fixed-size outputs padded like the device path

@@ -171,12 +171,188 @@ inline int action_encode(const Action& a) {
   }
   return -1;
 }
-// Observation::mask (observation/python.rs:98-111) for a seat that owes an action
-inline void encode_mask(const GameState& g, int pid, uint8_t* out82) {
-  memset(out82, 0, 82);
+// ---- sanma: Observation3P::encode (observation_3p/python.rs:402-708), 74 channels x 27 compact columns ----
+inline int compact3(int t34) {  // observation_3p/helpers.rs:8-15; -1 = None
+  if (t34 == 0) return 0;
+  if (t34 >= 8 && t34 <= 33) return t34 - 7;
+  return -1;
+}
+inline int obs_next_tile_sanma(int tile) {  // observation_3p/helpers.rs:41-50
+  int t34 = tile / 4;
+  if (t34 == 0) return 8 * 4;
+  if (t34 == 8) return 0;
+  if (t34 >= 1 && t34 <= 7) return tile;
+  return obs_next_tile(tile);
+}
+// out: 74*27 floats, channel-major
+inline void encode_obs_3p(const GameState& g, int pid, float* arr) {
+  const int W = 27, NP3 = 3;
+  auto A = [&](int ch, int col) -> float& { return arr[ch * W + col]; };
+  auto set = [&](int ch, int tile) {
+    int c = compact3(tile / 4);
+    if (c >= 0) A(ch, c) = 1.0f;
+  };
+  for (int i = 0; i < 74 * W; i++) arr[i] = 0.0f;
+  const auto& hand = g.players[pid].hand;
+  HandEvaluator he(hand, g.players[pid].melds, true);   // state_3p/mod.rs:189-194
+  std::vector<uint8_t> waits = he.get_waits_u8();
+  bool is_tenpai = !waits.empty();
+  int rel[3] = {pid, (pid + 1) % 3, (pid + 2) % 3};      // observation_3p/mod.rs:120-123
+  uint8_t counts[27] = {0};
+  for (uint8_t t : hand) {
+    int idx = compact3(t / 4);
+    if (idx < 0) continue;
+    counts[idx]++;
+    if (t == 16 || t == 52 || t == 88) A(4, idx) = 1.0f;
+  }
+  for (int i = 0; i < W; i++)
+    for (int k = 1; k <= 4; k++)
+      if (counts[i] >= k) A(k - 1, i) = 1.0f;
+  {
+    int m_idx = 0;
+    for (auto& m : g.players[pid].melds) {
+      if (m_idx >= 4) break;
+      for (uint8_t t : m.tiles) set(5 + m_idx, t);
+      m_idx++;
+    }
+  }
+  for (uint8_t t : g.dora_indicators) set(9, t);
+  auto tail = [&](int p, int skip, int take, int ch_base) {
+    const auto& d = g.players[p].discards;
+    int i = 0;
+    for (int k = (int)d.size() - 1 - skip; k >= 0 && i < take; k--, i++) set(ch_base + i, d[k]);
+  };
+  tail(pid, 0, 4, 10);
+  for (int i = 1; i < NP3; i++) tail((pid + i) % NP3, 0, 4, 14 + (i - 1) * 4);
+  for (int c = 0; c < NP3; c++) {
+    float v = (float)g.players[rel[c]].discards.size() / 24.0f;
+    for (int k = 0; k < W; k++) A(26 + c, k) = v;
+  }
+  {
+    int used = 0;
+    for (int p = 0; p < NP3; p++) used += (int)g.players[p].discards.size();
+    for (int p = 0; p < NP3; p++)
+      for (auto& m : g.players[p].melds) used += (int)m.tiles.size();
+    used += (int)hand.size();
+    used += (int)g.dora_indicators.size();
+    float v = (float)std::max(108 - used, 0) / 70.0f;
+    for (int k = 0; k < W; k++) A(30, k) = v;
+  }
+  if (g.players[pid].riichi_declared)
+    for (int k = 0; k < W; k++) A(31, k) = 1.0f;
+  for (int i = 1; i < NP3; i++)
+    if (g.players[(pid + i) % NP3].riichi_declared)
+      for (int k = 0; k < W; k++) A(32 + i - 1, k) = 1.0f;
+  {
+    int c = compact3(27 + g.round_wind);
+    if (c >= 0) A(35, c) = 1.0f;
+    c = compact3(27 + (pid + NP3 - g.oya) % NP3);
+    if (c >= 0) A(36, c) = 1.0f;
+  }
+  for (int k = 0; k < W; k++) {
+    A(37, k) = (float)g.honba / 10.0f;
+    A(38, k) = (float)g.riichi_sticks / 5.0f;
+  }
+  for (int c = 0; c < NP3; c++) {
+    int s = g.players[rel[c]].score;
+    float v1 = (float)std::min(std::max(s, 0), 100000) / 100000.0f;
+    float v2 = (float)std::min(std::max(s, 0), 30000) / 30000.0f;
+    for (int k = 0; k < W; k++) {
+      A(39 + c, k) = v1;
+      A(43 + c, k) = v2;
+    }
+  }
+  for (uint8_t t : waits) {
+    int c = compact3(t);
+    if (c >= 0) A(47, c) = 1.0f;
+  }
+  for (int k = 0; k < W; k++) A(48, k) = is_tenpai ? 1.0f : 0.0f;
+  {
+    int rank = 0;
+    for (int p = 0; p < NP3; p++)
+      if (g.players[p].score > g.players[pid].score) rank++;
+    if (rank < NP3)
+      for (int k = 0; k < W; k++) A(49 + rank, k) = 1.0f;
+  }
+  for (int k = 0; k < W; k++) {
+    A(53, k) = (float)g.kyoku_idx / 8.0f;
+    A(54, k) = ((float)g.round_wind * 4.0f + (float)g.kyoku_idx) / 7.0f;
+  }
+  {
+    uint8_t dc[3] = {0, 0, 0};
+    for (int p = 0; p < NP3; p++) {
+      for (auto& m : g.players[p].melds)
+        for (uint8_t t : m.tiles)
+          for (uint8_t di : g.dora_indicators)
+            if (t / 4 == obs_next_tile_sanma(di) / 4) dc[p]++;
+      for (uint8_t t : g.players[p].discards)
+        for (uint8_t di : g.dora_indicators)
+          if (t / 4 == obs_next_tile_sanma(di) / 4) dc[p]++;
+    }
+    for (uint8_t t : hand)
+      for (uint8_t di : g.dora_indicators)
+        if (t / 4 == obs_next_tile_sanma(di) / 4) dc[pid]++;
+    for (int c = 0; c < NP3; c++) {
+      float v = (float)dc[rel[c]] / 12.0f;
+      for (int k = 0; k < W; k++) A(55 + c, k) = v;
+    }
+  }
+  for (int c = 0; c < NP3; c++) {
+    float v = (float)g.players[rel[c]].melds.size() / 4.0f;
+    for (int k = 0; k < W; k++) A(59 + c, k) = v;
+  }
+  {
+    uint8_t seen[27] = {0};
+    auto see = [&](uint8_t t) {
+      int c = compact3(t / 4);
+      if (c >= 0) seen[c]++;
+    };
+    for (uint8_t t : hand) see(t);
+    for (int p = 0; p < NP3; p++)
+      for (auto& m : g.players[p].melds)
+        for (uint8_t t : m.tiles) see(t);
+    for (int p = 0; p < NP3; p++)
+      for (uint8_t t : g.players[p].discards) see(t);
+    for (uint8_t t : g.dora_indicators) see(t);
+    for (int i = 0; i < W; i++) A(63, i) = (float)seen[i] / 4.0f;
+  }
+  tail(pid, 4, 4, 64);
+  tail((pid + 1) % NP3, 4, 2, 68);
+  // 70-72: tsumogiri_flags is always empty in the live env (observation_3p/mod.rs:100)
+}
+// ActionEncoder::encode_3p (action.rs:262-346); -1 on error
+inline int action_encode_3p(const Action& a) {
+  switch (a.type) {
+    case RV_DISCARD: return a.tile < 0 ? -1 : compact3(a.tile / 4);
+    case RV_RIICHI: return 27;
+    case RV_CHI: return -1;
+    case RV_PON: return 28;
+    case RV_DAIMINKAN: {
+      int c = a.tile < 0 ? -1 : compact3(a.tile / 4);
+      return c < 0 ? -1 : 29 + c;
+    }
+    case RV_ANKAN:
+    case RV_KAKAN: {
+      int c = a.consume.empty() ? -1 : compact3(a.consume[0] / 4);
+      return c < 0 ? -1 : 29 + c;
+    }
+    case RV_RON:
+    case RV_TSUMO: return 56;
+    case RV_KYUSHU_KYUHAI: return 57;
+    case RV_PASS: return 58;
+    case RV_KITA: return 59;
+  }
+  return -1;
+}
+// Observation::mask (observation/python.rs:98-111; 3P: observation_3p/python.rs:102-114) for a seat that owes an action:
+// 82 bytes (4P) or 60 bytes (3P)
+inline void encode_mask(const GameState& g, int pid, uint8_t* out) {
+  const bool sanma = g.np == 3;
+  const int ids = sanma ? 60 : 82;
+  memset(out, 0, ids);
   for (auto& a : g._get_legal_actions_internal(pid)) {
-    int id = action_encode(a);
-    if (id >= 0 && id < 82) out82[id] = 1;
+    int id = sanma ? action_encode_3p(a) : action_encode(a);
+    if (id >= 0 && id < ids) out[id] = 1;
   }
 }
 

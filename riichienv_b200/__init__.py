@@ -5,12 +5,12 @@ C ABI in include/riichienv_b200.h.  Importing this package does not need a GPU; 
 """
 from . import _abi  # noqa: F401
 
-__all__ = ["RiichiEnv", "VecRiichiEnv", "Observation", "Action", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
+__all__ = ["RiichiEnv", "VecRiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
            "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "tid_to_mjai"]
 
 
 def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
-    if name in ("RiichiEnv", "Observation", "Action", "ActionType", "Phase", "Meld", "MeldType", "GameRule", "GameType", "Wind",
+    if name in ("RiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule", "GameType", "Wind",
                 "tid_to_mjai"):
         from . import env
 

@@ -9,6 +9,11 @@
 //   BCAST : one value in all 34 columns                (counts / scores / flags, each = small int / const,
 //                                                       IEEE f32 division as the reference does)
 //   SEEN  : per-kind visible count / 4                 (channel 63)
+//
+// Sanma (Observation3P::encode, observation_3p/python.rs:402-708; mask 102-114; ActionEncoder::encode_3p,
+// action.rs:262-346): the same 74 channels over 27 compact columns (1m, 9m, 1-9p, 1-9s, honors —
+// observation_3p/helpers.rs:8-15), three relative seats per group (the fourth channel of each group stays zero),
+// 108 tiles, the 1m<->9m dora wrap, a 60-id action space.  `SANMA` selects it at compile time.
 #pragma once
 #include "game.cuh"
 
@@ -16,6 +21,10 @@ namespace rv {
 
 constexpr int OBS_CH = 74;
 constexpr int OBS_W = 34;
+constexpr int OBS_W3 = 27;     // TILE_DIM_3P
+constexpr int OBS_IDS = 82, OBS_IDS3 = 60;
+// compact column -> tile kind (inverse of tile34_to_compact, observation_3p/helpers.rs:8-15)
+__device__ __forceinline__ int obs_col_kind3(int col) { return col == 0 ? 0 : col + 7; }
 enum { OBS_MASK = 0, OBS_BCAST = 1, OBS_SEEN = 2 };
 
 __device__ __forceinline__ uint64_t river_tail_mask(const G& g, int p, int from_last) {
@@ -29,11 +38,18 @@ __device__ __forceinline__ int obs_next_kind(int k) {  // observation/helpers.rs
   if (k < 31) return 27 + (k - 27 + 1) % 4;
   return 31 + (k - 31 + 1) % 3;
 }
-// visible dora count of seat q as seen by pid (observation/python.rs:684-725)
+__device__ __forceinline__ int obs_next_kind_sanma(int k) {  // observation_3p/helpers.rs:41-50
+  if (k == 0) return 8;
+  if (k == 8) return 0;
+  if (k <= 7) return k;
+  return obs_next_kind(k);
+}
+// visible dora count of seat q as seen by pid (observation/python.rs:684-725, observation_3p/python.rs:595-630)
+template <bool SANMA>
 __device__ inline int obs_dora_count(const G& g, int pid, int q) {
   int cnt = 0;
   for (int d = 0; d < g.n_dora; d++) {
-    int dk = obs_next_kind(g.dora_ind[d] >> 2);
+    int dk = SANMA ? obs_next_kind_sanma(g.dora_ind[d] >> 2) : obs_next_kind(g.dora_ind[d] >> 2);
     for (int m = 0; m < g.n_melds[q]; m++)
       for (int k = 0; k < 4; k++) {
         int t = g.meld_tiles[q][m][k];
@@ -47,11 +63,15 @@ __device__ inline int obs_dora_count(const G& g, int pid, int q) {
   return cnt & 0xFF;
 }
 
+template <bool SANMA>
 __device__ inline void obs_channel(const G& g, int pid, int ch, int& kind, uint64_t& mask, float& val) {
   kind = OBS_MASK;
   mask = 0;
   val = 0.0f;
-  auto rel = [&](int i) { return (pid + i) & 3; };
+  constexpr int NPV = SANMA ? 3 : 4;
+  auto rel = [&](int i) { return SANMA ? (pid + i) % 3 : (pid + i) & 3; };
+  // sanma: each per-seat group has three channels; the fourth (22-25, 29, 34, 42, 46, 52, 58, 62) is never written
+  if (SANMA && ((ch >= 22 && ch <= 25) || ch == 29 || ch == 34 || ch == 42 || ch == 46 || ch == 52 || ch == 58 || ch == 62)) return;
   auto bc = [&](float v) { kind = OBS_BCAST; val = v; };
   if (ch <= 3) {           // hand count >= ch+1
     for (int su = 0; su < 4; su++) {
@@ -82,18 +102,18 @@ __device__ inline void obs_channel(const G& g, int pid, int ch, int& kind, uint6
     bc((float)g.n_river[rel(ch - 26)] / 24.0f);
   } else if (ch == 30) {
     int used = g.hand_len[pid] + g.n_dora;
-    for (int p = 0; p < 4; p++) {
+    for (int p = 0; p < NPV; p++) {
       used += g.n_river[p];
       for (int m = 0; m < g.n_melds[p]; m++) used += (g.meld_tiles[p][m][3] != RV_NONE) ? 4 : 3;
     }
-    int left = 136 - used;
+    int left = (SANMA ? 108 : 136) - used;
     bc((float)(left < 0 ? 0 : left) / 70.0f);
   } else if (ch <= 34) {
     bc((g.flags[rel(ch - 31)] & RV_F_RIICHI_DECLARED) ? 1.0f : 0.0f);
   } else if (ch == 35) {
     if (27 + g.round_wind < 34) mask = 1ull << (27 + g.round_wind);
   } else if (ch == 36) {
-    mask = 1ull << (27 + ((pid + 4 - g.oya) & 3));
+    mask = 1ull << (27 + (SANMA ? (pid + 3 - g.oya) % 3 : (pid + 4 - g.oya) & 3));
   } else if (ch == 37) {
     bc((float)g.honba / 10.0f);
   } else if (ch == 38) {
@@ -112,7 +132,7 @@ __device__ inline void obs_channel(const G& g, int pid, int ch, int& kind, uint6
     bc(g.c_waits[pid] != 0 ? 1.0f : 0.0f);
   } else if (ch <= 52) {
     int rank = 0;
-    for (int p = 0; p < 4; p++)
+    for (int p = 0; p < NPV; p++)
       if (g.score[p] > g.score[pid]) rank++;
     bc(rank == ch - 49 ? 1.0f : 0.0f);
   } else if (ch == 53) {
@@ -120,7 +140,7 @@ __device__ inline void obs_channel(const G& g, int pid, int ch, int& kind, uint6
   } else if (ch == 54) {
     bc(((float)g.round_wind * 4.0f + (float)g.kyoku_idx) / 7.0f);
   } else if (ch <= 58) {
-    bc((float)obs_dora_count(g, pid, rel(ch - 55)) / 12.0f);
+    bc((float)obs_dora_count<SANMA>(g, pid, rel(ch - 55)) / 12.0f);
   } else if (ch <= 62) {
     bc((float)g.n_melds[rel(ch - 59)] / 4.0f);
   } else if (ch == 63) {
@@ -130,13 +150,13 @@ __device__ inline void obs_channel(const G& g, int pid, int ch, int& kind, uint6
   } else if (ch <= 69) {
     mask = river_tail_mask(g, rel(1), 4 + (ch - 68));
   } else {
-    // 70-73: tsumogiri flags are always empty in the live env (observation/mod.rs:105) -> zeros
+    // 70-73: tsumogiri flags are always empty in the live env (observation/mod.rs:105, observation_3p/mod.rs:100) -> zeros
   }
 }
 // channel 63: own hand + all melds + all rivers + dora indicators, per kind
 __device__ inline int obs_seen(const G& g, int pid, int kind) {
   int c = (int)((g.c_cnt[pid][kind / 9] >> (4 * (kind % 9))) & 15);
-  for (int p = 0; p < 4; p++) {
+  for (int p = 0, np = num_players(g); p < np; p++) {
     for (int m = 0; m < g.n_melds[p]; m++)
       for (int k = 0; k < 4; k++) {
         int t = g.meld_tiles[p][m][k];
@@ -156,6 +176,31 @@ __device__ __forceinline__ float obs_value(int kind, uint64_t mask, float val, i
   return ((mask >> col) & 1) ? 1.0f : 0.0f;
 }
 
+// ActionEncoder::encode_3p (action.rs:262-346); -1 if not encodable
+__device__ inline int action_id_3p(const rv_action& a) {
+  auto compact = [](int t34) { return t34 == 0 ? 0 : (t34 >= 8 && t34 < 34 ? t34 - 7 : -1); };
+  switch (a.type) {
+    case RV_DISCARD: return a.tile == RV_NONE ? -1 : compact(a.tile >> 2);
+    case RV_RIICHI: return 27;
+    case RV_CHI: return -1;
+    case RV_PON: return 28;
+    case RV_DAIMINKAN: {
+      int c = a.tile == RV_NONE ? -1 : compact(a.tile >> 2);
+      return c < 0 ? -1 : 29 + c;
+    }
+    case RV_ANKAN:
+    case RV_KAKAN: {
+      int c = a.n_consume == 0 ? -1 : compact(a.consume[0] >> 2);
+      return c < 0 ? -1 : 29 + c;
+    }
+    case RV_RON:
+    case RV_TSUMO: return 56;
+    case RV_KYUSHU_KYUHAI: return 57;
+    case RV_PASS: return 58;
+    case RV_KITA: return 59;
+  }
+  return -1;
+}
 // Action::encode (action.rs:158-227); -1 if not encodable
 __device__ inline int action_id(const rv_action& a) {
   switch (a.type) {

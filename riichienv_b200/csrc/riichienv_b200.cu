@@ -708,9 +708,12 @@ __global__ void obs_count_kernel(const G* states, int64_t n, int32_t* counts) {
 }
 
 // One warp per game; for each seat that owes an action the warp (1) describes the 74 channels
-// (lane L takes channels L, L+32, L+64), (2) streams the 2,516 floats out with 16-byte stores.
+// (lane L takes channels L, L+32, L+64), (2) streams the 2,516 floats (sanma: 1,998) out with 16-byte
+// (sanma: 8-byte — a 7,992 B row is only 8-byte aligned) streaming stores.
+template <bool SANMA>
 __global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* states, int64_t n, const int32_t* offsets,
                                                          float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
+  constexpr int W = SANMA ? OBS_W3 : OBS_W, IDS = SANMA ? OBS_IDS3 : OBS_IDS, VEC = SANMA ? 2 : 4;
   __shared__ uint64_t s_mask[4][OBS_CH];
   __shared__ float s_val[4][OBS_CH];
   __shared__ uint8_t s_kind[4][OBS_CH];
@@ -729,28 +732,31 @@ __global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* stat
         int kind;
         uint64_t m;
         float v;
-        obs_channel(g, pid, ch, kind, m, v);
+        obs_channel<SANMA>(g, pid, ch, kind, m, v);
         s_kind[w][ch] = (uint8_t)kind;
         s_mask[w][ch] = m;
         s_val[w][ch] = v;
       }
       for (int k = lane; k < OBS_W; k += 32) s_seen[w][k] = (uint8_t)obs_seen(g, pid, k);
       __syncwarp();
-      float4* dst = reinterpret_cast<float4*>(obs + (size_t)row * (OBS_CH * OBS_W));
-      for (int j = lane; j < OBS_CH * OBS_W / 4; j += 32) {
-        float o[4];
+      float* dst = obs + (size_t)row * (OBS_CH * W);
+      for (int j = lane; j < OBS_CH * W / VEC; j += 32) {
+        float o[VEC];
         #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          int e = 4 * j + q, ch = e / OBS_W, col = e - ch * OBS_W;
-          o[q] = obs_value(s_kind[w][ch], s_mask[w][ch], s_val[w][ch], s_seen[w][col], col);
+        for (int q = 0; q < VEC; q++) {
+          int e = VEC * j + q, ch = e / W, col = e - ch * W;
+          int k34 = SANMA ? obs_col_kind3(col) : col;
+          o[q] = obs_value(s_kind[w][ch], s_mask[w][ch], s_val[w][ch], s_seen[w][k34], k34);
         }
-        __stcs(&dst[j], make_float4(o[0], o[1], o[2], o[3]));   // streaming store: write-once data
+        // streaming stores: write-once data
+        if constexpr (SANMA) __stcs(reinterpret_cast<float2*>(dst) + j, make_float2(o[0], o[1]));
+        else __stcs(reinterpret_cast<float4*>(dst) + j, make_float4(o[0], o[1], o[2], o[3]));
       }
       __syncwarp();
     }
     if (mask) {
-      uint8_t* mrow = mask + (size_t)row * 82;
-      for (int k = lane; k < 82; k += 32) mrow[k] = 0;
+      uint8_t* mrow = mask + (size_t)row * IDS;
+      for (int k = lane; k < IDS; k += 32) mrow[k] = 0;
       __syncwarp();
       if (lane == 0) {
         Ctx cx = make_ctx(T, nullptr, 0, gi);
@@ -758,8 +764,9 @@ __global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* stat
         int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
         if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
         for (int k = 0; k < cnt; k++) {
-          int id = action_id(expand_act(g, pid, packed[k]));
-          if (id >= 0 && id < 82) mrow[id] = 1;
+          rv_action a = expand_act(g, pid, packed[k]);
+          int id = SANMA ? action_id_3p(a) : action_id(a);
+          if (id >= 0 && id < IDS) mrow[id] = 1;
         }
       }
       __syncwarp();
@@ -1402,8 +1409,6 @@ int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, ui
   return RV_OK;
 }
 int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
-  if (v->game_mode >= 3)
-    return fail(RV_ERR_UNSUPPORTED, "3P observation tensors (observation_3p, 27 compact columns) are not built yet");
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   int64_t n = v->n;
@@ -1415,8 +1420,12 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
   }
   obs_count_kernel<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(v->d_states, n, v->d_obs_counts);
   CK(cub::DeviceScan::ExclusiveSum(v->d_scan_tmp, v->scan_tmp_bytes, v->d_obs_counts, v->d_obs_offsets, (int)(n + 1), c->stream));
-  if (d_obs || d_mask || d_index)
-    obs_encode_kernel<<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_obs_offsets, d_obs, d_mask, d_index, max_obs);
+  if (d_obs || d_mask || d_index) {
+    if (v->game_mode >= 3)
+      obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_obs_offsets, d_obs, d_mask, d_index, max_obs);
+    else
+      obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_obs_offsets, d_obs, d_mask, d_index, max_obs);
+  }
   CK(cudaGetLastError());
   if (n_obs) {
     int32_t total = 0;

@@ -160,10 +160,57 @@ class Action:
         a.actor = 255 if self.actor is None else self.actor
         return a
 
+    @classmethod
+    def _from_abi(cls, a: A.Action) -> "Action":
+        return cls(a.type, None if a.tile == 255 else a.tile, [a.consume[k] for k in range(a.n_consume)],
+                   None if a.actor == 255 else a.actor)
+
+
+class Action3P(Action):
+    """action.rs:434-467 — the sanma wrapper: same fields, 60-id action space (ActionEncoder::encode_3p, 262-346)."""
+
+    __slots__ = ()
+
+    def __repr__(self):
+        return (f"Action3P(action_type={self.action_type.name}, tile={self.tile}, consume_tiles={self.consume_tiles}, "
+                f"actor={self.actor})")
+
     @staticmethod
-    def _from_abi(a: A.Action) -> "Action":
-        return Action(a.type, None if a.tile == 255 else a.tile, [a.consume[k] for k in range(a.n_consume)],
-                      None if a.actor == 255 else a.actor)
+    def _compact(tile):
+        kind = tile // 4
+        if kind >= 34:
+            raise ValueError(f"Invalid tile type {kind} for 3P encode")
+        if 1 <= kind <= 7:
+            raise ValueError(f"Tile type {kind} (manzu 2-8) is not valid in 3P mode")
+        return 0 if kind == 0 else kind - 7
+
+    def encode(self) -> int:
+        at = self.action_type
+        if at == ActionType.DISCARD:
+            if self.tile is None:
+                raise ValueError("Discard action requires a tile")
+            return self._compact(self.tile)
+        if at == ActionType.RIICHI:
+            return 27
+        if at == ActionType.CHI:
+            raise ValueError("Chi is not allowed in 3P mode")
+        if at == ActionType.PON:
+            return 28
+        if at == ActionType.DAIMINKAN:
+            if self.tile is None:
+                raise ValueError("Daiminkan action requires a tile")
+            return 29 + self._compact(self.tile)
+        if at in (ActionType.ANKAN, ActionType.KAKAN):
+            if not self.consume_tiles:
+                raise ValueError("Ankan/Kakan action requires consumed tiles")
+            return 29 + self._compact(self.consume_tiles[0])
+        if at in (ActionType.RON, ActionType.TSUMO):
+            return 56
+        if at == ActionType.KYUSHU_KYUHAI:
+            return 57
+        if at == ActionType.PASS:
+            return 58
+        return 59  # Kita
 
 
 class Meld:  # types.rs:98-190
@@ -272,8 +319,12 @@ class Observation:
     def new_events(self):
         return list(self._new_events)
 
-    def mask(self):  # observation/python.rs:98-111
-        m = bytearray(82)
+    @property
+    def action_space_size(self):  # observation_3p/python.rs:116-118
+        return self._env.action_space_size
+
+    def mask(self):  # observation/python.rs:98-111, observation_3p/python.rs:102-114
+        m = bytearray(self._env.action_space_size)
         for a in self._legal_actions:
             try:
                 m[a.encode()] = 1
@@ -349,7 +400,8 @@ class Observation:
                 "riichi_sticks": self.riichi_sticks, "round_wind": self.round_wind, "oya": self.oya}
 
     def encode(self):
-        """(74, 34) float32 FEATURE_ENCODING tensor bytes (observation/python.rs:457-806), computed on the GPU."""
+        """(74, 34) float32 FEATURE_ENCODING tensor bytes (observation/python.rs:457-806); sanma: (74, 27)
+        (observation_3p/python.rs:402-708).  Computed on the GPU."""
         return self._env._encode(self.player_id)
 
     # ---- sequence features (observation/python.rs:1297-1364): raw bytes, as the reference returns them ----
@@ -377,6 +429,9 @@ class Observation:
     def encode_seq_candidates(self):
         _, _, _, ca, lens = self._seq_features()
         return ca[: lens[2]].tobytes()
+
+
+Observation3P = Observation   # observation_3p/mod.rs:19-46: the same snapshot over 3 seats (lists are sized by the env's seat count)
 
 
 class RiichiEnv:
@@ -476,7 +531,7 @@ class RiichiEnv:
 
     def _get_legal_actions(self, pid: int):
         acts, counts = self._v.legal_actions()
-        return [Action._from_abi(acts[pid * A.MAX_LEGAL + k]) for k in range(int(counts[0, pid]))]
+        return [self._action_cls._from_abi(acts[pid * A.MAX_LEGAL + k]) for k in range(int(counts[0, pid]))]
 
     # ---- logs -----------------------------------------------------------------------------------
     @property
@@ -504,7 +559,7 @@ class RiichiEnv:
         out = {}
         logs = {}
         for p in players:
-            legal = [Action._from_abi(acts[p * A.MAX_LEGAL + k]) for k in range(int(counts[0, p]))]
+            legal = [self._action_cls._from_abi(acts[p * A.MAX_LEGAL + k]) for k in range(int(counts[0, p]))]
             full = logs.setdefault(p, self._masked_log(p))
             new = full[self._event_counts[p]:]
             start_word = self._event_word_offset(self._event_counts[p])
@@ -546,11 +601,12 @@ class RiichiEnv:
         return sp[r].cpu().numpy(), nu[r].cpu().numpy(), pr[r].cpu().numpy(), ca[r].cpu().numpy(), lens
 
     def _encode(self, pid):
-        """bytes of the (74, 34) float32 tensor for seat `pid` (must owe an action), computed by obs_encode_kernel."""
+        """bytes of the (74, 34) — sanma (74, 27) — float32 tensor for seat `pid` (must owe an action), computed by
+        obs_encode_kernel."""
         import torch
 
         dev = f"cuda:{self._v.ctx.device}"
-        obs = torch.zeros((4, 74, 34), dtype=torch.float32, device=dev)
+        obs = torch.zeros((4, 74, 27 if self._np == 3 else 34), dtype=torch.float32, device=dev)
         idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
         n = self._v.encode(obs=obs, index=idx, max_obs=4)
         rows = idx[:n].tolist()
@@ -568,6 +624,7 @@ class RiichiEnv:
     is_done = property(lambda self: bool(self._state().is_done))
     num_players = property(lambda self: self._np)
     action_space_size = property(lambda self: 60 if self._np == 3 else 82)
+    _action_cls = property(lambda self: Action3P if self._np == 3 else Action)
     last_error = property(lambda self: None if self._state().last_error == 255 else
                           f"Error: Illegal Action by Player {self._state().last_error}")
     dora_indicators = property(lambda self: [self._state().dora_ind[k] for k in range(self._state().n_dora)])

@@ -337,6 +337,7 @@ uint32_t hs_game_events(void* p, uint32_t* out, uint32_t cap) {
 void hs_game_encode(void* p, int pid, float* obs, uint8_t* mask) {
   HS* h = (HS*)p;
   const G& g = h->g;
+  bool sanma = is_sanma(g);
   if (obs) {
     int seen[34];
     for (int k = 0; k < 34; k++) seen[k] = obs_seen(g, pid, k);
@@ -344,19 +345,28 @@ void hs_game_encode(void* p, int pid, float* obs, uint8_t* mask) {
       int kind;
       uint64_t m;
       float v;
-      obs_channel(g, pid, ch, kind, m, v);
-      for (int col = 0; col < OBS_W; col++) obs[ch * OBS_W + col] = obs_value(kind, m, v, seen[col], col);
+      if (sanma) {
+        obs_channel<true>(g, pid, ch, kind, m, v);
+        for (int col = 0; col < OBS_W3; col++) {
+          int k34 = obs_col_kind3(col);
+          obs[ch * OBS_W3 + col] = obs_value(kind, m, v, seen[k34], k34);
+        }
+      } else {
+        obs_channel<false>(g, pid, ch, kind, m, v);
+        for (int col = 0; col < OBS_W; col++) obs[ch * OBS_W + col] = obs_value(kind, m, v, seen[col], col);
+      }
     }
   }
   if (mask) {
-    memset(mask, 0, 82);
+    memset(mask, 0, sanma ? OBS_IDS3 : OBS_IDS);
     Ctx cx = hs_ctx(h);
     uint32_t packed[RV_MAX_LEGAL];
     int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
     if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
     for (int k = 0; k < cnt; k++) {
-      int id = action_id(expand_act(g, pid, packed[k]));
-      if (id >= 0 && id < 82) mask[id] = 1;
+      rv_action a = expand_act(g, pid, packed[k]);
+      int id = sanma ? action_id_3p(a) : action_id(a);
+      if (id >= 0 && id < (sanma ? OBS_IDS3 : OBS_IDS)) mask[id] = 1;
     }
   }
 }

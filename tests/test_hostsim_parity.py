@@ -177,6 +177,42 @@ def test_observation_encode_lockstep(libs):
     assert n_obs > 3000
 
 
+def test_observation_encode_lockstep_3p(libs):
+    """Sanma: Observation3P.encode() (74x27 f32) and mask() (60 ids) of every acting seat at every step: bit-equal."""
+    import numpy as np
+
+    orc, hs = libs
+    n_obs, kita_ids = 0, 0
+    for mode, seed in ((5, 21), (5, 22), (3, 23), (4, 24)):
+        o, h = OracleBackend(mode, seed), HostsimBackend(mode, seed)
+        o.reset()
+        h.reset()
+        a = np.full(74 * 27 + 8, 7.0, np.float32)    # guard words: the encoders must write exactly 74*27 floats / 60 bytes
+        b = np.full(74 * 27 + 8, 7.0, np.float32)
+        ma = np.full(64, 9, np.uint8)
+        mb = np.full(64, 9, np.uint8)
+        fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        up = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint8))
+        step = 0
+        while True:
+            s = o.get_state()
+            if s.is_done:
+                break
+            for p in range(3):
+                if (s.active_mask >> p) & 1:
+                    orc.orc_game_encode(o.h, p, fp(a), up(ma))
+                    hs.hs_game_encode(h.h, p, fp(b), up(mb))
+                    assert (a[74 * 27:] == 7.0).all() and (b[74 * 27:] == 7.0).all() and (ma[60:] == 9).all() and (mb[60:] == 9).all()
+                    assert a.tobytes() == b.tobytes(), f"seed {seed} step {step} seat {p}: channels {sorted(set(np.nonzero(a != b)[0] // 27))}"
+                    assert ma.tobytes() == mb.tobytes(), f"seed {seed} step {step} seat {p}: mask"
+                    kita_ids += int(ma[59])
+                    n_obs += 1
+            o.random_step(5, seed)
+            h.random_step(5, seed)
+            step += 1
+    assert n_obs > 1500 and kita_ids > 20
+
+
 def test_sequence_features_lockstep(libs):
     """encode_seq_{sparse,numeric,progression,candidates} of every acting seat at every step, over the seat's event delta
     since its previous observation (state/mod.rs:211-218): kernel source vs oracle, byte-equal."""
