@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--mode", type=int, default=2, help="2 = 4p-red-half")
     ap.add_argument("--cpu-sample-games", type=int, default=0, help="games in the cpu_baseline sample (0 = sized by time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split", action="store_true", help="rollout_obs: tensor rows by rv_vec_encode, masks + step by the fused kernel")
+    ap.add_argument("--unfused", action="store_true", help="rollout_obs: rv_vec_encode + rv_vec_step_random instead of the fused kernel")
     ap.add_argument("--workload", default="rollout", choices=["rollout", "rollout_obs", "hands"],
                     help="rollout: BASELINE configs[2]/[3] (headline); rollout_obs: configs[4] (encode()+mask() every step); "
                          "hands: configs[1] (batched shanten + agari/yaku/fu/score)")

@@ -331,9 +331,18 @@ int rv_wall_from_seed(uint64_t seed, uint64_t hand_index, int n_tiles /*136|108*
  * compactly in ascending (game, seat) order:
  *   d_obs   [max_obs][74][34] f32   (device, 16-byte aligned)      — may be NULL
  *   d_mask  [max_obs][82] u8        (device)                       — may be NULL
+ *           sanma (Observation3P::encode / mask, observation_3p/python.rs:402-708, 102-114): [74][27] f32 and [60] u8
  *   d_index [max_obs] i32           (device) game*4 + seat per row — may be NULL
  * *n_obs (host, may be NULL -> fully asynchronous) receives the number of rows; rows beyond max_obs are dropped. */
 int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
+
+/* Observe + step in one pass (BASELINE config 5: a random-agent rollout that emits FEATURE_ENCODING tensors at every step —
+ * the loop `obs = env.step({p: agent.act(o) ...})` of README.md:50-62 with the agent of rv_vec_step_random on the device).
+ * Exactly rv_vec_encode(v, d_obs, d_mask, d_index, max_obs, n_obs) followed by rv_vec_step_random_async(v, agent_seed, 1):
+ * the rows describe the decision point BEFORE the step, then every live game takes one env step.  One kernel reads each
+ * game record once: the tensors are written from the staged state and the masks from the legal lists the agent picks from. */
+int rv_vec_observe_step_random(rv_vec* v, uint64_t agent_seed, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs,
+                               int64_t* n_obs);
 
 /* Sequence features (observation/sequence_features.rs:331-835; docs/SEQUENCE_FEATURE_ENCODING.md) for every seat that
  * owes an action, rows in the same (game, seat) order as rv_vec_encode.  4P only (as in the reference); the vector

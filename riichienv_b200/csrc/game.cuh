@@ -29,6 +29,8 @@ struct Ctx {
   uint32_t log_cap;   // words
   bool defer_init;    // rollout kernels: next_round() parks the deal in g.pending_init so warps can batch it
   bool defer_tail;    // rollout kernels: act_fast() parks the follow-up of a discard it cannot finish inline in g.pending_tail
+  uint32_t* idbits;   // observe+step kernel: [MAXP][3] words; the random_step<true> routines leave here, per acting seat, the
+                      // set of action ids (Action::encode) of the legal list they picked from — Observation::mask for free
 };
 
 // The rollout kernels run on a shared-memory copy of the record's hot prefix (RV_HOT_BYTES); the word after that prefix
@@ -1705,6 +1707,19 @@ __host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uin
   return (uint32_t)(mix64(k) % n);
 }
 
+// Action::encode / ActionEncoder::encode_3p (defined in obs.cuh)
+__device__ inline int action_id(const rv_action& a);
+__device__ inline int action_id_3p(const rv_action& a);
+__device__ __forceinline__ void ids_clear(const Ctx& cx, int seat) {
+  cx.idbits[3 * seat] = cx.idbits[3 * seat + 1] = cx.idbits[3 * seat + 2] = 0;
+}
+__device__ __forceinline__ void ids_add(const Ctx& cx, const G& g, int seat, uint32_t packed) {
+  const rv_action a = expand_act(g, seat, packed);
+  const bool sanma = is_sanma(g);
+  const int id = sanma ? action_id_3p(a) : action_id(a);
+  if (id >= 0 && id < (sanma ? 60 : 82)) cx.idbits[3 * seat + (id >> 5)] |= 1u << (id & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fast path of the ACT phase.  The generic turn code (legal-action enumeration, action expansion, the
 // apply switch) is ~90 KB of hot SASS and a long chain of dependent loads; the overwhelmingly common
@@ -1779,6 +1794,7 @@ __device__ __noinline__ void run_pending_tail(const Ctx& cx, G& g) {
   g.pending_tail[1] = 0;
   resolve_discard(cx, g, g.current_player, tile, tsumogiri, claim_seats);
 }
+template <bool IDS = false>
 __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   const int np = num_players(g);
   RV_STAT(10);
@@ -1827,6 +1843,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   const uint32_t sc = g.step_count;
   int pick;
   const int f0 = g.forbidden[pid][0], f1 = g.forbidden[pid][1];
+  uint32_t legal_rows = (1u << hl) - 1;            // hand rows that are legal discards
   if ((f0 & f1) == RV_NONE) {
     pick = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)hl);
   } else {
@@ -1839,6 +1856,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     }
     const int n_ok = __popc(ok);
     if (n_ok == 0) return RV_DECLINE(20);
+    legal_rows = ok;
     int r = (int)agent_pick(agent_seed, game_id, sc, pid, (uint32_t)n_ok);
     for (; r > 0; r--) ok &= ok - 1;              // r-th set bit
     pick = __ffs(ok) - 1;
@@ -1864,6 +1882,16 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     }
   }
   const bool claims = claim_seats != 0;
+  if (IDS) {
+    // the legal list is exactly the discards of `legal_rows`: ids = their tile kinds (4P id space; sanma declined above)
+    uint64_t kinds = 0;
+    #pragma unroll
+    for (int j = 0; j < RV_HAND_CAP; j++)
+      if ((legal_rows >> j) & 1) kinds |= 1ull << (row_get(hx, j) >> 2);
+    cx.idbits[3 * pid] = (uint32_t)kinds;
+    cx.idbits[3 * pid + 1] = (uint32_t)(kinds >> 32);
+    cx.idbits[3 * pid + 2] = 0;
+  }
   // ================= commit: nothing below can fail =================
   RV_STAT(9);
   g.step_count = sc + 1;
@@ -1974,6 +2002,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
 
 // One env step with the on-device random agent, split by phase so that phase-sorted kernels only carry
 // the code of their own phase.
+template <bool IDS = false>
 __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   const int np = num_players(g);
   rv_action acts[MAXP];
@@ -1982,6 +2011,7 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
   RV_STAT(3);
   RV_STAT(4);
   int pid = g.current_player;
+  if (IDS) ids_clear(cx, pid);
   TurnInfo ti;
   turn_info(cx, g, pid, ti);
   uint32_t fl = g.flags[pid];
@@ -2014,6 +2044,14 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
       }
     }
     acts[pid] = expand_act(g, pid, chosen);
+    if (IDS) {
+      if (ti.can_tsumo) ids_add(cx, g, pid, pack_act(RV_TSUMO, g.drawn_tile, RV_NONE, RV_NONE));
+      for (int j = 0; j < hl; j++) ids_add(cx, g, pid, pack_act(RV_DISCARD, g.hand[pid][j], RV_NONE, RV_NONE));
+      if (ti.can_riichi) ids_add(cx, g, pid, pack_act(RV_RIICHI, RV_NONE, RV_NONE, RV_NONE));
+      uint64_t q = ti.quads;
+      for (int z = 0; z < nq; z++, q &= q - 1) ids_add(cx, g, pid, pack_act(RV_ANKAN, (__ffsll((long long)q) - 1) * 4, RV_NONE, RV_NONE));
+      if (ti.kyushu) ids_add(cx, g, pid, pack_act(RV_KYUSHU_KYUHAI, RV_NONE, RV_NONE, RV_NONE));
+    }
   } else {
     int n = enum_turn_actions(g, pid, ti, [](uint32_t) {});
     if (n == 0) {
@@ -2031,6 +2069,7 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
       enum_turn_actions(g, pid, ti, [&](uint32_t a) {
         if (idx == pick) chosen = a;
         idx++;
+        if (IDS) ids_add(cx, g, pid, a);
       });
       acts[pid] = expand_act(g, pid, chosen);
     }
@@ -2038,6 +2077,7 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
   g.step_count = sc + 1;
   step_apply_act(cx, g, acts);
 }
+template <bool IDS = false>
 __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   const int np = num_players(g);
   rv_action acts[MAXP];
@@ -2046,6 +2086,11 @@ __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agen
   RV_STAT(3);
   for (int p = 0; p < np; p++) {
     if (!((g.active_mask >> p) & 1)) continue;
+    if (IDS) {
+      ids_clear(cx, p);
+      for (int k = 0; k < g.n_claims[p]; k++) ids_add(cx, g, p, cold(g).claims[p][k]);
+      ids_add(cx, g, p, pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE));
+    }
     int n = g.n_claims[p] + 1;
     int pick = (int)agent_pick(agent_seed, game_id, sc, p, (uint32_t)n);
     uint32_t chosen = pick < g.n_claims[p] ? cold(g).claims[p][pick] : pack_act(RV_PASS, RV_NONE, RV_NONE, RV_NONE);
@@ -2054,11 +2099,12 @@ __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agen
   g.step_count = sc + 1;
   step_apply_resp(cx, g, acts);
 }
+template <bool IDS = false>
 __device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
   if (g.phase == RV_WAIT_ACT) {
-    if (!act_fast(cx, g, agent_seed, game_id)) random_step_act(cx, g, agent_seed, game_id);
+    if (!act_fast<IDS>(cx, g, agent_seed, game_id)) random_step_act<IDS>(cx, g, agent_seed, game_id);
   }
-  else random_step_resp(cx, g, agent_seed, game_id);
+  else random_step_resp<IDS>(cx, g, agent_seed, game_id);
 }
 
 }  // namespace rv

@@ -226,3 +226,230 @@ __device__ inline int action_id(const rv_action& a) {
 }
 
 }  // namespace rv
+
+#ifdef __CUDACC__
+namespace rv {
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-cooperative encoder (the production path; obs_channel/obs_value above are the per-element statement of the same
+// tensor, kept for single observations and for the host-compiled parity tests).
+//
+// One warp writes one observation row.  The work is arranged so that lanes run the same instructions:
+//   gather      every lane owns one 4-byte word of the seat-major river array (32 words = the four 32-tile rivers), lanes
+//               0-15 one meld each, lanes 0-4 one dora indicator, and lane k the hand count of tile kind k; per-kind "seen"
+//               counts, per-seat dora counts and the last eight discards of every seat land in shared memory through
+//               shared-memory atomics, the hand>=k masks come out of warp ballots;
+//   describe    a channel is (34-bit column mask, value): lane L describes channels L, L+32, L+64 from those gathered
+//               pieces (a handful of instructions per branch — no loops over tiles);
+//   stream      2,516 floats (sanma 1,998) leave as 16-byte (8-byte) streaming stores, each built from two table reads
+//               and a funnel of the masks of the (at most two) channels it spans.  Channel 63 (seen/4) is patched in.
+struct ObsScratch {
+  uint64_t mask[OBS_CH + 2];
+  float val[OBS_CH + 2];
+  int seen[36];
+  int dora[4];
+  uint8_t rtail[4][8];   // kind of the j-th most recent discard of seat q, 0xFF = none
+};
+__device__ __forceinline__ uint64_t obs_compact3(uint64_t m) { return (m & 1) | ((m >> 7) & ~1ull); }   // 34 kinds -> 27 columns
+
+template <bool SANMA>
+__device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river, int pid, float* dst, ObsScratch& S, int lane) {
+  constexpr int NPV = SANMA ? 3 : 4, W = SANMA ? OBS_W3 : OBS_W, VEC = SANMA ? 2 : 4;
+  constexpr uint64_t ALL = (1ull << W) - 1;
+  auto rel = [&](int i) { return SANMA ? (pid + i) % 3 : (pid + i) & 3; };
+  // ---- gather
+  S.seen[lane] = 0;
+  if (lane < 4) S.seen[32 + lane] = 0, S.dora[lane] = 0;
+  S.rtail[lane >> 3][lane & 7] = 0xFF;
+  const int nd = g.n_dora;
+  uint64_t dkp = ~0ull;                                     // dora kinds, one per byte
+  for (int d = 0; d < nd; d++) {
+    int k = g.dora_ind[d] >> 2;
+    k = SANMA ? obs_next_kind_sanma(k) : obs_next_kind(k);
+    dkp = (dkp & ~(0xFFull << (8 * d))) | ((uint64_t)k << (8 * d));
+  }
+  auto dmatch = [&](int kind) {
+    int c = 0;
+    for (int d = 0; d < nd; d++) c += ((int)((dkp >> (8 * d)) & 0xFF) == kind) ? 1 : 0;
+    return c;
+  };
+  __syncwarp();
+  {
+    const int q = lane >> 3, w = lane & 7;
+    const int n = min((int)g.n_river[q], RV_RIVER_CAP);
+    if (4 * w < n) {
+      const uint32_t rw = reinterpret_cast<const uint32_t*>(river)[lane];
+      #pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int i = 4 * w + b;
+        if (i < n) {
+          const int kind = (int)((rw >> (8 * b)) & 0xFF) >> 2;
+          atomicAdd(&S.seen[kind], 1);
+          const int dm = dmatch(kind);
+          if (dm) atomicAdd(&S.dora[q], dm);
+          const int fl = n - 1 - i;
+          if (fl < 8) S.rtail[q][fl] = (uint8_t)kind;
+        }
+      }
+    }
+  }
+  if (lane < 16) {
+    const int q = lane >> 2, m = lane & 3;
+    if (m < g.n_melds[q]) {
+      const uint32_t mw = *reinterpret_cast<const uint32_t*>(&g.meld_tiles[q][m][0]);
+      #pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int t = (int)((mw >> (8 * b)) & 0xFF);
+        if (t != RV_NONE) {
+          atomicAdd(&S.seen[t >> 2], 1);
+          const int dm = dmatch(t >> 2);
+          if (dm) atomicAdd(&S.dora[q], dm);
+        }
+      }
+    }
+  }
+  if (lane < nd) atomicAdd(&S.seen[g.dora_ind[lane] >> 2], 1);
+  uint64_t hge[4];                                          // hand count >= 1..4, per kind
+  {
+    const int c = (int)((g.c_cnt[pid][lane / 9] >> (4 * (lane % 9))) & 15);                 // kinds 0..31
+    const int c2 = lane < 2 ? (int)((g.c_cnt[pid][3] >> (4 * (lane + 5))) & 15) : 0;        // kinds 32, 33
+    if (c) {
+      atomicAdd(&S.seen[lane], c);
+      const int dm = dmatch(lane);
+      if (dm) atomicAdd(&S.dora[pid], c * dm);
+    }
+    if (c2) {
+      atomicAdd(&S.seen[32 + lane], c2);
+      const int dm = dmatch(32 + lane);
+      if (dm) atomicAdd(&S.dora[pid], c2 * dm);
+    }
+    #pragma unroll
+    for (int k = 0; k < 4; k++)
+      hge[k] = (uint64_t)__ballot_sync(0xFFFFFFFFu, c > k) | ((uint64_t)(__ballot_sync(0xFFFFFFFFu, c2 > k) & 3u) << 32);
+  }
+  uint64_t red;
+  {
+    const int t = lane < g.hand_len[pid] ? g.hand[pid][lane < RV_HAND_CAP ? lane : 0] : RV_NONE;
+    red = (__any_sync(0xFFFFFFFFu, t == 16) ? 1ull << 4 : 0) | (__any_sync(0xFFFFFFFFu, t == 52) ? 1ull << 13 : 0) |
+          (__any_sync(0xFFFFFFFFu, t == 88) ? 1ull << 22 : 0);
+  }
+  __syncwarp();
+  int used = S.seen[lane] + (lane < 2 ? S.seen[32 + lane] : 0);      // tiles visible to the seat = rivers + melds + hand + indicators
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xFFFFFFFFu, used, o);
+  // ---- describe
+  for (int ch = lane; ch < OBS_CH + 2; ch += 32) {
+    uint64_t m = 0;
+    float v = 1.0f;
+    bool bcast = false;
+    auto bc = [&](float x) { bcast = true; v = x; };
+    auto tail = [&](int q, int j) { int k = S.rtail[q][j]; return k != 0xFF ? 1ull << k : 0ull; };
+    const bool dead = ch >= OBS_CH ||
+                      (SANMA && ((ch >= 22 && ch <= 25) || ch == 29 || ch == 34 || ch == 42 || ch == 46 || ch == 52 || ch == 58 || ch == 62));
+    if (dead) {
+    } else if (ch <= 3) {
+      m = hge[ch];
+    } else if (ch == 4) {
+      m = red;
+    } else if (ch <= 8) {
+      const int mi = ch - 5;
+      if (mi < g.n_melds[pid]) {
+        const uint32_t mw = *reinterpret_cast<const uint32_t*>(&g.meld_tiles[pid][mi][0]);
+        #pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int t = (int)((mw >> (8 * b)) & 0xFF);
+          if (t != RV_NONE) m |= 1ull << (t >> 2);
+        }
+      }
+    } else if (ch == 9) {
+      for (int d = 0; d < nd; d++) m |= 1ull << (g.dora_ind[d] >> 2);
+    } else if (ch <= 13) {
+      m = tail(pid, ch - 10);
+    } else if (ch <= 25) {
+      m = tail(rel(((ch - 14) >> 2) + 1), (ch - 14) & 3);
+    } else if (ch <= 29) {
+      bc((float)g.n_river[rel(ch - 26)] / 24.0f);
+    } else if (ch == 30) {
+      const int left = (SANMA ? 108 : 136) - used;
+      bc((float)(left < 0 ? 0 : left) / 70.0f);
+    } else if (ch <= 34) {
+      bc((g.flags[rel(ch - 31)] & RV_F_RIICHI_DECLARED) ? 1.0f : 0.0f);
+    } else if (ch == 35) {
+      if (27 + g.round_wind < 34) m = 1ull << (27 + g.round_wind);
+    } else if (ch == 36) {
+      m = 1ull << (27 + (SANMA ? (pid + 3 - g.oya) % 3 : (pid + 4 - g.oya) & 3));
+    } else if (ch == 37) {
+      bc((float)g.honba / 10.0f);
+    } else if (ch == 38) {
+      bc((float)g.riichi_sticks / 5.0f);
+    } else if (ch <= 46) {
+      const bool wide = ch <= 42;
+      int s = g.score[rel(wide ? ch - 39 : ch - 43)];
+      const int cap = wide ? 100000 : 30000;
+      s = s < 0 ? 0 : (s > cap ? cap : s);
+      bc(wide ? (float)s / 100000.0f : (float)s / 30000.0f);
+    } else if (ch == 47) {
+      m = g.c_waits[pid];
+    } else if (ch == 48) {
+      bc(g.c_waits[pid] != 0 ? 1.0f : 0.0f);
+    } else if (ch <= 52) {
+      int rank = 0;
+      #pragma unroll
+      for (int p = 0; p < NPV; p++) rank += g.score[p] > g.score[pid] ? 1 : 0;
+      bc(rank == ch - 49 ? 1.0f : 0.0f);
+    } else if (ch == 53) {
+      bc((float)g.kyoku_idx / 8.0f);
+    } else if (ch == 54) {
+      bc(((float)g.round_wind * 4.0f + (float)g.kyoku_idx) / 7.0f);
+    } else if (ch <= 58) {
+      bc((float)(S.dora[rel(ch - 55)] & 0xFF) / 12.0f);
+    } else if (ch <= 62) {
+      bc((float)g.n_melds[rel(ch - 59)] / 4.0f);
+    } else if (ch == 63) {
+      // seen/4: patched in by the store loop
+    } else if (ch <= 67) {
+      m = tail(pid, 4 + (ch - 64));
+    } else if (ch <= 69) {
+      m = tail(rel(1), 4 + (ch - 68));
+    }
+    // 70-73: tsumogiri flags are always empty in the live env -> zeros
+    if (bcast) m = ALL;
+    else if (SANMA) m = obs_compact3(m);
+    S.mask[ch] = m & ALL;
+    S.val[ch] = v;
+  }
+  __syncwarp();
+  // ---- stream
+  for (int j = lane; j < OBS_CH * W / VEC; j += 32) {
+    const int e0 = VEC * j, ch0 = e0 / W, col0 = e0 - ch0 * W, rem = W - col0;   // elements q < rem belong to ch0
+    const uint64_t bits = (S.mask[ch0] >> col0) | (S.mask[ch0 + 1] << rem);
+    const float v0 = S.val[ch0], v1 = S.val[ch0 + 1];
+    float o[VEC];
+    #pragma unroll
+    for (int q = 0; q < VEC; q++) o[q] = ((bits >> q) & 1) ? (q < rem ? v0 : v1) : 0.0f;
+    if (ch0 == 63 || (ch0 == 62 && rem < VEC)) {
+      #pragma unroll
+      for (int q = 0; q < VEC; q++) {
+        const int ch = q < rem ? ch0 : ch0 + 1, col = q < rem ? col0 + q : q - rem;
+        if (ch == 63) o[q] = (float)S.seen[SANMA ? obs_col_kind3(col) : col] / 4.0f;
+      }
+    }
+    if constexpr (SANMA) __stcs(reinterpret_cast<float2*>(dst) + j, make_float2(o[0], o[1]));
+    else __stcs(reinterpret_cast<float4*>(dst) + j, make_float4(o[0], o[1], o[2], o[3]));
+  }
+  __syncwarp();
+}
+
+// 82 (sanma 60) mask bytes of one row from the id bitset (3 words) — lanes write 4 bytes each when the row is 4-byte aligned
+template <bool SANMA>
+__device__ __forceinline__ void obs_mask_row_warp(const uint32_t bits[3], uint8_t* mrow, int lane) {
+  constexpr int IDS = SANMA ? OBS_IDS3 : OBS_IDS;
+  for (int k = lane; k < IDS; k += 32) mrow[k] = (uint8_t)((bits[k >> 5] >> (k & 31)) & 1);
+}
+// id bitset of a legal-action list
+template <bool SANMA>
+__device__ __forceinline__ void obs_id_set(uint32_t bits[3], const rv_action& a) {
+  const int id = SANMA ? action_id_3p(a) : action_id(a);
+  if (id >= 0 && id < (SANMA ? OBS_IDS3 : OBS_IDS)) bits[id >> 5] |= 1u << (id & 31);
+}
+}  // namespace rv
+#endif

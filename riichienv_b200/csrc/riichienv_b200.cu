@@ -1,6 +1,7 @@
 // Kernels + extern "C" entry points of libriichienv_b200.so (see include/riichienv_b200.h).
 // There is NO CPU fallback in this file: every compute entry point launches CUDA kernels
 // and returns RV_ERR_CUDA if the device is unavailable.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,8 +28,15 @@ static int fail(int code, const std::string& msg) {
       return fail(RV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
   } while (0)
 
+struct HandStage {              // rv_hand_eval_batch: persistent staging (allocated on first use)
+  rv_hand_query *d_q[2] = {nullptr, nullptr}, *h_q[2] = {nullptr, nullptr};
+  rv_hand_result *d_r[2] = {nullptr, nullptr}, *h_r[2] = {nullptr, nullptr};
+  cudaStream_t st[2];
+  cudaEvent_t done[2];
+};
 struct rv_ctx {
   int device;
+  HandStage hands;
   cudaStream_t stream;
   cudaEvent_t ev[8];
   cudaStream_t aux[3];          // phase pipeline: RESPOND, DEAL and SLOW kernels run beside ACT
@@ -49,6 +57,8 @@ struct rv_vec {
   uint32_t log_cap;
   uint64_t* d_seeds;            // scratch for rv_vec_reseed
   int32_t *d_obs_counts, *d_obs_offsets;   // encode: active seats per game and their exclusive scan (n + 1)
+  uint32_t* d_idbits;                      // encode: action-id sets [n][4][3]
+  int32_t* h_obs_total;                    // pinned: row count of the last encode
   void* d_scan_tmp;
   unsigned char *d_gather, *h_gather;   // results/counters staging (device, pinned host)
   uint32_t* d_seq_cursor;       // [n][4] event-log word offset of each seat's previous observation (rv_vec_encode_seq)
@@ -126,6 +136,7 @@ __device__ __forceinline__ Ctx make_ctx(const Tables& T, uint32_t* log, uint32_t
   cx.log_cap = cap;
   cx.defer_init = false;
   cx.defer_tail = false;
+  cx.idbits = nullptr;
   return cx;
 }
 
@@ -707,17 +718,33 @@ __global__ void obs_count_kernel(const G* states, int64_t n, int32_t* counts) {
   counts[i] = c;   // counts[n] = 0 so that offsets[n] is the total
 }
 
-// One warp per game; for each seat that owes an action the warp (1) describes the 74 channels
-// (lane L takes channels L, L+32, L+64), (2) streams the 2,516 floats (sanma: 1,998) out with 16-byte
-// (sanma: 8-byte — a 7,992 B row is only 8-byte aligned) streaming stores.
+// Action-id sets (Observation::mask as a 96-bit set) of every seat that owes an action: one thread per game runs the
+// generic legal-action enumeration once; obs_encode_kernel expands the bits into mask bytes.
 template <bool SANMA>
-__global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* states, int64_t n, const int32_t* offsets,
+__global__ void __launch_bounds__(128) legal_ids_kernel(Tables T, const G* states, int64_t n, uint32_t* idbits) {
+  int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n) return;
+  const G& g = states[gi];
+  if (g.is_done) return;
+  Ctx cx = make_ctx(T, nullptr, 0, gi);
+  for (int pid = 0; pid < MAXP; pid++) {
+    if (!((g.active_mask >> pid) & 1)) continue;
+    uint32_t packed[RV_MAX_LEGAL];
+    int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
+    if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+    uint32_t bits[3] = {0, 0, 0};
+    for (int k = 0; k < cnt; k++) obs_id_set<SANMA>(bits, expand_act(g, pid, packed[k]));
+    uint32_t* o = idbits + ((size_t)gi * MAXP + pid) * 3;
+    o[0] = bits[0], o[1] = bits[1], o[2] = bits[2];
+  }
+}
+// One warp per game; for each seat that owes an action the warp writes the row with obs_encode_warp (obs.cuh) and
+// expands the seat's action-id set into the 82 (sanma 60) mask bytes.
+template <bool SANMA>
+__global__ void __launch_bounds__(128) obs_encode_kernel(const G* states, int64_t n, const int32_t* offsets, const uint32_t* idbits,
                                                          float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
-  constexpr int W = SANMA ? OBS_W3 : OBS_W, IDS = SANMA ? OBS_IDS3 : OBS_IDS, VEC = SANMA ? 2 : 4;
-  __shared__ uint64_t s_mask[4][OBS_CH];
-  __shared__ float s_val[4][OBS_CH];
-  __shared__ uint8_t s_kind[4][OBS_CH];
-  __shared__ uint8_t s_seen[4][36];
+  constexpr int W = SANMA ? OBS_W3 : OBS_W, IDS = SANMA ? OBS_IDS3 : OBS_IDS;
+  __shared__ ObsScratch scratch[4];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t gi = (int64_t)blockIdx.x * 4 + w;
   if (gi >= n) return;
@@ -727,52 +754,113 @@ __global__ void __launch_bounds__(128) obs_encode_kernel(Tables T, const G* stat
   for (int pid = 0; pid < MAXP; pid++) {
     if (!((g.active_mask >> pid) & 1)) continue;
     if (row >= max_obs) break;
-    if (obs) {
-      for (int ch = lane; ch < OBS_CH; ch += 32) {
-        int kind;
-        uint64_t m;
-        float v;
-        obs_channel<SANMA>(g, pid, ch, kind, m, v);
-        s_kind[w][ch] = (uint8_t)kind;
-        s_mask[w][ch] = m;
-        s_val[w][ch] = v;
-      }
-      for (int k = lane; k < OBS_W; k += 32) s_seen[w][k] = (uint8_t)obs_seen(g, pid, k);
-      __syncwarp();
-      float* dst = obs + (size_t)row * (OBS_CH * W);
-      for (int j = lane; j < OBS_CH * W / VEC; j += 32) {
-        float o[VEC];
-        #pragma unroll
-        for (int q = 0; q < VEC; q++) {
-          int e = VEC * j + q, ch = e / W, col = e - ch * W;
-          int k34 = SANMA ? obs_col_kind3(col) : col;
-          o[q] = obs_value(s_kind[w][ch], s_mask[w][ch], s_val[w][ch], s_seen[w][k34], k34);
-        }
-        // streaming stores: write-once data
-        if constexpr (SANMA) __stcs(reinterpret_cast<float2*>(dst) + j, make_float2(o[0], o[1]));
-        else __stcs(reinterpret_cast<float4*>(dst) + j, make_float4(o[0], o[1], o[2], o[3]));
-      }
-      __syncwarp();
-    }
-    if (mask) {
-      uint8_t* mrow = mask + (size_t)row * IDS;
-      for (int k = lane; k < IDS; k += 32) mrow[k] = 0;
-      __syncwarp();
-      if (lane == 0) {
-        Ctx cx = make_ctx(T, nullptr, 0, gi);
-        uint32_t packed[RV_MAX_LEGAL];
-        int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
-        if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
-        for (int k = 0; k < cnt; k++) {
-          rv_action a = expand_act(g, pid, packed[k]);
-          int id = SANMA ? action_id_3p(a) : action_id(a);
-          if (id >= 0 && id < IDS) mrow[id] = 1;
-        }
-      }
-      __syncwarp();
-    }
+    if (obs) obs_encode_warp<SANMA>(g, &g.river[0][0], pid, obs + (size_t)row * (OBS_CH * W), scratch[w], lane);
+    if (mask) obs_mask_row_warp<SANMA>(idbits + ((size_t)gi * MAXP + pid) * 3, mask + (size_t)row * IDS, lane);
     if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
     row++;
+  }
+}
+
+// Observe + step, fused (BASELINE config 5: a rollout that emits FEATURE_ENCODING tensors and masks at every step).
+// One warp owns 32 games.  Their hot prefixes are staged in shared memory with one bulk copy per game; then
+//   1. the warp walks its games and writes the tensor row of every seat that owes an action (obs_encode_warp), all lanes
+//      streaming one row at a time, straight from the staged state;
+//   2. every lane takes its own game's env step with the on-device agent (random_step<true>): the routine that builds the
+//      legal list to pick from leaves the list's action-id set in shared memory;
+//   3. the warp expands those sets into the mask rows;
+//   4. lanes whose round ended deal the next one together, and the records are stored back with one bulk copy each.
+// The state is read once and written once per step; the observation rows are the only other HBM traffic.
+template <bool SANMA>
+__global__ void __launch_bounds__(32) observe_step_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
+                                                          const int32_t* offsets, float* obs, uint8_t* mask, int32_t* index,
+                                                          int64_t max_obs, unsigned long long* counters) {
+  constexpr int W = SANMA ? OBS_W3 : OBS_W, IDS = SANMA ? OBS_IDS3 : OBS_IDS;
+  __shared__ __align__(128) unsigned char stage[32 * STG_STRIDE];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ ObsScratch scratch;
+  __shared__ uint32_t s_bits[32][MAXP][3];
+  const int lane = threadIdx.x;
+  const int64_t gi = (int64_t)blockIdx.x * 32 + lane;
+  const bool have = gi < n;
+  unsigned char* slot = stage + lane * STG_STRIDE;
+  const uint32_t bar = smem_u32(&mbar);
+  const int take = (int)min((int64_t)32, n - (int64_t)blockIdx.x * 32);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)take * (uint32_t)RV_HOT_BYTES) : "memory");
+  }
+  __syncwarp();
+  if (have) {
+    stage_in(slot, &states[gi], bar);
+    *reinterpret_cast<G**>(slot + RV_HOT_BYTES) = &states[gi];
+  }
+  {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok)
+                   : "r"(bar), "r"(0u)
+                   : "memory");
+  }
+  __syncwarp();
+  G& g = *reinterpret_cast<G*>(slot);
+  const bool live = have && !g.is_done;
+  const uint32_t am = live ? (g.active_mask & 0xFu) : 0u;
+  const int row0 = have ? offsets[gi] : 0;
+  // 1. tensor rows, one at a time, all lanes
+  const unsigned any_obs = __ballot_sync(0xFFFFFFFFu, am != 0);
+  if (obs || index) {
+    for (unsigned rest = any_obs; rest; rest &= rest - 1) {
+      const int src = __ffs(rest) - 1;
+      uint32_t am_s = __shfl_sync(0xFFFFFFFFu, am, src);
+      int row = __shfl_sync(0xFFFFFFFFu, row0, src);
+      const int64_t gi_s = (int64_t)blockIdx.x * 32 + src;
+      const G& gs = *reinterpret_cast<const G*>(stage + src * STG_STRIDE);
+      for (; am_s; am_s &= am_s - 1, row++) {
+        const int pid = __ffs(am_s) - 1;
+        if (row >= max_obs) break;
+        if (obs) obs_encode_warp<SANMA>(gs, &states[gi_s].river[0][0], pid, obs + (size_t)row * (OBS_CH * W), scratch, lane);
+        if (index && lane == 0) index[row] = (int32_t)(gi_s * 4 + pid);
+      }
+    }
+  }
+  // 2. the env step (leaves the id sets of the acting seats in s_bits)
+  Ctx cx = make_ctx(T, log, cap, have ? gi : 0);
+  cx.defer_init = true;
+  cx.idbits = &s_bits[lane][0][0];
+  unsigned long long stepped = 0, finished = 0;
+  if (live) {
+    random_step<true>(cx, g, agent_seed, g.seed);
+    stepped = 1;
+  }
+  __syncwarp();
+  // 3. mask rows
+  if (mask) {
+    for (unsigned rest = any_obs; rest; rest &= rest - 1) {
+      const int src = __ffs(rest) - 1;
+      uint32_t am_s = __shfl_sync(0xFFFFFFFFu, am, src);
+      int row = __shfl_sync(0xFFFFFFFFu, row0, src);
+      for (; am_s; am_s &= am_s - 1, row++) {
+        const int pid = __ffs(am_s) - 1;
+        if (row >= max_obs) break;
+        obs_mask_row_warp<SANMA>(s_bits[src][pid], mask + (size_t)row * IDS, lane);
+      }
+    }
+  }
+  // 4. deal the rounds that ended in this step (convergent over the lanes that need it), store back
+  if (live) {
+    if (g.pending_init[0] != RV_NONE) run_pending_init(cx, g);
+    finished = g.is_done ? 1 : 0;
+    stage_out(&states[gi], slot);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    stepped += __shfl_down_sync(0xFFFFFFFFu, stepped, o);
+    finished += __shfl_down_sync(0xFFFFFFFFu, finished, o);
+  }
+  if (lane == 0 && stepped) {
+    atomicAdd(&counters[0], stepped);
+    if (finished) atomicAdd(&counters[1], finished);
   }
 }
 
@@ -891,6 +979,15 @@ int rv_ctx_destroy(rv_ctx* c) {
   cudaFree(c->honor_info);
   cudaFree(c->suit_cost);
   cudaFree(c->honor_cost);
+  if (c->hands.d_q[0])
+    for (int b = 0; b < 2; b++) {
+      cudaFree(c->hands.d_q[b]);
+      cudaFree(c->hands.d_r[b]);
+      cudaFreeHost(c->hands.h_q[b]);
+      cudaFreeHost(c->hands.h_r[b]);
+      cudaStreamDestroy(c->hands.st[b]);
+      cudaEventDestroy(c->hands.done[b]);
+    }
   cudaStreamDestroy(c->stream);
   delete c;
   return RV_OK;
@@ -922,22 +1019,65 @@ int rv_hand_eval_batch_device(rv_ctx* c, const rv_hand_query* d_q, rv_hand_resul
   CK(cudaGetLastError());
   return RV_OK;
 }
+// Host buffers: a two-deep pipeline over persistent pinned staging buffers and two streams, so that the host-side copy of
+// chunk k+1 into pinned memory, the H2D/D2H transfers and the kernel of chunk k overlap.  Buffers the caller already
+// pinned (cudaHostAlloc / cudaHostRegister) are transferred directly.
+static constexpr int64_t HAND_CHUNK = 1 << 18;
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
 int rv_hand_eval_batch(rv_ctx* c, const rv_hand_query* q, rv_hand_result* out, int64_t n) {
   if (n <= 0) return RV_OK;
   CK(cudaSetDevice(c->device));
-  rv_hand_query* dq;
-  rv_hand_result* dr;
-  CK(cudaMalloc(&dq, sizeof(rv_hand_query) * n));
-  CK(cudaMalloc(&dr, sizeof(rv_hand_result) * n));
-  CK(cudaMemcpyAsync(dq, q, sizeof(rv_hand_query) * n, cudaMemcpyHostToDevice, c->stream));
-  int rc = rv_hand_eval_batch_device(c, dq, dr, n);
-  if (rc == RV_OK) {
-    CK(cudaMemcpyAsync(out, dr, sizeof(rv_hand_result) * n, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+  HandStage& hs = c->hands;
+  if (!hs.d_q[0]) {
+    for (int b = 0; b < 2; b++) {
+      CK(cudaMalloc(&hs.d_q[b], sizeof(rv_hand_query) * HAND_CHUNK));
+      CK(cudaMalloc(&hs.d_r[b], sizeof(rv_hand_result) * HAND_CHUNK));
+      CK(cudaMallocHost(&hs.h_q[b], sizeof(rv_hand_query) * HAND_CHUNK));
+      CK(cudaMallocHost(&hs.h_r[b], sizeof(rv_hand_result) * HAND_CHUNK));
+      CK(cudaStreamCreateWithFlags(&hs.st[b], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&hs.done[b], cudaEventDisableTiming));
+    }
   }
-  cudaFree(dq);
-  cudaFree(dr);
-  return rc;
+  CK(cudaStreamSynchronize(c->stream));       // earlier work of this context (table generation) is complete
+  const bool pin_in = is_pinned(q), pin_out = is_pinned(out);
+  const int64_t chunks = (n + HAND_CHUNK - 1) / HAND_CHUNK;
+  auto drain = [&](int64_t k) -> int {        // results of chunk k -> caller
+    const int b = (int)(k & 1);
+    CK(cudaEventSynchronize(hs.done[b]));
+    const int64_t lo = k * HAND_CHUNK, m = std::min(HAND_CHUNK, n - lo);
+    if (!pin_out) memcpy(out + lo, hs.h_r[b], sizeof(rv_hand_result) * m);
+    return RV_OK;
+  };
+  for (int64_t k = 0; k < chunks; k++) {
+    const int b = (int)(k & 1);
+    if (k >= 2) {
+      int rc = drain(k - 2);
+      if (rc != RV_OK) return rc;
+    }
+    const int64_t lo = k * HAND_CHUNK, m = std::min(HAND_CHUNK, n - lo);
+    const rv_hand_query* src = q + lo;
+    if (!pin_in) {
+      memcpy(hs.h_q[b], src, sizeof(rv_hand_query) * m);
+      src = hs.h_q[b];
+    }
+    CK(cudaMemcpyAsync(hs.d_q[b], src, sizeof(rv_hand_query) * m, cudaMemcpyHostToDevice, hs.st[b]));
+    hand_eval_kernel<<<grid_for(m, 128), 128, 0, hs.st[b]>>>(c->T, hs.d_q[b], hs.d_r[b], m);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pin_out ? out + lo : hs.h_r[b], hs.d_r[b], sizeof(rv_hand_result) * m, cudaMemcpyDeviceToHost, hs.st[b]));
+    CK(cudaEventRecord(hs.done[b], hs.st[b]));
+  }
+  for (int64_t k = std::max<int64_t>(0, chunks - 2); k < chunks; k++) {
+    int rc = drain(k);
+    if (rc != RV_OK) return rc;
+  }
+  return RV_OK;
 }
 int rv_calculate_score(int han, int fu, int is_oya, int is_tsumo, uint32_t honba, int num_players, uint32_t out[4]) {
   uint32_t total = 0;
@@ -968,6 +1108,8 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_log = nullptr;
   v->d_seeds = nullptr;
   v->d_obs_counts = v->d_obs_offsets = nullptr;
+  v->d_idbits = nullptr;
+  v->h_obs_total = nullptr;
   v->d_scan_tmp = nullptr;
   v->scan_tmp_bytes = 0;
   v->d_lists = nullptr;
@@ -1018,6 +1160,8 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_log) cudaFree(v->d_log);
   if (v->d_seeds) cudaFree(v->d_seeds);
   if (v->d_obs_counts) cudaFree(v->d_obs_counts);
+  if (v->d_idbits) cudaFree(v->d_idbits);
+  if (v->h_obs_total) cudaFreeHost(v->h_obs_total);
   if (v->d_obs_offsets) cudaFree(v->d_obs_offsets);
   if (v->d_scan_tmp) cudaFree(v->d_scan_tmp);
   if (v->d_lists) cudaFree(v->d_lists);
@@ -1408,9 +1552,9 @@ int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, ui
   }
   return RV_OK;
 }
-int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
+// rows of the observation buffers: active seats per game and their exclusive scan (offsets[n] = total)
+static int obs_offsets(rv_vec* v) {
   rv_ctx* c = v->ctx;
-  CK(cudaSetDevice(c->device));
   int64_t n = v->n;
   if (!v->d_obs_counts) {
     CK(cudaMalloc(&v->d_obs_counts, sizeof(int32_t) * (n + 1)));
@@ -1420,20 +1564,54 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
   }
   obs_count_kernel<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(v->d_states, n, v->d_obs_counts);
   CK(cub::DeviceScan::ExclusiveSum(v->d_scan_tmp, v->scan_tmp_bytes, v->d_obs_counts, v->d_obs_offsets, (int)(n + 1), c->stream));
+  return RV_OK;
+}
+static int obs_row_count(rv_vec* v, int64_t* n_obs) {
+  if (!n_obs) return RV_OK;
+  rv_ctx* c = v->ctx;
+  if (!v->h_obs_total) CK(cudaMallocHost(&v->h_obs_total, sizeof(int32_t)));
+  CK(cudaMemcpyAsync(v->h_obs_total, v->d_obs_offsets + v->n, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n_obs = *v->h_obs_total;
+  return RV_OK;
+}
+int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  int64_t n = v->n;
+  int rc = obs_offsets(v);
+  if (rc != RV_OK) return rc;
+  const bool sanma = v->game_mode >= 3;
+  if (d_mask) {
+    if (!v->d_idbits) CK(cudaMalloc(&v->d_idbits, sizeof(uint32_t) * 3 * MAXP * n));
+    if (sanma) legal_ids_kernel<true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_idbits);
+    else legal_ids_kernel<false><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_idbits);
+  }
   if (d_obs || d_mask || d_index) {
-    if (v->game_mode >= 3)
-      obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_obs_offsets, d_obs, d_mask, d_index, max_obs);
+    if (sanma)
+      obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, v->d_idbits, d_obs, d_mask, d_index, max_obs);
     else
-      obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_obs_offsets, d_obs, d_mask, d_index, max_obs);
+      obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, v->d_idbits, d_obs, d_mask, d_index, max_obs);
   }
   CK(cudaGetLastError());
-  if (n_obs) {
-    int32_t total = 0;
-    CK(cudaMemcpyAsync(&total, v->d_obs_offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    *n_obs = total;
-  }
-  return RV_OK;
+  return obs_row_count(v, n_obs);
+}
+int rv_vec_observe_step_random(rv_vec* v, uint64_t agent_seed, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs,
+                               int64_t* n_obs) {
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  int64_t n = v->n;
+  int rc = obs_offsets(v);
+  if (rc != RV_OK) return rc;
+  const unsigned grid = (unsigned)((n + 31) / 32);
+  if (v->game_mode >= 3)
+    observe_step_kernel<true><<<grid, 32, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_obs_offsets, d_obs,
+                                                          d_mask, d_index, max_obs, v->d_steps);
+  else
+    observe_step_kernel<false><<<grid, 32, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_obs_offsets, d_obs,
+                                                           d_mask, d_index, max_obs, v->d_steps);
+  CK(cudaGetLastError());
+  return obs_row_count(v, n_obs);
 }
 int rv_vec_encode_seq(rv_vec* v, int game_style, const uint32_t* start_words, uint16_t* d_sparse, float* d_numeric, uint16_t* d_prog,
                       int max_prog, uint16_t* d_cand, uint16_t* d_lens, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {

@@ -102,6 +102,18 @@ class VecRiichiEnv:
         check(lib().rv_vec_encode(self.handle, ptr(obs), ptr(mask), ptr(index), int(max_obs), C.byref(n) if sync else None))
         return int(n.value) if sync else None
 
+    def observe_step_random(self, agent_seed, obs=None, mask=None, index=None, max_obs=None, sync=False):
+        """encode(obs, mask, index) of the current decision point, then one env step of every live game with the on-device
+        agent — one fused kernel (rv_vec_observe_step_random).  Returns the row count when sync=True."""
+        def ptr(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        if max_obs is None:
+            max_obs = min(t.shape[0] for t in (obs, mask, index) if t is not None)
+        n = C.c_int64(0)
+        check(lib().rv_vec_observe_step_random(self.handle, int(agent_seed), ptr(obs), ptr(mask), ptr(index), int(max_obs),
+                                               C.byref(n) if sync else None))
+        return int(n.value) if sync else None
+
     def encode_seq(self, sparse=None, numeric=None, prog=None, cand=None, lens=None, index=None, game_style=1, max_obs=None,
                    start_words=None, sync=True):
         """Sequence features (Observation.encode_seq_sparse/numeric/progression/candidates) of every seat that owes an

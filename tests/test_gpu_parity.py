@@ -219,6 +219,71 @@ def test_external_actions_step(orc):
 
 
 @pytest.mark.parametrize("mode", [2, 5])
+def test_observe_step_fused_vs_oracle(orc, mode):
+    """rv_vec_observe_step_random (fused observe + step kernel): at every step of 192 games the tensor and mask rows equal the
+    oracle's encode()/mask() of the state BEFORE the step, and the games end with the oracle's scores and event hashes."""
+    import torch
+
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n = 192
+    W, IDS = (27, 60) if mode >= 3 else (34, 82)
+    v = VecRiichiEnv(n, mode, A.RULE_DEFAULT_TENHOU, seed_base=7700)
+    v.reset()
+    games = [orc.orc_game_new(mode, 7700 + g, 0, A.RULE_DEFAULT_TENHOU, 0) for g in range(n)]
+    for h in games:
+        orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    obs = torch.empty((n * 3, 74, W), dtype=torch.float32, device="cuda")
+    mask = torch.empty((n * 3, IDS), dtype=torch.uint8, device="cuda")
+    idx = torch.empty((n * 3,), dtype=torch.int32, device="cuda")
+    a = np.zeros(74 * W, np.float32)
+    m = np.zeros(IDS, np.uint8)
+    st = A.GameState()
+    checked = 0
+    for it in range(400):
+        check_now = it < 40 or it % 7 == 0
+        obs.fill_(-1.0)
+        mask.fill_(7)
+        rows = v.observe_step_random(33, obs=obs, mask=mask, index=idx, sync=True)
+        if check_now:
+            h_obs, h_mask, h_idx = obs[:rows].cpu().numpy(), mask[:rows].cpu().numpy(), idx[:rows].cpu().numpy()
+            r = 0
+            for g in range(n):
+                orc.orc_game_snapshot(games[g], C.byref(st))
+                if st.is_done:
+                    continue
+                for p in range(4):
+                    if (st.active_mask >> p) & 1:
+                        assert h_idx[r] == g * 4 + p
+                        orc.orc_game_encode(games[g], p, a.ctypes.data_as(C.POINTER(C.c_float)), m.ctypes.data_as(C.POINTER(C.c_uint8)))
+                        assert h_obs[r].tobytes() == a.tobytes(), f"iter {it} game {g} seat {p}: channels {sorted(set(np.nonzero(h_obs[r].ravel() != a)[0] // W))}"
+                        assert h_mask[r].tobytes() == m.tobytes(), f"iter {it} game {g} seat {p} mask"
+                        r += 1
+                        checked += 1
+            assert r == rows
+            assert (obs[rows:] == -1.0).all() and (mask[rows:] == 7).all()     # nothing written past the last row
+        for g in range(n):
+            orc.orc_game_random_step(games[g], 33, 7700 + g)
+    # run both to the end: same results
+    while True:
+        rows = v.observe_step_random(33, obs=obs, mask=mask, index=idx, sync=True)
+        if rows == 0:
+            break
+    done, scores, _ = v.results()
+    _, _, _, eh = v.counters()
+    assert done.all()
+    for g in range(n):
+        while True:
+            orc.orc_game_snapshot(games[g], C.byref(st))
+            if st.is_done:
+                break
+            orc.orc_game_random_step(games[g], 33, 7700 + g)
+        assert [st.score[p] for p in range(4)] == list(scores[g]) and st.ev_hash == eh[g], f"game {g}"
+        orc.orc_game_free(games[g])
+    assert checked > 5000
+
+
+@pytest.mark.parametrize("mode", [2, 5])
 def test_observation_encode_vs_oracle(orc, mode):
     """rv_vec_encode: every acting seat of 256 games at several points of the rollout, bytes equal to the oracle's
     Observation::encode / mask restatement (4P: 74x34 + 82 ids; sanma: 74x27 + 60 ids); row order ascending (game, seat)."""
