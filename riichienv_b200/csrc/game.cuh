@@ -1710,8 +1710,15 @@ __host__ __device__ __forceinline__ uint32_t agent_pick(uint64_t agent_seed, uin
 // Action::encode / ActionEncoder::encode_3p (defined in obs.cuh)
 __device__ inline int action_id(const rv_action& a);
 __device__ inline int action_id_3p(const rv_action& a);
+// Layout per seat: three words = ids 0..95; bit 31 of the third word marks "this seat owed an action at this step".
+constexpr uint32_t IDS_VALID = 0x80000000u;
+__device__ __forceinline__ void ids_reset(const Ctx& cx) {        // start of an env step: no seat acts yet
+  #pragma unroll
+  for (int k = 0; k < 3 * MAXP; k++) cx.idbits[k] = 0;
+}
 __device__ __forceinline__ void ids_clear(const Ctx& cx, int seat) {
-  cx.idbits[3 * seat] = cx.idbits[3 * seat + 1] = cx.idbits[3 * seat + 2] = 0;
+  cx.idbits[3 * seat] = cx.idbits[3 * seat + 1] = 0;
+  cx.idbits[3 * seat + 2] = IDS_VALID;
 }
 __device__ __forceinline__ void ids_add(const Ctx& cx, const G& g, int seat, uint32_t packed) {
   const rv_action a = expand_act(g, seat, packed);
@@ -1726,7 +1733,7 @@ __device__ __forceinline__ void ids_add(const Ctx& cx, const G& g, int seat, uin
 // turn — "the only legal actions are discards" — is restated here as one compact routine.  It either
 // performs the WHOLE env step exactly as random_step_act would, or returns false BEFORE touching the
 // state so the game is handed to the generic kernel (agari shape, riichi / kan / kyushu options, a
-// declared riichi, sanma).  The discard itself is committed here; what FOLLOWS the discard is
+// declared riichi, a North tile in a sanma hand).  The discard itself is committed here; what FOLLOWS the discard is
 //   * inline, when it is the plain case (nobody can claim, ordinary draw, no kan dora business), or
 //   * the generic resolve_discard() (claims, first turn, after a call or a kan, last tile) — the very
 //     function the generic path runs, entered with the same state.
@@ -1801,10 +1808,11 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   const int pid = g.current_player;
   const int drawn = g.drawn_tile;
   const int hl = g.hand_len[pid], nm = g.n_melds[pid];
-  if (np != 4) return RV_DECLINE(16);   // sanma takes the generic path (kita, seat arithmetic mod 3)
+  const bool sanma = np == 3;
   if (g.flags[pid] & (RV_F_RIICHI_DECLARED | RV_F_RIICHI_STAGE)) return RV_DECLINE(19);
   if (hl + 3 * nm != 14) return RV_DECLINE(21);
   const uint64_t c0 = g.c_cnt[pid][0], c1 = g.c_cnt[pid][1], c2 = g.c_cnt[pid][2], c3 = g.c_cnt[pid][3];
+  if (sanma && ((c3 >> 12) & 15)) return RV_DECLINE(16);   // a North tile in hand: Kita may be legal (state_3p/sanma.rs:146-169)
   if ((c0 | c1 | c2 | c3) & 0x4444444444444444ull) return RV_DECLINE(22);             // four of a kind: ankan may be legal
   const uint32_t e0 = __ldg(&cx.T.suit_info[g.c_key[pid][0]]), e1 = __ldg(&cx.T.suit_info[g.c_key[pid][1]]),
                  e2 = __ldg(&cx.T.suit_info[g.c_key[pid][2]]), e3 = __ldg(&cx.T.honor_info[g.c_key[pid][3]]);
@@ -1836,7 +1844,8 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     if (tk >= (first ? 9 : 12)) return RV_DECLINE(25);
   }
   if (complete == 4) return RV_DECLINE(26);                                            // standard agari shape: tsumo evaluation
-  if (complete >= 2 && !open_meld && g.score[pid] >= 1000 && g.drawable_count >= 4) return RV_DECLINE(27);   // riichi may be legal
+  if (complete >= 2 && !open_meld && g.score[pid] >= 1000 && (sanma ? g.drawable_count > 0 : g.drawable_count >= 4))
+    return RV_DECLINE(27);   // riichi may be legal (3P: state_3p/legal_actions.rs:116)
   // ---- the action: every hand tile that kuikae does not forbid is a legal discard, nothing else is legal
   uint8_t* const hrow = g.hand[pid];
   Row14 hx = row_load(hrow);
@@ -1867,13 +1876,13 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   uint32_t claim_seats = 0;                                                   // seats gen_claims has to look at
   #pragma unroll 1
   for (int d = 1; d < np; d++) {
-    int i = (pid + d) & 3;
+    int i = sanma ? (pid + d) % 3 : (pid + d) & 3;
     if ((g.c_waits[i] >> kind) & 1) claim_seats |= 1u << i;                   // ron shape
     if (g.flags[i] & RV_F_RIICHI_DECLARED) continue;
     if (g.hand_len[i] < 3) continue;
     uint64_t x = g.c_cnt[i][ksu];
     if (((x >> (4 * kr)) & 15) >= 2) claim_seats |= 1u << i;                  // pon / daiminkan
-    if (d == 1 && ksu < 3) {                                                  // chi (shimocha)
+    if (d == 1 && ksu < 3 && !sanma) {                                        // chi (shimocha; none in sanma)
       uint64_t y = x << 8;                                                    // nibble kr+2 of y == nibble kr of x
       int m2 = (y >> (4 * kr)) & 15, m1 = (y >> (4 * kr + 4)) & 15, p1 = (y >> (4 * kr + 12)) & 15, p2 = (y >> (4 * kr + 16)) & 15;
       if (kr >= 8) p1 = 0;
@@ -1888,9 +1897,10 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     #pragma unroll
     for (int j = 0; j < RV_HAND_CAP; j++)
       if ((legal_rows >> j) & 1) kinds |= 1ull << (row_get(hx, j) >> 2);
+    ids_reset(cx);
     cx.idbits[3 * pid] = (uint32_t)kinds;
     cx.idbits[3 * pid + 1] = (uint32_t)(kinds >> 32);
-    cx.idbits[3 * pid + 2] = 0;
+    cx.idbits[3 * pid + 2] = IDS_VALID;
   }
   // ================= commit: nothing below can fail =================
   RV_STAT(9);
@@ -1939,6 +1949,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     return act_fast_tail(cx, g, pid, tile, tsumogiri, claim_seats);
   }
   // _resolve_discard (state/mod.rs:1317-1413), no-claims branch
+  if (sanma) g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;   // state_3p/mod.rs:1224-1227
   g.flags[pid] &= ~(RV_F_IPPATSU_CYCLE | RV_F_MISSED_AGARI_DOUJUN);
   if (!tid_terminal(tile)) g.flags[pid] &= ~RV_F_NAGASHI_ELIGIBLE;
   const int nr = g.n_river[pid];
@@ -1966,8 +1977,8 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   g.n_claims[0] = g.n_claims[1] = g.n_claims[2] = g.n_claims[3] = 0;
   // the next seat draws (_deal_next, state/mod.rs:1569-1593)
   g.turn_count++;
-  if (first && g.turn_count >= 4) g.is_first_turn = 0;
-  const int nxt = (pid + 1) & 3;
+  if (first && g.turn_count >= (uint32_t)np) g.is_first_turn = 0;
+  const int nxt = sanma ? (pid + 1) % 3 : (pid + 1) & 3;
   g.current_player = (uint8_t)nxt;
   const int t2 = cold(g).wall[g.wall_top - 1];
   g.wall_top--;
@@ -2011,7 +2022,10 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
   RV_STAT(3);
   RV_STAT(4);
   int pid = g.current_player;
-  if (IDS) ids_clear(cx, pid);
+  if (IDS) {
+    ids_reset(cx);
+    ids_clear(cx, pid);
+  }
   TurnInfo ti;
   turn_info(cx, g, pid, ti);
   uint32_t fl = g.flags[pid];
@@ -2084,6 +2098,7 @@ __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agen
   for (int p = 0; p < np; p++) acts[p].type = RV_NO_ACTION;
   uint32_t sc = g.step_count;
   RV_STAT(3);
+  if (IDS) ids_reset(cx);
   for (int p = 0; p < np; p++) {
     if (!((g.active_mask >> p) & 1)) continue;
     if (IDS) {

@@ -59,6 +59,7 @@ struct rv_vec {
   int32_t *d_obs_counts, *d_obs_offsets;   // encode: active seats per game and their exclusive scan (n + 1)
   uint32_t* d_idbits;                      // encode: action-id sets [n][4][3]
   int32_t* h_obs_total;                    // pinned: row count of the last encode
+  int32_t* d_row_index;                    // observe+step: row -> game*4+seat when the caller does not ask for it
   void* d_scan_tmp;
   unsigned char *d_gather, *h_gather;   // results/counters staging (device, pinned host)
   uint32_t* d_seq_cursor;       // [n][4] event-log word offset of each seat's previous observation (rv_vec_encode_seq)
@@ -183,21 +184,25 @@ __global__ void reset_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint
 #ifndef RV_INIT_BATCH
 #define RV_INIT_BATCH 8
 #endif
+// IDS (one-step launches of the observation pipeline): the legal lists' action-id sets go to idbits[game][seat][3].
+template <bool IDS>
 __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
-                                                          uint64_t agent_seed, uint32_t max_steps, unsigned long long* counters) {
+                                                          uint64_t agent_seed, uint32_t max_steps, unsigned long long* counters,
+                                                          uint32_t* idbits) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long my_steps = 0, my_done = 0;
   bool alive = i < n;
   G& g = states[alive ? i : 0];
   Ctx cx = make_ctx(T, log, cap, alive ? i : 0);
   cx.defer_init = true;
+  if (IDS) cx.idbits = idbits + (size_t)(alive ? i : 0) * (3 * MAXP);
   uint64_t gid = alive ? g.seed : 0;
   uint32_t taken = 0;
   while (true) {
     bool parked = alive && g.pending_init[0] != RV_NONE;
     bool can = alive && !parked && !g.is_done && taken < max_steps;
     if (can) {
-      random_step(cx, g, agent_seed, gid);
+      random_step<IDS>(cx, g, agent_seed, gid);
       taken++;
       my_steps++;
       parked = g.pending_init[0] != RV_NONE;
@@ -761,6 +766,17 @@ __global__ void __launch_bounds__(128) obs_encode_kernel(const G* states, int64_
   }
 }
 
+// Mask rows from the id sets a one-step rollout left in HBM: one warp per row, (game, seat) from the row index.
+template <bool SANMA>
+__global__ void __launch_bounds__(256) obs_mask_rows_kernel(const int32_t* index, const int32_t* total, const uint32_t* idbits, uint8_t* mask,
+                                                            int64_t max_obs) {
+  constexpr int IDS = SANMA ? OBS_IDS3 : OBS_IDS;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= max_obs || row >= *total) return;
+  const int gs = index[row];                       // game * 4 + seat
+  obs_mask_row_warp<SANMA>(idbits + (size_t)gs * 3, mask + (size_t)row * IDS, threadIdx.x & 31);
+}
+
 // Observe + step, fused (BASELINE config 5: a rollout that emits FEATURE_ENCODING tensors and masks at every step).
 // One warp owns 32 games.  Their hot prefixes are staged in shared memory with one bulk copy per game; then
 //   1. the warp walks its games and writes the tensor row of every seat that owes an action (obs_encode_warp), all lanes
@@ -1110,6 +1126,7 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_obs_counts = v->d_obs_offsets = nullptr;
   v->d_idbits = nullptr;
   v->h_obs_total = nullptr;
+  v->d_row_index = nullptr;
   v->d_scan_tmp = nullptr;
   v->scan_tmp_bytes = 0;
   v->d_lists = nullptr;
@@ -1162,6 +1179,7 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_obs_counts) cudaFree(v->d_obs_counts);
   if (v->d_idbits) cudaFree(v->d_idbits);
   if (v->h_obs_total) cudaFreeHost(v->h_obs_total);
+  if (v->d_row_index) cudaFree(v->d_row_index);
   if (v->d_obs_offsets) cudaFree(v->d_obs_offsets);
   if (v->d_scan_tmp) cudaFree(v->d_scan_tmp);
   if (v->d_lists) cudaFree(v->d_lists);
@@ -1244,8 +1262,8 @@ int rv_vec_step(rv_vec* v, const rv_action* actions) {
 
 static int rollout_mono(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
-  step_random_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, agent_seed,
-                                                                 max_steps, v->d_steps);
+  step_random_kernel<false><<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, agent_seed,
+                                                                        max_steps, v->d_steps, nullptr);
   CK(cudaGetLastError());
   return RV_OK;
 }
@@ -1432,7 +1450,8 @@ int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps)
   // short calls (lock-step drivers, per-step observation loops) use the single persistent kernel: the phase pipeline
   // needs a few dozen iterations to drain its deferred lists and only pays off for long rollouts
   const int mode = rollout_mode();
-  if (mode == 0 || max_steps < 32) return rollout_mono(v, agent_seed, max_steps);
+  static const uint32_t mono_below = (uint32_t)env_int("RV_MONO_BELOW", 32);
+  if (mode == 0 || max_steps < mono_below) return rollout_mono(v, agent_seed, max_steps);
   return mode == 1 ? rollout_phased(v, agent_seed, max_steps) : rollout_persistent(v, agent_seed, max_steps);
 }
 int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done) {
@@ -1603,6 +1622,33 @@ int rv_vec_observe_step_random(rv_vec* v, uint64_t agent_seed, float* d_obs, uin
   int64_t n = v->n;
   int rc = obs_offsets(v);
   if (rc != RV_OK) return rc;
+  const char* impl = getenv("RV_OBS_STEP");                // "fused" selects the single kernel; read per call (the parity
+  const bool use_queue = !(impl && strcmp(impl, "fused") == 0);   // tests exercise both implementations in one process)
+  if (use_queue) {
+    // tensor rows from the state as it is (many warps per SM: the encoder is a streaming kernel); then ONE env step per game
+    // (thread per game — few, fat warps), which leaves the legal lists' id sets in HBM; then the mask rows.  Measured on a
+    // B200 (65,536 hanchan): 203 + 270 + 10 us per step against 814 us for the single fused kernel, whose 2,048 one-warp
+    // CTAs (168 registers, 24 KB of staging) leave the encoder 9 warps per SM.  A one-step launch of the class-queue
+    // scheduler is no alternative: 194 us at best, milliseconds when the last games of a class keep SMs switching.
+    const bool sanma = v->game_mode >= 3;
+    if (!v->d_idbits) CK(cudaMalloc(&v->d_idbits, sizeof(uint32_t) * 3 * MAXP * n));
+    if (!d_index) {
+      if (!v->d_row_index) CK(cudaMalloc(&v->d_row_index, sizeof(int32_t) * MAXP * n));
+      d_index = v->d_row_index;
+      if (max_obs > (int64_t)MAXP * n) max_obs = (int64_t)MAXP * n;
+    }
+    if (sanma) obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs);
+    else obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs);
+    step_random_kernel<true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, 1, v->d_steps,
+                                                                      v->d_idbits);
+    if (d_mask) {
+      const int64_t rows_cap = std::min<int64_t>(max_obs, (int64_t)MAXP * n);
+      if (sanma) obs_mask_rows_kernel<true><<<grid_for(rows_cap, 8), 256, 0, c->stream>>>(d_index, v->d_obs_offsets + n, v->d_idbits, d_mask, max_obs);
+      else obs_mask_rows_kernel<false><<<grid_for(rows_cap, 8), 256, 0, c->stream>>>(d_index, v->d_obs_offsets + n, v->d_idbits, d_mask, max_obs);
+    }
+    CK(cudaGetLastError());
+    return obs_row_count(v, n_obs);
+  }
   const unsigned grid = (unsigned)((n + 31) / 32);
   if (v->game_mode >= 3)
     observe_step_kernel<true><<<grid, 32, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_obs_offsets, d_obs,

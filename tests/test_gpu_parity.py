@@ -218,11 +218,14 @@ def test_external_actions_step(orc):
     assert np.array_equal(a.counters()[3], b.counters()[3])
 
 
-@pytest.mark.parametrize("mode", [2, 5])
-def test_observe_step_fused_vs_oracle(orc, mode):
-    """rv_vec_observe_step_random (fused observe + step kernel): at every step of 192 games the tensor and mask rows equal the
-    oracle's encode()/mask() of the state BEFORE the step, and the games end with the oracle's scores and event hashes."""
+@pytest.mark.parametrize("mode,impl", [(2, "queue"), (5, "queue"), (2, "fused"), (5, "fused")])
+def test_observe_step_fused_vs_oracle(orc, mode, impl, monkeypatch):
+    """rv_vec_observe_step_random — both implementations (queue: encode kernel + one-step class-queue rollout + mask rows;
+    fused: the single kernel): at every step of 192 games the tensor and mask rows equal the oracle's encode()/mask()
+    of the state BEFORE the step, and the games end with the oracle's scores and event hashes."""
     import torch
+
+    monkeypatch.setenv("RV_OBS_STEP", impl)
 
     from riichienv_b200.vec_env import VecRiichiEnv
 
