@@ -139,7 +139,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = args.cpu_sample_games or max(2 * threads, 256)
+    per_step = args.cpu_sample_games or max(64 * threads, 2048)   # ~1-2 s of work per step on all cores
     for w in range(args.warmup):
         run_oracle_sample(args.mode, max(threads, per_step // 8), 30_000_000 + w * per_step, 1, threads)
     tot_steps, tot_t = 0, 0.0

@@ -1721,7 +1721,15 @@ __device__ __forceinline__ void ids_clear(const Ctx& cx, int seat) {
   cx.idbits[3 * seat + 2] = IDS_VALID;
 }
 __device__ __forceinline__ void ids_add(const Ctx& cx, const G& g, int seat, uint32_t packed) {
-  const rv_action a = expand_act(g, seat, packed);
+  // the id depends on the type, the tile kind and (chi) the two consumed kinds: all in the packed word — no expand_act.
+  // (ankan / kakan: consume_tiles[0] has the kind of the packed tile, whichever physical tiles expand_act picks)
+  rv_action a;
+  a.type = (uint8_t)(packed & 0xFF);
+  a.tile = (uint8_t)((packed >> 8) & 0xFF);
+  const bool kan = a.type == RV_ANKAN || a.type == RV_KAKAN;
+  a.consume[0] = kan ? a.tile : (uint8_t)((packed >> 16) & 0xFF);
+  a.consume[1] = (uint8_t)(packed >> 24);
+  a.n_consume = kan ? 1 : (a.type == RV_CHI ? 2 : 0);
   const bool sanma = is_sanma(g);
   const int id = sanma ? action_id_3p(a) : action_id(a);
   if (id >= 0 && id < (sanma ? 60 : 82)) cx.idbits[3 * seat + (id >> 5)] |= 1u << (id & 31);
@@ -1801,9 +1809,11 @@ __device__ __noinline__ void run_pending_tail(const Ctx& cx, G& g) {
   g.pending_tail[1] = 0;
   resolve_discard(cx, g, g.current_player, tile, tsumogiri, claim_seats);
 }
-template <bool IDS = false>
+// NPC: seat count known at compile time (the rollout kernel is instantiated per variant so that the 4P hot path carries no
+// sanma arithmetic), or 0 = read it from the record.
+template <bool IDS = false, int NPC = 0>
 __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_seed, uint64_t game_id) {
-  const int np = num_players(g);
+  const int np = NPC ? NPC : num_players(g);
   RV_STAT(10);
   const int pid = g.current_player;
   const int drawn = g.drawn_tile;
@@ -1892,11 +1902,12 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   }
   const bool claims = claim_seats != 0;
   if (IDS) {
-    // the legal list is exactly the discards of `legal_rows`: ids = their tile kinds (4P id space; sanma declined above)
+    // the legal list is exactly the discards of `legal_rows`: ids = their tile kinds (sanma: compact columns, action.rs:262-279)
     uint64_t kinds = 0;
     #pragma unroll
     for (int j = 0; j < RV_HAND_CAP; j++)
       if ((legal_rows >> j) & 1) kinds |= 1ull << (row_get(hx, j) >> 2);
+    if (sanma) kinds = (kinds & 1) | ((kinds >> 7) & ~1ull);
     ids_reset(cx);
     cx.idbits[3 * pid] = (uint32_t)kinds;
     cx.idbits[3 * pid + 1] = (uint32_t)(kinds >> 32);

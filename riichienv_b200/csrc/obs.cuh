@@ -242,18 +242,23 @@ namespace rv {
 //               pieces (a handful of instructions per branch — no loops over tiles);
 //   stream      2,516 floats (sanma 1,998) leave as 16-byte (8-byte) streaming stores, each built from two table reads
 //               and a funnel of the masks of the (at most two) channels it spans.  Channel 63 (seen/4) is patched in.
+struct __align__(16) ObsDesc {   // one channel: out[col] = (mask >> col) & 1 ? val : 0
+  uint64_t mask;
+  float val;
+  uint32_t pad;
+};
 struct ObsScratch {
-  uint64_t mask[OBS_CH + 2];
-  float val[OBS_CH + 2];
+  ObsDesc d[OBS_CH + 2];
   int seen[36];
   int dora[4];
   uint8_t rtail[4][8];   // kind of the j-th most recent discard of seat q, 0xFF = none
+  uint8_t dm[36];        // per tile kind: how many dora indicators point at it
 };
 __device__ __forceinline__ uint64_t obs_compact3(uint64_t m) { return (m & 1) | ((m >> 7) & ~1ull); }   // 34 kinds -> 27 columns
 
 template <bool SANMA>
 __device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river, int pid, float* dst, ObsScratch& S, int lane) {
-  constexpr int NPV = SANMA ? 3 : 4, W = SANMA ? OBS_W3 : OBS_W, VEC = SANMA ? 2 : 4;
+  constexpr int NPV = SANMA ? 3 : 4, W = SANMA ? OBS_W3 : OBS_W;
   constexpr uint64_t ALL = (1ull << W) - 1;
   auto rel = [&](int i) { return SANMA ? (pid + i) % 3 : (pid + i) & 3; };
   // ---- gather
@@ -267,12 +272,18 @@ __device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river
     k = SANMA ? obs_next_kind_sanma(k) : obs_next_kind(k);
     dkp = (dkp & ~(0xFFull << (8 * d))) | ((uint64_t)k << (8 * d));
   }
-  auto dmatch = [&](int kind) {
-    int c = 0;
-    for (int d = 0; d < nd; d++) c += ((int)((dkp >> (8 * d)) & 0xFF) == kind) ? 1 : 0;
-    return c;
-  };
+  {
+    int c = 0, c2 = 0;
+    for (int d = 0; d < nd; d++) {
+      const int k = (int)((dkp >> (8 * d)) & 0xFF);
+      c += k == lane ? 1 : 0;
+      c2 += k == 32 + lane ? 1 : 0;
+    }
+    S.dm[lane] = (uint8_t)c;
+    if (lane < 2) S.dm[32 + lane] = (uint8_t)c2;
+  }
   __syncwarp();
+  auto dmatch = [&](int kind) { return (int)S.dm[kind]; };
   {
     const int q = lane >> 3, w = lane & 7;
     const int n = min((int)g.n_river[q], RV_RIVER_CAP);
@@ -414,27 +425,56 @@ __device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river
     // 70-73: tsumogiri flags are always empty in the live env -> zeros
     if (bcast) m = ALL;
     else if (SANMA) m = obs_compact3(m);
-    S.mask[ch] = m & ALL;
-    S.val[ch] = v;
+    S.d[ch].mask = m & ALL;
+    S.d[ch].val = v;
   }
   __syncwarp();
   // ---- stream
-  for (int j = lane; j < OBS_CH * W / VEC; j += 32) {
-    const int e0 = VEC * j, ch0 = e0 / W, col0 = e0 - ch0 * W, rem = W - col0;   // elements q < rem belong to ch0
-    const uint64_t bits = (S.mask[ch0] >> col0) | (S.mask[ch0 + 1] << rem);
-    const float v0 = S.val[ch0], v1 = S.val[ch0 + 1];
-    float o[VEC];
-    #pragma unroll
-    for (int q = 0; q < VEC; q++) o[q] = ((bits >> q) & 1) ? (q < rem ? v0 : v1) : 0.0f;
-    if (ch0 == 63 || (ch0 == 62 && rem < VEC)) {
-      #pragma unroll
-      for (int q = 0; q < VEC; q++) {
-        const int ch = q < rem ? ch0 : ch0 + 1, col = q < rem ? col0 + q : q - rem;
-        if (ch == 63) o[q] = (float)S.seen[SANMA ? obs_col_kind3(col) : col] / 4.0f;
-      }
+  if constexpr (!SANMA) {
+    // Two channels are 68 floats = 17 sixteen-byte stores: 8 inside the even channel, one straddling both (columns 32,33 |
+    // 0,1), 8 inside the odd channel.  The 16 one-channel stores of a pair are item (p, u): u = lane & 15 never changes for
+    // a lane, so column and half are loop invariants and a store costs one 16-byte table read, one funnel shift and four
+    // bit-field-extract + and pairs.  The 37 straddling stores are a second, short pass.
+    auto bit_and = [](uint32_t bits, int q, uint32_t v) {
+      int m;
+      asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(bits), "r"(q));   // 0 or -1
+      return __uint_as_float(v & (uint32_t)m);
+    };
+    const int u = lane & 15, odd = u >> 3, col = odd ? 4 * u - 30 : 4 * u;
+    float4* const out4 = reinterpret_cast<float4*>(dst);
+    for (int pr = lane >> 4; pr < OBS_CH / 2; pr += 2) {
+      const int ch = 2 * pr + odd;
+      const uint4 dsc = *reinterpret_cast<const uint4*>(&S.d[ch]);
+      const uint32_t bits = __funnelshift_r(dsc.x, dsc.y, col);
+      float4 o = make_float4(bit_and(bits, 0, dsc.z), bit_and(bits, 1, dsc.z), bit_and(bits, 2, dsc.z), bit_and(bits, 3, dsc.z));
+      if (ch == 63) o = make_float4((float)S.seen[col] / 4.0f, (float)S.seen[col + 1] / 4.0f, (float)S.seen[col + 2] / 4.0f,
+                                    (float)S.seen[col + 3] / 4.0f);
+      __stcs(out4 + 17 * pr + u + odd, o);
     }
-    if constexpr (SANMA) __stcs(reinterpret_cast<float2*>(dst) + j, make_float2(o[0], o[1]));
-    else __stcs(reinterpret_cast<float4*>(dst) + j, make_float4(o[0], o[1], o[2], o[3]));
+    for (int pr = lane; pr < OBS_CH / 2; pr += 32) {
+      const uint4 a = *reinterpret_cast<const uint4*>(&S.d[2 * pr]), b = *reinterpret_cast<const uint4*>(&S.d[2 * pr + 1]);
+      float4 o = make_float4(bit_and(a.y, 0, a.z), bit_and(a.y, 1, a.z), bit_and(b.x, 0, b.z), bit_and(b.x, 1, b.z));   // a: columns 32, 33
+      if (2 * pr + 1 == 63) o.z = (float)S.seen[0] / 4.0f, o.w = (float)S.seen[1] / 4.0f;
+      __stcs(out4 + 17 * pr + 8, o);
+    }
+  } else {
+    constexpr int VEC = 2;
+    for (int j = lane; j < OBS_CH * W / VEC; j += 32) {
+      const int e0 = VEC * j, ch0 = e0 / W, col0 = e0 - ch0 * W, rem = W - col0;   // elements q < rem belong to ch0
+      const uint64_t bits = (S.d[ch0].mask >> col0) | (S.d[ch0 + 1].mask << rem);
+      const float v0 = S.d[ch0].val, v1 = S.d[ch0 + 1].val;
+      float o[VEC];
+      #pragma unroll
+      for (int q = 0; q < VEC; q++) o[q] = ((bits >> q) & 1) ? (q < rem ? v0 : v1) : 0.0f;
+      if (ch0 == 63 || (ch0 == 62 && rem < VEC)) {
+        #pragma unroll
+        for (int q = 0; q < VEC; q++) {
+          const int ch = q < rem ? ch0 : ch0 + 1, col = q < rem ? col0 + q : q - rem;
+          if (ch == 63) o[q] = (float)S.seen[obs_col_kind3(col)] / 4.0f;
+        }
+      }
+      __stcs(reinterpret_cast<float2*>(dst) + j, make_float2(o[0], o[1]));
+    }
   }
   __syncwarp();
 }

@@ -193,9 +193,17 @@ __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, i
   unsigned long long my_steps = 0, my_done = 0;
   bool alive = i < n;
   G& g = states[alive ? i : 0];
+  if (IDS && alive) {
+    // one-step launches of the observation pipeline: the rows streamed out since the last step have pushed the records out
+    // of the L2; ask for all 14 lines of this game's record at once instead of meeting them one dependent miss at a time
+    const char* rec = reinterpret_cast<const char*>(&g);
+    #pragma unroll
+    for (int k = 0; k < (int)((sizeof(G) + 127) / 128); k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 128 * k));
+  }
   Ctx cx = make_ctx(T, log, cap, alive ? i : 0);
   cx.defer_init = true;
-  if (IDS) cx.idbits = idbits + (size_t)(alive ? i : 0) * (3 * MAXP);
+  uint32_t my_ids[3 * MAXP];          // built in (L1-cached) local memory, stored once: not a read-modify-write per id in HBM
+  if (IDS) cx.idbits = my_ids;
   uint64_t gid = alive ? g.seed : 0;
   uint32_t taken = 0;
   while (true) {
@@ -203,6 +211,12 @@ __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, i
     bool can = alive && !parked && !g.is_done && taken < max_steps;
     if (can) {
       random_step<IDS>(cx, g, agent_seed, gid);
+      if (IDS) {
+        uint4* o = reinterpret_cast<uint4*>(idbits + (size_t)i * (3 * MAXP));
+        o[0] = make_uint4(my_ids[0], my_ids[1], my_ids[2], my_ids[3]);
+        o[1] = make_uint4(my_ids[4], my_ids[5], my_ids[6], my_ids[7]);
+        o[2] = make_uint4(my_ids[8], my_ids[9], my_ids[10], my_ids[11]);
+      }
       taken++;
       my_steps++;
       parked = g.pending_init[0] != RV_NONE;
@@ -231,6 +245,110 @@ __global__ void __launch_bounds__(128) step_random_kernel(Tables T, G* states, i
   if (threadIdx.x == 0) {
     atomicAdd(&counters[0], sh[0]);
     atomicAdd(&counters[1], sh[1]);
+  }
+}
+
+// One env step per game, lock-step, with the work regrouped inside the block so that warps run ONE kind of transition.
+// (A thread-per-game warp executes the union of the code paths its 32 games need: ncu on the one-step launches of the
+// observation pipeline shows 5.2 of 32 lanes active per instruction and 8,700 instructions per warp.)  A block owns 256 games:
+//   1. every thread classifies its own game; the turns the compact act_fast routine can take are taken right here — all
+//      lanes run the same routine — with the follow-up of a discard that somebody may claim parked (pending_tail);
+//   2. the games that are left — claim windows (RESP), parked follow-ups (TAIL), turns act_fast declined (SLOW) — are compacted
+//      into per-kind lists in shared memory and handed out again in warp-aligned ranges: a warp now runs one generic routine
+//      on up to 32 games of that kind; a round that ends is dealt by the same thread right away.
+// Id sets (IDS) are built in shared memory and stored once per game.
+constexpr int SB = 256;
+template <bool IDS>
+__global__ void __launch_bounds__(SB) step_sorted_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
+                                                         unsigned long long* counters, uint32_t* idbits) {
+  enum { K_RESP = 0, K_TAIL = 1, K_SLOW = 2, K_NONE = 3 };
+  __shared__ uint16_t list[3][SB];
+  __shared__ int cnt[3];
+  __shared__ uint32_t s_ids[IDS ? SB : 1][3 * MAXP];
+  __shared__ unsigned long long sh[2];
+  const int t = threadIdx.x, lane = t & 31;
+  const int64_t base = (int64_t)blockIdx.x * SB, i = base + t;
+  if (t < 3) cnt[t] = 0;
+  if (t == 0) sh[0] = sh[1] = 0;
+  __syncthreads();
+  const bool alive = i < n;
+  G& g = states[alive ? i : 0];
+  if (IDS && alive) {
+    const char* rec = reinterpret_cast<const char*>(&g);
+    #pragma unroll
+    for (int k = 0; k < (int)((sizeof(G) + 127) / 128); k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 128 * k));
+  }
+  const bool live = alive && !g.is_done;
+  int kind = K_NONE;
+  if (live) {
+    if (g.phase == RV_WAIT_ACT) {
+      Ctx cx = make_ctx(T, log, cap, i);
+      cx.defer_init = true;
+      cx.defer_tail = true;
+      if (IDS) cx.idbits = s_ids[t];
+      if (!act_fast<IDS>(cx, g, agent_seed, g.seed)) kind = K_SLOW;
+      else if (g.pending_tail[0] != RV_NONE) kind = K_TAIL;
+    } else {
+      kind = K_RESP;
+    }
+  }
+  #pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, kind == k);
+    if (m == 0) continue;
+    int b = 0;
+    if (lane == __ffs(m) - 1) b = atomicAdd(&cnt[k], __popc(m));
+    b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
+    if (kind == k) list[k][b + __popc(m & ((1u << lane) - 1))] = (uint16_t)t;
+  }
+  __syncthreads();
+  {
+    const int n_resp = cnt[K_RESP], n_tail = cnt[K_TAIL], n_slow = cnt[K_SLOW];
+    const int o_tail = (n_resp + 31) & ~31, o_slow = o_tail + ((n_tail + 31) & ~31), total = o_slow + n_slow;
+    for (int slot = t; slot < ((total + 31) & ~31); slot += SB) {
+      int k = K_NONE, li = 0;
+      if (slot < n_resp) k = K_RESP, li = list[K_RESP][slot];
+      else if (slot >= o_tail && slot < o_tail + n_tail) k = K_TAIL, li = list[K_TAIL][slot - o_tail];
+      else if (slot >= o_slow && slot < total) k = K_SLOW, li = list[K_SLOW][slot - o_slow];
+      if (k != K_NONE) {
+        const int64_t gi = base + li;
+        G& h = states[gi];
+        Ctx cx = make_ctx(T, log, cap, gi);
+        cx.defer_init = true;
+        if (IDS) cx.idbits = s_ids[li];
+        if (k == K_RESP) random_step_resp<IDS>(cx, h, agent_seed, h.seed);
+        else if (k == K_TAIL) run_pending_tail(cx, h);
+        else random_step_act<IDS>(cx, h, agent_seed, h.seed);
+      }
+      // rounds that ended in this warp are dealt together, by the threads that ended them
+      const bool parked = k != K_NONE && states[base + li].pending_init[0] != RV_NONE;
+      if (parked) {
+        Ctx cx = make_ctx(T, log, cap, base + li);
+        run_pending_init(cx, states[base + li]);
+      }
+    }
+  }
+  __syncthreads();
+  if (IDS && live) {
+    uint4* o = reinterpret_cast<uint4*>(idbits + (size_t)i * (3 * MAXP));
+    const uint32_t* b = s_ids[t];
+    o[0] = make_uint4(b[0], b[1], b[2], b[3]);
+    o[1] = make_uint4(b[4], b[5], b[6], b[7]);
+    o[2] = make_uint4(b[8], b[9], b[10], b[11]);
+  }
+  unsigned long long my_steps = live ? 1 : 0, my_done = (live && g.is_done) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) {
+    my_steps += __shfl_down_sync(0xFFFFFFFFu, my_steps, o);
+    my_done += __shfl_down_sync(0xFFFFFFFFu, my_done, o);
+  }
+  if (lane == 0 && my_steps) {
+    atomicAdd(&sh[0], my_steps);
+    atomicAdd(&sh[1], my_done);
+  }
+  __syncthreads();
+  if (t == 0 && sh[0]) {
+    atomicAdd(&counters[0], sh[0]);
+    if (sh[1]) atomicAdd(&counters[1], sh[1]);
   }
 }
 
@@ -297,6 +415,7 @@ __global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, 
 // The cold arrays (wall, river, claims) stay in HBM; game code reaches them through cold(g) (game.cuh).
 constexpr int PHB = 32;                              // threads (= games) per block: one warp, own barrier, own exit
 constexpr int STG_STRIDE = RV_HOT_BYTES + 32;        // 656 B = 164 words (== 4 mod 32: same-field accesses are 4-way conflicts)
+static_assert(offsetof(G, river) % 8 == 0, "river alignment");
 static_assert(offsetof(G, wall) == RV_HOT_BYTES && RV_HOT_BYTES % 16 == 0 && sizeof(G) % 16 == 0, "hot prefix layout");
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void stage_in(unsigned char* slot, const G* src, uint32_t bar) {
@@ -470,6 +589,7 @@ __device__ __forceinline__ int q_claim(const Queues& q, int c, uint32_t& h, unsi
   h = atomicAdd(&q.ctl[Q_HEAD + 32 * c], (uint32_t)want);
   return want;
 }
+template <int NPC>   // seat count of every game of the vector (4, or 3 for sanma)
 __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
                                                                  uint64_t agent_seed, uint32_t* budget, Queues q,
                                                                  unsigned long long* counters, int reps) {
@@ -594,7 +714,7 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
       const uint32_t b0 = b;
       if (cls == PH_ACT) {
         for (int r = 0; r < reps; r++) {
-          if (!act_fast(cx, g, agent_seed, g.seed)) {
+          if (!act_fast<false, NPC>(cx, g, agent_seed, g.seed)) {
             next = PH_SLOW;
             break;
           }
@@ -745,21 +865,46 @@ __global__ void __launch_bounds__(128) legal_ids_kernel(Tables T, const G* state
 }
 // One warp per game; for each seat that owes an action the warp writes the row with obs_encode_warp (obs.cuh) and
 // expands the seat's action-id set into the 82 (sanma 60) mask bytes.
+// The warp first copies the record's hot prefix and the rivers into shared memory with independent 16- and 8-byte loads (at
+// most two per lane, all in flight together): read field by field the record costs a chain of ~8 dependent DRAM
+// round trips per warp — the records are not L2-resident here, every step streams 0.67 GB of rows through the L2 — and that
+// chain, not issue slots or HBM bandwidth, bounded the kernel (ncu: 2.9 TB/s of writes at 40 % DRAM utilisation, and a 29 %
+// cut of the instruction count left the duration unchanged).
+// (A persistent variant — 8 blocks per SM, each warp walking several games with the next record prefetched into registers —
+// measured slower, 194 us against 157 us per 65,536 rows: with one short-lived warp per game the block scheduler keeps
+// every SM topped up and other warps cover the one remaining round trip.)
+constexpr int OBS_STAGE_BYTES = RV_HOT_BYTES + MAXP * RV_RIVER_CAP;   // 640 + 128
 template <bool SANMA>
-__global__ void __launch_bounds__(128) obs_encode_kernel(const G* states, int64_t n, const int32_t* offsets, const uint32_t* idbits,
-                                                         float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
+__global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int64_t n, const int32_t* offsets, const uint32_t* idbits,
+                                                            float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
   constexpr int W = SANMA ? OBS_W3 : OBS_W, IDS = SANMA ? OBS_IDS3 : OBS_IDS;
   __shared__ ObsScratch scratch[4];
+  __shared__ __align__(16) unsigned char staged[4][OBS_STAGE_BYTES];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t gi = (int64_t)blockIdx.x * 4 + w;
   if (gi >= n) return;
-  const G& g = states[gi];
-  if (g.is_done) return;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(&states[gi]);
+    const uint2* riv = reinterpret_cast<const uint2*>(&states[gi].river[0][0]);   // offset 776: 8-byte aligned only
+    uint4* dst = reinterpret_cast<uint4*>(staged[w]);
+    const uint4 a = __ldcs(src + lane);                                      // hot bytes 0..511
+    uint4 b = make_uint4(0, 0, 0, 0);
+    uint2 r = make_uint2(0, 0);
+    if (lane < 8) b = __ldcs(src + 32 + lane);                               // hot bytes 512..639
+    else if (lane >= 16) r = __ldcs(riv + (lane - 16));                      // rivers, 16 x 8 bytes
+    dst[lane] = a;
+    if (lane < 8) dst[32 + lane] = b;
+    else if (lane >= 16) reinterpret_cast<uint2*>(staged[w] + RV_HOT_BYTES)[lane - 16] = r;
+  }
   int row = offsets[gi];
+  __syncwarp();
+  const G& g = *reinterpret_cast<const G*>(staged[w]);     // hot fields only; the rivers are passed separately
+  const uint8_t* river = staged[w] + RV_HOT_BYTES;
+  if (g.is_done) return;
   for (int pid = 0; pid < MAXP; pid++) {
     if (!((g.active_mask >> pid) & 1)) continue;
     if (row >= max_obs) break;
-    if (obs) obs_encode_warp<SANMA>(g, &g.river[0][0], pid, obs + (size_t)row * (OBS_CH * W), scratch[w], lane);
+    if (obs) obs_encode_warp<SANMA>(g, river, pid, obs + (size_t)row * (OBS_CH * W), scratch[w], lane);
     if (mask) obs_mask_row_warp<SANMA>(idbits + ((size_t)gi * MAXP + pid) * 3, mask + (size_t)row * IDS, lane);
     if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
     row++;
@@ -771,10 +916,11 @@ template <bool SANMA>
 __global__ void __launch_bounds__(256) obs_mask_rows_kernel(const int32_t* index, const int32_t* total, const uint32_t* idbits, uint8_t* mask,
                                                             int64_t max_obs) {
   constexpr int IDS = SANMA ? OBS_IDS3 : OBS_IDS;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= max_obs || row >= *total) return;
-  const int gs = index[row];                       // game * 4 + seat
-  obs_mask_row_warp<SANMA>(idbits + (size_t)gs * 3, mask + (size_t)row * IDS, threadIdx.x & 31);
+  const int64_t rows = min((int64_t)*total, max_obs);   // the row count is only known on the device: grid-stride over it
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 8) {
+    const int gs = index[row];                       // game * 4 + seat
+    obs_mask_row_warp<SANMA>(idbits + (size_t)gs * 3, mask + (size_t)row * IDS, threadIdx.x & 31);
+  }
 }
 
 // Observe + step, fused (BASELINE config 5: a rollout that emits FEATURE_ENCODING tensors and masks at every step).
@@ -1260,8 +1406,16 @@ int rv_vec_step(rv_vec* v, const rv_action* actions) {
   return RV_OK;
 }
 
+static int env_int(const char* name, int dflt);
 static int rollout_mono(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
+  static const int sorted = env_int("RV_STEP_SORTED", 2) - 1;
+  if (max_steps == 1 && sorted) {      // lock-step drivers: one env step per game, regrouped by kind inside the block
+    step_sorted_kernel<false><<<grid_for(v->n, SB), SB, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, agent_seed, v->d_steps,
+                                                                        nullptr);
+    CK(cudaGetLastError());
+    return RV_OK;
+  }
   step_random_kernel<false><<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, agent_seed,
                                                                         max_steps, v->d_steps, nullptr);
   CK(cudaGetLastError());
@@ -1430,8 +1584,12 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
   CK(cudaMemsetAsync(v->d_q_slots, 0xFF, sizeof(int32_t) * N_QUEUES * (size_t)v->q_cap, c->stream));   // every slot empty (abandoned marks of the last call included)
   q_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, q);
   int64_t crew = (int64_t)c->sm_count * warps_per_sm, need = (n + PHB - 1) / PHB;
-  rollout_persistent_kernel<<<(int)(crew < need ? crew : need), PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed,
-                                                                                    v->d_budget, q, v->d_steps, act_reps);
+  if (v->game_mode >= 3)
+    rollout_persistent_kernel<3><<<(int)(crew < need ? crew : need), PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed,
+                                                                                         v->d_budget, q, v->d_steps, act_reps);
+  else
+    rollout_persistent_kernel<4><<<(int)(crew < need ? crew : need), PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed,
+                                                                                         v->d_budget, q, v->d_steps, act_reps);
   CK(cudaGetLastError());
   return RV_OK;
 }
@@ -1639,12 +1797,16 @@ int rv_vec_observe_step_random(rv_vec* v, uint64_t agent_seed, float* d_obs, uin
     }
     if (sanma) obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs);
     else obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs);
-    step_random_kernel<true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, 1, v->d_steps,
-                                                                      v->d_idbits);
+    static const int sorted = env_int("RV_STEP_SORTED", 2) - 1;    // RV_STEP_SORTED=1: the thread-per-game kernel (A/B)
+    if (sorted)
+      step_sorted_kernel<true><<<grid_for(n, SB), SB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_steps, v->d_idbits);
+    else
+      step_random_kernel<true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, 1, v->d_steps,
+                                                                        v->d_idbits);
     if (d_mask) {
-      const int64_t rows_cap = std::min<int64_t>(max_obs, (int64_t)MAXP * n);
-      if (sanma) obs_mask_rows_kernel<true><<<grid_for(rows_cap, 8), 256, 0, c->stream>>>(d_index, v->d_obs_offsets + n, v->d_idbits, d_mask, max_obs);
-      else obs_mask_rows_kernel<false><<<grid_for(rows_cap, 8), 256, 0, c->stream>>>(d_index, v->d_obs_offsets + n, v->d_idbits, d_mask, max_obs);
+      const int grid = (int)std::min<int64_t>(grid_for(std::min<int64_t>(max_obs, (int64_t)MAXP * n), 8), (int64_t)c->sm_count * 8);
+      if (sanma) obs_mask_rows_kernel<true><<<grid, 256, 0, c->stream>>>(d_index, v->d_obs_offsets + n, v->d_idbits, d_mask, max_obs);
+      else obs_mask_rows_kernel<false><<<grid, 256, 0, c->stream>>>(d_index, v->d_obs_offsets + n, v->d_idbits, d_mask, max_obs);
     }
     CK(cudaGetLastError());
     return obs_row_count(v, n_obs);
