@@ -578,21 +578,22 @@ __global__ void q_init_kernel(const G* states, int64_t n, uint32_t* budget, uint
   q_push(q, cls, (int32_t)i);
 }
 // lane 0 only: take up to PHB consumer tickets of class c if the queue looks non-empty; returns the count and the first ticket
-__device__ __forceinline__ int q_claim(const Queues& q, int c, uint32_t& h, unsigned long long* dbg = nullptr) {
+__device__ __forceinline__ int q_claim(const Queues& q, int c, uint32_t& h, unsigned long long* dbg = nullptr, int cap = PHB) {
   uint32_t hh = ld_volatile_u32(&q.ctl[Q_HEAD + 32 * c]), tt = ld_volatile_u32(&q.ctl[Q_TAIL + 32 * c]);
   int avail = (int)(tt - hh);
   if (avail <= 0) {
     if (dbg) dbg[1]++;
     return 0;
   }
-  int want = avail < PHB ? avail : PHB;
+  int want = avail < cap ? avail : cap;
   h = atomicAdd(&q.ctl[Q_HEAD + 32 * c], (uint32_t)want);
   return want;
 }
 template <int NPC>   // seat count of every game of the vector (4, or 3 for sanma)
 __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
                                                                  uint64_t agent_seed, uint32_t* budget, Queues q,
-                                                                 unsigned long long* counters, int reps) {
+                                                                 unsigned long long* counters, int reps, uint32_t endgame_live,
+                                                                 int endgame_take) {
   __shared__ __align__(128) unsigned char stage[PHB * STG_STRIDE];
   __shared__ __align__(8) uint64_t mbar;
   const int lane = threadIdx.x;
@@ -627,10 +628,23 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
   while (true) {
     int cls = PH_NONE, take = 0;
     uint32_t h = 0;
+    // Endgame.  A hanchan is a chain of ~1,000 dependent steps and a queue visit is tens of microseconds, so once fewer
+    // games are live than the crew can keep busy the rollout is bound by the latency of the longest games, not by
+    // throughput (per-class accounting: 39 % of all warp cycles were idle polls).  Below `endgame_live` live games a warp
+    // takes a few games from ANY class and plays them to the end in place, every transition inline, no queue round trips.
+    bool endgame = false;
     if (lane == 0) {
+      endgame = ld_volatile_u32(&q.ctl[Q_LIVE]) < endgame_live;
+      if (endgame) {
+        for (int c = 0; c < N_QUEUES && take == 0; c++) {
+          cls = c;
+          take = q_claim(q, c, h, QDBG, endgame_take);
+        }
+      } else {
       cls = (int)ld_volatile_u32(my_class);
       take = q_claim(q, cls, h, QDBG);
-      if (take == 0 && idle >= 3) {
+      }
+      if (!endgame && take == 0 && idle >= 3) {
         // move the SM: longest queue wins
         int best = -1, best_len = 0;
         for (int c = 0; c < N_QUEUES; c++) {
@@ -669,6 +683,7 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
     idle = 0;
     cls = __shfl_sync(0xFFFFFFFFu, cls, 0);
     h = __shfl_sync(0xFFFFFFFFu, h, 0);
+    endgame = __shfl_sync(0xFFFFFFFFu, (int)endgame, 0) != 0;
     int32_t gi = -1;
     if (lane < take) {
       int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + ((h + (uint32_t)lane) & q.mask);
@@ -712,7 +727,21 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
       cx.defer_tail = true;
       uint32_t b = budget[gi];
       const uint32_t b0 = b;
-      if (cls == PH_ACT) {
+      if (endgame) {
+        cx.defer_init = false;
+        cx.defer_tail = false;
+        while (true) {
+          if (g.pending_tail[0] != RV_NONE) run_pending_tail(cx, g);          // parked by an earlier visit
+          else if (g.pending_init[0] != RV_NONE) run_pending_init(cx, g);
+          else if (g.is_done || b == 0) break;
+          else {
+            if (g.phase != RV_WAIT_ACT) random_step_resp(cx, g, agent_seed, g.seed);
+            else if (!act_fast<false, NPC>(cx, g, agent_seed, g.seed)) random_step_act(cx, g, agent_seed, g.seed);
+            b--;
+          }
+        }
+        next = PH_NONE;
+      } else if (cls == PH_ACT) {
         for (int r = 0; r < reps; r++) {
           if (!act_fast<false, NPC>(cx, g, agent_seed, g.seed)) {
             next = PH_SLOW;
@@ -1579,17 +1608,22 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
     if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
   }
   static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 10);
+  // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 4 = 1 game per
+  // warp), warps own RV_ENDGAME_TAKE games each and play them out in place (see the kernel)
+  static int eg_quarters = env_int("RV_ENDGAME_Q", 4), eg_take = env_int("RV_ENDGAME_TAKE", 1);
   Queues q{v->d_q_slots, v->d_q_ctl, v->q_cap - 1};
   CK(cudaMemsetAsync(v->d_q_ctl, 0, sizeof(uint32_t) * Q_CTL_WORDS, c->stream));
   CK(cudaMemsetAsync(v->d_q_slots, 0xFF, sizeof(int32_t) * N_QUEUES * (size_t)v->q_cap, c->stream));   // every slot empty (abandoned marks of the last call included)
   q_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, q);
   int64_t crew = (int64_t)c->sm_count * warps_per_sm, need = (n + PHB - 1) / PHB;
+  const int grid = (int)(crew < need ? crew : need);
+  const uint32_t eg_live = getenv("RV_ENDGAME_OFF") ? 0u : (uint32_t)((int64_t)grid * eg_quarters / 4);
   if (v->game_mode >= 3)
-    rollout_persistent_kernel<3><<<(int)(crew < need ? crew : need), PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed,
-                                                                                         v->d_budget, q, v->d_steps, act_reps);
+    rollout_persistent_kernel<3><<<grid, PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, q,
+                                                             v->d_steps, act_reps, eg_live, eg_take);
   else
-    rollout_persistent_kernel<4><<<(int)(crew < need ? crew : need), PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed,
-                                                                                         v->d_budget, q, v->d_steps, act_reps);
+    rollout_persistent_kernel<4><<<grid, PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, q,
+                                                             v->d_steps, act_reps, eg_live, eg_take);
   CK(cudaGetLastError());
   return RV_OK;
 }
