@@ -763,6 +763,8 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
         else if (cls == PH_SLOW) random_step_act(cx, g, agent_seed, g.seed), b--;
         else random_step_resp(cx, g, agent_seed, g.seed), b--;
         next = classify(g, b);
+        // (taking the plain turn most games leave these visits with right here, instead of through the ACT queue, measured
+        // slower: 1.36 -> 1.30 / 1.26 G steps/s for one / two inline turns — the lanes of a generic batch diverge again)
       }
       if (b != b0) {
         budget[gi] = b;
@@ -1608,9 +1610,9 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
     if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
   }
   static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 10);
-  // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 4 = 1 game per
+  // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 8 = 2 games per
   // warp), warps own RV_ENDGAME_TAKE games each and play them out in place (see the kernel)
-  static int eg_quarters = env_int("RV_ENDGAME_Q", 4), eg_take = env_int("RV_ENDGAME_TAKE", 1);
+  static int eg_quarters = env_int("RV_ENDGAME_Q", 8), eg_take = env_int("RV_ENDGAME_TAKE", 1);
   Queues q{v->d_q_slots, v->d_q_ctl, v->q_cap - 1};
   CK(cudaMemsetAsync(v->d_q_ctl, 0, sizeof(uint32_t) * Q_CTL_WORDS, c->stream));
   CK(cudaMemsetAsync(v->d_q_slots, 0xFF, sizeof(int32_t) * N_QUEUES * (size_t)v->q_cap, c->stream));   // every slot empty (abandoned marks of the last call included)
