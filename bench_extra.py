@@ -27,9 +27,18 @@ def run(args, rank, world, local_rank):
 
     from riichienv_b200 import _abi as A
     from riichienv_b200._lib import Context, check, lib
+    from riichienv_b200.multi_gpu import RunStats, reduce_stats, shard_range
     from riichienv_b200.vec_env import VecRiichiEnv
 
-    assert world == 1, "secondary workloads are single-GPU"
+    dist = None
+    if world > 1:
+        assert args.workload == "rollout_obs", "the hands workload is single-GPU"
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
     torch.cuda.set_device(local_rank)
     ctx = Context.get(local_rank)
     peak, peak_src = _peak()
@@ -88,12 +97,14 @@ def run(args, rank, world, local_rank):
     G = args.games
     v = VecRiichiEnv(G, args.mode, device=local_rank)
     max_obs = G * 2
-    obs = torch.empty((max_obs, 74, 34), dtype=torch.float32, device="cuda")
-    mask = torch.empty((max_obs, 82), dtype=torch.uint8, device="cuda")
+    W, IDS = (27, 60) if args.mode >= 3 else (34, 82)     # sanma: Observation3P (74 x 27, 60 ids)
+    b_obs = 74 * W * 4 + IDS
+    obs = torch.empty((max_obs, 74, W), dtype=torch.float32, device="cuda")
+    mask = torch.empty((max_obs, IDS), dtype=torch.uint8, device="cuda")
     idx = torch.empty((max_obs,), dtype=torch.int32, device="cuda")
 
     def one(k):
-        v.reseed(None, k * G)
+        v.reseed(None, shard_range(k, world, rank, G)[0])   # disjoint global game ids per (bench step, rank)
         v.reset()
         n_obs = 0
         it = 0
@@ -117,6 +128,8 @@ def run(args, rank, world, local_rank):
     for w in range(max(1, args.warmup // 3)):
         one(1000 + w)
     ctx.sync()
+    if dist is not None:
+        dist.barrier()
     tot_ms, tot_steps, tot_obs, iters = 0.0, 0, 0, 0
     for k in range(args.steps):
         ctx.sync()
@@ -128,18 +141,24 @@ def run(args, rank, world, local_rank):
         tot_steps += s
         tot_obs += n_obs
         iters += it
-    val = tot_steps / (tot_ms / 1000)
-    ach = (tot_steps * 1024 + tot_obs * B_OBS) / (tot_ms / 1000) / 1e9
+    ach = (tot_steps * 1024 + tot_obs * b_obs) / (tot_ms / 1000) / 1e9      # this rank's kernels
+    red = reduce_stats(RunStats(elapsed_ms=tot_ms, env_steps=float(tot_steps), games=float(tot_obs)), dist, torch, f"cuda:{local_rank}")
+    tot_ms, all_steps, all_obs = red.elapsed_ms, red.env_steps, red.games      # max time over ranks, summed steps / rows
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    val = all_steps / (tot_ms / 1000)
     print(json.dumps({
-        "metric": "env_steps_per_sec", "value": val, "unit": "env steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": "env_steps_per_sec", "value": val, "unit": "env steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 + f32 obs",
         "data": "synthetic",
-        "config": {"workload": f"4p-red-half hanchan, {G:,} games, encode() (74x34 f32) + mask() for every acting seat at every "
-                               "env step (BASELINE.json configs[4] on one GPU)", "games_per_gpu": G,
-                   "observations_per_env_step": tot_obs / max(1, tot_steps), "l2": "observation buffer 1.3 GB per iteration > L2"},
+        "config": {"workload": f"{'3p-red-half (sanma)' if args.mode >= 3 else '4p-red-half'} hanchan, {G:,} games per GPU, encode() (74x{W} f32) + mask() for every acting seat at every "
+                               "env step (BASELINE.json configs[4]; games sharded over the GPUs)", "games_per_gpu": G,
+                   "observations_per_env_step": all_obs / max(1, all_steps), "l2": "observation buffer 1.3 GB per iteration > L2"},
         "e2e": {"value": val, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (iters // 64)},
         "gpu_launches": iters * (6 if args.unfused else 4),
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "kernel": "obs_encode_kernel + step_random_kernel" if args.unfused else "observe_step_kernel", "peak_source": peak_src,
-                     "bytes_per_observation": B_OBS},
+                     "bytes_per_observation": b_obs},
     }))
