@@ -273,6 +273,11 @@ int orc_calculate_score(int han, int fu, int is_oya, int is_tsumo, uint32_t honb
   out[3] = s.total;
   return 0;
 }
+// known-answer hook: n output words of ChaCha(rounds) keyed by 8 raw words, counter 0
+void orc_chacha_words(const uint32_t* key, int rounds, int n, uint32_t* out) {
+  ChaCha12 rng(key, rounds);
+  for (int i = 0; i < n; i++) out[i] = rng.next_u32();
+}
 int orc_wall_from_seed(uint64_t seed, uint64_t hand_index, int n_tiles, uint8_t* out) {
   auto w = wall_from_seed(seed, hand_index, n_tiles);
   memcpy(out, w.data(), w.size());

@@ -9,8 +9,12 @@
 //     output consumed as consecutive little-endian u32 words
 //   * SliceRandom::shuffle = partial_shuffle(len) with IncreasingUniform chunking
 //   * random_range(..bound) for u32 = widening multiply with one bias-correction draw
-// PARITY UNPINNED at this boundary: no reference test pins (seed -> wall)
+// PARITY PARTLY PINNED at this boundary: no reference test pins (seed -> wall)
 // (tests/env/test_riichienv.py:56-58 declines to), and the crates cannot be built here.
+// What IS pinned (tests/test_oracle_golden.py::test_chacha_known_answers): the ChaCha block
+// function and word order on the published ChaCha20/ChaCha12 zero-key keystreams and on the
+// constant of rand's own `test_stdrng_construction` (StdRng::from_seed -> next_u64).  The
+// PCG32 seed expansion and the chunked shuffle are restated from the crate sources, unpinned.
 // Everything is isolated in wall_from_seed() so it can be corrected in one place.
 #pragma once
 #include <cstdint>
@@ -31,6 +35,7 @@ struct ChaCha12 {
   uint64_t counter = 0;
   uint32_t buf[16];
   int idx = 16;
+  int double_rounds = 6;  // StdRng: 12 rounds; the known-answer tests also run 20
 
   static inline uint32_t rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
   static inline void qr(uint32_t* s, int a, int b, int c, int d) {
@@ -48,6 +53,10 @@ struct ChaCha12 {
       key[i] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
     }
   }
+  // raw 32-byte key (SeedableRng::from_seed) — used by the known-answer tests
+  ChaCha12(const uint32_t* k, int rounds) : double_rounds(rounds / 2) {
+    for (int i = 0; i < 8; i++) key[i] = k[i];
+  }
   void refill() {
     uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
     for (int i = 0; i < 8; i++) in[4 + i] = key[i];
@@ -57,7 +66,7 @@ struct ChaCha12 {
     in[15] = 0;
     uint32_t s[16];
     for (int i = 0; i < 16; i++) s[i] = in[i];
-    for (int r = 0; r < 6; r++) {
+    for (int r = 0; r < double_rounds; r++) {
       qr(s, 0, 4, 8, 12); qr(s, 1, 5, 9, 13); qr(s, 2, 6, 10, 14); qr(s, 3, 7, 11, 15);
       qr(s, 0, 5, 10, 15); qr(s, 1, 6, 11, 12); qr(s, 2, 7, 8, 13); qr(s, 3, 4, 9, 14);
     }

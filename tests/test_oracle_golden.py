@@ -174,3 +174,36 @@ def test_sequence_feature_known_answers():
             pons.add(o.orc_seq_encode_pon(4 * kind + c[0], 4 * kind + c[1], 4 * kind + c[2]))
     assert min(chis) == 0 and max(chis) == 89 and len(chis) == 90
     assert min(pons) == 0 and max(pons) == 39 and len(pons) == 40
+
+
+def test_chacha_known_answers():
+    """Partial pin of the seeded-wall boundary (state/wall.rs:38-48 -> crates rand 0.10 / chacha20 0.10, not vendored).
+
+    The ChaCha block function, state layout (constants | key | 64-bit counter | stream 0) and the little-endian word
+    order the wall shuffle consumes are checked against published vectors:
+      * ChaCha20, zero key/nonce, block 0 (the IETF / djb keystream that rand_chacha's `test_chacha_true_values_a` holds),
+      * ChaCha12, zero key/nonce, block 0 (draft-strombergson-chacha-test-vectors TC1, 256-bit key, 12 rounds),
+      * rand `src/rngs/std.rs::test_stdrng_construction`: StdRng::from_seed([1,0,0,0, 23,0,0,0, 200,1,0,0, 210,30,0,0, 0...])
+        .next_u64() == 10719222850664546238 — which also pins StdRng == ChaCha with 12 rounds.
+    """
+    import ctypes as C
+    import struct
+
+    o = oracle.load()
+
+    def words(key, rounds, n):
+        k = (C.c_uint32 * 8)(*key)
+        out = (C.c_uint32 * n)()
+        o.orc_chacha_words(k, rounds, n, out)
+        return list(out)
+
+    z = [0] * 8
+    assert struct.pack("<16I", *words(z, 20, 16)).hex() == (
+        "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+        "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
+    assert struct.pack("<16I", *words(z, 12, 16)).hex() == (
+        "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+        "0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be")
+    seed = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
+    w = words(struct.unpack("<8I", seed), 12, 2)
+    assert (w[0] | (w[1] << 32)) == 10719222850664546238
