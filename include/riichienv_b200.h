@@ -336,6 +336,14 @@ int rv_wall_from_seed(uint64_t seed, uint64_t hand_index, int n_tiles /*136|108*
  * *n_obs (host, may be NULL -> fully asynchronous) receives the number of rows; rows beyond max_obs are dropped. */
 int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
 
+/* Extended observation tensors: Observation::encode_extended (observation/python.rs:1272-1294; channel blocks
+ * observation/encode.rs:12-584) — base 74 channels + discard decay, shanten efficiency (shanten.rs:250-393), ankan / fuuro
+ * overview, action availability, discard candidates, pass context, last tedashi, riichi sutehai = 215 channels.  4P only
+ * (RV_ERR_UNSUPPORTED for a sanma vector).  Same row order and arguments as rv_vec_encode:
+ *   d_obs   [max_obs][215][34] f32  (device, 8-byte aligned)       — may be NULL
+ *   d_mask  [max_obs][82] u8, d_index [max_obs] i32                — may be NULL */
+int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
+
 /* Observe + step in one pass (BASELINE config 5: a random-agent rollout that emits FEATURE_ENCODING tensors at every step —
  * the loop `obs = env.step({p: agent.act(o) ...})` of README.md:50-62 with the agent of rv_vec_step_random on the device).
  * Exactly rv_vec_encode(v, d_obs, d_mask, d_index, max_obs, n_obs) followed by rv_vec_step_random_async(v, agent_seed, 1):

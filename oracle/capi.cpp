@@ -370,6 +370,15 @@ extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {
   if (obs) g->np == 3 ? encode_obs_3p(*g, pid, obs) : encode_obs(*g, pid, obs);   // 74x34 (4P) / 74x27 (3P) floats
   if (mask) encode_mask(*g, pid, mask);
 }
+// Observation::encode_extended: 215x34 floats (4P only)
+extern "C" void orc_game_encode_ext(void* h, int pid, float* obs) { encode_obs_extended(*(GameState*)h, pid, obs); }
+// shanten.rs:250-393 on tid lists (known-answer hooks): out = {shanten, effective_with_discard, best_ukeire}
+extern "C" void orc_ukeire(const int* hand, int n, const int* visible, int nv, int* out) {
+  std::vector<int> h(hand, hand + n), v(visible, visible + nv);
+  out[0] = shanten_tiles(h);
+  out[1] = effective_tiles_with_discard(h);
+  out[2] = best_ukeire(h, v);
+}
 // sequence features of seat pid over the event delta [w0, w1) (words); fixed-size outputs padded like the device path
 extern "C" void orc_game_encode_seq(void* h, int pid, uint32_t w0, uint32_t w1, int game_style, uint16_t* sparse, float* numeric,
                                     uint16_t* prog, int max_prog, uint16_t* cand, uint16_t* lens) {

@@ -5,6 +5,8 @@
 // (state/mod.rs:189-263).  Channel spec: docs/FEATURE_ENCODING.md:8-82.
 #pragma once
 #include "game.hpp"
+#include "shanten.hpp"
+#include <cmath>
 
 namespace orc {
 
@@ -344,6 +346,213 @@ inline int action_encode_3p(const Action& a) {
   }
   return -1;
 }
+// ---- extended encoders: Observation::encode_extended (observation/python.rs:1272-1294), 215 channels x 34 -------------
+// shanten.rs:250-261 on a tid list
+inline int shanten_tiles(const std::vector<int>& tiles) {
+  uint8_t cnt[34] = {0};
+  int n = 0;
+  for (int t : tiles)
+    if (t / 4 < 34) cnt[t / 4]++, n++;
+  return shanten_from_counts(cnt, n / 3);
+}
+// shanten.rs:265-296 (caller guarantees a 3n+1 hand)
+inline int effective_tiles(const std::vector<int>& hand) {
+  int cur = shanten_tiles(hand), eff = 0;
+  uint8_t hc[34] = {0};
+  for (int t : hand)
+    if (t / 4 < 34) hc[t / 4]++;
+  for (int k = 0; k < 34; k++) {
+    if (hc[k] >= 4) continue;
+    std::vector<int> nh = hand;
+    nh.push_back(k * 4);
+    if (shanten_tiles(nh) < cur) eff++;
+  }
+  return eff;
+}
+// shanten.rs:301-327
+inline int effective_tiles_with_discard(const std::vector<int>& hand) {
+  if (hand.size() % 3 == 1) return effective_tiles(hand);
+  int sh = shanten_tiles(hand), best = 0;
+  for (size_t idx = 0; idx < hand.size(); idx++) {
+    std::vector<int> sub;
+    for (size_t i = 0; i < hand.size(); i++)
+      if (i != idx) sub.push_back(hand[i]);
+    if (shanten_tiles(sub) <= sh) best = std::max(best, effective_tiles(sub));
+  }
+  return best;
+}
+// shanten.rs:331-393
+inline int best_ukeire(const std::vector<int>& hand, const std::vector<int>& visible) {
+  int best = 0;
+  uint32_t vis[34] = {0};
+  for (int t : visible)
+    if (t / 4 < 34) vis[t / 4]++;
+  int cur = shanten_tiles(hand);
+  uint8_t base[34] = {0};
+  for (int t : hand)
+    if (t / 4 < 34) base[t / 4]++;
+  for (size_t idx = 0; idx < hand.size(); idx++) {
+    std::vector<int> sub;
+    for (size_t i = 0; i < hand.size(); i++)
+      if (i != idx) sub.push_back(hand[i]);
+    uint8_t nc[34];
+    memcpy(nc, base, 34);
+    nc[hand[idx] / 4]--;
+    int ns = shanten_tiles(sub);
+    if (ns > cur) continue;
+    uint32_t uke = 0;
+    for (int k = 0; k < 34; k++) {
+      if (nc[k] >= 4) continue;
+      std::vector<int> th = sub;
+      th.push_back(k * 4);
+      if (shanten_tiles(th) < ns) {
+        uint32_t rem = 4u > vis[k] ? 4u - vis[k] : 0u;          // saturating_sub twice
+        rem = rem > nc[k] ? rem - nc[k] : 0u;
+        uke += rem;
+      }
+    }
+    best = std::max(best, (int)uke);
+  }
+  return best;
+}
+
+// out: 215*34 floats, channel-major.  Channel blocks (python.rs:1281-1290): base 0, decay 74, shanten 78, ankan 94,
+// fuuro 98, action availability 178, discard candidates 189, pass context 194, last tedashi 197, riichi sutehai 206.
+inline void encode_obs_extended(const GameState& g, int pid, float* arr) {
+  auto A = [&](int ch, int col) -> float& { return arr[ch * 34 + col]; };
+  auto B = [&](int ch, float v) { for (int k = 0; k < 34; k++) arr[ch * 34 + k] = v; };
+  for (int i = 0; i < 215 * 34; i++) arr[i] = 0.0f;
+  encode_obs(g, pid, arr);   // observation/encode.rs:12-291 == python.rs:457-806 except channel 30 (below)
+  const int rel[4] = {pid, (pid + 1) % 4, (pid + 2) % 4, (pid + 3) % 4};
+  std::vector<int> hand(g.players[pid].hand.begin(), g.players[pid].hand.end());
+  {
+    // encode.rs:94-110: encode_base_into counts a called meld one tile short ("already counted in discards");
+    // Observation::encode (python.rs) does not.  Both kept as they are.
+    int used = 0;
+    for (auto& p : g.players) used += (int)p.discards.size();
+    for (auto& p : g.players)
+      for (auto& m : p.melds) used += (int)m.tiles.size() - (m.called_tile >= 0 ? 1 : 0);
+    used += (int)hand.size() + (int)g.dora_indicators.size();
+    B(30, (float)std::max(136 - used, 0) / 70.0f);
+  }
+  // decay (encode.rs:295-313)
+  for (int c = 0; c < 4; c++) {
+    const auto& d = g.players[rel[c]].discards;
+    for (size_t turn = 0; turn < d.size(); turn++) {
+      float age = (float)(d.size() - 1 - turn);
+      A(74 + c, d[turn] / 4) += expf(-0.2f * age);
+    }
+  }
+  // shanten efficiency (encode.rs:317-350)
+  {
+    std::vector<int> vis;
+    for (auto& p : g.players)
+      for (uint8_t t : p.discards) vis.push_back(t);
+    for (auto& p : g.players)
+      for (auto& m : p.melds)
+        for (uint8_t t : m.tiles) vis.push_back(t);
+    for (uint8_t t : g.dora_indicators) vis.push_back(t);
+    for (int c = 0; c < 4; c++) {
+      int b = 78 + c * 4;
+      if (c == 0) {
+        int sv = shanten_tiles(hand);
+        B(b, std::max((float)sv, 0.0f) / 8.0f);
+        B(b + 1, (float)effective_tiles_with_discard(hand) / 34.0f);
+        B(b + 2, (float)best_ukeire(hand, vis) / 80.0f);
+      } else {
+        B(b, 0.5f), B(b + 1, 0.5f), B(b + 2, 0.5f);
+      }
+      B(b + 3, std::min((float)g.players[rel[c]].discards.size() / 18.0f, 1.0f));
+    }
+  }
+  // ankan (encode.rs:354-368), fuuro (encode.rs:372-396)
+  for (int c = 0; c < 4; c++) {
+    int mi = 0;
+    for (auto& m : g.players[rel[c]].melds) {
+      if (m.meld_type == Ankan && !m.tiles.empty()) A(94 + c, m.tiles[0] / 4) = 1.0f;
+      if (mi < 4) {
+        int slot = 0;
+        for (uint8_t t : m.tiles) {
+          if (slot >= 4) break;
+          A(98 + c * 20 + mi * 5 + slot, t / 4) = 1.0f;
+          if (t == 16 || t == 52 || t == 88) A(98 + c * 20 + mi * 5 + 4, t / 4) = 1.0f;
+          slot++;
+        }
+      }
+      mi++;
+    }
+  }
+  // action availability (encode.rs:399-430) over the seat's legal list (empty unless the seat owes an action)
+  {
+    bool may = !g.is_done && ((g.phase == RV_WAIT_ACT && g.current_player == pid) ||
+                              (g.phase == RV_WAIT_RESPONSE &&
+                               std::find(g.active_players.begin(), g.active_players.end(), (uint8_t)pid) != g.active_players.end()));
+    if (may)
+      for (auto& a : g._get_legal_actions_internal(pid)) {
+        switch (a.type) {
+          case RV_RIICHI: B(178, 1.0f); break;
+          case RV_CHI:
+            if (a.consume.size() == 2) {
+              int t0 = a.consume[0] / 4, t1 = a.consume[1] / 4, diff = std::abs(t1 - t0);
+              if (diff == 1) B(t0 < t1 ? 179 : 181, 1.0f);
+              else if (diff == 2) B(180, 1.0f);
+            }
+            break;
+          case RV_PON: B(182, 1.0f); break;
+          case RV_DAIMINKAN: B(183, 1.0f); break;
+          case RV_ANKAN: B(184, 1.0f); break;
+          case RV_KAKAN: B(185, 1.0f); break;
+          case RV_TSUMO:
+          case RV_RON: B(186, 1.0f); break;
+          case RV_KYUSHU_KYUHAI: B(187, 1.0f); break;
+          case RV_PASS: B(188, 1.0f); break;
+          default: break;
+        }
+      }
+  }
+  // discard candidates (encode.rs:433-476)
+  {
+    int cur = shanten_tiles(hand), keep = 0, inc = 0;
+    B(189, (float)hand.size() / 34.0f);
+    for (size_t idx = 0; idx < hand.size(); idx++) {
+      std::vector<int> sub;
+      for (size_t i = 0; i < hand.size(); i++)
+        if (i != idx) sub.push_back(hand[i]);
+      int ns = shanten_tiles(sub);
+      if (ns == cur) keep++;
+      else if (ns > cur) inc++;
+    }
+    if (!hand.empty()) {
+      B(190, (float)keep / (float)hand.size());
+      B(191, (float)inc / (float)hand.size());
+    }
+    B(192, cur == -1 ? 1.0f : 0.0f);
+    B(193, g.players[pid].riichi_declared ? 1.0f : 0.0f);
+  }
+  std::vector<uint8_t> dora_tiles;   // tids of copy 0 of each dora kind (helpers.rs:25-50 returns a tid)
+  for (uint8_t di : g.dora_indicators) dora_tiles.push_back((uint8_t)obs_next_tile(di));
+  auto is_dora_tid = [&](int tid) { return std::find(dora_tiles.begin(), dora_tiles.end(), (uint8_t)tid) != dora_tiles.end(); };
+  auto tile_ctx = [&](int ch, int tile) {
+    B(ch, (float)(tile / 4) / 33.0f);
+    B(ch + 1, (tile == 16 || tile == 52 || tile == 88) ? 1.0f : 0.0f);
+    B(ch + 2, is_dora_tid(tile) ? 1.0f : 0.0f);   // compares a TID with kind*4: only copy 0 of a dora kind matches
+  };
+  // pass context (encode.rs:479-510).  state/mod.rs:252 builds Observation.last_discard with
+  // `self.last_discard.map(|(tile, _pid)| tile as u32)` on a tuple stored as (pid, tile) (state/mod.rs:1329): the value
+  // the encoder sees is the DISCARDER'S SEAT, not the tile.  Restated as is.
+  if (g.last_discard_pid >= 0) tile_ctx(194, g.last_discard_pid);
+  // last tedashi (encode.rs:513-547), riichi sutehai (encode.rs:550-584): opponents in ABSOLUTE seat order
+  {
+    int opp = 0;
+    for (int p = 0; p < 4; p++) {
+      if (p == pid) continue;
+      if (g.last_tedashis[p] >= 0) tile_ctx(197 + opp * 3, g.last_tedashis[p]);
+      if (g.riichi_sutehais[p] >= 0) tile_ctx(206 + opp * 3, g.riichi_sutehais[p]);
+      opp++;
+    }
+  }
+}
+
 // Observation::mask (observation/python.rs:98-111; 3P: observation_3p/python.rs:102-114) for a seat that owes an action:
 // 82 bytes (4P) or 60 bytes (3P)
 inline void encode_mask(const GameState& g, int pid, uint8_t* out) {

@@ -1,0 +1,34 @@
+#!/usr/bin/env python3
+"""Times rv_vec_encode_ext (215x34 rows) and rv_vec_encode (74x34 rows) on 65,536 mid-game hanchan (CUDA events, 10 reps)."""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from riichienv_b200 import _abi as A
+from riichienv_b200.vec_env import VecRiichiEnv
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=0)
+v.reset()
+v.step_random(1, 300)
+cap = n + n // 4
+ext = torch.empty((cap, 215, 34), dtype=torch.float32, device="cuda")
+base = torch.empty((cap, 74, 34), dtype=torch.float32, device="cuda")
+mask = torch.empty((cap, 82), dtype=torch.uint8, device="cuda")
+idx = torch.empty((cap,), dtype=torch.int32, device="cuda")
+out = {}
+for name, fn, buf in (("encode_ext", v.encode_extended, ext), ("encode", v.encode, base)):
+    rows = fn(obs=buf, mask=mask, index=idx)
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(obs=buf, mask=mask, index=idx, sync=False)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[len(ts) // 2]
+    out[name] = {"rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3, "GBps": rows * buf[0].numel() * 4 / ms / 1e6}
+print(json.dumps(out))

@@ -256,8 +256,11 @@ struct ObsScratch {
 };
 __device__ __forceinline__ uint64_t obs_compact3(uint64_t m) { return (m & 1) | ((m >> 7) & ~1ull); }   // 34 kinds -> 27 columns
 
+// gather + describe: leaves the channel descriptors S.d[0..73] and the per-kind seen counts S.seen.  `ch30_adj` is added to
+// the "tiles left" count of channel 30 (0 for Observation::encode; encode_base_into, which encode_extended uses, counts every
+// called meld one tile short — observation/encode.rs:94-110).
 template <bool SANMA>
-__device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river, int pid, float* dst, ObsScratch& S, int lane) {
+__device__ __forceinline__ void obs_describe_warp(const G& g, const uint8_t* river, int pid, ObsScratch& S, int lane, int ch30_adj = 0) {
   constexpr int NPV = SANMA ? 3 : 4, W = SANMA ? OBS_W3 : OBS_W;
   constexpr uint64_t ALL = (1ull << W) - 1;
   auto rel = [&](int i) { return SANMA ? (pid + i) % 3 : (pid + i) & 3; };
@@ -380,7 +383,7 @@ __device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river
     } else if (ch <= 29) {
       bc((float)g.n_river[rel(ch - 26)] / 24.0f);
     } else if (ch == 30) {
-      const int left = (SANMA ? 108 : 136) - used;
+      const int left = (SANMA ? 108 : 136) - used + ch30_adj;
       bc((float)(left < 0 ? 0 : left) / 70.0f);
     } else if (ch <= 34) {
       bc((g.flags[rel(ch - 31)] & RV_F_RIICHI_DECLARED) ? 1.0f : 0.0f);
@@ -429,7 +432,11 @@ __device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river
     S.d[ch].val = v;
   }
   __syncwarp();
-  // ---- stream
+}
+// stream: the descriptors of one row -> 74 x 34 (sanma 74 x 27) floats
+template <bool SANMA>
+__device__ __forceinline__ void obs_stream_warp(float* dst, ObsScratch& S, int lane) {
+  constexpr int W = SANMA ? OBS_W3 : OBS_W;
   if constexpr (!SANMA) {
     // Two channels are 68 floats = 17 sixteen-byte stores: 8 inside the even channel, one straddling both (columns 32,33 |
     // 0,1), 8 inside the odd channel.  The 16 one-channel stores of a pair are item (p, u): u = lane & 15 never changes for
@@ -477,6 +484,11 @@ __device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river
     }
   }
   __syncwarp();
+}
+template <bool SANMA>
+__device__ __forceinline__ void obs_encode_warp(const G& g, const uint8_t* river, int pid, float* dst, ObsScratch& S, int lane) {
+  obs_describe_warp<SANMA>(g, river, pid, S, lane);
+  obs_stream_warp<SANMA>(dst, S, lane);
 }
 
 // 82 (sanma 60) mask bytes of one row from the id bitset (3 words) — lanes write 4 bytes each when the row is 4-byte aligned

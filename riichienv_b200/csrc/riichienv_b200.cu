@@ -11,6 +11,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "obs.cuh"
+#include "obs_ext.cuh"
 #include "seq.cuh"
 
 using namespace rv;
@@ -876,7 +877,9 @@ __global__ void obs_count_kernel(const G* states, int64_t n, int32_t* counts) {
 
 // Action-id sets (Observation::mask as a 96-bit set) of every seat that owes an action: one thread per game runs the
 // generic legal-action enumeration once; obs_encode_kernel expands the bits into mask bytes.
-template <bool SANMA>
+// AVAIL (4P, rv_vec_encode_ext): bits 82..92 of the set carry the 11 action-availability flags of encode.rs:399-430.
+constexpr int OBS_AVAIL_SHIFT = 18;   // bit 82 = word 2, bit 18
+template <bool SANMA, bool AVAIL = false>
 __global__ void __launch_bounds__(128) legal_ids_kernel(Tables T, const G* states, int64_t n, uint32_t* idbits) {
   int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= n) return;
@@ -889,7 +892,11 @@ __global__ void __launch_bounds__(128) legal_ids_kernel(Tables T, const G* state
     int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
     if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
     uint32_t bits[3] = {0, 0, 0};
-    for (int k = 0; k < cnt; k++) obs_id_set<SANMA>(bits, expand_act(g, pid, packed[k]));
+    for (int k = 0; k < cnt; k++) {
+      const rv_action a = expand_act(g, pid, packed[k]);
+      obs_id_set<SANMA>(bits, a);
+      if (AVAIL) bits[2] |= obs_avail_bit(a) << OBS_AVAIL_SHIFT;
+    }
     uint32_t* o = idbits + ((size_t)gi * MAXP + pid) * 3;
     o[0] = bits[0], o[1] = bits[1], o[2] = bits[2];
   }
@@ -937,6 +944,45 @@ __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int
     if (row >= max_obs) break;
     if (obs) obs_encode_warp<SANMA>(g, river, pid, obs + (size_t)row * (OBS_CH * W), scratch[w], lane);
     if (mask) obs_mask_row_warp<SANMA>(idbits + ((size_t)gi * MAXP + pid) * 3, mask + (size_t)row * IDS, lane);
+    if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
+    row++;
+  }
+}
+
+// Extended rows (Observation::encode_extended, 215 x 34): one warp per game, staged like obs_encode_kernel; obs_ext.cuh.
+__global__ void __launch_bounds__(128) obs_ext_kernel(Tables T, DecayTab D, const G* states, int64_t n, const int32_t* offsets,
+                                                      const uint32_t* idbits, float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
+  __shared__ ObsScratch scratch[4];
+  __shared__ ObsExtScratch xscratch[4];
+  __shared__ __align__(16) unsigned char staged[4][OBS_STAGE_BYTES];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t gi = (int64_t)blockIdx.x * 4 + w;
+  if (gi >= n) return;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(&states[gi]);
+    const uint2* riv = reinterpret_cast<const uint2*>(&states[gi].river[0][0]);
+    uint4* dst = reinterpret_cast<uint4*>(staged[w]);
+    const uint4 a = __ldcs(src + lane);
+    uint4 b = make_uint4(0, 0, 0, 0);
+    uint2 r = make_uint2(0, 0);
+    if (lane < 8) b = __ldcs(src + 32 + lane);
+    else if (lane >= 16) r = __ldcs(riv + (lane - 16));
+    dst[lane] = a;
+    if (lane < 8) dst[32 + lane] = b;
+    else if (lane >= 16) reinterpret_cast<uint2*>(staged[w] + RV_HOT_BYTES)[lane - 16] = r;
+  }
+  int row = offsets[gi];
+  __syncwarp();
+  const G& g = *reinterpret_cast<const G*>(staged[w]);
+  const uint8_t* river = staged[w] + RV_HOT_BYTES;
+  if (g.is_done) return;
+  for (int pid = 0; pid < MAXP; pid++) {
+    if (!((g.active_mask >> pid) & 1)) continue;
+    if (row >= max_obs) break;
+    const uint32_t* bits = idbits + ((size_t)gi * MAXP + pid) * 3;
+    if (obs) obs_ext_encode_warp(T, D, g, river, pid, (bits[2] >> OBS_AVAIL_SHIFT) & 0x7FFu, obs + (size_t)row * (OBSX_CH * OBS_W),
+                                 scratch[w], xscratch[w], lane);
+    if (mask) obs_mask_row_warp<false>(bits, mask + (size_t)row * OBS_IDS, lane);
     if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
     row++;
   }
@@ -1806,6 +1852,24 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
     else
       obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, v->d_idbits, d_obs, d_mask, d_index, max_obs);
   }
+  CK(cudaGetLastError());
+  return obs_row_count(v, n_obs);
+}
+int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
+  rv_ctx* c = v->ctx;
+  if (v->game_mode >= 3) return RV_ERR_UNSUPPORTED;    // 4P rows only (Observation3P has its own 27-column encoders)
+  CK(cudaSetDevice(c->device));
+  int64_t n = v->n;
+  int rc = obs_offsets(v);
+  if (rc != RV_OK) return rc;
+  static DecayTab D = [] {
+    DecayTab d;
+    for (int age = 0; age < RV_RIVER_CAP; age++) d.w[age] = expf(-0.2f * (float)age);   // encode.rs:296-308, the C library's expf
+    return d;
+  }();
+  if (!v->d_idbits) CK(cudaMalloc(&v->d_idbits, sizeof(uint32_t) * 3 * MAXP * n));
+  legal_ids_kernel<false, true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_idbits);
+  obs_ext_kernel<<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, D, v->d_states, n, v->d_obs_offsets, v->d_idbits, d_obs, d_mask, d_index, max_obs);
   CK(cudaGetLastError());
   return obs_row_count(v, n_obs);
 }

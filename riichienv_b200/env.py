@@ -404,6 +404,12 @@ class Observation:
         (observation_3p/python.rs:402-708).  Computed on the GPU."""
         return self._env._encode(self.player_id)
 
+    def encode_extended(self):  # observation/python.rs:1272-1294 (4P)
+        if self._token != self._env._token:
+            raise RuntimeError("tensors are computed on the device from the live game: call encode_extended() on the "
+                               "observations of the latest reset()/step()")
+        return self._env._encode(self.player_id, extended=True)
+
     # ---- sequence features (observation/python.rs:1297-1364): raw bytes, as the reference returns them ----
     def _seq_features(self):
         if self._seq is None:
@@ -600,15 +606,21 @@ class RiichiEnv:
         lens = le[r].cpu().numpy()
         return sp[r].cpu().numpy(), nu[r].cpu().numpy(), pr[r].cpu().numpy(), ca[r].cpu().numpy(), lens
 
-    def _encode(self, pid):
+    def _encode(self, pid, extended=False):
         """bytes of the (74, 34) — sanma (74, 27) — float32 tensor for seat `pid` (must owe an action), computed by
-        obs_encode_kernel."""
+        obs_encode_kernel; extended=True: the (215, 34) tensor of encode_extended (obs_ext_kernel, 4P)."""
         import torch
 
         dev = f"cuda:{self._v.ctx.device}"
-        obs = torch.zeros((4, 74, 27 if self._np == 3 else 34), dtype=torch.float32, device=dev)
         idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
-        n = self._v.encode(obs=obs, index=idx, max_obs=4)
+        if extended:
+            if self._np == 3:
+                raise NotImplementedError("encode_extended: 4-player observations only")
+            obs = torch.zeros((4, 215, 34), dtype=torch.float32, device=dev)
+            n = self._v.encode_extended(obs=obs, index=idx, max_obs=4)
+        else:
+            obs = torch.zeros((4, 74, 27 if self._np == 3 else 34), dtype=torch.float32, device=dev)
+            n = self._v.encode(obs=obs, index=idx, max_obs=4)
         rows = idx[:n].tolist()
         if pid not in rows:
             raise ValueError(f"seat {pid} owes no action; encode() is defined for the observations step()/reset() return")

@@ -68,6 +68,13 @@ class OracleBackend(Backend):
     def _step(self, arr):
         self.lib.orc_game_step(self.h, arr)
 
+    def encode_ext(self, pid):
+        import numpy as np
+
+        a = np.zeros((215, 34), np.float32)
+        self.lib.orc_game_encode_ext(self.h, pid, a.ctypes.data_as(C.POINTER(C.c_float)))
+        return a
+
     def random_step(self, agent_seed, game_id):
         self.lib.orc_game_random_step(self.h, agent_seed, game_id)
 
@@ -108,6 +115,13 @@ class HostsimBackend(Backend):
     def _step(self, arr):
         self.lib.hs_game_step(self.h, arr)
 
+    def encode_ext(self, pid):
+        import numpy as np
+
+        a = np.zeros((215, 34), np.float32)
+        self.lib.hs_game_encode_ext(self.h, pid, a.ctypes.data_as(C.POINTER(C.c_float)))
+        return a
+
     def random_step(self, agent_seed, game_id):
         self.lib.hs_game_random_step(self.h, agent_seed, game_id)
 
@@ -147,6 +161,16 @@ class GpuBackend(Backend):
 
     def _step(self, arr):
         self.v.step(arr)
+
+    def encode_ext(self, pid):
+        """row of seat pid (which must owe an action) through rv_vec_encode_ext"""
+        import torch
+
+        obs = torch.zeros((4, 215, 34), dtype=torch.float32, device="cuda")
+        idx = torch.full((4,), -1, dtype=torch.int32, device="cuda")
+        n = self.v.encode_extended(obs=obs, index=idx, max_obs=4)
+        rows = idx[:n].tolist()
+        return obs[rows.index(pid)].cpu().numpy()
 
     def random_step(self, agent_seed, game_id):
         self.v.step_random(agent_seed, 1)

@@ -169,6 +169,108 @@ def gen_shanten():
         assert ref_shanten(T, c, sum(c) // 3) == exp, hs
 
 
+def structured_hand(rng, n):
+    """n tiles built from mentsu/pairs then perturbed (shanten -1..2 coverage)."""
+    cnt = [0] * 34
+    left = n
+    while left >= 3:
+        if rng.random() < 0.5:
+            t = rng.randrange(34)
+            if cnt[t] <= 1:
+                cnt[t] += 3
+                left -= 3
+        else:
+            s = rng.randrange(3) * 9 + rng.randrange(7)
+            if max(cnt[s:s + 3]) <= 3:
+                for k in range(3):
+                    cnt[s + k] += 1
+                left -= 3
+    while left > 0:
+        t = rng.randrange(34)
+        if cnt[t] < 4:
+            cnt[t] += 1
+            left -= 1
+    for _ in range(rng.randrange(3)):
+        a = rng.choice([i for i in range(34) if cnt[i] > 0])
+        b = rng.choice([i for i in range(34) if cnt[i] < 4])
+        cnt[a] -= 1
+        cnt[b] += 1
+    return cnt
+
+
+def gen_ukeire():
+    """shanten.rs:250-393 (calculate_shanten / calculate_effective_tiles_with_discard / calculate_best_ukeire) restated on
+    top of the reference's own tables: hands of 13/14 (closed), 10/11, 7/8, 4/5 tiles and a random visible-tile list."""
+    T = load_shanten_tables()
+    rng = random.Random(20261017)
+
+    def sh(tiles):
+        cnt = [0] * 34
+        for t in tiles:
+            cnt[t // 4] += 1
+        return ref_shanten(T, cnt, len(tiles) // 3)
+
+    def effective(hand):
+        cur = sh(hand)
+        hc = [0] * 34
+        for t in hand:
+            hc[t // 4] += 1
+        return sum(1 for k in range(34) if hc[k] < 4 and sh(hand + [k * 4]) < cur)
+
+    def effective_with_discard(hand):
+        if len(hand) % 3 == 1:
+            return effective(hand)
+        s0 = sh(hand)
+        best = 0
+        for i in range(len(hand)):
+            sub = hand[:i] + hand[i + 1:]
+            if sh(sub) <= s0:
+                best = max(best, effective(sub))
+        return best
+
+    def best_ukeire(hand, visible):
+        vis = [0] * 34
+        for t in visible:
+            vis[t // 4] += 1
+        cur = sh(hand)
+        base = [0] * 34
+        for t in hand:
+            base[t // 4] += 1
+        best = 0
+        for i in range(len(hand)):
+            sub = hand[:i] + hand[i + 1:]
+            nc = list(base)
+            nc[hand[i] // 4] -= 1
+            ns = sh(sub)
+            if ns > cur:
+                continue
+            uke = 0
+            for k in range(34):
+                if nc[k] >= 4:
+                    continue
+                if sh(sub + [k * 4]) < ns:
+                    uke += max(0, max(0, 4 - vis[k]) - nc[k])
+            best = max(best, uke)
+        return best
+
+    lines = []
+    for it in range(400):
+        n = rng.choice([13, 14, 13, 14, 13, 14, 10, 11, 7, 8, 4, 5])
+        if it % 4 == 0:
+            hand = sorted(rng.sample(range(136), n))
+        else:
+            cnt = structured_hand(rng, n)
+            hand = [t * 4 + k for t in range(34) for k in range(cnt[t])]
+        rest = [t for t in range(136) if t not in hand]
+        visible = rng.sample(rest, rng.randrange(0, 60))
+        lines.append(",".join(map(str, hand)) + " | " + ",".join(map(str, visible)) +
+                     f" | {sh(hand)} {effective_with_discard(hand)} {best_ukeire(hand, visible)}\n")
+    with open(os.path.join(OUT, "ukeire_golden.txt"), "w") as f:
+        f.write("# hand tids | visible tids | shanten effective_tiles_with_discard best_ukeire   [reference tables' answers]\n")
+        f.writelines(lines)
+    print("ukeire_golden.txt", len(lines))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference checkout not found: fixtures are committed, nothing to do")
@@ -176,3 +278,4 @@ if __name__ == "__main__":
     conv_agari("agari_3p.json", "agari_3p.txt")
     conv_negative()
     gen_shanten()
+    gen_ukeire()

@@ -20,7 +20,7 @@ def load():
     so = os.path.join(_HERE, "libhostsim.so")
     csrc = os.path.join(_HERE, "..", "..", "riichienv_b200", "csrc")
     srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "cuda_shim.h")] + [
-        os.path.join(csrc, f) for f in ("game.cuh", "hand.cuh", "tables.cuh", "obs.cuh")]
+        os.path.join(csrc, f) for f in ("game.cuh", "hand.cuh", "tables.cuh", "obs.cuh", "obs_ext.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", so,
                                os.path.join(_HERE, "hostsim.cpp")])
@@ -46,6 +46,7 @@ def load():
     lib.hs_game_events.restype = C.c_uint32
     lib.hs_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.hs_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]
+    lib.hs_game_encode_ext.argtypes = [C.c_void_p, C.c_int, P(C.c_float)]
     lib.hs_game_encode_seq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(C.c_uint16), P(C.c_float),
                                        P(C.c_uint16), C.c_int, P(C.c_uint16), P(C.c_uint16)]
     lib.hs_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]

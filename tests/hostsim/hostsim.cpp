@@ -15,6 +15,8 @@ static thread_local rv_game_state* hs_home = nullptr;
 #include <vector>
 
 #include "../../riichienv_b200/csrc/obs.cuh"
+#include "../../riichienv_b200/csrc/obs_ext.cuh"
+#include <cmath>
 #include "../../riichienv_b200/csrc/seq.cuh"
 
 using namespace rv;
@@ -368,6 +370,54 @@ void hs_game_encode(void* p, int pid, float* obs, uint8_t* mask) {
       int id = sanma ? action_id_3p(a) : action_id(a);
       if (id >= 0 && id < (sanma ? OBS_IDS3 : OBS_IDS)) mask[id] = 1;
     }
+  }
+}
+// Observation::encode_extended through the scalar definitions of obs_ext.cuh (4P): 215 x 34 floats
+void hs_game_encode_ext(void* p, int pid, float* obs) {
+  HS* h = (HS*)p;
+  const G& g = h->g;
+  int seen[34], vis[34], called = 0;
+  for (int k = 0; k < 34; k++) {
+    seen[k] = obs_seen(g, pid, k);
+    vis[k] = seen[k] - (int)((g.c_cnt[pid][k / 9] >> (4 * (k % 9))) & 15);
+  }
+  for (int q = 0; q < 4; q++)
+    for (int m = 0; m < g.n_melds[q]; m++) called += g.meld_called[q][m] != RV_NONE;
+  for (int ch = 0; ch < OBS_CH; ch++) {
+    int kind;
+    uint64_t m;
+    float v;
+    obs_channel<false>(g, pid, ch, kind, m, v);
+    for (int col = 0; col < OBS_W; col++) obs[ch * OBS_W + col] = obs_value(kind, m, v, seen[col], col);
+  }
+  {
+    int used = 0;
+    for (int k = 0; k < 34; k++) used += seen[k];
+    int left = 136 - used + called;
+    for (int col = 0; col < OBS_W; col++) obs[30 * OBS_W + col] = (float)(left < 0 ? 0 : left) / 70.0f;
+  }
+  DecayTab D;
+  for (int age = 0; age < RV_RIVER_CAP; age++) D.w[age] = expf(-0.2f * (float)age);
+  for (int r = 0; r < 4; r++) {
+    float* row = obs + (74 + r) * OBS_W;
+    for (int col = 0; col < OBS_W; col++) row[col] = 0.0f;
+    obs_ext_decay_row(g, &g.river[0][0], (pid + r) & 3, D, row);
+  }
+  ObsExtInfo I;
+  Ctx cx = hs_ctx(h);
+  obs_ext_shanten_scalar(g_T, g, pid, vis, I);
+  I.avail = 0;
+  if (!g.is_done && ((g.active_mask >> pid) & 1)) {
+    uint32_t packed[RV_MAX_LEGAL];
+    int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
+    if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+    for (int k = 0; k < cnt; k++) I.avail |= obs_avail_bit(expand_act(g, pid, packed[k]));
+  }
+  for (int ch = 78; ch < OBSX_CH; ch++) {
+    uint64_t m;
+    float v;
+    obs_ext_channel(g, pid, ch, I, m, v);
+    for (int col = 0; col < OBS_W; col++) obs[ch * OBS_W + col] = ((m >> col) & 1) ? v : 0.0f;
   }
 }
 void hs_game_encode_seq(void* p, int pid, uint32_t w0, uint32_t w1, int game_style, uint16_t* sparse, float* numeric, uint16_t* prog,

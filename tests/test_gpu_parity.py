@@ -336,6 +336,77 @@ def test_observation_encode_vs_oracle(orc, mode):
     assert checked > (5000 if mode >= 3 else 10000)
 
 
+def test_observation_encode_extended_vs_oracle(orc):
+    """rv_vec_encode_ext: Observation::encode_extended (215x34) + mask of every acting seat of 192 hanchan at many points of
+    the rollout, bytes equal to the oracle's restatement (observation/encode.rs:12-584); nothing written past the last row."""
+    import torch
+
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n = 192
+    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=9500)
+    v.reset()
+    games = [orc.orc_game_new(2, 9500 + g, 0, A.RULE_DEFAULT_TENHOU, 0) for g in range(n)]
+    for h in games:
+        orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    obs = torch.empty((n * 3, 215, 34), dtype=torch.float32, device="cuda")
+    mask = torch.empty((n * 3, 82), dtype=torch.uint8, device="cuda")
+    idx = torch.empty((n * 3,), dtype=torch.int32, device="cuda")
+    a = np.zeros(215 * 34, np.float32)
+    m = np.zeros(82, np.uint8)
+    checked = 0
+    seen_channels = np.zeros(215, bool)
+    for it in range(50):
+        obs.fill_(-3.0)
+        rows = v.encode_extended(obs=obs, mask=mask, index=idx)
+        assert (obs[rows:] == -3.0).all()
+        h_obs, h_mask, h_idx = obs[:rows].cpu().numpy(), mask[:rows].cpu().numpy(), idx[:rows].cpu().numpy()
+        assert (np.diff(h_idx) > 0).all()
+        st = A.GameState()
+        expect_rows = 0
+        for g in range(n):
+            orc.orc_game_snapshot(games[g], C.byref(st))
+            if st.is_done:
+                continue
+            for p in range(4):
+                if (st.active_mask >> p) & 1:
+                    assert h_idx[expect_rows] == g * 4 + p
+                    orc.orc_game_encode_ext(games[g], p, a.ctypes.data_as(C.POINTER(C.c_float)))
+                    orc.orc_game_encode(games[g], p, None, m.ctypes.data_as(C.POINTER(C.c_uint8)))
+                    if h_obs[expect_rows].tobytes() != a.tobytes():
+                        bad = sorted(set(np.nonzero(h_obs[expect_rows].ravel() != a)[0] // 34))
+                        raise AssertionError(f"iter {it} game {g} seat {p}: channels {bad}")
+                    assert h_mask[expect_rows].tobytes() == m.tobytes(), f"iter {it} game {g} seat {p} mask"
+                    seen_channels |= a.reshape(215, 34).any(axis=1)
+                    expect_rows += 1
+                    checked += 1
+        assert expect_rows == rows
+        stride = 1 if it < 20 else 41
+        v.step_random(23, stride)
+        for g in range(n):
+            for _ in range(stride):
+                orc.orc_game_random_step(games[g], 23, 9500 + g)
+    for h in games:
+        orc.orc_game_free(h)
+    assert checked > 6000
+    # every block of the extended layout was exercised with non-zero content
+    for lo, hi in ((74, 78), (78, 94), (94, 98), (98, 178), (178, 189), (189, 194), (197, 206), (206, 215)):
+        assert seen_channels[lo:hi].any(), (lo, hi)
+
+
+def test_shim_observation_encode_extended(orc):
+    from riichienv_b200 import RiichiEnv
+
+    env = RiichiEnv(game_mode=0, seed=5)
+    obs = env.reset()
+    b = obs[0].encode_extended()
+    assert len(b) == 215 * 34 * 4
+    arr = np.frombuffer(b, dtype=np.float32).reshape(215, 34)
+    base = np.frombuffer(obs[0].encode(), dtype=np.float32).reshape(74, 34)
+    assert (arr[:74] == base).all()                       # no melds yet: channel 30 agrees too
+    assert (arr[82] == 0.5).all() and (arr[189] == np.float32(14) / np.float32(34)).all()
+
+
 def test_sequence_features_vs_oracle(orc):
     """rv_vec_encode_seq: sparse / numeric / progression / candidates of every acting seat of 128 games, observed after
     single steps and after multi-step strides (so the per-seat event deltas span several steps), bytes equal to the

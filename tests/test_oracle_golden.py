@@ -207,3 +207,26 @@ def test_chacha_known_answers():
     seed = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
     w = words(struct.unpack("<8I", seed), 12, 2)
     assert (w[0] | (w[1] << 32)) == 10719222850664546238
+
+
+def test_ukeire_golden():
+    """shanten.rs:250-393 (calculate_shanten / effective_tiles_with_discard / best_ukeire — what the extended encoders'
+    shanten channels call) against answers computed from the reference's own nyanten tables (tests/golden/make_golden.py)."""
+    import ctypes as C
+    import os
+
+    o = oracle.load()
+    path = os.path.join(os.path.dirname(__file__), "golden", "ukeire_golden.txt")
+    n = 0
+    for line in open(path):
+        if line.startswith("#"):
+            continue
+        hs, vs, es = [x.strip() for x in line.split("|")]
+        hand = [int(x) for x in hs.split(",")]
+        vis = [int(x) for x in vs.split(",")] if vs else []
+        exp = [int(x) for x in es.split()]
+        out = (C.c_int * 3)()
+        o.orc_ukeire((C.c_int * len(hand))(*hand), len(hand), (C.c_int * max(1, len(vis)))(*vis), len(vis), out)
+        assert list(out) == exp, (hand, vis, list(out), exp)
+        n += 1
+    assert n == 400

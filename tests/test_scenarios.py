@@ -348,3 +348,58 @@ def test_sanma_kita(backend):  # state_3p/sanma.rs:9-204, tests/env/test_sanma.p
     types = [x["type"] for x in ev(env)]
     assert types[-2:] == ["kita", "tsumo"]
     assert s.is_first_turn == 0
+
+
+# ---- extended encoders: the reference's own unit tests (observation/encode.rs:593-800) -----------------------------------
+_OBS_HANDS = [[0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48], [1, 5, 9, 13, 17, 21, 25, 29, 33, 37, 41, 45, 49],
+              [2, 6, 10, 14, 18, 22, 26, 30, 34, 38, 42, 46, 50], [3, 7, 11, 15, 19, 23, 27, 31, 35, 39, 43, 47, 51]]
+
+
+def _ext(backend, pid, discards=None, melds=None):
+    """make_obs (encode.rs:593-621) as a live state: seat `pid` is the one observed (it owes the action)."""
+    env = setup_env(BACKENDS[backend], seed=3, hands=_OBS_HANDS, current_player=pid, active_players=[pid],
+                    discards=discards or [[], [], [], []], melds=melds)
+    return env.encode_ext(pid)
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_ext_discard_decay_relative_order(backend):  # encode.rs:633-662, 785-803
+    d = [[0], [], [36], []]
+    b0, b2 = _ext(backend, 0, d), _ext(backend, 2, d)
+    assert b0[74, 0] > 0 and b0[76, 9] > 0
+    assert b2[74, 9] > 0 and b2[76, 0] > 0
+    assert b0[74, 0] == b2[74, 9] == 1.0
+    d = [[0], [4], [8], [12]]
+    for pid in range(4):
+        assert _ext(backend, pid, d)[74, d[pid][0] // 4] > 0
+    # exp(-0.2 * age): two discards of one kind accumulate, oldest first
+    import numpy as np
+    b = _ext(backend, 1, [[], [0, 1, 40], [], []])
+    w = [np.float32(np.exp(np.float32(-0.2) * np.float32(a))) for a in (2, 1)]
+    assert abs(b[74, 0] - (w[0] + w[1])) < 1e-6 and b[74, 10] == 1.0
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_ext_shanten_relative_order(backend):  # encode.rs:665-702
+    d = [[0, 4], [8], [12, 16, 20], []]
+    b0, b2 = _ext(backend, 0, d), _ext(backend, 2, d)
+    assert abs(b0[78 + 3, 0] - b2[78 + 2 * 4 + 3, 0]) < 1e-6
+    assert b0[78 + 4, 0] == 0.5 and abs(b0[78, 0] - 0.5) > 1e-6
+    assert b2[78 + 4, 0] == 0.5 and abs(b2[78, 0] - 0.5) > 1e-6
+    assert (b0[78 + 3] == b0[78 + 3, 0]).all()      # broadcast
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_ext_ankan_and_fuuro_relative_order(backend):  # encode.rs:705-782
+    ankan = [None, [(3, [0, 1, 2, 3], 0, None)], None, None]
+    b0, b3 = _ext(backend, 0, melds=ankan), _ext(backend, 3, melds=ankan)
+    assert b0[94 + 1, 0] == 1.0 and b0[94, 0] == 0.0
+    assert b3[94 + 2, 0] == 1.0 and b3[94 + 1, 0] == 0.0
+    chi = [None, None, [(0, [0, 4, 8], 1, 0)], None]
+    b0, b1 = _ext(backend, 0, melds=chi), _ext(backend, 1, melds=chi)
+    assert b0[98 + 40, 0] == 1.0 and b0[98 + 41, 1] == 1.0
+    assert b1[98 + 20, 0] == 1.0 and b1[98 + 21, 1] == 1.0
+    # a called meld counts one tile short in channel 30 of encode_base_into (encode.rs:94-110)
+    import numpy as np
+    used = 13 + 1 + 3 - 1      # own hand, the dora indicator, the chi minus its called tile
+    assert b0[30, 0] == np.float32(136 - used) / np.float32(70.0)
