@@ -23,12 +23,10 @@ for name, fn, buf in (("encode_ext", v.encode_extended, ext), ("encode", v.encod
     rows = fn(obs=buf, mask=mask, index=idx)
     ts = []
     for _ in range(10):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        v.ctx.timer_mark(0)          # CUDA events on the library's own stream
         fn(obs=buf, mask=mask, index=idx, sync=False)
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        v.ctx.timer_mark(1)
+        ts.append(v.ctx.timer_elapsed(0, 1))
     ms = sorted(ts)[len(ts) // 2]
     out[name] = {"rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3, "GBps": rows * buf[0].numel() * 4 / ms / 1e6}
 print(json.dumps(out))

@@ -17,8 +17,8 @@
 // channel; the decay rows are accumulated in the reference's order (oldest discard first) by one lane per seat from a table of
 // exp(-0.2 * age) computed on the host with the C library's expf (the reference calls the same libm through f32::exp), so the
 // row is bit-identical to the oracle's.  The shanten channels cost up to 14 x 34 + 15 shanten evaluations
-// (shanten.rs:331-393 removes each hand tile and tries each of the 34 kinds): lane k evaluates "draw kind k" for the warp's
-// current discard, the per-discard reductions are ballots and shuffles.
+// (shanten.rs:331-393 removes each hand tile and tries each of the 34 kinds): the (discard, draw) pairs are dealt out flat
+// over the lanes (obs_ext_shanten_warp).
 #pragma once
 #include "obs.cuh"
 
@@ -188,62 +188,79 @@ __device__ inline void obs_ext_channel(const G& g, int pid, int ch, const ObsExt
 struct ObsExtScratch {
   ObsDesc d[OBSX_CH - 78 + 1];     // channels 78..214
   float decay[4][36];
-  int info[6];
+  int uke[16], eff[16];          // per compacted discard (obs_ext_shanten_warp)
+  uint16_t vk[16];               // compacted discards: kind | (shanten after the discard + 2) << 8; kind 0xFF = no discard
 };
 
-// shanten.rs:250-393, one warp: lane k = "draw kind k" (lanes 0,1 also kinds 32,33); uniform loop over the kinds in hand
-__device__ __forceinline__ void obs_ext_shanten_warp(const Tables& T, const G& g, int pid, const int* seen, int lane, ObsExtInfo& I) {
+// shanten.rs:250-393, one warp.  Three passes, each one shanten evaluation per lane:
+//   1. lane l = the l-th distinct tile kind of the hand: shanten after discarding it (keep / increase counts come from here);
+//      the discards that do not raise shanten are compacted into a list (+ one pseudo entry "no discard" for a 3n+1 hand,
+//      whose effective-tile count is taken on the hand itself, shanten.rs:265-296);
+//   2. the (discard, draw kind) pairs of that list, 34 per discard, are dealt out flat over the lanes: a draw that lowers the
+//      shanten adds its unseen copies to the discard's ukeire and 1 to its effective-tile count (shared-memory atomics);
+//   3. maxima over the list.
+// A hand has at most 14 distinct kinds, so pass 2 is at most 15 rounds (the per-discard loop it replaces took 3 per discard).
+__device__ __forceinline__ void obs_ext_shanten_warp(const Tables& T, const G& g, int pid, const int* seen, int lane, ObsExtScratch& X,
+                                                    ObsExtInfo& I) {
   const Cnt c = obs_hand_cnt(g, pid);
   const int n = g.hand_len[pid];
   const int cur = shanten_counts(T, c, n / 3);
-  const int hcA = cnt_get(c, lane), hcB = lane < 2 ? cnt_get(c, 32 + lane) : 4;
-  const int visA = seen[lane] - hcA, visB = lane < 2 ? seen[32 + lane] - hcB : 0;    // seen = hand + rivers + melds + indicators
-  int keep = 0, inc = 0, best_uke = 0, best_eff = 0;
+  // pass 1
   uint64_t present = cnt_present(c);
-  while (present) {
-    const int d = __ffsll((long long)present) - 1;
+  const int D = __popcll(present);
+  int kind = -1;
+  for (int i = 0; i < 14; i++) {
+    if (i == lane && present) kind = __ffsll((long long)present) - 1;
     present &= present - 1;
-    const int cd = cnt_get(c, d);
+  }
+  int ss = 99, cd = 0;
+  if (lane < D) {
+    cd = cnt_get(c, kind);
     Cnt sub = c;
-    cnt_sub(sub, d);
-    const int ss = shanten_counts(T, sub, (n - 1) / 3);
-    keep += ss == cur ? cd : 0;
-    inc += ss > cur ? cd : 0;
-    if (ss > cur) continue;
-    const int scA = hcA - (lane == d ? 1 : 0), scB = hcB - (32 + lane == d ? 1 : 0);
-    bool goodA = false, goodB = false;
-    if (scA < 4) {
-      Cnt t = sub;
-      cnt_add(t, lane);
-      goodA = shanten_counts(T, t, n / 3) < ss;
-    }
-    if (scB < 4) {
-      Cnt t = sub;
-      cnt_add(t, 32 + lane);
-      goodB = shanten_counts(T, t, n / 3) < ss;
-    }
-    int uke = (goodA ? max(max(4 - visA, 0) - scA, 0) : 0) + (goodB ? max(max(4 - visB, 0) - scB, 0) : 0);
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) uke += __shfl_xor_sync(0xFFFFFFFFu, uke, o);
-    const int eff = __popc(__ballot_sync(0xFFFFFFFFu, goodA)) + __popc(__ballot_sync(0xFFFFFFFFu, goodB));
-    best_uke = max(best_uke, uke);
-    best_eff = max(best_eff, eff);
+    cnt_sub(sub, kind);
+    ss = shanten_counts(T, sub, (n - 1) / 3);
   }
-  if (n % 3 == 1) {
-    bool goodA = false, goodB = false;
-    if (hcA < 4) {
-      Cnt t = c;
-      cnt_add(t, lane);
-      goodA = shanten_counts(T, t, (n + 1) / 3) < cur;
-    }
-    if (hcB < 4) {
-      Cnt t = c;
-      cnt_add(t, 32 + lane);
-      goodB = shanten_counts(T, t, (n + 1) / 3) < cur;
-    }
-    best_eff = __popc(__ballot_sync(0xFFFFFFFFu, goodA)) + __popc(__ballot_sync(0xFFFFFFFFu, goodB));
+  int keep = ss == cur ? cd : 0, inc = (lane < D && ss > cur) ? cd : 0;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    keep += __shfl_xor_sync(0xFFFFFFFFu, keep, o);
+    inc += __shfl_xor_sync(0xFFFFFFFFu, inc, o);
   }
-  I.shanten = cur, I.eff = best_eff, I.uke = best_uke, I.keep = keep, I.inc = inc;
+  const bool valid = lane < D && ss <= cur;
+  const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+  int V = __popc(vmask);
+  if (valid) X.vk[__popc(vmask & ((1u << lane) - 1))] = (uint16_t)(kind | ((ss + 2) << 8));
+  const bool self13 = n % 3 == 1;
+  if (lane == 0 && self13) X.vk[V] = (uint16_t)(0xFF | ((cur + 2) << 8));
+  if (lane < 16) X.uke[lane] = 0, X.eff[lane] = 0;
+  __syncwarp();
+  // pass 2
+  const int total = (V + (self13 ? 1 : 0)) * 34;
+  for (int j = lane; j < total; j += 32) {
+    const int di = j / 34, k = j - di * 34;
+    const int e = X.vk[di], dk = e & 0xFF, base_s = (e >> 8) - 2;
+    Cnt t = c;
+    if (dk != 0xFF) cnt_sub(t, dk);
+    const int sc = cnt_get(t, k);
+    if (sc < 4) {
+      cnt_add(t, k);
+      if (shanten_counts(T, t, dk != 0xFF ? n / 3 : (n + 1) / 3) < base_s) {
+        const int vis = seen[k] - cnt_get(c, k);           // seen = hand + rivers + melds + indicators
+        atomicAdd(&X.uke[di], max(max(4 - vis, 0) - sc, 0));
+        atomicAdd(&X.eff[di], 1);
+      }
+    }
+  }
+  __syncwarp();
+  // pass 3
+  int uke = lane < V ? X.uke[lane] : 0;
+  int eff = self13 ? (lane == V ? X.eff[lane] : 0) : (lane < V ? X.eff[lane] : 0);
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uke = max(uke, __shfl_xor_sync(0xFFFFFFFFu, uke, o));
+    eff = max(eff, __shfl_xor_sync(0xFFFFFFFFu, eff, o));
+  }
+  I.shanten = cur, I.eff = eff, I.uke = uke, I.keep = keep, I.inc = inc;
 }
 
 // One warp, one row: base gather + describe (obs.cuh), extended describe, then 3,655 eight-byte streaming stores
@@ -258,7 +275,7 @@ __device__ __forceinline__ void obs_ext_encode_warp(const Tables& T, const Decay
   __syncwarp();
   if (lane < 4) obs_ext_decay_row(g, river, (pid + lane) & 3, D, X.decay[lane]);
   ObsExtInfo I;
-  obs_ext_shanten_warp(T, g, pid, S.seen, lane, I);
+  obs_ext_shanten_warp(T, g, pid, S.seen, lane, X, I);
   I.avail = avail;
   for (int ch = 78 + lane; ch < OBSX_CH; ch += 32) {
     uint64_t m;

@@ -403,3 +403,37 @@ def test_ext_ankan_and_fuuro_relative_order(backend):  # encode.rs:705-782
     import numpy as np
     used = 13 + 1 + 3 - 1      # own hand, the dora indicator, the chi minus its called tile
     assert b0[30, 0] == np.float32(136 - used) / np.float32(70.0)
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_ext_tile_context_channels(backend):
+    """pass context / last tedashi / riichi sutehai (encode.rs:479-584) from injected state: opponents in ABSOLUTE seat order,
+    "is dora" only for copy 0 of the dora kind (a tile id is compared with get_next_tile's id), and the pass context is fed
+    the discarder's SEAT (state/mod.rs:252 destructures the (pid, tile) tuple the other way round)."""
+    import numpy as np
+
+    env = setup_env(BACKENDS[backend], seed=3, hands=_OBS_HANDS, current_player=1, active_players=[1])
+    s = env.get_state()
+    s.n_dora = 1
+    s.dora_ind[0] = 4 * 12 + 2          # indicator 4p -> dora 5p (kind 13): only tile id 52 "is dora"
+    s.riichi_sutehai[0], s.riichi_sutehai[2], s.riichi_sutehai[3] = 52, 53, 255
+    s.last_tedashi[0], s.last_tedashi[2], s.last_tedashi[3] = 255, 88, 135
+    s.last_discard_pid, s.last_discard_tile = 2, 52
+    env.set_state(s)
+    b = env.encode_ext(1)
+    f = np.float32
+    # riichi sutehai: opponents of seat 1 in absolute order are 0, 2, 3
+    assert (b[206] == f(13) / f(33)).all() and (b[207] == 1).all() and (b[208] == 1).all()     # 52: red 5p, copy 0 -> dora
+    assert (b[209] == f(13) / f(33)).all() and (b[210] == 0).all() and (b[211] == 0).all()     # 53: same kind, not copy 0
+    assert not b[212:215].any()
+    # last tedashi
+    assert not b[197:200].any()
+    assert (b[200] == f(22) / f(33)).all() and (b[201] == 1).all() and (b[202] == 0).all()     # 88: red 5s
+    assert (b[203] == f(33) / f(33)).all() and (b[204] == 0).all() and (b[205] == 0).all()
+    # pass context sees "tile" 2 (the discarder's seat): kind 0, not red, not dora
+    assert not b[194:197].any()
+    s.dora_ind[0] = 4 * 8               # indicator 9m -> dora 1m (kind 0, copy 0 = tile id 0)
+    s.last_discard_pid = 0
+    env.set_state(s)
+    b = env.encode_ext(1)
+    assert (b[194] == 0).all() and (b[195] == 0).all() and (b[196] == 1).all()                  # seat 0 "is" tile id 0
