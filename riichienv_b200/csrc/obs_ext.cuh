@@ -107,6 +107,169 @@ __device__ inline void obs_ext_shanten_scalar(const Tables& T, const G& g, int p
   I.shanten = cur, I.eff = best_eff, I.uke = best_uke, I.keep = keep, I.inc = inc;
 }
 
+// ---- shanten of "hand - one tile + one tile" without the full four-suit combination --------------------------------------
+// shanten_counts (hand.cuh) folds the four suits' cost vectors (tiles missing for k mentsu, with / without the pair) with three
+// (min,+) convolutions.  Discarding a tile and drawing one changes at most two suits, so per hand the convolutions of the
+// UNCHANGED suits are taken once (R1[A]: all suits but A; R2[A,B]: the two suits other than A and B), per discard one
+// convolution per other suit (Y), and a (discard, draw) pair costs one table load and the single entry [m mentsu, with pair]
+// of the last convolution.  Chiitoitsu / kokushi (shanten.rs:198-239, hands without melds) follow from four counters.
+// Vectors are packed like the cost table: byte k = c0[k] | c1[k] << 4 (every entry <= 14).
+__device__ __forceinline__ uint64_t sh_conv(uint64_t a, uint64_t b) {
+  uint64_t out = 0;
+  #pragma unroll
+  for (int k = 0; k < 5; k++) {
+    int n0 = 99, n1 = 99;
+    #pragma unroll
+    for (int i = 0; i <= k; i++) {
+      const int a0 = (int)(a >> (8 * i)) & 15, a1 = (int)(a >> (8 * i + 4)) & 15;
+      const int b0 = (int)(b >> (8 * (k - i))) & 15, b1 = (int)(b >> (8 * (k - i) + 4)) & 15;
+      n0 = min(n0, a0 + b0);
+      n1 = min(n1, min(a1 + b0, a0 + b1));
+    }
+    out |= (uint64_t)(n0 | (n1 << 4)) << (8 * k);
+  }
+  return out;
+}
+// entry [m][with pair] of sh_conv(a, b)
+__device__ __forceinline__ int sh_single(uint64_t a, uint64_t b, int m) {
+  int best = 99;
+  #pragma unroll
+  for (int i = 0; i < 5; i++) {
+    if (i > m) break;
+    const int a0 = (int)(a >> (8 * i)) & 15, a1 = (int)(a >> (8 * i + 4)) & 15;
+    const int b0 = (int)(b >> (8 * (m - i))) & 15, b1 = (int)(b >> (8 * (m - i) + 4)) & 15;
+    best = min(best, min(a1 + b0, a0 + b1));
+  }
+  return best;
+}
+__device__ __forceinline__ uint64_t sh_cost(const Tables& T, int suit, int key) {
+  return suit == 3 ? __ldg(&T.honor_cost[key]) : __ldg(&T.suit_cost[key]);
+}
+__device__ __forceinline__ int sh_pair_index(int a, int b) {   // unordered pair of distinct suits -> 0..5
+  const int lo = a < b ? a : b, hi = a < b ? b : a;
+  return lo == 0 ? hi - 1 : lo + hi;                            // 01 02 03 12 13 23 -> 0 1 2 3 4 5
+}
+struct ShStats {   // what calc_chitoi / calc_kokushi need
+  int kinds, pairs, tk, tp2;   // kinds present, kinds with >= 2, terminal/honor kinds present, terminal/honor kinds with >= 2
+};
+__device__ __forceinline__ bool sh_is_terminal(int k) { return (MASK_TERMINAL_HONOR >> k) & 1; }
+__device__ __forceinline__ void sh_remove(ShStats& s, int k, int cnt_before) {
+  s.kinds -= cnt_before == 1, s.pairs -= cnt_before == 2;
+  if (sh_is_terminal(k)) s.tk -= cnt_before == 1, s.tp2 -= cnt_before == 2;
+}
+__device__ __forceinline__ void sh_add(ShStats& s, int k, int cnt_before) {
+  s.kinds += cnt_before == 0, s.pairs += cnt_before == 1;
+  if (sh_is_terminal(k)) s.tk += cnt_before == 0, s.tp2 += cnt_before == 1;
+}
+// shanten.rs:228-239 from the normal-form replacement number and the counters
+__device__ __forceinline__ int sh_finish(int normal_repl, int m, const ShStats& st) {
+  int sh = normal_repl - 1;
+  if (sh <= 0 || m < 4) return sh;
+  sh = min(sh, 7 - st.pairs + (st.kinds < 7 ? 7 - st.kinds : 0) - 1);
+  if (sh > 0) sh = min(sh, 14 - st.tk - (st.tp2 > 0 ? 1 : 0) - 1);
+  return sh;
+}
+struct ShHand {    // per hand
+  uint64_t cs[4];  // cost vectors of the four suits
+  uint64_t R2[6];  // sh_pair_index(A, B) -> convolution of the two suits other than A, B
+  uint64_t R1[4];  // A -> convolution of the three suits other than A
+  int key[4];
+  ShStats st;
+};
+__device__ inline void sh_hand_init(const Tables& T, const G& g, int pid, ShHand& H) {
+  const Cnt c = obs_hand_cnt(g, pid);
+  for (int s = 0; s < 4; s++) {
+    H.key[s] = (int)g.c_key[pid][s];
+    H.cs[s] = sh_cost(T, s, H.key[s]);
+  }
+  for (int a = 0; a < 4; a++)
+    for (int b = a + 1; b < 4; b++) {
+      int o[2], no = 0;
+      for (int s = 0; s < 4; s++)
+        if (s != a && s != b) o[no++] = s;
+      H.R2[sh_pair_index(a, b)] = sh_conv(H.cs[o[0]], H.cs[o[1]]);
+    }
+  for (int a = 0; a < 4; a++) {
+    const int b = a == 0 ? 1 : 0;                                   // R1[a] = cs[b] (x) (the two suits other than a, b)
+    H.R1[a] = sh_conv(H.cs[b], H.R2[sh_pair_index(a, b)]);
+  }
+  const uint64_t present = cnt_present(c);
+  H.st.kinds = __popcll(present);
+  H.st.tk = __popcll(present & MASK_TERMINAL_HONOR);
+  H.st.pairs = H.st.tp2 = 0;
+  for (int k = 0; k < 34; k++)
+    if (cnt_get(c, k) >= 2) H.st.pairs++, H.st.tp2 += sh_is_terminal(k);
+}
+// shanten of the hand itself (m = len / 3)
+__device__ __forceinline__ int sh_hand_shanten(const ShHand& H, int m) { return sh_finish(sh_single(H.R1[0], H.cs[0], m), m, H.st); }
+// hand minus one tile of kind d (cd copies before): shanten, the suit's new vector, the counters
+__device__ __forceinline__ int sh_discard(const Tables& T, const ShHand& H, int d, int cd, int m, uint64_t& xa, ShStats& st) {
+  const int A = d / 9;
+  xa = sh_cost(T, A, H.key[A] - pow5(d - 9 * A));
+  st = H.st;
+  sh_remove(st, d, cd);
+  return sh_finish(sh_single(H.R1[A], xa, m), m, st);
+}
+// (hand minus d) plus one tile of kind k (ck copies after the discard).  d < 0: no discard.  y = sh_conv(xa, R2[A, B]) for
+// B != A (precomputed per discard by the caller), ignored otherwise.
+__device__ __forceinline__ int sh_draw(const Tables& T, const ShHand& H, int d, int k, int ck, int m, uint64_t y, ShStats st) {
+  const int B = k / 9, b = k - 9 * B;
+  int repl;
+  if (d < 0) {
+    repl = sh_single(H.R1[B], sh_cost(T, B, H.key[B] + pow5(b)), m);
+  } else {
+    const int A = d / 9;
+    if (A == B) repl = sh_single(H.R1[A], sh_cost(T, A, H.key[A] - pow5(d - 9 * A) + pow5(b)), m);
+    else repl = sh_single(y, sh_cost(T, B, H.key[B] + pow5(b)), m);
+  }
+  sh_add(st, k, ck);
+  return sh_finish(repl, m, st);
+}
+// the definition above, evaluated through the fast path (one thread): must equal obs_ext_shanten_scalar
+__device__ inline void obs_ext_shanten_fast_scalar(const Tables& T, const G& g, int pid, const int* vis, ObsExtInfo& I) {
+  ShHand H;
+  sh_hand_init(T, g, pid, H);
+  const Cnt c = obs_hand_cnt(g, pid);
+  const int n = g.hand_len[pid];
+  const int cur = sh_hand_shanten(H, n / 3);
+  int keep = 0, inc = 0, best_uke = 0, best_eff = 0;
+  for (int d = 0; d < 34; d++) {
+    const int cd = cnt_get(c, d);
+    if (!cd) continue;
+    uint64_t xa;
+    ShStats st;
+    const int ss = sh_discard(T, H, d, cd, (n - 1) / 3, xa, st);
+    if (ss == cur) keep += cd;
+    else if (ss > cur) inc += cd;
+    if (ss > cur) continue;
+    int uke = 0, eff = 0;
+    for (int k = 0; k < 34; k++) {
+      const int sc = cnt_get(c, k) - (k == d ? 1 : 0);
+      if (sc >= 4) continue;
+      const int A = d / 9, B = k / 9;
+      const uint64_t y = A != B ? sh_conv(xa, H.R2[sh_pair_index(A, B)]) : 0;
+      if (sh_draw(T, H, d, k, sc, n / 3, y, st) < ss) {
+        int rem = 4 - vis[k];
+        rem = rem < 0 ? 0 : rem;
+        rem -= sc;
+        uke += rem < 0 ? 0 : rem;
+        eff++;
+      }
+    }
+    best_uke = max(best_uke, uke);
+    best_eff = max(best_eff, eff);
+  }
+  if (n % 3 == 1) {
+    best_eff = 0;
+    for (int k = 0; k < 34; k++) {
+      const int sc = cnt_get(c, k);
+      if (sc >= 4) continue;
+      if (sh_draw(T, H, -1, k, sc, (n + 1) / 3, 0, H.st) < cur) best_eff++;
+    }
+  }
+  I.shanten = cur, I.eff = best_eff, I.uke = best_uke, I.keep = keep, I.inc = inc;
+}
+
 // discard decay row of seat q (encode.rs:295-313): row[kind] += exp(-0.2 * age), oldest discard first
 __device__ inline void obs_ext_decay_row(const G& g, const uint8_t* river, int q, const DecayTab& D, float* row) {
   const int n = min((int)g.n_river[q], RV_RIVER_CAP);
@@ -190,35 +353,72 @@ struct ObsExtScratch {
   float decay[4][36];
   int uke[16], eff[16];          // per compacted discard (obs_ext_shanten_warp)
   uint16_t vk[16];               // compacted discards: kind | (shanten after the discard + 2) << 8; kind 0xFF = no discard
+  uint32_t vst[16];              // their chiitoi / kokushi counters (ShStats, a byte each)
+  uint64_t Y[16][4];             // their cross-suit vectors: Y[B] = (suit of the discard, after it) (x) R2[A, B]
+  ShHand H;
 };
 
-// shanten.rs:250-393, one warp.  Three passes, each one shanten evaluation per lane:
+// shanten.rs:250-393, one warp, on the incremental evaluation above (sh_*).  Passes:
+//   0. lanes 0-5 take the six two-suit convolutions, lanes 0-3 then the four three-suit ones (ShHand in shared memory);
 //   1. lane l = the l-th distinct tile kind of the hand: shanten after discarding it (keep / increase counts come from here);
-//      the discards that do not raise shanten are compacted into a list (+ one pseudo entry "no discard" for a 3n+1 hand,
-//      whose effective-tile count is taken on the hand itself, shanten.rs:265-296);
-//   2. the (discard, draw kind) pairs of that list, 34 per discard, are dealt out flat over the lanes: a draw that lowers the
-//      shanten adds its unseen copies to the discard's ukeire and 1 to its effective-tile count (shared-memory atomics);
+//      the discards that do not raise shanten are compacted into a list together with their three cross-suit vectors Y
+//      (+ one pseudo entry "no discard" for a 3n+1 hand, whose effective-tile count is taken on the hand itself,
+//      shanten.rs:265-296);
+//   2. the (discard, draw kind) pairs of that list, 34 per discard, are dealt out flat over the lanes — one table load and
+//      one five-term minimum each; a draw that lowers the shanten adds its unseen copies to the discard's ukeire and 1 to
+//      its effective-tile count (shared-memory atomics);
 //   3. maxima over the list.
-// A hand has at most 14 distinct kinds, so pass 2 is at most 15 rounds (the per-discard loop it replaces took 3 per discard).
 __device__ __forceinline__ void obs_ext_shanten_warp(const Tables& T, const G& g, int pid, const int* seen, int lane, ObsExtScratch& X,
                                                     ObsExtInfo& I) {
   const Cnt c = obs_hand_cnt(g, pid);
   const int n = g.hand_len[pid];
-  const int cur = shanten_counts(T, c, n / 3);
-  // pass 1
+  ShHand& H = X.H;
+  // pass 0
+  if (lane < 4) {
+    H.key[lane] = (int)g.c_key[pid][lane];
+    H.cs[lane] = sh_cost(T, lane, H.key[lane]);
+  }
+  __syncwarp();
+  if (lane < 6) {
+    const int a = lane < 3 ? 0 : lane < 5 ? 1 : 2, b = lane < 3 ? lane + 1 : lane < 5 ? lane - 1 : 3;   // 01 02 03 12 13 23
+    int o0 = -1, o1 = -1;
+    #pragma unroll
+    for (int s = 0; s < 4; s++)
+      if (s != a && s != b) (o0 < 0 ? o0 : o1) = s;
+    H.R2[lane] = sh_conv(H.cs[o0], H.cs[o1]);
+  }
+  __syncwarp();
+  if (lane < 4) {
+    const int b = lane == 0 ? 1 : 0;
+    H.R1[lane] = sh_conv(H.cs[b], H.R2[sh_pair_index(lane, b)]);
+  }
   uint64_t present = cnt_present(c);
-  const int D = __popcll(present);
+  ShStats st0;
+  st0.kinds = __popcll(present);
+  st0.tk = __popcll(present & MASK_TERMINAL_HONOR);
+  {
+    const int cA = cnt_get(c, lane), cB = lane < 2 ? cnt_get(c, 32 + lane) : 0;
+    const uint32_t p2 = __ballot_sync(0xFFFFFFFFu, cA >= 2), p2b = __ballot_sync(0xFFFFFFFFu, cB >= 2) & 3u;
+    const uint64_t ge2 = (uint64_t)p2 | ((uint64_t)p2b << 32);
+    st0.pairs = __popcll(ge2);
+    st0.tp2 = __popcll(ge2 & MASK_TERMINAL_HONOR);
+  }
+  if (lane == 0) H.st = st0;
+  __syncwarp();
+  const int cur = sh_finish(sh_single(H.R1[0], H.cs[0], n / 3), n / 3, st0);
+  // pass 1
+  const int D = st0.kinds;
   int kind = -1;
   for (int i = 0; i < 14; i++) {
     if (i == lane && present) kind = __ffsll((long long)present) - 1;
     present &= present - 1;
   }
   int ss = 99, cd = 0;
+  uint64_t xa = 0;
+  ShStats st1 = st0;
   if (lane < D) {
     cd = cnt_get(c, kind);
-    Cnt sub = c;
-    cnt_sub(sub, kind);
-    ss = shanten_counts(T, sub, (n - 1) / 3);
+    ss = sh_discard(T, H, kind, cd, (n - 1) / 3, xa, st1);
   }
   int keep = ss == cur ? cd : 0, inc = (lane < D && ss > cur) ? cd : 0;
   #pragma unroll
@@ -228,10 +428,20 @@ __device__ __forceinline__ void obs_ext_shanten_warp(const Tables& T, const G& g
   }
   const bool valid = lane < D && ss <= cur;
   const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-  int V = __popc(vmask);
-  if (valid) X.vk[__popc(vmask & ((1u << lane) - 1))] = (uint16_t)(kind | ((ss + 2) << 8));
+  const int V = __popc(vmask);
+  if (valid) {
+    const int slot = __popc(vmask & ((1u << lane) - 1)), A = kind / 9;
+    X.vk[slot] = (uint16_t)(kind | ((ss + 2) << 8));
+    X.vst[slot] = (uint32_t)st1.kinds | ((uint32_t)st1.pairs << 8) | ((uint32_t)st1.tk << 16) | ((uint32_t)st1.tp2 << 24);
+    #pragma unroll
+    for (int B = 0; B < 4; B++)
+      if (B != A) X.Y[slot][B] = sh_conv(xa, H.R2[sh_pair_index(A, B)]);
+  }
   const bool self13 = n % 3 == 1;
-  if (lane == 0 && self13) X.vk[V] = (uint16_t)(0xFF | ((cur + 2) << 8));
+  if (lane == 0 && self13) {
+    X.vk[V] = (uint16_t)(0xFF | ((cur + 2) << 8));
+    X.vst[V] = (uint32_t)st0.kinds | ((uint32_t)st0.pairs << 8) | ((uint32_t)st0.tk << 16) | ((uint32_t)st0.tp2 << 24);
+  }
   if (lane < 16) X.uke[lane] = 0, X.eff[lane] = 0;
   __syncwarp();
   // pass 2
@@ -239,13 +449,16 @@ __device__ __forceinline__ void obs_ext_shanten_warp(const Tables& T, const G& g
   for (int j = lane; j < total; j += 32) {
     const int di = j / 34, k = j - di * 34;
     const int e = X.vk[di], dk = e & 0xFF, base_s = (e >> 8) - 2;
-    Cnt t = c;
-    if (dk != 0xFF) cnt_sub(t, dk);
-    const int sc = cnt_get(t, k);
+    const bool none = dk == 0xFF;
+    const int ck = cnt_get(c, k), sc = ck - ((!none && dk == k) ? 1 : 0);
     if (sc < 4) {
-      cnt_add(t, k);
-      if (shanten_counts(T, t, dk != 0xFF ? n / 3 : (n + 1) / 3) < base_s) {
-        const int vis = seen[k] - cnt_get(c, k);           // seen = hand + rivers + melds + indicators
+      const uint32_t pv = X.vst[di];
+      ShStats st;
+      st.kinds = pv & 0xFF, st.pairs = (pv >> 8) & 0xFF, st.tk = (pv >> 16) & 0xFF, st.tp2 = pv >> 24;
+      const int B = k / 9;
+      const uint64_t y = (!none && dk / 9 != B) ? X.Y[di][B] : 0;
+      if (sh_draw(T, H, none ? -1 : dk, k, sc, none ? (n + 1) / 3 : n / 3, y, st) < base_s) {
+        const int vis = seen[k] - ck;                       // seen = hand + rivers + melds + indicators
         atomicAdd(&X.uke[di], max(max(4 - vis, 0) - sc, 0));
         atomicAdd(&X.eff[di], 1);
       }

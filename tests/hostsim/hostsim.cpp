@@ -406,6 +406,12 @@ void hs_game_encode_ext(void* p, int pid, float* obs) {
   ObsExtInfo I;
   Ctx cx = hs_ctx(h);
   obs_ext_shanten_scalar(g_T, g, pid, vis, I);
+  {
+    // the incremental evaluation the warp kernel uses (sh_* in obs_ext.cuh) must give the same five numbers
+    ObsExtInfo F;
+    obs_ext_shanten_fast_scalar(g_T, g, pid, vis, F);
+    if (F.shanten != I.shanten || F.eff != I.eff || F.uke != I.uke || F.keep != I.keep || F.inc != I.inc) I.shanten = -77;
+  }
   I.avail = 0;
   if (!g.is_done && ((g.active_mask >> pid) & 1)) {
     uint32_t packed[RV_MAX_LEGAL];
