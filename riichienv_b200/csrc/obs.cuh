@@ -33,10 +33,10 @@ __device__ __forceinline__ uint64_t river_tail_mask(const G& g, int p, int from_
   int i = n - 1 - from_last;
   return i >= 0 ? 1ull << (cold(g).river[p][i] >> 2) : 0;
 }
-__device__ __forceinline__ int obs_next_kind(int k) {  // observation/helpers.rs:25-50
-  if (k < 27) return (k % 9 == 8) ? k - 8 : k + 1;
-  if (k < 31) return 27 + (k - 27 + 1) % 4;
-  return 31 + (k - 31 + 1) % 3;
+__device__ __forceinline__ int obs_next_kind(int k) {  // observation/helpers.rs:25-50, k in 0..33
+  // k + 1, wrapping 9 -> 1 inside a suit, North -> East, Red -> White (no integer modulo: this is inlined many times)
+  constexpr uint64_t NINES = (1ull << 8) | (1ull << 17) | (1ull << 26);
+  return k + 1 - (int)((NINES >> k) & 1) * 9 - (k == 30 ? 4 : 0) - (k == 33 ? 3 : 0);
 }
 __device__ __forceinline__ int obs_next_kind_sanma(int k) {  // observation_3p/helpers.rs:41-50
   if (k == 0) return 8;

@@ -30,8 +30,14 @@ struct DecayTab {
 };
 struct ObsExtInfo {
   int shanten, eff, uke, keep, inc;
-  uint32_t avail;   // bit i = channel 178 + i
+  uint32_t avail;        // bit i = channel 178 + i
+  uint64_t dora_kinds;   // bit k = some indicator points at kind k (obs_ext_dora_kinds)
 };
+__device__ __forceinline__ uint64_t obs_ext_dora_kinds(const G& g) {
+  uint64_t m = 0;
+  for (int d = 0; d < g.n_dora; d++) m |= 1ull << obs_next_kind(g.dora_ind[d] >> 2);
+  return m;
+}
 
 // encode.rs:399-430: which availability channel a legal action raises (0 = none)
 __device__ inline uint32_t obs_avail_bit(const rv_action& a) {
@@ -114,7 +120,7 @@ __device__ inline void obs_ext_shanten_scalar(const Tables& T, const G& g, int p
 // convolution per other suit (Y), and a (discard, draw) pair costs one table load and the single entry [m mentsu, with pair]
 // of the last convolution.  Chiitoitsu / kokushi (shanten.rs:198-239, hands without melds) follow from four counters.
 // Vectors are packed like the cost table: byte k = c0[k] | c1[k] << 4 (every entry <= 14).
-__device__ __forceinline__ uint64_t sh_conv(uint64_t a, uint64_t b) {
+__device__ __noinline__ uint64_t sh_conv(uint64_t a, uint64_t b) {
   uint64_t out = 0;
   #pragma unroll
   for (int k = 0; k < 5; k++) {
@@ -273,6 +279,7 @@ __device__ inline void obs_ext_shanten_fast_scalar(const Tables& T, const G& g, 
 // discard decay row of seat q (encode.rs:295-313): row[kind] += exp(-0.2 * age), oldest discard first
 __device__ inline void obs_ext_decay_row(const G& g, const uint8_t* river, int q, const DecayTab& D, float* row) {
   const int n = min((int)g.n_river[q], RV_RIVER_CAP);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) row[river[q * RV_RIVER_CAP + i] >> 2] += D.w[n - 1 - i];
 }
 
@@ -288,11 +295,7 @@ __device__ inline void obs_ext_channel(const G& g, int pid, int ch, const ObsExt
   auto tile_ctx = [&](int f, int tile) {
     if (f == 0) bc((float)(tile >> 2) / 33.0f);
     else if (f == 1) bc((tile == 16 || tile == 52 || tile == 88) ? 1.0f : 0.0f);
-    else {
-      bool dora = false;
-      for (int d = 0; d < g.n_dora; d++) dora |= obs_next_kind(g.dora_ind[d] >> 2) * 4 == tile;
-      bc(dora ? 1.0f : 0.0f);
-    }
+    else bc(((tile & 3) == 0 && ((I.dora_kinds >> (tile >> 2)) & 1)) ? 1.0f : 0.0f);
   };
   if (ch < 94) {                                   // shanten efficiency
     const int r = (ch - 78) >> 2, f = (ch - 78) & 3;
@@ -490,6 +493,7 @@ __device__ __forceinline__ void obs_ext_encode_warp(const Tables& T, const Decay
   ObsExtInfo I;
   obs_ext_shanten_warp(T, g, pid, S.seen, lane, X, I);
   I.avail = avail;
+  I.dora_kinds = obs_ext_dora_kinds(g);
   for (int ch = 78 + lane; ch < OBSX_CH; ch += 32) {
     uint64_t m;
     float v;
@@ -499,19 +503,21 @@ __device__ __forceinline__ void obs_ext_encode_warp(const Tables& T, const Decay
   }
   __syncwarp();
   float2* const out2 = reinterpret_cast<float2*>(dst);
+  // the five channels with per-column values (63: seen / 4; 74-77: decay) first: 85 pairs
+  for (int j = lane; j < 5 * 17; j += 32) {
+    const int r = j / 17, col = 2 * (j - r * 17);
+    const float2 o = r == 0 ? make_float2((float)S.seen[col] * 0.25f, (float)S.seen[col + 1] * 0.25f)   // == / 4.0f, exactly
+                            : make_float2(X.decay[r - 1][col], X.decay[r - 1][col + 1]);
+    __stcs(out2 + (r == 0 ? 63 : 73 + r) * 17 + (j - r * 17), o);
+  }
+  // every other channel is (mask, value)
+  #pragma unroll 1
   for (int j = lane; j < OBSX_CH * 17; j += 32) {
-    const int ch = j / 17, col = 2 * (j - ch * 17);
-    float2 o;
-    if (ch == 63) {
-      o = make_float2((float)S.seen[col] / 4.0f, (float)S.seen[col + 1] / 4.0f);
-    } else if (ch >= 74 && ch < 78) {
-      o = make_float2(X.decay[ch - 74][col], X.decay[ch - 74][col + 1]);
-    } else {
-      const ObsDesc& dd = ch < OBS_CH ? S.d[ch] : X.d[ch - 78];
-      const uint32_t bits = (uint32_t)(dd.mask >> col);
-      o = make_float2((bits & 1) ? dd.val : 0.0f, (bits & 2) ? dd.val : 0.0f);
-    }
-    __stcs(out2 + j, o);
+    const int ch = (j * 3856) >> 16, col = 2 * (j - ch * 17);            // j / 17 for j < 3,655
+    if (ch == 63 || (ch >= 74 && ch < 78)) continue;
+    const uint4 dd = *reinterpret_cast<const uint4*>(ch < OBS_CH ? &S.d[ch] : &X.d[ch - 78]);
+    const uint32_t bits = __funnelshift_rc(dd.x, dd.y, col);        // clamped: col == 32 takes the high word
+    __stcs(out2 + j, make_float2(__uint_as_float((bits & 1) ? dd.z : 0u), __uint_as_float((bits & 2) ? dd.z : 0u)));
   }
   __syncwarp();
 }

@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int
 }
 
 // Extended rows (Observation::encode_extended, 215 x 34): one warp per game, staged like obs_encode_kernel; obs_ext.cuh.
-__global__ void __launch_bounds__(128) obs_ext_kernel(Tables T, DecayTab D, const G* states, int64_t n, const int32_t* offsets,
+__global__ void __launch_bounds__(128, 6) obs_ext_kernel(Tables T, DecayTab D, const G* states, int64_t n, const int32_t* offsets,
                                                       const uint32_t* idbits, float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
   __shared__ ObsScratch scratch[4];
   __shared__ ObsExtScratch xscratch[4];

@@ -413,6 +413,7 @@ void hs_game_encode_ext(void* p, int pid, float* obs) {
     if (F.shanten != I.shanten || F.eff != I.eff || F.uke != I.uke || F.keep != I.keep || F.inc != I.inc) I.shanten = -77;
   }
   I.avail = 0;
+  I.dora_kinds = obs_ext_dora_kinds(g);
   if (!g.is_done && ((g.active_mask >> pid) & 1)) {
     uint32_t packed[RV_MAX_LEGAL];
     int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);

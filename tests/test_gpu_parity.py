@@ -413,7 +413,7 @@ def test_shim_observation_encode_extended(orc):
     assert (se[1:, :3] == 0.5).all() and se[0, 0] == arr[78, 0] and se[0, 3] == 0.0
     assert f(obs[0].encode_fuuro_overview(), 4, 4, 5, 34).sum() == 0 and f(obs[0].encode_ankan_overview(), 4, 34).sum() == 0
     av = f(obs[0].encode_action_availability(), 11)
-    types = {int(a.type) for a in obs[0].legal_actions()}
+    types = {int(a.action_type) for a in obs[0].legal_actions()}
     assert av[0] == (1.0 if 5 in types else 0.0) and av[10] == 0.0          # Riichi = 5 (action.rs:55-68); no Pass on own turn
     dc = f(obs[0].encode_discard_candidates(), 5)
     assert dc[0] == np.float32(14) / np.float32(34) and 0.0 <= dc[1] + dc[2] <= 1.0
