@@ -352,7 +352,7 @@ __device__ inline void obs_ext_channel(const G& g, int pid, int ch, const ObsExt
 
 #ifdef __CUDACC__
 struct ObsExtScratch {
-  ObsDesc d[OBSX_CH - 78 + 1];     // channels 78..214
+  ObsDesc d[OBSX_CH + 1];          // all channels: 0..73 copied from the base describe, 63 and 74..77 empty (streamed apart)
   float decay[4][36];
   int uke[16], eff[16];          // per compacted discard (obs_ext_shanten_warp)
   uint16_t vk[16];               // compacted discards: kind | (shanten after the discard + 2) << 8; kind 0xFF = no discard
@@ -494,30 +494,42 @@ __device__ __forceinline__ void obs_ext_encode_warp(const Tables& T, const Decay
   obs_ext_shanten_warp(T, g, pid, S.seen, lane, X, I);
   I.avail = avail;
   I.dora_kinds = obs_ext_dora_kinds(g);
+  for (int ch = lane; ch < 78; ch += 32) {          // base descriptors next to the extended ones: one array for the stream
+    uint4 dd = make_uint4(0, 0, 0, 0);
+    if (ch < OBS_CH && ch != 63) dd = *reinterpret_cast<const uint4*>(&S.d[ch]);
+    *reinterpret_cast<uint4*>(&X.d[ch]) = dd;
+  }
   for (int ch = 78 + lane; ch < OBSX_CH; ch += 32) {
     uint64_t m;
     float v;
     obs_ext_channel(g, pid, ch, I, m, v);
-    X.d[ch - 78].mask = m;
-    X.d[ch - 78].val = v;
+    X.d[ch].mask = m;
+    X.d[ch].val = v;
   }
   __syncwarp();
   float2* const out2 = reinterpret_cast<float2*>(dst);
-  // the five channels with per-column values (63: seen / 4; 74-77: decay) first: 85 pairs
+  // (mask, value) channels: pair j = lane + 32 t covers columns 2p, 2p+1 of channel ch, (ch, p) = divmod(j, 17) kept
+  // incrementally (32 = 17 + 15).  Channels 63 and 74-77 have empty descriptors here and are written below.
+  {
+    int ch = lane >= 17 ? 1 : 0, p = lane >= 17 ? lane - 17 : lane;
+    float2* o = out2 + lane;
+    #pragma unroll 1
+    for (int j = lane; j < OBSX_CH * 17; j += 32) {
+      const uint4 dd = *reinterpret_cast<const uint4*>(&X.d[ch]);
+      const uint32_t bits = __funnelshift_rc(dd.x, dd.y, 2 * p);            // clamped: p == 16 takes the high word
+      __stcs(o, make_float2(__uint_as_float((bits & 1) ? dd.z : 0u), __uint_as_float((bits & 2) ? dd.z : 0u)));
+      o += 32;
+      p += 15, ch += 1;
+      if (p >= 17) p -= 17, ch += 1;
+    }
+  }
+  __syncwarp();                                        // the per-column channels overwrite zeros: order the two passes
+  // the five channels with per-column values (63: seen / 4; 74-77: decay): 85 pairs
   for (int j = lane; j < 5 * 17; j += 32) {
     const int r = j / 17, col = 2 * (j - r * 17);
     const float2 o = r == 0 ? make_float2((float)S.seen[col] * 0.25f, (float)S.seen[col + 1] * 0.25f)   // == / 4.0f, exactly
                             : make_float2(X.decay[r - 1][col], X.decay[r - 1][col + 1]);
     __stcs(out2 + (r == 0 ? 63 : 73 + r) * 17 + (j - r * 17), o);
-  }
-  // every other channel is (mask, value)
-  #pragma unroll 1
-  for (int j = lane; j < OBSX_CH * 17; j += 32) {
-    const int ch = (j * 3856) >> 16, col = 2 * (j - ch * 17);            // j / 17 for j < 3,655
-    if (ch == 63 || (ch >= 74 && ch < 78)) continue;
-    const uint4 dd = *reinterpret_cast<const uint4*>(ch < OBS_CH ? &S.d[ch] : &X.d[ch - 78]);
-    const uint32_t bits = __funnelshift_rc(dd.x, dd.y, col);        // clamped: col == 32 takes the high word
-    __stcs(out2 + j, make_float2(__uint_as_float((bits & 1) ? dd.z : 0u), __uint_as_float((bits & 2) ? dd.z : 0u)));
   }
   __syncwarp();
 }
