@@ -707,55 +707,59 @@ __device__ __noinline__ bool gen_claims(const Ctx& cx, G& g, int i, int pid, int
   uint64_t sc = g.c_cnt[i][su];
   int n_same = (int)((sc >> (4 * r9)) & 15);
   bool kuikae = rule(g, RV_RULE_KUIKAE_FORBIDDEN);
+  // Which neighbours a chi needs (shimocha only, number suits; no chi in 3P: state_3p/legal_actions.rs:386)
+  const bool chi_seat = np == 4 && i == (pid + 1) % np && su < 3;
+  auto at = [&](int r) -> int { return (r < 0 || r > 8) ? 0 : (int)((sc >> (4 * r)) & 15); };
+  int m2 = 0, m1 = 0, p1 = 0, p2 = 0;
+  if (chi_seat) m2 = at(r9 - 2), m1 = at(r9 - 1), p1 = at(r9 + 1), p2 = at(r9 + 2);
+  const bool chi_any = (m2 && m1) || (m1 && p1) || (p1 && p2);
+  if (n_same < 2 && !chi_any) return missed;
+  // ONE pass over the hand collects, in hand order, the tile ids of the five kinds involved (kind-2 .. kind+2): a byte
+  // queue per kind, packed in a 32-bit word (at most four copies).  The claim lists below are cross products of these.
+  uint32_t q[5] = {0, 0, 0, 0, 0};
+  int qn[5] = {0, 0, 0, 0, 0};
+  #pragma unroll 1
+  for (int k = 0; k < hl; k++) {
+    const int t = g.hand[i][k];
+    const unsigned d = (unsigned)((t >> 2) - kind + 2);
+    if (d < 5u) {   // (a neighbour kind across a suit boundary is collected but never used: its pattern is off)
+      #pragma unroll
+      for (int e = 0; e < 5; e++)
+        if (d == (unsigned)e && qn[e] < 4) q[e] |= (uint32_t)t << (8 * qn[e]), qn[e]++;
+    }
+  }
   // 2. Pon / Daiminkan
   if (n_same >= 2) {
     RV_STAT(7);
-    uint8_t match[4];
-    int cnt = 0;
-    #pragma unroll 1
-    for (int k = 0; k < hl; k++) {
-      int t = g.hand[i][k];
-      if ((t >> 2) == kind && cnt < 4) match[cnt++] = (uint8_t)t;
-    }
+    const int cnt = qn[2];
     // kuikae: some tile other than the consumed pair must be discardable (legal_actions.rs:316-338)
     bool ok = kuikae ? (hl - cnt) > 0 : true;
     if (ok)
       #pragma unroll 1
       for (int a = 0; a < cnt; a++)
         #pragma unroll 1
-        for (int b = a + 1; b < cnt; b++) claim_push(g, i, pack_act(RV_PON, tile, match[a], match[b]));
-    if (cnt >= 3) claim_push(g, i, pack_act(RV_DAIMINKAN, tile, match[0], match[1]));
+        for (int b = a + 1; b < cnt; b++) claim_push(g, i, pack_act(RV_PON, tile, (q[2] >> (8 * a)) & 0xFF, (q[2] >> (8 * b)) & 0xFF));
+    if (cnt >= 3) claim_push(g, i, pack_act(RV_DAIMINKAN, tile, q[2] & 0xFF, (q[2] >> 8) & 0xFF));
   }
-  // 3. Chi (shimocha only, number suits)
-  if (np == 4 && i == (pid + 1) % np && su < 3) {   // no chi in 3P (state_3p/legal_actions.rs:386)
-    auto at = [&](int r) -> int { return (r < 0 || r > 8) ? 0 : (int)((sc >> (4 * r)) & 15); };
-    int m2 = at(r9 - 2), m1 = at(r9 - 1), p1 = at(r9 + 1), p2 = at(r9 + 2);
-    if ((m2 && m1) || (m1 && p1) || (p1 && p2)) {
-      RV_STAT(8);
+  // 3. Chi
+  if (chi_any) {
+    RV_STAT(8);
+    #pragma unroll 1
+    for (int pat = 0; pat < 3; pat++) {
+      int forb2 = -1;
+      if (pat == 0) { if (!(m2 && m1)) continue; if (r9 >= 3) forb2 = kind - 3; }
+      else if (pat == 1) { if (!(m1 && p1)) continue; }
+      else { if (!(p1 && p2)) continue; if (r9 <= 5) forb2 = kind + 3; }
+      // leftover tiles (hand minus c1,c2) need one tile that is neither `kind` nor forb2 (legal_actions.rs:394-431)
+      int free_tiles = hl;
+      if (kuikae) free_tiles -= n_same + (forb2 >= 0 ? at(forb2 - 9 * su) : 0);
+      if (free_tiles - 2 <= 0) continue;
+      const uint32_t qa = pat == 0 ? q[0] : pat == 1 ? q[1] : q[3], qb = pat == 0 ? q[1] : pat == 1 ? q[3] : q[4];
+      const int na = pat == 0 ? qn[0] : pat == 1 ? qn[1] : qn[3], nb = pat == 0 ? qn[1] : pat == 1 ? qn[3] : qn[4];
       #pragma unroll 1
-      for (int pat = 0; pat < 3; pat++) {
-        int ka, kb, forb2 = -1;
-        if (pat == 0) { if (!(m2 && m1)) continue; ka = kind - 2; kb = kind - 1; if (r9 >= 3) forb2 = kind - 3; }
-        else if (pat == 1) { if (!(m1 && p1)) continue; ka = kind - 1; kb = kind + 1; }
-        else { if (!(p1 && p2)) continue; ka = kind + 1; kb = kind + 2; if (r9 <= 5) forb2 = kind + 3; }
-        // leftover tiles (hand minus c1,c2) need one tile that is neither `kind` nor forb2 (legal_actions.rs:394-431)
-        int free_tiles = hl;
-        if (kuikae) free_tiles -= n_same + (forb2 >= 0 ? at(forb2 - 9 * su) : 0);
-        if (free_tiles - 2 <= 0) continue;
-        // one pass over the hand collects the candidate tile ids (hand order), then the cross product
-        uint8_t ta[4], tb[4];
-        int na = 0, nb = 0;
+      for (int a = 0; a < na; a++)
         #pragma unroll 1
-        for (int k = 0; k < hl; k++) {
-          int t = g.hand[i][k], tk = t >> 2;
-          if (tk == ka && na < 4) ta[na++] = (uint8_t)t;
-          if (tk == kb && nb < 4) tb[nb++] = (uint8_t)t;
-        }
-        #pragma unroll 1
-        for (int a = 0; a < na; a++)
-          #pragma unroll 1
-          for (int b = 0; b < nb; b++) claim_push(g, i, pack_act(RV_CHI, tile, ta[a], tb[b]));
-      }
+        for (int b = 0; b < nb; b++) claim_push(g, i, pack_act(RV_CHI, tile, (qa >> (8 * a)) & 0xFF, (qb >> (8 * b)) & 0xFF));
     }
   }
   return missed;
@@ -1559,10 +1563,15 @@ __device__ __noinline__ void resp_ron(const Ctx& cx, G& g, int ron_mask) {
 __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_action* acts) {
   const int np = num_players(g);
   // missed agari (state/mod.rs:902-917): every seat holding a Ron claim (stale ones included) that did not ron
+  // (a Ron claim is either the first entry of a list — gen_claims pushes it before the calls — or was appended to a
+  // possibly stale list by chankan_ronners: looking at the two ends is the same as scanning the list)
   for (int p = 0; p < np; p++) {
+    const int nc = g.n_claims[p];
     bool has_ron = false;
-    for (int k = 0; k < g.n_claims[p]; k++)
-      if ((cold(g).claims[p][k] & 0xFF) == RV_RON) has_ron = true;
+    if (nc > 0) {
+      const uint32_t* cl = cold(g).claims[p];
+      has_ron = (cl[0] & 0xFF) == RV_RON || (cl[nc - 1] & 0xFF) == RV_RON;
+    }
     if (has_ron && acts[p].type != RV_RON) {
       g.flags[p] |= RV_F_MISSED_AGARI_DOUJUN;
       if (g.flags[p] & RV_F_RIICHI_DECLARED) g.flags[p] |= RV_F_MISSED_AGARI_RIICHI;
