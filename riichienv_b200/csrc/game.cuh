@@ -419,30 +419,37 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   g.pending_tail[0] = RV_NONE;
   g.pending_tail[1] = 0;
   const int wl = np == 3 ? 108 : 136;
+  // The wall is built in a local array, written to the record with 8-byte stores and DEALT FROM THE LOCAL COPY: reading the
+  // 53 dealt tiles back from the record one byte at a time was a chain of 53 dependent L2 round trips (the cold part of the
+  // record lives in global memory) — most of the 17 k cycles a deal took in the rollout's DEAL class.
+  alignas(8) uint8_t w[136];
   if (custom_wall) {
-    for (int i = 0; i < wl; i++) cold(g).wall[i] = custom_wall[wl - 1 - i];  // wall.rs:69-72 / state_3p/wall.rs:148-149
+    for (int i = 0; i < wl; i++) w[i] = custom_wall[wl - 1 - i];  // wall.rs:69-72 / state_3p/wall.rs:148-149
   } else {
-    uint8_t w[136];
     wall_from_seed(g.seed, g.hand_index, wl, w);
     g.hand_index++;
-    for (int i = 0; i < wl; i++) cold(g).wall[i] = w[i];
   }
-  for (int i = wl; i < 136; i++) cold(g).wall[i] = RV_NONE;
+  for (int i = wl; i < 136; i++) w[i] = RV_NONE;
+  {
+    uint64_t* dst = reinterpret_cast<uint64_t*>(cold(g).wall);          // offset RV_HOT_BYTES of a 16-byte aligned record
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(w);
+    for (int i = 0; i < 136 / 8; i++) dst[i] = src[i];
+  }
   g.wall_len = (uint8_t)wl;
   g.wall_top = (uint8_t)wl;
   g.n_dora = 1;
-  g.dora_ind[0] = cold(g).wall[np == 3 ? 8 : 4];   // state_3p/wall.rs:104-112
+  g.dora_ind[0] = w[np == 3 ? 8 : 4];   // state_3p/wall.rs:104-112
   for (int i = 1; i < 5; i++) g.dora_ind[i] = RV_NONE;
   g.kyoku_count++;
   // deal: 3 x (4 tiles per seat from oya), then 1 each; tiles pop from the back
   for (int r = 0; r < 3; r++)
     for (int idx = 0; idx < np; idx++) {
       int p = (idx + oya) % np;
-      for (int k = 0; k < 4; k++) hand_push(g, p, cold(g).wall[--g.wall_top]);
+      for (int k = 0; k < 4; k++) hand_push(g, p, w[--g.wall_top]);
     }
   for (int idx = 0; idx < np; idx++) {
     int p = (idx + oya) % np;
-    hand_push(g, p, cold(g).wall[--g.wall_top]);
+    hand_push(g, p, w[--g.wall_top]);
   }
   for (int p = 0; p < np; p++) {
     hand_sort(g, p);
@@ -450,11 +457,11 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   }
   g.drawable_count = (uint8_t)(g.wall_top - 14);
   {  // start_kyoku: 4P 19 words, 3P 15 words (np scores, 13*np tehai bytes)
-    uint32_t w[19];
+    uint32_t ew[19];
     const int nb = 13 * np, ntw = (nb + 3) / 4, nwords = 2 + np + ntw;
-    w[0] = ev_w0(RV_EV_START_KYOKU, nwords, round_wind % 4, oya);
-    w[1] = (uint32_t)honba | ((uint32_t)g.dora_ind[0] << 8) | ((kyotaku & 0xFFFF) << 16);
-    for (int i = 0; i < np; i++) w[2 + i] = (uint32_t)g.score[i];
+    ew[0] = ev_w0(RV_EV_START_KYOKU, nwords, round_wind % 4, oya);
+    ew[1] = (uint32_t)honba | ((uint32_t)g.dora_ind[0] << 8) | ((kyotaku & 0xFFFF) << 16);
+    for (int i = 0; i < np; i++) ew[2 + i] = (uint32_t)g.score[i];
     for (int k = 0; k < ntw; k++) {
       uint32_t v = 0;
       for (int b = 0; b < 4; b++) {
@@ -462,14 +469,14 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
         int t = flat < nb ? g.hand[flat / 13][flat % 13] : RV_NONE;
         v |= (uint32_t)t << (8 * b);
       }
-      w[2 + np + k] = v;
+      ew[2 + np + k] = v;
     }
-    ev_push(cx, g, w, nwords);
+    ev_push(cx, g, ew, nwords);
   }
   g.phase = RV_WAIT_ACT;
   g.active_mask = (uint8_t)(1u << oya);
   {
-    int t = cold(g).wall[--g.wall_top];
+    int t = w[--g.wall_top];
     g.drawable_count--;
     hand_push(g, oya, t);
     g.drawn_tile = (uint8_t)t;
