@@ -214,9 +214,9 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 struct ChaCha12 {
   uint32_t key[8];
-  uint32_t buf[16];
+  uint32_t buf[64];     // output words of blocks 0..3, in order.  A 136-tile shuffle draws at most 28 chunks x 2 words.
   uint64_t counter;
-  int idx;
+  int idx, filled;
   __host__ __device__ static inline uint32_t rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
   __host__ __device__ inline void init(uint64_t state) {
     // rand_core SeedableRng::seed_from_u64: PCG32 (XSH-RR) expansion
@@ -227,9 +227,14 @@ struct ChaCha12 {
       key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
     }
     counter = 0;
-    idx = 16;
+    idx = 0;
+    filled = 0;
+    // Three blocks up front, the same instructions in every lane of a warp: drawn on demand, the lanes of a warp cross a block
+    // boundary at different iterations (the bias-correction draw of random_below is data dependent), so each refill ran
+    // with a handful of lanes active — ~10 block computations per warp and shuffle instead of 3.
+    for (int b = 0; b < 3; b++) refill();
   }
-  __host__ __device__ inline void refill() {
+  __host__ __device__ inline void refill() {   // appends block `counter`
     uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
                        key[4], key[5], key[6], key[7], (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
     uint32_t s[16];
@@ -242,13 +247,14 @@ struct ChaCha12 {
       RV_QR(0, 5, 10, 15) RV_QR(1, 6, 11, 12) RV_QR(2, 7, 8, 13) RV_QR(3, 4, 9, 14)
     }
 #undef RV_QR
-    for (int i = 0; i < 16; i++) buf[i] = s[i] + in[i];
+    const int o = filled & 63;            // (a fifth block cannot be needed; the mask only keeps the store in bounds)
+    for (int i = 0; i < 16; i++) buf[o + i] = s[i] + in[i];
     counter++;
-    idx = 0;
+    filled += 16;
   }
   __host__ __device__ inline uint32_t next_u32() {
-    if (idx >= 16) refill();
-    return buf[idx++];
+    if (idx >= filled) refill();
+    return buf[(idx++) & 63];
   }
 };
 // rand UniformInt<u32>::sample_single_inclusive(0, range-1): widening multiply + one bias-correction draw
@@ -263,7 +269,10 @@ __host__ __device__ inline uint32_t random_below(ChaCha12& rng, uint32_t range) 
 }
 // SliceRandom::shuffle via IncreasingUniform (one u32 draw feeds several indices), then reverse.
 // `out` receives the reference's `wall.tiles` order.  n = 136 (4P) or 108 (3P tile set).
+__host__ __device__ __forceinline__ uint32_t rv_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 __host__ __device__ __noinline__ void wall_from_seed(uint64_t seed, uint64_t hand_index, int n, uint8_t* out) {
+  static const uint32_t RECIP[137] = {   // floor(2^32 / d) (d = 1: 2^32 - 1; the fix-ups below absorb the difference)
+      0u, 0xFFFFFFFFu, 2147483648u, 1431655765u, 1073741824u, 858993459u, 715827882u, 613566756u, 536870912u, 477218588u, 429496729u, 390451572u, 357913941u, 330382099u, 306783378u, 286331153u, 268435456u, 252645135u, 238609294u, 226050910u, 214748364u, 204522252u, 195225786u, 186737708u, 178956970u, 171798691u, 165191049u, 159072862u, 153391689u, 148102320u, 143165576u, 138547332u, 134217728u, 130150524u, 126322567u, 122713351u, 119304647u, 116080197u, 113025455u, 110127366u, 107374182u, 104755299u, 102261126u, 99882960u, 97612893u, 95443717u, 93368854u, 91382282u, 89478485u, 87652393u, 85899345u, 84215045u, 82595524u, 81037118u, 79536431u, 78090314u, 76695844u, 75350303u, 74051160u, 72796055u, 71582788u, 70409299u, 69273666u, 68174084u, 67108864u, 66076419u, 65075262u, 64103989u, 63161283u, 62245902u, 61356675u, 60492497u, 59652323u, 58835168u, 58040098u, 57266230u, 56512727u, 55778796u, 55063683u, 54366674u, 53687091u, 53024287u, 52377649u, 51746593u, 51130563u, 50529027u, 49941480u, 49367440u, 48806446u, 48258059u, 47721858u, 47197442u, 46684427u, 46182444u, 45691141u, 45210182u, 44739242u, 44278013u, 43826196u, 43383508u, 42949672u, 42524428u, 42107522u, 41698711u, 41297762u, 40904450u, 40518559u, 40139881u, 39768215u, 39403369u, 39045157u, 38693399u, 38347922u, 38008560u, 37675151u, 37347541u, 37025580u, 36709122u, 36398027u, 36092162u, 35791394u, 35495597u, 35204649u, 34918433u, 34636833u, 34359738u, 34087042u, 33818640u, 33554432u, 33294320u, 33038209u, 32786009u, 32537631u, 32292987u, 32051994u, 31814572u, 31580641u};
   uint8_t w[136];
   if (n == 136) {
     for (int i = 0; i < 136; i++) w[i] = (uint8_t)i;
@@ -297,8 +306,14 @@ __host__ __device__ __noinline__ void wall_from_seed(uint64_t seed, uint64_t han
     if (rem == 0) {
       j = chunk;
     } else {
-      j = chunk % next_n;
-      chunk /= next_n;
+      // chunk / next_n and chunk % next_n without an integer division (~25 instructions each on the GPU, 108 of them per
+      // shuffle): q = hi32(chunk * floor(2^32 / d)) is q or short of it by at most 2
+      uint32_t q = rv_umulhi(chunk, RECIP[next_n]);
+      uint32_t r = chunk - q * next_n;
+      if (r >= next_n) r -= next_n, q++;
+      if (r >= next_n) r -= next_n, q++;
+      j = r;
+      chunk = q;
     }
     remaining = rem;
     cur_n = next_n;
