@@ -99,13 +99,11 @@ typedef struct rv_game_state {
   uint64_t c_river_kinds[RV_NP];  /* bit k: some own discard has kind k (furiten test)                     */
   uint64_t c_waits[RV_NP];        /* get_waits_u8 of the seat's hand when it is 13-tile-equivalent, else 0 */
   uint64_t seed;                  /* wall.seed */
-  uint64_t hand_index;            /* wall.hand_index */
   uint64_t ev_hash;               /* FNV-1a-64 over the 32-bit words of the binary event stream */
   uint32_t c_key[RV_NP][4];       /* base-5 suit keys of c_cnt (table indices)                             */
   uint32_t river_tedashi[RV_NP];  /* bit i = discard_from_hand[i] */
   uint32_t river_riichi[RV_NP];   /* bit i = discard_is_riichi[i] */
   int32_t score[RV_NP];
-  int32_t score_delta[RV_NP];
   uint32_t riichi_sticks;
   uint32_t turn_count;
   /* counters (not in the reference): */
@@ -118,13 +116,10 @@ typedef struct rv_game_state {
   uint8_t hand_len[RV_NP];
   uint8_t meld_tiles[RV_NP][4][4];  /* tids, order as stored by the reference (sorted); RV_NONE pad */
   uint8_t meld_type[RV_NP][4];      /* rv_meld_type */
-  uint8_t meld_from[RV_NP][4];      /* from_who, RV_NONE == -1 */
-  uint8_t meld_called[RV_NP][4];    /* called_tile or RV_NONE */
   uint8_t n_melds[RV_NP];
   uint8_t n_river[RV_NP];
   uint8_t riichi_decl_idx[RV_NP];   /* riichi_declaration_index or RV_NONE */
   uint8_t flags[RV_NP];             /* RV_F_* */
-  uint8_t pao[RV_NP][2];            /* [seat][0]: liable seat for yaku 37, [1]: for yaku 50; RV_NONE */
   uint8_t forbidden[RV_NP][2];      /* forbidden_discards (tids), RV_NONE pad */
   uint8_t riichi_sutehai[RV_NP];    /* state/mod.rs:89 */
   uint8_t last_tedashi[RV_NP];      /* state/mod.rs:90 */
@@ -159,9 +154,15 @@ typedef struct rv_game_state {
   uint8_t river[RV_NP][RV_RIVER_CAP]; /* discards */
   /* current_claims (state/mod.rs:47): packed type | tile<<8 | c0<<16 | c1<<24 */
   uint32_t claims[RV_NP][RV_MAX_CLAIMS];
+  /* fields a step rarely reads: kept out of the staged prefix so that more games fit in an SM's shared memory */
+  uint64_t hand_index;              /* wall.hand_index */
+  int32_t score_delta[RV_NP];
+  uint8_t meld_from[RV_NP][4];      /* from_who, RV_NONE == -1 */
+  uint8_t meld_called[RV_NP][4];    /* called_tile or RV_NONE */
+  uint8_t pao[RV_NP][2];            /* [seat][0]: liable seat for yaku 37, [1]: for yaku 50; RV_NONE */
   uint8_t reserved[8];            /* keeps sizeof a multiple of 16 (bulk-copy granularity) */
 } rv_game_state;
-#define RV_HOT_BYTES 640          /* == offsetof(rv_game_state, wall); a multiple of 16 */
+#define RV_HOT_BYTES 576          /* == offsetof(rv_game_state, wall); a multiple of 16 */
 
 /* ---- binary event stream (replaces _push_mjai_event, state/mod.rs:2094-2148)
  * A sequence of 32-bit words.  word0 = type | nwords<<8 | a<<16 | b<<24.

@@ -52,15 +52,15 @@ class GameState(C.Structure):
     _fields_ = [
         # hot part (first HOT_BYTES bytes)
         ("c_cnt", (u64 * 4) * NP), ("c_river_kinds", u64 * NP), ("c_waits", u64 * NP),
-        ("seed", u64), ("hand_index", u64), ("ev_hash", u64),
+        ("seed", u64), ("ev_hash", u64),
         ("c_key", (u32 * 4) * NP), ("river_tedashi", u32 * NP), ("river_riichi", u32 * NP),
-        ("score", i32 * NP), ("score_delta", i32 * NP),
+        ("score", i32 * NP),
         ("riichi_sticks", u32), ("turn_count", u32),
         ("step_count", u32), ("kyoku_count", u32), ("ev_count", u32), ("ev_words", u32),
         ("hand", (u8 * HAND_CAP) * NP), ("hand_len", u8 * NP), ("meld_tiles", ((u8 * 4) * 4) * NP),
-        ("meld_type", (u8 * 4) * NP), ("meld_from", (u8 * 4) * NP), ("meld_called", (u8 * 4) * NP),
+        ("meld_type", (u8 * 4) * NP),
         ("n_melds", u8 * NP), ("n_river", u8 * NP), ("riichi_decl_idx", u8 * NP), ("flags", u8 * NP),
-        ("pao", (u8 * 2) * NP), ("forbidden", (u8 * 2) * NP), ("riichi_sutehai", u8 * NP), ("last_tedashi", u8 * NP),
+        ("forbidden", (u8 * 2) * NP), ("riichi_sutehai", u8 * NP), ("last_tedashi", u8 * NP),
         ("wall_len", u8), ("wall_top", u8), ("rinshan_draw_count", u8),
         ("pending_kan_dora_count", u8), ("drawable_count", u8), ("n_dora", u8), ("dora_ind", u8 * 5), ("phase", u8),
         ("current_player", u8), ("oya", u8), ("honba", u8), ("kyoku_idx", u8),
@@ -72,11 +72,12 @@ class GameState(C.Structure):
         ("pending_tail", u8 * 2), ("hot_reserved", u8 * 14),
         # cold part
         ("wall", u8 * 136), ("river", (u8 * RIVER_CAP) * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
-        ("reserved", u8 * 8),
+        ("hand_index", u64), ("score_delta", i32 * NP), ("meld_from", (u8 * 4) * NP), ("meld_called", (u8 * 4) * NP),
+        ("pao", (u8 * 2) * NP), ("reserved", u8 * 8),
     ]
 
 
-HOT_BYTES = 640
+HOT_BYTES = 576
 assert GameState.wall.offset == HOT_BYTES and C.sizeof(GameState) % 16 == 0
 
 

@@ -352,7 +352,7 @@ __device__ __noinline__ void accept_riichi(const Ctx& cx, G& g) {
   int p = g.riichi_pending_acceptance;
   if (p != RV_NONE) {
     g.score[p] -= 1000;
-    g.score_delta[p] -= 1000;
+    cold(g).score_delta[p] -= 1000;
     g.riichi_sticks += 1;
     g.flags[p] |= RV_F_RIICHI_DECLARED | RV_F_IPPATSU_CYCLE;
     ev_simple(cx, g, RV_EV_REACH_ACCEPTED, p);
@@ -397,7 +397,7 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
     g.hand_len[p] = 0;
     for (int m = 0; m < 4; m++) {
       for (int k = 0; k < 4; k++) g.meld_tiles[p][m][k] = RV_NONE;
-      g.meld_type[p][m] = g.meld_from[p][m] = g.meld_called[p][m] = RV_NONE;
+      g.meld_type[p][m] = cold(g).meld_from[p][m] = cold(g).meld_called[p][m] = RV_NONE;
     }
     g.n_melds[p] = 0;
     for (int i = 0; i < RV_RIVER_CAP; i++) cold(g).river[p][i] = RV_NONE;
@@ -405,9 +405,9 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
     g.river_tedashi[p] = g.river_riichi[p] = 0;
     g.riichi_decl_idx[p] = RV_NONE;
     g.flags[p] = RV_F_NAGASHI_ELIGIBLE;
-    g.pao[p][0] = g.pao[p][1] = RV_NONE;
+    cold(g).pao[p][0] = cold(g).pao[p][1] = RV_NONE;
     g.forbidden[p][0] = g.forbidden[p][1] = RV_NONE;
-    g.score_delta[p] = 0;
+    cold(g).score_delta[p] = 0;
     g.n_claims[p] = 0;
     g.riichi_sutehai[p] = g.last_tedashi[p] = RV_NONE;
     g.n_kita[p] = 0;
@@ -441,8 +441,8 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   if (custom_wall) {
     for (int i = 0; i < wl; i++) w[i] = custom_wall[wl - 1 - i];  // wall.rs:69-72 / state_3p/wall.rs:148-149
   } else {
-    wall_from_seed(g.seed, g.hand_index, wl, w);
-    g.hand_index++;
+    wall_from_seed(g.seed, cold(g).hand_index, wl, w);
+    cold(g).hand_index++;
   }
   for (int i = wl; i < 136; i++) w[i] = RV_NONE;
   {
@@ -606,9 +606,9 @@ __device__ __noinline__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason) {
           if (i == w) continue;
           int32_t pay = is_oya ? 4000 : (i == oya ? 4000 : 2000);
           g.score[i] -= pay;
-          g.score_delta[i] -= pay;
+          cold(g).score_delta[i] -= pay;
           g.score[w] += pay;
-          g.score_delta[w] += pay;
+          cold(g).score_delta[w] += pay;
         }
       }
     } else {
@@ -620,7 +620,7 @@ __device__ __noinline__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason) {
         for (int i = 0; i < np; i++) {
           int32_t d = tenpai[i] ? pk : -pn;
           g.score[i] += d;
-          g.score_delta[i] = d;
+          cold(g).score_delta[i] = d;
         }
       }
     }
@@ -631,13 +631,13 @@ __device__ __noinline__ void trigger_ryukyoku(const Ctx& cx, G& g, int reason) {
       if (pid == oya) d = (i == pid) ? -4000 * (np - 1) : 4000;
       else d = (i == pid) ? -(4000 + 2000 * (np - 2)) : (i == oya ? 4000 : 2000);
       g.score[i] += d;
-      g.score_delta[i] = d;
+      cold(g).score_delta[i] = d;
     }
   }
   bool renchan = final_reason == RV_RK_EXHAUSTIVE ? tenpai[oya]
                : final_reason == RV_RK_NAGASHI ? ((nagashi_mask >> oya) & 1) != 0 : true;
-  uint32_t w[5] = {ev_w0(RV_EV_RYUKYOKU, 1 + np, final_reason, 0), (uint32_t)g.score_delta[0], (uint32_t)g.score_delta[1],
-                   (uint32_t)g.score_delta[2], (uint32_t)g.score_delta[3]};
+  uint32_t w[5] = {ev_w0(RV_EV_RYUKYOKU, 1 + np, final_reason, 0), (uint32_t)cold(g).score_delta[0], (uint32_t)cold(g).score_delta[1],
+                   (uint32_t)cold(g).score_delta[2], (uint32_t)cold(g).score_delta[3]};
   ev_push(cx, g, w, 1 + np);
   next_round(cx, g, renchan, true);
 }
@@ -1107,9 +1107,9 @@ __device__ __noinline__ void register_pao(G& g, int claimer, int tile, int disca
     if (t >= 27 && t <= 30) winds++;
   }
   if (tv >= 31 && tv <= 33) {
-    if (dragons == 3) g.pao[claimer][0] = (uint8_t)discarder;
+    if (dragons == 3) cold(g).pao[claimer][0] = (uint8_t)discarder;
   } else if (tv >= 27 && tv <= 30) {
-    if (winds == 4) g.pao[claimer][1] = (uint8_t)discarder;
+    if (winds == 4) cold(g).pao[claimer][1] = (uint8_t)discarder;
   }
 }
 __device__ __forceinline__ int yakuman_val(const G& g, int yid) {
@@ -1170,15 +1170,15 @@ __device__ __noinline__ void resolve_kan(const Ctx& cx, G& g, int pid, const rv_
       for (int k = 0; k < act.n_consume && k < 4; k++) tl[n++] = act.consume[k];
       if (act.type == RV_ANKAN) {
         g.meld_type[pid][m] = RV_MELD_ANKAN;
-        g.meld_from[pid][m] = RV_NONE;
-        g.meld_called[pid][m] = RV_NONE;
+        cold(g).meld_from[pid][m] = RV_NONE;
+        cold(g).meld_called[pid][m] = RV_NONE;
       } else {
         if (n < 4) tl[n++] = g.last_discard_tile;
         for (int x = 1; x < n; x++)
           for (int y = x; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
         g.meld_type[pid][m] = RV_MELD_DAIMINKAN;
-        g.meld_from[pid][m] = g.last_discard_pid;
-        g.meld_called[pid][m] = g.last_discard_tile;
+        cold(g).meld_from[pid][m] = g.last_discard_pid;
+        cold(g).meld_called[pid][m] = g.last_discard_tile;
       }
       for (int k = 0; k < 4; k++) g.meld_tiles[pid][m][k] = tl[k];
       g.n_melds[pid] = (uint8_t)(m + 1);
@@ -1463,7 +1463,7 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
             m &= m - 1;
             int v = yakuman_val(g, y);
             total_val += v;
-            int liable = y == 37 ? g.pao[pid][0] : y == 50 ? g.pao[pid][1] : RV_NONE;
+            int liable = y == 37 ? cold(g).pao[pid][0] : y == 50 ? cold(g).pao[pid][1] : RV_NONE;
             if (liable != RV_NONE) { pao_val += v; pao_payer = liable; }
           }
         }
@@ -1500,7 +1500,7 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
         d[pid] += total_win;
         for (int i = 0; i < np; i++) {
           g.score[i] += d[i];
-          g.score_delta[i] = d[i];
+          cold(g).score_delta[i] = d[i];
         }
         ev_hora(cx, g, pid, pid, true, r, d, riichi);
         next_round(cx, g, pid == oya, false);
@@ -1552,7 +1552,7 @@ __device__ __noinline__ void resp_ron(const Ctx& cx, G& g, int ron_mask) {
           m &= m - 1;
           int v = yakuman_val(g, y);
           total_val += v;
-          int liable = y == 37 ? g.pao[w][0] : y == 50 ? g.pao[w][1] : RV_NONE;
+          int liable = y == 37 ? cold(g).pao[w][0] : y == 50 ? cold(g).pao[w][1] : RV_NONE;
           if (liable != RV_NONE) { has_pao = true; pao_payer = liable; pao_val += v; }
         }
         if (has_pao) {
@@ -1578,7 +1578,7 @@ __device__ __noinline__ void resp_ron(const Ctx& cx, G& g, int ron_mask) {
   }
   for (int i = 0; i < np; i++) {
     g.score[i] += total[i];
-    g.score_delta[i] = total[i];
+    cold(g).score_delta[i] = total[i];
   }
   next_round(cx, g, oya_won, false);
 }
@@ -1644,8 +1644,8 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
         for (int y = x; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t t = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = t; }
       for (int k = 0; k < 4; k++) g.meld_tiles[claimer][m][k] = tl[k];
       g.meld_type[claimer][m] = act.type == RV_PON ? RV_MELD_PON : RV_MELD_CHI;
-      g.meld_from[claimer][m] = (uint8_t)discarder;
-      g.meld_called[claimer][m] = (uint8_t)tile;
+      cold(g).meld_from[claimer][m] = (uint8_t)discarder;
+      cold(g).meld_called[claimer][m] = (uint8_t)tile;
       g.n_melds[claimer] = (uint8_t)(m + 1);
     } else {
       g.overflow = 1;

@@ -481,10 +481,10 @@ __device__ __forceinline__ void obs_ext_shanten_warp(const Tables& T, const G& g
 
 // One warp, one row: base gather + describe (obs.cuh), extended describe, then 3,655 eight-byte streaming stores
 // (a 29,240-byte row is 8-byte aligned; 34 columns = 17 pairs, so a pair never straddles two channels).
-__device__ __forceinline__ void obs_ext_encode_warp(const Tables& T, const DecayTab& D, const G& g, const uint8_t* river, int pid,
+__device__ __forceinline__ void obs_ext_encode_warp(const Tables& T, const DecayTab& D, const G& g, const G& rec, const uint8_t* river, int pid,
                                                     uint32_t avail, float* dst, ObsScratch& S, ObsExtScratch& X, int lane) {
   int called = 0;                                 // channel 30 of encode_base_into: called melds count one tile short
-  if (lane < 16 && (lane & 3) < g.n_melds[lane >> 2] && g.meld_called[lane >> 2][lane & 3] != RV_NONE) called = 1;
+  if (lane < 16 && (lane & 3) < g.n_melds[lane >> 2] && rec.meld_called[lane >> 2][lane & 3] != RV_NONE) called = 1;   // `rec`: the HBM record (cold field)
   called = __popc(__ballot_sync(0xFFFFFFFFu, called));
   obs_describe_warp<false>(g, river, pid, S, lane, called);
   for (int i = lane; i < 4 * 36; i += 32) (&X.decay[0][0])[i] = 0.0f;

@@ -411,11 +411,11 @@ __global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, 
 // ---- shared-memory staging of the hot prefix (per-lane bulk copies, TMA engine) ----
 // A lane's game record is 13 cache lines of HBM and a step touches most of the hot ones through dependent, uncoalesced
 // loads (every warp-level load waits for its slowest lane: ncu showed ~20 warps stalled on long_scoreboard per issue).
-// So each lane pulls its record's hot prefix (RV_HOT_BYTES = 624 B) into shared memory with ONE cp.async.bulk, all 32
+// So each lane pulls its record's hot prefix (RV_HOT_BYTES = 576 B) into shared memory with ONE cp.async.bulk, all 32
 // copies of the warp in flight together, runs the step(s) there, and writes the prefix back with one bulk store.
 // The cold arrays (wall, river, claims) stay in HBM; game code reaches them through cold(g) (game.cuh).
 constexpr int PHB = 32;                              // threads (= games) per block: one warp, own barrier, own exit
-constexpr int STG_STRIDE = RV_HOT_BYTES + 32;        // 656 B = 164 words (== 4 mod 32: same-field accesses are 4-way conflicts)
+constexpr int STG_STRIDE = RV_HOT_BYTES + 16;        // 592 B = 148 words (== 20 mod 32, gcd 4: same-field accesses are 4-way conflicts)
 static_assert(offsetof(G, river) % 8 == 0, "river alignment");
 static_assert(offsetof(G, wall) == RV_HOT_BYTES && RV_HOT_BYTES % 16 == 0 && sizeof(G) % 16 == 0, "hot prefix layout");
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(128) legal_ids_kernel(Tables T, const G* state
 // (A persistent variant — 8 blocks per SM, each warp walking several games with the next record prefetched into registers —
 // measured slower, 194 us against 157 us per 65,536 rows: with one short-lived warp per game the block scheduler keeps
 // every SM topped up and other warps cover the one remaining round trip.)
-constexpr int OBS_STAGE_BYTES = RV_HOT_BYTES + MAXP * RV_RIVER_CAP;   // 640 + 128
+constexpr int OBS_STAGE_BYTES = RV_HOT_BYTES + MAXP * RV_RIVER_CAP;   // 576 + 128
 template <bool SANMA>
 __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int64_t n, const int32_t* offsets, const uint32_t* idbits,
                                                             float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
@@ -928,10 +928,10 @@ __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int
     const uint4 a = __ldcs(src + lane);                                      // hot bytes 0..511
     uint4 b = make_uint4(0, 0, 0, 0);
     uint2 r = make_uint2(0, 0);
-    if (lane < 8) b = __ldcs(src + 32 + lane);                               // hot bytes 512..639
+    if (lane < (RV_HOT_BYTES - 512) / 16) b = __ldcs(src + 32 + lane);      // hot bytes 512..RV_HOT_BYTES-1
     else if (lane >= 16) r = __ldcs(riv + (lane - 16));                      // rivers, 16 x 8 bytes
     dst[lane] = a;
-    if (lane < 8) dst[32 + lane] = b;
+    if (lane < (RV_HOT_BYTES - 512) / 16) dst[32 + lane] = b;
     else if (lane >= 16) reinterpret_cast<uint2*>(staged[w] + RV_HOT_BYTES)[lane - 16] = r;
   }
   int row = offsets[gi];
@@ -965,10 +965,10 @@ __global__ void __launch_bounds__(128, 6) obs_ext_kernel(Tables T, DecayTab D, c
     const uint4 a = __ldcs(src + lane);
     uint4 b = make_uint4(0, 0, 0, 0);
     uint2 r = make_uint2(0, 0);
-    if (lane < 8) b = __ldcs(src + 32 + lane);
+    if (lane < (RV_HOT_BYTES - 512) / 16) b = __ldcs(src + 32 + lane);
     else if (lane >= 16) r = __ldcs(riv + (lane - 16));
     dst[lane] = a;
-    if (lane < 8) dst[32 + lane] = b;
+    if (lane < (RV_HOT_BYTES - 512) / 16) dst[32 + lane] = b;
     else if (lane >= 16) reinterpret_cast<uint2*>(staged[w] + RV_HOT_BYTES)[lane - 16] = r;
   }
   int row = offsets[gi];
@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(128, 6) obs_ext_kernel(Tables T, DecayTab D, c
     if (!((g.active_mask >> pid) & 1)) continue;
     if (row >= max_obs) break;
     const uint32_t* bits = idbits + ((size_t)gi * MAXP + pid) * 3;
-    if (obs) obs_ext_encode_warp(T, D, g, river, pid, (bits[2] >> OBS_AVAIL_SHIFT) & 0x7FFu, obs + (size_t)row * (OBSX_CH * OBS_W),
+    if (obs) obs_ext_encode_warp(T, D, g, states[gi], river, pid, (bits[2] >> OBS_AVAIL_SHIFT) & 0x7FFu, obs + (size_t)row * (OBSX_CH * OBS_W),
                                  scratch[w], xscratch[w], lane);
     if (mask) obs_mask_row_warp<false>(bits, mask + (size_t)row * OBS_IDS, lane);
     if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
@@ -1655,7 +1655,7 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
     CK(cudaMalloc(&v->d_q_ctl, sizeof(uint32_t) * Q_CTL_WORDS));
     if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
   }
-  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 10);
+  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 11);
   // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 8 = 2 games per
   // warp), warps own RV_ENDGAME_TAKE games each and play them out in place (see the kernel)
   static int eg_quarters = env_int("RV_ENDGAME_Q", 8), eg_take = env_int("RV_ENDGAME_TAKE", 1);
