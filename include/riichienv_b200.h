@@ -108,7 +108,6 @@ typedef struct rv_game_state {
   uint32_t turn_count;
   /* counters (not in the reference): */
   uint32_t step_count;            /* env steps taken (RiichiEnv.step calls that were not no-ops on a done game) */
-  uint32_t kyoku_count;           /* rounds dealt since reset */
   uint32_t ev_count;              /* events pushed since reset */
   uint32_t ev_words;              /* 32-bit words pushed since reset (log length, even when the log is capped/off) */
 
@@ -118,11 +117,8 @@ typedef struct rv_game_state {
   uint8_t meld_type[RV_NP][4];      /* rv_meld_type */
   uint8_t n_melds[RV_NP];
   uint8_t n_river[RV_NP];
-  uint8_t riichi_decl_idx[RV_NP];   /* riichi_declaration_index or RV_NONE */
   uint8_t flags[RV_NP];             /* RV_F_* */
   uint8_t forbidden[RV_NP][2];      /* forbidden_discards (tids), RV_NONE pad */
-  uint8_t riichi_sutehai[RV_NP];    /* state/mod.rs:89 */
-  uint8_t last_tedashi[RV_NP];      /* state/mod.rs:90 */
 
   uint8_t wall_len;               /* 136 (4P) or 108 (3P) */
   uint8_t wall_top;               /* tiles not yet popped from the back (absolute index + 1) */
@@ -141,13 +137,12 @@ typedef struct rv_game_state {
   uint8_t last_error;             /* RV_NONE or offending seat (state/mod.rs:395-399) */
   uint8_t game_mode, rule_bits;
   uint8_t overflow;               /* bit0: a fixed capacity (river/claims/log) was exceeded; bit1: game retired on a dead end */
-  uint8_t n_kita[RV_NP];          /* 3P: kita count per seat */
   uint8_t pending_init[3];        /* {oya, round_wind, honba} of a round whose deal is deferred inside a rollout kernel;
                                      pending_init[0]==RV_NONE outside kernels (always, as seen through this API)      */
   uint8_t n_claims[RV_NP];        /* lengths of claims[] below */
   uint8_t pending_tail[2];        /* {tile, tsumogiri} of a discard whose follow-up (_resolve_discard) is deferred inside a rollout
                                      kernel; pending_tail[0]==RV_NONE outside kernels (always, as seen through this API) */
-  uint8_t hot_reserved[14];
+  uint8_t hot_reserved[2];
 
   /* ---- cold part (offset RV_HOT_BYTES): large arrays touched a byte or a few words at a time ---- */
   uint8_t wall[136];
@@ -160,9 +155,14 @@ typedef struct rv_game_state {
   uint8_t meld_from[RV_NP][4];      /* from_who, RV_NONE == -1 */
   uint8_t meld_called[RV_NP][4];    /* called_tile or RV_NONE */
   uint8_t pao[RV_NP][2];            /* [seat][0]: liable seat for yaku 37, [1]: for yaku 50; RV_NONE */
-  uint8_t reserved[8];            /* keeps sizeof a multiple of 16 (bulk-copy granularity) */
+  uint32_t kyoku_count;             /* rounds dealt since reset (counter, not in the reference) */
+  uint8_t riichi_decl_idx[RV_NP];   /* riichi_declaration_index or RV_NONE */
+  uint8_t riichi_sutehai[RV_NP];    /* state/mod.rs:89 */
+  uint8_t last_tedashi[RV_NP];      /* state/mod.rs:90 */
+  uint8_t n_kita[RV_NP];            /* 3P: kita count per seat */
+  uint8_t reserved[20];             /* keeps sizeof a multiple of 16 (bulk-copy granularity) */
 } rv_game_state;
-#define RV_HOT_BYTES 576          /* == offsetof(rv_game_state, wall); a multiple of 16 */
+#define RV_HOT_BYTES 544          /* == offsetof(rv_game_state, wall); a multiple of 16 */
 
 /* ---- binary event stream (replaces _push_mjai_event, state/mod.rs:2094-2148)
  * A sequence of 32-bit words.  word0 = type | nwords<<8 | a<<16 | b<<24.

@@ -56,11 +56,11 @@ class GameState(C.Structure):
         ("c_key", (u32 * 4) * NP), ("river_tedashi", u32 * NP), ("river_riichi", u32 * NP),
         ("score", i32 * NP),
         ("riichi_sticks", u32), ("turn_count", u32),
-        ("step_count", u32), ("kyoku_count", u32), ("ev_count", u32), ("ev_words", u32),
+        ("step_count", u32), ("ev_count", u32), ("ev_words", u32),
         ("hand", (u8 * HAND_CAP) * NP), ("hand_len", u8 * NP), ("meld_tiles", ((u8 * 4) * 4) * NP),
         ("meld_type", (u8 * 4) * NP),
-        ("n_melds", u8 * NP), ("n_river", u8 * NP), ("riichi_decl_idx", u8 * NP), ("flags", u8 * NP),
-        ("forbidden", (u8 * 2) * NP), ("riichi_sutehai", u8 * NP), ("last_tedashi", u8 * NP),
+        ("n_melds", u8 * NP), ("n_river", u8 * NP), ("flags", u8 * NP),
+        ("forbidden", (u8 * 2) * NP),
         ("wall_len", u8), ("wall_top", u8), ("rinshan_draw_count", u8),
         ("pending_kan_dora_count", u8), ("drawable_count", u8), ("n_dora", u8), ("dora_ind", u8 * 5), ("phase", u8),
         ("current_player", u8), ("oya", u8), ("honba", u8), ("kyoku_idx", u8),
@@ -68,16 +68,17 @@ class GameState(C.Structure):
         ("is_rinshan_flag", u8), ("riichi_pending_acceptance", u8), ("drawn_tile", u8), ("last_discard_pid", u8),
         ("last_discard_tile", u8), ("pending_kan_pid", u8), ("pending_kan_type", u8), ("pending_kan_tile", u8),
         ("active_mask", u8), ("last_error", u8), ("game_mode", u8), ("rule_bits", u8),
-        ("overflow", u8), ("n_kita", u8 * NP), ("pending_init", u8 * 3), ("n_claims", u8 * NP),
-        ("pending_tail", u8 * 2), ("hot_reserved", u8 * 14),
+        ("overflow", u8), ("pending_init", u8 * 3), ("n_claims", u8 * NP),
+        ("pending_tail", u8 * 2), ("hot_reserved", u8 * 2),
         # cold part
         ("wall", u8 * 136), ("river", (u8 * RIVER_CAP) * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
         ("hand_index", u64), ("score_delta", i32 * NP), ("meld_from", (u8 * 4) * NP), ("meld_called", (u8 * 4) * NP),
-        ("pao", (u8 * 2) * NP), ("reserved", u8 * 8),
+        ("pao", (u8 * 2) * NP), ("kyoku_count", u32), ("riichi_decl_idx", u8 * NP), ("riichi_sutehai", u8 * NP),
+        ("last_tedashi", u8 * NP), ("n_kita", u8 * NP), ("reserved", u8 * 20),
     ]
 
 
-HOT_BYTES = 576
+HOT_BYTES = 544
 assert GameState.wall.offset == HOT_BYTES and C.sizeof(GameState) % 16 == 0
 
 

@@ -202,7 +202,7 @@ __device__ inline WinRes seat_calc(const Ctx& cx, const G& g, int p, int win_til
   int n_ura = with_ura ? ura_indicators(g, ura) : 0;
   return hand_calc(cx.T, g.hand[p], g.hand_len[p], g.n_melds[p], g.meld_type[p], g.meld_tiles[p], win_tile, g.dora_ind,
                    g.n_dora, ura, n_ura, cond, (p + np - g.oya) % np, g.round_wind % 4, honba, is_sanma(g),
-                   with_kita ? g.n_kita[p] : 0);
+                   with_kita ? cold(g).n_kita[p] : 0);
 }
 
 // ------------------------------------------------------------------ wall (state/wall.rs:36-88)
@@ -403,14 +403,14 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
     for (int i = 0; i < RV_RIVER_CAP; i++) cold(g).river[p][i] = RV_NONE;
     g.n_river[p] = 0;
     g.river_tedashi[p] = g.river_riichi[p] = 0;
-    g.riichi_decl_idx[p] = RV_NONE;
+    cold(g).riichi_decl_idx[p] = RV_NONE;
     g.flags[p] = RV_F_NAGASHI_ELIGIBLE;
     cold(g).pao[p][0] = cold(g).pao[p][1] = RV_NONE;
     g.forbidden[p][0] = g.forbidden[p][1] = RV_NONE;
     cold(g).score_delta[p] = 0;
     g.n_claims[p] = 0;
-    g.riichi_sutehai[p] = g.last_tedashi[p] = RV_NONE;
-    g.n_kita[p] = 0;
+    cold(g).riichi_sutehai[p] = cold(g).last_tedashi[p] = RV_NONE;
+    cold(g).n_kita[p] = 0;
     for (int k = 0; k < 4; k++) g.c_cnt[p][k] = 0, g.c_key[p][k] = 0;
     g.c_river_kinds[p] = 0;
     g.c_waits[p] = 0;
@@ -455,7 +455,7 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
   g.n_dora = 1;
   g.dora_ind[0] = w[np == 3 ? 8 : 4];   // state_3p/wall.rs:104-112
   for (int i = 1; i < 5; i++) g.dora_ind[i] = RV_NONE;
-  g.kyoku_count++;
+  cold(g).kyoku_count++;
   // deal: 3 x (4 tiles per seat from oya), then 1 each; tiles pop from the back
   for (int r = 0; r < 3; r++)
     for (int idx = 0; idx < np; idx++) {
@@ -505,7 +505,7 @@ __device__ __noinline__ void game_reset(const Ctx& cx, G& g, int oya, int round_
                                   const uint8_t* custom_wall, const int32_t* scores) {
   const int np = num_players(g);
   g.ev_hash = 0xcbf29ce484222325ull;
-  g.ev_count = g.ev_words = g.step_count = g.kyoku_count = 0;
+  g.ev_count = g.ev_words = g.step_count = cold(g).kyoku_count = 0;
   g.last_error = RV_NONE;   // NOTE: the reference never clears last_error on reset (state/mod.rs:171-187); a fresh
                             // VecEnv has none, and rv_vec_reset is documented to clear it.
   g.overflow = 0;
@@ -1235,12 +1235,12 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
   g.last_discard_pid = (uint8_t)pid;
   g.last_discard_tile = (uint8_t)tile;
   g.drawn_tile = RV_NONE;
-  if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)tile;
+  if (!tsumogiri) cold(g).last_tedashi[pid] = (uint8_t)tile;
   g.needs_tsumo = 1;
   if (stage) {
     g.flags[pid] |= RV_F_RIICHI_DECLARED;
     if (g.is_first_turn) g.flags[pid] |= RV_F_DOUBLE_RIICHI;
-    g.riichi_decl_idx[pid] = (uint8_t)nr;
+    cold(g).riichi_decl_idx[pid] = (uint8_t)nr;
     g.flags[pid] &= ~RV_F_RIICHI_STAGE;
     g.riichi_pending_acceptance = (uint8_t)pid;
   }
@@ -1333,7 +1333,7 @@ __device__ __noinline__ void handle_kita(const Ctx& cx, G& g, int pid, const rv_
     if (tile < 0) tile = act.tile != RV_NONE ? act.tile : (act.n_consume ? act.consume[0] : 0);
   }
   hand_remove_first(g, pid, tile);
-  g.n_kita[pid]++;
+  cold(g).n_kita[pid]++;
   g.is_first_turn = 0;
   ev_simple(cx, g, RV_EV_KITA, pid, tile);
   flush_pending_kan_dora(cx, g);
@@ -1382,8 +1382,8 @@ __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action
         if (act.tile != RV_NONE) {
           int t = act.tile;
           bool tsumogiri = g.drawn_tile != RV_NONE && g.drawn_tile == t;
-          g.riichi_sutehai[pid] = (uint8_t)t;
-          if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)t;
+          cold(g).riichi_sutehai[pid] = (uint8_t)t;
+          if (!tsumogiri) cold(g).last_tedashi[pid] = (uint8_t)t;
           if (hand_remove_first(g, pid, t)) hand_sort(g, pid);
           resolve_discard(cx, g, pid, t, tsumogiri);
         }
@@ -2015,7 +2015,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   }
   g.last_discard_pid = (uint8_t)pid;
   g.last_discard_tile = (uint8_t)tile;
-  if (!tsumogiri) g.last_tedashi[pid] = (uint8_t)tile;
+  if (!tsumogiri) cold(g).last_tedashi[pid] = (uint8_t)tile;
   g.n_claims[0] = g.n_claims[1] = g.n_claims[2] = g.n_claims[3] = 0;
   // the next seat draws (_deal_next, state/mod.rs:1569-1593)
   g.turn_count++;

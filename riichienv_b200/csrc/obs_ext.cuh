@@ -284,7 +284,8 @@ __device__ inline void obs_ext_decay_row(const G& g, const uint8_t* river, int q
 }
 
 // channels 78..214 as (mask, value): out[col] = (mask >> col) & 1 ? val : 0
-__device__ inline void obs_ext_channel(const G& g, int pid, int ch, const ObsExtInfo& I, uint64_t& mask, float& val) {
+// `rec`: the record in HBM, for the cold fields (last_tedashi, riichi_sutehai); `g` may be a staged copy of the hot prefix
+__device__ inline void obs_ext_channel(const G& g, const G& rec, int pid, int ch, const ObsExtInfo& I, uint64_t& mask, float& val) {
   constexpr uint64_t ALL = (1ull << OBS_W) - 1;
   mask = 0;
   val = 1.0f;
@@ -345,7 +346,7 @@ __device__ inline void obs_ext_channel(const G& g, int pid, int ch, const ObsExt
   } else {                                         // last tedashi / riichi sutehai, opponents in absolute seat order
     const bool ted = ch < 206;
     const int x = ch - (ted ? 197 : 206), o = x / 3, p = o < pid ? o : o + 1;
-    const int t = ted ? g.last_tedashi[p] : g.riichi_sutehai[p];
+    const int t = ted ? rec.last_tedashi[p] : rec.riichi_sutehai[p];
     if (t != RV_NONE) tile_ctx(x % 3, t);
   }
 }
@@ -502,7 +503,7 @@ __device__ __forceinline__ void obs_ext_encode_warp(const Tables& T, const Decay
   for (int ch = 78 + lane; ch < OBSX_CH; ch += 32) {
     uint64_t m;
     float v;
-    obs_ext_channel(g, pid, ch, I, m, v);
+    obs_ext_channel(g, rec, pid, ch, I, m, v);
     X.d[ch].mask = m;
     X.d[ch].val = v;
   }

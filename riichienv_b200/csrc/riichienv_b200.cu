@@ -411,11 +411,11 @@ __global__ void sched_init_kernel(const G* states, int64_t n, uint32_t* budget, 
 // ---- shared-memory staging of the hot prefix (per-lane bulk copies, TMA engine) ----
 // A lane's game record is 13 cache lines of HBM and a step touches most of the hot ones through dependent, uncoalesced
 // loads (every warp-level load waits for its slowest lane: ncu showed ~20 warps stalled on long_scoreboard per issue).
-// So each lane pulls its record's hot prefix (RV_HOT_BYTES = 576 B) into shared memory with ONE cp.async.bulk, all 32
+// So each lane pulls its record's hot prefix (RV_HOT_BYTES = 544 B) into shared memory with ONE cp.async.bulk, all 32
 // copies of the warp in flight together, runs the step(s) there, and writes the prefix back with one bulk store.
 // The cold arrays (wall, river, claims) stay in HBM; game code reaches them through cold(g) (game.cuh).
 constexpr int PHB = 32;                              // threads (= games) per block: one warp, own barrier, own exit
-constexpr int STG_STRIDE = RV_HOT_BYTES + 16;        // 592 B = 148 words (== 20 mod 32, gcd 4: same-field accesses are 4-way conflicts)
+constexpr int STG_STRIDE = RV_HOT_BYTES + 16;        // 560 B = 140 words (== 12 mod 32, gcd 4: same-field accesses are 4-way conflicts)
 static_assert(offsetof(G, river) % 8 == 0, "river alignment");
 static_assert(offsetof(G, wall) == RV_HOT_BYTES && RV_HOT_BYTES % 16 == 0 && sizeof(G) % 16 == 0, "hot prefix layout");
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(128) legal_ids_kernel(Tables T, const G* state
 // (A persistent variant — 8 blocks per SM, each warp walking several games with the next record prefetched into registers —
 // measured slower, 194 us against 157 us per 65,536 rows: with one short-lived warp per game the block scheduler keeps
 // every SM topped up and other warps cover the one remaining round trip.)
-constexpr int OBS_STAGE_BYTES = RV_HOT_BYTES + MAXP * RV_RIVER_CAP;   // 576 + 128
+constexpr int OBS_STAGE_BYTES = RV_HOT_BYTES + MAXP * RV_RIVER_CAP;   // 544 + 128
 template <bool SANMA>
 __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int64_t n, const int32_t* offsets, const uint32_t* idbits,
                                                             float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
@@ -1655,7 +1655,7 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
     CK(cudaMalloc(&v->d_q_ctl, sizeof(uint32_t) * Q_CTL_WORDS));
     if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
   }
-  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 11);
+  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 12);
   // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 8 = 2 games per
   // warp), warps own RV_ENDGAME_TAKE games each and play them out in place (see the kernel)
   static int eg_quarters = env_int("RV_ENDGAME_Q", 8), eg_take = env_int("RV_ENDGAME_TAKE", 1);

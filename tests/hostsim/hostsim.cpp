@@ -423,7 +423,7 @@ void hs_game_encode_ext(void* p, int pid, float* obs) {
   for (int ch = 78; ch < OBSX_CH; ch++) {
     uint64_t m;
     float v;
-    obs_ext_channel(g, pid, ch, I, m, v);
+    obs_ext_channel(g, g, pid, ch, I, m, v);
     for (int col = 0; col < OBS_W; col++) obs[ch * OBS_W + col] = ((m >> col) & 1) ? v : 0.0f;
   }
 }
