@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 
 B_STEP = 1024  # algorithmic bytes per env step without observations (SURVEY.md §8 d)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_persistent_kernel launch (65,536 hanchan, 69.3 M env steps)
-# from the ncu --set full capture profiles/r01s3f_persist_raw.csv: 1.59 GB read + 6.78 GB written
-TRAFFIC_BYTES_PER_LAUNCH = 8.37e9
+# from the ncu --set full capture profiles/r01s3g_persist_raw.csv: 1.77 GB read + 7.50 GB written
+TRAFFIC_BYTES_PER_LAUNCH = 9.27e9
 MODE_NAMES = {0: "4p-red-single kyoku", 1: "4p-red-east", 2: "4p-red-half hanchan", 3: "3p-red-single kyoku", 4: "3p-red-east",
               5: "3p-red-half hanchan (sanma)"}
 METRIC = "env_steps_per_sec"
