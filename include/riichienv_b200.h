@@ -345,6 +345,10 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
  *   d_mask  [max_obs][82] u8, d_index [max_obs] i32                — may be NULL */
 int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
 
+/* Observation::encode_kawa_overview (observation/python.rs:881-930) for every seat that owes an action, same row order as
+ * rv_vec_encode: d_out [max_obs][4][7][34] f32 (device, 16-byte aligned), seats in absolute order; 4P only. */
+int rv_vec_encode_kawa(rv_vec* v, float* d_out, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
+
 /* Observe + step in one pass (BASELINE config 5: a random-agent rollout that emits FEATURE_ENCODING tensors at every step —
  * the loop `obs = env.step({p: agent.act(o) ...})` of README.md:50-62 with the agent of rv_vec_step_random on the device).
  * Exactly rv_vec_encode(v, d_obs, d_mask, d_index, max_obs, n_obs) followed by rv_vec_step_random_async(v, agent_seed, 1):

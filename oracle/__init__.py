@@ -52,6 +52,7 @@ def load():
     lib.orc_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.orc_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]
     lib.orc_game_encode_ext.argtypes = [C.c_void_p, C.c_int, P(C.c_float)]
+    lib.orc_game_encode_kawa.argtypes = [C.c_void_p, P(C.c_float)]
     lib.orc_ukeire.argtypes = [P(C.c_int), C.c_int, P(C.c_int), C.c_int, P(C.c_int)]
     lib.orc_game_encode_seq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(C.c_uint16), P(C.c_float),
                                         P(C.c_uint16), C.c_int, P(C.c_uint16), P(C.c_uint16)]

@@ -372,6 +372,8 @@ extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {
 }
 // Observation::encode_extended: 215x34 floats (4P only)
 extern "C" void orc_game_encode_ext(void* h, int pid, float* obs) { encode_obs_extended(*(GameState*)h, pid, obs); }
+// Observation::encode_kawa_overview: 4x7x34 floats (4P)
+extern "C" void orc_game_encode_kawa(void* h, float* out) { encode_kawa_overview(*(GameState*)h, out); }
 // shanten.rs:250-393 on tid lists (known-answer hooks): out = {shanten, effective_with_discard, best_ukeire}
 extern "C" void orc_ukeire(const int* hand, int n, const int* visible, int nv, int* out) {
   std::vector<int> h(hand, hand + n), v(visible, visible + nv);

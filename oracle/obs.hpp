@@ -553,6 +553,29 @@ inline void encode_obs_extended(const GameState& g, int pid, float* arr) {
   }
 }
 
+// Observation::encode_kawa_overview (observation/python.rs:881-930): (4, 7, 34) floats, seats in ABSOLUTE order.
+// Channels 0-3: the n-th copy of a kind a seat discarded (n capped at 4); 4-6: "aka" flags, which the reference raises for
+// tile ids 20 / 24 / 28 (not 16 / 52 / 88) at columns 5 / 14 / 23 — restated as is.
+inline void encode_kawa_overview(const GameState& g, float* arr) {
+  for (int i = 0; i < 4 * 7 * 34; i++) arr[i] = 0.0f;
+  for (int p = 0; p < 4; p++) {
+    uint8_t cnt[34] = {0};
+    bool aka[3] = {false, false, false};
+    for (uint8_t t : g.players[p].discards) {
+      int k = t / 4;
+      if (k < 34) {
+        arr[(p * 7 + std::min<int>(cnt[k], 3)) * 34 + k] = 1.0f;
+        if (cnt[k] < 255) cnt[k]++;
+      }
+      if (t == 20) aka[0] = true;
+      else if (t == 24) aka[1] = true;
+      else if (t == 28) aka[2] = true;
+    }
+    for (int i = 0; i < 3; i++)
+      if (aka[i]) arr[(p * 7 + 4 + i) * 34 + 5 + i * 9] = 1.0f;
+  }
+}
+
 // Observation::mask (observation/python.rs:98-111; 3P: observation_3p/python.rs:102-114) for a seat that owes an action:
 // 82 bytes (4P) or 60 bytes (3P)
 inline void encode_mask(const GameState& g, int pid, uint8_t* out) {

@@ -61,6 +61,7 @@ def lib():
     L.rv_event_to_json.argtypes = [P(C.c_uint32), C.c_uint32, C.c_int, C.c_char_p, C.c_uint32]
     L.rv_vec_encode.argtypes = [vp, vp, vp, vp, C.c_int64, P(C.c_int64)]
     L.rv_vec_encode_ext.argtypes = [vp, vp, vp, vp, C.c_int64, P(C.c_int64)]
+    L.rv_vec_encode_kawa.argtypes = [vp, vp, vp, C.c_int64, P(C.c_int64)]
     L.rv_vec_observe_step_random.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_int64, P(C.c_int64)]
     L.rv_vec_encode_seq.argtypes = [vp, C.c_int, P(C.c_uint32), vp, vp, vp, C.c_int, vp, vp, vp, C.c_int64, P(C.c_int64)]
     L.rv_sizeof.argtypes = [C.c_int]

@@ -426,6 +426,22 @@ class Observation:
     def encode_shanten_efficiency(self):  # python.rs:820-878 -> (4, 4)
         return self._ext_row()[78:94, 0].tobytes()
 
+    def encode_kawa_overview(self):  # python.rs:881-930 -> (4, 7, 34), seats in absolute order (obs_kawa_kernel)
+        import torch
+
+        if self._token != self._env._token:
+            raise RuntimeError("tensors are computed on the device from the live game: call encode_kawa_overview() on the "
+                               "observations of the latest reset()/step()")
+        env = self._env
+        dev = f"cuda:{env._v.ctx.device}"
+        out = torch.zeros((4, 4, 7, 34), dtype=torch.float32, device=dev)
+        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
+        n = env._v.encode_kawa_overview(out=out, index=idx, max_obs=4)
+        rows = idx[:n].tolist()
+        if self.player_id not in rows:
+            raise ValueError(f"seat {self.player_id} owes no action")
+        return out[rows.index(self.player_id)].cpu().numpy().tobytes()
+
     def encode_ankan_overview(self):  # python.rs:976-1010 -> (4, 34)
         return self._ext_row()[94:98].tobytes()
 

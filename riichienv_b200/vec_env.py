@@ -113,6 +113,17 @@ class VecRiichiEnv:
         check(lib().rv_vec_encode_ext(self.handle, ptr(obs), ptr(mask), ptr(index), int(max_obs), C.byref(n) if sync else None))
         return int(n.value) if sync else None
 
+    def encode_kawa_overview(self, out=None, index=None, max_obs=None, sync=True):
+        """Observation.encode_kawa_overview rows (observation/python.rs:881-930) of every seat that owes an action, into DEVICE
+        buffers: out [max_obs,4,7,34] f32, index [max_obs] i32.  4P only.  Returns the row count."""
+        def ptr(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        if max_obs is None:
+            max_obs = min(t.shape[0] for t in (out, index) if t is not None)
+        n = C.c_int64(0)
+        check(lib().rv_vec_encode_kawa(self.handle, ptr(out), ptr(index), int(max_obs), C.byref(n) if sync else None))
+        return int(n.value) if sync else None
+
     def observe_step_random(self, agent_seed, obs=None, mask=None, index=None, max_obs=None, sync=False):
         """encode(obs, mask, index) of the current decision point, then one env step of every live game with the on-device
         agent — one fused kernel (rv_vec_observe_step_random).  Returns the row count when sync=True."""

@@ -47,6 +47,7 @@ def load():
     lib.hs_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.hs_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]
     lib.hs_game_encode_ext.argtypes = [C.c_void_p, C.c_int, P(C.c_float)]
+    lib.hs_game_encode_kawa.argtypes = [C.c_void_p, P(C.c_float)]
     lib.hs_game_encode_seq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(C.c_uint16), P(C.c_float),
                                        P(C.c_uint16), C.c_int, P(C.c_uint16), P(C.c_uint16)]
     lib.hs_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]

@@ -395,6 +395,50 @@ def test_observation_encode_extended_vs_oracle(orc):
         assert seen_channels[lo:hi].any(), (lo, hi)
 
 
+def test_kawa_overview_vs_oracle(orc):
+    """rv_vec_encode_kawa: Observation::encode_kawa_overview (4x7x34) rows of 128 hanchan at several points of the rollout."""
+    import torch
+
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n = 128
+    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=9700)
+    v.reset()
+    games = [orc.orc_game_new(2, 9700 + g, 0, A.RULE_DEFAULT_TENHOU, 0) for g in range(n)]
+    for h in games:
+        orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    out = torch.empty((n * 3, 4, 7, 34), dtype=torch.float32, device="cuda")
+    idx = torch.empty((n * 3,), dtype=torch.int32, device="cuda")
+    a = np.zeros(4 * 7 * 34, np.float32)
+    checked = 0
+    for it in range(12):
+        out.fill_(-3.0)
+        rows = v.encode_kawa_overview(out=out, index=idx)
+        assert (out[rows:] == -3.0).all()
+        h_out, h_idx = out[:rows].cpu().numpy(), idx[:rows].cpu().numpy()
+        st = A.GameState()
+        r = 0
+        for g in range(n):
+            orc.orc_game_snapshot(games[g], C.byref(st))
+            if st.is_done:
+                continue
+            for p in range(4):
+                if (st.active_mask >> p) & 1:
+                    assert h_idx[r] == g * 4 + p
+                    orc.orc_game_encode_kawa(games[g], a.ctypes.data_as(C.POINTER(C.c_float)))
+                    assert h_out[r].tobytes() == a.tobytes(), f"iter {it} game {g} seat {p}"
+                    r += 1
+                    checked += 1
+        assert r == rows
+        v.step_random(29, 53)
+        for g in range(n):
+            for _ in range(53):
+                orc.orc_game_random_step(games[g], 29, 9700 + g)
+    for h in games:
+        orc.orc_game_free(h)
+    assert checked > 1000
+
+
 def test_shim_observation_encode_extended(orc):
     from riichienv_b200 import RiichiEnv
 
@@ -419,6 +463,7 @@ def test_shim_observation_encode_extended(orc):
     assert dc[0] == np.float32(14) / np.float32(34) and 0.0 <= dc[1] + dc[2] <= 1.0
     assert f(obs[0].encode_pass_context(), 3).sum() == 0                       # nothing discarded yet
     assert f(obs[0].encode_last_tedashis(), 3, 3).sum() == 0 and f(obs[0].encode_riichi_sutehais(), 3, 3).sum() == 0
+    assert f(obs[0].encode_kawa_overview(), 4, 7, 34).sum() == 0                # nothing discarded yet
 
 
 def test_sequence_features_vs_oracle(orc):

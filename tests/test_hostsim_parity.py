@@ -208,6 +208,30 @@ def test_observation_encode_extended_lockstep(libs):
     assert n_obs > 2000
 
 
+def test_kawa_overview_lockstep(libs):
+    """encode_kawa_overview() (4x7x34 f32, observer independent) at every step of a seeded hanchan: bit-equal."""
+    import numpy as np
+
+    orc, hs = libs
+    o, h = OracleBackend(2, 31), HostsimBackend(2, 31)
+    o.reset()
+    h.reset()
+    a = np.full(4 * 7 * 34 + 8, 7.0, np.float32)
+    b = np.full(4 * 7 * 34 + 8, 7.0, np.float32)
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    n = 0
+    nonzero = 0
+    while not o.get_state().is_done:
+        orc.orc_game_encode_kawa(o.h, fp(a))
+        hs.hs_game_encode_kawa(h.h, fp(b))
+        assert a.tobytes() == b.tobytes(), f"step {n}"
+        nonzero = max(nonzero, int(a[:4 * 7 * 34].sum()))
+        o.random_step(5, 31)
+        h.random_step(5, 31)
+        n += 1
+    assert n > 500 and nonzero > 40
+
+
 def test_observation_encode_lockstep_3p(libs):
     """Sanma: Observation3P.encode() (74x27 f32) and mask() (60 ids) of every acting seat at every step: bit-equal."""
     import numpy as np
