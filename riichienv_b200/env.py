@@ -442,6 +442,13 @@ class Observation:
             raise ValueError(f"seat {self.player_id} owes no action")
         return out[rows.index(self.player_id)].cpu().numpy().tobytes()
 
+    def encode_furiten_ron_possibility(self):  # python.rs:251-293 -> (4, 21)
+        """All ones: the encoder only clears a seat's row after three consecutive tsumogiri flags, and the live env never
+        fills `tsumogiri_flags` (observation/mod.rs:105) — a constant, so nothing is computed."""
+        import numpy as np
+
+        return np.ones((4, 21), np.float32).tobytes()
+
     def encode_ankan_overview(self):  # python.rs:976-1010 -> (4, 34)
         return self._ext_row()[94:98].tobytes()
 
