@@ -36,6 +36,7 @@ def load():
     lib.orc_is_agari.argtypes = [P(C.c_uint8)]
     lib.orc_is_tenpai_counts.argtypes = [P(C.c_uint8)]
     lib.orc_shanten_counts.argtypes = [P(C.c_uint8), C.c_int]
+    lib.orc_shanten_counts_3p.argtypes = [P(C.c_uint8), C.c_int]
     lib.orc_calculate_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, P(C.c_uint32)]
     lib.orc_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]
     lib.orc_chacha_words.argtypes = [P(C.c_uint32), C.c_int, C.c_int, P(C.c_uint32)]

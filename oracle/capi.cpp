@@ -214,14 +214,15 @@ static void eval_one(const rv_hand_query& q, rv_hand_result& r) {
       cnt[q.win_tile / 4]++;
       n++;
     }
-    r.shanten = (int8_t)shanten_from_counts(cnt, n / 3);
+    // sanma queries: calculate_shanten_3p (shanten.rs:470-484)
+    r.shanten = (int8_t)(sanma ? shanten_from_counts_3p(cnt, n / 3) : shanten_from_counts(cnt, n / 3));
     uint8_t c13[34] = {0};
     int n13 = 0;
     for (uint8_t t : t13) {
       c13[t / 4]++;
       n13++;
     }
-    r.shanten13 = ok13 ? (int8_t)shanten_from_counts(c13, n13 / 3) : (int8_t)127;
+    r.shanten13 = ok13 ? (int8_t)(sanma ? shanten_from_counts_3p(c13, n13 / 3) : shanten_from_counts(c13, n13 / 3)) : (int8_t)127;
   }
 }
 
@@ -265,6 +266,7 @@ int orc_is_tenpai_counts(const uint8_t* counts34) {  // agari.rs:15-61 semantics
   return 0;
 }
 int orc_shanten_counts(const uint8_t* counts34, int len_div3) { return shanten_from_counts(counts34, len_div3); }
+int orc_shanten_counts_3p(const uint8_t* counts34, int len_div3) { return shanten_from_counts_3p(counts34, len_div3); }
 int orc_calculate_score(int han, int fu, int is_oya, int is_tsumo, uint32_t honba, int np, uint32_t out[4]) {
   Score s = calculate_score((uint8_t)han, (uint8_t)fu, is_oya, is_tsumo, honba, (uint8_t)np);
   out[0] = s.pay_ron;

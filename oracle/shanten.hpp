@@ -127,4 +127,45 @@ inline int shanten_from_counts(const uint8_t* t, int len_div3) {
   return s;
 }
 
+// shanten.rs:407-435 — 3P normal form: 1m / 9m cannot form sequences, so their counts are relocated into EMPTY honor slots
+// (the honor part of the tables is koutsu / pair only and position independent) before the 4P lookup; when no empty slot is
+// left the count stays in manzu (the reference's overflow fallback, kept)
+inline int shanten_normal_3p(const uint8_t* tiles, int m) {
+  uint8_t t[34];
+  memcpy(t, tiles, 34);
+  const uint8_t mc[2] = {t[0], t[8]};
+  const int mp[2] = {0, 8};
+  t[0] = t[8] = 0;
+  int next_slot = 27;
+  for (int i = 0; i < 2; i++) {
+    if (mc[i] == 0) continue;
+    while (next_slot < 34 && t[next_slot] != 0) next_slot++;
+    if (next_slot < 34) t[next_slot++] = mc[i];
+    else t[mp[i]] = mc[i];
+  }
+  return shanten_normal(t, m);
+}
+// shanten.rs:437-453 — 2m-8m (kinds 1..7) do not exist in 3P and are skipped
+inline int shanten_chitoi_3p(const uint8_t* t) {
+  int pairs = 0, kinds = 0;
+  for (int i = 0; i < 34; i++) {
+    if (i >= 1 && i <= 7) continue;
+    if (t[i] > 0) {
+      kinds++;
+      if (t[i] >= 2) pairs++;
+    }
+  }
+  int red = kinds < 7 ? 7 - kinds : 0;
+  return 7 - pairs + red - 1;
+}
+// shanten.rs:455-468
+inline int shanten_from_counts_3p(const uint8_t* t, int len_div3) {
+  if (len_div3 > 4) len_div3 = 4;
+  int s = shanten_normal_3p(t, len_div3);
+  if (s <= 0 || len_div3 < 4) return s;
+  s = std::min(s, shanten_chitoi_3p(t));
+  if (s > 0) return std::min(s, shanten_kokushi(t));
+  return s;
+}
+
 }  // namespace orc

@@ -6,7 +6,7 @@ C ABI in include/riichienv_b200.h.  Importing this package does not need a GPU; 
 from . import _abi  # noqa: F401
 
 __all__ = ["RiichiEnv", "VecRiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
-           "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "tid_to_mjai"]
+           "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "tid_to_mjai"]
 
 
 def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
@@ -19,7 +19,7 @@ def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
         from .vec_env import VecRiichiEnv
 
         return VecRiichiEnv
-    if name in ("HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "WinResult"):
+    if name in ("HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "WinResult"):
         from . import hand
 
         return getattr(hand, name)

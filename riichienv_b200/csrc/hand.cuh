@@ -229,7 +229,8 @@ __device__ __forceinline__ uint64_t waits13(const Tables& T, const Cnt& c) {
 }
 
 // ------------------------------------------------------------------ shanten
-__device__ __noinline__ int shanten_counts(const Tables& T, const Cnt& c, int len_div3) {
+// normal-form replacement number minus one (shanten.rs:186-196): three (min,+) convolutions of the four suits' cost vectors
+__device__ __noinline__ int shanten_normal(const Tables& T, const Cnt& c, int m) {
   uint64_t cs[4] = {__ldg(&T.suit_cost[suit_key<9>(c.s[0])]), __ldg(&T.suit_cost[suit_key<9>(c.s[1])]),
                     __ldg(&T.suit_cost[suit_key<9>(c.s[2])]), __ldg(&T.honor_cost[suit_key<7>(c.s[3])])};
   int b0[5], b1[5];
@@ -258,23 +259,31 @@ __device__ __noinline__ int shanten_counts(const Tables& T, const Cnt& c, int le
       b1[k] = n1[k];
     }
   }
-  int m = len_div3 > 4 ? 4 : len_div3;
   int sh = 99;
   #pragma unroll
   for (int k = 0; k < 5; k++)
     if (k == m) sh = b1[k] - 1;
+  return sh;
+}
+// chiitoitsu / kokushi closing of shanten.rs:198-239; `skip` = tile kinds chiitoitsu ignores (3P: 2m-8m, shanten.rs:437-453)
+__device__ __forceinline__ int shanten_close(int sh, int m, const Cnt& c, uint64_t skip) {
   if (sh <= 0 || m < 4) return sh;
-  // shanten.rs:198-226
-  uint64_t present = cnt_present(c);
-  int kinds = __popcll(present), pairs = 0;
+  const uint64_t present = cnt_present(c);
+  int kinds = __popcll(present & ~skip), pairs = 0;
   int tk = __popcll(present & MASK_TERMINAL_HONOR);
   bool tpair = false;
   #pragma unroll
   for (int k = 0; k < 4; k++) {
     uint64_t x = c.s[k];
-    uint64_t ge2 = (x | (x >> 1)) >> 1;  // bit 4i set if nibble >= 2
-    ge2 = ((x >> 1) | (x >> 2)) & 0x1111111111111111ull;
-    pairs += __popcll(ge2);
+    uint64_t ge2 = ((x >> 1) | (x >> 2)) & 0x1111111111111111ull;   // bit 4i set if nibble i >= 2
+    if (k == 0) {
+      uint64_t sk = 0;                                                // nibble mask of the skipped manzu kinds
+      #pragma unroll
+      for (int i = 0; i < 9; i++) sk |= ((skip >> i) & 1) << (4 * i);
+      pairs += __popcll(ge2 & ~sk);
+    } else {
+      pairs += __popcll(ge2);
+    }
     uint64_t tm = (k == 3) ? 0x1111111ull : 0x100000001ull;
     if (ge2 & tm) tpair = true;
   }
@@ -282,6 +291,32 @@ __device__ __noinline__ int shanten_counts(const Tables& T, const Cnt& c, int le
   sh = min(sh, chi);
   if (sh > 0) sh = min(sh, 14 - tk - (tpair ? 1 : 0) - 1);
   return sh;
+}
+__device__ __noinline__ int shanten_counts(const Tables& T, const Cnt& c, int len_div3) {
+  const int m = len_div3 > 4 ? 4 : len_div3;
+  return shanten_close(shanten_normal(T, c, m), m, c, 0);
+}
+// calc_shanten_from_counts_3p (shanten.rs:407-468): 1m / 9m are relocated into EMPTY honor slots before the normal-form lookup
+// (they cannot form sequences; the honor tables are position independent), staying in manzu when no slot is left — the
+// reference's overflow fallback; chiitoitsu skips 2m-8m; kokushi as in 4P.
+__device__ __noinline__ int shanten_counts_3p(const Tables& T, const Cnt& c, int len_div3) {
+  const int m = len_div3 > 4 ? 4 : len_div3;
+  Cnt t = c;
+  const int mc[2] = {(int)(c.s[0] & 15), (int)((c.s[0] >> 32) & 15)};
+  t.s[0] &= ~(0xFull | (0xFull << 32));
+  int slot = 0;
+  #pragma unroll
+  for (int i = 0; i < 2; i++) {
+    if (mc[i] == 0) continue;
+    while (slot < 7 && ((t.s[3] >> (4 * slot)) & 15) != 0) slot++;
+    if (slot < 7) {
+      t.s[3] |= (uint64_t)mc[i] << (4 * slot);
+      slot++;
+    } else {
+      t.s[0] |= (uint64_t)mc[i] << (i == 0 ? 0 : 32);
+    }
+  }
+  return shanten_close(shanten_normal(T, t, m), m, c, 0xFEull);
 }
 
 // ------------------------------------------------------------------ score.rs

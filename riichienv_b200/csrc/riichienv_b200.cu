@@ -126,8 +126,9 @@ __global__ void hand_eval_kernel(Tables T, const rv_hand_query* __restrict__ q, 
     cnt_add(r14, win34);
     n14++;
   }
-  o.shanten = (int8_t)shanten_counts(T, r14, n14 / 3);
-  o.shanten13 = ok13 ? (int8_t)shanten_counts(T, r13, cnt_total(r13) / 3) : (int8_t)127;
+  // sanma queries: calculate_shanten_3p (shanten.rs:470-484)
+  o.shanten = (int8_t)((h.sanma & 1) ? shanten_counts_3p(T, r14, n14 / 3) : shanten_counts(T, r14, n14 / 3));
+  o.shanten13 = ok13 ? (int8_t)((h.sanma & 1) ? shanten_counts_3p(T, r13, cnt_total(r13) / 3) : shanten_counts(T, r13, cnt_total(r13) / 3)) : (int8_t)127;
   out[i] = o;
 }
 

@@ -127,3 +127,12 @@ def calculate_shanten(hand_tiles) -> int:  # shanten.rs:250-261 (len_div3 = n_ti
     r = eval_queries([q])[0]
     # the kernel adds the win tile to 13-tile hands (HandEvaluator::calc semantics); `shanten13` is the raw 13-tile figure
     return r.shanten13 if len(tiles) == 13 else r.shanten
+
+
+def calculate_shanten_3p(hand_tiles) -> int:  # shanten.rs:470-484 (1m / 9m koutsu-only, chiitoi without 2m-8m)
+    tiles = [t for t in hand_tiles if t // 4 < 34][:14]
+    if not tiles:
+        return 0
+    q = make_query(tiles, (), tiles[-1], (), (), Conditions(is_sanma=True))
+    r = eval_queries([q])[0]
+    return r.shanten13 if len(tiles) == 13 else r.shanten

@@ -271,6 +271,109 @@ def gen_ukeire():
     print("ukeire_golden.txt", len(lines))
 
 
+def ref_shanten_3p(T, cnt, m):
+    """shanten.rs:407-468 restated (relocation of 1m / 9m into empty honor slots, chiitoi without 2m-8m)."""
+    t = list(cnt)
+    mc = [t[0], t[8]]
+    t[0] = t[8] = 0
+    slot = 27
+    for i in range(2):
+        if mc[i] == 0:
+            continue
+        while slot < 34 and t[slot] != 0:
+            slot += 1
+        if slot < 34:
+            t[slot] = mc[i]
+            slot += 1
+        else:
+            t[(0, 8)[i]] = mc[i]
+    # normal form through the 4P table walk (without its chiitoi / kokushi closing)
+    def h(tab, tiles):
+        n = 0
+        hv = 0
+        for i, c in enumerate(tiles):
+            n += c
+            hv += tab[i][n][c]
+        return hv
+    k0m = T["sk"][h(T["shupai"], t[0:9])]
+    k0p = T["sk"][h(T["shupai"], t[9:18])]
+    k1 = T["k1"][k0m * 126 + k0p]
+    k0s = T["sk"][h(T["shupai"], t[18:27])]
+    k2 = T["k2"][k1 * 126 + k0s]
+    k0z = T["zk"][h(T["zipai"], t[27:34])]
+    s = T["k3"][(k2 * 55 + k0z) * 5 + m] - 1
+    if s <= 0 or m < 4:
+        return s
+    kinds = sum(1 for i, c in enumerate(cnt) if c > 0 and not 1 <= i <= 7)
+    pairs = sum(1 for i, c in enumerate(cnt) if c >= 2 and not 1 <= i <= 7)
+    s = min(s, 7 - pairs + max(0, 7 - kinds) - 1)
+    if s > 0:
+        term = [0, 8, 9, 17, 18, 26, 27, 28, 29, 30, 31, 32, 33]
+        k = sum(1 for i in term if cnt[i] > 0)
+        p = any(cnt[i] >= 2 for i in term)
+        s = min(s, 14 - k - int(p) - 1)
+    return s
+
+
+def gen_shanten_3p():
+    T = load_shanten_tables()
+    rng = random.Random(20261018)
+    valid = [0] + list(range(8, 34))
+    lines = []
+    for it in range(3000):
+        n = rng.choice([13, 14, 13, 14, 13, 14, 10, 11, 7, 8, 4, 5, 12, 9])
+        cnt = [0] * 34
+        if it % 10 == 0:
+            # overflow of the relocation: every honor present, plus 1m and 9m
+            for k in range(27, 34):
+                cnt[k] = 1
+            cnt[0] = rng.randrange(1, 4)
+            cnt[8] = rng.randrange(1, 4)
+            left = max(0, 14 - sum(cnt))
+        elif it % 10 == 1:
+            left = n                      # arbitrary tids, 2m-8m included (the functions accept them)
+            valid_here = list(range(34))
+        else:
+            left = n
+        pool = valid_here if it % 10 == 1 else valid
+        if it % 3 == 0 or it % 10 <= 1:
+            while left > 0:
+                t = rng.choice(pool)
+                if cnt[t] < 4:
+                    cnt[t] += 1
+                    left -= 1
+        else:
+            while left >= 3:
+                if rng.random() < 0.5:
+                    t = rng.choice(pool)
+                    if cnt[t] <= 1:
+                        cnt[t] += 3
+                        left -= 3
+                else:
+                    s0 = rng.choice([9, 18]) + rng.randrange(7)
+                    if max(cnt[s0:s0 + 3]) <= 3:
+                        for k in range(3):
+                            cnt[s0 + k] += 1
+                        left -= 3
+            while left > 0:
+                t = rng.choice(pool)
+                if cnt[t] < 4:
+                    cnt[t] += 1
+                    left -= 1
+            for _ in range(rng.randrange(3)):
+                a = rng.choice([i for i in range(34) if cnt[i] > 0])
+                b = rng.choice([i for i in pool if cnt[i] < 4])
+                cnt[a] -= 1
+                cnt[b] += 1
+        s = ref_shanten_3p(T, cnt, sum(cnt) // 3)
+        lines.append("".join(map(str, cnt)) + f" {s}\n")
+    with open(os.path.join(OUT, "shanten3p_golden.txt"), "w") as f:
+        f.write("# counts_34 (34 digits) shanten_3p   [reference tables' answer through calc_shanten_from_counts_3p, len_div3 = n // 3]\n")
+        f.writelines(lines)
+    print("shanten3p_golden.txt", len(lines))
+    # tests/test_shanten.py known answers for calculate_shanten_3p
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference checkout not found: fixtures are committed, nothing to do")
@@ -279,3 +382,4 @@ if __name__ == "__main__":
     conv_negative()
     gen_shanten()
     gen_ukeire()
+    gen_shanten_3p()

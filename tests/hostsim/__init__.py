@@ -29,6 +29,7 @@ def load():
     lib.hs_init.argtypes = [C.c_char_p, C.c_int]
     lib.hs_hand_eval.argtypes = [P(A.HandQuery), P(A.HandResult), C.c_int64]
     lib.hs_shanten_counts.argtypes = [P(C.c_uint8), C.c_int]
+    lib.hs_shanten_counts_3p.argtypes = [P(C.c_uint8), C.c_int]
     lib.hs_is_agari.argtypes = [P(C.c_uint8)]
     lib.hs_waits.restype = C.c_uint64
     lib.hs_waits.argtypes = [P(C.c_uint8)]

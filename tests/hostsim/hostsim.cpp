@@ -192,6 +192,12 @@ int hs_shanten_counts(const uint8_t* cnt34, int len_div3) {
   for (int i = 0; i < 34; i++) cnt_add(c, i, cnt34[i]);
   return shanten_counts(g_T, c, len_div3);
 }
+int hs_shanten_counts_3p(const uint8_t* cnt34, int len_div3) {
+  Cnt c;
+  cnt_zero(c);
+  for (int i = 0; i < 34; i++) cnt_add(c, i, cnt34[i]);
+  return shanten_counts_3p(g_T, c, len_div3);
+}
 int hs_is_agari(const uint8_t* cnt34) {
   Cnt c;
   cnt_zero(c);

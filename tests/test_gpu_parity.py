@@ -89,6 +89,30 @@ def test_shanten_golden_via_hand_eval(ctx):
         assert out[i].shanten == sh, f"hand {i}"
 
 
+def test_shanten_3p_golden_via_hand_eval(ctx):
+    """calculate_shanten_3p through rv_hand_eval_batch (sanma queries): the reference tables' answers of
+    tests/golden/shanten3p_golden.txt, and the shim function on a known answer of tests/test_shanten.py."""
+    cases = H.load_counts_file("shanten3p_golden.txt")
+    qs = []
+    keep = []
+    for cnt, sh in cases:
+        tiles = [t * 4 + k for t in range(34) for k in range(cnt[t])]
+        if len(tiles) % 3 != 2 or len(tiles) > 14:
+            continue
+        q = H.make_query(tiles, [], tiles[-1], [], [], 0, 0, 0, 0)
+        q.sanma = 1
+        qs.append(q)
+        keep.append(sh)
+    out = gpu_eval(ctx, H.query_array(qs), len(qs))
+    assert len(qs) > 700
+    for i, sh in enumerate(keep):
+        assert out[i].shanten == sh, f"hand {i}"
+    from riichienv_b200 import calculate_shanten, calculate_shanten_3p
+
+    hand = [0, 1, 2, 3, 108, 109, 110, 111, 112, 113, 114, 116, 117]      # 1111m111122233z (tests/test_shanten.py:4-13)
+    assert calculate_shanten(hand) == 1 and calculate_shanten_3p(hand) == 2
+
+
 def run_both(orc, n, mode, rule, seed_base, agent_seed, max_steps=100000):
     from riichienv_b200.vec_env import VecRiichiEnv
 

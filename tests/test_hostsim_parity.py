@@ -232,6 +232,28 @@ def test_kawa_overview_lockstep(libs):
     assert n > 500 and nonzero > 40
 
 
+def test_shanten_3p_kernel_source_vs_oracle(libs):
+    """shanten_counts_3p (hand.cuh) against the oracle on the 3P golden hands and on random 4-14 tile hands."""
+    import os
+    import random
+
+    orc, hs = libs
+    rng = random.Random(7)
+    hands = []
+    for line in open(os.path.join(os.path.dirname(__file__), "golden", "shanten3p_golden.txt")):
+        if not line.startswith("#"):
+            hands.append([int(c) for c in line.split()[0]])
+    for _ in range(3000):
+        cnt = [0] * 34
+        for t in rng.sample(range(136), rng.randrange(4, 15)):
+            cnt[t // 4] += 1
+        hands.append(cnt)
+    for cnt in hands:
+        a = (C.c_uint8 * 34)(*cnt)
+        assert orc.orc_shanten_counts_3p(a, sum(cnt) // 3) == hs.hs_shanten_counts_3p(a, sum(cnt) // 3), cnt
+        assert orc.orc_shanten_counts(a, sum(cnt) // 3) == hs.hs_shanten_counts(a, sum(cnt) // 3), cnt
+
+
 def test_observation_encode_lockstep_3p(libs):
     """Sanma: Observation3P.encode() (74x27 f32) and mask() (60 ids) of every acting seat at every step: bit-equal."""
     import numpy as np

@@ -230,3 +230,51 @@ def test_ukeire_golden():
         assert list(out) == exp, (hand, vis, list(out), exp)
         n += 1
     assert n == 400
+
+
+def _parse_counts(hs):
+    cnt = [0] * 34
+    digs = []
+    for ch in hs:
+        if ch.isdigit():
+            digs.append(int(ch))
+        else:
+            base = {"m": 0, "p": 9, "s": 18, "z": 27}[ch]
+            for d in digs:
+                cnt[base + d - 1] += 1
+            digs = []
+    return cnt
+
+
+def test_shanten_3p_golden_and_known_answers():
+    """calculate_shanten_3p (shanten.rs:407-484): 3,000 answers computed from the reference's own tables
+    (tests/golden/make_golden.py, incl. the relocation-overflow hands and hands with 2m-8m) and the known answers of the
+    reference's tests/test_shanten.py:4-75."""
+    import ctypes as C
+    import os
+
+    o = oracle.load()
+
+    def sh3(cnt):
+        return o.orc_shanten_counts_3p((C.c_uint8 * 34)(*cnt), sum(cnt) // 3)
+
+    def sh4(cnt):
+        return o.orc_shanten_counts((C.c_uint8 * 34)(*cnt), sum(cnt) // 3)
+
+    n = 0
+    for line in open(os.path.join(os.path.dirname(__file__), "golden", "shanten3p_golden.txt")):
+        if line.startswith("#"):
+            continue
+        digits, exp = line.split()
+        cnt = [int(c) for c in digits]
+        assert sh3(cnt) == int(exp), (digits, sh3(cnt), exp)
+        n += 1
+    assert n == 3000
+    for hs, e4, e3 in (("1111m111122233z", 1, 2), ("111m111z222z333z44z", -1, -1), ("123456789p11222z", -1, -1),
+                       ("111m123456789s11z", -1, -1), ("19m19p19s1234567z", 0, 0), ("111m999m123p789s1z", 0, 0),
+                       ("1199m1199p1199s1z", 0, 0), ("11m99m123p456s111z", 0, 0), ("111m999m123p13s7z", 1, 1),
+                       ("11119999m22345s", 1, 2), ("1111m9m1234567z", 3, 3), ("111m999m111p11z", -1, -1),
+                       ("111m123456789p1z", 0, 0), ("999m111222333z1p", 0, 0), ("11m99m11p99p11s99s1z", 0, 0),
+                       ("111999m111999p1z", 0, 0), ("19m147p258s12345z", 5, 5)):
+        c = _parse_counts(hs)
+        assert sh4(c) == e4 and sh3(c) == e3, hs
