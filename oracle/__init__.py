@@ -47,6 +47,8 @@ def load():
     lib.orc_game_legal.argtypes = [C.c_void_p, C.c_int, P(A.Action)]
     lib.orc_game_step.argtypes = [C.c_void_p, P(A.Action)]
     lib.orc_game_random_step.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.orc_games_legal_batch.argtypes = [P(C.c_void_p), C.c_int64, P(A.Action), P(C.c_uint8)]
+    lib.orc_games_random_step_batch.argtypes = [P(C.c_void_p), C.c_int64, C.c_uint64, C.c_uint64]
     lib.orc_game_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.orc_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.orc_game_events.restype = C.c_uint32

@@ -307,6 +307,12 @@ int orc_game_legal(void* h, int pid, rv_action* out) {
   for (int i = 0; i < n; i++) to_rv_action(l[i], out[i]);
   return n;
 }
+// batch helpers for the lock-step parity gate (tests/test_gpu_parity.py): legal lists of every seat of n games as
+// [n][4][RV_MAX_LEGAL] rv_action + counts [n][4]; one keyed random step of every game (game id = seed_base + i)
+void orc_games_legal_batch(void** hs, int64_t n, rv_action* out, uint8_t* counts) {
+  for (int64_t i = 0; i < n; i++)
+    for (int p = 0; p < 4; p++) counts[i * 4 + p] = (uint8_t)orc_game_legal(hs[i], p, out + ((size_t)i * 4 + p) * RV_MAX_LEGAL);
+}
 void orc_game_step(void* h, const rv_action* acts) {
   GameState* g = (GameState*)h;
   std::optional<Action> a[MAXP];
@@ -316,6 +322,9 @@ void orc_game_step(void* h, const rv_action* acts) {
 }
 int orc_game_random_step(void* h, uint64_t agent_seed, uint64_t game_id) {
   return random_step(*(GameState*)h, agent_seed, game_id) ? 1 : 0;
+}
+void orc_games_random_step_batch(void** hs, int64_t n, uint64_t agent_seed, uint64_t seed_base) {
+  for (int64_t i = 0; i < n; i++) orc_game_random_step(hs[i], agent_seed, seed_base + (uint64_t)i);
 }
 void orc_game_snapshot(void* h, rv_game_state* out) { ((GameState*)h)->to_snapshot(*out); }
 void orc_game_load_snapshot(void* h, const rv_game_state* in) { load_snapshot(*(GameState*)h, *in); }

@@ -205,6 +205,56 @@ def test_lockstep_snapshots_legal_and_events(orc):
         assert g.events_json() == o.events_json()
 
 
+def test_lockstep_legal_lists_1024_games(orc):
+    """The parity gate of SURVEY 8(d) on 1,024 hanchan driven in lock-step: the legal-action list of every seat at EVERY
+    decision point (rv_vec_legal_actions vs the oracle, entries and order), then the complete binary event log of every game
+    (what the MJAI JSON is rendered from), final scores and ranks."""
+    from riichienv_b200._lib import events_to_json
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n, seed_base, agent = 1024, 31000, 17
+    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=seed_base, log_cap_words=1 << 14)
+    v.reset()
+    hs = (C.c_void_p * n)(*[orc.orc_game_new(2, seed_base + g, 0, A.RULE_DEFAULT_TENHOU, 1) for g in range(n)])
+    for h in hs:
+        orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    o_acts = (A.Action * (n * 4 * A.MAX_LEGAL))()
+    o_cnt = np.zeros((n, 4), np.uint8)
+    k_idx = np.arange(A.MAX_LEGAL)[None, None, :]
+    steps = lists = 0
+    while True:
+        g_acts, g_cnt = v.legal_actions()
+        orc.orc_games_legal_batch(hs, n, o_acts, o_cnt.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert np.array_equal(g_cnt, o_cnt), f"step {steps}: legal-list lengths differ in games {np.nonzero((g_cnt != o_cnt).any(1))[0][:8]}"
+        if not g_cnt.any():
+            break
+        ga = np.frombuffer(g_acts, np.uint8).reshape(n, 4, A.MAX_LEGAL, C.sizeof(A.Action))
+        oa = np.frombuffer(o_acts, np.uint8).reshape(n, 4, A.MAX_LEGAL, C.sizeof(A.Action))
+        live = (k_idx < g_cnt[:, :, None])[..., None]
+        bad = ((ga != oa) & live).any(axis=(1, 2, 3))
+        assert not bad.any(), f"step {steps}: legal lists differ in games {np.nonzero(bad)[0][:8]}"
+        lists += int((g_cnt > 0).sum())
+        v.step_random(agent, 1)
+        orc.orc_games_random_step_batch(hs, n, agent, seed_base)
+        steps += 1
+        assert steps < 6000
+    done, scores, ranks = v.results()
+    assert done.all() and lists > 900_000
+    buf = (C.c_uint32 * (1 << 14))()
+    st = A.GameState()
+    for g in range(n):
+        words = v.events(g)
+        nw = orc.orc_game_events(hs[g], buf, 1 << 14)
+        assert nw == len(words) and list(buf[:nw]) == words, f"game {g}: event logs differ"
+        orc.orc_game_snapshot(hs[g], C.byref(st))
+        assert [st.score[p] for p in range(4)] == list(scores[g])
+        if g % 64 == 0:
+            js = events_to_json(words)
+            assert js[0] == '{"type":"start_game"}' and js[-1] == '{"type":"end_game"}'
+    for h in hs:
+        orc.orc_game_free(h)
+
+
 def test_external_actions_step(orc):
     """rv_vec_step with host-chosen actions (legal list -> keyed pick on the host) matches the on-device agent."""
     from riichienv_b200.vec_env import VecRiichiEnv
