@@ -57,6 +57,7 @@ def load():
     lib.orc_game_encode_ext.argtypes = [C.c_void_p, C.c_int, P(C.c_float)]
     lib.orc_game_encode_kawa.argtypes = [C.c_void_p, P(C.c_float)]
     lib.orc_ukeire.argtypes = [P(C.c_int), C.c_int, P(C.c_int), C.c_int, P(C.c_int)]
+    lib.orc_ukeire_3p.argtypes = [P(C.c_int), C.c_int, P(C.c_int), C.c_int, P(C.c_int)]
     lib.orc_game_encode_seq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(C.c_uint16), P(C.c_float),
                                         P(C.c_uint16), C.c_int, P(C.c_uint16), P(C.c_uint16)]
     for name in ("orc_seq_encode_chi", "orc_seq_encode_pon"):

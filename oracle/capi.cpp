@@ -392,6 +392,12 @@ extern "C" void orc_ukeire(const int* hand, int n, const int* visible, int nv, i
   out[1] = effective_tiles_with_discard(h);
   out[2] = best_ukeire(h, v);
 }
+extern "C" void orc_ukeire_3p(const int* hand, int n, const int* visible, int nv, int* out) {   // shanten.rs:470-615
+  std::vector<int> h(hand, hand + n), v(visible, visible + nv);
+  out[0] = shanten_tiles_3p(h);
+  out[1] = effective_tiles_3p_with_discard(h);
+  out[2] = best_ukeire_3p(h, v);
+}
 // sequence features of seat pid over the event delta [w0, w1) (words); fixed-size outputs padded like the device path
 extern "C" void orc_game_encode_seq(void* h, int pid, uint32_t w0, uint32_t w1, int game_style, uint16_t* sparse, float* numeric,
                                     uint16_t* prog, int max_prog, uint16_t* cand, uint16_t* lens) {

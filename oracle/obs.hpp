@@ -416,6 +416,74 @@ inline int best_ukeire(const std::vector<int>& hand, const std::vector<int>& vis
   return best;
 }
 
+// ---- 3P variants (shanten.rs:470-615), groundwork for Observation3P::encode_extended: draws range over the 27 tile kinds
+// that exist in sanma (SANMA_VALID_TILE_TYPES, shanten.rs:241-247)
+inline int shanten_tiles_3p(const std::vector<int>& tiles) {
+  uint8_t cnt[34] = {0};
+  int n = 0;
+  for (int t : tiles)
+    if (t / 4 < 34) cnt[t / 4]++, n++;
+  return shanten_from_counts_3p(cnt, n / 3);
+}
+inline bool sanma_kind(int k) { return k == 0 || (k >= 8 && k < 34); }
+inline int effective_tiles_3p(const std::vector<int>& hand) {
+  int cur = shanten_tiles_3p(hand), eff = 0;
+  uint8_t hc[34] = {0};
+  for (int t : hand)
+    if (t / 4 < 34) hc[t / 4]++;
+  for (int k = 0; k < 34; k++) {
+    if (!sanma_kind(k) || hc[k] >= 4) continue;
+    std::vector<int> nh = hand;
+    nh.push_back(k * 4);
+    if (shanten_tiles_3p(nh) < cur) eff++;
+  }
+  return eff;
+}
+inline int effective_tiles_3p_with_discard(const std::vector<int>& hand) {
+  if (hand.size() % 3 == 1) return effective_tiles_3p(hand);
+  int sh = shanten_tiles_3p(hand), best = 0;
+  for (size_t idx = 0; idx < hand.size(); idx++) {
+    std::vector<int> sub;
+    for (size_t i = 0; i < hand.size(); i++)
+      if (i != idx) sub.push_back(hand[i]);
+    if (shanten_tiles_3p(sub) <= sh) best = std::max(best, effective_tiles_3p(sub));
+  }
+  return best;
+}
+inline int best_ukeire_3p(const std::vector<int>& hand, const std::vector<int>& visible) {
+  int best = 0;
+  uint32_t vis[34] = {0};
+  for (int t : visible)
+    if (t / 4 < 34) vis[t / 4]++;
+  int cur = shanten_tiles_3p(hand);
+  uint8_t base[34] = {0};
+  for (int t : hand)
+    if (t / 4 < 34) base[t / 4]++;
+  for (size_t idx = 0; idx < hand.size(); idx++) {
+    std::vector<int> sub;
+    for (size_t i = 0; i < hand.size(); i++)
+      if (i != idx) sub.push_back(hand[i]);
+    uint8_t nc[34];
+    memcpy(nc, base, 34);
+    nc[hand[idx] / 4]--;
+    int ns = shanten_tiles_3p(sub);
+    if (ns > cur) continue;
+    uint32_t uke = 0;
+    for (int k = 0; k < 34; k++) {
+      if (!sanma_kind(k) || nc[k] >= 4) continue;
+      std::vector<int> th = sub;
+      th.push_back(k * 4);
+      if (shanten_tiles_3p(th) < ns) {
+        uint32_t rem = 4u > vis[k] ? 4u - vis[k] : 0u;
+        rem = rem > nc[k] ? rem - nc[k] : 0u;
+        uke += rem;
+      }
+    }
+    best = std::max(best, (int)uke);
+  }
+  return best;
+}
+
 // out: 215*34 floats, channel-major.  Channel blocks (python.rs:1281-1290): base 0, decay 74, shanten 78, ankan 94,
 // fuuro 98, action availability 178, discard candidates 189, pass context 194, last tedashi 197, riichi sutehai 206.
 inline void encode_obs_extended(const GameState& g, int pid, float* arr) {

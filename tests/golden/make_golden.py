@@ -374,6 +374,99 @@ def gen_shanten_3p():
     # tests/test_shanten.py known answers for calculate_shanten_3p
 
 
+def gen_ukeire_3p():
+    """shanten.rs:470-615 (calculate_shanten_3p / calculate_effective_tiles_3p_with_discard / calculate_best_ukeire_3p)
+    restated on top of the reference's own tables."""
+    T = load_shanten_tables()
+    rng = random.Random(20261019)
+    valid = [0] + list(range(8, 34))
+
+    def sh(tiles):
+        cnt = [0] * 34
+        for t in tiles:
+            cnt[t // 4] += 1
+        return ref_shanten_3p(T, cnt, len(tiles) // 3)
+
+    def effective(hand):
+        cur = sh(hand)
+        hc = [0] * 34
+        for t in hand:
+            hc[t // 4] += 1
+        return sum(1 for k in valid if hc[k] < 4 and sh(hand + [k * 4]) < cur)
+
+    def effective_with_discard(hand):
+        if len(hand) % 3 == 1:
+            return effective(hand)
+        s0 = sh(hand)
+        best = 0
+        for i in range(len(hand)):
+            sub = hand[:i] + hand[i + 1:]
+            if sh(sub) <= s0:
+                best = max(best, effective(sub))
+        return best
+
+    def best_ukeire(hand, visible):
+        vis = [0] * 34
+        for t in visible:
+            vis[t // 4] += 1
+        cur = sh(hand)
+        base = [0] * 34
+        for t in hand:
+            base[t // 4] += 1
+        best = 0
+        for i in range(len(hand)):
+            sub = hand[:i] + hand[i + 1:]
+            nc = list(base)
+            nc[hand[i] // 4] -= 1
+            ns = sh(sub)
+            if ns > cur:
+                continue
+            uke = 0
+            for k in valid:
+                if nc[k] >= 4:
+                    continue
+                if sh(sub + [k * 4]) < ns:
+                    uke += max(0, max(0, 4 - vis[k]) - nc[k])
+            best = max(best, uke)
+        return best
+
+    tiles108 = [t for t in range(136) if (t // 4) in valid]
+    lines = []
+    for it in range(300):
+        n = rng.choice([13, 14, 13, 14, 13, 14, 10, 11, 7, 8, 4, 5])
+        if it % 4 == 0:
+            hand = sorted(rng.sample(tiles108, n))
+        else:
+            cnt = [0] * 34
+            left = n
+            while left >= 3:
+                if rng.random() < 0.5:
+                    t = rng.choice(valid)
+                    if cnt[t] <= 1:
+                        cnt[t] += 3
+                        left -= 3
+                else:
+                    s0 = rng.choice([9, 18]) + rng.randrange(7)
+                    if max(cnt[s0:s0 + 3]) <= 3:
+                        for k in range(3):
+                            cnt[s0 + k] += 1
+                        left -= 3
+            while left > 0:
+                t = rng.choice(valid)
+                if cnt[t] < 4:
+                    cnt[t] += 1
+                    left -= 1
+            hand = [t * 4 + k for t in range(34) for k in range(cnt[t])]
+        rest = [t for t in tiles108 if t not in hand]
+        visible = rng.sample(rest, rng.randrange(0, 50))
+        lines.append(",".join(map(str, hand)) + " | " + ",".join(map(str, visible)) +
+                     f" | {sh(hand)} {effective_with_discard(hand)} {best_ukeire(hand, visible)}\n")
+    with open(os.path.join(OUT, "ukeire3p_golden.txt"), "w") as f:
+        f.write("# hand tids | visible tids | shanten_3p effective_tiles_3p_with_discard best_ukeire_3p   [reference tables' answers]\n")
+        f.writelines(lines)
+    print("ukeire3p_golden.txt", len(lines))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference checkout not found: fixtures are committed, nothing to do")
@@ -383,3 +476,4 @@ if __name__ == "__main__":
     gen_shanten()
     gen_ukeire()
     gen_shanten_3p()
+    gen_ukeire_3p()

@@ -278,3 +278,24 @@ def test_shanten_3p_golden_and_known_answers():
                        ("111999m111999p1z", 0, 0), ("19m147p258s12345z", 5, 5)):
         c = _parse_counts(hs)
         assert sh4(c) == e4 and sh3(c) == e3, hs
+
+
+def test_ukeire_3p_golden():
+    """shanten.rs:470-615 (the 3P shanten / effective-tile / ukeire helpers Observation3P's extended encoders call) against
+    answers computed from the reference's own tables (tests/golden/make_golden.py)."""
+    import ctypes as C
+    import os
+
+    o = oracle.load()
+    n = 0
+    for line in open(os.path.join(os.path.dirname(__file__), "golden", "ukeire3p_golden.txt")):
+        if line.startswith("#"):
+            continue
+        hs, vs, es = [x.strip() for x in line.split("|")]
+        hand = [int(x) for x in hs.split(",")]
+        vis = [int(x) for x in vs.split(",")] if vs else []
+        out = (C.c_int * 3)()
+        o.orc_ukeire_3p((C.c_int * len(hand))(*hand), len(hand), (C.c_int * max(1, len(vis)))(*vis), len(vis), out)
+        assert list(out) == [int(x) for x in es.split()], (hand, vis, list(out), es)
+        n += 1
+    assert n == 300
