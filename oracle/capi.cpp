@@ -382,7 +382,10 @@ extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {
   if (mask) encode_mask(*g, pid, mask);
 }
 // Observation::encode_extended: 215x34 floats (4P only)
-extern "C" void orc_game_encode_ext(void* h, int pid, float* obs) { encode_obs_extended(*(GameState*)h, pid, obs); }
+extern "C" void orc_game_encode_ext(void* h, int pid, float* obs) {
+  GameState* g = (GameState*)h;
+  g->np == 3 ? encode_obs_3p_extended(*g, pid, obs) : encode_obs_extended(*g, pid, obs);   // 215x34 (4P) / 215x27 (3P)
+}
 // Observation::encode_kawa_overview: 4x7x34 floats (4P)
 extern "C" void orc_game_encode_kawa(void* h, float* out) { encode_kawa_overview(*(GameState*)h, out); }
 // shanten.rs:250-393 on tid lists (known-answer hooks): out = {shanten, effective_with_discard, best_ukeire}

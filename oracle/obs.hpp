@@ -644,6 +644,137 @@ inline void encode_kawa_overview(const GameState& g, float* arr) {
   }
 }
 
+// Observation3P::encode_extended (observation_3p/python.rs:1117-1140; blocks observation_3p/encode.rs:22-620): 215 x 27 floats.
+// Same block offsets as 4P; three relative seats per group (the fourth channel of a group stays zero), two opponents in the
+// absolute-order blocks, compact columns, tile kind / 26, effective tiles / 27, the sanma dora successor, and the same two
+// quirks (called melds count one tile short in channel 30; the pass context is fed the discarder's seat,
+// state_3p/mod.rs:220).  A statement-level diff of encode_base_into against Observation3P::encode shows channel 30 as the only
+// difference.  (Oracle only so far: the device kernel for these rows is round-2 work.)
+inline void encode_obs_3p_extended(const GameState& g, int pid, float* arr) {
+  const int W = 27;
+  auto A = [&](int ch, int col) -> float& { return arr[ch * W + col]; };
+  auto B = [&](int ch, float v) { for (int k = 0; k < W; k++) arr[ch * W + k] = v; };
+  for (int i = 0; i < 215 * W; i++) arr[i] = 0.0f;
+  encode_obs_3p(g, pid, arr);
+  const int rel[3] = {pid, (pid + 1) % 3, (pid + 2) % 3};
+  std::vector<int> hand(g.players[pid].hand.begin(), g.players[pid].hand.end());
+  {
+    int used = 0;
+    for (int p = 0; p < 3; p++) used += (int)g.players[p].discards.size();
+    for (int p = 0; p < 3; p++)
+      for (auto& m : g.players[p].melds) used += (int)m.tiles.size() - (m.called_tile >= 0 ? 1 : 0);
+    used += (int)hand.size() + (int)g.dora_indicators.size();
+    B(30, (float)std::max(108 - used, 0) / 70.0f);
+  }
+  for (int c = 0; c < 3; c++) {   // decay (encode.rs:315-333)
+    const auto& d = g.players[rel[c]].discards;
+    for (size_t turn = 0; turn < d.size(); turn++) {
+      int col = compact3(d[turn] / 4);
+      if (col >= 0) A(74 + c, col) += expf(-0.2f * (float)(d.size() - 1 - turn));
+    }
+  }
+  {   // shanten efficiency (encode.rs:337-370)
+    std::vector<int> vis;
+    for (int p = 0; p < 3; p++)
+      for (uint8_t t : g.players[p].discards) vis.push_back(t);
+    for (int p = 0; p < 3; p++)
+      for (auto& m : g.players[p].melds)
+        for (uint8_t t : m.tiles) vis.push_back(t);
+    for (uint8_t t : g.dora_indicators) vis.push_back(t);
+    for (int c = 0; c < 3; c++) {
+      int b = 78 + c * 4;
+      if (c == 0) {
+        B(b, std::max((float)shanten_tiles_3p(hand), 0.0f) / 8.0f);
+        B(b + 1, (float)effective_tiles_3p_with_discard(hand) / 27.0f);
+        B(b + 2, (float)best_ukeire_3p(hand, vis) / 80.0f);
+      } else {
+        B(b, 0.5f), B(b + 1, 0.5f), B(b + 2, 0.5f);
+      }
+      B(b + 3, std::min((float)g.players[rel[c]].discards.size() / 18.0f, 1.0f));
+    }
+  }
+  for (int c = 0; c < 3; c++) {   // ankan (encode.rs:374-387), fuuro (encode.rs:392-418)
+    int mi = 0;
+    for (auto& m : g.players[rel[c]].melds) {
+      if (m.meld_type == Ankan && !m.tiles.empty() && compact3(m.tiles[0] / 4) >= 0) A(94 + c, compact3(m.tiles[0] / 4)) = 1.0f;
+      if (mi < 4) {
+        int slot = 0;
+        for (uint8_t t : m.tiles) {
+          if (slot >= 4) break;
+          int col = compact3(t / 4);
+          if (col >= 0) A(98 + c * 20 + mi * 5 + slot, col) = 1.0f;
+          if ((t == 16 || t == 52 || t == 88) && col >= 0) A(98 + c * 20 + mi * 5 + 4, col) = 1.0f;
+          slot++;
+        }
+      }
+      mi++;
+    }
+  }
+  {   // action availability (encode.rs:420-452)
+    bool may = !g.is_done && ((g.phase == RV_WAIT_ACT && g.current_player == pid) ||
+                              (g.phase == RV_WAIT_RESPONSE &&
+                               std::find(g.active_players.begin(), g.active_players.end(), (uint8_t)pid) != g.active_players.end()));
+    if (may)
+      for (auto& a : g._get_legal_actions_internal(pid)) {
+        switch (a.type) {
+          case RV_RIICHI: B(178, 1.0f); break;
+          case RV_CHI:
+            if (a.consume.size() == 2) {
+              int t0 = a.consume[0] / 4, t1 = a.consume[1] / 4, diff = std::abs(t1 - t0);
+              if (diff == 1) B(t0 < t1 ? 179 : 181, 1.0f);
+              else if (diff == 2) B(180, 1.0f);
+            }
+            break;
+          case RV_PON: B(182, 1.0f); break;
+          case RV_DAIMINKAN: B(183, 1.0f); break;
+          case RV_ANKAN: B(184, 1.0f); break;
+          case RV_KAKAN: B(185, 1.0f); break;
+          case RV_TSUMO:
+          case RV_RON: B(186, 1.0f); break;
+          case RV_KYUSHU_KYUHAI: B(187, 1.0f); break;
+          case RV_PASS: B(188, 1.0f); break;
+          default: break;   // Kita raises no channel
+        }
+      }
+  }
+  {   // discard candidates (encode.rs:455-498)
+    int cur = shanten_tiles_3p(hand), keep = 0, inc = 0;
+    B(189, (float)hand.size() / 34.0f);
+    for (size_t idx = 0; idx < hand.size(); idx++) {
+      std::vector<int> sub;
+      for (size_t i = 0; i < hand.size(); i++)
+        if (i != idx) sub.push_back(hand[i]);
+      int ns = shanten_tiles_3p(sub);
+      if (ns == cur) keep++;
+      else if (ns > cur) inc++;
+    }
+    if (!hand.empty()) {
+      B(190, (float)keep / (float)hand.size());
+      B(191, (float)inc / (float)hand.size());
+    }
+    B(192, cur == -1 ? 1.0f : 0.0f);
+    B(193, g.players[pid].riichi_declared ? 1.0f : 0.0f);
+  }
+  std::vector<uint8_t> dora_tiles;
+  for (uint8_t di : g.dora_indicators) dora_tiles.push_back((uint8_t)obs_next_tile_sanma(di));
+  auto tile_ctx = [&](int ch, int tile) {
+    int col = compact3(tile / 4);
+    if (col >= 0) B(ch, (float)col / 26.0f);
+    B(ch + 1, (tile == 16 || tile == 52 || tile == 88) ? 1.0f : 0.0f);
+    B(ch + 2, std::find(dora_tiles.begin(), dora_tiles.end(), (uint8_t)tile) != dora_tiles.end() ? 1.0f : 0.0f);
+  };
+  if (g.last_discard_pid >= 0) tile_ctx(194, g.last_discard_pid);   // the discarder's seat, as in 4P (state_3p/mod.rs:220)
+  {
+    int opp = 0;
+    for (int p = 0; p < 3; p++) {
+      if (p == pid) continue;
+      if (g.last_tedashis[p] >= 0) tile_ctx(197 + opp * 3, g.last_tedashis[p]);
+      if (g.riichi_sutehais[p] >= 0) tile_ctx(206 + opp * 3, g.riichi_sutehais[p]);
+      opp++;
+    }
+  }
+}
+
 // Observation::mask (observation/python.rs:98-111; 3P: observation_3p/python.rs:102-114) for a seat that owes an action:
 // 82 bytes (4P) or 60 bytes (3P)
 inline void encode_mask(const GameState& g, int pid, uint8_t* out) {

@@ -299,3 +299,49 @@ def test_ukeire_3p_golden():
         assert list(out) == [int(x) for x in es.split()], (hand, vis, list(out), es)
         n += 1
     assert n == 300
+
+
+def test_oracle_3p_extended_encoder_consistency():
+    """Observation3P::encode_extended restatement (oracle only so far): over a seeded sanma hanchan the base block equals
+    Observation3P::encode except channel 30, the shanten channels equal the pinned 3P helpers, every block keeps its shape
+    (fourth relative seat and third opponent empty)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from tests.backends import OracleBackend
+
+    o = oracle.load()
+    g = OracleBackend(5, 41)
+    g.reset()
+    ext = np.full(215 * 27 + 8, 7.0, np.float32)
+    base = np.zeros(74 * 27, np.float32)
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    n = 0
+    while True:
+        s = g.get_state()
+        if s.is_done:
+            break
+        for p in range(3):
+            if not (s.active_mask >> p) & 1:
+                continue
+            o.orc_game_encode_ext(g.h, p, fp(ext))
+            o.orc_game_encode(g.h, p, fp(base), None)
+            assert (ext[215 * 27:] == 7.0).all()
+            e, b = ext[:215 * 27].reshape(215, 27), base.reshape(74, 27)
+            keep = [c for c in range(74) if c != 30]
+            assert (e[keep] == b[keep]).all() and (e[30] >= b[30]).all()
+            hand = [s.hand[p][k] for k in range(s.hand_len[p])]
+            vis = [s.river[q][k] for q in range(3) for k in range(s.n_river[q])]
+            vis += [s.meld_tiles[q][m][k] for q in range(3) for m in range(s.n_melds[q]) for k in range(4) if s.meld_tiles[q][m][k] != 255]
+            vis += [s.dora_ind[k] for k in range(s.n_dora)]
+            out = (C.c_int * 3)()
+            o.orc_ukeire_3p((C.c_int * len(hand))(*hand), len(hand), (C.c_int * max(1, len(vis)))(*vis), len(vis), out)
+            f = np.float32
+            assert (e[78] == f(max(out[0], 0)) / f(8)).all() and (e[79] == f(out[1]) / f(27)).all() and (e[80] == f(out[2]) / f(80)).all()
+            assert not e[77].any() and not e[90:94].any() and not e[97].any() and not e[158:178].any()
+            assert not e[203:206].any() and not e[212:215].any()
+            assert np.isfinite(e).all()
+            n += 1
+        g.random_step(3, 41)
+    assert n > 300
