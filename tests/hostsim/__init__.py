@@ -20,7 +20,7 @@ def load():
     so = os.path.join(_HERE, "libhostsim.so")
     csrc = os.path.join(_HERE, "..", "..", "riichienv_b200", "csrc")
     srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "cuda_shim.h")] + [
-        os.path.join(csrc, f) for f in ("game.cuh", "hand.cuh", "tables.cuh", "obs.cuh", "obs_ext.cuh")]
+        os.path.join(csrc, f) for f in ("game.cuh", "hand.cuh", "tables.cuh", "obs.cuh", "obs_ext.cuh", "obs_ext3.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", so,
                                os.path.join(_HERE, "hostsim.cpp")])

@@ -16,6 +16,7 @@ static thread_local rv_game_state* hs_home = nullptr;
 
 #include "../../riichienv_b200/csrc/obs.cuh"
 #include "../../riichienv_b200/csrc/obs_ext.cuh"
+#include "../../riichienv_b200/csrc/obs_ext3.cuh"
 #include <cmath>
 #include "../../riichienv_b200/csrc/seq.cuh"
 
@@ -379,8 +380,63 @@ void hs_game_encode(void* p, int pid, float* obs, uint8_t* mask) {
   }
 }
 // Observation::encode_extended through the scalar definitions of obs_ext.cuh (4P): 215 x 34 floats
+// sanma rows (Observation3P::encode_extended, 215 x 27) through the scalar definitions of obs_ext3.cuh
+static void hs_encode_ext3(HS* h, int pid, float* obs) {
+  const G& g = h->g;
+  int seen[34], vis[34], called = 0;
+  for (int k = 0; k < 34; k++) {
+    seen[k] = obs_seen(g, pid, k);
+    vis[k] = seen[k] - (int)((g.c_cnt[pid][k / 9] >> (4 * (k % 9))) & 15);
+  }
+  for (int q = 0; q < 3; q++)
+    for (int m = 0; m < g.n_melds[q]; m++) called += g.meld_called[q][m] != RV_NONE;
+  for (int ch = 0; ch < OBS_CH; ch++) {
+    int kind;
+    uint64_t m;
+    float v;
+    obs_channel<true>(g, pid, ch, kind, m, v);
+    for (int col = 0; col < OBS_W3; col++) {
+      int k34 = obs_col_kind3(col);
+      obs[ch * OBS_W3 + col] = obs_value(kind, m, v, seen[k34], k34);
+    }
+  }
+  {
+    int used = 0;
+    for (int k = 0; k < 34; k++) used += seen[k];
+    int left = 108 - used + called;
+    for (int col = 0; col < OBS_W3; col++) obs[30 * OBS_W3 + col] = (float)(left < 0 ? 0 : left) / 70.0f;
+  }
+  DecayTab D;
+  for (int age = 0; age < RV_RIVER_CAP; age++) D.w[age] = expf(-0.2f * (float)age);
+  for (int r = 0; r < 4; r++) {
+    float* row = obs + (74 + r) * OBS_W3;
+    for (int col = 0; col < OBS_W3; col++) row[col] = 0.0f;
+    if (r < 3) obs_ext3_decay_row(g, &g.river[0][0], (pid + r) % 3, D, row);
+  }
+  ObsExtInfo I;
+  Ctx cx = hs_ctx(h);
+  obs_ext3_shanten_scalar(g_T, g, pid, vis, I);
+  I.avail = 0;
+  I.dora_kinds = obs_ext3_dora_kinds(g);
+  if (!g.is_done && ((g.active_mask >> pid) & 1)) {
+    uint32_t packed[RV_MAX_LEGAL];
+    int cnt = legal_actions(cx, g, pid, packed, -1, nullptr);
+    if (cnt > RV_MAX_LEGAL) cnt = RV_MAX_LEGAL;
+    for (int k = 0; k < cnt; k++) I.avail |= obs_avail_bit(expand_act(g, pid, packed[k]));
+  }
+  for (int ch = 78; ch < OBSX_CH; ch++) {
+    uint64_t m;
+    float v;
+    obs_ext3_channel(g, g, pid, ch, I, m, v);
+    for (int col = 0; col < OBS_W3; col++) obs[ch * OBS_W3 + col] = ((m >> col) & 1) ? v : 0.0f;
+  }
+}
 void hs_game_encode_ext(void* p, int pid, float* obs) {
   HS* h = (HS*)p;
+  if (is_sanma(h->g)) {
+    hs_encode_ext3(h, pid, obs);
+    return;
+  }
   const G& g = h->g;
   int seen[34], vis[34], called = 0;
   for (int k = 0; k < 34; k++) {

@@ -254,6 +254,37 @@ def test_shanten_3p_kernel_source_vs_oracle(libs):
         assert orc.orc_shanten_counts(a, sum(cnt) // 3) == hs.hs_shanten_counts(a, sum(cnt) // 3), cnt
 
 
+def test_observation_encode_extended_lockstep_3p(libs):
+    """Sanma: Observation3P.encode_extended() (215x27 f32) of every acting seat — and of every seat every 16th step — over a
+    seeded sanma hanchan: the scalar definitions of obs_ext3.cuh against the oracle, bit-equal."""
+    import numpy as np
+
+    orc, hs = libs
+    n_obs = 0
+    for seed in (51, 52):
+        o, h = OracleBackend(5, seed), HostsimBackend(5, seed)
+        o.reset()
+        h.reset()
+        a = np.full(215 * 27 + 8, 7.0, np.float32)
+        b = np.full(215 * 27 + 8, 7.0, np.float32)
+        fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        step = 0
+        while True:
+            s = o.get_state()
+            if s.is_done:
+                break
+            for p in range(3):
+                if (s.active_mask >> p) & 1 or step % 16 == 0:
+                    orc.orc_game_encode_ext(o.h, p, fp(a))
+                    hs.hs_game_encode_ext(h.h, p, fp(b))
+                    assert a.tobytes() == b.tobytes(), f"seed {seed} step {step} seat {p}: channels {sorted(set(np.nonzero(a != b)[0] // 27))}"
+                    n_obs += 1
+            o.random_step(5, seed)
+            h.random_step(5, seed)
+            step += 1
+    assert n_obs > 1000
+
+
 def test_observation_encode_lockstep_3p(libs):
     """Sanma: Observation3P.encode() (74x27 f32) and mask() (60 ids) of every acting seat at every step: bit-equal."""
     import numpy as np
