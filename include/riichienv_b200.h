@@ -339,10 +339,11 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
 
 /* Extended observation tensors: Observation::encode_extended (observation/python.rs:1272-1294; channel blocks
  * observation/encode.rs:12-584) — base 74 channels + discard decay, shanten efficiency (shanten.rs:250-393), ankan / fuuro
- * overview, action availability, discard candidates, pass context, last tedashi, riichi sutehai = 215 channels.  4P only
- * (RV_ERR_UNSUPPORTED for a sanma vector).  Same row order and arguments as rv_vec_encode:
+ * overview, action availability, discard candidates, pass context, last tedashi, riichi sutehai = 215 channels.
+ * Same row order and arguments as rv_vec_encode:
  *   d_obs   [max_obs][215][34] f32  (device, 8-byte aligned)       — may be NULL
- *   d_mask  [max_obs][82] u8, d_index [max_obs] i32                — may be NULL */
+ *   d_mask  [max_obs][82] u8, d_index [max_obs] i32                — may be NULL
+ *   sanma (Observation3P::encode_extended, observation_3p/python.rs:1117-1140): [215][27] f32 (4-byte aligned) and [60] u8 */
 int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
 
 /* Observation::encode_kawa_overview (observation/python.rs:881-930) for every seat that owes an action, same row order as

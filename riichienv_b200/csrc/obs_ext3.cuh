@@ -160,4 +160,110 @@ __device__ inline void obs_ext3_channel(const G& g, const G& rec, int pid, int c
   mask = bcast ? ALL : (((m34 & 1) | ((m34 >> 7) & ~1ull)) & ALL);   // 34 kinds -> 27 columns
 }
 
+#ifdef __CUDACC__
+// shanten.rs:470-615, one warp: lane l = the l-th distinct kind in hand (shanten after discarding it); the discards that do
+// not raise shanten are compacted (+ a "no discard" entry for a 3n+1 hand) and their (discard, draw) pairs — 27 draws each —
+// are dealt out flat over the lanes, one full shanten_counts_3p per pair (the incremental evaluation of obs_ext.cuh does not
+// carry over: relocating 1m / 9m into honor slots couples the manzu and honor suits).
+__device__ __forceinline__ void obs_ext3_shanten_warp(const Tables& T, const G& g, int pid, const int* seen, int lane, ObsExtScratch& X,
+                                                     ObsExtInfo& I) {
+  const Cnt c = obs_hand_cnt(g, pid);
+  const int n = g.hand_len[pid];
+  const int cur = shanten_counts_3p(T, c, n / 3);
+  uint64_t present = cnt_present(c);
+  const int D = __popcll(present);
+  int kind = -1;
+  for (int i = 0; i < 14; i++) {
+    if (i == lane && present) kind = __ffsll((long long)present) - 1;
+    present &= present - 1;
+  }
+  int ss = 99, cd = 0;
+  if (lane < D) {
+    cd = cnt_get(c, kind);
+    Cnt sub = c;
+    cnt_sub(sub, kind);
+    ss = shanten_counts_3p(T, sub, (n - 1) / 3);
+  }
+  int keep = ss == cur ? cd : 0, inc = (lane < D && ss > cur) ? cd : 0;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    keep += __shfl_xor_sync(0xFFFFFFFFu, keep, o);
+    inc += __shfl_xor_sync(0xFFFFFFFFu, inc, o);
+  }
+  const bool valid = lane < D && ss <= cur;
+  const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+  const int V = __popc(vmask);
+  if (valid) X.vk[__popc(vmask & ((1u << lane) - 1))] = (uint16_t)(kind | ((ss + 2) << 8));
+  const bool self13 = n % 3 == 1;
+  if (lane == 0 && self13) X.vk[V] = (uint16_t)(0xFF | ((cur + 2) << 8));
+  if (lane < 16) X.uke[lane] = 0, X.eff[lane] = 0;
+  __syncwarp();
+  const int total = (V + (self13 ? 1 : 0)) * OBS_W3;
+  for (int j = lane; j < total; j += 32) {
+    const int di = j / OBS_W3, k = obs_col_kind3(j - di * OBS_W3);
+    const int e = X.vk[di], dk = e & 0xFF, base_s = (e >> 8) - 2;
+    Cnt t = c;
+    if (dk != 0xFF) cnt_sub(t, dk);
+    const int sc = cnt_get(t, k);
+    if (sc < 4) {
+      cnt_add(t, k);
+      if (shanten_counts_3p(T, t, dk != 0xFF ? n / 3 : (n + 1) / 3) < base_s) {
+        const int vis = seen[k] - cnt_get(c, k);           // seen = hand + rivers + melds + indicators
+        atomicAdd(&X.uke[di], max(max(4 - vis, 0) - sc, 0));
+        atomicAdd(&X.eff[di], 1);
+      }
+    }
+  }
+  __syncwarp();
+  int uke = lane < V ? X.uke[lane] : 0;
+  int eff = self13 ? (lane == V ? X.eff[lane] : 0) : (lane < V ? X.eff[lane] : 0);
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uke = max(uke, __shfl_xor_sync(0xFFFFFFFFu, uke, o));
+    eff = max(eff, __shfl_xor_sync(0xFFFFFFFFu, eff, o));
+  }
+  I.shanten = cur, I.eff = eff, I.uke = uke, I.keep = keep, I.inc = inc;
+}
+
+// One warp, one sanma row: base gather + describe (obs.cuh, SANMA), the extended descriptors, 5,805 four-byte streaming stores
+// (a 23,220-byte row is only 4-byte aligned).
+__device__ __forceinline__ void obs_ext3_encode_warp(const Tables& T, const DecayTab& D, const G& g, const G& rec, const uint8_t* river,
+                                                     int pid, uint32_t avail, float* dst, ObsScratch& S, ObsExtScratch& X, int lane) {
+  int called = 0;
+  if (lane < 12 && (lane & 3) < g.n_melds[lane >> 2] && rec.meld_called[lane >> 2][lane & 3] != RV_NONE) called = 1;
+  called = __popc(__ballot_sync(0xFFFFFFFFu, called));
+  obs_describe_warp<true>(g, river, pid, S, lane, called);
+  for (int i = lane; i < 4 * 36; i += 32) (&X.decay[0][0])[i] = 0.0f;
+  __syncwarp();
+  if (lane < 3) obs_ext3_decay_row(g, river, (pid + lane) % 3, D, X.decay[lane]);
+  ObsExtInfo I;
+  obs_ext3_shanten_warp(T, g, pid, S.seen, lane, X, I);
+  I.avail = avail;
+  I.dora_kinds = obs_ext3_dora_kinds(g);
+  for (int ch = lane; ch < 78; ch += 32) {
+    uint4 dd = make_uint4(0, 0, 0, 0);
+    if (ch < OBS_CH && ch != 63) dd = *reinterpret_cast<const uint4*>(&S.d[ch]);
+    *reinterpret_cast<uint4*>(&X.d[ch]) = dd;
+  }
+  for (int ch = 78 + lane; ch < OBSX_CH; ch += 32) {
+    uint64_t m;
+    float v;
+    obs_ext3_channel(g, rec, pid, ch, I, m, v);
+    X.d[ch].mask = m;
+    X.d[ch].val = v;
+  }
+  __syncwarp();
+  #pragma unroll 1
+  for (int e = lane; e < OBSX3_FLOATS; e += 32) {
+    const int ch = e / OBS_W3, col = e - ch * OBS_W3;
+    float o;
+    if (ch == 63) o = (float)S.seen[obs_col_kind3(col)] * 0.25f;
+    else if (ch >= 74 && ch < 78) o = X.decay[ch - 74][col];
+    else o = ((X.d[ch].mask >> col) & 1) ? X.d[ch].val : 0.0f;
+    __stcs(dst + e, o);
+  }
+  __syncwarp();
+}
+#endif
+
 }  // namespace rv

@@ -12,6 +12,7 @@
 
 #include "obs.cuh"
 #include "obs_ext.cuh"
+#include "obs_ext3.cuh"
 #include "seq.cuh"
 
 using namespace rv;
@@ -951,6 +952,7 @@ __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int
 }
 
 // Extended rows (Observation::encode_extended, 215 x 34): one warp per game, staged like obs_encode_kernel; obs_ext.cuh.
+template <bool SANMA>
 __global__ void __launch_bounds__(128, 6) obs_ext_kernel(Tables T, DecayTab D, const G* states, int64_t n, const int32_t* offsets,
                                                       const uint32_t* idbits, float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
   __shared__ ObsScratch scratch[4];
@@ -981,9 +983,15 @@ __global__ void __launch_bounds__(128, 6) obs_ext_kernel(Tables T, DecayTab D, c
     if (!((g.active_mask >> pid) & 1)) continue;
     if (row >= max_obs) break;
     const uint32_t* bits = idbits + ((size_t)gi * MAXP + pid) * 3;
-    if (obs) obs_ext_encode_warp(T, D, g, states[gi], river, pid, (bits[2] >> OBS_AVAIL_SHIFT) & 0x7FFu, obs + (size_t)row * (OBSX_CH * OBS_W),
-                                 scratch[w], xscratch[w], lane);
-    if (mask) obs_mask_row_warp<false>(bits, mask + (size_t)row * OBS_IDS, lane);
+    if (obs) {
+      if constexpr (SANMA)
+        obs_ext3_encode_warp(T, D, g, states[gi], river, pid, (bits[2] >> OBS_AVAIL_SHIFT) & 0x7FFu, obs + (size_t)row * OBSX3_FLOATS,
+                             scratch[w], xscratch[w], lane);
+      else
+        obs_ext_encode_warp(T, D, g, states[gi], river, pid, (bits[2] >> OBS_AVAIL_SHIFT) & 0x7FFu, obs + (size_t)row * (OBSX_CH * OBS_W),
+                            scratch[w], xscratch[w], lane);
+    }
+    if (mask) obs_mask_row_warp<SANMA>(bits, mask + (size_t)row * (SANMA ? OBS_IDS3 : OBS_IDS), lane);
     if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
     row++;
   }
@@ -1886,7 +1894,7 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
 }
 int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
   rv_ctx* c = v->ctx;
-  if (v->game_mode >= 3) return RV_ERR_UNSUPPORTED;    // 4P rows only (Observation3P has its own 27-column encoders)
+  const bool sanma = v->game_mode >= 3;                // sanma: Observation3P::encode_extended, 215 x 27 (obs_ext3.cuh)
   CK(cudaSetDevice(c->device));
   int64_t n = v->n;
   int rc = obs_offsets(v);
@@ -1897,8 +1905,13 @@ int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index
     return d;
   }();
   if (!v->d_idbits) CK(cudaMalloc(&v->d_idbits, sizeof(uint32_t) * 3 * MAXP * n));
-  legal_ids_kernel<false, true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_idbits);
-  obs_ext_kernel<<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, D, v->d_states, n, v->d_obs_offsets, v->d_idbits, d_obs, d_mask, d_index, max_obs);
+  if (sanma) {
+    legal_ids_kernel<true, true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_idbits);
+    obs_ext_kernel<true><<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, D, v->d_states, n, v->d_obs_offsets, v->d_idbits, d_obs, d_mask, d_index, max_obs);
+  } else {
+    legal_ids_kernel<false, true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_idbits);
+    obs_ext_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(c->T, D, v->d_states, n, v->d_obs_offsets, v->d_idbits, d_obs, d_mask, d_index, max_obs);
+  }
   CK(cudaGetLastError());
   return obs_row_count(v, n_obs);
 }

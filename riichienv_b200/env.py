@@ -415,7 +415,7 @@ class Observation:
             if self._token != self._env._token:
                 raise RuntimeError("tensors are computed on the device from the live game: call the extended encoders on "
                                    "the observations of the latest reset()/step()")
-            self._ext = np.frombuffer(self._env._encode(self.player_id, extended=True), dtype=np.float32).reshape(215, 34)
+            self._ext = np.frombuffer(self._env._encode(self.player_id, extended=True), dtype=np.float32).reshape(215, -1)
         return self._ext
 
     # The standalone encoders of observation/python.rs:195-1270 are the channel blocks of encode_extended
@@ -674,9 +674,7 @@ class RiichiEnv:
         dev = f"cuda:{self._v.ctx.device}"
         idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
         if extended:
-            if self._np == 3:
-                raise NotImplementedError("encode_extended: 4-player observations only")
-            obs = torch.zeros((4, 215, 34), dtype=torch.float32, device=dev)
+            obs = torch.zeros((4, 215, 27 if self._np == 3 else 34), dtype=torch.float32, device=dev)
             n = self._v.encode_extended(obs=obs, index=idx, max_obs=4)
         else:
             obs = torch.zeros((4, 74, 27 if self._np == 3 else 34), dtype=torch.float32, device=dev)

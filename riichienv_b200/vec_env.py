@@ -104,7 +104,8 @@ class VecRiichiEnv:
 
     def encode_extended(self, obs=None, mask=None, index=None, max_obs=None, sync=True):
         """Observation.encode_extended rows (observation/python.rs:1272-1294) of every seat that owes an action, into DEVICE
-        buffers: obs [max_obs,215,34] f32, mask [max_obs,82] u8, index [max_obs] i32.  4P only.  Returns the row count."""
+        buffers: obs [max_obs,215,34] f32, mask [max_obs,82] u8, index [max_obs] i32 (sanma: Observation3P.encode_extended,
+        [max_obs,215,27] and 60 mask ids).  Returns the row count."""
         def ptr(t):
             return None if t is None else C.c_void_p(t.data_ptr())
         if max_obs is None:

@@ -410,24 +410,27 @@ def test_observation_encode_vs_oracle(orc, mode):
     assert checked > (5000 if mode >= 3 else 10000)
 
 
-def test_observation_encode_extended_vs_oracle(orc):
-    """rv_vec_encode_ext: Observation::encode_extended (215x34) + mask of every acting seat of 192 hanchan at many points of
-    the rollout, bytes equal to the oracle's restatement (observation/encode.rs:12-584); nothing written past the last row."""
+@pytest.mark.parametrize("mode", [2, 5])
+def test_observation_encode_extended_vs_oracle(orc, mode):
+    """rv_vec_encode_ext: Observation::encode_extended (215x34; sanma 215x27) + mask of every acting seat of 192 hanchan at many
+    points of the rollout, bytes equal to the oracle's restatement (observation/encode.rs:12-584, observation_3p/encode.rs:22-620);
+    nothing written past the last row."""
     import torch
 
     from riichienv_b200.vec_env import VecRiichiEnv
 
     n = 192
-    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=9500)
+    W, IDS = (27, 60) if mode >= 3 else (34, 82)
+    v = VecRiichiEnv(n, mode, A.RULE_DEFAULT_TENHOU, seed_base=9500)
     v.reset()
-    games = [orc.orc_game_new(2, 9500 + g, 0, A.RULE_DEFAULT_TENHOU, 0) for g in range(n)]
+    games = [orc.orc_game_new(mode, 9500 + g, 0, A.RULE_DEFAULT_TENHOU, 0) for g in range(n)]
     for h in games:
         orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
-    obs = torch.empty((n * 3, 215, 34), dtype=torch.float32, device="cuda")
-    mask = torch.empty((n * 3, 82), dtype=torch.uint8, device="cuda")
+    obs = torch.empty((n * 3, 215, W), dtype=torch.float32, device="cuda")
+    mask = torch.empty((n * 3, IDS), dtype=torch.uint8, device="cuda")
     idx = torch.empty((n * 3,), dtype=torch.int32, device="cuda")
-    a = np.zeros(215 * 34, np.float32)
-    m = np.zeros(82, np.uint8)
+    a = np.zeros(215 * W, np.float32)
+    m = np.zeros(IDS, np.uint8)
     checked = 0
     seen_channels = np.zeros(215, bool)
     for it in range(50):
@@ -448,10 +451,10 @@ def test_observation_encode_extended_vs_oracle(orc):
                     orc.orc_game_encode_ext(games[g], p, a.ctypes.data_as(C.POINTER(C.c_float)))
                     orc.orc_game_encode(games[g], p, None, m.ctypes.data_as(C.POINTER(C.c_uint8)))
                     if h_obs[expect_rows].tobytes() != a.tobytes():
-                        bad = sorted(set(np.nonzero(h_obs[expect_rows].ravel() != a)[0] // 34))
+                        bad = sorted(set(np.nonzero(h_obs[expect_rows].ravel() != a)[0] // W))
                         raise AssertionError(f"iter {it} game {g} seat {p}: channels {bad}")
                     assert h_mask[expect_rows].tobytes() == m.tobytes(), f"iter {it} game {g} seat {p} mask"
-                    seen_channels |= a.reshape(215, 34).any(axis=1)
+                    seen_channels |= a.reshape(215, W).any(axis=1)
                     expect_rows += 1
                     checked += 1
         assert expect_rows == rows
@@ -462,11 +465,11 @@ def test_observation_encode_extended_vs_oracle(orc):
                 orc.orc_game_random_step(games[g], 23, 9500 + g)
     for h in games:
         orc.orc_game_free(h)
-    assert checked > 6000
+    assert checked > (3000 if mode >= 3 else 6000)
     # every block of the extended layout was exercised with non-zero content
     # (riichi sutehai, 206-214, needs an opponent's riichi: tests/test_scenarios.py::test_ext_tile_context_channels)
     for lo, hi in ((74, 78), (78, 94), (94, 98), (98, 178), (178, 189), (189, 194), (197, 206)):
-        assert seen_channels[lo:hi].any(), (lo, hi)
+        assert mode >= 3 or seen_channels[lo:hi].any(), (lo, hi)
 
 
 def test_kawa_overview_vs_oracle(orc):
