@@ -418,13 +418,18 @@ class Observation:
             self._ext = np.frombuffer(self._env._encode(self.player_id, extended=True), dtype=np.float32).reshape(215, -1)
         return self._ext
 
+    def _ext_4p(self):
+        if self._env._np == 3:   # Observation3P's standalone encoders have their own shapes (3 seats, 27 columns)
+            raise NotImplementedError("standalone extended encoders: 4-player observations only (encode_extended() covers sanma)")
+        return self._ext_row()
+
     # The standalone encoders of observation/python.rs:195-1270 are the channel blocks of encode_extended
     # (observation/encode.rs:293-584 holds the same bodies as `_into` variants): slices of the device-computed row.
     def encode_discard_history_decay(self):  # python.rs:196-249 -> (4, 34)
-        return self._ext_row()[74:78].tobytes()
+        return self._ext_4p()[74:78].tobytes()
 
     def encode_shanten_efficiency(self):  # python.rs:820-878 -> (4, 4)
-        return self._ext_row()[78:94, 0].tobytes()
+        return self._ext_4p()[78:94, 0].tobytes()
 
     def encode_kawa_overview(self):  # python.rs:881-930 -> (4, 7, 34), seats in absolute order (obs_kawa_kernel)
         import torch
@@ -450,25 +455,25 @@ class Observation:
         return np.ones((4, 21), np.float32).tobytes()
 
     def encode_ankan_overview(self):  # python.rs:976-1010 -> (4, 34)
-        return self._ext_row()[94:98].tobytes()
+        return self._ext_4p()[94:98].tobytes()
 
     def encode_fuuro_overview(self):  # python.rs:931-974 -> (4, 4, 5, 34)
-        return self._ext_row()[98:178].tobytes()
+        return self._ext_4p()[98:178].tobytes()
 
     def encode_action_availability(self):  # python.rs:1012-1065 -> (11,)
-        return self._ext_row()[178:189, 0].tobytes()
+        return self._ext_4p()[178:189, 0].tobytes()
 
     def encode_discard_candidates(self):  # python.rs:1208-1270 -> (5,)
-        return self._ext_row()[189:194, 0].tobytes()
+        return self._ext_4p()[189:194, 0].tobytes()
 
     def encode_pass_context(self):  # python.rs:1165-1206 -> (3,)
-        return self._ext_row()[194:197, 0].tobytes()
+        return self._ext_4p()[194:197, 0].tobytes()
 
     def encode_last_tedashis(self):  # python.rs:1117-1163 -> (3, 3)
-        return self._ext_row()[197:206, 0].tobytes()
+        return self._ext_4p()[197:206, 0].tobytes()
 
     def encode_riichi_sutehais(self):  # python.rs:1067-1115 -> (3, 3)
-        return self._ext_row()[206:215, 0].tobytes()
+        return self._ext_4p()[206:215, 0].tobytes()
 
     # ---- sequence features (observation/python.rs:1297-1364): raw bytes, as the reference returns them ----
     def _seq_features(self):
