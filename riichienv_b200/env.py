@@ -418,20 +418,50 @@ class Observation:
             self._ext = np.frombuffer(self._env._encode(self.player_id, extended=True), dtype=np.float32).reshape(215, -1)
         return self._ext
 
-    def _ext_4p(self):
-        if self._env._np == 3:   # Observation3P's standalone encoders have their own shapes (3 seats, 27 columns)
-            raise NotImplementedError("standalone extended encoders: 4-player observations only (encode_extended() covers sanma)")
-        return self._ext_row()
+    # The standalone encoders of observation/python.rs:195-1270 (sanma: observation_3p/python.rs:198-1115) are the channel
+    # blocks of encode_extended — encode.rs holds the same bodies as `_into` variants; a statement-level diff shows only
+    # renames — so they are slices of the device-computed row.  Sanma rows carry three relative seats per group and two
+    # opponents (NP = 3): the slices stop there.
+    def _seats(self):
+        return 3 if self._env._np == 3 else 4
 
-    # The standalone encoders of observation/python.rs:195-1270 are the channel blocks of encode_extended
-    # (observation/encode.rs:293-584 holds the same bodies as `_into` variants): slices of the device-computed row.
-    def encode_discard_history_decay(self):  # python.rs:196-249 -> (4, 34)
-        return self._ext_4p()[74:78].tobytes()
+    def encode_discard_history_decay(self, decay_rate=None):  # python.rs:196-249 -> (NP, W)
+        if decay_rate is not None and float(decay_rate) != 0.2:
+            raise NotImplementedError("the device table holds exp(-0.2 * age): only the default decay_rate")
+        return self._ext_row()[74:74 + self._seats()].tobytes()
 
-    def encode_shanten_efficiency(self):  # python.rs:820-878 -> (4, 4)
-        return self._ext_4p()[78:94, 0].tobytes()
+    def encode_shanten_efficiency(self):  # python.rs:820-878 -> (NP, 4)
+        return self._ext_row()[78:78 + 4 * self._seats(), 0].tobytes()
 
-    def encode_kawa_overview(self):  # python.rs:881-930 -> (4, 7, 34), seats in absolute order (obs_kawa_kernel)
+    def encode_ankan_overview(self):  # python.rs:976-1010 -> (NP, W)
+        return self._ext_row()[94:94 + self._seats()].tobytes()
+
+    def encode_fuuro_overview(self):  # python.rs:931-974 -> (NP, 4, 5, W)
+        return self._ext_row()[98:98 + 20 * self._seats()].tobytes()
+
+    def encode_action_availability(self):  # python.rs:1012-1065 -> (11,)
+        return self._ext_row()[178:189, 0].tobytes()
+
+    def encode_discard_candidates(self):  # python.rs:1208-1270 -> (5,)
+        return self._ext_row()[189:194, 0].tobytes()
+
+    def encode_pass_context(self):  # python.rs:1165-1206 -> (3,)
+        return self._ext_row()[194:197, 0].tobytes()
+
+    def encode_last_tedashis(self):  # python.rs:1117-1163 -> (NP - 1, 3)
+        return self._ext_row()[197:197 + 3 * (self._seats() - 1), 0].tobytes()
+
+    def encode_riichi_sutehais(self):  # python.rs:1067-1115 -> (NP - 1, 3)
+        return self._ext_row()[206:206 + 3 * (self._seats() - 1), 0].tobytes()
+
+    def encode_furiten_ron_possibility(self):  # python.rs:251-293 -> (NP, 21)
+        """All ones: the encoder only clears a seat's row after three consecutive tsumogiri flags, and the live env never
+        fills `tsumogiri_flags` (observation/mod.rs:105) — a constant, so nothing is computed."""
+        import numpy as np
+
+        return np.ones((self._seats(), 21), np.float32).tobytes()
+
+    def encode_kawa_overview(self):  # python.rs:881-930 -> (4, 7, 34), seats in absolute order (obs_kawa_kernel; 4P)
         import torch
 
         if self._token != self._env._token:
@@ -446,34 +476,6 @@ class Observation:
         if self.player_id not in rows:
             raise ValueError(f"seat {self.player_id} owes no action")
         return out[rows.index(self.player_id)].cpu().numpy().tobytes()
-
-    def encode_furiten_ron_possibility(self):  # python.rs:251-293 -> (4, 21)
-        """All ones: the encoder only clears a seat's row after three consecutive tsumogiri flags, and the live env never
-        fills `tsumogiri_flags` (observation/mod.rs:105) — a constant, so nothing is computed."""
-        import numpy as np
-
-        return np.ones((4, 21), np.float32).tobytes()
-
-    def encode_ankan_overview(self):  # python.rs:976-1010 -> (4, 34)
-        return self._ext_4p()[94:98].tobytes()
-
-    def encode_fuuro_overview(self):  # python.rs:931-974 -> (4, 4, 5, 34)
-        return self._ext_4p()[98:178].tobytes()
-
-    def encode_action_availability(self):  # python.rs:1012-1065 -> (11,)
-        return self._ext_4p()[178:189, 0].tobytes()
-
-    def encode_discard_candidates(self):  # python.rs:1208-1270 -> (5,)
-        return self._ext_4p()[189:194, 0].tobytes()
-
-    def encode_pass_context(self):  # python.rs:1165-1206 -> (3,)
-        return self._ext_4p()[194:197, 0].tobytes()
-
-    def encode_last_tedashis(self):  # python.rs:1117-1163 -> (3, 3)
-        return self._ext_4p()[197:206, 0].tobytes()
-
-    def encode_riichi_sutehais(self):  # python.rs:1067-1115 -> (3, 3)
-        return self._ext_4p()[206:215, 0].tobytes()
 
     # ---- sequence features (observation/python.rs:1297-1364): raw bytes, as the reference returns them ----
     def _seq_features(self):
