@@ -61,7 +61,7 @@ enum rv_game_mode {
 
 #define RV_NONE 0xFFu /* Option::None for u8 fields */
 #define RV_NP 4
-#define RV_HAND_CAP 14
+#define RV_HAND_CAP 16 /* 13 + the drawn tile; the reference's hands are unbounded Vecs and its own tests park up to 15 tiles in one */
 #define RV_RIVER_CAP 32
 #define RV_MAX_CLAIMS 48
 #define RV_MAX_LEGAL 64
@@ -98,11 +98,12 @@ typedef struct rv_game_state {
   uint64_t c_cnt[RV_NP][4];       /* concealed-hand histogram, 4-bit count per tile kind; [seat][m,p,s,z] */
   uint64_t c_river_kinds[RV_NP];  /* bit k: some own discard has kind k (furiten test)                     */
   uint64_t c_waits[RV_NP];        /* get_waits_u8 of the seat's hand when it is 13-tile-equivalent, else 0 */
-  uint64_t seed;                  /* wall.seed */
+  uint8_t hand[RV_NP][RV_HAND_CAP]; /* ordered as the reference's Vec (legal_actions.rs:102-110 lists discards in this order);
+                                       RV_NONE pad; each row is 16-byte aligned (offset 192 + 16 seat): one 128-bit load */
+  uint64_t seed;                  /* wall.seed; also the game id that keys the on-device agent */
   uint64_t ev_hash;               /* FNV-1a-64 over the 32-bit words of the binary event stream */
   uint32_t c_key[RV_NP][4];       /* base-5 suit keys of c_cnt (table indices)                             */
   uint32_t river_tedashi[RV_NP];  /* bit i = discard_from_hand[i] */
-  uint32_t river_riichi[RV_NP];   /* bit i = discard_is_riichi[i] */
   int32_t score[RV_NP];
   uint32_t riichi_sticks;
   uint32_t turn_count;
@@ -111,7 +112,6 @@ typedef struct rv_game_state {
   uint32_t ev_count;              /* events pushed since reset */
   uint32_t ev_words;              /* 32-bit words pushed since reset (log length, even when the log is capped/off) */
 
-  uint8_t hand[RV_NP][RV_HAND_CAP]; /* ordered as the reference's Vec (legal_actions.rs:102-110 lists discards in this order) */
   uint8_t hand_len[RV_NP];
   uint8_t meld_tiles[RV_NP][4][4];  /* tids, order as stored by the reference (sorted); RV_NONE pad */
   uint8_t meld_type[RV_NP][4];      /* rv_meld_type */
@@ -142,7 +142,7 @@ typedef struct rv_game_state {
   uint8_t n_claims[RV_NP];        /* lengths of claims[] below */
   uint8_t pending_tail[2];        /* {tile, tsumogiri} of a discard whose follow-up (_resolve_discard) is deferred inside a rollout
                                      kernel; pending_tail[0]==RV_NONE outside kernels (always, as seen through this API) */
-  uint8_t hot_reserved[2];
+  uint8_t hot_reserved[10];
 
   /* ---- cold part (offset RV_HOT_BYTES): large arrays touched a byte or a few words at a time ---- */
   uint8_t wall[136];
@@ -151,6 +151,7 @@ typedef struct rv_game_state {
   uint32_t claims[RV_NP][RV_MAX_CLAIMS];
   /* fields a step rarely reads: kept out of the staged prefix so that more games fit in an SM's shared memory */
   uint64_t hand_index;              /* wall.hand_index */
+  uint32_t river_riichi[RV_NP];     /* bit i = discard_is_riichi[i] (written by a riichi discard, read by nobody on the step path) */
   int32_t score_delta[RV_NP];
   uint8_t meld_from[RV_NP][4];      /* from_who, RV_NONE == -1 */
   uint8_t meld_called[RV_NP][4];    /* called_tile or RV_NONE */
@@ -160,7 +161,7 @@ typedef struct rv_game_state {
   uint8_t riichi_sutehai[RV_NP];    /* state/mod.rs:89 */
   uint8_t last_tedashi[RV_NP];      /* state/mod.rs:90 */
   uint8_t n_kita[RV_NP];            /* 3P: kita count per seat */
-  uint8_t reserved[20];             /* keeps sizeof a multiple of 16 (bulk-copy granularity) */
+  uint8_t reserved[4];              /* keeps sizeof a multiple of 16 (bulk-copy granularity) */
 } rv_game_state;
 #define RV_HOT_BYTES 544          /* == offsetof(rv_game_state, wall); a multiple of 16 */
 
@@ -313,6 +314,13 @@ int rv_vec_counters(rv_vec* v, uint32_t* step_count, uint32_t* kyoku_count, uint
 /* Snapshot get/set (RiichiEnv getters/setters, env.rs:134-635; clone() 358-372). */
 int rv_vec_get_state(rv_vec* v, int64_t game, rv_game_state* out);
 int rv_vec_set_state(rv_vec* v, int64_t game, const rv_game_state* in);
+/* RiichiEnv::clone / __copy__ / __deepcopy__ (env.rs:358-372): an independent vector with the same games — records,
+ * event logs and sequence-feature cursors copied device to device.                                             */
+int rv_vec_clone(rv_vec* v, rv_vec** out);
+/* RiichiEnv::_reveal_kan_dora (op 0; *n_out = number of dora indicators afterwards) and RiichiEnv::_get_ura_markers
+ * (op 1; out_tiles[5] = ura indicator tile ids, RV_NONE pad, *n_out = how many) of env.rs:624-631: the reference exposes
+ * these two internals to its tests (tests/env/test_paishan.py); they run the device routines the step path uses. */
+int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out);
 /* Device pointer to the state records (for zero-copy consumers). */
 int rv_vec_state_device_ptr(rv_vec* v, void** d_states);
 

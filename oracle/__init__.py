@@ -51,6 +51,8 @@ def load():
     lib.orc_games_random_step_batch.argtypes = [P(C.c_void_p), C.c_int64, C.c_uint64, C.c_uint64]
     lib.orc_game_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.orc_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
+    lib.orc_game_call.argtypes = [C.c_void_p, C.c_int, P(C.c_uint8)]
+    lib.orc_game_copy_log.argtypes = [C.c_void_p, C.c_void_p]
     lib.orc_game_events.restype = C.c_uint32
     lib.orc_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.orc_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]

@@ -328,6 +328,22 @@ void orc_games_random_step_batch(void** hs, int64_t n, uint64_t agent_seed, uint
 }
 void orc_game_snapshot(void* h, rv_game_state* out) { ((GameState*)h)->to_snapshot(*out); }
 void orc_game_load_snapshot(void* h, const rv_game_state* in) { load_snapshot(*(GameState*)h, *in); }
+// test hooks of the PyO3 class (env.rs:624-631): op 0 = _reveal_kan_dora() -> number of indicators;
+// op 1 = _get_ura_markers() -> tile ids into out[5], returns how many
+int orc_game_call(void* h, int op, uint8_t* out) {
+  GameState* g = (GameState*)h;
+  if (op == 0) {
+    g->_reveal_kan_dora();
+    return (int)g->dora_indicators.size();
+  }
+  if (op == 1) {
+    auto u = g->_get_ura_indicators();
+    for (size_t i = 0; i < u.size() && i < 5; i++) out[i] = u[i];
+    return (int)std::min<size_t>(u.size(), 5);
+  }
+  return -1;
+}
+void orc_game_copy_log(void* dst, void* src) { ((GameState*)dst)->log = ((GameState*)src)->log; }
 uint32_t orc_game_events(void* h, uint32_t* out, uint32_t cap) {
   GameState* g = (GameState*)h;
   uint32_t n = (uint32_t)g->log.size();

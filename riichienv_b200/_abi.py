@@ -6,7 +6,7 @@ Host-side plumbing only: the layouts must match the C header byte for byte
 import ctypes as C
 
 NP = 4
-HAND_CAP = 14
+HAND_CAP = 16
 RIVER_CAP = 32
 MAX_CLAIMS = 48
 MAX_LEGAL = 64
@@ -52,12 +52,12 @@ class GameState(C.Structure):
     _fields_ = [
         # hot part (first HOT_BYTES bytes)
         ("c_cnt", (u64 * 4) * NP), ("c_river_kinds", u64 * NP), ("c_waits", u64 * NP),
-        ("seed", u64), ("ev_hash", u64),
-        ("c_key", (u32 * 4) * NP), ("river_tedashi", u32 * NP), ("river_riichi", u32 * NP),
+        ("hand", (u8 * HAND_CAP) * NP), ("seed", u64), ("ev_hash", u64),
+        ("c_key", (u32 * 4) * NP), ("river_tedashi", u32 * NP),
         ("score", i32 * NP),
         ("riichi_sticks", u32), ("turn_count", u32),
         ("step_count", u32), ("ev_count", u32), ("ev_words", u32),
-        ("hand", (u8 * HAND_CAP) * NP), ("hand_len", u8 * NP), ("meld_tiles", ((u8 * 4) * 4) * NP),
+        ("hand_len", u8 * NP), ("meld_tiles", ((u8 * 4) * 4) * NP),
         ("meld_type", (u8 * 4) * NP),
         ("n_melds", u8 * NP), ("n_river", u8 * NP), ("flags", u8 * NP),
         ("forbidden", (u8 * 2) * NP),
@@ -69,12 +69,12 @@ class GameState(C.Structure):
         ("last_discard_tile", u8), ("pending_kan_pid", u8), ("pending_kan_type", u8), ("pending_kan_tile", u8),
         ("active_mask", u8), ("last_error", u8), ("game_mode", u8), ("rule_bits", u8),
         ("overflow", u8), ("pending_init", u8 * 3), ("n_claims", u8 * NP),
-        ("pending_tail", u8 * 2), ("hot_reserved", u8 * 2),
+        ("pending_tail", u8 * 2), ("hot_reserved", u8 * 10),
         # cold part
         ("wall", u8 * 136), ("river", (u8 * RIVER_CAP) * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
-        ("hand_index", u64), ("score_delta", i32 * NP), ("meld_from", (u8 * 4) * NP), ("meld_called", (u8 * 4) * NP),
+        ("hand_index", u64), ("river_riichi", u32 * NP), ("score_delta", i32 * NP), ("meld_from", (u8 * 4) * NP), ("meld_called", (u8 * 4) * NP),
         ("pao", (u8 * 2) * NP), ("kyoku_count", u32), ("riichi_decl_idx", u8 * NP), ("riichi_sutehai", u8 * NP),
-        ("last_tedashi", u8 * NP), ("n_kita", u8 * NP), ("reserved", u8 * 20),
+        ("last_tedashi", u8 * NP), ("n_kita", u8 * NP), ("reserved", u8 * 4),
     ]
 
 

@@ -57,6 +57,8 @@ def lib():
     L.rv_vec_get_state.argtypes = [vp, C.c_int64, P(A.GameState)]
     L.rv_vec_set_state.argtypes = [vp, C.c_int64, P(A.GameState)]
     L.rv_vec_state_device_ptr.argtypes = [vp, P(vp)]
+    L.rv_vec_clone.argtypes = [vp, P(vp)]
+    L.rv_vec_debug_call.argtypes = [vp, C.c_int64, C.c_int, P(C.c_uint8), P(C.c_int)]
     L.rv_vec_events.argtypes = [vp, C.c_int64, P(C.c_uint32), C.c_uint32, P(C.c_uint32)]
     L.rv_event_to_json.argtypes = [P(C.c_uint32), C.c_uint32, C.c_int, C.c_char_p, C.c_uint32]
     L.rv_vec_encode.argtypes = [vp, vp, vp, vp, C.c_int64, P(C.c_int64)]

@@ -130,10 +130,10 @@ __device__ __forceinline__ Cnt hand_cnt(const G& g, int p) {
   return c;
 }
 __device__ __forceinline__ void hand_info(const Tables& T, const G& g, int p, SuitInfo& si) {
-  si.e[0] = __ldg(&T.suit_info[g.c_key[p][0]]);
-  si.e[1] = __ldg(&T.suit_info[g.c_key[p][1]]);
-  si.e[2] = __ldg(&T.suit_info[g.c_key[p][2]]);
-  si.e[3] = __ldg(&T.honor_info[g.c_key[p][3]]);
+  si.e[0] = __ldg(&T.suit_info[clamp_key9(g.c_key[p][0])]);
+  si.e[1] = __ldg(&T.suit_info[clamp_key9(g.c_key[p][1])]);
+  si.e[2] = __ldg(&T.suit_info[clamp_key9(g.c_key[p][2])]);
+  si.e[3] = __ldg(&T.honor_info[clamp_key7(g.c_key[p][3])]);
 }
 __device__ __forceinline__ uint64_t river_kinds(const G& g, int p) { return g.c_river_kinds[p]; }
 // c_waits[p] = get_waits_u8 when the hand is 13-tile-equivalent, else 0 (hand_evaluator.rs:196-201)
@@ -402,7 +402,8 @@ __device__ __noinline__ void init_round(const Ctx& cx, G& g, int oya, int round_
     g.n_melds[p] = 0;
     for (int i = 0; i < RV_RIVER_CAP; i++) cold(g).river[p][i] = RV_NONE;
     g.n_river[p] = 0;
-    g.river_tedashi[p] = g.river_riichi[p] = 0;
+    g.river_tedashi[p] = 0;
+    cold(g).river_riichi[p] = 0;
     cold(g).riichi_decl_idx[p] = RV_NONE;
     g.flags[p] = RV_F_NAGASHI_ELIGIBLE;
     cold(g).pao[p][0] = cold(g).pao[p][1] = RV_NONE;
@@ -863,7 +864,7 @@ __device__ __noinline__ uint16_t tenpai_discard_mask(const Ctx& cx, const G& g, 
       SuitInfo s2 = si;
       int su = kind / 9;
       uint32_t key = g.c_key[p][su] - (uint32_t)pow5(kind - 9 * su);
-      uint32_t e = su == 3 ? __ldg(&cx.T.honor_info[key]) : __ldg(&cx.T.suit_info[key]);
+      uint32_t e = su == 3 ? __ldg(&cx.T.honor_info[clamp_key7(key)]) : __ldg(&cx.T.suit_info[clamp_key9(key)]);
       s2.e[0] = su == 0 ? e : si.e[0];
       s2.e[1] = su == 1 ? e : si.e[1];
       s2.e[2] = su == 2 ? e : si.e[2];
@@ -967,7 +968,11 @@ __device__ __noinline__ void turn_info(const Ctx& cx, const G& g, int pid, TurnI
   SuitInfo si;
   hand_info(cx.T, g, pid, si);
   if (drawn != RV_NONE && !stage) {
-    if (hl + 3 * nm == 14 && (standard_agari(si) || chiitoi14(c) || kokushi14(c))) {
+    // HandEvaluator::calc adds the win tile to a 13-tile hand (hand_evaluator.rs:93-96): a record injected through the
+    // setters may carry `drawn_tile` without the tile in the hand — the cached wait set answers for that shape
+    const bool shape = hl + 3 * nm == 14 ? (standard_agari(si) || chiitoi14(c) || kokushi14(c))
+                                         : (hl + 3 * nm == 13 && ((g.c_waits[pid] >> (drawn >> 2)) & 1));
+    if (shape) {
       uint32_t cond = base_cond(g, pid) | RV_C_TSUMO;
       if (g.drawable_count == 0 && !g.is_rinshan_flag) cond |= RV_C_HAITEI;
       if (g.is_rinshan_flag) cond |= RV_C_RINSHAN;
@@ -1225,7 +1230,7 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
   if (nr < RV_RIVER_CAP) {
     cold(g).river[pid][nr] = (uint8_t)tile;
     if (!tsumogiri) g.river_tedashi[pid] |= 1u << nr;
-    if (stage) g.river_riichi[pid] |= 1u << nr;
+    if (stage) cold(g).river_riichi[pid] |= 1u << nr;
   } else {
     g.overflow = 1;
   }
@@ -1776,22 +1781,17 @@ __device__ __forceinline__ void ids_add(const Ctx& cx, const G& g, int seat, uin
 //   * inline, when it is the plain case (nobody can claim, ordinary draw, no kan dora business), or
 //   * the generic resolve_discard() (claims, first turn, after a call or a kan, last tile) — the very
 //     function the generic path runs, entered with the same state.
-// A hand row (14 tile ids, RV_NONE padded) held in two registers: bytes 0..7 in lo, 8..13 in hi (hi's top 16 bits stay 0xFFFF).
-struct Row14 {
+// A hand row held in two registers: bytes 0..7 in lo, 8..15 in hi.  The fast path only runs on hands of at most 14 tiles
+// (hl + 3 nm == 14), so bytes 14 and 15 are RV_NONE padding throughout; rows are 16-byte aligned (offset 192 + 16 seat).
+constexpr int ACT_ROW = 14;
+struct alignas(16) Row14 {
   uint64_t lo, hi;
 };
-__device__ __forceinline__ Row14 row_load(const uint8_t* h) {       // hand rows are 2-byte aligned (offset 368 + 14 p)
-  const uint16_t* q = reinterpret_cast<const uint16_t*>(h);
-  Row14 r;
-  r.lo = (uint64_t)q[0] | ((uint64_t)q[1] << 16) | ((uint64_t)q[2] << 32) | ((uint64_t)q[3] << 48);
-  r.hi = (uint64_t)q[4] | ((uint64_t)q[5] << 16) | ((uint64_t)q[6] << 32) | 0xFFFF000000000000ull;
-  return r;
+__device__ __forceinline__ Row14 row_load(const uint8_t* h) {
+  static_assert(sizeof(Row14) == 16 && alignof(Row14) == 16, "one 128-bit access per row");
+  return *reinterpret_cast<const Row14*>(h);
 }
-__device__ __forceinline__ void row_store(uint8_t* h, const Row14& r) {
-  uint16_t* q = reinterpret_cast<uint16_t*>(h);
-  q[0] = (uint16_t)r.lo, q[1] = (uint16_t)(r.lo >> 16), q[2] = (uint16_t)(r.lo >> 32), q[3] = (uint16_t)(r.lo >> 48);
-  q[4] = (uint16_t)r.hi, q[5] = (uint16_t)(r.hi >> 16), q[6] = (uint16_t)(r.hi >> 32);
-}
+__device__ __forceinline__ void row_store(uint8_t* h, const Row14& r) { *reinterpret_cast<Row14*>(h) = r; }
 __device__ __forceinline__ int row_get(const Row14& r, int j) {
   return (int)(((j < 8 ? r.lo : r.hi) >> (8 * (j & 7))) & 0xFF);
 }
@@ -1855,8 +1855,8 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   const uint64_t c0 = g.c_cnt[pid][0], c1 = g.c_cnt[pid][1], c2 = g.c_cnt[pid][2], c3 = g.c_cnt[pid][3];
   if (sanma && ((c3 >> 12) & 15)) return RV_DECLINE(16);   // a North tile in hand: Kita may be legal (state_3p/sanma.rs:146-169)
   if ((c0 | c1 | c2 | c3) & 0x4444444444444444ull) return RV_DECLINE(22);             // four of a kind: ankan may be legal
-  const uint32_t e0 = __ldg(&cx.T.suit_info[g.c_key[pid][0]]), e1 = __ldg(&cx.T.suit_info[g.c_key[pid][1]]),
-                 e2 = __ldg(&cx.T.suit_info[g.c_key[pid][2]]), e3 = __ldg(&cx.T.honor_info[g.c_key[pid][3]]);
+  const uint32_t e0 = __ldg(&cx.T.suit_info[clamp_key9(g.c_key[pid][0])]), e1 = __ldg(&cx.T.suit_info[clamp_key9(g.c_key[pid][1])]),
+                 e2 = __ldg(&cx.T.suit_info[clamp_key9(g.c_key[pid][2])]), e3 = __ldg(&cx.T.honor_info[clamp_key7(g.c_key[pid][3])]);
   // suits that are complete (M or P).  agari needs 4 of them, "some discard leaves tenpai" needs >= 2
   const int complete = ((e0 | (e0 >> 1)) & 1) + ((e1 | (e1 >> 1)) & 1) + ((e2 | (e2 >> 1)) & 1) + ((e3 | (e3 >> 1)) & 1);
   bool open_meld = false;
@@ -1900,7 +1900,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     const int k0 = f0 == RV_NONE ? 99 : f0 >> 2, k1 = f1 == RV_NONE ? 99 : f1 >> 2;
     uint32_t ok = 0;
     #pragma unroll
-    for (int j = 0; j < RV_HAND_CAP; j++) {
+    for (int j = 0; j < ACT_ROW; j++) {
       int k = row_get(hx, j) >> 2;
       if (j < hl && k != k0 && k != k1) ok |= 1u << j;
     }
@@ -1936,7 +1936,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     // the legal list is exactly the discards of `legal_rows`: ids = their tile kinds (sanma: compact columns, action.rs:262-279)
     uint64_t kinds = 0;
     #pragma unroll
-    for (int j = 0; j < RV_HAND_CAP; j++)
+    for (int j = 0; j < ACT_ROW; j++)
       if ((legal_rows >> j) & 1) kinds |= 1ull << (row_get(hx, j) >> 2);
     if (sanma) kinds = (kinds & 1) | ((kinds >> 7) & ~1ull);
     ids_reset(cx);
@@ -1964,7 +1964,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
     row_drop(hx, pick);                            // ... drop the pick (pick < hl - 1 here) ...
     int pos = 0;                                   // ... and count the tiles below the drawn one (pads are 0xFF)
     #pragma unroll
-    for (int j = 0; j < RV_HAND_CAP - 2; j++) pos += row_get(hx, j) < drawn ? 1 : 0;
+    for (int j = 0; j < ACT_ROW - 2; j++) pos += row_get(hx, j) < drawn ? 1 : 0;
     row_insert(hx, pos, drawn);
   }
   row_store(hrow, hx);
@@ -2006,7 +2006,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   {
     // waits of the 13-tile hand: only the discarded tile's suit entry changed
     const uint32_t key = g.c_key[pid][ksu];
-    const uint32_t en = ksu == 3 ? __ldg(&cx.T.honor_info[key]) : __ldg(&cx.T.suit_info[key]);
+    const uint32_t en = ksu == 3 ? __ldg(&cx.T.honor_info[clamp_key7(key)]) : __ldg(&cx.T.suit_info[clamp_key9(key)]);
     SuitInfo si;
     si.e[0] = ksu == 0 ? en : e0, si.e[1] = ksu == 1 ? en : e1, si.e[2] = ksu == 2 ? en : e2, si.e[3] = ksu == 3 ? en : e3;
     // standard-form waits only: a seven-pairs or kokushi wait after this discard needs >= 6 pairs / >= 12 terminal kinds in

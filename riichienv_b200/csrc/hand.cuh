@@ -79,13 +79,19 @@ __device__ __forceinline__ uint64_t cnt_present(const Cnt& c) {
   }
   return m;
 }
+// Base-5 table index of a suit histogram.  Physical hands hold at most four copies of a kind; a record injected through
+// the API may not (the reference's own tests park thirteen copies of one tile in seats they do not care about), so the
+// index is clamped: such a seat gets meaningless answers, never an out-of-bounds table read.
 template <int N>
 __device__ __forceinline__ int suit_key(uint64_t x) {
   int k = 0;
   #pragma unroll
   for (int i = N - 1; i >= 0; i--) k = k * 5 + (int)((x >> (4 * i)) & 15);
-  return k;
+  constexpr int LAST = (N == 9 ? 1953125 : 78125) - 1;
+  return min(max(k, 0), LAST);
 }
+__device__ __forceinline__ uint32_t clamp_key9(uint32_t k) { return min(k, 1953124u); }   // cached keys (c_key), same reason
+__device__ __forceinline__ uint32_t clamp_key7(uint32_t k) { return min(k, 78124u); }
 
 constexpr uint64_t MASK_TERMINAL_HONOR =
     (1ull << 0) | (1ull << 8) | (1ull << 9) | (1ull << 17) | (1ull << 18) | (1ull << 26) | (0x7Full << 27);
@@ -864,6 +870,73 @@ __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, 
   out.oya = sc.pay_oya;
   out.ko = sc.pay_ko;
   return out;
+}
+
+// One query of rv_hand_eval_batch: HandEvaluator::new + calc + get_waits_u8 (hand_evaluator.rs:24-213) and
+// calculate_shanten[_3p] (shanten.rs:250-261, 470-484).  A query that is not a hand (more than 14 concealed tiles or 4
+// melds, a tile id outside 0..135, a histogram beyond four copies — the suit tables are indexed by base-5 keys) gets a
+// zeroed result with shanten = shanten13 = 127 instead of out-of-bounds table reads.
+__device__ __noinline__ void hand_eval_one(const Tables& T, const rv_hand_query& h, rv_hand_result& o) {
+  memset(&o, 0, sizeof o);
+  bool valid = h.n_tiles <= 14 && h.n_melds <= 4 && h.win_tile < 136 && h.n_dora <= 5 && h.n_ura <= 5 && h.player_wind < 4 &&
+               h.round_wind < 4;
+  Cnt c;
+  cnt_zero(c);
+  for (int k = 0; valid && k < h.n_tiles; k++) {
+    if (h.tiles[k] >= 136 || cnt_get(c, h.tiles[k] >> 2) >= 4) valid = false;
+    else cnt_add(c, h.tiles[k] >> 2);
+  }
+  for (int m = 0; valid && m < h.n_melds; m++) {
+    if (h.meld_type[m] > RV_MELD_KAKAN) valid = false;
+    for (int k = 0; k < 3; k++)
+      if (h.meld_tiles[m][k] >= 136) valid = false;
+    if (h.meld_tiles[m][3] >= 136 && h.meld_tiles[m][3] != RV_NONE) valid = false;
+  }
+  for (int k = 0; valid && k < h.n_dora; k++) valid = h.dora_ind[k] < 136;
+  for (int k = 0; valid && k < h.n_ura; k++) valid = h.ura_ind[k] < 136;
+  if (!valid) {
+    o.shanten = o.shanten13 = 127;
+    return;
+  }
+  WinRes r = hand_calc(T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
+                       h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count);
+  o.is_win = r.is_win;
+  o.yakuman = r.yakuman;
+  o.has_win_shape = r.has_shape;
+  o.han = (uint8_t)r.han;
+  o.fu = (uint8_t)r.fu;
+  o.ron_agari = r.ron;
+  o.tsumo_agari_oya = r.oya;
+  o.tsumo_agari_ko = r.ko;
+  o.yaku_mask = r.yaku_mask;
+  o.n_yaku = (uint8_t)__popcll(r.yaku_mask);
+  // concealed histogram (kan melds whose tiles are also listed count 3, as HandEvaluator::new)
+  Cnt raw = c;
+  for (int m = 0; m < h.n_melds; m++)
+    if (h.meld_type[m] >= RV_MELD_DAIMINKAN) {
+      int kind = h.meld_tiles[m][0] >> 2;
+      if (cnt_get(c, kind) == 4) cnt_sub(c, kind, 1);
+    }
+  int total = cnt_total(c) + 3 * h.n_melds;
+  int win34 = h.win_tile >> 2;
+  Cnt c13 = c, r13 = raw;
+  bool ok13 = total == 13;
+  if (total == 14 && cnt_get(c, win34) > 0) {
+    cnt_sub(c13, win34);
+    cnt_sub(r13, win34);
+    ok13 = true;
+  }
+  o.wait_mask = ok13 ? waits13(T, c13) : 0;
+  Cnt r14 = raw;
+  int n14 = h.n_tiles;
+  if (total == 13 && cnt_get(r14, win34) < 4) {
+    cnt_add(r14, win34);
+    n14++;
+  }
+  const bool sanma = h.sanma & 1;   // sanma queries: calculate_shanten_3p (shanten.rs:470-484)
+  o.shanten = (int8_t)(sanma ? shanten_counts_3p(T, r14, n14 / 3) : shanten_counts(T, r14, n14 / 3));
+  o.shanten13 = ok13 ? (int8_t)(sanma ? shanten_counts_3p(T, r13, cnt_total(r13) / 3) : shanten_counts(T, r13, cnt_total(r13) / 3))
+                     : (int8_t)127;
 }
 
 }  // namespace rv

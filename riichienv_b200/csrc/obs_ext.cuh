@@ -149,7 +149,7 @@ __device__ __forceinline__ int sh_single(uint64_t a, uint64_t b, int m) {
   return best;
 }
 __device__ __forceinline__ uint64_t sh_cost(const Tables& T, int suit, int key) {
-  return suit == 3 ? __ldg(&T.honor_cost[key]) : __ldg(&T.suit_cost[key]);
+  return suit == 3 ? __ldg(&T.honor_cost[clamp_key7((uint32_t)key)]) : __ldg(&T.suit_cost[clamp_key9((uint32_t)key)]);
 }
 __device__ __forceinline__ int sh_pair_index(int a, int b) {   // unordered pair of distinct suits -> 0..5
   const int lo = a < b ? a : b, hi = a < b ? b : a;
@@ -433,7 +433,7 @@ __device__ __forceinline__ void obs_ext_shanten_warp(const Tables& T, const G& g
   // pass 1
   const int D = st0.kinds;
   int kind = -1;
-  for (int i = 0; i < 14; i++) {
+  for (int i = 0; i < RV_HAND_CAP; i++) {
     if (i == lane && present) kind = __ffsll((long long)present) - 1;
     present &= present - 1;
   }

@@ -173,7 +173,7 @@ __device__ __forceinline__ void obs_ext3_shanten_warp(const Tables& T, const G& 
   uint64_t present = cnt_present(c);
   const int D = __popcll(present);
   int kind = -1;
-  for (int i = 0; i < 14; i++) {
+  for (int i = 0; i < RV_HAND_CAP; i++) {
     if (i == lane && present) kind = __ffsll((long long)present) - 1;
     present &= present - 1;
   }

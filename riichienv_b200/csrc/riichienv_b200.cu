@@ -14,6 +14,7 @@
 #include "obs_ext.cuh"
 #include "obs_ext3.cuh"
 #include "seq.cuh"
+#include "validate.h"
 
 using namespace rv;
 
@@ -87,49 +88,8 @@ __global__ void hand_eval_kernel(Tables T, const rv_hand_query* __restrict__ q, 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   rv_hand_query h = q[i];
-  WinRes r = hand_calc(T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
-                       h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count);
   rv_hand_result o;
-  memset(&o, 0, sizeof o);
-  o.is_win = r.is_win;
-  o.yakuman = r.yakuman;
-  o.has_win_shape = r.has_shape;
-  o.han = (uint8_t)r.han;
-  o.fu = (uint8_t)r.fu;
-  o.ron_agari = r.ron;
-  o.tsumo_agari_oya = r.oya;
-  o.tsumo_agari_ko = r.ko;
-  o.yaku_mask = r.yaku_mask;
-  o.n_yaku = (uint8_t)__popcll(r.yaku_mask);
-  // concealed histogram (kan melds whose tiles are also listed count 3, as HandEvaluator::new)
-  Cnt c;
-  cnt_zero(c);
-  for (int k = 0; k < h.n_tiles; k++) cnt_add(c, h.tiles[k] >> 2);
-  Cnt raw = c;
-  for (int m = 0; m < h.n_melds; m++)
-    if (h.meld_type[m] >= RV_MELD_DAIMINKAN) {
-      int kind = h.meld_tiles[m][0] >> 2;
-      if (cnt_get(c, kind) == 4) cnt_sub(c, kind, 1);
-    }
-  int total = cnt_total(c) + 3 * h.n_melds;
-  int win34 = h.win_tile >> 2;
-  Cnt c13 = c, r13 = raw;
-  bool ok13 = total == 13;
-  if (total == 14 && cnt_get(c, win34) > 0) {
-    cnt_sub(c13, win34);
-    cnt_sub(r13, win34);
-    ok13 = true;
-  }
-  o.wait_mask = ok13 ? waits13(T, c13) : 0;
-  Cnt r14 = raw;
-  int n14 = h.n_tiles;
-  if (total == 13) {
-    cnt_add(r14, win34);
-    n14++;
-  }
-  // sanma queries: calculate_shanten_3p (shanten.rs:470-484)
-  o.shanten = (int8_t)((h.sanma & 1) ? shanten_counts_3p(T, r14, n14 / 3) : shanten_counts(T, r14, n14 / 3));
-  o.shanten13 = ok13 ? (int8_t)((h.sanma & 1) ? shanten_counts_3p(T, r13, cnt_total(r13) / 3) : shanten_counts(T, r13, cnt_total(r13) / 3)) : (int8_t)127;
+  hand_eval_one(T, h, o);
   out[i] = o;
 }
 
@@ -162,6 +122,17 @@ __global__ void create_kernel(G* states, int64_t n, int game_mode, uint32_t rule
 }
 
 __global__ void refresh_kernel(Tables T, G* state) { refresh_caches(T, *state); }
+// RiichiEnv::_reveal_kan_dora / _get_ura_markers (env.rs:624-631): the device routines the step path itself uses, run on one game
+__global__ void debug_call_kernel(Tables T, G* state, uint32_t* log, uint32_t cap, int64_t game, int op, uint8_t* out) {
+  G& g = *state;
+  Ctx cx = make_ctx(T, log, cap, game);
+  if (op == 0) {
+    reveal_kan_dora(cx, g);
+    out[7] = g.n_dora;
+  } else {
+    out[7] = (uint8_t)ura_indicators(g, out);
+  }
+}
 
 __global__ void reseed_kernel(G* states, int64_t n, const uint64_t* seeds, uint64_t seed_base) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1819,12 +1790,54 @@ int rv_vec_get_state(rv_vec* v, int64_t game, rv_game_state* out) {
 }
 int rv_vec_set_state(rv_vec* v, int64_t game, const rv_game_state* in) {
   if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
+  if (const char* why = rv_state_defect(*in)) return fail(RV_ERR_INVALID, why);
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   CK(cudaMemcpyAsync(v->d_states + game, in, sizeof(G), cudaMemcpyHostToDevice, c->stream));
   refresh_kernel<<<1, 1, 0, c->stream>>>(c->T, v->d_states + game);   // derived caches follow the canonical fields
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
+int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out) {
+  if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
+  if (op != 0 && op != 1) return fail(RV_ERR_INVALID, "op must be 0 (reveal kan dora) or 1 (ura indicators)");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  uint8_t* d_out = nullptr;
+  CK(cudaMalloc(&d_out, 8));
+  debug_call_kernel<<<1, 1, 0, c->stream>>>(c->T, v->d_states + game, v->d_log, v->log_cap, game, op, d_out);
+  uint8_t h[8] = {0};
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_out);
+  CK(e);
+  if (n_out) *n_out = h[7];
+  if (out_tiles && op == 1)
+    for (int k = 0; k < 5; k++) out_tiles[k] = k < h[7] ? h[k] : RV_NONE;
+  return RV_OK;
+}
+int rv_vec_clone(rv_vec* v, rv_vec** out) {
+  if (!v || !out) return fail(RV_ERR_INVALID, "bad arguments");
+  rv_ctx* c = v->ctx;
+  rv_vec* w = nullptr;
+  int rc = rv_vec_create(c, v->n, v->game_mode, v->rule_bits, nullptr, 0, v->log_cap, &w);
+  if (rc != RV_OK) return rc;
+  cudaError_t e = cudaMemcpyAsync(w->d_states, v->d_states, sizeof(G) * v->n, cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess && v->d_log)
+    e = cudaMemcpyAsync(w->d_log, v->d_log, sizeof(uint32_t) * (size_t)v->n * v->log_cap, cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess && v->d_seq_cursor) {
+    e = cudaMalloc(&w->d_seq_cursor, sizeof(uint32_t) * v->n * MAXP);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(w->d_seq_cursor, v->d_seq_cursor, sizeof(uint32_t) * v->n * MAXP, cudaMemcpyDeviceToDevice, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    rv_vec_destroy(w);
+    CK(e);
+  }
+  *out = w;
   return RV_OK;
 }
 int rv_vec_state_device_ptr(rv_vec* v, void** d_states) {

@@ -273,36 +273,105 @@ def _melds_of(s: A.GameState, p: int):
 
 
 class Observation:
-    """observation/mod.rs:24-160 — a by-value snapshot for one seat."""
+    """observation/mod.rs:24-160 — a by-value snapshot for one seat.  The constructor takes the reference's argument
+    list (Observation::new, observation/mod.rs:62-110); observations returned by RiichiEnv are additionally bound to the
+    live game so that the tensor encoders can run on the device."""
 
-    def __init__(self, env: "RiichiEnv", s: A.GameState, pid: int, legal, new_events, seq_start_word=0):
-        self.player_id = pid
-        n = env._np
-        self.hands = [[s.hand[p][k] for k in range(s.hand_len[p])] if p == pid else [] for p in range(n)]
-        self.melds = [_melds_of(s, p) for p in range(n)]
-        self.discards = [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(n)]
-        self.dora_indicators = [s.dora_ind[k] for k in range(s.n_dora)]
-        self.scores = [s.score[p] for p in range(n)]
-        self.riichi_declared = [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(n)]
-        self._legal_actions = legal
-        self._new_events = new_events
-        self._env = env
-        self._seq_start_word = seq_start_word
-        self._token = env._token
+    _NP = 4
+
+    def __init__(self, player_id, hands, melds, discards, dora_indicators, scores, riichi_declared, legal_actions, events,
+                 honba=0, riichi_sticks=0, round_wind=0, oya=0, kyoku_index=0, waits=(), is_tenpai=False,
+                 riichi_sutehais=None, last_tedashis=None, last_discard=None, drawn_tile=None):
+        n = self._NP
+        self.player_id = int(player_id)
+        self.hands = [list(h) for h in hands]
+        self.melds = [list(m) for m in melds]
+        self.discards = [list(d) for d in discards]
+        self.dora_indicators = list(dora_indicators)
+        self.scores = list(scores)
+        self.riichi_declared = [bool(x) for x in riichi_declared]
+        self._legal_actions = list(legal_actions)
+        self._new_events = list(events)
+        self.honba, self.riichi_sticks, self.round_wind, self.oya = honba, riichi_sticks, round_wind, oya
+        self.kyoku_index = kyoku_index
+        self.waits = list(waits)
+        self.is_tenpai = bool(is_tenpai)
+        self.tsumogiri_flags = [[] for _ in range(n)]  # always empty in the live env (observation/mod.rs:105)
+        self.riichi_sutehais = list(riichi_sutehais) if riichi_sutehais is not None else [None] * n
+        self.last_tedashis = list(last_tedashis) if last_tedashis is not None else [None] * n
+        self.last_discard = last_discard
+        self.drawn_tile = drawn_tile
+        self._env = None
+        self._token = None
+        self._seq_start_word = 0
         self._seq = None
-        self.honba = s.honba
-        self.riichi_sticks = s.riichi_sticks
-        self.round_wind = s.round_wind
-        self.oya = s.oya
-        self.kyoku_index = s.kyoku_idx
-        self.waits = [k for k in range(34) if (s.c_waits[pid] >> k) & 1]
-        self.is_tenpai = bool(self.waits)
-        self.tsumogiri_flags = [[], [], [], []]  # always empty in the live env (observation/mod.rs:105)
-        self.riichi_sutehais = [None if s.riichi_sutehai[p] == 255 else s.riichi_sutehai[p] for p in range(n)]
-        self.last_tedashis = [None if s.last_tedashi[p] == 255 else s.last_tedashi[p] for p in range(n)]
-        # state/mod.rs:252 destructures (pid, tile) as (tile, _pid): the field carries the DISCARDER'S SEAT
-        self.last_discard = None if s.last_discard_pid == 255 else s.last_discard_pid
-        self.drawn_tile = None if s.drawn_tile == 255 else s.drawn_tile
+
+    @classmethod
+    def _from_state(cls, env: "RiichiEnv", s: A.GameState, pid: int, legal, new_events, seq_start_word=0):
+        n = env._np
+        waits = [k for k in range(34) if (s.c_waits[pid] >> k) & 1]
+        o = cls(pid,
+                [[s.hand[p][k] for k in range(s.hand_len[p])] if p == pid else [] for p in range(n)],
+                [_melds_of(s, p) for p in range(n)],
+                [[s.river[p][k] for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(n)],
+                [s.dora_ind[k] for k in range(s.n_dora)], [s.score[p] for p in range(n)],
+                [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(n)], legal, new_events,
+                s.honba, s.riichi_sticks, s.round_wind, s.oya, s.kyoku_idx, waits, bool(waits),
+                [None if s.riichi_sutehai[p] == 255 else s.riichi_sutehai[p] for p in range(n)],
+                [None if s.last_tedashi[p] == 255 else s.last_tedashi[p] for p in range(n)],
+                # state/mod.rs:252 destructures (pid, tile) as (tile, _pid): the field carries the DISCARDER'S SEAT
+                None if s.last_discard_pid == 255 else s.last_discard_pid,
+                None if s.drawn_tile == 255 else s.drawn_tile)
+        o._env, o._token, o._seq_start_word = env, env._token, seq_start_word
+        return o
+
+    def _live(self, what):
+        if self._env is None or self._token != self._env._token:
+            raise RuntimeError(f"{what} is computed on the device from the live game: call it on the observations of the "
+                               "latest reset()/step()")
+        return self._env
+
+    # ---- serde (observation/mod.rs:143-160): base64 of the struct's JSON, field names as serde derives them ----
+    def serialize_to_base64(self) -> str:
+        import base64
+
+        def meld(m):
+            return {"meld_type": m.meld_type.name, "tiles": m.tiles, "opened": m.opened, "from_who": m.from_who,
+                    "called_tile": m.called_tile}
+
+        def act(a):
+            return {"action_type": _ACTION_SERDE[a.action_type], "tile": a.tile, "consume_tiles": a.consume_tiles, "actor": a.actor}
+        d = {"player_id": self.player_id, "hands": self.hands, "melds": [[meld(m) for m in ms] for ms in self.melds],
+             "discards": self.discards, "dora_indicators": self.dora_indicators, "scores": self.scores,
+             "riichi_declared": self.riichi_declared, "_legal_actions": [act(a) for a in self._legal_actions],
+             "events": self._new_events, "honba": self.honba, "riichi_sticks": self.riichi_sticks, "round_wind": self.round_wind,
+             "oya": self.oya, "kyoku_index": self.kyoku_index, "waits": self.waits, "is_tenpai": self.is_tenpai,
+             "tsumogiri_flags": self.tsumogiri_flags, "riichi_sutehais": self.riichi_sutehais,
+             "last_tedashis": self.last_tedashis, "last_discard": self.last_discard, "drawn_tile": self.drawn_tile}
+        return base64.b64encode(json.dumps(d, separators=(",", ":")).encode()).decode()
+
+    @classmethod
+    def deserialize_from_base64(cls, text: str):
+        import base64
+        import binascii
+
+        try:
+            raw = base64.b64decode(text, validate=True)
+        except (binascii.Error, ValueError) as e:
+            raise ValueError(f"Serialization error: base64 decode failed: {e}") from None
+        try:
+            d = json.loads(raw)
+            names = {v: k for k, v in _ACTION_SERDE.items()}
+            acts = [cls._ACTION(names[a["action_type"]], a["tile"], a["consume_tiles"], a["actor"]) for a in d["_legal_actions"]]
+            melds = [[Meld(MeldType[m["meld_type"]], m["tiles"], m["opened"], m["from_who"], m.get("called_tile")) for m in ms]
+                     for ms in d["melds"]]
+            o = cls(d["player_id"], d["hands"], melds, d["discards"], d["dora_indicators"], d["scores"], d["riichi_declared"],
+                    acts, d["events"], d["honba"], d["riichi_sticks"], d["round_wind"], d["oya"], d["kyoku_index"], d["waits"],
+                    d["is_tenpai"], d["riichi_sutehais"], d["last_tedashis"], d["last_discard"], d.get("drawn_tile"))
+            o.tsumogiri_flags = d["tsumogiri_flags"]
+            return o
+        except (KeyError, TypeError, ValueError) as e:
+            raise ValueError(f"Serialization error: JSON deserialize failed: {e}") from None
 
     @property
     def hand(self):
@@ -310,8 +379,8 @@ class Observation:
 
     @property
     def events(self):
-        """Full per-player masked log up to this observation (parsed dicts)."""
-        return [json.loads(x) for x in self._env._masked_log(self.player_id)]
+        """the event delta of this observation as parsed objects (observation/python.rs:81-92)"""
+        return [json.loads(x) for x in self._new_events]
 
     def legal_actions(self):
         return list(self._legal_actions)
@@ -320,11 +389,11 @@ class Observation:
         return list(self._new_events)
 
     @property
-    def action_space_size(self):  # observation_3p/python.rs:116-118
-        return self._env.action_space_size
+    def action_space_size(self):  # observation/python.rs:113-116, observation_3p/python.rs:116-118
+        return 60 if self._NP == 3 else 82
 
     def mask(self):  # observation/python.rs:98-111, observation_3p/python.rs:102-114
-        m = bytearray(self._env.action_space_size)
+        m = bytearray(self.action_space_size)
         for a in self._legal_actions:
             try:
                 m[a.encode()] = 1
@@ -402,7 +471,7 @@ class Observation:
     def encode(self):
         """(74, 34) float32 FEATURE_ENCODING tensor bytes (observation/python.rs:457-806); sanma: (74, 27)
         (observation_3p/python.rs:402-708).  Computed on the GPU."""
-        return self._env._encode(self.player_id)
+        return self._live("encode()")._encode(self.player_id)
 
     def encode_extended(self):  # observation/python.rs:1272-1294 (4P)
         return self._ext_row().tobytes()
@@ -412,10 +481,8 @@ class Observation:
         import numpy as np
 
         if getattr(self, "_ext", None) is None:
-            if self._token != self._env._token:
-                raise RuntimeError("tensors are computed on the device from the live game: call the extended encoders on "
-                                   "the observations of the latest reset()/step()")
-            self._ext = np.frombuffer(self._env._encode(self.player_id, extended=True), dtype=np.float32).reshape(215, -1)
+            env = self._live("encode_extended()")
+            self._ext = np.frombuffer(env._encode(self.player_id, extended=True), dtype=np.float32).reshape(215, -1)
         return self._ext
 
     # The standalone encoders of observation/python.rs:195-1270 (sanma: observation_3p/python.rs:198-1115) are the channel
@@ -423,7 +490,7 @@ class Observation:
     # renames — so they are slices of the device-computed row.  Sanma rows carry three relative seats per group and two
     # opponents (NP = 3): the slices stop there.
     def _seats(self):
-        return 3 if self._env._np == 3 else 4
+        return self._NP
 
     def encode_discard_history_decay(self, decay_rate=None):  # python.rs:196-249 -> (NP, W)
         if decay_rate is not None and float(decay_rate) != 0.2:
@@ -462,28 +529,12 @@ class Observation:
         return np.ones((self._seats(), 21), np.float32).tobytes()
 
     def encode_kawa_overview(self):  # python.rs:881-930 -> (4, 7, 34), seats in absolute order (obs_kawa_kernel; 4P)
-        import torch
-
-        if self._token != self._env._token:
-            raise RuntimeError("tensors are computed on the device from the live game: call encode_kawa_overview() on the "
-                               "observations of the latest reset()/step()")
-        env = self._env
-        dev = f"cuda:{env._v.ctx.device}"
-        out = torch.zeros((4, 4, 7, 34), dtype=torch.float32, device=dev)
-        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
-        n = env._v.encode_kawa_overview(out=out, index=idx, max_obs=4)
-        rows = idx[:n].tolist()
-        if self.player_id not in rows:
-            raise ValueError(f"seat {self.player_id} owes no action")
-        return out[rows.index(self.player_id)].cpu().numpy().tobytes()
+        return self._live("encode_kawa_overview()")._v.encode_kawa_single(self.player_id)
 
     # ---- sequence features (observation/python.rs:1297-1364): raw bytes, as the reference returns them ----
     def _seq_features(self):
         if self._seq is None:
-            if self._token != self._env._token:
-                raise RuntimeError("sequence features are computed on the device from the live game: call them on the "
-                                   "observations of the latest reset()/step()")
-            self._seq = self._env._encode_seq(self.player_id, self._seq_start_word)
+            self._seq = self._live("sequence features")._encode_seq(self.player_id, self._seq_start_word)
         return self._seq
 
     def encode_seq_sparse(self, game_style=1):
@@ -504,7 +555,18 @@ class Observation:
         return ca[: lens[2]].tobytes()
 
 
-Observation3P = Observation   # observation_3p/mod.rs:19-46: the same snapshot over 3 seats (lists are sized by the env's seat count)
+class Observation3P(Observation):
+    """observation_3p/mod.rs:19-46: the same snapshot over 3 seats, 27 tile columns and the 60-id action space"""
+
+    _NP = 3
+
+
+_ACTION_SERDE = {ActionType.DISCARD: "Discard", ActionType.CHI: "Chi", ActionType.PON: "Pon", ActionType.DAIMINKAN: "Daiminkan",
+                 ActionType.RON: "Ron", ActionType.RIICHI: "Riichi", ActionType.TSUMO: "Tsumo", ActionType.PASS: "Pass",
+                 ActionType.ANKAN: "Ankan", ActionType.KAKAN: "Kakan", ActionType.KYUSHU_KYUHAI: "KyushuKyuhai",
+                 ActionType.KITA: "Kita"}
+Observation._ACTION = Action
+Observation3P._ACTION = Action3P
 
 
 class RiichiEnv:
@@ -602,6 +664,8 @@ class RiichiEnv:
     def get_observations(self, players=None):
         return self._observations(list(range(self._np)) if players is None else list(players))
 
+    get_obs_py = get_observations   # env.rs:780 (private in the reference, used by one of its tests)
+
     def _get_legal_actions(self, pid: int):
         acts, counts = self._v.legal_actions()
         return [self._action_cls._from_abi(acts[pid * A.MAX_LEGAL + k]) for k in range(int(counts[0, pid]))]
@@ -637,7 +701,7 @@ class RiichiEnv:
             new = full[self._event_counts[p]:]
             start_word = self._event_word_offset(self._event_counts[p])
             self._event_counts[p] = len(full)  # state/mod.rs:211-218: the delta advances on every observation
-            out[p] = Observation(self, s, p, legal, new, start_word)
+            out[p] = (Observation3P if self._np == 3 else Observation)._from_state(self, s, p, legal, new, start_word)
         return out
 
     def _event_word_offset(self, k):
@@ -651,81 +715,87 @@ class RiichiEnv:
         return i
 
     def _encode_seq(self, pid, start_word):
-        import numpy as np
-        import torch
-
         if self.skip_mjai_logging:
             raise ValueError("sequence features need the MJAI log (skip_mjai_logging=False)")
-        dev = f"cuda:{self._v.ctx.device}"
-        sp = torch.zeros((4, 25), dtype=torch.uint16, device=dev)
-        nu = torch.zeros((4, 12), dtype=torch.float32, device=dev)
-        pr = torch.zeros((4, 512, 5), dtype=torch.uint16, device=dev)
-        ca = torch.zeros((4, 64, 4), dtype=torch.uint16, device=dev)
-        le = torch.zeros((4, 3), dtype=torch.uint16, device=dev)
-        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
-        start = np.zeros((1, 4), np.uint32)
-        start[0, pid] = start_word
-        n = self._v.encode_seq(sparse=sp, numeric=nu, prog=pr, cand=ca, lens=le, index=idx, game_style=1, max_obs=4, start_words=start)
-        rows = idx[:n].tolist()
-        if pid not in rows:
-            raise ValueError(f"seat {pid} owes no action")
-        r = rows.index(pid)
-        lens = le[r].cpu().numpy()
-        return sp[r].cpu().numpy(), nu[r].cpu().numpy(), pr[r].cpu().numpy(), ca[r].cpu().numpy(), lens
+        return self._v.encode_seq_single(pid, start_word)
 
     def _encode(self, pid, extended=False):
         """bytes of the (74, 34) — sanma (74, 27) — float32 tensor for seat `pid` (must owe an action), computed by
-        obs_encode_kernel; extended=True: the (215, 34) tensor of encode_extended (obs_ext_kernel, 4P)."""
-        import torch
-
-        dev = f"cuda:{self._v.ctx.device}"
-        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
-        if extended:
-            obs = torch.zeros((4, 215, 27 if self._np == 3 else 34), dtype=torch.float32, device=dev)
-            n = self._v.encode_extended(obs=obs, index=idx, max_obs=4)
-        else:
-            obs = torch.zeros((4, 74, 27 if self._np == 3 else 34), dtype=torch.float32, device=dev)
-            n = self._v.encode(obs=obs, index=idx, max_obs=4)
-        rows = idx[:n].tolist()
-        if pid not in rows:
-            raise ValueError(f"seat {pid} owes no action; encode() is defined for the observations step()/reset() return")
-        return obs[rows.index(pid)].cpu().numpy().tobytes()
+        obs_encode_kernel; extended=True: the (215, W) tensor of encode_extended (obs_ext_kernel)."""
+        return self._v.encode_single(pid, extended)
 
     # ---- getters / setters used by callers and by the reference's tests (env.rs:134-635) --------------
-    kyoku_idx = property(lambda self: self._state().kyoku_idx)
-    round_wind = property(lambda self: self._state().round_wind)
-    oya = property(lambda self: self._state().oya)
-    honba = property(lambda self: self._state().honba)
-    riichi_sticks = property(lambda self: self._state().riichi_sticks)
-    turn_count = property(lambda self: self._state().turn_count)
-    is_done = property(lambda self: bool(self._state().is_done))
+    # Every property reads / writes the game's snapshot record (rv_vec_get_state / rv_vec_set_state); the library
+    # recomputes the derived caches of a record it is handed.  Lists are by-value copies, as in PyO3: mutate and assign back.
     num_players = property(lambda self: self._np)
     action_space_size = property(lambda self: 60 if self._np == 3 else 82)
     _action_cls = property(lambda self: Action3P if self._np == 3 else Action)
+    kyoku_idx = property(lambda self: self._state().kyoku_idx)
+    _custom_round_wind = property(lambda self: self._state().round_wind)   # env.rs:633
     last_error = property(lambda self: None if self._state().last_error == 255 else
                           f"Error: Illegal Action by Player {self._state().last_error}")
-    dora_indicators = property(lambda self: [self._state().dora_ind[k] for k in range(self._state().n_dora)])
+    score_deltas = property(lambda self: [self._state().score_delta[p] for p in range(self._np)])   # env.rs:611
 
     def _mutate(self, fn):
         s = self._state()
         fn(s)
         self._v.set_state(0, s)
 
+    def _scalar(name, conv=int, get=None):  # noqa: N805 — property factory, evaluated in the class body
+        def fget(self):
+            v = getattr(self._state(), name)
+            return get(v) if get else v
+
+        def fset(self, v):
+            self._mutate(lambda s: setattr(s, name, conv(v)))
+        return property(fget, fset)
+
+    def _seat_flag(bit):  # noqa: N805
+        def fget(self):
+            s = self._state()
+            return [bool(s.flags[p] & bit) for p in range(self._np)]
+
+        def fset(self, v):
+            if len(v) != self._np:      # the PyO3 setters ignore a list of the wrong length (env.rs:450-459)
+                return
+
+            def f(s):
+                for p in range(self._np):
+                    s.flags[p] = (s.flags[p] | bit) if v[p] else (s.flags[p] & ~bit)
+            self._mutate(f)
+        return property(fget, fset)
+
+    def _opt_u8(v):  # noqa: N805
+        return 255 if v is None else int(v)
+
+    current_player = _scalar("current_player")
+    oya = _scalar("oya")
+    honba = _scalar("honba")
+    round_wind = _scalar("round_wind")
+    riichi_sticks = _scalar("riichi_sticks")
+    turn_count = _scalar("turn_count")
+    pending_kan_dora_count = _scalar("pending_kan_dora_count")
+    is_done = _scalar("is_done", lambda v: int(bool(v)), bool)
+    needs_tsumo = _scalar("needs_tsumo", lambda v: int(bool(v)), bool)
+    is_first_turn = _scalar("is_first_turn", lambda v: int(bool(v)), bool)
+    is_rinshan_flag = _scalar("is_rinshan_flag", lambda v: int(bool(v)), bool)
+    drawn_tile = _scalar("drawn_tile", _opt_u8, lambda t: None if t == 255 else t)
+    riichi_declared = _seat_flag(A.F_RIICHI_DECLARED)
+    riichi_stage = _seat_flag(A.F_RIICHI_STAGE)
+    missed_agari_doujun = _seat_flag(A.F_MISSED_AGARI_DOUJUN)
+    # state/mod.rs:84,335-338: armed by nothing in the live 4P env and consumed at the top of step(); the records carry no
+    # such flag because a finished round is re-dealt inside the step that ends it
+    needs_initialize_next_round = property(lambda self: False, lambda self, v: None)
+
     @property
     def phase(self):
         return Phase(self._state().phase)
 
     @phase.setter
-    def phase(self, v):
-        self._mutate(lambda s: setattr(s, "phase", int(v)))
-
-    @property
-    def current_player(self):
-        return self._state().current_player
-
-    @current_player.setter
-    def current_player(self, v):
-        self._mutate(lambda s: setattr(s, "current_player", int(v)))
+    def phase(self, v):  # env.rs:482-498: Phase or int, unknown ints -> WaitAct
+        if not isinstance(v, (int, Phase)):
+            raise TypeError("Expected Phase or int")
+        self._mutate(lambda s: setattr(s, "phase", 1 if int(v) == 1 else 0))
 
     @property
     def active_players(self):
@@ -733,24 +803,7 @@ class RiichiEnv:
 
     @active_players.setter
     def active_players(self, v):
-        self._mutate(lambda s: setattr(s, "active_mask", sum(1 << int(p) for p in v)))
-
-    @property
-    def needs_tsumo(self):
-        return bool(self._state().needs_tsumo)
-
-    @needs_tsumo.setter
-    def needs_tsumo(self, v):
-        self._mutate(lambda s: setattr(s, "needs_tsumo", int(bool(v))))
-
-    @property
-    def drawn_tile(self):
-        t = self._state().drawn_tile
-        return None if t == 255 else t
-
-    @drawn_tile.setter
-    def drawn_tile(self, v):
-        self._mutate(lambda s: setattr(s, "drawn_tile", 255 if v is None else int(v)))
+        self._mutate(lambda s: setattr(s, "active_mask", sum(1 << int(p) for p in set(v))))
 
     @property
     def hands(self):
@@ -759,9 +812,14 @@ class RiichiEnv:
 
     @hands.setter
     def hands(self, v):
+        if len(v) != self._np:
+            return
+
         def f(s):
             for p in range(self._np):
-                tiles = list(v[p])[: A.HAND_CAP]
+                tiles = [int(t) for t in v[p]]
+                if len(tiles) > A.HAND_CAP:
+                    raise ValueError(f"a hand holds at most {A.HAND_CAP} tiles, got {len(tiles)}")
                 for k in range(A.HAND_CAP):
                     s.hand[p][k] = tiles[k] if k < len(tiles) else 255
                 s.hand_len[p] = len(tiles)
@@ -774,12 +832,17 @@ class RiichiEnv:
 
     @melds.setter
     def melds(self, v):
+        if len(v) != self._np:
+            return
+
         def f(s):
             for p in range(self._np):
-                ms = list(v[p])[:4]
+                ms = list(v[p])
+                if len(ms) > 4:
+                    raise ValueError(f"a seat holds at most 4 melds, got {len(ms)}")
                 s.n_melds[p] = len(ms)
-                for m in range(self._np):
-                    for k in range(self._np):
+                for m in range(4):          # the storage is 4 melds x 4 tiles whatever the seat count
+                    for k in range(4):
                         s.meld_tiles[p][m][k] = 255
                     s.meld_type[p][m] = s.meld_from[p][m] = s.meld_called[p][m] = 255
                 for m, md in enumerate(ms):
@@ -797,26 +860,48 @@ class RiichiEnv:
 
     @discards.setter
     def discards(self, v):
+        """PlayerState.discards only (env.rs:193-202): the parallel discard_from_hand / discard_is_riichi vectors keep
+        their contents — bits past the new length are dead storage, bits below it survive."""
+        if len(v) != self._np:
+            return
+
         def f(s):
             for p in range(self._np):
-                d = list(v[p])[: A.RIVER_CAP]
+                d = [int(t) for t in v[p]]
+                if len(d) > A.RIVER_CAP:
+                    raise ValueError(f"a river holds at most {A.RIVER_CAP} discards, got {len(d)}")
                 s.n_river[p] = len(d)
-                s.river_tedashi[p] = (1 << len(d)) - 1
                 for k in range(A.RIVER_CAP):
                     s.river[p][k] = d[k] if k < len(d) else 255
         self._mutate(f)
 
-    @property
-    def riichi_declared(self):
-        s = self._state()
-        return [bool(s.flags[p] & A.F_RIICHI_DECLARED) for p in range(self._np)]
+    def _river_bits(name):  # noqa: N805
+        def fget(self):
+            s = self._state()
+            return [[bool((getattr(s, name)[p] >> k) & 1) for k in range(min(s.n_river[p], A.RIVER_CAP))] for p in range(self._np)]
 
-    @riichi_declared.setter
-    def riichi_declared(self, v):
-        def f(s):
-            for p in range(self._np):
-                s.flags[p] = (s.flags[p] | A.F_RIICHI_DECLARED) if v[p] else (s.flags[p] & ~A.F_RIICHI_DECLARED)
-        self._mutate(f)
+        def fset(self, v):
+            if len(v) != self._np:
+                return
+
+            def f(s):
+                for p in range(self._np):
+                    getattr(s, name)[p] = sum(1 << k for k, b in enumerate(list(v[p])[: A.RIVER_CAP]) if b)
+            self._mutate(f)
+        return property(fget, fset)
+
+    discard_from_hand = _river_bits("river_tedashi")      # env.rs:205-222
+    discard_is_riichi = _river_bits("river_riichi")       # env.rs:225-242
+
+    @property
+    def riichi_declaration_index(self):                   # env.rs:287-304
+        s = self._state()
+        return [None if s.riichi_decl_idx[p] == 255 else s.riichi_decl_idx[p] for p in range(self._np)]
+
+    @riichi_declaration_index.setter
+    def riichi_declaration_index(self, v):
+        if len(v) == self._np:
+            self._mutate(lambda s: [s.riichi_decl_idx.__setitem__(p, 255 if v[p] is None else int(v[p])) for p in range(self._np)])
 
     @property
     def wall(self):
@@ -824,20 +909,187 @@ class RiichiEnv:
         s = self._state()
         return [s.wall[i] for i in range(s.rinshan_draw_count, s.wall_top)]
 
-    def set_scores(self, pts):
-        self._mutate(lambda s: [s.score.__setitem__(p, int(pts[p])) for p in range(self._np)])
+    @staticmethod
+    def _store_wall(s, tiles, front):
+        """Vec index i lives at absolute slot front + i: the dora / ura indicators of the reference's
+        `(4 + 2k) - rinshan_draw_count` (state/mod.rs:2026,2051) are then the fixed slots 4 + 2k / 5 + 2k."""
+        if front + len(tiles) > len(s.wall):
+            raise ValueError(f"wall of {len(tiles)} tiles does not fit behind {front} rinshan draws")
+        for i in range(len(s.wall)):
+            s.wall[i] = 255
+        for i, t in enumerate(tiles):
+            s.wall[front + i] = int(t)
+        s.rinshan_draw_count = front
+        s.wall_top = front + len(tiles)
 
-    def set_state(self, oya=None, round_wind=None, honba=None, kyotaku=None, scores=None):  # env.rs:636-671
+    @wall.setter
+    def wall(self, v):                                    # env.rs:139-142 — replaces the Vec, counters untouched
+        self._mutate(lambda s: self._store_wall(s, list(v), s.rinshan_draw_count))
+
+    @property
+    def rinshan_draw_count(self):
+        return self._state().rinshan_draw_count
+
+    @rinshan_draw_count.setter
+    def rinshan_draw_count(self, v):                      # env.rs:264-266 — the counter alone; the Vec stays as it is
+        self._mutate(lambda s: self._store_wall(s, [s.wall[i] for i in range(s.rinshan_draw_count, s.wall_top)], int(v)))
+
+    @property
+    def dora_indicators(self):
+        s = self._state()
+        return [s.dora_ind[k] for k in range(s.n_dora)]
+
+    @dora_indicators.setter
+    def dora_indicators(self, v):                         # env.rs:254-257
+        v = [int(t) for t in v]
+        if len(v) > 5:
+            raise ValueError("at most 5 dora indicators")
+
+        def f(s):
+            s.n_dora = len(v)
+            for k in range(5):
+                s.dora_ind[k] = v[k] if k < len(v) else 255
+        self._mutate(f)
+
+    @property
+    def last_discard(self):                               # env.rs:560-567: (seat, tile)
+        s = self._state()
+        return None if s.last_discard_pid == 255 else (s.last_discard_pid, s.last_discard_tile)
+
+    @last_discard.setter
+    def last_discard(self, v):
+        def f(s):
+            s.last_discard_pid, s.last_discard_tile = (255, 255) if v is None else (int(v[0]), int(v[1]))
+        self._mutate(f)
+
+    @property
+    def current_claims(self):                             # env.rs:551-557: {seat: [Action]} (seats without claims absent)
+        s = self._state()
+        out = {}
+        for p in range(self._np):
+            if s.n_claims[p]:
+                out[p] = [self._claim_action(s.claims[p][k], p) for k in range(min(s.n_claims[p], A.MAX_CLAIMS))]
+        return out
+
+    def _claim_action(self, w, p):
+        ty, tile, c = w & 0xFF, (w >> 8) & 0xFF, [(w >> 16) & 0xFF, (w >> 24) & 0xFF]
+        cons = [t for t in c if t != 255]
+        if ty == ActionType.DAIMINKAN and cons:   # three consumed tiles: the third is the remaining copy of the kind
+            kind = cons[0] // 4
+            cons = [t for t in range(4 * kind, 4 * kind + 4) if t != tile]
+        return self._action_cls(ty, None if tile == 255 else tile, cons, p)
+
+    @current_claims.setter
+    def current_claims(self, v):
+        def f(s):
+            for p in range(4):
+                acts = list(v.get(p, ())) if p < self._np else []
+                if len(acts) > A.MAX_CLAIMS:
+                    raise ValueError(f"at most {A.MAX_CLAIMS} claims per seat")
+                s.n_claims[p] = len(acts)
+                for k, a in enumerate(acts):
+                    c = list(a.consume_tiles[:2]) + [255, 255]
+                    s.claims[p][k] = int(a.action_type) | ((255 if a.tile is None else a.tile) << 8) | (c[0] << 16) | (c[1] << 24)
+        self._mutate(f)
+
+    @property
+    def pao(self):                                        # env.rs:570-583: per seat {yaku id: liable seat}
+        s = self._state()
+        return [{y: s.pao[p][k] for k, y in enumerate((37, 50)) if s.pao[p][k] != 255} for p in range(self._np)]
+
+    @pao.setter
+    def pao(self, v):
+        if len(v) != self._np:
+            return
+
+        def f(s):
+            for p in range(self._np):
+                for k, y in enumerate((37, 50)):
+                    s.pao[p][k] = int(v[p][y]) if y in v[p] else 255
+        self._mutate(f)
+
+    @property
+    def kita_tiles(self):                                 # env.rs:331-337 (3P): North tiles set aside, per seat
+        out = [[] for _ in range(self._np)]
+        if self._np == 3 and not self.skip_mjai_logging:
+            for w in self._kyoku_events():
+                if w[0] & 0xFF == A.EV_KITA:
+                    out[(w[0] >> 16) & 0xFF].append((w[0] >> 24) & 0xFF)
+        return out
+
+    @property
+    def win_results(self):
+        """{seat: WinResult} of the wins declared since the last deal (state/mod.rs:863,1107; cleared by
+        _initialize_round, 1729) — rebuilt from the hora events of the binary log."""
+        from .hand import WinResult, ordered_yaku
+
+        out = {}
+        if self.skip_mjai_logging:
+            return out
+        s = self._state()
+        for w in self._kyoku_events():
+            if w[0] & 0xFF != A.EV_HORA:
+                continue
+            actor, tsumo = (w[0] >> 16) & 0xFF, bool(w[1] & 0xFF)
+            han, fu, yakuman = (w[1] >> 16) & 0xFF, (w[1] >> 24) & 0xFF, bool((w[3] >> 8) & 0xFF)
+            yaku = ordered_yaku(w[8] | (w[9] << 32))
+            pay = (C.c_uint32 * 4)()
+            from ._lib import check, lib
+
+            # hand_evaluator.rs:142-155: kazoe scores as 13 han; the evaluator always scores for four seats (3P: three)
+            check(lib().rv_calculate_score(13 if (not yakuman and han >= 13) else han, fu, int(actor == s.oya), int(tsumo),
+                                           0, self._np, pay))
+            pao = next((s.pao[actor][k] for k, y in enumerate((37, 50)) if y in yaku and s.pao[actor][k] != 255), None)
+            out[actor] = WinResult(True, yakuman, pay[0], pay[1], pay[2], yaku, han, fu, pao, True)
+        return out
+
+    def _kyoku_events(self):
+        """events of the binary log since the last start_kyoku, as lists of words"""
+        words = self._v.events(0)
+        evs, i = [], 0
+        while i < len(words):
+            n = max(1, (int(words[i]) >> 8) & 0xFF)
+            if words[i] & 0xFF == A.EV_START_KYOKU:
+                evs = []
+            evs.append([int(x) for x in words[i:i + n]])
+            i += n
+        return evs
+
+    def _reveal_kan_dora(self):                           # env.rs:624-626
+        self._v.call(0)
+
+    def _get_ura_markers(self):                           # env.rs:628-630: MJAI strings
+        return [tid_to_mjai(t) for t in self._v.call(1)]
+
+    def set_scores(self, pts):                            # env.rs:406-414
+        if len(pts) == self._np:
+            self._mutate(lambda s: [s.score.__setitem__(p, int(pts[p])) for p in range(self._np)])
+
+    def set_state(self, oya=None, honba=None, riichi_sticks=None, scores=None, round_wind=None):  # env.rs:639-671
         def f(s):
             if oya is not None:
                 s.oya = s.kyoku_idx = int(oya)
-            if round_wind is not None:
-                s.round_wind = int(round_wind)
             if honba is not None:
                 s.honba = int(honba)
-            if kyotaku is not None:
-                s.riichi_sticks = int(kyotaku)
+            if riichi_sticks is not None:
+                s.riichi_sticks = int(riichi_sticks)
             if scores is not None and len(scores) == self._np:
                 for p in range(self._np):
                     s.score[p] = int(scores[p])
+            if round_wind is not None:
+                s.round_wind = int(round_wind)
         self._mutate(f)
+
+    def clone(self):                                      # env.rs:359-372: deep copy (record + event log)
+        import copy
+
+        return copy.deepcopy(self)
+
+    def __deepcopy__(self, memo):
+        o = object.__new__(type(self))
+        o.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_v"})
+        o._event_counts = list(self._event_counts)
+        o._v = self._v.clone()
+        return o
+
+    __copy__ = clone

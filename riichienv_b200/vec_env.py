@@ -182,6 +182,21 @@ class VecRiichiEnv:
     def set_state(self, game, state):
         check(lib().rv_vec_set_state(self.handle, int(game), C.byref(state)))
 
+    def clone(self):
+        """independent copy of every game (RiichiEnv.clone, env.rs:358-372)"""
+        o = object.__new__(type(self))
+        o.ctx, o.n, o.game_mode = self.ctx, self.n, self.game_mode
+        o.handle = C.c_void_p()
+        check(lib().rv_vec_clone(self.handle, C.byref(o.handle)))
+        return o
+
+    def call(self, op, game=0):
+        """env.rs:624-631 hooks: op 0 reveal_kan_dora -> indicator count; op 1 -> list of ura indicator tile ids"""
+        out = (C.c_uint8 * 5)()
+        n = C.c_int(0)
+        check(lib().rv_vec_debug_call(self.handle, int(game), int(op), out, C.byref(n)))
+        return n.value if op == 0 else list(out[: n.value])
+
     def state_device_ptr(self):
         p = C.c_void_p()
         check(lib().rv_vec_state_device_ptr(self.handle, C.byref(p)))
@@ -196,3 +211,47 @@ class VecRiichiEnv:
 
     def mjai_log(self, game=0, viewer=-1):
         return events_to_json(self.events(game), viewer)
+
+    # ---- one-row conveniences for the single-env shim (a RiichiEnv is a vector of one game) ----
+    def _row_of(self, idx, n, pid):
+        rows = idx[:n].tolist()
+        if pid not in rows:
+            raise ValueError(f"seat {pid} owes no action; the tensors are defined for the observations step()/reset() return")
+        return rows.index(pid)
+
+    def encode_single(self, pid, extended=False):
+        """bytes of the (74, W) / extended (215, W) float32 tensor of seat `pid` of game 0 (W = 34, sanma 27)."""
+        import torch
+
+        dev = f"cuda:{self.ctx.device}"
+        w = 27 if self.game_mode >= 3 else 34
+        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
+        obs = torch.zeros((4, 215 if extended else 74, w), dtype=torch.float32, device=dev)
+        n = (self.encode_extended if extended else self.encode)(obs=obs, index=idx, max_obs=4)
+        return obs[self._row_of(idx, n, pid)].cpu().numpy().tobytes()
+
+    def encode_kawa_single(self, pid):
+        import torch
+
+        dev = f"cuda:{self.ctx.device}"
+        out = torch.zeros((4, 4, 7, 34), dtype=torch.float32, device=dev)
+        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
+        n = self.encode_kawa_overview(out=out, index=idx, max_obs=4)
+        return out[self._row_of(idx, n, pid)].cpu().numpy().tobytes()
+
+    def encode_seq_single(self, pid, start_word):
+        """(sparse[25] u16, numeric[12] f32, prog[512,5] u16, cand[64,4] u16, lens[3]) numpy arrays of seat `pid`."""
+        import torch
+
+        dev = f"cuda:{self.ctx.device}"
+        sp = torch.zeros((4, 25), dtype=torch.uint16, device=dev)
+        nu = torch.zeros((4, 12), dtype=torch.float32, device=dev)
+        pr = torch.zeros((4, 512, 5), dtype=torch.uint16, device=dev)
+        ca = torch.zeros((4, 64, 4), dtype=torch.uint16, device=dev)
+        le = torch.zeros((4, 3), dtype=torch.uint16, device=dev)
+        idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
+        start = np.zeros((1, 4), np.uint32)
+        start[0, pid] = start_word
+        n = self.encode_seq(sparse=sp, numeric=nu, prog=pr, cand=ca, lens=le, index=idx, game_style=1, max_obs=4, start_words=start)
+        r = self._row_of(idx, n, pid)
+        return sp[r].cpu().numpy(), nu[r].cpu().numpy(), pr[r].cpu().numpy(), ca[r].cpu().numpy(), le[r].cpu().numpy()

@@ -20,7 +20,7 @@ def load():
     so = os.path.join(_HERE, "libhostsim.so")
     csrc = os.path.join(_HERE, "..", "..", "riichienv_b200", "csrc")
     srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "cuda_shim.h")] + [
-        os.path.join(csrc, f) for f in ("game.cuh", "hand.cuh", "tables.cuh", "obs.cuh", "obs_ext.cuh", "obs_ext3.cuh")]
+        os.path.join(csrc, f) for f in ("game.cuh", "hand.cuh", "tables.cuh", "obs.cuh", "obs_ext.cuh", "obs_ext3.cuh", "seq.cuh", "validate.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", so,
                                os.path.join(_HERE, "hostsim.cpp")])
@@ -44,6 +44,10 @@ def load():
     lib.hs_game_random_step_deferred.restype = C.c_int
     lib.hs_game_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.hs_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
+    lib.hs_state_defect.restype = C.c_char_p
+    lib.hs_state_defect.argtypes = [P(A.GameState)]
+    lib.hs_game_call.argtypes = [C.c_void_p, C.c_int, P(C.c_uint8)]
+    lib.hs_game_copy_log.argtypes = [C.c_void_p, C.c_void_p]
     lib.hs_game_events.restype = C.c_uint32
     lib.hs_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.hs_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]

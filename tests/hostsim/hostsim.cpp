@@ -19,6 +19,7 @@ static thread_local rv_game_state* hs_home = nullptr;
 #include "../../riichienv_b200/csrc/obs_ext3.cuh"
 #include <cmath>
 #include "../../riichienv_b200/csrc/seq.cuh"
+#include "../../riichienv_b200/csrc/validate.h"
 
 using namespace rv;
 
@@ -140,51 +141,7 @@ int hs_init(const char* cache_path, int threads) {
 }
 
 int hs_hand_eval(const rv_hand_query* q, rv_hand_result* out, int64_t n) {
-  for (int64_t i = 0; i < n; i++) {
-    rv_hand_query h = q[i];
-    WinRes r = hand_calc(g_T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
-                         h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count);
-    rv_hand_result o;
-    memset(&o, 0, sizeof o);
-    o.is_win = r.is_win;
-    o.yakuman = r.yakuman;
-    o.has_win_shape = r.has_shape;
-    o.han = (uint8_t)r.han;
-    o.fu = (uint8_t)r.fu;
-    o.ron_agari = r.ron;
-    o.tsumo_agari_oya = r.oya;
-    o.tsumo_agari_ko = r.ko;
-    o.yaku_mask = r.yaku_mask;
-    o.n_yaku = (uint8_t)__popcll(r.yaku_mask);
-    Cnt c;
-    cnt_zero(c);
-    for (int k = 0; k < h.n_tiles; k++) cnt_add(c, h.tiles[k] >> 2);
-    Cnt raw = c;
-    for (int m = 0; m < h.n_melds; m++)
-      if (h.meld_type[m] >= RV_MELD_DAIMINKAN) {
-        int kind = h.meld_tiles[m][0] >> 2;
-        if (cnt_get(c, kind) == 4) cnt_sub(c, kind, 1);
-      }
-    int total = cnt_total(c) + 3 * h.n_melds;
-    int win34 = h.win_tile >> 2;
-    Cnt c13 = c, r13 = raw;
-    bool ok13 = total == 13;
-    if (total == 14 && cnt_get(c, win34) > 0) {
-      cnt_sub(c13, win34);
-      cnt_sub(r13, win34);
-      ok13 = true;
-    }
-    o.wait_mask = ok13 ? waits13(g_T, c13) : 0;
-    Cnt r14 = raw;
-    int n14 = h.n_tiles;
-    if (total == 13) {
-      cnt_add(r14, win34);
-      n14++;
-    }
-    o.shanten = (int8_t)shanten_counts(g_T, r14, n14 / 3);
-    o.shanten13 = ok13 ? (int8_t)shanten_counts(g_T, r13, cnt_total(r13) / 3) : (int8_t)127;
-    out[i] = o;
-  }
+  for (int64_t i = 0; i < n; i++) hand_eval_one(g_T, q[i], out[i]);
   return 0;
 }
 int hs_shanten_counts(const uint8_t* cnt34, int len_div3) {
@@ -333,10 +290,24 @@ int hs_game_random_step_deferred(void* p, uint64_t agent_seed, uint64_t game_id)
   return 1;
 }
 void hs_game_snapshot(void* p, rv_game_state* out) { *out = ((HS*)p)->g; }
-void hs_game_load_snapshot(void* p, const rv_game_state* in) {
+int hs_game_load_snapshot(void* p, const rv_game_state* in) {   // as rv_vec_set_state: -1 for a record that is not a position
+  if (rv_state_defect(*in)) return -1;
   ((HS*)p)->g = *in;
   refresh_caches(g_T, ((HS*)p)->g);
+  return 0;
 }
+const char* hs_state_defect(const rv_game_state* in) { return rv_state_defect(*in); }
+int hs_game_call(void* p, int op, uint8_t* out) {   // env.rs:624-631 test hooks, as orc_game_call
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  if (op == 0) {
+    reveal_kan_dora(cx, h->g);
+    return h->g.n_dora;
+  }
+  if (op == 1) return ura_indicators(h->g, out);
+  return -1;
+}
+void hs_game_copy_log(void* dst, void* src) { ((HS*)dst)->log = ((HS*)src)->log; }
 uint32_t hs_game_events(void* p, uint32_t* out, uint32_t cap) {
   HS* h = (HS*)p;
   uint32_t n = std::min<uint32_t>(h->g.ev_words, (uint32_t)h->log.size());
