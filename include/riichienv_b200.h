@@ -355,7 +355,8 @@ int rv_vec_encode(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, in
 int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
 
 /* Observation::encode_kawa_overview (observation/python.rs:881-930) for every seat that owes an action, same row order as
- * rv_vec_encode: d_out [max_obs][4][7][34] f32 (device, 16-byte aligned), seats in absolute order; 4P only. */
+ * rv_vec_encode: d_out [max_obs][4][7][34] f32 (device, 16-byte aligned), seats in absolute order;
+ * sanma (Observation3P::encode_kawa_overview, observation_3p/python.rs:760-808): [max_obs][3][7][27] f32 (4-byte aligned). */
 int rv_vec_encode_kawa(rv_vec* v, float* d_out, int32_t* d_index, int64_t max_obs, int64_t* n_obs);
 
 /* Observe + step in one pass (BASELINE config 5: a random-agent rollout that emits FEATURE_ENCODING tensors at every step —

@@ -15,7 +15,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "game.hpp", "hand.hpp", "wall.hpp", "shanten.hpp", "obs.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "game.hpp", "hand.hpp", "wall.hpp", "shanten.hpp", "obs.hpp", "seq.hpp", "json.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "riichienv_b200.h"))
     stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
     if force or stale:
@@ -53,6 +53,8 @@ def load():
     lib.orc_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.orc_game_call.argtypes = [C.c_void_p, C.c_int, P(C.c_uint8)]
     lib.orc_game_copy_log.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_game_mjai_log.restype = C.c_uint32
+    lib.orc_game_mjai_log.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32]
     lib.orc_game_events.restype = C.c_uint32
     lib.orc_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.orc_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]

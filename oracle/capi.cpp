@@ -343,7 +343,24 @@ int orc_game_call(void* h, int op, uint8_t* out) {
   }
   return -1;
 }
-void orc_game_copy_log(void* dst, void* src) { ((GameState*)dst)->log = ((GameState*)src)->log; }
+void orc_game_copy_log(void* dst, void* src) {
+  ((GameState*)dst)->log = ((GameState*)src)->log;
+  ((GameState*)dst)->text = ((GameState*)src)->text;
+}
+// the oracle's own MJAI text log (json.hpp): viewer -1 = mjai_log, 0..3 = mjai_log_per_player[viewer]; lines joined by '\n'.
+// Returns the byte length (without terminator); copies at most cap - 1 bytes.
+uint32_t orc_game_mjai_log(void* h, int viewer, char* out, uint32_t cap) {
+  GameState* g = (GameState*)h;
+  const std::vector<std::string>& v = viewer < 0 ? g->text.all : g->text.seat[viewer & 3];
+  std::string s;
+  for (size_t i = 0; i < v.size(); i++) s += (i ? "\n" : "") + v[i];
+  if (out && cap) {
+    size_t n = std::min<size_t>(s.size(), cap - 1);
+    memcpy(out, s.data(), n);
+    out[n] = 0;
+  }
+  return (uint32_t)s.size();
+}
 uint32_t orc_game_events(void* h, uint32_t* out, uint32_t cap) {
   GameState* g = (GameState*)h;
   uint32_t n = (uint32_t)g->log.size();
@@ -402,8 +419,12 @@ extern "C" void orc_game_encode_ext(void* h, int pid, float* obs) {
   GameState* g = (GameState*)h;
   g->np == 3 ? encode_obs_3p_extended(*g, pid, obs) : encode_obs_extended(*g, pid, obs);   // 215x34 (4P) / 215x27 (3P)
 }
-// Observation::encode_kawa_overview: 4x7x34 floats (4P)
-extern "C" void orc_game_encode_kawa(void* h, float* out) { encode_kawa_overview(*(GameState*)h, out); }
+// Observation::encode_kawa_overview: 4x7x34 floats (4P), 3x7x27 (sanma)
+extern "C" void orc_game_encode_kawa(void* h, float* out) {
+  GameState* g = (GameState*)h;
+  if (g->sanma) encode_kawa_overview_3p(*g, out);
+  else encode_kawa_overview(*g, out);
+}
 // shanten.rs:250-393 on tid lists (known-answer hooks): out = {shanten, effective_with_discard, best_ukeire}
 extern "C" void orc_ukeire(const int* hand, int n, const int* visible, int nv, int* out) {
   std::vector<int> h(hand, hand + n), v(visible, visible + nv);

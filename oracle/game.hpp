@@ -20,6 +20,7 @@
 
 #include "../include/riichienv_b200.h"
 #include "hand.hpp"
+#include "json.hpp"
 #include "wall.hpp"
 
 namespace orc {
@@ -107,6 +108,7 @@ struct GameState {
   // event stream
   bool keep_log = true;
   std::vector<uint32_t> log;
+  MjaiLog text;                 // mjai_log / mjai_log_per_player as the reference writes them (json.hpp)
   uint64_t ev_hash = 0xcbf29ce484222325ull;
   uint32_t ev_count = 0, step_count = 0, kyoku_count = 0, ev_words = 0;
   // per-winner results of the last settlement (win_results, state/mod.rs:60)
@@ -131,10 +133,46 @@ struct GameState {
   void ev_simple(int type, int a = 0, int b = 0) {
     uint32_t w = w0(type, 1, a, b);
     push_words(&w, 1);
+    if (!keep_log) return;
+    text.np = np;
+    JsonObj ev;
+    switch (type) {
+      case RV_EV_START_GAME: text.push(ev.str("type", "start_game")); break;                            // mod.rs:158-162
+      case RV_EV_END_KYOKU: text.push(ev.str("type", "end_kyoku")); break;                              // mod.rs:1674, 2075
+      case RV_EV_END_GAME: text.push(ev.str("type", "end_game")); break;                                // mod.rs:2079
+      case RV_EV_TSUMO: text.push(ev.str("type", "tsumo").num("actor", a).str("pai", mjai_tile(b)), nullptr, a); break;
+      case RV_EV_DAHAI:                                                                                 // mod.rs:1365-1368
+      case RV_EV_DAHAI_TSUMOGIRI:
+        text.push(ev.str("type", "dahai").num("actor", a).str("pai", mjai_tile(b)).boolean("tsumogiri", type == RV_EV_DAHAI_TSUMOGIRI));
+        break;
+      case RV_EV_REACH: text.push(ev.str("type", "reach").num("actor", a)); break;                      // mod.rs:454-455
+      case RV_EV_REACH_ACCEPTED: text.push(ev.str("type", "reach_accepted").num("actor", a)); break;    // mod.rs:1556-1563
+      case RV_EV_DORA: text.push(ev.str("type", "dora").str("dora_marker", mjai_tile(b))); break;       // mod.rs:2031-2036
+      case RV_EV_KITA: text.push(ev.str("type", "kita").num("actor", a).str("pai", mjai_tile(b))); break;   // sanma.rs:47-54
+      default: break;
+    }
   }
   void ev_deltas(int type, int a, const int32_t* d) {   // 1 + np words
     uint32_t w[5] = {w0(type, 1 + np, a, 0), (uint32_t)d[0], (uint32_t)d[1], (uint32_t)d[2], (uint32_t)d[3]};
     push_words(w, 1 + np);
+    if (!keep_log) return;
+    static const char* reasons[] = {"exhaustive_draw", "nagashimangan", "kyushu_kyuhai", "sufuurenta", "suukansansen",
+                                    "suucha_riichi", "sanchaho"};
+    std::string reason = a < RV_RK_ILLEGAL_BASE ? reasons[a] : "Error: Illegal Action by Player " + std::to_string(a - RV_RK_ILLEGAL_BASE);
+    text.np = np;
+    text.push(JsonObj().str("type", "ryukyoku").str("reason", reason).nums("deltas", d, d + np));       // mod.rs:1957-1963
+  }
+  // pon / chi / daiminkan / ankan / kakan (mod.rs:1195-1224, 1498-1517, 571-581)
+  void text_meld(const char* type, int actor, int target, int tile, const std::vector<uint8_t>& consumed) {
+    if (!keep_log) return;
+    JsonObj ev;
+    ev.str("type", type).num("actor", actor);
+    if (target >= 0) ev.num("target", target);
+    if (tile >= 0) ev.str("pai", mjai_tile(tile));
+    std::vector<std::string> c;
+    for (uint8_t t : consumed) c.push_back(mjai_tile(t));
+    text.np = np;
+    text.push(ev.strs("consumed", c));
   }
 
   // ------------------------------------------------------------ ctor / reset
@@ -151,6 +189,7 @@ struct GameState {
   void reset(uint8_t oya_ = 0, uint8_t rw = 0, uint8_t honba_ = 0, uint32_t kyotaku = 0,
              const std::vector<uint8_t>* wall = nullptr, const int32_t* scores = nullptr) {
     log.clear();
+    text.clear();
     stalled = false;
     ev_hash = 0xcbf29ce484222325ull;
     ev_count = 0;
@@ -256,6 +295,22 @@ struct GameState {
         for (size_t k = 0; k < players[i].hand.size() && k < 13; k++) th[i * 13 + k] = players[i].hand[k];
       memcpy(&w[2 + np], th, (size_t)((nb + 3) / 4) * 4);
       push_words(w, nwords);
+      if (keep_log) {   // mod.rs:1785-1819
+        static const char* winds[4] = {"E", "S", "W", "N"};
+        JsonObj ev;
+        ev.str("type", "start_kyoku").str("bakaze", winds[round_wind % 4]).num("kyoku", oya + 1).num("honba", honba);
+        ev.num("kyotaku", riichi_sticks).num("oya", oya).str("dora_marker", mjai_tile(dora_indicators[0]));
+        std::vector<int32_t> sc;
+        std::vector<std::vector<std::string>> tehais;
+        for (int i = 0; i < np; i++) {
+          sc.push_back(players[i].score);
+          tehais.emplace_back();
+          for (uint8_t t : players[i].hand) tehais.back().push_back(mjai_tile(t));
+        }
+        ev.nums("scores", sc.begin(), sc.end());
+        text.np = np;
+        text.push(ev, &tehais);
+      }
     }
     current_player = oya;
     phase = RV_WAIT_ACT;
@@ -641,6 +696,15 @@ struct GameState {
     w[4 + np] = (uint32_t)mask;
     w[5 + np] = (uint32_t)(mask >> 32);
     push_words(w, nw);
+    if (keep_log) {   // mod.rs:867-884 (tsumo), 1115-1131 (ron)
+      JsonObj ev;
+      ev.str("type", "hora").num("actor", actor).num("target", target).nums("deltas", deltas, deltas + np);
+      if (tsumo) ev.boolean("tsumo", true);
+      std::vector<std::string> um;
+      for (uint8_t t : ura) um.push_back(mjai_tile(t));
+      text.np = np;
+      text.push(ev.strs("ura_markers", um));
+    }
   }
 
   // acts[pid].has_value() <=> key present in the reference's HashMap
@@ -761,6 +825,7 @@ struct GameState {
             uint32_t w[2] = {w0(RV_EV_KAKAN, 2, pid, tile), 0};
             memcpy(&w[1], c, 4);
             push_words(w, 2);
+            text_meld("kakan", pid, -1, tile, act.consume);
           }
           while (pending_kan_dora_count > 0) {
             pending_kan_dora_count--;
@@ -1054,6 +1119,7 @@ struct GameState {
           uint32_t w[2] = {w0(action.type == RV_PON ? RV_EV_PON : RV_EV_CHI, 2, claimer, tile), 0};
           memcpy(&w[1], c, 4);
           push_words(w, 2);
+          text_meld(action.type == RV_PON ? "pon" : "chi", claimer, discarder, tile, action.consume);
         }
         if (m.meld_type == Pon) register_pao(claimer, tile, discarder);
         current_player = (uint8_t)claimer;
@@ -1224,12 +1290,14 @@ struct GameState {
         uint32_t w[2] = {w0(RV_EV_ANKAN, 2, pid, tile), 0};
         memcpy(&w[1], c, 4);
         push_words(w, 2);
+        text_meld("ankan", pid, -1, tile, action.consume);
       } else if (action.type == RV_DAIMINKAN) {
         uint8_t c[4] = {(uint8_t)last_discard_pid, 0xFF, 0xFF, 0xFF};
         for (size_t k = 0; k < action.consume.size() && k < 3; k++) c[1 + k] = action.consume[k];
         uint32_t w[2] = {w0(RV_EV_DAIMINKAN, 2, pid, last_discard_tile), 0};
         memcpy(&w[1], c, 4);
         push_words(w, 2);
+        text_meld("daiminkan", pid, last_discard_pid, last_discard_tile, action.consume);
       }
       while (pending_kan_dora_count > 0) {
         pending_kan_dora_count--;

@@ -644,6 +644,31 @@ inline void encode_kawa_overview(const GameState& g, float* arr) {
   }
 }
 
+// Observation3P::encode_kawa_overview (observation_3p/python.rs:760-808): (3, 7, 27) floats over the compact columns.  The aka
+// flags test tile ids 20 / 24 / 28 as in 4P; id 20's kind (5m... the reference's comment) has no sanma column, ids 24 / 28 raise
+// channel 5 at compact(13) = 6 and channel 6 at compact(22) = 15 — restated as is (no sanma wall holds those ids).
+inline void encode_kawa_overview_3p(const GameState& g, float* arr) {
+  const int W = 27;
+  auto compact = [](int k) { return k == 0 ? 0 : (k >= 8 && k < 34 ? k - 7 : -1); };
+  for (int i = 0; i < 3 * 7 * W; i++) arr[i] = 0.0f;
+  for (int p = 0; p < 3; p++) {
+    uint8_t cnt[27] = {0};
+    bool aka[3] = {false, false, false};
+    for (uint8_t t : g.players[p].discards) {
+      int idx = compact(t / 4);
+      if (idx >= 0) {
+        arr[(p * 7 + std::min<int>(cnt[idx], 3)) * W + idx] = 1.0f;
+        if (cnt[idx] < 255) cnt[idx]++;
+      }
+      if (t == 20) aka[0] = true;
+      else if (t == 24) aka[1] = true;
+      else if (t == 28) aka[2] = true;
+    }
+    if (aka[1]) arr[(p * 7 + 5) * W + 6] = 1.0f;
+    if (aka[2]) arr[(p * 7 + 6) * W + 15] = 1.0f;
+  }
+}
+
 // Observation3P::encode_extended (observation_3p/python.rs:1117-1140; blocks observation_3p/encode.rs:22-620): 215 x 27 floats.
 // Same block offsets as 4P; three relative seats per group (the fourth channel of a group stays zero), two opponents in the
 // absolute-order blocks, compact columns, tile kind / 26, effective tiles / 27, the sanma dora successor, and the same two

@@ -354,20 +354,33 @@ __device__ inline void obs_ext_channel(const G& g, const G& rec, int pid, int ch
 // Observation::encode_kawa_overview (observation/python.rs:881-930) of seat p into a ZEROED (7, 34) block: the n-th copy of a
 // kind the seat discarded (n capped at 4) raises channel n-1; channels 4-6 are the reference's "aka" flags, raised for tile
 // ids 20 / 24 / 28 at columns 5 / 14 / 23.  `river` = the [4][32] discard bytes.
+// Sanma (observation_3p/python.rs:760-808): 3 seats over the 27 compact columns; id 20 has no column, ids 24 / 28 raise channel
+// 5 at column 6 and channel 6 at column 15.
 constexpr int KAWA_FLOATS = 4 * 7 * OBS_W;
+constexpr int KAWA_FLOATS3 = 3 * 7 * OBS_W3;
+template <bool SANMA = false>
 __device__ inline void obs_kawa_seat(const G& g, const uint8_t* river, int p, float* out) {
+  constexpr int W = SANMA ? OBS_W3 : OBS_W;
   const int n = min((int)g.n_river[p], RV_RIVER_CAP);
   uint64_t c0 = 0, c1 = 0;            // 3-bit counters per kind: kinds 0..20 in c0, 21..33 in c1
   #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const int t = river[p * RV_RIVER_CAP + i], k = t >> 2;
-    uint64_t& c = k < 21 ? c0 : c1;
-    const int sh = 3 * (k < 21 ? k : k - 21), have = (int)((c >> sh) & 7);
-    out[(have < 3 ? have : 3) * OBS_W + k] = 1.0f;
-    if (have < 7) c += 1ull << sh;
-    if (t == 20) out[4 * OBS_W + 5] = 1.0f;
-    else if (t == 24) out[5 * OBS_W + 14] = 1.0f;
-    else if (t == 28) out[6 * OBS_W + 23] = 1.0f;
+    const int col = SANMA ? (k == 0 ? 0 : (k >= 8 ? k - 7 : -1)) : k;
+    if (col >= 0) {
+      uint64_t& c = k < 21 ? c0 : c1;
+      const int sh = 3 * (k < 21 ? k : k - 21), have = (int)((c >> sh) & 7);
+      out[(have < 3 ? have : 3) * W + col] = 1.0f;
+      if (have < 7) c += 1ull << sh;
+    }
+    if (SANMA) {
+      if (t == 24) out[5 * W + 6] = 1.0f;
+      else if (t == 28) out[6 * W + 15] = 1.0f;
+    } else {
+      if (t == 20) out[4 * W + 5] = 1.0f;
+      else if (t == 24) out[5 * W + 14] = 1.0f;
+      else if (t == 28) out[6 * W + 23] = 1.0f;
+    }
   }
 }
 

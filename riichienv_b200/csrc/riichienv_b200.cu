@@ -968,28 +968,35 @@ __global__ void __launch_bounds__(128, 6) obs_ext_kernel(Tables T, DecayTab D, c
   }
 }
 
-// Kawa overview rows (Observation::encode_kawa_overview, 4 x 7 x 34): one warp per game builds the block in shared memory
-// (lanes 0-3 walk one river each) and streams it out once per acting seat — the block does not depend on the observer.
+// Kawa overview rows (Observation::encode_kawa_overview, 4 x 7 x 34; sanma 3 x 7 x 27): one warp per game builds the block in
+// shared memory (one lane per seat walks that seat's river) and streams it out once per acting seat — the block does not
+// depend on the observer.
+template <bool SANMA>
 __global__ void __launch_bounds__(128) obs_kawa_kernel(const G* states, int64_t n, const int32_t* offsets, float* out, int32_t* index,
                                                        int64_t max_obs) {
+  constexpr int FL = SANMA ? KAWA_FLOATS3 : KAWA_FLOATS, W = SANMA ? OBS_W3 : OBS_W, NPL = SANMA ? 3 : 4;
   __shared__ __align__(16) float blk[4][KAWA_FLOATS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gi = (int64_t)blockIdx.x * 4 + w;
   if (gi >= n) return;
   const G& g = states[gi];
   if (g.is_done || (g.active_mask & 0xF) == 0) return;
-  float4* b4 = reinterpret_cast<float4*>(blk[w]);
-  for (int i = lane; i < KAWA_FLOATS / 4; i += 32) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < FL; i += 32) blk[w][i] = 0.f;
   __syncwarp();
-  if (lane < 4) obs_kawa_seat(g, &g.river[0][0], lane, blk[w] + lane * 7 * OBS_W);
+  if (lane < NPL) obs_kawa_seat<SANMA>(g, &g.river[0][0], lane, blk[w] + lane * 7 * W);
   __syncwarp();
   int row = offsets[gi];
-  for (int pid = 0; pid < MAXP; pid++) {
+  for (int pid = 0; pid < NPL; pid++) {
     if (!((g.active_mask >> pid) & 1)) continue;
     if (row >= max_obs) break;
     if (out) {
-      float4* o = reinterpret_cast<float4*>(out + (size_t)row * KAWA_FLOATS);
-      for (int i = lane; i < KAWA_FLOATS / 4; i += 32) __stcs(o + i, b4[i]);
+      float* o = out + (size_t)row * FL;               // a sanma row (2,268 B) is only 4-byte aligned
+      if (SANMA) {
+        for (int i = lane; i < FL; i += 32) __stcs(o + i, blk[w][i]);
+      } else {
+        const float4* b4 = reinterpret_cast<const float4*>(blk[w]);
+        for (int i = lane; i < FL / 4; i += 32) __stcs(reinterpret_cast<float4*>(o) + i, b4[i]);
+      }
     }
     if (index && lane == 0) index[row] = (int32_t)(gi * 4 + pid);
     row++;
@@ -1930,11 +1937,11 @@ int rv_vec_encode_ext(rv_vec* v, float* d_obs, uint8_t* d_mask, int32_t* d_index
 }
 int rv_vec_encode_kawa(rv_vec* v, float* d_out, int32_t* d_index, int64_t max_obs, int64_t* n_obs) {
   rv_ctx* c = v->ctx;
-  if (v->game_mode >= 3) return RV_ERR_UNSUPPORTED;    // 4P rows only
   CK(cudaSetDevice(c->device));
   int rc = obs_offsets(v);
   if (rc != RV_OK) return rc;
-  obs_kawa_kernel<<<grid_for(v->n, 4), 128, 0, c->stream>>>(v->d_states, v->n, v->d_obs_offsets, d_out, d_index, max_obs);
+  if (v->game_mode >= 3) obs_kawa_kernel<true><<<grid_for(v->n, 4), 128, 0, c->stream>>>(v->d_states, v->n, v->d_obs_offsets, d_out, d_index, max_obs);
+  else obs_kawa_kernel<false><<<grid_for(v->n, 4), 128, 0, c->stream>>>(v->d_states, v->n, v->d_obs_offsets, d_out, d_index, max_obs);
   CK(cudaGetLastError());
   return obs_row_count(v, n_obs);
 }

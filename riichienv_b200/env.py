@@ -592,6 +592,7 @@ class RiichiEnv:
         self._v = VecRiichiEnv(1, gm, self.rule.bits(), seeds=[self.seed], log_cap_words=0 if skip_mjai_logging else 1 << 16,
                                device=device)
         self._event_counts = [0, 0, 0, 0]
+        self._log_cache = {}
         self._token = getattr(self, "_token", 0) + 1
         # GameState::new deals a first round immediately (state/mod.rs:165); mirror it so getters work before reset().
         # That constructor deal uses shuffle #0; the library's create already accounts for it (hand_index = 1), so we
@@ -607,11 +608,22 @@ class RiichiEnv:
             raise ValueError(f"scores length {len(scores)} does not match number of players {self._np}")
         # reset(seed=) sets GameState.seed which nothing reads (env.rs:835-837): the wall is NOT reseeded.
         self._event_counts = [0, 0, 0, 0]
+        self._log_cache = {}
         self._token = getattr(self, "_token", 0) + 1
         self._v.reset(oya=0 if oya is None else oya, round_wind=0 if round_wind is None else round_wind,
                       honba=0 if honba is None else honba, kyotaku=0 if kyotaku is None else kyotaku,
-                      scores=None if scores is None else [list(scores)], walls=None if wall is None else [list(wall)])
+                      scores=None if scores is None else [list(scores)], walls=None if wall is None else [self._fit_wall(wall)])
         return self._observations(self.active_players)
+
+    def _fit_wall(self, wall):
+        """reset(wall=) -> load_wall (state/wall.rs:69-80) takes any Vec; the record holds the 136 (108) tiles of a real wall.
+        A longer list keeps its first tiles — the ones dealt and drawn first (the reference's tests pass 200-entry walls and
+        only ever reach the first few dozen); a shorter one is refused."""
+        need = 108 if self._np == 3 else 136
+        wall = [int(t) for t in wall]
+        if len(wall) < need:
+            raise ValueError(f"wall holds {len(wall)} tiles, the {self._np}-player game needs {need}")
+        return wall[:need]
 
     def step(self, actions):
         self._token += 1
@@ -675,12 +687,18 @@ class RiichiEnv:
     def mjai_log(self):
         if self.skip_mjai_logging:
             return []
-        return [json.loads(x) for x in self._v.mjai_log(0)]
+        return [json.loads(x) for x in self._log_text(-1)]
 
     def _masked_log(self, pid):
         if self.skip_mjai_logging:
             return []
-        return events_to_json(self._v.events(0), pid)
+        return self._log_text(pid)
+
+    def _log_text(self, viewer):
+        """rendered log of one viewer (-1: the all-seeing log); only the events pushed since the last call are rendered"""
+        have = self._log_cache.setdefault(viewer, [])
+        have.extend(self._v.mjai_log(0, viewer, skip_events=len(have)))
+        return have
 
     # ---- internals ------------------------------------------------------------------------------
     def _state(self) -> A.GameState:
@@ -1089,6 +1107,7 @@ class RiichiEnv:
         o = object.__new__(type(self))
         o.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_v"})
         o._event_counts = list(self._event_counts)
+        o._log_cache = {k: list(v) for k, v in self._log_cache.items()}
         o._v = self._v.clone()
         return o
 

@@ -148,6 +148,26 @@ class HandEvaluator:
         ura = sorted(parse_hand(ura_indicators)[0]) if ura_indicators else []
         return HandEvaluator(sorted(tiles), melds).calc(tiles[-1], dora, conditions, ura)
 
+    def to_text(self) -> str:  # hand.py:68-93: concealed tiles grouped by suit, then the melds with a 0 call index
+        def digit(t):
+            return "0" if t in (16, 52, 88) else str((t // 4) % 9 + 1 if t < 108 else (t - 108) // 4 + 1)
+
+        def suit(t):
+            return "mpsz"[min(t // 36, 3)]
+        out = ""
+        tiles = sorted(self.tiles_136)
+        for su in "mpsz":
+            ds = "".join(digit(t) for t in tiles if suit(t) == su)
+            out += ds + su if ds else ""
+        for m in self.melds:
+            t0 = m.tiles[0]
+            if int(m.meld_type) == 0:
+                ds = "".join(digit(t) for t in m.tiles)
+            else:
+                ds = "0" if any(t in (16, 52, 88) for t in m.tiles) else digit(t0)
+            out += f"({['', 'p', 'k', 'k', 's'][int(m.meld_type)]}{ds}{suit(t0)}0)"
+        return out
+
     def _conditions(self, conditions):
         c = conditions or Conditions()
         if self._sanma:

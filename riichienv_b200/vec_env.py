@@ -209,8 +209,16 @@ class VecRiichiEnv:
         check(lib().rv_vec_events(self.handle, int(game), buf, n.value, C.byref(n)))
         return list(buf[: n.value])
 
-    def mjai_log(self, game=0, viewer=-1):
-        return events_to_json(self.events(game), viewer)
+    def mjai_log(self, game=0, viewer=-1, skip_events=0):
+        """MJAI JSON lines of one game's log (viewer -1: all-seeing; 0..3: that seat's masked view), from event
+        `skip_events` on"""
+        words = self.events(game)
+        i = 0
+        for _ in range(skip_events):
+            if i >= len(words):
+                break
+            i += max(1, (int(words[i]) >> 8) & 0xFF)
+        return events_to_json(words[i:], viewer)
 
     # ---- one-row conveniences for the single-env shim (a RiichiEnv is a vector of one game) ----
     def _row_of(self, idx, n, pid):
@@ -234,7 +242,8 @@ class VecRiichiEnv:
         import torch
 
         dev = f"cuda:{self.ctx.device}"
-        out = torch.zeros((4, 4, 7, 34), dtype=torch.float32, device=dev)
+        shape = (4, 3, 7, 27) if self.game_mode >= 3 else (4, 4, 7, 34)
+        out = torch.zeros(shape, dtype=torch.float32, device=dev)
         idx = torch.full((4,), -1, dtype=torch.int32, device=dev)
         n = self.encode_kawa_overview(out=out, index=idx, max_obs=4)
         return out[self._row_of(idx, n, pid)].cpu().numpy().tobytes()

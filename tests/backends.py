@@ -83,6 +83,13 @@ class OracleBackend(Backend):
         n = self.lib.orc_game_legal(self.h, pid, out)
         return list(out[:n])
 
+    def events_json(self, viewer=-1):
+        """the oracle's OWN text log (oracle/json.hpp), not the product's renderer over the oracle's words"""
+        n = self.lib.orc_game_mjai_log(self.h, viewer, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.lib.orc_game_mjai_log(self.h, viewer, buf, n + 1)
+        return buf.value.decode().split("\n") if n else []
+
     def events(self):
         n = self.lib.orc_game_events(self.h, None, 0)
         buf = (C.c_uint32 * max(n, 1))()

@@ -462,8 +462,13 @@ void hs_game_encode_ext(void* p, int pid, float* obs) {
 }
 void hs_game_encode_kawa(void* p, float* out) {
   const G& g = ((HS*)p)->g;
+  if (is_sanma(g)) {
+    for (int i = 0; i < KAWA_FLOATS3; i++) out[i] = 0.0f;
+    for (int q = 0; q < 3; q++) obs_kawa_seat<true>(g, &g.river[0][0], q, out + q * 7 * OBS_W3);
+    return;
+  }
   for (int i = 0; i < KAWA_FLOATS; i++) out[i] = 0.0f;
-  for (int q = 0; q < 4; q++) obs_kawa_seat(g, &g.river[0][0], q, out + q * 7 * OBS_W);
+  for (int q = 0; q < 4; q++) obs_kawa_seat<false>(g, &g.river[0][0], q, out + q * 7 * OBS_W);
 }
 void hs_game_encode_seq(void* p, int pid, uint32_t w0, uint32_t w1, int game_style, uint16_t* sparse, float* numeric, uint16_t* prog,
                         int max_prog, uint16_t* cand, uint16_t* lens) {

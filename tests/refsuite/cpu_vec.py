@@ -88,26 +88,21 @@ class CpuVec:
         self._f("game_events")(self.h, buf, n)
         return list(buf[:n])
 
-    def mjai_log(self, game=0, viewer=-1):
-        return self.render(self.events(), viewer)
-
-    def render(self, words, viewer=-1):
-        """the oracle renders with its own MJAI renderer (oracle/json.hpp), hostsim with the product's host code"""
-        if self.backend == "oracle" and hasattr(self.lib, "orc_event_to_json"):
-            n = len(words)
-            arr = (C.c_uint32 * max(n, 1))(*words)
-            buf = C.create_string_buffer(4096)
-            out, i = [], 0
-            while i < n:
-                used = self.lib.orc_event_to_json(C.cast(C.byref(arr, 4 * i), C.POINTER(C.c_uint32)), n - i, viewer, buf, 4096)
-                if used <= 0:
-                    raise ValueError(f"malformed event stream at word {i}")
-                out.append(buf.value.decode())
-                i += used
-            return out
+    def mjai_log(self, game=0, viewer=-1, skip_events=0):
+        """oracle: its own text log, written at event time (oracle/json.hpp); hostsim: the product's renderer over the words"""
+        if self.backend == "oracle":
+            n = self.lib.orc_game_mjai_log(self.h, viewer, None, 0)
+            buf = C.create_string_buffer(n + 1)
+            self.lib.orc_game_mjai_log(self.h, viewer, buf, n + 1)
+            return (buf.value.decode().split("\n") if n else [])[skip_events:]
         from riichienv_b200._lib import events_to_json
 
-        return events_to_json(words, viewer)
+        words, i = self.events(), 0
+        for _ in range(skip_events):
+            if i >= len(words):
+                break
+            i += max(1, (int(words[i]) >> 8) & 0xFF)
+        return events_to_json(words[i:], viewer)
 
     def call(self, op):
         """env.rs:624-631 hooks: op 0 reveal_kan_dora -> indicator count; op 1 -> list of ura indicator tile ids"""
@@ -140,8 +135,8 @@ class CpuVec:
 
     def encode_kawa_single(self, pid):
         self._owes(pid)
-        a = np.zeros((4, 7, 34), np.float32)
-        self.lib.orc_game_encode_kawa(self.h, a.ctypes.data_as(C.POINTER(C.c_float)))
+        a = np.zeros((3, 7, 27) if self.game_mode >= 3 else (4, 7, 34), np.float32)
+        self._f("game_encode_kawa")(self.h, a.ctypes.data_as(C.POINTER(C.c_float)))
         return a.tobytes()
 
     def encode_seq_single(self, pid, start_word):

@@ -1,5 +1,6 @@
 """The C-ABI library loads without a GPU and exports every symbol include/riichienv_b200.h declares."""
 import ctypes as C
+import json
 import os
 import re
 
@@ -83,3 +84,61 @@ def test_host_only_entry_points():
         '{"actor":3,"deltas":[-4000,-2000,-2000,10000],"target":3,"tsumo":true,"type":"hora","ura_markers":["1s"]}']
     ry = [w0(A.EV_RYUKYOKU, 5, 0, 0), 1500, d(-1500), 1500, d(-1500)]
     assert events_to_json(ry) == ['{"deltas":[1500,-1500,1500,-1500],"reason":"exhaustive_draw","type":"ryukyoku"}']
+    # the remaining event types, as the reference builds them (keys sorted, serde_json BTreeMap):
+    #   reach / reach_accepted state/mod.rs:454-455, 1556-1563; chi / daiminkan 1195-1224, 1498-1517; kakan 571-581;
+    #   kita state_3p/sanma.rs:47-54; start_kyoku 1785-1819 with the per-seat masking of 2109-2131; end markers 1674, 2075-2080
+    assert events_to_json([w0(A.EV_START_GAME, 1, 0, 0)]) == ['{"type":"start_game"}']
+    assert events_to_json([w0(A.EV_REACH, 1, 2, 0)]) == ['{"actor":2,"type":"reach"}']
+    assert events_to_json([w0(A.EV_REACH_ACCEPTED, 1, 2, 0)]) == ['{"actor":2,"type":"reach_accepted"}']
+    assert events_to_json([w0(A.EV_DAHAI_TSUMOGIRI, 1, 3, 135)]) == ['{"actor":3,"pai":"C","tsumogiri":true,"type":"dahai"}']
+    assert events_to_json([w0(A.EV_CHI, 2, 1, 8), 0 | (12 << 8) | (16 << 16) | (255 << 24)]) == [
+        '{"actor":1,"consumed":["4m","5mr"],"pai":"3m","target":0,"type":"chi"}']
+    assert events_to_json([w0(A.EV_DAIMINKAN, 2, 3, 110), 1 | (108 << 8) | (109 << 16) | (111 << 24)]) == [
+        '{"actor":3,"consumed":["E","E","E"],"pai":"E","target":1,"type":"daiminkan"}']
+    assert events_to_json([w0(A.EV_KAKAN, 2, 0, 91), 88 | (89 << 8) | (90 << 16) | (255 << 24)]) == [
+        '{"actor":0,"consumed":["5sr","5s","5s"],"pai":"5s","type":"kakan"}']
+    assert events_to_json([w0(A.EV_KITA, 1, 2, 121)]) == ['{"actor":2,"pai":"N","type":"kita"}']
+    assert events_to_json([w0(A.EV_END_KYOKU, 1, 0, 0), w0(A.EV_END_GAME, 1, 0, 0)]) == ['{"type":"end_kyoku"}', '{"type":"end_game"}']
+    assert events_to_json([w0(A.EV_RYUKYOKU, 5, 8 + 2, 0), 4000, 4000, d(-12000), 4000]) == [
+        '{"deltas":[4000,4000,-12000,4000],"reason":"Error: Illegal Action by Player 2","type":"ryukyoku"}']
+    hands = [[4 * (4 * p + k) + 1 for k in range(13)] for p in range(4)]   # copy 1 of kinds 4p .. 4p+12 (no red fives)
+    th = bytes(t for h in hands for t in h)
+    sk = [w0(A.EV_START_KYOKU, 19, 1, 2), 3 | (52 << 8) | (1 << 16), 25000, 24000, 26000, 25000] + [
+        int.from_bytes(th[i:i + 4], "little") for i in range(0, 52, 4)]
+    names = lambda h: "[" + ",".join('"%d%s"' % ((t % 36) // 4 + 1, "mps"[t // 36]) for t in h) + "]"
+    full = "[" + ",".join(names(h) for h in hands) + "]"
+    assert events_to_json(sk) == ['{"bakaze":"S","dora_marker":"5pr","honba":3,"kyoku":3,"kyotaku":1,"oya":2,'
+                                  '"scores":[25000,24000,26000,25000],"tehais":%s,"type":"start_kyoku"}' % full]
+    q13 = "[" + ",".join(['"?"'] * 13) + "]"
+    masked = "[" + ",".join(names(hands[p]) if p == 2 else q13 for p in range(4)) + "]"
+    assert events_to_json(sk, viewer=2)[0].split('"tehais":')[1] == masked + ',"type":"start_kyoku"}'
+
+
+def test_text_log_two_renderers():
+    """The oracle writes its MJAI text at event time (oracle/json.hpp, following the reference's event builders); the product
+    renders binary event words on the host (csrc/json.cpp).  Full hanchan, 4P and sanma, every viewer: the texts are equal."""
+    import oracle
+    from riichienv_b200._lib import events_to_json
+
+    o = oracle.load()
+    for mode, n_games in ((2, 12), (5, 8), (0, 8)):
+        for seed in range(n_games):
+            h = o.orc_game_new(mode, seed, 0, A.RULE_DEFAULT_TENHOU if seed % 2 == 0 else A.RULE_DEFAULT_MJSOUL, 1)
+            o.orc_game_reset(h, 0, 0, 0, 0, None, None)
+            for _ in range(4000):
+                if not o.orc_game_random_step(h, 7, seed):
+                    break
+            n = o.orc_game_events(h, None, 0)
+            buf = (C.c_uint32 * max(n, 1))()
+            o.orc_game_events(h, buf, n)
+            words = list(buf[:n])
+            kinds = set()
+            for viewer in [-1] + list(range(3 if mode >= 3 else 4)):
+                ln = o.orc_game_mjai_log(h, viewer, None, 0)
+                tb = C.create_string_buffer(ln + 1)
+                o.orc_game_mjai_log(h, viewer, tb, ln + 1)
+                text = tb.value.decode().split("\n")
+                assert text == events_to_json(words, viewer), (mode, seed, viewer)
+                kinds |= {json.loads(x)["type"] for x in text}
+            assert {"start_game", "start_kyoku", "tsumo", "dahai", "end_kyoku"} <= kinds
+            o.orc_game_free(h)

@@ -202,7 +202,8 @@ def test_lockstep_snapshots_legal_and_events(orc):
             o.random_step(99, seed)
             steps += 1
         assert g.events() == o.events()
-        assert g.events_json() == o.events_json()
+        for viewer in [-1] + list(range(3 if mode >= 3 else 4)):     # the all-seeing log and every seat's masked view:
+            assert g.events_json(viewer) == o.events_json(viewer)    # product renderer vs the oracle's own text log
 
 
 def test_lockstep_legal_lists_1024_games(orc):
@@ -248,8 +249,14 @@ def test_lockstep_legal_lists_1024_games(orc):
         assert nw == len(words) and list(buf[:nw]) == words, f"game {g}: event logs differ"
         orc.orc_game_snapshot(hs[g], C.byref(st))
         assert [st.score[p] for p in range(4)] == list(scores[g])
-        if g % 64 == 0:
-            js = events_to_json(words)
+        # full MJAI text of every game: the product's renderer against the text the oracle wrote at event time
+        # (oracle/json.hpp), the all-seeing log of every game and the four masked views of every 16th
+        for viewer in ([-1, 0, 1, 2, 3] if g % 16 == 0 else [-1]):
+            ln = orc.orc_game_mjai_log(hs[g], viewer, None, 0)
+            tb = C.create_string_buffer(ln + 1)
+            orc.orc_game_mjai_log(hs[g], viewer, tb, ln + 1)
+            js = events_to_json(words, viewer)
+            assert js == tb.value.decode().split("\n"), f"game {g} viewer {viewer}: MJAI text differs"
             assert js[0] == '{"type":"start_game"}' and js[-1] == '{"type":"end_game"}'
     for h in hs:
         orc.orc_game_free(h)
