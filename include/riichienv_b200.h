@@ -136,7 +136,8 @@ typedef struct rv_game_state {
   uint8_t active_mask;            /* active_players as a seat bitmask (always ascending seat order in the reference) */
   uint8_t last_error;             /* RV_NONE or offending seat (state/mod.rs:395-399) */
   uint8_t game_mode, rule_bits;
-  uint8_t overflow;               /* bit0: a fixed capacity (river/claims/log) was exceeded; bit1: game retired on a dead end */
+  uint8_t overflow;               /* bit0: a fixed capacity (river / claims / hand) was exceeded; bit1: game retired on a dead end;
+                                     bit2: the event log is full — later events were dropped (hash and counters go on) */
   uint8_t pending_init[3];        /* {oya, round_wind, honba} of a round whose deal is deferred inside a rollout kernel;
                                      pending_init[0]==RV_NONE outside kernels (always, as seen through this API)      */
   uint8_t n_claims[RV_NP];        /* lengths of claims[] below */
@@ -305,6 +306,15 @@ int rv_vec_step_random(rv_vec* v, uint64_t agent_seed, uint32_t max_steps, uint6
 int rv_vec_step_random_async(rv_vec* v, uint64_t agent_seed, uint32_t max_steps);
 int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done);
 
+/* The same loop with a selectable on-device agent (README.md:50-62 with `agent.act` on the device):
+ *   RV_AGENT_RANDOM  the uniform keyed agent of rv_vec_step_random (src/riichienv/agents/random_agent.py:6-15)
+ *   RV_AGENT_GREEDY  a keyed "greedy-win" agent: every Tsumo / Ron, every Riichi, Pon / Kan / Kita with probability 1/4, Chi
+ *                    with 1/8, otherwise the discard that leaves the lowest shanten (ties keyed).  Its rollouts end ~60 % of
+ *                    the rounds in a win; it exists so that parity runs exercise the settlement path (state/mod.rs:685-893,
+ *                    919-1142).  Thread-per-game kernel: an evaluation path, not the throughput path.                       */
+enum rv_agent_policy { RV_AGENT_RANDOM = 0, RV_AGENT_GREEDY = 1 };
+int rv_vec_step_agent(rv_vec* v, int policy, uint64_t agent_seed, uint32_t max_steps, uint64_t* steps_done);
+
 /* RiichiEnv::{done,scores,ranks} (env.rs:353,401,673-689).  Host outputs:
  * done[n], scores[n*NP], ranks[n*NP] (1-based), any may be NULL.            */
 int rv_vec_results(rv_vec* v, uint8_t* done, int32_t* scores, uint8_t* ranks);
@@ -324,8 +334,9 @@ int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int
 /* Device pointer to the state records (for zero-copy consumers). */
 int rv_vec_state_device_ptr(rv_vec* v, void** d_states);
 
-/* Binary event log of one game (mjai_log, env.rs:729-739).  Copies up to cap
- * words; *n_words receives the full length.                                 */
+/* Binary event log of one game (mjai_log, env.rs:729-739).  Copies up to cap words; *n_words receives the readable
+ * length: the words the log holds, cut back to the last whole event if the per-game capacity was exceeded (the record's
+ * overflow bit 2 says so; rv_vec_counters' ev_count / ev_hash still cover every event).                                */
 int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, uint32_t* n_words);
 /* Render one binary event as MJAI JSON (alphabetical keys, as serde_json
  * without preserve_order).  viewer = seat for the per-player masked log

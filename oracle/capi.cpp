@@ -3,6 +3,7 @@
 // bench.py's cpu_baseline / --impl reference legs.  Speaks the same structs as
 // include/riichienv_b200.h so results can be compared byte for byte.
 #include <atomic>
+#include <mutex>
 #include <thread>
 
 #include "game.hpp"
@@ -370,22 +371,59 @@ uint32_t orc_game_events(void* h, uint32_t* out, uint32_t cap) {
 
 // Run n seeded games (game g: seed = seed_base + g, RiichiEnv(seed).reset() then the
 // keyed agent) for at most max_steps env steps each.  All outputs optional.
-int64_t orc_run_random(int mode, uint32_t rule, uint64_t seed_base, int64_t n, uint64_t agent_seed, uint32_t max_steps,
-                       int threads, int32_t* scores, uint8_t* ranks, uint8_t* done, uint32_t* steps, uint32_t* kyoku,
-                       uint32_t* evcount, uint64_t* hash, uint32_t* max_river) {
+// policy: 0 = uniform random agent, 1 = greedy-win agent (game.hpp greedy_pick).
+// hist (optional, 128 x u64, summed over all games from their event logs): [y] for y < 64 = hora events whose yaku set
+// holds id y; [64] hora events, [65] of them tsumo, [66] ron, [67] discards / kans that were ronned by two or more seats,
+// [68] hora settlements with a pao payer, [69] rounds dealt, [70] ryukyoku events, [71 + reason] ryukyoku by reason code
+// (0..7), [80] yakuman hora, [81] kazoe (>= 13 han, no yakuman), [82] games finished.
+static int64_t run_agent(int policy, int mode, uint32_t rule, uint64_t seed_base, int64_t n, uint64_t agent_seed, uint32_t max_steps,
+                         int threads, int32_t* scores, uint8_t* ranks, uint8_t* done, uint32_t* steps, uint32_t* kyoku,
+                         uint32_t* evcount, uint64_t* hash, uint32_t* max_river, uint64_t* hist) {
   std::atomic<int64_t> next{0};
   std::atomic<int64_t> total{0};
+  std::mutex hist_mu;
   auto work = [&] {
+    uint64_t local[128] = {0};
     while (true) {
       int64_t g = next.fetch_add(1);
       if (g >= n) break;
-      GameState gs((uint8_t)mode, seed_base + (uint64_t)g, 0, rule, false);
+      GameState gs((uint8_t)mode, seed_base + (uint64_t)g, 0, rule, hist != nullptr);
       gs.reset();
       uint32_t mr = 0;
       while (!gs.is_done && gs.step_count < max_steps) {
-        random_step(gs, agent_seed, seed_base + (uint64_t)g);
+        agent_step(gs, policy, agent_seed, seed_base + (uint64_t)g);
         if (max_river)
           for (auto& p : gs.players) mr = std::max<uint32_t>(mr, (uint32_t)p.discards.size());
+      }
+      if (hist) {
+        const std::vector<uint32_t>& w = gs.log;
+        int run = 0;   // consecutive hora events (a multi-ron settles in one step)
+        for (size_t i = 0; i < w.size();) {
+          int type = w[i] & 0xFF, nw = std::max<int>(1, (w[i] >> 8) & 0xFF);
+          if (type == RV_EV_HORA) {
+            uint64_t mask = (uint64_t)w[i + 4 + gs.np] | ((uint64_t)w[i + 5 + gs.np] << 32);
+            for (int y = 0; y < 64; y++)
+              if ((mask >> y) & 1) local[y]++;
+            local[64]++;
+            local[(w[i + 1] & 0xFF) ? 65 : 66]++;
+            int han = (w[i + 1] >> 16) & 0xFF;
+            bool yakuman = (w[i + 3] >> 8) & 0xFF;
+            if (yakuman) local[80]++;
+            else if (han >= 13) local[81]++;
+            if (++run == 2) local[67]++;
+          } else {
+            run = 0;
+            if (type == RV_EV_START_KYOKU) local[69]++;
+            if (type == RV_EV_RYUKYOKU) {
+              local[70]++;
+              int reason = (w[i] >> 16) & 0xFF;
+              local[71 + std::min(reason, 8)]++;
+            }
+          }
+          i += nw;
+        }
+        local[68] += gs.stat_pao;
+        local[82] += gs.is_done ? 1 : 0;
       }
       total += gs.step_count;
       if (scores)
@@ -398,6 +436,10 @@ int64_t orc_run_random(int mode, uint32_t rule, uint64_t seed_base, int64_t n, u
       if (hash) hash[g] = gs.ev_hash;
       if (max_river) max_river[g] = mr;
     }
+    if (hist) {
+      std::lock_guard<std::mutex> lk(hist_mu);
+      for (int i = 0; i < 128; i++) hist[i] += local[i];
+    }
   };
   if (threads <= 1) {
     work();
@@ -407,6 +449,21 @@ int64_t orc_run_random(int mode, uint32_t rule, uint64_t seed_base, int64_t n, u
     for (auto& t : th) t.join();
   }
   return total.load();
+}
+int64_t orc_run_random(int mode, uint32_t rule, uint64_t seed_base, int64_t n, uint64_t agent_seed, uint32_t max_steps,
+                       int threads, int32_t* scores, uint8_t* ranks, uint8_t* done, uint32_t* steps, uint32_t* kyoku,
+                       uint32_t* evcount, uint64_t* hash, uint32_t* max_river) {
+  return run_agent(0, mode, rule, seed_base, n, agent_seed, max_steps, threads, scores, ranks, done, steps, kyoku, evcount, hash,
+                   max_river, nullptr);
+}
+int64_t orc_run_agent(int policy, int mode, uint32_t rule, uint64_t seed_base, int64_t n, uint64_t agent_seed, uint32_t max_steps,
+                      int threads, int32_t* scores, uint8_t* ranks, uint8_t* done, uint32_t* steps, uint32_t* kyoku,
+                      uint32_t* evcount, uint64_t* hash, uint64_t* hist) {
+  return run_agent(policy, mode, rule, seed_base, n, agent_seed, max_steps, threads, scores, ranks, done, steps, kyoku, evcount,
+                   hash, nullptr, hist);
+}
+int orc_game_agent_step(void* h, int policy, uint64_t agent_seed, uint64_t game_id) {
+  return agent_step(*(GameState*)h, policy, agent_seed, game_id) ? 1 : 0;
 }
 }
 extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {

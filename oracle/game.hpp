@@ -21,6 +21,7 @@
 #include "../include/riichienv_b200.h"
 #include "hand.hpp"
 #include "json.hpp"
+#include "shanten.hpp"
 #include "wall.hpp"
 
 namespace orc {
@@ -108,6 +109,7 @@ struct GameState {
   // event stream
   bool keep_log = true;
   std::vector<uint32_t> log;
+  uint32_t stat_pao = 0;        // settlements that charged a pao payer (test statistics only)
   MjaiLog text;                 // mjai_log / mjai_log_per_player as the reference writes them (json.hpp)
   uint64_t ev_hash = 0xcbf29ce484222325ull;
   uint32_t ev_count = 0, step_count = 0, kyoku_count = 0, ev_words = 0;
@@ -897,6 +899,7 @@ struct GameState {
                 }
               }
             if (pao_val > 0) {
+              stat_pao++;
               // state_3p/mod.rs:713-721: per-yakuman tsumo total depends on the player count
               int32_t unit = pid == oya ? (np - 1) * 16000 : 16000 + (np - 2) * 8000;
               int32_t honba_total = (int32_t)honba * (np - 1) * 100;
@@ -1048,6 +1051,7 @@ struct GameState {
                 }
               }
               if (has_pao) {
+                stat_pao++;
                 int32_t unit = (w_pid == oya) ? 48000 : 32000;
                 int32_t honba_ron = (int32_t)ron_honba * (np - 1) * 100;
                 int32_t split_base = rb(RV_RULE_PAO_LIABILITY_ONLY) ? pao_val * unit : total_val * unit;
@@ -1779,6 +1783,95 @@ inline bool random_step(GameState& g, uint64_t agent_seed, uint64_t game_id) {
     for (uint8_t pid : g.active_players) {
       auto legals = g._get_legal_actions_internal(pid);
       if (!legals.empty()) acts[pid] = legals[agent_pick(agent_seed, game_id, sc, pid, (uint32_t)legals.size())];
+    }
+  }
+  g.step(acts);
+  return true;
+}
+
+// ---- the keyed "greedy-win" agent (test agent #1; shared definition with the kernel, csrc/game.cuh greedy_pick) ----
+// Uniform random play almost never completes a hand (~0.3 % of rounds end in a win), which leaves the settlement code
+// (state/mod.rs:685-893, 919-1142) statistically untested.  This agent plays towards wins:
+//   r = mix64(agent_seed ^ game_id * 0x9E3779B97F4A7C15 ^ step_count << 8 ^ seat)
+//   1. the first Tsumo / Ron of the legal list, if any;  2. else the first Riichi;
+//   3. else, u = (r >> 40) & 0xFF: with u < 64 a uniformly keyed ((r >> 8) mod count) action among Pon / Daiminkan / Ankan /
+//      Kakan / Kita if there is one; with 64 <= u < 96 likewise among the Chi actions;
+//   4. else, in a claim window: Pass;  5. else, on the own turn: among the Discard actions the ones that leave the lowest
+//      shanten (calculate_shanten / calculate_shanten_3p of the remaining tiles), one of them keyed by (r >> 8) mod count.
+inline int greedy_pick(const GameState& g, int pid, const std::vector<Action>& L, uint64_t agent_seed, uint64_t game_id) {
+  const uint64_t r = mix64(agent_seed ^ (game_id * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)g.step_count << 8) ^ (uint64_t)pid);
+  const int n = (int)L.size();
+  for (int i = 0; i < n; i++)
+    if (L[i].type == RV_TSUMO || L[i].type == RV_RON) return i;
+  for (int i = 0; i < n; i++)
+    if (L[i].type == RV_RIICHI) return i;
+  const uint32_t u = (uint32_t)(r >> 40) & 0xFF, v = (uint32_t)(r >> 8);
+  auto nth_of = [&](auto pred) -> int {
+    int cnt = 0;
+    for (int i = 0; i < n; i++) cnt += pred(L[i]) ? 1 : 0;
+    if (cnt == 0) return -1;
+    int want = (int)(v % (uint32_t)cnt);
+    for (int i = 0; i < n; i++)
+      if (pred(L[i]) && want-- == 0) return i;
+    return -1;
+  };
+  auto is_k = [](const Action& a) { return a.type == RV_PON || a.type == RV_DAIMINKAN || a.type == RV_ANKAN || a.type == RV_KAKAN || a.type == RV_KITA; };
+  auto is_c = [](const Action& a) { return a.type == RV_CHI; };
+  if (u < 64) {
+    int i = nth_of(is_k);
+    if (i >= 0) return i;
+  } else if (u < 96) {
+    int i = nth_of(is_c);
+    if (i >= 0) return i;
+  }
+  if (g.phase == RV_WAIT_RESPONSE) {
+    for (int i = 0; i < n; i++)
+      if (L[i].type == RV_PASS) return i;
+    return n - 1;
+  }
+  // discards by shanten of what remains
+  uint8_t cnt[34] = {0};
+  const auto& hand = g.players[pid].hand;
+  for (uint8_t t : hand)
+    if (t / 4 < 34) cnt[t / 4]++;
+  const int len_div3 = ((int)hand.size() - 1) / 3;
+  int best = 99, nbest = 0;
+  std::vector<int> sh(n, 99);
+  for (int i = 0; i < n; i++) {
+    if (L[i].type != RV_DISCARD || L[i].tile < 0) continue;
+    const int k = L[i].tile / 4;
+    cnt[k]--;
+    sh[i] = g.sanma ? shanten_from_counts_3p(cnt, len_div3) : shanten_from_counts(cnt, len_div3);
+    cnt[k]++;
+    if (sh[i] < best) best = sh[i], nbest = 0;
+    if (sh[i] == best) nbest++;
+  }
+  if (nbest == 0) return (int)(v % (uint32_t)n);   // no discard in the list (cannot happen on a live turn)
+  int want = (int)(v % (uint32_t)nbest);
+  for (int i = 0; i < n; i++)
+    if (sh[i] == best && want-- == 0) return i;
+  return 0;
+}
+
+// One env step with agent `policy` (0 = uniform random, 1 = greedy-win).  Returns false if the game is done.
+inline bool agent_step(GameState& g, int policy, uint64_t agent_seed, uint64_t game_id) {
+  if (policy == 0) return random_step(g, agent_seed, game_id);
+  if (g.is_done) return false;
+  std::optional<Action> acts[MAXP];
+  if (g.phase == RV_WAIT_ACT) {
+    int pid = g.current_player;
+    auto legals = g._get_legal_actions_internal(pid);
+    if (legals.empty()) {   // the reference's 3P dead end, as in random_step
+      g.step_count++;
+      g.is_done = true;
+      g.stalled = true;
+      return true;
+    }
+    acts[pid] = legals[greedy_pick(g, pid, legals, agent_seed, game_id)];
+  } else {
+    for (uint8_t pid : g.active_players) {
+      auto legals = g._get_legal_actions_internal(pid);
+      if (!legals.empty()) acts[pid] = legals[greedy_pick(g, pid, legals, agent_seed, game_id)];
     }
   }
   g.step(acts);

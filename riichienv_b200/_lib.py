@@ -50,6 +50,7 @@ def lib():
     L.rv_vec_legal_actions.argtypes = [vp, P(A.Action), P(C.c_uint8)]
     L.rv_vec_step.argtypes = [vp, P(A.Action)]
     L.rv_vec_step_random.argtypes = [vp, C.c_uint64, C.c_uint32, P(C.c_uint64)]
+    L.rv_vec_step_agent.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint32, P(C.c_uint64)]
     L.rv_vec_step_random_async.argtypes = [vp, C.c_uint64, C.c_uint32]
     L.rv_vec_steps_total.argtypes = [vp, P(C.c_uint64), P(C.c_int64)]
     L.rv_vec_results.argtypes = [vp, P(C.c_uint8), P(C.c_int32), P(C.c_uint8)]

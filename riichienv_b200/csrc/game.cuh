@@ -57,6 +57,7 @@ __device__ __noinline__ void ev_push(const Ctx& cx, G& g, const uint32_t* w, int
     h = (h ^ w[i]) * 0x100000001b3ull;
     if (cx.log && base + i < cx.log_cap) cx.log[base + i] = w[i];
   }
+  if (cx.log && base + n > cx.log_cap) g.overflow |= 4;   // the log is full: words dropped (hash and counters go on)
   g.ev_hash = h;
   g.ev_words = base + n;
   g.ev_count++;
@@ -2162,6 +2163,94 @@ __device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uin
     if (!act_fast<IDS>(cx, g, agent_seed, game_id)) random_step_act<IDS>(cx, g, agent_seed, game_id);
   }
   else random_step_resp<IDS>(cx, g, agent_seed, game_id);
+}
+
+// ---- agent #1: keyed "greedy-win" (definition shared with the oracle, oracle/game.hpp greedy_pick) ----
+// Test agent: takes every Tsumo / Ron, declares every Riichi, calls Pon / Kan / Kita with probability 1/4 and Chi with 1/8, and
+// discards towards the lowest shanten — so rollouts end in wins (~60 % of the rounds) and exercise the settlement code that
+// uniform random play reaches in 0.3 % of them.  L = the packed legal list in the reference's order.
+__device__ __noinline__ int greedy_pick(const Ctx& cx, const G& g, int pid, const uint32_t* L, int n, uint64_t agent_seed,
+                                        uint64_t game_id) {
+  const uint64_t r = mix64(agent_seed ^ (game_id * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)g.step_count << 8) ^ (uint64_t)pid);
+  for (int i = 0; i < n; i++) {
+    int ty = L[i] & 0xFF;
+    if (ty == RV_TSUMO || ty == RV_RON) return i;
+  }
+  for (int i = 0; i < n; i++)
+    if ((L[i] & 0xFF) == RV_RIICHI) return i;
+  const uint32_t u = (uint32_t)(r >> 40) & 0xFF, v = (uint32_t)(r >> 8);
+  if (u < 96) {
+    const bool calls = u < 64;   // Pon / Daiminkan / Ankan / Kakan / Kita, else Chi
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+      int ty = L[i] & 0xFF;
+      bool k = ty == RV_PON || ty == RV_DAIMINKAN || ty == RV_ANKAN || ty == RV_KAKAN || ty == RV_KITA;
+      cnt += (calls ? k : ty == RV_CHI) ? 1 : 0;
+    }
+    if (cnt > 0) {
+      int want = (int)(v % (uint32_t)cnt);
+      for (int i = 0; i < n; i++) {
+        int ty = L[i] & 0xFF;
+        bool k = ty == RV_PON || ty == RV_DAIMINKAN || ty == RV_ANKAN || ty == RV_KAKAN || ty == RV_KITA;
+        if ((calls ? k : ty == RV_CHI) && want-- == 0) return i;
+      }
+    }
+  }
+  if (g.phase == RV_WAIT_RESPONSE) {
+    for (int i = 0; i < n; i++)
+      if ((L[i] & 0xFF) == RV_PASS) return i;
+    return n - 1;
+  }
+  Cnt c = hand_cnt(g, pid);
+  const int len_div3 = (g.hand_len[pid] - 1) / 3;
+  const bool sanma = is_sanma(g);
+  int best = 99, nbest = 0;
+  int8_t sh[RV_MAX_LEGAL];
+  for (int i = 0; i < n && i < RV_MAX_LEGAL; i++) {
+    sh[i] = 99;
+    if ((L[i] & 0xFF) != RV_DISCARD || ((L[i] >> 8) & 0xFF) == RV_NONE) continue;
+    const int k = ((L[i] >> 8) & 0xFF) >> 2;
+    Cnt t = c;
+    cnt_sub(t, k);
+    sh[i] = (int8_t)(sanma ? shanten_counts_3p(cx.T, t, len_div3) : shanten_counts(cx.T, t, len_div3));
+    if (sh[i] < best) best = sh[i], nbest = 0;
+    if (sh[i] == best) nbest++;
+  }
+  if (nbest == 0) return (int)(v % (uint32_t)n);
+  int want = (int)(v % (uint32_t)nbest);
+  for (int i = 0; i < n && i < RV_MAX_LEGAL; i++)
+    if (sh[i] == best && want-- == 0) return i;
+  return 0;
+}
+// One env step with agent `policy` (0 = uniform random: random_step; 1 = greedy-win) through the generic legal-list path.
+__device__ __noinline__ void agent_step(const Ctx& cx, G& g, int policy, uint64_t agent_seed, uint64_t game_id) {
+  if (policy == 0) {
+    random_step(cx, g, agent_seed, game_id);
+    return;
+  }
+  const int np = num_players(g);
+  rv_action acts[MAXP];
+  for (int p = 0; p < MAXP; p++) acts[p].type = RV_NO_ACTION;
+  uint32_t L[RV_MAX_LEGAL];
+  if (g.phase == RV_WAIT_ACT) {
+    const int pid = g.current_player;
+    const int n = min(legal_actions(cx, g, pid, L, -1, nullptr), RV_MAX_LEGAL);
+    if (n == 0) {   // the reference's 3P dead end, retired as in random_step_act
+      g.step_count++;
+      g.is_done = 1;
+      g.overflow |= 2;
+      return;
+    }
+    acts[pid] = expand_act(g, pid, L[greedy_pick(cx, g, pid, L, n, agent_seed, game_id)]);
+  } else {
+    for (int p = 0; p < np; p++) {
+      if (!((g.active_mask >> p) & 1)) continue;
+      const int n = min(legal_actions(cx, g, p, L, -1, nullptr), RV_MAX_LEGAL);
+      if (n > 0) acts[p] = expand_act(g, p, L[greedy_pick(cx, g, p, L, n, agent_seed, game_id)]);
+    }
+  }
+  g.step_count++;
+  step_apply(cx, g, acts);
 }
 
 }  // namespace rv

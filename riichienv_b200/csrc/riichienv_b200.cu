@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,7 @@ struct HandStage {              // rv_hand_eval_batch: persistent staging (alloc
 };
 struct rv_ctx {
   int device;
+  std::mutex hands_mu;          // rv_hand_eval_batch shares one pair of staging buffers per context
   HandStage hands;
   cudaStream_t stream;
   cudaEvent_t ev[8];
@@ -81,9 +83,14 @@ struct rv_vec {
   uint64_t graph_seed;
   int graph_period;
   unsigned long long* d_steps;  // [0] = env steps executed, [1] = games finished (by step kernels)
+  void *d_io_a, *d_io_c;        // staging of rv_vec_step / rv_vec_legal_actions (grow-only)
+  size_t io_a_bytes, io_c_bytes;
 };
 
 // ------------------------------------------------------------------ kernels
+// rv_vec_step_agent: thread per game, every class of work inline (a test / evaluation path, not the throughput path)
+__global__ void __launch_bounds__(128) agent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, int policy,
+                                                    uint64_t agent_seed, uint32_t max_steps, unsigned long long* counters);
 __global__ void hand_eval_kernel(Tables T, const rv_hand_query* __restrict__ q, rv_hand_result* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -93,6 +100,19 @@ __global__ void hand_eval_kernel(Tables T, const rv_hand_query* __restrict__ q, 
   out[i] = o;
 }
 
+__device__ __forceinline__ Ctx make_ctx(const Tables& T, uint32_t* log, uint32_t cap, int64_t i);
+__global__ void __launch_bounds__(128) agent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, int policy,
+                                                    uint64_t agent_seed, uint32_t max_steps, unsigned long long* counters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G& g = states[i];
+  Ctx cx = make_ctx(T, log, cap, i);
+  unsigned long long steps = 0;
+  const bool was_done = g.is_done;
+  for (uint32_t k = 0; k < max_steps && !g.is_done; k++, steps++) agent_step(cx, g, policy, agent_seed, g.seed);
+  if (steps) atomicAdd(&counters[0], steps);
+  if (!was_done && g.is_done) atomicAdd(&counters[1], 1ull);
+}
 __device__ __forceinline__ Ctx make_ctx(const Tables& T, uint32_t* log, uint32_t cap, int64_t i) {
   Ctx cx;
   cx.T = T;
@@ -1175,12 +1195,32 @@ __global__ void results_kernel(const G* states, int64_t n, uint8_t* done, int32_
 // ------------------------------------------------------------------ host API
 static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
+// Device scratch that is released on every return path (CK returns early on a CUDA error).
 template <class T>
-static int upload(rv_ctx* c, const T* h, size_t count, T** d) {
-  *d = nullptr;
+struct Scratch {
+  T* p = nullptr;
+  Scratch() = default;
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  ~Scratch() {
+    if (p) cudaFree(p);
+  }
+};
+template <class T>
+static int upload(rv_ctx* c, const T* h, size_t count, Scratch<T>& d) {
   if (!h) return RV_OK;
-  CK(cudaMalloc(d, sizeof(T) * count));
-  CK(cudaMemcpyAsync(*d, h, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMalloc(&d.p, sizeof(T) * count));
+  CK(cudaMemcpyAsync(d.p, h, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
+  return RV_OK;
+}
+// Grow-only device buffer owned by a vector (staging of rv_vec_step / rv_vec_legal_actions: no allocation per call).
+static int ensure(void** p, size_t* have, size_t need) {
+  if (*have >= need) return RV_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  CK(cudaMalloc(p, need));
+  *have = need;
   return RV_OK;
 }
 
@@ -1287,6 +1327,8 @@ static bool is_pinned(const void* p) {
 }
 int rv_hand_eval_batch(rv_ctx* c, const rv_hand_query* q, rv_hand_result* out, int64_t n) {
   if (n <= 0) return RV_OK;
+  if (!q || !out) return fail(RV_ERR_INVALID, "null buffer");
+  std::lock_guard<std::mutex> lock(c->hands_mu);   // callers on several host threads take turns
   CK(cudaSetDevice(c->device));
   HandStage& hs = c->hands;
   if (!hs.d_q[0]) {
@@ -1378,6 +1420,8 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_seq_start = nullptr;
   v->d_q_slots = nullptr;
   v->d_q_ctl = nullptr;
+  v->d_io_a = v->d_io_c = nullptr;
+  v->io_a_bytes = v->io_c_bytes = 0;
   v->q_cap = 0;
   v->graph_seed = 0;
   v->graph_period = 0;
@@ -1431,6 +1475,8 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_seq_start) cudaFree(v->d_seq_start);
   if (v->d_q_slots) cudaFree(v->d_q_slots);
   if (v->d_q_ctl) cudaFree(v->d_q_ctl);
+  if (v->d_io_a) cudaFree(v->d_io_a);
+  if (v->d_io_c) cudaFree(v->d_io_c);
   cudaFree(v->d_steps);
   delete v;
   return RV_OK;
@@ -1441,60 +1487,54 @@ int rv_vec_reset(rv_vec* v, const uint8_t* oya, const uint8_t* round_wind, const
                  const int32_t* scores, const uint8_t* walls) {
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
-  uint8_t *d_oya, *d_rw, *d_honba, *d_walls;
-  uint32_t* d_ky;
-  int32_t* d_sc;
+  Scratch<uint8_t> d_oya, d_rw, d_honba, d_walls;    // freed on every return path
+  Scratch<uint32_t> d_ky;
+  Scratch<int32_t> d_sc;
   int rc;
-  if ((rc = upload(c, oya, v->n, &d_oya))) return rc;
-  if ((rc = upload(c, round_wind, v->n, &d_rw))) return rc;
-  if ((rc = upload(c, honba, v->n, &d_honba))) return rc;
-  if ((rc = upload(c, kyotaku, v->n, &d_ky))) return rc;
-  if ((rc = upload(c, scores, v->n * MAXP, &d_sc))) return rc;
-  if ((rc = upload(c, walls, v->n * (v->game_mode >= 3 ? 108 : 136), &d_walls))) return rc;
+  if ((rc = upload(c, oya, v->n, d_oya))) return rc;
+  if ((rc = upload(c, round_wind, v->n, d_rw))) return rc;
+  if ((rc = upload(c, honba, v->n, d_honba))) return rc;
+  if ((rc = upload(c, kyotaku, v->n, d_ky))) return rc;
+  if ((rc = upload(c, scores, v->n * MAXP, d_sc))) return rc;
+  if ((rc = upload(c, walls, v->n * (v->game_mode >= 3 ? 108 : 136), d_walls))) return rc;
   if (v->d_seq_cursor) CK(cudaMemsetAsync(v->d_seq_cursor, 0, sizeof(uint32_t) * 4 * v->n, c->stream));   // player_event_counts = [0; NP]
   CK(cudaMemsetAsync(v->d_steps, 0, sizeof(unsigned long long) * 32, c->stream));
-  reset_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_oya, d_rw, d_honba,
-                                                           d_ky, d_sc, d_walls);
+  reset_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_oya.p, d_rw.p, d_honba.p,
+                                                           d_ky.p, d_sc.p, d_walls.p);
   CK(cudaGetLastError());
   bool any = oya || round_wind || honba || kyotaku || scores || walls;
-  if (any) CK(cudaStreamSynchronize(c->stream));   // staging buffers are freed below; default reset stays asynchronous
-  cudaFree(d_oya);
-  cudaFree(d_rw);
-  cudaFree(d_honba);
-  cudaFree(d_ky);
-  cudaFree(d_sc);
-  cudaFree(d_walls);
+  if (any) CK(cudaStreamSynchronize(c->stream));   // the staging buffers go out of scope; a default reset stays asynchronous
   return RV_OK;
 }
 
 int rv_vec_legal_actions(rv_vec* v, rv_action* out_actions, uint8_t* out_counts) {
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
-  rv_action* d_a;
-  uint8_t* d_c;
   size_t na = (size_t)v->n * MAXP * RV_MAX_LEGAL;
-  CK(cudaMalloc(&d_a, sizeof(rv_action) * na));
-  CK(cudaMalloc(&d_c, (size_t)v->n * MAXP));
+  int rc = ensure(&v->d_io_a, &v->io_a_bytes, sizeof(rv_action) * na);
+  if (rc == RV_OK) rc = ensure(&v->d_io_c, &v->io_c_bytes, (size_t)v->n * MAXP);
+  if (rc != RV_OK) return rc;
+  rv_action* d_a = (rv_action*)v->d_io_a;
+  uint8_t* d_c = (uint8_t*)v->d_io_c;
   legal_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, d_a, d_c);
   CK(cudaGetLastError());
   if (out_actions) CK(cudaMemcpyAsync(out_actions, d_a, sizeof(rv_action) * na, cudaMemcpyDeviceToHost, c->stream));
   if (out_counts) CK(cudaMemcpyAsync(out_counts, d_c, (size_t)v->n * MAXP, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_a);
-  cudaFree(d_c);
   return RV_OK;
 }
 
 int rv_vec_step(rv_vec* v, const rv_action* actions) {
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
-  rv_action* d_a;
-  CK(cudaMalloc(&d_a, sizeof(rv_action) * v->n * MAXP));
+  if (!actions) return fail(RV_ERR_INVALID, "actions is null");
+  int rc = ensure(&v->d_io_a, &v->io_a_bytes, sizeof(rv_action) * v->n * MAXP);
+  if (rc != RV_OK) return rc;
+  rv_action* d_a = (rv_action*)v->d_io_a;
   CK(cudaMemcpyAsync(d_a, actions, sizeof(rv_action) * v->n * MAXP, cudaMemcpyHostToDevice, c->stream));
   step_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, d_a, v->d_steps);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_a);
   return RV_OK;
 }
 
@@ -1806,6 +1846,21 @@ int rv_vec_set_state(rv_vec* v, int64_t game, const rv_game_state* in) {
   CK(cudaStreamSynchronize(c->stream));
   return RV_OK;
 }
+int rv_vec_step_agent(rv_vec* v, int policy, uint64_t agent_seed, uint32_t max_steps, uint64_t* steps_done) {
+  if (policy != RV_AGENT_RANDOM && policy != RV_AGENT_GREEDY) return fail(RV_ERR_INVALID, "unknown agent policy");
+  if (policy == RV_AGENT_RANDOM) return rv_vec_step_random(v, agent_seed, max_steps, steps_done);
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  unsigned long long before = 0, after = 0;
+  CK(cudaMemcpyAsync(&before, v->d_steps, sizeof before, cudaMemcpyDeviceToHost, c->stream));
+  agent_kernel<<<grid_for(v->n, 128), 128, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_log, v->log_cap, policy, agent_seed, max_steps,
+                                                          v->d_steps);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&after, v->d_steps, sizeof after, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (steps_done) *steps_done = after - before;
+  return RV_OK;
+}
 int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out) {
   if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
   if (op != 0 && op != 1) return fail(RV_ERR_INVALID, "op must be 0 (reveal kan dora) or 1 (ura indicators)");
@@ -1858,9 +1913,28 @@ int rv_vec_events(rv_vec* v, int64_t game, uint32_t* out_words, uint32_t cap, ui
   G g;
   CK(cudaMemcpyAsync(&g, v->d_states + game, sizeof(G), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (n_words) *n_words = g.ev_words;
-  if (!v->d_log) return fail(RV_ERR_INVALID, "event logging is off for this VecEnv (log_cap_words == 0)");
+  if (!v->d_log) {
+    if (n_words) *n_words = 0;
+    return fail(RV_ERR_INVALID, "event logging is off for this VecEnv (log_cap_words == 0)");
+  }
+  // readable length: what the log holds, cut back to the last whole event when the capacity was exceeded (ev_push
+  // sets overflow bit 2 and drops the words that do not fit, possibly in the middle of an event)
   uint32_t have = g.ev_words < v->log_cap ? g.ev_words : v->log_cap;
+  if (g.ev_words > v->log_cap) {
+    std::vector<uint32_t> all(have);
+    if (have) {
+      CK(cudaMemcpyAsync(all.data(), v->d_log + (size_t)game * v->log_cap, sizeof(uint32_t) * have, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    uint32_t i = 0;
+    while (i < have) {
+      uint32_t nw = (all[i] >> 8) & 0xFF;
+      if (nw == 0 || i + nw > have) break;
+      i += nw;
+    }
+    have = i;
+  }
+  if (n_words) *n_words = have;
   uint32_t ncopy = have < cap ? have : cap;
   if (out_words && ncopy) {
     CK(cudaMemcpyAsync(out_words, v->d_log + (size_t)game * v->log_cap, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, c->stream));

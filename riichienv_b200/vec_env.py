@@ -73,6 +73,12 @@ class VecRiichiEnv:
         check(lib().rv_vec_step_random(self.handle, int(agent_seed), int(max_steps), C.byref(done)))
         return int(done.value)
 
+    def step_agent(self, policy, agent_seed, max_steps=1):
+        """up to max_steps env steps per game with on-device agent `policy` (0 = uniform random, 1 = greedy-win)"""
+        done = C.c_uint64(0)
+        check(lib().rv_vec_step_agent(self.handle, int(policy), int(agent_seed), int(max_steps), C.byref(done)))
+        return int(done.value)
+
     def step_random_async(self, agent_seed, max_steps):
         check(lib().rv_vec_step_random_async(self.handle, int(agent_seed), int(max_steps)))
 

@@ -78,6 +78,9 @@ class OracleBackend(Backend):
     def random_step(self, agent_seed, game_id):
         self.lib.orc_game_random_step(self.h, agent_seed, game_id)
 
+    def agent_step(self, policy, agent_seed, game_id):
+        self.lib.orc_game_agent_step(self.h, policy, agent_seed, game_id)
+
     def legal(self, pid):
         out = (A.Action * A.MAX_LEGAL)()
         n = self.lib.orc_game_legal(self.h, pid, out)
@@ -132,6 +135,9 @@ class HostsimBackend(Backend):
     def random_step(self, agent_seed, game_id):
         self.lib.hs_game_random_step(self.h, agent_seed, game_id)
 
+    def agent_step(self, policy, agent_seed, game_id):
+        self.lib.hs_game_agent_step(self.h, policy, agent_seed, game_id)
+
     def visit_deferred(self, agent_seed, game_id):
         """One scheduler visit of the rollout kernels (parked discard tails / deals run on their own visit)."""
         return self.lib.hs_game_random_step_deferred(self.h, agent_seed, game_id)
@@ -181,6 +187,9 @@ class GpuBackend(Backend):
 
     def random_step(self, agent_seed, game_id):
         self.v.step_random(agent_seed, 1)
+
+    def agent_step(self, policy, agent_seed, game_id):
+        self.v.step_agent(policy, agent_seed, 1)
 
     def legal(self, pid):
         acts, counts = self.v.legal_actions()

@@ -40,6 +40,7 @@ def load():
     lib.hs_game_legal.argtypes = [C.c_void_p, C.c_int, P(A.Action)]
     lib.hs_game_step.argtypes = [C.c_void_p, P(A.Action)]
     lib.hs_game_random_step.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.hs_game_agent_step.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     lib.hs_game_random_step_deferred.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.hs_game_random_step_deferred.restype = C.c_int
     lib.hs_game_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
@@ -56,7 +57,14 @@ def load():
     lib.hs_game_encode_seq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(C.c_uint16), P(C.c_float),
                                        P(C.c_uint16), C.c_int, P(C.c_uint16), P(C.c_uint16)]
     lib.hs_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]
-    cache = os.environ.get("RV_HOSTSIM_CACHE", "/tmp/rv_hostsim_tables.bin")
+    # table cache beside the library (git-ignored), named after the sources that define the tables and checksummed
+    import hashlib
+
+    tag = hashlib.sha1(b"".join(open(os.path.join(csrc, f), "rb").read() for f in ("tables.cuh", "hand.cuh"))).hexdigest()[:12]
+    cache = os.environ.get("RV_HOSTSIM_CACHE", os.path.join(_HERE, f"_tables_{tag}.bin"))
+    for old in os.listdir(_HERE):
+        if old.startswith("_tables_") and old.endswith(".bin") and old != os.path.basename(cache):
+            os.remove(os.path.join(_HERE, old))
     lib.hs_init(cache.encode(), os.cpu_count() or 1)
     _LIB = lib
     return lib

@@ -10,6 +10,8 @@ static thread_local rv_game_state* hs_home = nullptr;
 #define RV_COLD_HOOK(g) (&(g) == hs_staged ? *hs_home : (g))
 
 #include <atomic>
+#include <string>
+#include <unistd.h>
 #include <cstdio>
 #include <thread>
 #include <vector>
@@ -101,6 +103,18 @@ static void gen(std::vector<uint64_t>& cost, std::vector<uint32_t>& info, int n_
   }
 }
 
+static uint64_t tables_checksum() {   // FNV-1a over the four tables: a stale or damaged cache file is regenerated
+  uint64_t h = 0xcbf29ce484222325ull;
+  auto eat = [&](const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 0x100000001b3ull;
+  };
+  eat(g_suit_info.data(), 4 * g_suit_info.size());
+  eat(g_honor_info.data(), 4 * g_honor_info.size());
+  eat(g_suit_cost.data(), 8 * g_suit_cost.size());
+  eat(g_honor_cost.data(), 8 * g_honor_cost.size());
+  return h;
+}
 extern "C" {
 int hs_init(const char* cache_path, int threads) {
   if (g_ready) return 0;
@@ -114,21 +128,27 @@ int hs_init(const char* cache_path, int threads) {
       g_honor_cost.resize(HONOR_KEYS);
       size_t ok = fread(g_suit_info.data(), 4, SUIT_KEYS, f) + fread(g_honor_info.data(), 4, HONOR_KEYS, f) +
                   fread(g_suit_cost.data(), 8, SUIT_KEYS, f) + fread(g_honor_cost.data(), 8, HONOR_KEYS, f);
+      uint64_t sum = 0;
+      size_t got = fread(&sum, 8, 1, f);
       fclose(f);
-      loaded = ok == (size_t)2 * SUIT_KEYS + 2 * HONOR_KEYS;
+      loaded = ok == (size_t)2 * SUIT_KEYS + 2 * HONOR_KEYS && got == 1 && sum == tables_checksum();
     }
   }
   if (!loaded) {
     gen<9, true>(g_suit_cost, g_suit_info, SUIT_KEYS, threads);
     gen<7, false>(g_honor_cost, g_honor_info, HONOR_KEYS, threads);
     if (cache_path) {
-      FILE* f = fopen(cache_path, "wb");
+      std::string tmp = std::string(cache_path) + ".tmp" + std::to_string((long long)getpid());
+      FILE* f = fopen(tmp.c_str(), "wb");   // written beside the cache and renamed into place: readers never see half a file
       if (f) {
         fwrite(g_suit_info.data(), 4, SUIT_KEYS, f);
         fwrite(g_honor_info.data(), 4, HONOR_KEYS, f);
         fwrite(g_suit_cost.data(), 8, SUIT_KEYS, f);
         fwrite(g_honor_cost.data(), 8, HONOR_KEYS, f);
+        uint64_t sum = tables_checksum();
+        fwrite(&sum, 8, 1, f);
         fclose(f);
+        rename(tmp.c_str(), cache_path);
       }
     }
   }
@@ -267,6 +287,12 @@ void hs_game_random_step(void* p, uint64_t agent_seed, uint64_t game_id) {
   if (h->g.is_done) return;
   Staged st(h->g);
   random_step(cx, st.g(), agent_seed, game_id);
+}
+void hs_game_agent_step(void* p, int policy, uint64_t agent_seed, uint64_t game_id) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  if (h->g.is_done) return;
+  agent_step(cx, h->g, policy, agent_seed, game_id);
 }
 // One scheduler visit as the rollout kernels make it: a parked discard tail or a parked deal is run on its own visit,
 // otherwise the game takes one random step with both deferrals armed.  Returns 1 if an env step was taken.

@@ -160,6 +160,64 @@ def test_parity_gate_100k_games(orc):
     assert g[1].all() and g[0] > 1000 * n
 
 
+def run_both_agent(orc, policy, n, mode, rule, seed_base, agent_seed, hist=None, max_steps=200000):
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    v = VecRiichiEnv(n, mode, rule, seed_base=seed_base)
+    v.reset()
+    total = v.step_agent(policy, agent_seed, max_steps)
+    done, scores, ranks = v.results()
+    sc, kc, ec, eh = v.counters()
+    v.close()
+    o_scores, o_ranks, o_done = np.zeros((n, 4), np.int32), np.zeros((n, 4), np.uint8), np.zeros(n, np.uint8)
+    o_steps, o_ky, o_ec, o_h = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint64)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    import os
+
+    o_total = orc.orc_run_agent(policy, mode, rule, seed_base, n, agent_seed, max_steps, os.cpu_count() or 1, p(o_scores, C.c_int32),
+                                p(o_ranks, C.c_uint8), p(o_done, C.c_uint8), p(o_steps, C.c_uint32), p(o_ky, C.c_uint32),
+                                p(o_ec, C.c_uint32), p(o_h, C.c_uint64), None if hist is None else p(hist, C.c_uint64))
+    return (total, done, scores, ranks, sc, kc, ec, eh), (o_total, o_done, o_scores, o_ranks, o_steps, o_ky, o_ec, o_h)
+
+
+@pytest.mark.parametrize("mode,rule,n", [(2, A.RULE_DEFAULT_MJSOUL, 4096), (0, A.RULE_DEFAULT_TENHOU, 8192), (1, A.RULE_DEFAULT_MJSOUL, 2048),
+                                          (5, A.RULE_DEFAULT_TENHOU, 4096), (5, A.RULE_DEFAULT_MJSOUL, 4096), (3, A.RULE_DEFAULT_MJSOUL, 8192)])
+def test_greedy_agent_games_vs_oracle(orc, mode, rule, n):
+    """rv_vec_step_agent(RV_AGENT_GREEDY): every mode and both rule presets, final records and event hashes vs the oracle."""
+    g, o = run_both_agent(orc, 1, n, mode, rule, seed_base=7000 * (mode + 1), agent_seed=0xFACE)
+    assert g[0] == o[0], "total env steps"
+    for name, a, b in zip(["done", "scores", "ranks", "step_count", "kyoku_count", "ev_count", "ev_hash"], g[1:], o[1:]):
+        assert np.array_equal(a, b), f"{name} differs in {int((a != b).sum())} entries"
+    assert g[1].all()
+
+
+def test_settlement_gate_100k_greedy_games(orc):
+    """A5 (tsumo / ron settlement, state/mod.rs:685-893, 919-1142) at the size of the headline parity gate: 102,400 hanchan
+    played by the greedy-win agent — about 60 % of ~1.1 M rounds end in a win — with done / scores / ranks / step, round and
+    event counts and the 64-bit hash of the event stream (every hora event carries han, fu, the yaku set, deltas and ura
+    markers) equal between the CUDA path and the oracle.  The histogram (from the oracle's logs, which the hashes prove equal
+    to the GPU's) asserts that the quirk-laden branches were actually taken."""
+    n = 102400
+    hist = np.zeros(128, np.uint64)
+    g, o = run_both_agent(orc, 1, n, 2, A.RULE_DEFAULT_TENHOU, seed_base=9_000_000, agent_seed=0xA5A5, hist=hist)
+    assert g[0] == o[0], "total env steps"
+    for name, a, b in zip(["done", "scores", "ranks", "step_count", "kyoku_count", "ev_count", "ev_hash"], g[1:], o[1:]):
+        assert np.array_equal(a, b), f"{name} differs in {int((a != b).sum())} entries"
+    assert g[1].all()
+    H = {k: int(hist[i]) for k, i in dict(hora=64, tsumo=65, ron=66, multi_ron=67, pao=68, rounds=69, ryukyoku=70,
+                                          yakuman=80, kazoe=81).items()}
+    yaku = {y: int(hist[y]) for y in range(64) if hist[y]}
+    print("greedy gate:", H, "yaku:", yaku, "ryukyoku by reason:", [int(x) for x in hist[71:80]])
+    assert H["hora"] > 0.3 * H["rounds"], "more than 30 % of the rounds must end in a win"
+    assert H["tsumo"] > 10000 and H["ron"] > 10000 and H["multi_ron"] > 100
+    # chankan 3, rinshan 4, haitei 5, houtei 6, ippatsu 30, ura 33, double riichi 18; yakuman: at least daisangen / suuankou
+    # (tanki) / kokushi (13-wait) families; suucha riichi (reason 5) and sanchaho (reason 6) draws
+    for y in (1, 2, 3, 4, 5, 6, 18, 30, 31, 32, 33):
+        assert yaku.get(y, 0) > 0, f"yaku {y} never occurred"
+    assert yaku.get(37, 0) > 0 and yaku.get(38, 0) + yaku.get(48, 0) > 0 and yaku.get(42, 0) + yaku.get(49, 0) > 0
+    assert H["yakuman"] >= 100 and hist[71 + 5] > 0 and hist[71 + 6] > 0
+
+
 def test_partial_rollout_and_resume(orc):
     """max_steps < game length: state must carry over between launches exactly."""
     from riichienv_b200.vec_env import VecRiichiEnv

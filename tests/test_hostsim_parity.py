@@ -82,7 +82,7 @@ def test_wall_matches_oracle(libs):
                 assert len(set(bytes(a)[:n])) == n
 
 
-def lockstep(seed, mode, rule, agent_seed, check_legal=True):
+def lockstep(seed, mode, rule, agent_seed, check_legal=True, policy=0):
     o, h = OracleBackend(mode, seed, rule), HostsimBackend(mode, seed, rule)
     o.reset()
     h.reset()
@@ -96,10 +96,16 @@ def lockstep(seed, mode, rule, agent_seed, check_legal=True):
         if check_legal:
             for p in range(4):
                 assert o.legal_tuples(p) == h.legal_tuples(p), f"seed {seed} step {steps} seat {p}"
-        o.random_step(agent_seed, seed)
-        h.random_step(agent_seed, seed)
+        if policy:
+            o.agent_step(policy, agent_seed, seed)
+            h.agent_step(policy, agent_seed, seed)
+        else:
+            o.random_step(agent_seed, seed)
+            h.random_step(agent_seed, seed)
         steps += 1
     assert o.events() == h.events()
+    for viewer in (-1, 0, 1, 2):
+        assert o.events_json(viewer) == h.events_json(viewer)   # the oracle's own text log vs the product renderer
     return steps
 
 
@@ -111,6 +117,18 @@ def test_random_games_lockstep(mode, rule, n):
     total = 0
     for seed in range(100 * mode, 100 * mode + n):
         total += lockstep(seed, mode, rule, agent_seed=0xC0FFEE + mode)
+    assert total > 40 * n
+
+
+@pytest.mark.parametrize("mode,rule,n", [(2, A.RULE_DEFAULT_TENHOU, 16), (2, A.RULE_DEFAULT_MJSOUL, 16), (5, A.RULE_DEFAULT_TENHOU, 12),
+                                          (5, A.RULE_DEFAULT_MJSOUL, 8), (0, A.RULE_DEFAULT_MJSOUL, 24), (3, A.RULE_DEFAULT_TENHOU, 24)])
+def test_greedy_agent_games_lockstep(mode, rule, n):
+    """The greedy-win agent (every Tsumo / Ron / Riichi, calls with probability 1/4, discards towards the lowest shanten):
+    ~60 % of the rounds end in a win, so this is the lock-step gate of the settlement path (state/mod.rs:685-893, 919-1142).
+    Full record after every step, every legal list, the event words and the MJAI text of the kernel code vs the oracle."""
+    total = wins = 0
+    for seed in range(500 + 100 * mode, 500 + 100 * mode + n):
+        total += lockstep(seed, mode, rule, agent_seed=0xBEEF + mode, policy=1)
     assert total > 40 * n
 
 
