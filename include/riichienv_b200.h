@@ -260,6 +260,10 @@ int rv_sizeof(int which);
 int rv_hand_eval_batch(rv_ctx* ctx, const rv_hand_query* q, rv_hand_result* out, int64_t n);
 /* Same with DEVICE buffers; asynchronous on the context's stream. */
 int rv_hand_eval_batch_device(rv_ctx* ctx, const rv_hand_query* d_q, rv_hand_result* d_out, int64_t n);
+/* The seeded synthetic hand stream of BASELINE.json configs[1] (definition: include/rv_synth.h): queries first .. first+n-1
+ * written into a DEVICE buffer, asynchronous on the context's stream; the _host variant builds one query on the CPU. */
+int rv_hand_queries_seeded(rv_ctx* ctx, rv_hand_query* d_q, uint64_t first, int64_t n);
+int rv_hand_query_seeded_host(uint64_t h, rv_hand_query* out);
 /* score.rs:13-52 on host (no device work): out[0]=pay_ron out[1]=pay_tsumo_oya out[2]=pay_tsumo_ko out[3]=total */
 int rv_calculate_score(int han, int fu, int is_oya, int is_tsumo, uint32_t honba, int num_players, uint32_t out[4]);
 

@@ -33,6 +33,7 @@ def load():
     P = C.POINTER
     lib.orc_hand_eval.argtypes = [P(A.HandQuery), P(A.HandResult), C.c_int64]
     lib.orc_hand_eval_mt.argtypes = [P(A.HandQuery), P(A.HandResult), C.c_int64, C.c_int]
+    lib.orc_hand_queries_seeded.argtypes = [P(A.HandQuery), C.c_uint64, C.c_int64]
     lib.orc_is_agari.argtypes = [P(C.c_uint8)]
     lib.orc_is_tenpai_counts.argtypes = [P(C.c_uint8)]
     lib.orc_shanten_counts.argtypes = [P(C.c_uint8), C.c_int]

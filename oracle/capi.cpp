@@ -6,6 +6,7 @@
 #include <mutex>
 #include <thread>
 
+#include "../include/rv_synth.h"
 #include "game.hpp"
 #include "obs.hpp"
 #include "seq.hpp"
@@ -247,6 +248,11 @@ int orc_hand_eval_mt(const rv_hand_query* q, rv_hand_result* out, int64_t n, int
       }
     });
   for (auto& t : th) t.join();
+  return 0;
+}
+// the seeded synthetic hand stream of BASELINE.json configs[1] (input data; one definition in include/rv_synth.h)
+int orc_hand_queries_seeded(rv_hand_query* q, uint64_t first, int64_t n) {
+  for (int64_t i = 0; i < n; i++) rv_synth_hand(first + (uint64_t)i, &q[i]);
   return 0;
 }
 int orc_is_agari(const uint8_t* counts34) {

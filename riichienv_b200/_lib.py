@@ -40,6 +40,8 @@ def lib():
     L.rv_vec_reseed.argtypes = [vp, P(C.c_uint64), C.c_uint64]
     L.rv_hand_eval_batch.argtypes = [vp, P(A.HandQuery), P(A.HandResult), C.c_int64]
     L.rv_hand_eval_batch_device.argtypes = [vp, vp, vp, C.c_int64]
+    L.rv_hand_queries_seeded.argtypes = [vp, vp, C.c_uint64, C.c_int64]
+    L.rv_hand_query_seeded_host.argtypes = [C.c_uint64, P(A.HandQuery)]
     L.rv_calculate_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, P(C.c_uint32)]
     L.rv_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]
     L.rv_vec_create.argtypes = [vp, C.c_int64, C.c_int, C.c_uint32, P(C.c_uint64), C.c_uint64, C.c_uint32, P(vp)]

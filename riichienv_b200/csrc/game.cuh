@@ -583,6 +583,272 @@ __device__ __noinline__ void run_pending_init(const Ctx& cx, G& g) {
   init_round(cx, g, no, nw, nh, g.riichi_sticks, nullptr, nullptr);
 }
 
+// ---- the deal, one warp per game -------------------------------------------------------------------------------------
+// init_round above is ~18 k serial instructions (ChaCha blocks, the chunked shuffle, dealing, sorting, wait sets, the
+// start_kyoku event).  A lock-step launch (one env step for every game, the observation pipeline of BASELINE configs[4])
+// waits for whichever thread happens to deal a round — ~190 us, longer than the rest of the step.  Here a whole warp deals
+// ONE round: lanes 0-3 compute the four ChaCha blocks, the chunk draws and the swaps stay serial (they are a dependency
+// chain) but run out of shared memory, and everything else — clearing the record, writing the wall, dealing the 53 tiles,
+// rank-sorting the hands, histograms, wait sets, the event words — is spread over the lanes.  Same record, bit for bit.
+// Written as lane loops between warp barriers so that the host compile of these sources (tests/hostsim) runs the same code
+// with the lanes in sequence.
+#ifdef __CUDA_ARCH__
+#define RV_FOR_LANES(l) for (int l = (int)(threadIdx.x & 31), rv_once_ = 1; rv_once_; rv_once_ = 0)
+#define RV_WARP_BARRIER() __syncwarp()
+#else
+#define RV_FOR_LANES(l) for (int l = 0; l < 32; l++)
+#define RV_WARP_BARRIER()
+#endif
+struct DealScratch {            // per warp, in shared memory (on the host: on the stack)
+  uint32_t words[64];           // ChaCha12 output of blocks 0..3
+  alignas(8) uint8_t w[136];    // the wall being shuffled, then reversed in place
+  alignas(8) uint8_t rev[136];
+  uint8_t idx[136];             // swap partner of position i
+  uint32_t recip[137];          // floor((2^32 - 1) / d): the chunk / n, chunk % n of the shuffle without integer divisions
+  uint8_t hand[MAXP][16];       // dealt tiles per seat (13), unsorted
+};
+// One ChaCha12 block (key, 64-bit counter `ctr`, nonce 0) -> 16 words.
+__host__ __device__ inline void chacha12_block(const uint32_t* key, uint64_t ctr, uint32_t* out) {
+  uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                     key[4], key[5], key[6], key[7], (uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+  uint32_t s[16];
+  for (int i = 0; i < 16; i++) s[i] = in[i];
+#define RV_ROTL(v, n) (((v) << (n)) | ((v) >> (32 - (n))))
+#define RV_QR2(a, b, c, d)                                                      \
+  s[a] += s[b]; s[d] ^= s[a]; s[d] = RV_ROTL(s[d], 16); s[c] += s[d]; s[b] ^= s[c]; s[b] = RV_ROTL(s[b], 12); \
+  s[a] += s[b]; s[d] ^= s[a]; s[d] = RV_ROTL(s[d], 8);  s[c] += s[d]; s[b] ^= s[c]; s[b] = RV_ROTL(s[b], 7);
+  for (int r = 0; r < 6; r++) {
+    RV_QR2(0, 4, 8, 12) RV_QR2(1, 5, 9, 13) RV_QR2(2, 6, 10, 14) RV_QR2(3, 7, 11, 15)
+    RV_QR2(0, 5, 10, 15) RV_QR2(1, 6, 11, 12) RV_QR2(2, 7, 8, 13) RV_QR2(3, 4, 9, 14)
+  }
+#undef RV_QR2
+#undef RV_ROTL
+  for (int i = 0; i < 16; i++) out[i] = s[i] + in[i];
+}
+// Every lane of the warp calls this with the same arguments; `S` is the warp's scratch.  Seeded walls only (the rollout
+// never passes a custom wall or scores).
+__device__ __noinline__ void init_round_coop(const Ctx& cx, G& g, DealScratch& S, int oya, int round_wind, int honba, uint32_t kyotaku) {
+  const int np = num_players(g);
+  const int wl = np == 3 ? 108 : 136;
+  G& cg = cold(g);
+  // ---- phase 1: ChaCha blocks (lanes 0-3), identity wall (all lanes), per-seat reset (lanes 4-7), scalars (lane 8)
+  uint32_t key[8];
+  {
+    uint64_t state = splitmix64(g.seed + cg.hand_index);   // rand_core SeedableRng::seed_from_u64: PCG32 (XSH-RR) expansion
+    for (int i = 0; i < 8; i++) {
+      state = state * 6364136223846793005ull + 11634580027462260723ull;
+      uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
+      uint32_t rot = (uint32_t)(state >> 59);
+      key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+  }
+  RV_WARP_BARRIER();   // every lane has read hand_index before lane 8 advances it
+  RV_FOR_LANES(l) {
+    if (l < 4) chacha12_block(key, (uint64_t)l, S.words + 16 * l);
+    for (int i = l + 1; i <= 136; i += 32) S.recip[i] = 0xFFFFFFFFu / (uint32_t)i;
+    for (int i = l; i < 136; i += 32) {
+      int t = i;
+      if (np == 3) {                       // the 108-tile set: kinds 1..7 (2m-8m) removed (state_3p/wall.rs:77-79)
+        t = i < 4 ? i : i + 28;
+        if (i >= 108) t = RV_NONE;
+      }
+      S.w[i] = (uint8_t)t;
+    }
+    if (l >= 4 && l < 8) {                 // PlayerState::reset_round (state/player.rs:66-86)
+      const int p = l - 4;
+      for (int i = 0; i < RV_HAND_CAP; i++) g.hand[p][i] = RV_NONE;
+      g.hand_len[p] = 0;
+      for (int m = 0; m < 4; m++) {
+        for (int k = 0; k < 4; k++) g.meld_tiles[p][m][k] = RV_NONE;
+        g.meld_type[p][m] = cg.meld_from[p][m] = cg.meld_called[p][m] = RV_NONE;
+      }
+      g.n_melds[p] = 0;
+      for (int i = 0; i < RV_RIVER_CAP; i++) cg.river[p][i] = RV_NONE;
+      g.n_river[p] = 0;
+      g.river_tedashi[p] = 0;
+      cg.river_riichi[p] = 0;
+      cg.riichi_decl_idx[p] = RV_NONE;
+      g.flags[p] = (np == 3 && p == 3) ? 0 : RV_F_NAGASHI_ELIGIBLE;
+      cg.pao[p][0] = cg.pao[p][1] = RV_NONE;
+      g.forbidden[p][0] = g.forbidden[p][1] = RV_NONE;
+      cg.score_delta[p] = 0;
+      g.n_claims[p] = 0;
+      cg.riichi_sutehai[p] = cg.last_tedashi[p] = RV_NONE;
+      cg.n_kita[p] = 0;
+      g.c_river_kinds[p] = 0;
+      g.c_waits[p] = 0;
+      if (np == 3 && p == 3) g.score[3] = 0;
+    }
+    if (l == 8) {
+      g.oya = g.kyoku_idx = g.current_player = (uint8_t)oya;
+      g.honba = (uint8_t)honba;
+      g.riichi_sticks = kyotaku;
+      g.round_wind = (uint8_t)round_wind;
+      g.is_done = 0;
+      g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
+      g.is_rinshan_flag = 0;
+      g.rinshan_draw_count = 0;
+      g.pending_kan_dora_count = 0;
+      g.is_first_turn = 1;
+      g.riichi_pending_acceptance = RV_NONE;
+      g.turn_count = 0;
+      g.last_discard_pid = g.last_discard_tile = RV_NONE;
+      g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
+      g.pending_tail[0] = RV_NONE;
+      g.pending_tail[1] = 0;
+      g.wall_len = (uint8_t)wl;
+      g.n_dora = 1;
+      for (int i = 1; i < 5; i++) g.dora_ind[i] = RV_NONE;
+      cg.hand_index++;
+      cg.kyoku_count++;
+    }
+  }
+  RV_WARP_BARRIER();
+  // ---- phase 2 (lane 0): the chunk draws and the swap partners (IncreasingUniform; as wall_from_seed)
+  RV_FOR_LANES(l) {
+    if (l == 0) {
+      int widx = 0;
+      uint32_t cur_n = 0, chunk = 0, remaining = 1;
+      for (int i = 0; i < wl; i++) {
+        uint32_t next_n = cur_n + 1, rem;
+        if (remaining == 0) {
+          uint32_t product = next_n, current = next_n + 1;
+          while (true) {
+            uint64_t pr = (uint64_t)product * current;
+            if (pr > 0xFFFFFFFFull) break;
+            product = (uint32_t)pr;
+            current++;
+          }
+          uint64_t m = (uint64_t)S.words[widx++ & 63] * product;      // random_below: widening multiply + one bias draw
+          uint32_t hi = (uint32_t)(m >> 32), lo = (uint32_t)m;
+          if (lo > (uint32_t)(0u - product)) {
+            uint64_t m2 = (uint64_t)S.words[widx++ & 63] * product;
+            if ((uint64_t)lo + (uint32_t)(m2 >> 32) > 0xFFFFFFFFull) hi += 1;
+          }
+          chunk = hi;
+          rem = (current - next_n) - 1;
+        } else {
+          rem = remaining - 1;
+        }
+        uint32_t j;
+        if (rem == 0) {
+          j = chunk;
+        } else {
+          uint32_t q = rv_umulhi(chunk, S.recip[next_n]);   // q or short of it by at most 2
+          uint32_t r = chunk - q * next_n;
+          if (r >= next_n) r -= next_n, q++;
+          if (r >= next_n) r -= next_n, q++;
+          j = r;
+          chunk = q;
+        }
+        remaining = rem;
+        cur_n = next_n;
+        S.idx[i] = (uint8_t)j;
+      }
+      for (int i = 0; i < wl; i++) {       // the swaps: a chain through memory, kept in shared memory
+        const int j = S.idx[i];
+        uint8_t t = S.w[i];
+        S.w[i] = S.w[j];
+        S.w[j] = t;
+      }
+    }
+  }
+  RV_WARP_BARRIER();
+  // ---- phase 3: reverse (wall.rs:57-58), dead-wall pad, dealt tiles per seat
+  RV_FOR_LANES(l) {
+    for (int i = l; i < 136; i += 32) S.rev[i] = i < wl ? S.w[wl - 1 - i] : (uint8_t)RV_NONE;
+  }
+  RV_WARP_BARRIER();
+  RV_FOR_LANES(l) {
+    if (l < 17) reinterpret_cast<uint64_t*>(cg.wall)[l] = reinterpret_cast<const uint64_t*>(S.rev)[l];
+    // deal (state/mod.rs:1750-1765): 3 rounds of 4 tiles per seat from the dealer, then one each; pop from the back
+    for (int d = l; d < 13 * np; d += 32) {
+      int idx, k;                           // d-th tile dealt: seat slot idx (from the dealer), position k in that hand
+      if (d < 12 * np) {
+        const int r = d / (4 * np), within = d % (4 * np);
+        idx = within / 4;
+        k = 4 * r + (within & 3);
+      } else {
+        idx = d - 12 * np;
+        k = 12;
+      }
+      S.hand[(idx + oya) % np][k] = S.rev[wl - 1 - d];
+    }
+    if (l == 31) g.dora_ind[0] = S.rev[np == 3 ? 8 : 4];   // state_3p/wall.rs:104-112
+  }
+  RV_WARP_BARRIER();
+  // ---- phase 4: rank sort (tile ids are distinct), 13 lanes at a time per seat; the dealer's 14th tile goes last
+  const int drawn = S.rev[wl - 1 - 13 * np];
+  RV_FOR_LANES(l) {
+    for (int e = l; e < 13 * np; e += 32) {
+      const int p = e / 13, k = e - 13 * p, t = S.hand[p][k];
+      int rank = 0;
+      for (int j = 0; j < 13; j++) rank += S.hand[p][j] < t ? 1 : 0;
+      g.hand[p][rank] = (uint8_t)t;
+    }
+  }
+  RV_WARP_BARRIER();
+  // ---- phase 5: histograms + wait sets (one lane per seat), event (lane 4 builds it once the hands are in place)
+  RV_FOR_LANES(l) {
+    if (l < np) {
+      const int p = l;
+      uint64_t c[4] = {0, 0, 0, 0};
+      uint32_t key5[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 13; k++) {
+        const int kind = g.hand[p][k] >> 2, su = kind / 9, pos = kind - 9 * su;
+        c[su] += 1ull << (4 * pos);
+        key5[su] += (uint32_t)pow5(pos);
+      }
+      for (int k = 0; k < 4; k++) g.c_cnt[p][k] = c[k], g.c_key[p][k] = key5[k];
+      g.hand_len[p] = 13;
+      if (p != oya) {
+        waits_update(cx.T, g, p);
+      } else {
+        g.hand[p][13] = (uint8_t)drawn;      // the dealer draws right away
+        g.hand_len[p] = 14;
+        cache_add(g, p, drawn >> 2);
+      }
+    } else if (l < 4) {                      // sanma: the unused fourth seat keeps empty caches
+      for (int k = 0; k < 4; k++) g.c_cnt[l][k] = 0, g.c_key[l][k] = 0;
+    }
+  }
+  RV_WARP_BARRIER();
+  RV_FOR_LANES(l) {
+    if (l == 0) {
+      g.wall_top = (uint8_t)(wl - 13 * np - 1);
+      g.drawable_count = (uint8_t)(wl - 13 * np - 14 - 1);
+      uint32_t ew[19];
+      const int nb = 13 * np, ntw = (nb + 3) / 4, nwords = 2 + np + ntw;
+      ew[0] = ev_w0(RV_EV_START_KYOKU, nwords, round_wind % 4, oya);
+      ew[1] = (uint32_t)honba | ((uint32_t)g.dora_ind[0] << 8) | ((kyotaku & 0xFFFF) << 16);
+      for (int i = 0; i < np; i++) ew[2 + i] = (uint32_t)g.score[i];
+      for (int k = 0; k < ntw; k++) {
+        uint32_t v = 0;
+        for (int b = 0; b < 4; b++) {
+          int flat = k * 4 + b;
+          int t = flat < nb ? g.hand[flat / 13][flat % 13] : RV_NONE;
+          v |= (uint32_t)t << (8 * b);
+        }
+        ew[2 + np + k] = v;
+      }
+      ev_push(cx, g, ew, nwords);
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << oya);
+      g.drawn_tile = (uint8_t)drawn;
+      g.needs_tsumo = 0;
+      ev_simple(cx, g, RV_EV_TSUMO, oya, drawn);
+    }
+  }
+  RV_WARP_BARRIER();
+}
+// the parked deal of `g`, by the whole warp (every lane calls with the same game)
+__device__ __forceinline__ void run_pending_init_coop(const Ctx& cx, G& g, DealScratch& S) {
+  const int no = g.pending_init[0], nw = g.pending_init[1], nh = g.pending_init[2];
+  const uint32_t ky = g.riichi_sticks;
+  RV_WARP_BARRIER();              // every lane has read the parked parameters before lane 8 clears them
+  init_round_coop(cx, g, S, no, nw, nh, ky);
+}
+
 // is_tenpai of a seat's 13-tile-equivalent hand (hand_evaluator.rs:178-194)
 __device__ __forceinline__ bool seat_tenpai(const Ctx& cx, const G& g, int p) { return g.c_waits[p] != 0; }
 

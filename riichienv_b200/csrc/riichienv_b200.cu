@@ -16,6 +16,7 @@
 #include "obs_ext3.cuh"
 #include "seq.cuh"
 #include "validate.h"
+#include "../../include/rv_synth.h"
 
 using namespace rv;
 
@@ -88,6 +89,13 @@ struct rv_vec {
 };
 
 // ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) synth_hands_kernel(rv_hand_query* q, uint64_t first, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rv_hand_query h;
+  rv_synth_hand(first + (uint64_t)i, &h);
+  q[i] = h;
+}
 // rv_vec_step_agent: thread per game, every class of work inline (a test / evaluation path, not the throughput path)
 __global__ void __launch_bounds__(128) agent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, int policy,
                                                     uint64_t agent_seed, uint32_t max_steps, unsigned long long* counters);
@@ -256,13 +264,14 @@ template <bool IDS>
 __global__ void __launch_bounds__(SB) step_sorted_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, uint64_t agent_seed,
                                                          unsigned long long* counters, uint32_t* idbits) {
   enum { K_RESP = 0, K_TAIL = 1, K_SLOW = 2, K_NONE = 3 };
-  __shared__ uint16_t list[3][SB];
-  __shared__ int cnt[3];
+  __shared__ uint16_t list[4][SB];          // [3]: games whose round ended in this launch (dealt below, a warp per game)
+  __shared__ int cnt[4];
   __shared__ uint32_t s_ids[IDS ? SB : 1][3 * MAXP];
   __shared__ unsigned long long sh[2];
+  __shared__ DealScratch deal_scratch[SB / 32];
   const int t = threadIdx.x, lane = t & 31;
   const int64_t base = (int64_t)blockIdx.x * SB, i = base + t;
-  if (t < 3) cnt[t] = 0;
+  if (t < 4) cnt[t] = 0;
   if (t == 0) sh[0] = sh[1] = 0;
   __syncthreads();
   const bool alive = i < n;
@@ -314,12 +323,18 @@ __global__ void __launch_bounds__(SB) step_sorted_kernel(Tables T, G* states, in
         else if (k == K_TAIL) run_pending_tail(cx, h);
         else random_step_act<IDS>(cx, h, agent_seed, h.seed);
       }
-      // rounds that ended in this warp are dealt together, by the threads that ended them
+      // a round that ended: the deal (~18 k instructions on one thread) is handed to a whole warp below
       const bool parked = k != K_NONE && states[base + li].pending_init[0] != RV_NONE;
-      if (parked) {
-        Ctx cx = make_ctx(T, log, cap, base + li);
-        run_pending_init(cx, states[base + li]);
-      }
+      if (parked) list[3][atomicAdd(&cnt[3], 1)] = (uint16_t)li;
+    }
+  }
+  __syncthreads();
+  {
+    const int n_deal = cnt[3];
+    for (int d = t >> 5; d < n_deal; d += SB / 32) {
+      const int64_t gi = base + list[3][d];
+      Ctx cx = make_ctx(T, log, cap, gi);
+      run_pending_init_coop(cx, states[gi], deal_scratch[t >> 5]);
     }
   }
   __syncthreads();
@@ -1373,6 +1388,19 @@ int rv_hand_eval_batch(rv_ctx* c, const rv_hand_query* q, rv_hand_result* out, i
     int rc = drain(k);
     if (rc != RV_OK) return rc;
   }
+  return RV_OK;
+}
+int rv_hand_queries_seeded(rv_ctx* c, rv_hand_query* d_q, uint64_t first, int64_t n) {
+  if (n <= 0) return RV_OK;
+  if (!d_q) return fail(RV_ERR_INVALID, "null buffer");
+  CK(cudaSetDevice(c->device));
+  synth_hands_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(d_q, first, n);
+  CK(cudaGetLastError());
+  return RV_OK;
+}
+int rv_hand_query_seeded_host(uint64_t h, rv_hand_query* out) {
+  if (!out) return fail(RV_ERR_INVALID, "null buffer");
+  rv_synth_hand(h, out);
   return RV_OK;
 }
 int rv_calculate_score(int han, int fu, int is_oya, int is_tsumo, uint32_t honba, int num_players, uint32_t out[4]) {

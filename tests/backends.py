@@ -138,6 +138,10 @@ class HostsimBackend(Backend):
     def agent_step(self, policy, agent_seed, game_id):
         self.lib.hs_game_agent_step(self.h, policy, agent_seed, game_id)
 
+    def random_step_coopdeal(self, agent_seed, game_id):
+        """a random step whose round deal runs through init_round_coop (the warp-cooperative deal of the lock-step kernels)"""
+        self.lib.hs_game_random_step_coopdeal(self.h, agent_seed, game_id)
+
     def visit_deferred(self, agent_seed, game_id):
         """One scheduler visit of the rollout kernels (parked discard tails / deals run on their own visit)."""
         return self.lib.hs_game_random_step_deferred(self.h, agent_seed, game_id)

@@ -288,6 +288,18 @@ void hs_game_random_step(void* p, uint64_t agent_seed, uint64_t game_id) {
   Staged st(h->g);
   random_step(cx, st.g(), agent_seed, game_id);
 }
+// one random step as the lock-step kernels take it: the round's deal is parked and then run by the warp-cooperative routine
+void hs_game_random_step_coopdeal(void* p, uint64_t agent_seed, uint64_t game_id) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  if (h->g.is_done) return;
+  cx.defer_init = true;
+  random_step(cx, h->g, agent_seed, game_id);
+  if (h->g.pending_init[0] != RV_NONE) {
+    DealScratch S;
+    run_pending_init_coop(cx, h->g, S);
+  }
+}
 void hs_game_agent_step(void* p, int policy, uint64_t agent_seed, uint64_t game_id) {
   HS* h = (HS*)p;
   Ctx cx = hs_ctx(h);

@@ -132,6 +132,28 @@ def test_greedy_agent_games_lockstep(mode, rule, n):
     assert total > 40 * n
 
 
+@pytest.mark.parametrize("mode,rule,n", [(2, A.RULE_DEFAULT_TENHOU, 12), (5, A.RULE_DEFAULT_TENHOU, 12), (1, A.RULE_DEFAULT_MJSOUL, 6),
+                                          (4, A.RULE_DEFAULT_MJSOUL, 6)])
+def test_cooperative_deal_matches_oracle(mode, rule, n):
+    """init_round_coop — one warp deals one round (ChaCha blocks, shuffle, deal, rank sort, wait sets, start_kyoku spread over
+    the lanes) — leaves the record init_round leaves: full record after every step of whole games, 4P and sanma."""
+    for seed in range(900 + 10 * mode, 900 + 10 * mode + n):
+        o, h = OracleBackend(mode, seed, rule), HostsimBackend(mode, seed, rule)
+        o.reset()
+        h.reset()
+        steps = 0
+        while True:
+            so, sh = o.get_state(), h.get_state()
+            d = A.state_fields_equal(so, sh)
+            assert not d, f"seed {seed} step {steps}: state differs in {d}"
+            if so.is_done:
+                break
+            o.random_step(0xD1CE, seed)
+            h.random_step_coopdeal(0xD1CE, seed)
+            steps += 1
+        assert o.events() == h.events() and so.kyoku_count > (1 if mode not in (0, 3) else 0)
+
+
 @pytest.mark.parametrize("mode", [2, 5])
 def test_deferred_visits_match_oracle(mode):
     """The rollout kernels park the follow-up of some discards (pending_tail) and the next round's deal (pending_init)
