@@ -26,9 +26,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_STEP = 1024  # algorithmic bytes per env step without observations (SURVEY.md §8 d)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_persistent_kernel launch (65,536 hanchan, 69.3 M env steps)
-# from the ncu --set full capture profiles/r01s3g_persist_raw.csv: 1.77 GB read + 7.50 GB written
-TRAFFIC_BYTES_PER_LAUNCH = 9.27e9
 MODE_NAMES = {0: "4p-red-single kyoku", 1: "4p-red-east", 2: "4p-red-half hanchan", 3: "3p-red-single kyoku", 4: "3p-red-east",
               5: "3p-red-half hanchan (sanma)"}
 METRIC = "env_steps_per_sec"
@@ -61,6 +58,43 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+def source_fingerprint():
+    """sha1 over the CUDA sources: ncu facts are only quoted for the build they were measured on"""
+    import hashlib
+
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "riichienv_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_facts(kernel):
+    """DRAM bytes per launch and issue-slot utilisation of `kernel` from the committed `ncu --set full` capture of this build
+    (profiles/ncu_facts.json, written by profiles/summarize_ncu.py --facts); None when the capture belongs to other sources,
+    so the numbers cannot go stale silently."""
+    try:
+        facts = json.load(open(os.path.join(ROOT, "profiles", "ncu_facts.json")))
+    except Exception:
+        return None
+    f = facts.get(kernel)
+    if not f or f.get("src") != source_fingerprint():
+        return None
+    return f
+
+
+def workload_config(mode, games_per_gpu):
+    return {"workload": (f"{MODE_NAMES[mode]}, default Tenhou rules, {games_per_gpu:,} parallel seeded random-agent games per GPU "
+                         f"(BASELINE.json configs[{3 if mode >= 3 else 2}]), reset -> done"),
+            "games_per_gpu": games_per_gpu, "game_mode": mode}
+
+
+def cpu_sample_games(args):
+    """hanchan per CPU step: the same bounded sample for the cpu_baseline leg and the --impl reference arm"""
+    return args.cpu_sample_games or max(64 * (os.cpu_count() or 1), 2048)
 
 
 class ClockSampler:
@@ -122,24 +156,27 @@ def run_oracle_sample(mode, n_games, seed_base, agent_seed, threads):
     return int(steps), time.perf_counter() - t0
 
 
-def cpu_baseline(mode, sample_games):
+def cpu_baseline(mode, sample_games, reps=6):
+    """the oracle port on every host core: `reps` steps of the same bounded sample the --impl reference arm plays per step"""
     threads = os.cpu_count() or 1
-    if sample_games <= 0:
-        # probe, then size the sample for ~12 s of CPU work
-        s, dt = run_oracle_sample(mode, 4 * threads, 10_000_000, 1, threads)
-        rate = s / max(dt, 1e-6)
-        sample_games = max(4 * threads, int(12.0 * rate / 1060))
-    steps, dt = run_oracle_sample(mode, sample_games, 20_000_000, 1, threads)
+    run_oracle_sample(mode, max(threads, sample_games // 8), 10_000_000, 1, threads)      # warm-up
+    steps = 0
+    dt = 0.0
+    for k in range(reps):
+        s_, d_ = run_oracle_sample(mode, sample_games, 20_000_000 + k * sample_games, 1, threads)
+        steps += s_
+        dt += d_
     return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{sample_games} seeded 4p-red-half hanchan ({steps} env steps, {dt:.1f} s) through the C++ oracle "
-                      f"(restatement of riichienv-core; the Rust reference cannot be built here), {threads} threads"}
+            "sample": f"{reps} x {sample_games} seeded {MODE_NAMES[mode]} ({steps} env steps, {dt:.1f} s) through the C++ oracle "
+                      f"port (oracle/: a restatement of riichienv-core; the Rust reference cannot be built here or on the GPU box, "
+                      f"profiles/r02_probe.txt), {threads} threads"}
 
 
 def reference_arm(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = args.cpu_sample_games or max(64 * threads, 2048)   # ~1-2 s of work per step on all cores
+    per_step = cpu_sample_games(args)                              # ~1-2 s of work per step on all cores
     for w in range(args.warmup):
         run_oracle_sample(args.mode, max(threads, per_step // 8), 30_000_000 + w * per_step, 1, threads)
     tot_steps, tot_t = 0, 0.0
@@ -148,14 +185,16 @@ def reference_arm(args, rank, world):
         tot_steps += s
         tot_t += dt
     val = tot_steps / tot_t
-    sample = (f"{per_step} seeded hanchan per step x {args.steps} steps ({tot_steps} env steps) through the C++ oracle "
-              f"(CPU restatement of riichienv-core; Rust toolchain absent so oracle/_ref cannot exist), {threads} threads")
+    sample = (f"{per_step} seeded hanchan per step x {args.steps} steps ({tot_steps} env steps) through the C++ oracle port "
+              f"(CPU restatement of riichienv-core; no Rust toolchain here or on the GPU box, so oracle/_ref cannot exist), "
+              f"{threads} threads")
+    cfg = workload_config(args.mode, args.games)
+    cfg.update({"cpu_arm": "oracle port (kind=port), not riichienv-core itself", "sample_games_per_step": per_step})
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
-        "config": {"workload": "4p-red-half hanchan, default Tenhou rules, seeded keyed random agents (bounded CPU sample)",
-                   "games_per_step": per_step, "game_mode": args.mode},
+        "config": cfg,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -280,24 +319,30 @@ def main():
         peak, peak_src = measured_peaks()
         value = all_steps / (tot_ms / 1000.0)
         achieved = (tot_steps * B_STEP) / (tot_kernel_ms / 1000.0) / 1e9  # this rank's dominant kernel
+        kname = "rollout_persistent_kernel<3>" if args.mode >= 3 else "rollout_persistent_kernel<4>"
+        facts = ncu_facts(kname) if (G == 65536 and args.mode in (2, 5)) else None
+        cfg = workload_config(args.mode, G)
+        cfg.update({"l2": "256 MiB flush write between timed iterations",
+                    "games_per_sec": (G * args.steps * world) / (tot_ms / 1000.0),
+                    "env_steps_per_game": all_steps / (G * args.steps * world)})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot_ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/i32", "data": "synthetic",
-            "config": {"workload": (f"{MODE_NAMES[args.mode]}, default Tenhou rules, {G:,} parallel seeded random-agent games per GPU "
-                                    f"(BASELINE.json configs[{3 if args.mode >= 3 else 2}]), reset -> done"),
-                       "games_per_gpu": G, "game_mode": args.mode, "l2": "256 MiB flush write between timed iterations",
-                       "games_per_sec": (G * args.steps * world) / (tot_ms / 1000.0),
-                       "env_steps_per_game": all_steps / (G * args.steps * world)},
+            "config": cfg,
             "e2e": {"value": all_e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "kernel": "rollout_persistent_kernel (one launch per rollout)", "peak_source": peak_src,
+                         # traffic / issue_frac: from the committed ncu --set full capture of THIS build (else null)
+                         "traffic": facts["dram_bytes"] if facts else None,
+                         "issue_frac": facts["issue_active_pct"] / 100.0 if facts else None,
+                         "ncu_capture": facts["capture"] if facts else None,
+                         "kernel": "rollout_persistent_kernel (one launch per rollout)", "peak_source": peak_src,
                          "bytes_per_env_step": B_STEP, "kernel_share_of_step": tot_kernel_ms / tot_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.mode, args.cpu_sample_games)
+            line["cpu_baseline"] = cpu_baseline(args.mode, cpu_sample_games(args))
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -400,6 +400,32 @@ int rv_vec_encode_seq(rv_vec* v, int game_style, const uint32_t* start_words, ui
                       uint16_t* d_prog, int max_prog, uint16_t* d_cand, uint16_t* d_lens, int32_t* d_index, int64_t max_obs,
                       int64_t* n_obs);
 
+/* ---- several GPUs behind one handle (SURVEY.md §8 e) -------------------------------------------------------------
+ * Replaces what the reference does with one Python list of RiichiEnv per Ray actor (riichienv-ml/.../_ppo_worker.py:13,39).
+ * Device k of G owns the contiguous global game ids [k*N/G, (k+1)*N/G); game g is seeded seed_base + g for any G, so scores,
+ * ranks and event hashes do not depend on the number of devices.  Every call runs one host thread per device, each on its
+ * device's own context and stream; no data crosses devices on the step path.  rv_multi_stats sums the per-device episode
+ * statistics on the host (the only reduction).  Host output arrays are in global game order.                              */
+typedef struct rv_multi rv_multi; /* opaque */
+typedef struct rv_run_stats {
+  int64_t games, games_done, env_steps, rounds;
+  int64_t score_sum[RV_NP];          /* sum of final scores per seat */
+  int64_t rank_hist[RV_NP][RV_NP];   /* [seat][rank - 1] over finished games */
+} rv_run_stats;
+int rv_multi_create(const int* devices, int n_devices, int64_t n_games, int game_mode, uint32_t rule_bits, uint64_t seed_base,
+                    uint32_t log_cap_words, rv_multi** out);
+int rv_multi_destroy(rv_multi* m);
+int rv_multi_devices(const rv_multi* m);
+int64_t rv_multi_size(const rv_multi* m);
+/* the vector of shard k (for the per-device calls: encoders, snapshots) and its range of global game ids */
+int rv_multi_shard(rv_multi* m, int k, rv_vec** vec, int64_t* first_game, int64_t* n_games);
+int rv_multi_reset(rv_multi* m);                           /* RiichiEnv::reset() defaults for every game */
+int rv_multi_reseed(rv_multi* m, uint64_t seed_base);      /* as rv_vec_reseed with seed seed_base + global id */
+int rv_multi_step_random(rv_multi* m, uint64_t agent_seed, uint32_t max_steps, uint64_t* steps_done);
+int rv_multi_results(rv_multi* m, uint8_t* done, int32_t* scores, uint8_t* ranks);
+int rv_multi_counters(rv_multi* m, uint32_t* step_count, uint32_t* kyoku_count, uint32_t* ev_count, uint64_t* ev_hash);
+int rv_multi_stats(rv_multi* m, rv_run_stats* out);
+
 #ifdef __cplusplus
 }
 #endif

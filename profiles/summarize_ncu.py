@@ -43,3 +43,25 @@ for h in sorted(col):
             print(f"  {h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]:22s} {v:.2f}")
 r, w = float(vals[col["dram__bytes_read.sum"]]), float(vals[col["dram__bytes_write.sum"]])
 print(f"\nDRAM traffic of the launch: {r + w:.3f} {units[col['dram__bytes_read.sum']]} (read {r:.3f} + write {w:.3f})")
+
+# --facts NAME CAPTURE: record this launch's DRAM bytes and issue utilisation in profiles/ncu_facts.json, keyed by kernel and
+# stamped with the fingerprint of the CUDA sources (bench.py quotes them only while the sources are unchanged)
+if "--facts" in sys.argv:
+    import json
+    import os
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import bench
+
+    k = sys.argv.index("--facts")
+    name, capture = sys.argv[k + 1], sys.argv[k + 2]
+    unit = units[col["dram__bytes_read.sum"]].lower()
+    mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_facts.json")
+    facts = json.load(open(path)) if os.path.exists(path) else {}
+    facts[name] = {"dram_bytes": (r + w) * mult, "issue_active_pct": float(vals[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+                   "duration_ms": float(vals[col["gpu__time_duration.sum"]]) * {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(
+                       units[col["gpu__time_duration.sum"]].lower().replace("usecond", "us").replace("msecond", "ms").replace("nsecond", "ns").replace("second", "s"), 1),
+                   "capture": capture, "src": bench.source_fingerprint()}
+    json.dump(facts, open(path, "w"), indent=1, sort_keys=True)
+    print(f"\nrecorded {name} in {path}")

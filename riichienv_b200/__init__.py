@@ -5,7 +5,7 @@ C ABI in include/riichienv_b200.h.  Importing this package does not need a GPU; 
 """
 from . import _abi  # noqa: F401
 
-__all__ = ["RiichiEnv", "VecRiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
+__all__ = ["RiichiEnv", "VecRiichiEnv", "MultiVecRiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
            "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "tid_to_mjai"]
 
 
@@ -15,10 +15,10 @@ def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
         from . import env
 
         return getattr(env, name)
-    if name == "VecRiichiEnv":
-        from .vec_env import VecRiichiEnv
+    if name in ("VecRiichiEnv", "MultiVecRiichiEnv"):
+        from . import vec_env
 
-        return VecRiichiEnv
+        return getattr(vec_env, name)
     if name in ("HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "WinResult"):
         from . import hand
 

@@ -98,6 +98,11 @@ class HandResult(C.Structure):
     ]
 
 
+class RunStats(C.Structure):
+    _fields_ = [("games", C.c_int64), ("games_done", C.c_int64), ("env_steps", C.c_int64), ("rounds", C.c_int64),
+                ("score_sum", C.c_int64 * NP), ("rank_hist", (C.c_int64 * NP) * NP)]
+
+
 def state_fields_equal(a: "GameState", b: "GameState", skip=()):
     """Field-by-field comparison; returns list of differing field names."""
     diff = []

@@ -69,6 +69,18 @@ def lib():
     L.rv_vec_encode_kawa.argtypes = [vp, vp, vp, C.c_int64, P(C.c_int64)]
     L.rv_vec_observe_step_random.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_int64, P(C.c_int64)]
     L.rv_vec_encode_seq.argtypes = [vp, C.c_int, P(C.c_uint32), vp, vp, vp, C.c_int, vp, vp, vp, C.c_int64, P(C.c_int64)]
+    L.rv_multi_create.argtypes = [P(C.c_int), C.c_int, C.c_int64, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, P(vp)]
+    L.rv_multi_destroy.argtypes = [vp]
+    L.rv_multi_devices.argtypes = [vp]
+    L.rv_multi_size.restype = C.c_int64
+    L.rv_multi_size.argtypes = [vp]
+    L.rv_multi_shard.argtypes = [vp, C.c_int, P(vp), P(C.c_int64), P(C.c_int64)]
+    L.rv_multi_reset.argtypes = [vp]
+    L.rv_multi_reseed.argtypes = [vp, C.c_uint64]
+    L.rv_multi_step_random.argtypes = [vp, C.c_uint64, C.c_uint32, P(C.c_uint64)]
+    L.rv_multi_results.argtypes = [vp, P(C.c_uint8), P(C.c_int32), P(C.c_uint8)]
+    L.rv_multi_counters.argtypes = [vp, P(C.c_uint32), P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]
+    L.rv_multi_stats.argtypes = [vp, P(A.RunStats)]
     L.rv_sizeof.argtypes = [C.c_int]
     for i, T in enumerate((A.GameState, A.HandQuery, A.HandResult, A.Action)):
         if L.rv_sizeof(i) != C.sizeof(T):

@@ -399,11 +399,12 @@ __device__ __forceinline__ void static_yaku(YakuRes& r, const WinCtx& x) {  // y
 }
 
 struct Division {
-  int head;        // tile kind, or -1 for the chiitoitsu pseudo-division
-  int nb;
+  int8_t head;     // tile kind, or -1 for the chiitoitsu pseudo-division
+  int8_t nb;
   uint8_t bt[4];   // body tile (start tile for shuntsu)
   uint8_t bk[4];   // 1 = koutsu, 0 = shuntsu
 };
+constexpr int YAKU_CAND_CAP = 12;   // (division, winning group) candidates kept before a flush; more are flushed in batches
 
 // yaku.rs:892-1055.  `all` = kinds present in hand_14 or any meld; wg = -1 for head.
 __device__ __noinline__ void yakuman_eval(YakuRes& r, const Cnt& hand, uint64_t all, const MeldView& mv, const WinCtx& x,
@@ -671,6 +672,17 @@ __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand,
   }
   // enumerate divisions in the reference's order: head ascending, then DFS over the
   // remaining tiles (lowest tile first; koutsu before shuntsu) — agari.rs:73-139
+  Division cand[YAKU_CAND_CAP];
+  int8_t cand_wg[YAKU_CAND_CAP];
+  int ncand = 0;
+  auto flush = [&]() {            // candidates in discovery order: the first maximum wins, as in the reference's loop
+    for (int k = 0; k < ncand; k++) {
+      YakuRes r = eval_division(hand, all, mv, x, cand[k], cand_wg[k], win);
+      if (r.han >= 13 && r.yakuman > 0) { if (r.han > best.han) best = r; }
+      else if (r.han > best.han || (r.han == best.han && r.fu > best.fu)) best = r;
+    }
+    ncand = 0;
+  };
   Cnt work = hand;
   for (int head = 0; head < 34; head++) {
     if (cnt_get(work, head) < 2) continue;
@@ -680,7 +692,7 @@ __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand,
     load_info(T, work, si);
     if ((si.e[0] & si.e[1] & si.e[2] & si.e[3] & 1) != 0) {
       Division d;
-      d.head = head;
+      d.head = (int8_t)head;
       d.nb = 0;
       // explicit DFS stack: stage[l] = 0 try koutsu, 1 try shuntsu, 2 exhausted
       int pos[5], stage[5];
@@ -695,18 +707,21 @@ __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand,
           pos[depth] = i;
         }
         if (i >= 34) {
-          // complete division: evaluate every winning group
+          // complete division: every winning group is a candidate.  Candidates are only RECORDED here and evaluated in one
+          // loop after the search (flush): eval_division is ~90 % of the instructions of a winning hand, and called from
+          // inside this data-dependent search the lanes of a warp reached it at different iterations — ncu counted 2 of 32
+          // lanes active per instruction.  In the flush loop the lanes run it together.
           if (d.head == win) {
-            YakuRes r = eval_division(hand, all, mv, x, d, -1, win);
-            if (r.han >= 13 && r.yakuman > 0) { if (r.han > best.han) best = r; }
-            else if (r.han > best.han || (r.han == best.han && r.fu > best.fu)) best = r;
+            if (ncand == YAKU_CAND_CAP) flush();
+            cand[ncand] = d;
+            cand_wg[ncand++] = -1;
           }
           for (int g = 0; g < d.nb; g++) {
             bool hit = d.bk[g] ? (d.bt[g] == win) : (win >= d.bt[g] && win <= d.bt[g] + 2);
             if (!hit) continue;
-            YakuRes r = eval_division(hand, all, mv, x, d, g, win);
-            if (r.han >= 13 && r.yakuman > 0) { if (r.han > best.han) best = r; }
-            else if (r.han > best.han || (r.han == best.han && r.fu > best.fu)) best = r;
+            if (ncand == YAKU_CAND_CAP) flush();
+            cand[ncand] = d;
+            cand_wg[ncand++] = (int8_t)g;
           }
           depth--;
           if (depth >= 0) {
@@ -758,6 +773,7 @@ __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand,
     }
     cnt_add(work, head, 2);
   }
+  flush();
   return best;
 }
 
@@ -872,11 +888,12 @@ __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, 
   return out;
 }
 
-// One query of rv_hand_eval_batch: HandEvaluator::new + calc + get_waits_u8 (hand_evaluator.rs:24-213) and
-// calculate_shanten[_3p] (shanten.rs:250-261, 470-484).  A query that is not a hand (more than 14 concealed tiles or 4
-// melds, a tile id outside 0..135, a histogram beyond four copies — the suit tables are indexed by base-5 keys) gets a
-// zeroed result with shanten = shanten13 = 127 instead of out-of-bounds table reads.
-__device__ __noinline__ void hand_eval_one(const Tables& T, const rv_hand_query& h, rv_hand_result& o) {
+// Split in two so that a batch can run the uniform part on every hand and the yaku evaluation — long, divergent, and needed by
+// the few hands that have a winning shape — on a compacted list (hand_shape_kernel / hand_yaku_kernel):
+//   hand_eval_shape  validation, histograms, wait set, both shanten numbers; returns true when hand_calc has work to do
+//                    (the 14-tile-equivalent hand is a standard, seven-pairs or thirteen-orphans shape);
+//   hand_eval_win    hand_calc and the win fields of the result.
+__device__ __forceinline__ bool hand_eval_shape(const Tables& T, const rv_hand_query& h, rv_hand_result& o) {
   memset(&o, 0, sizeof o);
   bool valid = h.n_tiles <= 14 && h.n_melds <= 4 && h.win_tile < 136 && h.n_dora <= 5 && h.n_ura <= 5 && h.player_wind < 4 &&
                h.round_wind < 4;
@@ -896,8 +913,39 @@ __device__ __noinline__ void hand_eval_one(const Tables& T, const rv_hand_query&
   for (int k = 0; valid && k < h.n_ura; k++) valid = h.ura_ind[k] < 136;
   if (!valid) {
     o.shanten = o.shanten13 = 127;
-    return;
+    return false;
   }
+  // concealed histogram (kan melds whose tiles are also listed count 3, as HandEvaluator::new)
+  Cnt raw = c;
+  for (int m = 0; m < h.n_melds; m++)
+    if (h.meld_type[m] >= RV_MELD_DAIMINKAN) {
+      int kind = h.meld_tiles[m][0] >> 2;
+      if (cnt_get(c, kind) == 4) cnt_sub(c, kind, 1);
+    }
+  int total = cnt_total(c) + 3 * h.n_melds;
+  int win34 = h.win_tile >> 2;
+  Cnt c13 = c, r13 = raw, c14 = c;
+  bool ok13 = total == 13;
+  if (total == 14 && cnt_get(c, win34) > 0) {
+    cnt_sub(c13, win34);
+    cnt_sub(r13, win34);
+    ok13 = true;
+  }
+  if (total == 13) cnt_add(c14, win34);            // HandEvaluator::calc adds the win tile to a 13-tile hand
+  o.wait_mask = ok13 ? waits13(T, c13) : 0;
+  Cnt r14 = raw;
+  int n14 = h.n_tiles;
+  if (total == 13 && cnt_get(r14, win34) < 4) {
+    cnt_add(r14, win34);
+    n14++;
+  }
+  const bool sanma = h.sanma & 1;   // sanma queries: calculate_shanten_3p (shanten.rs:470-484)
+  o.shanten = (int8_t)(sanma ? shanten_counts_3p(T, r14, n14 / 3) : shanten_counts(T, r14, n14 / 3));
+  o.shanten13 = ok13 ? (int8_t)(sanma ? shanten_counts_3p(T, r13, cnt_total(r13) / 3) : shanten_counts(T, r13, cnt_total(r13) / 3))
+                     : (int8_t)127;
+  return agari14(T, c14);           // the shape test hand_calc starts with (a five-of-a-kind c14 is clamped, hence no shape)
+}
+__device__ __noinline__ void hand_eval_win(const Tables& T, const rv_hand_query& h, rv_hand_result& o) {
   WinRes r = hand_calc(T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
                        h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count);
   o.is_win = r.is_win;
@@ -910,33 +958,12 @@ __device__ __noinline__ void hand_eval_one(const Tables& T, const rv_hand_query&
   o.tsumo_agari_ko = r.ko;
   o.yaku_mask = r.yaku_mask;
   o.n_yaku = (uint8_t)__popcll(r.yaku_mask);
-  // concealed histogram (kan melds whose tiles are also listed count 3, as HandEvaluator::new)
-  Cnt raw = c;
-  for (int m = 0; m < h.n_melds; m++)
-    if (h.meld_type[m] >= RV_MELD_DAIMINKAN) {
-      int kind = h.meld_tiles[m][0] >> 2;
-      if (cnt_get(c, kind) == 4) cnt_sub(c, kind, 1);
-    }
-  int total = cnt_total(c) + 3 * h.n_melds;
-  int win34 = h.win_tile >> 2;
-  Cnt c13 = c, r13 = raw;
-  bool ok13 = total == 13;
-  if (total == 14 && cnt_get(c, win34) > 0) {
-    cnt_sub(c13, win34);
-    cnt_sub(r13, win34);
-    ok13 = true;
-  }
-  o.wait_mask = ok13 ? waits13(T, c13) : 0;
-  Cnt r14 = raw;
-  int n14 = h.n_tiles;
-  if (total == 13 && cnt_get(r14, win34) < 4) {
-    cnt_add(r14, win34);
-    n14++;
-  }
-  const bool sanma = h.sanma & 1;   // sanma queries: calculate_shanten_3p (shanten.rs:470-484)
-  o.shanten = (int8_t)(sanma ? shanten_counts_3p(T, r14, n14 / 3) : shanten_counts(T, r14, n14 / 3));
-  o.shanten13 = ok13 ? (int8_t)(sanma ? shanten_counts_3p(T, r13, cnt_total(r13) / 3) : shanten_counts(T, r13, cnt_total(r13) / 3))
-                     : (int8_t)127;
+}
+// One query of rv_hand_eval_batch: HandEvaluator::new + calc + get_waits_u8 (hand_evaluator.rs:24-213) and
+// calculate_shanten[_3p] (shanten.rs:250-261, 470-484).  A query that is not a hand (more than 14 concealed tiles or 4
+// melds, a tile id outside 0..135, more than four copies of a kind) gets a zeroed result with shanten = shanten13 = 127.
+__device__ __noinline__ void hand_eval_one(const Tables& T, const rv_hand_query& h, rv_hand_result& o) {
+  if (hand_eval_shape(T, h, o)) hand_eval_win(T, h, o);
 }
 
 }  // namespace rv

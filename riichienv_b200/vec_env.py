@@ -270,3 +270,69 @@ class VecRiichiEnv:
         n = self.encode_seq(sparse=sp, numeric=nu, prog=pr, cand=ca, lens=le, index=idx, game_style=1, max_obs=4, start_words=start)
         r = self._row_of(idx, n, pid)
         return sp[r].cpu().numpy(), nu[r].cpu().numpy(), pr[r].cpu().numpy(), ca[r].cpu().numpy(), le[r].cpu().numpy()
+
+
+class MultiVecRiichiEnv:
+    """N games sharded over several GPUs behind one handle (rv_multi_*): device k owns the contiguous global game ids
+    [k*N/G, (k+1)*N/G), game g is seeded seed_base + g whatever G is, one host thread and stream per device, no traffic between
+    devices on the step path; `stats()` is the end-of-run reduction.  What the reference does with a list of RiichiEnv per Ray
+    actor (riichienv-ml/src/riichienv_ml/.../_ppo_worker.py:13,39)."""
+
+    def __init__(self, n, game_mode="4p-red-half", rule_bits=A.RULE_DEFAULT_TENHOU, seed_base=0, log_cap_words=0, devices=(0,)):
+        if isinstance(game_mode, str):
+            game_mode = GAME_MODES.get(game_mode, 0)
+        self.n, self.game_mode, self.devices = int(n), int(game_mode), [int(d) for d in devices]
+        self.handle = C.c_void_p()
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        check(lib().rv_multi_create(dev, len(self.devices), self.n, self.game_mode, int(rule_bits), int(seed_base), int(log_cap_words),
+                                    C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            lib().rv_multi_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, k):
+        """(VecRiichiEnv view of device k's games, first global id, count) — for the per-device calls (encoders, snapshots)"""
+        vec, first, cnt = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+        check(lib().rv_multi_shard(self.handle, int(k), C.byref(vec), C.byref(first), C.byref(cnt)))
+        v = object.__new__(VecRiichiEnv)
+        v.ctx, v.n, v.game_mode, v.handle = None, int(cnt.value), self.game_mode, vec
+        v.close = lambda: None            # owned by the multi-device handle
+        return v, int(first.value), int(cnt.value)
+
+    def reset(self):
+        check(lib().rv_multi_reset(self.handle))
+
+    def reseed(self, seed_base=0):
+        check(lib().rv_multi_reseed(self.handle, int(seed_base)))
+
+    def step_random(self, agent_seed, max_steps=1):
+        done = C.c_uint64(0)
+        check(lib().rv_multi_step_random(self.handle, int(agent_seed), int(max_steps), C.byref(done)))
+        return int(done.value)
+
+    def results(self):
+        done = np.zeros(self.n, np.uint8)
+        scores = np.zeros((self.n, A.NP), np.int32)
+        ranks = np.zeros((self.n, A.NP), np.uint8)
+        check(lib().rv_multi_results(self.handle, _ptr(done, C.c_uint8), _ptr(scores, C.c_int32), _ptr(ranks, C.c_uint8)))
+        return done, scores, ranks
+
+    def counters(self):
+        sc, kc, ec = np.zeros(self.n, np.uint32), np.zeros(self.n, np.uint32), np.zeros(self.n, np.uint32)
+        eh = np.zeros(self.n, np.uint64)
+        check(lib().rv_multi_counters(self.handle, _ptr(sc, C.c_uint32), _ptr(kc, C.c_uint32), _ptr(ec, C.c_uint32), _ptr(eh, C.c_uint64)))
+        return sc, kc, ec, eh
+
+    def stats(self):
+        s = A.RunStats()
+        check(lib().rv_multi_stats(self.handle, C.byref(s)))
+        return {"games": s.games, "games_done": s.games_done, "env_steps": s.env_steps, "rounds": s.rounds,
+                "score_sum": list(s.score_sum), "rank_hist": [list(r) for r in s.rank_hist]}

@@ -73,6 +73,38 @@ def test_hand_eval_random_vs_oracle(ctx, orc):
     assert int(a[:, 28].sum()) > 10_000  # is_win column: positive stratum exercised
 
 
+def test_hand_eval_config2_full_stream(ctx, orc):
+    """BASELINE.json configs[1] at its stated size: the 10^7 DISTINCT seeded hands of include/rv_synth.h, generated on the device
+    (rv_hand_queries_seeded), evaluated by the two-kernel path (rv_hand_eval_batch_device) and compared byte for byte with the
+    oracle on the same stream (orc_hand_queries_seeded + orc_hand_eval_mt), in chunks of 10^6."""
+    import os
+
+    import torch
+
+    from riichienv_b200._lib import check, lib
+
+    total, chunk = 10_000_000, 1_000_000
+    qs, rs = C.sizeof(A.HandQuery), C.sizeof(A.HandResult)
+    d_q = torch.empty((chunk, qs), dtype=torch.uint8, device="cuda")
+    d_r = torch.empty((chunk, rs), dtype=torch.uint8, device="cuda")
+    h_q = (A.HandQuery * chunk)()
+    h_r = (A.HandResult * chunk)()
+    wins = shapes = 0
+    for first in range(0, total, chunk):
+        check(lib().rv_hand_queries_seeded(ctx.handle, C.c_void_p(d_q.data_ptr()), first, chunk))
+        check(lib().rv_hand_eval_batch_device(ctx.handle, C.c_void_p(d_q.data_ptr()), C.c_void_p(d_r.data_ptr()), chunk))
+        ctx.sync()
+        orc.orc_hand_queries_seeded(h_q, first, chunk)
+        assert np.array_equal(d_q.cpu().numpy(), np.frombuffer(h_q, np.uint8).reshape(chunk, qs)), "query streams differ"
+        orc.orc_hand_eval_mt(h_q, h_r, chunk, os.cpu_count() or 1)
+        a, b = d_r.cpu().numpy(), np.frombuffer(h_r, np.uint8).reshape(chunk, rs)
+        bad = np.nonzero((a != b).any(axis=1))[0]
+        assert bad.size == 0, f"chunk at {first}: {bad.size} hands differ, first {first + int(bad[0])}"
+        wins += int(a[:, 28].sum())
+        shapes += int(a[:, 30].sum())
+    assert shapes > 0.09 * total and wins > 0.07 * total    # the positive stratum (every tenth hand) reaches yaku / fu / score
+
+
 def test_shanten_golden_via_hand_eval(ctx):
     cases = H.load_counts_file("shanten_golden.txt")
     qs = []
@@ -216,6 +248,44 @@ def test_settlement_gate_100k_greedy_games(orc):
         assert yaku.get(y, 0) > 0, f"yaku {y} never occurred"
     assert yaku.get(37, 0) > 0 and yaku.get(38, 0) + yaku.get(48, 0) > 0 and yaku.get(42, 0) + yaku.get(49, 0) > 0
     assert H["yakuman"] >= 100 and hist[71 + 5] > 0 and hist[71 + 6] > 0
+
+
+@pytest.mark.parametrize("devices", [(0,), (0, 0, 0), "all"])
+def test_multi_device_results_do_not_depend_on_device_count(devices):
+    """rv_multi_*: the same 65,536 seeded hanchan as ONE vector and sharded — over three shards on one GPU (exercises the
+    partitioning and the per-device host threads on a single-GPU box) and over every GPU of the box.  Scores, ranks and event
+    hashes are identical game by game; the statistics reduction adds up."""
+    import torch
+
+    from riichienv_b200.vec_env import MultiVecRiichiEnv, VecRiichiEnv
+
+    if devices == "all":
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs at least two GPUs")
+        devices = tuple(range(torch.cuda.device_count()))
+    n, seed_base = 65536, 123_000
+    v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=seed_base)
+    v.reset()
+    total = v.step_random(0xABBA, 100000)
+    done, scores, ranks = v.results()
+    sc, kc, ec, eh = v.counters()
+    v.close()
+    m = MultiVecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=seed_base, devices=devices)
+    m.reset()
+    m_total = m.step_random(0xABBA, 100000)
+    m_done, m_scores, m_ranks = m.results()
+    m_sc, m_kc, m_ec, m_eh = m.counters()
+    st = m.stats()
+    first = [m.shard(k)[1] for k in range(len(devices))]
+    m.close()
+    assert first == [n * k // len(devices) for k in range(len(devices))]
+    assert m_total == total and done.all() and m_done.all()
+    for name, a, b in (("scores", scores, m_scores), ("ranks", ranks, m_ranks), ("steps", sc, m_sc), ("rounds", kc, m_kc),
+                       ("events", ec, m_ec), ("hash", eh, m_eh)):
+        assert np.array_equal(a, b), f"{name} differ in {int((a != b).sum())} entries"
+    assert st["games"] == n and st["games_done"] == n and st["env_steps"] == total and st["rounds"] == int(kc.sum())
+    assert st["score_sum"] == [int(x) for x in scores.sum(0)]
+    assert sum(st["rank_hist"][0]) == n and st["rank_hist"][2][0] == int((ranks[:, 2] == 1).sum())
 
 
 def test_partial_rollout_and_resume(orc):
