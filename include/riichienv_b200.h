@@ -253,7 +253,8 @@ void* rv_ctx_stream(rv_ctx* ctx);
 /* CUDA-event timers on the context stream: mark records event idx; elapsed synchronises on idx_b and returns ms. */
 int rv_timer_mark(rv_ctx* ctx, int idx /*0..7*/);
 int rv_timer_elapsed(rv_ctx* ctx, int idx_a, int idx_b, float* ms);
-/* sizeof() of the public structs as compiled: 0 rv_game_state, 1 rv_hand_query, 2 rv_hand_result, 3 rv_action */
+/* sizeof() of the public structs as compiled: 0 rv_game_state, 1 rv_hand_query, 2 rv_hand_result, 3 rv_action,
+ * 4 rv_mjai_event, 5 rv_run_stats */
 int rv_sizeof(int which);
 
 /* Batched hand evaluation with HOST buffers (copies inside the call). */
@@ -333,7 +334,10 @@ int rv_vec_set_state(rv_vec* v, int64_t game, const rv_game_state* in);
 int rv_vec_clone(rv_vec* v, rv_vec** out);
 /* RiichiEnv::_reveal_kan_dora (op 0; *n_out = number of dora indicators afterwards) and RiichiEnv::_get_ura_markers
  * (op 1; out_tiles[5] = ura indicator tile ids, RV_NONE pad, *n_out = how many) of env.rs:624-631: the reference exposes
- * these two internals to its tests (tests/env/test_paishan.py); they run the device routines the step path uses. */
+ * these two internals to its tests (tests/env/test_paishan.py); they run the device routines the step path uses.
+ * Ops 2-5 are what the reference's Rust unit tests call directly on a GameState (riichienv-core/src/tests.rs:172-262,
+ * 375-428): 2 = _trigger_ryukyoku("exhaustive_draw"); 3 / 4 / 5 = _initialize_next_round(false,false) / (true,false) /
+ * (false,true); *n_out = is_done afterwards.                                                                     */
 int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out);
 /* Device pointer to the state records (for zero-copy consumers). */
 int rv_vec_state_device_ptr(rv_vec* v, void** d_states);
@@ -399,6 +403,30 @@ int rv_vec_observe_step_random(rv_vec* v, uint64_t agent_seed, float* d_obs, uin
 int rv_vec_encode_seq(rv_vec* v, int game_style, const uint32_t* start_words, uint16_t* d_sparse, float* d_numeric,
                       uint16_t* d_prog, int max_prog, uint16_t* d_cand, uint16_t* d_lens, int32_t* d_index, int64_t max_obs,
                       int64_t* n_obs);
+
+/* ---- MJAI-driven state tracking (RiichiEnv::apply_event / observe_event, env.rs:880-948) -------------------------------
+ * One parsed MJAI event; tiles are ids 0..135 — mjai_to_tid (parser.rs:336-385) on the host, an unparsable tile ("?") is 0
+ * as in event_handler.rs:8-10.  `type` is an rv_event_type; RV_EV_NONE (0) = no event for this game / an event type the
+ * reference ignores.  Fields beyond those an event type carries are ignored.                                              */
+#define RV_EV_NONE 0
+typedef struct rv_mjai_event {
+  uint8_t type;          /* rv_event_type; daiminkan ("kan") = RV_EV_DAIMINKAN; dahai with tsumogiri = RV_EV_DAHAI_TSUMOGIRI */
+  uint8_t actor, target;
+  uint8_t pai;           /* tile id (dora: the dora_marker) */
+  uint8_t n_consumed;
+  uint8_t consumed[4];
+  uint8_t bakaze;        /* start_kyoku: 0..3 = E S W N */
+  uint8_t kyoku, honba, oya, dora_marker;
+  uint8_t tehai_len[RV_NP];
+  uint8_t tehais[RV_NP][14];
+  uint8_t _pad[3];
+  uint32_t kyotaku;
+  int32_t scores[RV_NP];
+} rv_mjai_event;
+/* GameState::apply_mjai_event (state/event_handler.rs:18-330; sanma state_3p/event_handler.rs:19-362) for every game:
+ * events[n], type RV_EV_NONE = leave that game alone.  A start_game event also resets the game's logs (env.rs:56-72).
+ * The event is NOT appended to the device event log: the caller keeps the text it fed (RiichiEnv.apply_event does).     */
+int rv_vec_apply_events(rv_vec* v, const rv_mjai_event* events);
 
 /* ---- several GPUs behind one handle (SURVEY.md §8 e) -------------------------------------------------------------
  * Replaces what the reference does with one Python list of RiichiEnv per Ray actor (riichienv-ml/.../_ppo_worker.py:13,39).

@@ -77,6 +77,7 @@ def load():
     lib.orc_run_agent.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_int,
                                   P(C.c_int32), P(C.c_uint8), P(C.c_uint8), P(C.c_uint32), P(C.c_uint32),
                                   P(C.c_uint32), P(C.c_uint64), P(C.c_uint64)]
+    lib.orc_game_apply_event.argtypes = [C.c_void_p, P(A.MjaiEvent)]
     lib.orc_game_agent_step.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     _LIB = lib
     return lib

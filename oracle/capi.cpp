@@ -348,6 +348,14 @@ int orc_game_call(void* h, int op, uint8_t* out) {
     for (size_t i = 0; i < u.size() && i < 5; i++) out[i] = u[i];
     return (int)std::min<size_t>(u.size(), 5);
   }
+  if (op == 2) {        // tests.rs:172-262
+    g->_trigger_ryukyoku(RV_RK_EXHAUSTIVE);
+    return g->is_done ? 1 : 0;
+  }
+  if (op >= 3 && op <= 5) {   // tests.rs:375-428
+    g->_initialize_next_round(op == 4, op == 5);
+    return g->is_done ? 1 : 0;
+  }
   return -1;
 }
 void orc_game_copy_log(void* dst, void* src) {
@@ -468,6 +476,7 @@ int64_t orc_run_agent(int policy, int mode, uint32_t rule, uint64_t seed_base, i
   return run_agent(policy, mode, rule, seed_base, n, agent_seed, max_steps, threads, scores, ranks, done, steps, kyoku, evcount,
                    hash, nullptr, hist);
 }
+void orc_game_apply_event(void* h, const rv_mjai_event* e) { apply_mjai_event(*(GameState*)h, *e); }
 int orc_game_agent_step(void* h, int policy, uint64_t agent_seed, uint64_t game_id) {
   return agent_step(*(GameState*)h, policy, agent_seed, game_id) ? 1 : 0;
 }

@@ -1679,8 +1679,8 @@ struct GameState {
       for (size_t k = 0; k < P.discards.size(); k++) {
         if (k < RV_RIVER_CAP) {
           s.river[p][k] = P.discards[k];
-          if (P.discard_from_hand[k]) s.river_tedashi[p] |= 1u << k;
-          if (P.discard_is_riichi[k]) s.river_riichi[p] |= 1u << k;
+          if (k < P.discard_from_hand.size() && P.discard_from_hand[k]) s.river_tedashi[p] |= 1u << k;   // (the event handler pushes discards only)
+          if (k < P.discard_is_riichi.size() && P.discard_is_riichi[k]) s.river_riichi[p] |= 1u << k;
         } else {
           s.overflow = 1;
         }
@@ -1787,6 +1787,261 @@ inline bool random_step(GameState& g, uint64_t agent_seed, uint64_t game_id) {
   }
   g.step(acts);
   return true;
+}
+
+// ---- GameState::apply_mjai_event (state/event_handler.rs:18-330; sanma: state_3p/event_handler.rs:19-362) ----
+// `e` is the parsed event (include/riichienv_b200.h rv_mjai_event: tiles already through mjai_to_tid, "?" -> 0).
+inline void apply_mjai_event(GameState& g, const rv_mjai_event& e) {
+  const int np = g.np;
+  const int actor = e.actor < np ? e.actor : 0;
+  auto tid = [](uint8_t t) -> uint8_t { return t < 136 ? t : 0; };
+  auto remove_first = [](std::vector<uint8_t>& v, uint8_t t) {
+    for (size_t i = 0; i < v.size(); i++)
+      if (v[i] == t) {
+        v.erase(v.begin() + i);
+        return;
+      }
+  };
+  auto claims_after = [&](uint8_t tile, bool ron_only) {          // event_handler.rs:112-138 / 3P 316-356
+    for (int i = 0; i < MAXP; i++) {
+      g.current_claims[i].clear();
+      g.has_claims_entry[i] = false;
+    }
+    g.active_players.clear();
+    std::vector<uint8_t> claim_active;
+    for (int i = 0; i < np; i++) {
+      if (i == actor) continue;
+      auto [legals, missed] = g._get_claim_actions_for_player(i, actor, tile);
+      (void)missed;
+      if (ron_only) {
+        std::vector<Action> r;
+        for (auto& a : legals)
+          if (a.type == RV_RON) r.push_back(a);
+        legals = r;
+      }
+      if (!legals.empty()) {
+        claim_active.push_back((uint8_t)i);
+        g.current_claims[i] = legals;
+        g.has_claims_entry[i] = true;
+      }
+    }
+    if (!claim_active.empty()) {
+      g.phase = RV_WAIT_RESPONSE;
+      g.active_players = claim_active;
+    } else {
+      g.phase = RV_WAIT_ACT;
+      g.active_players.clear();
+      g.current_player = 0xFF;
+    }
+    g.needs_tsumo = true;
+  };
+  switch (e.type) {
+    case RV_EV_START_GAME:     // env.rs:56-72 (reset(): logs and counters) + event_handler.rs:21-26
+      g.log.clear();
+      g.text.clear();
+      g.ev_hash = 0xcbf29ce484222325ull;
+      g.ev_count = g.ev_words = g.step_count = g.kyoku_count = 0;
+      g.stalled = false;
+      g.current_player = 0xFF;
+      g.active_players.clear();
+      break;
+    case RV_EV_START_KYOKU: {
+      g.honba = e.honba;
+      g.riichi_sticks = e.kyotaku;
+      g.round_wind = e.bakaze < 4 ? e.bakaze : 0;
+      g.oya = e.oya;
+      g.kyoku_idx = e.kyoku > 0 ? e.kyoku - 1 : 0;
+      g.current_player = 0xFF;
+      g.turn_count = 0;
+      g.is_done = false;
+      g.needs_tsumo = true;
+      g.phase = RV_WAIT_ACT;
+      g.active_players.clear();
+      g.last_discard_pid = g.last_discard_tile = -1;
+      for (int i = 0; i < MAXP; i++) {
+        g.current_claims[i].clear();
+        g.has_claims_entry[i] = false;
+      }
+      g.pending_kan = false;
+      g.is_rinshan_flag = false;
+      g.is_first_turn = true;
+      g.riichi_pending_acceptance = -1;
+      g.drawn_tile = -1;
+      g.win_results.clear();
+      g.last_error = -1;
+      for (int p = 0; p < MAXP; p++) g.riichi_sutehais[p] = g.last_tedashis[p] = -1;
+      const int wl = g.sanma ? 108 : 136, left = wl - 13 * np;
+      g.wall_tiles.assign(left, 0);
+      g.wall_abs.assign(wl, 0xFF);
+      for (int i = 0; i < left; i++) g.wall_abs[i] = 0;
+      g.dora_indicators = {tid(e.dora_marker)};
+      g.rinshan_draw_count = 0;
+      g.pending_kan_dora_count = 0;
+      g.drawable_count = (uint8_t)(left - 14);
+      for (int p = 0; p < MAXP; p++) {
+        g.players[p].reset_round();
+        g.n_kita[p] = 0;
+      }
+      for (int p = 0; p < np; p++) {
+        g.players[p].score = e.scores[p];
+        std::vector<uint8_t> hand;
+        for (int k = 0; k < e.tehai_len[p] && k < 14; k++) hand.push_back(tid(e.tehais[p][k]));
+        std::sort(hand.begin(), hand.end());
+        g.players[p].hand = hand;
+      }
+      break;
+    }
+    case RV_EV_TSUMO: {
+      const uint8_t tile = tid(e.pai);
+      g.current_player = (uint8_t)actor;
+      g.drawn_tile = tile;
+      g.players[actor].hand.push_back(tile);
+      std::sort(g.players[actor].hand.begin(), g.players[actor].hand.end());
+      g.players[actor].forbidden_discards.clear();
+      if (!g.wall_tiles.empty()) {
+        g.wall_tiles.pop_back();
+        g.drawable_count = g.drawable_count > 0 ? g.drawable_count - 1 : 0;
+      }
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {(uint8_t)actor};
+      g.needs_tsumo = false;
+      break;
+    }
+    case RV_EV_DAHAI:
+    case RV_EV_DAHAI_TSUMOGIRI: {
+      const uint8_t tile = tid(e.pai);
+      g.current_player = (uint8_t)actor;
+      remove_first(g.players[actor].hand, tile);
+      g.players[actor].discards.push_back(tile);
+      g.last_discard_pid = actor;
+      g.last_discard_tile = tile;
+      g.drawn_tile = -1;
+      if (g.players[actor].riichi_stage) {
+        g.players[actor].riichi_declared = true;
+        g.players[actor].riichi_stage = false;
+      }
+      claims_after(tile, false);
+      break;
+    }
+    case RV_EV_PON:
+    case RV_EV_CHI:
+    case RV_EV_DAIMINKAN: {
+      const uint8_t tile = tid(e.pai);
+      g.current_player = (uint8_t)actor;
+      const int want = e.type == RV_EV_DAIMINKAN ? 3 : 2;
+      const int nc = e.n_consumed < want ? e.n_consumed : want;
+      Meld m;
+      m.meld_type = e.type == RV_EV_PON ? Pon : e.type == RV_EV_CHI ? Chi : Daiminkan;
+      m.tiles.push_back(tile);
+      for (int k = 0; k < nc; k++) {
+        m.tiles.push_back(tid(e.consumed[k]));
+        remove_first(g.players[actor].hand, tid(e.consumed[k]));
+      }
+      m.opened = true;
+      m.from_who = -1;
+      m.called_tile = tile;
+      g.players[actor].melds.push_back(m);
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {(uint8_t)actor};
+      if (e.type == RV_EV_DAIMINKAN) {
+        g.needs_tsumo = true;
+        break;
+      }
+      g.drawn_tile = -1;
+      g.needs_tsumo = false;
+      if (e.type == RV_EV_CHI && g.sanma) break;      // the 3P handler leaves forbidden_discards alone on a chi
+      g.players[actor].forbidden_discards.clear();
+      if (g.rb(RV_RULE_KUIKAE_FORBIDDEN)) {
+        g.players[actor].forbidden_discards.push_back(tile);
+        if (e.type == RV_EV_CHI && nc == 2) {
+          const int t34 = tile / 4;
+          int c0 = tid(e.consumed[0]) / 4, c1 = tid(e.consumed[1]) / 4;
+          if (c0 > c1) std::swap(c0, c1);
+          if (c0 == t34 + 1 && c1 == t34 + 2) {
+            if (t34 % 9 <= 5) g.players[actor].forbidden_discards.push_back((uint8_t)((t34 + 3) * 4));
+          } else if (t34 >= 2 && c1 == t34 - 1 && c0 == t34 - 2 && t34 % 9 >= 3) {
+            g.players[actor].forbidden_discards.push_back((uint8_t)((t34 - 3) * 4));
+          }
+        }
+      }
+      break;
+    }
+    case RV_EV_ANKAN: {
+      Meld m;
+      m.meld_type = Ankan;
+      for (int k = 0; k < e.n_consumed && k < 4; k++) {
+        m.tiles.push_back(tid(e.consumed[k]));
+        remove_first(g.players[actor].hand, tid(e.consumed[k]));
+      }
+      m.opened = false;
+      m.from_who = -1;
+      m.called_tile = -1;
+      g.players[actor].melds.push_back(m);
+      g.current_player = (uint8_t)actor;
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {(uint8_t)actor};
+      g.needs_tsumo = true;
+      break;
+    }
+    case RV_EV_KAKAN: {
+      const uint8_t tile = tid(e.pai);
+      remove_first(g.players[actor].hand, tile);
+      for (auto& m : g.players[actor].melds)
+        if (m.meld_type == Pon && m.tiles[0] / 4 == tile / 4) {
+          m.meld_type = Kakan;
+          m.tiles.push_back(tile);
+          break;
+        }
+      g.current_player = (uint8_t)actor;
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {(uint8_t)actor};
+      g.needs_tsumo = true;
+      break;
+    }
+    case RV_EV_REACH:
+      g.players[actor].riichi_stage = true;
+      break;
+    case RV_EV_REACH_ACCEPTED:
+      g.players[actor].riichi_declared = true;
+      g.riichi_sticks += 1;
+      g.players[actor].score -= 1000;
+      break;
+    case RV_EV_DORA:
+      g.dora_indicators.push_back(tid(e.pai));
+      break;
+    case RV_EV_KITA:
+      if (g.sanma) {
+        int kita = -1;
+        for (uint8_t t : g.players[actor].hand)
+          if (t / 4 == 30) {
+            kita = t;
+            break;
+          }
+        g.current_player = (uint8_t)actor;
+        if (kita >= 0) {
+          remove_first(g.players[actor].hand, (uint8_t)kita);
+          g.n_kita[actor]++;
+          claims_after((uint8_t)kita, true);
+        } else {
+          for (int i = 0; i < MAXP; i++) {
+            g.current_claims[i].clear();
+            g.has_claims_entry[i] = false;
+          }
+          g.phase = RV_WAIT_ACT;
+          g.active_players.clear();
+          g.current_player = 0xFF;
+          g.needs_tsumo = true;
+        }
+      }
+      break;
+    case RV_EV_HORA:
+    case RV_EV_RYUKYOKU:
+    case RV_EV_END_KYOKU:
+      g.is_done = true;
+      break;
+    default:
+      break;
+  }
 }
 
 // ---- the keyed "greedy-win" agent (test agent #1; shared definition with the kernel, csrc/game.cuh greedy_pick) ----

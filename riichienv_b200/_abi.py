@@ -98,6 +98,12 @@ class HandResult(C.Structure):
     ]
 
 
+class MjaiEvent(C.Structure):
+    _fields_ = [("type", u8), ("actor", u8), ("target", u8), ("pai", u8), ("n_consumed", u8), ("consumed", u8 * 4), ("bakaze", u8),
+                ("kyoku", u8), ("honba", u8), ("oya", u8), ("dora_marker", u8), ("tehai_len", u8 * NP), ("tehais", (u8 * 14) * NP),
+                ("_pad", u8 * 3), ("kyotaku", u32), ("scores", i32 * NP)]
+
+
 class RunStats(C.Structure):
     _fields_ = [("games", C.c_int64), ("games_done", C.c_int64), ("env_steps", C.c_int64), ("rounds", C.c_int64),
                 ("score_sum", C.c_int64 * NP), ("rank_hist", (C.c_int64 * NP) * NP)]

@@ -82,7 +82,8 @@ def lib():
     L.rv_multi_counters.argtypes = [vp, P(C.c_uint32), P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]
     L.rv_multi_stats.argtypes = [vp, P(A.RunStats)]
     L.rv_sizeof.argtypes = [C.c_int]
-    for i, T in enumerate((A.GameState, A.HandQuery, A.HandResult, A.Action)):
+    L.rv_vec_apply_events.argtypes = [vp, P(A.MjaiEvent)]
+    for i, T in enumerate((A.GameState, A.HandQuery, A.HandResult, A.Action, A.MjaiEvent, A.RunStats)):
         if L.rv_sizeof(i) != C.sizeof(T):
             raise ImportError(f"ABI mismatch for {T.__name__}: C {L.rv_sizeof(i)} != ctypes {C.sizeof(T)}")
     _LIB = L

@@ -1628,6 +1628,7 @@ __device__ __noinline__ void handle_kita(const Ctx& cx, G& g, int pid, const rv_
 __device__ __noinline__ void step_apply_act(const Ctx& cx, G& g, const rv_action* acts) {
   const int np = num_players(g);
   int pid = g.current_player;
+  if (pid >= np) return;      // nobody to act: `actions.get(&self.current_player)` finds nothing (state/mod.rs:405-407)
   const rv_action& act = acts[pid];
   switch (act.type) {
     case RV_DISCARD: {
@@ -2114,6 +2115,7 @@ __device__ __forceinline__ bool act_fast(const Ctx& cx, G& g, uint64_t agent_see
   const int np = NPC ? NPC : num_players(g);
   RV_STAT(10);
   const int pid = g.current_player;
+  if (pid >= np) return RV_DECLINE(18);   // event-driven record between turns (current_player = RV_NONE): nobody acts
   const int drawn = g.drawn_tile;
   const int hl = g.hand_len[pid], nm = g.n_melds[pid];
   const bool sanma = np == 3;
@@ -2331,6 +2333,10 @@ __device__ __noinline__ void random_step_act(const Ctx& cx, G& g, uint64_t agent
   RV_STAT(3);
   RV_STAT(4);
   int pid = g.current_player;
+  if (pid >= np) {            // nobody to act (an event-driven record between turns): the step is a no-op, as in the reference
+    g.step_count = sc + 1;
+    return;
+  }
   if (IDS) {
     ids_reset(cx);
     ids_clear(cx, pid);
@@ -2431,6 +2437,276 @@ __device__ inline void random_step(const Ctx& cx, G& g, uint64_t agent_seed, uin
   else random_step_resp<IDS>(cx, g, agent_seed, game_id);
 }
 
+// ---- MJAI-driven state tracking: GameState::apply_mjai_event (state/event_handler.rs:18-330; 3P state_3p/event_handler.rs) ----
+// The record follows a game that is played elsewhere (a replay, an online table): events arrive one at a time, nothing is
+// drawn from the wall, and the claim windows are rebuilt from the event itself.  Only bookkeeping — but it is the
+// bookkeeping the legal-action and observation paths then read, so it lives with them.  `current_player` = RV_NONE is the
+// reference's u8::MAX "nobody to act" marker.
+__device__ __forceinline__ void hand_remove_if_present(G& g, int p, int tile) { hand_remove_first(g, p, tile); }
+__device__ __noinline__ void claims_after_tile(const Ctx& cx, G& g, int actor, int tile, bool ron_only) {
+  const int np = num_players(g);
+  uint32_t active = 0;
+  for (int i = 0; i < MAXP; i++) g.n_claims[i] = 0;                 // current_claims.clear()
+  for (int i = 0; i < np; i++) {
+    if (i == actor) continue;
+    gen_claims(cx, g, i, actor, tile);
+    if (ron_only) {                                                 // kita: only Ron survives (3P event_handler.rs:333-341)
+      int n = 0;
+      for (int k = 0; k < g.n_claims[i]; k++)
+        if ((cold(g).claims[i][k] & 0xFF) == RV_RON) cold(g).claims[i][n++] = cold(g).claims[i][k];
+      g.n_claims[i] = (uint8_t)n;
+    }
+    if (g.n_claims[i] > 0) active |= 1u << i;
+  }
+  if (active) {
+    g.phase = RV_WAIT_RESPONSE;
+    g.active_mask = (uint8_t)active;
+  } else {
+    g.phase = RV_WAIT_ACT;
+    g.active_mask = 0;
+    g.current_player = RV_NONE;
+  }
+  g.needs_tsumo = 1;
+}
+__device__ __noinline__ void apply_mjai_event(const Ctx& cx, G& g, const rv_mjai_event& e) {
+  const int np = num_players(g);
+  const bool sanma = np == 3;
+  const int actor = e.actor < np ? e.actor : 0;
+  switch (e.type) {
+    case RV_EV_START_GAME:
+      // env.rs:56-72: reset() (logs, counters) and then the handler's own lines (event_handler.rs:21-26)
+      g.ev_hash = 0xcbf29ce484222325ull;
+      g.ev_count = g.ev_words = g.step_count = 0;
+      cold(g).kyoku_count = 0;
+      g.overflow = 0;
+      g.current_player = RV_NONE;
+      g.active_mask = 0;
+      break;
+    case RV_EV_START_KYOKU: {
+      g.honba = e.honba;
+      g.riichi_sticks = e.kyotaku;
+      g.round_wind = e.bakaze < 4 ? e.bakaze : 0;
+      g.oya = e.oya;
+      g.kyoku_idx = e.kyoku > 0 ? (uint8_t)(e.kyoku - 1) : 0;
+      g.current_player = RV_NONE;
+      g.turn_count = 0;
+      g.is_done = 0;
+      g.needs_tsumo = 1;
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = 0;
+      g.last_discard_pid = g.last_discard_tile = RV_NONE;
+      g.pending_kan_pid = g.pending_kan_type = g.pending_kan_tile = RV_NONE;
+      g.is_rinshan_flag = 0;
+      g.is_first_turn = 1;
+      g.riichi_pending_acceptance = RV_NONE;
+      g.drawn_tile = RV_NONE;
+      g.last_error = RV_NONE;
+      g.pending_init[0] = g.pending_init[1] = g.pending_init[2] = RV_NONE;
+      g.pending_tail[0] = RV_NONE;
+      g.pending_tail[1] = 0;
+      // wall.tiles = vec![0; TILES - 13 * np]: a placeholder of the pre-draw length, nothing is ever read from it
+      const int wl = sanma ? 108 : 136, left = wl - 13 * np;
+      for (int i = 0; i < 136; i++) cold(g).wall[i] = i < left ? 0 : RV_NONE;
+      g.wall_len = (uint8_t)wl;
+      g.wall_top = (uint8_t)left;
+      g.rinshan_draw_count = 0;
+      g.pending_kan_dora_count = 0;
+      g.drawable_count = (uint8_t)(left - 14);
+      g.n_dora = 1;
+      g.dora_ind[0] = e.dora_marker;
+      for (int i = 1; i < 5; i++) g.dora_ind[i] = RV_NONE;
+      for (int p = 0; p < MAXP; p++) {                             // PlayerState::reset_round
+        for (int i = 0; i < RV_HAND_CAP; i++) g.hand[p][i] = RV_NONE;
+        g.hand_len[p] = 0;
+        for (int m = 0; m < 4; m++) {
+          for (int k = 0; k < 4; k++) g.meld_tiles[p][m][k] = RV_NONE;
+          g.meld_type[p][m] = cold(g).meld_from[p][m] = cold(g).meld_called[p][m] = RV_NONE;
+        }
+        g.n_melds[p] = 0;
+        for (int i = 0; i < RV_RIVER_CAP; i++) cold(g).river[p][i] = RV_NONE;
+        g.n_river[p] = 0;
+        g.river_tedashi[p] = 0;
+        cold(g).river_riichi[p] = 0;
+        cold(g).riichi_decl_idx[p] = RV_NONE;
+        g.flags[p] = (sanma && p == 3) ? 0 : RV_F_NAGASHI_ELIGIBLE;
+        cold(g).pao[p][0] = cold(g).pao[p][1] = RV_NONE;
+        g.forbidden[p][0] = g.forbidden[p][1] = RV_NONE;
+        cold(g).score_delta[p] = 0;
+        g.n_claims[p] = 0;
+        cold(g).riichi_sutehai[p] = cold(g).last_tedashi[p] = RV_NONE;
+        cold(g).n_kita[p] = 0;
+        for (int k = 0; k < 4; k++) g.c_cnt[p][k] = 0, g.c_key[p][k] = 0;
+        g.c_river_kinds[p] = 0;
+        g.c_waits[p] = 0;
+        if (p < np) {
+          g.score[p] = e.scores[p];
+          const int n = e.tehai_len[p] < 14 ? e.tehai_len[p] : 14;
+          for (int k = 0; k < n; k++) hand_push(g, p, e.tehais[p][k] < 136 ? e.tehais[p][k] : 0);
+          hand_sort(g, p);
+          waits_update(cx.T, g, p);
+        }
+      }
+      break;
+    }
+    case RV_EV_TSUMO: {
+      const int tile = e.pai < 136 ? e.pai : 0;
+      g.current_player = (uint8_t)actor;
+      g.drawn_tile = (uint8_t)tile;
+      hand_push(g, actor, tile);
+      hand_sort(g, actor);                                          // the handler sorts after the push
+      g.forbidden[actor][0] = g.forbidden[actor][1] = RV_NONE;
+      if (g.wall_top > g.rinshan_draw_count) {
+        g.wall_top--;
+        g.drawable_count = g.drawable_count > 0 ? (uint8_t)(g.drawable_count - 1) : 0;
+      }
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << actor);
+      g.needs_tsumo = 0;
+      waits_update(cx.T, g, actor);
+      break;
+    }
+    case RV_EV_DAHAI:
+    case RV_EV_DAHAI_TSUMOGIRI: {
+      const int tile = e.pai < 136 ? e.pai : 0;
+      g.current_player = (uint8_t)actor;
+      hand_remove_if_present(g, actor, tile);
+      const int nr = g.n_river[actor];
+      if (nr < RV_RIVER_CAP) cold(g).river[actor][nr] = (uint8_t)tile;
+      else g.overflow |= 1;
+      g.n_river[actor] = (uint8_t)(nr + 1);
+      g.c_river_kinds[actor] |= 1ull << (tile >> 2);
+      g.last_discard_pid = (uint8_t)actor;
+      g.last_discard_tile = (uint8_t)tile;
+      g.drawn_tile = RV_NONE;
+      if (g.flags[actor] & RV_F_RIICHI_STAGE) g.flags[actor] = (uint8_t)((g.flags[actor] | RV_F_RIICHI_DECLARED) & ~RV_F_RIICHI_STAGE);
+      waits_update(cx.T, g, actor);
+      claims_after_tile(cx, g, actor, tile, false);
+      break;
+    }
+    case RV_EV_PON:
+    case RV_EV_CHI:
+    case RV_EV_DAIMINKAN: {
+      const int tile = e.pai < 136 ? e.pai : 0;
+      g.current_player = (uint8_t)actor;
+      const int nc = e.n_consumed < (e.type == RV_EV_DAIMINKAN ? 3 : 2) ? e.n_consumed : (e.type == RV_EV_DAIMINKAN ? 3 : 2);
+      for (int k = 0; k < nc; k++) hand_remove_if_present(g, actor, e.consumed[k] < 136 ? e.consumed[k] : 0);
+      const int m = g.n_melds[actor];
+      if (m < 4) {                                                  // tiles = [called, consumed...] — NOT sorted by the handler
+        g.meld_tiles[actor][m][0] = (uint8_t)tile;
+        for (int k = 0; k < 3; k++) g.meld_tiles[actor][m][1 + k] = k < nc ? (uint8_t)(e.consumed[k] < 136 ? e.consumed[k] : 0) : (uint8_t)RV_NONE;
+        g.meld_type[actor][m] = e.type == RV_EV_PON ? RV_MELD_PON : e.type == RV_EV_CHI ? RV_MELD_CHI : RV_MELD_DAIMINKAN;
+        cold(g).meld_from[actor][m] = RV_NONE;                      // from_who: -1
+        cold(g).meld_called[actor][m] = (uint8_t)tile;
+        g.n_melds[actor] = (uint8_t)(m + 1);
+      } else {
+        g.overflow |= 1;
+      }
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << actor);
+      if (e.type == RV_EV_DAIMINKAN) {
+        g.needs_tsumo = 1;
+      } else {
+        g.drawn_tile = RV_NONE;
+        g.needs_tsumo = 0;
+        if (e.type == RV_EV_CHI && sanma) {
+          // the 3P handler accepts a chi "gracefully" and leaves forbidden_discards alone (state_3p/event_handler.rs:182-204)
+        } else {
+        g.forbidden[actor][0] = g.forbidden[actor][1] = RV_NONE;
+        if (rule(g, RV_RULE_KUIKAE_FORBIDDEN)) {
+          g.forbidden[actor][0] = (uint8_t)tile;
+          if (e.type == RV_EV_CHI && !sanma && nc == 2) {           // the 3P handler has no suji rule (chi does not exist there)
+            const int t34 = tile >> 2;
+            int c0 = (e.consumed[0] < 136 ? e.consumed[0] : 0) >> 2, c1 = (e.consumed[1] < 136 ? e.consumed[1] : 0) >> 2;
+            if (c0 > c1) { int t = c0; c0 = c1; c1 = t; }
+            if (c0 == t34 + 1 && c1 == t34 + 2) {
+              if (t34 % 9 <= 5) g.forbidden[actor][1] = (uint8_t)((t34 + 3) * 4);
+            } else if (t34 >= 2 && c1 == t34 - 1 && c0 == t34 - 2 && t34 % 9 >= 3) {
+              g.forbidden[actor][1] = (uint8_t)((t34 - 3) * 4);
+            }
+          }
+        }
+        }
+      }
+      waits_update(cx.T, g, actor);
+      break;
+    }
+    case RV_EV_ANKAN: {
+      const int nc = e.n_consumed < 4 ? e.n_consumed : 4;
+      const int m = g.n_melds[actor];
+      for (int k = 0; k < nc; k++) hand_remove_if_present(g, actor, e.consumed[k] < 136 ? e.consumed[k] : 0);
+      if (m < 4) {
+        for (int k = 0; k < 4; k++) g.meld_tiles[actor][m][k] = k < nc ? (uint8_t)(e.consumed[k] < 136 ? e.consumed[k] : 0) : (uint8_t)RV_NONE;
+        g.meld_type[actor][m] = RV_MELD_ANKAN;
+        cold(g).meld_from[actor][m] = RV_NONE;
+        cold(g).meld_called[actor][m] = RV_NONE;
+        g.n_melds[actor] = (uint8_t)(m + 1);
+      } else {
+        g.overflow |= 1;
+      }
+      g.current_player = (uint8_t)actor;
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << actor);
+      g.needs_tsumo = 1;
+      waits_update(cx.T, g, actor);
+      break;
+    }
+    case RV_EV_KAKAN: {
+      const int tile = e.pai < 136 ? e.pai : 0;
+      hand_remove_if_present(g, actor, tile);
+      for (int m = 0; m < g.n_melds[actor]; m++)
+        if (g.meld_type[actor][m] == RV_MELD_PON && (g.meld_tiles[actor][m][0] >> 2) == (tile >> 2)) {
+          g.meld_type[actor][m] = RV_MELD_KAKAN;
+          g.meld_tiles[actor][m][3] = (uint8_t)tile;                // pushed at the end, not re-sorted
+          break;
+        }
+      g.current_player = (uint8_t)actor;
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << actor);
+      g.needs_tsumo = 1;
+      waits_update(cx.T, g, actor);
+      break;
+    }
+    case RV_EV_REACH:
+      g.flags[actor] |= RV_F_RIICHI_STAGE;
+      break;
+    case RV_EV_REACH_ACCEPTED:
+      g.flags[actor] |= RV_F_RIICHI_DECLARED;
+      g.riichi_sticks += 1;
+      g.score[actor] -= 1000;
+      break;
+    case RV_EV_DORA:
+      if (g.n_dora < 5) g.dora_ind[g.n_dora++] = e.pai < 136 ? e.pai : 0;
+      break;
+    case RV_EV_KITA:
+      if (sanma) {                                                  // 4P: ignored (event_handler.rs:305-307)
+        int kita = -1;
+        for (int k = 0; k < g.hand_len[actor]; k++)
+          if ((g.hand[actor][k] >> 2) == 30) { kita = g.hand[actor][k]; break; }
+        g.current_player = (uint8_t)actor;
+        if (kita >= 0) {
+          hand_remove_first(g, actor, kita);
+          cold(g).n_kita[actor]++;
+          waits_update(cx.T, g, actor);
+          claims_after_tile(cx, g, actor, kita, true);
+        } else {
+          for (int i = 0; i < MAXP; i++) g.n_claims[i] = 0;
+          g.phase = RV_WAIT_ACT;
+          g.active_mask = 0;
+          g.current_player = RV_NONE;
+          g.needs_tsumo = 1;
+        }
+      }
+      break;
+    case RV_EV_HORA:
+    case RV_EV_RYUKYOKU:
+    case RV_EV_END_KYOKU:
+      g.is_done = 1;
+      break;
+    default:
+      break;
+  }
+}
+
 // ---- agent #1: keyed "greedy-win" (definition shared with the oracle, oracle/game.hpp greedy_pick) ----
 // Test agent: takes every Tsumo / Ron, declares every Riichi, calls Pon / Kan / Kita with probability 1/4 and Chi with 1/8, and
 // discards towards the lowest shanten — so rollouts end in wins (~60 % of the rounds) and exercise the settlement code that
@@ -2500,6 +2776,10 @@ __device__ __noinline__ void agent_step(const Ctx& cx, G& g, int policy, uint64_
   uint32_t L[RV_MAX_LEGAL];
   if (g.phase == RV_WAIT_ACT) {
     const int pid = g.current_player;
+    if (pid >= np) {
+      g.step_count++;
+      return;
+    }
     const int n = min(legal_actions(cx, g, pid, L, -1, nullptr), RV_MAX_LEGAL);
     if (n == 0) {   // the reference's 3P dead end, retired as in random_step_act
       g.step_count++;

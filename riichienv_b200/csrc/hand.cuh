@@ -82,6 +82,19 @@ __device__ __forceinline__ uint64_t cnt_present(const Cnt& c) {
 // Base-5 table index of a suit histogram.  Physical hands hold at most four copies of a kind; a record injected through
 // the API may not (the reference's own tests park thirteen copies of one tile in seats they do not care about), so the
 // index is clamped: such a seat gets meaningless answers, never an out-of-bounds table read.
+// lowest tile kind >= i with a nonzero count, 34 if there is none (one find-first-set per suit word instead of a scan)
+__device__ __forceinline__ int cnt_next(const Cnt& c, int i) {
+  if (i >= 34) return 34;
+  const int su = i / 9;
+  #pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (k < su) continue;
+    uint64_t x = c.s[k];
+    if (k == su) x &= ~0ull << (4 * (i - 9 * su));
+    if (x) return 9 * k + ((__ffsll((long long)x) - 1) >> 2);
+  }
+  return 34;
+}
 template <int N>
 __device__ __forceinline__ int suit_key(uint64_t x) {
   int k = 0;
@@ -703,7 +716,7 @@ __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand,
         // advance to first nonzero tile
         int i = pos[depth];
         if (stage[depth] == 0) {
-          while (i < 34 && cnt_get(work, i) == 0) i++;
+          i = cnt_next(work, i);            // lowest kind >= i still in the hand (34: none)
           pos[depth] = i;
         }
         if (i >= 34) {

@@ -88,6 +88,7 @@ struct rv_vec {
   uint64_t graph_seed;
   int graph_period;
   unsigned long long* d_steps;  // [0] = env steps executed, [1] = games finished (by step kernels)
+  unsigned char* d_obs_snap;    // rv_vec_observe_step_random: packed snapshot of what the encoder reads (n x OBS_STAGE_BYTES)
   void *d_io_a, *d_io_c;        // staging of rv_vec_step / rv_vec_legal_actions (grow-only)
   size_t io_a_bytes, io_c_bytes;
 };
@@ -99,6 +100,18 @@ __global__ void __launch_bounds__(128) synth_hands_kernel(rv_hand_query* q, uint
   rv_hand_query h;
   rv_synth_hand(first + (uint64_t)i, &h);
   q[i] = h;
+}
+// rv_vec_apply_events: thread per game
+__global__ void __launch_bounds__(64) apply_events_kernel(Tables T, G* states, int64_t n, const rv_mjai_event* events) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || events[i].type == RV_EV_NONE) return;
+  Ctx cx;
+  cx.T = T;
+  cx.log = nullptr;            // fed events are not appended to the device log (the caller keeps their text)
+  cx.log_cap = 0;
+  cx.defer_init = cx.defer_tail = false;
+  cx.idbits = nullptr;
+  apply_mjai_event(cx, states[i], events[i]);
 }
 // rv_vec_step_agent: thread per game, every class of work inline (a test / evaluation path, not the throughput path)
 __global__ void __launch_bounds__(128) agent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, int policy,
@@ -198,8 +211,14 @@ __global__ void debug_call_kernel(Tables T, G* state, uint32_t* log, uint32_t ca
   if (op == 0) {
     reveal_kan_dora(cx, g);
     out[7] = g.n_dora;
-  } else {
+  } else if (op == 1) {
     out[7] = (uint8_t)ura_indicators(g, out);
+  } else if (op == 2) {
+    trigger_ryukyoku(cx, g, RV_RK_EXHAUSTIVE);
+    out[7] = g.is_done;
+  } else {
+    next_round(cx, g, op == 4, op == 5);       // 3: (false, false)  4: (oya_won, false)  5: (false, is_draw)
+    out[7] = g.is_done;
   }
 }
 
@@ -425,6 +444,7 @@ __device__ __forceinline__ int classify(const G& g, uint32_t budget) {
   if (g.pending_tail[0] != RV_NONE) return PH_TAIL;      // (persistent scheduler only; flushed even when the budget is spent)
   if (g.pending_init[0] != RV_NONE) return PH_DEAL;      // must be flushed even when the budget is spent
   if (g.is_done || budget == 0) return PH_NONE;
+  if (g.phase == RV_WAIT_ACT && g.current_player == RV_NONE) return PH_NONE;   // event-driven record between turns: nothing to roll out
   return g.phase == RV_WAIT_ACT ? PH_ACT : PH_RESP;
 }
 // every lane of the warp must call this (cls = PH_NONE for lanes without a game).
@@ -1101,9 +1121,25 @@ __global__ void __launch_bounds__(128) legal_ids_kernel(Tables T, const G* state
 // measured slower, 194 us against 157 us per 65,536 rows: with one short-lived warp per game the block scheduler keeps
 // every SM topped up and other warps cover the one remaining round trip.)
 constexpr int OBS_STAGE_BYTES = RV_HOT_BYTES + MAXP * RV_RIVER_CAP;   // 544 + 128
+// Snapshot of what the encoder reads of every record (hot prefix + rivers, OBS_STAGE_BYTES per game, packed): taken before an
+// env step so that the rows of the decision point can be streamed out WHILE the step kernel already advances the games
+// (rv_vec_observe_step_random: the encoder is HBM-bound, the one-step kernel latency-bound — side by side they cost the longer
+// of the two instead of the sum).
+__global__ void __launch_bounds__(256) obs_snapshot_kernel(const G* states, int64_t n, unsigned char* snap) {
+  const int64_t gi = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gi >= n) return;
+  const uint4* src = reinterpret_cast<const uint4*>(&states[gi]);
+  const uint2* riv = reinterpret_cast<const uint2*>(&states[gi].river[0][0]);
+  uint4* dst = reinterpret_cast<uint4*>(snap + (size_t)gi * OBS_STAGE_BYTES);
+  __stcs(dst + lane, __ldcs(src + lane));
+  if (lane < (RV_HOT_BYTES - 512) / 16) __stcs(dst + 32 + lane, __ldcs(src + 32 + lane));
+  else if (lane >= 16) __stcs(reinterpret_cast<uint2*>(snap + (size_t)gi * OBS_STAGE_BYTES + RV_HOT_BYTES) + (lane - 16), __ldcs(riv + (lane - 16)));
+}
 template <bool SANMA>
 __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int64_t n, const int32_t* offsets, const uint32_t* idbits,
-                                                            float* obs, uint8_t* mask, int32_t* index, int64_t max_obs) {
+                                                            float* obs, uint8_t* mask, int32_t* index, int64_t max_obs,
+                                                            const unsigned char* snap = nullptr) {
   constexpr int W = SANMA ? OBS_W3 : OBS_W, IDS = SANMA ? OBS_IDS3 : OBS_IDS;
   __shared__ ObsScratch scratch[4];
   __shared__ __align__(16) unsigned char staged[4][OBS_STAGE_BYTES];
@@ -1111,8 +1147,10 @@ __global__ void __launch_bounds__(128, 8) obs_encode_kernel(const G* states, int
   int64_t gi = (int64_t)blockIdx.x * 4 + w;
   if (gi >= n) return;
   {
-    const uint4* src = reinterpret_cast<const uint4*>(&states[gi]);
-    const uint2* riv = reinterpret_cast<const uint2*>(&states[gi].river[0][0]);   // offset 776: 8-byte aligned only
+    // source: the record itself, or its packed snapshot (hot prefix followed by the rivers)
+    const uint4* src = snap ? reinterpret_cast<const uint4*>(snap + (size_t)gi * OBS_STAGE_BYTES) : reinterpret_cast<const uint4*>(&states[gi]);
+    const uint2* riv = snap ? reinterpret_cast<const uint2*>(snap + (size_t)gi * OBS_STAGE_BYTES + RV_HOT_BYTES)
+                            : reinterpret_cast<const uint2*>(&states[gi].river[0][0]);   // offset 776: 8-byte aligned only
     uint4* dst = reinterpret_cast<uint4*>(staged[w]);
     const uint4 a = __ldcs(src + lane);                                      // hot bytes 0..511
     uint4 b = make_uint4(0, 0, 0, 0);
@@ -1457,7 +1495,14 @@ int rv_ctx_create(int device, rv_ctx** out) {
   CK(cudaSetDevice(device));
   rv_ctx* c = new rv_ctx();
   c->device = device;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // the context stream outranks the side streams: when the observation encoder (side stream, 16 k short blocks, HBM-bound)
+    // runs beside the one-step kernel (context stream, a few hundred long, latency-bound blocks), freed SM resources go to
+    // the step kernel first
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+  }
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->ev[i]));
   for (int i = 0; i < 3; i++) {
     CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
@@ -1659,6 +1704,7 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_q_slots = nullptr;
   v->d_q_ctl = nullptr;
   v->d_io_a = v->d_io_c = nullptr;
+  v->d_obs_snap = nullptr;
   v->io_a_bytes = v->io_c_bytes = 0;
   v->q_cap = 0;
   v->graph_seed = 0;
@@ -1713,6 +1759,7 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_seq_start) cudaFree(v->d_seq_start);
   if (v->d_q_slots) cudaFree(v->d_q_slots);
   if (v->d_q_ctl) cudaFree(v->d_q_ctl);
+  if (v->d_obs_snap) cudaFree(v->d_obs_snap);
   if (v->d_io_a) cudaFree(v->d_io_a);
   if (v->d_io_c) cudaFree(v->d_io_c);
   cudaFree(v->d_steps);
@@ -2103,9 +2150,22 @@ int rv_vec_step_agent(rv_vec* v, int policy, uint64_t agent_seed, uint32_t max_s
   if (steps_done) *steps_done = after - before;
   return RV_OK;
 }
+int rv_vec_apply_events(rv_vec* v, const rv_mjai_event* events) {
+  if (!events) return fail(RV_ERR_INVALID, "events is null");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure(&v->d_io_a, &v->io_a_bytes, sizeof(rv_mjai_event) * (size_t)v->n);
+  if (rc != RV_OK) return rc;
+  rv_mjai_event* d_ev = (rv_mjai_event*)v->d_io_a;
+  CK(cudaMemcpyAsync(d_ev, events, sizeof(rv_mjai_event) * (size_t)v->n, cudaMemcpyHostToDevice, c->stream));
+  apply_events_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, d_ev);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
 int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out) {
   if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
-  if (op != 0 && op != 1) return fail(RV_ERR_INVALID, "op must be 0 (reveal kan dora) or 1 (ura indicators)");
+  if (op < 0 || op > 5) return fail(RV_ERR_INVALID, "op must be 0..5");
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   uint8_t* d_out = nullptr;
@@ -2283,8 +2343,25 @@ int rv_vec_observe_step_random(rv_vec* v, uint64_t agent_seed, float* d_obs, uin
       d_index = v->d_row_index;
       if (max_obs > (int64_t)MAXP * n) max_obs = (int64_t)MAXP * n;
     }
-    if (sanma) obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs);
-    else obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, c->stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs);
+    // RV_OBS_OVERLAP (default on): snapshot what the encoder reads, then stream the rows out on a side stream while the step
+    // kernel advances the games on the context stream; the streams join before the mask rows.
+    static const int overlap = env_int("RV_OBS_OVERLAP", 2) - 1;
+    const unsigned char* snap = nullptr;
+    cudaStream_t enc_stream = c->stream;
+    if (overlap && d_obs) {
+      if (!v->d_obs_snap) CK(cudaMalloc(&v->d_obs_snap, (size_t)n * OBS_STAGE_BYTES));
+      obs_snapshot_kernel<<<grid_for(n, 8), 256, 0, c->stream>>>(v->d_states, n, v->d_obs_snap);
+      CK(cudaEventRecord(c->fork_ev, c->stream));
+      CK(cudaStreamWaitEvent(c->aux[0], c->fork_ev, 0));
+      snap = v->d_obs_snap;
+      enc_stream = c->aux[0];
+    }
+    // overlapped: the step kernel is issued FIRST (its few long blocks take their SM share), the encoder fills what is left
+    if (!snap) {
+      if (sanma) obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, enc_stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs, snap);
+      else obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, enc_stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs, snap);
+      if (snap) CK(cudaEventRecord(c->join_ev[0], c->aux[0]));
+    }
     static const int sorted = env_int("RV_STEP_SORTED", 3) - 1;    // RV_STEP_SORTED=1: thread per game, 2: regrouped, 3: staged (A/B)
     if (sorted == 2)
       CK(launch_step_staged<true>(c, v, agent_seed, v->d_idbits));
@@ -2293,6 +2370,12 @@ int rv_vec_observe_step_random(rv_vec* v, uint64_t agent_seed, float* d_obs, uin
     else
       step_random_kernel<true><<<grid_for(n, 128), 128, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, 1, v->d_steps,
                                                                         v->d_idbits);
+    if (snap) {
+      if (sanma) obs_encode_kernel<true><<<grid_for(n, 4), 128, 0, enc_stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs, snap);
+      else obs_encode_kernel<false><<<grid_for(n, 4), 128, 0, enc_stream>>>(v->d_states, n, v->d_obs_offsets, nullptr, d_obs, nullptr, d_index, max_obs, snap);
+      if (snap) CK(cudaEventRecord(c->join_ev[0], c->aux[0]));
+    }
+    if (snap) CK(cudaStreamWaitEvent(c->stream, c->join_ev[0], 0));   // rows (and the row index) are complete from here on
     if (d_mask) {
       const int grid = (int)std::min<int64_t>(grid_for(std::min<int64_t>(max_obs, (int64_t)MAXP * n), 8), (int64_t)c->sm_count * 8);
       if (sanma) obs_mask_rows_kernel<true><<<grid, 256, 0, c->stream>>>(d_index, v->d_obs_offsets + n, v->d_idbits, d_mask, max_obs);
@@ -2481,6 +2564,8 @@ int rv_sizeof(int which) {
     case 1: return (int)sizeof(rv_hand_query);
     case 2: return (int)sizeof(rv_hand_result);
     case 3: return (int)sizeof(rv_action);
+    case 4: return (int)sizeof(rv_mjai_event);
+    case 5: return (int)sizeof(rv_run_stats);
   }
   return -1;
 }

@@ -14,7 +14,7 @@ inline const char* rv_state_defect(const rv_game_state& s) {
   if (s.wall_top > 136 || s.rinshan_draw_count > s.wall_top) return "wall cursors out of range";
   if (s.n_dora > 5) return "more than 5 dora indicators";
   if (s.phase > 1) return "phase must be 0 or 1";
-  if (s.current_player >= np) return "current_player out of range";
+  if (s.current_player >= np && s.current_player != RV_NONE) return "current_player out of range";   // RV_NONE: nobody to act (event-driven records)
   if (s.oya >= np) return "oya out of range";
   for (int p = 0; p < RV_NP; p++) {
     if (s.hand_len[p] > RV_HAND_CAP) return "a hand holds at most 16 tiles";

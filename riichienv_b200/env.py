@@ -593,6 +593,7 @@ class RiichiEnv:
                                device=device)
         self._event_counts = [0, 0, 0, 0]
         self._log_cache = {}
+        self._ext_log = None
         self._token = getattr(self, "_token", 0) + 1
         # GameState::new deals a first round immediately (state/mod.rs:165); mirror it so getters work before reset().
         # That constructor deal uses shuffle #0; the library's create already accounts for it (hand_index = 1), so we
@@ -609,6 +610,7 @@ class RiichiEnv:
         # reset(seed=) sets GameState.seed which nothing reads (env.rs:835-837): the wall is NOT reseeded.
         self._event_counts = [0, 0, 0, 0]
         self._log_cache = {}
+        self._ext_log = None
         self._token = getattr(self, "_token", 0) + 1
         self._v.reset(oya=0 if oya is None else oya, round_wind=0 if round_wind is None else round_wind,
                       honba=0 if honba is None else honba, kyotaku=0 if kyotaku is None else kyotaku,
@@ -682,12 +684,153 @@ class RiichiEnv:
         acts, counts = self._v.legal_actions()
         return [self._action_cls._from_abi(acts[pid * A.MAX_LEGAL + k]) for k in range(int(counts[0, pid]))]
 
+    # ---- MJAI-driven state tracking (env.rs:880-948 over state/event_handler.rs:18-330) -------------
+    _EVENT_TYPES = {"start_game": A.EV_START_GAME, "start_kyoku": A.EV_START_KYOKU, "tsumo": A.EV_TSUMO, "dahai": A.EV_DAHAI,
+                    "pon": A.EV_PON, "chi": A.EV_CHI, "kan": A.EV_DAIMINKAN, "daiminkan": A.EV_DAIMINKAN, "kakan": A.EV_KAKAN,
+                    "ankan": A.EV_ANKAN, "dora": A.EV_DORA, "reach": A.EV_REACH, "reach_accepted": A.EV_REACH_ACCEPTED,
+                    "hora": A.EV_HORA, "ryukyoku": A.EV_RYUKYOKU, "kita": A.EV_KITA, "end_game": A.EV_END_GAME,
+                    "end_kyoku": A.EV_END_KYOKU}
+    _NO_DECISION = ("start_game", "start_kyoku", "reach_accepted", "dora", "hora", "ryukyoku", "end_kyoku", "end_game")
+
+    @staticmethod
+    def _tile(s):
+        """parse_mjai_tile (event_handler.rs:8-10): mjai_to_tid, an unparsable tile (\"?\") is 0"""
+        from .convert import mjai_to_tid
+
+        try:
+            return mjai_to_tid(s)
+        except (ValueError, TypeError):
+            return 0
+
+    def _parse_event(self, event):
+        """Python dict -> (rv_mjai_event, canonical JSON text); what serde does with MjaiEvent (replay/mjai_replay.rs:67-156):
+        required fields missing or of the wrong type raise ValueError, unknown types are MjaiEvent::Other (ignored)."""
+        try:
+            text = json.dumps(event, sort_keys=True, separators=(",", ":"), ensure_ascii=False)
+        except (TypeError, ValueError) as e:
+            raise ValueError(f"JSON Parse Error: {e}") from None
+        ev = json.loads(text)
+        if not isinstance(ev, dict) or not isinstance(ev.get("type"), str):
+            raise ValueError("JSON Parse Error: missing field `type`")
+        kind = ev["type"]
+        e = A.MjaiEvent()
+        e.type = self._EVENT_TYPES.get(kind, 0)
+
+        def need(name, ty):
+            v = ev.get(name)
+            if not isinstance(v, ty) or isinstance(v, bool) and ty is int:
+                raise ValueError(f"JSON Parse Error: missing field `{name}`")
+            return v
+
+        def seat(name):
+            v = need(name, int)
+            if v < 0:
+                raise ValueError(f"JSON Parse Error: invalid value for `{name}`")
+            return min(v, 255)
+
+        def consumed():
+            c = need("consumed", list)
+            e.n_consumed = min(4, len(c))
+            for k in range(e.n_consumed):
+                e.consumed[k] = self._tile(c[k])
+
+        if kind == "start_kyoku":
+            e.bakaze = {"E": 0, "S": 1, "W": 2, "N": 3}.get(need("bakaze", str), 0)
+            e.kyoku, e.honba, e.oya = need("kyoku", int) & 0xFF, need("honba", int) & 0xFF, need("oya", int) & 0xFF
+            ky = ev.get("kyoutaku", ev.get("kyotaku"))
+            if not isinstance(ky, int):
+                raise ValueError("JSON Parse Error: missing field `kyoutaku`")
+            e.kyotaku = ky & 0xFF                      # serde field type u8
+            scores, tehais = need("scores", list), need("tehais", list)
+            e.dora_marker = self._tile(need("dora_marker", str))
+            for p in range(min(4, len(scores))):
+                e.scores[p] = int(scores[p])
+            for p in range(min(4, len(tehais))):
+                e.tehai_len[p] = min(14, len(tehais[p]))
+                for k in range(e.tehai_len[p]):
+                    e.tehais[p][k] = self._tile(tehais[p][k])
+            if len(scores) < self._np or len(tehais) < self._np:
+                raise ValueError("start_kyoku needs scores and tehais for every seat")
+        elif kind in ("tsumo", "kakan"):
+            e.actor, e.pai = seat("actor"), self._tile(need("pai", str))
+        elif kind == "dahai":
+            e.actor, e.pai = seat("actor"), self._tile(need("pai", str))
+            if need("tsumogiri", bool):
+                e.type = A.EV_DAHAI_TSUMOGIRI
+        elif kind in ("pon", "chi", "kan", "daiminkan"):
+            e.actor, e.target, e.pai = seat("actor"), seat("target"), self._tile(need("pai", str))
+            consumed()
+            if kind != "kan" and kind != "daiminkan" and e.n_consumed < 2:
+                raise IndexError("consumed needs two tiles")
+        elif kind == "ankan":
+            e.actor = seat("actor")
+            consumed()
+        elif kind == "dora":
+            e.pai = self._tile(need("dora_marker", str))
+        elif kind in ("reach", "reach_accepted", "kita"):
+            e.actor = seat("actor")
+        elif kind == "hora":
+            e.actor, e.target = seat("actor"), seat("target")
+        if kind in ("tsumo", "dahai", "pon", "chi", "kan", "daiminkan", "kakan", "ankan", "reach", "reach_accepted", "kita") \
+                and e.actor >= self._np:
+            raise IndexError(f"actor {e.actor} out of range")
+        return e, text, kind
+
+    def _apply(self, event):
+        e, text, kind = self._parse_event(event)
+        if kind == "start_game":          # env.rs:56-68: logs and counters restart with the caller's own start_game line
+            self._ext_log = []
+            self._event_counts = [0, 0, 0, 0]
+            self._log_cache = {}
+        elif self._ext_log is None:        # events fed on top of a played game: the text log continues from what was played
+            played = [self._log_text(v) for v in [-1] + list(range(self._np))]
+            self._ext_log = [[played[v][k] for v in range(self._np + 1)] for k in range(len(played[0]))]
+        self._token += 1
+        self._v.apply_events((A.MjaiEvent * 1)(e))
+        self._ext_log.append(self._masked_variants(text, kind))
+        return kind
+
+    def _masked_variants(self, text, kind):
+        """[all-seeing, seat 0, seat 1, ...] renderings of one fed event: _push_mjai_event's masking (state/mod.rs:2109-2143)"""
+        out = [text]
+        ev = json.loads(text)
+        for pid in range(self._np):
+            m = text
+            if kind == "start_kyoku" and isinstance(ev.get("tehais"), list):
+                d = dict(ev)
+                d["tehais"] = [h if i == pid else ["?"] * (len(h) if isinstance(h, list) else 13) for i, h in enumerate(ev["tehais"])]
+                m = json.dumps(d, sort_keys=True, separators=(",", ":"), ensure_ascii=False)
+            elif kind == "tsumo" and isinstance(ev.get("actor"), int) and ev["actor"] != pid:
+                d = dict(ev)
+                d["pai"] = "?"
+                m = json.dumps(d, sort_keys=True, separators=(",", ":"), ensure_ascii=False)
+            out.append(m)
+        return out
+
+    def apply_event(self, event):
+        """Apply one MJAI event (dict) to the tracked state without returning an observation (env.rs:880-887)."""
+        self._apply(event)
+
+    def observe_event(self, event, player_id):
+        """Apply one MJAI event and return `player_id`'s observation if that seat now has legal actions, else None
+        (env.rs:894-948)."""
+        kind = self._apply(event)
+        if kind in self._NO_DECISION or kind not in self._EVENT_TYPES:
+            return None
+        obs = self._observations([int(player_id)])[int(player_id)]
+        return obs if obs.legal_actions() else None
+
     # ---- logs -----------------------------------------------------------------------------------
     @property
     def mjai_log(self):
         if self.skip_mjai_logging:
             return []
         return [json.loads(x) for x in self._log_text(-1)]
+
+    @mjai_log.setter
+    def mjai_log(self, v):     # tests/env/helper.py assigns a list of dicts; the reference's setter takes JSON objects
+        self._ext_log = [self._masked_variants(json.dumps(e, sort_keys=True, separators=(",", ":"), ensure_ascii=False),
+                                               e.get("type", "") if isinstance(e, dict) else "") for e in v]
 
     def _masked_log(self, pid):
         if self.skip_mjai_logging:
@@ -696,6 +839,8 @@ class RiichiEnv:
 
     def _log_text(self, viewer):
         """rendered log of one viewer (-1: the all-seeing log); only the events pushed since the last call are rendered"""
+        if self._ext_log is not None:      # event-driven mode: the log is the text that was fed (apply_event keeps it)
+            return [row[viewer + 1] for row in self._ext_log]
         have = self._log_cache.setdefault(viewer, [])
         have.extend(self._v.mjai_log(0, viewer, skip_events=len(have)))
         return have
@@ -717,9 +862,9 @@ class RiichiEnv:
             legal = [self._action_cls._from_abi(acts[p * A.MAX_LEGAL + k]) for k in range(int(counts[0, p]))]
             full = logs.setdefault(p, self._masked_log(p))
             new = full[self._event_counts[p]:]
-            start_word = self._event_word_offset(self._event_counts[p])
+            first_new = self._event_counts[p]   # (its word offset in the binary log is only looked up if sequence features are asked for)
             self._event_counts[p] = len(full)  # state/mod.rs:211-218: the delta advances on every observation
-            out[p] = (Observation3P if self._np == 3 else Observation)._from_state(self, s, p, legal, new, start_word)
+            out[p] = (Observation3P if self._np == 3 else Observation)._from_state(self, s, p, legal, new, first_new)
         return out
 
     def _event_word_offset(self, k):
@@ -732,10 +877,12 @@ class RiichiEnv:
             i += max(1, (int(words[i]) >> 8) & 0xFF)
         return i
 
-    def _encode_seq(self, pid, start_word):
+    def _encode_seq(self, pid, first_new_event):
         if self.skip_mjai_logging:
             raise ValueError("sequence features need the MJAI log (skip_mjai_logging=False)")
-        return self._v.encode_seq_single(pid, start_word)
+        if self._ext_log is not None:
+            raise NotImplementedError("sequence features read the device event log; a game fed through apply_event has none")
+        return self._v.encode_seq_single(pid, self._event_word_offset(first_new_event))
 
     def _encode(self, pid, extended=False):
         """bytes of the (74, 34) — sanma (74, 27) — float32 tensor for seat `pid` (must owe an action), computed by
@@ -1108,6 +1255,7 @@ class RiichiEnv:
         o.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_v"})
         o._event_counts = list(self._event_counts)
         o._log_cache = {k: list(v) for k, v in self._log_cache.items()}
+        o._ext_log = None if self._ext_log is None else [list(r) for r in self._ext_log]
         o._v = self._v.clone()
         return o
 

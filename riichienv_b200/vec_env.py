@@ -188,6 +188,10 @@ class VecRiichiEnv:
     def set_state(self, game, state):
         check(lib().rv_vec_set_state(self.handle, int(game), C.byref(state)))
 
+    def apply_events(self, events):
+        """GameState::apply_mjai_event for every game: `events` = ctypes array (A.MjaiEvent * n), type 0 = no event"""
+        check(lib().rv_vec_apply_events(self.handle, events))
+
     def clone(self):
         """independent copy of every game (RiichiEnv.clone, env.rs:358-372)"""
         o = object.__new__(type(self))
@@ -197,11 +201,12 @@ class VecRiichiEnv:
         return o
 
     def call(self, op, game=0):
-        """env.rs:624-631 hooks: op 0 reveal_kan_dora -> indicator count; op 1 -> list of ura indicator tile ids"""
+        """env.rs:624-631 hooks: op 0 reveal_kan_dora -> indicator count; op 1 -> list of ura indicator tile ids;
+        ops 2-5 (tests.rs): _trigger_ryukyoku("exhaustive_draw") / _initialize_next_round variants -> is_done"""
         out = (C.c_uint8 * 5)()
         n = C.c_int(0)
         check(lib().rv_vec_debug_call(self.handle, int(game), int(op), out, C.byref(n)))
-        return n.value if op == 0 else list(out[: n.value])
+        return list(out[: n.value]) if op == 1 else n.value
 
     def state_device_ptr(self):
         p = C.c_void_p()

@@ -81,6 +81,10 @@ class OracleBackend(Backend):
     def agent_step(self, policy, agent_seed, game_id):
         self.lib.orc_game_agent_step(self.h, policy, agent_seed, game_id)
 
+    def call(self, op):
+        out = (C.c_uint8 * 8)()
+        return self.lib.orc_game_call(self.h, op, out)
+
     def legal(self, pid):
         out = (A.Action * A.MAX_LEGAL)()
         n = self.lib.orc_game_legal(self.h, pid, out)
@@ -138,6 +142,10 @@ class HostsimBackend(Backend):
     def agent_step(self, policy, agent_seed, game_id):
         self.lib.hs_game_agent_step(self.h, policy, agent_seed, game_id)
 
+    def call(self, op):
+        out = (C.c_uint8 * 8)()
+        return self.lib.hs_game_call(self.h, op, out)
+
     def random_step_coopdeal(self, agent_seed, game_id):
         """a random step whose round deal runs through init_round_coop (the warp-cooperative deal of the lock-step kernels)"""
         self.lib.hs_game_random_step_coopdeal(self.h, agent_seed, game_id)
@@ -194,6 +202,9 @@ class GpuBackend(Backend):
 
     def agent_step(self, policy, agent_seed, game_id):
         self.v.step_agent(policy, agent_seed, 1)
+
+    def call(self, op):
+        return self.v.call(op)
 
     def legal(self, pid):
         acts, counts = self.v.legal_actions()

@@ -41,6 +41,7 @@ def load():
     lib.hs_game_step.argtypes = [C.c_void_p, P(A.Action)]
     lib.hs_game_random_step.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.hs_game_random_step_coopdeal.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.hs_game_apply_event.argtypes = [C.c_void_p, P(A.MjaiEvent)]
     lib.hs_game_agent_step.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     lib.hs_game_random_step_deferred.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.hs_game_random_step_deferred.restype = C.c_int

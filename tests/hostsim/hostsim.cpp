@@ -300,6 +300,13 @@ void hs_game_random_step_coopdeal(void* p, uint64_t agent_seed, uint64_t game_id
     run_pending_init_coop(cx, h->g, S);
   }
 }
+void hs_game_apply_event(void* p, const rv_mjai_event* e) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  cx.log = nullptr;
+  cx.log_cap = 0;
+  if (e->type != RV_EV_NONE) apply_mjai_event(cx, h->g, *e);
+}
 void hs_game_agent_step(void* p, int policy, uint64_t agent_seed, uint64_t game_id) {
   HS* h = (HS*)p;
   Ctx cx = hs_ctx(h);
@@ -343,6 +350,14 @@ int hs_game_call(void* p, int op, uint8_t* out) {   // env.rs:624-631 test hooks
     return h->g.n_dora;
   }
   if (op == 1) return ura_indicators(h->g, out);
+  if (op == 2) {
+    trigger_ryukyoku(cx, h->g, RV_RK_EXHAUSTIVE);
+    return h->g.is_done;
+  }
+  if (op >= 3 && op <= 5) {
+    next_round(cx, h->g, op == 4, op == 5);
+    return h->g.is_done;
+  }
   return -1;
 }
 void hs_game_copy_log(void* dst, void* src) { ((HS*)dst)->log = ((HS*)src)->log; }

@@ -104,11 +104,14 @@ class CpuVec:
             i += max(1, (int(words[i]) >> 8) & 0xFF)
         return events_to_json(words[i:], viewer)
 
+    def apply_events(self, events):
+        self._f("game_apply_event")(self.h, events)
+
     def call(self, op):
         """env.rs:624-631 hooks: op 0 reveal_kan_dora -> indicator count; op 1 -> list of ura indicator tile ids"""
         out = (C.c_uint8 * 8)()
         n = self._f("game_call")(self.h, int(op), out)
-        return n if op == 0 else list(out[:n])
+        return list(out[:n]) if op == 1 else n
 
     def clone(self):
         o = type(self)(1, self.game_mode, self.rule_bits, seeds=[self.seed], log_cap_words=self.log_cap_words)

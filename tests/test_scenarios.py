@@ -437,3 +437,67 @@ def test_ext_tile_context_channels(backend):
     env.set_state(s)
     b = env.encode_ext(1)
     assert (b[194] == 0).all() and (b[195] == 0).all() and (b[196] == 1).all()                  # seat 0 "is" tile id 0
+
+
+# ---- round / game flow (state/mod.rs:1595-1688), re-expressed from the reference's Rust unit tests and tests/test_oyayame_tiebreak.py.
+# The Rust tests call _trigger_ryukyoku / _initialize_next_round directly on a GameState; ops 2-5 of the debug call do the same here.
+def _flow_env(backend, mode=2, **fields):
+    env = BACKENDS[backend](mode, 7)
+    env.reset()
+    s = env.get_state()
+    for k, v in fields.items():
+        if k == "scores":
+            for p, x in enumerate(v):
+                s.score[p] = x
+        elif k == "nagashi_off":
+            for p in range(4):
+                s.flags[p] &= ~A.F_NAGASHI_ELIGIBLE
+        else:
+            setattr(s, k, v)
+    env.set_state(s)
+    return env
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_sudden_death_hanchan_logic(backend):  # riichienv-core/src/tests.rs:172-233
+    env = _flow_env(backend, round_wind=1, kyoku_idx=3, oya=3, scores=[25000] * 4, nagashi_off=True)
+    assert env.call(2) == 0                       # exhaustive draw in South 4 with nobody at 30000: the game goes on
+    s = env.get_state()
+    assert (s.round_wind, s.kyoku_idx, s.oya, s.is_done) == (2, 0, 0, 0)     # West 1, dealer seat 0
+    for p, x in enumerate([31000, 25000, 24000, 20000]):
+        s.score[p] = x
+    for p in range(4):
+        s.flags[p] &= ~A.F_NAGASHI_ELIGIBLE
+    env.set_state(s)
+    assert env.call(2) == 1                       # somebody at 30000 in the West round: over
+    types = [x["type"] for x in ev(env)]
+    assert types[-1] == "end_game" and "ryukyoku" in types
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_tobi_ends_game(backend):  # tests.rs:375-409
+    env = _flow_env(backend, scores=[30000, 40000, 35000, -5000])
+    assert env.call(3) == 1
+    types = [x["type"] for x in ev(env)]
+    assert "end_kyoku" in types and types.index("end_kyoku") < types.index("end_game")
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_oyayame_requires_target_in_orasu(backend):  # tests.rs:411-427, tests/test_oyayame_tiebreak.py:75-87
+    env = _flow_env(backend, round_wind=1, oya=3, kyoku_idx=3, scores=[28900, 20000, 20100, 29000])
+    assert env.call(4) == 0                       # dealer top but below 30000: renchan, the game continues
+    s = env.get_state()
+    assert (s.oya, s.round_wind, s.honba) == (3, 1, 1)
+
+
+@pytest.mark.parametrize("backend", ALL)
+def test_oyayame_tiebreak_last_round(backend):  # tests/test_oyayame_tiebreak.py:44-72 on the env's own rule
+    # South 4, dealer (seat 3) tied with seat 0 at 30000: the tie goes to the lower seat, the dealer is not top -> no agari-yame
+    env = _flow_env(backend, round_wind=1, oya=3, kyoku_idx=3, scores=[30000, 20000, 20000, 30000])
+    assert env.call(4) == 0
+    # dealer sole top at 30000 -> the game ends on the dealer's win
+    env = _flow_env(backend, round_wind=1, oya=3, kyoku_idx=3, scores=[29000, 20000, 21000, 30000])
+    assert env.call(4) == 1
+    # dealer seat 0 ties seat 1 for top (ties go to the lower seat = the dealer): only the LAST dealer can stop; South 1 goes on
+    env = _flow_env(backend, round_wind=1, oya=0, kyoku_idx=0, scores=[35000, 35000, 15000, 15000])
+    assert env.call(4) == 0
