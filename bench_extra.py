@@ -130,20 +130,38 @@ def run(args, rank, world, local_rank):
     ctx.sync()
     if dist is not None:
         dist.barrier()
-    tot_ms, tot_steps, tot_obs, iters = 0.0, 0, 0, 0
+    tot_ms, tot_steps, tot_obs, iters, wall_s = 0.0, 0, 0, 0, 0.0
     for k in range(args.steps):
         ctx.sync()
+        t_host = time.perf_counter()
         ctx.timer_mark(0)
         it, n_obs = one(k)
         ctx.timer_mark(1)
         tot_ms += ctx.timer_elapsed(0, 1)
+        wall_s += time.perf_counter() - t_host        # e2e: the same public calls on the host clock (launches, syncs, row counts)
         s, _ = v.steps_total()
         tot_steps += s
         tot_obs += n_obs
         iters += it
-    ach = (tot_steps * 1024 + tot_obs * b_obs) / (tot_ms / 1000) / 1e9      # this rank's kernels
-    red = reduce_stats(RunStats(elapsed_ms=tot_ms, env_steps=float(tot_steps), games=float(tot_obs)), dist, torch, f"cuda:{local_rank}")
+    # the dominant kernel alone: tensor rows of a mid-game decision point through rv_vec_encode (count + scan + obs_encode_kernel),
+    # CUDA events on the context stream, rows >> L2
+    v.reseed(None, shard_range(9000, world, rank, G)[0])
+    v.reset()
+    v.step_random_async(0x5EED, 300)
+    ctx.sync()
+    reps = 20
+    rows = v.encode(obs=obs, index=idx, max_obs=max_obs, sync=True)
+    ctx.timer_mark(2)
+    for _ in range(reps):
+        v.encode(obs=obs, index=idx, max_obs=max_obs, sync=False)
+    ctx.timer_mark(3)
+    enc_ms = ctx.timer_elapsed(2, 3) / reps
+    enc_gbs = rows * (74 * W * 4) / (enc_ms / 1000) / 1e9
+    ach = (tot_steps * 1024 + tot_obs * b_obs) / (tot_ms / 1000) / 1e9      # this rank's whole pipeline
+    red = reduce_stats(RunStats(elapsed_ms=tot_ms, env_steps=float(tot_steps), games=float(tot_obs), e2e_s=wall_s, e2e_steps=float(tot_steps)),
+                       dist, torch, f"cuda:{local_rank}")
     tot_ms, all_steps, all_obs = red.elapsed_ms, red.env_steps, red.games      # max time over ranks, summed steps / rows
+    wall_s = red.e2e_s
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
@@ -156,9 +174,13 @@ def run(args, rank, world, local_rank):
         "config": {"workload": f"{'3p-red-half (sanma)' if args.mode >= 3 else '4p-red-half'} hanchan, {G:,} games per GPU, encode() (74x{W} f32) + mask() for every acting seat at every "
                                "env step (BASELINE.json configs[4]; games sharded over the GPUs)", "games_per_gpu": G,
                    "observations_per_env_step": all_obs / max(1, all_steps), "l2": "observation buffer 1.3 GB per iteration > L2"},
-        "e2e": {"value": val, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (iters // 64)},
-        "gpu_launches": iters * (6 if args.unfused else 4),
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "kernel": "obs_encode_kernel + step_random_kernel" if args.unfused else "observe_step_kernel", "peak_source": peak_src,
-                     "bytes_per_observation": b_obs},
+        "e2e": {"value": all_steps / wall_s, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * (iters // 64) // max(1, args.steps),
+                "note": "the same rv_vec_observe_step_random loop on the host clock (ctypes launches, a row-count read-back every 64 "
+                        "iterations); the tensors are consumed on the device, as by the reference's GPU policy workers"},
+        "gpu_launches": iters * (8 if not args.unfused else 6),
+        "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak, "traffic": None,
+                     "kernel": "obs_encode_kernel (dominant: tensor rows, timed alone through rv_vec_encode)", "peak_source": peak_src,
+                     "bytes_per_observation": b_obs, "rows_per_launch": rows, "kernel_ms": enc_ms,
+                     "kernel_share_of_step": enc_ms * iters / max(1e-9, tot_ms),
+                     "pipeline_achieved": ach, "pipeline_frac": ach / peak},
     }))

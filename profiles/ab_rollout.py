@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""A/B of the headline rollout between two builds of the library in ONE process on ONE box (fresh boxes differ by a few %):
+usage: ab_rollout.py lib_a.so lib_b.so [games] — alternates the builds, 5 rollouts each, prints G env steps/s per rollout."""
+import ctypes as C
+import sys
+
+import torch  # noqa: F401  (brings the CUDA runtime libraries into the process)
+
+
+def load(path):
+    import os
+
+    L = C.CDLL(os.path.abspath(path))
+    vp = C.c_void_p
+    L.rv_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.rv_vec_create.argtypes = [vp, C.c_int64, C.c_int, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32, C.POINTER(vp)]
+    L.rv_vec_reset.argtypes = [vp] + [vp] * 6
+    L.rv_vec_reseed.argtypes = [vp, vp, C.c_uint64]
+    L.rv_vec_step_random.argtypes = [vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+    L.rv_timer_mark.argtypes = [vp, C.c_int]
+    L.rv_timer_elapsed.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.rv_ctx_sync.argtypes = [vp]
+    ctx, v = vp(), vp()
+    assert L.rv_ctx_create(0, C.byref(ctx)) == 0
+    return L, ctx
+
+
+def rollout(L, ctx, v, k):
+    L.rv_vec_reseed(v, None, 1000000 * k)
+    L.rv_vec_reset(v, None, None, None, None, None, None)
+    L.rv_ctx_sync(ctx)
+    n = C.c_uint64(0)
+    L.rv_timer_mark(ctx, 0)
+    L.rv_vec_step_random(v, 0x5EED, 1 << 30, C.byref(n))
+    L.rv_timer_mark(ctx, 1)
+    ms = C.c_float(0)
+    L.rv_timer_elapsed(ctx, 0, 1, C.byref(ms))
+    return n.value / ms.value / 1e6
+
+
+games = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
+libs = []
+for path in sys.argv[1:3]:
+    L, ctx = load(path)
+    v = C.c_void_p()
+    assert L.rv_vec_create(ctx, games, 2, 0xC0, None, 0, 0, C.byref(v)) == 0
+    libs.append((path, L, ctx, v))
+res = {p: [] for p, *_ in libs}
+for k in range(7):
+    for path, L, ctx, v in libs:
+        r = rollout(L, ctx, v, k)
+        if k >= 2:
+            res[path].append(r)
+for p, r in res.items():
+    print(f"{p}: {' '.join(f'{x:.3f}' for x in r)}  median {sorted(r)[len(r) // 2]:.3f} G env steps/s")

@@ -82,6 +82,20 @@ __device__ __forceinline__ uint64_t cnt_present(const Cnt& c) {
 // Base-5 table index of a suit histogram.  Physical hands hold at most four copies of a kind; a record injected through
 // the API may not (the reference's own tests park thirteen copies of one tile in seats they do not care about), so the
 // index is clamped: such a seat gets meaningless answers, never an out-of-bounds table read.
+// 34-bit mask of tile kinds held at least twice
+__device__ __forceinline__ uint64_t cnt_ge2(const Cnt& c) {
+  uint64_t m = 0;
+  #pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint64_t x = c.s[k];
+    x = ((x >> 1) | (x >> 2)) & 0x1111111111111111ull;   // bit 4i set if nibble i >= 2
+    uint32_t r = 0;
+    #pragma unroll
+    for (int i = 0; i < 9; i++) r |= (uint32_t)((x >> (4 * i)) & 1) << i;
+    m |= (uint64_t)r << (9 * k);
+  }
+  return m;
+}
 // lowest tile kind >= i with a nonzero count, 34 if there is none (one find-first-set per suit word instead of a scan)
 __device__ __forceinline__ int cnt_next(const Cnt& c, int i) {
   if (i >= 34) return 34;
@@ -697,13 +711,32 @@ __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand,
     ncand = 0;
   };
   Cnt work = hand;
-  for (int head = 0; head < 34; head++) {
-    if (cnt_get(work, head) < 2) continue;
+  // heads in ascending order, but each lane walks only ITS candidate heads (kinds held at least twice): in a loop over all
+  // 34 kinds a warp spent every iteration with the few lanes that happen to hold that pair (ncu: 3 of 32 lanes active)
+  uint64_t heads = cnt_ge2(hand);
+  {
+    // first the quick reject for every candidate (cheap, all lanes busy): without the pair every suit must be mentsu-only;
+    // only the suit of the pair changes, the other three entries are those of the full hand
+    SuitInfo full;
+    load_info(T, hand, full);
+    uint64_t keep = 0, cand_heads = heads;
+    while (cand_heads) {
+      const int head = __ffsll((long long)cand_heads) - 1;
+      cand_heads &= cand_heads - 1;
+      const int su = head / 9;
+      cnt_sub(work, head, 2);
+      const uint32_t e = load_info_suit(T, cnt_suit(work, su), su);
+      cnt_add(work, head, 2);
+      const uint32_t e0 = su == 0 ? e : full.e[0], e1 = su == 1 ? e : full.e[1], e2 = su == 2 ? e : full.e[2], e3 = su == 3 ? e : full.e[3];
+      if ((e0 & e1 & e2 & e3 & 1) != 0) keep |= 1ull << head;
+    }
+    heads = keep;
+  }
+  while (heads) {
+    const int head = __ffsll((long long)heads) - 1;
+    heads &= heads - 1;
     cnt_sub(work, head, 2);
-    // quick reject: every suit of the remainder must be mentsu-only
-    SuitInfo si;
-    load_info(T, work, si);
-    if ((si.e[0] & si.e[1] & si.e[2] & si.e[3] & 1) != 0) {
+    {
       Division d;
       d.head = (int8_t)head;
       d.nb = 0;

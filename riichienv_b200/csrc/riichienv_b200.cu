@@ -787,6 +787,8 @@ __global__ void q_init_kernel(const G* states, int64_t n, uint32_t* budget, uint
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&q.ctl[Q_LIVE], (uint32_t)__popc(m));
   q_push(q, cls, (int32_t)i);
 }
+// Fault injection for the watchdog test (RV_FAULT_INJECT=lost_game): one more live game than the queues hold
+__global__ void q_fault_kernel(Queues q) { atomicAdd(&q.ctl[Q_LIVE], 1u); }
 // lane 0 only: take up to PHB consumer tickets of class c if the queue looks non-empty; returns the count and the first ticket
 __device__ __forceinline__ int q_claim(const Queues& q, int c, uint32_t& h, unsigned long long* dbg = nullptr, int cap = PHB) {
   uint32_t hh = ld_volatile_u32(&q.ctl[Q_HEAD + 32 * c]), tt = ld_volatile_u32(&q.ctl[Q_TAIL + 32 * c]);
@@ -2007,6 +2009,10 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
   CK(cudaMemsetAsync(v->d_q_ctl, 0, sizeof(uint32_t) * Q_CTL_WORDS, c->stream));
   CK(cudaMemsetAsync(v->d_q_slots, 0xFF, sizeof(int32_t) * N_QUEUES * (size_t)v->q_cap, c->stream));   // every slot empty (abandoned marks of the last call included)
   q_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, q);
+  {
+    const char* fault = getenv("RV_FAULT_INJECT");     // read per call: the watchdog test arms it for one rollout
+    if (fault && strcmp(fault, "lost_game") == 0) q_fault_kernel<<<1, 1, 0, c->stream>>>(q);
+  }
   int64_t crew = (int64_t)c->sm_count * warps_per_sm, need = (n + PHB - 1) / PHB;
   const int grid = (int)(crew < need ? crew : need);
   const uint32_t eg_live = getenv("RV_ENDGAME_OFF") ? 0u : (uint32_t)((int64_t)grid * eg_quarters / 4);
@@ -2046,7 +2052,10 @@ int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done) {
   CK(cudaMemcpyAsync(h, v->d_steps, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   if (v->d_q_ctl) CK(cudaMemcpyAsync(&sched_err, v->d_q_ctl + Q_ERR, sizeof sched_err, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (sched_err) return fail(RV_ERR_CUDA, "rollout scheduler watchdog: live games but no queued work");
+  if (sched_err) {   // reported once: the flag is cleared so that the vector stays usable
+    CK(cudaMemsetAsync(v->d_q_ctl + Q_ERR, 0, sizeof(uint32_t), c->stream));
+    return fail(RV_ERR_CUDA, "rollout scheduler watchdog: live games but no queued work");
+  }
 #ifdef RV_QPROF
   {
     unsigned long long p[32];

@@ -288,6 +288,35 @@ def test_multi_device_results_do_not_depend_on_device_count(devices):
     assert sum(st["rank_hist"][0]) == n and st["rank_hist"][2][0] == int((ranks[:, 2] == 1).sum())
 
 
+def test_scheduler_watchdog_reports_instead_of_hanging():
+    """The persistent rollout ends when its live-game counter reaches zero.  With one more live game than the queues hold
+    (fault injection) the crew can never finish: the watchdog must flag the launch — rv_vec_steps_total returns RV_ERR_CUDA —
+    within seconds instead of hanging the GPU, and the next rollout on the same vector must be clean."""
+    import os
+    import time
+
+    from riichienv_b200._lib import RvError
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    v = VecRiichiEnv(2048, 2, A.RULE_DEFAULT_TENHOU, seed_base=4242)
+    v.reset()
+    os.environ["RV_FAULT_INJECT"] = "lost_game"
+    try:
+        t0 = time.time()
+        with pytest.raises(RvError, match="watchdog"):
+            v.step_random(3, 100000)
+        assert time.time() - t0 < 60
+    finally:
+        del os.environ["RV_FAULT_INJECT"]
+    done, _, _ = v.results()
+    assert done.all()                       # the games themselves were played out; only the termination was sabotaged
+    v.reset()
+    total = v.step_random(3, 100000)
+    done, scores, _ = v.results()
+    assert done.all() and total > 2048 * 500
+    v.close()
+
+
 def test_partial_rollout_and_resume(orc):
     """max_steps < game length: state must carry over between launches exactly."""
     from riichienv_b200.vec_env import VecRiichiEnv
