@@ -59,6 +59,8 @@ def load():
     lib.orc_game_events.restype = C.c_uint32
     lib.orc_game_events.argtypes = [C.c_void_p, P(C.c_uint32), C.c_uint32]
     lib.orc_game_encode.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_uint8)]
+    lib.orc_games_encode_batch.restype = C.c_int64
+    lib.orc_games_encode_batch.argtypes = [P(C.c_void_p), C.c_int64, P(C.c_float), P(C.c_uint8), P(C.c_int32), C.c_int64]
     lib.orc_game_encode_ext.argtypes = [C.c_void_p, C.c_int, P(C.c_float)]
     lib.orc_game_encode_kawa.argtypes = [C.c_void_p, P(C.c_float)]
     lib.orc_ukeire.argtypes = [P(C.c_int), C.c_int, P(C.c_int), C.c_int, P(C.c_int)]

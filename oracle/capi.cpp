@@ -486,6 +486,27 @@ extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask) {
   if (obs) g->np == 3 ? encode_obs_3p(*g, pid, obs) : encode_obs(*g, pid, obs);   // 74x34 (4P) / 74x27 (3P) floats
   if (mask) encode_mask(*g, pid, mask);
 }
+extern "C" void orc_game_encode(void* h, int pid, float* obs, uint8_t* mask);
+// encode() + mask() rows of every seat that owes an action, n games, ascending (game, seat) order — the row order of
+// rv_vec_encode.  obs [max_rows][74][W], mask [max_rows][IDS], index [max_rows] = game * 4 + seat.  Returns the row count.
+extern "C" int64_t orc_games_encode_batch(void** hs, int64_t n, float* obs, uint8_t* mask, int32_t* index, int64_t max_rows) {
+  int64_t row = 0;
+  for (int64_t i = 0; i < n; i++) {
+    GameState* g = (GameState*)hs[i];
+    if (g->is_done) continue;
+    const int W = g->np == 3 ? 27 : 34, IDS = g->np == 3 ? 60 : 82;
+    for (int p = 0; p < g->np; p++) {
+      bool owes = (g->phase == RV_WAIT_ACT && g->current_player == p) ||
+                  (g->phase == RV_WAIT_RESPONSE &&
+                   std::find(g->active_players.begin(), g->active_players.end(), (uint8_t)p) != g->active_players.end());
+      if (!owes || row >= max_rows) continue;
+      orc_game_encode(g, p, obs + row * 74 * W, mask + row * IDS);
+      index[row] = (int32_t)(i * 4 + p);
+      row++;
+    }
+  }
+  return row;
+}
 // Observation::encode_extended: 215x34 floats (4P only)
 extern "C" void orc_game_encode_ext(void* h, int pid, float* obs) {
   GameState* g = (GameState*)h;

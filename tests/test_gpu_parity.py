@@ -181,6 +181,16 @@ def test_random_games_vs_oracle(orc, mode, rule, n):
     assert g[1].all()   # incl. the rare stalled 3P games, which the rollout retires (overflow bit 1)
 
 
+def test_sanma_config_size_65536_games(orc):
+    """BASELINE configs[3] at its stated size: 65,536 sanma hanchan (3p-red-half), done / scores / ranks / counters / event hash."""
+    n = 65536
+    g, o = run_both(orc, n, 5, A.RULE_DEFAULT_TENHOU, seed_base=6_000_000, agent_seed=0x3A3A)
+    assert g[0] == o[0], "total env steps"
+    for name, a, b in zip(["done", "scores", "ranks", "step_count", "kyoku_count", "ev_count", "ev_hash"], g[1:], o[1:]):
+        assert np.array_equal(a, b), f"{name} differs in {int((a != b).sum())} entries"
+    assert g[1].all()
+
+
 def test_parity_gate_100k_games(orc):
     """The parity gate that accompanies the headline number (SURVEY.md section 8 d): >= 10^5 hanchan, final done / scores /
     ranks / step count / round count / event count / 64-bit event-stream hash equal between the CUDA rollout and the oracle."""
@@ -575,6 +585,49 @@ def test_observation_encode_vs_oracle(orc, mode):
 
 
 @pytest.mark.parametrize("mode", [2, 5])
+@pytest.mark.parametrize("mode", [2, 5])
+def test_observation_encode_100k_rows(orc, mode):
+    """SURVEY §8 d: encode() bytes equal on >= 10^5 observations.  2,048 hanchan, every acting seat at 64 decision points
+    spread over the rollout (rv_vec_encode vs the oracle's encode / mask restatement, whole buffers compared at once)."""
+    import torch
+
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n, seed_base, agent = 2048, 9100, 71
+    W, IDS = (27, 60) if mode >= 3 else (34, 82)
+    v = VecRiichiEnv(n, mode, A.RULE_DEFAULT_TENHOU, seed_base=seed_base)
+    v.reset()
+    hs = (C.c_void_p * n)(*[orc.orc_game_new(mode, seed_base + g, 0, A.RULE_DEFAULT_TENHOU, 0) for g in range(n)])
+    for h in hs:
+        orc.orc_game_reset(h, 0, 0, 0, 0, None, None)
+    cap = n * 3
+    obs = torch.empty((cap, 74, W), dtype=torch.float32, device="cuda")
+    mask = torch.empty((cap, IDS), dtype=torch.uint8, device="cuda")
+    idx = torch.empty((cap,), dtype=torch.int32, device="cuda")
+    o_obs, o_mask, o_idx = np.zeros((cap, 74, W), np.float32), np.zeros((cap, IDS), np.uint8), np.zeros(cap, np.int32)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    total = 0
+    for point in range(64):
+        rows = v.encode(obs=obs, mask=mask, index=idx)
+        o_rows = orc.orc_games_encode_batch(hs, n, p(o_obs, C.c_float), p(o_mask, C.c_uint8), p(o_idx, C.c_int32), cap)
+        assert rows == o_rows, f"point {point}: {rows} rows vs {o_rows}"
+        if rows == 0:
+            break
+        assert np.array_equal(idx[:rows].cpu().numpy(), o_idx[:rows])
+        g_obs = obs[:rows].cpu().numpy()
+        bad = np.nonzero((g_obs.view(np.uint32) != o_obs[:rows].view(np.uint32)).any(axis=(1, 2)))[0]
+        assert bad.size == 0, f"point {point}: {bad.size} tensor rows differ, first row {int(bad[0])} (game*4+seat {int(o_idx[bad[0]])})"
+        assert np.array_equal(mask[:rows].cpu().numpy(), o_mask[:rows]), f"point {point}: mask rows differ"
+        total += rows
+        steps = 1 if point < 8 else 19             # the first turns one by one, then strides through the hanchan
+        v.step_random(agent, steps)
+        for _ in range(steps):
+            orc.orc_games_random_step_batch(hs, n, agent, seed_base)
+    assert total >= 100_000, total
+    for h in hs:
+        orc.orc_game_free(h)
+
+
 def test_observation_encode_extended_vs_oracle(orc, mode):
     """rv_vec_encode_ext: Observation::encode_extended (215x34; sanma 215x27) + mask of every acting seat of 192 hanchan at many
     points of the rollout, bytes equal to the oracle's restatement (observation/encode.rs:12-584, observation_3p/encode.rs:22-620);
