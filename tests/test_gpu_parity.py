@@ -585,7 +585,6 @@ def test_observation_encode_vs_oracle(orc, mode):
 
 
 @pytest.mark.parametrize("mode", [2, 5])
-@pytest.mark.parametrize("mode", [2, 5])
 def test_observation_encode_100k_rows(orc, mode):
     """SURVEY §8 d: encode() bytes equal on >= 10^5 observations.  2,048 hanchan, every acting seat at 64 decision points
     spread over the rollout (rv_vec_encode vs the oracle's encode / mask restatement, whole buffers compared at once)."""
@@ -628,6 +627,7 @@ def test_observation_encode_100k_rows(orc, mode):
         orc.orc_game_free(h)
 
 
+@pytest.mark.parametrize("mode", [2, 5])
 def test_observation_encode_extended_vs_oracle(orc, mode):
     """rv_vec_encode_ext: Observation::encode_extended (215x34; sanma 215x27) + mask of every acting seat of 192 hanchan at many
     points of the rollout, bytes equal to the oracle's restatement (observation/encode.rs:12-584, observation_3p/encode.rs:22-620);
