@@ -143,7 +143,8 @@ typedef struct rv_game_state {
   uint8_t n_claims[RV_NP];        /* lengths of claims[] below */
   uint8_t pending_tail[2];        /* {tile, tsumogiri} of a discard whose follow-up (_resolve_discard) is deferred inside a rollout
                                      kernel; pending_tail[0]==RV_NONE outside kernels (always, as seen through this API) */
-  uint8_t hot_reserved[10];
+  uint8_t is_after_kan;           /* state/mod.rs:87 — replay only (apply_log_action): the next DealTile is a rinshan draw */
+  uint8_t hot_reserved[9];
 
   /* ---- cold part (offset RV_HOT_BYTES): large arrays touched a byte or a few words at a time ---- */
   uint8_t wall[136];
@@ -254,7 +255,7 @@ void* rv_ctx_stream(rv_ctx* ctx);
 int rv_timer_mark(rv_ctx* ctx, int idx /*0..7*/);
 int rv_timer_elapsed(rv_ctx* ctx, int idx_a, int idx_b, float* ms);
 /* sizeof() of the public structs as compiled: 0 rv_game_state, 1 rv_hand_query, 2 rv_hand_result, 3 rv_action,
- * 4 rv_mjai_event, 5 rv_run_stats */
+ * 4 rv_mjai_event, 5 rv_run_stats, 6 rv_log_action, 7 rv_log_kyoku */
 int rv_sizeof(int which);
 
 /* Batched hand evaluation with HOST buffers (copies inside the call). */
@@ -337,7 +338,9 @@ int rv_vec_clone(rv_vec* v, rv_vec** out);
  * these two internals to its tests (tests/env/test_paishan.py); they run the device routines the step path uses.
  * Ops 2-5 are what the reference's Rust unit tests call directly on a GameState (riichienv-core/src/tests.rs:172-262,
  * 375-428): 2 = _trigger_ryukyoku("exhaustive_draw"); 3 / 4 / 5 = _initialize_next_round(false,false) / (true,false) /
- * (false,true); *n_out = is_done afterwards.                                                                     */
+ * (false,true); *n_out = is_done afterwards.  Op 6 is the replay iterator's `_get_claim_actions_for_player` for every seat
+ * against the game's last discard (replay/mod.rs:130-181): claim lists, active seats and phase are left in the record
+ * (the caller reads them with rv_vec_get_state and puts the record back); *n_out = number of seats with a claim.        */
 int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out);
 /* Device pointer to the state records (for zero-copy consumers). */
 int rv_vec_state_device_ptr(rv_vec* v, void** d_states);
@@ -427,6 +430,77 @@ typedef struct rv_mjai_event {
  * events[n], type RV_EV_NONE = leave that game alone.  A start_game event also resets the game's logs (env.rs:56-72).
  * The event is NOT appended to the device event log: the caller keeps the text it fed (RiichiEnv.apply_event does).     */
 int rv_vec_apply_events(rv_vec* v, const rv_mjai_event* events);
+
+/* ---- replay ingestion: MJAI logs -> kyoku records + log actions -> batched state tracking ----------------
+ * Replaces MjaiReplay::from_jsonl / KyokuBuilder (riichienv-core/src/replay/mjai_replay.rs:184-633), the replay `Action`
+ * enum (replay/mod.rs:35-96), the state set-up of LogKyoku::steps (replay/mod.rs:1094-1292) and GameState::apply_log_action
+ * (state/event_handler.rs:332-894; sanma state_3p/event_handler.rs:365-808).  One game record follows one kyoku: a batch of
+ * N kyoku is replayed in lock-step, one log action per record per call, and the decision points in between are read with
+ * the ordinary observation calls (rv_vec_legal_actions, rv_vec_encode, ...).                                                */
+enum rv_log_action_type {
+  RV_LA_NONE = 0,            /* no action for this record / Action::Other */
+  RV_LA_DISCARD = 1,         /* DiscardTile  {seat, tile, flags bit0 is_liqi, bit1 is_wliqi} */
+  RV_LA_DEAL = 2,            /* DealTile     {seat, tile} */
+  RV_LA_CHI_PENG_GANG = 3,   /* ChiPengGang  {seat, meld_type, tiles[n_tiles], froms[n_tiles]}: tiles[0] = the called tile */
+  RV_LA_ANGANG_ADDGANG = 4,  /* AnGangAddGang{seat, meld_type (RV_MELD_ANKAN | RV_MELD_KAKAN), tiles[n_tiles]} */
+  RV_LA_DORA = 5,            /* Dora         {tile = dora_marker} */
+  RV_LA_HULE = 6,            /* Hule         {hules[n_hule]} */
+  RV_LA_NOTILE = 7,          /* NoTile (exhaustive draw) */
+  RV_LA_BABEI = 8,           /* BaBei        {seat, flags bit0 moqie} (sanma Kita) */
+  RV_LA_LIUJU = 9            /* LiuJu        {seat, tile = lj_type} (abortive draw) */
+};
+typedef struct rv_hule {       /* HuleData, replay/mod.rs:82-96 */
+  uint8_t seat, hu_tile, zimo, yiman;
+  uint8_t n_li_doras;          /* 0xFF = li_doras is None */
+  uint8_t li_doras[5];
+  uint8_t _pad[2];
+  uint32_t count, fu;          /* han (or yakuman count), fu */
+  uint32_t point_rong, point_zimo_qin, point_zimo_xian;
+  uint64_t fans;               /* bit y = yaku id y is in `fans` */
+} rv_hule;
+typedef struct rv_log_action {
+  uint8_t type;                /* rv_log_action_type */
+  uint8_t seat, tile, flags;
+  uint8_t meld_type, n_tiles;
+  uint8_t tiles[4], froms[4];
+  uint8_t n_hule;
+  uint8_t _pad;
+  rv_hule hules[3];
+} rv_log_action;
+#define RV_LOG_MAX_DORAS 8
+typedef struct rv_log_kyoku {  /* LogKyoku, replay/mod.rs:1010-1029 (+ what LogKyoku::steps derives before the first action) */
+  uint8_t np;                  /* scores.len(): 4, or 3 for sanma */
+  uint8_t chang, ju, ben, liqibang, left_tile_count;
+  uint8_t n_doras, n_ura_doras;
+  uint8_t doras[RV_LOG_MAX_DORAS], ura_doras[RV_LOG_MAX_DORAS];
+  uint8_t hand_len[RV_NP];
+  uint8_t hands[RV_NP][14];
+  uint8_t wliqi[RV_NP];
+  uint8_t oya;                 /* steps(): ju % np, or the seat dealt 14 tiles (replay/mod.rs:1125-1132) */
+  uint8_t oya_drawn_tile;      /* steps(): drawn tile of a 14-tile dealer read off the first action, RV_NONE for 13-tile deals */
+  uint8_t has_game_end_scores;
+  uint8_t _pad[3];
+  uint32_t rule_bits;
+  int32_t n_actions;
+  int32_t scores[RV_NP], end_scores[RV_NP], game_end_scores[RV_NP];
+} rv_log_kyoku;
+typedef struct rv_replay rv_replay; /* opaque: the rounds of one parsed log (host memory only) */
+/* MjaiReplay::from_jsonl (mjai_replay.rs:276-370): JSON lines, gzip detected by its magic bytes.  rule_bits: RV_RULE_* preset
+ * stored with every kyoku.  RV_ERR_INVALID with rv_last_error() = "Failed to open file…" / "Parse error…" as the reference raises. */
+int rv_replay_from_jsonl(const char* path, uint32_t rule_bits, rv_replay** out);
+/* the same parser over text already in memory (len bytes of JSON lines, not compressed) */
+int rv_replay_from_text(const char* text, size_t len, uint32_t rule_bits, rv_replay** out);
+int rv_replay_free(rv_replay* r);
+int rv_replay_num_rounds(const rv_replay* r);                                  /* MjaiReplay::num_rounds */
+int rv_replay_kyoku(const rv_replay* r, int round, rv_log_kyoku* out);
+/* copies min(cap, n_actions) actions of the round; *n_out = n_actions */
+int rv_replay_actions(const rv_replay* r, int round, rv_log_action* out, int cap, int* n_out);
+/* LogKyoku::steps' state set-up for every game of the vector: kyokus[n] (HOST).  Each game is re-initialised as
+ * `_initialize_round(oya, chang, ben, liqibang, None, scores)` does and then patched with the logged hands, dora markers and the
+ * dealer's draw.  The vector's game mode must have kyoku.np seats.                                                          */
+int rv_vec_replay_begin(rv_vec* v, const rv_log_kyoku* kyokus);
+/* GameState::apply_log_action for every game: actions[n] (HOST), type RV_LA_NONE = leave that game alone. */
+int rv_vec_apply_log_actions(rv_vec* v, const rv_log_action* actions);
 
 /* ---- several GPUs behind one handle (SURVEY.md §8 e) -------------------------------------------------------------
  * Replaces what the reference does with one Python list of RiichiEnv per Ray actor (riichienv-ml/.../_ppo_worker.py:13,39).

@@ -51,6 +51,8 @@ def load():
     lib.orc_games_legal_batch.argtypes = [P(C.c_void_p), C.c_int64, P(A.Action), P(C.c_uint8)]
     lib.orc_games_random_step_batch.argtypes = [P(C.c_void_p), C.c_int64, C.c_uint64, C.c_uint64]
     lib.orc_game_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
+    lib.orc_game_apply_log_action.argtypes = [C.c_void_p, P(A.LogAction)]
+    lib.orc_game_replay_begin.argtypes = [C.c_void_p, P(A.LogKyoku)]
     lib.orc_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.orc_game_call.argtypes = [C.c_void_p, C.c_int, P(C.c_uint8)]
     lib.orc_game_copy_log.argtypes = [C.c_void_p, C.c_void_p]

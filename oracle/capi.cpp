@@ -113,6 +113,7 @@ static void load_snapshot(GameState& g, const rv_game_state& s) {
   g.needs_tsumo = s.needs_tsumo;
   g.is_first_turn = s.is_first_turn;
   g.is_rinshan_flag = s.is_rinshan_flag;
+  g.is_after_kan = s.is_after_kan;
   g.riichi_pending_acceptance = s.riichi_pending_acceptance == 0xFF ? -1 : s.riichi_pending_acceptance;
   g.drawn_tile = s.drawn_tile == 0xFF ? -1 : s.drawn_tile;
   g.last_discard_pid = s.last_discard_pid == 0xFF ? -1 : s.last_discard_pid;
@@ -352,6 +353,10 @@ int orc_game_call(void* h, int op, uint8_t* out) {
     g->_trigger_ryukyoku(RV_RK_EXHAUSTIVE);
     return g->is_done ? 1 : 0;
   }
+  if (op == 6) {        // replay: claim lists of every seat against the last discard
+    claims_for_last_discard(*g);
+    return (int)g->active_players.size();
+  }
   if (op >= 3 && op <= 5) {   // tests.rs:375-428
     g->_initialize_next_round(op == 4, op == 5);
     return g->is_done ? 1 : 0;
@@ -477,6 +482,16 @@ int64_t orc_run_agent(int policy, int mode, uint32_t rule, uint64_t seed_base, i
                    hash, nullptr, hist);
 }
 void orc_game_apply_event(void* h, const rv_mjai_event* e) { apply_mjai_event(*(GameState*)h, *e); }
+// replay ingestion (test oracle of rv_vec_replay_begin / rv_vec_apply_log_actions)
+void orc_game_apply_log_action(void* h, const rv_log_action* a) {
+  if (a->type != RV_LA_NONE) apply_log_action(*(GameState*)h, *a);
+}
+void orc_game_replay_begin(void* h, const rv_log_kyoku* k) {
+  GameState* g = (GameState*)h;
+  int32_t sc[4] = {k->scores[0], k->scores[1], k->scores[2], k->scores[3]};
+  g->reset((uint8_t)(k->oya < g->np ? k->oya : 0), (uint8_t)(k->chang < 4 ? k->chang : 0), k->ben, k->liqibang, nullptr, sc);
+  replay_begin_patch(*g, *k);
+}
 int orc_game_agent_step(void* h, int policy, uint64_t agent_seed, uint64_t game_id) {
   return agent_step(*(GameState*)h, policy, agent_seed, game_id) ? 1 : 0;
 }

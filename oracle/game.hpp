@@ -95,6 +95,7 @@ struct GameState {
   Action pending_kan_act;
   uint8_t oya = 0, honba = 0, kyoku_idx = 0, round_wind = 0;
   bool is_rinshan_flag = false, is_first_turn = true;
+  bool is_after_kan = false;   // state/mod.rs:87 (replay only)
   int riichi_pending_acceptance = -1;
   int drawn_tile = -1;
   uint8_t game_mode = 0;
@@ -1648,7 +1649,9 @@ struct GameState {
     s.rinshan_draw_count = rinshan_draw_count;
     s.pending_kan_dora_count = pending_kan_dora_count;
     s.drawable_count = drawable_count;
-    s.n_dora = (uint8_t)dora_indicators.size();
+    s.n_dora = (uint8_t)std::min<size_t>(dora_indicators.size(), 5);   // the record holds five; a replay can push more (overflow bit 0)
+    if (dora_indicators.size() > 5) s.overflow |= 1;
+    s.is_after_kan = is_after_kan;
     memset(s.dora_ind, 0xFF, 5);
     for (size_t i = 0; i < dora_indicators.size() && i < 5; i++) s.dora_ind[i] = dora_indicators[i];
     s.phase = phase;
@@ -2042,6 +2045,400 @@ inline void apply_mjai_event(GameState& g, const rv_mjai_event& e) {
     default:
       break;
   }
+}
+
+// ---- replay ingestion: GameState::apply_log_action (state/event_handler.rs:332-894; sanma state_3p/event_handler.rs:365-808) ----
+// `a` is one replay `Action` (replay/mod.rs:35-80) in the fixed layout of include/riichienv_b200.h (rv_log_action).
+inline void apply_log_action(GameState& g, const rv_log_action& a) {
+  const int np = g.np;
+  const bool sanma = g.sanma;
+  const int seat = a.seat < np ? a.seat : 0;
+  auto tid = [](uint8_t t) -> uint8_t { return t < 136 ? t : 0; };
+  auto remove_first = [](std::vector<uint8_t>& v, uint8_t t) {
+    for (size_t i = 0; i < v.size(); i++)
+      if (v[i] == t) {
+        v.erase(v.begin() + i);
+        return;
+      }
+  };
+  auto accept_pending = [&]() {                               // `if let Some(rp) = self.riichi_pending_acceptance.take()`
+    if (g.riichi_pending_acceptance >= 0) {
+      g.players[g.riichi_pending_acceptance].score -= 1000;
+      g.riichi_sticks += 1;
+      g.riichi_pending_acceptance = -1;
+    }
+  };
+  PlayerState& P = g.players[seat];
+  switch (a.type) {
+    case RV_LA_DISCARD: {                                     // event_handler.rs:334-416 / 3P 368-414
+      const uint8_t t = tid(a.tile);
+      const bool is_liqi = a.flags & 1, is_wliqi = a.flags & 2;
+      const bool tsumogiri = g.drawn_tile >= 0 && g.drawn_tile == t;
+      remove_first(P.hand, t);
+      std::sort(P.hand.begin(), P.hand.end());
+      P.discards.push_back(t);
+      P.discard_from_hand.push_back(!tsumogiri);
+      P.discard_is_riichi.push_back(is_liqi || is_wliqi);
+      g.last_discard_pid = seat;
+      g.last_discard_tile = t;
+      g.drawn_tile = -1;
+      P.missed_agari_doujun = false;
+      if (!sanma) {
+        P.nagashi_eligible = P.nagashi_eligible && is_terminal_tile(t);
+        if (is_liqi || is_wliqi) {
+          if (!P.riichi_declared) {
+            P.riichi_declared = true;
+            if (is_wliqi) P.double_riichi_declared = true;
+            g.riichi_pending_acceptance = seat;
+          }
+          P.riichi_declaration_index = (int)P.discards.size() - 1;
+        }
+      } else {
+        P.riichi_declared = P.riichi_declared || is_liqi || is_wliqi;
+        if (is_wliqi) P.double_riichi_declared = true;
+        if (is_liqi || is_wliqi) {
+          P.riichi_declaration_index = (int)P.discards.size() - 1;
+          g.riichi_pending_acceptance = seat;
+        }
+        P.nagashi_eligible = P.nagashi_eligible && is_terminal_tile(t);
+      }
+      g.current_player = (uint8_t)((seat + 1) % np);
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {g.current_player};
+      g.needs_tsumo = true;
+      g.is_first_turn = false;
+      g.is_after_kan = false;
+      break;
+    }
+    case RV_LA_DEAL: {                                        // 417-436
+      const uint8_t t = tid(a.tile);
+      accept_pending();
+      P.hand.push_back(t);
+      g.drawn_tile = t;
+      g.current_player = (uint8_t)seat;
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {g.current_player};
+      g.is_rinshan_flag = g.is_after_kan && seat == g.current_player;
+      g.needs_tsumo = false;
+      g.is_after_kan = false;
+      std::sort(P.hand.begin(), P.hand.end());
+      if (!g.wall_tiles.empty()) {
+        g.wall_tiles.pop_back();
+        g.drawable_count = g.drawable_count > 0 ? g.drawable_count - 1 : 0;
+      }
+      break;
+    }
+    case RV_LA_CHI_PENG_GANG: {                               // 437-567
+      accept_pending();
+      if (g.last_discard_pid >= 0) g.players[g.last_discard_pid].nagashi_eligible = false;
+      const int n = a.n_tiles < 4 ? a.n_tiles : 4;
+      for (int i = 0; i < n; i++)
+        if (a.froms[i] == seat) remove_first(P.hand, tid(a.tiles[i]));
+      std::sort(P.hand.begin(), P.hand.end());
+      int from_who = -1, ct = -1;
+      for (int i = 0; i < n; i++)
+        if (a.froms[i] != seat) {
+          from_who = a.froms[i];
+          ct = tid(a.tiles[i]);
+          break;
+        }
+      const uint8_t discarder = (uint8_t)(from_who < 0 ? 0 : from_who);
+      Meld m;
+      m.meld_type = (MeldType)a.meld_type;
+      for (int i = 0; i < n; i++) m.tiles.push_back(tid(a.tiles[i]));
+      m.opened = true;
+      m.from_who = (int8_t)from_who;
+      m.called_tile = (int16_t)ct;
+      P.melds.push_back(m);
+      if ((m.meld_type == Pon || m.meld_type == Daiminkan) && ct >= 0) {
+        const int tv = ct / 4;
+        auto count = [&](int lo, int hi) {
+          int c = 0;
+          for (auto& x : P.melds) {
+            const int t = x.tiles[0] / 4;
+            if (t >= lo && t <= hi && x.meld_type != Chi) c++;
+          }
+          return c;
+        };
+        if (tv >= 31 && tv <= 33) {
+          if (count(31, 33) == 3) P.pao37 = discarder;
+        } else if (tv >= 27 && tv <= 30) {
+          if (count(27, 30) == 4) P.pao50 = discarder;
+        }
+      }
+      g.current_player = (uint8_t)seat;
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {g.current_player};
+      const bool gang = m.meld_type == Daiminkan;
+      g.needs_tsumo = gang;
+      g.is_first_turn = false;
+      g.is_after_kan = gang;
+      break;
+    }
+    case RV_LA_ANGANG_ADDGANG: {                              // 568-663
+      const uint8_t t0 = tid(a.n_tiles ? a.tiles[0] : 0);
+      if (a.meld_type == RV_MELD_ANKAN) {
+        const uint8_t tv = t0 / 4;
+        for (int r = 0; r < 4; r++)
+          for (size_t i = 0; i < P.hand.size(); i++)
+            if (P.hand[i] / 4 == tv) {
+              P.hand.erase(P.hand.begin() + i);
+              break;
+            }
+        Meld m;
+        m.meld_type = Ankan;
+        m.tiles = {(uint8_t)(tv * 4), (uint8_t)(tv * 4 + 1), (uint8_t)(tv * 4 + 2), (uint8_t)(tv * 4 + 3)};
+        m.opened = false;
+        m.from_who = -1;
+        m.called_tile = -1;
+        P.melds.push_back(m);
+      } else {
+        remove_first(P.hand, t0);
+        for (auto& m : P.melds)
+          if (m.meld_type == Pon && m.tiles[0] / 4 == t0 / 4) {
+            m.meld_type = Kakan;
+            m.tiles.push_back(t0);
+            std::sort(m.tiles.begin(), m.tiles.end());
+            break;
+          }
+        g.last_discard_pid = seat;                            // chankan target
+        g.last_discard_tile = t0;
+      }
+      std::sort(P.hand.begin(), P.hand.end());
+      g.current_player = (uint8_t)seat;
+      g.phase = RV_WAIT_ACT;
+      g.active_players = {g.current_player};
+      g.needs_tsumo = true;
+      g.is_first_turn = false;
+      g.is_after_kan = true;
+      if (sanma || a.meld_type == RV_MELD_ANKAN) {            // kokushi can ron a closed kan (3P: set for both kinds)
+        g.last_discard_pid = seat;
+        g.last_discard_tile = t0;
+      }
+      break;
+    }
+    case RV_LA_DORA:                                          // 664-666
+      g.dora_indicators.push_back(tid(a.tile));
+      break;
+    case RV_LA_BABEI:                                         // 3P 573-595; the 4P match has no arm for it
+      if (sanma) {
+        accept_pending();
+        for (size_t i = 0; i < P.hand.size(); i++)
+          if (P.hand[i] / 4 == 30) {
+            const uint8_t t = P.hand[i];
+            P.hand.erase(P.hand.begin() + i);
+            g.n_kita[seat]++;
+            g.last_discard_pid = seat;
+            g.last_discard_tile = t;
+            break;
+          }
+        std::sort(P.hand.begin(), P.hand.end());
+        g.current_player = (uint8_t)seat;
+        g.phase = RV_WAIT_ACT;
+        g.active_players = {g.current_player};
+        g.needs_tsumo = true;
+        g.is_first_turn = false;
+        g.is_after_kan = true;
+      }
+      break;
+    case RV_LA_HULE: {                                        // 667-818 / 3P 596-735
+      const int nh = a.n_hule < 3 ? a.n_hule : 3;
+      auto real_tsumo = [&](const rv_hule& h) { return sanma ? (h.zimo && h.seat == g.current_player) : (h.zimo != 0); };
+      if (nh > 0 && !real_tsumo(a.hules[0])) g.riichi_pending_acceptance = -1;
+      const int32_t honba = g.honba;
+      const uint32_t sticks = g.riichi_sticks;
+      bool honba_taken = false;
+      for (int k = 0; k < nh; k++) {
+        const rv_hule& h = a.hules[k];
+        const int w = h.seat < np ? h.seat : 0;
+        const bool is_oya = w == g.oya;
+        const bool tsumo = real_tsumo(h);
+        int pao_payer = -1, pao_val = 0, total_val = 0;
+        if (h.yiman)
+          for (int y = 0; y < 64; y++) {
+            if (!((h.fans >> y) & 1)) continue;
+            const int val = (y >= 47 && y <= 50) ? 2 : 1;
+            total_val += val;
+            const int liable = y == 37 ? g.players[w].pao37 : y == 50 ? g.players[w].pao50 : -1;
+            if (liable >= 0) {
+              pao_val += val;
+              pao_payer = liable;
+              if (!sanma && !tsumo) break;
+            }
+          }
+        if (tsumo) {
+          if (pao_val > 0) {
+            int32_t pao_amt, non_pao, tsumo_total = 0;
+            if (sanma) {
+              tsumo_total = is_oya ? (int32_t)h.point_zimo_xian * (np - 1) : (int32_t)h.point_zimo_qin + (int32_t)h.point_zimo_xian * (np - 2);
+              pao_amt = total_val > 0 ? tsumo_total * pao_val / total_val : tsumo_total;
+              non_pao = tsumo_total - pao_amt;
+            } else {
+              const int32_t unit = is_oya ? 48000 : 32000;
+              pao_amt = pao_val * unit;
+              non_pao = (total_val - pao_val) * unit;
+            }
+            if (pao_payer >= 0) {
+              g.players[pao_payer].score -= pao_amt;
+              g.players[w].score += pao_amt;
+            }
+            if (non_pao > 0)
+              for (int i = 0; i < np; i++) {
+                if (i == w) continue;
+                int32_t share;
+                if (sanma)
+                  share = is_oya ? non_pao / (np - 1)
+                                 : (i == g.oya ? (int32_t)h.point_zimo_qin : (int32_t)h.point_zimo_xian) * non_pao / (tsumo_total ? tsumo_total : 1);
+                else
+                  share = is_oya ? non_pao / 3 : (i == g.oya ? non_pao / 2 : non_pao / 4);
+                g.players[i].score -= share;
+                g.players[w].score += share;
+              }
+            if (pao_payer >= 0) {
+              const int32_t hb = sanma ? honba * (np - 1) * 100 : honba * 300;
+              g.players[pao_payer].score -= hb;
+              g.players[w].score += hb;
+            }
+          } else {
+            for (int i = 0; i < np; i++) {
+              if (i == w) continue;
+              const int32_t base = is_oya ? h.point_zimo_xian : (i == g.oya ? h.point_zimo_qin : h.point_zimo_xian);
+              const int32_t pay = base + honba * 100;
+              g.players[i].score -= pay;
+              g.players[w].score += pay;
+            }
+          }
+        } else if (g.last_discard_pid >= 0) {
+          const int d = g.last_discard_pid;
+          const int32_t ron_honba = honba_taken ? 0 : honba;
+          honba_taken = true;
+          const int32_t hb = sanma ? ron_honba * (np - 1) * 100 : ron_honba * 300;
+          if (sanma ? pao_val > 0 : pao_payer >= 0) {
+            if (sanma) {
+              const int pp = pao_payer >= 0 ? pao_payer : d;
+              const int32_t ron_total = (int32_t)h.point_rong;
+              const int32_t pao_amt = ron_total * pao_val / (total_val ? total_val : 1);
+              const int32_t pao_share = pao_amt / 2 + hb, disc_share = ron_total - pao_amt / 2;
+              g.players[pp].score -= pao_share;
+              g.players[d].score -= disc_share;
+              g.players[w].score += pao_share + disc_share;
+            } else {
+              const int32_t half = (int32_t)h.point_rong / 2;
+              g.players[pao_payer].score -= half + hb;
+              g.players[d].score -= half;
+              g.players[w].score += (int32_t)h.point_rong + hb;
+            }
+          } else {
+            const int32_t pay = (int32_t)h.point_rong + hb;
+            g.players[d].score -= pay;
+            g.players[w].score += pay;
+          }
+        }
+      }
+      if (nh > 0) {
+        g.players[a.hules[0].seat < np ? a.hules[0].seat : 0].score += (int32_t)sticks * 1000;
+        g.riichi_sticks = 0;
+      }
+      g.is_done = true;
+      break;
+    }
+    case RV_LA_NOTILE: {                                      // 819-882
+      accept_pending();
+      std::vector<int> nagashi;
+      for (int i = 0; i < np; i++)
+        if (g.players[i].nagashi_eligible) nagashi.push_back(i);
+      if (!nagashi.empty()) {
+        for (int w : nagashi) {
+          const bool is_oya = w == g.oya;
+          Score sc = calculate_score(5, 30, is_oya, true, 0, (uint8_t)np);
+          for (int i = 0; i < np; i++) {
+            if (i == w) continue;
+            const int32_t pay = is_oya ? (int32_t)sc.pay_tsumo_ko : (i == g.oya ? (int32_t)sc.pay_tsumo_oya : (int32_t)sc.pay_tsumo_ko);
+            g.players[i].score -= pay;
+            g.players[w].score += pay;
+          }
+        }
+      } else {
+        bool tenpai[MAXP] = {false, false, false, false};
+        int ntp = 0;
+        for (int i = 0; i < np; i++) {
+          HandEvaluator calc(g.players[i].hand, g.players[i].melds, sanma);
+          tenpai[i] = calc.is_tenpai();
+          ntp += tenpai[i];
+        }
+        if (ntp > 0 && ntp < np) {
+          const int32_t pool = sanma ? 2000 : 3000;
+          const int32_t pk = pool / ntp, pn = pool / (np - ntp);
+          for (int i = 0; i < np; i++) g.players[i].score += tenpai[i] ? pk : -pn;
+        }
+      }
+      g.is_done = true;
+      break;
+    }
+    case RV_LA_LIUJU:                                         // 883-890 (the 3P arm does not settle the deposit)
+      if (!sanma) accept_pending();
+      g.is_done = true;
+      break;
+    default:
+      break;
+  }
+}
+// KyokuStepIterator::_collect_pass_observations (replay/mod.rs:130-181) asks `_get_claim_actions_for_player(i, discarder, tile)`
+// of every other seat after a logged discard: here for all seats at once, left in current_claims / active_players / phase
+// (the caller snapshots the record, reads the lists and puts the record back).
+inline void claims_for_last_discard(GameState& g) {
+  if (g.last_discard_pid < 0) return;
+  const int actor = g.last_discard_pid;
+  const uint8_t tile = (uint8_t)g.last_discard_tile;
+  for (int i = 0; i < MAXP; i++) {
+    g.current_claims[i].clear();
+    g.has_claims_entry[i] = false;
+  }
+  g.active_players.clear();
+  for (int i = 0; i < g.np; i++) {
+    if (i == actor) continue;
+    auto [legals, missed] = g._get_claim_actions_for_player(i, actor, tile);
+    (void)missed;
+    if (!legals.empty()) {
+      g.active_players.push_back((uint8_t)i);
+      g.current_claims[i] = legals;
+      g.has_claims_entry[i] = true;
+    }
+  }
+  if (!g.active_players.empty()) {
+    g.phase = RV_WAIT_RESPONSE;
+  } else {
+    g.phase = RV_WAIT_ACT;
+    g.current_player = 0xFF;
+  }
+  g.needs_tsumo = true;
+}
+// LogKyoku::steps (replay/mod.rs:1094-1292), the part after `_initialize_round(oya, bakaze, ben, liqibang, None, scores)`
+inline void replay_begin_patch(GameState& g, const rv_log_kyoku& k) {
+  const int np = g.np;
+  const int oya = k.oya < np ? k.oya : 0;
+  for (int i = 0; i < np; i++) {
+    std::vector<uint8_t> h;
+    for (int j = 0; j < k.hand_len[i] && j < 14; j++) h.push_back(k.hands[i][j] < 136 ? k.hands[i][j] : 0);
+    g.players[i].hand = h;
+  }
+  if (g.players[oya].hand.size() == 14) {
+    g.drawn_tile = k.oya_drawn_tile == 0xFF ? -1 : k.oya_drawn_tile;
+    g.needs_tsumo = false;
+  } else {
+    if (g.drawn_tile >= 0) {
+      const size_t top = g.wall_tiles.size() + g.rinshan_draw_count;
+      g.wall_tiles.push_back((uint8_t)g.drawn_tile);
+      if (top < g.wall_abs.size()) g.wall_abs[top] = (uint8_t)g.drawn_tile;
+      g.drawable_count += 1;
+    }
+    g.drawn_tile = -1;
+    g.needs_tsumo = true;
+  }
+  for (int i = 0; i < np; i++) std::sort(g.players[i].hand.begin(), g.players[i].hand.end());
+  g.dora_indicators.clear();
+  for (int i = 0; i < k.n_doras && i < RV_LOG_MAX_DORAS; i++) g.dora_indicators.push_back(k.doras[i] < 136 ? k.doras[i] : 0);
+  g.is_after_kan = false;
 }
 
 // ---- the keyed "greedy-win" agent (test agent #1; shared definition with the kernel, csrc/game.cuh greedy_pick) ----

@@ -69,7 +69,7 @@ class GameState(C.Structure):
         ("last_discard_tile", u8), ("pending_kan_pid", u8), ("pending_kan_type", u8), ("pending_kan_tile", u8),
         ("active_mask", u8), ("last_error", u8), ("game_mode", u8), ("rule_bits", u8),
         ("overflow", u8), ("pending_init", u8 * 3), ("n_claims", u8 * NP),
-        ("pending_tail", u8 * 2), ("hot_reserved", u8 * 10),
+        ("pending_tail", u8 * 2), ("is_after_kan", u8), ("hot_reserved", u8 * 9),
         # cold part
         ("wall", u8 * 136), ("river", (u8 * RIVER_CAP) * NP), ("claims", (u32 * MAX_CLAIMS) * NP),
         ("hand_index", u64), ("river_riichi", u32 * NP), ("score_delta", i32 * NP), ("meld_from", (u8 * 4) * NP), ("meld_called", (u8 * 4) * NP),
@@ -102,6 +102,29 @@ class MjaiEvent(C.Structure):
     _fields_ = [("type", u8), ("actor", u8), ("target", u8), ("pai", u8), ("n_consumed", u8), ("consumed", u8 * 4), ("bakaze", u8),
                 ("kyoku", u8), ("honba", u8), ("oya", u8), ("dora_marker", u8), ("tehai_len", u8 * NP), ("tehais", (u8 * 14) * NP),
                 ("_pad", u8 * 3), ("kyotaku", u32), ("scores", i32 * NP)]
+
+
+# replay ingestion (include/riichienv_b200.h: rv_log_action_type, rv_hule, rv_log_action, rv_log_kyoku)
+LA_NONE, LA_DISCARD, LA_DEAL, LA_CHI_PENG_GANG, LA_ANGANG_ADDGANG, LA_DORA, LA_HULE, LA_NOTILE, LA_BABEI, LA_LIUJU = range(10)
+LOG_MAX_DORAS = 8
+
+
+class Hule(C.Structure):
+    _fields_ = [("seat", u8), ("hu_tile", u8), ("zimo", u8), ("yiman", u8), ("n_li_doras", u8), ("li_doras", u8 * 5), ("_pad", u8 * 2),
+                ("count", u32), ("fu", u32), ("point_rong", u32), ("point_zimo_qin", u32), ("point_zimo_xian", u32), ("fans", u64)]
+
+
+class LogAction(C.Structure):
+    _fields_ = [("type", u8), ("seat", u8), ("tile", u8), ("flags", u8), ("meld_type", u8), ("n_tiles", u8), ("tiles", u8 * 4),
+                ("froms", u8 * 4), ("n_hule", u8), ("_pad", u8), ("hules", Hule * 3)]
+
+
+class LogKyoku(C.Structure):
+    _fields_ = [("np", u8), ("chang", u8), ("ju", u8), ("ben", u8), ("liqibang", u8), ("left_tile_count", u8), ("n_doras", u8),
+                ("n_ura_doras", u8), ("doras", u8 * LOG_MAX_DORAS), ("ura_doras", u8 * LOG_MAX_DORAS), ("hand_len", u8 * NP),
+                ("hands", (u8 * 14) * NP), ("wliqi", u8 * NP), ("oya", u8), ("oya_drawn_tile", u8), ("has_game_end_scores", u8),
+                ("_pad", u8 * 3), ("rule_bits", u32), ("n_actions", i32), ("scores", i32 * NP), ("end_scores", i32 * NP),
+                ("game_end_scores", i32 * NP)]
 
 
 class RunStats(C.Structure):

@@ -83,7 +83,15 @@ def lib():
     L.rv_multi_stats.argtypes = [vp, P(A.RunStats)]
     L.rv_sizeof.argtypes = [C.c_int]
     L.rv_vec_apply_events.argtypes = [vp, P(A.MjaiEvent)]
-    for i, T in enumerate((A.GameState, A.HandQuery, A.HandResult, A.Action, A.MjaiEvent, A.RunStats)):
+    L.rv_replay_from_jsonl.argtypes = [C.c_char_p, C.c_uint32, P(vp)]
+    L.rv_replay_from_text.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, P(vp)]
+    L.rv_replay_free.argtypes = [vp]
+    L.rv_replay_num_rounds.argtypes = [vp]
+    L.rv_replay_kyoku.argtypes = [vp, C.c_int, P(A.LogKyoku)]
+    L.rv_replay_actions.argtypes = [vp, C.c_int, P(A.LogAction), C.c_int, P(C.c_int)]
+    L.rv_vec_replay_begin.argtypes = [vp, P(A.LogKyoku)]
+    L.rv_vec_apply_log_actions.argtypes = [vp, P(A.LogAction)]
+    for i, T in enumerate((A.GameState, A.HandQuery, A.HandResult, A.Action, A.MjaiEvent, A.RunStats, A.LogAction, A.LogKyoku)):
         if L.rv_sizeof(i) != C.sizeof(T):
             raise ImportError(f"ABI mismatch for {T.__name__}: C {L.rv_sizeof(i)} != ctypes {C.sizeof(T)}")
     _LIB = L

@@ -1523,8 +1523,14 @@ __device__ __noinline__ void resolve_discard(const Ctx& cx, G& g, int pid, int t
   for (int i = 0; i < np; i++) g.n_claims[i] = 0;
   g.active_mask = 0;
   int claim_mask = 0;
-  for (int i = 0; i < np; i++) {
-    if (i == pid || !((claim_seats >> i) & 1)) continue;
+  // seats in increasing order, as the reference walks them; the loop runs over the SET BITS so that the lanes of a warp enter
+  // gen_claims together (each game usually has one candidate seat, but not the same one: a loop over 0..np-1 called
+  // gen_claims three times with ~2 of 32 lanes active, 5 % of all instructions of a rollout)
+  uint32_t todo = claim_seats & ((1u << np) - 1) & ~(1u << pid);
+  #pragma unroll 1
+  while (todo) {
+    const int i = __ffs(todo) - 1;
+    todo &= todo - 1;
     bool missed = gen_claims(cx, g, i, pid, tile);
     if (missed) g.flags[i] |= RV_F_MISSED_AGARI_DOUJUN;
     if (g.n_claims[i] > 0) claim_mask |= 1 << i;
@@ -1860,13 +1866,16 @@ __device__ __noinline__ void step_apply_resp(const Ctx& cx, G& g, const rv_actio
   // missed agari (state/mod.rs:902-917): every seat holding a Ron claim (stale ones included) that did not ron
   // (a Ron claim is either the first entry of a list — gen_claims pushes it before the calls — or was appended to a
   // possibly stale list by chankan_ronners: looking at the two ends is the same as scanning the list)
-  for (int p = 0; p < np; p++) {
+  uint32_t listed = 0;
+  for (int p = 0; p < np; p++) listed |= g.n_claims[p] ? 1u << p : 0u;
+  #pragma unroll 1
+  while (listed) {        // over the set bits: the lanes of a warp read their (usually single) list together
+    const int p = __ffs(listed) - 1;
+    listed &= listed - 1;
     const int nc = g.n_claims[p];
-    bool has_ron = false;
-    if (nc > 0) {
-      const uint32_t* cl = cold(g).claims[p];
-      has_ron = (cl[0] & 0xFF) == RV_RON || (cl[nc - 1] & 0xFF) == RV_RON;
-    }
+    const uint32_t* cl = cold(g).claims[p];
+    const uint32_t first = cl[0], last = cl[nc - 1];
+    const bool has_ron = (first & 0xFF) == RV_RON || (last & 0xFF) == RV_RON;
     if (has_ron && acts[p].type != RV_RON) {
       g.flags[p] |= RV_F_MISSED_AGARI_DOUJUN;
       if (g.flags[p] & RV_F_RIICHI_DECLARED) g.flags[p] |= RV_F_MISSED_AGARI_RIICHI;
@@ -2414,8 +2423,11 @@ __device__ __noinline__ void random_step_resp(const Ctx& cx, G& g, uint64_t agen
   uint32_t sc = g.step_count;
   RV_STAT(3);
   if (IDS) ids_reset(cx);
-  for (int p = 0; p < np; p++) {
-    if (!((g.active_mask >> p) & 1)) continue;
+  uint32_t todo = g.active_mask & ((1u << np) - 1);   // set bits in increasing order: the lanes of a warp answer their first claim together
+  #pragma unroll 1
+  while (todo) {
+    const int p = __ffs(todo) - 1;
+    todo &= todo - 1;
     if (IDS) {
       ids_clear(cx, p);
       for (int k = 0; k < g.n_claims[p]; k++) ids_add(cx, g, p, cold(g).claims[p][k]);
@@ -2705,6 +2717,358 @@ __device__ __noinline__ void apply_mjai_event(const Ctx& cx, G& g, const rv_mjai
     default:
       break;
   }
+}
+
+// ---- replay ingestion: GameState::apply_log_action (state/event_handler.rs:332-894; 3P state_3p/event_handler.rs:365-808) ----
+// One record follows one kyoku of a parsed log (rv_log_kyoku / rv_log_action, include/riichienv_b200.h).  Pure bookkeeping:
+// nothing is drawn from the wall and no event is pushed; the decision points between two actions are read with the
+// ordinary legal-action / observation code.
+__device__ __forceinline__ void log_accept_riichi(G& g) {          // `if let Some(rp) = self.riichi_pending_acceptance.take()`
+  const int rp = g.riichi_pending_acceptance;
+  if (rp != RV_NONE) {
+    g.score[rp & 3] -= 1000;
+    g.riichi_sticks += 1;
+    g.riichi_pending_acceptance = RV_NONE;
+  }
+}
+__device__ __forceinline__ int hule_yakuman_val(int yid) { return (yid >= 47 && yid <= 50) ? 2 : 1; }
+__device__ __noinline__ void apply_log_hule(G& g, const rv_log_action& a) {
+  const int np = num_players(g);
+  const bool sanma = np == 3;
+  const int nh = a.n_hule < 3 ? a.n_hule : 3;
+  auto real_tsumo = [&](const rv_hule& h) { return sanma ? (h.zimo && h.seat == g.current_player) : (h.zimo != 0); };
+  if (nh > 0 && !real_tsumo(a.hules[0])) g.riichi_pending_acceptance = RV_NONE;      // the deposit is void when the discard is ronned
+  const int32_t honba = g.honba;
+  const uint32_t sticks = g.riichi_sticks;
+  bool honba_taken = false;
+  for (int k = 0; k < nh; k++) {
+    const rv_hule& h = a.hules[k];
+    const int w = h.seat < np ? h.seat : 0;
+    const bool is_oya = w == g.oya;
+    // PAO: which of the winner's yakuman has a liable seat (pao map filled by ChiPengGang below)
+    int pao_payer = -1, pao_val = 0, total_val = 0;
+    if (h.yiman)
+      for (int y = 0; y < 64; y++)
+        if ((h.fans >> y) & 1) {
+          const int val = hule_yakuman_val(y);
+          total_val += val;
+          const int liable = y == 37 ? cold(g).pao[w][0] : y == 50 ? cold(g).pao[w][1] : RV_NONE;
+          if (liable != RV_NONE) {
+            pao_val += val;
+            pao_payer = liable;
+            if (!sanma && !real_tsumo(h)) break;        // the 4P ron branch stops at the first liable yaku
+          }
+        }
+    if (real_tsumo(h)) {
+      if (pao_val > 0) {
+        int32_t pao_amt, non_pao, tsumo_total = 0;
+        if (sanma) {
+          tsumo_total = is_oya ? (int32_t)h.point_zimo_xian * (np - 1) : (int32_t)h.point_zimo_qin + (int32_t)h.point_zimo_xian * (np - 2);
+          pao_amt = total_val > 0 ? tsumo_total * pao_val / total_val : tsumo_total;
+          non_pao = tsumo_total - pao_amt;
+        } else {
+          const int32_t unit = is_oya ? 48000 : 32000;
+          pao_amt = pao_val * unit;
+          non_pao = (total_val - pao_val) * unit;
+        }
+        if (pao_payer >= 0) {
+          g.score[pao_payer & 3] -= pao_amt;
+          g.score[w] += pao_amt;
+        }
+        if (non_pao > 0)
+          for (int i = 0; i < np; i++) {
+            if (i == w) continue;
+            int32_t share;
+            if (sanma) share = is_oya ? non_pao / (np - 1) : (i == g.oya ? (int32_t)h.point_zimo_qin : (int32_t)h.point_zimo_xian) * non_pao / (tsumo_total ? tsumo_total : 1);
+            else share = is_oya ? non_pao / 3 : (i == g.oya ? non_pao / 2 : non_pao / 4);
+            g.score[i] -= share;
+            g.score[w] += share;
+          }
+        if (pao_payer >= 0) {
+          const int32_t hb = sanma ? honba * (np - 1) * 100 : honba * 300;
+          g.score[pao_payer & 3] -= hb;
+          g.score[w] += hb;
+        }
+      } else {
+        for (int i = 0; i < np; i++) {
+          if (i == w) continue;
+          const int32_t base = is_oya ? h.point_zimo_xian : (i == g.oya ? h.point_zimo_qin : h.point_zimo_xian);
+          const int32_t pay = base + honba * 100;
+          g.score[i] -= pay;
+          g.score[w] += pay;
+        }
+      }
+    } else if (g.last_discard_pid != RV_NONE) {
+      const int d = g.last_discard_pid & 3;
+      const int32_t ron_honba = honba_taken ? 0 : honba;
+      honba_taken = true;
+      const int32_t hb = sanma ? ron_honba * (np - 1) * 100 : ron_honba * 300;
+      if (sanma ? pao_val > 0 : pao_payer >= 0) {
+        if (sanma) {
+          const int pp = pao_payer >= 0 ? pao_payer & 3 : d;
+          const int32_t ron_total = (int32_t)h.point_rong;
+          const int32_t pao_amt = ron_total * pao_val / (total_val ? total_val : 1);
+          const int32_t pao_share = pao_amt / 2 + hb, disc_share = ron_total - pao_amt / 2;
+          g.score[pp] -= pao_share;
+          g.score[d] -= disc_share;
+          g.score[w] += pao_share + disc_share;
+        } else {
+          const int32_t half = (int32_t)h.point_rong / 2;
+          g.score[pao_payer & 3] -= half + hb;
+          g.score[d] -= half;
+          g.score[w] += (int32_t)h.point_rong + hb;
+        }
+      } else {
+        const int32_t pay = (int32_t)h.point_rong + hb;
+        g.score[d] -= pay;
+        g.score[w] += pay;
+      }
+    }
+  }
+  if (nh > 0) {
+    g.score[a.hules[0].seat < np ? a.hules[0].seat : 0] += (int32_t)sticks * 1000;
+    g.riichi_sticks = 0;
+  }
+  g.is_done = 1;
+}
+__device__ __noinline__ void apply_log_action(const Ctx& cx, G& g, const rv_log_action& a) {
+  const int np = num_players(g);
+  const bool sanma = np == 3;
+  const int s = a.seat < np ? a.seat : 0;
+  auto tid = [](int t) { return t < 136 ? t : 0; };
+  switch (a.type) {
+    case RV_LA_DISCARD: {
+      const int t = tid(a.tile);
+      const bool liqi = (a.flags & 3) != 0, wliqi = (a.flags & 2) != 0;
+      const bool tsumogiri = g.drawn_tile != RV_NONE && g.drawn_tile == t;
+      hand_remove_first(g, s, t);
+      hand_sort(g, s);
+      const int nr = g.n_river[s];
+      if (nr < RV_RIVER_CAP) {
+        cold(g).river[s][nr] = (uint8_t)t;
+        if (!tsumogiri) g.river_tedashi[s] |= 1u << nr;
+        if (liqi) cold(g).river_riichi[s] |= 1u << nr;
+      } else {
+        g.overflow |= 1;
+      }
+      g.n_river[s] = (uint8_t)(nr + 1);
+      g.c_river_kinds[s] |= 1ull << (t >> 2);
+      g.last_discard_pid = (uint8_t)s;
+      g.last_discard_tile = (uint8_t)t;
+      g.drawn_tile = RV_NONE;
+      g.flags[s] &= ~RV_F_MISSED_AGARI_DOUJUN;
+      if (!tid_terminal(t)) g.flags[s] &= ~RV_F_NAGASHI_ELIGIBLE;
+      if (liqi) {
+        if (sanma) {                                  // 3P: the flags and the pending deposit are (re)written unconditionally
+          g.flags[s] |= RV_F_RIICHI_DECLARED;
+          if (wliqi) g.flags[s] |= RV_F_DOUBLE_RIICHI;
+          g.riichi_pending_acceptance = (uint8_t)s;
+        } else if (!(g.flags[s] & RV_F_RIICHI_DECLARED)) {
+          g.flags[s] |= RV_F_RIICHI_DECLARED;
+          if (wliqi) g.flags[s] |= RV_F_DOUBLE_RIICHI;
+          g.riichi_pending_acceptance = (uint8_t)s;
+        }
+        cold(g).riichi_decl_idx[s] = (uint8_t)nr;
+      }
+      g.current_player = (uint8_t)((s + 1) % np);
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << g.current_player);
+      g.needs_tsumo = 1;
+      g.is_first_turn = 0;
+      g.is_after_kan = 0;
+      waits_update(cx.T, g, s);
+      break;
+    }
+    case RV_LA_DEAL: {
+      const int t = tid(a.tile);
+      log_accept_riichi(g);
+      hand_push(g, s, t);
+      g.drawn_tile = (uint8_t)t;
+      g.current_player = (uint8_t)s;
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << s);
+      g.is_rinshan_flag = g.is_after_kan ? 1 : 0;
+      g.needs_tsumo = 0;
+      g.is_after_kan = 0;
+      hand_sort(g, s);
+      if (g.wall_top > g.rinshan_draw_count) {       // `if !self.wall.tiles.is_empty()`
+        g.wall_top--;
+        g.drawable_count = g.drawable_count > 0 ? (uint8_t)(g.drawable_count - 1) : 0;
+      }
+      waits_update(cx.T, g, s);
+      break;
+    }
+    case RV_LA_CHI_PENG_GANG: {
+      log_accept_riichi(g);
+      if (g.last_discard_pid != RV_NONE) g.flags[g.last_discard_pid & 3] &= ~RV_F_NAGASHI_ELIGIBLE;
+      const int n = a.n_tiles < 4 ? a.n_tiles : 4;
+      int from_who = -1, called = -1;
+      for (int k = 0; k < n; k++) {
+        if (a.froms[k] == s) hand_remove_first(g, s, tid(a.tiles[k]));
+        else if (from_who < 0) from_who = a.froms[k], called = tid(a.tiles[k]);
+      }
+      hand_sort(g, s);
+      const int m = g.n_melds[s];
+      if (m < 4) {                                    // tiles as logged ([called, consumed...]), not sorted
+        for (int k = 0; k < 4; k++) g.meld_tiles[s][m][k] = k < n ? (uint8_t)tid(a.tiles[k]) : (uint8_t)RV_NONE;
+        g.meld_type[s][m] = a.meld_type;
+        cold(g).meld_from[s][m] = from_who < 0 ? (uint8_t)RV_NONE : (uint8_t)from_who;
+        cold(g).meld_called[s][m] = called < 0 ? (uint8_t)RV_NONE : (uint8_t)called;
+        g.n_melds[s] = (uint8_t)(m + 1);
+        if ((a.meld_type == RV_MELD_PON || a.meld_type == RV_MELD_DAIMINKAN) && called >= 0)
+          register_pao(g, s, called, from_who < 0 ? 0 : from_who);
+      } else {
+        g.overflow |= 1;
+      }
+      g.current_player = (uint8_t)s;
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << s);
+      const bool gang = a.meld_type == RV_MELD_DAIMINKAN;
+      g.needs_tsumo = gang ? 1 : 0;
+      g.is_first_turn = 0;
+      g.is_after_kan = gang ? 1 : 0;
+      waits_update(cx.T, g, s);
+      break;
+    }
+    case RV_LA_ANGANG_ADDGANG: {
+      const int t0 = tid(a.n_tiles ? a.tiles[0] : 0);
+      if (a.meld_type == RV_MELD_ANKAN) {
+        const int kind = t0 >> 2;
+        for (int r = 0; r < 4; r++)
+          for (int k = 0; k < g.hand_len[s]; k++)
+            if ((g.hand[s][k] >> 2) == kind) {
+              hand_remove_first(g, s, g.hand[s][k]);
+              break;
+            }
+        const int m = g.n_melds[s];
+        if (m < 4) {
+          for (int k = 0; k < 4; k++) g.meld_tiles[s][m][k] = (uint8_t)(kind * 4 + k);
+          g.meld_type[s][m] = RV_MELD_ANKAN;
+          cold(g).meld_from[s][m] = RV_NONE;
+          cold(g).meld_called[s][m] = RV_NONE;
+          g.n_melds[s] = (uint8_t)(m + 1);
+        } else {
+          g.overflow |= 1;
+        }
+      } else {
+        hand_remove_first(g, s, t0);
+        for (int m = 0; m < g.n_melds[s]; m++)
+          if (g.meld_type[s][m] == RV_MELD_PON && (g.meld_tiles[s][m][0] >> 2) == (t0 >> 2)) {
+            g.meld_type[s][m] = RV_MELD_KAKAN;
+            uint8_t* tl = g.meld_tiles[s][m];           // push + sort
+            tl[3] = (uint8_t)t0;
+            for (int x = 1; x < 4; x++)
+              for (int y = x; y > 0 && tl[y - 1] > tl[y]; y--) { uint8_t v = tl[y]; tl[y] = tl[y - 1]; tl[y - 1] = v; }
+            break;
+          }
+      }
+      g.last_discard_pid = (uint8_t)s;                 // chankan / kokushi-on-ankan target
+      g.last_discard_tile = (uint8_t)t0;
+      hand_sort(g, s);
+      g.current_player = (uint8_t)s;
+      g.phase = RV_WAIT_ACT;
+      g.active_mask = (uint8_t)(1u << s);
+      g.needs_tsumo = 1;
+      g.is_first_turn = 0;
+      g.is_after_kan = 1;
+      waits_update(cx.T, g, s);
+      break;
+    }
+    case RV_LA_DORA:
+      if (g.n_dora < 5) g.dora_ind[g.n_dora++] = (uint8_t)tid(a.tile);
+      else g.overflow |= 1;                             // the reference's Vec keeps growing (steps() preloads every marker of the kyoku)
+      break;
+    case RV_LA_BABEI:
+      if (sanma) {                                      // 4P: `_ => {}`
+        log_accept_riichi(g);
+        for (int k = 0; k < g.hand_len[s]; k++)
+          if ((g.hand[s][k] >> 2) == 30) {
+            const int t = g.hand[s][k];
+            hand_remove_first(g, s, t);
+            cold(g).n_kita[s]++;
+            g.last_discard_pid = (uint8_t)s;
+            g.last_discard_tile = (uint8_t)t;
+            break;
+          }
+        hand_sort(g, s);
+        g.current_player = (uint8_t)s;
+        g.phase = RV_WAIT_ACT;
+        g.active_mask = (uint8_t)(1u << s);
+        g.needs_tsumo = 1;
+        g.is_first_turn = 0;
+        g.is_after_kan = 1;
+        waits_update(cx.T, g, s);
+      }
+      break;
+    case RV_LA_HULE:
+      apply_log_hule(g, a);
+      break;
+    case RV_LA_NOTILE: {
+      log_accept_riichi(g);
+      int nagashi = 0;
+      for (int p = 0; p < np; p++)
+        if (g.flags[p] & RV_F_NAGASHI_ELIGIBLE) nagashi |= 1 << p;
+      if (nagashi) {
+        for (int w = 0; w < np; w++) {
+          if (!((nagashi >> w) & 1)) continue;
+          const bool is_oya = w == g.oya;                // calculate_score(5, 30, is_oya, true, 0, np): 4000 all / 2000-4000
+          for (int i = 0; i < np; i++) {
+            if (i == w) continue;
+            const int32_t pay = is_oya ? 4000 : (i == g.oya ? 4000 : 2000);
+            g.score[i] -= pay;
+            g.score[w] += pay;
+          }
+        }
+      } else {
+        int ntp = 0;
+        for (int p = 0; p < np; p++) ntp += g.c_waits[p] != 0;
+        if (ntp > 0 && ntp < np) {
+          const int32_t pool = sanma ? 2000 : 3000;
+          const int32_t pk = pool / ntp, pn = pool / (np - ntp);
+          for (int p = 0; p < np; p++) g.score[p] += g.c_waits[p] != 0 ? pk : -pn;
+        }
+      }
+      g.is_done = 1;
+      break;
+    }
+    case RV_LA_LIUJU:
+      if (!sanma) log_accept_riichi(g);
+      g.is_done = 1;
+      break;
+    default:
+      break;
+  }
+}
+// LogKyoku::steps (replay/mod.rs:1094-1292) after `_initialize_round(oya, chang, ben, liqibang, None, scores)` has run: the
+// logged hands replace the dealt ones, the dealer's 14th tile goes back to the wall when the log deals it separately, and
+// EVERY dora marker the kyoku will show is installed up front (as the reference does).
+__device__ __noinline__ void replay_begin_patch(const Ctx& cx, G& g, const rv_log_kyoku& k) {
+  const int np = num_players(g);
+  const int oya = k.oya < np ? k.oya : 0;
+  for (int p = 0; p < np; p++) {
+    const int n = k.hand_len[p] < 14 ? k.hand_len[p] : 14;
+    for (int i = 0; i < RV_HAND_CAP; i++) g.hand[p][i] = i < n ? (uint8_t)(k.hands[p][i] < 136 ? k.hands[p][i] : 0) : (uint8_t)RV_NONE;
+    g.hand_len[p] = (uint8_t)n;
+  }
+  if (g.hand_len[oya] == 14) {
+    g.drawn_tile = k.oya_drawn_tile;
+    g.needs_tsumo = 0;
+  } else {
+    if (g.drawn_tile != RV_NONE) {                      // wall.tiles.push(dt); drawable_count += 1
+      cold(g).wall[g.wall_top] = g.drawn_tile;
+      g.wall_top++;
+      g.drawable_count++;
+    }
+    g.drawn_tile = RV_NONE;
+    g.needs_tsumo = 1;
+  }
+  for (int p = 0; p < np; p++) hand_sort(g, p);
+  const int nd = k.n_doras < 5 ? k.n_doras : 5;
+  for (int i = 0; i < 5; i++) g.dora_ind[i] = i < nd ? (uint8_t)(k.doras[i] < 136 ? k.doras[i] : 0) : (uint8_t)RV_NONE;
+  g.n_dora = (uint8_t)nd;
+  if (k.n_doras > 5) g.overflow |= 1;
+  g.is_after_kan = 0;
+  refresh_caches(cx.T, g);
 }
 
 // ---- agent #1: keyed "greedy-win" (definition shared with the oracle, oracle/game.hpp greedy_pick) ----

@@ -1,0 +1,504 @@
+// Host-side MJAI log reader of the replay-ingestion path: JSON lines (optionally gzip) -> one rv_log_kyoku
+// plus a list of rv_log_action per round.  Replaces MjaiReplay::from_jsonl and KyokuBuilder
+// (riichienv-core/src/replay/mjai_replay.rs:184-633; tile names: parser.rs:336-395 `mjai_to_tid`).  The records feed
+// rv_vec_replay_begin / rv_vec_apply_log_actions, which track the kyoku on the device.
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/riichienv_b200.h"
+
+int rv_internal_fail(int code, const std::string& msg);   // riichienv_b200.cu: sets rv_last_error()
+
+namespace {
+// ---------------------------------------------------------------- a small JSON reader (objects, arrays, strings, numbers, literals)
+struct JVal {
+  enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
+  bool b = false;
+  double num = 0;
+  std::string str;
+  std::vector<JVal> arr;
+  std::vector<std::pair<std::string, JVal>> obj;
+  const JVal* get(const char* key) const {
+    for (auto& kv : obj)
+      if (kv.first == key) return &kv.second;
+    return nullptr;
+  }
+};
+struct JParser {
+  const char* p;
+  const char* end;
+  std::string err;
+  void ws() {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) p++;
+  }
+  bool fail(const char* m) {
+    if (err.empty()) err = m;
+    return false;
+  }
+  bool str(std::string& out) {
+    if (p >= end || *p != '"') return fail("expected string");
+    p++;
+    while (p < end && *p != '"') {
+      if (*p == '\\') {
+        if (++p >= end) return fail("bad escape");
+        switch (*p) {
+          case 'n': out += '\n'; break;
+          case 't': out += '\t'; break;
+          case 'r': out += '\r'; break;
+          case 'b': out += '\b'; break;
+          case 'f': out += '\f'; break;
+          case 'u': {                                     // names only: keep the code point as UTF-8 (BMP)
+            if (end - p < 5) return fail("bad \\u escape");
+            unsigned cp = 0;
+            for (int k = 1; k <= 4; k++) {
+              char c = p[k];
+              cp = cp * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : 0);
+            }
+            p += 4;
+            if (cp < 0x80) out += (char)cp;
+            else if (cp < 0x800) out += (char)(0xC0 | (cp >> 6)), out += (char)(0x80 | (cp & 0x3F));
+            else out += (char)(0xE0 | (cp >> 12)), out += (char)(0x80 | ((cp >> 6) & 0x3F)), out += (char)(0x80 | (cp & 0x3F));
+            break;
+          }
+          default: out += *p;
+        }
+        p++;
+      } else {
+        out += *p++;
+      }
+    }
+    if (p >= end) return fail("unterminated string");
+    p++;
+    return true;
+  }
+  bool value(JVal& v, int depth = 0) {
+    if (depth > 32) return fail("nesting too deep");
+    ws();
+    if (p >= end) return fail("EOF while parsing a value");
+    if (*p == '{') {
+      v.kind = JVal::Obj;
+      p++;
+      ws();
+      if (p < end && *p == '}') return p++, true;
+      while (true) {
+        ws();
+        std::string k;
+        if (!str(k)) return false;
+        ws();
+        if (p >= end || *p != ':') return fail("expected ':'");
+        p++;
+        JVal c;
+        if (!value(c, depth + 1)) return false;
+        v.obj.emplace_back(std::move(k), std::move(c));
+        ws();
+        if (p < end && *p == ',') { p++; continue; }
+        if (p < end && *p == '}') return p++, true;
+        return fail("expected ',' or '}'");
+      }
+    }
+    if (*p == '[') {
+      v.kind = JVal::Arr;
+      p++;
+      ws();
+      if (p < end && *p == ']') return p++, true;
+      while (true) {
+        JVal c;
+        if (!value(c, depth + 1)) return false;
+        v.arr.push_back(std::move(c));
+        ws();
+        if (p < end && *p == ',') { p++; continue; }
+        if (p < end && *p == ']') return p++, true;
+        return fail("expected ',' or ']'");
+      }
+    }
+    if (*p == '"') {
+      v.kind = JVal::Str;
+      return str(v.str);
+    }
+    if (end - p >= 4 && !strncmp(p, "true", 4)) return v.kind = JVal::Bool, v.b = true, p += 4, true;
+    if (end - p >= 5 && !strncmp(p, "false", 5)) return v.kind = JVal::Bool, v.b = false, p += 5, true;
+    if (end - p >= 4 && !strncmp(p, "null", 4)) return v.kind = JVal::Null, p += 4, true;
+    char* e = nullptr;
+    std::string tmp(p, (size_t)std::min<ptrdiff_t>(end - p, 40));
+    double d = strtod(tmp.c_str(), &e);
+    if (e == tmp.c_str()) return fail("expected value");
+    v.kind = JVal::Num;
+    v.num = d;
+    p += e - tmp.c_str();
+    return true;
+  }
+};
+
+// parser.rs:336-395: "5mr" red fives are copy 0 of the five (16 / 52 / 88), a plain five is copy 1, everything else copy 0;
+// honors by letter (E S W N P F C) or as 1z..7z.  Unknown strings -> None -> the caller's unwrap_or(0).
+int mjai_to_tid(const std::string& s) {
+  static const char* honors[7] = {"E", "S", "W", "N", "P", "F", "C"};
+  for (int k = 0; k < 7; k++)
+    if (s == honors[k]) return 108 + 4 * k;
+  if (s == "5mr") return 16;
+  if (s == "5pr") return 52;
+  if (s == "5sr") return 88;
+  if (s.size() < 2 || s[0] < '0' || s[0] > '9') return -1;   // only the first two characters are looked at
+  const int num = s[0] - '0';
+  const int suit = s[1] == 'm' ? 0 : s[1] == 'p' ? 1 : s[1] == 's' ? 2 : s[1] == 'z' ? 3 : -1;
+  if (suit < 0) return -1;
+  if (num == 0) return suit < 3 ? suit * 36 + 16 : -1;
+  if (suit == 3) return 108 + (num - 1) * 4;                  // 8z / 9z give 136 / 140 as in the reference; consumers clamp
+  return suit * 36 + (num - 1) * 4 + (num == 5 ? 1 : 0);
+}
+uint8_t tile_of(const JVal* v) {
+  if (!v || v->kind != JVal::Str) return 0;
+  int t = mjai_to_tid(v->str);
+  return (uint8_t)(t < 0 ? 0 : t);   // parse_mjai_tile: unwrap_or(0)
+}
+
+struct Kyoku {
+  rv_log_kyoku k;
+  std::vector<rv_log_action> actions;
+};
+// KyokuBuilder (mjai_replay.rs:159-270)
+struct Builder {
+  Kyoku out;
+  int np = 4;
+  bool liqi[4] = {}, wliqi[4] = {}, reach_accepted[4] = {}, reached[4] = {}, first_discard[4] = {true, true, true, true};
+  bool has_calls = false;
+  std::vector<rv_hule> pending_hule;
+  void flush_hule() {
+    if (pending_hule.empty()) return;
+    rv_log_action a;
+    memset(&a, 0, sizeof a);
+    a.type = RV_LA_HULE;
+    a.n_hule = (uint8_t)std::min<size_t>(pending_hule.size(), 3);
+    for (int i = 0; i < a.n_hule; i++) a.hules[i] = pending_hule[i];
+    out.actions.push_back(a);
+    pending_hule.clear();
+  }
+};
+rv_log_action blank(int type, int seat) {
+  rv_log_action a;
+  memset(&a, 0, sizeof a);
+  a.type = (uint8_t)type;
+  a.seat = (uint8_t)seat;
+  a.tile = RV_NONE;
+  memset(a.tiles, RV_NONE, 4);
+  memset(a.froms, RV_NONE, 4);
+  return a;
+}
+int geti(const JVal& o, const char* key, int dflt = 0) {
+  const JVal* v = o.get(key);
+  return v && v->kind == JVal::Num ? (int)v->num : dflt;
+}
+}  // namespace
+
+struct rv_replay {
+  std::vector<Kyoku> rounds;
+};
+
+namespace {
+// serde's derive: a missing required field or a wrong type is a parse error, unknown `type` strings are MjaiEvent::Other
+bool require(const JVal& o, const char* key, JVal::Kind kind, std::string& err) {
+  const JVal* v = o.get(key);
+  if (!v) return err = std::string("missing field `") + key + "`", false;
+  if (v->kind != kind) return err = std::string("invalid type for field `") + key + "`", false;
+  return true;
+}
+bool finish_builder(std::unique_ptr<Builder>& b, rv_replay* r) {
+  if (!b) return false;
+  b->flush_hule();
+  rv_log_kyoku& k = b->out.k;
+  for (int p = 0; p < 4; p++) k.wliqi[p] = b->wliqi[p];
+  k.n_actions = (int32_t)b->out.actions.size();
+  // LogKyoku::steps (replay/mod.rs:1125-1132, 1214-1247): the dealer and, for a 14-tile deal, the tile it holds as "drawn"
+  int oya = k.ju % k.np;
+  for (int p = 0; p < k.np; p++)
+    if (k.hand_len[p] == 14) { oya = p; break; }
+  k.oya = (uint8_t)oya;
+  k.oya_drawn_tile = RV_NONE;
+  if (k.hand_len[oya] == 14) {
+    int dt = k.hands[oya][13];
+    if (!b->out.actions.empty()) {
+      const rv_log_action& a = b->out.actions[0];
+      if (a.type == RV_LA_HULE) {
+        for (int i = 0; i < a.n_hule; i++)
+          if (a.hules[i].seat == oya && a.hules[i].zimo) { dt = a.hules[i].hu_tile; break; }
+      } else if (a.type == RV_LA_DISCARD) {
+        if (a.seat == oya) dt = a.tile;
+      } else if (a.type == RV_LA_ANGANG_ADDGANG) {
+        if (a.seat == oya && a.n_tiles) dt = a.tiles[0];
+      }
+    }
+    k.oya_drawn_tile = (uint8_t)dt;
+  }
+  r->rounds.push_back(std::move(b->out));
+  b.reset();
+  return true;
+}
+// MjaiReplay::process_event (mjai_replay.rs:388-632)
+void process_event(Builder& b, const std::string& type, const JVal& e) {
+  if (type != "hora") b.flush_hule();
+  const int np = b.np;
+  auto seat = [&](const char* key) { int a = geti(e, key); return a < 0 || a >= np ? 0 : a; };
+  rv_log_kyoku& k = b.out.k;
+  if (type == "tsumo") {
+    rv_log_action a = blank(RV_LA_DEAL, seat("actor"));
+    a.tile = tile_of(e.get("pai"));
+    b.out.actions.push_back(a);
+    if (k.left_tile_count > 0) k.left_tile_count--;
+  } else if (type == "dahai") {
+    const int s = seat("actor");
+    rv_log_action a = blank(RV_LA_DISCARD, s);
+    a.tile = tile_of(e.get("pai"));
+    const bool is_liqi = b.liqi[s];
+    const bool is_wliqi = is_liqi && b.first_discard[s] && !b.has_calls;
+    if (is_wliqi) b.wliqi[s] = true;
+    a.flags = (uint8_t)((is_liqi ? 1 : 0) | (is_wliqi ? 2 : 0));
+    b.out.actions.push_back(a);
+    b.first_discard[s] = false;
+    if (is_liqi) b.liqi[s] = false;
+  } else if (type == "reach") {
+    const int s = seat("actor");
+    b.liqi[s] = true;
+    b.reached[s] = true;
+  } else if (type == "reach_accepted") {
+    b.reach_accepted[seat("actor")] = true;
+  } else if (type == "chi" || type == "pon" || type == "kan" || type == "daiminkan") {
+    b.has_calls = true;
+    const int s = seat("actor"), target = seat("target");
+    rv_log_action a = blank(RV_LA_CHI_PENG_GANG, s);
+    a.meld_type = type == "chi" ? RV_MELD_CHI : type == "pon" ? RV_MELD_PON : RV_MELD_DAIMINKAN;
+    a.tiles[0] = tile_of(e.get("pai"));
+    a.froms[0] = (uint8_t)target;
+    int n = 1;
+    if (const JVal* c = e.get("consumed"))
+      for (size_t i = 0; i < c->arr.size() && n < 4; i++) a.tiles[n] = tile_of(&c->arr[i]), a.froms[n] = (uint8_t)s, n++;
+    a.n_tiles = (uint8_t)n;
+    a.tile = a.tiles[0];
+    b.out.actions.push_back(a);
+  } else if (type == "ankan") {
+    b.has_calls = true;
+    rv_log_action a = blank(RV_LA_ANGANG_ADDGANG, seat("actor"));
+    a.meld_type = RV_MELD_ANKAN;
+    int n = 0;
+    if (const JVal* c = e.get("consumed"))
+      for (size_t i = 0; i < c->arr.size() && n < 4; i++) a.tiles[n++] = tile_of(&c->arr[i]);
+    a.n_tiles = (uint8_t)n;
+    b.out.actions.push_back(a);
+  } else if (type == "kakan") {
+    b.has_calls = true;
+    rv_log_action a = blank(RV_LA_ANGANG_ADDGANG, seat("actor"));
+    a.meld_type = RV_MELD_KAKAN;
+    a.tiles[0] = tile_of(e.get("pai"));
+    a.n_tiles = 1;
+    b.out.actions.push_back(a);
+  } else if (type == "dora") {
+    const uint8_t m = tile_of(e.get("dora_marker"));
+    if (k.n_doras < RV_LOG_MAX_DORAS) k.doras[k.n_doras++] = m;
+    rv_log_action a = blank(RV_LA_DORA, 0);
+    a.tile = m;
+    b.out.actions.push_back(a);
+  } else if (type == "hora") {
+    const int actor = seat("actor"), target = seat("target");
+    rv_hule h;
+    memset(&h, 0, sizeof h);
+    const JVal* pai = e.get("pai");
+    if (pai && pai->kind == JVal::Str) {
+      h.hu_tile = tile_of(pai);
+    } else if (!b.out.actions.empty()) {              // infer from the last action
+      const rv_log_action& last = b.out.actions.back();
+      if (last.type == RV_LA_DEAL || last.type == RV_LA_DISCARD) h.hu_tile = last.tile;
+      else if (last.type == RV_LA_ANGANG_ADDGANG) h.hu_tile = last.tiles[0];
+    }
+    h.seat = (uint8_t)actor;
+    h.zimo = actor == target;
+    h.count = (uint32_t)geti(e, "han");
+    h.fu = (uint32_t)geti(e, "fu");
+    h.n_li_doras = 0xFF;
+    const JVal* ura = e.get("uradora_markers");
+    if (!ura) ura = e.get("ura_markers");
+    if (ura && ura->kind == JVal::Arr) {
+      h.n_li_doras = (uint8_t)std::min<size_t>(ura->arr.size(), 5);
+      k.n_ura_doras = 0;
+      for (size_t i = 0; i < ura->arr.size(); i++) {
+        const uint8_t t = tile_of(&ura->arr[i]);
+        if (i < 5) h.li_doras[i] = t;
+        if (k.n_ura_doras < RV_LOG_MAX_DORAS) k.ura_doras[k.n_ura_doras++] = t;
+      }
+    }
+    const JVal* scores = e.get("scores");
+    const JVal* delta = e.get("delta");
+    if (!delta) delta = e.get("deltas");
+    if (scores && scores->kind == JVal::Arr) {
+      for (size_t i = 0; i < scores->arr.size() && i < 4; i++) k.end_scores[i] = (int32_t)scores->arr[i].num;
+    } else if (delta && delta->kind == JVal::Arr) {
+      const bool first = b.pending_hule.empty();
+      for (size_t i = 0; i < delta->arr.size() && i < (size_t)np; i++) {
+        const int32_t d = (int32_t)delta->arr[i].num;
+        if (first) k.end_scores[i] = k.scores[i] + d - (b.reach_accepted[i] ? 1000 : 0);
+        else k.end_scores[i] += d;
+      }
+    }
+    b.pending_hule.push_back(h);
+  } else if (type == "kita") {
+    b.out.actions.push_back(blank(RV_LA_BABEI, seat("actor")));
+  } else if (type == "ryukyoku") {
+    const JVal* scores = e.get("scores");
+    const JVal* delta = e.get("delta");
+    if (!delta) delta = e.get("deltas");
+    if (scores && scores->kind == JVal::Arr) {
+      for (size_t i = 0; i < scores->arr.size() && i < 4; i++) k.end_scores[i] = (int32_t)scores->arr[i].num;
+    } else if (delta && delta->kind == JVal::Arr) {
+      for (size_t i = 0; i < delta->arr.size() && i < (size_t)np; i++)
+        k.end_scores[i] = k.scores[i] + (int32_t)delta->arr[i].num - (b.reached[i] ? 1000 : 0);
+    }
+    b.out.actions.push_back(blank(RV_LA_NOTILE, 0));
+  }
+}
+
+int parse_lines(const char* text, size_t len, uint32_t rule_bits, rv_replay** out) {
+  std::unique_ptr<rv_replay> r(new rv_replay);
+  std::unique_ptr<Builder> b;
+  const char* p = text;
+  const char* end = text + len;
+  int line_no = 0;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    line_no++;
+    const char* a = p;
+    const char* z = le;
+    while (a < z && (*a == ' ' || *a == '\t' || *a == '\r')) a++;
+    while (z > a && (z[-1] == ' ' || z[-1] == '\t' || z[-1] == '\r')) z--;
+    p = nl ? nl + 1 : end;
+    if (a == z) continue;
+    JParser jp{a, z, {}};
+    JVal e;
+    bool ok = jp.value(e);
+    if (ok) {
+      jp.ws();
+      if (jp.p != z) ok = jp.fail("trailing characters");
+    }
+    if (ok && e.kind != JVal::Obj) ok = jp.fail("invalid type: expected an event object");
+    std::string type;
+    if (ok) {
+      const JVal* t = e.get("type");
+      if (!t || t->kind != JVal::Str) ok = jp.fail("missing field `type`");
+      else type = t->str;
+    }
+    std::string err = jp.err;
+    if (ok) {
+      // field checks of the serde enum (mjai_replay.rs:67-156) for the variants this reader consumes
+      if (type == "start_kyoku") {
+        ok = require(e, "bakaze", JVal::Str, err) && require(e, "kyoku", JVal::Num, err) && require(e, "honba", JVal::Num, err) &&
+             (e.get("kyoutaku") ? require(e, "kyoutaku", JVal::Num, err) : require(e, "kyotaku", JVal::Num, err)) &&
+             require(e, "oya", JVal::Num, err) && require(e, "scores", JVal::Arr, err) && require(e, "dora_marker", JVal::Str, err) &&
+             require(e, "tehais", JVal::Arr, err);
+      } else if (type == "tsumo") {
+        ok = require(e, "actor", JVal::Num, err) && require(e, "pai", JVal::Str, err);
+      } else if (type == "dahai") {
+        ok = require(e, "actor", JVal::Num, err) && require(e, "pai", JVal::Str, err) && require(e, "tsumogiri", JVal::Bool, err);
+      } else if (type == "pon" || type == "chi" || type == "kan" || type == "daiminkan") {
+        ok = require(e, "actor", JVal::Num, err) && require(e, "target", JVal::Num, err) && require(e, "pai", JVal::Str, err) &&
+             require(e, "consumed", JVal::Arr, err);
+      } else if (type == "kakan") {
+        ok = require(e, "actor", JVal::Num, err) && require(e, "pai", JVal::Str, err);
+      } else if (type == "ankan") {
+        ok = require(e, "actor", JVal::Num, err) && require(e, "consumed", JVal::Arr, err);
+      } else if (type == "dora") {
+        ok = require(e, "dora_marker", JVal::Str, err);
+      } else if (type == "reach" || type == "reach_accepted" || type == "kita") {
+        ok = require(e, "actor", JVal::Num, err);
+      } else if (type == "hora") {
+        ok = require(e, "actor", JVal::Num, err) && require(e, "target", JVal::Num, err);
+      }
+    }
+    if (!ok) return rv_internal_fail(RV_ERR_INVALID, "Parse error: " + err + " at line " + std::to_string(line_no));
+    if (type == "start_kyoku") {
+      if (b) finish_builder(b, r.get());
+      b.reset(new Builder);
+      rv_log_kyoku& k = b->out.k;
+      memset(&k, 0, sizeof k);
+      const JVal& scores = *e.get("scores");
+      const int np = (int)scores.arr.size();
+      if (np != 3 && np != 4)
+        return rv_internal_fail(RV_ERR_INVALID, "Parse error: start_kyoku with " + std::to_string(np) + " scores at line " + std::to_string(line_no));
+      b->np = np;
+      k.np = (uint8_t)np;
+      const std::string& bk = e.get("bakaze")->str;
+      k.chang = bk == "S" ? 1 : bk == "W" ? 2 : bk == "N" ? 3 : 0;
+      k.ju = (uint8_t)(geti(e, "kyoku") - 1);
+      k.ben = (uint8_t)geti(e, "honba");
+      k.liqibang = (uint8_t)geti(e, e.get("kyoutaku") ? "kyoutaku" : "kyotaku");
+      k.left_tile_count = np == 3 ? 55 : 70;
+      k.rule_bits = rule_bits;
+      for (int p = 0; p < np; p++) k.scores[p] = k.end_scores[p] = (int32_t)scores.arr[p].num;
+      memset(k.doras, RV_NONE, sizeof k.doras);
+      memset(k.ura_doras, RV_NONE, sizeof k.ura_doras);
+      memset(k.hands, RV_NONE, sizeof k.hands);
+      k.doras[0] = tile_of(e.get("dora_marker"));
+      k.n_doras = 1;
+      const JVal& th = *e.get("tehais");
+      for (size_t p = 0; p < th.arr.size() && p < (size_t)np; p++) {
+        int n = 0;
+        for (size_t i = 0; i < th.arr[p].arr.size() && n < 14; i++) k.hands[p][n++] = tile_of(&th.arr[p].arr[i]);
+        k.hand_len[p] = (uint8_t)n;
+      }
+    } else if (type == "end_kyoku" || type == "end_game") {
+      if (b) finish_builder(b, r.get());
+    } else if (b) {
+      process_event(*b, type, e);
+    }
+  }
+  if (b) finish_builder(b, r.get());
+  // the next round's start scores are the authoritative post-round scores of every non-final round
+  for (size_t i = 0; i + 1 < r->rounds.size(); i++)
+    for (int p = 0; p < 4; p++) r->rounds[i].k.end_scores[p] = r->rounds[i + 1].k.scores[p];
+  *out = r.release();
+  return RV_OK;
+}
+}  // namespace
+
+extern "C" {
+int rv_replay_from_text(const char* text, size_t len, uint32_t rule_bits, rv_replay** out) {
+  if (!text || !out) return rv_internal_fail(RV_ERR_INVALID, "text / out is null");
+  return parse_lines(text, len, rule_bits, out);
+}
+int rv_replay_from_jsonl(const char* path, uint32_t rule_bits, rv_replay** out) {
+  if (!path || !out) return rv_internal_fail(RV_ERR_INVALID, "path / out is null");
+  // gzopen reads plain files transparently and inflates those that start with the gzip magic bytes (0x1f 0x8b) —
+  // detection by content, not by extension, as the reference does
+  gzFile f = gzopen(path, "rb");
+  if (!f) return rv_internal_fail(RV_ERR_INVALID, std::string("Failed to open file: ") + path);
+  std::string text;
+  char buf[1 << 16];
+  int n;
+  while ((n = gzread(f, buf, sizeof buf)) > 0) text.append(buf, (size_t)n);
+  const bool bad = n < 0;
+  gzclose(f);
+  if (bad) return rv_internal_fail(RV_ERR_INVALID, std::string("Read error: ") + path);
+  return parse_lines(text.data(), text.size(), rule_bits, out);
+}
+int rv_replay_free(rv_replay* r) {
+  delete r;
+  return RV_OK;
+}
+int rv_replay_num_rounds(const rv_replay* r) { return r ? (int)r->rounds.size() : 0; }
+int rv_replay_kyoku(const rv_replay* r, int round, rv_log_kyoku* out) {
+  if (!r || !out || round < 0 || round >= (int)r->rounds.size()) return rv_internal_fail(RV_ERR_INVALID, "round out of range");
+  *out = r->rounds[round].k;
+  return RV_OK;
+}
+int rv_replay_actions(const rv_replay* r, int round, rv_log_action* out, int cap, int* n_out) {
+  if (!r || round < 0 || round >= (int)r->rounds.size()) return rv_internal_fail(RV_ERR_INVALID, "round out of range");
+  const auto& a = r->rounds[round].actions;
+  if (n_out) *n_out = (int)a.size();
+  if (out)
+    for (int i = 0; i < cap && i < (int)a.size(); i++) out[i] = a[i];
+  return RV_OK;
+}
+}  // extern "C"

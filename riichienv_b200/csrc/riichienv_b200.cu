@@ -27,6 +27,7 @@ static int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+int rv_internal_fail(int code, const std::string& msg) { return fail(code, msg); }   // for the host-only sources (replay.cpp)
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -112,6 +113,29 @@ __global__ void __launch_bounds__(64) apply_events_kernel(Tables T, G* states, i
   cx.defer_init = cx.defer_tail = false;
   cx.idbits = nullptr;
   apply_mjai_event(cx, states[i], events[i]);
+}
+// rv_vec_apply_log_actions / rv_vec_replay_begin: thread per game (one record follows one kyoku of a parsed log)
+__global__ void __launch_bounds__(64) apply_log_actions_kernel(Tables T, G* states, int64_t n, const rv_log_action* acts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || acts[i].type == RV_LA_NONE) return;
+  Ctx cx;
+  cx.T = T;
+  cx.log = nullptr;
+  cx.log_cap = 0;
+  cx.defer_init = cx.defer_tail = false;
+  cx.idbits = nullptr;
+  apply_log_action(cx, states[i], acts[i]);
+}
+__global__ void __launch_bounds__(64) replay_begin_kernel(Tables T, G* states, int64_t n, const rv_log_kyoku* kyokus) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ctx cx;
+  cx.T = T;
+  cx.log = nullptr;
+  cx.log_cap = 0;
+  cx.defer_init = cx.defer_tail = false;
+  cx.idbits = nullptr;
+  replay_begin_patch(cx, states[i], kyokus[i]);
 }
 // rv_vec_step_agent: thread per game, every class of work inline (a test / evaluation path, not the throughput path)
 __global__ void __launch_bounds__(128) agent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap, int policy,
@@ -216,6 +240,9 @@ __global__ void debug_call_kernel(Tables T, G* state, uint32_t* log, uint32_t ca
   } else if (op == 2) {
     trigger_ryukyoku(cx, g, RV_RK_EXHAUSTIVE);
     out[7] = g.is_done;
+  } else if (op == 6) {                          // replay: claim lists of every seat against the last discard
+    if (g.last_discard_pid != RV_NONE) claims_after_tile(cx, g, g.last_discard_pid, g.last_discard_tile, false);
+    out[7] = (uint8_t)__popc(g.active_mask);
   } else {
     next_round(cx, g, op == 4, op == 5);       // 3: (false, false)  4: (oya_won, false)  5: (false, is_draw)
     out[7] = g.is_done;
@@ -844,58 +871,76 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
     // games are live than the crew can keep busy the rollout is bound by the latency of the longest games, not by
     // throughput (per-class accounting: 39 % of all warp cycles were idle polls).  Below `endgame_live` live games a warp
     // takes a few games from ANY class and plays them to the end in place, every transition inline, no queue round trips.
+    // ONE round trip for everything the decision needs: lane 0 reads the live-game counter, lane 1 the SM's class, lane 2 the
+    // error flag, lanes 4.. the head and lanes 12.. the tail of every class queue; the warp then decides uniformly and lane 0
+    // draws the tickets.  (Read one after the other by lane 0 these were four dependent L2 round trips per visit.)
     bool endgame = false;
-    if (lane == 0) {
-      endgame = ld_volatile_u32(&q.ctl[Q_LIVE]) < endgame_live;
+    uint32_t ctl_v = 0;
+    {
+      const uint32_t* a = nullptr;
+      if (lane == 0) a = &q.ctl[Q_LIVE];
+      else if (lane == 1) a = my_class;
+      else if (lane == 2) a = &q.ctl[Q_ERR];
+      else if (lane >= 4 && lane < 4 + N_QUEUES) a = &q.ctl[Q_HEAD + 32 * (lane - 4)];
+      else if (lane >= 12 && lane < 12 + N_QUEUES) a = &q.ctl[Q_TAIL + 32 * (lane - 12)];
+      if (a) ctl_v = ld_volatile_u32(a);
+    }
+    const uint32_t live_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 0);
+    const uint32_t err_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 2);
+    auto q_len = [&](int c) { return (int)(__shfl_sync(0xFFFFFFFFu, ctl_v, 12 + c) - __shfl_sync(0xFFFFFFFFu, ctl_v, 4 + c)); };
+    endgame = live_now < endgame_live;
+    {
+      int want_cap = PHB;
       if (endgame) {
-        for (int c = 0; c < N_QUEUES && take == 0; c++) {
-          cls = c;
-          take = q_claim(q, c, h, QDBG, endgame_take);
-        }
+        cls = PH_NONE;
+        want_cap = endgame_take;
+        for (int c = N_QUEUES - 1; c >= 0; c--)
+          if (q_len(c) > 0) cls = c;                       // first non-empty class
       } else {
-      cls = (int)ld_volatile_u32(my_class);
-      take = q_claim(q, cls, h, QDBG);
-      }
-      if (!endgame && take == 0 && idle >= 3) {
-        // move the SM: longest queue wins
-        int best = -1, best_len = 0;
-        for (int c = 0; c < N_QUEUES; c++) {
-          int len = (int)(ld_volatile_u32(&q.ctl[Q_TAIL + 32 * c]) - ld_volatile_u32(&q.ctl[Q_HEAD + 32 * c]));
-          if (len > best_len) best_len = len, best = c;
-        }
-        if (best >= 0) {
-          *reinterpret_cast<volatile uint32_t*>(my_class) = (uint32_t)best;
-          cls = best;
-          take = q_claim(q, cls, h, QDBG);
-          idle = 0;
+        cls = (int)__shfl_sync(0xFFFFFFFFu, ctl_v, 1);
+        const bool empty = q_len(cls) <= 0;
 #ifdef RV_QPROF
-          dbg[3]++;
+        if (empty && lane == 0) dbg[1]++;
 #endif
+        if (empty && idle >= 3) {
+          // move the SM: longest queue wins
+          int best = -1, best_len = 0;
+          for (int c = 0; c < N_QUEUES; c++) {
+            const int len = q_len(c);
+            if (len > best_len) best_len = len, best = c;
+          }
+          if (best >= 0) {
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(my_class) = (uint32_t)best;
+            cls = best;
+            idle = 0;
+#ifdef RV_QPROF
+            dbg[3]++;
+#endif
+          } else {
+            cls = PH_NONE;
+          }
+        } else if (empty) {
+          cls = PH_NONE;
         }
+      }
+      if (cls != PH_NONE) {
+        const int avail = q_len(cls);
+        take = avail < want_cap ? avail : want_cap;
+        if (lane == 0) h = atomicAdd(&q.ctl[Q_HEAD + 32 * cls], (uint32_t)take);
+        h = __shfl_sync(0xFFFFFFFFu, h, 0);
       }
     }
-    take = __shfl_sync(0xFFFFFFFFu, take, 0);
     if (take == 0) {
-      uint32_t live = 0, err = 0;
-      if (lane == 0) {
-        live = ld_volatile_u32(&q.ctl[Q_LIVE]);
-        err = ld_volatile_u32(&q.ctl[Q_ERR]);
-        if (live != 0 && err == 0 && ++idle > (1u << 22)) {     // watchdog: seconds without work while games are live
-          atomicExch(&q.ctl[Q_ERR], 1u);
-          err = 1;
-        }
+      if (live_now != 0 && err_now == 0 && ++idle > (1u << 22)) {     // watchdog: seconds without work while games are live
+        if (lane == 0) atomicExch(&q.ctl[Q_ERR], 1u);
+        break;
       }
-      live = __shfl_sync(0xFFFFFFFFu, live, 0);
-      err = __shfl_sync(0xFFFFFFFFu, err, 0);
-      if (live == 0 || err != 0) break;
+      if (live_now == 0 || err_now != 0) break;
       __nanosleep(300);
       QP(0);
       continue;
     }
     idle = 0;
-    cls = __shfl_sync(0xFFFFFFFFu, cls, 0);
-    h = __shfl_sync(0xFFFFFFFFu, h, 0);
-    endgame = __shfl_sync(0xFFFFFFFFu, (int)endgame, 0) != 0;
     int32_t gi = -1;
     if (lane < take) {
       int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + ((h + (uint32_t)lane) & q.mask);
@@ -917,9 +962,11 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
     if (lane == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)take * (uint32_t)RV_HOT_BYTES) : "memory");
     __syncwarp();
+    uint32_t b_in = 0;
     if (have) {
       stage_in(slot, &states[gi], bar);
       *reinterpret_cast<G**>(slot + RV_HOT_BYTES) = &states[gi];
+      b_in = budget[gi];          // in flight together with the bulk copy
     }
     {
       uint32_t ok = 0;
@@ -937,7 +984,7 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
       Ctx cx = make_ctx(T, log, cap, gi);
       cx.defer_init = true;
       cx.defer_tail = true;
-      uint32_t b = budget[gi];
+      uint32_t b = b_in;
       const uint32_t b0 = b;
       if (endgame) {
         cx.defer_init = false;
@@ -2172,9 +2219,49 @@ int rv_vec_apply_events(rv_vec* v, const rv_mjai_event* events) {
   CK(cudaStreamSynchronize(c->stream));
   return RV_OK;
 }
+int rv_vec_apply_log_actions(rv_vec* v, const rv_log_action* actions) {
+  if (!actions) return fail(RV_ERR_INVALID, "actions is null");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure(&v->d_io_a, &v->io_a_bytes, sizeof(rv_log_action) * (size_t)v->n);
+  if (rc != RV_OK) return rc;
+  rv_log_action* d_a = (rv_log_action*)v->d_io_a;
+  CK(cudaMemcpyAsync(d_a, actions, sizeof(rv_log_action) * (size_t)v->n, cudaMemcpyHostToDevice, c->stream));
+  apply_log_actions_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, d_a);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
+int rv_vec_replay_begin(rv_vec* v, const rv_log_kyoku* kyokus) {
+  if (!kyokus) return fail(RV_ERR_INVALID, "kyokus is null");
+  const int np = v->game_mode >= 3 ? 3 : 4;
+  std::vector<uint8_t> oya(v->n), rw(v->n), honba(v->n);
+  std::vector<uint32_t> ky(v->n);
+  std::vector<int32_t> sc((size_t)v->n * MAXP, 0);
+  for (int64_t i = 0; i < v->n; i++) {
+    const rv_log_kyoku& k = kyokus[i];
+    if (k.np != np) return fail(RV_ERR_INVALID, "kyoku " + std::to_string(i) + " has " + std::to_string(k.np) + " seats, the vector's game mode " + std::to_string(np));
+    oya[i] = k.oya < np ? k.oya : 0;
+    rw[i] = k.chang < 4 ? k.chang : 0;                       // LogKyoku::steps: chang -> Wind, anything else East
+    honba[i] = k.ben;
+    ky[i] = k.liqibang;
+    for (int p = 0; p < np; p++) sc[(size_t)i * MAXP + p] = k.scores[p];
+  }
+  int rc = rv_vec_reset(v, oya.data(), rw.data(), honba.data(), ky.data(), sc.data(), nullptr);   // _initialize_round(.., None, scores)
+  if (rc != RV_OK) return rc;
+  rv_ctx* c = v->ctx;
+  rc = ensure(&v->d_io_a, &v->io_a_bytes, sizeof(rv_log_kyoku) * (size_t)v->n);
+  if (rc != RV_OK) return rc;
+  rv_log_kyoku* d_k = (rv_log_kyoku*)v->d_io_a;
+  CK(cudaMemcpyAsync(d_k, kyokus, sizeof(rv_log_kyoku) * (size_t)v->n, cudaMemcpyHostToDevice, c->stream));
+  replay_begin_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, d_k);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
 int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out) {
   if (game < 0 || game >= v->n) return fail(RV_ERR_INVALID, "game index out of range");
-  if (op < 0 || op > 5) return fail(RV_ERR_INVALID, "op must be 0..5");
+  if (op < 0 || op > 6) return fail(RV_ERR_INVALID, "op must be 0..6");
   rv_ctx* c = v->ctx;
   CK(cudaSetDevice(c->device));
   uint8_t* d_out = nullptr;
@@ -2575,6 +2662,8 @@ int rv_sizeof(int which) {
     case 3: return (int)sizeof(rv_action);
     case 4: return (int)sizeof(rv_mjai_event);
     case 5: return (int)sizeof(rv_run_stats);
+    case 6: return (int)sizeof(rv_log_action);
+    case 7: return (int)sizeof(rv_log_kyoku);
   }
   return -1;
 }

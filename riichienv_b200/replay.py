@@ -1,0 +1,521 @@
+"""Replay ingestion: the reference's `MjaiReplay` / `Kyoku` / step-iterator surface.
+
+Reference: riichienv-core/src/replay/mjai_replay.rs (reader), replay/mod.rs:99-1010 (KyokuStepIterator, KyokuStepIterator3P),
+replay/mod.rs:1010-1590 (LogKyoku).  What runs where:
+
+* the log is parsed by the library (`rv_replay_from_jsonl`, csrc/replay.cpp) into fixed records: one `rv_log_kyoku` and a
+  list of `rv_log_action` per round;
+* the kyoku is tracked by the same game records the simulator uses: `rv_vec_replay_begin` (LogKyoku::steps' set-up) and
+  `rv_vec_apply_log_actions` (GameState::apply_log_action) run on the device, and the decision points in between are read
+  with the ordinary legal-action / observation calls;
+* this file is the host logic of the iterator (which decision a log action stands for, pass observations, the
+  reach → discard split), a line-for-line mirror of replay/mod.rs:206-532.
+
+`ReplayBatch` is the batched form the data-parallel path wants: K kyoku replayed in lock-step on one vector of K records.
+"""
+import ctypes as C
+
+from . import _abi as A
+from ._lib import check, lib
+from .env import Action, Action3P, ActionType, GameRule, MeldType, Observation, Observation3P, Phase, RiichiEnv
+
+
+def _tile_str(t: int) -> str:  # TileConverter::to_string (replay/mod.rs:2224-2241): red fives are "0m" / "0p" / "0s"
+    t34 = t // 4
+    if t34 // 9 > 3:
+        return "?"
+    if t in (16, 52, 88):
+        return "0" + "mpsz"[t34 // 9]
+    return f"{t34 % 9 + 1}{'mpsz'[t34 // 9]}"
+
+
+class _ActionView:
+    """one replay `Action` (replay/mod.rs:35-80) read off an rv_log_action"""
+
+    __slots__ = ("raw", "type", "seat", "tile", "is_liqi", "is_wliqi", "meld_type", "tiles", "froms", "hules", "moqie")
+
+    def __init__(self, a: A.LogAction):
+        self.raw = a
+        self.type, self.seat, self.tile = a.type, a.seat, a.tile
+        self.is_liqi, self.is_wliqi = bool(a.flags & 1), bool(a.flags & 2)
+        self.moqie = bool(a.flags & 1)
+        self.meld_type = a.meld_type
+        self.tiles = [a.tiles[k] for k in range(a.n_tiles)]
+        self.froms = [a.froms[k] for k in range(a.n_tiles)]
+        self.hules = [a.hules[k] for k in range(a.n_hule)]
+
+
+class LogKyoku:
+    """replay/mod.rs:1010-1590 (pyclass `Kyoku`)"""
+
+    def __init__(self, k: A.LogKyoku, actions, rule: GameRule):
+        self._k = k
+        self._actions = actions                  # ctypes array (A.LogAction * n)
+        self._views = [_ActionView(a) for a in actions]
+        self.rule = rule
+        n = k.np
+        self.scores = [k.scores[p] for p in range(n)]
+        self.end_scores = [k.end_scores[p] for p in range(n)]
+        self.doras = [k.doras[i] for i in range(min(k.n_doras, A.LOG_MAX_DORAS))]
+        self.ura_doras = [k.ura_doras[i] for i in range(min(k.n_ura_doras, A.LOG_MAX_DORAS))]
+        self.hands = [[k.hands[p][i] for i in range(k.hand_len[p])] for p in range(n)]
+        self.chang, self.ju, self.ben, self.liqibang = k.chang, k.ju, k.ben, k.liqibang
+        self.left_tile_count = k.left_tile_count
+        self.wliqi = [bool(k.wliqi[p]) for p in range(n)]
+        self.paishan = None                      # MJAI logs carry no wall
+        self.game_end_scores = [k.game_end_scores[p] for p in range(n)] if k.has_game_end_scores else None
+
+    # ---- features ----------------------------------------------------------------------------------
+    def grp_features(self):  # replay/mod.rs:1502-1522
+        d = [e - s for s, e in zip(self.scores, self.end_scores)] if len(self.scores) == len(self.end_scores) else []
+        return {"chang": self.chang, "ju": self.ju, "ben": self.ben, "liqibang": self.liqibang, "scores": list(self.scores),
+                "end_scores": list(self.end_scores), "wliqi": list(self.wliqi), "delta_scores": d}
+
+    def take_grp_features(self):  # replay/mod.rs:1524-1590
+        def ranks(scores):  # descending by score, lower seat wins ties
+            order = sorted(range(len(scores)), key=lambda i: (-scores[i], i))
+            out = [0] * len(scores)
+            for r, seat in enumerate(order):
+                out[seat] = r
+            return out
+
+        init = list(self.scores)
+        end = list(self.end_scores) if self.end_scores else init
+        ri, re = ranks(init), ranks(end)
+        d = {"chang": self.chang, "ju": self.ju, "ben": self.ben, "liqibang": self.liqibang,
+             "round_initial_scores": init, "round_end_scores": end, "round_delta_scores": [e - s for s, e in zip(init, end)],
+             "round_initial_ranks": ri, "round_end_ranks": list(re), "round_delta_ranks": [e - s for s, e in zip(ri, re)],
+             "final_ranks": ranks(self.game_end_scores) if self.game_end_scores is not None else re}
+        for i, h in enumerate(self.hands):
+            d[f"player{i}_initial_hand_tids"] = list(h)
+        return d
+
+    def events(self):  # replay/mod.rs:1294-1500
+        data = {"scores": list(self.scores), "doras": [_tile_str(t) for t in self.doras]}
+        if self.doras:
+            data["dora_marker"] = _tile_str(self.doras[0])
+        for i, h in enumerate(self.hands):
+            data[f"tiles{i}"] = [_tile_str(t) for t in h]
+        data.update(chang=self.chang, ju=self.ju, ben=self.ben, liqibang=self.liqibang, left_tile_count=self.left_tile_count)
+        if self.ura_doras:
+            data["ura_doras"] = [_tile_str(t) for t in self.ura_doras]
+        out = [{"name": "NewRound", "data": data}]
+        for a in self._views:
+            if a.type == A.LA_DISCARD:
+                ev = ("DiscardTile", {"seat": a.seat, "tile": _tile_str(a.tile), "is_liqi": a.is_liqi, "is_wliqi": a.is_wliqi})
+            elif a.type == A.LA_DEAL:
+                ev = ("DealTile", {"seat": a.seat, "tile": _tile_str(a.tile)})
+            elif a.type == A.LA_CHI_PENG_GANG:
+                mt = {MeldType.Chi: 0, MeldType.Pon: 1, MeldType.Daiminkan: 2, MeldType.Ankan: 3, MeldType.Kakan: 2}[MeldType(a.meld_type)]
+                ev = ("ChiPengGang", {"seat": a.seat, "type": mt, "tiles": [_tile_str(t) for t in a.tiles], "froms": list(a.froms)})
+            elif a.type == A.LA_ANGANG_ADDGANG:
+                d = {"seat": a.seat, "type": 3 if a.meld_type == MeldType.Ankan else 2}
+                if a.tiles:
+                    d["tiles"] = _tile_str(a.tiles[0])
+                ev = ("AnGangAddGang", d)
+            elif a.type == A.LA_HULE:
+                hs = []
+                for h in a.hules:
+                    hd = {"seat": h.seat, "hu_tile": _tile_str(h.hu_tile), "zimo": bool(h.zimo), "count": h.count, "fu": h.fu,
+                          "fans": [{"id": y} for y in range(64) if (h.fans >> y) & 1], "point_rong": h.point_rong,
+                          "point_zimo_qin": h.point_zimo_qin, "point_zimo_xian": h.point_zimo_xian, "yiman": bool(h.yiman)}
+                    if h.n_li_doras != 0xFF:
+                        hd["li_doras"] = [_tile_str(h.li_doras[i]) for i in range(min(h.n_li_doras, 5))]
+                    hs.append(hd)
+                ev = ("Hule", {"hules": hs})
+            elif a.type == A.LA_DORA:
+                ev = ("Dora", {"dora_marker": _tile_str(a.tile)})
+            elif a.type == A.LA_BABEI:
+                ev = ("BaBei", {"seat": a.seat, "moqie": a.moqie})
+            elif a.type == A.LA_NOTILE:
+                ev = ("NoTile", {})
+            elif a.type == A.LA_LIUJU:
+                ev = ("LiuJu", {"type": a.tile, "seat": a.seat, "tiles": [_tile_str(t) for t in a.tiles]})
+            else:
+                continue
+            out.append({"name": ev[0], "data": ev[1]})
+        return out
+
+    def take_win_result_contexts(self):
+        raise NotImplementedError("WinResultContextIterator (replay/mod.rs:1594-2180) verifies MjSoul paifu fans; MJAI logs carry "
+                                  "none — not built (SURVEY.md §8 f4 covers the step path)")
+
+    # ---- the step iterator -------------------------------------------------------------------------
+    def steps(self, seat=None, rule=None, skip_single_action=None):  # replay/mod.rs:1094-1292
+        return KyokuStepIterator(self, seat, rule or self.rule, True if skip_single_action is None else bool(skip_single_action))
+
+
+Kyoku = LogKyoku
+
+
+class _ReplayObsEnv:
+    """What a replay observation is bound to: the record it was taken from (by value).  The tensor encoders load it into
+    the iterator's game vector, run the device encoder and put the live record back."""
+
+    def __init__(self, it, record):
+        self._it, self._record = it, record
+        self._token = 0
+        self._np = it._np
+        self.skip_mjai_logging = False
+        self._ext_log = None
+
+    def _encode(self, pid, extended=False):
+        v = self._it._env._v
+        live = v.get_state(0)
+        v.set_state(0, self._record)
+        try:
+            return v.encode_single(pid, extended)
+        finally:
+            v.set_state(0, live)
+
+    def _encode_seq(self, pid, first_new_event):
+        raise NotImplementedError("sequence features of replay observations (the reference's progression cache, replay/mod.rs:1280) "
+                                  "are not built")
+
+
+class KyokuStepIterator:
+    """replay/mod.rs:99-532 (4P) and 113-1008 (3P): yields (obs, action) for `seat`, or (seat, obs, action) for seat=None."""
+
+    def __init__(self, kyoku: LogKyoku, seat, rule: GameRule, skip_single_action: bool):
+        self._kyoku = kyoku
+        self._np = kyoku._k.np
+        self._acls = Action3P if self._np == 3 else Action
+        # GameState::new(0, false, None, 0, rule): single-round mode, MJAI logging on.  (The reference seeds this scratch state
+        # from entropy; its wall only feeds the start_kyoku text of the event log, the logged hands replace the deal.)
+        self._env = RiichiEnv(game_mode=3 if self._np == 3 else 0, rule=rule, seed=0)
+        arr = (A.LogKyoku * 1)(kyoku._k)
+        self._env._v.replay_begin(arr)
+        self._env._event_counts = [0, 0, 0, 0]
+        self._env._log_cache = {}
+        self._env._token += 1
+        self._actions = kyoku._views
+        self._idx = 0
+        self._pending_action = None
+        self._filter = seat
+        self._skip_single = skip_single_action
+        self._pending_pass = []
+
+    def __iter__(self):
+        return self
+
+    # ---- state access -----------------------------------------------------------------------------
+    def _apply(self, a: _ActionView):
+        self._env._v.apply_log_actions((A.LogAction * 1)(a.raw))
+        self._env._token += 1
+
+    def _observe(self, pid):
+        """GameState::get_observation(pid) of the record as it stands, bound by value to that record"""
+        env = self._env
+        env._token += 1
+        s = env._state()
+        obs = env._observations([pid], s)[pid]
+        obs._env = _ReplayObsEnv(self, s)
+        obs._token = 0
+        return obs
+
+    def _get_observation_for_replay(self, pid, action, what):  # state/mod.rs:265-328
+        env = self._env
+        orig = env._state()
+        if action.action_type in (ActionType.RON, ActionType.CHI, ActionType.PON, ActionType.DAIMINKAN):
+            s = env._state()
+            s.phase = int(Phase.WaitResponse)
+            s.active_mask = 1 << pid
+            n = s.n_claims[pid]
+            if n < A.MAX_CLAIMS:                      # current_claims.entry(pid).or_default().push(env_action)
+                own = [t for t in action.consume_tiles if t != action.tile] or list(action.consume_tiles)
+                c = (own + [255, 255])[:2]
+                s.claims[pid][n] = int(action.action_type) | ((255 if action.tile is None else action.tile) << 8) | (c[0] << 16) | (c[1] << 24)
+                s.n_claims[pid] = n + 1
+            env._v.set_state(0, s)
+        obs = self._observe(pid)
+        if action.action_type == ActionType.KITA:      # 3P: any North tile is equivalent (state_3p/mod.rs:250-257)
+            exists = any(a.action_type == ActionType.KITA for a in obs._legal_actions)
+        else:
+            exists = any(a.action_type == action.action_type and a.tile == action.tile for a in obs._legal_actions)
+        keep_riichi_cleared = False
+        if not exists and action.action_type == ActionType.DISCARD and (orig.flags[pid] & A.F_RIICHI_DECLARED):
+            s = env._state()
+            s.flags[pid] &= ~A.F_RIICHI_DECLARED
+            env._v.set_state(0, s)
+            new_obs = self._observe(pid)
+            if any(a.action_type == ActionType.DISCARD and a.tile == action.tile for a in new_obs._legal_actions):
+                obs, exists, keep_riichi_cleared = new_obs, True, True
+        if keep_riichi_cleared:                       # the reference leaves riichi_declared cleared in this branch
+            orig.flags[pid] &= ~A.F_RIICHI_DECLARED
+        env._v.set_state(0, orig)                     # phase, active_players, current_claims (and the flag) back
+        if not exists:
+            raise RuntimeError(f"Replay desync:\n  Env action: {action!r}\n  Log action: {what}\n  Self state:\n"
+                               f"    phase: {Phase(orig.phase)!r}\n    drawn: {None if orig.drawn_tile == 255 else orig.drawn_tile}")
+        return obs
+
+    def _collect_pass_observations(self, discarder, tile, claimers):  # replay/mod.rs:130-181
+        env = self._env
+        orig = env._state()
+        env._v.call(6)                                # _get_claim_actions_for_player(i, discarder, tile) for every seat
+        listed = env._state()
+        for i in range(self._np):
+            if i == discarder or i in claimers or listed.n_claims[i] == 0:
+                continue
+            n = min(listed.n_claims[i], A.MAX_CLAIMS)
+            had_ron = any((listed.claims[i][k] & 0xFF) == ActionType.RON for k in range(n))
+            tmp = A.GameState.from_buffer_copy(bytes(orig))
+            tmp.phase = int(Phase.WaitResponse)
+            tmp.active_mask = 1 << i
+            for p in range(4):
+                tmp.n_claims[p] = 0
+            tmp.n_claims[i] = n
+            for k in range(n):
+                tmp.claims[i][k] = listed.claims[i][k]
+            env._v.set_state(0, tmp)
+            self._pending_pass.append((i, self._observe(i)))
+            if had_ron:                               # passing on a ron: same-turn furiten (permanent in riichi)
+                orig.flags[i] |= A.F_MISSED_AGARI_DOUJUN
+                if orig.flags[i] & A.F_RIICHI_DECLARED:
+                    orig.flags[i] |= A.F_MISSED_AGARI_RIICHI
+        env._v.set_state(0, orig)
+
+    def _peek_next_claimers(self):  # replay/mod.rs:183-198
+        if self._idx >= len(self._actions):
+            return []
+        a = self._actions[self._idx]
+        if a.type == A.LA_CHI_PENG_GANG:
+            return [a.seat]
+        if a.type == A.LA_HULE:
+            return [h.seat for h in a.hules if not h.zimo]
+        return []
+
+    def _emit(self, pid, obs, action, single_filter=True):
+        """the tail every arm of __next__ shares: filter by seat, drop forced decisions; None = keep iterating"""
+        if self._filter is not None:
+            if pid != self._filter:
+                return None
+            if single_filter and self._skip_single and len(obs._legal_actions) <= 1:
+                return None
+            return (obs, action)
+        return (pid, obs, action)
+
+    # ---- __next__ (replay/mod.rs:206-532; the 3P iterator differs in BaBei / Kita handling only) ----
+    def __next__(self):
+        acts = self._actions
+        A_ = self._acls
+        while True:
+            if self._pending_pass:
+                pid, obs = self._pending_pass.pop()
+                out = self._emit(pid, obs, A_(ActionType.PASS, None, [], pid))
+                if out is not None:
+                    return out
+                continue
+            if self._pending_action is not None:
+                pid, action = self._pending_action
+                self._pending_action = None
+                s = self._env._state()
+                staged = False
+                if action.action_type == ActionType.DISCARD and not (s.flags[pid] & (A.F_RIICHI_DECLARED | A.F_RIICHI_STAGE)):
+                    s.flags[pid] |= A.F_RIICHI_STAGE      # the discard after a reach: legal actions of a declared riichi
+                    self._env._v.set_state(0, s)
+                    staged = True
+                try:
+                    obs = self._get_observation_for_replay(pid, action, repr(acts[self._idx].raw.type))
+                finally:
+                    if staged:
+                        s = self._env._state()
+                        s.flags[pid] &= ~A.F_RIICHI_STAGE
+                        self._env._v.set_state(0, s)
+                self._apply(acts[self._idx])
+                self._idx += 1
+                if action.action_type == ActionType.DISCARD and action.tile is not None:
+                    self._collect_pass_observations(pid, action.tile, self._peek_next_claimers())
+                out = self._emit(pid, obs, action)
+                if out is not None:
+                    return out
+                continue
+            if self._idx >= len(acts):
+                raise StopIteration
+            a = acts[self._idx]
+            if a.type in (A.LA_DEAL, A.LA_DORA, A.LA_NOTILE, A.LA_LIUJU) or (a.type == A.LA_BABEI and self._np == 4):
+                self._apply(a)
+                self._idx += 1
+            elif a.type == A.LA_NONE:
+                self._idx += 1
+            elif a.type == A.LA_BABEI:                    # 3P: a Kita decision (replay/mod.rs:723-755)
+                pid = a.seat
+                action = A_(ActionType.KITA, None, [], None)
+                obs = self._get_observation_for_replay(pid, action, "BaBei")
+                self._apply(a)
+                self._idx += 1
+                out = self._emit(pid, obs, action)
+                if out is not None:
+                    return out
+            elif a.type == A.LA_DISCARD:
+                pid = a.seat
+                action = A_(ActionType.DISCARD, a.tile, [], None)
+                if a.is_liqi:
+                    riichi = A_(ActionType.RIICHI, None, [], None)
+                    obs = self._get_observation_for_replay(pid, riichi, "DiscardTile")
+                    self._pending_action = (pid, action)
+                    out = self._emit(pid, obs, riichi, single_filter=False)
+                    if out is not None:
+                        return out
+                else:
+                    obs = self._get_observation_for_replay(pid, action, "DiscardTile")
+                    self._apply(a)
+                    self._idx += 1
+                    self._collect_pass_observations(pid, a.tile, self._peek_next_claimers())
+                    out = self._emit(pid, obs, action)
+                    if out is not None:
+                        return out
+            elif a.type == A.LA_CHI_PENG_GANG:
+                pid = a.seat
+                ty = {MeldType.Chi: ActionType.CHI, MeldType.Pon: ActionType.PON, MeldType.Daiminkan: ActionType.DAIMINKAN}.get(
+                    MeldType(a.meld_type), ActionType.CHI)
+                action = A_(ty, a.tiles[0] if a.tiles else None, list(a.tiles), None)
+                obs = self._get_observation_for_replay(pid, action, "ChiPengGang")
+                self._apply(a)
+                self._idx += 1
+                out = self._emit(pid, obs, action)
+                if out is not None:
+                    return out
+            elif a.type == A.LA_ANGANG_ADDGANG:
+                pid = a.seat
+                t0 = a.tiles[0] if a.tiles else 0
+                if a.meld_type == MeldType.Kakan:
+                    cons = []
+                    for m in self._env.melds[pid]:
+                        if m.meld_type == MeldType.Pon and m.tiles[0] // 4 == t0 // 4:
+                            cons = list(m.tiles)
+                            break
+                    action = A_(ActionType.KAKAN, t0, cons, None)
+                else:
+                    lo = (t0 // 4) * 4
+                    action = A_(ActionType.ANKAN, lo, [lo, lo + 1, lo + 2, lo + 3], None)
+                obs = self._get_observation_for_replay(pid, action, "AnGangAddGang")
+                self._apply(a)
+                self._idx += 1
+                out = self._emit(pid, obs, action)
+                if out is not None:
+                    return out
+            elif a.type == A.LA_HULE:
+                first = a.hules[0]
+                pid = first.seat
+                s = self._env._state()
+                tsumo = bool(first.zimo) and pid == s.current_player
+                if tsumo:
+                    action = A_(ActionType.TSUMO, None if s.drawn_tile == 255 else s.drawn_tile, [], None)
+                else:
+                    action = A_(ActionType.RON, None if s.last_discard_pid == 255 else s.last_discard_tile, [], None)
+                obs = self._get_observation_for_replay(pid, action, "Hule")
+                self._apply(a)
+                self._idx += 1
+                out = self._emit(pid, obs, action)
+                if out is not None:
+                    return out
+            else:
+                self._idx += 1
+
+
+KyokuStepIterator3P = KyokuStepIterator
+
+
+class KyokuIterator:
+    """mjai_replay.rs:36-62"""
+
+    def __init__(self, replay):
+        self._replay, self._i = replay, 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._i >= len(self._replay.rounds):
+            raise StopIteration
+        self._i += 1
+        return self._replay.rounds[self._i - 1]
+
+
+class MjaiReplay:
+    """mjai_replay.rs:28-385: `MjaiReplay.from_jsonl(path, rule=None)` — plain or gzip JSON lines (detected by content)."""
+
+    def __init__(self, rounds):
+        self.rounds = rounds
+
+    @staticmethod
+    def _rule(rule):
+        if rule is None or rule == "tenhou":
+            return GameRule.default_tenhou()
+        if rule == "mjsoul":
+            return GameRule.default_mjsoul()
+        raise ValueError(f"Unknown rule: '{rule}'. Expected 'tenhou' or 'mjsoul'")
+
+    @classmethod
+    def _from_handle(cls, h, rule):
+        try:
+            rounds = []
+            for r in range(lib().rv_replay_num_rounds(h)):
+                k = A.LogKyoku()
+                check(lib().rv_replay_kyoku(h, r, C.byref(k)))
+                acts = (A.LogAction * max(1, k.n_actions))()
+                n = C.c_int(0)
+                check(lib().rv_replay_actions(h, r, acts, k.n_actions, C.byref(n)))
+                rounds.append(LogKyoku(k, (A.LogAction * k.n_actions).from_buffer_copy(bytes(acts)[: C.sizeof(A.LogAction) * k.n_actions])
+                                       if k.n_actions else (A.LogAction * 0)(), rule))
+            return cls(rounds)
+        finally:
+            lib().rv_replay_free(h)
+
+    @classmethod
+    def from_jsonl(cls, path, rule=None):
+        g = cls._rule(rule)
+        h = C.c_void_p()
+        check(lib().rv_replay_from_jsonl(str(path).encode(), g.bits(), C.byref(h)))
+        return cls._from_handle(h, g)
+
+    @classmethod
+    def from_text(cls, text, rule=None):
+        """the same reader over JSON lines already in memory (not in the reference: its reader only takes a path)"""
+        g = cls._rule(rule)
+        data = text.encode() if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        check(lib().rv_replay_from_text(data, len(data), g.bits(), C.byref(h)))
+        return cls._from_handle(h, g)
+
+    def num_rounds(self):
+        return len(self.rounds)
+
+    def take_kyokus(self):
+        return KyokuIterator(self)
+
+
+class ReplayBatch:
+    """K kyoku replayed in lock-step on ONE vector of K game records (the data-parallel form of `Kyoku.steps`): call
+    `advance()` until it returns False; after each call `self.vec` holds every kyoku one log action further, and the usual
+    batched readers (legal_actions, encode, encode_extended, get_state) see all K positions at once."""
+
+    def __init__(self, kyokus, device=0):
+        from .vec_env import VecRiichiEnv
+
+        kyokus = list(kyokus)
+        if not kyokus:
+            raise ValueError("no kyoku")
+        np_ = kyokus[0]._k.np
+        if any(k._k.np != np_ for k in kyokus):
+            raise ValueError("a batch holds kyoku of one variant (all 4P or all sanma)")
+        self.kyokus = kyokus
+        self.n = len(kyokus)
+        self.vec = VecRiichiEnv(self.n, 3 if np_ == 3 else 0, kyokus[0].rule.bits(), seed_base=0, log_cap_words=0, device=device)
+        self.vec.replay_begin((A.LogKyoku * self.n)(*[k._k for k in kyokus]))
+        self.cursor = [0] * self.n
+
+    def advance(self):
+        """apply the next log action of every kyoku that has one; returns False when every kyoku is exhausted"""
+        arr = (A.LogAction * self.n)()
+        live = False
+        for i, k in enumerate(self.kyokus):
+            if self.cursor[i] < len(k._views):
+                arr[i] = k._views[self.cursor[i]].raw
+                self.cursor[i] += 1
+                live = True
+            else:
+                arr[i].type = A.LA_NONE
+        if live:
+            self.vec.apply_log_actions(arr)
+        return live

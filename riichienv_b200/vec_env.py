@@ -192,6 +192,14 @@ class VecRiichiEnv:
         """GameState::apply_mjai_event for every game: `events` = ctypes array (A.MjaiEvent * n), type 0 = no event"""
         check(lib().rv_vec_apply_events(self.handle, events))
 
+    def replay_begin(self, kyokus):
+        """LogKyoku::steps' state set-up for every game: `kyokus` = ctypes array (A.LogKyoku * n)"""
+        check(lib().rv_vec_replay_begin(self.handle, kyokus))
+
+    def apply_log_actions(self, actions):
+        """GameState::apply_log_action for every game: `actions` = ctypes array (A.LogAction * n), type 0 = no action"""
+        check(lib().rv_vec_apply_log_actions(self.handle, actions))
+
     def clone(self):
         """independent copy of every game (RiichiEnv.clone, env.rs:358-372)"""
         o = object.__new__(type(self))

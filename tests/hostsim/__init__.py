@@ -46,6 +46,8 @@ def load():
     lib.hs_game_random_step_deferred.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.hs_game_random_step_deferred.restype = C.c_int
     lib.hs_game_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
+    lib.hs_game_apply_log_action.argtypes = [C.c_void_p, P(A.LogAction)]
+    lib.hs_game_replay_begin.argtypes = [C.c_void_p, P(A.LogKyoku)]
     lib.hs_game_load_snapshot.argtypes = [C.c_void_p, P(A.GameState)]
     lib.hs_state_defect.restype = C.c_char_p
     lib.hs_state_defect.argtypes = [P(A.GameState)]

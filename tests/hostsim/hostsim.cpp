@@ -307,6 +307,23 @@ void hs_game_apply_event(void* p, const rv_mjai_event* e) {
   cx.log_cap = 0;
   if (e->type != RV_EV_NONE) apply_mjai_event(cx, h->g, *e);
 }
+void hs_game_apply_log_action(void* p, const rv_log_action* a) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  cx.log = nullptr;
+  cx.log_cap = 0;
+  if (a->type != RV_LA_NONE) apply_log_action(cx, h->g, *a);
+}
+void hs_game_replay_begin(void* p, const rv_log_kyoku* k) {
+  HS* h = (HS*)p;
+  Ctx cx = hs_ctx(h);
+  const int np = h->g.game_mode >= 3 ? 3 : 4;
+  int32_t sc[4] = {k->scores[0], k->scores[1], k->scores[2], k->scores[3]};
+  game_reset(cx, h->g, k->oya < np ? k->oya : 0, k->chang < 4 ? k->chang : 0, k->ben, k->liqibang, nullptr, sc);
+  cx.log = nullptr;
+  cx.log_cap = 0;
+  replay_begin_patch(cx, h->g, *k);
+}
 void hs_game_agent_step(void* p, int policy, uint64_t agent_seed, uint64_t game_id) {
   HS* h = (HS*)p;
   Ctx cx = hs_ctx(h);
@@ -353,6 +370,10 @@ int hs_game_call(void* p, int op, uint8_t* out) {   // env.rs:624-631 test hooks
   if (op == 2) {
     trigger_ryukyoku(cx, h->g, RV_RK_EXHAUSTIVE);
     return h->g.is_done;
+  }
+  if (op == 6) {
+    if (h->g.last_discard_pid != RV_NONE) claims_after_tile(cx, h->g, h->g.last_discard_pid, h->g.last_discard_tile, false);
+    return __builtin_popcount(h->g.active_mask);
   }
   if (op >= 3 && op <= 5) {
     next_round(cx, h->g, op == 4, op == 5);

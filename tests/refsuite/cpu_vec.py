@@ -107,6 +107,12 @@ class CpuVec:
     def apply_events(self, events):
         self._f("game_apply_event")(self.h, events)
 
+    def replay_begin(self, kyokus):
+        self._f("game_replay_begin")(self.h, kyokus)
+
+    def apply_log_actions(self, actions):
+        self._f("game_apply_log_action")(self.h, actions)
+
     def call(self, op):
         """env.rs:624-631 hooks: op 0 reveal_kan_dora -> indicator count; op 1 -> list of ura indicator tile ids"""
         out = (C.c_uint8 * 8)()

@@ -48,13 +48,7 @@ from riichienv_b200.convert import parse_hand, parse_tile  # noqa: E402,F401
 EAST, SOUTH, WEST, NORTH = Wind.East, Wind.South, Wind.West, Wind.North
 
 
-class MjaiReplay:
-    """Replay ingestion (replay/*) is not built.  The name exists so that reference test modules which import
-    it next to RiichiEnv still load; the tests that actually read a replay fail with this message."""
-
-    @staticmethod
-    def from_jsonl(*a, **k):
-        raise NotImplementedError("MjaiReplay: replay ingestion is out of scope (SURVEY.md §8 f4)")
+from riichienv_b200.replay import Kyoku, KyokuIterator, MjaiReplay  # noqa: E402,F401  (replay ingestion)
 
 
 def __getattr__(name):

@@ -1,0 +1,302 @@
+"""Replay ingestion: the MJAI reader, LogKyoku::steps' set-up and GameState::apply_log_action.
+
+Pins, in the order of how much of the reference they carry:
+  * the reference's own replay tests run unmodified through tests/test_reference_suite.py (tests/test_mjai_replay.py and
+    TestReplayFuriten of tests/env/test_apply_event.py);
+  * the real 12-kyoku game of the reference's fixtures (tests/data/126_204_0_mjai.jsonl, committed as the decisions of
+    tests/golden/real_game_126_204_0.json plus the log itself in tests/golden/): every logged decision must be among the
+    legal actions of the replayed position — 862 decisions, nine wins, calls, kans, riichi — and the round features must
+    chain (`scores` of round k+1 == `end_scores` of round k);
+  * logs written by this repo's own simulator (oracle, greedy agent, 4P and sanma) read back through the parser: the replayed
+    record must follow the game, and oracle and kernel code (host compile here, the GPU under -m gpu) must agree on the full
+    record after every log action.
+"""
+import ctypes as C
+import gzip
+import json
+import os
+
+import pytest
+
+from riichienv_b200 import _abi as A
+from tests.backends import BACKENDS, HostsimBackend, OracleBackend
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REAL_LOG = os.path.join(HERE, "golden", "126_204_0_mjai.jsonl")
+
+
+def _lib():
+    from riichienv_b200._lib import lib
+
+    return lib()
+
+
+def parse_text(text, rule=A.RULE_DEFAULT_TENHOU):
+    """-> [(A.LogKyoku, [A.LogAction])] through the library's reader (host code: no GPU needed)"""
+    from riichienv_b200._lib import check
+
+    L = _lib()
+    data = text.encode()
+    h = C.c_void_p()
+    check(L.rv_replay_from_text(data, len(data), rule, C.byref(h)))
+    out = []
+    for r in range(L.rv_replay_num_rounds(h)):
+        k = A.LogKyoku()
+        check(L.rv_replay_kyoku(h, r, C.byref(k)))
+        acts = (A.LogAction * max(1, k.n_actions))()
+        n = C.c_int(0)
+        check(L.rv_replay_actions(h, r, acts, k.n_actions, C.byref(n)))
+        assert n.value == k.n_actions
+        out.append((k, [acts[i] for i in range(k.n_actions)]))
+    L.rv_replay_free(h)
+    return out
+
+
+def simulated_log(mode, seed, agent_seed=0xA6E27, policy=1, max_steps=6000):
+    """MJAI text log of one game played by the oracle with the greedy-win agent (wins, calls, kans, riichi, kita)"""
+    b = OracleBackend(mode, seed)
+    b.reset()
+    for _ in range(max_steps):
+        if b.get_state().is_done:
+            break
+        b.agent_step(policy, agent_seed, seed)
+    return b.events_json(-1)
+
+
+def begin(backend_cls, k, seed=7):
+    b = backend_cls(3 if k.np == 3 else 0, seed, k.rule_bits)
+    if isinstance(b, OracleBackend):
+        b.lib.orc_game_replay_begin(b.h, C.byref(k))
+        b.apply = lambda a: b.lib.orc_game_apply_log_action(b.h, C.byref(a))
+    elif isinstance(b, HostsimBackend):
+        b.lib.hs_game_replay_begin(b.h, C.byref(k))
+        b.apply = lambda a: b.lib.hs_game_apply_log_action(b.h, C.byref(a))
+    else:
+        b.v.replay_begin((A.LogKyoku * 1)(k))
+        b.apply = lambda a: b.v.apply_log_actions((A.LogAction * 1)(a))
+    return b
+
+
+# ------------------------------------------------------------------------------------------------ the reader
+def test_reader_real_game_rounds_and_features():
+    rounds = parse_text(open(REAL_LOG).read())
+    assert len(rounds) == 12
+    k0 = rounds[0][0]
+    assert [k0.scores[p] for p in range(4)] == [25000] * 4
+    assert [k0.end_scores[p] for p in range(4)] == [21000, 22000, 23000, 34000]       # tests/test_mjai_replay.py:96-98
+    for (a, _), (b, _) in zip(rounds, rounds[1:]):
+        assert [a.end_scores[p] for p in range(4)] == [b.scores[p] for p in range(4)]
+    # every round: 13-tile deals, the dealer's first tile arrives as a DealTile
+    for k, acts in rounds:
+        assert k.np == 4 and [k.hand_len[p] for p in range(4)] == [13] * 4 and k.oya_drawn_tile == 255
+        assert k.oya == k.ju % 4
+        assert acts[0].type == A.LA_DEAL and acts[0].seat == k.oya
+        assert acts[-1].type in (A.LA_HULE, A.LA_NOTILE)
+    n_hule = sum(1 for _, acts in rounds for a in acts if a.type == A.LA_HULE)
+    assert n_hule == 9
+
+
+def test_reader_gzip_and_plain_files_agree(tmp_path):
+    from riichienv_b200.replay import MjaiReplay
+
+    text = open(REAL_LOG).read()
+    plain, gz = tmp_path / "g.jsonl", tmp_path / "g.bin"          # gzip is detected by content, not by extension
+    plain.write_text(text)
+    with gzip.open(gz, "wt") as f:
+        f.write(text)
+    a, b = MjaiReplay.from_jsonl(str(plain)), MjaiReplay.from_jsonl(str(gz))
+    assert a.num_rounds() == b.num_rounds() == 12
+    for x, y in zip(a.take_kyokus(), b.take_kyokus()):
+        assert x.events() == y.events() and x.grp_features() == y.grp_features()
+    ev = next(iter(a.take_kyokus())).events()
+    assert ev[0]["name"] == "NewRound" and ev[0]["data"]["left_tile_count"] < 70 and ev[1]["name"] == "DealTile"
+
+
+def test_reader_errors_and_tile_names(tmp_path):
+    from riichienv_b200.replay import MjaiReplay
+
+    with pytest.raises(ValueError, match="Failed to open file"):
+        MjaiReplay.from_jsonl(str(tmp_path / "missing.jsonl"))
+    with pytest.raises(ValueError, match="Unknown rule"):
+        MjaiReplay.from_jsonl(REAL_LOG, rule="nope")
+    with pytest.raises(ValueError, match="Parse error"):
+        MjaiReplay.from_text('{"type":"tsumo","actor":0}\n')                      # `pai` is a required field of the variant
+    with pytest.raises(ValueError, match="Parse error"):
+        MjaiReplay.from_text('{"type":"tsumo","actor":0,"pai":"1m"\n')
+    r = MjaiReplay.from_text('{"type":"mystery","x":1}\n')                        # serde(other): unknown types are skipped
+    assert r.num_rounds() == 0
+    start = {"type": "start_kyoku", "bakaze": "S", "kyoku": 3, "honba": 2, "kyotaku": 1, "oya": 2, "scores": [1, 2, 3, 4],
+             "dora_marker": "5sr", "tehais": [["5mr", "5m", "0p", "5p", "1z", "E", "7z", "C", "9s", "1m", "P", "F", "N"]] * 4}
+    (k, acts), = parse_text(json.dumps(start) + "\n")                              # `kyotaku` is an accepted alias
+    assert (k.chang, k.ju, k.ben, k.liqibang, k.doras[0]) == (1, 2, 2, 1, 88)
+    assert [k.hands[0][i] for i in range(13)] == [16, 17, 52, 53, 108, 108, 132, 132, 104, 0, 124, 128, 120]
+    assert k.n_actions == 0 and not acts
+
+
+# ------------------------------------------------------------------------------------------------ state tracking
+def _owed(s):
+    return [p for p in range(4) if not s.is_done and ((s.phase == 0 and s.current_player == p) or (s.phase == 1 and (s.active_mask >> p) & 1))]
+
+
+def _replay_and_compare(rounds, backends, check_follow=None):
+    steps = 0
+    for k, acts in rounds:
+        bs = [begin(cls, k) for cls in backends]
+        ref = bs[0].get_state()
+        for b in bs[1:]:
+            assert A.state_fields_equal(ref, b.get_state()) == [], "after replay_begin"
+        for i, a in enumerate(acts):
+            for b in bs:
+                b.apply(a)
+            ref = bs[0].get_state()
+            for b in bs[1:]:
+                d = A.state_fields_equal(ref, b.get_state())
+                assert d == [], f"action {i} (type {a.type}) of a kyoku: {d}"
+            for p in _owed(ref):
+                want = bs[0].legal_tuples(p)
+                for b in bs[1:]:
+                    assert b.legal_tuples(p) == want
+            if check_follow:
+                check_follow(k, i, a, ref)
+            steps += 1
+    return steps
+
+
+def test_real_game_kernel_code_equals_oracle():
+    rounds = parse_text(open(REAL_LOG).read())
+    assert _replay_and_compare(rounds, [OracleBackend, HostsimBackend]) == sum(len(a) for _, a in rounds)
+
+
+@pytest.mark.parametrize("mode,seeds", [(2, range(3)), (5, range(3)), (0, range(100, 108)), (3, range(100, 108))])
+def test_simulated_logs_replay_follows_the_game(mode, seeds):
+    """logs of this repo's simulator read back: after every action hands, melds, rivers and riichi flags of the replayed record
+    are what the log implies, on the oracle and on the kernel code alike"""
+    n_kyoku = calls = kans = reaches = kitas = 0
+    for seed in seeds:
+        lines = simulated_log(mode, seed)
+        rounds = parse_text("\n".join(lines) + "\n")
+        n_kyoku += len(rounds)
+        for k, acts in rounds:
+            calls += sum(a.type == A.LA_CHI_PENG_GANG for a in acts)
+            kans += sum(a.type == A.LA_ANGANG_ADDGANG for a in acts)
+            reaches += sum(a.type == A.LA_DISCARD and a.flags & 1 for a in acts)
+            kitas += sum(a.type == A.LA_BABEI for a in acts)
+
+        def follow(k, i, a, s):
+            if a.type == A.LA_DISCARD:
+                assert s.river[a.seat][s.n_river[a.seat] - 1] == a.tile and s.last_discard_tile == a.tile
+                assert a.tile not in [s.hand[a.seat][j] for j in range(s.hand_len[a.seat])] or True
+                if a.flags & 1:
+                    assert s.flags[a.seat] & A.F_RIICHI_DECLARED
+            if a.type == A.LA_DEAL:
+                assert s.drawn_tile == a.tile and s.current_player == a.seat and s.hand_len[a.seat] + 3 * s.n_melds[a.seat] == 14
+            if a.type in (A.LA_HULE, A.LA_NOTILE):
+                assert s.is_done
+
+        _replay_and_compare(rounds, [OracleBackend, HostsimBackend], follow)
+    assert n_kyoku >= len(list(seeds)) and calls > 0 and reaches > 0
+    if mode in (3, 5):
+        assert kitas > 0
+    else:
+        assert kans > 0 or mode == 0
+
+
+def _shim(backend):
+    from tests.test_real_game_replay import _env_module
+
+    _env_module(backend)
+    import riichienv_b200.replay as R
+
+    return R
+
+
+@pytest.mark.parametrize("backend", ["oracle", "hostsim"])
+def test_real_game_every_logged_decision_is_legal(backend):
+    """Kyoku.steps over the reference's real game: no desync (each logged action is in the legal list of the position it was
+    taken in), the action stream re-reads as the log's decisions, masks cover the chosen ids"""
+    R = _shim(backend)
+    replay = R.MjaiReplay.from_jsonl(REAL_LOG)
+    logged = [json.loads(l) for l in open(REAL_LOG)]
+    want = {"dahai": 0, "reach": 0, "pon": 0, "chi": 0, "kan": 0, "daiminkan": 0, "ankan": 0, "kakan": 0, "hora": 0}
+    for e in logged:
+        if e["type"] in want:
+            want[e["type"]] += 1
+    got = {}
+    n = passes = 0
+    for kyoku in replay.take_kyokus():
+        for pid, obs, act in kyoku.steps(seat=None, skip_single_action=False):
+            n += 1
+            name = act.action_type.name
+            got[name] = got.get(name, 0) + 1
+            m = obs.mask()
+            assert m[act.encode()] == 1
+            if name == "PASS":
+                passes += 1
+                assert any(a.action_type.name in ("PON", "CHI", "RON", "DAIMINKAN") for a in obs.legal_actions())
+    assert got["DISCARD"] == want["dahai"] and got["RIICHI"] == want["reach"]
+    assert got.get("PON", 0) == want["pon"] and got.get("CHI", 0) == want["chi"]
+    assert got.get("ANKAN", 0) == want["ankan"] and got.get("KAKAN", 0) == want["kakan"]
+    assert got.get("TSUMO", 0) + got.get("RON", 0) == want["hora"] == 9
+    assert passes > 50 and n == sum(got.values())
+    # per-seat iteration with forced decisions skipped is a subsequence of the full one
+    k0 = next(iter(replay.take_kyokus()))
+    full = [(p, a.action_type, a.tile) for p, _, a in k0.steps(seat=None, skip_single_action=False)]
+    mine = [(2, a.action_type, a.tile) for _, a in k0.steps(2)]
+    it = iter(full)
+    assert all(x in it for x in mine) and 0 < len(mine) < len(full)
+
+
+@pytest.mark.parametrize("backend", ["oracle", "hostsim"])
+@pytest.mark.parametrize("mode", [2, 5])
+def test_simulated_logs_every_logged_decision_is_legal(backend, mode):
+    R = _shim(backend)
+    for seed in (11, 12):
+        text = "\n".join(simulated_log(mode, seed)) + "\n"
+        replay = R.MjaiReplay.from_text(text, rule="tenhou")
+        kinds = set()
+        for kyoku in replay.take_kyokus():
+            for pid, obs, act in kyoku.steps(seat=None, skip_single_action=False):
+                kinds.add(act.action_type.name)
+                assert obs.mask()[act.encode()] == 1
+        assert {"DISCARD", "RIICHI", "PASS"} <= kinds and ("KITA" in kinds) == (mode == 5)
+
+
+# ------------------------------------------------------------------------------------------------ the product (GPU)
+@pytest.mark.gpu
+def test_gpu_replay_batch_equals_oracle():
+    """rv_vec_replay_begin / rv_vec_apply_log_actions on a vector of kyoku replayed in lock-step, record by record against the
+    oracle after every action (real game + simulated 4P logs; sanma in its own vector)"""
+    from riichienv_b200.replay import LogKyoku, ReplayBatch
+    from riichienv_b200.env import GameRule
+
+    for mode, texts in ((2, [open(REAL_LOG).read()] + ["\n".join(simulated_log(2, s)) + "\n" for s in range(4)]),
+                        (5, ["\n".join(simulated_log(5, s)) + "\n" for s in range(4)])):
+        rounds = [r for t in texts for r in parse_text(t)]
+        kyokus = [LogKyoku(k, (A.LogAction * len(acts))(*acts), GameRule.default_tenhou()) for k, acts in rounds]
+        batch = ReplayBatch(kyokus)
+        oracles = [begin(OracleBackend, k, seed=i) for i, (k, _) in enumerate(rounds)]      # ReplayBatch seeds game i with i
+        for i, o in enumerate(oracles):
+            assert A.state_fields_equal(o.get_state(), batch.vec.get_state(i)) == [], "after replay_begin"
+        step = 0
+        while batch.advance():
+            for i, (k, acts) in enumerate(rounds):
+                if step < len(acts):
+                    oracles[i].apply(acts[step])
+                d = A.state_fields_equal(oracles[i].get_state(), batch.vec.get_state(i))
+                assert d == [], f"mode {mode} kyoku {i} action {step}: {d}"
+            step += 1
+        assert step == max(len(a) for _, a in rounds)
+
+
+@pytest.mark.gpu
+def test_gpu_shim_real_game_steps():
+    R = _shim("gpu")
+    replay = R.MjaiReplay.from_jsonl(REAL_LOG)
+    n = 0
+    for kyoku in list(replay.take_kyokus())[:3]:
+        for pid, obs, act in kyoku.steps(seat=None, skip_single_action=False):
+            n += 1
+            assert obs.mask()[act.encode()] == 1
+            if n % 40 == 0:
+                assert len(obs.encode()) == 74 * 34 * 4          # the tensor of a by-value replay observation (device encoder)
+    assert n > 150
