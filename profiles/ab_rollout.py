@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""A/B of the headline rollout between two builds of the library in ONE process on ONE box (fresh boxes differ by a few %):
-usage: ab_rollout.py lib_a.so lib_b.so [games] — alternates the builds, 5 rollouts each, prints G env steps/s per rollout."""
+"""A/B of the headline rollout between builds / knob settings in ONE process on ONE box (fresh boxes differ by a few %):
+usage: ab_rollout.py SPEC SPEC [SPEC ...] [--games N] — SPEC = lib.so[:VAR=val[,VAR=val...]] (environment knobs the library
+reads per call, e.g. RV_ACT_HOLD=0); alternates the variants, 5 timed rollouts each, prints G env steps/s per rollout."""
 import ctypes as C
 import sys
 
@@ -38,18 +39,32 @@ def rollout(L, ctx, v, k):
     return n.value / ms.value / 1e6
 
 
-games = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
-libs = []
-for path in sys.argv[1:3]:
-    L, ctx = load(path)
-    v = C.c_void_p()
-    assert L.rv_vec_create(ctx, games, 2, 0xC0, None, 0, 0, C.byref(v)) == 0
-    libs.append((path, L, ctx, v))
-res = {p: [] for p, *_ in libs}
+import os
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+games = 65536
+if "--games" in sys.argv:
+    games = int(sys.argv[sys.argv.index("--games") + 1])
+    args.remove(str(games))
+libs, loaded = [], {}
+for spec in args:
+    path, _, knobs = spec.partition(":")
+    env = dict(kv.split("=", 1) for kv in knobs.split(",") if kv)
+    if path not in loaded:
+        L, ctx = load(path)
+        v = C.c_void_p()
+        assert L.rv_vec_create(ctx, games, 2, 0xC0, None, 0, 0, C.byref(v)) == 0
+        loaded[path] = (L, ctx, v)
+    libs.append((spec, env) + loaded[path])
+res = {spec: [] for spec, *_ in libs}
+knob_names = sorted({k for _, env, *_ in libs for k in env})
 for k in range(7):
-    for path, L, ctx, v in libs:
+    for spec, env, L, ctx, v in libs:
+        for name in knob_names:
+            os.environ.pop(name, None)
+        os.environ.update(env)
         r = rollout(L, ctx, v, k)
         if k >= 2:
-            res[path].append(r)
+            res[spec].append(r)
 for p, r in res.items():
     print(f"{p}: {' '.join(f'{x:.3f}' for x in r)}  median {sorted(r)[len(r) // 2]:.3f} G env steps/s")

@@ -798,7 +798,7 @@ __device__ __forceinline__ void q_push(const Queues& q, int cls, int32_t gi) {
     }
   }
 }
-__global__ void q_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, Queues q) {
+__global__ void q_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, Queues q, int init_dist) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cls = PH_NONE;
   if (i < n) {
@@ -808,7 +808,8 @@ __global__ void q_init_kernel(const G* states, int64_t n, uint32_t* budget, uint
   if (i < 256) {
     // initial class of every SM; shares follow the measured per-class warp time
     const int r = (int)i & 15;
-    q.ctl[Q_SMCLASS + i] = r < 7 ? PH_ACT : r < 10 ? PH_TAIL : r < 13 ? PH_RESP : r < 15 ? PH_SLOW : PH_DEAL;
+    if (init_dist == 0) q.ctl[Q_SMCLASS + i] = r < 7 ? PH_ACT : r < 10 ? PH_TAIL : r < 13 ? PH_RESP : r < 15 ? PH_SLOW : PH_DEAL;
+    else q.ctl[Q_SMCLASS + i] = r < 6 ? PH_ACT : r < 13 ? PH_TAIL : r < 15 ? PH_SLOW : PH_DEAL;   // measured warp-time shares; RESP rides on TAIL
   }
   unsigned m = __ballot_sync(0xFFFFFFFFu, cls != PH_NONE);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&q.ctl[Q_LIVE], (uint32_t)__popc(m));
@@ -828,22 +829,17 @@ __device__ __forceinline__ int q_claim(const Queues& q, int c, uint32_t& h, unsi
   h = atomicAdd(&q.ctl[Q_HEAD + 32 * c], (uint32_t)want);
   return want;
 }
+// The per-warp scheduler loop (one warp = 32 staged games, its own mbarrier): runs until no game is live.  `stage` / `mbar` are
+// the warp's shared memory (initialised by the caller), `parity` the phase its mbarrier is in.
 template <int NPC>   // seat count of every game of the vector (4, or 3 for sanma)
-__global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
-                                                                 uint64_t agent_seed, uint32_t* budget, Queues q,
-                                                                 unsigned long long* counters, int reps, uint32_t endgame_live,
-                                                                 int endgame_take) {
-  __shared__ __align__(128) unsigned char stage[PHB * STG_STRIDE];
-  __shared__ __align__(8) uint64_t mbar;
-  const int lane = threadIdx.x;
+__device__ __forceinline__ void persistent_warp_loop(const Tables& T, G* states, int64_t n, uint32_t* log, uint32_t cap,
+                                                     uint64_t agent_seed, uint32_t* budget, const Queues& q,
+                                                     unsigned long long* counters, int reps, uint32_t endgame_live,
+                                                     int endgame_take, uint32_t switch_knobs, unsigned char* stage, uint64_t* mbar,
+                                                     uint32_t parity) {
+  const int lane = threadIdx.x & 31;
   unsigned char* slot = stage + lane * STG_STRIDE;
-  const uint32_t bar = smem_u32(&mbar);
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint32_t parity = 0;
+  const uint32_t bar = smem_u32(mbar);
   // All warps of an SM work on the SAME class (its code stays in the SM's instruction cache: the per-class hot code is
   // tens of KB, the L1.5 I-cache 32 KB).  The class is a per-SM word in global memory; a warp that finds its SM's class
   // empty twice in a row moves the whole SM to the class with the longest queue.
@@ -852,6 +848,17 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
   uint32_t* const my_class = &q.ctl[Q_SMCLASS + (smid & 255)];
   unsigned long long stepped_total = 0, finished_total = 0;
   uint32_t idle = 0;
+  // Lane refill.  A game whose next step is again a plain turn (ACT -> ACT, the most frequent transition) stays staged in its
+  // lane between iterations instead of going through store / push / claim / load: the warp keeps such games, pushes the ones
+  // that leave the class and refills only the FREE lanes from the ACT queue.  Every iteration then runs act_fast on a full
+  // warp (the `reps` loop alone decays: ~16 of 32 lanes active), and an ACT -> ACT step costs no queue round trip.
+  // when an SM changes class: after `switch_idle` empty looks in a row, and only to a queue of at least `switch_minlen` games
+  const uint32_t switch_idle = switch_knobs & 0xFFFF;
+  const int switch_minlen = (int)(switch_knobs >> 16);
+  const bool hold_enabled = (reps >> 8) & 1;
+  reps &= 0xFF;
+  int32_t held_gi = -1;                 // the game kept in this lane's slot (class ACT only), -1 = the lane is free
+  uint32_t held_b = 0, held_b0 = 0;     // its budget now / as last read from memory
 #ifdef RV_QPROF
   // per-warp cycle accounting: [0] idle polls, [1] claim+slots+fence, [2] stage in, [3..7] compute per class, [8] stage out+fence,
   // [9] push; [10..14] batches per class, [15..19] games per class
@@ -889,22 +896,33 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
     const uint32_t err_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 2);
     auto q_len = [&](int c) { return (int)(__shfl_sync(0xFFFFFFFFu, ctl_v, 12 + c) - __shfl_sync(0xFFFFFFFFu, ctl_v, 4 + c)); };
     endgame = live_now < endgame_live;
+    const unsigned held_mask = __ballot_sync(0xFFFFFFFFu, held_gi >= 0);
+    const int n_held = __popc(held_mask);
+    const int sm_cls = (int)__shfl_sync(0xFFFFFFFFu, ctl_v, 1);
+    // games may be kept (and free lanes refilled) while the SM still serves ACT and the rollout is not in its endgame
+    const bool hold_ok = hold_enabled && !endgame && sm_cls == PH_ACT;
     {
       int want_cap = PHB;
-      if (endgame) {
+      if (n_held > 0) {
+        cls = PH_ACT;
+        want_cap = hold_ok ? PHB - n_held : 0;
+      } else if (endgame) {
         cls = PH_NONE;
         want_cap = endgame_take;
         for (int c = N_QUEUES - 1; c >= 0; c--)
           if (q_len(c) > 0) cls = c;                       // first non-empty class
       } else {
-        cls = (int)__shfl_sync(0xFFFFFFFFu, ctl_v, 1);
+        cls = sm_cls;
+        // claim windows reached outside a TAIL visit are few (0.5 % of the visits) and their code is part of the TAIL code:
+        // the TAIL SMs serve them too, no SM is ever switched to RESP for them
+        if (cls == PH_TAIL && q_len(PH_TAIL) <= 0 && q_len(PH_RESP) > 0) cls = PH_RESP;
         const bool empty = q_len(cls) <= 0;
 #ifdef RV_QPROF
         if (empty && lane == 0) dbg[1]++;
 #endif
-        if (empty && idle >= 3) {
+        if (empty && idle >= switch_idle) {
           // move the SM: longest queue wins
-          int best = -1, best_len = 0;
+          int best = -1, best_len = switch_minlen - 1;
           for (int c = 0; c < N_QUEUES; c++) {
             const int len = q_len(c);
             if (len > best_len) best_len = len, best = c;
@@ -923,14 +941,17 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
           cls = PH_NONE;
         }
       }
-      if (cls != PH_NONE) {
+      if (cls != PH_NONE && want_cap > 0) {
         const int avail = q_len(cls);
         take = avail < want_cap ? avail : want_cap;
-        if (lane == 0) h = atomicAdd(&q.ctl[Q_HEAD + 32 * cls], (uint32_t)take);
-        h = __shfl_sync(0xFFFFFFFFu, h, 0);
+        if (take < 0) take = 0;
+        if (take > 0) {
+          if (lane == 0) h = atomicAdd(&q.ctl[Q_HEAD + 32 * cls], (uint32_t)take);
+          h = __shfl_sync(0xFFFFFFFFu, h, 0);
+        }
       }
     }
-    if (take == 0) {
+    if (take == 0 && n_held == 0) {
       if (live_now != 0 && err_now == 0 && ++idle > (1u << 22)) {     // watchdog: seconds without work while games are live
         if (lane == 0) atomicExch(&q.ctl[Q_ERR], 1u);
         break;
@@ -942,8 +963,10 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
     }
     idle = 0;
     int32_t gi = -1;
-    if (lane < take) {
-      int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + ((h + (uint32_t)lane) & q.mask);
+    // the free lanes draw the tickets, in lane order
+    const int my_ticket = held_gi >= 0 ? PHB : __popc(~held_mask & ((1u << lane) - 1));
+    if (my_ticket < take) {
+      int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + ((h + (uint32_t)my_ticket) & q.mask);
       for (int poll = 0; poll < 6 && gi < 0; poll++) gi = *reinterpret_cast<volatile int32_t*>(sl);
       if (gi < 0) {
         gi = atomicCAS(sl, -1, -2);          // racing consumers over-claimed, or the producer is slow: abandon the ticket
@@ -953,22 +976,21 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
       }
       if (gi >= 0) *reinterpret_cast<volatile int32_t*>(sl) = -1;
     }
-    const bool have = gi >= 0;
-    const unsigned have_mask = __ballot_sync(0xFFFFFFFFu, have);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    const bool fresh = gi >= 0;                                     // a game taken from the queue in this iteration
+    const unsigned fresh_mask = __ballot_sync(0xFFFFFFFFu, fresh);
+    if (take > 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
     QP(1);
-    if (have_mask == 0) continue;
-    take = __popc(have_mask);
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)take * (uint32_t)RV_HOT_BYTES) : "memory");
-    __syncwarp();
+    if (fresh_mask == 0 && n_held == 0) continue;
     uint32_t b_in = 0;
-    if (have) {
-      stage_in(slot, &states[gi], bar);
-      *reinterpret_cast<G**>(slot + RV_HOT_BYTES) = &states[gi];
-      b_in = budget[gi];          // in flight together with the bulk copy
-    }
-    {
+    if (fresh_mask != 0) {
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)__popc(fresh_mask) * (uint32_t)RV_HOT_BYTES) : "memory");
+      __syncwarp();
+      if (fresh) {
+        stage_in(slot, &states[gi], bar);
+        *reinterpret_cast<G**>(slot + RV_HOT_BYTES) = &states[gi];
+        b_in = budget[gi];          // in flight together with the bulk copy
+      }
       uint32_t ok = 0;
       while (!ok)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -978,15 +1000,20 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
       parity ^= 1;
     }
     QP(2);
+    if (!fresh && held_gi >= 0) gi = held_gi;
+    const bool have = gi >= 0;
+    take = __popc(__ballot_sync(0xFFFFFFFFu, have));
     int next = PH_NONE;
+    bool leave = true;                                              // the game goes back to HBM and into a queue after this visit
     if (have) {
       G& g = *reinterpret_cast<G*>(slot);
       Ctx cx = make_ctx(T, log, cap, gi);
       cx.defer_init = true;
       cx.defer_tail = true;
-      uint32_t b = b_in;
-      const uint32_t b0 = b;
-      if (endgame) {
+      uint32_t b = fresh ? b_in : held_b;
+      const uint32_t b0 = fresh ? b_in : held_b0;
+      held_gi = -1;
+      if (endgame && n_held == 0) {
         cx.defer_init = false;
         cx.defer_tail = false;
         while (true) {
@@ -1010,6 +1037,12 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
           next = classify(g, b);
           if (next != PH_ACT) break;
         }
+        if (next == PH_ACT && hold_ok) {       // stays in this lane: no store, no push, no claim, no load
+          leave = false;
+          held_gi = gi;
+          held_b = b;
+          held_b0 = b0;
+        }
       } else {
         if (cls == PH_TAIL) {
           // the parked follow-up of a discard; when it opens a claim window the answers are taken in the same visit
@@ -1025,7 +1058,7 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
         // (taking the plain turn most games leave these visits with right here, instead of through the ACT queue, measured
         // slower: 1.36 -> 1.30 / 1.26 G steps/s for one / two inline turns — the lanes of a generic batch diverge again)
       }
-      if (b != b0) {
+      if (leave && b != b0) {
         budget[gi] = b;
         stepped_total += b0 - b;
         finished_total += g.is_done ? 1 : 0;
@@ -1037,15 +1070,16 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
     prof[10 + cls]++;
     prof[15 + cls] += take;
 #endif
-    if (have) {
+    const bool out = have && leave;
+    if (out) {
       stage_out(&states[gi], slot);
       __threadfence();
     }
     __syncwarp();
     QP(8);
-    {
-      unsigned retired = __ballot_sync(0xFFFFFFFFu, have && next == PH_NONE);
-      q_push(q, next, gi);
+    if (__any_sync(0xFFFFFFFFu, out)) {
+      unsigned retired = __ballot_sync(0xFFFFFFFFu, out && next == PH_NONE);
+      q_push(q, out ? next : (int)PH_NONE, gi);
       if (lane == 0 && retired) atomicSub(&q.ctl[Q_LIVE], (uint32_t)__popc(retired));
     }
     QP(9);
@@ -1065,6 +1099,213 @@ __global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* st
     atomicAdd(&counters[0], stepped_total);
     if (finished_total) atomicAdd(&counters[1], finished_total);
   }
+}
+
+template <int NPC>
+__global__ void __launch_bounds__(PHB) rollout_persistent_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
+                                                                 uint64_t agent_seed, uint32_t* budget, Queues q,
+                                                                 unsigned long long* counters, int reps, uint32_t endgame_live,
+                                                                 int endgame_take, uint32_t switch_knobs) {
+  __shared__ __align__(128) unsigned char stage[PHB * STG_STRIDE];
+  __shared__ __align__(8) uint64_t mbar;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  persistent_warp_loop<NPC>(T, states, n, log, cap, agent_seed, budget, q, counters, reps, endgame_live, endgame_take, switch_knobs,
+                            stage, &mbar, 0u);
+}
+
+// ---- the crew kernel: ONE block per SM, its warps in step ---------------------------------------------------------------
+// ncu on the per-warp scheduler (profiles/r02i_*): a batch visit executes ~7.5 k warp instructions = ~1,000 instruction-cache
+// lines and ~420 of them MISS the SM's instruction cache (hit rate 60 %; the GPC-level cache behind it runs at 70 % of its
+// request rate); at ~200 cycles a miss that IS the 55-130 k cycles of a visit.  The 12 one-warp blocks of an SM work on the same
+// class but each at its own point of 40-60 KB of code, so they evict each other's lines.  Here the warps of an SM form one block:
+// warp 0 reads the queue heads once and draws the tickets for the whole block, a block barrier starts the visit, and the warps
+// then run the same class's code at the same time — a line is fetched once and used by all of them while it is resident.
+// A short queue fills the first warps completely instead of every warp partially.  When the rollout reaches its endgame (or
+// nothing is live any more) the warps leave the barrier loop and finish in persistent_warp_loop, each on its own.
+struct CrewCtl {
+  uint32_t mode, cls, take, h;      // mode: 0 = visit, 1 = nothing to do right now, 2 = leave the lock-step phase
+};
+template <int NPC>
+__global__ void __launch_bounds__(384, 1) rollout_crew_kernel(Tables T, G* states, int64_t n, uint32_t* log, uint32_t cap,
+                                                              uint64_t agent_seed, uint32_t* budget, Queues q,
+                                                              unsigned long long* counters, int reps_knobs, uint32_t endgame_live,
+                                                              int endgame_take, uint32_t switch_knobs) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  unsigned char* stage = dyn_smem + (size_t)warp * PHB * STG_STRIDE;
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(dyn_smem + (size_t)n_warps * PHB * STG_STRIDE);
+  CrewCtl* ctl2 = reinterpret_cast<CrewCtl*>(mbars + n_warps);            // double-buffered by iteration parity
+  uint64_t* mbar = mbars + warp;
+  unsigned char* slot = stage + lane * STG_STRIDE;
+  const uint32_t bar = smem_u32(mbar);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  uint32_t* const my_class = &q.ctl[Q_SMCLASS + (smid & 255)];
+  const uint32_t switch_idle = switch_knobs & 0xFFFF;
+  const int switch_minlen = (int)(switch_knobs >> 16);
+  const int reps = reps_knobs & 0xFF;
+  unsigned long long stepped_total = 0, finished_total = 0;
+  uint32_t idle = 0;
+  for (uint32_t iter = 0;; iter++) {
+    CrewCtl* cc = ctl2 + (iter & 1);
+    if (warp == 0) {
+      uint32_t ctl_v = 0;
+      {
+        const uint32_t* a = nullptr;
+        if (lane == 0) a = &q.ctl[Q_LIVE];
+        else if (lane == 1) a = my_class;
+        else if (lane == 2) a = &q.ctl[Q_ERR];
+        else if (lane >= 4 && lane < 4 + N_QUEUES) a = &q.ctl[Q_HEAD + 32 * (lane - 4)];
+        else if (lane >= 12 && lane < 12 + N_QUEUES) a = &q.ctl[Q_TAIL + 32 * (lane - 12)];
+        if (a) ctl_v = ld_volatile_u32(a);
+      }
+      const uint32_t live_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 0);
+      const uint32_t err_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 2);
+      auto q_len = [&](int c) { return (int)(__shfl_sync(0xFFFFFFFFu, ctl_v, 12 + c) - __shfl_sync(0xFFFFFFFFu, ctl_v, 4 + c)); };
+      uint32_t mode = 0, take = 0, h = 0;
+      int cls = (int)__shfl_sync(0xFFFFFFFFu, ctl_v, 1);
+      if (live_now < endgame_live || live_now == 0 || err_now != 0) {
+        mode = 2;
+      } else {
+        if (cls == PH_TAIL && q_len(PH_TAIL) <= 0 && q_len(PH_RESP) > 0) cls = PH_RESP;
+        bool empty = q_len(cls) <= 0;
+        if (empty && idle >= switch_idle) {
+          int best = -1, best_len = switch_minlen - 1;
+          for (int c = 0; c < N_QUEUES; c++) {
+            const int len = q_len(c);
+            if (len > best_len) best_len = len, best = c;
+          }
+          if (best >= 0) {
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(my_class) = (uint32_t)best;
+            cls = best;
+            idle = 0;
+            empty = false;
+          }
+        }
+        if (empty) {
+          mode = 1;
+          if (++idle > (1u << 22)) {                      // watchdog, as in the per-warp loop
+            if (lane == 0) atomicExch(&q.ctl[Q_ERR], 1u);
+            mode = 2;
+          }
+        } else {
+          idle = 0;
+          const int avail = q_len(cls), cap_all = (int)blockDim.x;
+          take = (uint32_t)(avail < cap_all ? avail : cap_all);
+          if (lane == 0) h = atomicAdd(&q.ctl[Q_HEAD + 32 * cls], take);
+        }
+      }
+      if (lane == 0) {
+        cc->mode = mode;
+        cc->cls = (uint32_t)cls;
+        cc->take = take;
+        cc->h = h;
+      }
+    }
+    __syncthreads();
+    const uint32_t mode = cc->mode;
+    if (mode == 2) break;
+    if (mode == 1) {
+      __nanosleep(300);
+      continue;
+    }
+    const int cls = (int)cc->cls;
+    const uint32_t take = cc->take, h = cc->h;
+    if ((uint32_t)warp * 32u >= take) continue;            // a short queue fills the first warps; the others wait at the barrier
+    int32_t gi = -1;
+    if (threadIdx.x < take) {
+      int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + ((h + threadIdx.x) & q.mask);
+      for (int poll = 0; poll < 6 && gi < 0; poll++) gi = *reinterpret_cast<volatile int32_t*>(sl);
+      if (gi < 0) gi = atomicCAS(sl, -1, -2);
+      if (gi >= 0) *reinterpret_cast<volatile int32_t*>(sl) = -1;
+    }
+    const bool have = gi >= 0;
+    const unsigned have_mask = __ballot_sync(0xFFFFFFFFu, have);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    if (have_mask == 0) continue;
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)__popc(have_mask) * (uint32_t)RV_HOT_BYTES) : "memory");
+    __syncwarp();
+    uint32_t b = 0;
+    if (have) {
+      stage_in(slot, &states[gi], bar);
+      *reinterpret_cast<G**>(slot + RV_HOT_BYTES) = &states[gi];
+      b = budget[gi];
+    }
+    {
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+      parity ^= 1;
+    }
+    int next = PH_NONE;
+    if (have) {
+      G& g = *reinterpret_cast<G*>(slot);
+      Ctx cx = make_ctx(T, log, cap, gi);
+      cx.defer_init = true;
+      cx.defer_tail = true;
+      const uint32_t b0 = b;
+      if (cls == PH_ACT) {
+        for (int r = 0; r < reps; r++) {
+          if (!act_fast<false, NPC>(cx, g, agent_seed, g.seed)) {
+            next = PH_SLOW;
+            break;
+          }
+          b--;
+          next = classify(g, b);
+          if (next != PH_ACT) break;
+        }
+      } else {
+        if (cls == PH_TAIL) {
+          run_pending_tail(cx, g);
+          if (b > 0 && !g.is_done && g.pending_init[0] == RV_NONE && g.phase == RV_WAIT_RESPONSE) {
+            random_step_resp(cx, g, agent_seed, g.seed);
+            b--;
+          }
+        } else if (cls == PH_DEAL) run_pending_init(cx, g);
+        else if (cls == PH_SLOW) random_step_act(cx, g, agent_seed, g.seed), b--;
+        else random_step_resp(cx, g, agent_seed, g.seed), b--;
+        next = classify(g, b);
+      }
+      if (b != b0) {
+        budget[gi] = b;
+        stepped_total += b0 - b;
+        finished_total += g.is_done ? 1 : 0;
+      }
+      stage_out(&states[gi], slot);
+      __threadfence();
+    }
+    __syncwarp();
+    {
+      unsigned retired = __ballot_sync(0xFFFFFFFFu, have && next == PH_NONE);
+      q_push(q, next, gi);
+      if (lane == 0 && retired) atomicSub(&q.ctl[Q_LIVE], (uint32_t)__popc(retired));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    stepped_total += __shfl_down_sync(0xFFFFFFFFu, stepped_total, o);
+    finished_total += __shfl_down_sync(0xFFFFFFFFu, finished_total, o);
+  }
+  if (lane == 0 && stepped_total) {
+    atomicAdd(&counters[0], stepped_total);
+    if (finished_total) atomicAdd(&counters[1], finished_total);
+  }
+  // endgame / termination: every warp on its own
+  persistent_warp_loop<NPC>(T, states, n, log, cap, agent_seed, budget, q, counters, reps_knobs & 0xFF, endgame_live, endgame_take,
+                            switch_knobs, stage, mbar, parity);
 }
 
 __global__ void legal_kernel(Tables T, const G* states, int64_t n, rv_action* out, uint8_t* counts) {
@@ -1873,6 +2114,7 @@ int rv_vec_step(rv_vec* v, const rv_action* actions) {
 }
 
 static int env_int(const char* name, int dflt);
+static int env_int0(const char* name, int dflt);
 static int rollout_mono(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
   static const int sorted = env_int("RV_STEP_SORTED", 3) - 1;   // 1: thread per game; 2: regrouped in the block; 3: + staged records
@@ -1899,6 +2141,11 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   int v = e ? atoi(e) : dflt;
   return v < 1 ? 1 : v;
+}
+static int env_int0(const char* name, int dflt) {      // knobs for which 0 is a value (switches)
+  const char* e = getenv(name);
+  int v = e ? atoi(e) : dflt;
+  return v < 0 ? 0 : v;
 }
 static int rollout_phased(rv_vec* v, uint64_t agent_seed, uint32_t max_steps) {
   rv_ctx* c = v->ctx;
@@ -2048,14 +2295,17 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
     CK(cudaMalloc(&v->d_q_ctl, sizeof(uint32_t) * Q_CTL_WORDS));
     if (!v->d_budget) CK(cudaMalloc(&v->d_budget, sizeof(uint32_t) * n));
   }
-  static int act_reps = env_int("RV_ACT_REPS", 4), warps_per_sm = env_int("RV_WARPS_PER_SM", 12);
+  static int warps_per_sm = env_int("RV_WARPS_PER_SM", 12);
+  // read per call (A/B in one process): reps of act_fast per iteration; RV_ACT_HOLD=0 turns the lane refill off
+  const int act_reps = (env_int("RV_ACT_REPS", 4) & 0xFF) | (env_int0("RV_ACT_HOLD", 0) ? 0x100 : 0);
   // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 8 = 2 games per
   // warp), warps own RV_ENDGAME_TAKE games each and play them out in place (see the kernel)
   static int eg_quarters = env_int("RV_ENDGAME_Q", 8), eg_take = env_int("RV_ENDGAME_TAKE", 1);
+  const uint32_t switch_knobs = ((uint32_t)env_int("RV_SWITCH_IDLE", 3) & 0xFFFF) | ((uint32_t)env_int("RV_SWITCH_MINLEN", 1) << 16);
   Queues q{v->d_q_slots, v->d_q_ctl, v->q_cap - 1};
   CK(cudaMemsetAsync(v->d_q_ctl, 0, sizeof(uint32_t) * Q_CTL_WORDS, c->stream));
   CK(cudaMemsetAsync(v->d_q_slots, 0xFF, sizeof(int32_t) * N_QUEUES * (size_t)v->q_cap, c->stream));   // every slot empty (abandoned marks of the last call included)
-  q_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, q);
+  q_init_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(v->d_states, n, v->d_budget, max_steps, q, env_int0("RV_INIT_DIST", 1));
   {
     const char* fault = getenv("RV_FAULT_INJECT");     // read per call: the watchdog test arms it for one rollout
     if (fault && strcmp(fault, "lost_game") == 0) q_fault_kernel<<<1, 1, 0, c->stream>>>(q);
@@ -2063,12 +2313,31 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
   int64_t crew = (int64_t)c->sm_count * warps_per_sm, need = (n + PHB - 1) / PHB;
   const int grid = (int)(crew < need ? crew : need);
   const uint32_t eg_live = getenv("RV_ENDGAME_OFF") ? 0u : (uint32_t)((int64_t)grid * eg_quarters / 4);
-  if (v->game_mode >= 3)
+  if (env_int0("RV_CREW", 1)) {
+    // one block per SM, warps_per_sm warps each (see rollout_crew_kernel); the endgame threshold counts warps as before
+    const int threads = 32 * warps_per_sm;
+    const size_t smem = (size_t)warps_per_sm * PHB * STG_STRIDE + sizeof(uint64_t) * warps_per_sm + 2 * sizeof(CrewCtl);
+    const int64_t need_b = (n + threads - 1) / threads;
+    const int blocks = (int)(c->sm_count < need_b ? c->sm_count : need_b);
+    const uint32_t eg_live_c = getenv("RV_ENDGAME_OFF") ? 0u : (uint32_t)((int64_t)blocks * warps_per_sm * eg_quarters / 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(rollout_crew_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(rollout_crew_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    if (v->game_mode >= 3)
+      rollout_crew_kernel<3><<<blocks, threads, smem, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, q,
+                                                                  v->d_steps, act_reps, eg_live_c, eg_take, switch_knobs);
+    else
+      rollout_crew_kernel<4><<<blocks, threads, smem, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, q,
+                                                                  v->d_steps, act_reps, eg_live_c, eg_take, switch_knobs);
+  } else if (v->game_mode >= 3)
     rollout_persistent_kernel<3><<<grid, PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, q,
-                                                             v->d_steps, act_reps, eg_live, eg_take);
+                                                             v->d_steps, act_reps, eg_live, eg_take, switch_knobs);
   else
     rollout_persistent_kernel<4><<<grid, PHB, 0, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, q,
-                                                             v->d_steps, act_reps, eg_live, eg_take);
+                                                             v->d_steps, act_reps, eg_live, eg_take, switch_knobs);
   CK(cudaGetLastError());
   return RV_OK;
 }
