@@ -3,6 +3,7 @@
 usage: ab_rollout.py SPEC SPEC [SPEC ...] [--games N] — SPEC = lib.so[:VAR=val[,VAR=val...]] (environment knobs the library
 reads per call, e.g. RV_ACT_HOLD=0); alternates the variants, 5 timed rollouts each, prints G env steps/s per rollout."""
 import ctypes as C
+import os
 import sys
 
 import torch  # noqa: F401  (brings the CUDA runtime libraries into the process)
@@ -32,7 +33,10 @@ def rollout(L, ctx, v, k):
     L.rv_ctx_sync(ctx)
     n = C.c_uint64(0)
     L.rv_timer_mark(ctx, 0)
-    L.rv_vec_step_random(v, 0x5EED, 1 << 30, C.byref(n))
+    rc = L.rv_vec_step_random(v, 0x5EED, 1 << 30, C.byref(n))
+    if rc != 0:
+        L.rv_last_error.restype = C.c_char_p
+        raise RuntimeError(f"rv_vec_step_random -> {rc}: {L.rv_last_error().decode()} (env: {[(k, v2) for k, v2 in os.environ.items() if k.startswith('RV_')]})")
     L.rv_timer_mark(ctx, 1)
     ms = C.c_float(0)
     L.rv_timer_elapsed(ctx, 0, 1, C.byref(ms))

@@ -1154,85 +1154,139 @@ __global__ void __launch_bounds__(384, 1) rollout_crew_kernel(Tables T, G* state
   const uint32_t switch_idle = switch_knobs & 0xFFFF;
   const int switch_minlen = (int)(switch_knobs >> 16);
   const int reps = reps_knobs & 0xFF;
+  const int slot_polls = (reps_knobs >> 16) & 0xFF;      // looks at an empty slot before the ticket is abandoned
   unsigned long long stepped_total = 0, finished_total = 0;
   uint32_t idle = 0;
-  for (uint32_t iter = 0;; iter++) {
-    CrewCtl* cc = ctl2 + (iter & 1);
-    if (warp == 0) {
-      uint32_t ctl_v = 0;
-      {
-        const uint32_t* a = nullptr;
-        if (lane == 0) a = &q.ctl[Q_LIVE];
-        else if (lane == 1) a = my_class;
-        else if (lane == 2) a = &q.ctl[Q_ERR];
-        else if (lane >= 4 && lane < 4 + N_QUEUES) a = &q.ctl[Q_HEAD + 32 * (lane - 4)];
-        else if (lane >= 12 && lane < 12 + N_QUEUES) a = &q.ctl[Q_TAIL + 32 * (lane - 12)];
-        if (a) ctl_v = ld_volatile_u32(a);
-      }
-      const uint32_t live_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 0);
-      const uint32_t err_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 2);
-      auto q_len = [&](int c) { return (int)(__shfl_sync(0xFFFFFFFFu, ctl_v, 12 + c) - __shfl_sync(0xFFFFFFFFu, ctl_v, 4 + c)); };
-      uint32_t mode = 0, take = 0, h = 0;
-      int cls = (int)__shfl_sync(0xFFFFFFFFu, ctl_v, 1);
-      if (live_now < endgame_live || live_now == 0 || err_now != 0) {
-        mode = 2;
-      } else {
-        if (cls == PH_TAIL && q_len(PH_TAIL) <= 0 && q_len(PH_RESP) > 0) cls = PH_RESP;
-        bool empty = q_len(cls) <= 0;
-        if (empty && idle >= switch_idle) {
-          int best = -1, best_len = switch_minlen - 1;
-          for (int c = 0; c < N_QUEUES; c++) {
-            const int len = q_len(c);
-            if (len > best_len) best_len = len, best = c;
-          }
-          if (best >= 0) {
-            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(my_class) = (uint32_t)best;
-            cls = best;
-            idle = 0;
-            empty = false;
-          }
+#ifdef RV_QPROF
+  // per-warp cycles of the lock-step phase: [0] decision (warp 0), [1] barrier wait, [2] idle sleeps, [3] iterations without a ticket
+  // (counts), [4] iterations (counts), [5] class changes (warp 0), [6] visit (claim .. push), [7] visits (counts)
+  unsigned long long cp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long ct0 = clock64();
+#define CQP(i) { long long t1 = clock64(); cp[i] += (unsigned long long)(t1 - ct0); ct0 = t1; }
+#else
+#define CQP(i)
+#endif
+  // warp 0's decision: (1) ONE load instruction for everything it needs (lane 0 the live-game counter, lane 1 the SM's class,
+  // lane 2 the error flag, lanes 4.. / 12.. head and tail of every class queue), (2) the choice and the tickets.
+  auto ctl_load = [&]() -> uint32_t {
+    const uint32_t* a = nullptr;
+    if (lane == 0) a = &q.ctl[Q_LIVE];
+    else if (lane == 1) a = my_class;
+    else if (lane == 2) a = &q.ctl[Q_ERR];
+    else if (lane >= 4 && lane < 4 + N_QUEUES) a = &q.ctl[Q_HEAD + 32 * (lane - 4)];
+    else if (lane >= 12 && lane < 12 + N_QUEUES) a = &q.ctl[Q_TAIL + 32 * (lane - 12)];
+    return a ? ld_volatile_u32(a) : 0u;
+  };
+  auto decide = [&](uint32_t ctl_v, CrewCtl& out) {        // warp 0, all lanes; `out` is a register copy, published by lane 0 later
+    const uint32_t live_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 0);
+    const uint32_t err_now = __shfl_sync(0xFFFFFFFFu, ctl_v, 2);
+    auto q_len = [&](int c) { return (int)(__shfl_sync(0xFFFFFFFFu, ctl_v, 12 + c) - __shfl_sync(0xFFFFFFFFu, ctl_v, 4 + c)); };
+    uint32_t mode = 0, take = 0, h = 0;
+    int cls = (int)__shfl_sync(0xFFFFFFFFu, ctl_v, 1);
+    if (live_now < endgame_live || live_now == 0 || err_now != 0) {
+      mode = 2;
+    } else {
+      if (cls == PH_TAIL && q_len(PH_TAIL) <= 0 && q_len(PH_RESP) > 0) cls = PH_RESP;
+      bool empty = q_len(cls) <= 0;
+      // greedy variant (bit 9 of reps_knobs): a queue that cannot fill the block is left for one at least twice as long
+      const bool short_q = ((reps_knobs >> 9) & 1) && q_len(cls) < (int)blockDim.x;
+      if ((empty && idle >= switch_idle) || short_q) {
+        int best = -1, best_len = short_q && !empty ? 2 * q_len(cls) : switch_minlen - 1;
+        for (int c = 0; c < N_QUEUES; c++) {
+          const int len = q_len(c);
+          if (len > best_len) best_len = len, best = c;
         }
-        if (empty) {
-          mode = 1;
-          if (++idle > (1u << 22)) {                      // watchdog, as in the per-warp loop
-            if (lane == 0) atomicExch(&q.ctl[Q_ERR], 1u);
-            mode = 2;
-          }
-        } else {
+        if (best >= 0) {
+          if (lane == 0) *reinterpret_cast<volatile uint32_t*>(my_class) = (uint32_t)best;
+          cls = best;
           idle = 0;
-          const int avail = q_len(cls), cap_all = (int)blockDim.x;
-          take = (uint32_t)(avail < cap_all ? avail : cap_all);
-          if (lane == 0) h = atomicAdd(&q.ctl[Q_HEAD + 32 * cls], take);
+          empty = false;
+#ifdef RV_QPROF
+          cp[5]++;
+#endif
         }
       }
-      if (lane == 0) {
-        cc->mode = mode;
-        cc->cls = (uint32_t)cls;
-        cc->take = take;
-        cc->h = h;
+      if (empty) {
+        mode = 1;
+        if (++idle > (1u << 22)) {                      // watchdog, as in the per-warp loop
+          if (lane == 0) atomicExch(&q.ctl[Q_ERR], 1u);
+          mode = 2;
+        }
+      } else {
+        idle = 0;
+        // A blind fetch-add, not a compare-and-swap on exact tickets: deciders that race for a short queue over-claim, and the
+        // tickets beyond the tail are RESERVATIONS — the next games pushed go straight into slots somebody is already polling.
+        // Measured (profiles/r02p_ab_rollout.txt): exact tickets 2.05 G env steps/s, fetch-add 2.35 G.
+        const int avail = q_len(cls), cap_all = (int)blockDim.x;
+        take = (uint32_t)(avail < cap_all ? avail : cap_all);
+        if (lane == 0) h = atomicAdd(&q.ctl[Q_HEAD + 32 * cls], take);
       }
     }
+    out.mode = mode;
+    out.cls = (uint32_t)cls;
+    out.take = take;
+    out.h = h;                                             // lane 0's copy holds the first ticket
+  };
+  // (Taking the decision one iteration ahead — loads issued before warp 0 polls its own slots, tickets drawn while its
+  // records are in flight — was measured slower: 1.91 against 2.32 G env steps/s; the queue lengths it acts on are an
+  // iteration old and the SMs over-claim by whole blocks.  profiles/r02o_*.)
+  if (warp == 0) {                                         // the first decision
+    CrewCtl d;
+    decide(ctl_load(), d);
+    if (lane == 0) ctl2[0] = d;
+  }
+  for (uint32_t iter = 0;; iter++) {
+    CrewCtl* cc = ctl2 + (iter & 1);
+    CrewCtl* cc_next = ctl2 + ((iter + 1) & 1);
+    CQP(0);
     __syncthreads();
+    CQP(1);
+#ifdef RV_QPROF
+    cp[4]++;
+#endif
     const uint32_t mode = cc->mode;
     if (mode == 2) break;
+    CrewCtl nd;
     if (mode == 1) {
       __nanosleep(300);
+      if (warp == 0) {
+        decide(ctl_load(), nd);
+        if (lane == 0) *cc_next = nd;
+      }
+      CQP(2);
       continue;
     }
     const int cls = (int)cc->cls;
     const uint32_t take = cc->take, h = cc->h;
-    if ((uint32_t)warp * 32u >= take) continue;            // a short queue fills the first warps; the others wait at the barrier
+    if ((uint32_t)warp * 32u >= take) {                   // a short queue fills the first warps; the others wait at the barrier
+#ifdef RV_QPROF
+      cp[3]++;
+#endif
+      continue;                                            // (never warp 0: take > 0 here)
+    }
     int32_t gi = -1;
     if (threadIdx.x < take) {
       int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + ((h + threadIdx.x) & q.mask);
-      for (int poll = 0; poll < 6 && gi < 0; poll++) gi = *reinterpret_cast<volatile int32_t*>(sl);
+      for (int poll = 0; poll < slot_polls && gi < 0; poll++) gi = *reinterpret_cast<volatile int32_t*>(sl);
       if (gi < 0) gi = atomicCAS(sl, -1, -2);
       if (gi >= 0) *reinterpret_cast<volatile int32_t*>(sl) = -1;
+#ifdef RV_CREW_DEBUG
+      if (gi >= n || cls < 0 || cls >= N_QUEUES) {
+        printf("crew: bad ticket: block %d thread %d iter %u cls %d take %u h %u gi %d\n", blockIdx.x, threadIdx.x, iter, cls, take, h, gi);
+        gi = -1;
+      }
+#endif
     }
     const bool have = gi >= 0;
     const unsigned have_mask = __ballot_sync(0xFFFFFFFFu, have);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    if (have_mask == 0) continue;
+    if (have_mask == 0) {
+      if (warp == 0) {
+        decide(ctl_load(), nd);
+        if (lane == 0) *cc_next = nd;
+      }
+      continue;
+    }
     if (lane == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)__popc(have_mask) * (uint32_t)RV_HOT_BYTES) : "memory");
     __syncwarp();
@@ -1294,7 +1348,19 @@ __global__ void __launch_bounds__(384, 1) rollout_crew_kernel(Tables T, G* state
       q_push(q, next, gi);
       if (lane == 0 && retired) atomicSub(&q.ctl[Q_LIVE], (uint32_t)__popc(retired));
     }
+    if (warp == 0) {                                       // the decision for the next iteration, published by the barrier
+      decide(ctl_load(), nd);
+      if (lane == 0) *cc_next = nd;
+    }
+    CQP(6);
+#ifdef RV_QPROF
+    cp[7]++;
+#endif
   }
+#ifdef RV_QPROF
+  if (lane == 0)
+    for (int i = 0; i < 6; i++) atomicAdd(&counters[2 + i], i == 0 ? cp[1] : i == 1 ? cp[4] : i == 2 ? cp[3] : i == 3 ? cp[5] : i == 4 ? cp[2] : cp[6]);
+#endif
   for (int o = 16; o > 0; o >>= 1) {
     stepped_total += __shfl_down_sync(0xFFFFFFFFu, stepped_total, o);
     finished_total += __shfl_down_sync(0xFFFFFFFFu, finished_total, o);
@@ -2297,7 +2363,7 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
   }
   static int warps_per_sm = env_int("RV_WARPS_PER_SM", 12);
   // read per call (A/B in one process): reps of act_fast per iteration; RV_ACT_HOLD=0 turns the lane refill off
-  const int act_reps = (env_int("RV_ACT_REPS", 4) & 0xFF) | (env_int0("RV_ACT_HOLD", 0) ? 0x100 : 0);
+  const int act_reps = (env_int("RV_ACT_REPS", 4) & 0xFF) | (env_int0("RV_ACT_HOLD", 0) ? 0x100 : 0) | (env_int0("RV_CREW_GREEDY", 1) ? 0x200 : 0) | ((env_int("RV_SLOT_POLLS", 64) & 0xFF) << 16);
   // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 8 = 2 games per
   // warp), warps own RV_ENDGAME_TAKE games each and play them out in place (see the kernel)
   static int eg_quarters = env_int("RV_ENDGAME_Q", 8), eg_take = env_int("RV_ENDGAME_TAKE", 1);
@@ -2379,6 +2445,9 @@ int rv_vec_steps_total(rv_vec* v, uint64_t* steps_total, int64_t* games_done) {
     const char* nm[10] = {"idle", "claim", "stage_in", "ACT", "RESP", "DEAL", "SLOW", "TAIL", "stage_out", "push"};
     unsigned long long tot = 0;
     for (int i = 0; i < 10; i++) tot += p[8 + i];
+    if (p[3])
+      fprintf(stderr, "[qprof] crew phase: warp-iterations=%llu without ticket=%llu (%.1f%%) class changes=%llu | warp-cycles: barrier=%llu "
+              "idle sleeps=%llu visits=%llu\n", p[3], p[4], 100.0 * p[4] / p[3], p[5], p[2], p[6], p[7]);
     if (tot) fprintf(stderr, "[qprof] steps=%llu total warp-cycles=%llu\n", h[0], tot);
     for (int i = 0; i < 10 && tot; i++) fprintf(stderr, "[qprof] %-9s %6.2f%%\n", nm[i], 100.0 * p[8 + i] / (tot ? tot : 1));
     if (tot) fprintf(stderr, "[qprof] (unused)=%llu empty_looks=%llu tickets_abandoned=%llu sm_switches=%llu\n", p[28], p[29], p[30], p[31]);
