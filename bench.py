@@ -276,7 +276,7 @@ def main():
         tot_ms += ms
         tot_kernel_ms += kms
         tot_steps += st
-        launches += 4                         # reseed_kernel + reset_kernel + q_init_kernel + rollout_persistent_kernel
+        launches += 4                         # reseed_kernel + reset_kernel + q_init_kernel + rollout_crew_kernel
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
@@ -319,7 +319,7 @@ def main():
         peak, peak_src = measured_peaks()
         value = all_steps / (tot_ms / 1000.0)
         achieved = (tot_steps * B_STEP) / (tot_kernel_ms / 1000.0) / 1e9  # this rank's dominant kernel
-        kname = "rollout_persistent_kernel<3>" if args.mode >= 3 else "rollout_persistent_kernel<4>"
+        kname = "rollout_crew_kernel<3>" if args.mode >= 3 else "rollout_crew_kernel<4>"
         facts = ncu_facts(kname) if (G == 65536 and args.mode in (2, 5)) else None
         cfg = workload_config(args.mode, G)
         cfg.update({"l2": "256 MiB flush write between timed iterations",
@@ -338,7 +338,7 @@ def main():
                          "traffic": facts["dram_bytes"] if facts else None,
                          "issue_frac": facts["issue_active_pct"] / 100.0 if facts else None,
                          "ncu_capture": facts["capture"] if facts else None,
-                         "kernel": "rollout_persistent_kernel (one launch per rollout)", "peak_source": peak_src,
+                         "kernel": "rollout_crew_kernel (one launch per rollout)", "peak_source": peak_src,
                          "bytes_per_env_step": B_STEP, "kernel_share_of_step": tot_kernel_ms / tot_ms},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -1155,6 +1155,7 @@ __global__ void __launch_bounds__(384, 1) rollout_crew_kernel(Tables T, G* state
   const int switch_minlen = (int)(switch_knobs >> 16);
   const int reps = reps_knobs & 0xFF;
   const int slot_polls = (reps_knobs >> 16) & 0xFF;      // looks at an empty slot before the ticket is abandoned
+  const int follow_reps = (reps_knobs >> 24) & 0xF;      // plain turns taken at the end of a non-ACT visit
   unsigned long long stepped_total = 0, finished_total = 0;
   uint32_t idle = 0;
 #ifdef RV_QPROF
@@ -1333,6 +1334,16 @@ __global__ void __launch_bounds__(384, 1) rollout_crew_kernel(Tables T, G* state
         else if (cls == PH_SLOW) random_step_act(cx, g, agent_seed, g.seed), b--;
         else random_step_resp(cx, g, agent_seed, g.seed), b--;
         next = classify(g, b);
+        // most games leave these visits with a plain turn next: take up to `follow_reps` of them here instead of through the
+        // ACT queue (a queue round trip is a whole iteration of latency for the game)
+        for (int r = 0; r < follow_reps && next == PH_ACT; r++) {
+          if (!act_fast<false, NPC>(cx, g, agent_seed, g.seed)) {
+            next = PH_SLOW;
+            break;
+          }
+          b--;
+          next = classify(g, b);
+        }
       }
       if (b != b0) {
         budget[gi] = b;
@@ -2363,7 +2374,7 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
   }
   static int warps_per_sm = env_int("RV_WARPS_PER_SM", 12);
   // read per call (A/B in one process): reps of act_fast per iteration; RV_ACT_HOLD=0 turns the lane refill off
-  const int act_reps = (env_int("RV_ACT_REPS", 4) & 0xFF) | (env_int0("RV_ACT_HOLD", 0) ? 0x100 : 0) | (env_int0("RV_CREW_GREEDY", 1) ? 0x200 : 0) | ((env_int("RV_SLOT_POLLS", 64) & 0xFF) << 16);
+  const int act_reps = (env_int("RV_ACT_REPS", 4) & 0xFF) | (env_int0("RV_ACT_HOLD", 0) ? 0x100 : 0) | (env_int0("RV_CREW_GREEDY", 1) ? 0x200 : 0) | ((env_int("RV_SLOT_POLLS", 64) & 0xFF) << 16) | ((env_int0("RV_FOLLOW_REPS", 4) & 0xF) << 24);
   // endgame: below RV_ENDGAME_PER_WARP live games per crew warp (x1/4: the knob is in quarter games, default 8 = 2 games per
   // warp), warps own RV_ENDGAME_TAKE games each and play them out in place (see the kernel)
   static int eg_quarters = env_int("RV_ENDGAME_Q", 8), eg_take = env_int("RV_ENDGAME_TAKE", 1);
@@ -2381,17 +2392,15 @@ static int rollout_persistent(rv_vec* v, uint64_t agent_seed, uint32_t max_steps
   const uint32_t eg_live = getenv("RV_ENDGAME_OFF") ? 0u : (uint32_t)((int64_t)grid * eg_quarters / 4);
   if (env_int0("RV_CREW", 1)) {
     // one block per SM, warps_per_sm warps each (see rollout_crew_kernel); the endgame threshold counts warps as before
-    const int threads = 32 * warps_per_sm;
-    const size_t smem = (size_t)warps_per_sm * PHB * STG_STRIDE + sizeof(uint64_t) * warps_per_sm + 2 * sizeof(CrewCtl);
+    const int crew_warps = warps_per_sm > 12 ? 12 : warps_per_sm;   // 12 x (32 x 560 B) of staging fill the SM's shared memory; 168 registers x 384 threads its register file
+    const int threads = 32 * crew_warps;
+    const size_t smem = (size_t)crew_warps * PHB * STG_STRIDE + sizeof(uint64_t) * crew_warps + 2 * sizeof(CrewCtl);
     const int64_t need_b = (n + threads - 1) / threads;
     const int blocks = (int)(c->sm_count < need_b ? c->sm_count : need_b);
-    const uint32_t eg_live_c = getenv("RV_ENDGAME_OFF") ? 0u : (uint32_t)((int64_t)blocks * warps_per_sm * eg_quarters / 4);
-    static bool attr_set = false;
-    if (!attr_set) {
-      CK(cudaFuncSetAttribute(rollout_crew_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      CK(cudaFuncSetAttribute(rollout_crew_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
-    }
+    const uint32_t eg_live_c = getenv("RV_ENDGAME_OFF") ? 0u : (uint32_t)((int64_t)blocks * crew_warps * eg_quarters / 4);
+    // per launch: the attribute belongs to the device's context, and an rv_multi handle drives several devices from one process
+    if (v->game_mode >= 3) CK(cudaFuncSetAttribute(rollout_crew_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(rollout_crew_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (v->game_mode >= 3)
       rollout_crew_kernel<3><<<blocks, threads, smem, c->stream>>>(c->T, v->d_states, n, v->d_log, v->log_cap, agent_seed, v->d_budget, q,
                                                                   v->d_steps, act_reps, eg_live_c, eg_take, switch_knobs);

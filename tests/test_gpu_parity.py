@@ -592,7 +592,7 @@ def test_observation_encode_100k_rows(orc, mode):
 
     from riichienv_b200.vec_env import VecRiichiEnv
 
-    n, seed_base, agent = 2048, 9100, 71
+    n, seed_base, agent = (4096 if mode >= 3 else 2048), 9100, 71      # sanma hanchan are shorter: fewer rows per game
     W, IDS = (27, 60) if mode >= 3 else (34, 82)
     v = VecRiichiEnv(n, mode, A.RULE_DEFAULT_TENHOU, seed_base=seed_base)
     v.reset()
