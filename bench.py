@@ -61,13 +61,14 @@ def measured_peaks():
 
 
 def source_fingerprint():
-    """sha1 over the CUDA sources: ncu facts are only quoted for the build they were measured on"""
+    """sha1 over the CUDA sources (kernels and the headers they include; the host-only .cpp files — JSON renderer, log reader —
+    cannot change a kernel): ncu facts are only quoted for the build they were measured on"""
     import hashlib
 
     h = hashlib.sha1()
     d = os.path.join(ROOT, "riichienv_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+        if f.endswith((".cu", ".cuh", ".h")):
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -490,6 +490,11 @@ typedef struct rv_replay rv_replay; /* opaque: the rounds of one parsed log (hos
 int rv_replay_from_jsonl(const char* path, uint32_t rule_bits, rv_replay** out);
 /* the same parser over text already in memory (len bytes of JSON lines, not compressed) */
 int rv_replay_from_text(const char* text, size_t len, uint32_t rule_bits, rv_replay** out);
+/* MjSoulReplay::from_json / from_dict (replay/mjsoul_replay.rs:174-343): a paifu as JSON — {"rounds": [[{"name", "data"}, ...]]},
+ * {"header", "data": [[...]]} or the bare list of rounds; _json reads a (gzip) file, _text takes the JSON text.  The first
+ * action of every round (NewRound) is kept as an RV_LA_NONE placeholder, as the reference keeps Action::Other.             */
+int rv_replay_from_mjsoul_json(const char* path, uint32_t rule_bits, rv_replay** out);
+int rv_replay_from_mjsoul_text(const char* text, size_t len, uint32_t rule_bits, rv_replay** out);
 int rv_replay_free(rv_replay* r);
 int rv_replay_num_rounds(const rv_replay* r);                                  /* MjaiReplay::num_rounds */
 int rv_replay_kyoku(const rv_replay* r, int round, rv_log_kyoku* out);

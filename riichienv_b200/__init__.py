@@ -7,7 +7,7 @@ from . import _abi  # noqa: F401
 
 __all__ = ["RiichiEnv", "VecRiichiEnv", "MultiVecRiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
            "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "tid_to_mjai",
-           "MjaiReplay", "Kyoku", "ReplayBatch"]
+           "MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch"]
 
 
 def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
@@ -24,7 +24,7 @@ def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
         from . import hand
 
         return getattr(hand, name)
-    if name in ("MjaiReplay", "Kyoku", "ReplayBatch"):
+    if name in ("MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch"):
         from . import replay
 
         return getattr(replay, name)

@@ -85,6 +85,8 @@ def lib():
     L.rv_vec_apply_events.argtypes = [vp, P(A.MjaiEvent)]
     L.rv_replay_from_jsonl.argtypes = [C.c_char_p, C.c_uint32, P(vp)]
     L.rv_replay_from_text.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, P(vp)]
+    L.rv_replay_from_mjsoul_json.argtypes = [C.c_char_p, C.c_uint32, P(vp)]
+    L.rv_replay_from_mjsoul_text.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, P(vp)]
     L.rv_replay_free.argtypes = [vp]
     L.rv_replay_num_rounds.argtypes = [vp]
     L.rv_replay_kyoku.argtypes = [vp, C.c_int, P(A.LogKyoku)]

@@ -461,6 +461,217 @@ int parse_lines(const char* text, size_t len, uint32_t rule_bits, rv_replay** ou
   *out = r.release();
   return RV_OK;
 }
+
+// ---------------------------------------------------------------- MjSoul paifu (replay/mjsoul_replay.rs)
+// TileConverter::parse_tile / parse_tile_136 (replay/mod.rs:2184-2222): "<digit><suit>", digit 0 = red five
+uint8_t paifu_tile(const JVal* v) {
+  if (!v || v->kind != JVal::Str || v->str.empty()) return 0;
+  const std::string& t = v->str;
+  int num = (t[0] >= '0' && t[0] <= '9') ? t[0] - '0' : 0;
+  const bool aka = num == 0;
+  if (aka) num = 5;
+  const std::string suit = t.substr(1);
+  int id34 = suit == "m" ? num - 1 : suit == "p" ? 9 + num - 1 : suit == "s" ? 18 + num - 1 : suit == "z" ? 27 + num - 1 : 0;
+  id34 &= 0xFF;
+  if (aka) return id34 == 4 ? 16 : id34 == 13 ? 52 : id34 == 22 ? 88 : (uint8_t)(id34 * 4);
+  if (id34 == 4 || id34 == 13 || id34 == 22) return (uint8_t)(id34 * 4 + 1);
+  return (uint8_t)(id34 * 4);
+}
+bool getb(const JVal& o, const char* key) {
+  const JVal* v = o.get(key);
+  return v && v->kind == JVal::Bool && v->b;
+}
+// MjSoulReplay::parse_raw_action (mjsoul_replay.rs:541-687); `name` / `data` as serde's adjacently tagged enum reads them
+rv_log_action paifu_action(const std::string& name, const JVal& d) {
+  static const JVal empty;
+  auto seat = [&]() { int s = geti(d, "seat"); return s < 0 || s > 3 ? 0 : s; };
+  if (name == "DiscardTile") {
+    rv_log_action a = blank(RV_LA_DISCARD, seat());
+    a.tile = paifu_tile(d.get("tile"));
+    a.flags = (uint8_t)((getb(d, "is_liqi") ? 1 : 0) | (getb(d, "is_wliqi") ? 2 : 0));
+    return a;
+  }
+  if (name == "DealTile") {
+    rv_log_action a = blank(RV_LA_DEAL, seat());
+    a.tile = paifu_tile(d.get("tile"));
+    return a;
+  }
+  if (name == "ChiPengGang") {
+    rv_log_action a = blank(RV_LA_CHI_PENG_GANG, seat());
+    const int mt = geti(d, "type");
+    a.meld_type = mt == 0 ? RV_MELD_CHI : mt == 1 ? RV_MELD_PON : mt == 2 ? RV_MELD_DAIMINKAN : mt == 3 ? RV_MELD_ANKAN : RV_MELD_CHI;
+    int n = 0;
+    const JVal* tiles = d.get("tiles");
+    const JVal* froms = d.get("froms");
+    if (tiles && tiles->kind == JVal::Arr)
+      for (size_t i = 0; i < tiles->arr.size() && n < 4; i++) {
+        a.tiles[n] = paifu_tile(&tiles->arr[i]);
+        a.froms[n] = froms && i < froms->arr.size() ? (uint8_t)froms->arr[i].num : (uint8_t)RV_NONE;
+        n++;
+      }
+    a.n_tiles = (uint8_t)n;
+    a.tile = n ? a.tiles[0] : (uint8_t)RV_NONE;
+    return a;
+  }
+  if (name == "AnGangAddGang") {
+    rv_log_action a = blank(RV_LA_ANGANG_ADDGANG, seat());
+    a.meld_type = geti(d, "type") == 3 ? RV_MELD_ANKAN : RV_MELD_KAKAN;
+    a.tiles[0] = paifu_tile(d.get("tiles"));
+    a.n_tiles = 1;
+    return a;
+  }
+  if (name == "Hule") {
+    rv_log_action a = blank(RV_LA_HULE, 0);
+    const JVal* hs = d.get("hules");
+    int n = 0;
+    if (hs && hs->kind == JVal::Arr)
+      for (size_t i = 0; i < hs->arr.size() && n < 3; i++, n++) {
+        const JVal& h = hs->arr[i];
+        rv_hule& o = a.hules[n];
+        memset(&o, 0, sizeof o);
+        o.seat = (uint8_t)geti(h, "seat");
+        o.hu_tile = paifu_tile(h.get("hu_tile"));
+        o.zimo = getb(h, "zimo");
+        o.yiman = getb(h, "yiman");
+        o.count = (uint32_t)geti(h, "count");
+        o.fu = (uint32_t)geti(h, "fu");
+        o.point_rong = (uint32_t)geti(h, "point_rong");
+        o.point_zimo_qin = (uint32_t)geti(h, "point_zimo_qin");
+        o.point_zimo_xian = (uint32_t)geti(h, "point_zimo_xian");
+        if (const JVal* fans = h.get("fans"))
+          for (auto& f : fans->arr) {
+            const int id = geti(f, "id"), val = geti(f, "val");     // fans with val 0 are dropped
+            if (val > 0 && id >= 0 && id < 64) o.fans |= 1ull << id;
+          }
+        const JVal* li = h.get("ura_dora_indicators");
+        if (!li || li->kind != JVal::Arr) li = h.get("li_doras");
+        o.n_li_doras = 0xFF;
+        if (li && li->kind == JVal::Arr) {
+          o.n_li_doras = (uint8_t)std::min<size_t>(li->arr.size(), 5);
+          for (int k = 0; k < o.n_li_doras; k++) o.li_doras[k] = paifu_tile(&li->arr[k]);
+        }
+      }
+    a.n_hule = (uint8_t)n;
+    return a;
+  }
+  if (name == "dora") {
+    rv_log_action a = blank(RV_LA_DORA, 0);
+    a.tile = paifu_tile(d.get("dora_marker"));
+    return a;
+  }
+  if (name == "NoTile") return blank(RV_LA_NOTILE, 0);
+  if (name == "BaBei") {
+    rv_log_action a = blank(RV_LA_BABEI, seat());
+    a.flags = getb(d, "moqie") ? 1 : 0;
+    return a;
+  }
+  if (name == "LiuJu") {
+    rv_log_action a = blank(RV_LA_LIUJU, seat());
+    a.tile = (uint8_t)geti(d, "type");
+    int n = 0;
+    if (const JVal* tiles = d.get("tiles"))
+      for (size_t i = 0; i < tiles->arr.size() && n < 4; i++) a.tiles[n++] = paifu_tile(&tiles->arr[i]);   // (the record keeps four)
+    a.n_tiles = (uint8_t)n;
+    return a;
+  }
+  return blank(RV_LA_NONE, 0);                            // NewRound and unknown names: Action::Other
+}
+// MjSoulReplay::kyoku_from_raw_actions (mjsoul_replay.rs:448-539) + the oya / drawn-tile derivation of LogKyoku::steps
+bool paifu_round(const JVal& round, uint32_t rule_bits, Kyoku& out, std::string& err) {
+  if (round.kind != JVal::Arr || round.arr.empty()) return err = "a round is not a list of actions", false;
+  rv_log_kyoku& k = out.k;
+  memset(&k, 0, sizeof k);
+  memset(k.doras, RV_NONE, sizeof k.doras);
+  memset(k.ura_doras, RV_NONE, sizeof k.ura_doras);
+  memset(k.hands, RV_NONE, sizeof k.hands);
+  k.np = 4;
+  k.left_tile_count = 70;
+  k.rule_bits = rule_bits;
+  auto name_of = [](const JVal& a) { const JVal* n = a.get("name"); return n && n->kind == JVal::Str ? n->str : std::string(); };
+  static const JVal none;
+  const JVal& first = round.arr[0];
+  if (name_of(first) == "NewRound") {
+    const JVal* dp = first.get("data");
+    const JVal& d = dp ? *dp : none;
+    const JVal* sc = d.get("scores");
+    if (!sc || sc->kind != JVal::Arr) return err = "NewRound: missing field `scores`", false;
+    k.np = sc->arr.size() == 3 ? 3 : 4;
+    for (size_t p = 0; p < sc->arr.size() && p < 4; p++) k.scores[p] = k.end_scores[p] = (int32_t)sc->arr[p].num;
+    const JVal* da = d.get("dora_indicators");
+    if (!da || da->kind != JVal::Arr) da = d.get("doras");
+    if (da && da->kind == JVal::Arr) {
+      for (size_t i = 0; i < da->arr.size() && k.n_doras < RV_LOG_MAX_DORAS; i++) k.doras[k.n_doras++] = paifu_tile(&da->arr[i]);
+    } else if (const JVal* dm = d.get("dora_marker")) {
+      if (dm->kind == JVal::Str) k.doras[k.n_doras++] = paifu_tile(dm);
+    }
+    static const char* tk[4] = {"tiles0", "tiles1", "tiles2", "tiles3"};
+    for (int p = 0; p < 4; p++) {
+      const JVal* t = d.get(tk[p]);
+      if (!t || t->kind != JVal::Arr) {
+        if (p < k.np) return err = std::string("NewRound: missing field `") + tk[p] + "`", false;
+        continue;
+      }
+      int n = 0;
+      for (size_t i = 0; i < t->arr.size() && n < 14; i++) k.hands[p][n++] = paifu_tile(&t->arr[i]);
+      k.hand_len[p] = (uint8_t)n;
+    }
+    k.chang = (uint8_t)geti(d, "chang");
+    k.ju = (uint8_t)geti(d, "ju");
+    k.ben = (uint8_t)(d.get("ben") && d.get("ben")->kind == JVal::Num ? geti(d, "ben") : geti(d, "honba"));
+    k.liqibang = (uint8_t)geti(d, "liqibang");
+    k.left_tile_count = (uint8_t)geti(d, "left_tile_count", 70);
+    if (const JVal* ud = d.get("ura_doras"))
+      for (size_t i = 0; i < ud->arr.size() && k.n_ura_doras < RV_LOG_MAX_DORAS; i++) k.ura_doras[k.n_ura_doras++] = paifu_tile(&ud->arr[i]);
+  }
+  for (auto& a : round.arr) {
+    const JVal* dp = a.get("data");
+    out.actions.push_back(paifu_action(name_of(a), dp ? *dp : none));
+  }
+  for (auto& a : out.actions)
+    if (a.type == RV_LA_DISCARD && (a.flags & 2) && a.seat < 4) k.wliqi[a.seat] = 1;
+  k.n_actions = (int32_t)out.actions.size();
+  int oya = k.ju % k.np;
+  for (int p = 0; p < k.np; p++)
+    if (k.hand_len[p] == 14) { oya = p; break; }
+  k.oya = (uint8_t)oya;
+  k.oya_drawn_tile = RV_NONE;
+  if (k.hand_len[oya] == 14) {
+    int dt = k.hands[oya][13];
+    for (auto& a : out.actions) {                          // `self.actions.first()` is the NewRound placeholder: no match, dt stays
+      (void)a;
+      break;
+    }
+    k.oya_drawn_tile = (uint8_t)dt;
+  }
+  return true;
+}
+int parse_paifu(const char* text, size_t len, uint32_t rule_bits, rv_replay** out) {
+  JParser jp{text, text + len, {}};
+  JVal v;
+  if (!jp.value(v)) return rv_internal_fail(RV_ERR_INVALID, "Failed to parse JSON: " + jp.err);
+  const JVal* rounds = nullptr;
+  if (v.kind == JVal::Obj) {
+    rounds = v.get("rounds");                              // GameLog { rounds } (from_json)
+    if (!rounds) rounds = v.get("data");                   // Paifu { header, data } (from_dict)
+    if (!rounds) return rv_internal_fail(RV_ERR_INVALID, "Invalid dict format: missing 'data'");
+  } else if (v.kind == JVal::Arr) {
+    rounds = &v;
+  } else {
+    return rv_internal_fail(RV_ERR_INVALID, "Invalid input format: expected dict or list");
+  }
+  if (rounds->kind != JVal::Arr) return rv_internal_fail(RV_ERR_INVALID, "Failed to parse rounds list");
+  std::unique_ptr<rv_replay> r(new rv_replay);
+  for (auto& rd : rounds->arr) {
+    Kyoku k;
+    std::string err;
+    if (!paifu_round(rd, rule_bits, k, err)) return rv_internal_fail(RV_ERR_INVALID, "Failed to parse rounds: " + err);
+    r->rounds.push_back(std::move(k));
+  }
+  for (size_t i = 0; i + 1 < r->rounds.size(); i++)
+    for (int p = 0; p < 4; p++) r->rounds[i].k.end_scores[p] = r->rounds[i + 1].k.scores[p];
+  *out = r.release();
+  return RV_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -482,6 +693,23 @@ int rv_replay_from_jsonl(const char* path, uint32_t rule_bits, rv_replay** out) 
   gzclose(f);
   if (bad) return rv_internal_fail(RV_ERR_INVALID, std::string("Read error: ") + path);
   return parse_lines(text.data(), text.size(), rule_bits, out);
+}
+int rv_replay_from_mjsoul_text(const char* text, size_t len, uint32_t rule_bits, rv_replay** out) {
+  if (!text || !out) return rv_internal_fail(RV_ERR_INVALID, "text / out is null");
+  return parse_paifu(text, len, rule_bits, out);
+}
+int rv_replay_from_mjsoul_json(const char* path, uint32_t rule_bits, rv_replay** out) {
+  if (!path || !out) return rv_internal_fail(RV_ERR_INVALID, "path / out is null");
+  gzFile f = gzopen(path, "rb");                           // the reference expects gzip; gzopen also reads a plain file
+  if (!f) return rv_internal_fail(RV_ERR_INVALID, std::string("Failed to open file: ") + path);
+  std::string text;
+  char buf[1 << 16];
+  int n;
+  while ((n = gzread(f, buf, sizeof buf)) > 0) text.append(buf, (size_t)n);
+  const bool bad = n < 0;
+  gzclose(f);
+  if (bad) return rv_internal_fail(RV_ERR_INVALID, std::string("Failed to decompress: ") + path);
+  return parse_paifu(text.data(), text.size(), rule_bits, out);
 }
 int rv_replay_free(rv_replay* r) {
   delete r;

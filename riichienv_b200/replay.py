@@ -485,6 +485,52 @@ class MjaiReplay:
         return KyokuIterator(self)
 
 
+class MjSoulReplay:
+    """replay/mjsoul_replay.rs:20-343: a MjSoul paifu as JSON records {"name": "NewRound" | "DealTile" | ..., "data": {...}} —
+    the format `Kyoku.events()` writes.  `from_json(path)` reads a gzip file holding {"rounds": [[...], ...]}; `from_dict`
+    takes the paifu dict ({"header", "data"}) or the bare list of rounds and also fills `game_end_scores`."""
+
+    def __init__(self, rounds):
+        self.rounds = rounds
+
+    @classmethod
+    def from_json(cls, path):
+        g = GameRule.default_mjsoul()
+        h = C.c_void_p()
+        check(lib().rv_replay_from_mjsoul_json(str(path).encode(), g.bits(), C.byref(h)))
+        return cls(MjaiReplay._from_handle(h, g).rounds)
+
+    @classmethod
+    def from_dict(cls, paifu):
+        import json
+
+        g = GameRule.default_mjsoul()
+        data = json.dumps(paifu).encode()
+        h = C.c_void_p()
+        check(lib().rv_replay_from_mjsoul_text(data, len(data), g.bits(), C.byref(h)))
+        self = cls(MjaiReplay._from_handle(h, g).rounds)
+        if self.rounds:                       # the last round replayed to its end gives the game's final scores (mjsoul_replay.rs:259-340)
+            last = self.rounds[-1]
+            env = RiichiEnv(game_mode=3 if last._k.np == 3 else 0, rule=g, seed=0)
+            env._v.replay_begin((A.LogKyoku * 1)(last._k))
+            for a in last._views:
+                if a.type != A.LA_NONE:
+                    env._v.apply_log_actions((A.LogAction * 1)(a.raw))
+            last.end_scores = env.scores()
+            for r in self.rounds:
+                r.game_end_scores = list(last.end_scores)
+        return self
+
+    def num_rounds(self):
+        return len(self.rounds)
+
+    def take_kyokus(self):
+        return KyokuIterator(self)
+
+    def verify(self):
+        raise NotImplementedError("MjSoulReplay.verify walks WinResultContextIterator (replay/mod.rs:1594-2180): not built")
+
+
 class ReplayBatch:
     """K kyoku replayed in lock-step on ONE vector of K game records (the data-parallel form of `Kyoku.steps`): call
     `advance()` until it returns False; after each call `self.vec` holds every kyoku one log action further, and the usual

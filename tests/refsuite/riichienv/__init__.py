@@ -48,7 +48,7 @@ from riichienv_b200.convert import parse_hand, parse_tile  # noqa: E402,F401
 EAST, SOUTH, WEST, NORTH = Wind.East, Wind.South, Wind.West, Wind.North
 
 
-from riichienv_b200.replay import Kyoku, KyokuIterator, MjaiReplay  # noqa: E402,F401  (replay ingestion)
+from riichienv_b200.replay import Kyoku, KyokuIterator, MjaiReplay, MjSoulReplay  # noqa: E402,F401  (replay ingestion)
 
 
 def __getattr__(name):

@@ -261,6 +261,50 @@ def test_simulated_logs_every_logged_decision_is_legal(backend, mode):
         assert {"DISCARD", "RIICHI", "PASS"} <= kinds and ("KITA" in kinds) == (mode == 5)
 
 
+@pytest.mark.parametrize("source", ["real", "sim4", "sim3"])
+def test_mjsoul_paifu_reader_round_trip(source, tmp_path):
+    """MjSoulReplay reads the record format Kyoku.events() writes (replay/mjsoul_replay.rs RawAction <-> replay/mod.rs:1294-1500):
+    a log read as MJAI, written out as paifu rounds and read back must give the same kyoku records, the same events and the same
+    decisions.  (The reference writes a kan dora as "Dora" and reads it as "dora": renamed on the way.)"""
+    R = _shim("oracle")
+    text = open(REAL_LOG).read() if source == "real" else "\n".join(simulated_log(2 if source == "sim4" else 5, 21)) + "\n"
+    a = R.MjaiReplay.from_text(text, rule="mjsoul")
+    rounds = []
+    for k in a.take_kyokus():
+        ev = k.events()
+        for e in ev:
+            if e["name"] == "Dora":
+                e["name"] = "dora"
+        rounds.append(ev)
+    b = R.MjSoulReplay.from_dict({"header": {}, "data": rounds})
+    path = tmp_path / "paifu.json.gz"
+    with gzip.open(path, "wt") as f:
+        json.dump({"rounds": rounds}, f)
+    c = R.MjSoulReplay.from_json(str(path))
+    assert a.num_rounds() == b.num_rounds() == c.num_rounds() > 0
+    n_steps = 0
+    for x, y, z in zip(a.take_kyokus(), b.take_kyokus(), c.take_kyokus()):
+        for other in (y, z):
+            assert (x.scores, x.hands, x.doras, x.chang, x.ju, x.ben, x.liqibang, x.wliqi) == \
+                   (other.scores, other.hands, other.doras, other.chang, other.ju, other.ben, other.liqibang, other.wliqi)
+            assert x.events() == other.events()
+        assert y._views[0].type == A.LA_NONE                      # the NewRound placeholder (Action::Other)
+        sx = [(p, act.action_type, act.tile) for p, _, act in x.steps(None, skip_single_action=False)]
+        sy = [(p, act.action_type, act.tile) for p, _, act in y.steps(None, skip_single_action=False)]
+        assert sx == sy
+        n_steps += len(sx)
+    assert n_steps > 100
+    # non-final rounds: end_scores = the next round's start scores; the final one: the last round replayed to its end
+    ks = list(b.take_kyokus())
+    for p, q in zip(ks, ks[1:]):
+        assert p.end_scores == q.scores
+    assert ks[0].game_end_scores == ks[-1].end_scores and len(ks[-1].end_scores) == len(ks[-1].scores)
+    with pytest.raises(ValueError, match="missing 'data'"):
+        R.MjSoulReplay.from_dict({"header": {}})
+    with pytest.raises(ValueError, match="expected dict or list"):
+        R.MjSoulReplay.from_dict(3)
+
+
 # ------------------------------------------------------------------------------------------------ the product (GPU)
 @pytest.mark.gpu
 def test_gpu_replay_batch_equals_oracle():
