@@ -41,6 +41,9 @@ def load():
     lib.orc_calculate_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, P(C.c_uint32)]
     lib.orc_wall_from_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_int, P(C.c_uint8)]
     lib.orc_chacha_words.argtypes = [P(C.c_uint32), C.c_int, C.c_int, P(C.c_uint32)]
+    lib.orc_run_agent_walls.restype = C.c_int64
+    lib.orc_run_agent_walls.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, P(C.c_uint8),
+                                        P(C.c_int32), P(C.c_uint8), P(C.c_uint8), P(C.c_uint32), P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]
     lib.orc_game_new.restype = C.c_void_p
     lib.orc_game_new.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint32, C.c_int]
     lib.orc_game_free.argtypes = [C.c_void_p]

@@ -397,7 +397,7 @@ uint32_t orc_game_events(void* h, uint32_t* out, uint32_t cap) {
 // (0..7), [80] yakuman hora, [81] kazoe (>= 13 han, no yakuman), [82] games finished.
 static int64_t run_agent(int policy, int mode, uint32_t rule, uint64_t seed_base, int64_t n, uint64_t agent_seed, uint32_t max_steps,
                          int threads, int32_t* scores, uint8_t* ranks, uint8_t* done, uint32_t* steps, uint32_t* kyoku,
-                         uint32_t* evcount, uint64_t* hash, uint32_t* max_river, uint64_t* hist) {
+                         uint32_t* evcount, uint64_t* hash, uint32_t* max_river, uint64_t* hist, const uint8_t* walls = nullptr) {
   std::atomic<int64_t> next{0};
   std::atomic<int64_t> total{0};
   std::mutex hist_mu;
@@ -407,7 +407,13 @@ static int64_t run_agent(int policy, int mode, uint32_t rule, uint64_t seed_base
       int64_t g = next.fetch_add(1);
       if (g >= n) break;
       GameState gs((uint8_t)mode, seed_base + (uint64_t)g, 0, rule, hist != nullptr);
-      gs.reset();
+      if (walls) {              // reset(wall=...) -> load_wall (state/wall.rs:69-80): the first round is dealt from the caller's tiles
+        const int wl = mode >= 3 ? 108 : 136;
+        std::vector<uint8_t> w(walls + (size_t)g * wl, walls + (size_t)(g + 1) * wl);
+        gs.reset(0, 0, 0, 0, &w, nullptr);
+      } else {
+        gs.reset();
+      }
       uint32_t mr = 0;
       while (!gs.is_done && gs.step_count < max_steps) {
         agent_step(gs, policy, agent_seed, seed_base + (uint64_t)g);
@@ -480,6 +486,13 @@ int64_t orc_run_agent(int policy, int mode, uint32_t rule, uint64_t seed_base, i
                       uint32_t* evcount, uint64_t* hash, uint64_t* hist) {
   return run_agent(policy, mode, rule, seed_base, n, agent_seed, max_steps, threads, scores, ranks, done, steps, kyoku, evcount,
                    hash, nullptr, hist);
+}
+// the same with explicit walls (n x 136 / 108 tiles): single-round modes never reach the seeded shuffle
+int64_t orc_run_agent_walls(int policy, int mode, uint32_t rule, uint64_t seed_base, int64_t n, uint64_t agent_seed, uint32_t max_steps,
+                            int threads, const uint8_t* walls, int32_t* scores, uint8_t* ranks, uint8_t* done, uint32_t* steps,
+                            uint32_t* kyoku, uint32_t* evcount, uint64_t* hash) {
+  return run_agent(policy, mode, rule, seed_base, n, agent_seed, max_steps, threads, scores, ranks, done, steps, kyoku, evcount,
+                   hash, nullptr, nullptr, walls);
 }
 void orc_game_apply_event(void* h, const rv_mjai_event* e) { apply_mjai_event(*(GameState*)h, *e); }
 // replay ingestion (test oracle of rv_vec_replay_begin / rv_vec_apply_log_actions)

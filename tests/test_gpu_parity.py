@@ -202,6 +202,44 @@ def test_parity_gate_100k_games(orc):
     assert g[1].all() and g[0] > 1000 * n
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,policy", [(0, 0), (0, 1), (3, 0), (3, 1)])
+def test_explicit_wall_gate_100k_rounds(orc, mode, policy):
+    """The parity gate WITHOUT the seeded shuffle (the one function whose parity with the reference cannot be pinned here):
+    102,400 single-round games dealt from caller-supplied walls (reset(wall=) -> load_wall, state/wall.rs:69-80; numpy
+    permutations of the 136 / 108 tile ids), played to the end by the random (policy 0) and the greedy-win agent (policy 1)."""
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    n, seed_base, agent_seed = 102400, 77_000_000, 0xE7A11
+    wl = 108 if mode >= 3 else 136
+    tiles = np.array([t for t in range(136) if mode < 3 or not (4 <= t < 32)], np.uint8)      # sanma: no 2m-8m
+    assert tiles.size == wl
+    rng = np.random.default_rng(20260117 + mode)
+    walls = np.ascontiguousarray(rng.permuted(np.broadcast_to(tiles, (n, wl)), axis=1))
+    v = VecRiichiEnv(n, mode, A.RULE_DEFAULT_TENHOU, seed_base=seed_base)
+    v.reset(walls=walls)
+    # policy 0 goes through the rollout scheduler (the crew kernel), policy 1 through the agent kernel
+    total = v.step_random(agent_seed, 100000) if policy == 0 else v.step_agent(policy, agent_seed, 100000)
+    done, scores, ranks = v.results()
+    sc, kc, ec, eh = v.counters()
+    v.close()
+    o_scores, o_ranks, o_done = np.zeros((n, 4), np.int32), np.zeros((n, 4), np.uint8), np.zeros(n, np.uint8)
+    o_steps, o_ky, o_ec, o_h = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint64)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    import os
+
+    o_total = orc.orc_run_agent_walls(policy, mode, A.RULE_DEFAULT_TENHOU, seed_base, n, agent_seed, 100000, os.cpu_count() or 1,
+                                      p(walls, C.c_uint8), p(o_scores, C.c_int32), p(o_ranks, C.c_uint8), p(o_done, C.c_uint8),
+                                      p(o_steps, C.c_uint32), p(o_ky, C.c_uint32), p(o_ec, C.c_uint32), p(o_h, C.c_uint64))
+    assert total == o_total and done.all() and o_done.all()
+    for name, a, b in zip(["scores", "ranks", "step_count", "kyoku_count", "ev_count", "ev_hash"], [scores, ranks, sc, kc, ec, eh],
+                          [o_scores, o_ranks, o_steps, o_ky, o_ec, o_h]):
+        assert np.array_equal(a, b), f"{name} differs in {int((a != b).sum())} entries"
+    assert (kc == 1).all()                                     # one round each: the seeded shuffle is never reached
+    if policy == 1:
+        assert (scores[:, : 3 if mode >= 3 else 4] != (35000 if mode >= 3 else 25000)).any(axis=1).mean() > 0.5   # most rounds are won
+
+
 def run_both_agent(orc, policy, n, mode, rule, seed_base, agent_seed, hist=None, max_steps=200000):
     from riichienv_b200.vec_env import VecRiichiEnv
 
