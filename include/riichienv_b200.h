@@ -506,6 +506,12 @@ int rv_replay_actions(const rv_replay* r, int round, rv_log_action* out, int cap
 int rv_vec_replay_begin(rv_vec* v, const rv_log_kyoku* kyokus);
 /* GameState::apply_log_action for every game: actions[n] (HOST), type RV_LA_NONE = leave that game alone. */
 int rv_vec_apply_log_actions(rv_vec* v, const rv_log_action* actions);
+/* The same with the logs resident in HBM: rv_vec_replay_load = rv_vec_replay_begin + ONE upload of every record's action
+ * list (actions of record i = actions[first[i] .. first[i + 1]), first[n + 1] HOST offsets); each rv_vec_replay_advance then
+ * applies the next action of every record that has one left (nothing crosses PCIe), *n_applied = how many records did
+ * (0 = every kyoku is exhausted; NULL = do not wait for the kernel).                                                     */
+int rv_vec_replay_load(rv_vec* v, const rv_log_kyoku* kyokus, const rv_log_action* actions, const int64_t* first);
+int rv_vec_replay_advance(rv_vec* v, int64_t* n_applied);
 
 /* ---- several GPUs behind one handle (SURVEY.md §8 e) -------------------------------------------------------------
  * Replaces what the reference does with one Python list of RiichiEnv per Ray actor (riichienv-ml/.../_ppo_worker.py:13,39).

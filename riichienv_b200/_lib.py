@@ -93,6 +93,8 @@ def lib():
     L.rv_replay_actions.argtypes = [vp, C.c_int, P(A.LogAction), C.c_int, P(C.c_int)]
     L.rv_vec_replay_begin.argtypes = [vp, P(A.LogKyoku)]
     L.rv_vec_apply_log_actions.argtypes = [vp, P(A.LogAction)]
+    L.rv_vec_replay_load.argtypes = [vp, P(A.LogKyoku), P(A.LogAction), P(C.c_int64)]
+    L.rv_vec_replay_advance.argtypes = [vp, P(C.c_int64)]
     for i, T in enumerate((A.GameState, A.HandQuery, A.HandResult, A.Action, A.MjaiEvent, A.RunStats, A.LogAction, A.LogKyoku)):
         if L.rv_sizeof(i) != C.sizeof(T):
             raise ImportError(f"ABI mismatch for {T.__name__}: C {L.rv_sizeof(i)} != ctypes {C.sizeof(T)}")

@@ -92,6 +92,11 @@ struct rv_vec {
   unsigned char* d_obs_snap;    // rv_vec_observe_step_random: packed snapshot of what the encoder reads (n x OBS_STAGE_BYTES)
   void *d_io_a, *d_io_c;        // staging of rv_vec_step / rv_vec_legal_actions (grow-only)
   size_t io_a_bytes, io_c_bytes;
+  // replay ingestion with the log resident in HBM (rv_vec_replay_load / rv_vec_replay_advance)
+  rv_log_action* d_rp_actions;  // the log actions of every record's kyoku, concatenated
+  int64_t* d_rp_first;          // [n + 1] offsets into d_rp_actions
+  int32_t* d_rp_cursor;         // [n] actions of the record's kyoku applied so far
+  int32_t* d_rp_live;           // records that still had an action in the last advance
 };
 
 // ------------------------------------------------------------------ kernels
@@ -125,6 +130,29 @@ __global__ void __launch_bounds__(64) apply_log_actions_kernel(Tables T, G* stat
   cx.defer_init = cx.defer_tail = false;
   cx.idbits = nullptr;
   apply_log_action(cx, states[i], acts[i]);
+}
+// rv_vec_replay_advance: every record applies the next action of its own kyoku, read from the log resident in HBM
+__global__ void __launch_bounds__(64) replay_advance_kernel(Tables T, G* states, int64_t n, const rv_log_action* __restrict__ acts,
+                                                            const int64_t* __restrict__ first, int32_t* cursor, int32_t* live) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool did = false;
+  if (i < n) {
+    const int32_t c = cursor[i];
+    const int64_t at = first[i] + c;
+    if (at < first[i + 1]) {
+      Ctx cx;
+      cx.T = T;
+      cx.log = nullptr;
+      cx.log_cap = 0;
+      cx.defer_init = cx.defer_tail = false;
+      cx.idbits = nullptr;
+      if (acts[at].type != RV_LA_NONE) apply_log_action(cx, states[i], acts[at]);
+      cursor[i] = c + 1;
+      did = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, did);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(live, __popc(m));
 }
 __global__ void __launch_bounds__(64) replay_begin_kernel(Tables T, G* states, int64_t n, const rv_log_kyoku* kyokus) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2073,6 +2101,9 @@ int rv_vec_create(rv_ctx* c, int64_t n, int game_mode, uint32_t rule_bits, const
   v->d_io_a = v->d_io_c = nullptr;
   v->d_obs_snap = nullptr;
   v->io_a_bytes = v->io_c_bytes = 0;
+  v->d_rp_actions = nullptr;
+  v->d_rp_first = nullptr;
+  v->d_rp_cursor = v->d_rp_live = nullptr;
   v->q_cap = 0;
   v->graph_seed = 0;
   v->graph_period = 0;
@@ -2129,6 +2160,10 @@ int rv_vec_destroy(rv_vec* v) {
   if (v->d_obs_snap) cudaFree(v->d_obs_snap);
   if (v->d_io_a) cudaFree(v->d_io_a);
   if (v->d_io_c) cudaFree(v->d_io_c);
+  if (v->d_rp_actions) cudaFree(v->d_rp_actions);
+  if (v->d_rp_first) cudaFree(v->d_rp_first);
+  if (v->d_rp_cursor) cudaFree(v->d_rp_cursor);
+  if (v->d_rp_live) cudaFree(v->d_rp_live);
   cudaFree(v->d_steps);
   delete v;
   return RV_OK;
@@ -2604,6 +2639,48 @@ int rv_vec_replay_begin(rv_vec* v, const rv_log_kyoku* kyokus) {
   replay_begin_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, d_k);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
+int rv_vec_replay_load(rv_vec* v, const rv_log_kyoku* kyokus, const rv_log_action* actions, const int64_t* first) {
+  if (!kyokus || !first) return fail(RV_ERR_INVALID, "kyokus / first is null");
+  const int64_t total = first[v->n];
+  if (first[0] != 0 || total < 0) return fail(RV_ERR_INVALID, "first[] must start at 0 and be non-decreasing");
+  for (int64_t i = 0; i < v->n; i++)
+    if (first[i + 1] < first[i]) return fail(RV_ERR_INVALID, "first[] must start at 0 and be non-decreasing");
+  if (total > 0 && !actions) return fail(RV_ERR_INVALID, "actions is null");
+  int rc = rv_vec_replay_begin(v, kyokus);
+  if (rc != RV_OK) return rc;
+  rv_ctx* c = v->ctx;
+  if (v->d_rp_actions) CK(cudaFree(v->d_rp_actions));
+  v->d_rp_actions = nullptr;
+  if (!v->d_rp_first) {
+    CK(cudaMalloc(&v->d_rp_first, sizeof(int64_t) * (size_t)(v->n + 1)));
+    CK(cudaMalloc(&v->d_rp_cursor, sizeof(int32_t) * (size_t)v->n));
+    CK(cudaMalloc(&v->d_rp_live, sizeof(int32_t)));
+  }
+  if (total > 0) {
+    CK(cudaMalloc(&v->d_rp_actions, sizeof(rv_log_action) * (size_t)total));
+    CK(cudaMemcpyAsync(v->d_rp_actions, actions, sizeof(rv_log_action) * (size_t)total, cudaMemcpyHostToDevice, c->stream));
+  }
+  CK(cudaMemcpyAsync(v->d_rp_first, first, sizeof(int64_t) * (size_t)(v->n + 1), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(v->d_rp_cursor, 0, sizeof(int32_t) * (size_t)v->n, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RV_OK;
+}
+int rv_vec_replay_advance(rv_vec* v, int64_t* n_applied) {
+  if (!v->d_rp_first) return fail(RV_ERR_INVALID, "no log loaded (rv_vec_replay_load)");
+  rv_ctx* c = v->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(v->d_rp_live, 0, sizeof(int32_t), c->stream));
+  replay_advance_kernel<<<grid_for(v->n, 64), 64, 0, c->stream>>>(c->T, v->d_states, v->n, v->d_rp_actions, v->d_rp_first, v->d_rp_cursor,
+                                                                 v->d_rp_live);
+  CK(cudaGetLastError());
+  if (n_applied) {                                   // NULL: asynchronous on the context's stream
+    int32_t live = 0;
+    CK(cudaMemcpyAsync(&live, v->d_rp_live, sizeof live, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *n_applied = live;
+  }
   return RV_OK;
 }
 int rv_vec_debug_call(rv_vec* v, int64_t game, int op, uint8_t out_tiles[5], int* n_out) {

@@ -548,20 +548,19 @@ class ReplayBatch:
         self.kyokus = kyokus
         self.n = len(kyokus)
         self.vec = VecRiichiEnv(self.n, 3 if np_ == 3 else 0, kyokus[0].rule.bits(), seed_base=0, log_cap_words=0, device=device)
-        self.vec.replay_begin((A.LogKyoku * self.n)(*[k._k for k in kyokus]))
-        self.cursor = [0] * self.n
+        # the logs go to the device ONCE (rv_vec_replay_load); every advance() is then a kernel launch, nothing crosses PCIe
+        first = (C.c_int64 * (self.n + 1))()
+        for i, k in enumerate(kyokus):
+            first[i + 1] = first[i] + len(k._views)
+        total = first[self.n]
+        blob = b"".join(bytes(k._actions) for k in kyokus)
+        acts = (A.LogAction * max(1, total)).from_buffer_copy(blob.ljust(C.sizeof(A.LogAction) * max(1, total), b"\0"))
+        self.vec.replay_load((A.LogKyoku * self.n)(*[k._k for k in kyokus]), acts, first)
+        self.position = 0
 
     def advance(self):
         """apply the next log action of every kyoku that has one; returns False when every kyoku is exhausted"""
-        arr = (A.LogAction * self.n)()
-        live = False
-        for i, k in enumerate(self.kyokus):
-            if self.cursor[i] < len(k._views):
-                arr[i] = k._views[self.cursor[i]].raw
-                self.cursor[i] += 1
-                live = True
-            else:
-                arr[i].type = A.LA_NONE
-        if live:
-            self.vec.apply_log_actions(arr)
-        return live
+        if self.vec.replay_advance() == 0:
+            return False
+        self.position += 1
+        return True

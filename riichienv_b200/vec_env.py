@@ -196,6 +196,16 @@ class VecRiichiEnv:
         """LogKyoku::steps' state set-up for every game: `kyokus` = ctypes array (A.LogKyoku * n)"""
         check(lib().rv_vec_replay_begin(self.handle, kyokus))
 
+    def replay_load(self, kyokus, actions, first):
+        """rv_vec_replay_begin + one upload of every record's action list (first = n + 1 offsets into `actions`)"""
+        check(lib().rv_vec_replay_load(self.handle, kyokus, actions, first))
+
+    def replay_advance(self, sync=True):
+        """the next log action of every record that has one left, from the log in HBM; returns how many records did"""
+        n = C.c_int64(0)
+        check(lib().rv_vec_replay_advance(self.handle, C.byref(n) if sync else None))
+        return int(n.value) if sync else None
+
     def apply_log_actions(self, actions):
         """GameState::apply_log_action for every game: `actions` = ctypes array (A.LogAction * n), type 0 = no action"""
         check(lib().rv_vec_apply_log_actions(self.handle, actions))
