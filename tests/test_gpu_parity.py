@@ -181,6 +181,26 @@ def test_random_games_vs_oracle(orc, mode, rule, n):
     assert g[1].all()   # incl. the rare stalled 3P games, which the rollout retires (overflow bit 1)
 
 
+@pytest.mark.parametrize("n", [1, 31, 33, 383, 385, 12 * 32 * 148 + 1])
+def test_rollout_scheduler_odd_sizes(orc, n):
+    """vector sizes around the scheduler's granules (a warp = 32 games, a block = 384, the crew = 148 blocks), incl. step budgets
+    that end the call in the middle of a game and a resume"""
+    from riichienv_b200.vec_env import VecRiichiEnv
+
+    g, o = run_both(orc, n, 2, A.RULE_DEFAULT_TENHOU, seed_base=31_000 + n, agent_seed=0x0DD)
+    assert g[0] == o[0]
+    for a, b in zip(g[1:], o[1:]):
+        assert np.array_equal(a, b)
+    if n <= 385:
+        v = VecRiichiEnv(n, 2, A.RULE_DEFAULT_TENHOU, seed_base=31_000 + n)
+        v.reset()
+        total = 0
+        for budget in (40, 333, 100000):                 # three calls: the rollout resumes where the budget stopped it
+            total += v.step_random(0x0DD, budget)
+        assert total == g[0] and np.array_equal(v.results()[1], g[2]) and np.array_equal(v.counters()[3], g[7])
+        v.close()
+
+
 def test_sanma_config_size_65536_games(orc):
     """BASELINE configs[3] at its stated size: 65,536 sanma hanchan (3p-red-half), done / scores / ranks / counters / event hash."""
     n = 65536
