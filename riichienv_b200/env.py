@@ -521,6 +521,11 @@ class Observation:
     def encode_riichi_sutehais(self):  # python.rs:1067-1115 -> (NP - 1, 3)
         return self._ext_row()[206:206 + 3 * (self._seats() - 1), 0].tobytes()
 
+    def encode_yaku_possibility(self):  # observation/python.rs:327-449, observation_3p/python.rs:275-395 -> (NP, 21, 2)
+        from . import yaku_possibility
+
+        return yaku_possibility.encode(self, self._NP)
+
     def encode_furiten_ron_possibility(self):  # python.rs:251-293 -> (NP, 21)
         """All ones: the encoder only clears a seat's row after three consecutive tsumogiri flags, and the live env never
         fills `tsumogiri_flags` (observation/mod.rs:105) — a constant, so nothing is computed."""

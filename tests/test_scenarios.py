@@ -501,3 +501,30 @@ def test_oyayame_tiebreak_last_round(backend):  # tests/test_oyayame_tiebreak.py
     # dealer seat 0 ties seat 1 for top (ties go to the lower seat = the dealer): only the LAST dealer can stop; South 1 goes on
     env = _flow_env(backend, round_wind=1, oya=0, kyoku_idx=0, scores=[35000, 35000, 15000, 15000])
     assert env.call(4) == 0
+
+
+def test_yaku_possibility_known_answers():
+    """riichienv-core/src/yaku_checker.rs:413-467 (the reference's unit tests) and the shape of encode_yaku_possibility"""
+    from types import SimpleNamespace as NS
+
+    import numpy as np
+
+    from riichienv_b200 import yaku_possibility as Y
+
+    M = lambda tiles: NS(tiles=list(tiles))
+    assert Y.check_tanyao([]) == Y.UNKNOWN
+    assert Y.check_tanyao([M([0, 1, 2])]) == Y.IMPOSSIBLE          # 1m pon
+    assert Y.check_tanyao([M([16, 17, 18])]) == Y.UNKNOWN           # 5m pon
+    assert Y.check_toitoi([M([0, 4, 8])]) == Y.IMPOSSIBLE           # 1m-2m-3m
+    assert Y.check_toitoi([M([16, 17, 18])]) == Y.POSSIBLE
+    assert Y.check_yakuhai(31, [M([124, 125, 126])], [], []) == Y.POSSIBLE
+    assert Y.check_yakuhai(31, [], [124, 125], [126]) == Y.IMPOSSIBLE      # three of four visible
+    assert Y.check_flush([M([0, 4, 8]), M([108, 109, 110])]) == (Y.POSSIBLE, Y.IMPOSSIBLE)
+    assert Y.check_flush([M([0, 4, 8]), M([36, 40, 44])]) == (Y.IMPOSSIBLE, Y.IMPOSSIBLE)
+    assert Y.check_daisangen([], [124, 125], []) == Y.IMPOSSIBLE and Y.check_kokushi([M([0, 1, 2])], [], []) == Y.IMPOSSIBLE
+    obs = NS(melds=[[M([0, 4, 8])], [], [], []], discards=[[], [124, 125, 126], [], []], dora_indicators=[0], round_wind=0, oya=1)
+    a = np.frombuffer(Y.encode(obs, 4), np.float32).reshape(4, 21, 2)
+    assert a.shape == (4, 21, 2) and (a[:, :, 0] == a[:, :, 1]).all()
+    assert a[0, 0, 0] == 0.0 and a[0, 8, 0] == 0.0 and a[0, 9, 0] == 0.0 and a[0, 19, 0] == 0.0       # tanyao, toitoi, chiitoi, iipeikou
+    assert a[1, 1, 0] == 0.0 and a[0, 1, 0] == 1.0 and a[2].min() == 1.0                             # seat 1 discarded three haku
+    assert len(Y.encode(NS(melds=[[], [], []], discards=[[], [], []], dora_indicators=[], round_wind=0, oya=0), 3)) == 3 * 21 * 2 * 4
