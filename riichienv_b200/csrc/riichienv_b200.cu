@@ -826,6 +826,35 @@ __device__ __forceinline__ void q_push(const Queues& q, int cls, int32_t gi) {
     }
   }
 }
+// q_push in two halves, for callers that can put work between them: the ticket (one warp-aggregated fetch-add per class, nothing
+// is published by it) and the publication (the slot store, after the game's record has reached memory).
+__device__ __forceinline__ uint32_t q_ticket(const Queues& q, int cls) {
+  const int lane = threadIdx.x & 31;
+  uint32_t t = 0;
+  #pragma unroll
+  for (int c = 0; c < N_QUEUES; c++) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+    if (m == 0) continue;
+    int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&q.ctl[Q_TAIL + 32 * c], (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (cls == c) t = base + __popc(m & ((1u << lane) - 1));
+  }
+  return t;
+}
+__device__ __forceinline__ void q_publish(const Queues& q, int cls, uint32_t t, int32_t gi) {
+  if (cls < 0 || cls >= N_QUEUES) return;
+  while (true) {
+    int32_t* sl = q.slots + (size_t)cls * (q.mask + 1) + (t & q.mask);
+    int32_t old = atomicCAS(sl, -1, gi);
+    if (old == -1) break;
+    if (old == -2) {                                     // the consumer of this ticket gave up: clear, draw a new ticket
+      *reinterpret_cast<volatile int32_t*>(sl) = -1;
+      t = atomicAdd(&q.ctl[Q_TAIL + 32 * cls], 1u);
+    }
+  }
+}
 __global__ void q_init_kernel(const G* states, int64_t n, uint32_t* budget, uint32_t max_steps, Queues q, int init_dist) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cls = PH_NONE;
@@ -1378,13 +1407,18 @@ __global__ void __launch_bounds__(384, 1) rollout_crew_kernel(Tables T, G* state
         stepped_total += b0 - b;
         finished_total += g.is_done ? 1 : 0;
       }
-      stage_out(&states[gi], slot);
-      __threadfence();
     }
     __syncwarp();
     {
+      // the ticket is drawn BEFORE the record is stored (its round trip runs under the bulk store), the game is published after
+      const int dest = have ? next : (int)PH_NONE;
+      const uint32_t ticket = q_ticket(q, dest);
+      if (have) {
+        stage_out(&states[gi], slot);
+        __threadfence();
+      }
       unsigned retired = __ballot_sync(0xFFFFFFFFu, have && next == PH_NONE);
-      q_push(q, next, gi);
+      q_publish(q, dest, ticket, gi);
       if (lane == 0 && retired) atomicSub(&q.ctl[Q_LIVE], (uint32_t)__popc(retired));
     }
     if (warp == 0) {                                       // the decision for the next iteration, published by the barrier
