@@ -75,6 +75,17 @@ def run(args, rank, world, local_rank):
         reps = 5
         for _ in range(reps):
             check(lib().rv_hand_eval_batch(ctx.handle, pq, po, ne))
+        e2e_pageable = reps * ne / (time.perf_counter() - t0)
+        # the same call on PINNED host buffers (what the bench contract asks for; the library sees that the caller's memory is
+        # page-locked and copies straight from / into it)
+        p_in = torch.from_numpy(h_in).pin_memory()
+        p_out = torch.empty((ne, C.sizeof(A.HandResult)), dtype=torch.uint8).pin_memory()
+        ppq, ppo = C.cast(p_in.data_ptr(), C.POINTER(A.HandQuery)), C.cast(p_out.data_ptr(), C.POINTER(A.HandResult))
+        check(lib().rv_hand_eval_batch(ctx.handle, ppq, ppo, ne))
+        assert bytes(p_out.numpy()[:4096].tobytes()) == h_out[:4096].tobytes()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            check(lib().rv_hand_eval_batch(ctx.handle, ppq, ppo, ne))
         e2e = reps * ne / (time.perf_counter() - t0)
         val = n * args.steps / (ms / 1000)
         ach = val * B_HAND / 1e9
@@ -87,7 +98,7 @@ def run(args, rank, world, local_rank):
                                    "score (BASELINE.json configs[1])", "hands": n,
                        "l2": "inputs+outputs 960 MB per step > 126 MB L2"},
             "e2e": {"value": e2e, "unit": "hands/s", "h2d_bytes_per_step": ne * 56, "d2h_bytes_per_step": ne * 40,
-                    "note": "rv_hand_eval_batch on pageable host buffers, 2M hands per call"},
+                    "note": "rv_hand_eval_batch on pinned host buffers, 2M hands per call", "pageable": e2e_pageable},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "kernel": "hand_eval_kernel", "peak_source": peak_src, "bytes_per_hand": B_HAND},
