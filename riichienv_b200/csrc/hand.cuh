@@ -668,10 +668,41 @@ __device__ __noinline__ YakuRes eval_division(const Cnt& hand, uint64_t all, con
 }
 
 // yaku::calculate_yaku (yaku.rs:232-559) on the concealed 3n+2 hand.
+// A soft block-wide rendezvous for kernels whose threads each run a long, data-dependent routine (hand_yaku_kernel): every
+// thread ARRIVES once per generation — as early as it knows that it will not take the expensive path — and the threads that do
+// take it WAIT (bounded spin, so a thread that never arrives costs time, never a hang) until the whole block has arrived.
+// The point: 28 warps of an SM at 28 different places of ~80 KB of yaku code miss the instruction cache on four lines out of
+// ten; after the rendezvous they run the candidate evaluation — 90 % of the instructions — at the same time.
+struct BlockPace {
+  unsigned* cnt;        // shared memory, monotonic
+  unsigned target;      // arrivals that complete the current generation
+  bool arrived;
+};
+__device__ __forceinline__ void pace_arrive(BlockPace* p) {
+#ifdef __CUDA_ARCH__
+  if (p && !p->arrived) {
+    atomicAdd(p->cnt, 1u);
+    p->arrived = true;
+  }
+#else
+  (void)p;
+#endif
+}
+__device__ __forceinline__ void pace_wait(BlockPace* p) {
+#ifdef __CUDA_ARCH__
+  if (!p) return;
+  pace_arrive(p);
+  for (int spins = 0; spins < 4096; spins++)
+    if ((int)(*reinterpret_cast<volatile unsigned*>(p->cnt) - p->target) >= 0) break;
+#else
+  (void)p;
+#endif
+}
 __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand, uint64_t all, const MeldView& mv,
-                                         const WinCtx& x, int win, bool std_shape) {
+                                         const WinCtx& x, int win, bool std_shape, BlockPace* pace = nullptr) {
   YakuRes best{0, 0, 0, 0};
   if (!std_shape) {
+    pace_arrive(pace);                       // no candidate evaluation on this path
     if (kokushi14(hand)) {
       if (cnt_get(hand, win) == 2) { best.han = 26; best.yakuman = 2; best.mask = 1ull << 49; }
       else { best.han = 13; best.yakuman = 1; best.mask = 1ull << 42; }
@@ -819,6 +850,7 @@ __device__ __noinline__ YakuRes calculate_yaku(const Tables& T, const Cnt& hand,
     }
     cnt_add(work, head, 2);
   }
+  pace_wait(pace);                           // the block evaluates its candidates together
   flush();
   return best;
 }
@@ -843,7 +875,7 @@ __device__ __forceinline__ bool tid_is_aka(int tid) { return tid == 16 || tid ==
 __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, int n, int n_melds, const uint8_t* meld_type,
                                    const uint8_t (*meld_tiles)[4], int win_tid, const uint8_t* dora, int n_dora,
                                    const uint8_t* ura, int n_ura, uint32_t cond, int player_wind, int round_wind,
-                                   uint32_t honba, bool sanma = false, int kita_count = 0) {
+                                   uint32_t honba, bool sanma = false, int kita_count = 0, BlockPace* pace = nullptr) {
   WinRes out{false, false, false, 0, 0, 0, 0, 0, 0};
   RV_STAT(0);
   Cnt hand, full;
@@ -888,7 +920,10 @@ __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, 
   SuitInfo si;
   load_info(T, hand, si);
   bool std_shape = standard_agari(si);
-  if (!std_shape && !chiitoi14(hand) && !kokushi14(hand)) return out;
+  if (!std_shape && !chiitoi14(hand) && !kokushi14(hand)) {
+    pace_arrive(pace);
+    return out;
+  }
   out.has_shape = true;
   RV_STAT(1);
   WinCtx x;
@@ -918,7 +953,7 @@ __device__ __noinline__ WinRes hand_calc(const Tables& T, const uint8_t* tiles, 
   x.round_wind = (uint8_t)(27 + round_wind);
   x.seat_wind = (uint8_t)(27 + player_wind);
   uint64_t all = cnt_present(hand) | meld_present;
-  YakuRes y = calculate_yaku(T, hand, all, mv, x, win34, std_shape);
+  YakuRes y = calculate_yaku(T, hand, all, mv, x, win34, std_shape, pace);
   bool is_oya = player_wind == 0;
   int scoring_han = (y.yakuman == 0 && y.han >= 13) ? 13 : y.han;
   ScoreRes sc = calc_score(scoring_han & 0xFF, y.fu, is_oya, x.tsumo, honba, sanma ? 3 : 4);
@@ -991,9 +1026,9 @@ __device__ __forceinline__ bool hand_eval_shape(const Tables& T, const rv_hand_q
                      : (int8_t)127;
   return agari14(T, c14);           // the shape test hand_calc starts with (a five-of-a-kind c14 is clamped, hence no shape)
 }
-__device__ __noinline__ void hand_eval_win(const Tables& T, const rv_hand_query& h, rv_hand_result& o) {
+__device__ __noinline__ void hand_eval_win(const Tables& T, const rv_hand_query& h, rv_hand_result& o, BlockPace* pace = nullptr) {
   WinRes r = hand_calc(T, h.tiles, h.n_tiles, h.n_melds, h.meld_type, h.meld_tiles, h.win_tile, h.dora_ind, h.n_dora,
-                       h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count);
+                       h.ura_ind, h.n_ura, h.cond, h.player_wind, h.round_wind, h.honba, h.sanma & 1, h.kita_count, pace);
   o.is_win = r.is_win;
   o.yakuman = r.yakuman;
   o.has_win_shape = r.has_shape;

@@ -193,15 +193,29 @@ __global__ void __launch_bounds__(256) hand_shape_kernel(Tables T, const rv_hand
     if (shape) list[base + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
   }
 }
-__global__ void __launch_bounds__(128) hand_yaku_kernel(Tables T, const rv_hand_query* __restrict__ q, rv_hand_result* __restrict__ out,
-                                                        const int32_t* __restrict__ list, const unsigned int* __restrict__ count) {
-  const unsigned total = *count;
-  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-    const int32_t i = list[k];
-    rv_hand_query h = q[i];
-    rv_hand_result o = out[i];
-    hand_eval_win(T, h, o);
-    out[i] = o;
+constexpr int YAKU_THREADS = 1024;  // one block per SM: 32 warps at 64 registers, paced by BlockPace (hand.cuh)
+__global__ void __launch_bounds__(YAKU_THREADS) hand_yaku_kernel(Tables T, const rv_hand_query* __restrict__ q, rv_hand_result* __restrict__ out,
+                                                                 const int32_t* __restrict__ list, const unsigned int* __restrict__ count,
+                                                                 int paced) {
+  __shared__ unsigned arrivals;
+  if (threadIdx.x == 0) arrivals = 0;
+  __syncthreads();
+  const unsigned total = *count, stride = gridDim.x * blockDim.x;
+  const unsigned iters = (total + stride - 1) / stride;            // the same for every thread: a generation per iteration
+  BlockPace pace{&arrivals, 0u, false};
+  for (unsigned it = 0; it < iters; it++) {
+    const unsigned k = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    pace.target = (it + 1) * blockDim.x;
+    pace.arrived = false;
+    if (paced > 1) __syncthreads();                                 // the division search starts together too (uniform loop: a real barrier)
+    if (k < total) {
+      const int32_t i = list[k];
+      rv_hand_query h = q[i];
+      rv_hand_result o = out[i];
+      hand_eval_win(T, h, o, paced ? &pace : nullptr);
+      out[i] = o;
+    }
+    if (paced) pace_arrive(&pace);                                 // threads without a hand, and any path that did not arrive
   }
 }
 // one launch pair on `st`; `list` holds n entries, `count` one word
@@ -210,7 +224,12 @@ static cudaError_t launch_hand_eval(const Tables& T, const rv_hand_query* d_q, r
   cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   hand_shape_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, d_q, d_out, n, list, count);
-  hand_yaku_kernel<<<sm_count * 8, 128, 0, st>>>(T, d_q, d_out, list, count);
+  {
+    const char* e = getenv("RV_YAKU_PACED");               // 0: eight 128-thread blocks per SM, no rendezvous (A/B)
+    const int paced = e ? atoi(e) : 2;
+    if (paced) hand_yaku_kernel<<<sm_count, YAKU_THREADS, 0, st>>>(T, d_q, d_out, list, count, paced);
+    else hand_yaku_kernel<<<sm_count * 8, 128, 0, st>>>(T, d_q, d_out, list, count, 0);
+  }
   return cudaGetLastError();
 }
 
