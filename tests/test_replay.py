@@ -133,6 +133,41 @@ def test_reader_errors_and_tile_names(tmp_path):
     assert k.n_actions == 0 and not acts
 
 
+def test_reader_survives_malformed_input():
+    """the C++ reader must refuse, not crash on, anything that is not a log (the data loaders skip unparseable files:
+    riichienv-ml/src/riichienv_ml/datasets/mjai_logs.py:86-90)"""
+    import random
+
+    from riichienv_b200.replay import MjaiReplay, MjSoulReplay
+
+    good = open(REAL_LOG).read()
+    rng = random.Random(7)
+    bad_inputs = ["{", "[1,2", '{"type":', '{"type":"start_kyoku"}', '{"type":"dahai","actor":"x","pai":1,"tsumogiri":0}',
+                  "[" * 100 + "]" * 100, '{"type":"tsumo","actor":1e99,"pai":"1m"}', "\x00\x01\x02", '"just a string"', "nul"]
+    for text in bad_inputs:
+        try:
+            MjaiReplay.from_text(text + "\n")
+        except ValueError:
+            pass
+    for _ in range(60):                                   # truncations and byte flips of a real log
+        cut = rng.randrange(1, len(good))
+        text = good[:cut]
+        if rng.random() < 0.5:
+            i = rng.randrange(len(text))
+            text = text[:i] + chr(rng.randrange(32, 127)) + text[i + 1:]
+        try:
+            r = MjaiReplay.from_text(text)
+            assert 0 <= r.num_rounds() <= 12
+        except ValueError:
+            pass
+    for obj in ({"data": 3}, {"data": [[{"name": "NewRound"}]]}, {"data": [[]]}, [[{"name": "NewRound", "data": {"scores": "x"}}]], [3]):
+        try:
+            MjSoulReplay.from_dict(obj)
+        except ValueError:
+            pass
+    assert MjaiReplay.from_text(good).num_rounds() == 12   # and the reader is still sane afterwards
+
+
 # ------------------------------------------------------------------------------------------------ state tracking
 def _owed(s):
     return [p for p in range(4) if not s.is_done and ((s.phase == 0 and s.current_player == p) or (s.phase == 1 and (s.active_mask >> p) & 1))]
