@@ -500,6 +500,37 @@ int rv_replay_num_rounds(const rv_replay* r);                                  /
 int rv_replay_kyoku(const rv_replay* r, int round, rv_log_kyoku* out);
 /* copies min(cap, n_actions) actions of the round; *n_out = n_actions */
 int rv_replay_actions(const rv_replay* r, int round, rv_log_action* out, int cap, int* n_out);
+/* The Option fields of the reference's Action that rv_log_action does not carry (state tracking never reads them; Kyoku.events()
+ * and the win-context walk do): one record per action of the round, as rv_replay_actions.  All "none" for MJAI logs.        */
+typedef struct rv_log_action_aux {
+  uint8_t n_doras;                 /* DiscardTile / DealTile `doras`; 0xFF = None */
+  uint8_t doras[RV_LOG_MAX_DORAS];
+  uint8_t left_tile_count;         /* DealTile `left_tile_count`; 0xFF = None */
+  uint8_t tile_raw_id;             /* AnGangAddGang `tile_raw_id` (kind 0..33; 0 in MJAI logs as in the reference) */
+  uint8_t _pad;
+} rv_log_action_aux;
+int rv_replay_actions_aux(const rv_replay* r, int round, rv_log_action_aux* out, int cap, int* n_out);
+/* LogKyoku.paishan (replay/mod.rs:1022,1077): the wall string a MjSoul NewRound record carries; copies min(cap, len) bytes (no
+ * terminator), *n_out = len, or -1 when the log has none (every MJAI log). */
+int rv_replay_paishan(const rv_replay* r, int round, char* out, int cap, int* n_out);
+/* WinResultContextIterator (replay/mod.rs:1594-2093): the walk over a kyoku that tracks hands, melds, dora markers and the win
+ * conditions up to every Hule.  One record per winner, in log order; `query` is what the iterator hands HandEvaluator::calc, so
+ * WinResultContext.actual of a whole log is ONE rv_hand_eval_batch over the records' queries (MjSoulReplay::verify,
+ * mjsoul_replay.rs:357-430, compares it with the expected_* fields the paifu recorded).  As the reference: the 4-player
+ * evaluator also for sanma logs, honba and riichi sticks 0.  round < 0 = every round of the log; copies min(cap, n) records,
+ * *n_out = n.  RV_ERR_INVALID for logs the reference's walk would panic on (a seat the kyoku lacks, more than 14 tiles).   */
+typedef struct rv_win_context {
+  rv_hand_query query;
+  uint64_t expected_yaku;      /* bit id = id in HuleData.fans (paifu fans with val > 0; none in MJAI logs) */
+  uint32_t expected_han, expected_fu;
+  int32_t round, action;       /* the kyoku and the index of the Hule action in it */
+  uint8_t seat;
+  int8_t meld_from[4];         /* Meld.from_who of query.meld_*[m] (-1: none) */
+  uint8_t meld_called[4];      /* Meld.called_tile (RV_NONE: none) */
+  uint8_t _pad[7];
+} rv_win_context;
+int rv_replay_win_contexts(const rv_replay* r, int round, rv_win_context* out, int cap, int* n_out);
+int rv_replay_sizeof(int which); /* sizeof() as compiled: 0 rv_win_context, 1 rv_log_action_aux (a binding's layout check, like rv_sizeof) */
 /* LogKyoku::steps' state set-up for every game of the vector: kyokus[n] (HOST).  Each game is re-initialised as
  * `_initialize_round(oya, chang, ben, liqibang, None, scores)` does and then patched with the logged hands, dora markers and the
  * dealer's draw.  The vector's game mode must have kyoku.np seats.                                                          */

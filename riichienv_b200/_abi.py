@@ -127,6 +127,15 @@ class LogKyoku(C.Structure):
                 ("game_end_scores", i32 * NP)]
 
 
+class LogActionAux(C.Structure):
+    _fields_ = [("n_doras", u8), ("doras", u8 * LOG_MAX_DORAS), ("left_tile_count", u8), ("tile_raw_id", u8), ("_pad", u8)]
+
+
+class WinContext(C.Structure):
+    _fields_ = [("query", HandQuery), ("expected_yaku", C.c_uint64), ("expected_han", C.c_uint32), ("expected_fu", C.c_uint32),
+                ("round", C.c_int32), ("action", C.c_int32), ("seat", u8), ("meld_from", i8 * 4), ("meld_called", u8 * 4), ("_pad", u8 * 7)]
+
+
 class RunStats(C.Structure):
     _fields_ = [("games", C.c_int64), ("games_done", C.c_int64), ("env_steps", C.c_int64), ("rounds", C.c_int64),
                 ("score_sum", C.c_int64 * NP), ("rank_hist", (C.c_int64 * NP) * NP)]

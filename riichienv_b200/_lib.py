@@ -91,6 +91,11 @@ def lib():
     L.rv_replay_num_rounds.argtypes = [vp]
     L.rv_replay_kyoku.argtypes = [vp, C.c_int, P(A.LogKyoku)]
     L.rv_replay_actions.argtypes = [vp, C.c_int, P(A.LogAction), C.c_int, P(C.c_int)]
+    L.rv_replay_paishan.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, P(C.c_int)]
+    L.rv_replay_win_contexts.argtypes = [vp, C.c_int, P(A.WinContext), C.c_int, P(C.c_int)]
+    L.rv_replay_actions_aux.argtypes = [vp, C.c_int, P(A.LogActionAux), C.c_int, P(C.c_int)]
+    if L.rv_replay_sizeof(0) != C.sizeof(A.WinContext) or L.rv_replay_sizeof(1) != C.sizeof(A.LogActionAux):
+        raise RuntimeError("ABI mismatch: rv_win_context / rv_log_action_aux")
     L.rv_vec_replay_begin.argtypes = [vp, P(A.LogKyoku)]
     L.rv_vec_apply_log_actions.argtypes = [vp, P(A.LogAction)]
     L.rv_vec_replay_load.argtypes = [vp, P(A.LogKyoku), P(A.LogAction), P(C.c_int64)]

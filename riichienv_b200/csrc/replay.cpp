@@ -4,6 +4,7 @@
 // rv_vec_replay_begin / rv_vec_apply_log_actions, which track the kyoku on the device.
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -158,9 +159,22 @@ uint8_t tile_of(const JVal* v) {
   return (uint8_t)(t < 0 ? 0 : t);   // parse_mjai_tile: unwrap_or(0)
 }
 
+// what the reference's Action carries besides the fields of rv_log_action (WinResultContextIterator and Kyoku.events() read them)
+struct ActAux : rv_log_action_aux {
+  ActAux() {
+    memset(static_cast<rv_log_action_aux*>(this), 0, sizeof(rv_log_action_aux));
+    n_doras = 0xFF;                       // DiscardTile / DealTile `doras`: None
+    left_tile_count = 0xFF;               // DealTile `left_tile_count`: None
+    tile_raw_id = 0;                      // AnGangAddGang `tile_raw_id` (0 in MJAI logs, mjai_replay.rs:507,518)
+  }
+};
 struct Kyoku {
   rv_log_kyoku k;
   std::vector<rv_log_action> actions;
+  std::vector<ActAux> aux;                // empty (all None) for MJAI logs, else one per action
+  std::vector<uint8_t> wall;              // LogKyoku.paishan as tids; empty = None
+  std::string paishan;                    // the string itself (Kyoku.paishan, the NewRound record of Kyoku.events())
+  bool has_paishan = false;
 };
 // KyokuBuilder (mjai_replay.rs:159-270)
 struct Builder {
@@ -576,6 +590,29 @@ rv_log_action paifu_action(const std::string& name, const JVal& d) {
   }
   return blank(RV_LA_NONE, 0);                            // NewRound and unknown names: Action::Other
 }
+// the Option fields of DiscardTile / DealTile / AnGangAddGang (mjsoul_replay.rs:547-640)
+ActAux paifu_aux(const std::string& name, const JVal& d) {
+  ActAux x;
+  auto list = [&](const JVal* v) {
+    if (!v || v->kind != JVal::Arr || v->arr.empty()) return false;
+    x.n_doras = (uint8_t)std::min<size_t>(v->arr.size(), RV_LOG_MAX_DORAS);
+    for (int i = 0; i < x.n_doras; i++) x.doras[i] = paifu_tile(&v->arr[i]);
+    return true;
+  };
+  if (name == "DiscardTile") {
+    list(d.get("doras"));
+  } else if (name == "DealTile") {
+    if (!list(d.get("doras"))) {
+      const JVal* dm = d.get("dora_marker");
+      if (dm && dm->kind == JVal::Str) x.n_doras = 1, x.doras[0] = paifu_tile(dm);
+    }
+    const JVal* lc = d.get("left_tile_count");
+    if (lc && lc->kind == JVal::Num) x.left_tile_count = (uint8_t)std::min(254, std::max(0, (int)lc->num));
+  } else if (name == "AnGangAddGang") {
+    x.tile_raw_id = (uint8_t)(paifu_tile(d.get("tiles")) >> 2);   // TileConverter::parse_tile_34(&tiles).0
+  }
+  return x;
+}
 // MjSoulReplay::kyoku_from_raw_actions (mjsoul_replay.rs:448-539) + the oya / drawn-tile derivation of LogKyoku::steps
 bool paifu_round(const JVal& round, uint32_t rule_bits, Kyoku& out, std::string& err) {
   if (round.kind != JVal::Arr || round.arr.empty()) return err = "a round is not a list of actions", false;
@@ -622,10 +659,22 @@ bool paifu_round(const JVal& round, uint32_t rule_bits, Kyoku& out, std::string&
     k.left_tile_count = (uint8_t)geti(d, "left_tile_count", 70);
     if (const JVal* ud = d.get("ura_doras"))
       for (size_t i = 0; i < ud->arr.size() && k.n_ura_doras < RV_LOG_MAX_DORAS; i++) k.ura_doras[k.n_ura_doras++] = paifu_tile(&ud->arr[i]);
+    if (const JVal* ps = d.get("paishan"))
+      if (ps->kind == JVal::Str) {                         // parse_paishan (replay/mod.rs:1631-1641): two characters per tile
+        out.paishan = ps->str;
+        out.has_paishan = true;
+        for (size_t i = 0; i + 1 < ps->str.size(); i += 2) {
+          JVal t;
+          t.kind = JVal::Str;
+          t.str = ps->str.substr(i, 2);
+          out.wall.push_back(paifu_tile(&t));
+        }
+      }
   }
   for (auto& a : round.arr) {
     const JVal* dp = a.get("data");
     out.actions.push_back(paifu_action(name_of(a), dp ? *dp : none));
+    out.aux.push_back(paifu_aux(name_of(a), dp ? *dp : none));
   }
   for (auto& a : out.actions)
     if (a.type == RV_LA_DISCARD && (a.flags & 2) && a.seat < 4) k.wliqi[a.seat] = 1;
@@ -672,6 +721,231 @@ int parse_paifu(const char* text, size_t len, uint32_t rule_bits, rv_replay** ou
   *out = r.release();
   return RV_OK;
 }
+// ---------------------------------------------------------------- WinResultContextIterator (replay/mod.rs:1594-2093)
+// The walk over one kyoku that tracks hands, melds and the win conditions up to every Hule and hands HandEvaluator::calc its
+// arguments.  Here it only BUILDS the queries: the evaluation is one rv_hand_eval_batch over every context of a log.
+struct WinWalk {
+  struct M { uint8_t type, n, t[4]; int8_t from; uint8_t called; };
+  const Kyoku& ky;
+  int np;
+  std::vector<uint8_t> hand[4];
+  std::vector<M> melds[4];
+  bool liqi[4] = {}, wliqi[4] = {}, ippatsu[4] = {}, rinshan[4] = {}, first_turn[4] = {true, true, true, true};
+  bool ippatsu_before_babei[4] = {};
+  bool last_kakan = false, last_babei = false;
+  int kakan_tile = -1;
+  std::vector<uint8_t> doras;
+  int left, dora_count = 1, pending_minkan = 0;
+  int kita[4] = {};
+  explicit WinWalk(const Kyoku& k) : ky(k), np(k.k.np), left(k.k.left_tile_count) {
+    for (int p = 0; p < np; p++) hand[p].assign(k.k.hands[p], k.k.hands[p] + k.k.hand_len[p]);
+    doras.assign(k.k.doras, k.k.doras + k.k.n_doras);
+  }
+  static void all(bool (&a)[4], bool v) { a[0] = a[1] = a[2] = a[3] = v; }
+  static bool match_and_remove(std::vector<uint8_t>& h, uint8_t t) {   // TileConverter::match_and_remove_u8 (2243-2255)
+    auto it = std::find(h.begin(), h.end(), t);
+    if (it == h.end()) it = std::find_if(h.begin(), h.end(), [&](uint8_t x) { return x / 4 == t / 4; });
+    if (it == h.end()) return false;
+    h.erase(it);
+    return true;
+  }
+  void recalc_doras() {                                                // 1679-1696
+    const size_t len = ky.wall.size();
+    if (!len) return;
+    doras.clear();
+    for (int i = 0; i < dora_count; i++)
+      if (len >= 5 + 2 * (size_t)i) doras.push_back(ky.wall[len - 5 - 2 * i]);
+  }
+  void sync_doras() {                                                  // 1698-1712
+    if (ky.wall.empty()) return;
+    if ((int)doras.size() > dora_count) dora_count = (int)doras.size(), pending_minkan = 0;
+    else if (dora_count > (int)doras.size()) recalc_doras();
+  }
+  std::vector<uint8_t> ura_from_wall() const {                         // 1714-1728
+    std::vector<uint8_t> u;
+    const size_t len = ky.wall.size();
+    for (int i = 0; i < dora_count; i++)
+      if (len >= 6 + 2 * (size_t)i) u.push_back(ky.wall[len - 6 - 2 * i]);
+    return u;
+  }
+  void after_kakan_reset() {
+    if (!last_kakan) return;
+    all(ippatsu, false), all(first_turn, false);
+    last_kakan = last_babei = false;
+    kakan_tile = -1;
+  }
+  void flush_pending() {
+    if (pending_minkan > 0) dora_count += pending_minkan, pending_minkan = 0;
+  }
+  bool run(int round, std::vector<rv_win_context>& out, std::string& err) {
+    static const ActAux none;
+    for (size_t ai = 0; ai < ky.actions.size(); ai++) {
+      const rv_log_action& a = ky.actions[ai];
+      const ActAux& x = ai < ky.aux.size() ? ky.aux[ai] : none;
+      if (a.type != RV_LA_HULE) {
+        all(rinshan, false);
+        if (a.type != RV_LA_BABEI) last_babei = false;
+      }
+      const int s = a.seat;
+      if ((a.type == RV_LA_DISCARD || a.type == RV_LA_DEAL || a.type == RV_LA_CHI_PENG_GANG || a.type == RV_LA_ANGANG_ADDGANG ||
+           a.type == RV_LA_BABEI) && s >= np)
+        return err = "action of a seat the kyoku does not have", false;
+      switch (a.type) {
+        case RV_LA_DISCARD:
+          after_kakan_reset();
+          if (a.flags & 2) wliqi[s] = ippatsu[s] = true;
+          if (a.flags & 1) liqi[s] = ippatsu[s] = true;
+          if (!(a.flags & 1)) ippatsu[s] = false;
+          first_turn[s] = false;
+          match_and_remove(hand[s], a.tile);
+          if (x.n_doras != 0xFF) doras.assign(x.doras, x.doras + x.n_doras);
+          flush_pending();
+          sync_doras();
+          break;
+        case RV_LA_DEAL:
+          after_kakan_reset();
+          hand[s].push_back(a.tile);
+          if (x.left_tile_count != 0xFF) left = x.left_tile_count;
+          else if (left > 0) left--;
+          if (x.n_doras != 0xFF) doras.assign(x.doras, x.doras + x.n_doras), rinshan[s] = true;
+          sync_doras();
+          break;
+        case RV_LA_CHI_PENG_GANG: {
+          all(rinshan, false), all(ippatsu, false), all(first_turn, false);
+          last_kakan = last_babei = false;
+          kakan_tile = -1;
+          M m{a.meld_type, a.n_tiles, {RV_NONE, RV_NONE, RV_NONE, RV_NONE}, -1, RV_NONE};
+          for (int i = 0; i < a.n_tiles; i++) {
+            m.t[i] = a.tiles[i];
+            if (a.froms[i] == s) match_and_remove(hand[s], a.tiles[i]);
+            else if (m.from < 0) m.from = (int8_t)a.froms[i], m.called = a.tiles[i];   // the first tile of another seat
+          }
+          melds[s].push_back(m);
+          if (a.meld_type == RV_MELD_DAIMINKAN) {
+            rinshan[s] = true;
+            flush_pending();
+            pending_minkan++;
+          }
+          break;
+        }
+        case RV_LA_DORA:
+          if (ky.wall.empty()) {
+            doras.push_back(a.tile);
+          } else {
+            dora_count++;
+            if (pending_minkan > 0) pending_minkan--;
+            sync_doras();
+          }
+          break;
+        case RV_LA_ANGANG_ADDGANG:
+          all(rinshan, false);
+          flush_pending();
+          if (a.meld_type == RV_MELD_ANKAN) {
+            all(ippatsu, false), all(first_turn, false);
+            last_kakan = last_babei = false;
+            kakan_tile = -1;
+            const int k34 = x.tile_raw_id;
+            for (int i = 0; i < 4; i++) {
+              auto it = std::find_if(hand[s].begin(), hand[s].end(), [&](uint8_t t) { return t / 4 == k34; });
+              if (it != hand[s].end()) hand[s].erase(it);
+            }
+            M m{RV_MELD_ANKAN, 4, {(uint8_t)(k34 * 4), (uint8_t)(k34 * 4 + 1), (uint8_t)(k34 * 4 + 2), (uint8_t)(k34 * 4 + 3)}, -1, RV_NONE};
+            melds[s].push_back(m);
+            rinshan[s] = true;
+            if (!ky.wall.empty()) dora_count++;
+          } else {
+            last_kakan = true;
+            kakan_tile = a.tiles[0];
+            rinshan[s] = true;
+            bool upgraded = false;
+            for (auto& m : melds[s])
+              if (m.type == RV_MELD_PON && m.t[0] / 4 == a.tiles[0] / 4) {
+                m.type = RV_MELD_KAKAN;
+                if (m.n < 4) m.t[m.n++] = a.tiles[0];
+                upgraded = true;
+                break;
+              }
+            if (!upgraded) {
+              M m{a.meld_type, a.n_tiles, {RV_NONE, RV_NONE, RV_NONE, RV_NONE}, -1, RV_NONE};
+              for (int i = 0; i < a.n_tiles; i++) m.t[i] = a.tiles[i];
+              melds[s].push_back(m);
+            }
+            match_and_remove(hand[s], a.tiles[0]);
+            pending_minkan++;
+          }
+          sync_doras();
+          break;
+        case RV_LA_BABEI: {
+          memcpy(ippatsu_before_babei, ippatsu, sizeof ippatsu);
+          all(ippatsu, false), all(first_turn, false);
+          last_babei = true;
+          auto it = std::find_if(hand[s].begin(), hand[s].end(), [](uint8_t t) { return t / 4 == 30; });
+          if (it != hand[s].end()) hand[s].erase(it);
+          kita[s]++;
+          rinshan[s] = true;
+          break;
+        }
+        case RV_LA_HULE:
+          for (int hi = 0; hi < a.n_hule; hi++) {
+            const rv_hule& h = a.hules[hi];
+            const int w = h.seat;
+            if (w >= np) return err = "hule of a seat the kyoku does not have", false;
+            const bool zimo = h.zimo;
+            const bool chankan = !zimo && last_kakan && kakan_tile >= 0 && kakan_tile / 4 == h.hu_tile / 4;
+            const bool ipp = !zimo && last_babei ? ippatsu_before_babei[w] : ippatsu[w];
+            std::vector<uint8_t> tiles = hand[w];
+            if (!zimo) tiles.push_back(h.hu_tile);
+            std::vector<uint8_t> ura;
+            if (liqi[w]) {
+              if (h.n_li_doras != 0xFF) ura.assign(h.li_doras, h.li_doras + h.n_li_doras);
+              else if (!ky.wall.empty()) ura = ura_from_wall();
+              else ura.assign(ky.k.ura_doras, ky.k.ura_doras + ky.k.n_ura_doras);
+            }
+            if (tiles.size() > 14 || melds[w].size() > 4)
+              return err = "a hand of more than 14 tiles or 4 melds at a hule", false;
+            rv_win_context c;
+            memset(&c, 0, sizeof c);
+            rv_hand_query& q = c.query;
+            memset(q.tiles, RV_NONE, sizeof q.tiles);
+            memset(q.meld_tiles, RV_NONE, sizeof q.meld_tiles);
+            q.n_tiles = (uint8_t)tiles.size();
+            std::copy(tiles.begin(), tiles.end(), q.tiles);
+            q.n_melds = (uint8_t)melds[w].size();
+            for (size_t m = 0; m < melds[w].size(); m++) {
+              q.meld_type[m] = melds[w][m].type;
+              memcpy(q.meld_tiles[m], melds[w][m].t, 4);
+              c.meld_from[m] = melds[w][m].from;
+              c.meld_called[m] = melds[w][m].called;
+            }
+            q.win_tile = h.hu_tile;
+            q.n_dora = (uint8_t)std::min<size_t>(doras.size(), 5);
+            std::copy(doras.begin(), doras.begin() + q.n_dora, q.dora_ind);
+            q.n_ura = (uint8_t)std::min<size_t>(ura.size(), 5);
+            std::copy(ura.begin(), ura.begin() + q.n_ura, q.ura_ind);
+            q.player_wind = (uint8_t)((w + np - ky.k.ju % np) % np);
+            q.round_wind = (uint8_t)(ky.k.chang & 3);
+            q.honba = 0;                                    // "Not tracked" (2008-2009)
+            q.cond = (uint16_t)((zimo ? RV_C_TSUMO : 0) | (liqi[w] ? RV_C_RIICHI : 0) | (wliqi[w] ? RV_C_DOUBLE_RIICHI : 0) |
+                                (ipp ? RV_C_IPPATSU : 0) | (left == 0 && zimo && !rinshan[w] ? RV_C_HAITEI : 0) |
+                                (left == 0 && !zimo && !rinshan[w] ? RV_C_HOUTEI : 0) | (rinshan[w] ? RV_C_RINSHAN : 0) |
+                                (chankan ? RV_C_CHANKAN : 0) | (first_turn[w] && zimo ? RV_C_TSUMO_FIRST_TURN : 0));
+            q.sanma = 0;                                    // the iterator always builds the 4-player HandEvaluator (2035)
+            q.kita_count = (uint8_t)kita[w];
+            c.expected_yaku = h.fans;
+            c.expected_han = h.count;
+            c.expected_fu = h.fu;
+            c.round = round;
+            c.action = (int32_t)ai;
+            c.seat = (uint8_t)w;
+            out.push_back(c);
+          }
+          break;
+        default: break;
+      }
+    }
+    return true;
+  }
+};
 }  // namespace
 
 extern "C" {
@@ -727,6 +1001,38 @@ int rv_replay_actions(const rv_replay* r, int round, rv_log_action* out, int cap
   if (n_out) *n_out = (int)a.size();
   if (out)
     for (int i = 0; i < cap && i < (int)a.size(); i++) out[i] = a[i];
+  return RV_OK;
+}
+int rv_replay_sizeof(int which) { return which == 0 ? (int)sizeof(rv_win_context) : which == 1 ? (int)sizeof(rv_log_action_aux) : -1; }
+int rv_replay_actions_aux(const rv_replay* r, int round, rv_log_action_aux* out, int cap, int* n_out) {
+  if (!r || round < 0 || round >= (int)r->rounds.size() || cap < 0 || (cap > 0 && !out))
+    return rv_internal_fail(RV_ERR_INVALID, "rv_replay_actions_aux: bad arguments");
+  const Kyoku& k = r->rounds[round];
+  static const ActAux none;
+  for (int i = 0; i < (int)k.actions.size() && i < cap; i++) out[i] = i < (int)k.aux.size() ? k.aux[i] : none;
+  if (n_out) *n_out = (int)k.actions.size();
+  return RV_OK;
+}
+int rv_replay_paishan(const rv_replay* r, int round, char* out, int cap, int* n_out) {
+  if (!r || round < 0 || round >= (int)r->rounds.size() || !n_out || cap < 0 || (cap > 0 && !out))
+    return rv_internal_fail(RV_ERR_INVALID, "rv_replay_paishan: bad arguments");
+  const Kyoku& k = r->rounds[round];
+  *n_out = k.has_paishan ? (int)k.paishan.size() : -1;
+  if (k.has_paishan) memcpy(out, k.paishan.data(), std::min<size_t>(cap, k.paishan.size()));
+  return RV_OK;
+}
+int rv_replay_win_contexts(const rv_replay* r, int round, rv_win_context* out, int cap, int* n_out) {
+  if (!r || round >= (int)r->rounds.size() || cap < 0 || (cap > 0 && !out))
+    return rv_internal_fail(RV_ERR_INVALID, "rv_replay_win_contexts: bad arguments");
+  std::vector<rv_win_context> ctxs;
+  std::string err;
+  const int lo = round < 0 ? 0 : round, hi = round < 0 ? (int)r->rounds.size() : round + 1;
+  for (int i = lo; i < hi; i++) {
+    WinWalk w(r->rounds[i]);
+    if (!w.run(i, ctxs, err)) return rv_internal_fail(RV_ERR_INVALID, "rv_replay_win_contexts: round " + std::to_string(i) + ": " + err);
+  }
+  for (size_t i = 0; i < ctxs.size() && (int)i < cap; i++) out[i] = ctxs[i];
+  if (n_out) *n_out = (int)ctxs.size();
   return RV_OK;
 }
 }  // extern "C"

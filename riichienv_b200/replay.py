@@ -17,7 +17,7 @@ import ctypes as C
 
 from . import _abi as A
 from ._lib import check, lib
-from .env import Action, Action3P, ActionType, GameRule, MeldType, Observation, Observation3P, Phase, RiichiEnv
+from .env import Action, Action3P, ActionType, GameRule, Meld, MeldType, Observation, Observation3P, Phase, RiichiEnv
 
 
 def _tile_str(t: int) -> str:  # TileConverter::to_string (replay/mod.rs:2224-2241): red fives are "0m" / "0p" / "0s"
@@ -32,10 +32,14 @@ def _tile_str(t: int) -> str:  # TileConverter::to_string (replay/mod.rs:2224-22
 class _ActionView:
     """one replay `Action` (replay/mod.rs:35-80) read off an rv_log_action"""
 
-    __slots__ = ("raw", "type", "seat", "tile", "is_liqi", "is_wliqi", "meld_type", "tiles", "froms", "hules", "moqie")
+    __slots__ = ("raw", "type", "seat", "tile", "is_liqi", "is_wliqi", "meld_type", "tiles", "froms", "hules", "moqie", "doras",
+                 "left_tile_count")
 
-    def __init__(self, a: A.LogAction):
+    def __init__(self, a: A.LogAction, aux=None):
         self.raw = a
+        # Option fields only a paifu carries (rv_log_action_aux): None for MJAI logs
+        self.doras = None if aux is None or aux.n_doras == 0xFF else [aux.doras[i] for i in range(min(aux.n_doras, A.LOG_MAX_DORAS))]
+        self.left_tile_count = None if aux is None or aux.left_tile_count == 0xFF else aux.left_tile_count
         self.type, self.seat, self.tile = a.type, a.seat, a.tile
         self.is_liqi, self.is_wliqi = bool(a.flags & 1), bool(a.flags & 2)
         self.moqie = bool(a.flags & 1)
@@ -48,10 +52,10 @@ class _ActionView:
 class LogKyoku:
     """replay/mod.rs:1010-1590 (pyclass `Kyoku`)"""
 
-    def __init__(self, k: A.LogKyoku, actions, rule: GameRule):
+    def __init__(self, k: A.LogKyoku, actions, rule: GameRule, aux=None):
         self._k = k
         self._actions = actions                  # ctypes array (A.LogAction * n)
-        self._views = [_ActionView(a) for a in actions]
+        self._views = [_ActionView(a, aux[i] if aux is not None else None) for i, a in enumerate(actions)]
         self.rule = rule
         n = k.np
         self.scores = [k.scores[p] for p in range(n)]
@@ -62,7 +66,8 @@ class LogKyoku:
         self.chang, self.ju, self.ben, self.liqibang = k.chang, k.ju, k.ben, k.liqibang
         self.left_tile_count = k.left_tile_count
         self.wliqi = [bool(k.wliqi[p]) for p in range(n)]
-        self.paishan = None                      # MJAI logs carry no wall
+        self.paishan = None                      # MJAI logs carry no wall; set by the paifu reader
+        self._win_ctx, self._win_error = [], None  # rv_replay_win_contexts of this round (filled by _from_handle)
         self.game_end_scores = [k.game_end_scores[p] for p in range(n)] if k.has_game_end_scores else None
 
     # ---- features ----------------------------------------------------------------------------------
@@ -99,12 +104,20 @@ class LogKyoku:
         data.update(chang=self.chang, ju=self.ju, ben=self.ben, liqibang=self.liqibang, left_tile_count=self.left_tile_count)
         if self.ura_doras:
             data["ura_doras"] = [_tile_str(t) for t in self.ura_doras]
+        if self.paishan is not None:
+            data["paishan"] = self.paishan
         out = [{"name": "NewRound", "data": data}]
         for a in self._views:
             if a.type == A.LA_DISCARD:
                 ev = ("DiscardTile", {"seat": a.seat, "tile": _tile_str(a.tile), "is_liqi": a.is_liqi, "is_wliqi": a.is_wliqi})
+                if a.doras is not None:
+                    ev[1]["doras"] = [_tile_str(t) for t in a.doras]
             elif a.type == A.LA_DEAL:
                 ev = ("DealTile", {"seat": a.seat, "tile": _tile_str(a.tile)})
+                if a.doras is not None:
+                    ev[1]["doras"] = [_tile_str(t) for t in a.doras]
+                if a.left_tile_count is not None:
+                    ev[1]["left_tile_count"] = a.left_tile_count
             elif a.type == A.LA_CHI_PENG_GANG:
                 mt = {MeldType.Chi: 0, MeldType.Pon: 1, MeldType.Daiminkan: 2, MeldType.Ankan: 3, MeldType.Kakan: 2}[MeldType(a.meld_type)]
                 ev = ("ChiPengGang", {"seat": a.seat, "type": mt, "tiles": [_tile_str(t) for t in a.tiles], "froms": list(a.froms)})
@@ -136,9 +149,8 @@ class LogKyoku:
             out.append({"name": ev[0], "data": ev[1]})
         return out
 
-    def take_win_result_contexts(self):
-        raise NotImplementedError("WinResultContextIterator (replay/mod.rs:1594-2180) verifies MjSoul paifu fans; MJAI logs carry "
-                                  "none — not built (SURVEY.md §8 f4 covers the step path)")
+    def take_win_result_contexts(self):  # replay/mod.rs:1089-1091
+        return WinResultContextIterator(self)
 
     # ---- the step iterator -------------------------------------------------------------------------
     def steps(self, seat=None, rule=None, skip_single_action=None):  # replay/mod.rs:1094-1292
@@ -146,6 +158,110 @@ class LogKyoku:
 
 
 Kyoku = LogKyoku
+
+
+class WinResultContext:
+    """replay/mod.rs:2097-2180: the hand, melds, indicators and win conditions at one Hule of a log, what the log recorded
+    (`expected_*`) and what the evaluator says (`actual`).  The walk that builds it is rv_replay_win_contexts (host); `actual`
+    comes from hand_eval_kernel — for all contexts of an iterator / a `verify()` in ONE rv_hand_eval_batch call."""
+
+    def __init__(self, c: A.WinContext, batch):
+        q = c.query
+        self._c, self._batch = c, batch
+        self.seat = c.seat
+        self.tiles = [q.tiles[i] for i in range(q.n_tiles)]
+        self.melds = []
+        for m in range(q.n_melds):
+            t = [q.meld_tiles[m][k] for k in range(4) if q.meld_tiles[m][k] != 255]
+            called = c.meld_called[m]
+            self.melds.append(Meld(q.meld_type[m], t, q.meld_type[m] != MeldType.Ankan, c.meld_from[m], None if called == 255 else called))
+        self.agari_tile = q.win_tile
+        self.dora_indicators = [q.dora_ind[i] for i in range(q.n_dora)]
+        self.ura_indicators = [q.ura_ind[i] for i in range(q.n_ura)]
+        from .hand import Conditions
+
+        b = q.cond
+        self.conditions = Conditions(*[bool(b >> i & 1) for i in range(9)], player_wind=q.player_wind, round_wind=q.round_wind,
+                                     riichi_sticks=0, honba=0, kita_count=q.kita_count)
+        self.expected_yaku = [y for y in range(64) if c.expected_yaku >> y & 1]   # ids of HuleData.fans (ascending)
+        self.expected_han, self.expected_fu = c.expected_han, c.expected_fu
+
+    @property
+    def actual(self):
+        return self._batch.result(self)
+
+    def create_calculator(self):
+        from .hand import HandEvaluator
+
+        return HandEvaluator(list(self.tiles), list(self.melds))
+
+    def calculate(self, calculator, conditions=None):
+        return calculator.calc(self.agari_tile, self.dora_indicators, conditions or self.conditions, self.ura_indicators)
+
+    def __repr__(self):
+        return (f"WinResultContext(seat={self.seat}, tiles={self.tiles}, agari_tile={self.agari_tile}, "
+                f"expected_han={self.expected_han}, expected_fu={self.expected_fu})")
+
+
+class _WinBatch:
+    """the contexts of one or many kyoku evaluated together: one rv_hand_eval_batch on first use of any `actual`"""
+
+    def __init__(self, ctxs):
+        self.ctxs = [WinResultContext(c, self) for c in ctxs]
+        self._raw = None
+
+    def raw(self):
+        if self._raw is None and self.ctxs:
+            from .hand import eval_queries
+
+            self._raw = eval_queries([c._c.query for c in self.ctxs])
+        return self._raw or []
+
+    def result(self, ctx):
+        from .hand import _to_result
+
+        return _to_result(self.raw()[self.ctxs.index(ctx)])
+
+
+def _verify_counts(batch):
+    """MjSoulReplay::verify (mjsoul_replay.rs:357-430): (wins, wins whose yaku / han / fu differ from the paifu's)"""
+    ignored = (1 << 31) | (1 << 32) | (1 << 33)                 # dora, aka dora, ura dora
+    yakuman_ids = sum(1 << y for y in range(35, 51))
+    mismatches = 0
+    for ctx, r in zip(batch.ctxs, batch.raw()):
+        exp, sim = ctx._c.expected_yaku, r.yaku_mask
+        exp_han = ctx.expected_han * 13 if exp & yakuman_ids and ctx.expected_han < 13 else ctx.expected_han
+        bad = (sim & ~ignored) != (exp & ~ignored)
+        if not bad:
+            want = exp_han - bin(exp & ignored).count("1") + bin(sim & ignored).count("1")
+            if exp_han < 13 and r.han != want:
+                bad = r.han != exp_han
+            elif (r.han >= 13) != (exp_han >= 13):
+                bad = True
+            if not bad and exp_han < 13 and r.fu != ctx.expected_fu:
+                bad = True
+        if bad:
+            mismatches += 1
+            print(f"Mismatch: seat={ctx.seat}, han=(sim={r.han}, exp={ctx.expected_han}), fu=(sim={r.fu}, exp={ctx.expected_fu})")
+            print(f"  Expected Yaku: {ctx.expected_yaku}")
+            print(f"  Actual Yaku: {ctx.actual.yaku}")
+            print(f"  Conditions: {ctx.conditions}")
+    return len(batch.ctxs), mismatches
+
+
+class WinResultContextIterator:
+    """replay/mod.rs:1594-1628"""
+
+    def __init__(self, kyoku: LogKyoku):
+        if kyoku._win_error:
+            raise ValueError(kyoku._win_error)
+        self._it = iter(_WinBatch(kyoku._win_ctx).ctxs)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return next(self._it)
 
 
 class _ReplayObsEnv:
@@ -456,8 +572,21 @@ class MjaiReplay:
                 acts = (A.LogAction * max(1, k.n_actions))()
                 n = C.c_int(0)
                 check(lib().rv_replay_actions(h, r, acts, k.n_actions, C.byref(n)))
+                aux = (A.LogActionAux * max(1, k.n_actions))()
+                check(lib().rv_replay_actions_aux(h, r, aux, k.n_actions, C.byref(n)))
                 rounds.append(LogKyoku(k, (A.LogAction * k.n_actions).from_buffer_copy(bytes(acts)[: C.sizeof(A.LogAction) * k.n_actions])
-                                       if k.n_actions else (A.LogAction * 0)(), rule))
+                                       if k.n_actions else (A.LogAction * 0)(), rule, aux))
+                ky = rounds[-1]
+                if lib().rv_replay_win_contexts(h, r, None, 0, C.byref(n)) == 0:
+                    ky._win_ctx = (A.WinContext * n.value)()
+                    check(lib().rv_replay_win_contexts(h, r, ky._win_ctx, n.value, C.byref(n)))
+                else:                        # a log the walk cannot follow: reported when the contexts are asked for
+                    ky._win_error = lib().rv_last_error().decode("utf-8", "replace")
+                check(lib().rv_replay_paishan(h, r, None, 0, C.byref(n)))
+                if n.value >= 0:
+                    buf = C.create_string_buffer(n.value + 1)
+                    check(lib().rv_replay_paishan(h, r, buf, n.value, C.byref(n)))
+                    ky.paishan = buf.raw[: n.value].decode()
             return cls(rounds)
         finally:
             lib().rv_replay_free(h)
@@ -527,8 +656,11 @@ class MjSoulReplay:
     def take_kyokus(self):
         return KyokuIterator(self)
 
-    def verify(self):
-        raise NotImplementedError("MjSoulReplay.verify walks WinResultContextIterator (replay/mod.rs:1594-2180): not built")
+    def verify(self):  # mjsoul_replay.rs:357-430 -> (total_agari, total_mismatches); every win of the game in one batch
+        for r in self.rounds:
+            if r._win_error:
+                raise ValueError(r._win_error)
+        return _verify_counts(_WinBatch([c for r in self.rounds for c in r._win_ctx]))
 
 
 class ReplayBatch:

@@ -340,6 +340,164 @@ def test_mjsoul_paifu_reader_round_trip(source, tmp_path):
         R.MjSoulReplay.from_dict(3)
 
 
+# ------------------------------------------------------------------------------------------------ win contexts / verify
+def _paifu_rounds(R, text, sanma):
+    """a log of this repo's simulator turned into paifu rounds as MjSoul records them: Kyoku.events() of the MJAI reading, with the
+    NewRound record holding only the first dora marker and the count of the live wall before the dealer's draw"""
+    rounds = []
+    for k in R.MjaiReplay.from_text(text, rule="mjsoul").take_kyokus():
+        ev = k.events()
+        ev[0]["data"]["doras"] = ev[0]["data"]["doras"][:1]
+        ev[0]["data"]["left_tile_count"] = 55 if sanma else 70
+        for e in ev:
+            if e["name"] == "Dora":
+                e["name"] = "dora"
+        rounds.append((k, ev))
+    return rounds
+
+
+def _check_payments(ctx_list, k, hora_events, np_):
+    """the evaluator's answer for the walk's hand + conditions against what the game paid (honba and sticks are not the
+    walk's business: WinResultContextIterator evaluates with honba 0, replay/mod.rs:2008-2009)"""
+    honba = k.ben
+    paid = {}
+    for c, e in zip(ctx_list, hora_events):
+        r = c.actual
+        assert r.is_win and c.seat == e["actor"], (c, e)
+        if e["actor"] == e["target"]:                    # tsumo: every other seat pays its share + 100 per honba
+            oya = k.ju % np_
+            for p in range(np_):
+                if p != c.seat:
+                    share = r.tsumo_agari_oya if p == oya else r.tsumo_agari_ko
+                    paid[p] = paid.get(p, 0) + share + 100 * honba
+        else:                                           # ron: the discarder pays ron_agari + 300 (200 in sanma) per honba
+            paid[e["target"]] = paid.get(e["target"], 0) + r.ron_agari + (np_ - 1) * 100 * honba
+    return paid
+
+
+@pytest.mark.parametrize("backend", ["oracle", "hostsim"])
+@pytest.mark.parametrize("mode,seeds", [(2, range(40, 52)), (5, range(60, 68))])
+def test_win_contexts_of_simulated_games_pay_what_the_game_paid(backend, mode, seeds):
+    """WinResultContextIterator (replay/mod.rs:1594-2093): hands, melds, dora markers and win conditions tracked by the walk
+    over a log, evaluated, must give the payments the game itself made — the game derives riichi / ippatsu / haitei / rinshan /
+    chankan from its own state, the walk from the log alone."""
+    R = _shim(backend)
+    sanma = mode >= 3
+    np_ = 3 if sanma else 4
+    wins = flags = 0
+    for seed in seeds:
+        lines = simulated_log(mode, seed)
+        text = "\n".join(lines) + "\n"
+        horas, cur = [], None
+        for l in lines:
+            e = json.loads(l)
+            if e["type"] == "start_kyoku":
+                cur = []
+                horas.append(cur)
+            elif e["type"] == "hora":
+                cur.append(e)
+        rounds = _paifu_rounds(R, text, sanma)
+        game = R.MjSoulReplay.from_dict({"header": {}, "data": [ev for _, ev in rounds]})
+        assert game.num_rounds() == len(horas)
+        for k, hs in zip(game.take_kyokus(), horas):
+            ctxs = list(k.take_win_result_contexts())
+            assert len(ctxs) == len(hs)
+            if not hs:
+                continue
+            # pao (a liable seat pays for a yakuman) is the one case where the payers differ from the plain split
+            if any(c.actual.yakuman for c in ctxs):
+                continue
+            paid = _check_payments(ctxs, k, hs, np_)
+            deltas = [0] * np_
+            for e in hs:                                 # the log's deltas are per hora event
+                deltas = [a + b for a, b in zip(deltas, e["deltas"][:np_])]
+            if sanma:
+                # the iterator builds the 4-player evaluator also for sanma logs (replay/mod.rs:2035): no nukidora, no 1m<->9m
+                # marker wrap, so only the walk is checked: who won, on what, with how many kita set aside
+                for c in ctxs:
+                    n_kita = sum(v.type == A.LA_BABEI and v.seat == c.seat for v in k._views)
+                    assert c.conditions.kita_count == n_kita and not c.conditions.is_sanma
+                    assert len(c.tiles) + 3 * len(c.melds) == 14
+                wins += len(ctxs)
+                flags += sum(c.conditions.kita_count > 0 for c in ctxs)
+                continue
+            for p, amount in paid.items():
+                # a loser who declared riichi in this kyoku also lost the stick: the hora deltas do not include it
+                assert -deltas[p] == amount, (seed, k.chang, k.ju, k.ben, p, deltas, paid, [c.conditions for c in ctxs])
+            wins += len(ctxs)
+            flags += sum(c.conditions.ippatsu or c.conditions.haitei or c.conditions.houtei or c.conditions.rinshan or
+                         c.conditions.chankan or c.conditions.riichi for c in ctxs)
+    assert wins > 40 and flags > 10, (wins, flags)
+
+
+def test_win_contexts_read_markers_off_the_wall_and_verify_counts_mismatches():
+    """a paifu with `paishan`: dora / ura markers come from the wall (replay/mod.rs:1679-1728), ankan reveals at once, the
+    recorded fans / count / fu are compared by MjSoulReplay.verify (mjsoul_replay.rs:357-430)"""
+    R = _shim("oracle")
+    names = [f"{n}{s}" for s in "mps" for n in range(1, 10)] + [f"{n}z" for n in range(1, 8)]
+    wall = [names[(i * 7) % 34] for i in range(136)]
+    paishan = "".join(wall)
+    # seat 0 (dealer): 1m x4 + 2m3m4m 5p6p7p 7s8s + 9s9s  -> ankan 1m, riichi, tsumo 6s / 9s
+    hand0 = ["1m", "1m", "1m", "1m", "2m", "3m", "4m", "5p", "6p", "7p", "7s", "8s", "9s", "9s"]
+    others = [["2p", "2p", "3p", "3p", "4p", "4p", "6m", "6m", "7m", "7m", "8m", "8m", "1z"] for _ in range(3)]
+    new_round = {"scores": [25000] * 4, "doras": [wall[136 - 5]], "tiles0": hand0, "tiles1": others[0], "tiles2": others[1],
+                 "tiles3": others[2], "chang": 0, "ju": 0, "ben": 0, "liqibang": 0, "left_tile_count": 69, "paishan": paishan}
+    def hule(fans, count, fu):
+        return {"name": "Hule", "data": {"hules": [{"seat": 0, "hu_tile": "6s", "zimo": True, "count": count, "fu": fu,
+                                                      "fans": [{"id": y, "val": 1} for y in fans]}]}}
+    actions = [{"name": "NewRound", "data": new_round},
+               {"name": "AnGangAddGang", "data": {"seat": 0, "type": 3, "tiles": "1m"}},
+               {"name": "DealTile", "data": {"seat": 0, "tile": "2z", "left_tile_count": 68}},
+               {"name": "DiscardTile", "data": {"seat": 0, "tile": "2z", "is_liqi": True, "is_wliqi": True}},
+               {"name": "DealTile", "data": {"seat": 1, "tile": "3z", "left_tile_count": 67}},
+               {"name": "DiscardTile", "data": {"seat": 1, "tile": "3z"}},
+               {"name": "DealTile", "data": {"seat": 2, "tile": "3z", "left_tile_count": 66}},
+               {"name": "DiscardTile", "data": {"seat": 2, "tile": "3z"}},
+               {"name": "DealTile", "data": {"seat": 3, "tile": "3z", "left_tile_count": 65}},
+               {"name": "DiscardTile", "data": {"seat": 3, "tile": "3z"}},
+               {"name": "DealTile", "data": {"seat": 0, "tile": "6s", "left_tile_count": 64}}]
+    game = R.MjSoulReplay.from_dict({"header": {}, "data": [actions + [hule([1, 2, 30], 3, 40)]]})
+    k = next(iter(game.take_kyokus()))
+    assert k.paishan == paishan and k.events()[0]["data"]["paishan"] == paishan
+    assert k.events()[2]["data"]["left_tile_count"] == 68
+    (c,) = list(k.take_win_result_contexts())
+    # the ankan revealed the second marker at once: markers = wall[-5], wall[-7]; ura = wall[-6], wall[-8]
+    from riichienv_b200.replay import _tile_str
+    assert [_tile_str(x) for x in c.dora_indicators] == [wall[131], wall[129]]
+    assert [_tile_str(x) for x in c.ura_indicators] == [wall[130], wall[128]]
+    assert c.seat == 0 and len(c.tiles) == 11 and [m.meld_type.name for m in c.melds] == ["Ankan"] and not c.melds[0].opened
+    cd = c.conditions
+    # the ankan ended the first go-around, so the riichi is a plain one for ippatsu purposes only in the flags the walk keeps
+    assert cd.tsumo and cd.riichi and cd.double_riichi and cd.ippatsu and not cd.rinshan and not cd.haitei and not cd.tsumo_first_turn
+    assert c.expected_yaku == [1, 2, 30] and (c.expected_han, c.expected_fu) == (3, 40)
+    r = c.actual
+    assert r.is_win and {1, 30}.issubset(r.yaku)
+    assert c.calculate(c.create_calculator()).han == r.han
+    # verify(): the recorded answer equal to the evaluator's is no mismatch; another yaku list, han or fu is one
+    right = [y for y in r.yaku if y not in (31, 32, 33)]
+    n_dora = sum(y in (31, 32, 33) for y in r.yaku)
+    def counts(fans, count, fu):
+        g = R.MjSoulReplay.from_dict({"header": {}, "data": [actions + [hule(fans, count, fu)]]})
+        return g.verify()
+    assert counts(right, r.han - n_dora, r.fu) == (1, 0)
+    assert counts(right, r.han, r.fu) == (1, 0)                   # han with the dora han counted is accepted too
+    assert counts(right, r.han + 1, r.fu) == (1, 1)
+    assert counts(right, r.han, r.fu + 10) == (1, 1)
+    assert counts(right[:-1], r.han, r.fu) == (1, 1)
+
+
+def test_win_contexts_refuse_logs_the_walk_cannot_follow():
+    R = _shim("oracle")
+    new_round = {"scores": [35000] * 3, "doras": ["1m"], "tiles0": ["1m"] * 13, "tiles1": ["2m"] * 13, "tiles2": ["3m"] * 13,
+                 "chang": 0, "ju": 0, "ben": 0, "liqibang": 0}
+    bad = [{"name": "NewRound", "data": new_round}, {"name": "DealTile", "data": {"seat": 3, "tile": "1m"}}]
+    game = R.MjSoulReplay.from_dict({"header": {}, "data": [bad]})
+    with pytest.raises(ValueError, match="seat the kyoku does not have"):
+        next(iter(game.take_kyokus())).take_win_result_contexts()
+    with pytest.raises(ValueError, match="seat the kyoku does not have"):
+        game.verify()
+
+
 # ------------------------------------------------------------------------------------------------ the product (GPU)
 @pytest.mark.gpu
 def test_gpu_replay_batch_equals_oracle():
@@ -379,3 +537,49 @@ def test_gpu_shim_real_game_steps():
             if n % 40 == 0:
                 assert len(obs.encode()) == 74 * 34 * 4          # the tensor of a by-value replay observation (device encoder)
     assert n > 150
+
+
+def _verify_and_collect(R, mode, seeds):
+    """games whose paifu records the evaluator's own answer for even rounds and a wrong fu for odd ones: verify() must count
+    exactly the odd ones; returns the walk's queries"""
+    queries = []
+    for seed in seeds:
+        text = "\n".join(simulated_log(mode, seed)) + "\n"
+        rounds = [ev for _, ev in _paifu_rounds(R, text, mode >= 3)]
+        n_bad = 0
+        game = R.MjSoulReplay.from_dict({"header": {}, "data": rounds})
+        for i, k in enumerate(game.take_kyokus()):
+            for c in k.take_win_result_contexts():
+                r = c.actual
+                for h in rounds[i][-1]["data"]["hules"]:
+                    if h["seat"] == c.seat:
+                        h["fans"] = [{"id": y, "val": 1} for y in r.yaku]
+                        h["count"], h["fu"] = r.han, r.fu + (10 if i % 2 else 0)
+                n_bad += (i % 2 == 1 and r.han < 13)
+                queries.append(c._c.query)
+        game = R.MjSoulReplay.from_dict({"header": {}, "data": rounds})
+        assert game.verify() == (sum(len(k._win_ctx) for k in game.rounds), n_bad), seed
+    return queries
+
+
+def test_verify_counts_exactly_the_altered_rounds(capsys):
+    assert len(_verify_and_collect(_shim("oracle"), 2, range(40, 43))) > 10
+    assert "Mismatch: seat=" in capsys.readouterr().out         # the reference prints every mismatch (mjsoul_replay.rs:423-432)
+
+
+@pytest.mark.gpu
+def test_gpu_win_contexts_and_verify_equal_oracle():
+    """MjSoulReplay.verify / WinResultContext.actual on the device: every win of 4P and sanma games (the walk's queries) evaluated
+    by rv_hand_eval_batch, byte for byte the oracle's answer for the same queries"""
+    import oracle
+    import riichienv_b200.replay as R
+    from riichienv_b200 import hand as H
+
+    for mode, seeds in ((2, range(40, 48)), (5, range(60, 64))):
+        queries = _verify_and_collect(R, mode, seeds)
+        n = len(queries)
+        assert n > 20
+        arr = (A.HandQuery * n)(*queries)
+        want = (A.HandResult * n)()
+        oracle.load().orc_hand_eval(arr, want, n)
+        assert bytes(H.eval_queries(queries)) == bytes(want)
