@@ -531,6 +531,12 @@ typedef struct rv_win_context {
 } rv_win_context;
 int rv_replay_win_contexts(const rv_replay* r, int round, rv_win_context* out, int cap, int* n_out);
 int rv_replay_sizeof(int which); /* sizeof() as compiled: 0 rv_win_context, 1 rv_log_action_aux (a binding's layout check, like rv_sizeof) */
+/* encode_seq_progression of a REPLAY observation: in replay mode GameState::apply_log_action keeps a progression cache
+ * (state/event_handler.rs:351-379, 443-486, 573-606 -> observation/sequence_features.rs:212-313) and the observation returns it
+ * as it stands (sequence_features.rs:505-507).  The tuples (actor, type, moqie, liqi, from) of actions[0..n); tsumogiri[i] != 0
+ * = the discard of action i was the tile just drawn (the state's drawn_tile at that point).  Writes min(cap, m) rows of 5
+ * uint16, *n_out = m.  Pure host arithmetic on the log.                                                                  */
+int rv_replay_progression(const rv_log_action* actions, const uint8_t* tsumogiri, int n, uint16_t* out, int cap, int* n_out);
 /* LogKyoku::steps' state set-up for every game of the vector: kyokus[n] (HOST).  Each game is re-initialised as
  * `_initialize_round(oya, chang, ben, liqibang, None, scores)` does and then patched with the logged hands, dora markers and the
  * dealer's draw.  The vector's game mode must have kyoku.np seats.                                                          */

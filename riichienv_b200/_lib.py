@@ -93,6 +93,7 @@ def lib():
     L.rv_replay_actions.argtypes = [vp, C.c_int, P(A.LogAction), C.c_int, P(C.c_int)]
     L.rv_replay_paishan.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, P(C.c_int)]
     L.rv_replay_win_contexts.argtypes = [vp, C.c_int, P(A.WinContext), C.c_int, P(C.c_int)]
+    L.rv_replay_progression.argtypes = [P(A.LogAction), P(C.c_uint8), C.c_int, P(C.c_uint16), C.c_int, P(C.c_int)]
     L.rv_replay_actions_aux.argtypes = [vp, C.c_int, P(A.LogActionAux), C.c_int, P(C.c_int)]
     if L.rv_replay_sizeof(0) != C.sizeof(A.WinContext) or L.rv_replay_sizeof(1) != C.sizeof(A.LogActionAux):
         raise RuntimeError("ABI mismatch: rv_win_context / rv_log_action_aux")

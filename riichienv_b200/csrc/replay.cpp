@@ -721,6 +721,85 @@ int parse_paifu(const char* text, size_t len, uint32_t rule_bits, rv_replay** ou
   *out = r.release();
   return RV_OK;
 }
+// ---------------------------------------------------------------- the progression cache of replay mode
+// GameState::apply_log_action with enable_seq_caching (state/event_handler.rs:351-379, 443-486, 573-606) feeds a synthesized
+// reach / dahai / chi / pon / daiminkan / ankan / kakan event to process_single_event_progression
+// (observation/sequence_features.rs:212-313); a replay observation's encode_seq_progression returns that list as it stands
+// (sequence_features.rs:505-507: no start marker, no 512 cap).  The tile codes are the ones of seq.cuh.
+bool prog_red(int t) { return t == 16 || t == 52 || t == 88; }
+int prog_kan37(int t) {
+  if (t == 16) return 0;
+  if (t == 52) return 10;
+  if (t == 88) return 20;
+  const int k = t >> 2;
+  return k < 9 ? k + 1 : k < 18 ? k + 2 : k + 3;
+}
+int prog_chi(const std::vector<int>& consumed, int called) {            // encode_chi (93-133)
+  std::vector<int> all(consumed);
+  all.push_back(called);
+  std::sort(all.begin(), all.end());
+  const int first = all[0] / 4, suit = first / 9, start = first - 9 * suit, call_pos = called / 4 - 9 * suit - start;
+  bool red = false;
+  for (int t : all) red |= prog_red(t);
+  const bool five = start <= 4 && 4 <= start + 2;
+  int off = 0;
+  for (int q = 0; q < start; q++) off += (q <= 4 && 4 <= q + 2) ? 6 : 3;
+  return suit * 30 + off + (five && red ? 3 + call_pos : call_pos);
+}
+int prog_pon(const std::vector<int>& consumed, int called) {            // encode_pon (144-183)
+  const int kind = called / 4, suit = kind / 9;
+  if (suit == 3) return 33 + kind - 27;
+  const int rank = kind - 9 * suit;
+  if (rank == 4) {
+    bool red = false;
+    for (int t : consumed) red |= prog_red(t);
+    return suit * 11 + 4 + (prog_red(called) ? 2 : red ? 1 : 0);
+  }
+  return suit * 11 + (rank < 4 ? rank : rank + 2);
+}
+}  // namespace
+
+extern "C" int rv_replay_progression(const rv_log_action* actions, const uint8_t* tsumogiri, int n, uint16_t* out, int cap, int* n_out) {
+  if (n < 0 || cap < 0 || (n > 0 && (!actions || !tsumogiri)) || (cap > 0 && !out) || !n_out)
+    return rv_internal_fail(RV_ERR_INVALID, "rv_replay_progression: bad arguments");
+  int m = 0;
+  auto push = [&](int actor, int type, int moqie, int liqi, int from) {
+    if (m < cap) {
+      uint16_t* r = out + 5 * m;
+      r[0] = (uint16_t)actor, r[1] = (uint16_t)type, r[2] = (uint16_t)moqie, r[3] = (uint16_t)liqi, r[4] = (uint16_t)from;
+    }
+    m++;
+  };
+  for (int i = 0; i < n; i++) {
+    const rv_log_action& a = actions[i];
+    const int s = a.seat;
+    if (a.type == RV_LA_DISCARD) {
+      if (a.tile < 136) push(s, 1 + prog_kan37(a.tile), tsumogiri[i] ? 1 : 0, (a.flags & 3) ? 1 : 0, 4);
+    } else if (a.type == RV_LA_CHI_PENG_GANG) {
+      if (a.meld_type != RV_MELD_CHI && a.meld_type != RV_MELD_PON && a.meld_type != RV_MELD_DAIMINKAN) continue;
+      int target = 0, called = -1;
+      bool have_target = false;
+      std::vector<int> consumed;
+      for (int k = 0; k < a.n_tiles && k < 4; k++) {
+        if (a.froms[k] != s) {
+          if (!have_target) have_target = true, target = a.froms[k], called = a.tiles[k];
+        } else if (a.tiles[k] < 136) {
+          consumed.push_back(a.tiles[k]);
+        }
+      }
+      if (called < 0 || called >= 136) continue;                        // pai "" does not parse: no entry
+      const int rel = ((target - s + 3) % 4 + 4) % 4;
+      if (a.meld_type == RV_MELD_DAIMINKAN) push(s, 168 + prog_kan37(called), 2, 2, rel);
+      else if (consumed.size() >= 2) push(s, a.meld_type == RV_MELD_CHI ? 38 + prog_chi(consumed, called) : 128 + prog_pon(consumed, called), 2, 2, rel);
+    } else if (a.type == RV_LA_ANGANG_ADDGANG && a.n_tiles > 0 && a.tiles[0] < 136) {
+      if (a.meld_type == RV_MELD_ANKAN) push(s, 205 + a.tiles[0] / 4, 2, 2, 4);
+      else push(s, 239 + prog_kan37(a.tiles[0]), 2, 2, 4);
+    }
+  }
+  *n_out = m;
+  return RV_OK;
+}
+namespace {
 // ---------------------------------------------------------------- WinResultContextIterator (replay/mod.rs:1594-2093)
 // The walk over one kyoku that tracks hands, melds and the win conditions up to every Hule and hands HandEvaluator::calc its
 // arguments.  Here it only BUILDS the queries: the evaluation is one rv_hand_eval_batch over every context of a log.

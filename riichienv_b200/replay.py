@@ -270,6 +270,7 @@ class _ReplayObsEnv:
 
     def __init__(self, it, record):
         self._it, self._record = it, record
+        self._n_applied = it._idx                # log actions applied when the observation was taken
         self._token = 0
         self._np = it._np
         self.skip_mjai_logging = False
@@ -285,8 +286,30 @@ class _ReplayObsEnv:
             v.set_state(0, live)
 
     def _encode_seq(self, pid, first_new_event):
-        raise NotImplementedError("sequence features of replay observations (the reference's progression cache, replay/mod.rs:1280) "
-                                  "are not built")
+        """sparse / numeric / candidates by the device encoder over the record and the event log LogKyoku::steps' set-up left
+        (start_kyoku + the dealer's scratch draw: apply_log_action pushes no events — so, as in the reference, numeric takes
+        its round-start values from that start_kyoku, and the event-derived `drawn` / `last discarder` see nothing after it);
+        progression = the replay-mode cache (rv_replay_progression over the actions applied before this observation)."""
+        import numpy as np
+
+        if self._np == 3:
+            raise NotImplementedError("the reference has no sequence features for sanma observations")
+        v = self._it._env._v
+        live = v.get_state(0)
+        v.set_state(0, self._record)
+        try:
+            sp, nu, _, ca, lens = v.encode_seq_single(pid, 0)
+        finally:
+            v.set_state(0, live)
+        n = self._n_applied
+        acts, flags = self._it._kyoku._actions, (C.c_uint8 * max(1, n))(*self._it._tsumogiri[:n])
+        m = C.c_int(0)
+        check(lib().rv_replay_progression(acts, flags, n, None, 0, C.byref(m)))
+        pr = np.zeros((max(1, m.value), 5), np.uint16)
+        check(lib().rv_replay_progression(acts, flags, n, pr.ctypes.data_as(C.POINTER(C.c_uint16)), m.value, C.byref(m)))
+        lens = lens.copy()
+        lens[1] = m.value
+        return sp, nu, pr, ca, lens
 
 
 class KyokuStepIterator:
@@ -305,6 +328,7 @@ class KyokuStepIterator:
         self._env._log_cache = {}
         self._env._token += 1
         self._actions = kyoku._views
+        self._tsumogiri = [0] * len(kyoku._views)   # per action: the discard was the tile just drawn (the progression cache's moqie)
         self._idx = 0
         self._pending_action = None
         self._filter = seat
@@ -316,6 +340,8 @@ class KyokuStepIterator:
 
     # ---- state access -----------------------------------------------------------------------------
     def _apply(self, a: _ActionView):
+        if a.type == A.LA_DISCARD and self._np == 4:
+            self._tsumogiri[self._idx] = int(self._env._state().drawn_tile == a.tile)   # state/event_handler.rs:343-347
         self._env._v.apply_log_actions((A.LogAction * 1)(a.raw))
         self._env._token += 1
 

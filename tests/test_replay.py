@@ -498,6 +498,89 @@ def test_win_contexts_refuse_logs_the_walk_cannot_follow():
         game.verify()
 
 
+# ------------------------------------------------------------------------------------------------ sequence features of replay observations
+def _progression_of_events(lines):
+    """per kyoku: the (actor, type, moqie, liqi, from) tuples of the MJAI text, by the rules of process_single_event_progression
+    (observation/sequence_features.rs:212-313) with the oracle's tile codes, without the start marker.  moqie as replay mode
+    sees it (state/event_handler.rs:343-347): the discard is the drawn tile — by tile NAME, a log does not say which copy."""
+    import oracle
+    from riichienv_b200.convert import mjai_to_tid
+
+    orc = oracle.load()
+    out, cur, pending, drawn = [], None, None, {}
+    for l in lines:
+        e = json.loads(l)
+        t = e["type"]
+        if t == "start_kyoku":
+            cur, pending, drawn = [], None, {}
+            out.append(cur)
+        elif t == "tsumo":
+            drawn = {e["actor"]: e["pai"]}
+        elif t == "reach":
+            pending = e["actor"]
+        elif t == "dahai":
+            liqi = int(pending == e["actor"])
+            if liqi:
+                pending = None
+            assert not e["tsumogiri"] or drawn.get(e["actor"]) == e["pai"]
+            cur.append((e["actor"], 1 + orc.orc_seq_kan37(mjai_to_tid(e["pai"])), int(drawn.get(e["actor"]) == e["pai"]), liqi, 4))
+            drawn = {}
+        elif t in ("chi", "pon"):
+            drawn = {}
+            c = [mjai_to_tid(x) for x in e["consumed"]]
+            code = (38 + orc.orc_seq_encode_chi(c[0], c[1], mjai_to_tid(e["pai"])) if t == "chi"
+                    else 128 + orc.orc_seq_encode_pon(c[0], c[1], mjai_to_tid(e["pai"])))
+            cur.append((e["actor"], code, 2, 2, orc.orc_seq_relative_from(e["actor"], e["target"])))
+        elif t == "daiminkan":
+            cur.append((e["actor"], 168 + orc.orc_seq_kan37(mjai_to_tid(e["pai"])), 2, 2, orc.orc_seq_relative_from(e["actor"], e["target"])))
+        elif t == "ankan":
+            cur.append((e["actor"], 205 + mjai_to_tid(e["consumed"][0]) // 4, 2, 2, 4))
+        elif t == "kakan":
+            cur.append((e["actor"], 239 + orc.orc_seq_kan37(mjai_to_tid(e["pai"])), 2, 2, 4))
+    return out
+
+
+def _check_replay_seq_features(R, seeds):
+    import numpy as np
+
+    n_obs = n_tuples = 0
+    kinds = set()
+    for seed in seeds:
+        lines = simulated_log(2, seed)
+        want = _progression_of_events(lines)
+        game = R.MjaiReplay.from_text("\n".join(lines) + "\n")
+        assert game.num_rounds() == len(want)
+        for k, tuples in zip(game.take_kyokus(), want):
+            # tuples so far after i log actions: one per discard / call / kan action
+            upto = [0]
+            for v in k._views:
+                upto.append(upto[-1] + (v.type in (A.LA_DISCARD, A.LA_CHI_PENG_GANG, A.LA_ANGANG_ADDGANG)))
+            assert upto[-1] == len(tuples)
+            for pid, obs, act in k.steps(None, skip_single_action=False):
+                m = upto[obs._env._n_applied]
+                pr = np.frombuffer(obs.encode_seq_progression(), np.uint16).reshape(-1, 5)
+                assert [tuple(r) for r in pr.tolist()] == tuples[:m], (seed, k.chang, k.ju, obs._env._n_applied)
+                nu = np.frombuffer(obs.encode_seq_numeric(), np.float32)
+                assert nu[0] == nu[6] == k.ben and nu[8:12].tolist() == [k.scores[(pid + i) % 4] for i in range(4)]
+                sp = np.frombuffer(obs.encode_seq_sparse(), np.uint16)
+                assert sp[1] == 2 + pid and sp[3] == 9 + k._k.oya
+                ca = np.frombuffer(obs.encode_seq_candidates(), np.uint16).reshape(-1, 4)
+                assert len(ca) <= len(obs.legal_actions())
+                n_obs += 1
+                n_tuples += m
+            kinds |= {t[1] // 1 for t in tuples if t[1] >= 38}
+    return n_obs, n_tuples, kinds
+
+
+def test_replay_observations_carry_the_progression_cache():
+    """encode_seq_* of replay observations (scripts/validate_logs.py:100-113 calls them on every step of a log): progression =
+    the replay-mode cache, equal at every decision to the tuples of the game's own MJAI text up to there (tsumogiri flags from
+    the replayed record's drawn tile, riichi from the log's flag), without the start marker"""
+    n_obs, n_tuples, kinds = _check_replay_seq_features(_shim("oracle"), range(30, 33))
+    assert n_obs > 1500 and n_tuples > 50_000
+    assert any(38 <= t < 128 for t in kinds) and any(128 <= t < 168 for t in kinds)       # chi and pon seen
+
+
 # ------------------------------------------------------------------------------------------------ the product (GPU)
 @pytest.mark.gpu
 def test_gpu_replay_batch_equals_oracle():
@@ -583,3 +666,11 @@ def test_gpu_win_contexts_and_verify_equal_oracle():
         want = (A.HandResult * n)()
         oracle.load().orc_hand_eval(arr, want, n)
         assert bytes(H.eval_queries(queries)) == bytes(want)
+
+
+@pytest.mark.gpu
+def test_gpu_replay_observations_carry_the_progression_cache():
+    import riichienv_b200.replay as R
+
+    n_obs, _, _ = _check_replay_seq_features(R, [30])
+    assert n_obs > 400
