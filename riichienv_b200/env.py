@@ -433,6 +433,8 @@ class Observation:
         tt = {"dahai": ActionType.DISCARD, "chi": ActionType.CHI, "pon": ActionType.PON, "kakan": ActionType.KAKAN,
               "daiminkan": ActionType.DAIMINKAN, "ankan": ActionType.ANKAN, "reach": ActionType.RIICHI,
               "ryukyoku": ActionType.KYUSHU_KYUHAI}.get(atype)
+        if self._NP == 3:                       # mjai_select.rs:112-119: sanma knows `kita` and has no chi
+            tt = ActionType.KITA if atype == "kita" else None if atype == "chi" else tt
         if tt is None:
             return None
         if tt == ActionType.DISCARD:

@@ -276,14 +276,28 @@ class _ReplayObsEnv:
         self.skip_mjai_logging = False
         self._ext_log = None
 
-    def _encode(self, pid, extended=False):
+    def _on_record(self, call):
         v = self._it._env._v
         live = v.get_state(0)
         v.set_state(0, self._record)
         try:
-            return v.encode_single(pid, extended)
+            return call(v)
         finally:
             v.set_state(0, live)
+
+    def _encode(self, pid, extended=False):
+        return self._on_record(lambda v: v.encode_single(pid, extended))
+
+    @property
+    def _v(self):
+        """the vector calls an Observation makes (encode_kawa_single, ...), run on this observation's record"""
+        outer = self
+
+        class _OnRecord:
+            def __getattr__(self, name):
+                return lambda *a, **k: outer._on_record(lambda v: getattr(v, name)(*a, **k))
+
+        return _OnRecord()
 
     def _encode_seq(self, pid, first_new_event):
         """sparse / numeric / candidates by the device encoder over the record and the event log LogKyoku::steps' set-up left
@@ -294,13 +308,7 @@ class _ReplayObsEnv:
 
         if self._np == 3:
             raise NotImplementedError("the reference has no sequence features for sanma observations")
-        v = self._it._env._v
-        live = v.get_state(0)
-        v.set_state(0, self._record)
-        try:
-            sp, nu, _, ca, lens = v.encode_seq_single(pid, 0)
-        finally:
-            v.set_state(0, live)
+        sp, nu, _, ca, lens = self._on_record(lambda v: v.encode_seq_single(pid, 0))
         n = self._n_applied
         acts, flags = self._it._kyoku._actions, (C.c_uint8 * max(1, n))(*self._it._tsumogiri[:n])
         m = C.c_int(0)

@@ -153,7 +153,8 @@ class CpuVec:
         sp, nu = np.zeros(25, np.uint16), np.zeros(12, np.float32)
         pr, ca, le = np.zeros((512, 5), np.uint16), np.zeros((64, 4), np.uint16), np.zeros(3, np.uint16)
         p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
-        self.lib.orc_game_encode_seq(self.h, pid, int(start_word), len(self.events()), 1, p16(sp),
+        fn = self.lib.orc_game_encode_seq if self.backend == "oracle" else self.lib.hs_game_encode_seq
+        fn(self.h, pid, int(start_word), len(self.events()), 1, p16(sp),
                                      nu.ctypes.data_as(C.POINTER(C.c_float)), p16(pr), 512, p16(ca), p16(le))
         return sp, nu, pr, ca, le
 

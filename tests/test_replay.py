@@ -581,6 +581,33 @@ def test_replay_observations_carry_the_progression_cache():
     assert any(38 <= t < 128 for t in kinds) and any(128 <= t < 168 for t in kinds)       # chi and pon seen
 
 
+def _run_validate_logs(backend, tmp_path):
+    """the reference's own log validator (scripts/validate_logs.py, unmodified; read from /root/reference or from the git-ignored
+    copy __graft_entry__.build() leaves in baseline/_ref/scripts) over the real game and simulated 4P / sanma hanchan: every
+    encoder on every replay observation, legality of every logged action, masks, score continuity, waits at wins"""
+    import shutil
+    import subprocess
+    import sys
+
+    script = next((p for p in ("/root/reference/scripts/validate_logs.py",
+                               os.path.join(os.path.dirname(HERE), "baseline", "_ref", "scripts", "validate_logs.py")) if os.path.exists(p)), None)
+    if script is None:
+        pytest.skip("reference scripts not present")
+    shutil.copy(REAL_LOG, tmp_path / "real.mjson")
+    (tmp_path / "sim4.mjson").write_text("\n".join(simulated_log(2, 31)) + "\n")
+    (tmp_path / "sim3.mjson").write_text("\n".join(simulated_log(5, 61)) + "\n")
+    root = os.path.dirname(HERE)
+    env = dict(os.environ, RV_REFSUITE_BACKEND=backend, PYTHONPATH=os.pathsep.join([os.path.join(HERE, "refsuite"), root]))
+    out = subprocess.run([sys.executable, os.path.join(HERE, "refsuite", "run_validate_logs.py"), script, str(tmp_path)],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "Done: 3/3 passed" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("backend", ["oracle", "hostsim"])
+def test_reference_validate_logs_script_passes(backend, tmp_path):
+    _run_validate_logs(backend, tmp_path)
+
+
 # ------------------------------------------------------------------------------------------------ the product (GPU)
 @pytest.mark.gpu
 def test_gpu_replay_batch_equals_oracle():
@@ -674,3 +701,8 @@ def test_gpu_replay_observations_carry_the_progression_cache():
 
     n_obs, _, _ = _check_replay_seq_features(R, [30])
     assert n_obs > 400
+
+
+@pytest.mark.gpu
+def test_gpu_reference_validate_logs_script_passes(tmp_path):
+    _run_validate_logs("gpu", tmp_path)
