@@ -486,6 +486,117 @@ def test_win_contexts_read_markers_off_the_wall_and_verify_counts_mismatches():
     assert counts(right[:-1], r.han, r.fu) == (1, 1)
 
 
+def _mini_paifu(R, actions, np_=4, hands=None, paishan=None, left=69, ju=0, chang=0):
+    """one round: NewRound with 13 filler tiles per seat (the dealer 14) + the given actions"""
+    fill = [["1m", "2m", "3m", "4m", "5m", "6m", "7m", "8m", "9m", "1p", "2p", "3p", "4p"] for _ in range(np_)]
+    fill[ju % np_] = fill[ju % np_] + ["5p"]
+    hands = hands or fill
+    nr = {"scores": [25000] * np_ if np_ == 4 else [35000] * 3, "doras": ["1z"], "chang": chang, "ju": ju, "ben": 0, "liqibang": 0,
+          "left_tile_count": left}
+    for p in range(np_):
+        nr[f"tiles{p}"] = hands[p]
+    if paishan:
+        nr["paishan"] = paishan
+        nr["doras"] = [paishan[2 * 131: 2 * 132]]
+    game = R.MjSoulReplay.from_dict({"header": {}, "data": [[{"name": "NewRound", "data": nr}] + actions]})
+    return list(next(iter(game.take_kyokus())).take_win_result_contexts())
+
+
+def _act(name, **data):
+    return {"name": name, "data": data}
+
+
+def _hule(seat, tile, zimo, **kw):
+    return _act("Hule", hules=[dict(seat=seat, hu_tile=tile, zimo=zimo, count=1, fu=30, fans=[], **kw)])
+
+
+def test_win_context_conditions_follow_the_walk():
+    """the flags WinResultContextIterator derives from the log (replay/mod.rs:1741-2060), one scenario each"""
+    R = _shim("oracle")
+    flags = lambda c: {n for n in ("tsumo", "riichi", "double_riichi", "ippatsu", "haitei", "houtei", "rinshan", "chankan",
+                                   "tsumo_first_turn") if getattr(c.conditions, n)}
+    base = ["1m", "2m", "3m", "4m", "5m", "6m", "7m", "8m", "9m", "1p", "2p"]
+    H = [base + ["3p", "4p", "5p"], base + ["3p", "4p"], base + ["9p", "9p"], base + ["3p", "4p"]]   # seat 2 can pon 9p
+    # tenhou: the dealer wins on the dealt hand
+    (c,) = _mini_paifu(R, [_hule(0, "5p", True)])
+    assert flags(c) == {"tsumo", "tsumo_first_turn"} and len(c.tiles) == 14 and c.conditions.player_wind == 0
+    # riichi + ippatsu tsumo; the same with a call in between: no ippatsu, no first turn for anybody
+    turn = [_act("DiscardTile", seat=0, tile="5p", is_liqi=True), _act("DealTile", seat=1, tile="9p", left_tile_count=68),
+            _act("DiscardTile", seat=1, tile="9p")]
+    (c,) = _mini_paifu(R, turn + [_act("DealTile", seat=0, tile="5p", left_tile_count=60), _hule(0, "5p", True)])
+    assert flags(c) == {"tsumo", "riichi", "ippatsu"}
+    call = [_act("ChiPengGang", seat=2, type=1, tiles=["9p", "9p", "9p"], froms=[1, 2, 2]), _act("DiscardTile", seat=2, tile="1m")]
+    (c,) = _mini_paifu(R, turn + call + [_act("DealTile", seat=0, tile="5p", left_tile_count=60), _hule(0, "5p", True)], hands=H)
+    assert flags(c) == {"tsumo", "riichi"}
+    (c,) = _mini_paifu(R, turn + call + [_hule(1, "1m", False)], hands=H)
+    assert flags(c) == set() and c.tiles[-1] == 0 and len(c.tiles) == 14            # ron: the win tile joins the hand
+    (c,) = _mini_paifu(R, turn + call + [_hule(2, "1m", True)], hands=H)
+    assert [m.meld_type.name for m in c.melds] == ["Pon"] and c.melds[0].from_who == 1 and c.melds[0].called_tile == 68 and c.melds[0].opened
+    assert len(c.tiles) == 13 - 2 - 1 and c.conditions.player_wind == 2
+    # double riichi (is_wliqi) keeps both flags
+    (c,) = _mini_paifu(R, [_act("DiscardTile", seat=0, tile="5p", is_liqi=True, is_wliqi=True), _hule(0, "5p", False)])
+    assert flags(c) == {"riichi", "double_riichi", "ippatsu"}
+    # last tile: haitei on a draw, houtei on the discard after it — but not off a replacement tile
+    (c,) = _mini_paifu(R, [_act("DiscardTile", seat=0, tile="5p"), _act("DealTile", seat=1, tile="9p", left_tile_count=0), _hule(1, "9p", True)])
+    assert flags(c) == {"tsumo", "haitei", "tsumo_first_turn"}     # first turn is per seat: seat 1 has not discarded, nobody called
+    (c,) = _mini_paifu(R, [_act("DiscardTile", seat=0, tile="5p"), _act("DealTile", seat=1, tile="9p", left_tile_count=0),
+                           _act("DiscardTile", seat=1, tile="9p"), _hule(2, "9p", False)])
+    assert flags(c) == {"houtei"}
+    # ankan + replacement draw (a DealTile that carries `doras`): rinshan, and never haitei
+    kan = [_act("AnGangAddGang", seat=0, type=3, tiles="1m"), _act("DealTile", seat=0, tile="5p", doras=["1z", "2z"], left_tile_count=0)]
+    hands = [["1m", "1m", "1m", "1m", "5m", "6m", "7m", "8m", "9m", "1p", "2p", "3p", "4p", "5p"]] + [["2m"] * 13] * 3
+    (c,) = _mini_paifu(R, kan + [_hule(0, "5p", True)], hands=hands)
+    assert flags(c) == {"tsumo", "rinshan"} and [m.meld_type.name for m in c.melds] == ["Ankan"] and len(c.tiles) == 11
+    assert c.dora_indicators == [108, 112]
+    # kakan robbed: pon of 9p, then the added 9p is ronned by seat 3 (ippatsu of the riichi player survives until the kan resolves)
+    rob = turn + call + [_act("DealTile", seat=3, tile="2z", left_tile_count=66), _act("DiscardTile", seat=3, tile="2z"),
+                         _act("DealTile", seat=0, tile="2z", left_tile_count=65), _act("DiscardTile", seat=0, tile="2z"),
+                         _act("DealTile", seat=1, tile="2z", left_tile_count=64), _act("DiscardTile", seat=1, tile="2z"),
+                         _act("DealTile", seat=2, tile="9p", left_tile_count=63), _act("AnGangAddGang", seat=2, type=2, tiles="9p")]
+    (c,) = _mini_paifu(R, rob + [_hule(3, "9p", False)], hands=H)
+    assert flags(c) == {"chankan"}
+    (c,) = _mini_paifu(R, rob + [_act("DealTile", seat=2, tile="3z", doras=["1z"], left_tile_count=62), _hule(2, "3z", True)], hands=H)
+    assert flags(c) == {"tsumo", "rinshan"} and [(m.meld_type.name, len(m.tiles), m.from_who) for m in c.melds] == [("Kakan", 4, 1)]
+    # sanma: a ron on the set-aside north uses the ippatsu of before the kita; kita are counted per seat
+    h3 = [["1m", "9m", "1p", "2p", "3p", "4p", "5p", "6p", "7p", "8p", "9p", "1s", "2s", "4z"], ["1s"] * 12 + ["4z"], ["2s"] * 13]
+    kita = [_act("DiscardTile", seat=0, tile="1m", is_liqi=True), _act("DealTile", seat=1, tile="4z", left_tile_count=50),
+            _act("BaBei", seat=1, moqie=True)]
+    (c,) = _mini_paifu(R, kita + [_hule(0, "4z", False)], np_=3, hands=h3, left=54)
+    assert flags(c) == {"riichi", "ippatsu"} and c.conditions.kita_count == 0 and c.conditions.player_wind == 0
+    (c,) = _mini_paifu(R, kita + [_act("DealTile", seat=1, tile="3s", doras=["1z"], left_tile_count=49), _hule(1, "3s", True)], np_=3, hands=h3, left=54)
+    assert flags(c) == {"tsumo", "rinshan"} and c.conditions.kita_count == 1 and len(c.tiles) == 14   # one north set aside, two tiles drawn
+    # seat winds turn with ju; the round wind is chang
+    (c,) = _mini_paifu(R, [_act("DiscardTile", seat=1, tile="5p"), _hule(0, "5p", False)], ju=1, chang=1)
+    assert (c.conditions.player_wind, c.conditions.round_wind) == (3, 1)
+
+
+def test_win_context_kan_doras_follow_the_wall():
+    """with `paishan` the markers are read off the wall: an ankan reveals at once, a daiminkan / kakan at the next discard or kan
+    (replay/mod.rs:1770-1776, 1843-1852, 1905-1936)"""
+    R = _shim("oracle")
+    names = [f"{n}{s}" for s in "mps" for n in range(1, 10)] + [f"{n}z" for n in range(1, 8)]
+    wall = [names[(i * 5 + 3) % 34] for i in range(136)]
+    from riichienv_b200.replay import _tile_str
+    marks = lambda c: [_tile_str(x) for x in c.dora_indicators]
+    hands = [["1m"] * 14, ["2m"] * 13, ["3m"] * 13, ["4m"] * 13]
+    first = [_act("DiscardTile", seat=0, tile="1m")]
+    dmk = first + [_act("ChiPengGang", seat=1, type=2, tiles=["1m", "1m", "1m", "1m"], froms=[0, 1, 1, 1]),
+                   _act("DealTile", seat=1, tile="7z", doras=[wall[131]], left_tile_count=60)]
+    def run(actions):
+        return _mini_paifu(R, actions, hands=hands, paishan="".join(wall))
+    (c,) = run(dmk + [_hule(1, "7z", True)])
+    assert marks(c) == [wall[131]] and c.conditions.rinshan            # the daiminkan's marker is not up at the rinshan win
+    (c,) = run(dmk + [_act("DiscardTile", seat=1, tile="7z"), _hule(2, "7z", False)])
+    assert marks(c) == [wall[131], wall[129]]                          # ... it is after the discard
+    (c,) = run(dmk + [_act("AnGangAddGang", seat=1, type=3, tiles="2m"), _act("DealTile", seat=1, tile="6z", left_tile_count=59),
+                      _hule(1, "6z", True)])
+    assert marks(c) == [wall[131], wall[129], wall[127]]                # a second kan flushes the pending one; the ankan shows its own
+    (c,) = run(first + [_act("DealTile", seat=1, tile="2m", left_tile_count=60), _act("DiscardTile", seat=1, tile="2m", is_liqi=True),
+                        _act("DealTile", seat=2, tile="2m", left_tile_count=59), _act("DiscardTile", seat=2, tile="2m"),
+                        _hule(1, "2m", False)])
+    assert marks(c) == [wall[131]] and [_tile_str(x) for x in c.ura_indicators] == [wall[130]]
+
+
 def test_win_contexts_refuse_logs_the_walk_cannot_follow():
     R = _shim("oracle")
     new_round = {"scores": [35000] * 3, "doras": ["1m"], "tiles0": ["1m"] * 13, "tiles1": ["2m"] * 13, "tiles2": ["3m"] * 13,
