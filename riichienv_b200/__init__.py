@@ -7,7 +7,8 @@ from . import _abi  # noqa: F401
 
 __all__ = ["RiichiEnv", "VecRiichiEnv", "MultiVecRiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
            "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "tid_to_mjai",
-           "MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch"]
+           "MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch", "WinResultContext", "WinResultContextIterator", "Yaku", "get_yaku_by_id", "get_all_yaku",
+           "check_riichi_candidates"]
 
 
 def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
@@ -20,11 +21,15 @@ def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
         from . import vec_env
 
         return getattr(vec_env, name)
-    if name in ("HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "WinResult"):
+    if name in ("Yaku", "get_yaku_by_id", "get_all_yaku"):
+        from . import yaku_table
+
+        return getattr(yaku_table, name)
+    if name in ("HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "WinResult", "check_riichi_candidates"):
         from . import hand
 
         return getattr(hand, name)
-    if name in ("MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch"):
+    if name in ("MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch", "WinResultContext", "WinResultContextIterator"):
         from . import replay
 
         return getattr(replay, name)

@@ -46,6 +46,11 @@ class WinResult:  # types.rs:281-295
     pao_payer: object = None
     has_win_shape: bool = False
 
+    def yaku_list(self):  # types.rs:356-361
+        from .yaku_table import get_yaku_by_id
+
+        return [y for y in map(get_yaku_by_id, self.yaku) if y is not None]
+
 
 def make_query(tiles_136, melds, win_tile, dora, ura, cond: Conditions) -> A.HandQuery:
     q = A.HandQuery()
@@ -226,6 +231,25 @@ def calculate_score(han, fu, is_oya, is_tsumo, honba=0, num_players=4) -> Score:
     out = (C.c_uint32 * 4)()
     check(lib().rv_calculate_score(int(han), int(fu), int(bool(is_oya)), int(bool(is_tsumo)), int(honba), int(num_players), out))
     return Score(out[0], out[1], out[2], out[3])
+
+
+def check_riichi_candidates(tiles_136):  # hand_evaluator.rs:263-284
+    """the tiles of a 3n+2 hand whose discard leaves a tenpai hand (agari::is_tenpai of the other tiles), in input order.
+    One wait query per candidate, evaluated in a single rv_hand_eval_batch; concealed hands shorter than 14 (calls made) are
+    padded with far-away dummy sets, which complete nothing."""
+    tiles = [int(t) for t in tiles_136]
+    n = len(tiles)
+    if n == 0:
+        return []
+    if n > 14 or n % 3 != 2:
+        raise ValueError("check_riichi_candidates takes the 3n+2 concealed tiles of a hand (at most 14)")
+    if any(not 0 <= t < 136 for t in tiles):
+        raise ValueError("tile ids must be in 0..135")
+    from .env import Meld, MeldType
+
+    pads = [Meld(MeldType.Pon, [4 * k, 4 * k + 1, 4 * k + 2], True) for k in (27, 28, 29, 30)][: (14 - n) // 3]
+    qs = [make_query(tiles[:i] + tiles[i + 1:], pads, 0, (), (), Conditions()) for i in range(n)]
+    return [t for t, r in zip(tiles, eval_queries(qs)) if r.wait_mask != 0]
 
 
 def calculate_shanten(hand_tiles) -> int:  # shanten.rs:250-261 (len_div3 = n_tiles // 3)

@@ -42,16 +42,19 @@ if BACKEND != "gpu":
 from riichienv_b200.env import (Action, Action3P, ActionType, GameRule, GameType, Meld, MeldType, Observation,  # noqa: E402,F401
                                 Observation3P, Phase, RiichiEnv, Wind)
 from riichienv_b200.hand import (Conditions, HandEvaluator, HandEvaluator3P, Score, WinResult, calculate_score,  # noqa: E402,F401
-                                 calculate_shanten, calculate_shanten_3p)
+                                 calculate_shanten, calculate_shanten_3p, check_riichi_candidates)
+from riichienv_b200.yaku_table import Yaku, get_all_yaku, get_yaku_by_id  # noqa: E402,F401
 from riichienv_b200.convert import parse_hand, parse_tile  # noqa: E402,F401
 
 EAST, SOUTH, WEST, NORTH = Wind.East, Wind.South, Wind.West, Wind.North
 
 
-from riichienv_b200.replay import Kyoku, KyokuIterator, MjaiReplay, MjSoulReplay  # noqa: E402,F401  (replay ingestion)
+from riichienv_b200.replay import (Kyoku, KyokuIterator, MjaiReplay, MjSoulReplay, WinResultContext,  # noqa: E402,F401  (replay ingestion)
+                                   WinResultContextIterator)
+from . import consts  # noqa: E402,F401
 
 
 def __getattr__(name):
-    # replay readers, viewer, yaku catalogue: out of scope; the tests that import them are
+    # viewer, legacy pure-Python rule classes: out of scope; the tests that import them are
     # recorded as out of scope in tests/refsuite/expected.txt
     raise AttributeError(f"riichienv_b200 does not provide {name} (out of scope, SURVEY.md §2)")
