@@ -7,7 +7,7 @@ from . import _abi  # noqa: F401
 
 __all__ = ["RiichiEnv", "VecRiichiEnv", "MultiVecRiichiEnv", "Observation", "Observation3P", "Action", "Action3P", "ActionType", "Phase", "Meld", "MeldType", "GameRule",
            "GameType", "Wind", "HandEvaluator", "Conditions", "calculate_score", "calculate_shanten", "calculate_shanten_3p", "tid_to_mjai",
-           "MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch", "WinResultContext", "WinResultContextIterator", "Yaku", "get_yaku_by_id", "get_all_yaku",
+           "MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch", "WinResultContext", "WinResultContextIterator", "KyokuStepIterator", "KyokuIterator", "Yaku", "get_yaku_by_id", "get_all_yaku",
            "check_riichi_candidates"]
 
 
@@ -29,7 +29,8 @@ def __getattr__(name):  # lazy: keep `import riichienv_b200` light and GPU-free
         from . import hand
 
         return getattr(hand, name)
-    if name in ("MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch", "WinResultContext", "WinResultContextIterator"):
+    if name in ("MjaiReplay", "MjSoulReplay", "Kyoku", "ReplayBatch", "WinResultContext", "WinResultContextIterator", "KyokuStepIterator",
+                "KyokuIterator"):
         from . import replay
 
         return getattr(replay, name)

@@ -49,7 +49,7 @@ from riichienv_b200.convert import parse_hand, parse_tile  # noqa: E402,F401
 EAST, SOUTH, WEST, NORTH = Wind.East, Wind.South, Wind.West, Wind.North
 
 
-from riichienv_b200.replay import (Kyoku, KyokuIterator, MjaiReplay, MjSoulReplay, WinResultContext,  # noqa: E402,F401  (replay ingestion)
+from riichienv_b200.replay import (Kyoku, KyokuIterator, KyokuStepIterator, MjaiReplay, MjSoulReplay, WinResultContext,  # noqa: E402,F401  (replay ingestion)
                                    WinResultContextIterator)
 from . import consts  # noqa: E402,F401
 
