@@ -724,6 +724,61 @@ class ReplayBatch:
         self.vec.replay_load((A.LogKyoku * self.n)(*[k._k for k in kyokus]), acts, first)
         self.position = 0
 
+    # ---- labels: what the seat on turn decided, read off the log -------------------------------------------------------
+    @staticmethod
+    def own_turn_label(a: _ActionView, np_):
+        """(seat, action id) when log action `a` is a decision of the seat on turn — the sample `Kyoku.steps` yields for it
+        (replay/mod.rs:206-532; ids: Action::encode, action.rs:158-227, sanma action_3p.rs) — else None.  A riichi discard is
+        the Riichi decision (the discard that follows it is taken in a state this walk does not stop at); calls and ron are
+        responses to another seat's discard, taken in states `get_observation_for_replay` builds: see `Kyoku.steps`."""
+        acls = Action3P if np_ == 3 else Action
+        if a.type == A.LA_DISCARD:
+            act = acls(ActionType.RIICHI, None, [], None) if a.is_liqi else acls(ActionType.DISCARD, a.tile, [], None)
+        elif a.type == A.LA_ANGANG_ADDGANG and a.tiles:
+            lo = (a.tiles[0] // 4) * 4
+            act = acls(ActionType.ANKAN if a.meld_type == MeldType.Ankan else ActionType.KAKAN, lo, [lo], None)
+        elif a.type == A.LA_HULE and a.hules and a.hules[0].zimo:
+            return a.hules[0].seat, acls(ActionType.TSUMO, None, [], None).encode()
+        elif a.type == A.LA_BABEI and np_ == 3:
+            act = acls(ActionType.KITA, None, [], None)
+        else:
+            return None
+        return a.seat, act.encode()
+
+    def labels(self):
+        """(seat, action_id): int16 arrays [K, T] (T = the longest log), -1 where log action t of kyoku k is not an own-turn
+        decision.  Row (k, seat) of `vec.encode(...)` taken at `position` t is the observation that decision was made on."""
+        import numpy as np
+
+        if getattr(self, "_labels", None) is None:
+            T = max(len(k._views) for k in self.kyokus)
+            seat = np.full((self.n, T), -1, np.int16)
+            aid = np.full((self.n, T), -1, np.int16)
+            np_ = self.kyokus[0]._k.np
+            for i, k in enumerate(self.kyokus):
+                for t, a in enumerate(k._views):
+                    lab = self.own_turn_label(a, np_)
+                    if lab is not None:
+                        seat[i, t], aid[i, t] = lab
+            self._labels = (seat, aid)
+        return self._labels
+
+    def labels_of_rows(self, index, n_rows):
+        """for the rows `vec.encode(..., index=index)` just wrote at the current position: the logged action id of each row's
+        (game, seat), or -1 when that seat's next logged action is not an own-turn decision (int64 tensor on `index`'s device)"""
+        import torch
+
+        seat, aid = self.labels()
+        t = self.position
+        if t >= seat.shape[1]:
+            return torch.full((n_rows,), -1, dtype=torch.int64, device=index.device)
+        if getattr(self, "_labels_dev", None) is None or self._labels_dev[0].device != index.device:
+            self._labels_dev = (torch.from_numpy(seat.astype("int64")).to(index.device), torch.from_numpy(aid.astype("int64")).to(index.device))
+        dseat, daid = self._labels_dev
+        idx = index[:n_rows].to(torch.int64)
+        g, s = idx // 4, idx % 4
+        return torch.where(dseat[g, t] == s, daid[g, t], torch.full_like(g, -1))
+
     def advance(self):
         """apply the next log action of every kyoku that has one; returns False when every kyoku is exhausted"""
         if self.vec.replay_advance() == 0:

@@ -719,6 +719,43 @@ def test_reference_validate_logs_script_passes(backend, tmp_path):
     _run_validate_logs(backend, tmp_path)
 
 
+# ------------------------------------------------------------------------------------------------ labels of the batched walk
+_OWN_TURN = ("DISCARD", "RIICHI", "ANKAN", "KAKAN", "TSUMO", "KITA")
+
+
+def _iterator_own_turn_samples(k):
+    """{(log action index, seat): action id} of the own-turn decisions Kyoku.steps yields (the first one per log action: a
+    riichi discard yields Riichi and then the discard)"""
+    out = {}
+    for pid, obs, act in k.steps(None, skip_single_action=False):
+        if act.action_type.name in _OWN_TURN:
+            out.setdefault((obs._env._n_applied, pid), (act.encode(), obs))
+    return out
+
+
+@pytest.mark.parametrize("source", ["real", "sim4", "sim3"])
+def test_batch_labels_are_the_iterators_own_turn_decisions(source):
+    """ReplayBatch.own_turn_label reads off the log, per action, what Kyoku.steps yields for the seat on turn: same positions,
+    same seats, same action ids — nothing missing, nothing extra"""
+    R = _shim("oracle")
+    text = open(REAL_LOG).read() if source == "real" else "\n".join(simulated_log(2 if source == "sim4" else 5, 33)) + "\n"
+    n = 0
+    ids = set()
+    for k in R.MjaiReplay.from_text(text).take_kyokus():
+        np_ = k._k.np
+        want = {key: v[0] for key, v in _iterator_own_turn_samples(k).items()}
+        got = {}
+        for t, a in enumerate(k._views):
+            lab = R.ReplayBatch.own_turn_label(a, np_)
+            if lab is not None:
+                got[(t, lab[0])] = lab[1]
+        assert got == want, (k.chang, k.ju, k.ben)
+        n += len(got)
+        ids |= set(got.values())
+    assert n > 200 and (37 in ids or 27 in ids) and (79 in ids or 56 in ids)          # riichi and tsumo seen
+    assert (59 in ids) == (source == "sim3")                                          # kita
+
+
 # ------------------------------------------------------------------------------------------------ the product (GPU)
 @pytest.mark.gpu
 def test_gpu_replay_batch_equals_oracle():
@@ -817,3 +854,44 @@ def test_gpu_replay_observations_carry_the_progression_cache():
 @pytest.mark.gpu
 def test_gpu_reference_validate_logs_script_passes(tmp_path):
     _run_validate_logs("gpu", tmp_path)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_rows_carry_their_labels():
+    """the batched extraction (ReplayBatch + rv_vec_encode + labels_of_rows): every own-turn decision of every kyoku gets a row
+    at its position, the logged action is legal in that row's mask, and tensors / masks equal what Kyoku.steps yields"""
+    import numpy as np
+    import torch
+    import riichienv_b200.replay as R
+
+    for mode, texts in ((2, [open(REAL_LOG).read(), "\n".join(simulated_log(2, 33)) + "\n"]), (5, ["\n".join(simulated_log(5, 33)) + "\n"])):
+        kyokus = [k for t in texts for k in R.MjaiReplay.from_text(t).take_kyokus()]
+        W, M = (27, 60) if mode == 5 else (34, 82)
+        batch = R.ReplayBatch(kyokus)
+        K = batch.n
+        obs = torch.empty((4 * K, 74, W), dtype=torch.float32, device="cuda")
+        mask = torch.empty((4 * K, M), dtype=torch.uint8, device="cuda")
+        idx = torch.empty((4 * K,), dtype=torch.int32, device="cuda")
+        seat, aid = batch.labels()
+        want_rows = int((aid >= 0).sum())
+        check_k = {0: _iterator_own_turn_samples(kyokus[0]), K - 1: _iterator_own_turn_samples(kyokus[K - 1])}
+        got_rows = compared = 0
+        while True:
+            n = batch.vec.encode(obs=obs, mask=mask, index=idx)
+            lab = batch.labels_of_rows(idx, n)
+            rows = torch.nonzero(lab >= 0).flatten()
+            got_rows += int(rows.numel())
+            if rows.numel():
+                assert bool((mask[rows, lab[rows]] == 1).all()), f"a logged action is not legal in its row's mask (position {batch.position})"
+                for r in rows.tolist():
+                    g, s = int(idx[r]) // 4, int(idx[r]) % 4
+                    assert seat[g, batch.position] == s
+                    if g in check_k:
+                        a_id, o = check_k[g][(batch.position, s)]
+                        assert a_id == int(lab[r])
+                        assert obs[r].cpu().numpy().tobytes() == o.encode() and mask[r].cpu().numpy().tobytes() == o.mask()
+                        compared += 1
+            if not batch.advance():
+                break
+        assert got_rows == want_rows > 500, (got_rows, want_rows)
+        assert compared > 50
