@@ -893,5 +893,5 @@ def test_gpu_batch_rows_carry_their_labels():
                         compared += 1
             if not batch.advance():
                 break
-        assert got_rows == want_rows > 500, (got_rows, want_rows)
+        assert got_rows == want_rows > 200, (got_rows, want_rows)
         assert compared > 50
