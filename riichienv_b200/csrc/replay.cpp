@@ -1097,7 +1097,7 @@ int rv_replay_paishan(const rv_replay* r, int round, char* out, int cap, int* n_
     return rv_internal_fail(RV_ERR_INVALID, "rv_replay_paishan: bad arguments");
   const Kyoku& k = r->rounds[round];
   *n_out = k.has_paishan ? (int)k.paishan.size() : -1;
-  if (k.has_paishan) memcpy(out, k.paishan.data(), std::min<size_t>(cap, k.paishan.size()));
+  if (k.has_paishan && cap > 0) memcpy(out, k.paishan.data(), std::min<size_t>(cap, k.paishan.size()));
   return RV_OK;
 }
 int rv_replay_win_contexts(const rv_replay* r, int round, rv_win_context* out, int cap, int* n_out) {

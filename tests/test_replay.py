@@ -168,6 +168,51 @@ def test_reader_survives_malformed_input():
     assert MjaiReplay.from_text(good).num_rounds() == 12   # and the reader is still sane afterwards
 
 
+def test_reader_fuzz_under_sanitizers(tmp_path):
+    """tests/fuzz/replay_fuzz.cpp: csrc/replay.cpp compiled with AddressSanitizer + UBSan, fed mutated paifu (with paishan, per-deal
+    dora lists and tile counts, fans) and mutated MJAI logs through every rv_replay_* entry point — no report, and the queries
+    of the win-context walk stay inside their arrays whatever the log says"""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    R = _shim("oracle")
+    names = [f"{n}{s}" for s in "mps" for n in range(1, 10)] + [f"{n}z" for n in range(1, 8)]
+    wall = "".join(names[(i * 5 + 3) % 34] for i in range(136))
+    rounds = []
+    for text in (open(REAL_LOG).read(), "\n".join(simulated_log(2, 40)) + "\n", "\n".join(simulated_log(5, 60)) + "\n"):
+        for i, (_, r) in enumerate(_paifu_rounds(R, text, False)):
+            if i % 2 == 0:
+                r[0]["data"]["paishan"] = wall
+            left = 70
+            for e in r:
+                if e["name"] == "DealTile":
+                    left -= 1
+                    if i % 3:
+                        e["data"]["left_tile_count"] = max(0, left)
+                    if i % 4 == 1:
+                        e["data"]["doras"] = r[0]["data"]["doras"]
+                if e["name"] == "Hule":
+                    for h in e["data"]["hules"]:
+                        h["fans"] = [{"id": 2, "val": 1}, {"id": 31, "val": 2}]
+            rounds.append(r)
+    paifu = tmp_path / "paifu.json"
+    paifu.write_text(json.dumps({"rounds": rounds}))
+    exe = tmp_path / "replay_fuzz"
+    root = os.path.dirname(HERE)
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-o", str(exe),
+                         os.path.join(HERE, "fuzz", "replay_fuzz.cpp"), os.path.join(root, "riichienv_b200", "csrc", "replay.cpp"), "-lz"],
+                        capture_output=True, text=True, cwd=os.path.join(HERE, "fuzz"))
+    if cc.returncode != 0 and "sanitize" in cc.stderr:
+        pytest.skip("sanitizer runtime not available: " + cc.stderr[-200:])
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    out = subprocess.run([str(exe), str(paifu), REAL_LOG, "400"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "runtime error" not in out.stderr and "AddressSanitizer" not in out.stderr, out.stderr[-3000:]
+    ok, bad, ctxs = (int(out.stdout.split()[i]) for i in (1, 3, 6))
+    assert ok > 100 and bad > 50 and ctxs > 1000, out.stdout
+
+
 # ------------------------------------------------------------------------------------------------ state tracking
 def _owed(s):
     return [p for p in range(4) if not s.is_done and ((s.phase == 0 and s.current_player == p) or (s.phase == 1 and (s.active_mask >> p) & 1))]
