@@ -46,6 +46,15 @@ extern "C" int rv_event_to_json(const uint32_t* w, uint32_t n_words, int viewer,
   if (!w || n_words == 0) return RV_ERR_INVALID;
   int type = w[0] & 0xFF, nw = (w[0] >> 8) & 0xFF, a = (w[0] >> 16) & 0xFF, b = (w[0] >> 24) & 0xFF;
   if (nw == 0 || (uint32_t)nw > n_words) return RV_ERR_INVALID;
+  // the record length every event type is written with (ev_push callers in game.cuh): a stream that disagrees is refused,
+  // not read past its end
+  switch (type) {
+    case RV_EV_START_KYOKU: if (nw != 19 && nw != 15) return RV_ERR_INVALID; break;
+    case RV_EV_PON: case RV_EV_CHI: case RV_EV_DAIMINKAN: case RV_EV_ANKAN: case RV_EV_KAKAN: if (nw < 2) return RV_ERR_INVALID; break;
+    case RV_EV_HORA: if (nw != 10 && nw != 9) return RV_ERR_INVALID; break;
+    case RV_EV_RYUKYOKU: if (nw != 5 && nw != 4) return RV_ERR_INVALID; break;
+    default: break;
+  }
   std::string s, tmp;
   auto cons = [&](uint32_t word, int from, int to) {
     std::string r = "[";

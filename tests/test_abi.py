@@ -114,6 +114,34 @@ def test_host_only_entry_points():
     assert events_to_json(sk, viewer=2)[0].split('"tehais":')[1] == masked + ',"type":"start_kyoku"}'
 
 
+def test_event_renderer_refuses_records_of_the_wrong_length():
+    """rv_event_to_json reads 1..19 words depending on the event type: a record whose length byte disagrees with its type is
+    refused (RV_ERR_INVALID), never read past its end (the renderer was run under ASan + UBSan over 2x10^6 random records)"""
+    import random
+
+    from riichienv_b200._lib import lib
+
+    L = lib()
+    out = C.create_string_buffer(4096)
+    w0 = lambda t, n, x, y: t | (n << 8) | (x << 16) | (y << 24)
+    for ty, good in ((A.EV_START_KYOKU, (19, 15)), (A.EV_HORA, (10, 9)), (A.EV_RYUKYOKU, (5, 4)), (A.EV_PON, (2,)), (A.EV_ANKAN, (2,))):
+        for nw in range(1, 20):
+            words = (C.c_uint32 * 19)(*([w0(ty, nw, 1, 40)] + [0x04030201] * 18))
+            rc = L.rv_event_to_json(words, 19, -1, out, 4096)
+            if nw in good or (len(good) == 1 and nw >= good[0]):
+                assert rc == nw and out.value.startswith(b"{") and out.value.endswith(b"}")
+            else:
+                assert rc == -1, (ty, nw, rc)
+    assert L.rv_event_to_json((C.c_uint32 * 1)(w0(A.EV_HORA, 10, 0, 0)), 1, -1, out, 4096) == -1     # record longer than the buffer
+    rng = random.Random(1)
+    for _ in range(20000):
+        n = rng.randrange(1, 12)
+        words = (C.c_uint32 * n)(*[rng.getrandbits(32) for _ in range(n)])
+        words[0] = w0(rng.randrange(24), rng.randrange(14), rng.randrange(6), rng.randrange(256))
+        rc = L.rv_event_to_json(words, n, rng.randrange(-1, 5), out, 4096)
+        assert rc == -1 or 1 <= rc <= n
+
+
 def test_text_log_two_renderers():
     """The oracle writes its MJAI text at event time (oracle/json.hpp, following the reference's event builders); the product
     renders binary event words on the host (csrc/json.cpp).  Full hanchan, 4P and sanma, every viewer: the texts are equal."""
