@@ -336,6 +336,7 @@ class KyokuStepIterator:
         self._env._log_cache = {}
         self._env._token += 1
         self._actions = kyoku._views
+        self._drawn_seen = (-1, 255)
         self._tsumogiri = [0] * len(kyoku._views)   # per action: the discard was the tile just drawn (the progression cache's moqie)
         self._idx = 0
         self._pending_action = None
@@ -348,8 +349,9 @@ class KyokuStepIterator:
 
     # ---- state access -----------------------------------------------------------------------------
     def _apply(self, a: _ActionView):
-        if a.type == A.LA_DISCARD and self._np == 4:
-            self._tsumogiri[self._idx] = int(self._env._state().drawn_tile == a.tile)   # state/event_handler.rs:343-347
+        if a.type == A.LA_DISCARD and self._np == 4:                                   # state/event_handler.rs:343-347
+            seen = self._drawn_seen if self._drawn_seen[0] == self._idx else (self._idx, self._env._state().drawn_tile)
+            self._tsumogiri[self._idx] = int(seen[1] == a.tile)
         self._env._v.apply_log_actions((A.LogAction * 1)(a.raw))
         self._env._token += 1
 
@@ -366,6 +368,7 @@ class KyokuStepIterator:
     def _get_observation_for_replay(self, pid, action, what):  # state/mod.rs:265-328
         env = self._env
         orig = env._state()
+        self._drawn_seen = (self._idx, orig.drawn_tile)     # (the record just read: saves _apply a second download)
         if action.action_type in (ActionType.RON, ActionType.CHI, ActionType.PON, ActionType.DAIMINKAN):
             s = env._state()
             s.phase = int(Phase.WaitResponse)
