@@ -495,6 +495,21 @@ int rv_replay_from_text(const char* text, size_t len, uint32_t rule_bits, rv_rep
  * action of every round (NewRound) is kept as an RV_LA_NONE placeholder, as the reference keeps Action::Other.             */
 int rv_replay_from_mjsoul_json(const char* path, uint32_t rule_bits, rv_replay** out);
 int rv_replay_from_mjsoul_text(const char* text, size_t len, uint32_t rule_bits, rv_replay** out);
+/* Bulk loading for a data loader (riichienv-ml/.../datasets/mjai_logs.py:73-84 opens the files one by one): n_paths files —
+ * format 0 = MJAI JSON lines (rv_replay_from_jsonl), 1 = MjSoul paifu (rv_replay_from_mjsoul_json) — parsed by `threads` host
+ * threads (<= 0: one per core) into ONE replay whose rounds follow the order of `paths`.  A file that does not open or parse is
+ * skipped and counted in *n_failed, as the reference's datasets skip it.                                                   */
+int rv_replay_from_files(const char* const* paths, int n_paths, int format, uint32_t rule_bits, int threads, rv_replay** out,
+                         int* n_failed);
+/* rounds with np seats and their actions in total; rv_replay_flatten writes exactly these: kyokus[n_rounds], the action lists
+ * back to back in actions[n_actions], first[n_rounds + 1] offsets (the arguments of rv_vec_replay_load) and, if not NULL, the
+ * index of each in the replay (round_index[n_rounds]).                                                                     */
+int rv_replay_totals(const rv_replay* r, int np, int64_t* n_rounds, int64_t* n_actions);
+int rv_replay_flatten(const rv_replay* r, int np, rv_log_kyoku* kyokus, rv_log_action* actions, int64_t* first, int32_t* round_index);
+/* What the seat on turn decided, per log action: seat[i] / action_id[i] (Action::encode ids, action.rs:158-227; sanma ids for
+ * np = 3) when action i is a discard (a riichi discard: the Riichi id), an ankan / kakan, a tsumo win or a kita — the samples
+ * Kyoku.steps yields for the seat on turn — else -1 / -1 (draws, calls and ron are not own-turn decisions).                 */
+int rv_replay_own_turn_labels(const rv_log_action* actions, int64_t n, int np, int16_t* seat, int16_t* action_id);
 int rv_replay_free(rv_replay* r);
 int rv_replay_num_rounds(const rv_replay* r);                                  /* MjaiReplay::num_rounds */
 int rv_replay_kyoku(const rv_replay* r, int round, rv_log_kyoku* out);

@@ -93,6 +93,10 @@ def lib():
     L.rv_replay_actions.argtypes = [vp, C.c_int, P(A.LogAction), C.c_int, P(C.c_int)]
     L.rv_replay_paishan.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, P(C.c_int)]
     L.rv_replay_win_contexts.argtypes = [vp, C.c_int, P(A.WinContext), C.c_int, P(C.c_int)]
+    L.rv_replay_from_files.argtypes = [P(C.c_char_p), C.c_int, C.c_int, C.c_uint32, C.c_int, P(vp), P(C.c_int)]
+    L.rv_replay_totals.argtypes = [vp, C.c_int, P(C.c_int64), P(C.c_int64)]
+    L.rv_replay_flatten.argtypes = [vp, C.c_int, P(A.LogKyoku), P(A.LogAction), P(C.c_int64), P(C.c_int32)]
+    L.rv_replay_own_turn_labels.argtypes = [P(A.LogAction), C.c_int64, C.c_int, P(C.c_int16), P(C.c_int16)]
     L.rv_replay_progression.argtypes = [P(A.LogAction), P(C.c_uint8), C.c_int, P(C.c_uint16), C.c_int, P(C.c_int)]
     L.rv_replay_actions_aux.argtypes = [vp, C.c_int, P(A.LogActionAux), C.c_int, P(C.c_int)]
     if L.rv_replay_sizeof(0) != C.sizeof(A.WinContext) or L.rv_replay_sizeof(1) != C.sizeof(A.LogActionAux):

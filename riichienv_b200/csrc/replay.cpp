@@ -9,7 +9,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/riichienv_b200.h"
@@ -1063,6 +1065,89 @@ int rv_replay_from_mjsoul_json(const char* path, uint32_t rule_bits, rv_replay**
   gzclose(f);
   if (bad) return rv_internal_fail(RV_ERR_INVALID, std::string("Failed to decompress: ") + path);
   return parse_paifu(text.data(), text.size(), rule_bits, out);
+}
+// ---- bulk loading for a data loader: many files parsed by a pool of host threads into ONE replay, then flat arrays ----------
+int rv_replay_from_files(const char* const* paths, int n_paths, int format, uint32_t rule_bits, int threads, rv_replay** out,
+                         int* n_failed) {
+  if (!paths || n_paths < 0 || !out || (format != 0 && format != 1))
+    return rv_internal_fail(RV_ERR_INVALID, "rv_replay_from_files: bad arguments");
+  std::vector<rv_replay*> parts((size_t)n_paths, nullptr);
+  std::atomic<int> next{0}, failed{0};
+  auto work = [&]() {
+    for (int i; (i = next.fetch_add(1)) < n_paths;) {
+      rv_replay* r = nullptr;
+      const int rc = !paths[i] ? RV_ERR_INVALID
+                   : format == 0 ? rv_replay_from_jsonl(paths[i], rule_bits, &r) : rv_replay_from_mjsoul_json(paths[i], rule_bits, &r);
+      if (rc == RV_OK) parts[(size_t)i] = r;
+      else failed.fetch_add(1);                            // a file that does not parse is skipped, as the reference's datasets do
+    }
+  };
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, std::max(1, n_paths)));
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  std::unique_ptr<rv_replay> all(new rv_replay);
+  for (rv_replay* r : parts) {
+    if (!r) continue;
+    for (auto& k : r->rounds) all->rounds.push_back(std::move(k));
+    delete r;
+  }
+  if (n_failed) *n_failed = failed.load();
+  *out = all.release();
+  return RV_OK;
+}
+int rv_replay_totals(const rv_replay* r, int np, int64_t* n_rounds, int64_t* n_actions) {
+  if (!r || (np != 3 && np != 4)) return rv_internal_fail(RV_ERR_INVALID, "rv_replay_totals: bad arguments");
+  int64_t nr = 0, na = 0;
+  for (auto& k : r->rounds)
+    if (k.k.np == np) nr++, na += (int64_t)k.actions.size();
+  if (n_rounds) *n_rounds = nr;
+  if (n_actions) *n_actions = na;
+  return RV_OK;
+}
+int rv_replay_flatten(const rv_replay* r, int np, rv_log_kyoku* kyokus, rv_log_action* actions, int64_t* first, int32_t* round_index) {
+  if (!r || (np != 3 && np != 4) || !kyokus || !actions || !first)
+    return rv_internal_fail(RV_ERR_INVALID, "rv_replay_flatten: bad arguments");
+  int64_t i = 0, a = 0;
+  first[0] = 0;
+  for (size_t k = 0; k < r->rounds.size(); k++) {
+    const Kyoku& ky = r->rounds[k];
+    if (ky.k.np != np) continue;
+    kyokus[i] = ky.k;
+    if (!ky.actions.empty()) memcpy(actions + a, ky.actions.data(), ky.actions.size() * sizeof(rv_log_action));
+    a += (int64_t)ky.actions.size();
+    if (round_index) round_index[i] = (int32_t)k;
+    first[++i] = a;
+  }
+  return RV_OK;
+}
+int rv_replay_own_turn_labels(const rv_log_action* actions, int64_t n, int np, int16_t* seat, int16_t* action_id) {
+  if (n < 0 || (n > 0 && (!actions || !seat || !action_id)) || (np != 3 && np != 4))
+    return rv_internal_fail(RV_ERR_INVALID, "rv_replay_own_turn_labels: bad arguments");
+  // Action::encode (action.rs:158-227): discard kind, 37 riichi, 42 + kind ankan / kakan, 79 tsumo; sanma (action_3p.rs) over
+  // the 27 kinds it has: kind 0 -> 0, kinds 8.. -> kind - 7; 27 riichi, 29 + compact kan, 56 tsumo, 59 kita
+  auto compact = [](int kind) { return kind == 0 ? 0 : kind >= 8 ? kind - 7 : -1; };
+  for (int64_t i = 0; i < n; i++) {
+    const rv_log_action& a = actions[i];
+    int s = a.seat, id = -1;
+    if (a.type == RV_LA_DISCARD) {
+      if (a.flags & 1) id = np == 3 ? 27 : 37;
+      else if (a.tile < 136) id = np == 3 ? compact(a.tile / 4) : a.tile / 4;
+    } else if (a.type == RV_LA_ANGANG_ADDGANG && a.n_tiles > 0 && a.tiles[0] < 136) {
+      const int c = np == 3 ? compact(a.tiles[0] / 4) : a.tiles[0] / 4;
+      id = c < 0 ? -1 : (np == 3 ? 29 : 42) + c;
+    } else if (a.type == RV_LA_HULE && a.n_hule > 0 && a.hules[0].zimo) {
+      s = a.hules[0].seat;
+      id = np == 3 ? 56 : 79;
+    } else if (a.type == RV_LA_BABEI && np == 3) {
+      id = 59;
+    }
+    seat[i] = (int16_t)(id >= 0 ? s : -1);
+    action_id[i] = (int16_t)id;
+  }
+  return RV_OK;
 }
 int rv_replay_free(rv_replay* r) {
   delete r;

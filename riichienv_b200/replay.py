@@ -727,6 +727,55 @@ class ReplayBatch:
         self.vec.replay_load((A.LogKyoku * self.n)(*[k._k for k in kyokus]), acts, first)
         self.position = 0
 
+    @classmethod
+    def from_files(cls, paths, rule=None, sanma=False, mjsoul=False, threads=0, device=0):
+        """The bulk form for a data loader: the files are parsed by a pool of host threads inside the library
+        (rv_replay_from_files), the rounds of the wanted variant flattened in C (rv_replay_flatten) and uploaded once — no Python
+        object per round or action.  Files that do not parse are skipped and counted in `self.n_failed`, as the reference's
+        datasets skip them (riichienv-ml/.../datasets/mjai_logs.py:80-84).  `self.round_index[i]` = position of kyoku i among all
+        rounds read (both variants), `self.kyokus` stays empty: labels come from rv_replay_own_turn_labels."""
+        import numpy as np
+
+        from .vec_env import VecRiichiEnv
+
+        g = GameRule.default_mjsoul() if (mjsoul and rule is None) else MjaiReplay._rule(rule)
+        paths = [str(p).encode() for p in paths]
+        arr = (C.c_char_p * max(1, len(paths)))(*paths)
+        h, failed = C.c_void_p(), C.c_int(0)
+        check(lib().rv_replay_from_files(arr, len(paths), 1 if mjsoul else 0, g.bits(), int(threads), C.byref(h), C.byref(failed)))
+        try:
+            np_ = 3 if sanma else 4
+            nr, na = C.c_int64(0), C.c_int64(0)
+            check(lib().rv_replay_totals(h, np_, C.byref(nr), C.byref(na)))
+            if nr.value == 0:
+                raise ValueError(f"no {'sanma' if sanma else '4-player'} kyoku in {len(paths)} files ({failed.value} unreadable)")
+            self = cls.__new__(cls)
+            self.kyokus, self.n, self.n_failed, self.position = [], nr.value, failed.value, 0
+            ky = (A.LogKyoku * nr.value)()
+            acts = (A.LogAction * max(1, na.value))()
+            first = (C.c_int64 * (nr.value + 1))()
+            self.round_index = np.zeros(nr.value, np.int32)
+            check(lib().rv_replay_flatten(h, np_, ky, acts, first, self.round_index.ctypes.data_as(C.POINTER(C.c_int32))))
+        finally:
+            lib().rv_replay_free(h)
+        self._first = np.frombuffer(first, np.int64).copy()
+        lens = np.diff(self._first)
+        T = int(lens.max()) if len(lens) else 0
+        seat_flat = np.zeros(max(1, na.value), np.int16)
+        id_flat = np.zeros(max(1, na.value), np.int16)
+        check(lib().rv_replay_own_turn_labels(acts, na.value, np_, seat_flat.ctypes.data_as(C.POINTER(C.c_int16)),
+                                              id_flat.ctypes.data_as(C.POINTER(C.c_int16))))
+        seat = np.full((self.n, T), -1, np.int16)
+        aid = np.full((self.n, T), -1, np.int16)
+        col = np.arange(T)[None, :]
+        inside = col < lens[:, None]
+        src = (self._first[:-1, None] + col)[inside]
+        seat[inside], aid[inside] = seat_flat[src], id_flat[src]
+        self._labels = (seat, aid)
+        self.vec = VecRiichiEnv(self.n, 3 if sanma else 0, g.bits(), seed_base=0, log_cap_words=0, device=device)
+        self.vec.replay_load(ky, acts, first)
+        return self
+
     # ---- labels: what the seat on turn decided, read off the log -------------------------------------------------------
     @staticmethod
     def own_turn_label(a: _ActionView, np_):

@@ -801,6 +801,65 @@ def test_batch_labels_are_the_iterators_own_turn_decisions(source):
     assert (59 in ids) == (source == "sim3")                                          # kita
 
 
+def _log_files(tmp_path):
+    """real game (plain), a 4P and a sanma simulated hanchan (gzip), one corrupt file, one missing path"""
+    paths = [tmp_path / "a_real.jsonl", tmp_path / "b_sim4.jsonl.gz", tmp_path / "c_bad.jsonl", tmp_path / "d_sim3.jsonl.gz",
+             tmp_path / "e_missing.jsonl", tmp_path / "f_sim4.jsonl"]
+    paths[0].write_text(open(REAL_LOG).read())
+    with gzip.open(paths[1], "wt") as f:
+        f.write("\n".join(simulated_log(2, 34)) + "\n")
+    paths[2].write_text('{"type":"start_game"}\n{"type":"start_kyoku","bakaze":"E"\n')
+    with gzip.open(paths[3], "wt") as f:
+        f.write("\n".join(simulated_log(5, 35)) + "\n")
+    paths[5].write_text("\n".join(simulated_log(2, 36)) + "\n")
+    return [str(p) for p in paths]
+
+
+def test_bulk_reader_equals_file_by_file(tmp_path):
+    """rv_replay_from_files (a pool of host threads) + rv_replay_flatten: the rounds of the readable files in the order of the
+    paths, byte for byte what reading each file alone gives, whatever the thread count; unreadable files are counted;
+    rv_replay_own_turn_labels equals the shim's own_turn_label on every action"""
+    import numpy as np
+
+    from riichienv_b200._lib import check
+
+    R = _shim("oracle")
+    L = _lib()
+    paths = _log_files(tmp_path)
+    single = {}
+    for np_ in (4, 3):
+        single[np_] = [(bytes(k), [bytes(a) for a in acts]) for p in paths if "bad" not in p and "missing" not in p
+                       for k, acts in parse_text(gzip.open(p, "rt").read() if p.endswith(".gz") else open(p).read()) if k.np == np_]
+    for threads in (1, 4, 0):
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        h, failed = C.c_void_p(), C.c_int(0)
+        check(L.rv_replay_from_files(arr, len(paths), 0, A.RULE_DEFAULT_TENHOU, threads, C.byref(h), C.byref(failed)))
+        assert failed.value == 2
+        assert L.rv_replay_num_rounds(h) == len(single[4]) + len(single[3])
+        for np_ in (4, 3):
+            nr, na = C.c_int64(0), C.c_int64(0)
+            check(L.rv_replay_totals(h, np_, C.byref(nr), C.byref(na)))
+            assert nr.value == len(single[np_]) and na.value == sum(len(a) for _, a in single[np_])
+            ky, acts = (A.LogKyoku * nr.value)(), (A.LogAction * na.value)()
+            first, ridx = (C.c_int64 * (nr.value + 1))(), (C.c_int32 * nr.value)()
+            check(L.rv_replay_flatten(h, np_, ky, acts, first, ridx))
+            assert list(ridx) == sorted(ridx) and first[nr.value] == na.value
+            for i, (kb, ab) in enumerate(single[np_]):
+                assert bytes(ky[i]) == kb and [bytes(acts[j]) for j in range(first[i], first[i + 1])] == ab
+            seat, aid = np.zeros(na.value, np.int16), np.zeros(na.value, np.int16)
+            p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int16))
+            check(L.rv_replay_own_turn_labels(acts, na.value, np_, p16(seat), p16(aid)))
+            from riichienv_b200.replay import _ActionView
+            n_lab = 0
+            for j in range(na.value):
+                lab = R.ReplayBatch.own_turn_label(_ActionView(acts[j]), np_)
+                assert (int(seat[j]), int(aid[j])) == (lab if lab is not None else (-1, -1)), j
+                n_lab += lab is not None
+            assert n_lab > 200
+        L.rv_replay_free(h)
+    assert L.rv_replay_from_files(None, 0, 0, 0, 1, C.byref(h), None) == -1
+
+
 # ------------------------------------------------------------------------------------------------ the product (GPU)
 @pytest.mark.gpu
 def test_gpu_replay_batch_equals_oracle():
@@ -940,3 +999,44 @@ def test_gpu_batch_rows_carry_their_labels():
                 break
         assert got_rows == want_rows > 200, (got_rows, want_rows)
         assert compared > 50
+
+
+@pytest.mark.gpu
+def test_gpu_batch_from_files_equals_batch_of_kyokus(tmp_path):
+    """ReplayBatch.from_files (parsed, flattened and labelled in the library) against ReplayBatch(kyokus) built round by round in
+    the shim: same labels, same tensor rows / masks / row index at every position"""
+    import numpy as np
+    import torch
+    import riichienv_b200.replay as R
+
+    paths = _log_files(tmp_path)
+    for sanma in (False, True):
+        a = R.ReplayBatch.from_files(paths, sanma=sanma, threads=3)
+        assert a.n_failed == 2
+        kyokus = []
+        for p in paths:
+            try:
+                kyokus += [k for k in R.MjaiReplay.from_jsonl(p).take_kyokus() if (k._k.np == 3) == sanma]
+            except ValueError:
+                pass
+        b = R.ReplayBatch(kyokus)
+        assert a.n == b.n > 10
+        for x, y in zip(a.labels(), b.labels()):
+            assert np.array_equal(x, y)
+        W, M = (27, 60) if sanma else (34, 82)
+        bufs = [(torch.zeros((4 * a.n, 74, W), device="cuda"), torch.zeros((4 * a.n, M), dtype=torch.uint8, device="cuda"),
+                 torch.zeros((4 * a.n,), dtype=torch.int32, device="cuda")) for _ in range(2)]
+        rows = 0
+        while True:
+            na = a.vec.encode(obs=bufs[0][0], mask=bufs[0][1], index=bufs[0][2])
+            nb = b.vec.encode(obs=bufs[1][0], mask=bufs[1][1], index=bufs[1][2])
+            assert na == nb
+            for t0, t1 in zip(bufs[0], bufs[1]):
+                assert torch.equal(t0[:na], t1[:na])
+            assert torch.equal(a.labels_of_rows(bufs[0][2], na), b.labels_of_rows(bufs[1][2], nb))
+            rows += na
+            more_a, more_b = a.advance(), b.advance()
+            assert more_a == more_b
+            if not more_a:
+                break
+        assert rows > 1000
