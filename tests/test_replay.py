@@ -1020,7 +1020,7 @@ def test_gpu_batch_from_files_equals_batch_of_kyokus(tmp_path):
             except ValueError:
                 pass
         b = R.ReplayBatch(kyokus)
-        assert a.n == b.n > 10
+        assert a.n == b.n > 5
         for x, y in zip(a.labels(), b.labels()):
             assert np.array_equal(x, y)
         W, M = (27, 60) if sanma else (34, 82)
@@ -1039,4 +1039,4 @@ def test_gpu_batch_from_files_equals_batch_of_kyokus(tmp_path):
             assert more_a == more_b
             if not more_a:
                 break
-        assert rows > 1000
+        assert rows > 300
