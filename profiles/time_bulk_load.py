@@ -47,7 +47,13 @@ for threads in (1, 8, 0):
         L.rv_replay_free(h)
     parse[str(threads or os.cpu_count())] = {"s": best, "files_per_sec": len(files) / best, "kyoku_per_sec": rounds / best}
 
-R.ReplayBatch.from_files(paths[:1], threads=1)        # warm-up: CUDA context, device tables (once per process)
+warm = R.ReplayBatch.from_files(paths[:1], threads=1)  # warm-up: CUDA context, device tables, torch's lazily loaded kernels (once per process)
+_o, _m, _i = (torch.empty((4 * warm.n, 74, 34), device="cuda"), torch.empty((4 * warm.n, 82), dtype=torch.uint8, device="cuda"),
+              torch.empty((4 * warm.n,), dtype=torch.int32, device="cuda"))
+for _ in range(3):
+    _n = warm.vec.encode(obs=_o, mask=_m, index=_i)
+    _ = (warm.labels_of_rows(_i, _n) >= 0).sum()
+    warm.advance()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 batch = R.ReplayBatch.from_files(files, threads=0)
