@@ -752,7 +752,7 @@ class ReplayBatch:
             self = cls.__new__(cls)
             self.kyokus, self.n, self.n_failed, self.position = [], nr.value, failed.value, 0
             ky = (A.LogKyoku * nr.value)()
-            # (numpy.empty: the action array of a large batch is ~170 B x millions of actions — not worth zeroing first)
+            # (numpy.empty: the action array of a large batch is 136 B x millions of actions — not worth zeroing first)
             acts_mem = np.empty(max(1, na.value) * C.sizeof(A.LogAction), np.uint8)
             acts = (A.LogAction * max(1, na.value)).from_buffer(acts_mem)
             first = (C.c_int64 * (nr.value + 1))()
