@@ -728,12 +728,15 @@ class ReplayBatch:
         self.position = 0
 
     @classmethod
-    def from_files(cls, paths, rule=None, sanma=False, mjsoul=False, threads=0, device=0):
+    def from_files(cls, paths, rule=None, sanma=False, mjsoul=False, threads=0, device=0, staging=None):
         """The bulk form for a data loader: the files are parsed by a pool of host threads inside the library
         (rv_replay_from_files), the rounds of the wanted variant flattened in C (rv_replay_flatten) and uploaded once — no Python
         object per round or action.  Files that do not parse are skipped and counted in `self.n_failed`, as the reference's
         datasets skip them (riichienv-ml/.../datasets/mjai_logs.py:80-84).  `self.round_index[i]` = position of kyoku i among all
-        rounds read (both variants), `self.kyokus` stays empty: labels come from rv_replay_own_turn_labels."""
+        rounds read (both variants), `self.kyokus` stays empty: labels come from rv_replay_own_turn_labels.
+        `staging`: an optional uint8 torch tensor in PINNED host memory that a loader keeps across batches; the action records
+        are flattened into it and uploaded from there (the records of a large batch are ~1 GB: from pageable memory the upload
+        is the largest part of the load)."""
         import numpy as np
 
         from .vec_env import VecRiichiEnv
@@ -753,8 +756,12 @@ class ReplayBatch:
             self.kyokus, self.n, self.n_failed, self.position = [], nr.value, failed.value, 0
             ky = (A.LogKyoku * nr.value)()
             # (numpy.empty: the action array of a large batch is 136 B x millions of actions — not worth zeroing first)
-            acts_mem = np.empty(max(1, na.value) * C.sizeof(A.LogAction), np.uint8)
-            acts = (A.LogAction * max(1, na.value)).from_buffer(acts_mem)
+            need = max(1, na.value) * C.sizeof(A.LogAction)
+            if staging is not None and staging.numel() * staging.element_size() >= need:
+                acts = (A.LogAction * max(1, na.value)).from_address(staging.data_ptr())
+            else:
+                acts_mem = np.empty(need, np.uint8)
+                acts = (A.LogAction * max(1, na.value)).from_buffer(acts_mem)
             first = (C.c_int64 * (nr.value + 1))()
             self.round_index = np.zeros(nr.value, np.int32)
             check(lib().rv_replay_flatten(h, np_, ky, acts, first, self.round_index.ctypes.data_as(C.POINTER(C.c_int32))))
