@@ -89,6 +89,7 @@ struct JParser {
       p++;
       ws();
       if (p < end && *p == '}') return p++, true;
+      v.obj.reserve(8);
       while (true) {
         ws();
         std::string k;
@@ -110,6 +111,7 @@ struct JParser {
       p++;
       ws();
       if (p < end && *p == ']') return p++, true;
+      v.arr.reserve(16);
       while (true) {
         JVal c;
         if (!value(c, depth + 1)) return false;
@@ -127,6 +129,20 @@ struct JParser {
     if (end - p >= 4 && !strncmp(p, "true", 4)) return v.kind = JVal::Bool, v.b = true, p += 4, true;
     if (end - p >= 5 && !strncmp(p, "false", 5)) return v.kind = JVal::Bool, v.b = false, p += 5, true;
     if (end - p >= 4 && !strncmp(p, "null", 4)) return v.kind = JVal::Null, p += 4, true;
+    {                                                     // plain integers (nearly every number of a log) without strtod
+      const char* q = p;
+      const bool neg = q < end && *q == '-';
+      if (neg) q++;
+      const char* d0 = q;
+      double acc = 0;
+      while (q < end && *q >= '0' && *q <= '9' && q - d0 < 15) acc = acc * 10 + (*q++ - '0');
+      if (q > d0 && (q >= end || (*q != '.' && *q != 'e' && *q != 'E' && !(*q >= '0' && *q <= '9') && *q != 'x' && *q != 'X'))) {
+        v.kind = JVal::Num;
+        v.num = neg ? -acc : acc;
+        p = q;
+        return true;
+      }
+    }
     char* e = nullptr;
     std::string tmp(p, (size_t)std::min<ptrdiff_t>(end - p, 40));
     double d = strtod(tmp.c_str(), &e);
@@ -437,6 +453,7 @@ int parse_lines(const char* text, size_t len, uint32_t rule_bits, rv_replay** ou
     if (type == "start_kyoku") {
       if (b) finish_builder(b, r.get());
       b.reset(new Builder);
+      b->out.actions.reserve(192);
       rv_log_kyoku& k = b->out.k;
       memset(&k, 0, sizeof k);
       const JVal& scores = *e.get("scores");
