@@ -271,6 +271,97 @@ bool finish_builder(std::unique_ptr<Builder>& b, rv_replay* r) {
   b.reset();
   return true;
 }
+// the two events that make up most of a log (mjai_replay.rs:392-433), shared by the DOM path and the flat-line scanner
+void on_tsumo(Builder& b, int s, uint8_t tile) {
+  rv_log_action a = blank(RV_LA_DEAL, s);
+  a.tile = tile;
+  b.out.actions.push_back(a);
+  if (b.out.k.left_tile_count > 0) b.out.k.left_tile_count--;
+}
+void on_dahai(Builder& b, int s, uint8_t tile) {
+  rv_log_action a = blank(RV_LA_DISCARD, s);
+  a.tile = tile;
+  const bool is_liqi = b.liqi[s];
+  const bool is_wliqi = is_liqi && b.first_discard[s] && !b.has_calls;
+  if (is_wliqi) b.wliqi[s] = true;
+  a.flags = (uint8_t)((is_liqi ? 1 : 0) | (is_wliqi ? 2 : 0));
+  b.out.actions.push_back(a);
+  b.first_discard[s] = false;
+  if (is_liqi) b.liqi[s] = false;
+}
+// A line that is a flat object of short plain strings, small non-negative integers and booleans — `tsumo` and `dahai`, most of
+// a log — read without building the DOM.  Returns false for anything else (escapes, nesting, negative or long numbers, floats,
+// a missing or mistyped field, another event type): the caller then takes the DOM path, which also words the errors.
+bool flat_tsumo_dahai(const char* p, const char* z, Builder& b) {
+  struct V { const char* k; int kl; int kind; const char* s; int sl; long num; } v[8];   // kind: 0 string, 1 integer, 2 bool
+  int n = 0;
+  auto ws = [&]() { while (p < z && (*p == ' ' || *p == '\t' || *p == '\r')) p++; };
+  ws();
+  if (p >= z || *p++ != '{') return false;
+  while (true) {
+    ws();
+    if (p >= z || *p++ != '"' || n == 8) return false;
+    V& x = v[n];
+    x.k = p;
+    while (p < z && *p != '"' && *p != '\\') p++;
+    if (p >= z || *p != '"') return false;
+    x.kl = (int)(p++ - x.k);
+    ws();
+    if (p >= z || *p++ != ':') return false;
+    ws();
+    if (p >= z) return false;
+    if (*p == '"') {
+      x.kind = 0;
+      x.s = ++p;
+      while (p < z && *p != '"' && *p != '\\') p++;
+      if (p >= z || *p != '"') return false;
+      x.sl = (int)(p++ - x.s);
+    } else if (*p >= '0' && *p <= '9') {
+      x.kind = 1;
+      x.num = 0;
+      const char* d0 = p;
+      while (p < z && *p >= '0' && *p <= '9' && p - d0 < 9) x.num = x.num * 10 + (*p++ - '0');
+      if (p < z && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == 'x' || *p == 'X')) return false;
+    } else if (z - p >= 4 && !strncmp(p, "true", 4)) {
+      x.kind = 2, x.num = 1, p += 4;
+    } else if (z - p >= 5 && !strncmp(p, "false", 5)) {
+      x.kind = 2, x.num = 0, p += 5;
+    } else {
+      return false;
+    }
+    n++;
+    ws();
+    if (p < z && *p == ',') { p++; continue; }
+    if (p < z && *p == '}') { p++; break; }
+    return false;
+  }
+  ws();
+  if (p != z) return false;
+  auto get = [&](const char* key) -> const V* {
+    const int kl = (int)strlen(key);
+    for (int i = 0; i < n; i++)
+      if (v[i].kl == kl && !memcmp(v[i].k, key, (size_t)kl)) return &v[i];
+    return nullptr;
+  };
+  const V* ty = get("type");
+  if (!ty || ty->kind != 0) return false;
+  const bool tsumo = ty->sl == 5 && !memcmp(ty->s, "tsumo", 5), dahai = ty->sl == 5 && !memcmp(ty->s, "dahai", 5);
+  if (!tsumo && !dahai) return false;
+  const V* actor = get("actor");
+  const V* pai = get("pai");
+  if (!actor || actor->kind != 1 || !pai || pai->kind != 0) return false;
+  if (dahai) {
+    const V* tg = get("tsumogiri");
+    if (!tg || tg->kind != 2) return false;
+  }
+  const int s = actor->num >= b.np ? 0 : (int)actor->num;
+  const int t = mjai_to_tid(std::string(pai->s, (size_t)pai->sl));
+  const uint8_t tile = (uint8_t)(t < 0 ? 0 : t);
+  b.flush_hule();
+  if (tsumo) on_tsumo(b, s, tile);
+  else on_dahai(b, s, tile);
+  return true;
+}
 // MjaiReplay::process_event (mjai_replay.rs:388-632)
 void process_event(Builder& b, const std::string& type, const JVal& e) {
   if (type != "hora") b.flush_hule();
@@ -278,21 +369,9 @@ void process_event(Builder& b, const std::string& type, const JVal& e) {
   auto seat = [&](const char* key) { int a = geti(e, key); return a < 0 || a >= np ? 0 : a; };
   rv_log_kyoku& k = b.out.k;
   if (type == "tsumo") {
-    rv_log_action a = blank(RV_LA_DEAL, seat("actor"));
-    a.tile = tile_of(e.get("pai"));
-    b.out.actions.push_back(a);
-    if (k.left_tile_count > 0) k.left_tile_count--;
+    on_tsumo(b, seat("actor"), tile_of(e.get("pai")));
   } else if (type == "dahai") {
-    const int s = seat("actor");
-    rv_log_action a = blank(RV_LA_DISCARD, s);
-    a.tile = tile_of(e.get("pai"));
-    const bool is_liqi = b.liqi[s];
-    const bool is_wliqi = is_liqi && b.first_discard[s] && !b.has_calls;
-    if (is_wliqi) b.wliqi[s] = true;
-    a.flags = (uint8_t)((is_liqi ? 1 : 0) | (is_wliqi ? 2 : 0));
-    b.out.actions.push_back(a);
-    b.first_discard[s] = false;
-    if (is_liqi) b.liqi[s] = false;
+    on_dahai(b, seat("actor"), tile_of(e.get("pai")));
   } else if (type == "reach") {
     const int s = seat("actor");
     b.liqi[s] = true;
@@ -408,6 +487,7 @@ int parse_lines(const char* text, size_t len, uint32_t rule_bits, rv_replay** ou
     while (z > a && (z[-1] == ' ' || z[-1] == '\t' || z[-1] == '\r')) z--;
     p = nl ? nl + 1 : end;
     if (a == z) continue;
+    if (b && flat_tsumo_dahai(a, z, *b)) continue;
     JParser jp{a, z, {}};
     JVal e;
     bool ok = jp.value(e);

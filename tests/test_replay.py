@@ -168,6 +168,35 @@ def test_reader_survives_malformed_input():
     assert MjaiReplay.from_text(good).num_rounds() == 12   # and the reader is still sane afterwards
 
 
+@pytest.mark.parametrize("source", ["real", "sim4", "sim3"])
+def test_reader_flat_line_scanner_equals_dom_path(source):
+    """tsumo / dahai lines are read by a scanner that builds no DOM; anything it does not recognise takes the DOM path.  The same
+    log with an (ignored) nested member in every line — which the scanner refuses — with members reordered and with spaces must
+    give byte-identical records"""
+    text = open(REAL_LOG).read() if source == "real" else "\n".join(simulated_log(2 if source == "sim4" else 5, 37)) + "\n"
+    want = [(bytes(k), [bytes(a) for a in acts]) for k, acts in parse_text(text)]
+    assert sum(len(a) for _, a in want) > 500
+    lines = [l for l in text.split("\n") if l.strip()]
+    nested = "\n".join('{"zz":[],' + l.strip()[1:] for l in lines) + "\n"
+    reordered = "\n".join(json.dumps(dict(reversed(list(json.loads(l).items()))), separators=(" , ", " : ")) for l in lines) + "\n"
+    for variant in (nested, reordered):
+        got = [(bytes(k), [bytes(a) for a in acts]) for k, acts in parse_text(variant)]
+        assert got == want
+    # what the scanner must hand over rather than guess: escapes, floats, negative / out-of-range seats, a missing member
+    head = "\n".join(lines[:2]) + "\n"
+    base = parse_text(head + '{"type":"tsumo","actor":1,"pai":"5m"}\n')
+    for line in ('{"type":"tsumo","actor":1.0,"pai":"5m"}', '{"type":"tsu\\u006do","actor":1,"pai":"5m"}', '{"type":"tsumo","actor":1,"pai":"5\\u006d"}'):
+        got = parse_text(head + line + "\n")
+        assert [bytes(a) for a in got[0][1]] == [bytes(a) for a in base[0][1]], line
+    seat0 = parse_text(head + '{"type":"tsumo","actor":0,"pai":"5m"}\n')
+    for line in ('{"type":"tsumo","actor":-1,"pai":"5m"}', '{"type":"tsumo","actor":7,"pai":"5m"}', '{"type":"tsumo","actor":12345678901,"pai":"5m"}'):
+        assert [bytes(a) for a in parse_text(head + line + "\n")[0][1]] == [bytes(a) for a in seat0[0][1]], line
+    for line, msg in (('{"type":"tsumo","actor":1}', "missing field `pai`"), ('{"type":"dahai","actor":1,"pai":"5m"}', "missing field `tsumogiri`"),
+                      ('{"type":"tsumo","actor":"1","pai":"5m"}', "invalid type"), ('{"type":"tsumo","actor":1,"pai":"5m"} x', "trailing characters")):
+        with pytest.raises(ValueError, match=msg):
+            parse_text(head + line + "\n")
+
+
 def test_reader_fuzz_under_sanitizers(tmp_path):
     """tests/fuzz/replay_fuzz.cpp: csrc/replay.cpp compiled with AddressSanitizer + UBSan, fed mutated paifu (with paishan, per-deal
     dora lists and tile counts, fans) and mutated MJAI logs through every rv_replay_* entry point — no report, and the queries
