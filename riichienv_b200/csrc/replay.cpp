@@ -1126,6 +1126,17 @@ struct WinWalk {
 };
 }  // namespace
 
+// run f(lo, hi) over [0, n) on a few host threads (the copies and the label pass of a large batch are memory-bound loops)
+template <class F>
+static void parallel_ranges(int64_t n, int64_t grain, F f) {
+  int nt = (int)std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 8u), (n + grain - 1) / std::max<int64_t>(grain, 1));
+  if (nt <= 1) return f((int64_t)0, n);
+  std::vector<std::thread> pool;
+  const int64_t step = (n + nt - 1) / nt;
+  for (int t = 1; t < nt; t++) pool.emplace_back(f, std::min(n, t * step), std::min(n, (t + 1) * step));
+  f((int64_t)0, std::min(n, step));
+  for (auto& t : pool) t.join();
+}
 extern "C" {
 int rv_replay_from_text(const char* text, size_t len, uint32_t rule_bits, rv_replay** out) {
   if (!text || !out) return rv_internal_fail(RV_ERR_INVALID, "text / out is null");
@@ -1207,17 +1218,24 @@ int rv_replay_totals(const rv_replay* r, int np, int64_t* n_rounds, int64_t* n_a
 int rv_replay_flatten(const rv_replay* r, int np, rv_log_kyoku* kyokus, rv_log_action* actions, int64_t* first, int32_t* round_index) {
   if (!r || (np != 3 && np != 4) || !kyokus || !actions || !first)
     return rv_internal_fail(RV_ERR_INVALID, "rv_replay_flatten: bad arguments");
-  int64_t i = 0, a = 0;
+  std::vector<const Kyoku*> sel;
+  int64_t a = 0;
   first[0] = 0;
   for (size_t k = 0; k < r->rounds.size(); k++) {
     const Kyoku& ky = r->rounds[k];
     if (ky.k.np != np) continue;
-    kyokus[i] = ky.k;
-    if (!ky.actions.empty()) memcpy(actions + a, ky.actions.data(), ky.actions.size() * sizeof(rv_log_action));
+    if (round_index) round_index[sel.size()] = (int32_t)k;
+    sel.push_back(&ky);
     a += (int64_t)ky.actions.size();
-    if (round_index) round_index[i] = (int32_t)k;
-    first[++i] = a;
+    first[sel.size()] = a;
   }
+  parallel_ranges((int64_t)sel.size(), 256, [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; i++) {
+      kyokus[i] = sel[(size_t)i]->k;
+      const auto& av = sel[(size_t)i]->actions;
+      if (!av.empty()) memcpy(actions + first[i], av.data(), av.size() * sizeof(rv_log_action));
+    }
+  });
   return RV_OK;
 }
 int rv_replay_own_turn_labels(const rv_log_action* actions, int64_t n, int np, int16_t* seat, int16_t* action_id) {
@@ -1226,7 +1244,8 @@ int rv_replay_own_turn_labels(const rv_log_action* actions, int64_t n, int np, i
   // Action::encode (action.rs:158-227): discard kind, 37 riichi, 42 + kind ankan / kakan, 79 tsumo; sanma (action_3p.rs) over
   // the 27 kinds it has: kind 0 -> 0, kinds 8.. -> kind - 7; 27 riichi, 29 + compact kan, 56 tsumo, 59 kita
   auto compact = [](int kind) { return kind == 0 ? 0 : kind >= 8 ? kind - 7 : -1; };
-  for (int64_t i = 0; i < n; i++) {
+  parallel_ranges(n, 1 << 16, [&](int64_t lo, int64_t hi) {
+  for (int64_t i = lo; i < hi; i++) {
     const rv_log_action& a = actions[i];
     int s = a.seat, id = -1;
     if (a.type == RV_LA_DISCARD) {
@@ -1244,6 +1263,7 @@ int rv_replay_own_turn_labels(const rv_log_action* actions, int64_t n, int np, i
     seat[i] = (int16_t)(id >= 0 ? s : -1);
     action_id[i] = (int16_t)id;
   }
+  });
   return RV_OK;
 }
 int rv_replay_free(rv_replay* r) {

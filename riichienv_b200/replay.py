@@ -768,19 +768,12 @@ class ReplayBatch:
         finally:
             lib().rv_replay_free(h)
         self._first = np.frombuffer(first, np.int64).copy()
-        lens = np.diff(self._first)
-        T = int(lens.max()) if len(lens) else 0
         seat_flat = np.zeros(max(1, na.value), np.int16)
         id_flat = np.zeros(max(1, na.value), np.int16)
         check(lib().rv_replay_own_turn_labels(acts, na.value, np_, seat_flat.ctypes.data_as(C.POINTER(C.c_int16)),
                                               id_flat.ctypes.data_as(C.POINTER(C.c_int16))))
-        seat = np.full((self.n, T), -1, np.int16)
-        aid = np.full((self.n, T), -1, np.int16)
-        col = np.arange(T)[None, :]
-        inside = col < lens[:, None]
-        src = (self._first[:-1, None] + col)[inside]
-        seat[inside], aid[inside] = seat_flat[src], id_flat[src]
-        self._labels = (seat, aid)
+        self._flat_labels = (seat_flat, id_flat)   # per action, in the order of the flattened logs; labels() makes them [K, T]
+        self._labels = None
         self.vec = VecRiichiEnv(self.n, 3 if sanma else 0, g.bits(), seed_base=0, log_cap_words=0, device=device)
         self.vec.replay_load(ky, acts, first)
         return self
@@ -811,6 +804,16 @@ class ReplayBatch:
         decision.  Row (k, seat) of `vec.encode(...)` taken at `position` t is the observation that decision was made on."""
         import numpy as np
 
+        if getattr(self, "_labels", None) is None and getattr(self, "_flat_labels", None) is not None:
+            lens = np.diff(self._first)
+            T = int(lens.max()) if len(lens) else 0
+            seat = np.full((self.n, T), -1, np.int16)
+            aid = np.full((self.n, T), -1, np.int16)
+            col = np.arange(T)[None, :]
+            inside = col < lens[:, None]
+            src = (self._first[:-1, None] + col)[inside]
+            seat[inside], aid[inside] = self._flat_labels[0][src], self._flat_labels[1][src]
+            self._labels = (seat, aid)
         if getattr(self, "_labels", None) is None:
             T = max(len(k._views) for k in self.kyokus)
             seat = np.full((self.n, T), -1, np.int16)
@@ -829,8 +832,18 @@ class ReplayBatch:
         (game, seat), or -1 when that seat's next logged action is not an own-turn decision (int64 tensor on `index`'s device)"""
         import torch
 
-        seat, aid = self.labels()
         t = self.position
+        if getattr(self, "_flat_labels", None) is not None:          # from_files: gather from the per-action arrays, no [K, T] table
+            if getattr(self, "_flat_dev", None) is None or self._flat_dev[0].device != index.device:
+                self._flat_dev = tuple(torch.from_numpy(a).to(index.device) for a in (self._first, *self._flat_labels))
+            first, fseat, fid = self._flat_dev
+            idx = index[:n_rows].to(torch.int64)
+            g, s = idx // 4, idx % 4
+            pos = first[g] + t
+            ok = pos < first[g + 1]
+            pos = torch.where(ok, pos, torch.zeros_like(pos))
+            return torch.where(ok & (fseat[pos] == s), fid[pos].to(torch.int64), torch.full_like(g, -1))
+        seat, aid = self.labels()
         if t >= seat.shape[1]:
             return torch.full((n_rows,), -1, dtype=torch.int64, device=index.device)
         if getattr(self, "_labels_dev", None) is None or self._labels_dev[0].device != index.device:
