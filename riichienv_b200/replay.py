@@ -693,6 +693,25 @@ class MjSoulReplay:
     def take_kyokus(self):
         return KyokuIterator(self)
 
+    @staticmethod
+    def verify_files(paths, threads=0):
+        """`verify()` over many paifu files at once: parsed by the library's host thread pool (rv_replay_from_files), every win
+        of every readable file walked (rv_replay_win_contexts) and evaluated in ONE rv_hand_eval_batch.
+        -> (total_agari, total_mismatches, unreadable_files)"""
+        g = GameRule.default_mjsoul()
+        paths = [str(p).encode() for p in paths]
+        arr = (C.c_char_p * max(1, len(paths)))(*paths)
+        h, failed, n = C.c_void_p(), C.c_int(0), C.c_int(0)
+        check(lib().rv_replay_from_files(arr, len(paths), 1, g.bits(), int(threads), C.byref(h), C.byref(failed)))
+        try:
+            check(lib().rv_replay_win_contexts(h, -1, None, 0, C.byref(n)))
+            ctxs = (A.WinContext * max(1, n.value))()
+            check(lib().rv_replay_win_contexts(h, -1, ctxs, n.value, C.byref(n)))
+        finally:
+            lib().rv_replay_free(h)
+        total, bad = _verify_counts(_WinBatch([ctxs[i] for i in range(n.value)]))
+        return total, bad, failed.value
+
     def verify(self):  # mjsoul_replay.rs:357-430 -> (total_agari, total_mismatches); every win of the game in one batch
         for r in self.rounds:
             if r._win_error:

@@ -953,6 +953,33 @@ def _verify_and_collect(R, mode, seeds):
     return queries
 
 
+def test_verify_files_sums_over_games(tmp_path, capsys):
+    """MjSoulReplay.verify_files: several paifu files (one unreadable) through the bulk reader, one evaluation batch"""
+    R = _shim("oracle")
+    paths, want_total, want_bad = [], 0, 0
+    for i, seed in enumerate((40, 41, 42)):
+        rounds = [ev for _, ev in _paifu_rounds(R, "\n".join(simulated_log(2, seed)) + "\n", False)]
+        game = R.MjSoulReplay.from_dict({"header": {}, "data": rounds})
+        for j, k in enumerate(game.take_kyokus()):
+            for c in k.take_win_result_contexts():
+                r = c.actual
+                for h in rounds[j][-1]["data"]["hules"]:
+                    if h["seat"] == c.seat:
+                        h["fans"] = [{"id": y, "val": 1} for y in r.yaku]
+                        h["count"], h["fu"] = r.han, r.fu + (10 if (i + j) % 3 == 0 else 0)
+                want_total += 1
+                want_bad += ((i + j) % 3 == 0 and r.han < 13)
+        p = tmp_path / f"game{i}.json.gz"
+        with gzip.open(p, "wt") as f:
+            json.dump({"rounds": rounds}, f)
+        paths.append(str(p))
+    (tmp_path / "broken.json.gz").write_bytes(b"not gzip, not json")
+    paths.insert(1, str(tmp_path / "broken.json.gz"))
+    assert R.MjSoulReplay.verify_files(paths, threads=2) == (want_total, want_bad, 1)
+    assert want_total > 10 and 0 < want_bad < want_total
+    assert capsys.readouterr().out.count("Mismatch: seat=") == want_bad
+
+
 def test_verify_counts_exactly_the_altered_rounds(capsys):
     assert len(_verify_and_collect(_shim("oracle"), 2, range(40, 43))) > 10
     assert "Mismatch: seat=" in capsys.readouterr().out         # the reference prints every mismatch (mjsoul_replay.rs:423-432)
