@@ -10,6 +10,13 @@ def shard_range(batch_index: int, world: int, rank: int, games_per_rank: int):
     return lo, lo + games_per_rank
 
 
+def shard_paths(paths, world: int, rank: int):
+    """Replay ingestion over several GPUs: logs are independent, so rank r reads every world-th file starting at r
+    (`ReplayBatch.from_files(shard_paths(paths, world, rank))` per rank, no exchange on the data path — what the reference's
+    datasets do per DataLoader worker, riichienv-ml/.../datasets/mjai_logs.py:66-69)."""
+    return list(paths)[rank::world]
+
+
 @dataclass
 class RunStats:
     elapsed_ms: float = 0.0       # device time of this rank's timed region
