@@ -980,6 +980,41 @@ def test_verify_files_sums_over_games(tmp_path, capsys):
     assert capsys.readouterr().out.count("Mismatch: seat=") == want_bad
 
 
+def test_bulk_reader_reads_paifu_files_too(tmp_path):
+    """format 1 of rv_replay_from_files = rv_replay_from_mjsoul_json per file, rounds in path order"""
+    from riichienv_b200._lib import check
+
+    R = _shim("oracle")
+    L = _lib()
+    paths, want = [], []
+    for i, (mode, seed) in enumerate(((2, 44), (5, 64), (2, 45))):
+        rounds = [ev for _, ev in _paifu_rounds(R, "\n".join(simulated_log(mode, seed)) + "\n", mode >= 3)]
+        p = tmp_path / f"p{i}.json.gz"
+        with gzip.open(p, "wt") as f:
+            json.dump({"rounds": rounds}, f)
+        paths.append(str(p))
+        h = C.c_void_p()
+        check(L.rv_replay_from_mjsoul_json(str(p).encode(), A.RULE_DEFAULT_MJSOUL, C.byref(h)))
+        for r in range(L.rv_replay_num_rounds(h)):
+            k = A.LogKyoku()
+            check(L.rv_replay_kyoku(h, r, C.byref(k)))
+            want.append(bytes(k))
+        L.rv_replay_free(h)
+    arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    h, failed = C.c_void_p(), C.c_int(0)
+    check(L.rv_replay_from_files(arr, len(paths), 1, A.RULE_DEFAULT_MJSOUL, 3, C.byref(h), C.byref(failed)))
+    got = []
+    for r in range(L.rv_replay_num_rounds(h)):
+        k = A.LogKyoku()
+        check(L.rv_replay_kyoku(h, r, C.byref(k)))
+        got.append(bytes(k))
+    n = C.c_int(0)
+    check(L.rv_replay_win_contexts(h, -1, None, 0, C.byref(n)))
+    L.rv_replay_free(h)
+    assert failed.value == 0 and got == want and len(got) > 20 and n.value > 10
+    assert {bytes(k)[0] for k in map(bytes, got)} == {3, 4}                 # both variants, in the order of the paths
+
+
 def test_verify_counts_exactly_the_altered_rounds(capsys):
     assert len(_verify_and_collect(_shim("oracle"), 2, range(40, 43))) > 10
     assert "Mismatch: seat=" in capsys.readouterr().out         # the reference prints every mismatch (mjsoul_replay.rs:423-432)
