@@ -55,7 +55,7 @@ class LogKyoku:
     def __init__(self, k: A.LogKyoku, actions, rule: GameRule, aux=None):
         self._k = k
         self._actions = actions                  # ctypes array (A.LogAction * n)
-        self._views = [_ActionView(a, aux[i] if aux is not None else None) for i, a in enumerate(actions)]
+        self._aux, self._views_cache = aux, None   # the per-action views are built on first use (steps / events / labels need them)
         self.rule = rule
         n = k.np
         self.scores = [k.scores[p] for p in range(n)]
@@ -69,6 +69,13 @@ class LogKyoku:
         self.paishan = None                      # MJAI logs carry no wall; set by the paifu reader
         self._win_ctx, self._win_error = [], None  # rv_replay_win_contexts of this round (filled by _from_handle)
         self.game_end_scores = [k.game_end_scores[p] for p in range(n)] if k.has_game_end_scores else None
+
+    @property
+    def _views(self):
+        if self._views_cache is None:
+            aux = self._aux
+            self._views_cache = [_ActionView(a, aux[i] if aux is not None else None) for i, a in enumerate(self._actions)]
+        return self._views_cache
 
     # ---- features ----------------------------------------------------------------------------------
     def grp_features(self):  # replay/mod.rs:1502-1522
