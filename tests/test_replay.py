@@ -671,6 +671,61 @@ def test_win_context_kan_doras_follow_the_wall():
     assert marks(c) == [wall[131]] and [_tile_str(x) for x in c.ura_indicators] == [wall[130]]
 
 
+def _paifu_tid(t):
+    """TileConverter::parse_tile_136 (replay/mod.rs:2184-2222): "0m" the red five, a plain five copy 1, anything else copy 0"""
+    num, suit = int(t[0]), "mpsz".index(t[1])
+    kind = 9 * suit + (5 if num == 0 else num) - 1
+    return {4: 16, 13: 52, 22: 88}[kind] if num == 0 else 4 * kind + (1 if kind in (4, 13, 22) else 0)
+
+
+def _contexts_as_tuples(k):
+    out = []
+    for c in k.take_win_result_contexts():
+        q = c._c.query
+        out.append((c.seat, c.tiles, [(int(m.meld_type), m.tiles) for m in c.melds], c.agari_tile, c.dora_indicators, c.ura_indicators,
+                    int(q.cond), q.player_wind, q.round_wind, q.kita_count))
+    return out
+
+
+@pytest.mark.parametrize("mode,seeds", [(2, range(40, 48)), (5, range(60, 66))])
+def test_win_context_walk_equals_the_python_restatement(mode, seeds):
+    """rv_replay_win_contexts (C++, in the reader) against tests/oracle_win_walk.py (a plain restatement of
+    WinResultContextIterator::do_next): hands, melds, markers, condition bits, winds, kita — on games as the simulator played them,
+    as paifu with tile counts / a wall, and with a third of every log's draws and discards dropped (hands the walk cannot
+    reconcile: both must go wrong the same way)"""
+    import random
+
+    from tests.oracle_win_walk import walk
+
+    R = _shim("oracle")
+    names = [f"{n}{s}" for s in "mps" for n in range(1, 10)] + [f"{n}z" for n in range(1, 8)]
+    wall_names = [names[(i * 11 + 5) % 34] for i in range(136)]
+    rng = random.Random(9)
+    n_ctx = 0
+    for seed in seeds:
+        text = "\n".join(simulated_log(mode, seed)) + "\n"
+        game = R.MjaiReplay.from_text(text)                                   # MJAI reading: no tile counts, tile_raw_id 0
+        for k in game.take_kyokus():
+            assert _contexts_as_tuples(k) == walk(k)
+        rounds = [ev for _, ev in _paifu_rounds(R, text, mode >= 3)]
+        for variant in range(3):
+            rs = json.loads(json.dumps(rounds))
+            for i, r in enumerate(rs):
+                if variant >= 1 and i % 2 == 0:
+                    r[0]["data"]["paishan"] = "".join(wall_names)
+                if variant == 2:
+                    r[1:] = [e for e in r[1:] if e["name"] not in ("DealTile", "DiscardTile") or rng.random() > 0.33]
+            g = R.MjSoulReplay.from_dict({"header": {}, "data": rs})
+            for k in g.take_kyokus():
+                wall = [_paifu_tid(k.paishan[j:j + 2]) for j in range(0, len(k.paishan), 2)] if k.paishan else []
+                if k._win_error:
+                    continue
+                got = _contexts_as_tuples(k)
+                assert got == walk(k, wall), (seed, variant, k.chang, k.ju, k.ben)
+                n_ctx += len(got)
+    assert n_ctx > 50
+
+
 def test_win_contexts_refuse_logs_the_walk_cannot_follow():
     R = _shim("oracle")
     new_round = {"scores": [35000] * 3, "doras": ["1m"], "tiles0": ["1m"] * 13, "tiles1": ["2m"] * 13, "tiles2": ["3m"] * 13,
