@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE: a plain-Python restatement of WinResultContextIterator::do_next (riichienv-core/src/replay/mod.rs:1741-2093)
+"""TEST INFRASTRUCTURE (oracle): a plain-Python restatement of WinResultContextIterator::do_next (riichienv-core/src/replay/mod.rs:1741-2093)
 over the shim's action views — the checker for rv_replay_win_contexts (csrc/replay.cpp).  Returns, per Hule, the tuple
 (seat, tiles, melds, win tile, dora markers, ura markers, condition bits, player wind, round wind, kita count)."""
 from riichienv_b200 import _abi as A

@@ -689,13 +689,13 @@ def _contexts_as_tuples(k):
 
 @pytest.mark.parametrize("mode,seeds", [(2, range(40, 48)), (5, range(60, 66))])
 def test_win_context_walk_equals_the_python_restatement(mode, seeds):
-    """rv_replay_win_contexts (C++, in the reader) against tests/oracle_win_walk.py (a plain restatement of
+    """rv_replay_win_contexts (C++, in the reader) against oracle/win_walk.py (a plain restatement of
     WinResultContextIterator::do_next): hands, melds, markers, condition bits, winds, kita — on games as the simulator played them,
     as paifu with tile counts / a wall, and with a third of every log's draws and discards dropped (hands the walk cannot
     reconcile: both must go wrong the same way)"""
     import random
 
-    from tests.oracle_win_walk import walk
+    from oracle.win_walk import walk
 
     R = _shim("oracle")
     names = [f"{n}{s}" for s in "mps" for n in range(1, 10)] + [f"{n}z" for n in range(1, 8)]
