@@ -1,7 +1,11 @@
 """TEST INFRASTRUCTURE (oracle): a plain-Python restatement of WinResultContextIterator::do_next (riichienv-core/src/replay/mod.rs:1741-2093)
 over the shim's action views — the checker for rv_replay_win_contexts (csrc/replay.cpp).  Returns, per Hule, the tuple
 (seat, tiles, melds, win tile, dora markers, ura markers, condition bits, player wind, round wind, kita count)."""
-from riichienv_b200 import _abi as A
+
+
+class A:  # rv_log_action_type (include/riichienv_b200.h), restated so that the checker imports nothing of the product
+    LA_DISCARD, LA_DEAL, LA_CHI_PENG_GANG, LA_ANGANG_ADDGANG, LA_DORA, LA_HULE, LA_NOTILE, LA_BABEI, LA_LIUJU = range(1, 10)
+
 
 PON, DAIMINKAN, ANKAN, KAKAN = 1, 2, 3, 4
 
