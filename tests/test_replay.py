@@ -191,6 +191,30 @@ def test_reader_flat_line_scanner_equals_dom_path(source):
     seat0 = parse_text(head + '{"type":"tsumo","actor":0,"pai":"5m"}\n')
     for line in ('{"type":"tsumo","actor":-1,"pai":"5m"}', '{"type":"tsumo","actor":7,"pai":"5m"}', '{"type":"tsumo","actor":12345678901,"pai":"5m"}'):
         assert [bytes(a) for a in parse_text(head + line + "\n")[0][1]] == [bytes(a) for a in seat0[0][1]], line
+    # random draw / discard lines — member order, spacing, odd seats and tile names, extra members — read by the scanner and,
+    # with a nested member that the scanner refuses, by the DOM path: same records or the same refusal
+    import random
+    rng = random.Random(11)
+    for _ in range(600):
+        ty = rng.choice(["tsumo", "dahai"])
+        members = [("type", json.dumps(ty)), ("actor", rng.choice(["0", "1", "2", "3", "4", "9", "007", "123456789", "1234567890"])),
+                   ("pai", json.dumps(rng.choice(["5m", "5mr", "E", "C", "9s", "?", "", "0p", "5m5", "x", "１ｍ"])))]
+        if ty == "dahai" or rng.random() < 0.2:
+            members.append(("tsumogiri", rng.choice(["true", "false"])))
+        if rng.random() < 0.3:
+            members.append((rng.choice(["note", "ts", "flag"]), rng.choice(['"abc"', "17", "true", "false"])))
+        if rng.random() < 0.2:
+            members.pop(rng.randrange(1, len(members)))          # a member missing (possibly a required one)
+        rng.shuffle(members)
+        sp = lambda: rng.choice(["", "", " ", "  ", "\t"])
+        line = "{" + ",".join(f"{sp()}{json.dumps(k)}{sp()}:{sp()}{v}{sp()}" for k, v in members) + "}" + sp()
+        forced = '{"zz":{"a":[1]},' + line[1:]
+        def read(text):
+            try:
+                return [[bytes(x) for x in acts] for _, acts in parse_text(text)]
+            except ValueError as e:
+                return str(e)
+        assert read(head + line + "\n") == read(head + forced + "\n"), line
     for line, msg in (('{"type":"tsumo","actor":1}', "missing field `pai`"), ('{"type":"dahai","actor":1,"pai":"5m"}', "missing field `tsumogiri`"),
                       ('{"type":"tsumo","actor":"1","pai":"5m"}', "invalid type"), ('{"type":"tsumo","actor":1,"pai":"5m"} x', "trailing characters")):
         with pytest.raises(ValueError, match=msg):
