@@ -690,8 +690,13 @@ class MjSoulReplay:
                 if a.type != A.LA_NONE:
                     env._v.apply_log_actions((A.LogAction * 1)(a.raw))
             last.end_scores = env.scores()
+            for p, v in enumerate(last.end_scores):
+                last._k.end_scores[p] = v
             for r in self.rounds:
                 r.game_end_scores = list(last.end_scores)
+                r._k.has_game_end_scores = 1           # (the records carry them too: ReplayBatch.round_features reads records)
+                for p, v in enumerate(last.end_scores):
+                    r._k.game_end_scores[p] = v
         return self
 
     def num_rounds(self):
@@ -798,11 +803,44 @@ class ReplayBatch:
         id_flat = np.zeros(max(1, na.value), np.int16)
         check(lib().rv_replay_own_turn_labels(acts, na.value, np_, seat_flat.ctypes.data_as(C.POINTER(C.c_int16)),
                                               id_flat.ctypes.data_as(C.POINTER(C.c_int16))))
+        self._ky = ky
         self._flat_labels = (seat_flat, id_flat)   # per action, in the order of the flattened logs; labels() makes them [K, T]
         self._labels = None
         self.vec = VecRiichiEnv(self.n, 3 if sanma else 0, g.bits(), seed_base=0, log_cap_words=0, device=device)
         self.vec.replay_load(ky, acts, first)
         return self
+
+    # ---- per-kyoku features for all K rounds at once --------------------------------------------------------------------
+    @staticmethod
+    def round_features_of(ky, np_):
+        """`Kyoku.take_grp_features()` (replay/mod.rs:1524-1590) of every record of an rv_log_kyoku array as numpy arrays:
+        chang / ju / ben / liqibang [K], round_initial_scores / round_end_scores / round_delta_scores [K, np],
+        round_initial_ranks / round_end_ranks / round_delta_ranks / final_ranks [K, np] (rank 0 = top, the lower seat wins ties)."""
+        import numpy as np
+
+        a = np.ctypeslib.as_array(ky)
+        out = {k: a[k].astype(np.int32) for k in ("chang", "ju", "ben", "liqibang")}
+        init = a["scores"][:, :np_].astype(np.int64)
+        end = a["end_scores"][:, :np_].astype(np.int64)
+
+        def ranks(sc):  # descending by score, then by seat
+            order = np.argsort(-sc, axis=1, kind="stable")
+            r = np.empty_like(order)
+            np.put_along_axis(r, order, np.arange(sc.shape[1])[None, :].repeat(sc.shape[0], 0), axis=1)
+            return r.astype(np.int32)
+
+        ri, re = ranks(init), ranks(end)
+        game_end = a["game_end_scores"][:, :np_].astype(np.int64)
+        has_final = a["has_game_end_scores"].astype(bool)
+        out.update(round_initial_scores=init.astype(np.int32), round_end_scores=end.astype(np.int32),
+                   round_delta_scores=(end - init).astype(np.int32), round_initial_ranks=ri, round_end_ranks=re,
+                   round_delta_ranks=re - ri, final_ranks=np.where(has_final[:, None], ranks(game_end), re))
+        return out
+
+    def round_features(self):
+        if getattr(self, "_ky", None) is None:
+            self._ky = (A.LogKyoku * self.n)(*[k._k for k in self.kyokus])
+        return self.round_features_of(self._ky, self._ky[0].np)
 
     # ---- labels: what the seat on turn decided, read off the log -------------------------------------------------------
     @staticmethod

@@ -1059,6 +1059,31 @@ def test_verify_files_sums_over_games(tmp_path, capsys):
     assert capsys.readouterr().out.count("Mismatch: seat=") == want_bad
 
 
+def test_batched_round_features_equal_take_grp_features():
+    """ReplayBatch.round_features_of over an rv_log_kyoku array = Kyoku.take_grp_features() of every round (replay/mod.rs:1524-1590),
+    incl. rank ties (the lower seat first) and final_ranks of a paifu's game_end_scores"""
+    import numpy as np
+
+    R = _shim("oracle")
+    games = [R.MjaiReplay.from_text(open(REAL_LOG).read()), R.MjaiReplay.from_text("\n".join(simulated_log(5, 62)) + "\n")]
+    text = "\n".join(simulated_log(2, 46)) + "\n"
+    games.append(R.MjSoulReplay.from_dict({"header": {}, "data": [ev for _, ev in _paifu_rounds(R, text, False)]}))
+    for g in games:
+        ks = list(g.take_kyokus())
+        ks[0]._k.scores[1] = ks[0]._k.scores[0]        # a tie in the start scores
+        ks[0].scores[1] = ks[0].scores[0]
+        np_ = ks[0]._k.np
+        got = R.ReplayBatch.round_features_of((A.LogKyoku * len(ks))(*[k._k for k in ks]), np_)
+        for i, k in enumerate(ks):
+            want = k.take_grp_features()
+            for key in ("chang", "ju", "ben", "liqibang"):
+                assert int(got[key][i]) == want[key]
+            for key in ("round_initial_scores", "round_end_scores", "round_delta_scores", "round_initial_ranks", "round_end_ranks",
+                        "round_delta_ranks", "final_ranks"):
+                assert got[key][i].tolist() == list(want[key]), (key, i)
+        assert got["round_end_scores"].shape == (len(ks), np_)
+
+
 def test_bulk_reader_reads_paifu_files_too(tmp_path):
     """format 1 of rv_replay_from_files = rv_replay_from_mjsoul_json per file, rounds in path order"""
     from riichienv_b200._lib import check
