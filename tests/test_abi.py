@@ -52,6 +52,23 @@ def test_no_cpu_fallback_without_gpu():
         Context(0)
 
 
+def test_product_never_imports_the_checker():
+    """oracle/ and tests/hostsim are test infrastructure: nothing under riichienv_b200/ (nor its C sources) may reference them"""
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "riichienv_b200")
+    bad = []
+    for d, _, files in os.walk(root):
+        if "_build" in d or "__pycache__" in d:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(d, f), errors="replace").read()
+                if re.search(r"^\s*(import|from)\s+(oracle|tests)\b", text, re.M) or re.search(r'#include\s+"[^"]*(oracle|hostsim)/', text):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
+
+
 def test_host_only_entry_points():
     """rv_calculate_score / rv_wall_from_seed / rv_event_to_json are pure host helpers of the ABI."""
     from riichienv_b200._lib import events_to_json, lib
